@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py — Msamples/s of the resample -> effects -> mix pipeline (BASELINE.json metric).
+
+Workload (config.workload = "cfg3_pipeline"): per GPU 4096 mono 44.1 kHz f32 streams of `--seconds`
+seconds, each `UniformSourceIterator(1 ch, 48 kHz) -> low_pass(200) -> amplify(1.2)`, summed by
+`mixer(1, 48000)` — the benches/pipeline.rs shape of BASELINE.json configs[2], which is the
+configuration the metric is quoted on and fits one GPU.  A step = one drain of the MixerSource over the
+whole batch.  "samples" = sum over streams of post-resample, pre-mix samples.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA path
+  python bench.py --impl reference ...                          # the reference's CPU algorithm (oracle port,
+                                                                # all host threads; rodio is Rust and cannot be built here)
+Under torchrun (N>1) every rank renders its own 4096 streams (weak scaling), the partial mixes are
+all-reduced (NCCL) inside the timed region, time = max over ranks of the CUDA-event time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MIX_CH, MIX_RATE, IN_RATE = 1, 48000, 44100
+LOW_PASS_HZ, AMPLIFY = 200, 1.2
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=4096, help="streams per GPU")
+    ap.add_argument("--seconds", type=float, default=5.0, help="audio seconds per stream")
+    ap.add_argument("--flags", type=int, default=0, help="rb_batch_create flags (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampled DURING the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def make_sources(rb, n_streams: int, frames: int, pcm=None):
+    """cfg3 sources.  `pcm` (n_streams x frames float32) may be None: the bench fills HBM directly."""
+    srcs = []
+    dummy = np.zeros(frames, dtype=np.float32)
+    for s in range(n_streams):
+        x = dummy if pcm is None else pcm[s]
+        srcs.append(rb.UniformSourceIterator(rb.TestSource(x, 1, IN_RATE), MIX_CH, MIX_RATE)
+                    .low_pass(LOW_PASS_HZ).amplify(AMPLIFY))
+    return srcs
+
+
+def cpu_reference(n_streams: int, frames: int, threads: int, seed: int = 1234):
+    """The reference's CPU algorithm (oracle port, pull iterators, virtual call per source per sample),
+    streams sharded over `threads` host threads.  Returns (Msamples/s, seconds, samples)."""
+    import oracle
+    import rodio_b200 as rb
+    rng = np.random.default_rng(seed)
+    pcm = rng.uniform(-1, 1, (n_streams, frames)).astype(np.float32)
+    srcs = make_sources(rb, n_streams, frames, pcm)
+    streams = [oracle.Stream(s.pcm, s.base_channels, s.base_rate, s.effects, s.span_len) for s in srcs]
+    out_frames = rb.plan(srcs[0], MIX_CH, MIX_RATE)[0]
+    _, secs = oracle.mixer_mt(streams, MIX_CH, MIX_RATE, threads, out_frames + 16)
+    samples = n_streams * out_frames
+    return samples / secs / 1e6, secs, samples
+
+
+def host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def run_reference(args):
+    from rodio_b200 import dist as rbd
+    rank, _, world = rbd.env_rank()
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    threads = host_threads()
+    # bounded sample of the same workload: sized for ~1-2 s of wall time per step on a many-core host
+    n_streams = max(threads, min(args.streams, 16 * threads))
+    frames = IN_RATE  # 1 s of audio per stream
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_reference(min(n_streams, threads), 4410, threads)
+    vals, secs_all, samples = [], 0.0, 0
+    steps = max(1, min(args.steps, 5))
+    for _ in range(steps):
+        v, secs, samples = cpu_reference(n_streams, frames, threads)
+        vals.append(v)
+        secs_all += secs
+    value = statistics.median(vals)
+    sample = f"{n_streams} streams x 1 s (of {args.streams} x {args.seconds} s), {steps} timed drains, all host threads"
+    line = {
+        "impl": "reference", "metric": "Msamples/s resample->low_pass->amplify->mix", "value": value,
+        "unit": "Msamples/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1,
+        "ms_per_step": 1e3 * secs_all / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg3_pipeline", "streams_per_gpu": args.streams, "seconds": args.seconds,
+                   "in_rate": IN_RATE, "mixer": [MIX_CH, MIX_RATE], "low_pass_hz": LOW_PASS_HZ, "amplify": AMPLIFY,
+                   "note": "C++ restatement of rodio's CPU pull-iterator path (Rust toolchain unavailable)"},
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import rodio_b200 as rb
+    from rodio_b200 import build as rb_build
+    from rodio_b200 import dist as rbd
+
+    rank, local_rank, world = rbd.env_rank()
+    if not os.path.exists(rb.capi.LIB_PATH):
+        rb_build.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: rodio_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        rbd.init_process_group("nccl")
+    dev = torch.device("cuda", local_rank)
+    ctx = rb.Context(local_rank)
+    ext = torch.cuda.ExternalStream(ctx.cuda_stream, device=dev)
+
+    S = args.streams
+    frames = int(round(args.seconds * IN_RATE))
+    srcs = make_sources(rb, S, frames)
+    batch = rb.Batch(srcs, MIX_CH, MIX_RATE, flags=args.flags, ctx=ctx)
+    out_frames = batch.stream_out_len(0)
+    mix_len = batch.mix_len
+    samples_per_step = S * out_frames * world
+    algo_bytes = batch.algorithmic_bytes
+    launches = batch.launches_per_render
+
+    # ---- inputs resident in HBM before the timed region (seeded, distinct per rank) ----
+    p0, _ = batch.input_device_ptr(0)
+    pitch = (batch.input_device_ptr(1)[0] - p0) // 4 if S > 1 else frames
+    for i in range(S):
+        batch.input_device_ptr(i)          # marks every stream as provided
+    arena = torch.as_tensor(rbd.DeviceArray(p0, pitch * (S - 1) + frames), device=dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(0x5EED + rank)
+    with torch.cuda.stream(ext):
+        arena.uniform_(-1.0, 1.0, generator=gen)
+    mix = torch.as_tensor(rbd.DeviceArray(batch.mix_device_ptr, max(1, mix_len)), device=dev)
+
+    def step():
+        batch.render_mix_device()
+        if world > 1:
+            with torch.cuda.stream(ext):
+                dist.all_reduce(mix, op=dist.ReduceOp.SUM)
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    fence()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fence()
+    e0.record(ext)
+    for _ in range(args.steps):
+        step()
+    e1.record(ext)
+    fence()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    ms_total = rbd.max_over_ranks(ms_total, dev)
+    ms_step = ms_total / args.steps
+    value = samples_per_step / (ms_step * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel: timed alone (no collective), CUDA events on its stream ----
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    k0.record(ext)
+    for _ in range(args.steps):
+        batch.render_mix_device()
+    k1.record(ext)
+    torch.cuda.synchronize(dev)
+    ms_kernel = k0.elapsed_time(k1) / args.steps
+    peak, peak_src = peaks()
+    achieved = algo_bytes / (ms_kernel * 1e-3) / 1e9
+
+    # ---- end to end through the public API with HOST buffers (H2D + render + D2H every step) ----
+    e2e = None
+    if not args.no_e2e:
+        host_in = torch.empty(S * frames, dtype=torch.float32, pin_memory=True)
+        with torch.cuda.stream(ext):
+            tmp = torch.empty(S * frames, dtype=torch.float32, device=dev)
+            tmp.uniform_(-1.0, 1.0, generator=gen)
+            host_in.copy_(tmp, non_blocking=False)
+        del tmp
+        host_out = torch.empty(max(1, mix_len), dtype=torch.float32, pin_memory=True)
+
+        def e2e_step():
+            batch.upload_packed(host_in.data_ptr(), S * frames)
+            if world > 1:
+                batch.render_mix_device()
+                with torch.cuda.stream(ext):
+                    dist.all_reduce(mix, op=dist.ReduceOp.SUM)
+                    host_out.copy_(mix, non_blocking=True)
+                ctx.sync()
+            else:
+                batch.render_mix_into(host_out.data_ptr(), mix_len)
+
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            e2e_step()
+        fence()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(ext)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        f1.record(ext)
+        fence()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        e2e_ms = rbd.max_over_ranks(max(f0.elapsed_time(f1), wall_ms) / e2e_steps, dev)
+        e2e = {"value": samples_per_step / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s",
+               "h2d_bytes_per_step": S * frames * 4, "d2h_bytes_per_step": mix_len * 4, "ms_per_step": e2e_ms,
+               "steps": e2e_steps, "note": "pinned host PCM -> rb_batch_upload_packed -> render -> host mix, per step"}
+
+    # ---- CPU baseline beside it (rank 0, N=1): bounded sample of the same workload ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+        oracle.build()
+        threads = host_threads()
+        n_cpu = max(threads, min(S, 16 * threads))
+        v, secs, smp = cpu_reference(n_cpu, IN_RATE, threads)
+        cpu = {"value": v, "unit": "Msamples/s", "cores": threads, "kind": "port",
+               "sample": f"{n_cpu} streams x 1 s of the same chain, one drain ({secs:.2f} s wall), oracle port "
+                         f"(pull iterators) sharded over {threads} host threads"}
+
+    if rank == 0:
+        line = {
+            "metric": "Msamples/s resample->low_pass->amplify->mix", "value": value, "unit": "Msamples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg3_pipeline", "streams_per_gpu": S, "seconds": args.seconds, "in_rate": IN_RATE,
+                       "mixer": [MIX_CH, MIX_RATE], "low_pass_hz": LOW_PASS_HZ, "amplify": AMPLIFY,
+                       "biquad": "exact sequential f32 order (bit-exact with the reference)",
+                       "l2": f"inputs {S * frames * 4 / 1e9:.2f} GB per GPU, larger than the 126 MB L2 (no flush needed)",
+                       "flags": args.flags},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel_ms": ms_kernel,
+                         "algorithmic_bytes_per_step": algo_bytes,
+                         "note": "whole render (all launches of one step) timed with CUDA events on the launch stream"},
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": launches * args.steps,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    batch.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,223 @@
+/*
+ * rodio_b200.h — C ABI of the B200-native block DSP path that sits behind rodio's
+ * `Source` / `Mixer` / `Player` surface.
+ *
+ * rodio itself has no FFI; the boundary it exposes for this path is the Rust trait
+ * `Source: Iterator<Item = f32>` (reference src/source/mod.rs:179-218) plus the
+ * constructors listed per entry point below.  A Rust shim (`bindings/rust/`, shown in
+ * INTEGRATION.md) implements `Source` on top of these functions by pulling *blocks*;
+ * the per-sample pull model survives only inside that shim.
+ *
+ * Conventions
+ *   - plain C types, caller-owned host memory, no exceptions/panics across the ABI:
+ *     every function returns an rb_status (0 = RB_OK); where rodio would panic
+ *     (zero rate / zero channels / frequency 0 / clamp(min > max)) the call fails
+ *     with RB_ERR_INVALID_ARGUMENT instead.
+ *   - thread-compatible: one caller per rb_context / rb_batch at a time.
+ *   - all device work is enqueued on the context's CUDA stream; functions that hand
+ *     results to the host synchronise that stream before returning, `*_device`
+ *     variants do not (use rb_context_sync).
+ *   - there is NO CPU fallback: if no CUDA device is usable, rb_context_create fails
+ *     with RB_ERR_CUDA and nothing else can be called.
+ */
+#ifndef RODIO_B200_H
+#define RODIO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB_ABI_VERSION 1
+
+typedef int32_t rb_status;
+enum {
+    RB_OK = 0,
+    RB_ERR_INVALID_ARGUMENT = 1, /* NULL pointer, zero rate/channels, bad enum, clamp(min>max) ... */
+    RB_ERR_CUDA = 2,             /* CUDA runtime error; text via rb_last_error() */
+    RB_ERR_OUT_OF_MEMORY = 3,
+    RB_ERR_UNSUPPORTED = 4,      /* a combination the block path does not implement (documented) */
+    RB_ERR_UNALIGNED_FRAMES = 5, /* input length is not a whole number of frames */
+    RB_ERR_RATIO_OVERFLOW = 6,   /* reduced from*to >= 2^32: rodio's u32 index math would wrap
+                                    (reference src/conversions/sample_rate.rs:45-47,:157-158,:173) */
+    RB_ERR_NOT_SUPPORTED_SEEK = 7, /* mirrors SeekError::NotSupported (src/source/mod.rs:767-810) */
+    RB_ERR_BUFFER_TOO_SMALL = 8,
+    RB_ERR_STATE = 9             /* call order violated (e.g. render before upload) */
+};
+
+/* Sample formats accepted at the input edge (rows a3 / K8 of SURVEY.md §8).
+ * Conversion to f32 follows dasp_sample 0.11.0 `conv` (reference call site
+ * src/conversions/sample.rs:42-44; decoder side src/decoder/wav.rs:119-151). */
+typedef enum {
+    RB_FMT_F32 = 0,
+    RB_FMT_I16 = 1,
+    RB_FMT_U16 = 2,
+    RB_FMT_I8  = 3,
+    RB_FMT_U8  = 4,
+    RB_FMT_I32 = 5,
+    RB_FMT_I24_IN_I32 = 6 /* 24-bit signed value sign-extended in an int32 (dasp I24) */
+} rb_sample_format;
+
+/* Effect kinds.  Each replaces one rodio adapter; parameters have the same meaning as
+ * the rodio constructor named in the comment. */
+typedef enum {
+    RB_FX_AMPLIFY = 1,        /* Source::amplify(value)              src/source/mod.rs:307-314, amplify.rs:63-65
+                                 f32[0] = factor                                                              */
+    RB_FX_SPEED = 2,          /* Source::speed(ratio)                src/source/speed.rs:103-105,:130-133
+                                 f32[0] = factor (samples untouched; reported rate changes)                   */
+    RB_FX_LOW_PASS = 3,       /* Source::low_pass_with_q(freq, q)    src/source/blt.rs:11-32,:502-560
+                                 u32[0] = freq Hz, f32[0] = q (low_pass(freq) == q 0.5)                       */
+    RB_FX_HIGH_PASS = 4,      /* Source::high_pass_with_q(freq, q)   src/source/blt.rs:19-40,:523-541         */
+    RB_FX_REVERB = 5,         /* Source::reverb(duration, amplitude) src/source/mod.rs:628-634 (mix.rs:43-53, delay.rs:8-16,:68-75)
+                                 ns[0] = delay, f32[0] = amplitude                                            */
+    RB_FX_AGC = 6,            /* Source::automatic_gain_control(settings) src/source/mod.rs:415-446, agc.rs:183-236,:433-504
+                                 f32[0] = target_level, f32[1] = absolute_max_gain, f32[2] = floor (set_floor, agc.rs:386-388)
+                                 ns[0] = attack_time, ns[1] = release_time (clamped to 10 s like mod.rs:432-433) */
+    RB_FX_LIMIT = 7,          /* Source::limit(LimitSettings)        src/source/limit.rs:94-130,:854-988
+                                 f32[0] = threshold dB, f32[1] = knee_width dB, ns[0] = attack, ns[1] = release */
+    RB_FX_SPATIAL = 8,        /* Spatial::new(input, emitter, left_ear, right_ear) src/source/spatial.rs:31-69
+                                 f32[0..3) emitter, f32[3..6) left ear, f32[6..9) right ear                    */
+    RB_FX_CHANNEL_VOLUME = 9, /* ChannelVolume::new(input, volumes)  src/source/channel_volume.rs:30-38,:71-88
+                                 u32[0] = number of output channels (1..12), f32[0..n) = volumes               */
+    RB_FX_UNIFORM = 10,       /* UniformSourceIterator::new(input, channels, rate) src/source/uniform.rs:33-47
+                                 u32[0] = target channels, u32[1] = target sample rate                        */
+    RB_FX_DELAY = 11          /* Source::delay(duration)             src/source/delay.rs:19-29,:68-75
+                                 ns[0] = delay                                                                */
+} rb_effect_kind;
+
+typedef struct rb_effect {
+    uint32_t kind;     /* rb_effect_kind */
+    uint32_t u32[3];
+    float    f32[12];
+    uint64_t ns[2];    /* std::time::Duration as whole nanoseconds */
+} rb_effect;           /* 80 bytes, no padding */
+
+/* One input stream = one rodio source handed to Mixer::add (src/mixer.rs:58-66):
+ * an in-memory PCM buffer (SamplesBuffer, src/buffer.rs:40-60) followed by a chain
+ * of adapters, applied in array order (effects[0] wraps the buffer first). */
+typedef struct rb_stream_desc {
+    uint32_t sample_rate;   /* > 0 */
+    uint16_t channels;      /* > 0 */
+    uint16_t format;        /* rb_sample_format of the uploaded PCM */
+    uint64_t n_samples;     /* interleaved samples (frames * channels); must be frame aligned */
+    uint32_t span_len;      /* what the source's current_span_len() reports: 0 = None (span-less, e.g.
+                               benches/shared.rs:32-34); n_samples for a SamplesBuffer (src/buffer.rs:76-82).
+                               UniformSourceIterator re-bootstraps every min(span_len, 32768) samples
+                               (src/source/uniform.rs:56,:83-96). */
+    uint32_t n_effects;
+    const rb_effect* effects;
+    uint64_t mix_start;     /* mixer output sample index at which Mixer::add was called; rounded up to
+                               the next frame boundary like src/mixer.rs:175-183 */
+} rb_stream_desc;
+
+typedef struct rb_context rb_context;
+typedef struct rb_batch rb_batch;
+
+/* rb_batch_create flags */
+enum {
+    RB_MIX_EXACT_ORDER = 1u << 0,   /* mixer sum strictly sequential in insertion order (bit-exact with
+                                       src/mixer.rs:185-198 on one GPU); default = per-group ordered partial
+                                       sums combined in group order (deterministic, <= 1e-5 * peak)          */
+    RB_NO_FUSION = 1u << 1,         /* run one kernel per adapter (debug / cross-check path)                  */
+    RB_BIQUAD_TIME_PARALLEL = 1u << 2, /* chunked-scan biquad: not bit-exact, tolerance-checked; off by default */
+    RB_KEEP_STREAM_OUTPUTS = 1u << 3   /* also keep every stream's post-chain (pre-mix) samples in HBM so
+                                          rb_batch_read_stream can return them                                */
+};
+
+const char* rb_status_string(rb_status s);
+/* Thread-local text of the last failure (CUDA error string, offending field ...). */
+const char* rb_last_error(void);
+uint32_t rb_abi_version(void);
+
+/* One context per GPU: owns the CUDA stream, workspaces and device properties. */
+rb_status rb_context_create(int device_ordinal, rb_context** out);
+rb_status rb_context_destroy(rb_context* ctx);
+rb_status rb_context_sync(rb_context* ctx);
+/* The cudaStream_t (as void*) every launch of this context goes to; for callers that
+ * time with CUDA events or enqueue a collective behind a render. */
+rb_status rb_context_stream(rb_context* ctx, void** cuda_stream_out);
+rb_status rb_context_sm_count(rb_context* ctx, int* out);
+
+/* mixer(channels, sample_rate) + Mixer::add for every desc, in array order
+ * (src/mixer.rs:25-43,:58-66).  Validates like the reference constructors would
+ * panic/accept, computes every stream's output length in closed form and allocates
+ * HBM.  `descs[i].effects` are copied. */
+rb_status rb_batch_create(rb_context* ctx, uint16_t mixer_channels, uint32_t mixer_sample_rate,
+                          const rb_stream_desc* descs, size_t n_streams, uint32_t flags,
+                          rb_batch** out);
+rb_status rb_batch_destroy(rb_batch* b);
+
+/* Host -> HBM copy of one stream's PCM in the desc's format (the SamplesBuffer::new data). */
+rb_status rb_batch_upload(rb_batch* b, size_t stream, const void* pcm, uint64_t n_samples);
+/* Upload for many streams laid out back to back in one pinned/pageable host buffer
+ * (stream i at element offset sum(n_samples[0..i))). */
+rb_status rb_batch_upload_packed(rb_batch* b, const void* pcm, uint64_t total_samples);
+/* Device pointer + capacity (in samples of the desc's format) of a stream's input region,
+ * for callers that produce PCM on the GPU (bench: inputs resident in HBM). */
+rb_status rb_batch_input_device_ptr(rb_batch* b, size_t stream, void** dptr, uint64_t* capacity);
+
+/* Closed-form lengths (samples): the stream after its whole chain incl. the mixer's
+ * UniformSourceIterator, and the mixer output. */
+rb_status rb_batch_stream_out_len(rb_batch* b, size_t stream, uint64_t* n_samples);
+rb_status rb_batch_mix_len(rb_batch* b, uint64_t* n_samples);
+/* Number of kernels one rb_batch_render_mix_device enqueues (bench "gpu_launches"). */
+rb_status rb_batch_launches_per_render(rb_batch* b, uint32_t* n);
+/* Algorithmic bytes of one render: 4*sum(in_samples)(or format size) + 4*mix_len. */
+rb_status rb_batch_algorithmic_bytes(rb_batch* b, uint64_t* bytes);
+
+/* Pure host query (no device needed): the number of samples MixerSource would pull from this
+ * source, i.e. the length of UniformSourceIterator::new(chain, mixer_channels, mixer_rate), plus the
+ * channel count / sample rate the chain itself reports (Source::channels / Source::sample_rate).
+ * Runs exactly the validation rb_batch_create runs.  Any out pointer may be NULL. */
+rb_status rb_stream_plan(const rb_stream_desc* desc, uint16_t mixer_channels, uint32_t mixer_sample_rate,
+                         uint64_t* out_len_samples, uint16_t* chain_channels, uint32_t* chain_sample_rate,
+                         uint64_t* chain_len_samples);
+
+/* Drain the MixerSource (src/mixer.rs:120-136) for the whole batch.
+ *   _device: enqueue only; result stays in HBM (rb_batch_mix_device_ptr), no sync.
+ *   host   : enqueue, copy `min(mix_len, max_samples)` samples to out_host, sync. */
+rb_status rb_batch_render_mix_device(rb_batch* b);
+rb_status rb_batch_mix_device_ptr(rb_batch* b, float** dptr);
+rb_status rb_batch_render_mix(rb_batch* b, float* out_host, uint64_t max_samples, uint64_t* written);
+
+/* Per-stream post-chain samples (what MixerSource would pull from that source), for
+ * parity tests; needs RB_KEEP_STREAM_OUTPUTS. Valid after a render. */
+rb_status rb_batch_read_stream(rb_batch* b, size_t stream, float* out_host, uint64_t max_samples,
+                               uint64_t* written);
+
+/* Stand-alone conversions (rows a1..a3 of SURVEY.md §8) on host buffers: H2D, one kernel, D2H.
+ *   rb_convert_sample_rate   = SampleRateConverter::new(input, from, to, channels).collect()
+ *                              (src/conversions/sample_rate.rs:52-201)
+ *   rb_convert_channels      = ChannelCountConverter::new(input, from, to).collect()
+ *                              (src/conversions/channels.rs:28,:57-85)
+ *   rb_convert_samples       = SampleTypeConverter<_, O>::new(input).collect()
+ *                              (src/conversions/sample.rs:14,:42-44)
+ * `*_len` query helpers give the exact output length first. */
+rb_status rb_sample_rate_out_len(uint64_t n_in, uint32_t from, uint32_t to, uint16_t channels, uint64_t* n_out);
+rb_status rb_convert_sample_rate(rb_context* ctx, const float* in, uint64_t n_in, uint32_t from, uint32_t to,
+                                 uint16_t channels, float* out, uint64_t cap, uint64_t* n_out);
+rb_status rb_channels_out_len(uint64_t n_in, uint16_t from, uint16_t to, uint64_t* n_out);
+rb_status rb_convert_channels(rb_context* ctx, const float* in, uint64_t n_in, uint16_t from, uint16_t to,
+                              float* out, uint64_t cap, uint64_t* n_out);
+rb_status rb_convert_samples(rb_context* ctx, const void* in, rb_sample_format in_fmt, void* out,
+                             rb_sample_format out_fmt, uint64_t n);
+
+/* Host-side helpers that mirror rodio's pure functions bit for bit (used by the shim so
+ * reported metadata matches):
+ *   rb_speed_sample_rate  = Speed::sample_rate()            src/source/speed.rs:130-133
+ *   rb_delay_samples      = delay::remaining_samples()      src/source/delay.rs:8-16
+ *   rb_db_to_linear / rb_linear_to_db                       src/math.rs:52-56,:87-90
+ *   rb_spatial_volumes    = Spatial::set_positions()        src/source/spatial.rs:48-69 */
+uint32_t rb_speed_sample_rate(uint32_t input_rate, float factor);
+uint64_t rb_delay_samples(uint64_t delay_ns, uint32_t sample_rate, uint16_t channels);
+float rb_db_to_linear(float decibels);
+float rb_linear_to_db(float linear);
+void rb_spatial_volumes(const float emitter[3], const float left_ear[3], const float right_ear[3],
+                        float out_volumes[2]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RODIO_B200_H */

@@ -1,0 +1,843 @@
+// rb_api.cu — C ABI (include/rodio_b200.h), host-side planner and launch sequencing.
+//
+// The planner turns every rb_stream_desc (a SamplesBuffer + adapter chain handed to Mixer::add,
+// reference src/mixer.rs:58-66) into a list of nodes with closed-form lengths, validates what the
+// reference constructors would panic on, lays the streams out in HBM and records the launch list.
+// Product code: there is no CPU compute path here — everything that touches samples is a kernel.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "rb_internal.h"
+#include "rb_fused.h"
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static rb_status fail(rb_status s, const std::string& msg) {
+    g_last_error = msg;
+    return s;
+}
+#define RB_CUDA(expr)                                                                      \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            return fail(_e == cudaErrorMemoryAllocation ? RB_ERR_OUT_OF_MEMORY : RB_ERR_CUDA, \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+        }                                                                                  \
+    } while (0)
+
+extern "C" const char* rb_status_string(rb_status s) {
+    switch (s) {
+        case RB_OK: return "ok";
+        case RB_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case RB_ERR_CUDA: return "CUDA error";
+        case RB_ERR_OUT_OF_MEMORY: return "out of device memory";
+        case RB_ERR_UNSUPPORTED: return "unsupported by the block path";
+        case RB_ERR_UNALIGNED_FRAMES: return "input is not a whole number of frames";
+        case RB_ERR_RATIO_OVERFLOW: return "reduced sample-rate ratio overflows rodio's u32 index math";
+        case RB_ERR_NOT_SUPPORTED_SEEK: return "seek not supported";
+        case RB_ERR_BUFFER_TOO_SMALL: return "output buffer too small";
+        case RB_ERR_STATE: return "call order violated";
+        default: return "unknown status";
+    }
+}
+extern "C" const char* rb_last_error(void) { return g_last_error.c_str(); }
+extern "C" uint32_t rb_abi_version(void) { return RB_ABI_VERSION; }
+
+// ------------------------------------------------------------------------------------------------
+// host restatements of rodio's pure helper functions (glibc libm == what rustc's std lowers to)
+// ------------------------------------------------------------------------------------------------
+namespace hostmath {
+constexpr float PI_F = 3.14159265358979323846264338327950288f;
+constexpr float LOG2_10_F = 3.32192809488736234787031942948939018f;
+constexpr float LOG10_2_F = 0.301029995663981195213738894724493027f;
+
+static float duration_secs_f32(uint64_t ns) {  // Duration::as_secs_f32
+    uint64_t secs = ns / 1000000000ull;
+    uint32_t nanos = (uint32_t)(ns % 1000000000ull);
+    volatile float a = (float)secs;
+    volatile float b = (float)nanos / 1000000000.0f;
+    return a + b;
+}
+static float duration_to_coefficient(uint64_t ns, uint32_t rate) {  // src/math.rs:111-113
+    volatile float d = duration_secs_f32(ns) * (float)rate;
+    volatile float q = -1.0f / d;
+    return expf(q);
+}
+struct Blt {
+    float b0, b1, b2, a1, a2;
+};
+static Blt blt(bool high, uint32_t freq, float q, uint32_t fs) {  // src/source/blt.rs:502-544
+    volatile float w0 = ((2.0f * PI_F) * (float)freq) / (float)fs;
+    volatile float cw = cosf(w0);
+    volatile float alpha = sinf(w0) / (2.0f * q);
+    volatile float b0, b1, b2;
+    if (!high) {
+        b1 = 1.0f - cw;
+        b0 = b1 / 2.0f;
+        b2 = b0;
+    } else {
+        b0 = (1.0f + cw) / 2.0f;
+        b1 = -1.0f - cw;
+        b2 = b0;
+    }
+    volatile float a0 = 1.0f + alpha;
+    volatile float a1 = -2.0f * cw;
+    volatile float a2 = 1.0f - alpha;
+    return {b0 / a0, b1 / a0, b2 / a0, a1 / a0, a2 / a0};
+}
+static float dist_sq(const float a[3], const float b[3]) {  // src/source/spatial.rs:19-24
+    volatile float s = 0.0f;
+    for (int i = 0; i < 3; i++) {
+        volatile float d = a[i] - b[i];
+        volatile float dd = d * d;
+        s = s + dd;
+    }
+    return s;
+}
+static void spatial_volumes(const float e[3], const float l[3], const float r[3], float out[2]) {  // spatial.rs:48-69
+    volatile float lds = dist_sq(l, e), rds = dist_sq(r, e);
+    volatile float max_diff = sqrtf(dist_sq(l, r));
+    volatile float ld = sqrtf(lds), rd = sqrtf(rds);
+    volatile float t1 = (ld - rd) / max_diff;
+    volatile float t2 = (t1 + 1.0f) / 4.0f;
+    volatile float ldm = fminf(t2 + 0.5f, 1.0f);
+    volatile float u1 = (rd - ld) / max_diff;
+    volatile float u2 = (u1 + 1.0f) / 4.0f;
+    volatile float rdm = fminf(u2 + 0.5f, 1.0f);
+    volatile float ldist = fminf(1.0f / lds, 1.0f);
+    volatile float rdist = fminf(1.0f / rds, 1.0f);
+    out[0] = ldm * ldist;
+    out[1] = rdm * rdist;
+}
+static uint32_t f32_as_u32(float v) {  // Rust `as u32`
+    if (!(v == v) || v <= 0.0f) return 0;
+    if (v >= 4294967296.0f) return 0xFFFFFFFFu;
+    return (uint32_t)v;
+}
+}  // namespace hostmath
+
+extern "C" uint32_t rb_speed_sample_rate(uint32_t input_rate, float factor) {  // src/source/speed.rs:130-133
+    volatile float r = (float)input_rate * factor;
+    return hostmath::f32_as_u32(fmaxf(r, 1.0f));
+}
+extern "C" uint64_t rb_delay_samples(uint64_t ns, uint32_t rate, uint16_t ch) {  // src/source/delay.rs:8-16
+    unsigned __int128 s = (unsigned __int128)ns * ch * rate / 1000000000ull;
+    return (uint64_t)s;
+}
+extern "C" float rb_db_to_linear(float d) {
+    volatile float t = d * 0.05f;
+    volatile float u = t * hostmath::LOG2_10_F;
+    return powf(2.0f, u);
+}
+extern "C" float rb_linear_to_db(float l) {
+    volatile float t = log2f(l) * hostmath::LOG10_2_F;
+    return t * 20.0f;
+}
+extern "C" void rb_spatial_volumes(const float e[3], const float l[3], const float r[3], float out[2]) {
+    hostmath::spatial_volumes(e, l, r, out);
+}
+
+// Output frames of SampleRateConverter on L input frames with reduced ratio from:to
+// (closed form of src/conversions/sample_rate.rs:131-201; derivation in DESIGN.md).
+static uint64_t src_out_frames(uint64_t L, uint32_t from, uint32_t to) {
+    if (from == to) return L;
+    if (L == 0) return 0;
+    unsigned __int128 a = (unsigned __int128)(L - 1) * to;
+    unsigned __int128 nstar = (a + from - 1) / from;                 // first n with floor(n*from/to) >= L-1
+    bool raw = nstar * from < (unsigned __int128)L * to;             // ... and it is exactly L-1
+    return (uint64_t)nstar + (raw ? 1 : 0);
+}
+
+static size_t fmt_size(uint32_t fmt) {
+    switch (fmt) {
+        case RB_FMT_F32: case RB_FMT_I32: case RB_FMT_I24_IN_I32: return 4;
+        case RB_FMT_I16: case RB_FMT_U16: return 2;
+        default: return 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct rb_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+};
+
+extern "C" rb_status rb_context_create(int device, rb_context** out) {
+    if (!out) return fail(RB_ERR_INVALID_ARGUMENT, "out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(RB_ERR_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") +
+                                     cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(RB_ERR_INVALID_ARGUMENT, "device ordinal out of range");
+    RB_CUDA(cudaSetDevice(device));
+    auto ctx = std::make_unique<rb_context>();
+    ctx->device = device;
+    RB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    RB_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
+    *out = ctx.release();
+    return RB_OK;
+}
+extern "C" rb_status rb_context_destroy(rb_context* ctx) {
+    if (!ctx) return RB_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return RB_OK;
+}
+extern "C" rb_status rb_context_sync(rb_context* ctx) {
+    if (!ctx) return fail(RB_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    RB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RB_OK;
+}
+extern "C" rb_status rb_context_stream(rb_context* ctx, void** out) {
+    if (!ctx || !out) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = (void*)ctx->stream;
+    return RB_OK;
+}
+extern "C" rb_status rb_context_sm_count(rb_context* ctx, int* out) {
+    if (!ctx || !out) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = ctx->sm_count;
+    return RB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// planner
+// ------------------------------------------------------------------------------------------------
+struct PlanNode {
+    rb_node_dev d{};       // src/dst filled at layout time
+    uint32_t rate_out = 0;
+    uint32_t span_out = 0;
+};
+struct PlanStream {
+    rb_stream_desc desc{};
+    std::vector<rb_effect> fx;
+    std::vector<PlanNode> nodes;
+    uint64_t out_len = 0;      // samples reaching the mixer
+    uint64_t mix_start = 0;
+    uint64_t chain_len = 0;    // samples of the chain itself (before the mixer's UniformSourceIterator)
+    uint32_t chain_channels = 0, chain_rate = 0;
+    // layout
+    size_t in_off = 0;         // byte offset in the input arena
+    size_t buf_off = 0;        // float offset in each ping-pong arena
+    uint64_t buf_cap = 0;      // floats
+    const float* final_ptr = nullptr;
+};
+
+static rb_uniform_seg uniform_seg(uint64_t in_samples, uint32_t c_in, uint32_t c_out, uint32_t from, uint32_t to) {
+    rb_uniform_seg g{};
+    g.L = in_samples / c_in;
+    g.p = (uint32_t)(in_samples % c_in);
+    if (from == to) {
+        g.full_out_frames = g.L;
+        g.flat_total = in_samples;
+    } else if (g.p == 0) {
+        g.full_out_frames = src_out_frames(g.L, from, to);
+        g.flat_total = g.full_out_frames * c_in;
+    } else {
+        // channels < p own L+1 frames; the others own L and never get their raw last frame
+        uint64_t n_a = 0;
+        if (g.L >= 1) {
+            unsigned __int128 a = (unsigned __int128)(g.L - 1) * to;
+            n_a = (uint64_t)((a + from - 1) / from);
+        }
+        g.full_out_frames = n_a;
+        g.flat_total = n_a * c_in + (src_out_frames(g.L + 1, from, to) - n_a) * g.p;
+    }
+    // ChannelCountConverter over the flat sequence: whole groups of c_in, then a trailing group that
+    // stops at the first missing input sample.
+    uint64_t groups = g.flat_total / c_in, k = g.flat_total % c_in;
+    g.out_samples = groups * c_out + std::min<uint64_t>(k, c_out);
+    return g;
+}
+
+// `cv_last_frame_start` >= 0: the input is a ChannelVolume/Spatial over a SamplesBuffer whose last output
+// frame starts there.  ChannelVolume forwards the *buffer's* span report (channel_volume.rs:106-108), and an
+// exhausted SamplesBuffer reports Some(0) (buffer.rs:76-82): a re-bootstrap that lands inside the last
+// frame therefore gets an empty Take and the rest of that frame is never pulled.
+static rb_status plan_uniform(PlanNode& nd, uint64_t n_in, uint32_t c_in, uint32_t rate_in, uint32_t span_in,
+                              uint32_t c_out, uint32_t rate_out, int64_t cv_last_frame_start = -1) {
+    if (c_out == 0 || rate_out == 0) return fail(RB_ERR_INVALID_ARGUMENT, "uniform: zero channels or rate");
+    if (c_out > RB_MAX_CHANNELS) return fail(RB_ERR_UNSUPPORTED, "uniform: more than 12 channels");
+    uint32_t g = std::gcd(rate_in, rate_out);
+    uint32_t from = rate_in / g, to = rate_out / g;
+    if (from != to && (uint64_t)from * to >= (1ull << 32))
+        return fail(RB_ERR_RATIO_OVERFLOW, "reduced from*to >= 2^32 (sample_rate.rs:45-47)");
+    rb_uniform_params u{};
+    u.from = from, u.to = to;
+    uint64_t chunk = 0;
+    if (span_in != 0) {
+        chunk = std::min(span_in, RB_UNIFORM_SPAN_CAP);   // uniform.rs:56
+        if (chunk >= n_in) chunk = 0;                      // a single chunk
+    }
+    if (chunk && cv_last_frame_start >= 0) {
+        uint64_t B = ((uint64_t)cv_last_frame_start / chunk + 1) * chunk;   // first re-bootstrap inside the last frame
+        if (B < n_in) n_in = B;
+    }
+    if (chunk) {
+        u.chunk_samples = chunk;
+        u.n_full_chunks = n_in / chunk;
+        u.full = uniform_seg(chunk, c_in, c_out, from, to);
+        u.tail = uniform_seg(n_in % chunk, c_in, c_out, from, to);
+    } else {
+        u.tail = uniform_seg(n_in, c_in, c_out, from, to);
+    }
+    nd.d.kind = RB_N_UNIFORM;
+    nd.d.c_in = c_in, nd.d.c_out = c_out;
+    nd.d.n_in = n_in, nd.d.n_out = u.n_full_chunks * u.full.out_samples + u.tail.out_samples;
+    nd.d.p.uni = u;
+    nd.rate_out = rate_out;
+    nd.span_out = 0;   // UniformSourceIterator::current_span_len() == None (uniform.rs:108-110)
+    return RB_OK;
+}
+
+static rb_status plan_stream(PlanStream& ps, uint16_t mixer_ch, uint32_t mixer_rate) {
+    const rb_stream_desc& d = ps.desc;
+    if (d.sample_rate == 0 || d.channels == 0) return fail(RB_ERR_INVALID_ARGUMENT, "zero sample rate or channels");
+    if (d.channels > RB_MAX_CHANNELS) return fail(RB_ERR_UNSUPPORTED, "more than 12 channels");
+    if (d.format > RB_FMT_I24_IN_I32) return fail(RB_ERR_INVALID_ARGUMENT, "unknown sample format");
+    if (d.n_samples % d.channels != 0) return fail(RB_ERR_UNALIGNED_FRAMES, "n_samples % channels != 0");
+    uint64_t n = d.n_samples;
+    uint32_t c = d.channels, rate = d.sample_rate, span = d.span_len;
+    const bool buffer_spans = d.span_len != 0 && (uint64_t)d.span_len == d.n_samples;   // SamplesBuffer semantics
+    int64_t cv_last = -1;
+    if (d.format != RB_FMT_F32) {
+        PlanNode nd;
+        nd.d.kind = RB_N_CONVERT, nd.d.fmt = d.format, nd.d.c_in = nd.d.c_out = c, nd.d.n_in = nd.d.n_out = n;
+        nd.rate_out = rate, nd.span_out = span;
+        ps.nodes.push_back(nd);
+    }
+    for (const rb_effect& e : ps.fx) {
+        PlanNode nd;
+        nd.d.c_in = nd.d.c_out = c, nd.d.n_in = nd.d.n_out = n;
+        nd.rate_out = rate, nd.span_out = span;
+        switch (e.kind) {
+            case RB_FX_AMPLIFY:
+                nd.d.kind = RB_N_AMPLIFY, nd.d.p.amp.factor = e.f32[0];
+                break;
+            case RB_FX_SPEED:
+                rate = rb_speed_sample_rate(rate, e.f32[0]);
+                continue;   // metadata only
+            case RB_FX_LOW_PASS:
+            case RB_FX_HIGH_PASS: {
+                hostmath::Blt k = hostmath::blt(e.kind == RB_FX_HIGH_PASS, e.u32[0], e.f32[0], rate);
+                nd.d.kind = RB_N_BIQUAD;
+                nd.d.p.blt = {k.b0, k.b1, k.b2, k.a1, k.a2};
+                break;
+            }
+            case RB_FX_REVERB: {
+                uint64_t D = rb_delay_samples(e.ns[0], rate, (uint16_t)c);
+                nd.d.kind = RB_N_ECHO, nd.d.p.echo.delay = D, nd.d.p.echo.amplitude = e.f32[0];
+                nd.d.n_out = n + D;
+                cv_last = -1;
+                nd.span_out = 0;   // Mix::current_span_len of two UniformSourceIterators == None
+                break;
+            }
+            case RB_FX_DELAY: {
+                uint64_t D = rb_delay_samples(e.ns[0], rate, (uint16_t)c);
+                if (span != 0 && (span < n || cv_last >= 0))
+                    return fail(RB_ERR_UNSUPPORTED, "delay on a source with short spans");
+                nd.d.kind = RB_N_DELAY, nd.d.p.echo.delay = D, nd.d.p.echo.amplitude = 1.0f;
+                nd.d.n_out = n + D;
+                if (span) nd.span_out = (uint32_t)std::min<uint64_t>((uint64_t)span + D, 0xFFFFFFFFull);
+                break;
+            }
+            case RB_FX_AGC: {
+                float mg = e.f32[1];
+                if (!(mg >= 0.1f)) return fail(RB_ERR_INVALID_ARGUMENT, "agc: clamp(0.1, absolute_max_gain) would panic");
+                uint64_t ten = 10ull * 1000000000ull;   // src/source/mod.rs:432-433
+                nd.d.kind = RB_N_AGC;
+                nd.d.p.agc.target = e.f32[0], nd.d.p.agc.max_gain = mg, nd.d.p.agc.floor = e.f32[2];
+                nd.d.p.agc.attack = hostmath::duration_to_coefficient(std::min(e.ns[0], ten), rate);
+                nd.d.p.agc.release = hostmath::duration_to_coefficient(std::min(e.ns[1], ten), rate);
+                break;
+            }
+            case RB_FX_LIMIT: {
+                nd.d.kind = RB_N_LIMIT;
+                nd.d.p.lim.threshold = e.f32[0], nd.d.p.lim.knee = e.f32[1];
+                volatile float k8 = 8.0f * e.f32[1];
+                nd.d.p.lim.inv_knee_8 = 1.0f / k8;   // limit.rs:877
+                nd.d.p.lim.attack = hostmath::duration_to_coefficient(e.ns[0], rate);
+                nd.d.p.lim.release = hostmath::duration_to_coefficient(e.ns[1], rate);
+                break;
+            }
+            case RB_FX_SPATIAL:
+            case RB_FX_CHANNEL_VOLUME: {
+                nd.d.kind = RB_N_CHANVOL;
+                uint32_t co;
+                if (e.kind == RB_FX_SPATIAL) {
+                    co = 2;
+                    hostmath::spatial_volumes(e.f32, e.f32 + 3, e.f32 + 6, nd.d.p.cv.vol);
+                } else {
+                    co = e.u32[0];
+                    if (co == 0 || co > RB_MAX_CHANNELS) return fail(RB_ERR_INVALID_ARGUMENT, "channel_volume: 1..12 volumes");
+                    for (uint32_t j = 0; j < co; j++) nd.d.p.cv.vol[j] = e.f32[j];
+                }
+                if (n % c != 0)
+                    return fail(RB_ERR_UNALIGNED_FRAMES, "channel_volume/spatial on a stream that is not frame aligned "
+                                                         "(e.g. after an odd-length delay)");
+                nd.d.c_out = co;
+                nd.d.n_out = (n / c) * co;
+                cv_last = (buffer_spans && span != 0 && n >= c) ? (int64_t)((n / c - 1) * co) : -1;
+                break;
+            }
+            case RB_FX_UNIFORM: {
+                rb_status s = plan_uniform(nd, n, c, rate, span, e.u32[0], e.u32[1], cv_last);
+                if (s != RB_OK) return s;
+                cv_last = -1;
+                if (nd.d.p.uni.from == nd.d.p.uni.to && nd.d.c_in == nd.d.c_out && nd.d.n_out == n) {   // identity: no kernel
+                    rate = nd.rate_out, span = 0;
+                    continue;
+                }
+                break;
+            }
+            default: return fail(RB_ERR_INVALID_ARGUMENT, "unknown effect kind");
+        }
+        ps.nodes.push_back(nd);
+        n = nd.d.n_out, c = nd.d.c_out, rate = nd.rate_out, span = nd.span_out;
+    }
+    ps.chain_len = n, ps.chain_channels = c, ps.chain_rate = rate;
+    // Mixer::add wraps the source in UniformSourceIterator::new(source, mixer_ch, mixer_rate) (mixer.rs:62-63)
+    {
+        PlanNode nd;
+        rb_status s = plan_uniform(nd, n, c, rate, span, mixer_ch, mixer_rate, cv_last);
+        if (s != RB_OK) return s;
+        if (!(nd.d.p.uni.from == nd.d.p.uni.to && nd.d.c_in == nd.d.c_out) || nd.d.n_out != n) {
+            ps.nodes.push_back(nd);
+            n = nd.d.n_out;
+        }
+    }
+    ps.out_len = n;
+    // start_pending_sources: a source joins at the next frame boundary (mixer.rs:175-183)
+    ps.mix_start = (d.mix_start + mixer_ch - 1) / mixer_ch * mixer_ch;
+    return RB_OK;
+}
+
+extern "C" rb_status rb_stream_plan(const rb_stream_desc* desc, uint16_t mixer_ch, uint32_t mixer_rate,
+                                    uint64_t* out_len, uint16_t* chain_channels, uint32_t* chain_rate,
+                                    uint64_t* chain_len) {
+    if (!desc) return fail(RB_ERR_INVALID_ARGUMENT, "desc is NULL");
+    if (mixer_ch == 0 || mixer_rate == 0) return fail(RB_ERR_INVALID_ARGUMENT, "mixer: zero channels or rate");
+    if (mixer_ch > RB_MAX_CHANNELS) return fail(RB_ERR_UNSUPPORTED, "mixer: more than 12 channels");
+    if (desc->n_effects && !desc->effects) return fail(RB_ERR_INVALID_ARGUMENT, "effects is NULL");
+    PlanStream ps;
+    ps.desc = *desc;
+    ps.fx.assign(desc->effects, desc->effects + desc->n_effects);
+    rb_status s = plan_stream(ps, mixer_ch, mixer_rate);
+    if (s != RB_OK) return s;
+    if (out_len) *out_len = ps.out_len;
+    if (chain_channels) *chain_channels = (uint16_t)ps.chain_channels;
+    if (chain_rate) *chain_rate = ps.chain_rate;
+    if (chain_len) *chain_len = ps.chain_len;
+    return RB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batch
+// ------------------------------------------------------------------------------------------------
+struct LaunchGroup {
+    uint32_t kind;
+    uint32_t first, count;   // range in d_nodes
+    uint64_t max_n_out;
+    uint32_t max_channels;
+};
+struct rb_batch {
+    rb_context* ctx = nullptr;
+    uint16_t mixer_ch = 0;
+    uint32_t mixer_rate = 0;
+    uint32_t flags = 0;
+    std::vector<PlanStream> streams;
+    uint64_t mix_len = 0;
+    uint64_t algo_bytes = 0;
+    // device memory
+    uint8_t* d_in = nullptr;
+    size_t in_bytes = 0;
+    float* d_buf[2] = {nullptr, nullptr};
+    size_t buf_floats = 0;
+    rb_node_dev* d_nodes = nullptr;
+    rb_mix_src* d_mix = nullptr;
+    float* d_out = nullptr;
+    std::vector<LaunchGroup> groups;
+    rb_fused_plan* fused = nullptr;   // non-null when the fused path serves this batch
+    uint32_t launches = 0;
+    bool rendered = false;
+    std::vector<uint8_t> uploaded;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" rb_status rb_batch_destroy(rb_batch* b) {
+    if (!b) return RB_OK;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    if (b->fused) rb_fused_destroy(b->fused);
+    cudaFree(b->d_in);
+    cudaFree(b->d_buf[0]);
+    cudaFree(b->d_buf[1]);
+    cudaFree(b->d_nodes);
+    cudaFree(b->d_mix);
+    cudaFree(b->d_out);
+    delete b;
+    return RB_OK;
+}
+
+extern "C" rb_status rb_batch_create(rb_context* ctx, uint16_t mixer_ch, uint32_t mixer_rate,
+                                     const rb_stream_desc* descs, size_t n_streams, uint32_t flags, rb_batch** out) {
+    if (!ctx || !out || (!descs && n_streams)) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (mixer_ch == 0 || mixer_rate == 0) return fail(RB_ERR_INVALID_ARGUMENT, "mixer: zero channels or rate");
+    if (mixer_ch > RB_MAX_CHANNELS) return fail(RB_ERR_UNSUPPORTED, "mixer: more than 12 channels");
+    if (n_streams > 0x7FFFFFFFull) return fail(RB_ERR_UNSUPPORTED, "too many streams");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    std::unique_ptr<rb_batch, rb_status (*)(rb_batch*)> b(new (std::nothrow) rb_batch, rb_batch_destroy);
+    if (!b) return fail(RB_ERR_OUT_OF_MEMORY, "host allocation failed");
+    b->ctx = ctx, b->mixer_ch = mixer_ch, b->mixer_rate = mixer_rate, b->flags = flags;
+    b->streams.resize(n_streams);
+    b->uploaded.assign(n_streams, 0);
+    size_t in_bytes = 0, buf_floats = 0;
+    uint64_t mix_len = 0, algo = 0;
+    size_t max_nodes = 0;
+    for (size_t i = 0; i < n_streams; i++) {
+        PlanStream& ps = b->streams[i];
+        ps.desc = descs[i];
+        if (descs[i].n_effects && !descs[i].effects) return fail(RB_ERR_INVALID_ARGUMENT, "effects is NULL");
+        ps.fx.assign(descs[i].effects, descs[i].effects + descs[i].n_effects);
+        ps.desc.effects = nullptr;
+        rb_status s = plan_stream(ps, mixer_ch, mixer_rate);
+        if (s != RB_OK) {
+            g_last_error = "stream " + std::to_string(i) + ": " + g_last_error;
+            return s;
+        }
+        ps.in_off = in_bytes;
+        in_bytes += align_up((size_t)ps.desc.n_samples * fmt_size(ps.desc.format) + 16, 128);
+        uint64_t cap = 0;
+        for (auto& nd : ps.nodes) cap = std::max(cap, nd.d.n_out);
+        ps.buf_cap = align_up((size_t)cap + 4, 32);
+        ps.buf_off = buf_floats;
+        buf_floats += ps.buf_cap;
+        max_nodes = std::max(max_nodes, ps.nodes.size());
+        if (ps.out_len) mix_len = std::max(mix_len, ps.mix_start + ps.out_len);
+        algo += ps.desc.n_samples * fmt_size(ps.desc.format);
+    }
+    b->mix_len = mix_len;
+    b->algo_bytes = algo + mix_len * 4;
+    b->in_bytes = in_bytes;
+
+    RB_CUDA(cudaMalloc(&b->d_in, std::max<size_t>(in_bytes, 256)));
+    RB_CUDA(cudaMalloc(&b->d_out, std::max<size_t>(mix_len * 4, 256)));
+
+    // Fast path: one fused kernel family when the whole batch has a chain shape it understands.
+    if (!(flags & RB_NO_FUSION)) {
+        std::vector<rb_fused_stream> fs(n_streams);
+        bool ok = true;
+        for (size_t i = 0; i < n_streams && ok; i++) {
+            PlanStream& ps = b->streams[i];
+            fs[i].in = b->d_in + ps.in_off;
+            fs[i].fmt = ps.desc.format;
+            fs[i].n_nodes = (uint32_t)ps.nodes.size();
+            fs[i].nodes = ps.nodes.empty() ? nullptr : &ps.nodes[0].d;
+            fs[i].node_stride = sizeof(PlanNode);
+            fs[i].out_len = ps.out_len;
+            fs[i].mix_start = ps.mix_start;
+            fs[i].n_in = ps.desc.n_samples;
+            fs[i].c_in = ps.desc.channels;
+        }
+        if (ok) {
+            rb_fused_plan* fp = nullptr;
+            cudaError_t e = rb_fused_try_create(fs.data(), n_streams, mixer_ch, b->d_out, mix_len, flags,
+                                                ctx->sm_count, ctx->stream, &fp);
+            if (e != cudaSuccess) return fail(RB_ERR_CUDA, std::string("fused plan: ") + cudaGetErrorString(e));
+            b->fused = fp;   // may be null: shape not covered -> general path
+        }
+    }
+
+    if (!b->fused || (flags & RB_KEEP_STREAM_OUTPUTS)) {
+        // general path: two ping-pong arenas, one kernel per adapter level and kind
+        b->buf_floats = buf_floats;
+        RB_CUDA(cudaMalloc(&b->d_buf[0], std::max<size_t>(buf_floats * 4, 256)));
+        RB_CUDA(cudaMalloc(&b->d_buf[1], std::max<size_t>(buf_floats * 4, 256)));
+        std::vector<rb_node_dev> host_nodes;
+        for (size_t lvl = 0; lvl < max_nodes; lvl++) {
+            for (uint32_t kind = 0; kind < RB_N_KINDS; kind++) {
+                LaunchGroup g{kind, (uint32_t)host_nodes.size(), 0, 0, 0};
+                for (auto& ps : b->streams) {
+                    if (lvl >= ps.nodes.size() || ps.nodes[lvl].d.kind != kind) continue;
+                    rb_node_dev nd = ps.nodes[lvl].d;
+                    nd.src = (lvl == 0) ? (const void*)(b->d_in + ps.in_off)
+                                        : (const void*)(b->d_buf[(lvl - 1) & 1] + ps.buf_off);
+                    nd.dst = b->d_buf[lvl & 1] + ps.buf_off;
+                    host_nodes.push_back(nd);
+                    g.count++;
+                    g.max_n_out = std::max(g.max_n_out, nd.n_out);
+                    g.max_channels = std::max(g.max_channels, nd.c_in);
+                }
+                if (g.count) b->groups.push_back(g);
+            }
+        }
+        RB_CUDA(cudaMalloc(&b->d_nodes, std::max<size_t>(host_nodes.size() * sizeof(rb_node_dev), 256)));
+        if (!host_nodes.empty())
+            RB_CUDA(cudaMemcpy(b->d_nodes, host_nodes.data(), host_nodes.size() * sizeof(rb_node_dev),
+                               cudaMemcpyHostToDevice));
+        std::vector<rb_mix_src> mix(n_streams);
+        for (size_t i = 0; i < n_streams; i++) {
+            PlanStream& ps = b->streams[i];
+            size_t k = ps.nodes.size();
+            ps.final_ptr = (k == 0) ? (const float*)(b->d_in + ps.in_off) : b->d_buf[(k - 1) & 1] + ps.buf_off;
+            mix[i] = {ps.final_ptr, ps.mix_start, ps.out_len};
+        }
+        RB_CUDA(cudaMalloc(&b->d_mix, std::max<size_t>(n_streams * sizeof(rb_mix_src), 256)));
+        if (n_streams)
+            RB_CUDA(cudaMemcpy(b->d_mix, mix.data(), n_streams * sizeof(rb_mix_src), cudaMemcpyHostToDevice));
+    }
+    b->launches = b->fused ? rb_fused_launch_count(b->fused)
+                           : (uint32_t)b->groups.size() + (mix_len ? 1u : 0u);
+    if (b->fused && (flags & RB_KEEP_STREAM_OUTPUTS)) b->launches += (uint32_t)b->groups.size();
+    *out = b.release();
+    return RB_OK;
+}
+
+static rb_status check_stream(rb_batch* b, size_t stream) {
+    if (!b) return fail(RB_ERR_INVALID_ARGUMENT, "batch is NULL");
+    if (stream >= b->streams.size()) return fail(RB_ERR_INVALID_ARGUMENT, "stream index out of range");
+    return RB_OK;
+}
+
+extern "C" rb_status rb_batch_upload(rb_batch* b, size_t stream, const void* pcm, uint64_t n_samples) {
+    rb_status s = check_stream(b, stream);
+    if (s != RB_OK) return s;
+    PlanStream& ps = b->streams[stream];
+    if (n_samples != ps.desc.n_samples) return fail(RB_ERR_INVALID_ARGUMENT, "n_samples differs from the descriptor");
+    if (!pcm && n_samples) return fail(RB_ERR_INVALID_ARGUMENT, "pcm is NULL");
+    RB_CUDA(cudaSetDevice(b->ctx->device));
+    if (n_samples)
+        RB_CUDA(cudaMemcpyAsync(b->d_in + ps.in_off, pcm, n_samples * fmt_size(ps.desc.format), cudaMemcpyHostToDevice,
+                                b->ctx->stream));
+    b->uploaded[stream] = 1;
+    return RB_OK;
+}
+
+extern "C" rb_status rb_batch_upload_packed(rb_batch* b, const void* pcm, uint64_t total_samples) {
+    if (!b || (!pcm && total_samples)) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
+    uint64_t tot = 0;
+    for (auto& ps : b->streams) tot += ps.desc.n_samples;
+    if (tot != total_samples) return fail(RB_ERR_INVALID_ARGUMENT, "total_samples differs from the descriptors");
+    RB_CUDA(cudaSetDevice(b->ctx->device));
+    const uint8_t* p = (const uint8_t*)pcm;
+    // Streams with equal byte sizes are laid out with a constant device pitch: one strided 2-D copy
+    // instead of one cudaMemcpyAsync per stream.
+    size_t i = 0, n = b->streams.size();
+    while (i < n) {
+        size_t bytes = (size_t)b->streams[i].desc.n_samples * fmt_size(b->streams[i].desc.format);
+        size_t j = i + 1;
+        size_t pitch = (j < n) ? b->streams[j].in_off - b->streams[i].in_off : 0;
+        while (j < n && (size_t)b->streams[j].desc.n_samples * fmt_size(b->streams[j].desc.format) == bytes &&
+               b->streams[j].in_off - b->streams[j - 1].in_off == pitch)
+            j++;
+        size_t rows = j - i;
+        if (bytes) {
+            if (rows > 1)
+                RB_CUDA(cudaMemcpy2DAsync(b->d_in + b->streams[i].in_off, pitch, p, bytes, bytes, rows,
+                                          cudaMemcpyHostToDevice, b->ctx->stream));
+            else
+                RB_CUDA(cudaMemcpyAsync(b->d_in + b->streams[i].in_off, p, bytes, cudaMemcpyHostToDevice,
+                                        b->ctx->stream));
+        }
+        p += bytes * rows;
+        for (size_t k = i; k < j; k++) b->uploaded[k] = 1;
+        i = j;
+    }
+    return RB_OK;
+}
+
+extern "C" rb_status rb_batch_input_device_ptr(rb_batch* b, size_t stream, void** dptr, uint64_t* capacity) {
+    rb_status s = check_stream(b, stream);
+    if (s != RB_OK) return s;
+    if (!dptr) return fail(RB_ERR_INVALID_ARGUMENT, "dptr is NULL");
+    PlanStream& ps = b->streams[stream];
+    *dptr = b->d_in + ps.in_off;
+    if (capacity) *capacity = ps.desc.n_samples;
+    b->uploaded[stream] = 1;   // the caller takes responsibility for the contents
+    return RB_OK;
+}
+
+extern "C" rb_status rb_batch_stream_out_len(rb_batch* b, size_t stream, uint64_t* n) {
+    rb_status s = check_stream(b, stream);
+    if (s != RB_OK) return s;
+    if (!n) return fail(RB_ERR_INVALID_ARGUMENT, "n is NULL");
+    *n = b->streams[stream].out_len;
+    return RB_OK;
+}
+extern "C" rb_status rb_batch_mix_len(rb_batch* b, uint64_t* n) {
+    if (!b || !n) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
+    *n = b->mix_len;
+    return RB_OK;
+}
+extern "C" rb_status rb_batch_launches_per_render(rb_batch* b, uint32_t* n) {
+    if (!b || !n) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
+    *n = b->launches;
+    return RB_OK;
+}
+extern "C" rb_status rb_batch_algorithmic_bytes(rb_batch* b, uint64_t* bytes) {
+    if (!b || !bytes) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
+    *bytes = b->algo_bytes;
+    return RB_OK;
+}
+
+static rb_status run_general(rb_batch* b, bool with_mix) {
+    cudaStream_t st = b->ctx->stream;
+    for (const LaunchGroup& g : b->groups)
+        RB_CUDA(rb_launch_nodes(g.kind, b->d_nodes + g.first, g.count, g.max_n_out, g.max_channels, st));
+    if (with_mix) RB_CUDA(rb_launch_mix(b->d_mix, (uint32_t)b->streams.size(), b->d_out, b->mix_len, st));
+    return RB_OK;
+}
+
+extern "C" rb_status rb_batch_render_mix_device(rb_batch* b) {
+    if (!b) return fail(RB_ERR_INVALID_ARGUMENT, "batch is NULL");
+    for (size_t i = 0; i < b->streams.size(); i++)
+        if (!b->uploaded[i] && b->streams[i].desc.n_samples)
+            return fail(RB_ERR_STATE, "stream " + std::to_string(i) + " was never uploaded");
+    RB_CUDA(cudaSetDevice(b->ctx->device));
+    if (b->fused) {
+        RB_CUDA(rb_fused_run(b->fused, b->ctx->stream));
+        if (b->flags & RB_KEEP_STREAM_OUTPUTS) {
+            rb_status s = run_general(b, false);
+            if (s != RB_OK) return s;
+        }
+    } else {
+        rb_status s = run_general(b, true);
+        if (s != RB_OK) return s;
+    }
+    b->rendered = true;
+    return RB_OK;
+}
+extern "C" rb_status rb_batch_mix_device_ptr(rb_batch* b, float** dptr) {
+    if (!b || !dptr) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
+    *dptr = b->d_out;
+    return RB_OK;
+}
+extern "C" rb_status rb_batch_render_mix(rb_batch* b, float* out_host, uint64_t max_samples, uint64_t* written) {
+    rb_status s = rb_batch_render_mix_device(b);
+    if (s != RB_OK) return s;
+    uint64_t n = std::min<uint64_t>(b->mix_len, max_samples);
+    if (n && !out_host) return fail(RB_ERR_INVALID_ARGUMENT, "out_host is NULL");
+    if (n) RB_CUDA(cudaMemcpyAsync(out_host, b->d_out, n * 4, cudaMemcpyDeviceToHost, b->ctx->stream));
+    RB_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    if (written) *written = n;
+    return RB_OK;
+}
+extern "C" rb_status rb_batch_read_stream(rb_batch* b, size_t stream, float* out_host, uint64_t max_samples,
+                                          uint64_t* written) {
+    rb_status s = check_stream(b, stream);
+    if (s != RB_OK) return s;
+    if (!b->rendered) return fail(RB_ERR_STATE, "render first");
+    PlanStream& ps = b->streams[stream];
+    if (!ps.final_ptr) return fail(RB_ERR_STATE, "per-stream outputs need RB_KEEP_STREAM_OUTPUTS on a fused batch");
+    if (ps.nodes.empty() && ps.desc.format != RB_FMT_F32) return fail(RB_ERR_STATE, "internal: unconverted stream");
+    uint64_t n = std::min<uint64_t>(ps.out_len, max_samples);
+    if (n && !out_host) return fail(RB_ERR_INVALID_ARGUMENT, "out_host is NULL");
+    RB_CUDA(cudaSetDevice(b->ctx->device));
+    if (n) RB_CUDA(cudaMemcpyAsync(out_host, ps.final_ptr, n * 4, cudaMemcpyDeviceToHost, b->ctx->stream));
+    RB_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    if (written) *written = n;
+    return RB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone conversions (SampleRateConverter / ChannelCountConverter / SampleTypeConverter)
+// ------------------------------------------------------------------------------------------------
+extern "C" rb_status rb_sample_rate_out_len(uint64_t n_in, uint32_t from, uint32_t to, uint16_t ch, uint64_t* n_out) {
+    if (!n_out) return fail(RB_ERR_INVALID_ARGUMENT, "n_out is NULL");
+    if (from == 0 || to == 0 || ch == 0) return fail(RB_ERR_INVALID_ARGUMENT, "zero rate or channels (rodio panics)");
+    if (n_in % ch) return fail(RB_ERR_UNALIGNED_FRAMES, "n_in % channels != 0");
+    uint32_t g = std::gcd(from, to);
+    uint32_t f = from / g, t = to / g;
+    if (f != t && (uint64_t)f * t >= (1ull << 32)) return fail(RB_ERR_RATIO_OVERFLOW, "reduced from*to >= 2^32");
+    *n_out = src_out_frames(n_in / ch, f, t) * ch;
+    return RB_OK;
+}
+extern "C" rb_status rb_channels_out_len(uint64_t n_in, uint16_t from, uint16_t to, uint64_t* n_out) {
+    if (!n_out) return fail(RB_ERR_INVALID_ARGUMENT, "n_out is NULL");
+    if (from == 0 || to == 0) return fail(RB_ERR_INVALID_ARGUMENT, "zero channels (rodio panics)");
+    if (n_in % from) return fail(RB_ERR_UNALIGNED_FRAMES, "n_in % from != 0");
+    *n_out = n_in / from * to;
+    return RB_OK;
+}
+
+static rb_status run_single_uniform(rb_context* ctx, const float* in, uint64_t n_in, uint32_t c_in, uint32_t rate_in,
+                                    uint32_t c_out, uint32_t rate_out, float* out, uint64_t cap, uint64_t* n_out) {
+    if (!ctx || (!in && n_in) || !n_out) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (c_in > RB_MAX_CHANNELS) return fail(RB_ERR_UNSUPPORTED, "more than 12 channels");
+    PlanNode nd;
+    rb_status s = plan_uniform(nd, n_in, c_in, rate_in, 0, c_out, rate_out);
+    if (s != RB_OK) return s;
+    *n_out = nd.d.n_out;
+    if (nd.d.n_out > cap) return fail(RB_ERR_BUFFER_TOO_SMALL, "output capacity too small");
+    if (nd.d.n_out == 0) return RB_OK;
+    if (!out) return fail(RB_ERR_INVALID_ARGUMENT, "out is NULL");
+    RB_CUDA(cudaSetDevice(ctx->device));
+    float *d_in = nullptr, *d_out = nullptr;
+    rb_node_dev* d_node = nullptr;
+    RB_CUDA(cudaMalloc(&d_in, n_in * 4 + 16));
+    RB_CUDA(cudaMalloc(&d_out, nd.d.n_out * 4));
+    RB_CUDA(cudaMalloc(&d_node, sizeof(rb_node_dev)));
+    nd.d.src = d_in, nd.d.dst = d_out;
+    cudaError_t e = cudaMemcpyAsync(d_in, in, n_in * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_node, &nd.d, sizeof(rb_node_dev), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = rb_launch_nodes(RB_N_UNIFORM, d_node, 1, nd.d.n_out, c_in, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, nd.d.n_out * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_in), cudaFree(d_out), cudaFree(d_node);
+    if (e != cudaSuccess) return fail(RB_ERR_CUDA, cudaGetErrorString(e));
+    return RB_OK;
+}
+
+extern "C" rb_status rb_convert_sample_rate(rb_context* ctx, const float* in, uint64_t n_in, uint32_t from, uint32_t to,
+                                            uint16_t channels, float* out, uint64_t cap, uint64_t* n_out) {
+    if (from == 0 || to == 0 || channels == 0) return fail(RB_ERR_INVALID_ARGUMENT, "zero rate or channels (rodio panics)");
+    if (n_in % channels) return fail(RB_ERR_UNALIGNED_FRAMES, "n_in % channels != 0");
+    return run_single_uniform(ctx, in, n_in, channels, from, channels, to, out, cap, n_out);
+}
+extern "C" rb_status rb_convert_channels(rb_context* ctx, const float* in, uint64_t n_in, uint16_t from, uint16_t to,
+                                         float* out, uint64_t cap, uint64_t* n_out) {
+    if (from == 0 || to == 0) return fail(RB_ERR_INVALID_ARGUMENT, "zero channels (rodio panics)");
+    if (n_in % from) return fail(RB_ERR_UNALIGNED_FRAMES, "n_in % from != 0");
+    if (from == to) {   // ChannelCountConverter with from == to is the identity map
+        if (!n_out) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
+        *n_out = n_in;
+        if (n_in > cap) return fail(RB_ERR_BUFFER_TOO_SMALL, "output capacity too small");
+        if (n_in) memcpy(out, in, n_in * 4);
+        return RB_OK;
+    }
+    return run_single_uniform(ctx, in, n_in, from, 48000, to, 48000, out, cap, n_out);
+}
+extern "C" rb_status rb_convert_samples(rb_context* ctx, const void* in, rb_sample_format in_fmt, void* out,
+                                        rb_sample_format out_fmt, uint64_t n) {
+    if (!ctx || ((!in || !out) && n)) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
+    if ((uint32_t)in_fmt > RB_FMT_I24_IN_I32 || (uint32_t)out_fmt > RB_FMT_I24_IN_I32)
+        return fail(RB_ERR_INVALID_ARGUMENT, "unknown sample format");
+    if (in_fmt != RB_FMT_F32 && out_fmt != RB_FMT_F32)
+        return fail(RB_ERR_UNSUPPORTED, "one side of the conversion must be f32 (the Source sample type)");
+    if (n == 0) return RB_OK;
+    RB_CUDA(cudaSetDevice(ctx->device));
+    void *d_in = nullptr, *d_out = nullptr;
+    RB_CUDA(cudaMalloc(&d_in, n * fmt_size(in_fmt)));
+    RB_CUDA(cudaMalloc(&d_out, n * fmt_size(out_fmt)));
+    cudaError_t e = cudaMemcpyAsync(d_in, in, n * fmt_size(in_fmt), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = rb_launch_convert(d_in, in_fmt, d_out, out_fmt, n, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, n * fmt_size(out_fmt), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_in), cudaFree(d_out);
+    if (e != cudaSuccess) return fail(RB_ERR_CUDA, cudaGetErrorString(e));
+    return RB_OK;
+}

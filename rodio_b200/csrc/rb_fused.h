@@ -1,0 +1,31 @@
+// rb_fused.h — interface between the planner (rb_api.cu) and the fused fast path (rb_fused.cu).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "rb_internal.h"
+
+// One mixer input as the fused planner sees it: the raw input region plus the planned node list
+// (rb_node_dev embedded at offset 0 of records `node_stride` bytes apart; src/dst not yet filled).
+struct rb_fused_stream {
+    const void* in;
+    uint32_t fmt;
+    uint32_t n_nodes;
+    const rb_node_dev* nodes;
+    size_t node_stride;
+    uint64_t out_len;
+    uint64_t mix_start;
+    uint64_t n_in;
+    uint32_t c_in;
+};
+
+struct rb_fused_plan;
+
+// Sets *out to a plan when every stream of the batch has a chain shape the fused kernels cover,
+// else leaves it NULL (the general per-adapter path then serves the batch).
+cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams, uint16_t mixer_channels, float* d_out,
+                                uint64_t mix_len, uint32_t flags, int sm_count, cudaStream_t st, rb_fused_plan** out);
+cudaError_t rb_fused_run(rb_fused_plan* plan, cudaStream_t st);
+void rb_fused_destroy(rb_fused_plan* plan);
+uint32_t rb_fused_launch_count(const rb_fused_plan* plan);

@@ -1,0 +1,264 @@
+// rb_kernels.cu — one kernel per rodio adapter (the general, un-fused path) plus the mixer sum.
+// Layout: every stream is a contiguous, 128-byte aligned run of interleaved f32 samples in HBM
+// ("planar by stream", interleaved inside a stream exactly like rodio, src/source/mod.rs:131-135).
+// Grid convention for the time-parallel kernels: blockIdx.x = node (stream) index, blockIdx.y walks
+// tiles of that stream; consecutive threads touch consecutive samples (coalesced).
+// The recurrences (biquad / AGC / limiter) keep the reference's sequential f32 order: one thread per
+// independent chain, lanes = chains.  The fused kernels in rb_fused.cu are the fast path; these stay as
+// the general path for arbitrary chains and as the cross-check (RB_NO_FUSION).
+#include "rb_dsp.cuh"
+
+using namespace rbd;
+
+namespace {
+
+constexpr int TPB = 256;
+constexpr int TILE = TPB * 4;
+
+// ---------------------------------------------------------------- time-parallel nodes
+template <class F>
+__device__ __forceinline__ void for_each_out(const rb_node_dev& nd, F f) {
+    for (uint64_t base = (uint64_t)blockIdx.y * TILE; base < nd.n_out; base += (uint64_t)gridDim.y * TILE) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint64_t o = base + (uint64_t)k * TPB + threadIdx.x;
+            if (o < nd.n_out) f(o);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TPB) k_convert(const rb_node_dev* __restrict__ nodes) {
+    const rb_node_dev& nd = nodes[blockIdx.x];
+    for_each_out(nd, [&](uint64_t o) { nd.dst[o] = load_as_f32(nd.src, nd.fmt, o); });
+}
+
+__global__ void __launch_bounds__(TPB) k_amplify(const rb_node_dev* __restrict__ nodes) {
+    const rb_node_dev& nd = nodes[blockIdx.x];
+    const float* __restrict__ x = (const float*)nd.src;
+    const float f = nd.p.amp.factor;
+    for_each_out(nd, [&](uint64_t o) { nd.dst[o] = mul(x[o], f); });
+}
+
+// reverb: Mix(x, Delay(Amplify(x))) — src/source/mix.rs:43-53, delay.rs:68-75, amplify.rs:63-65
+__global__ void __launch_bounds__(TPB) k_echo(const rb_node_dev* __restrict__ nodes) {
+    const rb_node_dev& nd = nodes[blockIdx.x];
+    const float* __restrict__ x = (const float*)nd.src;
+    const uint64_t D = nd.p.echo.delay, L = nd.n_in;
+    const float a = nd.p.echo.amplitude;
+    for_each_out(nd, [&](uint64_t o) {
+        float s2 = (o < D) ? 0.0f : mul(x[o - D], a);   // Delay emits literal 0.0 first
+        float y = (o < L) ? add(x[o], s2) : s2;          // (Some, Some) => s1 + s2 ; (None, Some) => s2
+        nd.dst[o] = y;
+    });
+}
+
+__global__ void __launch_bounds__(TPB) k_delay(const rb_node_dev* __restrict__ nodes) {
+    const rb_node_dev& nd = nodes[blockIdx.x];
+    const float* __restrict__ x = (const float*)nd.src;
+    const uint64_t D = nd.p.echo.delay;
+    for_each_out(nd, [&](uint64_t o) { nd.dst[o] = (o < D) ? 0.0f : x[o - D]; });
+}
+
+// ChannelVolume / Spatial — src/source/channel_volume.rs:71-88
+__global__ void __launch_bounds__(TPB) k_chanvol(const rb_node_dev* __restrict__ nodes) {
+    const rb_node_dev& nd = nodes[blockIdx.x];
+    const float* __restrict__ x = (const float*)nd.src;
+    const uint32_t ci = nd.c_in, co = nd.c_out;
+    const float cif = (float)ci;
+    for_each_out(nd, [&](uint64_t o) {
+        uint64_t f = o / co;
+        uint32_t j = (uint32_t)(o - f * co);
+        const float* fr = x + f * ci;
+        float m = 0.0f;                                  // Sample::EQUILIBRIUM
+        for (uint32_t c = 0; c < ci; c++) m = add(m, fr[c]);
+        m = divf(m, cif);
+        nd.dst[o] = mul(m, nd.p.cv.vol[j]);
+    });
+}
+
+// UniformSourceIterator = ChannelCountConverter(SampleRateConverter(Take(input))) — closed form
+__global__ void __launch_bounds__(TPB) k_uniform(const rb_node_dev* __restrict__ nodes) {
+    const rb_node_dev& nd = nodes[blockIdx.x];
+    const float* __restrict__ x = (const float*)nd.src;
+    const uint32_t ci = nd.c_in, co = nd.c_out;
+    const rb_uniform_params& u = nd.p.uni;
+    const float den_f = __uint2float_rn(u.to);
+    for_each_out(nd, [&](uint64_t o) { nd.dst[o] = uniform_sample(x, u, ci, co, den_f, o); });
+}
+
+// ---------------------------------------------------------------- sequential recurrences
+// One thread per (stream, channel) chain.
+__global__ void __launch_bounds__(128) k_biquad_seq(const rb_node_dev* __restrict__ nodes, uint32_t n_nodes,
+                                                    uint32_t max_c) {
+    uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t s = gid / max_c, c = gid % max_c;
+    if (s >= n_nodes) return;
+    const rb_node_dev& nd = nodes[s];
+    if (c >= nd.c_in) return;
+    const float* __restrict__ x = (const float*)nd.src;
+    float* __restrict__ y = nd.dst;
+    const float b0 = nd.p.blt.b0, b1 = nd.p.blt.b1, b2 = nd.p.blt.b2, a1 = nd.p.blt.a1, a2 = nd.p.blt.a2;
+    const uint32_t C = nd.c_in;
+    float x1 = 0.f, x2 = 0.f, y1 = 0.f, y2 = 0.f;
+    for (uint64_t i = c; i < nd.n_in; i += C) {      // flat position % C selects the state (blt.rs:472-476)
+        float xv = x[i];
+        float r = biquad(b0, b1, b2, a1, a2, xv, x1, x2, y1, y2);
+        y2 = y1, x2 = x1, y1 = r, x1 = xv;
+        y[i] = r;
+    }
+}
+
+// AGC: state shared across interleaved channels (src/source/agc.rs:524-557 applies it to the flat stream).
+__global__ void __launch_bounds__(128) k_agc_seq(const rb_node_dev* __restrict__ nodes, uint32_t n_nodes) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_nodes) return;
+    const rb_node_dev& nd = nodes[s];
+    const float* __restrict__ x = (const float*)nd.src;
+    float* __restrict__ y = nd.dst;
+    const float target = nd.p.agc.target, max_gain = nd.p.agc.max_gain, floor_v = nd.p.agc.floor;
+    const float attack = nd.p.agc.attack, release = nd.p.agc.release;
+    float gain = 1.0f, peak = 0.0f, sum = 0.0f;
+    for (uint64_t n = 0; n < nd.n_in; n++) {
+        float sample = x[n];
+        float v = fabsf(sample);
+        float coeff = (v > peak) ? 0.0f : release;                       // agc.rs:397-408
+        peak = add(mul(peak, coeff), mul(v, sub(1.0f, coeff)));
+        float sq = mul(v, v);                                            // agc.rs:413-418
+        float old = 0.0f;                                                // ring slot content = |x[n-8192]|^2
+        if (n >= 8192) {
+            float ov = fabsf(x[n - 8192]);
+            old = mul(ov, ov);
+        }
+        sum = add(sub(sum, old), sq);                                    // agc.rs:157
+        float rms = __fsqrt_rn(divf(sum, 8192.0f));
+        float rms_gain = (rms > 0.0f) ? divf(target, rms) : max_gain;
+        float peak_gain = (peak > 0.0f) ? fminf(divf(target, peak), max_gain) : max_gain;
+        float desired = fmaxf(fminf(rms_gain, peak_gain), floor_v);
+        float k = (desired > gain) ? attack : release;
+        gain = add(mul(gain, k), mul(desired, sub(1.0f, k)));
+        if (gain < 0.1f) gain = 0.1f;                                    // f32::clamp(0.1, max)
+        if (gain > max_gain) gain = max_gain;
+        y[n] = mul(sample, gain);
+    }
+}
+
+// Limiter: per-channel envelope state, channel-coupled gain, sample-sequential (limit.rs:927-988).
+__global__ void __launch_bounds__(128) k_limit_seq(const rb_node_dev* __restrict__ nodes, uint32_t n_nodes) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_nodes) return;
+    const rb_node_dev& nd = nodes[s];
+    const float* __restrict__ x = (const float*)nd.src;
+    float* __restrict__ y = nd.dst;
+    const float thr = nd.p.lim.threshold, knee = nd.p.lim.knee, ik8 = nd.p.lim.inv_knee_8;
+    const float att = nd.p.lim.attack, rel = nd.p.lim.release;
+    const uint32_t C = nd.c_in;
+    float integ[RB_MAX_CHANNELS], peaks[RB_MAX_CHANNELS];
+    for (uint32_t c = 0; c < RB_MAX_CHANNELS; c++) integ[c] = 0.f, peaks[c] = 0.f;
+    uint32_t c = 0;
+    for (uint64_t n = 0; n < nd.n_in; n++) {
+        float sample = x[n];
+        float ldb = limiter_db(sample, thr, knee, ik8);
+        float in_c = fmaxf(ldb, add(mul(rel, integ[c]), mul(sub(1.0f, rel), ldb)));   // limit.rs:909-912
+        integ[c] = in_c;
+        peaks[c] = add(mul(att, peaks[c]), mul(sub(1.0f, att), in_c));                 // limit.rs:913
+        float mp;
+        if (C == 1) mp = peaks[0];
+        else if (C == 2) mp = fmaxf(peaks[0], peaks[1]);
+        else {
+            mp = 0.0f;
+            for (uint32_t k = 0; k < C; k++) mp = fmaxf(mp, peaks[k]);
+        }
+        y[n] = mul(sample, db_to_linear(-mp));
+        c = (c + 1 == C) ? 0 : c + 1;
+    }
+}
+
+// ---------------------------------------------------------------- mixer
+// MixerSource::sum_current_sources (src/mixer.rs:185-198): acc = 0.0; for s in insertion order: acc += v_s.
+// One thread per output sample; the loop over sources keeps the reference's order, loads are issued
+// UNROLL at a time so enough bytes are in flight.
+constexpr int MIX_UNROLL = 8;
+__global__ void __launch_bounds__(256) k_mix_ordered(const rb_mix_src* __restrict__ srcs, uint32_t n_srcs,
+                                                     float* __restrict__ out, uint64_t out_len) {
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < out_len;
+         p += (uint64_t)gridDim.x * blockDim.x) {
+        float acc = 0.0f;
+        uint32_t s = 0;
+        for (; s + MIX_UNROLL <= n_srcs; s += MIX_UNROLL) {
+            float v[MIX_UNROLL];
+            bool on[MIX_UNROLL];
+#pragma unroll
+            for (int k = 0; k < MIX_UNROLL; k++) {
+                const rb_mix_src m = srcs[s + k];
+                uint64_t q = p - m.start;                 // wraps when p < start -> huge -> inactive
+                on[k] = q < m.len;
+                v[k] = on[k] ? __ldg(m.data + q) : 0.0f;
+            }
+#pragma unroll
+            for (int k = 0; k < MIX_UNROLL; k++)
+                if (on[k]) acc = add(acc, v[k]);
+        }
+        for (; s < n_srcs; s++) {
+            const rb_mix_src m = srcs[s];
+            uint64_t q = p - m.start;
+            if (q < m.len) acc = add(acc, __ldg(m.data + q));
+        }
+        out[p] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(TPB) k_convert_flat(const void* __restrict__ in, uint32_t in_fmt, void* __restrict__ out,
+                                                      uint32_t out_fmt, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        store_from_f32(out, out_fmt, i, load_as_f32(in, in_fmt, i));
+}
+
+}  // namespace
+
+cudaError_t rb_launch_nodes(uint32_t kind, const rb_node_dev* d_nodes, uint32_t n_nodes, uint64_t max_n_out,
+                            uint32_t max_channels, cudaStream_t st) {
+    if (n_nodes == 0) return cudaSuccess;
+    uint64_t tiles = (max_n_out + TILE - 1) / TILE;
+    if (tiles < 1) tiles = 1;
+    // enough blocks per stream to fill the machine, never more than the tiles there are
+    uint64_t want = (148ull * 16 + n_nodes - 1) / n_nodes;
+    if (want < 1) want = 1;
+    uint32_t gy = (uint32_t)(tiles < want ? tiles : want);
+    if (gy > 65535u) gy = 65535u;
+    dim3 grid(n_nodes, gy);
+    switch (kind) {
+        case RB_N_CONVERT: k_convert<<<grid, TPB, 0, st>>>(d_nodes); break;
+        case RB_N_AMPLIFY: k_amplify<<<grid, TPB, 0, st>>>(d_nodes); break;
+        case RB_N_ECHO: k_echo<<<grid, TPB, 0, st>>>(d_nodes); break;
+        case RB_N_DELAY: k_delay<<<grid, TPB, 0, st>>>(d_nodes); break;
+        case RB_N_CHANVOL: k_chanvol<<<grid, TPB, 0, st>>>(d_nodes); break;
+        case RB_N_UNIFORM: k_uniform<<<grid, TPB, 0, st>>>(d_nodes); break;
+        case RB_N_BIQUAD: {
+            if (max_channels < 1) max_channels = 1;
+            uint32_t threads = n_nodes * max_channels;
+            k_biquad_seq<<<(threads + 127) / 128, 128, 0, st>>>(d_nodes, n_nodes, max_channels);
+            break;
+        }
+        case RB_N_AGC: k_agc_seq<<<(n_nodes + 127) / 128, 128, 0, st>>>(d_nodes, n_nodes); break;
+        case RB_N_LIMIT: k_limit_seq<<<(n_nodes + 127) / 128, 128, 0, st>>>(d_nodes, n_nodes); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t rb_launch_mix(const rb_mix_src* d_srcs, uint32_t n_srcs, float* d_out, uint64_t out_len, cudaStream_t st) {
+    if (out_len == 0) return cudaSuccess;
+    uint64_t blocks = (out_len + 255) / 256;
+    if (blocks > 148ull * 8) blocks = 148ull * 8;
+    k_mix_ordered<<<(uint32_t)blocks, 256, 0, st>>>(d_srcs, n_srcs, d_out, out_len);
+    return cudaGetLastError();
+}
+
+cudaError_t rb_launch_convert(const void* d_in, uint32_t in_fmt, void* d_out, uint32_t out_fmt, uint64_t n,
+                              cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    uint64_t blocks = (n + TPB - 1) / TPB;
+    if (blocks > 148ull * 16) blocks = 148ull * 16;
+    k_convert_flat<<<(uint32_t)blocks, TPB, 0, st>>>(d_in, in_fmt, d_out, out_fmt, n);
+    return cudaGetLastError();
+}

@@ -1,0 +1,591 @@
+"""Host-side mirror of rodio's `Source` / `Mixer` surface for the B200 block path.
+
+Names, argument meaning and error behaviour follow the reference (file:line in each docstring);
+where rodio panics this raises ValueError / RodioB200Error.  Nothing here touches samples on the
+CPU: a `Source` is a PCM buffer plus a recorded adapter chain, and `MixerSource` drains it through
+the C ABI (include/rodio_b200.h) on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from fractions import Fraction
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _capi as capi
+from ._capi import check, lib
+
+_NP_OF_FMT = {
+    capi.RB_FMT_F32: np.float32, capi.RB_FMT_I16: np.int16, capi.RB_FMT_U16: np.uint16,
+    capi.RB_FMT_I8: np.int8, capi.RB_FMT_U8: np.uint8, capi.RB_FMT_I32: np.int32,
+}
+_FMT_OF_NP = {np.dtype(v): k for k, v in _NP_OF_FMT.items()}
+
+
+# ---------------------------------------------------------------------------------------------
+# std::time::Duration as whole nanoseconds
+# ---------------------------------------------------------------------------------------------
+class Duration(int):
+    """std::time::Duration; the value is whole nanoseconds."""
+
+    @staticmethod
+    def from_secs(s: int) -> "Duration":
+        return Duration(int(s) * 1_000_000_000)
+
+    @staticmethod
+    def from_millis(ms: int) -> "Duration":
+        return Duration(int(ms) * 1_000_000)
+
+    @staticmethod
+    def from_micros(us: int) -> "Duration":
+        return Duration(int(us) * 1_000)
+
+    @staticmethod
+    def from_nanos(ns: int) -> "Duration":
+        return Duration(int(ns))
+
+    @staticmethod
+    def from_secs_f32(secs: float) -> "Duration":
+        """Duration::from_secs_f32: the f32 value, rounded to the nearest nanosecond."""
+        v = Fraction(float(np.float32(secs)))
+        if v < 0:
+            raise ValueError("negative Duration (Duration::from_secs_f32 panics)")
+        ns = v * 1_000_000_000
+        fl = ns.numerator // ns.denominator
+        rem = ns - fl
+        if rem > Fraction(1, 2) or (rem == Fraction(1, 2) and fl % 2 == 1):
+            fl += 1
+        return Duration(fl)
+
+
+# ---------------------------------------------------------------------------------------------
+# effect records (one per rodio adapter)
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class Effect:
+    kind: int
+    u32: Tuple[int, int, int] = (0, 0, 0)
+    f32: Tuple[float, ...] = (0.0,) * 12
+    ns: Tuple[int, int] = (0, 0)
+
+    @staticmethod
+    def make(kind, u32=(), f32=(), ns=()):
+        u = tuple(int(x) for x in u32) + (0,) * (3 - len(u32))
+        f = tuple(float(x) for x in f32) + (0.0,) * (12 - len(f32))
+        n = tuple(int(x) for x in ns) + (0,) * (2 - len(ns))
+        return Effect(kind, u, f, n)
+
+
+@dataclass
+class AutomaticGainControlSettings:
+    """src/source/agc.rs:57-82 (defaults :73-82)."""
+    target_level: float = 1.0
+    attack_time: int = Duration.from_secs(4)
+    release_time: int = Duration.from_secs(0)
+    absolute_max_gain: float = 7.0
+    floor: float = 0.0   # AutomaticGainControl::set_floor (agc.rs:386-388); 0.0 == None
+
+
+@dataclass
+class LimitSettings:
+    """src/source/limit.rs:209-248 and the presets :284-438."""
+    threshold: float = -1.0
+    knee_width: float = 4.0
+    attack: int = Duration.from_millis(5)
+    release: int = Duration.from_millis(100)
+
+    @staticmethod
+    def default() -> "LimitSettings":
+        return LimitSettings()
+
+    @staticmethod
+    def dynamic_content() -> "LimitSettings":
+        return LimitSettings(threshold=-3.0, knee_width=6.0)
+
+    @staticmethod
+    def broadcast() -> "LimitSettings":
+        return LimitSettings(knee_width=2.0, attack=Duration.from_millis(3), release=Duration.from_millis(50))
+
+    @staticmethod
+    def mastering() -> "LimitSettings":
+        return LimitSettings(-0.5, 1.0, Duration.from_millis(1), Duration.from_millis(200))
+
+    @staticmethod
+    def live_performance() -> "LimitSettings":
+        return LimitSettings(-2.0, 3.0, Duration.from_micros(500), Duration.from_millis(30))
+
+    @staticmethod
+    def gaming() -> "LimitSettings":
+        return LimitSettings(-3.0, 3.0, Duration.from_millis(2), Duration.from_millis(75))
+
+    def with_threshold(self, v):
+        return LimitSettings(float(v), self.knee_width, self.attack, self.release)
+
+    def with_knee_width(self, v):
+        return LimitSettings(self.threshold, float(v), self.attack, self.release)
+
+    def with_attack(self, v):
+        return LimitSettings(self.threshold, self.knee_width, int(v), self.release)
+
+    def with_release(self, v):
+        return LimitSettings(self.threshold, self.knee_width, self.attack, int(v))
+
+
+# ---------------------------------------------------------------------------------------------
+# trait Source (src/source/mod.rs:179-759): PCM + recorded adapter chain
+# ---------------------------------------------------------------------------------------------
+class Source:
+    def __init__(self, pcm: np.ndarray, channels: int, sample_rate: int, span_len: int,
+                 effects: Optional[List[Effect]] = None, cur_channels: Optional[int] = None,
+                 cur_rate: Optional[int] = None):
+        if channels <= 0 or sample_rate <= 0:
+            raise ValueError("channels and sample_rate must be non-zero (NonZero in rodio)")
+        pcm = np.ascontiguousarray(pcm)
+        if pcm.dtype not in _FMT_OF_NP:
+            pcm = pcm.astype(np.float32)
+        self.pcm = pcm.reshape(-1)
+        self.base_channels = int(channels)
+        self.base_rate = int(sample_rate)
+        self.span_len = int(span_len)
+        self.effects: List[Effect] = list(effects or [])
+        self._channels = int(cur_channels if cur_channels is not None else channels)
+        self._rate = int(cur_rate if cur_rate is not None else sample_rate)
+
+    # -- metadata the trait reports --------------------------------------------------------
+    def channels(self) -> int:
+        return self._channels
+
+    def sample_rate(self) -> int:
+        return self._rate
+
+    def _with(self, e: Effect, channels=None, rate=None) -> "Source":
+        return Source(self.pcm, self.base_channels, self.base_rate, self.span_len, self.effects + [e],
+                      channels if channels is not None else self._channels,
+                      rate if rate is not None else self._rate)
+
+    # -- adapters ---------------------------------------------------------------------------
+    def amplify(self, value: float) -> "Source":
+        """Source::amplify — src/source/mod.rs:307-314."""
+        return self._with(Effect.make(capi.RB_FX_AMPLIFY, f32=[value]))
+
+    def amplify_decibel(self, value: float) -> "Source":
+        """Source::amplify_decibel — src/source/mod.rs:316-323 (math::db_to_linear)."""
+        return self.amplify(lib().rb_db_to_linear(C.c_float(value)))
+
+    def amplify_normalized(self, value: float) -> "Source":
+        """Source::amplify_normalized — src/source/mod.rs:325-349."""
+        v = np.float32(min(max(np.float32(value), np.float32(0.0)), np.float32(1.0)))
+        amp = np.float32(np.exp(np.float32(6.9077554) * v, dtype=np.float32) / np.float32(1000.0))
+        if v < np.float32(0.1):
+            amp = np.float32(amp * np.float32(v * np.float32(10.0)))
+        return self.amplify(float(amp))
+
+    def speed(self, ratio: float) -> "Source":
+        """Source::speed — src/source/speed.rs:103-105,:130-133 (samples untouched, rate rescaled)."""
+        new_rate = lib().rb_speed_sample_rate(self._rate, C.c_float(ratio))
+        return self._with(Effect.make(capi.RB_FX_SPEED, f32=[ratio]), rate=new_rate)
+
+    def low_pass(self, freq: int) -> "Source":
+        """Source::low_pass — src/source/mod.rs:686-692 (q = 0.5, blt.rs:11-16)."""
+        return self.low_pass_with_q(freq, 0.5)
+
+    def low_pass_with_q(self, freq: int, q: float) -> "Source":
+        return self._with(Effect.make(capi.RB_FX_LOW_PASS, u32=[freq], f32=[q]))
+
+    def high_pass(self, freq: int) -> "Source":
+        return self.high_pass_with_q(freq, 0.5)
+
+    def high_pass_with_q(self, freq: int, q: float) -> "Source":
+        return self._with(Effect.make(capi.RB_FX_HIGH_PASS, u32=[freq], f32=[q]))
+
+    def reverb(self, duration: int, amplitude: float) -> "Source":
+        """Source::reverb — src/source/mod.rs:628-634."""
+        return self._with(Effect.make(capi.RB_FX_REVERB, f32=[amplitude], ns=[duration]))
+
+    def delay(self, duration: int) -> "Source":
+        """Source::delay — src/source/delay.rs:19-29."""
+        return self._with(Effect.make(capi.RB_FX_DELAY, ns=[duration]))
+
+    def automatic_gain_control(self, settings: Optional[AutomaticGainControlSettings] = None) -> "Source":
+        """Source::automatic_gain_control — src/source/mod.rs:415-446."""
+        s = settings or AutomaticGainControlSettings()
+        return self._with(Effect.make(capi.RB_FX_AGC, f32=[s.target_level, s.absolute_max_gain, s.floor],
+                                      ns=[s.attack_time, s.release_time]))
+
+    def limit(self, settings: Optional[LimitSettings] = None) -> "Source":
+        """Source::limit — src/source/limit.rs:94-130."""
+        s = settings or LimitSettings()
+        return self._with(Effect.make(capi.RB_FX_LIMIT, f32=[s.threshold, s.knee_width], ns=[s.attack, s.release]))
+
+    # -- draining ----------------------------------------------------------------------------
+    def collect(self, ctx: Optional["Context"] = None) -> np.ndarray:
+        """`.collect::<Vec<f32>>()` of this source (chain only, no mixer conversion)."""
+        u = self if self.effects and self.effects[-1].kind == capi.RB_FX_UNIFORM else self
+        b = Batch([u], u.channels(), u.sample_rate(), flags=capi.RB_KEEP_STREAM_OUTPUTS | capi.RB_NO_FUSION, ctx=ctx)
+        try:
+            b.upload_all()
+            b.render_mix_device()
+            return b.read_stream(0)
+        finally:
+            b.close()
+
+
+class SamplesBuffer(Source):
+    """buffer::SamplesBuffer::new(channels, sample_rate, data) — src/buffer.rs:40-60.
+    `current_span_len()` reports the whole buffer (src/buffer.rs:76-82)."""
+
+    def __init__(self, channels: int, sample_rate: int, data):
+        data = np.asarray(data)
+        if data.dtype not in _FMT_OF_NP:
+            data = data.astype(np.float32)
+        super().__init__(data, channels, sample_rate, span_len=min(int(data.size), 0xFFFFFFFF))
+
+
+class TestSource(Source):
+    """benches/shared.rs:7-50 TestSource: a Vec-backed source whose span is `None` (forever)."""
+    __test__ = False
+
+    def __init__(self, samples, channels: int, sample_rate: int):
+        super().__init__(np.asarray(samples), channels, sample_rate, span_len=0)
+
+
+def ChannelVolume(input: Source, channel_volumes: Sequence[float]) -> Source:
+    """source::ChannelVolume::new(input, volumes) — src/source/channel_volume.rs:30-38."""
+    vols = [float(v) for v in channel_volumes]
+    if not 1 <= len(vols) <= 12:
+        raise ValueError("1..12 channel volumes")
+    return input._with(Effect.make(capi.RB_FX_CHANNEL_VOLUME, u32=[len(vols)], f32=vols), channels=len(vols))
+
+
+def Spatial(input: Source, emitter_position, left_ear, right_ear) -> Source:
+    """source::Spatial::new(input, emitter, left_ear, right_ear) — src/source/spatial.rs:31-45."""
+    f = [float(x) for x in list(emitter_position) + list(left_ear) + list(right_ear)]
+    return input._with(Effect.make(capi.RB_FX_SPATIAL, f32=f), channels=2)
+
+
+def UniformSourceIterator(input: Source, target_channels: int, target_sample_rate: int) -> Source:
+    """source::UniformSourceIterator::new(input, channels, rate) — src/source/uniform.rs:33-47."""
+    if target_channels <= 0 or target_sample_rate <= 0:
+        raise ValueError("target channels / rate must be non-zero")
+    return input._with(Effect.make(capi.RB_FX_UNIFORM, u32=[target_channels, target_sample_rate]),
+                       channels=target_channels, rate=target_sample_rate)
+
+
+# ---------------------------------------------------------------------------------------------
+# context / batch (thin RAII over the C ABI)
+# ---------------------------------------------------------------------------------------------
+class Context:
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        check(lib().rb_context_create(device, C.byref(self._h)), "rb_context_create")
+        self.device = device
+
+    def sync(self):
+        check(lib().rb_context_sync(self._h), "rb_context_sync")
+
+    @property
+    def cuda_stream(self) -> int:
+        p = C.c_void_p()
+        check(lib().rb_context_stream(self._h, C.byref(p)), "rb_context_stream")
+        return p.value or 0
+
+    @property
+    def sm_count(self) -> int:
+        n = C.c_int()
+        check(lib().rb_context_sm_count(self._h, C.byref(n)), "rb_context_sm_count")
+        return n.value
+
+    def close(self):
+        if self._h:
+            lib().rb_context_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+_default_ctx: dict = {}
+
+
+def default_context(device: int = 0) -> Context:
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+def pack_descs(sources: Sequence[Source], mix_starts: Optional[Sequence[int]] = None):
+    """Build the rb_stream_desc array for `sources` (returns the array and the objects it points into)."""
+    n = len(sources)
+    descs = (capi.rb_stream_desc * max(1, n))()
+    keep = []
+    for i, s in enumerate(sources):
+        fx = (capi.rb_effect * max(1, len(s.effects)))()
+        for j, e in enumerate(s.effects):
+            fx[j].kind = e.kind
+            for k in range(3):
+                fx[j].u32[k] = e.u32[k]
+            for k in range(12):
+                fx[j].f32[k] = e.f32[k]
+            for k in range(2):
+                fx[j].ns[k] = e.ns[k]
+        keep.append(fx)
+        d = descs[i]
+        d.sample_rate = s.base_rate
+        d.channels = s.base_channels
+        d.format = _FMT_OF_NP[s.pcm.dtype]
+        d.n_samples = s.pcm.size
+        d.span_len = s.span_len
+        d.n_effects = len(s.effects)
+        d.effects = C.cast(fx, C.POINTER(capi.rb_effect))
+        d.mix_start = int(mix_starts[i]) if mix_starts is not None else 0
+    return descs, keep
+
+
+def plan(source: Source, mixer_channels: int, mixer_rate: int):
+    """Host-only closed forms for one source: (samples the mixer pulls, chain channels, chain rate, chain samples)."""
+    descs, keep = pack_descs([source])
+    n, ch, rate, cn = C.c_uint64(), C.c_uint16(), C.c_uint32(), C.c_uint64()
+    check(lib().rb_stream_plan(C.byref(descs[0]), mixer_channels, mixer_rate, C.byref(n), C.byref(ch), C.byref(rate),
+                               C.byref(cn)), "rb_stream_plan")
+    return n.value, ch.value, rate.value, cn.value
+
+
+class Batch:
+    """mixer(channels, rate) + Mixer::add for every source, as one rb_batch."""
+
+    def __init__(self, sources: Sequence[Source], mixer_channels: int, mixer_rate: int, flags: int = 0,
+                 mix_starts: Optional[Sequence[int]] = None, ctx: Optional[Context] = None):
+        self.ctx = ctx or default_context()
+        self.sources = list(sources)
+        self._descs, self._keep = pack_descs(self.sources, mix_starts)
+        self._h = C.c_void_p()
+        check(lib().rb_batch_create(self.ctx._h, mixer_channels, mixer_rate, self._descs, len(self.sources), flags,
+                                    C.byref(self._h)), "rb_batch_create")
+
+    def close(self):
+        if self._h:
+            lib().rb_batch_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def upload(self, i: int, pcm: Optional[np.ndarray] = None):
+        a = self.sources[i].pcm if pcm is None else np.ascontiguousarray(pcm)
+        check(lib().rb_batch_upload(self._h, i, a.ctypes.data_as(C.c_void_p), a.size), "rb_batch_upload")
+
+    def upload_all(self):
+        for i in range(len(self.sources)):
+            self.upload(i)
+
+    def upload_packed(self, host_ptr: int, total_samples: int):
+        check(lib().rb_batch_upload_packed(self._h, C.c_void_p(host_ptr), total_samples), "rb_batch_upload_packed")
+
+    def input_device_ptr(self, i: int) -> Tuple[int, int]:
+        p, cap = C.c_void_p(), C.c_uint64()
+        check(lib().rb_batch_input_device_ptr(self._h, i, C.byref(p), C.byref(cap)), "rb_batch_input_device_ptr")
+        return p.value or 0, cap.value
+
+    def stream_out_len(self, i: int) -> int:
+        n = C.c_uint64()
+        check(lib().rb_batch_stream_out_len(self._h, i, C.byref(n)), "rb_batch_stream_out_len")
+        return n.value
+
+    @property
+    def mix_len(self) -> int:
+        n = C.c_uint64()
+        check(lib().rb_batch_mix_len(self._h, C.byref(n)), "rb_batch_mix_len")
+        return n.value
+
+    @property
+    def launches_per_render(self) -> int:
+        n = C.c_uint32()
+        check(lib().rb_batch_launches_per_render(self._h, C.byref(n)), "rb_batch_launches_per_render")
+        return n.value
+
+    @property
+    def algorithmic_bytes(self) -> int:
+        n = C.c_uint64()
+        check(lib().rb_batch_algorithmic_bytes(self._h, C.byref(n)), "rb_batch_algorithmic_bytes")
+        return n.value
+
+    def render_mix_device(self):
+        check(lib().rb_batch_render_mix_device(self._h), "rb_batch_render_mix_device")
+
+    @property
+    def mix_device_ptr(self) -> int:
+        p = C.c_void_p()
+        check(lib().rb_batch_mix_device_ptr(self._h, C.byref(p)), "rb_batch_mix_device_ptr")
+        return p.value or 0
+
+    def render_mix(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        n = self.mix_len
+        if out is None:
+            out = np.empty(n, dtype=np.float32)
+        w = C.c_uint64()
+        check(lib().rb_batch_render_mix(self._h, out.ctypes.data_as(C.c_void_p), out.size, C.byref(w)),
+              "rb_batch_render_mix")
+        return out[: w.value]
+
+    def render_mix_into(self, host_ptr: int, max_samples: int) -> int:
+        w = C.c_uint64()
+        check(lib().rb_batch_render_mix(self._h, C.c_void_p(host_ptr), max_samples, C.byref(w)), "rb_batch_render_mix")
+        return w.value
+
+    def read_stream(self, i: int) -> np.ndarray:
+        n = self.stream_out_len(i)
+        out = np.empty(n, dtype=np.float32)
+        w = C.c_uint64()
+        check(lib().rb_batch_read_stream(self._h, i, out.ctypes.data_as(C.c_void_p), n, C.byref(w)),
+              "rb_batch_read_stream")
+        return out[: w.value]
+
+
+# ---------------------------------------------------------------------------------------------
+# mixer::mixer(channels, sample_rate) -> (Mixer, MixerSource)   src/mixer.rs:25-43
+# ---------------------------------------------------------------------------------------------
+class _MixerShared:
+    def __init__(self, channels, rate, flags, ctx):
+        self.channels, self.rate, self.flags, self.ctx = channels, rate, flags, ctx
+        self.sources: List[Source] = []
+        self.starts: List[int] = []
+        self.pos = 0              # samples already handed out by MixerSource
+        self.rendered: Optional[np.ndarray] = None
+        self.active: Optional[np.ndarray] = None
+
+
+class Mixer:
+    """The input handle (`mixer::Mixer`, src/mixer.rs:47-66). `add` is infallible like the reference."""
+
+    def __init__(self, shared: _MixerShared):
+        self._s = shared
+
+    def add(self, source: Source):
+        s = self._s
+        s.sources.append(source)
+        s.starts.append(s.pos)    # joins at the next frame boundary (mixer.rs:175-183), done by the library
+        s.rendered = None
+
+
+class MixerSource:
+    """The output (`mixer::MixerSource`, src/mixer.rs:70-136): an iterator of f32 that implements Source."""
+
+    def __init__(self, shared: _MixerShared):
+        self._s = shared
+
+    def channels(self) -> int:
+        return self._s.channels
+
+    def sample_rate(self) -> int:
+        return self._s.rate
+
+    def current_span_len(self):
+        return None
+
+    def try_seek(self, pos):
+        raise capi.RodioB200Error(capi.RB_ERR_NOT_SUPPORTED_SEEK, "MixerSource::try_seek",
+                                  "SeekError::NotSupported (src/mixer.rs:109-113)")
+
+    def _render(self):
+        s = self._s
+        if s.rendered is not None:
+            return
+        if not s.sources:
+            s.rendered = np.zeros(0, dtype=np.float32)
+            s.active = np.zeros(0, dtype=bool)
+            return
+        with Batch(s.sources, s.channels, s.rate, flags=s.flags, mix_starts=s.starts, ctx=s.ctx) as b:
+            b.upload_all()
+            s.rendered = b.render_mix()
+            act = np.zeros(s.rendered.size + 1, dtype=np.int64)
+            for i in range(len(s.sources)):
+                n = b.stream_out_len(i)
+                if n:
+                    st = (s.starts[i] + s.channels - 1) // s.channels * s.channels
+                    act[st] += 1
+                    act[st + n] -= 1
+            s.active = np.cumsum(act)[:-1] > 0
+
+    def next(self) -> Optional[float]:
+        """Iterator::next — None when no source is playing at this position (src/mixer.rs:131-135)."""
+        s = self._s
+        self._render()
+        p = s.pos
+        s.pos += 1
+        if p < s.rendered.size and s.active[p]:
+            return float(s.rendered[p])
+        return None
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        v = self.next()
+        if v is None:
+            raise StopIteration
+        return v
+
+    def collect(self) -> np.ndarray:
+        """Drain until the mixer first reports None."""
+        s = self._s
+        self._render()
+        p = s.pos
+        q = p
+        while q < s.rendered.size and s.active[q]:
+            q += 1
+        s.pos = q + 1
+        return s.rendered[p:q].copy()
+
+
+def mixer(channels: int, sample_rate: int, flags: int = 0, ctx: Optional[Context] = None) -> Tuple[Mixer, MixerSource]:
+    """mixer::mixer(channels, sample_rate) — src/mixer.rs:25-43."""
+    if channels <= 0 or sample_rate <= 0:
+        raise ValueError("channels and sample_rate must be non-zero")
+    sh = _MixerShared(int(channels), int(sample_rate), flags, ctx)
+    return Mixer(sh), MixerSource(sh)
+
+
+# ---------------------------------------------------------------------------------------------
+# conversions::{SampleRateConverter, ChannelCountConverter, SampleTypeConverter}
+# ---------------------------------------------------------------------------------------------
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32).reshape(-1)
+
+
+def SampleRateConverter(input, from_rate: int, to_rate: int, num_channels: int, ctx: Optional[Context] = None) -> np.ndarray:
+    """conversions::SampleRateConverter::new(input, from, to, channels).collect() — sample_rate.rs:52-201."""
+    x = _f32(input)
+    ctx = ctx or default_context()
+    n = C.c_uint64()
+    check(lib().rb_sample_rate_out_len(x.size, from_rate, to_rate, num_channels, C.byref(n)), "rb_sample_rate_out_len")
+    out = np.empty(n.value, dtype=np.float32)
+    check(lib().rb_convert_sample_rate(ctx._h, x.ctypes.data_as(C.c_void_p), x.size, from_rate, to_rate, num_channels,
+                                       out.ctypes.data_as(C.c_void_p), out.size, C.byref(n)), "rb_convert_sample_rate")
+    return out[: n.value]
+
+
+def ChannelCountConverter(input, from_channels: int, to_channels: int, ctx: Optional[Context] = None) -> np.ndarray:
+    """conversions::ChannelCountConverter::new(input, from, to).collect() — channels.rs:28,:57-85."""
+    x = _f32(input)
+    ctx = ctx or default_context()
+    n = C.c_uint64()
+    check(lib().rb_channels_out_len(x.size, from_channels, to_channels, C.byref(n)), "rb_channels_out_len")
+    out = np.empty(n.value, dtype=np.float32)
+    check(lib().rb_convert_channels(ctx._h, x.ctypes.data_as(C.c_void_p), x.size, from_channels, to_channels,
+                                    out.ctypes.data_as(C.c_void_p), out.size, C.byref(n)), "rb_convert_channels")
+    return out[: n.value]
+
+
+def SampleTypeConverter(input: np.ndarray, out_fmt: int, in_fmt: Optional[int] = None, ctx: Optional[Context] = None) -> np.ndarray:
+    """conversions::SampleTypeConverter::<_, O>::new(input).collect() — sample.rs:14,:42-44."""
+    x = np.ascontiguousarray(input).reshape(-1)
+    if in_fmt is None:
+        in_fmt = _FMT_OF_NP[x.dtype]
+    ctx = ctx or default_context()
+    odt = np.int32 if out_fmt == capi.RB_FMT_I24_IN_I32 else _NP_OF_FMT[out_fmt]
+    out = np.empty(x.size, dtype=odt)
+    check(lib().rb_convert_samples(ctx._h, x.ctypes.data_as(C.c_void_p), in_fmt, out.ctypes.data_as(C.c_void_p),
+                                   out_fmt, x.size), "rb_convert_samples")
+    return out

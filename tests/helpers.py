@@ -1,0 +1,46 @@
+"""Test helpers: turn a rodio_b200 Source into the oracle's neutral Stream, compare results."""
+from __future__ import annotations
+
+import numpy as np
+
+import oracle
+import rodio_b200 as rb
+
+
+def to_oracle(src: rb.Source, mix_start: int = 0) -> oracle.Stream:
+    pcm = src.pcm
+    if pcm.dtype != np.float32:
+        fmt = {np.dtype(np.int16): 1, np.dtype(np.uint16): 2, np.dtype(np.int8): 3, np.dtype(np.uint8): 4,
+               np.dtype(np.int32): 5}[pcm.dtype]
+        pcm = oracle.convert(pcm, fmt, 0)
+    return oracle.Stream(pcm=pcm, channels=src.base_channels, sample_rate=src.base_rate, effects=src.effects,
+                         span_len=src.span_len, mix_start=mix_start)
+
+
+def bits(a: np.ndarray) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def assert_bit_exact(got: np.ndarray, want: np.ndarray, what: str = ""):
+    assert got.shape == want.shape, f"{what}: length {got.shape} != {want.shape}"
+    if got.size == 0:
+        return
+    g, w = bits(got), bits(want)
+    bad = np.nonzero(g != w)[0]
+    assert bad.size == 0, (f"{what}: {bad.size}/{got.size} samples differ, first at {bad[0]}: "
+                           f"got {got[bad[0]]!r} want {want[bad[0]]!r}")
+
+
+def assert_close_peak(got: np.ndarray, want: np.ndarray, tol: float = 1e-5, what: str = ""):
+    """Parity metric of the north star: max|got - want| <= tol * max|want| (peak-normalised)."""
+    assert got.shape == want.shape, f"{what}: length {got.shape} != {want.shape}"
+    if got.size == 0:
+        return
+    peak = float(np.max(np.abs(want)))
+    err = float(np.max(np.abs(got.astype(np.float64) - want.astype(np.float64))))
+    assert err <= tol * max(peak, 1e-30), f"{what}: max err {err:.3e} > {tol:g} * peak {peak:.3e}"
+
+
+def noise(n: int, seed: int, amp: float = 1.0) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    return (rng.uniform(-1.0, 1.0, n) * amp).astype(np.float32)

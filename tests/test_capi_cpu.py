@@ -1,0 +1,188 @@
+"""CPU-side checks of the product: the C-ABI library loads and exports every symbol the header
+declares, host-only helpers match the oracle bit for bit, closed-form lengths match the literal
+iterator, argument validation mirrors the reference's panics.  No compute call needs a GPU here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+import rodio_b200 as rb
+from rodio_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "rodio_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    names = header_functions()
+    assert len(names) >= 30
+    L = C.CDLL(capi.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/rodio_b200.h but not exported"
+    assert set(names) == set(capi.SYMBOLS), set(names) ^ set(capi.SYMBOLS)
+    assert rb.lib().rb_abi_version() == 1
+
+
+def test_struct_layout_matches_header(built):
+    assert C.sizeof(capi.rb_effect) == 80
+    assert C.sizeof(capi.rb_stream_desc) == 40
+    assert capi.rb_stream_desc.effects.offset == 24 and capi.rb_stream_desc.mix_start.offset == 32
+
+
+def test_no_gpu_fails_loudly(built):
+    h = C.c_void_p()
+    st = rb.lib().rb_context_create(0, C.byref(h))
+    if st == capi.RB_OK:
+        rb.lib().rb_context_destroy(h)
+        pytest.skip("a GPU is present")
+    assert st == capi.RB_ERR_CUDA
+    assert b"no CPU fallback" in rb.lib().rb_last_error()
+    with pytest.raises(rb.RodioB200Error):
+        rb.Context(0)
+
+
+def test_status_strings(built):
+    for s in range(0, 10):
+        assert rb.lib().rb_status_string(s)
+
+
+def _out_len(n, f, t, c):
+    v = C.c_uint64()
+    st = rb.lib().rb_sample_rate_out_len(n, f, t, c, C.byref(v))
+    return st, v.value
+
+
+def test_sample_rate_out_len_matches_literal_iterator(built):
+    rng = np.random.default_rng(7)
+    rates = [8000, 11025, 16000, 22050, 44100, 48000, 88200, 96000, 176400, 192000, 352800, 384000, 39690, 40000,
+             1, 2, 3, 7, 1000, 7000, 2400, 12000]
+    for _ in range(400):
+        f, t = int(rng.choice(rates)), int(rng.choice(rates))
+        c = int(rng.integers(1, 5))
+        frames = int(rng.integers(0, 700))
+        if frames * t / f > 100_000:      # keep the literal drain short
+            frames = int(100_000 * f / t)
+        x = rng.uniform(-1, 1, frames * c).astype(np.float32)
+        st, n = _out_len(x.size, f, t, c)
+        assert st == capi.RB_OK
+        assert n == oracle.sample_rate_converter(x, f, t, c).size, (f, t, c, frames)
+    for f, t, L, want in [(147, 160, 147, 160), (44100, 48000, 1000, 1089), (44100, 48000, 44100, 48000),
+                          (1, 1, 5, 5), (44100, 48000, 1, 1), (44100, 48000, 2, 3), (44100, 48000, 0, 0)]:
+        assert _out_len(L, f, t, 1) == (capi.RB_OK, want)
+
+
+def test_out_len_errors(built):
+    assert _out_len(10, 0, 48000, 1)[0] == capi.RB_ERR_INVALID_ARGUMENT
+    assert _out_len(10, 48000, 48000, 0)[0] == capi.RB_ERR_INVALID_ARGUMENT
+    assert _out_len(7, 44100, 48000, 2)[0] == capi.RB_ERR_UNALIGNED_FRAMES
+    assert _out_len(10, 96001, 192000, 1)[0] == capi.RB_ERR_RATIO_OVERFLOW
+    v = C.c_uint64()
+    assert rb.lib().rb_channels_out_len(6, 3, 2, C.byref(v)) == capi.RB_OK and v.value == 4
+    assert rb.lib().rb_channels_out_len(6, 0, 2, C.byref(v)) == capi.RB_ERR_INVALID_ARGUMENT
+    assert rb.lib().rb_channels_out_len(7, 2, 1, C.byref(v)) == capi.RB_ERR_UNALIGNED_FRAMES
+
+
+def test_host_helpers_bit_exact_with_oracle(built):
+    L, O = rb.lib(), oracle.lib()
+    rng = np.random.default_rng(11)
+    for _ in range(300):
+        rate = int(rng.integers(1, 400000))
+        fac = float(np.float32(rng.uniform(0.0, 4.0)))
+        assert L.rb_speed_sample_rate(rate, fac) == O.ro_speed_sample_rate(rate, fac)
+        ns = int(rng.integers(0, 5_000_000_000))
+        ch = int(rng.integers(1, 9))
+        assert L.rb_delay_samples(ns, rate, ch) == O.ro_delay_samples(ns, rate, ch)
+        db = float(np.float32(rng.uniform(-100, 100)))
+        assert np.float32(L.rb_db_to_linear(db)).view(np.uint32) == np.float32(O.ro_db_to_linear(db)).view(np.uint32)
+        lin = float(np.float32(rng.uniform(1e-6, 100)))
+        assert np.float32(L.rb_linear_to_db(lin)).view(np.uint32) == np.float32(O.ro_linear_to_db(lin)).view(np.uint32)
+    assert L.rb_speed_sample_rate(44100, 0.9) == 39690
+    assert L.rb_speed_sample_rate(5, 0.0) == 1                  # .max(1.0)
+    assert L.rb_delay_samples(50_000_000, 48000, 2) == 4800
+
+
+def test_spatial_volumes_bit_exact_with_oracle(built):
+    rng = np.random.default_rng(12)
+    for _ in range(200):
+        e, l, r = (rng.uniform(-5, 5, 3).astype(np.float32) for _ in range(3))
+        out = np.zeros(2, np.float32)
+        fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+        rb.lib().rb_spatial_volumes(fp(e), fp(l), fp(r), fp(out))
+        assert np.array_equal(out.view(np.uint32), oracle.spatial_volumes(e, l, r).view(np.uint32))
+
+
+def test_duration_from_secs_f32():
+    assert rb.Duration.from_secs_f32(0.5) == 500_000_000
+    assert rb.Duration.from_secs_f32(2.0) == 2_000_000_000
+    # 0.05f32 = 0.0500000007450580596923828125 -> 50_000_001 ns (rounded to nearest)
+    assert rb.Duration.from_secs_f32(0.05) == 50_000_001
+    assert rb.Duration.from_millis(5) == 5_000_000
+
+
+def test_source_metadata_follows_the_trait():
+    s = rb.SamplesBuffer(2, 44100, np.zeros(8, np.float32))
+    assert (s.channels(), s.sample_rate(), s.span_len) == (2, 44100, 8)
+    assert s.speed(0.9).sample_rate() == 39690 and s.speed(0.9).channels() == 2
+    sp = rb.Spatial(s, [0, 1, 0], [-1, 0, 0], [1, 0, 0])
+    assert sp.channels() == 2 and sp.sample_rate() == 44100
+    u = rb.UniformSourceIterator(s.amplify(2.0), 1, 48000)
+    assert (u.channels(), u.sample_rate()) == (1, 48000)
+    assert rb.TestSource(np.zeros(4, np.float32), 1, 48000).span_len == 0
+    with pytest.raises(ValueError):
+        rb.SamplesBuffer(0, 44100, [])
+    with pytest.raises(ValueError):
+        rb.mixer(1, 0)
+    _, out = rb.mixer(2, 48000)
+    assert out.channels() == 2 and out.sample_rate() == 48000 and out.current_span_len() is None
+    with pytest.raises(rb.RodioB200Error):
+        out.try_seek(0)
+
+
+# ---- planner closed forms vs the literal pull iterator (host only) --------------------------
+from chains import CHAINS, LIMIT_CHAINS  # noqa: E402
+from helpers import to_oracle  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(CHAINS) + sorted(LIMIT_CHAINS))
+def test_planner_lengths_match_literal_iterator(built, name):
+    src = {**CHAINS, **LIMIT_CHAINS}[name]()
+    want, ch, rate = oracle.chain(to_oracle(src))
+    for mix in [(1, 48000), (2, 48000), (2, 44100), (3, 32000)]:
+        n, pch, prate, cn = rb.plan(src, *mix)
+        assert (pch, prate, cn) == (ch, rate, want.size), name
+        assert n == oracle.chain_uniform(to_oracle(src), *mix).size, (name, mix)
+
+
+def test_planner_random_uniform_lengths(built):
+    """Spans, partial trailing frames, channel up/down-mix: closed form == literal iterator."""
+    rng = np.random.default_rng(31)
+    rates = [8000, 11025, 22050, 44100, 48000, 96000, 39690, 40000]
+    for i in range(300):
+        c = int(rng.integers(1, 5))
+        n = int(rng.integers(0, 5000))
+        kind = int(rng.integers(0, 3))
+        x = np.zeros(n, np.float32)
+        if kind == 0:
+            n -= n % c
+            src = rb.SamplesBuffer(c, int(rng.choice(rates)), x[:n])                      # spans
+        elif kind == 1:
+            n -= n % c
+            src = rb.Source(x[:n], c, int(rng.choice(rates)), span_len=int(c * rng.integers(1, 600)))
+        else:
+            n -= n % c
+            src = rb.TestSource(x[:n], c, int(rng.choice(rates))).delay(rb.Duration.from_nanos(int(rng.integers(0, 90000))))
+        mix = (int(rng.integers(1, 5)), int(rng.choice(rates)))
+        try:
+            got = rb.plan(src, *mix)[0]
+        except rb.RodioB200Error as e:
+            assert e.status in (capi.RB_ERR_UNSUPPORTED,), e
+            continue
+        assert got == oracle.chain_uniform(to_oracle(src), *mix).size, (i, kind, c, n, mix)

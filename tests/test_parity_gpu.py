@@ -1,0 +1,349 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs.  Bit-exact wherever the arithmetic is +,-,*,/,sqrt (everything except the limiter's
+log2/exp2, which is held to the north-star tolerance 1e-5 * peak)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+import rodio_b200 as rb
+from chains import CHAINS, LIMIT_CHAINS, _stereo
+from helpers import assert_bit_exact, assert_close_peak, noise, to_oracle
+from rodio_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+GENERAL = capi.RB_KEEP_STREAM_OUTPUTS | capi.RB_NO_FUSION | capi.RB_MIX_EXACT_ORDER
+
+
+def run_chain(src: rb.Source, ctx, mixer=None, flags=GENERAL) -> np.ndarray:
+    ch, rate = mixer if mixer else (src.channels(), src.sample_rate())
+    with rb.Batch([src], ch, rate, flags=flags, ctx=ctx) as b:
+        b.upload_all()
+        b.render_mix_device()
+        return b.read_stream(0)
+
+
+# ------------------------------------------------------------------ conversions (rows a1, a2, a3)
+def test_src_reference_vectors(ctx):
+    out = rb.SampleRateConverter([2.0, 16.0, 4.0, 18.0, 6.0, 20.0, 8.0, 22.0], 2000, 3000, 2, ctx=ctx)
+    assert np.trunc(out).tolist() == [2.0, 16.0, 3.0, 17.0, 4.0, 18.0, 6.0, 20.0, 7.0, 21.0, 8.0, 22.0]
+    out = rb.SampleRateConverter([1.0, 14.0], 1000, 7000, 1, ctx=ctx)
+    assert np.trunc(out).tolist() == [1.0, 2.0, 4.0, 6.0, 8.0, 10.0, 12.0, 14.0]
+    out = rb.SampleRateConverter(np.arange(17, dtype=np.float32), 12000, 2400, 1, ctx=ctx)
+    assert out.tolist() == [0.0, 5.0, 10.0, 15.0]
+
+
+COMMON_RATES = [8000, 11025, 16000, 22050, 44100, 48000, 88200, 96000, 176400, 192000, 352800, 384000]
+
+
+@pytest.mark.parametrize("to_rate", COMMON_RATES)
+def test_src_common_rates_bit_exact(ctx, to_rate):
+    """benches/resampler.rs:27-44 shape: stereo 44.1 kHz to each common rate."""
+    x = noise(2 * 4001, 100 + to_rate)
+    got = rb.SampleRateConverter(x, 44100, to_rate, 2, ctx=ctx)
+    assert_bit_exact(got, oracle.sample_rate_converter(x, 44100, to_rate, 2), f"44100->{to_rate}")
+
+
+def test_src_random_ratios_bit_exact(ctx):
+    rng = np.random.default_rng(21)
+    rates = COMMON_RATES + [39690, 40000, 1000, 7000, 2400, 12000, 3, 7]
+    for i in range(40):
+        f, t, c = int(rng.choice(rates)), int(rng.choice(rates)), int(rng.integers(1, 7))
+        frames = int(rng.integers(0, 3000))
+        if frames * t / f > 200_000:
+            frames = int(200_000 * f / t)
+        x = noise(frames * c, 1000 + i)
+        got = rb.SampleRateConverter(x, f, t, c, ctx=ctx)
+        assert_bit_exact(got, oracle.sample_rate_converter(x, f, t, c), f"{f}->{t} c={c} frames={frames}")
+
+
+def test_src_properties(ctx):
+    """quickcheck properties of sample_rate.rs:252-334 on the GPU path."""
+    rng = np.random.default_rng(22)
+    assert rb.SampleRateConverter(np.zeros(0, np.float32), 44100, 48000, 2, ctx=ctx).size == 0
+    for _ in range(10):
+        c, k = int(rng.integers(1, 5)), int(rng.integers(1, 9))
+        x = rng.integers(-32768, 32767, c * int(rng.integers(1, 500))).astype(np.float32)
+        assert np.array_equal(rb.SampleRateConverter(x, 12345, 12345, c, ctx=ctx), x)            # identity
+        out = rb.SampleRateConverter(x, 4800 * k, 4800, c, ctx=ctx)                               # divide
+        assert np.array_equal(out, x.reshape(-1, c)[::k].reshape(-1))
+        out = rb.SampleRateConverter(x, 4800, 4800 * k, c, ctx=ctx)                               # multiply
+        assert np.array_equal(out.reshape(-1, c)[::k].reshape(-1), x)
+
+
+@pytest.mark.parametrize("x,f,t,want", [
+    ([1, 2, 3, 4, 5, 6], 3, 2, [1, 2, 4, 5]),
+    ([1, 2, 3, 4, 5, 6, 7, 8], 4, 1, [1, 5]),
+    ([1, 2, 3, 4], 1, 2, [1, 1, 2, 2, 3, 3, 4, 4]),
+    ([1, 2], 1, 4, [1, 1, 0, 0, 2, 2, 0, 0]),
+    ([1, 2, 3, 4], 2, 4, [1, 2, 0, 0, 3, 4, 0, 0]),
+    ([1, 2, 3, 4], 2, 2, [1, 2, 3, 4]),
+])
+def test_channel_count_converter_vectors(ctx, x, f, t, want):
+    out = rb.ChannelCountConverter(np.array(x, np.float32), f, t, ctx=ctx)
+    assert out.tolist() == [float(v) for v in want]
+
+
+def test_channel_count_converter_random(ctx):
+    rng = np.random.default_rng(23)
+    for i in range(20):
+        f, t = int(rng.integers(1, 9)), int(rng.integers(1, 9))
+        x = noise(f * int(rng.integers(0, 2000)), 300 + i)
+        x[::7] = -0.0
+        assert_bit_exact(rb.ChannelCountConverter(x, f, t, ctx=ctx), oracle.channel_count_converter(x, f, t), f"{f}->{t}")
+
+
+@pytest.mark.parametrize("fmt,dt", [(1, np.int16), (2, np.uint16), (3, np.int8), (4, np.uint8), (5, np.int32), (6, np.int32)])
+def test_sample_type_converter(ctx, fmt, dt):
+    rng = np.random.default_rng(24 + fmt)
+    info = np.iinfo(dt)
+    lo, hi = (info.min, info.max) if fmt != 6 else (-(1 << 23), (1 << 23) - 1)
+    ints = np.concatenate([rng.integers(lo, hi, 5000, endpoint=True), [lo, hi, 0, 1, -1 if lo < 0 else 1]]).astype(dt)
+    got = rb.SampleTypeConverter(ints, capi.RB_FMT_F32, in_fmt=fmt, ctx=ctx)
+    assert_bit_exact(got, oracle.convert(ints, fmt, 0), f"fmt {fmt} -> f32")
+    f = np.concatenate([noise(5000, 77 + fmt, 1.2), np.array([1.0, -1.0, 0.0, -0.0, 2.0, -2.0, np.nan, np.inf, -np.inf,
+                                                               0.99999994, -0.99999994, 1e-9], np.float32)])
+    got = rb.SampleTypeConverter(f, fmt, ctx=ctx)
+    want = oracle.convert(f, 0, fmt)
+    assert got.dtype == want.dtype and np.array_equal(got, want), f"f32 -> fmt {fmt}"
+
+
+# ------------------------------------------------------------------ single adapters (rows a6..a12)
+@pytest.mark.parametrize("name", sorted(CHAINS))
+def test_chain_bit_exact(ctx, name):
+    src = CHAINS[name]()
+    want, ch, rate = oracle.chain(to_oracle(src))
+    assert (ch, rate) == (src.channels(), src.sample_rate())
+    got = run_chain(src, ctx)
+    assert_bit_exact(got, want, name)
+
+
+@pytest.mark.parametrize("name", sorted(LIMIT_CHAINS))
+def test_limiter_within_tolerance(ctx, name):
+    """log2f / exp2f on the device differ from glibc by <= 2 ulp: tolerance 1e-5 * peak (north star)."""
+    src = LIMIT_CHAINS[name]()
+    want = oracle.chain(to_oracle(src))[0]
+    assert_close_peak(run_chain(src, ctx), want, 1e-5, name)
+
+
+def test_limiter_reference_bands(ctx):
+    """tests/limit.rs:6-38 on the GPU path."""
+    st = rb.LimitSettings.default().with_threshold(-6.0).with_knee_width(0.5) \
+        .with_attack(rb.Duration.from_millis(3)).with_release(rb.Duration.from_millis(12))
+    out = run_chain(rb.TestSource(oracle.sine_wave(440.0, 2600), 1, 48000).amplify(3.0).limit(st), ctx)
+    assert 0.4 <= np.max(np.abs(out[1500:])) <= 0.6
+
+
+# ------------------------------------------------------------------ what the mixer pulls per stream (row a4)
+@pytest.mark.parametrize("name", ["amplify", "low_pass_stereo", "reverb", "spatial", "channel_volume_1_to_2",
+                                  "uniform_then_effects", "agc_default", "i16_input"])
+@pytest.mark.parametrize("mix", [(1, 48000), (2, 48000), (2, 44100), (4, 96000)])
+def test_chain_through_mixer_uniform(ctx, name, mix):
+    src = CHAINS[name]()
+    want = oracle.chain_uniform(to_oracle(src), *mix)
+    assert_bit_exact(run_chain(src, ctx, mixer=mix), want, f"{name} -> {mix}")
+
+
+# ------------------------------------------------------------------ mixer (row a5): src/mixer.rs:208-341
+def test_mixer_basic(ctx):
+    tx, rx = rb.mixer(1, 48000, ctx=ctx)
+    tx.add(rb.SamplesBuffer(1, 48000, [10.0, -10.0, 10.0, -10.0]))
+    tx.add(rb.SamplesBuffer(1, 48000, [5.0, 5.0, 5.0, 5.0]))
+    assert rx.channels() == 1 and rx.sample_rate() == 48000
+    assert [rx.next() for _ in range(5)] == [15.0, -5.0, 15.0, -5.0, None]
+
+
+def test_mixer_channels_conv(ctx):
+    tx, rx = rb.mixer(2, 48000, ctx=ctx)
+    tx.add(rb.SamplesBuffer(1, 48000, [10.0, -10.0, 10.0, -10.0]))
+    tx.add(rb.SamplesBuffer(1, 48000, [5.0, 5.0, 5.0, 5.0]))
+    assert [rx.next() for _ in range(9)] == [15.0, 15.0, -5.0, -5.0, 15.0, 15.0, -5.0, -5.0, None]
+
+
+def test_mixer_rate_conv(ctx):
+    tx, rx = rb.mixer(1, 96000, ctx=ctx)
+    tx.add(rb.SamplesBuffer(1, 48000, [10.0, -10.0, 10.0, -10.0]))
+    tx.add(rb.SamplesBuffer(1, 48000, [5.0, 5.0, 5.0, 5.0]))
+    assert [rx.next() for _ in range(8)] == [15.0, 5.0, -5.0, 5.0, 15.0, 5.0, -5.0, None]
+
+
+def test_mixer_start_afterwards(ctx):
+    tx, rx = rb.mixer(1, 48000, ctx=ctx)
+    tx.add(rb.SamplesBuffer(1, 48000, [10.0, -10.0, 10.0, -10.0]))
+    assert [rx.next(), rx.next()] == [10.0, -10.0]
+    tx.add(rb.SamplesBuffer(1, 48000, [5.0, 5.0, 6.0, 6.0, 7.0, 7.0, 7.0]))
+    assert [rx.next() for _ in range(4)] == [15.0, -5.0, 6.0, 6.0]
+    tx.add(rb.SamplesBuffer(1, 48000, [2.0]))
+    assert [rx.next() for _ in range(4)] == [9.0, 7.0, 7.0, None]
+
+
+def test_mixer_added_taking_phase_into_account(ctx):
+    tx, rx = rb.mixer(2, 48000, ctx=ctx)
+    tx.add(rb.SamplesBuffer(2, 48000, [10.0, -10.0, 10.0, -10.0]))
+    assert rx.next() == 10.0
+    tx.add(rb.SamplesBuffer(2, 48000, [5.0, -5.0, 6.0, -6.0]))
+    assert rx.next() == -10.0      # not yet mixed (out of phase)
+    assert rx.next() == 15.0       # mixing starts
+
+
+def test_mixer_empty(ctx):
+    tx, rx = rb.mixer(2, 48000, ctx=ctx)
+    assert rx.next() is None
+    with rb.Batch([], 2, 48000, ctx=ctx) as b:
+        assert b.mix_len == 0
+        assert b.render_mix().size == 0
+
+
+def _random_streams(rng, n, mixer_rate):
+    srcs, starts = [], []
+    for i in range(n):
+        ch = int(rng.choice([1, 2]))
+        rate = int(rng.choice([mixer_rate, 44100, 22050]))
+        frames = int(rng.integers(0, 3000))
+        x = noise(frames * ch, 5000 + i, 0.5)
+        s = rb.SamplesBuffer(ch, rate, x) if i % 2 else rb.TestSource(x, ch, rate)
+        k = int(rng.integers(0, 4))
+        if k == 1:
+            s = s.amplify(0.7)
+        elif k == 2:
+            s = s.low_pass(800)
+        elif k == 3:
+            s = s.reverb(rb.Duration.from_millis(3), 0.4)
+        srcs.append(s)
+        starts.append(int(rng.integers(0, 1500)) if i % 3 == 0 else 0)
+    return srcs, starts
+
+
+@pytest.mark.parametrize("mix", [(1, 48000), (2, 48000)])
+def test_mixer_random_streams_exact_order(ctx, mix):
+    """Heterogeneous chains, lengths, rates and late starts; ordered sum is bit-exact with the oracle."""
+    rng = np.random.default_rng(40 + mix[0])
+    srcs, starts = _random_streams(rng, 37, mix[1])
+    want = oracle.mixer([to_oracle(s, st) for s, st in zip(srcs, starts)], *mix)
+    with rb.Batch(srcs, *mix, flags=GENERAL, mix_starts=starts, ctx=ctx) as b:
+        b.upload_all()
+        got = b.render_mix()
+        for i, s in enumerate(srcs):
+            assert b.stream_out_len(i) == oracle.chain_uniform(to_oracle(s), *mix).size
+    assert_bit_exact(got, want, "random mixer")
+
+
+# ------------------------------------------------------------------ BASELINE configs at oracle-friendly sizes
+def _cfg3_sources(n_streams, frames, seed=0x5EED):
+    return [rb.UniformSourceIterator(rb.TestSource(noise(frames, seed + s), 1, 44100), 1, 48000)
+            .low_pass(200).amplify(1.2) for s in range(n_streams)]
+
+
+def test_cfg3_pipeline_small_exact(ctx):
+    """cfg3 shape: resample 44.1->48 k -> low_pass(200) -> amplify(1.2) -> mix, general path, bit-exact."""
+    srcs = _cfg3_sources(24, 4410)
+    want = oracle.mixer([to_oracle(s) for s in srcs], 1, 48000)
+    with rb.Batch(srcs, 1, 48000, flags=GENERAL, ctx=ctx) as b:
+        b.upload_all()
+        got = b.render_mix()
+    assert_bit_exact(got, want, "cfg3 small")
+
+
+@pytest.mark.parametrize("n_streams,frames", [(1, 4410), (5, 1000), (33, 2000), (150, 3000), (300, 700)])
+def test_cfg3_pipeline_default_path(ctx, n_streams, frames):
+    """Same shape through the default (fused) path: <= 1e-5 * peak of the sequential reference sum."""
+    srcs = _cfg3_sources(n_streams, frames, seed=900)
+    want = oracle.mixer([to_oracle(s) for s in srcs], 1, 48000)
+    with rb.Batch(srcs, 1, 48000, ctx=ctx) as b:
+        b.upload_all()
+        got = b.render_mix()
+        assert b.launches_per_render >= 1
+    assert_close_peak(got, want, 1e-5, f"cfg3 default S={n_streams}")
+
+
+def test_cfg2_mixer_of_sines(ctx):
+    """cfg2 shape: SineWave sources summed by mixer(1, 48000)."""
+    n, frames = 64, 4800
+    srcs = [rb.TestSource(oracle.sine_wave(110.0 * 2 ** (s / 12.0), frames), 1, 48000) for s in range(n)]
+    want = oracle.mixer([to_oracle(s) for s in srcs], 1, 48000)
+    with rb.Batch(srcs, 1, 48000, flags=GENERAL, ctx=ctx) as b:
+        b.upload_all()
+        assert_bit_exact(b.render_mix(), want, "cfg2 exact")
+    with rb.Batch(srcs, 1, 48000, ctx=ctx) as b:
+        b.upload_all()
+        assert_close_peak(b.render_mix(), want, 1e-5, "cfg2 default")
+
+
+def test_cfg4_effect_chain(ctx):
+    """cfg4 shape: spatial -> reverb(50 ms, 0.3) -> AGC(default) -> mix(2 ch)."""
+    n, frames = 12, 12000
+    srcs = []
+    for s in range(n):
+        t = np.arange(frames, dtype=np.float32)
+        l = np.sin(t * np.float32(0.02 + 0.001 * s)).astype(np.float32) * np.float32(0.4)
+        r = np.sin(t * np.float32(0.021 + 0.001 * s)).astype(np.float32) * np.float32(0.4)
+        x = np.stack([l, r], 1).reshape(-1) + noise(2 * frames, 700 + s, 0.1)
+        src = rb.Spatial(rb.TestSource(x, 2, 48000), [float(s % 7 - 3), 1.0, 0.0], [-1, 0, 0], [1, 0, 0]) \
+            .reverb(rb.Duration.from_millis(50), 0.3).automatic_gain_control()
+        srcs.append(src)
+    want = oracle.mixer([to_oracle(s) for s in srcs], 2, 48000)
+    with rb.Batch(srcs, 2, 48000, flags=GENERAL, ctx=ctx) as b:
+        b.upload_all()
+        got = b.render_mix()
+        for i in (0, n - 1):
+            assert_bit_exact(b.read_stream(i), oracle.chain_uniform(to_oracle(srcs[i]), 2, 48000), f"cfg4 stream {i}")
+    assert_bit_exact(got, want, "cfg4 mix")
+
+
+# ------------------------------------------------------------------ edge cases and errors
+def test_edge_cases(ctx):
+    for frames in [0, 1, 2, 3]:
+        src = rb.UniformSourceIterator(rb.SamplesBuffer(2, 44100, noise(2 * frames, 60 + frames)), 2, 48000).low_pass(100)
+        assert_bit_exact(run_chain(src, ctx), oracle.chain(to_oracle(src))[0], f"frames={frames}")
+    src = rb.SamplesBuffer(1, 48000, np.array([-0.0, 0.0, -0.0], np.float32)).reverb(rb.Duration.from_nanos(1), 1.0)
+    assert_bit_exact(run_chain(src, ctx), oracle.chain(to_oracle(src))[0], "negative zero")
+    tx, rx = rb.mixer(1, 48000, ctx=ctx)
+    tx.add(rb.SamplesBuffer(1, 48000, np.array([-0.0], np.float32)))
+    assert np.float32(rx.next()).view(np.uint32) == 0        # 0.0 + -0.0 == +0.0 like the reference sum
+
+
+def test_argument_errors(ctx):
+    with pytest.raises(rb.RodioB200Error) as e:
+        rb.Batch([rb.SamplesBuffer(2, 44100, np.zeros(3, np.float32))], 2, 48000, ctx=ctx)
+    assert e.value.status == capi.RB_ERR_UNALIGNED_FRAMES
+    with pytest.raises(rb.RodioB200Error) as e:
+        rb.Batch([rb.SamplesBuffer(1, 44100, np.zeros(4, np.float32)).automatic_gain_control(
+            rb.AutomaticGainControlSettings(absolute_max_gain=0.05))], 1, 48000, ctx=ctx)
+    assert e.value.status == capi.RB_ERR_INVALID_ARGUMENT
+    with pytest.raises(rb.RodioB200Error) as e:
+        rb.Batch([rb.SamplesBuffer(1, 96001, np.zeros(4, np.float32))], 1, 192000, ctx=ctx)
+    assert e.value.status == capi.RB_ERR_RATIO_OVERFLOW
+    with rb.Batch([rb.SamplesBuffer(1, 44100, np.zeros(4, np.float32))], 1, 48000, ctx=ctx) as b:
+        with pytest.raises(rb.RodioB200Error) as e:
+            b.render_mix()
+        assert e.value.status == capi.RB_ERR_STATE
+
+
+# ------------------------------------------------------------------ full-size, size-independent properties
+def test_full_size_properties(ctx):
+    """BASELINE cfg3 at full per-stream size (44 100 frames) on 512 streams: properties that need no oracle."""
+    S, frames = 512, 44100
+    rng = np.random.default_rng(99)
+    base = rng.uniform(-1, 1, (S, frames)).astype(np.float32)
+    mk = lambda amp: [rb.UniformSourceIterator(rb.TestSource(base[s], 1, 44100), 1, 48000).low_pass(200).amplify(amp)
+                      for s in range(S)]
+    with rb.Batch(mk(1.0), 1, 48000, ctx=ctx) as b:
+        b.upload_all()
+        assert b.mix_len == 48000
+        y1 = b.render_mix().copy()
+        y1b = b.render_mix().copy()
+    assert np.array_equal(y1, y1b), "render is deterministic / idempotent"
+    with rb.Batch(mk(2.0), 1, 48000, ctx=ctx) as b:     # scaling by a power of two commutes with every rounding
+        b.upload_all()
+        y2 = b.render_mix()
+    assert np.array_equal(y2, y1 * np.float32(2.0))
+    # spot-check 3 streams of the full-size batch against the oracle, through the exact general path
+    pick = [0, 255, 511]
+    srcs = [mk(1.0)[i] for i in pick]
+    want = oracle.mixer([to_oracle(s) for s in srcs], 1, 48000)
+    with rb.Batch(srcs, 1, 48000, flags=GENERAL, ctx=ctx) as b:
+        b.upload_all()
+        assert_bit_exact(b.render_mix(), want, "full-length spot check")
+    assert np.isfinite(y1).all() and np.max(np.abs(y1)) > 0
