@@ -109,7 +109,8 @@ typedef struct rb_stream_desc {
     uint32_t n_effects;
     const rb_effect* effects;
     uint64_t mix_start;     /* mixer output sample index at which Mixer::add was called; rounded up to
-                               the next frame boundary like src/mixer.rs:175-183 */
+                               the next frame boundary like src/mixer.rs:175-183.  The mixer sums in the
+                               order of the add calls: increasing mix_start, ties in array order. */
 } rb_stream_desc;
 
 typedef struct rb_context rb_context;

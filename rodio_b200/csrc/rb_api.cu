@@ -537,12 +537,20 @@ extern "C" rb_status rb_batch_create(rb_context* ctx, uint16_t mixer_ch, uint32_
     RB_CUDA(cudaMalloc(&b->d_in, std::max<size_t>(in_bytes, 256)));
     RB_CUDA(cudaMalloc(&b->d_out, std::max<size_t>(mix_len * 4, 256)));
 
+    // Mixer insertion order: Mixer::add calls arrive in increasing output position, ties in array order
+    // (src/mixer.rs:175-183 appends pending sources in arrival order) -> stable sort by mix_start.
+    std::vector<size_t> order(n_streams);
+    std::iota(order.begin(), order.end(), (size_t)0);
+    std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) {
+        return b->streams[x].desc.mix_start < b->streams[y].desc.mix_start;
+    });
+
     // Fast path: one fused kernel family when the whole batch has a chain shape it understands.
     if (!(flags & RB_NO_FUSION)) {
         std::vector<rb_fused_stream> fs(n_streams);
         bool ok = true;
         for (size_t i = 0; i < n_streams && ok; i++) {
-            PlanStream& ps = b->streams[i];
+            PlanStream& ps = b->streams[order[i]];
             fs[i].in = b->d_in + ps.in_off;
             fs[i].fmt = ps.desc.format;
             fs[i].n_nodes = (uint32_t)ps.nodes.size();
@@ -591,7 +599,7 @@ extern "C" rb_status rb_batch_create(rb_context* ctx, uint16_t mixer_ch, uint32_
                                cudaMemcpyHostToDevice));
         std::vector<rb_mix_src> mix(n_streams);
         for (size_t i = 0; i < n_streams; i++) {
-            PlanStream& ps = b->streams[i];
+            PlanStream& ps = b->streams[order[i]];
             size_t k = ps.nodes.size();
             ps.final_ptr = (k == 0) ? (const float*)(b->d_in + ps.in_off) : b->d_buf[(k - 1) & 1] + ps.buf_off;
             mix[i] = {ps.final_ptr, ps.mix_start, ps.out_len};

@@ -1,15 +1,507 @@
-// rb_fused.cu — fused resample -> channel-map -> effects -> mix kernels (fast path).
+// rb_fused.cu — the fused resample -> channel-map -> effects -> mix kernel (fast path).
+//
+// Shape covered (every stream of the batch must have the same adapter-kind sequence; parameters are
+// per stream):   [convert] [amplify]*  [uniform]?  [amplify]* [biquad]? [amplify]*   -> mixer sum
+// i.e. BASELINE cfg2 (plain mixer of sources) and cfg3 (resample -> low_pass -> amplify -> mix), in any
+// channel layout.  Everything else is served by the general per-adapter kernels (rb_kernels.cu).
+//
+// Work decomposition (B200: 148 SMs, 4 sub-partitions each, 1 warp-instruction / cycle / sub-partition):
+//   * a CTA owns G consecutive streams ("rows", insertion order) and walks the mixer timeline in tiles
+//     of TT samples; G is chosen so that the grid is one balanced wave over the SMs.
+//   * per tile three stages run CONCURRENTLY on three different tiles (software pipeline over a ring of
+//     three shared-memory tile buffers, one __syncthreads per tile):
+//       A  (all "parallel" warps)  tile k   : input taps -> pre-gains -> linear interpolation + channel map
+//                                             -> gains  => x[row][t] in shared memory; loads are coalesced
+//                                             along time and every input sample is fetched from HBM once.
+//       B  (recurrence warps)      tile k-1 : Direct-Form-I biquad, one lane per (row, channel) chain,
+//                                             strictly the reference's f32 operation order (bit-exact);
+//                                             state lives in registers across tiles.
+//       C  (parallel warps)        tile k-2 : post-gains and the ordered sum over the CTA's rows
+//                                             -> one partial-mix row per CTA in HBM.
+//     The recurrence is a 12-cycle dependent chain per sample (FMUL -> FADD -> FADD): it is the critical
+//     path at modest batch sizes, so stage B owns its warps and never waits for loads.
+//   * a second tiny kernel adds the per-CTA partial rows in CTA order (deterministic).  With one CTA the
+//     result equals the reference's strictly sequential sum bit for bit.
+//
+// Without a biquad the kernel degenerates to stage A + C in registers (no shared memory, no barrier).
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "rb_dsp.cuh"
 #include "rb_fused.h"
 
-struct rb_fused_plan {
-    int unused;
+using namespace rbd;
+
+namespace {
+
+constexpr int TT = 256;            // mixer-timeline samples per tile
+constexpr int ROW_STRIDE = TT + 4; // words; (TT+4)/4 odd -> LDS.128 by 8 lanes hits 8 distinct bank groups
+constexpr int MAX_G = 32;          // rows per CTA
+constexpr int NBUF = 3;
+constexpr int MAX_GAINS = 4;
+
+struct FusedRow {                  // one stream, device side
+    const void* in;
+    uint64_t n_in;
+    uint64_t out_len;              // samples on the mixer timeline
+    uint64_t mix_start;
+    uint32_t fmt, c_in;
+    uint32_t has_uniform, pad_;
+    rb_uniform_params uni;
+    float pre[MAX_GAINS];          // gains applied to raw input samples (before interpolation)
+    float mid[MAX_GAINS];          // gains between the uniform conversion and the biquad
+    float post[MAX_GAINS];         // gains after the biquad
+    float b0, b1, b2, a1, a2;
 };
 
-cudaError_t rb_fused_try_create(const rb_fused_stream*, size_t, uint16_t, float*, uint64_t, uint32_t, int, cudaStream_t,
-                                rb_fused_plan** out) {
-    *out = nullptr;   // first milestone: every batch goes through the general path
+struct FusedArgs {
+    const FusedRow* rows;
+    uint32_t n_rows;
+    uint32_t rows_per_cta;
+    uint32_t c_mix;                // mixer channels
+    uint32_t n_pre, n_mid, n_post;
+    uint32_t has_biquad;
+    float* partial;                // [n_ctas][mix_len]
+    uint64_t mix_len;
+    uint32_t direct;               // single CTA: `partial` is the mixer output itself, cover the whole timeline
+    uint32_t pad_;
+};
+
+// ---- per (row, tile) fast index state --------------------------------------------------------------
+struct RowTile {
+    uint32_t lo, hi;       // active tile positions [lo, hi)
+    uint32_t fast;         // 1: fast uniform path valid for the whole active range
+    uint32_t r0;           // (n0 * from) mod to at the first active frame
+    uint64_t i0;           // left input frame of the first active frame (absolute, in frames)
+    uint64_t L;            // frames in the segment (for the raw-last-frame test), absolute end frame
+    uint64_t o0;           // row-local output sample index at tile position `lo`
+    uint32_t j0;           // channel of that sample (o0 % c_mix)
+    uint32_t pad_;
+};
+
+__device__ __forceinline__ float apply_gains(float v, const float* g, uint32_t n) {
+#pragma unroll
+    for (int k = 0; k < MAX_GAINS; k++)
+        if (k < (int)n) v = mul(v, g[k]);
+    return v;
+}
+
+__device__ __forceinline__ float load_pre(const FusedRow& r, uint32_t n_pre, uint64_t idx) {
+    return apply_gains(load_as_f32(r.in, r.fmt, idx), r.pre, n_pre);
+}
+
+// Generic (any segment / partial frame / chunk boundary) sample of the row at local output index o.
+__device__ float row_sample_generic(const FusedRow& r, const FusedArgs& a, uint64_t o) {
+    if (!r.has_uniform) return apply_gains(load_pre(r, a.n_pre, o), r.mid, a.n_mid);
+    UniformTap t = uniform_tap(r.uni, r.c_in, a.c_mix, o);
+    float v = 0.0f;
+    if (t.kind != 0) {
+        float x0 = load_pre(r, a.n_pre, t.i0);
+        v = x0;
+        if (t.kind == 2) {
+            float x1 = load_pre(r, a.n_pre, t.i0 + r.c_in);
+            v = lerp_f(x0, x1, __uint2float_rn(t.num), __uint2float_rn(r.uni.to));
+        }
+    }
+    return apply_gains(v, r.mid, a.n_mid);
+}
+
+__device__ void row_tile_setup(const FusedRow& r, const FusedArgs& a, uint64_t m0, RowTile& rt) {
+    uint64_t s = r.mix_start, e = r.mix_start + r.out_len;
+    uint64_t lo = m0 > s ? m0 : s, hi = (m0 + TT) < e ? (m0 + TT) : e;
+    if (lo >= hi) {
+        rt.lo = rt.hi = 0, rt.fast = 0;
+        return;
+    }
+    rt.lo = (uint32_t)(lo - m0), rt.hi = (uint32_t)(hi - m0);
+    rt.o0 = lo - s;
+    rt.j0 = (uint32_t)(rt.o0 % a.c_mix);
+    rt.fast = 0;
+    if (!r.has_uniform) return;
+    const rb_uniform_params& u = r.uni;
+    if (u.from == u.to || u.chunk_samples != 0 || u.tail.p != 0) return;
+    if (u.from > (1u << 20) || u.to > (1u << 20)) return;
+    uint64_t o_last = hi - 1 - s;
+    if (o_last / a.c_mix >= u.tail.full_out_frames) return;          // stay inside the all-channels region
+    uint64_t n0 = rt.o0 / a.c_mix;
+    uint64_t prod = n0 * (uint64_t)u.from;
+    rt.i0 = prod / u.to;
+    rt.r0 = (uint32_t)(prod - rt.i0 * u.to);
+    rt.L = u.tail.L;
+    rt.fast = 1;
+}
+
+// Value of row `r` at tile position t (active), using the fast incremental index path when valid.
+__device__ __forceinline__ float row_sample(const FusedRow& r, const FusedArgs& a, const RowTile& rt, uint32_t t,
+                                            float den_f) {
+    uint64_t o = rt.o0 + (t - rt.lo);
+    if (!rt.fast) return row_sample_generic(r, a, o);
+    uint32_t c_mix = a.c_mix;
+    uint32_t rel = (t - rt.lo) + rt.j0;          // flat offset from the start of frame n0
+    uint32_t k = rel / c_mix, j = rel - k * c_mix;
+    int c = chan_map(j, r.c_in);
+    float v = 0.0f;
+    if (c >= 0) {
+        uint32_t prod = rt.r0 + k * r.uni.from;    // < 2^20 + 256 * 2^20
+        uint32_t di = prod / r.uni.to;
+        uint32_t num = prod - di * r.uni.to;
+        uint64_t i = rt.i0 + di;
+        uint64_t idx = i * r.c_in + (uint32_t)c;
+        float x0 = load_pre(r, a.n_pre, idx);
+        v = x0;
+        if (i + 1 < rt.L) {
+            float x1 = load_pre(r, a.n_pre, idx + r.c_in);
+            v = lerp_f(x0, x1, __uint2float_rn(num), den_f);
+        }
+    }
+    return apply_gains(v, r.mid, a.n_mid);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// no-biquad variant: stage A and C fused in registers, no shared memory
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fused_nobiquad(FusedArgs a) {
+    __shared__ RowTile s_rt[MAX_G];
+    const uint32_t row0 = blockIdx.x * a.rows_per_cta;
+    const uint32_t G = min(a.rows_per_cta, a.n_rows - row0);
+    const FusedRow* rows = a.rows + row0;
+    float* partial = a.partial + (uint64_t)blockIdx.x * a.mix_len;
+    // this CTA's span of the mixer timeline
+    uint64_t lo = ~0ull, hi = 0;
+    for (uint32_t g = 0; g < G; g++) {
+        if (rows[g].out_len == 0) continue;
+        lo = min(lo, rows[g].mix_start);
+        hi = max(hi, rows[g].mix_start + rows[g].out_len);
+    }
+    if (a.direct) lo = 0, hi = a.mix_len;
+    if (lo >= hi) return;
+    uint64_t m_begin = lo / TT * TT;
+    for (uint64_t m0 = m_begin + (uint64_t)blockIdx.y * TT; m0 < hi; m0 += (uint64_t)gridDim.y * TT) {
+        __syncthreads();
+        if (threadIdx.x < G) row_tile_setup(rows[threadIdx.x], a, m0, s_rt[threadIdx.x]);
+        __syncthreads();
+        uint32_t t = threadIdx.x;
+        if (m0 + t < a.mix_len) {
+            float acc = 0.0f;
+            for (uint32_t g = 0; g < G; g++) {
+                const RowTile& rt = s_rt[g];
+                if (t >= rt.lo && t < rt.hi) {
+                    const FusedRow& r = rows[g];
+                    float v = row_sample(r, a, rt, t, __uint2float_rn(r.uni.to));
+                    acc = add(acc, apply_gains(v, r.post, a.n_post));
+                }
+            }
+            partial[m0 + t] = acc;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// biquad variant: three-stage software pipeline over shared-memory tiles
+// ---------------------------------------------------------------------------------------------------
+template <int C_MIX_STATIC>   // 1: mono fast path (vectorised recurrence), 0: generic channel count
+__global__ void __launch_bounds__(512, 1) k_fused_biquad(FusedArgs a, uint32_t n_rec_warps) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ RowTile s_rt[NBUF][MAX_G];
+    const uint32_t row0 = blockIdx.x * a.rows_per_cta;
+    const uint32_t G = min(a.rows_per_cta, a.n_rows - row0);
+    const FusedRow* rows = a.rows + row0;
+    float* partial = a.partial + (uint64_t)blockIdx.x * a.mix_len;
+    const uint32_t c_mix = C_MIX_STATIC ? (uint32_t)C_MIX_STATIC : a.c_mix;
+
+    uint64_t lo = ~0ull, hi = 0;
+    for (uint32_t g = 0; g < G; g++) {
+        if (rows[g].out_len == 0) continue;
+        lo = min(lo, rows[g].mix_start);
+        hi = max(hi, rows[g].mix_start + rows[g].out_len);
+    }
+    if (a.direct) lo = 0, hi = a.mix_len;
+    if (lo >= hi) return;
+    const uint64_t m_begin = lo / TT * TT;
+    const uint32_t n_tiles = (uint32_t)((hi - m_begin + TT - 1) / TT);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t n_warps = blockDim.x >> 5;
+    const bool is_rec = warp < n_rec_warps;
+    const uint32_t n_par_threads = (n_warps - n_rec_warps) * 32;
+    const uint32_t par_tid = threadIdx.x - n_rec_warps * 32;
+
+    // recurrence lane -> chain (row, channel); state in registers for the whole stream
+    const uint32_t chain = warp * 32 + lane;
+    const uint32_t ch_row = chain / c_mix, ch_c = chain - ch_row * c_mix;
+    const bool chain_on = is_rec && ch_row < G;
+    float x1 = 0.f, x2 = 0.f, y1 = 0.f, y2 = 0.f;
+    float b0 = 0.f, b1 = 0.f, b2 = 0.f, a1 = 0.f, a2 = 0.f;
+    if (chain_on) {
+        const FusedRow& r = rows[ch_row];
+        b0 = r.b0, b1 = r.b1, b2 = r.b2, a1 = r.a1, a2 = r.a2;
+    }
+
+    for (uint32_t it = 0; it < n_tiles + 2; it++) {
+        // ---- stage A on tile `it` ----
+        if (!is_rec) {
+            if (it < n_tiles) {
+                const uint32_t buf = it % NBUF;
+                const uint64_t m0 = m_begin + (uint64_t)it * TT;
+                float* tile = smem + (size_t)buf * MAX_G * ROW_STRIDE;
+                // per-row index state for this tile (one thread per row), visible to the same warps only after
+                // a named barrier among the parallel warps
+                if (par_tid < G) row_tile_setup(rows[par_tid], a, m0, s_rt[buf][par_tid]);
+                asm volatile("bar.sync 1, %0;" ::"r"(n_par_threads));
+                for (uint32_t item = par_tid; item < G * TT; item += n_par_threads) {
+                    uint32_t g = item / TT, t = item - g * TT;
+                    const RowTile& rt = s_rt[buf][g];
+                    float v = 0.0f;
+                    if (t >= rt.lo && t < rt.hi) {
+                        const FusedRow& r = rows[g];
+                        v = row_sample(r, a, rt, t, __uint2float_rn(r.uni.to));
+                    }
+                    tile[g * ROW_STRIDE + t] = v;
+                }
+            }
+            // ---- stage C on tile `it - 2` ----
+            if (it >= 2) {
+                const uint32_t kt = it - 2;
+                const uint32_t buf = kt % NBUF;
+                const uint64_t m0 = m_begin + (uint64_t)kt * TT;
+                const float* tile = smem + (size_t)buf * MAX_G * ROW_STRIDE;
+                for (uint32_t t = par_tid; t < TT; t += n_par_threads) {
+                    if (m0 + t >= a.mix_len) continue;
+                    float acc = 0.0f;
+                    for (uint32_t g = 0; g < G; g++) {
+                        const RowTile& rt = s_rt[buf][g];
+                        if (t >= rt.lo && t < rt.hi)
+                            acc = add(acc, apply_gains(tile[g * ROW_STRIDE + t], rows[g].post, a.n_post));
+                    }
+                    partial[m0 + t] = acc;
+                }
+            }
+        } else if (it >= 1 && it <= n_tiles) {
+            // ---- stage B on tile `it - 1` ----
+            const uint32_t kt = it - 1;
+            const uint32_t buf = kt % NBUF;
+            if (chain_on) {
+                float* row = smem + (size_t)buf * MAX_G * ROW_STRIDE + ch_row * ROW_STRIDE;
+                const RowTile& rt = s_rt[buf][ch_row];
+                if (C_MIX_STATIC == 1) {
+                    uint32_t t = rt.lo, hi_t = rt.hi;
+                    for (; t < hi_t && (t & 3); t++) {               // head up to 16-byte alignment
+                        float xv = row[t];
+                        float y = biquad_fb(a1, a2, biquad_ff(b0, b1, b2, xv, x1, x2), y1, y2);
+                        x2 = x1, x1 = xv, y2 = y1, y1 = y;
+                        row[t] = y;
+                    }
+                    for (; t + 4 <= hi_t; t += 4) {
+                        float4 xv = *reinterpret_cast<const float4*>(row + t);
+                        float4 yv;
+                        float f0 = biquad_ff(b0, b1, b2, xv.x, x1, x2);
+                        float f1 = biquad_ff(b0, b1, b2, xv.y, xv.x, x1);
+                        float f2 = biquad_ff(b0, b1, b2, xv.z, xv.y, xv.x);
+                        float f3 = biquad_ff(b0, b1, b2, xv.w, xv.z, xv.y);
+                        yv.x = biquad_fb(a1, a2, f0, y1, y2);
+                        yv.y = biquad_fb(a1, a2, f1, yv.x, y1);
+                        yv.z = biquad_fb(a1, a2, f2, yv.y, yv.x);
+                        yv.w = biquad_fb(a1, a2, f3, yv.z, yv.y);
+                        x2 = xv.z, x1 = xv.w, y2 = yv.z, y1 = yv.w;
+                        *reinterpret_cast<float4*>(row + t) = yv;
+                    }
+                    for (; t < hi_t; t++) {
+                        float xv = row[t];
+                        float y = biquad_fb(a1, a2, biquad_ff(b0, b1, b2, xv, x1, x2), y1, y2);
+                        x2 = x1, x1 = xv, y2 = y1, y1 = y;
+                        row[t] = y;
+                    }
+                } else {
+                    // chain (row, c): positions whose mixer channel is c.  Streams join on a frame boundary
+                    // (mixer.rs:175-183) so channel == (m0 + t) % c_mix == (local index) % c_mix.
+                    const uint64_t m0 = m_begin + (uint64_t)kt * TT;
+                    uint32_t ph = (uint32_t)((m0 + rt.lo) % c_mix);
+                    uint32_t t = rt.lo + (ch_c + c_mix - ph) % c_mix;
+                    for (; t < rt.hi; t += c_mix) {
+                        float xv = row[t];
+                        float y = biquad_fb(a1, a2, biquad_ff(b0, b1, b2, xv, x1, x2), y1, y2);
+                        x2 = x1, x1 = xv, y2 = y1, y1 = y;
+                        row[t] = y;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ordered sum of the per-CTA partial rows
+__global__ void __launch_bounds__(256) k_sum_partials(const float* __restrict__ partial, uint32_t n_ctas,
+                                                      uint64_t mix_len, float* __restrict__ out) {
+    for (uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; m < mix_len;
+         m += (uint64_t)gridDim.x * blockDim.x) {
+        float acc = partial[m];
+        for (uint32_t c = 1; c < n_ctas; c++) acc = add(acc, partial[(uint64_t)c * mix_len + m]);
+        out[m] = acc;
+    }
+}
+
+}  // namespace
+
+// ----------------------------------------------------------------------------------------------------
+// host side: shape detection and launch
+// ----------------------------------------------------------------------------------------------------
+struct rb_fused_plan {
+    FusedArgs args{};
+    FusedRow* d_rows = nullptr;
+    float* d_partial = nullptr;
+    float* d_out = nullptr;
+    uint32_t n_ctas = 0;
+    uint32_t n_rec_warps = 0;
+    uint32_t grid_y = 1;
+    size_t smem_bytes = 0;
+    bool single_cta_direct = false;
+};
+
+static const rb_node_dev& node_at(const rb_fused_stream& s, uint32_t i) {
+    return *reinterpret_cast<const rb_node_dev*>(reinterpret_cast<const char*>(s.nodes) + (size_t)i * s.node_stride);
+}
+
+// Parse one stream into a FusedRow; returns false when its chain is outside the fused shape.
+static bool parse_row(const rb_fused_stream& s, uint16_t mixer_ch, FusedRow& r, uint32_t& n_pre, uint32_t& n_mid,
+                      uint32_t& n_post, uint32_t& has_uniform, uint32_t& has_biquad) {
+    memset(&r, 0, sizeof(r));
+    r.in = s.in, r.n_in = s.n_in, r.out_len = s.out_len, r.mix_start = s.mix_start;
+    r.fmt = s.fmt, r.c_in = s.c_in;
+    n_pre = n_mid = n_post = has_uniform = has_biquad = 0;
+    uint32_t cur_c = s.c_in;
+    for (uint32_t i = 0; i < s.n_nodes; i++) {
+        const rb_node_dev& nd = node_at(s, i);
+        switch (nd.kind) {
+            case RB_N_CONVERT:
+                if (i != 0) return false;
+                break;   // the format is applied at load time
+            case RB_N_AMPLIFY:
+                if (has_biquad) {
+                    if (n_post >= MAX_GAINS) return false;
+                    r.post[n_post++] = nd.p.amp.factor;
+                } else if (has_uniform) {
+                    if (n_mid >= MAX_GAINS) return false;
+                    r.mid[n_mid++] = nd.p.amp.factor;
+                } else {
+                    if (n_pre >= MAX_GAINS) return false;
+                    r.pre[n_pre++] = nd.p.amp.factor;
+                }
+                break;
+            case RB_N_UNIFORM:
+                if (has_uniform || has_biquad) return false;
+                has_uniform = 1;
+                r.uni = nd.p.uni;
+                if (nd.c_in != s.c_in) return false;
+                cur_c = nd.c_out;
+                break;
+            case RB_N_BIQUAD:
+                if (has_biquad) return false;
+                has_biquad = 1;
+                r.b0 = nd.p.blt.b0, r.b1 = nd.p.blt.b1, r.b2 = nd.p.blt.b2, r.a1 = nd.p.blt.a1, r.a2 = nd.p.blt.a2;
+                break;
+            default: return false;
+        }
+    }
+    if (cur_c != mixer_ch) return false;
+    if (!has_uniform) {
+        // gains before a (missing) uniform were collected as `pre`; keep that, n_mid stays 0
+    }
+    r.has_uniform = has_uniform;
+    return true;
+}
+
+cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams, uint16_t mixer_channels, float* d_out,
+                                uint64_t mix_len, uint32_t flags, int sm_count, cudaStream_t st, rb_fused_plan** out) {
+    *out = nullptr;
+    if (n_streams == 0 || mix_len == 0) return cudaSuccess;
+    if (flags & (RB_MIX_EXACT_ORDER | RB_BIQUAD_TIME_PARALLEL)) return cudaSuccess;   // served by the general path
+    std::vector<FusedRow> rows(n_streams);
+    uint32_t n_pre = 0, n_mid = 0, n_post = 0, has_u = 0, has_b = 0;
+    for (size_t i = 0; i < n_streams; i++) {
+        uint32_t p, m, q, u, b;
+        if (!parse_row(streams[i], mixer_channels, rows[i], p, m, q, u, b)) return cudaSuccess;
+        // a biquad directly on the input (no uniform) sees the `pre` gains as its input gains: move them
+        if (i == 0) n_pre = p, n_mid = m, n_post = q, has_u = u, has_b = b;
+        else if (p != n_pre || m != n_mid || q != n_post || u != has_u || b != has_b) return cudaSuccess;
+    }
+    if (has_b && (uint32_t)mixer_channels * 1u > 32u) return cudaSuccess;
+
+    auto plan = new rb_fused_plan;
+    // rows per CTA: one balanced wave over the SMs (k CTAs per SM when the batch is large)
+    uint32_t S = (uint32_t)n_streams;
+    uint32_t max_g = MAX_G;
+    if (has_b) {
+        while (max_g > 1 && max_g * mixer_channels > 128) max_g--;   // at most 4 recurrence warps
+    }
+    uint32_t k = (S + (uint32_t)sm_count * max_g - 1) / ((uint32_t)sm_count * max_g);
+    uint32_t G = (S + (uint32_t)sm_count * k - 1) / ((uint32_t)sm_count * k);
+    if (G > max_g) G = max_g;
+    if (G < 1) G = 1;
+    uint32_t n_ctas = (S + G - 1) / G;
+    plan->n_ctas = n_ctas;
+    plan->n_rec_warps = has_b ? (G * mixer_channels + 31) / 32 : 0;
+    plan->smem_bytes = has_b ? (size_t)NBUF * MAX_G * ROW_STRIDE * sizeof(float) : 0;
+    plan->d_out = d_out;
+
+    cudaError_t e = cudaMalloc(&plan->d_rows, n_streams * sizeof(FusedRow));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(plan->d_rows, rows.data(), n_streams * sizeof(FusedRow), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    plan->single_cta_direct = (n_ctas == 1);
+    if (e == cudaSuccess && !plan->single_cta_direct) e = cudaMalloc(&plan->d_partial, (size_t)n_ctas * mix_len * sizeof(float));
+    if (e == cudaSuccess && !plan->single_cta_direct) e = cudaMemsetAsync(plan->d_partial, 0, (size_t)n_ctas * mix_len * sizeof(float), st);
+    if (e == cudaSuccess && has_b) {
+        e = cudaFuncSetAttribute(k_fused_biquad<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(k_fused_biquad<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
+    }
+    if (e != cudaSuccess) {
+        rb_fused_destroy(plan);
+        return e;
+    }
+    FusedArgs& a = plan->args;
+    a.rows = plan->d_rows, a.n_rows = S, a.rows_per_cta = G, a.c_mix = mixer_channels;
+    a.n_pre = n_pre, a.n_mid = n_mid, a.n_post = n_post, a.has_biquad = has_b;
+    a.partial = plan->single_cta_direct ? d_out : plan->d_partial;
+    a.mix_len = mix_len;
+    a.direct = plan->single_cta_direct ? 1u : 0u;
+    // no-biquad variant: spread the timeline of each CTA over blockIdx.y so small batches still fill the GPU
+    uint64_t tiles = (mix_len + TT - 1) / TT;
+    uint64_t want_y = ((uint64_t)sm_count * 8 + n_ctas - 1) / n_ctas;
+    plan->grid_y = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(tiles, want_y), 65535));
+    *out = plan;
     return cudaSuccess;
 }
-cudaError_t rb_fused_run(rb_fused_plan*, cudaStream_t) { return cudaSuccess; }
-void rb_fused_destroy(rb_fused_plan* p) { delete p; }
-uint32_t rb_fused_launch_count(const rb_fused_plan*) { return 0; }
+
+cudaError_t rb_fused_run(rb_fused_plan* p, cudaStream_t st) {
+    const FusedArgs& a = p->args;
+    if (a.has_biquad) {
+        uint32_t threads = 512;
+        if (a.c_mix == 1)
+            k_fused_biquad<1><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
+        else
+            k_fused_biquad<0><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
+    } else {
+        k_fused_nobiquad<<<dim3(p->n_ctas, p->grid_y), 256, 0, st>>>(a);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (!p->single_cta_direct) {
+        uint64_t blocks = (a.mix_len + 255) / 256;
+        if (blocks > 148ull * 8) blocks = 148ull * 8;
+        k_sum_partials<<<(uint32_t)blocks, 256, 0, st>>>(p->d_partial, p->n_ctas, a.mix_len, p->d_out);
+        e = cudaGetLastError();
+    }
+    return e;
+}
+
+void rb_fused_destroy(rb_fused_plan* p) {
+    if (!p) return;
+    cudaFree(p->d_rows);
+    cudaFree(p->d_partial);
+    delete p;
+}
+
+uint32_t rb_fused_launch_count(const rb_fused_plan* p) { return p->single_cta_direct ? 1u : 2u; }

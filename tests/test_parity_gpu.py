@@ -347,3 +347,64 @@ def test_full_size_properties(ctx):
         b.upload_all()
         assert_bit_exact(b.render_mix(), want, "full-length spot check")
     assert np.isfinite(y1).all() and np.max(np.abs(y1)) > 0
+
+
+# ------------------------------------------------------------------ fused kernel shapes (default flags)
+def _fused_case(rng, i, S, c_in, rate_in, mix, biquad, fmt16, late):
+    srcs, starts = [], []
+    for s in range(S):
+        frames = int(rng.integers(200, 1500))
+        x = noise(frames * c_in, 9000 + 131 * i + s, 0.8)
+        if fmt16:
+            x = (x * 30000).astype(np.int16)
+        src = rb.TestSource(x, c_in, rate_in).amplify(0.9)
+        if (rate_in, c_in) != (mix[1], mix[0]):
+            src = rb.UniformSourceIterator(src, mix[0], mix[1])
+        src = src.amplify(1.1)
+        if biquad == "lp":
+            src = src.low_pass(300 + 10 * s)
+        elif biquad == "hp":
+            src = src.high_pass(150 + s)
+        src = src.amplify(1.2).amplify(0.5)
+        srcs.append(src)
+        starts.append(int(rng.integers(0, 700)) * (s % 3 == 0) if late else 0)
+    starts = sorted(starts)
+    return srcs, starts
+
+
+FUSED_CASES = [
+    # S, c_in, rate_in, mixer, biquad, i16, late starts
+    (7, 1, 44100, (1, 48000), "lp", False, False),
+    (40, 1, 44100, (1, 48000), "lp", False, True),
+    (200, 1, 44100, (1, 48000), "lp", False, False),
+    (333, 1, 48000, (1, 48000), "lp", False, True),
+    (19, 2, 44100, (2, 48000), "lp", False, True),
+    (170, 2, 44100, (2, 48000), "hp", True, False),
+    (21, 1, 22050, (2, 48000), "lp", False, True),
+    (9, 2, 48000, (1, 44100), "hp", False, False),
+    (12, 3, 32000, (3, 48000), "lp", False, True),
+    (50, 1, 44100, (1, 48000), None, False, True),
+    (500, 2, 48000, (2, 48000), None, True, False),
+    (33, 2, 44100, (4, 96000), None, False, True),
+    (5, 4, 48000, (2, 48000), "lp", False, False),
+]
+
+
+@pytest.mark.parametrize("case", range(len(FUSED_CASES)))
+def test_fused_shapes_match_oracle(ctx, case):
+    S, c_in, rate_in, mix, biquad, fmt16, late = FUSED_CASES[case]
+    rng = np.random.default_rng(1000 + case)
+    srcs, starts = _fused_case(rng, case, S, c_in, rate_in, mix, biquad, fmt16, late)
+    want = oracle.mixer([to_oracle(s, st) for s, st in zip(srcs, starts)], *mix)
+    with rb.Batch(srcs, *mix, mix_starts=starts, ctx=ctx) as b:
+        b.upload_all()
+        got = b.render_mix()
+        assert b.launches_per_render <= 2, "expected the fused path"
+    with rb.Batch(srcs, *mix, flags=GENERAL, mix_starts=starts, ctx=ctx) as b:
+        b.upload_all()
+        ref_general = b.render_mix()
+    assert_bit_exact(ref_general, want, f"general path case {case}")
+    if S <= 148:      # one stream per CTA: the partial-row sum is the reference's sequential order
+        assert_bit_exact(got, want, f"fused case {case}")
+    else:
+        assert_close_peak(got, want, 1e-5, f"fused case {case}")
