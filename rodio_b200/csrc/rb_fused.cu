@@ -48,12 +48,22 @@ struct FusedRow {                  // one stream, device side
     uint64_t out_len;              // samples on the mixer timeline
     uint64_t mix_start;
     uint32_t fmt, c_in;
-    uint32_t has_uniform, pad_;
+    uint32_t has_uniform;
+    uint32_t mode;                 // row-wide fast mode, see ROW_*
     rb_uniform_params uni;
+    uint32_t q32, r32;             // divmod(32 * from, to): index advance for a lane stride of 32 output frames
+    float den_f, rcp_den;          // (f32)to and RN(1 / (f32)to)
     float pre[MAX_GAINS];          // gains applied to raw input samples (before interpolation)
     float mid[MAX_GAINS];          // gains between the uniform conversion and the biquad
     float post[MAX_GAINS];         // gains after the biquad
     float b0, b1, b2, a1, a2;
+    uint32_t pad_[3];
+};
+enum : uint32_t {
+    ROW_GENERIC = 0,   // exact closed form per sample (span chunks, trailing partial frames, huge ratios)
+    ROW_DIRECT = 1,    // no conversion at all: out[o] = in[o]
+    ROW_PASS = 2,      // same rate, channel map only
+    ROW_LERP = 3       // linear interpolation on the reduced grid, one segment, whole frames
 };
 
 struct FusedArgs {
@@ -69,16 +79,13 @@ struct FusedArgs {
     uint32_t pad_;
 };
 
-// ---- per (row, tile) fast index state --------------------------------------------------------------
+// ---- per (row, tile) index state -------------------------------------------------------------------
 struct RowTile {
     uint32_t lo, hi;       // active tile positions [lo, hi)
-    uint32_t fast;         // 1: fast uniform path valid for the whole active range
-    uint32_t r0;           // (n0 * from) mod to at the first active frame
-    uint64_t i0;           // left input frame of the first active frame (absolute, in frames)
-    uint64_t L;            // frames in the segment (for the raw-last-frame test), absolute end frame
+    uint32_t r0;           // ROW_LERP: (n0 * from) mod to at frame n0
+    uint32_t j0;           // channel of the first active sample (o0 % c_mix)
+    uint64_t i0;           // ROW_LERP: left input frame of frame n0 ; ROW_PASS: n0
     uint64_t o0;           // row-local output sample index at tile position `lo`
-    uint32_t j0;           // channel of that sample (o0 % c_mix)
-    uint32_t pad_;
 };
 
 __device__ __forceinline__ float apply_gains(float v, const float* g, uint32_t n) {
@@ -88,136 +95,205 @@ __device__ __forceinline__ float apply_gains(float v, const float* g, uint32_t n
     return v;
 }
 
-__device__ __forceinline__ float load_pre(const FusedRow& r, uint32_t n_pre, uint64_t idx) {
-    return apply_gains(load_as_f32(r.in, r.fmt, idx), r.pre, n_pre);
+template <bool F32>
+__device__ __forceinline__ float load_in(const void* in, uint32_t fmt, uint64_t idx) {
+    if (F32) return __ldg((const float*)in + idx);
+    return load_as_f32(in, fmt, idx);
+}
+
+// (b - a) * num / den with the reference's rounding sequence, the division done as an exact
+// reciprocal refinement: q0 = RN(m * rcp); r = m - q0 * den (exact, FMA); q = RN(q0 + r * rcp) == RN(m / den)
+// (Markstein).  Outside the guarded range (zeros keep their sign, denormals, huge values) fall back to the
+// IEEE division.  Verified exhaustively against `/` for every den <= 4000 and the common rate pairs.
+__device__ __forceinline__ float lerp_rcp(float first, float second, float num_f, float den_f, float rcp_den) {
+    float m = mul(sub(second, first), num_f);
+    float am = fabsf(m);
+    float q;
+    if (am >= 1e-30f && am <= 1e30f) {
+        float q0 = mul(m, rcp_den);
+        float r = __fmaf_rn(-q0, den_f, m);
+        q = __fmaf_rn(r, rcp_den, q0);
+    } else {
+        q = divf(m, den_f);
+    }
+    return add(first, q);
 }
 
 // Generic (any segment / partial frame / chunk boundary) sample of the row at local output index o.
-__device__ float row_sample_generic(const FusedRow& r, const FusedArgs& a, uint64_t o) {
-    if (!r.has_uniform) return apply_gains(load_pre(r, a.n_pre, o), r.mid, a.n_mid);
-    UniformTap t = uniform_tap(r.uni, r.c_in, a.c_mix, o);
+template <bool F32>
+__device__ __noinline__ float row_sample_generic(const FusedRow& r, uint32_t c_mix, uint32_t n_pre, uint32_t n_mid,
+                                                 uint64_t o) {
+    if (!r.has_uniform) return apply_gains(apply_gains(load_in<F32>(r.in, r.fmt, o), r.pre, n_pre), r.mid, n_mid);
+    UniformTap t = uniform_tap(r.uni, r.c_in, c_mix, o);
     float v = 0.0f;
     if (t.kind != 0) {
-        float x0 = load_pre(r, a.n_pre, t.i0);
+        float x0 = apply_gains(load_in<F32>(r.in, r.fmt, t.i0), r.pre, n_pre);
         v = x0;
         if (t.kind == 2) {
-            float x1 = load_pre(r, a.n_pre, t.i0 + r.c_in);
-            v = lerp_f(x0, x1, __uint2float_rn(t.num), __uint2float_rn(r.uni.to));
+            float x1 = apply_gains(load_in<F32>(r.in, r.fmt, t.i0 + r.c_in), r.pre, n_pre);
+            v = lerp_f(x0, x1, __uint2float_rn(t.num), r.den_f);
         }
     }
-    return apply_gains(v, r.mid, a.n_mid);
+    return apply_gains(v, r.mid, n_mid);
 }
 
-__device__ void row_tile_setup(const FusedRow& r, const FusedArgs& a, uint64_t m0, RowTile& rt) {
+__device__ __forceinline__ void row_tile_setup(const FusedRow& r, uint32_t c_mix, uint64_t m0, RowTile& rt) {
     uint64_t s = r.mix_start, e = r.mix_start + r.out_len;
     uint64_t lo = m0 > s ? m0 : s, hi = (m0 + TT) < e ? (m0 + TT) : e;
-    if (lo >= hi) {
-        rt.lo = rt.hi = 0, rt.fast = 0;
-        return;
-    }
+    rt.lo = rt.hi = 0, rt.r0 = 0, rt.j0 = 0, rt.i0 = 0, rt.o0 = 0;
+    if (lo >= hi) return;
     rt.lo = (uint32_t)(lo - m0), rt.hi = (uint32_t)(hi - m0);
     rt.o0 = lo - s;
-    rt.j0 = (uint32_t)(rt.o0 % a.c_mix);
-    rt.fast = 0;
-    if (!r.has_uniform) return;
-    const rb_uniform_params& u = r.uni;
-    if (u.from == u.to || u.chunk_samples != 0 || u.tail.p != 0) return;
-    if (u.from > (1u << 20) || u.to > (1u << 20)) return;
-    uint64_t o_last = hi - 1 - s;
-    if (o_last / a.c_mix >= u.tail.full_out_frames) return;          // stay inside the all-channels region
-    uint64_t n0 = rt.o0 / a.c_mix;
-    uint64_t prod = n0 * (uint64_t)u.from;
-    rt.i0 = prod / u.to;
-    rt.r0 = (uint32_t)(prod - rt.i0 * u.to);
-    rt.L = u.tail.L;
-    rt.fast = 1;
+    uint64_t n0 = rt.o0 / c_mix;
+    rt.j0 = (uint32_t)(rt.o0 - n0 * c_mix);
+    if (r.mode == ROW_LERP) {
+        uint64_t prod = n0 * (uint64_t)r.uni.from;
+        rt.i0 = prod / r.uni.to;
+        rt.r0 = (uint32_t)(prod - rt.i0 * r.uni.to);
+    } else {
+        rt.i0 = n0;
+    }
 }
 
-// Value of row `r` at tile position t (active), using the fast incremental index path when valid.
-__device__ __forceinline__ float row_sample(const FusedRow& r, const FusedArgs& a, const RowTile& rt, uint32_t t,
-                                            float den_f) {
-    uint64_t o = rt.o0 + (t - rt.lo);
-    if (!rt.fast) return row_sample_generic(r, a, o);
-    uint32_t c_mix = a.c_mix;
-    uint32_t rel = (t - rt.lo) + rt.j0;          // flat offset from the start of frame n0
-    uint32_t k = rel / c_mix, j = rel - k * c_mix;
-    int c = chan_map(j, r.c_in);
-    float v = 0.0f;
-    if (c >= 0) {
-        uint32_t prod = rt.r0 + k * r.uni.from;    // < 2^20 + 256 * 2^20
-        uint32_t di = prod / r.uni.to;
-        uint32_t num = prod - di * r.uni.to;
-        uint64_t i = rt.i0 + di;
-        uint64_t idx = i * r.c_in + (uint32_t)c;
-        float x0 = load_pre(r, a.n_pre, idx);
-        v = x0;
-        if (i + 1 < rt.L) {
-            float x1 = load_pre(r, a.n_pre, idx + r.c_in);
-            v = lerp_f(x0, x1, __uint2float_rn(num), den_f);
+// Stage A for one (row, tile): the whole warp walks the row's active samples and writes them to `dst`
+// (dst[t] for tile position t).  dst may be shared memory (biquad variant) — `Store` abstracts it.
+template <bool F32, class Store>
+__device__ __forceinline__ void row_stage_a(const FusedRow& r, const RowTile& rt, uint32_t c_mix, uint32_t n_pre,
+                                            uint32_t n_mid, uint32_t lane, Store store) {
+    if (rt.lo >= rt.hi) return;
+    const void* in = r.in;
+    const uint32_t fmt = r.fmt, c_in = r.c_in, mode = r.mode;
+    float pre[MAX_GAINS], mid[MAX_GAINS];
+#pragma unroll
+    for (int k = 0; k < MAX_GAINS; k++) pre[k] = r.pre[k], mid[k] = r.mid[k];
+    if (mode == ROW_DIRECT) {
+        for (uint32_t t = rt.lo + lane; t < rt.hi; t += 32) {
+            float v = load_in<F32>(in, fmt, rt.o0 + (t - rt.lo));
+            store(t, apply_gains(apply_gains(v, pre, n_pre), mid, n_mid));
+        }
+    } else if (mode == ROW_GENERIC) {
+        for (uint32_t t = rt.lo + lane; t < rt.hi; t += 32)
+            store(t, row_sample_generic<F32>(r, c_mix, n_pre, n_mid, rt.o0 + (t - rt.lo)));
+    } else {
+        // lanes walk output FRAMES k = lane, lane+32, ... counted from frame n0 (the frame of position lo)
+        const uint32_t n_frames = (rt.hi - rt.lo + rt.j0 + c_mix - 1) / c_mix;
+        const uint32_t from = r.uni.from, to = r.uni.to, q32 = r.q32, r32 = r.r32;
+        const float den_f = r.den_f, rcp_den = r.rcp_den;
+        const uint64_t L = r.uni.tail.L;
+        uint32_t di = 0, num = 0;
+        if (mode == ROW_LERP) {
+            uint32_t prod = rt.r0 + lane * from;      // from, to <= 2^20 in this mode
+            di = prod / to;
+            num = prod - di * to;
+        }
+        for (uint32_t k = lane; k < n_frames; k += 32) {
+            const uint64_t i = (mode == ROW_LERP) ? rt.i0 + di : rt.i0 + k;
+            const bool interp = (mode == ROW_LERP) && (i + 1 < L);
+            const float num_f = __uint2float_rn(num);
+            const int tbase = (int)(rt.lo + k * c_mix) - (int)rt.j0;   // tile position of channel 0 of this frame
+            for (uint32_t j = 0; j < c_mix; j++) {
+                int t = tbase + (int)j;
+                if (t < (int)rt.lo || t >= (int)rt.hi) continue;
+                int c = chan_map(j, c_in);
+                float v = 0.0f;
+                if (c >= 0) {
+                    uint64_t idx = i * c_in + (uint32_t)c;
+                    float x0 = apply_gains(load_in<F32>(in, fmt, idx), pre, n_pre);
+                    v = x0;
+                    if (interp) {
+                        float x1 = apply_gains(load_in<F32>(in, fmt, idx + c_in), pre, n_pre);
+                        v = lerp_rcp(x0, x1, num_f, den_f, rcp_den);
+                    }
+                }
+                store((uint32_t)t, apply_gains(v, mid, n_mid));
+            }
+            if (mode == ROW_LERP) {
+                num += r32, di += q32;
+                if (num >= to) num -= to, di += 1;
+            }
         }
     }
-    return apply_gains(v, r.mid, a.n_mid);
+}
+
+// Copy this CTA's rows into shared memory once (row constants are then warp-broadcast LDS, not LDG).
+__device__ __forceinline__ void load_rows(FusedRow* s_rows, const FusedRow* rows, uint32_t G) {
+    const uint32_t words = G * (uint32_t)(sizeof(FusedRow) / 4);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(rows);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(s_rows);
+    for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+}
+
+__device__ __forceinline__ void cta_span(const FusedRow* s_rows, uint32_t G, const FusedArgs& a, uint64_t& lo,
+                                         uint64_t& hi) {
+    lo = ~0ull, hi = 0;
+    for (uint32_t g = 0; g < G; g++) {
+        if (s_rows[g].out_len == 0) continue;
+        lo = min(lo, s_rows[g].mix_start);
+        hi = max(hi, s_rows[g].mix_start + s_rows[g].out_len);
+    }
+    if (a.direct) lo = 0, hi = a.mix_len;
+}
+
+// Stage C for one tile position: post-gains and the ordered sum over the CTA's rows.
+__device__ __forceinline__ float mix_rows(const float* tile, const RowTile* rts, const FusedRow* s_rows, uint32_t G,
+                                          uint32_t n_post, uint32_t t) {
+    float acc = 0.0f;
+    for (uint32_t g = 0; g < G; g++) {
+        const uint2 r = *reinterpret_cast<const uint2*>(&rts[g].lo);   // (lo, hi)
+        if (t >= r.x && t < r.y) acc = add(acc, apply_gains(tile[g * ROW_STRIDE + t], s_rows[g].post, n_post));
+    }
+    return acc;
 }
 
 // ---------------------------------------------------------------------------------------------------
-// no-biquad variant: stage A and C fused in registers, no shared memory
+// no-biquad variant: stage A (warp per row) -> shared tile -> stage C (thread per position)
 // ---------------------------------------------------------------------------------------------------
+template <bool F32>
 __global__ void __launch_bounds__(256) k_fused_nobiquad(FusedArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ __align__(16) FusedRow s_rows[MAX_G];
     __shared__ RowTile s_rt[MAX_G];
     const uint32_t row0 = blockIdx.x * a.rows_per_cta;
     const uint32_t G = min(a.rows_per_cta, a.n_rows - row0);
-    const FusedRow* rows = a.rows + row0;
+    load_rows(s_rows, a.rows + row0, G);
+    __syncthreads();
     float* partial = a.partial + (uint64_t)blockIdx.x * a.mix_len;
-    // this CTA's span of the mixer timeline
-    uint64_t lo = ~0ull, hi = 0;
-    for (uint32_t g = 0; g < G; g++) {
-        if (rows[g].out_len == 0) continue;
-        lo = min(lo, rows[g].mix_start);
-        hi = max(hi, rows[g].mix_start + rows[g].out_len);
-    }
-    if (a.direct) lo = 0, hi = a.mix_len;
+    uint64_t lo, hi;
+    cta_span(s_rows, G, a, lo, hi);
     if (lo >= hi) return;
-    uint64_t m_begin = lo / TT * TT;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    float* tile = smem;
+    const uint64_t m_begin = lo / TT * TT;
     for (uint64_t m0 = m_begin + (uint64_t)blockIdx.y * TT; m0 < hi; m0 += (uint64_t)gridDim.y * TT) {
-        __syncthreads();
-        if (threadIdx.x < G) row_tile_setup(rows[threadIdx.x], a, m0, s_rt[threadIdx.x]);
-        __syncthreads();
-        uint32_t t = threadIdx.x;
-        if (m0 + t < a.mix_len) {
-            float acc = 0.0f;
-            for (uint32_t g = 0; g < G; g++) {
-                const RowTile& rt = s_rt[g];
-                if (t >= rt.lo && t < rt.hi) {
-                    const FusedRow& r = rows[g];
-                    float v = row_sample(r, a, rt, t, __uint2float_rn(r.uni.to));
-                    acc = add(acc, apply_gains(v, r.post, a.n_post));
-                }
-            }
-            partial[m0 + t] = acc;
+        for (uint32_t g = warp; g < G; g += n_warps) {
+            if (lane == 0) row_tile_setup(s_rows[g], a.c_mix, m0, s_rt[g]);
+            __syncwarp();
+            float* row = tile + g * ROW_STRIDE;
+            row_stage_a<F32>(s_rows[g], s_rt[g], a.c_mix, a.n_pre, a.n_mid, lane, [&](uint32_t t, float v) { row[t] = v; });
         }
+        __syncthreads();
+        for (uint32_t t = threadIdx.x; t < TT; t += blockDim.x)
+            if (m0 + t < a.mix_len) partial[m0 + t] = mix_rows(tile, s_rt, s_rows, G, a.n_post, t);
+        __syncthreads();
     }
 }
 
 // ---------------------------------------------------------------------------------------------------
 // biquad variant: three-stage software pipeline over shared-memory tiles
 // ---------------------------------------------------------------------------------------------------
-template <int C_MIX_STATIC>   // 1: mono fast path (vectorised recurrence), 0: generic channel count
+template <bool F32, int C_MIX_STATIC>   // C_MIX_STATIC 1: mono fast path (vectorised recurrence), 0: any channel count
 __global__ void __launch_bounds__(512, 1) k_fused_biquad(FusedArgs a, uint32_t n_rec_warps) {
     extern __shared__ __align__(16) float smem[];
+    __shared__ __align__(16) FusedRow s_rows[MAX_G];
     __shared__ RowTile s_rt[NBUF][MAX_G];
     const uint32_t row0 = blockIdx.x * a.rows_per_cta;
     const uint32_t G = min(a.rows_per_cta, a.n_rows - row0);
-    const FusedRow* rows = a.rows + row0;
+    load_rows(s_rows, a.rows + row0, G);
+    __syncthreads();
     float* partial = a.partial + (uint64_t)blockIdx.x * a.mix_len;
     const uint32_t c_mix = C_MIX_STATIC ? (uint32_t)C_MIX_STATIC : a.c_mix;
-
-    uint64_t lo = ~0ull, hi = 0;
-    for (uint32_t g = 0; g < G; g++) {
-        if (rows[g].out_len == 0) continue;
-        lo = min(lo, rows[g].mix_start);
-        hi = max(hi, rows[g].mix_start + rows[g].out_len);
-    }
-    if (a.direct) lo = 0, hi = a.mix_len;
+    uint64_t lo, hi;
+    cta_span(s_rows, G, a, lo, hi);
     if (lo >= hi) return;
     const uint64_t m_begin = lo / TT * TT;
     const uint32_t n_tiles = (uint32_t)((hi - m_begin + TT - 1) / TT);
@@ -225,8 +301,10 @@ __global__ void __launch_bounds__(512, 1) k_fused_biquad(FusedArgs a, uint32_t n
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t n_warps = blockDim.x >> 5;
     const bool is_rec = warp < n_rec_warps;
-    const uint32_t n_par_threads = (n_warps - n_rec_warps) * 32;
+    const uint32_t n_par_warps = n_warps - n_rec_warps;
+    const uint32_t n_par_threads = n_par_warps * 32;
     const uint32_t par_tid = threadIdx.x - n_rec_warps * 32;
+    const uint32_t par_warp = warp - n_rec_warps;
 
     // recurrence lane -> chain (row, channel); state in registers for the whole stream
     const uint32_t chain = warp * 32 + lane;
@@ -235,30 +313,23 @@ __global__ void __launch_bounds__(512, 1) k_fused_biquad(FusedArgs a, uint32_t n
     float x1 = 0.f, x2 = 0.f, y1 = 0.f, y2 = 0.f;
     float b0 = 0.f, b1 = 0.f, b2 = 0.f, a1 = 0.f, a2 = 0.f;
     if (chain_on) {
-        const FusedRow& r = rows[ch_row];
+        const FusedRow& r = s_rows[ch_row];
         b0 = r.b0, b1 = r.b1, b2 = r.b2, a1 = r.a1, a2 = r.a2;
     }
 
     for (uint32_t it = 0; it < n_tiles + 2; it++) {
-        // ---- stage A on tile `it` ----
         if (!is_rec) {
+            // ---- stage A on tile `it`: one warp per row ----
             if (it < n_tiles) {
                 const uint32_t buf = it % NBUF;
                 const uint64_t m0 = m_begin + (uint64_t)it * TT;
                 float* tile = smem + (size_t)buf * MAX_G * ROW_STRIDE;
-                // per-row index state for this tile (one thread per row), visible to the same warps only after
-                // a named barrier among the parallel warps
-                if (par_tid < G) row_tile_setup(rows[par_tid], a, m0, s_rt[buf][par_tid]);
-                asm volatile("bar.sync 1, %0;" ::"r"(n_par_threads));
-                for (uint32_t item = par_tid; item < G * TT; item += n_par_threads) {
-                    uint32_t g = item / TT, t = item - g * TT;
-                    const RowTile& rt = s_rt[buf][g];
-                    float v = 0.0f;
-                    if (t >= rt.lo && t < rt.hi) {
-                        const FusedRow& r = rows[g];
-                        v = row_sample(r, a, rt, t, __uint2float_rn(r.uni.to));
-                    }
-                    tile[g * ROW_STRIDE + t] = v;
+                for (uint32_t g = par_warp; g < G; g += n_par_warps) {
+                    if (lane == 0) row_tile_setup(s_rows[g], c_mix, m0, s_rt[buf][g]);
+                    __syncwarp();
+                    float* row = tile + g * ROW_STRIDE;
+                    row_stage_a<F32>(s_rows[g], s_rt[buf][g], c_mix, a.n_pre, a.n_mid, lane,
+                                     [&](uint32_t t, float v) { row[t] = v; });
                 }
             }
             // ---- stage C on tile `it - 2` ----
@@ -267,16 +338,8 @@ __global__ void __launch_bounds__(512, 1) k_fused_biquad(FusedArgs a, uint32_t n
                 const uint32_t buf = kt % NBUF;
                 const uint64_t m0 = m_begin + (uint64_t)kt * TT;
                 const float* tile = smem + (size_t)buf * MAX_G * ROW_STRIDE;
-                for (uint32_t t = par_tid; t < TT; t += n_par_threads) {
-                    if (m0 + t >= a.mix_len) continue;
-                    float acc = 0.0f;
-                    for (uint32_t g = 0; g < G; g++) {
-                        const RowTile& rt = s_rt[buf][g];
-                        if (t >= rt.lo && t < rt.hi)
-                            acc = add(acc, apply_gains(tile[g * ROW_STRIDE + t], rows[g].post, a.n_post));
-                    }
-                    partial[m0 + t] = acc;
-                }
+                for (uint32_t t = par_tid; t < TT; t += n_par_threads)
+                    if (m0 + t < a.mix_len) partial[m0 + t] = mix_rows(tile, s_rt[buf], s_rows, G, a.n_post, t);
             }
         } else if (it >= 1 && it <= n_tiles) {
             // ---- stage B on tile `it - 1` ----
@@ -284,9 +347,10 @@ __global__ void __launch_bounds__(512, 1) k_fused_biquad(FusedArgs a, uint32_t n
             const uint32_t buf = kt % NBUF;
             if (chain_on) {
                 float* row = smem + (size_t)buf * MAX_G * ROW_STRIDE + ch_row * ROW_STRIDE;
-                const RowTile& rt = s_rt[buf][ch_row];
+                const uint2 act = *reinterpret_cast<const uint2*>(&s_rt[buf][ch_row].lo);
+                const uint32_t lo_t = act.x, hi_t = act.y;
                 if (C_MIX_STATIC == 1) {
-                    uint32_t t = rt.lo, hi_t = rt.hi;
+                    uint32_t t = lo_t;
                     for (; t < hi_t && (t & 3); t++) {               // head up to 16-byte alignment
                         float xv = row[t];
                         float y = biquad_fb(a1, a2, biquad_ff(b0, b1, b2, xv, x1, x2), y1, y2);
@@ -317,9 +381,9 @@ __global__ void __launch_bounds__(512, 1) k_fused_biquad(FusedArgs a, uint32_t n
                     // chain (row, c): positions whose mixer channel is c.  Streams join on a frame boundary
                     // (mixer.rs:175-183) so channel == (m0 + t) % c_mix == (local index) % c_mix.
                     const uint64_t m0 = m_begin + (uint64_t)kt * TT;
-                    uint32_t ph = (uint32_t)((m0 + rt.lo) % c_mix);
-                    uint32_t t = rt.lo + (ch_c + c_mix - ph) % c_mix;
-                    for (; t < rt.hi; t += c_mix) {
+                    uint32_t ph = (uint32_t)((m0 + lo_t) % c_mix);
+                    uint32_t t = lo_t + (ch_c + c_mix - ph) % c_mix;
+                    for (; t < hi_t; t += c_mix) {
                         float xv = row[t];
                         float y = biquad_fb(a1, a2, biquad_ff(b0, b1, b2, xv, x1, x2), y1, y2);
                         x2 = x1, x1 = xv, y2 = y1, y1 = y;
@@ -358,6 +422,7 @@ struct rb_fused_plan {
     uint32_t grid_y = 1;
     size_t smem_bytes = 0;
     bool single_cta_direct = false;
+    bool all_f32 = true;
 };
 
 static const rb_node_dev& node_at(const rb_fused_stream& s, uint32_t i) {
@@ -410,6 +475,21 @@ static bool parse_row(const rb_fused_stream& s, uint16_t mixer_ch, FusedRow& r, 
         // gains before a (missing) uniform were collected as `pre`; keep that, n_mid stays 0
     }
     r.has_uniform = has_uniform;
+    r.mode = ROW_GENERIC;
+    if (!has_uniform) {
+        r.mode = ROW_DIRECT;
+    } else {
+        const rb_uniform_params& u = r.uni;
+        r.den_f = (float)u.to;
+        r.rcp_den = 1.0f / r.den_f;
+        if (u.from == u.to) {
+            if (u.tail.p == 0 && (u.chunk_samples == 0 || u.chunk_samples % s.c_in == 0)) r.mode = ROW_PASS;
+        } else if (u.chunk_samples == 0 && u.tail.p == 0 && u.from <= (1u << 20) && u.to <= (1u << 20)) {
+            r.mode = ROW_LERP;
+            r.q32 = (uint32_t)((32ull * u.from) / u.to);
+            r.r32 = (uint32_t)((32ull * u.from) % u.to);
+        }
+    }
     return true;
 }
 
@@ -443,7 +523,9 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     uint32_t n_ctas = (S + G - 1) / G;
     plan->n_ctas = n_ctas;
     plan->n_rec_warps = has_b ? (G * mixer_channels + 31) / 32 : 0;
-    plan->smem_bytes = has_b ? (size_t)NBUF * MAX_G * ROW_STRIDE * sizeof(float) : 0;
+    plan->smem_bytes = (size_t)(has_b ? NBUF : 1) * MAX_G * ROW_STRIDE * sizeof(float);
+    plan->all_f32 = true;
+    for (size_t i = 0; i < n_streams; i++) plan->all_f32 = plan->all_f32 && streams[i].fmt == RB_FMT_F32;
     plan->d_out = d_out;
 
     cudaError_t e = cudaMalloc(&plan->d_rows, n_streams * sizeof(FusedRow));
@@ -453,9 +535,11 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     if (e == cudaSuccess && !plan->single_cta_direct) e = cudaMalloc(&plan->d_partial, (size_t)n_ctas * mix_len * sizeof(float));
     if (e == cudaSuccess && !plan->single_cta_direct) e = cudaMemsetAsync(plan->d_partial, 0, (size_t)n_ctas * mix_len * sizeof(float), st);
     if (e == cudaSuccess && has_b) {
-        e = cudaFuncSetAttribute(k_fused_biquad<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(k_fused_biquad<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
+        const int sb = (int)plan->smem_bytes;
+        e = cudaFuncSetAttribute(k_fused_biquad<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused_biquad<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused_biquad<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused_biquad<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
     }
     if (e != cudaSuccess) {
         rb_fused_destroy(plan);
@@ -478,13 +562,15 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
 cudaError_t rb_fused_run(rb_fused_plan* p, cudaStream_t st) {
     const FusedArgs& a = p->args;
     if (a.has_biquad) {
-        uint32_t threads = 512;
-        if (a.c_mix == 1)
-            k_fused_biquad<1><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
-        else
-            k_fused_biquad<0><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
+        const uint32_t threads = 512;
+        const bool mono = a.c_mix == 1;
+        if (p->all_f32 && mono) k_fused_biquad<true, 1><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
+        else if (p->all_f32) k_fused_biquad<true, 0><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
+        else if (mono) k_fused_biquad<false, 1><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
+        else k_fused_biquad<false, 0><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
     } else {
-        k_fused_nobiquad<<<dim3(p->n_ctas, p->grid_y), 256, 0, st>>>(a);
+        if (p->all_f32) k_fused_nobiquad<true><<<dim3(p->n_ctas, p->grid_y), 256, p->smem_bytes, st>>>(a);
+        else k_fused_nobiquad<false><<<dim3(p->n_ctas, p->grid_y), 256, p->smem_bytes, st>>>(a);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
