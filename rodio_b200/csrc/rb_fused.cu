@@ -175,41 +175,60 @@ __device__ __forceinline__ void row_stage_a(const FusedRow& r, const RowTile& rt
         for (uint32_t t = rt.lo + lane; t < rt.hi; t += 32)
             store(t, row_sample_generic<F32>(r, c_mix, n_pre, n_mid, rt.o0 + (t - rt.lo)));
     } else {
-        // lanes walk output FRAMES k = lane, lane+32, ... counted from frame n0 (the frame of position lo)
+        // lanes walk output FRAMES k = lane, lane+32, ... counted from frame n0 (the frame of position lo).
+        // U frames per lane are handled per batch: all index math first, then all loads (2*U independent
+        // LDGs in flight per lane -- this stage must cover HBM latency by itself), then the arithmetic.
+        constexpr int U = 8;
         const uint32_t n_frames = (rt.hi - rt.lo + rt.j0 + c_mix - 1) / c_mix;
         const uint32_t from = r.uni.from, to = r.uni.to, q32 = r.q32, r32 = r.r32;
         const float den_f = r.den_f, rcp_den = r.rcp_den;
         const uint64_t L = r.uni.tail.L;
+        const bool lerp_mode = (mode == ROW_LERP);
         uint32_t di = 0, num = 0;
-        if (mode == ROW_LERP) {
+        if (lerp_mode) {
             uint32_t prod = rt.r0 + lane * from;      // from, to <= 2^20 in this mode
             di = prod / to;
             num = prod - di * to;
         }
-        for (uint32_t k = lane; k < n_frames; k += 32) {
-            const uint64_t i = (mode == ROW_LERP) ? rt.i0 + di : rt.i0 + k;
-            const bool interp = (mode == ROW_LERP) && (i + 1 < L);
-            const float num_f = __uint2float_rn(num);
-            const int tbase = (int)(rt.lo + k * c_mix) - (int)rt.j0;   // tile position of channel 0 of this frame
+        for (uint32_t kb = 0; kb < n_frames; kb += 32 * U) {
+            uint32_t dis[U], nums[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                dis[u] = lerp_mode ? di : (kb + lane + 32u * (uint32_t)u);
+                nums[u] = num;
+                if (lerp_mode) {
+                    num += r32, di += q32;
+                    if (num >= to) num -= to, di += 1;
+                }
+            }
             for (uint32_t j = 0; j < c_mix; j++) {
-                int t = tbase + (int)j;
-                if (t < (int)rt.lo || t >= (int)rt.hi) continue;
-                int c = chan_map(j, c_in);
-                float v = 0.0f;
-                if (c >= 0) {
-                    uint64_t idx = i * c_in + (uint32_t)c;
-                    float x0 = apply_gains(load_in<F32>(in, fmt, idx), pre, n_pre);
-                    v = x0;
-                    if (interp) {
-                        float x1 = apply_gains(load_in<F32>(in, fmt, idx + c_in), pre, n_pre);
-                        v = lerp_rcp(x0, x1, num_f, den_f, rcp_den);
+                const int c = chan_map(j, c_in);
+                float x0[U], x1[U];
+                bool itp[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const uint32_t k = kb + lane + 32u * (uint32_t)u;
+                    const uint64_t i = rt.i0 + dis[u];
+                    itp[u] = lerp_mode && (i + 1 < L);
+                    x0[u] = 0.0f, x1[u] = 0.0f;
+                    if (k < n_frames && c >= 0) {
+                        const uint64_t idx = i * c_in + (uint32_t)c;
+                        x0[u] = load_in<F32>(in, fmt, idx);
+                        if (itp[u]) x1[u] = load_in<F32>(in, fmt, idx + c_in);
                     }
                 }
-                store((uint32_t)t, apply_gains(v, mid, n_mid));
-            }
-            if (mode == ROW_LERP) {
-                num += r32, di += q32;
-                if (num >= to) num -= to, di += 1;
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const uint32_t k = kb + lane + 32u * (uint32_t)u;
+                    const int t = (int)(rt.lo + k * c_mix + j) - (int)rt.j0;
+                    if (k >= n_frames || t < (int)rt.lo || t >= (int)rt.hi) continue;
+                    float v = 0.0f;
+                    if (c >= 0) {
+                        v = apply_gains(x0[u], pre, n_pre);
+                        if (itp[u]) v = lerp_rcp(v, apply_gains(x1[u], pre, n_pre), __uint2float_rn(nums[u]), den_f, rcp_den);
+                    }
+                    store((uint32_t)t, apply_gains(v, mid, n_mid));
+                }
             }
         }
     }
