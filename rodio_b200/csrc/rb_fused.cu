@@ -95,6 +95,11 @@ __device__ __forceinline__ float apply_gains(float v, const float* g, uint32_t n
     return v;
 }
 
+template <bool NOGAIN>
+__device__ __forceinline__ float gains(float v, const float* g, uint32_t n) {
+    return NOGAIN ? v : apply_gains(v, g, n);
+}
+
 template <bool F32>
 __device__ __forceinline__ float load_in(const void* in, uint32_t fmt, uint64_t idx) {
     if (F32) return __ldg((const float*)in + idx);
@@ -155,11 +160,61 @@ __device__ __forceinline__ void row_tile_setup(const FusedRow& r, uint32_t c_mix
     }
 }
 
+// Stage A, hot case: mono source, mono mixer, linear interpolation (BASELINE cfg3).  One batch of 8 output
+// frames per lane covers the tile; indices are 32-bit offsets from the tile's first input frame.
+template <bool F32, bool NOGAIN>
+__device__ __forceinline__ void stage_a_mono_lerp(const FusedRow& r, const RowTile& rt, uint32_t n_pre, uint32_t n_mid,
+                                                  uint32_t lane, float* __restrict__ row) {
+    constexpr int U = TT / 32;
+    const uint32_t n = rt.hi - rt.lo;
+    const uint32_t to = r.uni.to, q32 = r.q32, r32 = r.r32, fmt = r.fmt;
+    const float den_f = r.den_f, rcp_den = r.rcp_den;
+    const uint64_t remain = r.uni.tail.L - 1 - rt.i0;              // frames to the right of i0
+    const uint32_t lim = remain > 0x7fffffffull ? 0x7fffffffu : (uint32_t)remain;   // interpolate iff di < lim
+    const float* __restrict__ base_f = (const float*)r.in + rt.i0;
+    float pre[MAX_GAINS], mid[MAX_GAINS];
+#pragma unroll
+    for (int k = 0; k < MAX_GAINS; k++) pre[k] = r.pre[k], mid[k] = r.mid[k];
+    uint32_t prod = rt.r0 + lane * r.uni.from;
+    uint32_t di = prod / to;
+    uint32_t num = prod - di * to;
+    uint32_t dis[U], nums[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        dis[u] = di, nums[u] = num;
+        num += r32, di += q32;
+        if (num >= to) num -= to, di += 1;
+    }
+    float x0[U], x1[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        x0[u] = 0.0f, x1[u] = 0.0f;
+        if (lane + 32u * (uint32_t)u < n) {
+            if (F32) {
+                x0[u] = __ldg(base_f + dis[u]);
+                if (dis[u] < lim) x1[u] = __ldg(base_f + dis[u] + 1);
+            } else {
+                x0[u] = load_as_f32(r.in, fmt, rt.i0 + dis[u]);
+                if (dis[u] < lim) x1[u] = load_as_f32(r.in, fmt, rt.i0 + dis[u] + 1);
+            }
+        }
+    }
+    float* __restrict__ out = row + rt.lo + lane;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        if (lane + 32u * (uint32_t)u < n) {
+            float v = gains<NOGAIN>(x0[u], pre, n_pre);
+            if (dis[u] < lim) v = lerp_rcp(v, gains<NOGAIN>(x1[u], pre, n_pre), __uint2float_rn(nums[u]), den_f, rcp_den);
+            out[32 * u] = gains<NOGAIN>(v, mid, n_mid);
+        }
+    }
+}
+
 // Stage A for one (row, tile): the whole warp walks the row's active samples and writes them to `dst`
 // (dst[t] for tile position t).  dst may be shared memory (biquad variant) — `Store` abstracts it.
 template <bool F32, class Store>
-__device__ __forceinline__ void row_stage_a(const FusedRow& r, const RowTile& rt, uint32_t c_mix, uint32_t n_pre,
-                                            uint32_t n_mid, uint32_t lane, Store store) {
+__device__ __forceinline__ void row_stage_a_any(const FusedRow& r, const RowTile& rt, uint32_t c_mix, uint32_t n_pre,
+                                                uint32_t n_mid, uint32_t lane, Store store) {
     if (rt.lo >= rt.hi) return;
     const void* in = r.in;
     const uint32_t fmt = r.fmt, c_in = r.c_in, mode = r.mode;
@@ -234,6 +289,18 @@ __device__ __forceinline__ void row_stage_a(const FusedRow& r, const RowTile& rt
     }
 }
 
+template <bool F32>
+__device__ __forceinline__ void row_stage_a(const FusedRow& r, const RowTile& rt, uint32_t c_mix, uint32_t n_pre,
+                                            uint32_t n_mid, uint32_t lane, float* row) {
+    if (rt.lo >= rt.hi) return;
+    if (r.mode == ROW_LERP && c_mix == 1 && r.c_in == 1) {
+        if (n_pre == 0 && n_mid == 0) stage_a_mono_lerp<F32, true>(r, rt, n_pre, n_mid, lane, row);
+        else stage_a_mono_lerp<F32, false>(r, rt, n_pre, n_mid, lane, row);
+        return;
+    }
+    row_stage_a_any<F32>(r, rt, c_mix, n_pre, n_mid, lane, [&](uint32_t t, float v) { row[t] = v; });
+}
+
 // Copy this CTA's rows into shared memory once (row constants are then warp-broadcast LDS, not LDG).
 __device__ __forceinline__ void load_rows(FusedRow* s_rows, const FusedRow* rows, uint32_t G) {
     const uint32_t words = G * (uint32_t)(sizeof(FusedRow) / 4);
@@ -254,14 +321,46 @@ __device__ __forceinline__ void cta_span(const FusedRow* s_rows, uint32_t G, con
 }
 
 // Stage C for one tile position: post-gains and the ordered sum over the CTA's rows.
-__device__ __forceinline__ float mix_rows(const float* tile, const RowTile* rts, const FusedRow* s_rows, uint32_t G,
-                                          uint32_t n_post, uint32_t t) {
+// `full`: every row of the CTA is active over the whole tile (the common interior case) -> no range checks.
+template <int NPOST>   // 0, 1 or -1 (runtime count)
+__device__ __forceinline__ float mix_rows_n(const float* tile, const RowTile* rts, const FusedRow* s_rows, uint32_t G,
+                                            uint32_t n_post, uint32_t t, bool full) {
     float acc = 0.0f;
-    for (uint32_t g = 0; g < G; g++) {
-        const uint2 r = *reinterpret_cast<const uint2*>(&rts[g].lo);   // (lo, hi)
-        if (t >= r.x && t < r.y) acc = add(acc, apply_gains(tile[g * ROW_STRIDE + t], s_rows[g].post, n_post));
+    if (full) {
+#pragma unroll 4
+        for (uint32_t g = 0; g < G; g++) {
+            float v = tile[g * ROW_STRIDE + t];
+            if (NPOST == 1) v = mul(v, s_rows[g].post[0]);
+            else if (NPOST < 0) v = apply_gains(v, s_rows[g].post, n_post);
+            acc = add(acc, v);
+        }
+    } else {
+        for (uint32_t g = 0; g < G; g++) {
+            const uint2 r = *reinterpret_cast<const uint2*>(&rts[g].lo);   // (lo, hi)
+            if (t >= r.x && t < r.y) {
+                float v = tile[g * ROW_STRIDE + t];
+                if (NPOST == 1) v = mul(v, s_rows[g].post[0]);
+                else if (NPOST < 0) v = apply_gains(v, s_rows[g].post, n_post);
+                acc = add(acc, v);
+            }
+        }
     }
     return acc;
+}
+__device__ __forceinline__ float mix_rows(const float* tile, const RowTile* rts, const FusedRow* s_rows, uint32_t G,
+                                          uint32_t n_post, uint32_t t, bool full) {
+    if (n_post == 0) return mix_rows_n<0>(tile, rts, s_rows, G, n_post, t, full);
+    if (n_post == 1) return mix_rows_n<1>(tile, rts, s_rows, G, n_post, t, full);
+    return mix_rows_n<-1>(tile, rts, s_rows, G, n_post, t, full);
+}
+
+// Mixer-timeline interval on which every row of the CTA is active: tiles inside it need no range checks.
+__device__ __forceinline__ void cta_full_span(const FusedRow* s_rows, uint32_t G, uint64_t& f_lo, uint64_t& f_hi) {
+    f_lo = 0, f_hi = ~0ull;
+    for (uint32_t g = 0; g < G; g++) {
+        f_lo = max(f_lo, s_rows[g].mix_start);
+        f_hi = min(f_hi, s_rows[g].mix_start + s_rows[g].out_len);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -283,16 +382,19 @@ __global__ void __launch_bounds__(256) k_fused_nobiquad(FusedArgs a) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
     float* tile = smem;
     const uint64_t m_begin = lo / TT * TT;
+    uint64_t f_lo, f_hi;
+    cta_full_span(s_rows, G, f_lo, f_hi);
     for (uint64_t m0 = m_begin + (uint64_t)blockIdx.y * TT; m0 < hi; m0 += (uint64_t)gridDim.y * TT) {
         for (uint32_t g = warp; g < G; g += n_warps) {
             if (lane == 0) row_tile_setup(s_rows[g], a.c_mix, m0, s_rt[g]);
             __syncwarp();
             float* row = tile + g * ROW_STRIDE;
-            row_stage_a<F32>(s_rows[g], s_rt[g], a.c_mix, a.n_pre, a.n_mid, lane, [&](uint32_t t, float v) { row[t] = v; });
+            row_stage_a<F32>(s_rows[g], s_rt[g], a.c_mix, a.n_pre, a.n_mid, lane, row);
         }
         __syncthreads();
+        const bool full = m0 >= f_lo && m0 + TT <= f_hi;
         for (uint32_t t = threadIdx.x; t < TT; t += blockDim.x)
-            if (m0 + t < a.mix_len) partial[m0 + t] = mix_rows(tile, s_rt, s_rows, G, a.n_post, t);
+            if (m0 + t < a.mix_len) partial[m0 + t] = mix_rows(tile, s_rt, s_rows, G, a.n_post, t, full);
         __syncthreads();
     }
 }
@@ -316,6 +418,8 @@ __global__ void __launch_bounds__(512, 1) k_fused_biquad(FusedArgs a, uint32_t n
     if (lo >= hi) return;
     const uint64_t m_begin = lo / TT * TT;
     const uint32_t n_tiles = (uint32_t)((hi - m_begin + TT - 1) / TT);
+    uint64_t f_lo, f_hi;
+    cta_full_span(s_rows, G, f_lo, f_hi);
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t n_warps = blockDim.x >> 5;
@@ -347,8 +451,7 @@ __global__ void __launch_bounds__(512, 1) k_fused_biquad(FusedArgs a, uint32_t n
                     if (lane == 0) row_tile_setup(s_rows[g], c_mix, m0, s_rt[buf][g]);
                     __syncwarp();
                     float* row = tile + g * ROW_STRIDE;
-                    row_stage_a<F32>(s_rows[g], s_rt[buf][g], c_mix, a.n_pre, a.n_mid, lane,
-                                     [&](uint32_t t, float v) { row[t] = v; });
+                    row_stage_a<F32>(s_rows[g], s_rt[buf][g], c_mix, a.n_pre, a.n_mid, lane, row);
                 }
             }
             // ---- stage C on tile `it - 2` ----
@@ -357,8 +460,9 @@ __global__ void __launch_bounds__(512, 1) k_fused_biquad(FusedArgs a, uint32_t n
                 const uint32_t buf = kt % NBUF;
                 const uint64_t m0 = m_begin + (uint64_t)kt * TT;
                 const float* tile = smem + (size_t)buf * MAX_G * ROW_STRIDE;
+                const bool full = m0 >= f_lo && m0 + TT <= f_hi;
                 for (uint32_t t = par_tid; t < TT; t += n_par_threads)
-                    if (m0 + t < a.mix_len) partial[m0 + t] = mix_rows(tile, s_rt[buf], s_rows, G, a.n_post, t);
+                    if (m0 + t < a.mix_len) partial[m0 + t] = mix_rows(tile, s_rt[buf], s_rows, G, a.n_post, t, full);
             }
         } else if (it >= 1 && it <= n_tiles) {
             // ---- stage B on tile `it - 1` ----
