@@ -113,14 +113,11 @@ __device__ __forceinline__ float load_in(const void* in, uint32_t fmt, uint64_t 
 __device__ __forceinline__ float lerp_rcp(float first, float second, float num_f, float den_f, float rcp_den) {
     float m = mul(sub(second, first), num_f);
     float am = fabsf(m);
-    float q;
-    if (am >= 1e-30f && am <= 1e30f) {
-        float q0 = mul(m, rcp_den);
-        float r = __fmaf_rn(-q0, den_f, m);
-        q = __fmaf_rn(r, rcp_den, q0);
-    } else {
-        q = divf(m, den_f);
-    }
+    float q0 = mul(m, rcp_den);
+    float r = __fmaf_rn(-q0, den_f, m);
+    float q = __fmaf_rn(r, rcp_den, q0);
+    q = (am == 0.0f) ? m : q;                                   // (+-0) / den keeps its sign
+    if (!(am <= 1e30f) || (am < 1e-30f && am != 0.0f)) q = divf(m, den_f);   // rare: denormal / huge / NaN
     return add(first, q);
 }
 
@@ -165,47 +162,74 @@ __device__ __forceinline__ void row_tile_setup(const FusedRow& r, uint32_t c_mix
 template <bool F32, bool NOGAIN>
 __device__ __forceinline__ void stage_a_mono_lerp(const FusedRow& r, const RowTile& rt, uint32_t n_pre, uint32_t n_mid,
                                                   uint32_t lane, float* __restrict__ row) {
-    constexpr int U = TT / 32;
+    constexpr int U = TT / 32;   // output frames per lane per tile
+    constexpr int H = 4;         // frames per half-batch: 2*H independent loads in flight per lane
     const uint32_t n = rt.hi - rt.lo;
     const uint32_t to = r.uni.to, q32 = r.q32, r32 = r.r32, fmt = r.fmt;
     const float den_f = r.den_f, rcp_den = r.rcp_den;
     const uint64_t remain = r.uni.tail.L - 1 - rt.i0;              // frames to the right of i0
     const uint32_t lim = remain > 0x7fffffffull ? 0x7fffffffu : (uint32_t)remain;   // interpolate iff di < lim
     const float* __restrict__ base_f = (const float*)r.in + rt.i0;
-    float pre[MAX_GAINS], mid[MAX_GAINS];
-#pragma unroll
-    for (int k = 0; k < MAX_GAINS; k++) pre[k] = r.pre[k], mid[k] = r.mid[k];
+    const float* pre = r.pre;   // shared memory (warp-broadcast reads); only touched when gains exist
+    const float* mid = r.mid;
     uint32_t prod = rt.r0 + lane * r.uni.from;
     uint32_t di = prod / to;
     uint32_t num = prod - di * to;
-    uint32_t dis[U], nums[U];
+    float* __restrict__ out = row + rt.lo + lane;
+    // last left index this lane will touch in the tile: di + (U-1) * (32*from/to) rounded up
+    const bool interior = F32 && n == (uint32_t)TT && (di + (uint32_t)(U - 1) * (q32 + 1) + 1) < lim;
+    if (interior) {
+        // every position active, every right neighbour exists -> no predicates at all
+#pragma unroll 1
+        for (int h = 0; h < U; h += H) {
+            uint32_t dis[H];
+            float nf[H], x0[H], x1[H];
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-        dis[u] = di, nums[u] = num;
-        num += r32, di += q32;
-        if (num >= to) num -= to, di += 1;
-    }
-    float x0[U], x1[U];
+            for (int u = 0; u < H; u++) {
+                dis[u] = di, nf[u] = __uint2float_rn(num);
+                num += r32, di += q32;
+                if (num >= to) num -= to, di += 1;
+            }
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-        x0[u] = 0.0f, x1[u] = 0.0f;
-        if (lane + 32u * (uint32_t)u < n) {
-            if (F32) {
-                x0[u] = __ldg(base_f + dis[u]);
-                if (dis[u] < lim) x1[u] = __ldg(base_f + dis[u] + 1);
-            } else {
-                x0[u] = load_as_f32(r.in, fmt, rt.i0 + dis[u]);
-                if (dis[u] < lim) x1[u] = load_as_f32(r.in, fmt, rt.i0 + dis[u] + 1);
+            for (int u = 0; u < H; u++) x0[u] = __ldg(base_f + dis[u]), x1[u] = __ldg(base_f + dis[u] + 1);
+#pragma unroll
+            for (int u = 0; u < H; u++) {
+                float v = lerp_rcp(gains<NOGAIN>(x0[u], pre, n_pre), gains<NOGAIN>(x1[u], pre, n_pre), nf[u], den_f, rcp_den);
+                out[32 * (h + u)] = gains<NOGAIN>(v, mid, n_mid);
             }
         }
+        return;
     }
-    float* __restrict__ out = row + rt.lo + lane;
+#pragma unroll 1
+    for (int h = 0; h < U; h += H) {
+        uint32_t dis[H];
+        float nf[H], x0[H], x1[H];
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-        if (lane + 32u * (uint32_t)u < n) {
-            float v = gains<NOGAIN>(x0[u], pre, n_pre);
-            if (dis[u] < lim) v = lerp_rcp(v, gains<NOGAIN>(x1[u], pre, n_pre), __uint2float_rn(nums[u]), den_f, rcp_den);
-            out[32 * u] = gains<NOGAIN>(v, mid, n_mid);
+        for (int u = 0; u < H; u++) {
+            dis[u] = di, nf[u] = __uint2float_rn(num);
+            num += r32, di += q32;
+            if (num >= to) num -= to, di += 1;
+        }
+#pragma unroll
+        for (int u = 0; u < H; u++) {
+            x0[u] = 0.0f, x1[u] = 0.0f;
+            if (lane + 32u * (uint32_t)(h + u) < n) {
+                if (F32) {
+                    x0[u] = __ldg(base_f + dis[u]);
+                    if (dis[u] < lim) x1[u] = __ldg(base_f + dis[u] + 1);
+                } else {
+                    x0[u] = load_as_f32(r.in, fmt, rt.i0 + dis[u]);
+                    if (dis[u] < lim) x1[u] = load_as_f32(r.in, fmt, rt.i0 + dis[u] + 1);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < H; u++) {
+            if (lane + 32u * (uint32_t)(h + u) < n) {
+                float v = gains<NOGAIN>(x0[u], pre, n_pre);
+                if (dis[u] < lim) v = lerp_rcp(v, gains<NOGAIN>(x1[u], pre, n_pre), nf[u], den_f, rcp_den);
+                out[32 * (h + u)] = gains<NOGAIN>(v, mid, n_mid);
+            }
         }
     }
 }
@@ -289,16 +313,16 @@ __device__ __forceinline__ void row_stage_a_any(const FusedRow& r, const RowTile
     }
 }
 
-template <bool F32>
+template <bool F32, bool HOT = false>   // HOT: the host guarantees every row is mono ROW_LERP
 __device__ __forceinline__ void row_stage_a(const FusedRow& r, const RowTile& rt, uint32_t c_mix, uint32_t n_pre,
                                             uint32_t n_mid, uint32_t lane, float* row) {
     if (rt.lo >= rt.hi) return;
-    if (r.mode == ROW_LERP && c_mix == 1 && r.c_in == 1) {
+    if (HOT || (r.mode == ROW_LERP && c_mix == 1 && r.c_in == 1)) {
         if (n_pre == 0 && n_mid == 0) stage_a_mono_lerp<F32, true>(r, rt, n_pre, n_mid, lane, row);
         else stage_a_mono_lerp<F32, false>(r, rt, n_pre, n_mid, lane, row);
         return;
     }
-    row_stage_a_any<F32>(r, rt, c_mix, n_pre, n_mid, lane, [&](uint32_t t, float v) { row[t] = v; });
+    if (!HOT) row_stage_a_any<F32>(r, rt, c_mix, n_pre, n_mid, lane, [&](uint32_t t, float v) { row[t] = v; });
 }
 
 // Copy this CTA's rows into shared memory once (row constants are then warp-broadcast LDS, not LDG).
@@ -402,8 +426,10 @@ __global__ void __launch_bounds__(256) k_fused_nobiquad(FusedArgs a) {
 // ---------------------------------------------------------------------------------------------------
 // biquad variant: three-stage software pipeline over shared-memory tiles
 // ---------------------------------------------------------------------------------------------------
-template <bool F32, int C_MIX_STATIC>   // C_MIX_STATIC 1: mono fast path (vectorised recurrence), 0: any channel count
-__global__ void __launch_bounds__(512, 1) k_fused_biquad(FusedArgs a, uint32_t n_rec_warps) {
+// C_MIX_STATIC 1: mono mixer (vectorised recurrence), 0: any channel count.
+// HOT: every row is a mono ROW_LERP f32 source (BASELINE cfg3): 1024 threads = one stage-A warp per row.
+template <bool F32, int C_MIX_STATIC, bool HOT>
+__global__ void __launch_bounds__(HOT ? 1024 : 512, 1) k_fused_biquad(FusedArgs a, uint32_t n_rec_warps) {
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(16) FusedRow s_rows[MAX_G];
     __shared__ RowTile s_rt[NBUF][MAX_G];
@@ -451,7 +477,7 @@ __global__ void __launch_bounds__(512, 1) k_fused_biquad(FusedArgs a, uint32_t n
                     if (lane == 0) row_tile_setup(s_rows[g], c_mix, m0, s_rt[buf][g]);
                     __syncwarp();
                     float* row = tile + g * ROW_STRIDE;
-                    row_stage_a<F32>(s_rows[g], s_rt[buf][g], c_mix, a.n_pre, a.n_mid, lane, row);
+                    row_stage_a<F32, HOT>(s_rows[g], s_rt[buf][g], c_mix, a.n_pre, a.n_mid, lane, row);
                 }
             }
             // ---- stage C on tile `it - 2` ----
@@ -546,6 +572,7 @@ struct rb_fused_plan {
     size_t smem_bytes = 0;
     bool single_cta_direct = false;
     bool all_f32 = true;
+    bool hot = false;
 };
 
 static const rb_node_dev& node_at(const rb_fused_stream& s, uint32_t i) {
@@ -649,6 +676,8 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     plan->smem_bytes = (size_t)(has_b ? NBUF : 1) * MAX_G * ROW_STRIDE * sizeof(float);
     plan->all_f32 = true;
     for (size_t i = 0; i < n_streams; i++) plan->all_f32 = plan->all_f32 && streams[i].fmt == RB_FMT_F32;
+    plan->hot = has_b && plan->all_f32 && mixer_channels == 1;
+    for (size_t i = 0; i < n_streams && plan->hot; i++) plan->hot = rows[i].mode == ROW_LERP && rows[i].c_in == 1;
     plan->d_out = d_out;
 
     cudaError_t e = cudaMalloc(&plan->d_rows, n_streams * sizeof(FusedRow));
@@ -659,10 +688,11 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     if (e == cudaSuccess && !plan->single_cta_direct) e = cudaMemsetAsync(plan->d_partial, 0, (size_t)n_ctas * mix_len * sizeof(float), st);
     if (e == cudaSuccess && has_b) {
         const int sb = (int)plan->smem_bytes;
-        e = cudaFuncSetAttribute(k_fused_biquad<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused_biquad<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused_biquad<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused_biquad<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+        e = cudaFuncSetAttribute(k_fused_biquad<true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused_biquad<true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused_biquad<true, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused_biquad<false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused_biquad<false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
     }
     if (e != cudaSuccess) {
         rb_fused_destroy(plan);
@@ -687,10 +717,11 @@ cudaError_t rb_fused_run(rb_fused_plan* p, cudaStream_t st) {
     if (a.has_biquad) {
         const uint32_t threads = 512;
         const bool mono = a.c_mix == 1;
-        if (p->all_f32 && mono) k_fused_biquad<true, 1><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
-        else if (p->all_f32) k_fused_biquad<true, 0><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
-        else if (mono) k_fused_biquad<false, 1><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
-        else k_fused_biquad<false, 0><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
+        if (p->hot) k_fused_biquad<true, 1, true><<<p->n_ctas, 1024, p->smem_bytes, st>>>(a, p->n_rec_warps);
+        else if (p->all_f32 && mono) k_fused_biquad<true, 1, false><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
+        else if (p->all_f32) k_fused_biquad<true, 0, false><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
+        else if (mono) k_fused_biquad<false, 1, false><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
+        else k_fused_biquad<false, 0, false><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
     } else {
         if (p->all_f32) k_fused_nobiquad<true><<<dim3(p->n_ctas, p->grid_y), 256, p->smem_bytes, st>>>(a);
         else k_fused_nobiquad<false><<<dim3(p->n_ctas, p->grid_y), 256, p->smem_bytes, st>>>(a);
