@@ -52,12 +52,13 @@ struct FusedRow {                  // one stream, device side
     uint32_t mode;                 // row-wide fast mode, see ROW_*
     rb_uniform_params uni;
     uint32_t q32, r32;             // divmod(32 * from, to): index advance for a lane stride of 32 output frames
+    uint32_t qT, rT;               // divmod(TT * from, to): index advance from one full tile to the next
     float den_f, rcp_den;          // (f32)to and RN(1 / (f32)to)
     float pre[MAX_GAINS];          // gains applied to raw input samples (before interpolation)
     float mid[MAX_GAINS];          // gains between the uniform conversion and the biquad
     float post[MAX_GAINS];         // gains after the biquad
     float b0, b1, b2, a1, a2;
-    uint32_t pad_[3];
+    uint32_t pad_[1];
 };
 enum : uint32_t {
     ROW_GENERIC = 0,   // exact closed form per sample (span chunks, trailing partial frames, huge ratios)
@@ -313,16 +314,16 @@ __device__ __forceinline__ void row_stage_a_any(const FusedRow& r, const RowTile
     }
 }
 
-template <bool F32, bool HOT = false>   // HOT: the host guarantees every row is mono ROW_LERP
+template <bool F32>
 __device__ __forceinline__ void row_stage_a(const FusedRow& r, const RowTile& rt, uint32_t c_mix, uint32_t n_pre,
                                             uint32_t n_mid, uint32_t lane, float* row) {
     if (rt.lo >= rt.hi) return;
-    if (HOT || (r.mode == ROW_LERP && c_mix == 1 && r.c_in == 1)) {
+    if (r.mode == ROW_LERP && c_mix == 1 && r.c_in == 1) {
         if (n_pre == 0 && n_mid == 0) stage_a_mono_lerp<F32, true>(r, rt, n_pre, n_mid, lane, row);
         else stage_a_mono_lerp<F32, false>(r, rt, n_pre, n_mid, lane, row);
         return;
     }
-    if (!HOT) row_stage_a_any<F32>(r, rt, c_mix, n_pre, n_mid, lane, [&](uint32_t t, float v) { row[t] = v; });
+    row_stage_a_any<F32>(r, rt, c_mix, n_pre, n_mid, lane, [&](uint32_t t, float v) { row[t] = v; });
 }
 
 // Copy this CTA's rows into shared memory once (row constants are then warp-broadcast LDS, not LDG).
@@ -427,9 +428,8 @@ __global__ void __launch_bounds__(256) k_fused_nobiquad(FusedArgs a) {
 // biquad variant: three-stage software pipeline over shared-memory tiles
 // ---------------------------------------------------------------------------------------------------
 // C_MIX_STATIC 1: mono mixer (vectorised recurrence), 0: any channel count.
-// HOT: every row is a mono ROW_LERP f32 source (BASELINE cfg3): 1024 threads = one stage-A warp per row.
-template <bool F32, int C_MIX_STATIC, bool HOT>
-__global__ void __launch_bounds__(HOT ? 1024 : 512, 1) k_fused_biquad(FusedArgs a, uint32_t n_rec_warps) {
+template <bool F32, int C_MIX_STATIC>
+__global__ void __launch_bounds__(512, 1) k_fused_biquad(FusedArgs a, uint32_t n_rec_warps) {
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(16) FusedRow s_rows[MAX_G];
     __shared__ RowTile s_rt[NBUF][MAX_G];
@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(HOT ? 1024 : 512, 1) k_fused_biquad(FusedArgs 
                     if (lane == 0) row_tile_setup(s_rows[g], c_mix, m0, s_rt[buf][g]);
                     __syncwarp();
                     float* row = tile + g * ROW_STRIDE;
-                    row_stage_a<F32, HOT>(s_rows[g], s_rt[buf][g], c_mix, a.n_pre, a.n_mid, lane, row);
+                    row_stage_a<F32>(s_rows[g], s_rt[buf][g], c_mix, a.n_pre, a.n_mid, lane, row);
                 }
             }
             // ---- stage C on tile `it - 2` ----
@@ -550,6 +550,286 @@ __global__ void __launch_bounds__(HOT ? 1024 : 512, 1) k_fused_biquad(FusedArgs 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// HOT variant (BASELINE cfg3): every row is a mono f32 source, linear interpolation with from <= to,
+// mono mixer, one biquad.  Same three-stage pipeline, plus a fourth, asynchronous stage in front:
+//   L  tile k+2 : each row's input window (<= TT+8 floats) is fetched by the bulk-copy engine
+//                 (cp.async.bulk global -> shared, completion counted on an mbarrier), two tiles ahead,
+//                 so stage A never touches global memory and never waits for HBM latency.
+// 1024 threads: one stage-A warp per row, the recurrence warp has the highest warp id.
+// ---------------------------------------------------------------------------------------------------
+constexpr int NWIN = 3;                 // input-window ring (tile k .. k+2)
+constexpr int WSTRIDE = TT + 8;         // floats per row window (>= 3 + TT*from/to + 2, multiple of 4)
+constexpr int NHT = 5;                  // per-(row,tile) index-state ring: written 2 tiles ahead, read until stage C
+
+struct HotTile {
+    uint32_t lo, hi;       // active tile positions
+    uint32_t r0;           // (n0 * from) mod to at position lo
+    uint32_t woff;         // i0 & 3: offset of frame i0 inside the 16-byte aligned window
+    uint64_t i0;           // left input frame of position lo
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA/bulk-copy engine; completes `bytes` on the mbarrier.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Index state of (row, tile) -- incremental from the previous tile when that one was a full interior tile.
+__device__ __forceinline__ void hot_tile_setup(const FusedRow& r, uint64_t m0, const HotTile* prev, HotTile& ht) {
+    const uint64_t s = r.mix_start, e = r.mix_start + r.out_len;
+    const uint64_t lo = m0 > s ? m0 : s, hi = (m0 + TT) < e ? (m0 + TT) : e;
+    ht.lo = ht.hi = 0, ht.r0 = 0, ht.woff = 0, ht.i0 = 0;
+    if (lo >= hi) return;
+    ht.lo = (uint32_t)(lo - m0), ht.hi = (uint32_t)(hi - m0);
+    if (prev && prev->lo == 0 && prev->hi == (uint32_t)TT && ht.lo == 0) {
+        uint32_t rr = prev->r0 + r.rT;
+        uint64_t ii = prev->i0 + r.qT;
+        if (rr >= r.uni.to) rr -= r.uni.to, ii += 1;
+        ht.r0 = rr, ht.i0 = ii;
+    } else {
+        const uint64_t prod = (lo - s) * (uint64_t)r.uni.from;
+        ht.i0 = prod / r.uni.to;
+        ht.r0 = (uint32_t)(prod - ht.i0 * r.uni.to);
+    }
+    ht.woff = (uint32_t)(ht.i0 & 3ull);
+}
+
+// Stage L for one (row, tile): arm the stage barrier and launch the bulk copy of the input window.
+__device__ __forceinline__ void hot_issue_window(const FusedRow& r, const HotTile& ht, float* win, uint64_t* bar) {
+    if (ht.lo >= ht.hi) {
+        mbar_arrive(bar);
+        return;
+    }
+    const uint32_t n = ht.hi - ht.lo;
+    const uint64_t L = r.uni.tail.L;
+    uint64_t taps = (uint64_t)((ht.r0 + (n - 1) * r.uni.from) / r.uni.to) + 2;   // 32-bit: from, to <= 2^20, n <= TT
+    if (ht.i0 + taps > L) taps = L - ht.i0;
+    const uint32_t frames = ht.woff + (uint32_t)taps;
+    const uint32_t bytes = (frames * 4u + 15u) & ~15u;                  // <= 12 bytes into the row's 16-byte tail pad
+    const float* src = (const float*)r.in + (ht.i0 - ht.woff);
+    mbar_arrive_expect_tx(bar, bytes);
+    bulk_g2s(win, src, bytes, bar);
+}
+
+// Stage A for one (row, tile) out of the shared-memory window.
+template <bool NOGAIN>
+__device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht, uint32_t n_pre, uint32_t n_mid,
+                                            uint32_t lane, const float* __restrict__ win, float* __restrict__ row) {
+    constexpr int U = TT / 32, H = 4;
+    const uint32_t n = ht.hi - ht.lo;
+    const uint32_t to = r.uni.to, q32 = r.q32, r32 = r.r32;
+    const float den_f = r.den_f, rcp_den = r.rcp_den;
+    const uint64_t remain = r.uni.tail.L - 1 - ht.i0;
+    const uint32_t lim = remain > 0x7fffffffull ? 0x7fffffffu : (uint32_t)remain;   // interpolate iff di < lim
+    const float* __restrict__ w = win + ht.woff;
+    const float* pre = r.pre;
+    const float* mid = r.mid;
+    uint32_t prod = ht.r0 + lane * r.uni.from;
+    uint32_t di = prod / to;
+    uint32_t num = prod - di * to;
+    float* __restrict__ out = row + ht.lo + lane;
+    const bool interior = n == (uint32_t)TT && (di + (uint32_t)(U - 1) * (q32 + 1) + 1) < lim;
+    if (interior) {
+#pragma unroll
+        for (int h = 0; h < U; h += H) {
+            uint32_t dis[H];
+            float nf[H], x0[H], x1[H];
+#pragma unroll
+            for (int u = 0; u < H; u++) {
+                dis[u] = di, nf[u] = __uint2float_rn(num);
+                num += r32, di += q32;
+                if (num >= to) num -= to, di += 1;
+            }
+#pragma unroll
+            for (int u = 0; u < H; u++) x0[u] = w[dis[u]], x1[u] = w[dis[u] + 1];
+#pragma unroll
+            for (int u = 0; u < H; u++) {
+                float v = lerp_rcp(gains<NOGAIN>(x0[u], pre, n_pre), gains<NOGAIN>(x1[u], pre, n_pre), nf[u], den_f, rcp_den);
+                out[32 * (h + u)] = gains<NOGAIN>(v, mid, n_mid);
+            }
+        }
+        return;
+    }
+#pragma unroll 1
+    for (int u = 0; u < U; u++) {
+        if (lane + 32u * (uint32_t)u < n) {
+            float v = gains<NOGAIN>(w[di], pre, n_pre);
+            if (di < lim) v = lerp_rcp(v, gains<NOGAIN>(w[di + 1], pre, n_pre), __uint2float_rn(num), den_f, rcp_den);
+            out[32 * u] = gains<NOGAIN>(v, mid, n_mid);
+        }
+        num += r32, di += q32;
+        if (num >= to) num -= to, di += 1;
+    }
+}
+
+__global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ __align__(16) FusedRow s_rows[MAX_G];
+    __shared__ __align__(8) HotTile s_ht[NHT][MAX_G];
+    __shared__ __align__(8) uint64_t s_full[NWIN];
+    const uint32_t row0 = blockIdx.x * a.rows_per_cta;
+    const uint32_t G = min(a.rows_per_cta, a.n_rows - row0);
+    load_rows(s_rows, a.rows + row0, G);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NWIN; i++) mbar_init(&s_full[i], G);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    float* tiles = smem;                                               // [NBUF][rows_per_cta][ROW_STRIDE]
+    float* wins = smem + (size_t)NBUF * a.rows_per_cta * ROW_STRIDE;   // [NWIN][rows_per_cta][WSTRIDE]
+    const size_t tile_sz = (size_t)a.rows_per_cta * ROW_STRIDE, win_sz = (size_t)a.rows_per_cta * WSTRIDE;
+    float* partial = a.partial + (uint64_t)blockIdx.x * a.mix_len;
+    uint64_t lo, hi;
+    cta_span(s_rows, G, a, lo, hi);
+    if (lo >= hi) return;
+    const uint64_t m_begin = lo / TT * TT;
+    const uint32_t n_tiles = (uint32_t)((hi - m_begin + TT - 1) / TT);
+    uint64_t f_lo, f_hi;
+    cta_full_span(s_rows, G, f_lo, f_hi);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t n_par_warps = (blockDim.x >> 5) - 1;   // the last warp runs the recurrence
+    const bool is_rec = warp == n_par_warps;
+    const uint32_t n_par_threads = n_par_warps * 32;
+    const bool nogain = a.n_pre == 0 && a.n_mid == 0;
+
+    const bool chain_on = is_rec && lane < G;
+    float x1 = 0.f, x2 = 0.f, y1 = 0.f, y2 = 0.f;
+    float b0 = 0.f, b1 = 0.f, b2 = 0.f, a1 = 0.f, a2 = 0.f;
+    if (chain_on) {
+        const FusedRow& r = s_rows[lane];
+        b0 = r.b0, b1 = r.b1, b2 = r.b2, a1 = r.a1, a2 = r.a2;
+    }
+
+    // prologue: windows of tiles 0 and 1
+    if (!is_rec && lane == 0) {
+        for (uint32_t g = warp; g < G; g += n_par_warps) {
+            for (uint32_t kt = 0; kt < 2 && kt < n_tiles; kt++) {
+                HotTile& ht = s_ht[kt % NHT][g];
+                hot_tile_setup(s_rows[g], m_begin + (uint64_t)kt * TT, kt ? &s_ht[(kt - 1) % NHT][g] : nullptr, ht);
+                hot_issue_window(s_rows[g], ht, wins + (kt % NWIN) * win_sz + g * WSTRIDE, &s_full[kt % NWIN]);
+            }
+        }
+    }
+    __syncthreads();
+
+    for (uint32_t it = 0; it < n_tiles + 2; it++) {
+        if (!is_rec) {
+            // ---- stage L on tile it+2 ----
+            if (lane == 0 && it + 2 < n_tiles) {
+                const uint32_t kt = it + 2;
+                for (uint32_t g = warp; g < G; g += n_par_warps) {
+                    HotTile& ht = s_ht[kt % NHT][g];
+                    hot_tile_setup(s_rows[g], m_begin + (uint64_t)kt * TT, &s_ht[(kt - 1) % NHT][g], ht);
+                    hot_issue_window(s_rows[g], ht, wins + (kt % NWIN) * win_sz + g * WSTRIDE, &s_full[kt % NWIN]);
+                }
+            }
+            // ---- stage A on tile it ----
+            if (it < n_tiles) {
+                mbar_wait(&s_full[it % NWIN], (it / NWIN) & 1u);
+                float* tile = tiles + (it % NBUF) * tile_sz;
+                const float* win = wins + (it % NWIN) * win_sz;
+                for (uint32_t g = warp; g < G; g += n_par_warps) {
+                    const HotTile& ht = s_ht[it % NHT][g];
+                    if (ht.lo >= ht.hi) continue;
+                    if (nogain) hot_stage_a<true>(s_rows[g], ht, a.n_pre, a.n_mid, lane, win + g * WSTRIDE, tile + g * ROW_STRIDE);
+                    else hot_stage_a<false>(s_rows[g], ht, a.n_pre, a.n_mid, lane, win + g * WSTRIDE, tile + g * ROW_STRIDE);
+                }
+            }
+            // ---- stage C on tile it-2 ----
+            if (it >= 2) {
+                const uint32_t kt = it - 2;
+                const uint64_t m0 = m_begin + (uint64_t)kt * TT;
+                const float* tile = tiles + (kt % NBUF) * tile_sz;
+                const HotTile* hts = s_ht[kt % NHT];
+                const bool full = m0 >= f_lo && m0 + TT <= f_hi;
+                for (uint32_t t = threadIdx.x; t < TT; t += n_par_threads) {
+                    if (m0 + t >= a.mix_len) continue;
+                    float acc = 0.0f;
+                    if (full) {
+#pragma unroll 4
+                        for (uint32_t g = 0; g < G; g++)
+                            acc = add(acc, apply_gains(tile[g * ROW_STRIDE + t], s_rows[g].post, a.n_post));
+                    } else {
+                        for (uint32_t g = 0; g < G; g++) {
+                            const uint2 r = *reinterpret_cast<const uint2*>(&hts[g].lo);
+                            if (t >= r.x && t < r.y)
+                                acc = add(acc, apply_gains(tile[g * ROW_STRIDE + t], s_rows[g].post, a.n_post));
+                        }
+                    }
+                    partial[m0 + t] = acc;
+                }
+            }
+        } else if (it >= 1 && it <= n_tiles) {
+            // ---- stage B on tile it-1 (recurrence warp, lane = row) ----
+            const uint32_t kt = it - 1;
+            if (chain_on) {
+                float* row = tiles + (kt % NBUF) * tile_sz + lane * ROW_STRIDE;
+                const uint2 act = *reinterpret_cast<const uint2*>(&s_ht[kt % NHT][lane].lo);
+                uint32_t t = act.x;
+                const uint32_t hi_t = act.y;
+                for (; t < hi_t && (t & 3); t++) {
+                    float xv = row[t];
+                    float y = biquad_fb(a1, a2, biquad_ff(b0, b1, b2, xv, x1, x2), y1, y2);
+                    x2 = x1, x1 = xv, y2 = y1, y1 = y;
+                    row[t] = y;
+                }
+                float4 nx = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t + 4 <= hi_t) nx = *reinterpret_cast<const float4*>(row + t);
+                for (; t + 4 <= hi_t; t += 4) {
+                    const float4 xv = nx;
+                    if (t + 8 <= hi_t) nx = *reinterpret_cast<const float4*>(row + t + 4);
+                    float4 yv;
+                    float f0 = biquad_ff(b0, b1, b2, xv.x, x1, x2);
+                    float f1 = biquad_ff(b0, b1, b2, xv.y, xv.x, x1);
+                    float f2 = biquad_ff(b0, b1, b2, xv.z, xv.y, xv.x);
+                    float f3 = biquad_ff(b0, b1, b2, xv.w, xv.z, xv.y);
+                    yv.x = biquad_fb(a1, a2, f0, y1, y2);
+                    yv.y = biquad_fb(a1, a2, f1, yv.x, y1);
+                    yv.z = biquad_fb(a1, a2, f2, yv.y, yv.x);
+                    yv.w = biquad_fb(a1, a2, f3, yv.z, yv.y);
+                    x2 = xv.z, x1 = xv.w, y2 = yv.z, y1 = yv.w;
+                    *reinterpret_cast<float4*>(row + t) = yv;
+                }
+                for (; t < hi_t; t++) {
+                    float xv = row[t];
+                    float y = biquad_fb(a1, a2, biquad_ff(b0, b1, b2, xv, x1, x2), y1, y2);
+                    x2 = x1, x1 = xv, y2 = y1, y1 = y;
+                    row[t] = y;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ordered sum of the per-CTA partial rows
 __global__ void __launch_bounds__(256) k_sum_partials(const float* __restrict__ partial, uint32_t n_ctas,
                                                       uint64_t mix_len, float* __restrict__ out) {
@@ -578,6 +858,7 @@ struct rb_fused_plan {
     bool single_cta_direct = false;
     bool all_f32 = true;
     bool hot = false;
+    size_t hot_smem = 0;
 };
 
 static const rb_node_dev& node_at(const rb_fused_stream& s, uint32_t i) {
@@ -643,6 +924,8 @@ static bool parse_row(const rb_fused_stream& s, uint16_t mixer_ch, FusedRow& r, 
             r.mode = ROW_LERP;
             r.q32 = (uint32_t)((32ull * u.from) / u.to);
             r.r32 = (uint32_t)((32ull * u.from) % u.to);
+            r.qT = (uint32_t)(((uint64_t)TT * u.from) / u.to);
+            r.rT = (uint32_t)(((uint64_t)TT * u.from) % u.to);
         }
     }
     return true;
@@ -682,7 +965,8 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     plan->all_f32 = true;
     for (size_t i = 0; i < n_streams; i++) plan->all_f32 = plan->all_f32 && streams[i].fmt == RB_FMT_F32;
     plan->hot = has_b && plan->all_f32 && mixer_channels == 1;
-    for (size_t i = 0; i < n_streams && plan->hot; i++) plan->hot = rows[i].mode == ROW_LERP && rows[i].c_in == 1;
+    for (size_t i = 0; i < n_streams && plan->hot; i++)
+        plan->hot = rows[i].mode == ROW_LERP && rows[i].c_in == 1 && rows[i].uni.from <= rows[i].uni.to;
     plan->d_out = d_out;
 
     cudaError_t e = cudaMalloc(&plan->d_rows, n_streams * sizeof(FusedRow));
@@ -693,11 +977,13 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     if (e == cudaSuccess && !plan->single_cta_direct) e = cudaMemsetAsync(plan->d_partial, 0, (size_t)n_ctas * mix_len * sizeof(float), st);
     if (e == cudaSuccess && has_b) {
         const int sb = (int)plan->smem_bytes;
-        e = cudaFuncSetAttribute(k_fused_biquad<true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused_biquad<true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused_biquad<true, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused_biquad<false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused_biquad<false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+        e = cudaFuncSetAttribute(k_fused_biquad<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused_biquad<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused_biquad<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused_biquad<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
+        plan->hot_smem = ((size_t)NBUF * ROW_STRIDE + (size_t)NWIN * WSTRIDE) * G * sizeof(float);
+        if (e == cudaSuccess && plan->hot)
+            e = cudaFuncSetAttribute(k_fused_hot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->hot_smem);
     }
     if (e != cudaSuccess) {
         rb_fused_destroy(plan);
@@ -722,11 +1008,11 @@ cudaError_t rb_fused_run(rb_fused_plan* p, cudaStream_t st) {
     if (a.has_biquad) {
         const uint32_t threads = 512;
         const bool mono = a.c_mix == 1;
-        if (p->hot) k_fused_biquad<true, 1, true><<<p->n_ctas, 1024, p->smem_bytes, st>>>(a, p->n_rec_warps);
-        else if (p->all_f32 && mono) k_fused_biquad<true, 1, false><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
-        else if (p->all_f32) k_fused_biquad<true, 0, false><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
-        else if (mono) k_fused_biquad<false, 1, false><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
-        else k_fused_biquad<false, 0, false><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
+        if (p->hot) k_fused_hot<<<p->n_ctas, 1024, p->hot_smem, st>>>(a);
+        else if (p->all_f32 && mono) k_fused_biquad<true, 1><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
+        else if (p->all_f32) k_fused_biquad<true, 0><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
+        else if (mono) k_fused_biquad<false, 1><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
+        else k_fused_biquad<false, 0><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
     } else {
         if (p->all_f32) k_fused_nobiquad<true><<<dim3(p->n_ctas, p->grid_y), 256, p->smem_bytes, st>>>(a);
         else k_fused_nobiquad<false><<<dim3(p->n_ctas, p->grid_y), 256, p->smem_bytes, st>>>(a);
