@@ -116,7 +116,7 @@ def cpu_reference(n_streams: int, frames: int, threads: int, seed: int = 1234):
     srcs = make_sources(rb, n_streams, frames, pcm)
     streams = [oracle.Stream(s.pcm, s.base_channels, s.base_rate, s.effects, s.span_len) for s in srcs]
     out_frames = rb.plan(srcs[0], MIX_CH, MIX_RATE)[0]
-    _, secs = oracle.mixer_mt(streams, MIX_CH, MIX_RATE, threads, out_frames + 16)
+    _, secs = oracle.mixer_mt(streams, MIX_CH, MIX_RATE, threads, out_frames + 16, static_dispatch=True)
     samples = n_streams * out_frames
     return samples / secs / 1e6, secs, samples
 

@@ -71,8 +71,9 @@ def lib():
         L.ro_speed_sample_rate.argtypes = [C.c_uint32, C.c_float]
         L.ro_delay_samples.restype = C.c_uint64
         L.ro_delay_samples.argtypes = [C.c_uint64, C.c_uint32, C.c_uint16]
-        L.ro_mixer_mt.argtypes = [C.POINTER(_Stream), C.c_uint64, C.c_uint16, C.c_uint32, C.c_int,
-                                  C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
+        for fn in (L.ro_mixer_mt, L.ro_mixer_mt_static):
+            fn.argtypes = [C.POINTER(_Stream), C.c_uint64, C.c_uint16, C.c_uint32, C.c_int,
+                           C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -196,14 +197,17 @@ def mixer(streams: Sequence[Stream], channels: int, rate: int, return_gaps: bool
     return (out, gaps.value) if return_gaps else out
 
 
-def mixer_mt(streams: Sequence[Stream], channels: int, rate: int, n_threads: int, out_cap: int):
-    """CPU baseline: pull-model mixer drain sharded over host threads.  Returns (mix, seconds)."""
+def mixer_mt(streams: Sequence[Stream], channels: int, rate: int, n_threads: int, out_cap: int,
+             static_dispatch: bool = False):
+    """CPU baseline: pull-model mixer drain sharded over host threads.  Returns (mix, seconds).
+    static_dispatch=True builds the bench chain shape from the monomorphised templates (what rustc emits)."""
     arr, keep = _pack(streams)
     L = lib()
     out = np.empty(out_cap, dtype=np.float32)
     n = C.c_uint64(0)
     secs = C.c_double(0.0)
-    rc = L.ro_mixer_mt(arr, C.c_uint64(len(streams)), C.c_uint16(channels), C.c_uint32(rate), C.c_int(n_threads),
+    fn = L.ro_mixer_mt_static if static_dispatch else L.ro_mixer_mt
+    rc = fn(arr, C.c_uint64(len(streams)), C.c_uint16(channels), C.c_uint32(rate), C.c_int(n_threads),
                        out.ctypes.data_as(C.c_void_p), C.c_uint64(out_cap), C.byref(n), C.byref(secs))
     if rc not in (0, 8):
         raise RuntimeError(f"ro_mixer_mt rc={rc}")

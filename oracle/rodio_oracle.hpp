@@ -744,6 +744,150 @@ struct MixerSource : Source {
     Src clone() const override { return nullptr; }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Statically dispatched variants (CPU baseline only).  rustc monomorphises an adapter chain such as
+// Amplify<BltFilter<UniformSourceIterator<TestSource>>> into one inlined next(); only the mixer holds
+// Box<dyn Source> (mixer.rs:72).  Timing the fully virtual classes above would understate the
+// reference, so the baseline builds the bench chain from these templates: same arithmetic, same
+// control flow, static dispatch inside a source, one virtual call per source per sample at the mixer.
+// tests/test_oracle_golden.py checks they are bit-identical to the virtual classes.
+// ---------------------------------------------------------------------------------------------
+struct VecT {   // benches/shared.rs TestSource (span-less)
+    const Sample* p;
+    size_t n, pos = 0;
+    uint16_t ch;
+    uint32_t rate;
+    inline std::optional<Sample> next() {
+        if (pos >= n) return std::nullopt;
+        return p[pos++];
+    }
+    std::optional<size_t> current_span_len() const { return std::nullopt; }
+    uint16_t channels() const { return ch; }
+    uint32_t sample_rate() const { return rate; }
+};
+template <class In>
+struct AmplifyT {
+    In in;
+    float factor;
+    inline std::optional<Sample> next() {
+        auto v = in.next();
+        if (!v) return std::nullopt;
+        return *v * factor;
+    }
+    std::optional<size_t> current_span_len() const { return in.current_span_len(); }
+    uint16_t channels() const { return in.channels(); }
+    uint32_t sample_rate() const { return in.sample_rate(); }
+};
+template <class In>
+struct BltT {   // mono / stereo / multi share one body here; state selection is position % channels
+    In in;
+    BltCoeffs k;
+    std::vector<float> x1, x2, y1, y2;
+    size_t position = 0;
+    BltT(In i, bool hp, uint32_t f, float q) : in(std::move(i)) {
+        k = hp ? blt_high_pass(f, q, in.sample_rate()) : blt_low_pass(f, q, in.sample_rate());
+        size_t n = in.channels();
+        x1.assign(n, 0.0f), x2.assign(n, 0.0f), y1.assign(n, 0.0f), y2.assign(n, 0.0f);
+    }
+    inline std::optional<Sample> next() {
+        auto s = in.next();
+        if (!s) return std::nullopt;
+        size_t c = position;
+        position = position + 1 == x1.size() ? 0 : position + 1;
+        float x = *s;
+        float r = k.b0 * x;
+        r = r + k.b1 * x1[c];
+        r = r + k.b2 * x2[c];
+        r = r - k.a1 * y1[c];
+        r = r - k.a2 * y2[c];
+        y2[c] = y1[c], x2[c] = x1[c], y1[c] = r, x1[c] = x;
+        return r;
+    }
+    std::optional<size_t> current_span_len() const { return in.current_span_len(); }
+    uint16_t channels() const { return in.channels(); }
+    uint32_t sample_rate() const { return in.sample_rate(); }
+};
+template <class In>
+struct UniformT {   // src/source/uniform.rs:33-97 with a concrete input type
+    struct Take {
+        In* iter;
+        std::optional<size_t> n;
+        inline std::optional<Sample> next() {
+            if (n) {
+                if (*n != 0) {
+                    *n -= 1;
+                    return iter->next();
+                }
+                return std::nullopt;
+            }
+            return iter->next();
+        }
+    };
+    struct Inner {
+        SampleRateConverter<Take> src;
+        ChannelCountConverter ccc;
+        Inner(Take t, uint32_t fr, uint32_t tr, uint16_t fc, uint16_t tc) : src(t, fr, tr, fc), ccc(fc, tc) {}
+    };
+    In input;
+    std::optional<Inner> inner;
+    uint16_t target_channels;
+    uint32_t target_sample_rate;
+    UniformT(In in, uint16_t ch, uint32_t rate) : input(std::move(in)), target_channels(ch), target_sample_rate(rate) {}
+    UniformT(UniformT&& o) noexcept
+        : input(std::move(o.input)), target_channels(o.target_channels), target_sample_rate(o.target_sample_rate) {}
+    void bootstrap() {
+        std::optional<size_t> span_len = input.current_span_len();
+        if (span_len) span_len = std::min<size_t>(*span_len, 32768);
+        inner.emplace(Take{&input, span_len}, input.sample_rate(), target_sample_rate, input.channels(), target_channels);
+    }
+    inline std::optional<Sample> next() {
+        if (inner) {
+            auto v = inner->ccc.next(inner->src);
+            if (v) return v;
+        }
+        bootstrap();
+        return inner->ccc.next(inner->src);
+    }
+    std::optional<size_t> current_span_len() const { return std::nullopt; }
+    uint16_t channels() const { return target_channels; }
+    uint32_t sample_rate() const { return target_sample_rate; }
+};
+// Box<dyn Source>: the one virtual boundary the mixer sees.
+template <class T>
+struct Boxed : Source {
+    T t;
+    explicit Boxed(T v) : t(std::move(v)) {}
+    std::optional<Sample> next() override { return t.next(); }
+    std::optional<size_t> current_span_len() const override { return t.current_span_len(); }
+    uint16_t channels() const override { return t.channels(); }
+    uint32_t sample_rate() const override { return t.sample_rate(); }
+    Src clone() const override { return nullptr; }
+};
+// MixerSource over already-uniform boxed sources (Mixer::add's wrap is part of the typed chain).
+struct MixerSourceBoxed {
+    std::vector<Src> current_sources;
+    uint16_t ch;
+    uint16_t current_channel = 0;
+    explicit MixerSourceBoxed(uint16_t c) : ch(c) {}
+    inline std::optional<Sample> next() {
+        float sum = 0.0f;
+        size_t w = 0;
+        for (size_t i = 0; i < current_sources.size(); i++) {
+            auto v = current_sources[i]->next();
+            if (v) {
+                sum += *v;
+                if (w != i) current_sources[w] = std::move(current_sources[i]);
+                w++;
+            }
+        }
+        current_sources.resize(w);
+        current_channel += 1;
+        if (current_channel >= ch) current_channel = 0;
+        if (current_sources.empty()) return std::nullopt;
+        return sum;
+    }
+};
+
 // dasp_sample 0.11.0 `conv` (un-vendored; PARITY UNPINNED).  Call site src/conversions/sample.rs:42-44.
 inline int32_t f32_as_i32_sat(float v) {  // Rust `as i32`
     if (!(v == v)) return 0;

@@ -237,6 +237,68 @@ int ro_mixer_mt(const ro_stream* streams, uint64_t n_streams, uint16_t ch, uint3
     return n <= cap ? 0 : 8;
 }
 
+// Statically dispatched build of the bench chain shape
+//   [UniformSourceIterator(ch, rate)] -> low_pass/high_pass -> amplify   (then Mixer::add's own uniform wrap)
+// Returns nullptr when the stream does not have exactly that shape.
+static Src build_static_cfg3(const ro_stream& s, uint16_t mix_ch, uint32_t mix_rate) {
+    if (s.span_len != 0 || s.n_effects != 3) return nullptr;
+    const ro_effect* e = s.effects;
+    if (e[0].kind != FX_UNIFORM || (e[1].kind != FX_LOW_PASS && e[1].kind != FX_HIGH_PASS) || e[2].kind != FX_AMPLIFY)
+        return nullptr;
+    using U1 = UniformT<VecT>;
+    using B = BltT<U1>;
+    using A = AmplifyT<B>;
+    using U2 = UniformT<A>;
+    VecT v{s.pcm, (size_t)s.n_samples, 0, s.channels, s.sample_rate};
+    U1 u1(v, (uint16_t)e[0].u32[0], e[0].u32[1]);
+    B b(std::move(u1), e[1].kind == FX_HIGH_PASS, e[1].u32[0], e[1].f32[0]);
+    A a{std::move(b), e[2].f32[0]};
+    return std::make_unique<Boxed<U2>>(U2(std::move(a), mix_ch, mix_rate));
+}
+
+// CPU baseline proper: like ro_mixer_mt, but every source is the monomorphised chain rustc would emit
+// (static dispatch inside a source, one virtual call per source per sample at the mixer).
+// Falls back to the virtual classes for streams of another shape.  mix_start must be 0.
+int ro_mixer_mt_static(const ro_stream* streams, uint64_t n_streams, uint16_t ch, uint32_t rate, int n_threads,
+                       float* out, uint64_t cap, uint64_t* n_out, double* seconds) {
+    if (n_threads < 1) n_threads = 1;
+    if ((uint64_t)n_threads > n_streams) n_threads = (int)std::max<uint64_t>(1, n_streams);
+    std::vector<std::vector<float>> partial(n_threads);
+    auto t0 = std::chrono::steady_clock::now();
+    auto work = [&](int t) {
+        uint64_t lo = n_streams * t / n_threads, hi = n_streams * (t + 1) / n_threads;
+        MixerSourceBoxed mx(ch);
+        for (uint64_t i = lo; i < hi; i++) {
+            Src s = build_static_cfg3(streams[i], ch, rate);
+            if (!s) s = std::make_unique<UniformSourceIterator>(build(streams[i]), ch, rate);
+            mx.current_sources.push_back(std::move(s));
+        }
+        auto& p = partial[t];
+        p.reserve(1 << 16);
+        while (true) {
+            auto v = mx.next();
+            if (!v) break;
+            p.push_back(*v);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto& t : th) t.join();
+    uint64_t n = 0;
+    for (auto& p : partial) n = std::max<uint64_t>(n, p.size());
+    for (uint64_t i = 0; i < n && i < cap; i++) {
+        float acc = 0.0f;
+        for (auto& p : partial)
+            if (i < p.size()) acc += p[i];
+        out[i] = acc;
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+    *n_out = n;
+    return n <= cap ? 0 : 8;
+}
+
 // dasp_sample conversions; formats numbered like rb_sample_format.
 int ro_convert(const void* in, int in_fmt, void* out, int out_fmt, uint64_t n) {
     for (uint64_t i = 0; i < n; i++) {

@@ -228,3 +228,19 @@ def test_volume_is_amplify():
 def test_blt_coefficients_known_values():
     k = oracle.blt_coeffs(False, 200, 0.5, 48000)
     assert np.allclose(k, [1.6696297e-4, 3.3392594e-4, 1.6696297e-4, -1.9483138, 0.94898164], rtol=2e-6)
+
+
+# ---- the statically dispatched baseline chain is the same arithmetic as the virtual classes ----
+def test_static_dispatch_baseline_is_bit_identical():
+    rng = np.random.default_rng(77)
+    srcs = [rb.UniformSourceIterator(rb.TestSource(rng.uniform(-1, 1, 3000).astype(np.float32), 1, 44100), 1, 48000)
+            .low_pass(200).amplify(1.2) for _ in range(9)]
+    streams = [to_oracle(s) for s in srcs]
+    want = oracle.mixer(streams, 1, 48000)
+    got_dyn, _ = oracle.mixer_mt(streams, 1, 48000, 1, want.size + 8)
+    got_static, _ = oracle.mixer_mt(streams, 1, 48000, 1, want.size + 8, static_dispatch=True)
+    assert np.array_equal(got_dyn.view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(got_static.view(np.uint32), want.view(np.uint32))
+    # sharded over threads: association across shards changes, values stay within the parity tolerance
+    got_mt, _ = oracle.mixer_mt(streams, 1, 48000, 3, want.size + 8, static_dispatch=True)
+    assert got_mt.shape == want.shape and np.max(np.abs(got_mt - want)) <= 1e-5 * np.max(np.abs(want))
