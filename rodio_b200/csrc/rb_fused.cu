@@ -641,9 +641,13 @@ __device__ __forceinline__ void hot_issue_window(const FusedRow& r, const HotTil
 }
 
 // Stage A for one (row, tile) out of the shared-memory window.
+// (lane_q, lane_r) = divmod(lane * from, to), computed once per kernel by the row's warp.
+// The exact-division fast path is used optimistically: a per-lane flag collects "operand outside the
+// guarded range" and ONE warp vote per row-tile decides whether the tile is redone with IEEE divisions.
 template <bool NOGAIN>
 __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht, uint32_t n_pre, uint32_t n_mid,
-                                            uint32_t lane, const float* __restrict__ win, float* __restrict__ row) {
+                                            uint32_t lane, uint32_t lane_q, uint32_t lane_r,
+                                            const float* __restrict__ win, float* __restrict__ row) {
     constexpr int U = TT / 32, H = 4;
     const uint32_t n = ht.hi - ht.lo;
     const uint32_t to = r.uni.to, q32 = r.q32, r32 = r.r32;
@@ -653,12 +657,14 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
     const float* __restrict__ w = win + ht.woff;
     const float* pre = r.pre;
     const float* mid = r.mid;
-    uint32_t prod = ht.r0 + lane * r.uni.from;
-    uint32_t di = prod / to;
-    uint32_t num = prod - di * to;
+    uint32_t num = ht.r0 + lane_r;
+    uint32_t di = lane_q;
+    if (num >= to) num -= to, di += 1;
     float* __restrict__ out = row + ht.lo + lane;
     const bool interior = n == (uint32_t)TT && (di + (uint32_t)(U - 1) * (q32 + 1) + 1) < lim;
     if (interior) {
+        const uint32_t di0 = di, num0 = num;
+        bool bad = false;
 #pragma unroll
         for (int h = 0; h < U; h += H) {
             uint32_t dis[H];
@@ -673,17 +679,24 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
             for (int u = 0; u < H; u++) x0[u] = w[dis[u]], x1[u] = w[dis[u] + 1];
 #pragma unroll
             for (int u = 0; u < H; u++) {
-                float v = lerp_rcp(gains<NOGAIN>(x0[u], pre, n_pre), gains<NOGAIN>(x1[u], pre, n_pre), nf[u], den_f, rcp_den);
-                out[32 * (h + u)] = gains<NOGAIN>(v, mid, n_mid);
+                const float a0 = gains<NOGAIN>(x0[u], pre, n_pre), a1 = gains<NOGAIN>(x1[u], pre, n_pre);
+                const float m = mul(sub(a1, a0), nf[u]);
+                const float q0 = mul(m, rcp_den);
+                float q = __fmaf_rn(__fmaf_rn(-q0, den_f, m), rcp_den, q0);
+                q = (m == 0.0f) ? m : q;
+                // guarded range as one unsigned compare on the exponent field: 2^-100 <= |m| < 2^100 (or m == 0)
+                bad |= ((__float_as_uint(m) & 0x7fffffffu) - 0x0d800000u >= 0x64000000u) && (m != 0.0f);
+                out[32 * (h + u)] = gains<NOGAIN>(add(a0, q), mid, n_mid);
             }
         }
-        return;
+        if (!__any_sync(0xffffffffu, bad)) return;
+        di = di0, num = num0;   // some operand was denormal / huge / NaN: redo this row-tile with IEEE divisions
     }
 #pragma unroll 1
     for (int u = 0; u < U; u++) {
         if (lane + 32u * (uint32_t)u < n) {
             float v = gains<NOGAIN>(w[di], pre, n_pre);
-            if (di < lim) v = lerp_rcp(v, gains<NOGAIN>(w[di + 1], pre, n_pre), __uint2float_rn(num), den_f, rcp_den);
+            if (di < lim) v = lerp_f(v, gains<NOGAIN>(w[di + 1], pre, n_pre), __uint2float_rn(num), den_f);
             out[32 * u] = gains<NOGAIN>(v, mid, n_mid);
         }
         num += r32, di += q32;
@@ -733,6 +746,13 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
     const bool is_rec = warp == HOT_REC_WARP, is_loader = warp == HOT_LOAD_WARP;
     const int slot = hot_row_slot(warp);
     const bool nogain = a.n_pre == 0 && a.n_mid == 0;
+    // (lane * from) divmod to for the rows this warp owns (first row in registers, wrapped rows recomputed)
+    uint32_t lane_q0 = 0, lane_r0 = 0;
+    if (slot >= 0 && (uint32_t)slot < G) {
+        const uint32_t p = lane * s_rows[slot].uni.from;
+        lane_q0 = p / s_rows[slot].uni.to;
+        lane_r0 = p - lane_q0 * s_rows[slot].uni.to;
+    }
 
     const bool chain_on = is_rec && lane < G;
     float x1 = 0.f, x2 = 0.f, y1 = 0.f, y2 = 0.f;
@@ -808,8 +828,14 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
                 for (uint32_t g = (uint32_t)slot; g < G; g += HOT_ROW_WARPS) {
                     const HotTile& ht = s_ht[it % NHT][g];
                     if (ht.lo >= ht.hi) continue;
-                    if (nogain) hot_stage_a<true>(s_rows[g], ht, a.n_pre, a.n_mid, lane, win + g * WSTRIDE, tile + g * ROW_STRIDE);
-                    else hot_stage_a<false>(s_rows[g], ht, a.n_pre, a.n_mid, lane, win + g * WSTRIDE, tile + g * ROW_STRIDE);
+                    uint32_t lq = lane_q0, lr = lane_r0;
+                    if (g != (uint32_t)slot) {
+                        const uint32_t p = lane * s_rows[g].uni.from;
+                        lq = p / s_rows[g].uni.to;
+                        lr = p - lq * s_rows[g].uni.to;
+                    }
+                    if (nogain) hot_stage_a<true>(s_rows[g], ht, a.n_pre, a.n_mid, lane, lq, lr, win + g * WSTRIDE, tile + g * ROW_STRIDE);
+                    else hot_stage_a<false>(s_rows[g], ht, a.n_pre, a.n_mid, lane, lq, lr, win + g * WSTRIDE, tile + g * ROW_STRIDE);
                 }
             }
             // ---- stage C on tile it-2: warps of slots 0..7 take 32 positions each ----
