@@ -661,7 +661,8 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
     uint32_t di = lane_q;
     if (num >= to) num -= to, di += 1;
     float* __restrict__ out = row + ht.lo + lane;
-    const bool interior = n == (uint32_t)TT && (di + (uint32_t)(U - 1) * (q32 + 1) + 1) < lim;
+    // warp-uniform: the vote below needs the whole warp on the same side of this branch
+    const bool interior = __all_sync(0xffffffffu, n == (uint32_t)TT && (di + (uint32_t)(U - 1) * (q32 + 1) + 1) < lim);
     if (interior) {
         const uint32_t di0 = di, num0 = num;
         bool bad = false;
