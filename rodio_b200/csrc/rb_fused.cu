@@ -38,6 +38,7 @@ namespace {
 
 constexpr int TT = 256;            // mixer-timeline samples per tile
 constexpr int ROW_STRIDE = TT + 4; // words; (TT+4)/4 odd -> LDS.128 by 8 lanes hits 8 distinct bank groups
+constexpr int HOT_PAD = 4;          // k_fused_hot: tile position 0 sits at word 4 of its row; words 2,3 hold x[-2], x[-1]
 constexpr int MAX_G = 32;          // rows per CTA
 constexpr int NBUF = 3;
 constexpr int MAX_GAINS = 4;
@@ -644,14 +645,23 @@ __device__ __forceinline__ void hot_issue_window(const FusedRow& r, const HotTil
 // (lane_q, lane_r) = divmod(lane * from, to), computed once per kernel by the row's warp.
 // The exact-division fast path is used optimistically: a per-lane flag collects "operand outside the
 // guarded range" and ONE warp vote per row-tile decides whether the tile is redone with IEEE divisions.
+//
+// The feed-forward half of the biquad, t[n] = (b0*x[n] + b1*x[n-1]) + b2*x[n-2], is computed HERE (same
+// three roundings as the reference, it does not depend on y): x goes to the tile row, the warp syncs,
+// every lane reads its two left neighbours, the warp syncs again and overwrites x with t in place.
+// A single warp issues roughly one instruction every two cycles, so the recurrence warp can only stay on
+// its 12-cycle dependent chain if it executes nothing but  y = (t - a1*y1) - a2*y2.
+// `row` points at tile position 0; row[-2], row[-1] are pad slots that receive the previous tile's last two
+// x values (`xtail`, kept in registers of lanes 30/31 across tiles) or zeros at the start of the stream.
 template <bool NOGAIN>
 __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht, uint32_t n_pre, uint32_t n_mid,
-                                            uint32_t lane, uint32_t lane_q, uint32_t lane_r,
+                                            uint32_t lane, uint32_t lane_q, uint32_t lane_r, float& xtail,
                                             const float* __restrict__ win, float* __restrict__ row) {
     constexpr int U = TT / 32, H = 4;
     const uint32_t n = ht.hi - ht.lo;
     const uint32_t to = r.uni.to, q32 = r.q32, r32 = r.r32;
     const float den_f = r.den_f, rcp_den = r.rcp_den;
+    const float b0 = r.b0, b1 = r.b1, b2 = r.b2;
     const uint64_t remain = r.uni.tail.L - 1 - ht.i0;
     const uint32_t lim = remain > 0x7fffffffull ? 0x7fffffffu : (uint32_t)remain;   // interpolate iff di < lim
     const float* __restrict__ w = win + ht.woff;
@@ -661,11 +671,16 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
     uint32_t di = lane_q;
     if (num >= to) num -= to, di += 1;
     float* __restrict__ out = row + ht.lo + lane;
+    // x[n-2], x[n-1] of the first active position: zeros when the stream starts in this tile (ht.lo > 0 or the
+    // very first tile), else the previous tile's tail
+    if (lane >= 30) row[(int)ht.lo - 32 + (int)lane] = (ht.i0 == 0 && ht.r0 == 0) ? 0.0f : xtail;
     // warp-uniform: the vote below needs the whole warp on the same side of this branch
     const bool interior = __all_sync(0xffffffffu, n == (uint32_t)TT && (di + (uint32_t)(U - 1) * (q32 + 1) + 1) < lim);
+    bool done = false;
     if (interior) {
         const uint32_t di0 = di, num0 = num;
         bool bad = false;
+        float xv[U];
 #pragma unroll
         for (int h = 0; h < U; h += H) {
             uint32_t dis[H];
@@ -687,12 +702,26 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
                 q = (m == 0.0f) ? m : q;
                 // guarded range as one unsigned compare on the exponent field: 2^-100 <= |m| < 2^100 (or m == 0)
                 bad |= ((__float_as_uint(m) & 0x7fffffffu) - 0x0d800000u >= 0x64000000u) && (m != 0.0f);
-                out[32 * (h + u)] = gains<NOGAIN>(add(a0, q), mid, n_mid);
+                xv[h + u] = gains<NOGAIN>(add(a0, q), mid, n_mid);
+                out[32 * (h + u)] = xv[h + u];
             }
         }
-        if (!__any_sync(0xffffffffu, bad)) return;
-        di = di0, num = num0;   // some operand was denormal / huge / NaN: redo this row-tile with IEEE divisions
+        if (!__any_sync(0xffffffffu, bad)) {
+            __syncwarp();
+            float xm1[U], xm2[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) xm1[u] = out[32 * u - 1], xm2[u] = out[32 * u - 2];
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < U; u++) out[32 * u] = biquad_ff(b0, b1, b2, xv[u], xm1[u], xm2[u]);
+            if (lane >= 30) xtail = xv[U - 1];     // positions TT-2 (lane 30) and TT-1 (lane 31)
+            done = true;
+        } else {
+            di = di0, num = num0;   // some operand was denormal / huge / NaN: redo this row-tile with IEEE divisions
+        }
     }
+    if (done) return;
+    // general path: partial tiles, end of stream, or the rare IEEE-division redo
 #pragma unroll 1
     for (int u = 0; u < U; u++) {
         if (lane + 32u * (uint32_t)u < n) {
@@ -703,6 +732,21 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
         num += r32, di += q32;
         if (num >= to) num -= to, di += 1;
     }
+    __syncwarp();
+    float xv[U], xm1[U], xm2[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        xv[u] = xm1[u] = xm2[u] = 0.0f;
+        if (lane + 32u * (uint32_t)u < n) xv[u] = out[32 * u], xm1[u] = out[32 * u - 1], xm2[u] = out[32 * u - 2];
+    }
+    // new tail = x at the last two active positions (n == 1: shift the old tail)
+    const float t_hi1 = row[(int)ht.hi - 1], t_hi2 = row[(int)ht.hi - 2];   // hi-2 >= lo-1 >= -1: inside the padded row
+    if (lane == 30) xtail = t_hi2;
+    if (lane == 31) xtail = t_hi1;
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < U; u++)
+        if (lane + 32u * (uint32_t)u < n) out[32 * u] = biquad_ff(b0, b1, b2, xv[u], xm1[u], xm2[u]);
 }
 
 // Warp roles (32 warps; sub-partition = warp % 4; the arbiter favours high warp ids):
@@ -757,12 +801,9 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
     }
 
     const bool chain_on = is_rec && lane < G;
-    float x1 = 0.f, x2 = 0.f, y1 = 0.f, y2 = 0.f;
-    float b0 = 0.f, b1 = 0.f, b2 = 0.f, a1 = 0.f, a2 = 0.f;
-    if (chain_on) {
-        const FusedRow& r = s_rows[lane];
-        b0 = r.b0, b1 = r.b1, b2 = r.b2, a1 = r.a1, a2 = r.a2;
-    }
+    float y1 = 0.f, y2 = 0.f, a1 = 0.f, a2 = 0.f;
+    if (chain_on) a1 = s_rows[lane].a1, a2 = s_rows[lane].a2;
+    float xtail0 = 0.f, xtail1 = 0.f;   // lanes 30/31: x at the last two positions of the previous tile, per owned row
 
     // prologue: the loader warp (lane = row) fetches the windows of tiles 0 and 1
     if (is_loader && lane < G) {
@@ -784,40 +825,35 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
                 hot_issue_window(s_rows[lane], ht, wins + (kt % NWIN) * win_sz + lane * WSTRIDE, &s_full[kt % NWIN]);
             }
         } else if (is_rec) {
-            // ---- stage B on tile it-1 (lane = row) ----
+            // ---- stage B on tile it-1 (lane = row): nothing but y = (t - a1*y1) - a2*y2 ----
             if (it >= 1 && it <= n_tiles && chain_on) {
                 const uint32_t kt = it - 1;
-                float* row = tiles + (kt % NBUF) * tile_sz + lane * ROW_STRIDE;
+                float* row = tiles + (kt % NBUF) * tile_sz + lane * ROW_STRIDE + HOT_PAD;
                 const uint2 act = *reinterpret_cast<const uint2*>(&s_ht[kt % NHT][lane].lo);
                 uint32_t t = act.x;
                 const uint32_t hi_t = act.y;
                 for (; t < hi_t && (t & 3); t++) {
-                    float xv = row[t];
-                    float y = biquad_fb(a1, a2, biquad_ff(b0, b1, b2, xv, x1, x2), y1, y2);
-                    x2 = x1, x1 = xv, y2 = y1, y1 = y;
+                    const float y = biquad_fb(a1, a2, row[t], y1, y2);
+                    y2 = y1, y1 = y;
                     row[t] = y;
                 }
                 float4 nx = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (t + 4 <= hi_t) nx = *reinterpret_cast<const float4*>(row + t);
+#pragma unroll 2
                 for (; t + 4 <= hi_t; t += 4) {
-                    const float4 xv = nx;
+                    const float4 f = nx;
                     if (t + 8 <= hi_t) nx = *reinterpret_cast<const float4*>(row + t + 4);
                     float4 yv;
-                    float f0 = biquad_ff(b0, b1, b2, xv.x, x1, x2);
-                    float f1 = biquad_ff(b0, b1, b2, xv.y, xv.x, x1);
-                    float f2 = biquad_ff(b0, b1, b2, xv.z, xv.y, xv.x);
-                    float f3 = biquad_ff(b0, b1, b2, xv.w, xv.z, xv.y);
-                    yv.x = biquad_fb(a1, a2, f0, y1, y2);
-                    yv.y = biquad_fb(a1, a2, f1, yv.x, y1);
-                    yv.z = biquad_fb(a1, a2, f2, yv.y, yv.x);
-                    yv.w = biquad_fb(a1, a2, f3, yv.z, yv.y);
-                    x2 = xv.z, x1 = xv.w, y2 = yv.z, y1 = yv.w;
+                    yv.x = biquad_fb(a1, a2, f.x, y1, y2);
+                    yv.y = biquad_fb(a1, a2, f.y, yv.x, y1);
+                    yv.z = biquad_fb(a1, a2, f.z, yv.y, yv.x);
+                    yv.w = biquad_fb(a1, a2, f.w, yv.z, yv.y);
+                    y2 = yv.z, y1 = yv.w;
                     *reinterpret_cast<float4*>(row + t) = yv;
                 }
                 for (; t < hi_t; t++) {
-                    float xv = row[t];
-                    float y = biquad_fb(a1, a2, biquad_ff(b0, b1, b2, xv, x1, x2), y1, y2);
-                    x2 = x1, x1 = xv, y2 = y1, y1 = y;
+                    const float y = biquad_fb(a1, a2, row[t], y1, y2);
+                    y2 = y1, y1 = y;
                     row[t] = y;
                 }
             }
@@ -836,8 +872,10 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
                         lq = p / s_rows[g].uni.to;
                         lr = p - lq * s_rows[g].uni.to;
                     }
-                    if (nogain) hot_stage_a<true>(s_rows[g], ht, a.n_pre, a.n_mid, lane, lq, lr, win + g * WSTRIDE, tile + g * ROW_STRIDE);
-                    else hot_stage_a<false>(s_rows[g], ht, a.n_pre, a.n_mid, lane, lq, lr, win + g * WSTRIDE, tile + g * ROW_STRIDE);
+                    float& xt = (g == (uint32_t)slot) ? xtail0 : xtail1;
+                    float* row = tile + g * ROW_STRIDE + HOT_PAD;
+                    if (nogain) hot_stage_a<true>(s_rows[g], ht, a.n_pre, a.n_mid, lane, lq, lr, xt, win + g * WSTRIDE, row);
+                    else hot_stage_a<false>(s_rows[g], ht, a.n_pre, a.n_mid, lane, lq, lr, xt, win + g * WSTRIDE, row);
                 }
             }
             // ---- stage C on tile it-2: warps of slots 0..7 take 32 positions each ----
@@ -847,7 +885,7 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
                 const uint32_t t = (uint32_t)slot * 32 + lane;
                 if (m0 + t < a.mix_len) {
                     const bool full = m0 >= f_lo && m0 + TT <= f_hi;
-                    partial[m0 + t] = mix_rows(tiles + (kt % NBUF) * tile_sz, s_ht[kt % NHT], s_rows, G, a.n_post, t, full);
+                    partial[m0 + t] = mix_rows(tiles + (kt % NBUF) * tile_sz + HOT_PAD, s_ht[kt % NHT], s_rows, G, a.n_post, t, full);
                 }
             }
         }
