@@ -749,18 +749,34 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
         if (lane + 32u * (uint32_t)u < n) out[32 * u] = biquad_ff(b0, b1, b2, xv[u], xm1[u], xm2[u]);
 }
 
-// Warp roles (32 warps; sub-partition = warp % 4; the arbiter favours high warp ids):
-//   warp 31          recurrence (stage B): ~1.8k instructions per tile on a 3.1k-cycle dependent chain;
-//                    highest warp id of sub-partition 3, so it wins every arbitration
-//   warp 27          loader (stage L, lane = row), ~100 instructions per tile
-//   warps 19, 23     idle (sub-partition 3 carries 4 rows instead of 8: the recurrence's share of issue slots)
-//   the other 28     stage A (one row each; rows >= 28 wrap around) and stage C
+// Warp roles (32 warps; sub-partition = warp % 4).  Measured: the recurrence warp must have its sub-partition
+// to itself -- co-resident throughput warps (even with lower warp ids) hold the issue port greedily and the
+// 12-cycle dependent chain doubles in length.
+//   warp 31                  recurrence (stage B)
+//   warp 27                  loader (stage L, lane = row), ~100 instructions per tile
+//   warps 3,7,..,23          idle
+//   the 24 warps with warp % 4 != 3: stage A, slot = (warp/4)*3 + warp%4 owns row `slot`; rows 24..27 go to
+//   slots {0,1,2,5} and the eight stage-C warps are chosen so that the three sub-partitions carry equal work.
 __device__ __forceinline__ int hot_row_slot(uint32_t warp) {
-    if (warp == 31 || warp == 27 || warp == 23 || warp == 19) return -1;
-    return (int)(warp - (warp > 19) - (warp > 23) - (warp > 27));   // 0..27
+    if ((warp & 3u) == 3u) return -1;
+    return (int)((warp >> 2) * 3u + (warp & 3u));   // 0..23
 }
-constexpr uint32_t HOT_ROW_WARPS = 28;
+constexpr uint32_t HOT_ROW_WARPS = 24;
+constexpr uint32_t HOT_MAX_ROWS = 28;   // 24 slots + 4 second rows
 constexpr uint32_t HOT_REC_WARP = 31, HOT_LOAD_WARP = 27;
+// second row of a slot (rows beyond 24), or -1
+__device__ __forceinline__ int hot_second_row(int slot) {
+    return slot == 0 ? 24 : slot == 1 ? 25 : slot == 2 ? 26 : slot == 5 ? 27 : -1;
+}
+// stage-C block (32 tile positions) handled by a slot, or -1
+__device__ __forceinline__ int hot_mix_block(int slot) {
+    switch (slot) {
+        case 3: return 0; case 6: return 1; case 9: return 2; case 12: return 3;   // sub-partition 0
+        case 4: return 4; case 7: return 5; case 10: return 6;                      // sub-partition 1
+        case 8: return 7;                                                           // sub-partition 2
+        default: return -1;
+    }
+}
 
 __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
     extern __shared__ __align__(16) float smem[];
@@ -863,7 +879,10 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
                 mbar_wait(&s_full[it % NWIN], (it / NWIN) & 1u);
                 float* tile = tiles + (it % NBUF) * tile_sz;
                 const float* win = wins + (it % NWIN) * win_sz;
-                for (uint32_t g = (uint32_t)slot; g < G; g += HOT_ROW_WARPS) {
+                for (int pass = 0; pass < 2; pass++) {
+                    const int gi = pass == 0 ? slot : hot_second_row(slot);
+                    if (gi < 0 || (uint32_t)gi >= G) continue;
+                    const uint32_t g = (uint32_t)gi;
                     const HotTile& ht = s_ht[it % NHT][g];
                     if (ht.lo >= ht.hi) continue;
                     uint32_t lq = lane_q0, lr = lane_r0;
@@ -878,11 +897,12 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
                     else hot_stage_a<false>(s_rows[g], ht, a.n_pre, a.n_mid, lane, lq, lr, xt, win + g * WSTRIDE, row);
                 }
             }
-            // ---- stage C on tile it-2: warps of slots 0..7 take 32 positions each ----
-            if (it >= 2 && slot < TT / 32) {
+            // ---- stage C on tile it-2: eight warps take 32 positions each ----
+            const int mix_block = hot_mix_block(slot);
+            if (it >= 2 && mix_block >= 0) {
                 const uint32_t kt = it - 2;
                 const uint64_t m0 = m_begin + (uint64_t)kt * TT;
-                const uint32_t t = (uint32_t)slot * 32 + lane;
+                const uint32_t t = (uint32_t)mix_block * 32 + lane;
                 if (m0 + t < a.mix_len) {
                     const bool full = m0 >= f_lo && m0 + TT <= f_hi;
                     partial[m0 + t] = mix_rows(tiles + (kt % NBUF) * tile_sz + HOT_PAD, s_ht[kt % NHT], s_rows, G, a.n_post, t, full);
@@ -1011,9 +1031,14 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     if (has_b && (uint32_t)mixer_channels * 1u > 32u) return cudaSuccess;
 
     auto plan = new rb_fused_plan;
+    plan->all_f32 = true;
+    for (size_t i = 0; i < n_streams; i++) plan->all_f32 = plan->all_f32 && streams[i].fmt == RB_FMT_F32;
+    plan->hot = has_b && plan->all_f32 && mixer_channels == 1;
+    for (size_t i = 0; i < n_streams && plan->hot; i++)
+        plan->hot = rows[i].mode == ROW_LERP && rows[i].c_in == 1 && rows[i].uni.from <= rows[i].uni.to;
     // rows per CTA: one balanced wave over the SMs (k CTAs per SM when the batch is large)
     uint32_t S = (uint32_t)n_streams;
-    uint32_t max_g = MAX_G;
+    uint32_t max_g = plan->hot ? HOT_MAX_ROWS : MAX_G;
     if (has_b) {
         while (max_g > 1 && max_g * mixer_channels > 128) max_g--;   // at most 4 recurrence warps
     }
@@ -1025,11 +1050,6 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     plan->n_ctas = n_ctas;
     plan->n_rec_warps = has_b ? (G * mixer_channels + 31) / 32 : 0;
     plan->smem_bytes = (size_t)(has_b ? NBUF : 1) * MAX_G * ROW_STRIDE * sizeof(float);
-    plan->all_f32 = true;
-    for (size_t i = 0; i < n_streams; i++) plan->all_f32 = plan->all_f32 && streams[i].fmt == RB_FMT_F32;
-    plan->hot = has_b && plan->all_f32 && mixer_channels == 1;
-    for (size_t i = 0; i < n_streams && plan->hot; i++)
-        plan->hot = rows[i].mode == ROW_LERP && rows[i].c_in == 1 && rows[i].uni.from <= rows[i].uni.to;
     plan->d_out = d_out;
 
     cudaError_t e = cudaMalloc(&plan->d_rows, n_streams * sizeof(FusedRow));
