@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=4096, help="streams per GPU")
-    ap.add_argument("--seconds", type=float, default=5.0, help="audio seconds per stream")
+    ap.add_argument("--seconds", type=float, default=2.0, help="audio seconds per stream")
     ap.add_argument("--flags", type=int, default=0, help="rb_batch_create flags (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -39,7 +39,12 @@ def init_process_group(backend: str = "nccl"):
     rank, local_rank, world = env_rank()
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        kw = {}
+        if backend == "nccl":
+            import torch
+            os.environ["NCCL_DEBUG"] = os.environ.get("RB_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+            kw["device_id"] = torch.device("cuda", local_rank)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
     return rank, local_rank, world
 
 
