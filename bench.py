@@ -298,6 +298,35 @@ def run_ours(args):
                "h2d_bytes_per_step": S * frames * 4, "d2h_bytes_per_step": mix_len * 4, "ms_per_step": e2e_ms,
                "steps": e2e_steps, "note": "pinned host PCM -> rb_batch_upload_packed -> render -> host mix, per step"}
 
+    # ---- BASELINE configs[1] beside it: DynamicMixer, 1024 mono 48 kHz sources summed (N=1 only) ----
+    also = None
+    if world == 1 and not args.no_e2e:
+        n2, frames2 = 1024, 48000 * 10
+        srcs2 = [rb.TestSource(np.zeros(frames2, np.float32), 1, MIX_RATE) for _ in range(n2)]
+        b2 = rb.Batch(srcs2, MIX_CH, MIX_RATE, flags=args.flags, ctx=ctx)
+        q0, _ = b2.input_device_ptr(0)
+        pitch2 = (b2.input_device_ptr(1)[0] - q0) // 4
+        for i in range(n2):
+            b2.input_device_ptr(i)
+        with torch.cuda.stream(ext):
+            torch.as_tensor(rbd.DeviceArray(q0, pitch2 * (n2 - 1) + frames2), device=dev).uniform_(-1.0, 1.0, generator=gen)
+        for _ in range(3):
+            b2.render_mix_device()
+        torch.cuda.synchronize(dev)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(ext)
+        for _ in range(args.steps):
+            b2.render_mix_device()
+        g1.record(ext)
+        torch.cuda.synchronize(dev)
+        ms2 = g0.elapsed_time(g1) / args.steps
+        also = {"cfg2_dynamic_mixer": {
+            "workload": "mixer(1, 48000) of 1024 mono 48 kHz f32 sources x 10 s, summed in insertion order (bit-exact)",
+            "value": n2 * frames2 / (ms2 * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms2,
+            "roofline": {"bound": "hbm", "achieved": b2.algorithmic_bytes / (ms2 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": b2.algorithmic_bytes / (ms2 * 1e-3) / 1e9 / peak, "kernel": "k_mix_ordered"}}}
+        b2.close()
+
     clocks = sampler.stop()   # sampled over the timed region, the kernel-only loop and the end-to-end loop
 
     # ---- CPU baseline beside it (rank 0, N=1): bounded sample of the same workload ----
@@ -329,6 +358,7 @@ def run_ours(args):
                          "note": "whole render (all launches of one step) timed with CUDA events on the launch stream"},
             "cpu_baseline": cpu,
             "e2e": e2e,
+            "also": also,
             "gpu_launches": launches * args.steps,
             "clocks": clocks,
         }

@@ -1030,6 +1030,13 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     }
     if (has_b && (uint32_t)mixer_channels * 1u > 32u) return cudaSuccess;
 
+    // Plain mixer of f32 sources at the mixer's own rate/channels (BASELINE cfg2): nothing to fuse -- the ordered
+    // mix kernel of the general path reads every source once with 16-byte loads and is bit-exact.
+    {
+        bool plain = !has_b && !has_u && n_pre == 0 && n_mid == 0 && n_post == 0;
+        for (size_t i = 0; i < n_streams && plain; i++) plain = streams[i].fmt == RB_FMT_F32 && streams[i].n_nodes == 0;
+        if (plain) return cudaSuccess;
+    }
     auto plan = new rb_fused_plan;
     plan->all_f32 = true;
     for (size_t i = 0; i < n_streams; i++) plan->all_f32 = plan->all_f32 && streams[i].fmt == RB_FMT_F32;

@@ -175,35 +175,65 @@ __global__ void __launch_bounds__(128) k_limit_seq(const rb_node_dev* __restrict
 
 // ---------------------------------------------------------------- mixer
 // MixerSource::sum_current_sources (src/mixer.rs:185-198): acc = 0.0; for s in insertion order: acc += v_s.
-// One thread per output sample; the loop over sources keeps the reference's order, loads are issued
-// UNROLL at a time so enough bytes are in flight.
+// One thread per FOUR consecutive output samples (one 16-byte load per source when the source covers all
+// four and is 16-byte aligned there, scalar loads otherwise); the loop over sources keeps the reference's
+// order, loads are issued MIX_UNROLL sources at a time so enough bytes are in flight.  HBM-bound:
+// algorithmic bytes = 4 * (sum of source samples + out_len).
 constexpr int MIX_UNROLL = 8;
+__device__ __forceinline__ float4 mix_fetch4(const rb_mix_src& m, uint64_t p, bool& any) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint64_t q = p - m.start;                       // wraps when p < start
+    any = false;
+    if (q < m.len && q + 3 < m.len && ((reinterpret_cast<uintptr_t>(m.data + q) & 15u) == 0)) {
+        v = __ldg(reinterpret_cast<const float4*>(m.data + q));
+        any = true;
+        return v;
+    }
+    // ragged edge / unaligned / late start inside the quad: per-sample, inactive samples flagged by NaN-free mask
+    return v;
+}
 __global__ void __launch_bounds__(256) k_mix_ordered(const rb_mix_src* __restrict__ srcs, uint32_t n_srcs,
                                                      float* __restrict__ out, uint64_t out_len) {
-    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < out_len;
-         p += (uint64_t)gridDim.x * blockDim.x) {
-        float acc = 0.0f;
+    const uint64_t n_quads = (out_len + 3) / 4;
+    for (uint64_t qd = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; qd < n_quads;
+         qd += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t p = qd * 4;
+        float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
         uint32_t s = 0;
         for (; s + MIX_UNROLL <= n_srcs; s += MIX_UNROLL) {
-            float v[MIX_UNROLL];
-            bool on[MIX_UNROLL];
+            float4 v[MIX_UNROLL];
+            bool fast[MIX_UNROLL];
+#pragma unroll
+            for (int k = 0; k < MIX_UNROLL; k++) v[k] = mix_fetch4(srcs[s + k], p, fast[k]);
 #pragma unroll
             for (int k = 0; k < MIX_UNROLL; k++) {
-                const rb_mix_src m = srcs[s + k];
-                uint64_t q = p - m.start;                 // wraps when p < start -> huge -> inactive
-                on[k] = q < m.len;
-                v[k] = on[k] ? __ldg(m.data + q) : 0.0f;
+                if (fast[k]) {
+                    acc0 = add(acc0, v[k].x), acc1 = add(acc1, v[k].y), acc2 = add(acc2, v[k].z), acc3 = add(acc3, v[k].w);
+                } else {
+                    const rb_mix_src m = srcs[s + k];
+                    const uint64_t q = p - m.start;
+                    if (q < m.len) acc0 = add(acc0, __ldg(m.data + q));
+                    if (q + 1 < m.len) acc1 = add(acc1, __ldg(m.data + q + 1));
+                    if (q + 2 < m.len) acc2 = add(acc2, __ldg(m.data + q + 2));
+                    if (q + 3 < m.len) acc3 = add(acc3, __ldg(m.data + q + 3));
+                }
             }
-#pragma unroll
-            for (int k = 0; k < MIX_UNROLL; k++)
-                if (on[k]) acc = add(acc, v[k]);
         }
         for (; s < n_srcs; s++) {
             const rb_mix_src m = srcs[s];
-            uint64_t q = p - m.start;
-            if (q < m.len) acc = add(acc, __ldg(m.data + q));
+            const uint64_t q = p - m.start;
+            if (q < m.len) acc0 = add(acc0, __ldg(m.data + q));
+            if (q + 1 < m.len) acc1 = add(acc1, __ldg(m.data + q + 1));
+            if (q + 2 < m.len) acc2 = add(acc2, __ldg(m.data + q + 2));
+            if (q + 3 < m.len) acc3 = add(acc3, __ldg(m.data + q + 3));
         }
-        out[p] = acc;
+        if (p + 3 < out_len) {
+            *reinterpret_cast<float4*>(out + p) = make_float4(acc0, acc1, acc2, acc3);
+        } else {
+            if (p < out_len) out[p] = acc0;
+            if (p + 1 < out_len) out[p + 1] = acc1;
+            if (p + 2 < out_len) out[p + 2] = acc2;
+        }
     }
 }
 
@@ -248,7 +278,7 @@ cudaError_t rb_launch_nodes(uint32_t kind, const rb_node_dev* d_nodes, uint32_t 
 
 cudaError_t rb_launch_mix(const rb_mix_src* d_srcs, uint32_t n_srcs, float* d_out, uint64_t out_len, cudaStream_t st) {
     if (out_len == 0) return cudaSuccess;
-    uint64_t blocks = (out_len + 255) / 256;
+    uint64_t blocks = ((out_len + 3) / 4 + 255) / 256;
     if (blocks > 148ull * 8) blocks = 148ull * 8;
     k_mix_ordered<<<(uint32_t)blocks, 256, 0, st>>>(d_srcs, n_srcs, d_out, out_len);
     return cudaGetLastError();

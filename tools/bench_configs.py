@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Time the other BASELINE.json configs (cfg2 mixer of sines, cfg4 effect chain, cfg5 sweep) on one GPU.
+Inputs are resident in HBM; times are CUDA events on the context's stream.  Prints one JSON line per case."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import rodio_b200 as rb
+from rodio_b200 import dist as rbd
+
+
+def time_batch(name, srcs, mixer, flags=0, steps=10, fill="uniform"):
+    ctx = rb.default_context(0)
+    dev = torch.device("cuda", 0)
+    ext = torch.cuda.ExternalStream(ctx.cuda_stream, device=dev)
+    with rb.Batch(srcs, *mixer, flags=flags, ctx=ctx) as b:
+        S = len(srcs)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(1)
+        for i in range(S):
+            p, cap = b.input_device_ptr(i)
+            t = torch.as_tensor(rbd.DeviceArray(p, cap), device=dev)
+            with torch.cuda.stream(ext):
+                t.uniform_(-0.5, 0.5, generator=gen)
+        for _ in range(3):
+            b.render_mix_device()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for _ in range(steps):
+            b.render_mix_device()
+        e1.record(ext)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        samples = sum(b.stream_out_len(i) for i in range(S))
+        out = {"case": name, "streams": S, "ms": round(ms, 4), "Msamples_s": round(samples / ms / 1e3, 1),
+               "algo_GBs": round(b.algorithmic_bytes / ms / 1e6, 1), "frac_6570": round(b.algorithmic_bytes / ms / 1e6 / 6570, 4),
+               "launches": b.launches_per_render}
+        print(json.dumps(out), flush=True)
+
+
+def main():
+    which = sys.argv[1:] or ["cfg2", "cfg4", "cfg3_stereo"]
+    z = lambda n: np.zeros(n, np.float32)
+    if "cfg2" in which:
+        for S, secs in [(1024, 10), (4096, 2), (16384, 1)]:
+            srcs = [rb.TestSource(z(48000 * secs), 1, 48000) for _ in range(S)]
+            time_batch(f"cfg2 mixer of {S} mono 48k sources x {secs}s (fused)", srcs, (1, 48000))
+        srcs = [rb.TestSource(z(48000 * 10), 1, 48000) for _ in range(1024)]
+        time_batch("cfg2 1024 x 10s exact-order general path", srcs, (1, 48000), flags=rb.capi.RB_MIX_EXACT_ORDER)
+    if "cfg4" in which:
+        S, frames = 512, 48000
+        srcs = [rb.Spatial(rb.TestSource(z(2 * frames), 2, 48000), [float(s % 7 - 3), 1.0, 0.0], [-1, 0, 0], [1, 0, 0])
+                .reverb(rb.Duration.from_millis(50), 0.3).automatic_gain_control() for s in range(S)]
+        time_batch("cfg4 512 stereo: spatial -> reverb -> agc -> mix (general path)", srcs, (2, 48000), steps=3)
+    if "cfg3_stereo" in which:
+        S, frames = 2048, 44100 * 2
+        srcs = [rb.UniformSourceIterator(rb.TestSource(z(2 * frames), 2, 44100), 2, 48000).low_pass(200).amplify(1.2)
+                for _ in range(S)]
+        time_batch("cfg3 shape, 2048 STEREO streams x 2s (generic fused kernel)", srcs, (2, 48000))
+        srcs = [rb.UniformSourceIterator(rb.TestSource(z(44100 * 2), 1, 44100), 1, 48000).low_pass(200).amplify(1.2)
+                for _ in range(4096)]
+        time_batch("cfg3 4096 mono x 2s, general path (RB_NO_FUSION)", srcs, (1, 48000), flags=rb.capi.RB_NO_FUSION, steps=3)
+
+
+if __name__ == "__main__":
+    main()
