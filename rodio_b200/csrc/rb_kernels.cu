@@ -179,38 +179,39 @@ __global__ void __launch_bounds__(128) k_limit_seq(const rb_node_dev* __restrict
 // four and is 16-byte aligned there, scalar loads otherwise); the loop over sources keeps the reference's
 // order, loads are issued MIX_UNROLL sources at a time so enough bytes are in flight.  HBM-bound:
 // algorithmic bytes = 4 * (sum of source samples + out_len).
-constexpr int MIX_UNROLL = 8;
-__device__ __forceinline__ float4 mix_fetch4(const rb_mix_src& m, uint64_t p, bool& any) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    const uint64_t q = p - m.start;                       // wraps when p < start
-    any = false;
-    if (q < m.len && q + 3 < m.len && ((reinterpret_cast<uintptr_t>(m.data + q) & 15u) == 0)) {
-        v = __ldg(reinterpret_cast<const float4*>(m.data + q));
-        any = true;
-        return v;
-    }
-    // ragged edge / unaligned / late start inside the quad: per-sample, inactive samples flagged by NaN-free mask
-    return v;
-}
+constexpr int MIX_CHUNK = 256;   // sources staged per shared-memory chunk (pointer / start / len are block-uniform)
+template <int U>
 __global__ void __launch_bounds__(256) k_mix_ordered(const rb_mix_src* __restrict__ srcs, uint32_t n_srcs,
                                                      float* __restrict__ out, uint64_t out_len) {
+    __shared__ rb_mix_src s_src[MIX_CHUNK];
     const uint64_t n_quads = (out_len + 3) / 4;
-    for (uint64_t qd = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; qd < n_quads;
-         qd += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t p = qd * 4;
-        float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
+    const uint64_t qd = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;   // grid covers every quad exactly once
+    const bool live = qd < n_quads;
+    const uint64_t p = qd * 4;
+    float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
+    for (uint32_t base = 0; base < n_srcs; base += MIX_CHUNK) {
+        const uint32_t cnt = min((uint32_t)MIX_CHUNK, n_srcs - base);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) s_src[i] = srcs[base + i];
+        __syncthreads();
+        if (!live) continue;
         uint32_t s = 0;
-        for (; s + MIX_UNROLL <= n_srcs; s += MIX_UNROLL) {
-            float4 v[MIX_UNROLL];
-            bool fast[MIX_UNROLL];
+        for (; s + U <= cnt; s += U) {
+            float4 v[U];
+            bool fast[U];
 #pragma unroll
-            for (int k = 0; k < MIX_UNROLL; k++) v[k] = mix_fetch4(srcs[s + k], p, fast[k]);
+            for (int k = 0; k < U; k++) {
+                const rb_mix_src& m = s_src[s + k];
+                const uint64_t q = p - m.start;                       // wraps when p < start
+                fast[k] = q < m.len && q + 3 < m.len && ((reinterpret_cast<uintptr_t>(m.data + q) & 15u) == 0);
+                v[k] = fast[k] ? __ldg(reinterpret_cast<const float4*>(m.data + q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
-            for (int k = 0; k < MIX_UNROLL; k++) {
+            for (int k = 0; k < U; k++) {
                 if (fast[k]) {
                     acc0 = add(acc0, v[k].x), acc1 = add(acc1, v[k].y), acc2 = add(acc2, v[k].z), acc3 = add(acc3, v[k].w);
-                } else {
-                    const rb_mix_src m = srcs[s + k];
+                } else {   // ragged edge / unaligned / a source that starts inside this quad
+                    const rb_mix_src& m = s_src[s + k];
                     const uint64_t q = p - m.start;
                     if (q < m.len) acc0 = add(acc0, __ldg(m.data + q));
                     if (q + 1 < m.len) acc1 = add(acc1, __ldg(m.data + q + 1));
@@ -219,21 +220,22 @@ __global__ void __launch_bounds__(256) k_mix_ordered(const rb_mix_src* __restric
                 }
             }
         }
-        for (; s < n_srcs; s++) {
-            const rb_mix_src m = srcs[s];
+        for (; s < cnt; s++) {
+            const rb_mix_src& m = s_src[s];
             const uint64_t q = p - m.start;
             if (q < m.len) acc0 = add(acc0, __ldg(m.data + q));
             if (q + 1 < m.len) acc1 = add(acc1, __ldg(m.data + q + 1));
             if (q + 2 < m.len) acc2 = add(acc2, __ldg(m.data + q + 2));
             if (q + 3 < m.len) acc3 = add(acc3, __ldg(m.data + q + 3));
         }
-        if (p + 3 < out_len) {
-            *reinterpret_cast<float4*>(out + p) = make_float4(acc0, acc1, acc2, acc3);
-        } else {
-            if (p < out_len) out[p] = acc0;
-            if (p + 1 < out_len) out[p + 1] = acc1;
-            if (p + 2 < out_len) out[p + 2] = acc2;
-        }
+    }
+    if (!live) return;
+    if (p + 3 < out_len) {
+        *reinterpret_cast<float4*>(out + p) = make_float4(acc0, acc1, acc2, acc3);
+    } else {
+        if (p < out_len) out[p] = acc0;
+        if (p + 1 < out_len) out[p + 1] = acc1;
+        if (p + 2 < out_len) out[p + 2] = acc2;
     }
 }
 
@@ -278,9 +280,12 @@ cudaError_t rb_launch_nodes(uint32_t kind, const rb_node_dev* d_nodes, uint32_t 
 
 cudaError_t rb_launch_mix(const rb_mix_src* d_srcs, uint32_t n_srcs, float* d_out, uint64_t out_len, cudaStream_t st) {
     if (out_len == 0) return cudaSuccess;
-    uint64_t blocks = ((out_len + 3) / 4 + 255) / 256;
-    if (blocks > 148ull * 8) blocks = 148ull * 8;
-    k_mix_ordered<<<(uint32_t)blocks, 256, 0, st>>>(d_srcs, n_srcs, d_out, out_len);
+    // one thread per 4 outputs; the fewer threads there are, the more 16-byte loads each keeps in flight
+    const uint64_t n_quads = (out_len + 3) / 4;
+    const uint64_t blocks = (n_quads + 255) / 256;
+    if (blocks > 0x7fffffffull) return cudaErrorInvalidValue;
+    if (n_quads >= 96 * 1024) k_mix_ordered<8><<<(uint32_t)blocks, 256, 0, st>>>(d_srcs, n_srcs, d_out, out_len);
+    else k_mix_ordered<16><<<(uint32_t)blocks, 256, 0, st>>>(d_srcs, n_srcs, d_out, out_len);
     return cudaGetLastError();
 }
 
