@@ -109,7 +109,12 @@ __global__ void __launch_bounds__(128) k_biquad_seq(const rb_node_dev* __restric
 }
 
 // AGC: state shared across interleaved channels (src/source/agc.rs:524-557 applies it to the flat stream).
-__global__ void __launch_bounds__(128) k_agc_seq(const rb_node_dev* __restrict__ nodes, uint32_t n_nodes) {
+// One thread per stream, the reference's strict f32 order.  The loop is blocked by AGC_K samples so that only
+// the three cheap loop-carried chains (running sum, peak follower, gain smoother) are sequential: the sqrt and
+// the two divisions of every sample depend on sum[n] / peak[n] only, so the block evaluates them back to back
+// with AGC_K-way instruction-level parallelism instead of exposing ~150 cycles of latency per sample.
+constexpr int AGC_K = 8;
+__global__ void __launch_bounds__(32) k_agc_seq(const rb_node_dev* __restrict__ nodes, uint32_t n_nodes) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_nodes) return;
     const rb_node_dev& nd = nodes[s];
@@ -118,32 +123,54 @@ __global__ void __launch_bounds__(128) k_agc_seq(const rb_node_dev* __restrict__
     const float target = nd.p.agc.target, max_gain = nd.p.agc.max_gain, floor_v = nd.p.agc.floor;
     const float attack = nd.p.agc.attack, release = nd.p.agc.release;
     float gain = 1.0f, peak = 0.0f, sum = 0.0f;
-    for (uint64_t n = 0; n < nd.n_in; n++) {
-        float sample = x[n];
-        float v = fabsf(sample);
-        float coeff = (v > peak) ? 0.0f : release;                       // agc.rs:397-408
-        peak = add(mul(peak, coeff), mul(v, sub(1.0f, coeff)));
-        float sq = mul(v, v);                                            // agc.rs:413-418
-        float old = 0.0f;                                                // ring slot content = |x[n-8192]|^2
-        if (n >= 8192) {
-            float ov = fabsf(x[n - 8192]);
-            old = mul(ov, ov);
+    const uint64_t N = nd.n_in;
+    for (uint64_t n0 = 0; n0 < N; n0 += AGC_K) {
+        const int cnt = (int)min((uint64_t)AGC_K, N - n0);
+        float xs[AGC_K], olds[AGC_K], sums[AGC_K], peaks[AGC_K], desired[AGC_K];
+#pragma unroll
+        for (int k = 0; k < AGC_K; k++) {
+            xs[k] = 0.0f, olds[k] = 0.0f;
+            if (k < cnt) {
+                xs[k] = x[n0 + k];
+                if (n0 + k >= 8192) {                                  // ring slot content = |x[n-8192]|^2
+                    float ov = fabsf(x[n0 + k - 8192]);
+                    olds[k] = mul(ov, ov);
+                }
+            }
         }
-        sum = add(sub(sum, old), sq);                                    // agc.rs:157
-        float rms = __fsqrt_rn(divf(sum, 8192.0f));
-        float rms_gain = (rms > 0.0f) ? divf(target, rms) : max_gain;
-        float peak_gain = (peak > 0.0f) ? fminf(divf(target, peak), max_gain) : max_gain;
-        float desired = fmaxf(fminf(rms_gain, peak_gain), floor_v);
-        float k = (desired > gain) ? attack : release;
-        gain = add(mul(gain, k), mul(desired, sub(1.0f, k)));
-        if (gain < 0.1f) gain = 0.1f;                                    // f32::clamp(0.1, max)
-        if (gain > max_gain) gain = max_gain;
-        y[n] = mul(sample, gain);
+#pragma unroll
+        for (int k = 0; k < AGC_K; k++) {                              // sequential, cheap
+            float v = fabsf(xs[k]);
+            float coeff = (v > peak) ? 0.0f : release;                 // agc.rs:397-408
+            peak = add(mul(peak, coeff), mul(v, sub(1.0f, coeff)));
+            sum = add(sub(sum, olds[k]), mul(v, v));                   // agc.rs:157
+            sums[k] = sum, peaks[k] = peak;
+        }
+#pragma unroll
+        for (int k = 0; k < AGC_K; k++) {                              // independent across k
+            float rms = __fsqrt_rn(divf(sums[k], 8192.0f));
+            float rms_gain = (rms > 0.0f) ? divf(target, rms) : max_gain;
+            float peak_gain = (peaks[k] > 0.0f) ? fminf(divf(target, peaks[k]), max_gain) : max_gain;
+            desired[k] = fmaxf(fminf(rms_gain, peak_gain), floor_v);
+        }
+#pragma unroll
+        for (int k = 0; k < AGC_K; k++) {                              // sequential, cheap
+            if (k < cnt) {
+                float kk = (desired[k] > gain) ? attack : release;
+                gain = add(mul(gain, kk), mul(desired[k], sub(1.0f, kk)));
+                if (gain < 0.1f) gain = 0.1f;                          // f32::clamp(0.1, max)
+                if (gain > max_gain) gain = max_gain;
+                y[n0 + k] = mul(xs[k], gain);
+            }
+        }
     }
 }
 
 // Limiter: per-channel envelope state, channel-coupled gain, sample-sequential (limit.rs:927-988).
-__global__ void __launch_bounds__(128) k_limit_seq(const rb_node_dev* __restrict__ nodes, uint32_t n_nodes) {
+// Blocked like the AGC: log2 (gain computer) and exp2 (dB -> linear) are feed-forward and evaluated with
+// LIM_K-way ILP around the short sequential envelope recurrences.
+constexpr int LIM_K = 8;
+__global__ void __launch_bounds__(32) k_limit_seq(const rb_node_dev* __restrict__ nodes, uint32_t n_nodes) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_nodes) return;
     const rb_node_dev& nd = nodes[s];
@@ -155,21 +182,35 @@ __global__ void __launch_bounds__(128) k_limit_seq(const rb_node_dev* __restrict
     float integ[RB_MAX_CHANNELS], peaks[RB_MAX_CHANNELS];
     for (uint32_t c = 0; c < RB_MAX_CHANNELS; c++) integ[c] = 0.f, peaks[c] = 0.f;
     uint32_t c = 0;
-    for (uint64_t n = 0; n < nd.n_in; n++) {
-        float sample = x[n];
-        float ldb = limiter_db(sample, thr, knee, ik8);
-        float in_c = fmaxf(ldb, add(mul(rel, integ[c]), mul(sub(1.0f, rel), ldb)));   // limit.rs:909-912
-        integ[c] = in_c;
-        peaks[c] = add(mul(att, peaks[c]), mul(sub(1.0f, att), in_c));                 // limit.rs:913
-        float mp;
-        if (C == 1) mp = peaks[0];
-        else if (C == 2) mp = fmaxf(peaks[0], peaks[1]);
-        else {
-            mp = 0.0f;
-            for (uint32_t k = 0; k < C; k++) mp = fmaxf(mp, peaks[k]);
+    const uint64_t N = nd.n_in;
+    for (uint64_t n0 = 0; n0 < N; n0 += LIM_K) {
+        const int cnt = (int)min((uint64_t)LIM_K, N - n0);
+        float xs[LIM_K], ldb[LIM_K], mp[LIM_K];
+#pragma unroll
+        for (int k = 0; k < LIM_K; k++) {
+            xs[k] = (k < cnt) ? x[n0 + k] : 0.0f;
+            ldb[k] = limiter_db(xs[k], thr, knee, ik8);
         }
-        y[n] = mul(sample, db_to_linear(-mp));
-        c = (c + 1 == C) ? 0 : c + 1;
+#pragma unroll
+        for (int k = 0; k < LIM_K; k++) {
+            if (k < cnt) {
+                float in_c = fmaxf(ldb[k], add(mul(rel, integ[c]), mul(sub(1.0f, rel), ldb[k])));   // limit.rs:909-912
+                integ[c] = in_c;
+                peaks[c] = add(mul(att, peaks[c]), mul(sub(1.0f, att), in_c));                       // limit.rs:913
+                float m;
+                if (C == 1) m = peaks[0];
+                else if (C == 2) m = fmaxf(peaks[0], peaks[1]);
+                else {
+                    m = 0.0f;
+                    for (uint32_t j = 0; j < C; j++) m = fmaxf(m, peaks[j]);
+                }
+                mp[k] = m;
+                c = (c + 1 == C) ? 0 : c + 1;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < LIM_K; k++)
+            if (k < cnt) y[n0 + k] = mul(xs[k], db_to_linear(-mp[k]));
     }
 }
 
@@ -271,8 +312,8 @@ cudaError_t rb_launch_nodes(uint32_t kind, const rb_node_dev* d_nodes, uint32_t 
             k_biquad_seq<<<(threads + 127) / 128, 128, 0, st>>>(d_nodes, n_nodes, max_channels);
             break;
         }
-        case RB_N_AGC: k_agc_seq<<<(n_nodes + 127) / 128, 128, 0, st>>>(d_nodes, n_nodes); break;
-        case RB_N_LIMIT: k_limit_seq<<<(n_nodes + 127) / 128, 128, 0, st>>>(d_nodes, n_nodes); break;
+        case RB_N_AGC: k_agc_seq<<<(n_nodes + 31) / 32, 32, 0, st>>>(d_nodes, n_nodes); break;
+        case RB_N_LIMIT: k_limit_seq<<<(n_nodes + 31) / 32, 32, 0, st>>>(d_nodes, n_nodes); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
