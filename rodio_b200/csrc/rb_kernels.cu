@@ -108,109 +108,186 @@ __global__ void __launch_bounds__(128) k_biquad_seq(const rb_node_dev* __restric
     }
 }
 
+// ---- sequential adapters with coalesced memory traffic -------------------------------------------------
+// One warp owns 32 streams (lane = stream, the reference's strict f32 order per stream).  Time advances in
+// tiles of RT samples: the warp loads tile k+1 of all its streams with coalesced 128-byte requests (one
+// stream per request, consecutive lanes on consecutive samples) into registers while every lane walks its
+// own stream's tile k out of a padded shared-memory transpose; results go back through the same transpose
+// and leave with coalesced stores.
+constexpr int RT = 32;            // samples per tile (one 128-byte line per stream)
+constexpr int RTS = RT + 1;       // padded row: lane r reading column k hits bank (r*33 + k) % 32 -> conflict-free
+
 // AGC: state shared across interleaved channels (src/source/agc.rs:524-557 applies it to the flat stream).
-// One thread per stream, the reference's strict f32 order.  The loop is blocked by AGC_K samples so that only
-// the three cheap loop-carried chains (running sum, peak follower, gain smoother) are sequential: the sqrt and
-// the two divisions of every sample depend on sum[n] / peak[n] only, so the block evaluates them back to back
-// with AGC_K-way instruction-level parallelism instead of exposing ~150 cycles of latency per sample.
+// Only the three cheap loop-carried chains (running sum, peak follower, gain smoother) are sequential; the
+// sqrt and the two divisions of a sample depend on sum[n] / peak[n] only and are evaluated AGC_K at a time.
 constexpr int AGC_K = 8;
-__global__ void __launch_bounds__(32) k_agc_seq(const rb_node_dev* __restrict__ nodes, uint32_t n_nodes) {
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_nodes) return;
-    const rb_node_dev& nd = nodes[s];
-    const float* __restrict__ x = (const float*)nd.src;
-    float* __restrict__ y = nd.dst;
-    const float target = nd.p.agc.target, max_gain = nd.p.agc.max_gain, floor_v = nd.p.agc.floor;
-    const float attack = nd.p.agc.attack, release = nd.p.agc.release;
+__global__ void __launch_bounds__(32) k_agc_tile(const rb_node_dev* __restrict__ nodes, uint32_t n_nodes) {
+    __shared__ float t_x[32 * RTS], t_old[32 * RTS];
+    const uint32_t lane = threadIdx.x;
+    const uint32_t s0 = blockIdx.x * 32;
+    const uint32_t cnt_rows = min(32u, n_nodes - s0);
+    const rb_node_dev* nds = nodes + s0;
+    // block-wide longest stream
+    uint64_t my_n = lane < cnt_rows ? nds[lane].n_in : 0;
+    uint64_t max_n = my_n;
+    for (int o = 16; o; o >>= 1) max_n = max(max_n, __shfl_xor_sync(0xffffffffu, max_n, o));
+    float target = 0.f, max_gain = 0.f, floor_v = 0.f, attack = 0.f, release = 0.f;
+    if (lane < cnt_rows) {
+        const rb_node_dev& nd = nds[lane];
+        target = nd.p.agc.target, max_gain = nd.p.agc.max_gain, floor_v = nd.p.agc.floor;
+        attack = nd.p.agc.attack, release = nd.p.agc.release;
+    }
     float gain = 1.0f, peak = 0.0f, sum = 0.0f;
-    const uint64_t N = nd.n_in;
-    for (uint64_t n0 = 0; n0 < N; n0 += AGC_K) {
-        const int cnt = (int)min((uint64_t)AGC_K, N - n0);
-        float xs[AGC_K], olds[AGC_K], sums[AGC_K], peaks[AGC_K], desired[AGC_K];
+    float rx[32], ro[32];
+    auto load_tile = [&](uint64_t n0) {
 #pragma unroll
-        for (int k = 0; k < AGC_K; k++) {
-            xs[k] = 0.0f, olds[k] = 0.0f;
-            if (k < cnt) {
-                xs[k] = x[n0 + k];
-                if (n0 + k >= 8192) {                                  // ring slot content = |x[n-8192]|^2
-                    float ov = fabsf(x[n0 + k - 8192]);
-                    olds[k] = mul(ov, ov);
+        for (int r = 0; r < 32; r++) {
+            rx[r] = 0.0f, ro[r] = 0.0f;
+            if ((uint32_t)r < cnt_rows) {
+                const rb_node_dev& nd = nds[r];
+                const uint64_t n = n0 + lane;
+                if (n < nd.n_in) {
+                    const float* x = (const float*)nd.src;
+                    rx[r] = __ldg(x + n);
+                    if (n >= 8192) ro[r] = __ldg(x + n - 8192);     // ring slot content = |x[n-8192]|^2
                 }
             }
         }
+    };
+    load_tile(0);
+    for (uint64_t n0 = 0; n0 < max_n; n0 += RT) {
+        __syncwarp();
 #pragma unroll
-        for (int k = 0; k < AGC_K; k++) {                              // sequential, cheap
-            float v = fabsf(xs[k]);
-            float coeff = (v > peak) ? 0.0f : release;                 // agc.rs:397-408
-            peak = add(mul(peak, coeff), mul(v, sub(1.0f, coeff)));
-            sum = add(sub(sum, olds[k]), mul(v, v));                   // agc.rs:157
-            sums[k] = sum, peaks[k] = peak;
+        for (int r = 0; r < 32; r++) t_x[r * RTS + lane] = rx[r], t_old[r * RTS + lane] = ro[r];
+        __syncwarp();
+        if (n0 + RT < max_n) load_tile(n0 + RT);                    // prefetch the next tile
+        const int cnt = (int)min((uint64_t)RT, my_n > n0 ? my_n - n0 : 0);
+        float* mx = t_x + lane * RTS;
+        const float* mo = t_old + lane * RTS;
+        for (int k0 = 0; k0 < cnt; k0 += AGC_K) {
+            float xs[AGC_K], sums[AGC_K], peaks[AGC_K], desired[AGC_K];
+#pragma unroll
+            for (int k = 0; k < AGC_K; k++) {                          // sequential, cheap
+                xs[k] = mx[k0 + k];
+                float ov = fabsf(mo[k0 + k]);
+                float v = fabsf(xs[k]);
+                float coeff = (v > peak) ? 0.0f : release;             // agc.rs:397-408
+                peak = add(mul(peak, coeff), mul(v, sub(1.0f, coeff)));
+                sum = add(sub(sum, mul(ov, ov)), mul(v, v));           // agc.rs:157
+                sums[k] = sum, peaks[k] = peak;
+            }
+#pragma unroll
+            for (int k = 0; k < AGC_K; k++) {                          // independent across k
+                float rms = __fsqrt_rn(divf(sums[k], 8192.0f));
+                float rms_gain = (rms > 0.0f) ? divf(target, rms) : max_gain;
+                float peak_gain = (peaks[k] > 0.0f) ? fminf(divf(target, peaks[k]), max_gain) : max_gain;
+                desired[k] = fmaxf(fminf(rms_gain, peak_gain), floor_v);
+            }
+#pragma unroll
+            for (int k = 0; k < AGC_K; k++) {                          // sequential, cheap
+                if (k0 + k < cnt) {
+                    float kk = (desired[k] > gain) ? attack : release;
+                    gain = add(mul(gain, kk), mul(desired[k], sub(1.0f, kk)));
+                    if (gain < 0.1f) gain = 0.1f;                      // f32::clamp(0.1, max)
+                    if (gain > max_gain) gain = max_gain;
+                    mx[k0 + k] = mul(xs[k], gain);
+                }
+            }
         }
+        __syncwarp();
 #pragma unroll
-        for (int k = 0; k < AGC_K; k++) {                              // independent across k
-            float rms = __fsqrt_rn(divf(sums[k], 8192.0f));
-            float rms_gain = (rms > 0.0f) ? divf(target, rms) : max_gain;
-            float peak_gain = (peaks[k] > 0.0f) ? fminf(divf(target, peaks[k]), max_gain) : max_gain;
-            desired[k] = fmaxf(fminf(rms_gain, peak_gain), floor_v);
-        }
-#pragma unroll
-        for (int k = 0; k < AGC_K; k++) {                              // sequential, cheap
-            if (k < cnt) {
-                float kk = (desired[k] > gain) ? attack : release;
-                gain = add(mul(gain, kk), mul(desired[k], sub(1.0f, kk)));
-                if (gain < 0.1f) gain = 0.1f;                          // f32::clamp(0.1, max)
-                if (gain > max_gain) gain = max_gain;
-                y[n0 + k] = mul(xs[k], gain);
+        for (int r = 0; r < 32; r++) {
+            if ((uint32_t)r < cnt_rows) {
+                const rb_node_dev& nd = nds[r];
+                const uint64_t n = n0 + lane;
+                if (n < nd.n_in) nd.dst[n] = t_x[r * RTS + lane];
             }
         }
     }
 }
 
 // Limiter: per-channel envelope state, channel-coupled gain, sample-sequential (limit.rs:927-988).
-// Blocked like the AGC: log2 (gain computer) and exp2 (dB -> linear) are feed-forward and evaluated with
-// LIM_K-way ILP around the short sequential envelope recurrences.
+// log2 (gain computer) and exp2 (dB -> linear) are feed-forward: evaluated LIM_K at a time around the
+// short sequential envelope recurrences.
 constexpr int LIM_K = 8;
-__global__ void __launch_bounds__(32) k_limit_seq(const rb_node_dev* __restrict__ nodes, uint32_t n_nodes) {
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_nodes) return;
-    const rb_node_dev& nd = nodes[s];
-    const float* __restrict__ x = (const float*)nd.src;
-    float* __restrict__ y = nd.dst;
-    const float thr = nd.p.lim.threshold, knee = nd.p.lim.knee, ik8 = nd.p.lim.inv_knee_8;
-    const float att = nd.p.lim.attack, rel = nd.p.lim.release;
-    const uint32_t C = nd.c_in;
+__global__ void __launch_bounds__(32) k_limit_tile(const rb_node_dev* __restrict__ nodes, uint32_t n_nodes) {
+    __shared__ float t_x[32 * RTS];
+    const uint32_t lane = threadIdx.x;
+    const uint32_t s0 = blockIdx.x * 32;
+    const uint32_t cnt_rows = min(32u, n_nodes - s0);
+    const rb_node_dev* nds = nodes + s0;
+    uint64_t my_n = lane < cnt_rows ? nds[lane].n_in : 0;
+    uint64_t max_n = my_n;
+    for (int o = 16; o; o >>= 1) max_n = max(max_n, __shfl_xor_sync(0xffffffffu, max_n, o));
+    float thr = 0.f, knee = 1.f, ik8 = 0.f, att = 0.f, rel = 0.f;
+    uint32_t C = 1;
+    if (lane < cnt_rows) {
+        const rb_node_dev& nd = nds[lane];
+        thr = nd.p.lim.threshold, knee = nd.p.lim.knee, ik8 = nd.p.lim.inv_knee_8;
+        att = nd.p.lim.attack, rel = nd.p.lim.release, C = nd.c_in;
+    }
     float integ[RB_MAX_CHANNELS], peaks[RB_MAX_CHANNELS];
     for (uint32_t c = 0; c < RB_MAX_CHANNELS; c++) integ[c] = 0.f, peaks[c] = 0.f;
     uint32_t c = 0;
-    const uint64_t N = nd.n_in;
-    for (uint64_t n0 = 0; n0 < N; n0 += LIM_K) {
-        const int cnt = (int)min((uint64_t)LIM_K, N - n0);
-        float xs[LIM_K], ldb[LIM_K], mp[LIM_K];
+    float rx[32];
+    auto load_tile = [&](uint64_t n0) {
 #pragma unroll
-        for (int k = 0; k < LIM_K; k++) {
-            xs[k] = (k < cnt) ? x[n0 + k] : 0.0f;
-            ldb[k] = limiter_db(xs[k], thr, knee, ik8);
-        }
-#pragma unroll
-        for (int k = 0; k < LIM_K; k++) {
-            if (k < cnt) {
-                float in_c = fmaxf(ldb[k], add(mul(rel, integ[c]), mul(sub(1.0f, rel), ldb[k])));   // limit.rs:909-912
-                integ[c] = in_c;
-                peaks[c] = add(mul(att, peaks[c]), mul(sub(1.0f, att), in_c));                       // limit.rs:913
-                float m;
-                if (C == 1) m = peaks[0];
-                else if (C == 2) m = fmaxf(peaks[0], peaks[1]);
-                else {
-                    m = 0.0f;
-                    for (uint32_t j = 0; j < C; j++) m = fmaxf(m, peaks[j]);
-                }
-                mp[k] = m;
-                c = (c + 1 == C) ? 0 : c + 1;
+        for (int r = 0; r < 32; r++) {
+            rx[r] = 0.0f;
+            if ((uint32_t)r < cnt_rows) {
+                const rb_node_dev& nd = nds[r];
+                const uint64_t n = n0 + lane;
+                if (n < nd.n_in) rx[r] = __ldg((const float*)nd.src + n);
             }
         }
+    };
+    load_tile(0);
+    for (uint64_t n0 = 0; n0 < max_n; n0 += RT) {
+        __syncwarp();
 #pragma unroll
-        for (int k = 0; k < LIM_K; k++)
-            if (k < cnt) y[n0 + k] = mul(xs[k], db_to_linear(-mp[k]));
+        for (int r = 0; r < 32; r++) t_x[r * RTS + lane] = rx[r];
+        __syncwarp();
+        if (n0 + RT < max_n) load_tile(n0 + RT);
+        const int cnt = (int)min((uint64_t)RT, my_n > n0 ? my_n - n0 : 0);
+        float* mx = t_x + lane * RTS;
+        for (int k0 = 0; k0 < cnt; k0 += LIM_K) {
+            float xs[LIM_K], ldb[LIM_K], mp[LIM_K];
+#pragma unroll
+            for (int k = 0; k < LIM_K; k++) {
+                xs[k] = mx[k0 + k];
+                ldb[k] = limiter_db(xs[k], thr, knee, ik8);
+            }
+#pragma unroll
+            for (int k = 0; k < LIM_K; k++) {
+                mp[k] = 0.0f;
+                if (k0 + k < cnt) {
+                    float in_c = fmaxf(ldb[k], add(mul(rel, integ[c]), mul(sub(1.0f, rel), ldb[k])));   // limit.rs:909-912
+                    integ[c] = in_c;
+                    peaks[c] = add(mul(att, peaks[c]), mul(sub(1.0f, att), in_c));                       // limit.rs:913
+                    float m;
+                    if (C == 1) m = peaks[0];
+                    else if (C == 2) m = fmaxf(peaks[0], peaks[1]);
+                    else {
+                        m = 0.0f;
+                        for (uint32_t j = 0; j < C; j++) m = fmaxf(m, peaks[j]);
+                    }
+                    mp[k] = m;
+                    c = (c + 1 == C) ? 0 : c + 1;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < LIM_K; k++)
+                if (k0 + k < cnt) mx[k0 + k] = mul(xs[k], db_to_linear(-mp[k]));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            if ((uint32_t)r < cnt_rows) {
+                const rb_node_dev& nd = nds[r];
+                const uint64_t n = n0 + lane;
+                if (n < nd.n_in) nd.dst[n] = t_x[r * RTS + lane];
+            }
+        }
     }
 }
 
@@ -312,8 +389,8 @@ cudaError_t rb_launch_nodes(uint32_t kind, const rb_node_dev* d_nodes, uint32_t 
             k_biquad_seq<<<(threads + 127) / 128, 128, 0, st>>>(d_nodes, n_nodes, max_channels);
             break;
         }
-        case RB_N_AGC: k_agc_seq<<<(n_nodes + 31) / 32, 32, 0, st>>>(d_nodes, n_nodes); break;
-        case RB_N_LIMIT: k_limit_seq<<<(n_nodes + 31) / 32, 32, 0, st>>>(d_nodes, n_nodes); break;
+        case RB_N_AGC: k_agc_tile<<<(n_nodes + 31) / 32, 32, 0, st>>>(d_nodes, n_nodes); break;
+        case RB_N_LIMIT: k_limit_tile<<<(n_nodes + 31) / 32, 32, 0, st>>>(d_nodes, n_nodes); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
