@@ -465,6 +465,7 @@ struct rb_batch {
     uint8_t* d_in = nullptr;
     size_t in_bytes = 0;
     float* d_buf[2] = {nullptr, nullptr};
+    float* d_aux[2] = {nullptr, nullptr};   // scratch rows for multi-pass adapters (AGC)
     size_t buf_floats = 0;
     rb_node_dev* d_nodes = nullptr;
     rb_mix_src* d_mix = nullptr;
@@ -486,6 +487,8 @@ extern "C" rb_status rb_batch_destroy(rb_batch* b) {
     cudaFree(b->d_in);
     cudaFree(b->d_buf[0]);
     cudaFree(b->d_buf[1]);
+    cudaFree(b->d_aux[0]);
+    cudaFree(b->d_aux[1]);
     cudaFree(b->d_nodes);
     cudaFree(b->d_mix);
     cudaFree(b->d_out);
@@ -575,6 +578,13 @@ extern "C" rb_status rb_batch_create(rb_context* ctx, uint16_t mixer_ch, uint32_
         b->buf_floats = buf_floats;
         RB_CUDA(cudaMalloc(&b->d_buf[0], std::max<size_t>(buf_floats * 4, 256)));
         RB_CUDA(cudaMalloc(&b->d_buf[1], std::max<size_t>(buf_floats * 4, 256)));
+        bool need_aux = false;
+        for (auto& ps : b->streams)
+            for (auto& nd : ps.nodes) need_aux = need_aux || nd.d.kind == RB_N_AGC;
+        if (need_aux) {
+            RB_CUDA(cudaMalloc(&b->d_aux[0], std::max<size_t>(buf_floats * 4, 256)));
+            RB_CUDA(cudaMalloc(&b->d_aux[1], std::max<size_t>(buf_floats * 4, 256)));
+        }
         std::vector<rb_node_dev> host_nodes;
         for (size_t lvl = 0; lvl < max_nodes; lvl++) {
             for (uint32_t kind = 0; kind < RB_N_KINDS; kind++) {
@@ -585,6 +595,8 @@ extern "C" rb_status rb_batch_create(rb_context* ctx, uint16_t mixer_ch, uint32_
                     nd.src = (lvl == 0) ? (const void*)(b->d_in + ps.in_off)
                                         : (const void*)(b->d_buf[(lvl - 1) & 1] + ps.buf_off);
                     nd.dst = b->d_buf[lvl & 1] + ps.buf_off;
+                    nd.aux0 = b->d_aux[0] ? b->d_aux[0] + ps.buf_off : nullptr;
+                    nd.aux1 = b->d_aux[1] ? b->d_aux[1] + ps.buf_off : nullptr;
                     host_nodes.push_back(nd);
                     g.count++;
                     g.max_n_out = std::max(g.max_n_out, nd.n_out);
@@ -608,9 +620,10 @@ extern "C" rb_status rb_batch_create(rb_context* ctx, uint16_t mixer_ch, uint32_
         if (n_streams)
             RB_CUDA(cudaMemcpy(b->d_mix, mix.data(), n_streams * sizeof(rb_mix_src), cudaMemcpyHostToDevice));
     }
-    b->launches = b->fused ? rb_fused_launch_count(b->fused)
-                           : (uint32_t)b->groups.size() + (mix_len ? 1u : 0u);
-    if (b->fused && (flags & RB_KEEP_STREAM_OUTPUTS)) b->launches += (uint32_t)b->groups.size();
+    uint32_t general_launches = 0;
+    for (const LaunchGroup& g : b->groups) general_launches += (g.kind == RB_N_AGC) ? 3u : 1u;
+    b->launches = b->fused ? rb_fused_launch_count(b->fused) : general_launches + (mix_len ? 1u : 0u);
+    if (b->fused && (flags & RB_KEEP_STREAM_OUTPUTS)) b->launches += general_launches;
     *out = b.release();
     return RB_OK;
 }

@@ -55,6 +55,8 @@ struct alignas(16) rb_node_dev {
     uint32_t c_in, c_out;  // channels
     uint32_t kind;
     uint32_t fmt;          // rb_sample_format of src (RB_N_CONVERT)
+    float* aux0;           // per-stream scratch rows (same capacity as dst) for multi-pass adapters (AGC)
+    float* aux1;
     union {
         struct { float factor; } amp;
         struct { float b0, b1, b2, a1, a2; } blt;

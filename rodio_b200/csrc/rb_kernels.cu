@@ -118,27 +118,29 @@ constexpr int RT = 32;            // samples per tile (one 128-byte line per str
 constexpr int RTS = RT + 1;       // padded row: lane r reading column k hits bank (r*33 + k) % 32 -> conflict-free
 
 // AGC: state shared across interleaved channels (src/source/agc.rs:524-557 applies it to the flat stream).
-// Only the three cheap loop-carried chains (running sum, peak follower, gain smoother) are sequential; the
-// sqrt and the two divisions of a sample depend on sum[n] / peak[n] only and are evaluated AGC_K at a time.
-constexpr int AGC_K = 8;
-__global__ void __launch_bounds__(32) k_agc_tile(const rb_node_dev* __restrict__ nodes, uint32_t n_nodes) {
-    __shared__ float t_x[32 * RTS], t_old[32 * RTS];
+// The reference's per-sample step splits into three passes with identical arithmetic (agc.rs:433-504):
+//   A (sequential, cheap)  peak follower + running sum of squares           -> aux0 = sum[n], aux1 = peak[n]
+//   B (time-parallel)      rms = sqrt(sum/8192); rms_gain; peak_gain; desired[n]     -> aux0 = desired[n]
+//   C (sequential, cheap)  gain smoother + clamp, y = x * gain
+// so the sqrt and the three IEEE divisions (≈ 500 cycles of dependent latency per sample in one thread)
+// leave the sequential chains.  A and C use the warp-transposed tiles above (lane = stream).
+template <int PASS>   // 0 = A, 2 = C
+__global__ void __launch_bounds__(32) k_agc_seq_pass(const rb_node_dev* __restrict__ nodes, uint32_t n_nodes) {
+    __shared__ float t_x[32 * RTS], t_y[32 * RTS];
     const uint32_t lane = threadIdx.x;
     const uint32_t s0 = blockIdx.x * 32;
     const uint32_t cnt_rows = min(32u, n_nodes - s0);
     const rb_node_dev* nds = nodes + s0;
-    // block-wide longest stream
     uint64_t my_n = lane < cnt_rows ? nds[lane].n_in : 0;
     uint64_t max_n = my_n;
     for (int o = 16; o; o >>= 1) max_n = max(max_n, __shfl_xor_sync(0xffffffffu, max_n, o));
-    float target = 0.f, max_gain = 0.f, floor_v = 0.f, attack = 0.f, release = 0.f;
+    float max_gain = 0.f, attack = 0.f, release = 0.f;
     if (lane < cnt_rows) {
         const rb_node_dev& nd = nds[lane];
-        target = nd.p.agc.target, max_gain = nd.p.agc.max_gain, floor_v = nd.p.agc.floor;
-        attack = nd.p.agc.attack, release = nd.p.agc.release;
+        max_gain = nd.p.agc.max_gain, attack = nd.p.agc.attack, release = nd.p.agc.release;
     }
     float gain = 1.0f, peak = 0.0f, sum = 0.0f;
-    float rx[32], ro[32];
+    float rx[32], ro[32];   // PASS A: x[n], x[n-8192] ; PASS C: x[n], desired[n]
     auto load_tile = [&](uint64_t n0) {
 #pragma unroll
         for (int r = 0; r < 32; r++) {
@@ -149,7 +151,11 @@ __global__ void __launch_bounds__(32) k_agc_tile(const rb_node_dev* __restrict__
                 if (n < nd.n_in) {
                     const float* x = (const float*)nd.src;
                     rx[r] = __ldg(x + n);
-                    if (n >= 8192) ro[r] = __ldg(x + n - 8192);     // ring slot content = |x[n-8192]|^2
+                    if (PASS == 0) {
+                        if (n >= 8192) ro[r] = __ldg(x + n - 8192);   // ring slot content = |x[n-8192]|^2
+                    } else {
+                        ro[r] = nd.aux0[n];
+                    }
                 }
             }
         }
@@ -158,40 +164,28 @@ __global__ void __launch_bounds__(32) k_agc_tile(const rb_node_dev* __restrict__
     for (uint64_t n0 = 0; n0 < max_n; n0 += RT) {
         __syncwarp();
 #pragma unroll
-        for (int r = 0; r < 32; r++) t_x[r * RTS + lane] = rx[r], t_old[r * RTS + lane] = ro[r];
+        for (int r = 0; r < 32; r++) t_x[r * RTS + lane] = rx[r], t_y[r * RTS + lane] = ro[r];
         __syncwarp();
         if (n0 + RT < max_n) load_tile(n0 + RT);                    // prefetch the next tile
         const int cnt = (int)min((uint64_t)RT, my_n > n0 ? my_n - n0 : 0);
         float* mx = t_x + lane * RTS;
-        const float* mo = t_old + lane * RTS;
-        for (int k0 = 0; k0 < cnt; k0 += AGC_K) {
-            float xs[AGC_K], sums[AGC_K], peaks[AGC_K], desired[AGC_K];
-#pragma unroll
-            for (int k = 0; k < AGC_K; k++) {                          // sequential, cheap
-                xs[k] = mx[k0 + k];
-                float ov = fabsf(mo[k0 + k]);
-                float v = fabsf(xs[k]);
+        float* my = t_y + lane * RTS;
+        if (PASS == 0) {
+            for (int k = 0; k < cnt; k++) {
+                float v = fabsf(mx[k]), ov = fabsf(my[k]);
                 float coeff = (v > peak) ? 0.0f : release;             // agc.rs:397-408
                 peak = add(mul(peak, coeff), mul(v, sub(1.0f, coeff)));
                 sum = add(sub(sum, mul(ov, ov)), mul(v, v));           // agc.rs:157
-                sums[k] = sum, peaks[k] = peak;
+                mx[k] = sum, my[k] = peak;
             }
-#pragma unroll
-            for (int k = 0; k < AGC_K; k++) {                          // independent across k
-                float rms = __fsqrt_rn(divf(sums[k], 8192.0f));
-                float rms_gain = (rms > 0.0f) ? divf(target, rms) : max_gain;
-                float peak_gain = (peaks[k] > 0.0f) ? fminf(divf(target, peaks[k]), max_gain) : max_gain;
-                desired[k] = fmaxf(fminf(rms_gain, peak_gain), floor_v);
-            }
-#pragma unroll
-            for (int k = 0; k < AGC_K; k++) {                          // sequential, cheap
-                if (k0 + k < cnt) {
-                    float kk = (desired[k] > gain) ? attack : release;
-                    gain = add(mul(gain, kk), mul(desired[k], sub(1.0f, kk)));
-                    if (gain < 0.1f) gain = 0.1f;                      // f32::clamp(0.1, max)
-                    if (gain > max_gain) gain = max_gain;
-                    mx[k0 + k] = mul(xs[k], gain);
-                }
+        } else {
+            for (int k = 0; k < cnt; k++) {
+                const float desired = my[k];
+                float kk = (desired > gain) ? attack : release;
+                gain = add(mul(gain, kk), mul(desired, sub(1.0f, kk)));
+                if (gain < 0.1f) gain = 0.1f;                          // f32::clamp(0.1, max)
+                if (gain > max_gain) gain = max_gain;
+                mx[k] = mul(mx[k], gain);
             }
         }
         __syncwarp();
@@ -200,10 +194,27 @@ __global__ void __launch_bounds__(32) k_agc_tile(const rb_node_dev* __restrict__
             if ((uint32_t)r < cnt_rows) {
                 const rb_node_dev& nd = nds[r];
                 const uint64_t n = n0 + lane;
-                if (n < nd.n_in) nd.dst[n] = t_x[r * RTS + lane];
+                if (n < nd.n_in) {
+                    if (PASS == 0) nd.aux0[n] = t_x[r * RTS + lane], nd.aux1[n] = t_y[r * RTS + lane];
+                    else nd.dst[n] = t_x[r * RTS + lane];
+                }
             }
         }
     }
+}
+// pass B: desired gain per sample, fully parallel (grid convention of the time-parallel kernels)
+__global__ void __launch_bounds__(TPB) k_agc_desired(const rb_node_dev* __restrict__ nodes) {
+    const rb_node_dev& nd = nodes[blockIdx.x];
+    const float target = nd.p.agc.target, max_gain = nd.p.agc.max_gain, floor_v = nd.p.agc.floor;
+    float* __restrict__ sums = nd.aux0;
+    const float* __restrict__ peaks = nd.aux1;
+    for_each_out(nd, [&](uint64_t o) {
+        float rms = __fsqrt_rn(divf(sums[o], 8192.0f));                                  // agc.rs:413-418
+        float rms_gain = (rms > 0.0f) ? divf(target, rms) : max_gain;
+        float pk = peaks[o];
+        float peak_gain = (pk > 0.0f) ? fminf(divf(target, pk), max_gain) : max_gain;    // agc.rs:424-431
+        sums[o] = fmaxf(fminf(rms_gain, peak_gain), floor_v);
+    });
 }
 
 // Limiter: per-channel envelope state, channel-coupled gain, sample-sequential (limit.rs:927-988).
@@ -389,7 +400,11 @@ cudaError_t rb_launch_nodes(uint32_t kind, const rb_node_dev* d_nodes, uint32_t 
             k_biquad_seq<<<(threads + 127) / 128, 128, 0, st>>>(d_nodes, n_nodes, max_channels);
             break;
         }
-        case RB_N_AGC: k_agc_tile<<<(n_nodes + 31) / 32, 32, 0, st>>>(d_nodes, n_nodes); break;
+        case RB_N_AGC:
+            k_agc_seq_pass<0><<<(n_nodes + 31) / 32, 32, 0, st>>>(d_nodes, n_nodes);
+            k_agc_desired<<<grid, TPB, 0, st>>>(d_nodes);
+            k_agc_seq_pass<2><<<(n_nodes + 31) / 32, 32, 0, st>>>(d_nodes, n_nodes);
+            break;
         case RB_N_LIMIT: k_limit_tile<<<(n_nodes + 31) / 32, 32, 0, st>>>(d_nodes, n_nodes); break;
         default: return cudaErrorInvalidValue;
     }
