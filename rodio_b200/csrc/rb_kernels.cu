@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(128) k_biquad_seq(const rb_node_dev* __restric
 // and leave with coalesced stores.
 constexpr int RT = 32;            // samples per tile (one 128-byte line per stream)
 constexpr int RTS = RT + 1;       // padded row: lane r reading column k hits bank (r*33 + k) % 32 -> conflict-free
+constexpr int RTV = RT + 4;       // padded row for 16-byte accesses: (r*36/4 + j) % 8 distinct per quarter-warp
 
 // AGC: state shared across interleaved channels (src/source/agc.rs:524-557 applies it to the flat stream).
 // The reference's per-sample step splits into three passes with identical arithmetic (agc.rs:433-504):
@@ -126,37 +127,42 @@ constexpr int RTS = RT + 1;       // padded row: lane r reading column k hits ba
 // leave the sequential chains.  A and C use the warp-transposed tiles above (lane = stream).
 template <int PASS>   // 0 = A, 2 = C
 __global__ void __launch_bounds__(32) k_agc_seq_pass(const rb_node_dev* __restrict__ nodes, uint32_t n_nodes) {
-    __shared__ float t_x[32 * RTS], t_y[32 * RTS];
+    __shared__ __align__(16) float t_x[32 * RTV], t_y[32 * RTV];
+    __shared__ const float* s_in0[32];
+    __shared__ const float* s_in1[32];
+    __shared__ float* s_out0[32];
+    __shared__ float* s_out1[32];
+    __shared__ uint64_t s_n[32];
     const uint32_t lane = threadIdx.x;
     const uint32_t s0 = blockIdx.x * 32;
     const uint32_t cnt_rows = min(32u, n_nodes - s0);
     const rb_node_dev* nds = nodes + s0;
-    uint64_t my_n = lane < cnt_rows ? nds[lane].n_in : 0;
-    uint64_t max_n = my_n;
-    for (int o = 16; o; o >>= 1) max_n = max(max_n, __shfl_xor_sync(0xffffffffu, max_n, o));
+    uint64_t my_n = 0;
     float max_gain = 0.f, attack = 0.f, release = 0.f;
+    s_n[lane] = 0;
     if (lane < cnt_rows) {
         const rb_node_dev& nd = nds[lane];
+        my_n = nd.n_in;
         max_gain = nd.p.agc.max_gain, attack = nd.p.agc.attack, release = nd.p.agc.release;
+        s_n[lane] = nd.n_in;
+        s_in0[lane] = (const float*)nd.src;
+        s_in1[lane] = PASS == 0 ? (const float*)nd.src - 8192 : nd.aux0;   // A: x[n-8192] (guarded by n >= 8192), C: desired[n]
+        s_out0[lane] = PASS == 0 ? nd.aux0 : nd.dst;
+        s_out1[lane] = nd.aux1;
     }
+    uint64_t max_n = my_n;
+    for (int o = 16; o; o >>= 1) max_n = max(max_n, __shfl_xor_sync(0xffffffffu, max_n, o));
+    __syncwarp();
     float gain = 1.0f, peak = 0.0f, sum = 0.0f;
     float rx[32], ro[32];   // PASS A: x[n], x[n-8192] ; PASS C: x[n], desired[n]
     auto load_tile = [&](uint64_t n0) {
+        const uint64_t n = n0 + lane;
 #pragma unroll
         for (int r = 0; r < 32; r++) {
             rx[r] = 0.0f, ro[r] = 0.0f;
-            if ((uint32_t)r < cnt_rows) {
-                const rb_node_dev& nd = nds[r];
-                const uint64_t n = n0 + lane;
-                if (n < nd.n_in) {
-                    const float* x = (const float*)nd.src;
-                    rx[r] = __ldg(x + n);
-                    if (PASS == 0) {
-                        if (n >= 8192) ro[r] = __ldg(x + n - 8192);   // ring slot content = |x[n-8192]|^2
-                    } else {
-                        ro[r] = nd.aux0[n];
-                    }
-                }
+            if (n < s_n[r]) {
+                rx[r] = __ldg(s_in0[r] + n);
+                if (PASS != 0 || n >= 8192) ro[r] = PASS == 0 ? __ldg(s_in1[r] + n) : s_in1[r][n];
             }
         }
     };
@@ -164,40 +170,44 @@ __global__ void __launch_bounds__(32) k_agc_seq_pass(const rb_node_dev* __restri
     for (uint64_t n0 = 0; n0 < max_n; n0 += RT) {
         __syncwarp();
 #pragma unroll
-        for (int r = 0; r < 32; r++) t_x[r * RTS + lane] = rx[r], t_y[r * RTS + lane] = ro[r];
+        for (int r = 0; r < 32; r++) t_x[r * RTV + lane] = rx[r], t_y[r * RTV + lane] = ro[r];
         __syncwarp();
         if (n0 + RT < max_n) load_tile(n0 + RT);                    // prefetch the next tile
         const int cnt = (int)min((uint64_t)RT, my_n > n0 ? my_n - n0 : 0);
-        float* mx = t_x + lane * RTS;
-        float* my = t_y + lane * RTS;
-        if (PASS == 0) {
-            for (int k = 0; k < cnt; k++) {
-                float v = fabsf(mx[k]), ov = fabsf(my[k]);
-                float coeff = (v > peak) ? 0.0f : release;             // agc.rs:397-408
-                peak = add(mul(peak, coeff), mul(v, sub(1.0f, coeff)));
-                sum = add(sub(sum, mul(ov, ov)), mul(v, v));           // agc.rs:157
-                mx[k] = sum, my[k] = peak;
+        float4* mx4 = reinterpret_cast<float4*>(t_x + lane * RTV);
+        float4* my4 = reinterpret_cast<float4*>(t_y + lane * RTV);
+        // whole float4 groups; positions >= cnt hold zeros / stale values and are never stored
+#pragma unroll 2
+        for (int k4 = 0; k4 * 4 < cnt; k4++) {
+            float4 a = mx4[k4], b = my4[k4];
+            float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (PASS == 0) {
+                    float v = fabsf(av[j]), ov = fabsf(bv[j]);
+                    float coeff = (v > peak) ? 0.0f : release;             // agc.rs:397-408
+                    peak = add(mul(peak, coeff), mul(v, sub(1.0f, coeff)));
+                    sum = add(sub(sum, mul(ov, ov)), mul(v, v));           // agc.rs:157
+                    av[j] = sum, bv[j] = peak;
+                } else if (k4 * 4 + j < cnt) {
+                    const float desired = bv[j];
+                    float kk = (desired > gain) ? attack : release;
+                    gain = add(mul(gain, kk), mul(desired, sub(1.0f, kk)));
+                    if (gain < 0.1f) gain = 0.1f;                          // f32::clamp(0.1, max)
+                    if (gain > max_gain) gain = max_gain;
+                    av[j] = mul(av[j], gain);
+                }
             }
-        } else {
-            for (int k = 0; k < cnt; k++) {
-                const float desired = my[k];
-                float kk = (desired > gain) ? attack : release;
-                gain = add(mul(gain, kk), mul(desired, sub(1.0f, kk)));
-                if (gain < 0.1f) gain = 0.1f;                          // f32::clamp(0.1, max)
-                if (gain > max_gain) gain = max_gain;
-                mx[k] = mul(mx[k], gain);
-            }
+            mx4[k4] = make_float4(av[0], av[1], av[2], av[3]);
+            if (PASS == 0) my4[k4] = make_float4(bv[0], bv[1], bv[2], bv[3]);
         }
         __syncwarp();
+        const uint64_t n = n0 + lane;
 #pragma unroll
         for (int r = 0; r < 32; r++) {
-            if ((uint32_t)r < cnt_rows) {
-                const rb_node_dev& nd = nds[r];
-                const uint64_t n = n0 + lane;
-                if (n < nd.n_in) {
-                    if (PASS == 0) nd.aux0[n] = t_x[r * RTS + lane], nd.aux1[n] = t_y[r * RTS + lane];
-                    else nd.dst[n] = t_x[r * RTS + lane];
-                }
+            if (n < s_n[r]) {
+                s_out0[r][n] = t_x[r * RTV + lane];
+                if (PASS == 0) s_out1[r][n] = t_y[r * RTV + lane];
             }
         }
     }
