@@ -1,0 +1,284 @@
+// rodio_b200.hpp — header-only C++ mirror of rodio's `Source` / `Mixer` surface on top of the C ABI
+// (include/rodio_b200.h).  rodio is compiled code, so this is the host-side binding a C++ caller links
+// against; the Rust shim in bindings/rust/ has the same shape.  Names and argument meaning follow the
+// reference (file:line in the comments); where rodio panics this throws std::invalid_argument /
+// rodio::Error.  Nothing here touches samples on the CPU: a Source records a PCM buffer and an adapter
+// chain, MixerSource drains it through the library in one block.
+#pragma once
+#include <chrono>
+#include <cstdint>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "rodio_b200.h"
+
+namespace rodio {
+
+using Sample = float;                       // src/common.rs:36,:48
+using Duration = std::chrono::nanoseconds;  // std::time::Duration
+
+struct Error : std::runtime_error {
+    rb_status status;
+    Error(rb_status s, const std::string& where)
+        : std::runtime_error(where + ": " + rb_status_string(s) + " (" + rb_last_error() + ")"), status(s) {}
+};
+inline void check(rb_status s, const char* where) {
+    if (s != RB_OK) throw Error(s, where);
+}
+
+// One rb_context per device, shared by everything in the process.
+class Context {
+  public:
+    static rb_context* get(int device = 0) {
+        static Context ctx(device);
+        return ctx.h_;
+    }
+
+  private:
+    explicit Context(int device) { check(rb_context_create(device, &h_), "rb_context_create"); }
+    ~Context() { rb_context_destroy(h_); }
+    rb_context* h_ = nullptr;
+};
+
+// AutomaticGainControlSettings — src/source/agc.rs:57-82
+struct AutomaticGainControlSettings {
+    float target_level = 1.0f;
+    Duration attack_time = std::chrono::seconds(4);
+    Duration release_time = std::chrono::seconds(0);
+    float absolute_max_gain = 7.0f;
+};
+// LimitSettings — src/source/limit.rs:209-248
+struct LimitSettings {
+    float threshold = -1.0f;
+    float knee_width = 4.0f;
+    Duration attack = std::chrono::milliseconds(5);
+    Duration release = std::chrono::milliseconds(100);
+    LimitSettings with_threshold(float v) const { auto s = *this; s.threshold = v; return s; }
+    LimitSettings with_knee_width(float v) const { auto s = *this; s.knee_width = v; return s; }
+    LimitSettings with_attack(Duration v) const { auto s = *this; s.attack = v; return s; }
+    LimitSettings with_release(Duration v) const { auto s = *this; s.release = v; return s; }
+};
+
+// trait Source (src/source/mod.rs:179-759) as a value: PCM + recorded adapters.
+class Source {
+  public:
+    Source(uint16_t channels, uint32_t sample_rate, std::vector<Sample> data, uint32_t span_len)
+        : pcm_(std::make_shared<std::vector<Sample>>(std::move(data))), base_channels_(channels), base_rate_(sample_rate),
+          span_len_(span_len), channels_(channels), rate_(sample_rate) {
+        if (channels == 0 || sample_rate == 0) throw std::invalid_argument("channels / sample_rate are NonZero in rodio");
+    }
+    uint16_t channels() const { return channels_; }        // Source::channels
+    uint32_t sample_rate() const { return rate_; }          // Source::sample_rate
+
+    Source amplify(float value) const { return with(fx(RB_FX_AMPLIFY, {}, {value}, {})); }                 // mod.rs:307-314
+    Source amplify_decibel(float value) const { return amplify(rb_db_to_linear(value)); }                  // mod.rs:316-323
+    Source speed(float ratio) const {                                                                        // speed.rs:103-133
+        Source s = with(fx(RB_FX_SPEED, {}, {ratio}, {}));
+        s.rate_ = rb_speed_sample_rate(rate_, ratio);
+        return s;
+    }
+    Source low_pass(uint32_t freq) const { return low_pass_with_q(freq, 0.5f); }                            // mod.rs:686-692
+    Source low_pass_with_q(uint32_t freq, float q) const { return with(fx(RB_FX_LOW_PASS, {freq}, {q}, {})); }
+    Source high_pass(uint32_t freq) const { return high_pass_with_q(freq, 0.5f); }
+    Source high_pass_with_q(uint32_t freq, float q) const { return with(fx(RB_FX_HIGH_PASS, {freq}, {q}, {})); }
+    Source reverb(Duration d, float amplitude) const { return with(fx(RB_FX_REVERB, {}, {amplitude}, {ns(d)})); }   // mod.rs:628-634
+    Source delay(Duration d) const { return with(fx(RB_FX_DELAY, {}, {}, {ns(d)})); }                        // delay.rs:19-29
+    Source automatic_gain_control(const AutomaticGainControlSettings& s = {}) const {                        // mod.rs:415-446
+        return with(fx(RB_FX_AGC, {}, {s.target_level, s.absolute_max_gain, 0.0f}, {ns(s.attack_time), ns(s.release_time)}));
+    }
+    Source limit(const LimitSettings& s = {}) const {                                                        // limit.rs:94-130
+        return with(fx(RB_FX_LIMIT, {}, {s.threshold, s.knee_width}, {ns(s.attack), ns(s.release)}));
+    }
+    // source::Spatial::new(input, emitter, left_ear, right_ear) — spatial.rs:31-45
+    Source spatial(const float (&e)[3], const float (&l)[3], const float (&r)[3]) const {
+        Source s = with(fx(RB_FX_SPATIAL, {}, {e[0], e[1], e[2], l[0], l[1], l[2], r[0], r[1], r[2]}, {}));
+        s.channels_ = 2;
+        return s;
+    }
+    // source::UniformSourceIterator::new(input, channels, rate) — uniform.rs:33-47
+    Source uniform(uint16_t channels, uint32_t rate) const {
+        if (channels == 0 || rate == 0) throw std::invalid_argument("target channels / rate must be non-zero");
+        Source s = with(fx(RB_FX_UNIFORM, {channels, rate}, {}, {}));
+        s.channels_ = channels, s.rate_ = rate;
+        return s;
+    }
+
+    // `.collect::<Vec<f32>>()` of this source (its own chain, no mixer conversion)
+    std::vector<Sample> collect() const;
+
+    rb_stream_desc desc(uint64_t mix_start = 0) const {
+        rb_stream_desc d{};
+        d.sample_rate = base_rate_, d.channels = base_channels_, d.format = RB_FMT_F32;
+        d.n_samples = pcm_->size(), d.span_len = span_len_;
+        d.n_effects = (uint32_t)effects_.size(), d.effects = effects_.data(), d.mix_start = mix_start;
+        return d;
+    }
+    const std::vector<Sample>& pcm() const { return *pcm_; }
+
+  private:
+    static uint64_t ns(Duration d) { return (uint64_t)d.count(); }
+    static rb_effect fx(uint32_t kind, std::initializer_list<uint32_t> u, std::initializer_list<float> f,
+                        std::initializer_list<uint64_t> n) {
+        rb_effect e{};
+        e.kind = kind;
+        size_t i = 0;
+        for (uint32_t v : u) e.u32[i++] = v;
+        i = 0;
+        for (float v : f) e.f32[i++] = v;
+        i = 0;
+        for (uint64_t v : n) e.ns[i++] = v;
+        return e;
+    }
+    Source with(const rb_effect& e) const {
+        Source s = *this;
+        s.effects_.push_back(e);
+        return s;
+    }
+    std::shared_ptr<std::vector<Sample>> pcm_;
+    uint16_t base_channels_;
+    uint32_t base_rate_, span_len_;
+    std::vector<rb_effect> effects_;
+    uint16_t channels_;
+    uint32_t rate_;
+};
+
+// buffer::SamplesBuffer::new(channels, sample_rate, data) — src/buffer.rs:40-60 (reports its length as the span)
+inline Source SamplesBuffer(uint16_t channels, uint32_t sample_rate, std::vector<Sample> data) {
+    uint32_t span = (uint32_t)std::min<size_t>(data.size(), 0xFFFFFFFFu);
+    return Source(channels, sample_rate, std::move(data), span);
+}
+// benches/shared.rs TestSource: span-less
+inline Source TestSource(std::vector<Sample> data, uint16_t channels, uint32_t sample_rate) {
+    return Source(channels, sample_rate, std::move(data), 0);
+}
+
+namespace detail {
+struct Batch {
+    rb_batch* h = nullptr;
+    Batch(const std::vector<rb_stream_desc>& descs, uint16_t ch, uint32_t rate, uint32_t flags) {
+        check(rb_batch_create(Context::get(), ch, rate, descs.data(), descs.size(), flags, &h), "rb_batch_create");
+    }
+    ~Batch() { rb_batch_destroy(h); }
+};
+}  // namespace detail
+
+inline std::vector<Sample> Source::collect() const {
+    std::vector<rb_stream_desc> d{desc()};
+    detail::Batch b(d, channels_, rate_, RB_KEEP_STREAM_OUTPUTS | RB_NO_FUSION);
+    check(rb_batch_upload(b.h, 0, pcm_->data(), pcm_->size()), "rb_batch_upload");
+    check(rb_batch_render_mix_device(b.h), "rb_batch_render_mix_device");
+    uint64_t n = 0, w = 0;
+    check(rb_batch_stream_out_len(b.h, 0, &n), "rb_batch_stream_out_len");
+    std::vector<Sample> out(n);
+    check(rb_batch_read_stream(b.h, 0, out.data(), n, &w), "rb_batch_read_stream");
+    out.resize(w);
+    return out;
+}
+
+namespace mixer {
+
+struct Shared {
+    uint16_t channels;
+    uint32_t rate;
+    std::vector<Source> sources;
+    std::vector<uint64_t> starts;
+    uint64_t pos = 0;                  // samples MixerSource already handed out
+    bool dirty = true;
+    std::vector<Sample> rendered;
+    std::vector<uint8_t> active;       // position has at least one source playing
+};
+
+// mixer::Mixer — src/mixer.rs:47-66 ; add is infallible like the reference
+class Mixer {
+  public:
+    explicit Mixer(std::shared_ptr<Shared> s) : s_(std::move(s)) {}
+    void add(const Source& source) {
+        s_->sources.push_back(source);
+        s_->starts.push_back(s_->pos);   // joins at the next frame boundary (mixer.rs:175-183), done by the library
+        s_->dirty = true;
+    }
+
+  private:
+    std::shared_ptr<Shared> s_;
+};
+
+// mixer::MixerSource — src/mixer.rs:70-136
+class MixerSource {
+  public:
+    explicit MixerSource(std::shared_ptr<Shared> s) : s_(std::move(s)) {}
+    uint16_t channels() const { return s_->channels; }
+    uint32_t sample_rate() const { return s_->rate; }
+    std::optional<size_t> current_span_len() const { return std::nullopt; }
+    // Iterator::next — None while no source is playing at this position (mixer.rs:131-135)
+    std::optional<Sample> next() {
+        render();
+        uint64_t p = s_->pos++;
+        if (p < s_->rendered.size() && s_->active[p]) return s_->rendered[p];
+        return std::nullopt;
+    }
+    void try_seek(Duration) { throw Error(RB_ERR_NOT_SUPPORTED_SEEK, "MixerSource::try_seek"); }   // mixer.rs:109-113
+
+  private:
+    void render() {
+        Shared& s = *s_;
+        if (!s.dirty) return;
+        s.dirty = false;
+        s.rendered.clear(), s.active.clear();
+        if (s.sources.empty()) return;
+        std::vector<rb_stream_desc> descs;
+        for (size_t i = 0; i < s.sources.size(); i++) descs.push_back(s.sources[i].desc(s.starts[i]));
+        detail::Batch b(descs, s.channels, s.rate, 0);
+        for (size_t i = 0; i < s.sources.size(); i++)
+            check(rb_batch_upload(b.h, i, s.sources[i].pcm().data(), s.sources[i].pcm().size()), "rb_batch_upload");
+        uint64_t n = 0, w = 0;
+        check(rb_batch_mix_len(b.h, &n), "rb_batch_mix_len");
+        s.rendered.resize(n);
+        check(rb_batch_render_mix(b.h, s.rendered.data(), n, &w), "rb_batch_render_mix");
+        s.active.assign(n, 0);
+        for (size_t i = 0; i < s.sources.size(); i++) {
+            uint64_t len = 0;
+            check(rb_batch_stream_out_len(b.h, i, &len), "rb_batch_stream_out_len");
+            uint64_t st = (s.starts[i] + s.channels - 1) / s.channels * s.channels;
+            for (uint64_t p = st; p < st + len && p < n; p++) s.active[p] = 1;
+        }
+    }
+    std::shared_ptr<Shared> s_;
+};
+
+// mixer::mixer(channels, sample_rate) -> (Mixer, MixerSource) — src/mixer.rs:25-43
+inline std::pair<Mixer, MixerSource> mixer(uint16_t channels, uint32_t sample_rate) {
+    if (channels == 0 || sample_rate == 0) throw std::invalid_argument("channels / sample_rate are NonZero in rodio");
+    auto s = std::make_shared<Shared>();
+    s->channels = channels, s->rate = sample_rate;
+    return {Mixer(s), MixerSource(s)};
+}
+
+}  // namespace mixer
+
+namespace conversions {
+// SampleRateConverter::new(input, from, to, channels).collect() — src/conversions/sample_rate.rs:52-201
+inline std::vector<Sample> SampleRateConverter(const std::vector<Sample>& input, uint32_t from, uint32_t to, uint16_t channels) {
+    uint64_t n = 0;
+    check(rb_sample_rate_out_len(input.size(), from, to, channels, &n), "rb_sample_rate_out_len");
+    std::vector<Sample> out(n);
+    check(rb_convert_sample_rate(Context::get(), input.data(), input.size(), from, to, channels, out.data(), n, &n),
+          "rb_convert_sample_rate");
+    out.resize(n);
+    return out;
+}
+// ChannelCountConverter::new(input, from, to).collect() — src/conversions/channels.rs:28,:57-85
+inline std::vector<Sample> ChannelCountConverter(const std::vector<Sample>& input, uint16_t from, uint16_t to) {
+    uint64_t n = 0;
+    check(rb_channels_out_len(input.size(), from, to, &n), "rb_channels_out_len");
+    std::vector<Sample> out(n);
+    check(rb_convert_channels(Context::get(), input.data(), input.size(), from, to, out.data(), n, &n), "rb_convert_channels");
+    out.resize(n);
+    return out;
+}
+}  // namespace conversions
+
+}  // namespace rodio

@@ -1,0 +1,31 @@
+"""The C++ host mirror (include/rodio_b200.hpp): compiles on CPU, runs the reference's own mixer /
+conversion unit tests on the GPU through the C ABI."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "cpp", "test_reference_api.cpp")
+EXE = os.path.join(ROOT, "tests", "cpp", "test_reference_api.bin")
+
+
+def _build():
+    lib_dir = os.path.join(ROOT, "rodio_b200")
+    cmd = ["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), SRC, "-o", EXE,
+           "-L", lib_dir, "-l:librodio_b200.so", f"-Wl,-rpath,{lib_dir}"]
+    subprocess.run(cmd, check=True, capture_output=True)
+
+
+def test_cpp_mirror_compiles_and_links(built):
+    _build()
+    assert os.path.exists(EXE)
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_runs_reference_tests(built):
+    if not os.path.exists(EXE):
+        _build()
+    r = subprocess.run([EXE], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all reference API tests passed" in r.stdout
