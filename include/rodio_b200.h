@@ -183,6 +183,11 @@ rb_status rb_batch_render_mix_device(rb_batch* b);
 rb_status rb_batch_mix_device_ptr(rb_batch* b, float** dptr);
 rb_status rb_batch_render_mix(rb_batch* b, float* out_host, uint64_t max_samples, uint64_t* written);
 
+/* Copy `n_samples` of the rendered mixer output starting at sample `offset` to the host (valid after a
+ * render; the block-pulling shim hands these out one block at a time).  Reads past mix_len are clipped;
+ * `written` receives the number of samples copied. */
+rb_status rb_batch_read_mix(rb_batch* b, uint64_t offset, float* out_host, uint64_t n_samples, uint64_t* written);
+
 /* Per-stream post-chain samples (what MixerSource would pull from that source), for
  * parity tests; needs RB_KEEP_STREAM_OUTPUTS. Valid after a render. */
 rb_status rb_batch_read_stream(rb_batch* b, size_t stream, float* out_host, uint64_t max_samples,

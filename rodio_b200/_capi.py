@@ -81,6 +81,7 @@ SYMBOLS = {
     "rb_batch_mix_device_ptr": (C.c_int32, [C.c_void_p, _vpp]),
     "rb_batch_render_mix": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, _u64p]),
     "rb_batch_read_stream": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint64, _u64p]),
+    "rb_batch_read_mix": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, _u64p]),
     "rb_sample_rate_out_len": (C.c_int32, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint16, _u64p]),
     "rb_convert_sample_rate": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint16,
                                            C.c_void_p, C.c_uint64, _u64p]),

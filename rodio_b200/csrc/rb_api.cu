@@ -757,6 +757,17 @@ extern "C" rb_status rb_batch_render_mix(rb_batch* b, float* out_host, uint64_t 
     if (written) *written = n;
     return RB_OK;
 }
+extern "C" rb_status rb_batch_read_mix(rb_batch* b, uint64_t offset, float* out_host, uint64_t n_samples, uint64_t* written) {
+    if (!b) return fail(RB_ERR_INVALID_ARGUMENT, "batch is NULL");
+    if (!b->rendered) return fail(RB_ERR_STATE, "render first");
+    uint64_t n = offset >= b->mix_len ? 0 : std::min<uint64_t>(n_samples, b->mix_len - offset);
+    if (n && !out_host) return fail(RB_ERR_INVALID_ARGUMENT, "out_host is NULL");
+    RB_CUDA(cudaSetDevice(b->ctx->device));
+    if (n) RB_CUDA(cudaMemcpyAsync(out_host, b->d_out + offset, n * 4, cudaMemcpyDeviceToHost, b->ctx->stream));
+    RB_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    if (written) *written = n;
+    return RB_OK;
+}
 extern "C" rb_status rb_batch_read_stream(rb_batch* b, size_t stream, float* out_host, uint64_t max_samples,
                                           uint64_t* written) {
     rb_status s = check_stream(b, stream);

@@ -434,6 +434,13 @@ class Batch:
         check(lib().rb_batch_render_mix(self._h, C.c_void_p(host_ptr), max_samples, C.byref(w)), "rb_batch_render_mix")
         return w.value
 
+    def read_mix(self, offset: int, n: int) -> np.ndarray:
+        """A block of the rendered mixer output (what a block-pulling `Source` shim hands out)."""
+        out = np.empty(n, dtype=np.float32)
+        w = C.c_uint64()
+        check(lib().rb_batch_read_mix(self._h, offset, out.ctypes.data_as(C.c_void_p), n, C.byref(w)), "rb_batch_read_mix")
+        return out[: w.value]
+
     def read_stream(self, i: int) -> np.ndarray:
         n = self.stream_out_len(i)
         out = np.empty(n, dtype=np.float32)

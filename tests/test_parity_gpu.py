@@ -408,3 +408,52 @@ def test_fused_shapes_match_oracle(ctx, case):
         assert_bit_exact(got, want, f"fused case {case}")
     else:
         assert_close_peak(got, want, 1e-5, f"fused case {case}")
+
+
+def test_fused_ragged_batch(ctx):
+    """HOT kernel with empty, one-frame, two-frame and long streams side by side, late starts, S > rows per CTA."""
+    rng = np.random.default_rng(4242)
+    lens = [0, 1, 2, 3, 255, 256, 257, 511, 513, 1000, 4410] * 16
+    srcs, starts = [], []
+    for i, n in enumerate(lens):
+        src = rb.UniformSourceIterator(rb.TestSource(noise(n, 7000 + i), 1, 44100), 1, 48000).low_pass(150 + i)
+        srcs.append(src.amplify(0.8))
+        starts.append(0 if i % 4 else int(rng.integers(0, 900)))
+    starts = sorted(starts)
+    want = oracle.mixer([to_oracle(s, st) for s, st in zip(srcs, starts)], 1, 48000)
+    with rb.Batch(srcs, 1, 48000, mix_starts=starts, ctx=ctx) as b:
+        b.upload_all()
+        got = b.render_mix()
+        assert b.launches_per_render <= 2
+    assert_close_peak(got, want, 1e-5, "ragged fused batch")
+    with rb.Batch(srcs[:100], 1, 48000, mix_starts=starts[:100], ctx=ctx) as b:   # one stream per CTA -> exact order
+        b.upload_all()
+        got = b.render_mix()
+    want = oracle.mixer([to_oracle(s, st) for s, st in zip(srcs[:100], starts[:100])], 1, 48000)
+    assert_bit_exact(got, want, "ragged fused batch, S <= 148")
+
+
+def test_fused_denormal_and_huge_inputs(ctx):
+    """The optimistic exact-division path must fall back to IEEE division for denormal / huge operands."""
+    x = noise(3000, 555)
+    x[100:200] *= np.float32(1e-38)        # denormal differences
+    x[300:320] = np.float32(3e30)          # huge
+    x[400] = np.float32(-0.0)
+    srcs = [rb.UniformSourceIterator(rb.TestSource(x if s == 0 else noise(3000, 556 + s), 1, 44100), 1, 48000)
+            .low_pass(5000) for s in range(3)]
+    want = oracle.mixer([to_oracle(s) for s in srcs], 1, 48000)
+    with rb.Batch(srcs, 1, 48000, ctx=ctx) as b:
+        b.upload_all()
+        got = b.render_mix()
+    assert_bit_exact(got, want, "denormal / huge inputs through the fused path")
+
+
+def test_read_mix_blocks(ctx):
+    srcs = _cfg3_sources(5, 3000, seed=77)
+    with rb.Batch(srcs, 1, 48000, ctx=ctx) as b:
+        b.upload_all()
+        with pytest.raises(rb.RodioB200Error):
+            b.read_mix(0, 10)                      # render first
+        full = b.render_mix().copy()
+        blocks = [b.read_mix(o, 1000) for o in range(0, full.size + 1000, 1000)]
+    assert np.array_equal(np.concatenate(blocks), full) and blocks[-1].size == 0
