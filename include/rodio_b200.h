@@ -83,8 +83,16 @@ typedef enum {
                                  u32[0] = number of output channels (1..12), f32[0..n) = volumes               */
     RB_FX_UNIFORM = 10,       /* UniformSourceIterator::new(input, channels, rate) src/source/uniform.rs:33-47
                                  u32[0] = target channels, u32[1] = target sample rate                        */
-    RB_FX_DELAY = 11          /* Source::delay(duration)             src/source/delay.rs:19-29,:68-75
+    RB_FX_DELAY = 11,         /* Source::delay(duration)             src/source/delay.rs:19-29,:68-75
                                  ns[0] = delay                                                                */
+    RB_FX_DISTORTION = 12,    /* Source::distortion(gain, threshold) src/source/distortion.rs:8-17,:66-72
+                                 f32[0] = gain, f32[1] = threshold (>= 0: clamp(-t, t) panics otherwise)      */
+    RB_FX_LINEAR_RAMP = 13,   /* Source::linear_gain_ramp(duration, start, end, clamp_end) src/source/linear_ramp.rs:9-34,:79-104
+                                 also fade_in(d) = ramp(d, 0, 1, false) (fadein.rs:8-15) and
+                                 fade_out(d) = ramp(d, 1, 0, true) (fadeout.rs:8-15)
+                                 ns[0] = duration (> 0), f32[0] = start_gain, f32[1] = end_gain, u32[0] = clamp_end */
+    RB_FX_TAKE_DURATION = 14  /* Source::take_duration(duration) [+ set_filter_fadeout] src/source/take.rs:9-26,:34-41,:107-148
+                                 ns[0] = duration, u32[0] = 1 when the fade-out filter is set                */
 } rb_effect_kind;
 
 typedef struct rb_effect {

@@ -87,6 +87,16 @@ class Source {
     Source high_pass_with_q(uint32_t freq, float q) const { return with(fx(RB_FX_HIGH_PASS, {freq}, {q}, {})); }
     Source reverb(Duration d, float amplitude) const { return with(fx(RB_FX_REVERB, {}, {amplitude}, {ns(d)})); }   // mod.rs:628-634
     Source delay(Duration d) const { return with(fx(RB_FX_DELAY, {}, {}, {ns(d)})); }                        // delay.rs:19-29
+    Source distortion(float gain, float threshold) const { return with(fx(RB_FX_DISTORTION, {}, {gain, threshold}, {})); }   // mod.rs:726-731
+    Source linear_gain_ramp(Duration d, float start, float end, bool clamp_end) const {                      // mod.rs:534-546
+        if (d.count() == 0) throw std::invalid_argument("duration must be greater than zero");
+        return with(fx(RB_FX_LINEAR_RAMP, {clamp_end ? 1u : 0u}, {start, end}, {ns(d)}));
+    }
+    Source fade_in(Duration d) const { return linear_gain_ramp(d, 0.0f, 1.0f, false); }                      // fadein.rs:8-15
+    Source fade_out(Duration d) const { return linear_gain_ramp(d, 1.0f, 0.0f, true); }                      // fadeout.rs:8-15
+    Source take_duration(Duration d, bool filter_fadeout = false) const {                                    // take.rs:9-26,:89-96
+        return with(fx(RB_FX_TAKE_DURATION, {filter_fadeout ? 1u : 0u}, {}, {ns(d)}));
+    }
     Source automatic_gain_control(const AutomaticGainControlSettings& s = {}) const {                        // mod.rs:415-446
         return with(fx(RB_FX_AGC, {}, {s.target_level, s.absolute_max_gain, 0.0f}, {ns(s.attack_time), ns(s.release_time)}));
     }

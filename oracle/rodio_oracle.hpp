@@ -330,6 +330,108 @@ struct Delay : Source {
     Src clone() const override { return std::make_unique<Delay>(in->clone(), remaining, 0); }
 };
 
+// src/source/distortion.rs:66-72
+struct Distortion : Source {
+    Src in;
+    float gain, threshold;
+    Distortion(Src i, float g, float t) : in(std::move(i)), gain(g), threshold(t) {}
+    std::optional<Sample> next() override {
+        auto v = in->next();
+        if (!v) return std::nullopt;
+        return clampf(*v * gain, -threshold, threshold);
+    }
+    std::optional<size_t> current_span_len() const override { return in->current_span_len(); }
+    uint16_t channels() const override { return in->channels(); }
+    uint32_t sample_rate() const override { return in->sample_rate(); }
+    Src clone() const override { return std::make_unique<Distortion>(in->clone(), gain, threshold); }
+};
+
+// src/source/linear_ramp.rs:9-34,:79-104 (fade_in = ramp(d, 0, 1, false), fade_out = ramp(d, 1, 0, true))
+struct LinearGainRamp : Source {
+    Src in;
+    uint64_t elapsed_ns = 0, total_ns;
+    float start_gain, end_gain;
+    bool clamp_end;
+    uint64_t sample_idx = 0;
+    LinearGainRamp(Src i, uint64_t d, float s, float e, bool c)
+        : in(std::move(i)), total_ns(d), start_gain(s), end_gain(e), clamp_end(c) {}
+    std::optional<Sample> next() override {
+        float factor;
+        if (elapsed_ns >= total_ns) {
+            factor = clamp_end ? end_gain : 1.0f;
+        } else {
+            sample_idx += 1;
+            float p = duration_secs_f32(elapsed_ns) / duration_secs_f32(total_ns);
+            factor = start_gain * (1.0f - p) + end_gain * p;
+        }
+        if (sample_idx % in->channels() == 0) elapsed_ns += 1000000000ull / in->sample_rate();   // :94-100
+        auto v = in->next();
+        if (!v) return std::nullopt;
+        return *v * factor;
+    }
+    std::optional<size_t> current_span_len() const override { return in->current_span_len(); }
+    uint16_t channels() const override { return in->channels(); }
+    uint32_t sample_rate() const override { return in->sample_rate(); }
+    Src clone() const override {
+        auto p = std::make_unique<LinearGainRamp>(in->clone(), total_ns, start_gain, end_gain, clamp_end);
+        p->elapsed_ns = elapsed_ns, p->sample_idx = sample_idx;
+        return p;
+    }
+};
+
+// src/source/take.rs:9-26,:34-41,:107-148,:180-196
+struct TakeDuration : Source {
+    Src in;
+    uint64_t remaining_ns, requested_ns, dps_ns;
+    bool fadeout;
+    size_t samples_in_current_frame = 0, silence_samples_remaining = 0;
+    TakeDuration(Src i, uint64_t d, bool f) : in(std::move(i)), remaining_ns(d), requested_ns(d), fadeout(f) {
+        dps_ns = 1000000000ull / ((uint64_t)in->sample_rate() * in->channels());   // :65-69
+    }
+    std::optional<Sample> next() override {
+        while (true) {
+            if (silence_samples_remaining > 0) {
+                silence_samples_remaining -= 1;
+                return 0.0f;
+            }
+            if (remaining_ns < dps_ns) {
+                silence_samples_remaining = samples_in_current_frame > 0 ? in->channels() - samples_in_current_frame : 0;
+                if (silence_samples_remaining > 0) {
+                    samples_in_current_frame = 0;
+                    continue;
+                }
+                return std::nullopt;
+            }
+            auto s = in->next();
+            if (!s) return std::nullopt;
+            samples_in_current_frame = (samples_in_current_frame + 1) % in->channels();
+            float sample = *s;
+            if (fadeout) {   // :34-41  sample * remaining / total
+                float remaining = (float)(remaining_ns / 1000000ull);
+                float total = (float)(requested_ns / 1000000ull);
+                sample = sample * remaining / total;
+            }
+            remaining_ns -= dps_ns;
+            return sample;
+        }
+    }
+    std::optional<size_t> current_span_len() const override {   // :180-196
+        if (dps_ns == 0 || remaining_ns == 0) return (size_t)0;
+        size_t remaining_samples = (size_t)(remaining_ns / dps_ns);
+        auto v = in->current_span_len();
+        if (v && *v < remaining_samples) return v;
+        return remaining_samples;
+    }
+    uint16_t channels() const override { return in->channels(); }
+    uint32_t sample_rate() const override { return in->sample_rate(); }
+    Src clone() const override {
+        auto p = std::make_unique<TakeDuration>(in->clone(), requested_ns, fadeout);
+        p->remaining_ns = remaining_ns, p->samples_in_current_frame = samples_in_current_frame;
+        p->silence_samples_remaining = silence_samples_remaining;
+        return p;
+    }
+};
+
 // src/conversions/channels.rs:57-85
 struct ChannelCountConverter {
     Source* input_src = nullptr;  // set by owner

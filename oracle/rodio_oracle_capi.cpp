@@ -30,7 +30,7 @@ struct ro_stream {
     const float* pcm;
 };
 enum { FX_AMPLIFY = 1, FX_SPEED, FX_LOW_PASS, FX_HIGH_PASS, FX_REVERB, FX_AGC, FX_LIMIT, FX_SPATIAL,
-       FX_CHANNEL_VOLUME, FX_UNIFORM, FX_DELAY };
+       FX_CHANNEL_VOLUME, FX_UNIFORM, FX_DELAY, FX_DISTORTION, FX_LINEAR_RAMP, FX_TAKE_DURATION };
 
 float ro_lerp(float a, float b, uint32_t num, uint32_t den) { return lerp(a, b, num, den); }
 float ro_db_to_linear(float d) { return db_to_linear(d); }
@@ -73,6 +73,11 @@ static Src apply_effects(Src src, const ro_effect* fx, uint32_t n) {
                 break;
             case FX_UNIFORM: src = std::make_unique<UniformSourceIterator>(std::move(src), (uint16_t)e.u32[0], e.u32[1]); break;
             case FX_DELAY: src = std::make_unique<Delay>(std::move(src), e.ns[0]); break;
+            case FX_DISTORTION: src = std::make_unique<Distortion>(std::move(src), e.f32[0], e.f32[1]); break;
+            case FX_LINEAR_RAMP:
+                src = std::make_unique<LinearGainRamp>(std::move(src), e.ns[0], e.f32[0], e.f32[1], e.u32[0] != 0);
+                break;
+            case FX_TAKE_DURATION: src = std::make_unique<TakeDuration>(std::move(src), e.ns[0], e.u32[0] != 0); break;
             default: return nullptr;
         }
     }

@@ -313,6 +313,7 @@ static rb_status plan_stream(PlanStream& ps, uint16_t mixer_ch, uint32_t mixer_r
     uint32_t c = d.channels, rate = d.sample_rate, span = d.span_len;
     const bool buffer_spans = d.span_len != 0 && (uint64_t)d.span_len == d.n_samples;   // SamplesBuffer semantics
     int64_t cv_last = -1;
+    uint64_t tail_pad = 0;   // zeros a TakeDuration appended to complete its last frame (take.rs:113-123)
     if (d.format != RB_FMT_F32) {
         PlanNode nd;
         nd.d.kind = RB_N_CONVERT, nd.d.fmt = d.format, nd.d.c_in = nd.d.c_out = c, nd.d.n_in = nd.d.n_out = n;
@@ -340,8 +341,12 @@ static rb_status plan_stream(PlanStream& ps, uint16_t mixer_ch, uint32_t mixer_r
             case RB_FX_REVERB: {
                 uint64_t D = rb_delay_samples(e.ns[0], rate, (uint16_t)c);
                 nd.d.kind = RB_N_ECHO, nd.d.p.echo.delay = D, nd.d.p.echo.amplitude = e.f32[0];
-                nd.d.n_out = n + D;
+                // Mix wraps both inputs in UniformSourceIterator (mix.rs:19-20): over a TakeDuration they never
+                // pull the frame padding (see RB_FX_UNIFORM below)
+                if (span && tail_pad) nd.d.n_in = n - tail_pad;
+                nd.d.n_out = nd.d.n_in + D;
                 cv_last = -1;
+                tail_pad = 0;
                 nd.span_out = 0;   // Mix::current_span_len of two UniformSourceIterators == None
                 break;
             }
@@ -385,6 +390,7 @@ static rb_status plan_stream(PlanStream& ps, uint16_t mixer_ch, uint32_t mixer_r
                     if (co == 0 || co > RB_MAX_CHANNELS) return fail(RB_ERR_INVALID_ARGUMENT, "channel_volume: 1..12 volumes");
                     for (uint32_t j = 0; j < co; j++) nd.d.p.cv.vol[j] = e.f32[j];
                 }
+                if (tail_pad) return fail(RB_ERR_UNSUPPORTED, "channel_volume/spatial directly on a padded take_duration");
                 if (n % c != 0)
                     return fail(RB_ERR_UNALIGNED_FRAMES, "channel_volume/spatial on a stream that is not frame aligned "
                                                          "(e.g. after an odd-length delay)");
@@ -393,10 +399,44 @@ static rb_status plan_stream(PlanStream& ps, uint16_t mixer_ch, uint32_t mixer_r
                 cv_last = (buffer_spans && span != 0 && n >= c) ? (int64_t)((n / c - 1) * co) : -1;
                 break;
             }
+            case RB_FX_DISTORTION: {
+                if (!(e.f32[1] >= 0.0f)) return fail(RB_ERR_INVALID_ARGUMENT, "distortion: clamp(-t, t) panics for t < 0 or NaN");
+                nd.d.kind = RB_N_DISTORT, nd.d.p.dist.gain = e.f32[0], nd.d.p.dist.threshold = e.f32[1];
+                break;
+            }
+            case RB_FX_LINEAR_RAMP: {
+                if (e.ns[0] == 0) return fail(RB_ERR_INVALID_ARGUMENT, "linear_gain_ramp: duration must be greater than zero");
+                nd.d.kind = RB_N_RAMP;
+                nd.d.p.ramp.total_ns = e.ns[0], nd.d.p.ramp.dt_ns = 1000000000ull / rate;   // linear_ramp.rs:97-99
+                nd.d.p.ramp.start = e.f32[0], nd.d.p.ramp.end = e.f32[1], nd.d.p.ramp.clamp_end = e.u32[0] ? 1u : 0u;
+                break;
+            }
+            case RB_FX_TAKE_DURATION: {
+                const uint64_t dps = 1000000000ull / ((uint64_t)rate * c);                   // take.rs:65-69
+                uint64_t take_n = dps ? e.ns[0] / dps : n;        // samples emitted before `remaining < dps`
+                uint64_t count = std::min<uint64_t>(n, take_n);
+                uint64_t pad = 0;
+                if (dps && take_n <= n && count % c) pad = c - count % c;   // duration expired first: pad the frame
+                nd.d.kind = RB_N_TAKE;
+                nd.d.p.take.total_ns = e.ns[0], nd.d.p.take.dps_ns = dps, nd.d.p.take.count = count;
+                nd.d.p.take.total_ms_f = (float)(e.ns[0] / 1000000ull);
+                nd.d.p.take.fadeout = e.u32[0] ? 1u : 0u;
+                nd.d.n_out = count + pad;
+                tail_pad = pad;
+                // TakeDuration::current_span_len: the inner span when it is shorter than what is left, else what is left
+                uint64_t so = span ? std::min<uint64_t>(span, take_n) : take_n;
+                nd.span_out = (uint32_t)std::min<uint64_t>(so, 0xFFFFFFFFull);
+                if (nd.span_out == 0) nd.span_out = 1;   // Some(0) at the very end only; never None
+                cv_last = -1;
+                break;
+            }
             case RB_FX_UNIFORM: {
-                rb_status s = plan_uniform(nd, n, c, rate, span, e.u32[0], e.u32[1], cv_last);
+                // a UniformSourceIterator over a TakeDuration asks for exactly the samples that are left
+                // (take.rs:180-196), so the frame padding is never pulled
+                rb_status s = plan_uniform(nd, (span && tail_pad) ? n - tail_pad : n, c, rate, span, e.u32[0], e.u32[1], cv_last);
                 if (s != RB_OK) return s;
                 cv_last = -1;
+                tail_pad = 0;
                 if (nd.d.p.uni.from == nd.d.p.uni.to && nd.d.c_in == nd.d.c_out && nd.d.n_out == n) {   // identity: no kernel
                     rate = nd.rate_out, span = 0;
                     continue;
@@ -412,7 +452,7 @@ static rb_status plan_stream(PlanStream& ps, uint16_t mixer_ch, uint32_t mixer_r
     // Mixer::add wraps the source in UniformSourceIterator::new(source, mixer_ch, mixer_rate) (mixer.rs:62-63)
     {
         PlanNode nd;
-        rb_status s = plan_uniform(nd, n, c, rate, span, mixer_ch, mixer_rate, cv_last);
+        rb_status s = plan_uniform(nd, (span && tail_pad) ? n - tail_pad : n, c, rate, span, mixer_ch, mixer_rate, cv_last);
         if (s != RB_OK) return s;
         if (!(nd.d.p.uni.from == nd.d.p.uni.to && nd.d.c_in == nd.d.c_out) || nd.d.n_out != n) {
             ps.nodes.push_back(nd);

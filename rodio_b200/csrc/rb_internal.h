@@ -21,7 +21,10 @@ enum rb_node_kind : uint32_t {
     RB_N_LIMIT = 6,     // src/source/limit.rs:854-988
     RB_N_CHANVOL = 7,   // src/source/channel_volume.rs:71-88 (also Spatial)
     RB_N_UNIFORM = 8,   // src/source/uniform.rs + conversions/{sample_rate,channels}.rs
-    RB_N_KINDS = 9
+    RB_N_DISTORT = 9,   // src/source/distortion.rs:66-72
+    RB_N_RAMP = 10,     // src/source/linear_ramp.rs:79-104 (also fade_in / fade_out)
+    RB_N_TAKE = 11,     // src/source/take.rs:107-148 (+ fade-out filter :34-41)
+    RB_N_KINDS = 12
 };
 
 // Closed-form description of one UniformSourceIterator application.
@@ -64,6 +67,9 @@ struct alignas(16) rb_node_dev {
         struct { float target, max_gain, floor, attack, release; } agc;
         struct { float threshold, knee, inv_knee_8, attack, release; } lim;
         struct { float vol[RB_MAX_CHANNELS]; } cv;
+        struct { float gain, threshold; } dist;
+        struct { uint64_t total_ns, dt_ns; float start, end; uint32_t clamp_end; } ramp;
+        struct { uint64_t total_ns, dps_ns, count; float total_ms_f; uint32_t fadeout; } take;
         rb_uniform_params uni;
     } p;
 };

@@ -59,6 +59,68 @@ __global__ void __launch_bounds__(TPB) k_delay(const rb_node_dev* __restrict__ n
     for_each_out(nd, [&](uint64_t o) { nd.dst[o] = (o < D) ? 0.0f : x[o - D]; });
 }
 
+// Distortion — src/source/distortion.rs:66-72 : (x * gain).clamp(-t, t)   (f32::clamp: NaN passes through)
+__global__ void __launch_bounds__(TPB) k_distort(const rb_node_dev* __restrict__ nodes) {
+    const rb_node_dev& nd = nodes[blockIdx.x];
+    const float* __restrict__ x = (const float*)nd.src;
+    const float g = nd.p.dist.gain, t = nd.p.dist.threshold;
+    for_each_out(nd, [&](uint64_t o) {
+        float v = mul(x[o], g);
+        if (v < -t) v = -t;
+        if (v > t) v = t;
+        nd.dst[o] = v;
+    });
+}
+
+// std::time::Duration::as_secs_f32 of `ns` nanoseconds: (secs as f32) + (nanos as f32) / 1e9
+__device__ __forceinline__ float duration_secs_f32(uint64_t ns) {
+    const uint64_t secs = ns / 1000000000ull;
+    const uint32_t nanos = (uint32_t)(ns - secs * 1000000000ull);
+    return add(__ull2float_rn(secs), divf(__uint2float_rn(nanos), 1000000000.0f));
+}
+
+// LinearGainRamp / fade_in / fade_out — src/source/linear_ramp.rs:79-104.  Frame f sees
+// elapsed = f * floor(1e9 / rate) ns (the elapsed time advances once per frame while the ramp is running).
+__global__ void __launch_bounds__(TPB) k_ramp(const rb_node_dev* __restrict__ nodes) {
+    const rb_node_dev& nd = nodes[blockIdx.x];
+    const float* __restrict__ x = (const float*)nd.src;
+    const uint64_t total = nd.p.ramp.total_ns, dt = nd.p.ramp.dt_ns;
+    const float start = nd.p.ramp.start, end = nd.p.ramp.end;
+    const float after = nd.p.ramp.clamp_end ? end : 1.0f;
+    const float total_f = duration_secs_f32(total);
+    const uint32_t C = nd.c_in;
+    for_each_out(nd, [&](uint64_t o) {
+        const uint64_t elapsed = (o / C) * dt;
+        float factor = after;
+        if (elapsed < total) {
+            const float p = divf(duration_secs_f32(elapsed), total_f);
+            factor = add(mul(start, sub(1.0f, p)), mul(end, p));
+        }
+        nd.dst[o] = mul(x[o], factor);
+    });
+}
+
+// TakeDuration (+ fade-out filter) — src/source/take.rs:107-148,:34-41.  `count` input samples pass, then
+// literal 0.0 pads the last frame.  Fade-out: sample * (remaining.as_millis() as f32) / (total.as_millis() as f32).
+__global__ void __launch_bounds__(TPB) k_take(const rb_node_dev* __restrict__ nodes) {
+    const rb_node_dev& nd = nodes[blockIdx.x];
+    const float* __restrict__ x = (const float*)nd.src;
+    const uint64_t total = nd.p.take.total_ns, dps = nd.p.take.dps_ns, count = nd.p.take.count;
+    const float total_ms = nd.p.take.total_ms_f;
+    const bool fade = nd.p.take.fadeout != 0;
+    for_each_out(nd, [&](uint64_t o) {
+        float v = 0.0f;                                   // Sample::EQUILIBRIUM padding
+        if (o < count) {
+            v = x[o];
+            if (fade) {
+                const uint64_t remaining_ms = (total - o * dps) / 1000000ull;
+                v = divf(mul(v, __ull2float_rn(remaining_ms)), total_ms);
+            }
+        }
+        nd.dst[o] = v;
+    });
+}
+
 // ChannelVolume / Spatial — src/source/channel_volume.rs:71-88
 __global__ void __launch_bounds__(TPB) k_chanvol(const rb_node_dev* __restrict__ nodes) {
     const rb_node_dev& nd = nodes[blockIdx.x];
@@ -403,6 +465,9 @@ cudaError_t rb_launch_nodes(uint32_t kind, const rb_node_dev* d_nodes, uint32_t 
         case RB_N_ECHO: k_echo<<<grid, TPB, 0, st>>>(d_nodes); break;
         case RB_N_DELAY: k_delay<<<grid, TPB, 0, st>>>(d_nodes); break;
         case RB_N_CHANVOL: k_chanvol<<<grid, TPB, 0, st>>>(d_nodes); break;
+        case RB_N_DISTORT: k_distort<<<grid, TPB, 0, st>>>(d_nodes); break;
+        case RB_N_RAMP: k_ramp<<<grid, TPB, 0, st>>>(d_nodes); break;
+        case RB_N_TAKE: k_take<<<grid, TPB, 0, st>>>(d_nodes); break;
         case RB_N_UNIFORM: k_uniform<<<grid, TPB, 0, st>>>(d_nodes); break;
         case RB_N_BIQUAD: {
             if (max_channels < 1) max_channels = 1;

@@ -208,6 +208,29 @@ class Source:
         """Source::delay — src/source/delay.rs:19-29."""
         return self._with(Effect.make(capi.RB_FX_DELAY, ns=[duration]))
 
+    def distortion(self, gain: float, threshold: float) -> "Source":
+        """Source::distortion — src/source/mod.rs:726-731 (distortion.rs:66-72)."""
+        return self._with(Effect.make(capi.RB_FX_DISTORTION, f32=[gain, threshold]))
+
+    def linear_gain_ramp(self, duration: int, start_value: float, end_value: float, clamp_end: bool) -> "Source":
+        """Source::linear_gain_ramp — src/source/mod.rs:534-546 (linear_ramp.rs:79-104)."""
+        if int(duration) == 0:
+            raise ValueError("duration must be greater than zero (linear_ramp.rs:19)")
+        return self._with(Effect.make(capi.RB_FX_LINEAR_RAMP, u32=[1 if clamp_end else 0], f32=[start_value, end_value],
+                                      ns=[duration]))
+
+    def fade_in(self, duration: int) -> "Source":
+        """Source::fade_in — src/source/fadein.rs:8-15."""
+        return self.linear_gain_ramp(duration, 0.0, 1.0, False)
+
+    def fade_out(self, duration: int) -> "Source":
+        """Source::fade_out — src/source/fadeout.rs:8-15."""
+        return self.linear_gain_ramp(duration, 1.0, 0.0, True)
+
+    def take_duration(self, duration: int, filter_fadeout: bool = False) -> "Source":
+        """Source::take_duration (+ TakeDuration::set_filter_fadeout) — src/source/take.rs:9-26,:89-96."""
+        return self._with(Effect.make(capi.RB_FX_TAKE_DURATION, u32=[1 if filter_fadeout else 0], ns=[duration]))
+
     def automatic_gain_control(self, settings: Optional[AutomaticGainControlSettings] = None) -> "Source":
         """Source::automatic_gain_control — src/source/mod.rs:415-446."""
         s = settings or AutomaticGainControlSettings()

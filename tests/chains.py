@@ -47,6 +47,20 @@ CHAINS = {
     "bench_long_shape": lambda: rb.UniformSourceIterator(
         rb.TestSource(_stereo(22050, 45), 2, 44100).high_pass(300).amplify(1.2).speed(0.9).automatic_gain_control()
         .delay(rb.Duration.from_secs_f32(0.5)).reverb(rb.Duration.from_secs_f32(0.05), 0.3), 2, 40000),
+    "distortion": lambda: rb.TestSource(_stereo(3000, 50), 2, 44100).distortion(4.0, 0.3),
+    "fade_in_stereo": lambda: rb.TestSource(_stereo(6000, 51), 2, 44100).fade_in(rb.Duration.from_millis(50)),
+    "fade_out_mono": lambda: rb.SamplesBuffer(1, 48000, noise(9000, 52)).fade_out(rb.Duration.from_millis(100)),
+    "linear_ramp_3ch": lambda: rb.TestSource(noise(3 * 2500, 53), 3, 32000).linear_gain_ramp(
+        rb.Duration.from_secs_f32(0.03), 0.25, 2.0, True),
+    "take_duration": lambda: rb.TestSource(_stereo(8000, 54), 2, 44100).take_duration(rb.Duration.from_millis(123)),
+    "take_duration_fadeout": lambda: rb.TestSource(noise(20000, 55), 1, 48000).take_duration(
+        rb.Duration.from_millis(300), filter_fadeout=True),
+    "take_longer_than_input": lambda: rb.SamplesBuffer(2, 44100, _stereo(1000, 56)).take_duration(rb.Duration.from_secs(3)),
+    "take_pads_frame": lambda: rb.TestSource(noise(3 * 4000, 57), 3, 44100).take_duration(rb.Duration.from_nanos(7_566_000)),
+    "bench_long_full": lambda: rb.UniformSourceIterator(
+        rb.TestSource(_stereo(44100, 58), 2, 44100).high_pass(300).amplify(1.2).speed(0.9).automatic_gain_control()
+        .delay(rb.Duration.from_secs_f32(0.1)).fade_in(rb.Duration.from_secs_f32(0.4))
+        .take_duration(rb.Duration.from_secs(1), filter_fadeout=True).reverb(rb.Duration.from_secs_f32(0.05), 0.3), 2, 40000),
     "i16_input": lambda: rb.SamplesBuffer(2, 44100, (noise(4000, 21) * 30000).astype(np.int16)).amplify(0.5).low_pass(500),
 }
 

@@ -186,3 +186,37 @@ def test_planner_random_uniform_lengths(built):
             assert e.status in (capi.RB_ERR_UNSUPPORTED,), e
             continue
         assert got == oracle.chain_uniform(to_oracle(src), *mix).size, (i, kind, c, n, mix)
+
+
+def test_planner_take_ramp_distortion_lengths(built):
+    """take_duration padding is never pulled through a UniformSourceIterator / reverb (take.rs:180-196)."""
+    rng = np.random.default_rng(9)
+    rates = [8000, 11025, 22050, 44100, 48000, 96000, 39690]
+    for i in range(400):
+        c = int(rng.integers(1, 5))
+        n = int(rng.integers(0, 600))
+        n -= n % c
+        x, r = np.zeros(n, np.float32), int(rng.choice(rates))
+        base = rb.SamplesBuffer(c, r, x) if i % 2 else rb.TestSource(x, c, r)
+        d = rb.Duration.from_nanos(int(rng.integers(0, 30_000_000)))
+        k = i % 5
+        if k == 0:
+            src = base.take_duration(d)
+        elif k == 1:
+            src = base.take_duration(d, True).amplify(0.5).low_pass(300)
+        elif k == 2:
+            src = base.fade_in(rb.Duration.from_millis(3)).take_duration(d).reverb(rb.Duration.from_micros(int(rng.integers(0, 900))), 0.3)
+        elif k == 3:
+            src = base.delay(rb.Duration.from_micros(int(rng.integers(0, 900)))).take_duration(d).distortion(2.0, 0.5)
+        else:
+            src = rb.UniformSourceIterator(base.take_duration(d), int(rng.integers(1, 4)), int(rng.choice(rates))) \
+                .fade_out(rb.Duration.from_millis(2))
+        mix = (int(rng.integers(1, 5)), int(rng.choice(rates)))
+        got = rb.plan(src, *mix)
+        w, ch, rate = oracle.chain(to_oracle(src))
+        assert (got[1], got[2], got[3]) == (ch, rate, w.size), (i, k)
+        assert got[0] == oracle.chain_uniform(to_oracle(src), *mix).size, (i, k)
+    with pytest.raises(ValueError):
+        rb.TestSource(np.zeros(4, np.float32), 1, 48000).fade_in(0)
+    with pytest.raises(rb.RodioB200Error):
+        rb.plan(rb.TestSource(np.zeros(4, np.float32), 1, 48000).distortion(2.0, -1.0), 1, 48000)
