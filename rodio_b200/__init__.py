@@ -8,12 +8,12 @@ the first call that needs a device fails loudly.
 from . import _capi as capi
 from ._capi import RodioB200Error, lib
 from .source import (AutomaticGainControlSettings, Batch, ChannelCountConverter, ChannelVolume, Context, Duration,
-                     Effect, LimitSettings, Mixer, MixerSource, SampleRateConverter, SamplesBuffer,
+                     Effect, LimitSettings, Mixer, MixerSource, Player, SampleRateConverter, SamplesBuffer,
                      SampleTypeConverter, Source, Spatial, TestSource, UniformSourceIterator, default_context, mixer, plan)
 
 __all__ = [
     "capi", "lib", "RodioB200Error", "AutomaticGainControlSettings", "Batch", "ChannelCountConverter",
-    "ChannelVolume", "Context", "Duration", "Effect", "LimitSettings", "Mixer", "MixerSource",
+    "ChannelVolume", "Context", "Duration", "Effect", "LimitSettings", "Mixer", "MixerSource", "Player",
     "SampleRateConverter", "SamplesBuffer", "SampleTypeConverter", "Source", "Spatial", "TestSource",
     "UniformSourceIterator", "default_context", "mixer", "plan",
 ]

@@ -578,6 +578,63 @@ def mixer(channels: int, sample_rate: int, flags: int = 0, ctx: Optional[Context
 
 
 # ---------------------------------------------------------------------------------------------
+# Player ("Sink" in rodio <= 0.20): the control handle, on blocks        src/player.rs:20-351
+# ---------------------------------------------------------------------------------------------
+class Player:
+    """`Player::connect_new(&mixer)` + `append` / `set_volume` / `set_speed` / `len` / `empty` for offline drains.
+
+    rodio wraps every appended source in speed -> track_position -> pausable -> amplify(volume) -> skippable ->
+    stoppable (src/player.rs:122-166) and samples the controls every 5 ms of audio.  On blocks the controls are
+    read when a source is appended: its chain becomes `source.speed(speed).amplify(volume)` and it is queued
+    behind the sources appended before it (src/queue.rs: one source after the other, each converted to the
+    mixer's format on its own).  Pausing / skipping / seeking mid-playback are control-plane features of the
+    real-time callback and are out of scope."""
+
+    def __init__(self, mixer: "Mixer"):
+        self._mixer = mixer
+        self._volume = 1.0
+        self._speed = 1.0
+        self._next_start = mixer._s.pos
+        self._count = 0
+
+    @staticmethod
+    def connect_new(mixer: "Mixer") -> "Player":
+        return Player(mixer)
+
+    def volume(self) -> float:
+        return self._volume
+
+    def set_volume(self, value: float):
+        """Player::set_volume — multiplies every sample (src/player.rs:180-186); == Source::amplify(value)."""
+        self._volume = float(value)
+
+    def speed(self) -> float:
+        return self._speed
+
+    def set_speed(self, value: float):
+        """Player::set_speed (src/player.rs:203-207): rescales the reported sample rate like Source::speed."""
+        self._speed = float(value)
+
+    def append(self, source: Source):
+        """Player::append — src/player.rs:104-170."""
+        s = self._mixer._s
+        chain = source.speed(self._speed).amplify(self._volume)
+        n = plan(chain, s.channels, s.rate)[0]
+        start = (self._next_start + s.channels - 1) // s.channels * s.channels
+        s.sources.append(chain)
+        s.starts.append(start)
+        s.rendered = None
+        self._next_start = start + n
+        self._count += 1
+
+    def len(self) -> int:
+        return self._count
+
+    def empty(self) -> bool:
+        return self._count == 0
+
+
+# ---------------------------------------------------------------------------------------------
 # conversions::{SampleRateConverter, ChannelCountConverter, SampleTypeConverter}
 # ---------------------------------------------------------------------------------------------
 def _f32(a) -> np.ndarray:

@@ -461,3 +461,23 @@ def test_read_mix_blocks(ctx):
         full = b.render_mix().copy()
         blocks = [b.read_mix(o, 1000) for o in range(0, full.size + 1000, 1000)]
     assert np.array_equal(np.concatenate(blocks), full) and blocks[-1].size == 0
+
+
+def test_player_volume_speed_and_queueing(ctx):
+    """src/player.rs:454-470 (`set_volume(0.5)` == amplify(0.5)) and sequential playback of appended sources."""
+    a = noise(3000, 901)
+    b = noise(2 * 2000, 902)
+    tx, rx = rb.mixer(2, 48000, ctx=ctx)
+    player = rb.Player.connect_new(tx)
+    assert player.empty()
+    player.set_volume(0.5)
+    player.append(rb.SamplesBuffer(1, 44100, a))
+    player.set_speed(0.9)
+    player.append(rb.SamplesBuffer(2, 48000, b))
+    assert player.len() == 2
+    got = rx.collect()
+    first = oracle.chain_uniform(to_oracle(rb.SamplesBuffer(1, 44100, a).speed(1.0).amplify(0.5)), 2, 48000)
+    second = oracle.chain_uniform(to_oracle(rb.SamplesBuffer(2, 48000, b).speed(0.9).amplify(0.5)), 2, 48000)
+    # the mixer adds +0.0 before every sample (mixer.rs:186-189): -0.0 becomes +0.0, everything else is unchanged
+    want = np.concatenate([first, second]) + np.float32(0.0)
+    assert_bit_exact(got, want, "player queue")
