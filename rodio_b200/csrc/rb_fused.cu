@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(512, 1) k_fused_biquad(FusedArgs a, uint32_t n
 // 1024 threads: one stage-A warp per row, the recurrence warp has the highest warp id.
 // ---------------------------------------------------------------------------------------------------
 constexpr int NWIN = 3;                 // input-window ring (tile k .. k+2)
-constexpr int WSTRIDE = TT + 8;         // floats per row window (>= 3 + TT*from/to + 2, multiple of 4)
+constexpr int WSTRIDE = 320;            // floats per row window (>= 3 + TT*from/to + 3, multiple of 4): from/to <= 1.2
 constexpr int NHT = 5;                  // per-(row,tile) index-state ring: written 2 tiles ahead, read until stage C
 
 struct HotTile {
@@ -675,7 +675,8 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
     // very first tile), else the previous tile's tail
     if (lane >= 30) row[(int)ht.lo - 32 + (int)lane] = (ht.i0 == 0 && ht.r0 == 0) ? 0.0f : xtail;
     // warp-uniform: the vote below needs the whole warp on the same side of this branch
-    const bool interior = __all_sync(0xffffffffu, n == (uint32_t)TT && (di + (uint32_t)(U - 1) * (q32 + 1) + 1) < lim);
+    const bool pass = r.mode != ROW_LERP;   // same-rate rows: x[n] = in[n], no interpolation (from = to = 1 in the row)
+    const bool interior = !pass && __all_sync(0xffffffffu, n == (uint32_t)TT && (di + (uint32_t)(U - 1) * (q32 + 1) + 1) < lim);
     bool done = false;
     if (interior) {
         const uint32_t di0 = di, num0 = num;
@@ -726,7 +727,7 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
     for (int u = 0; u < U; u++) {
         if (lane + 32u * (uint32_t)u < n) {
             float v = gains<NOGAIN>(w[di], pre, n_pre);
-            if (di < lim) v = lerp_f(v, gains<NOGAIN>(w[di + 1], pre, n_pre), __uint2float_rn(num), den_f);
+            if (!pass && di < lim) v = lerp_f(v, gains<NOGAIN>(w[di + 1], pre, n_pre), __uint2float_rn(num), den_f);
             out[32 * u] = gains<NOGAIN>(v, mid, n_mid);
         }
         num += r32, di += q32;
@@ -997,12 +998,19 @@ static bool parse_row(const rb_fused_stream& s, uint16_t mixer_ch, FusedRow& r, 
     r.mode = ROW_GENERIC;
     if (!has_uniform) {
         r.mode = ROW_DIRECT;
+        // the HOT kernel walks same-rate rows as a 1:1 "ratio"
+        r.uni.from = r.uni.to = 1, r.uni.tail.L = s.n_in / (s.c_in ? s.c_in : 1);
+        r.q32 = 32, r.r32 = 0, r.qT = TT, r.rT = 0, r.den_f = 1.0f, r.rcp_den = 1.0f;
     } else {
         const rb_uniform_params& u = r.uni;
         r.den_f = (float)u.to;
         r.rcp_den = 1.0f / r.den_f;
         if (u.from == u.to) {
-            if (u.tail.p == 0 && (u.chunk_samples == 0 || u.chunk_samples % s.c_in == 0)) r.mode = ROW_PASS;
+            if (u.tail.p == 0 && (u.chunk_samples == 0 || u.chunk_samples % s.c_in == 0)) {
+                r.mode = ROW_PASS;
+                r.uni.tail.L = r.n_in / (s.c_in ? s.c_in : 1);   // chunks are irrelevant for a whole-frame pass-through
+                r.q32 = 32, r.r32 = 0, r.qT = TT, r.rT = 0;
+            }
         } else if (u.chunk_samples == 0 && u.tail.p == 0 && u.from <= (1u << 20) && u.to <= (1u << 20)) {
             r.mode = ROW_LERP;
             r.q32 = (uint32_t)((32ull * u.from) / u.to);
@@ -1041,8 +1049,11 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     plan->all_f32 = true;
     for (size_t i = 0; i < n_streams; i++) plan->all_f32 = plan->all_f32 && streams[i].fmt == RB_FMT_F32;
     plan->hot = has_b && plan->all_f32 && mixer_channels == 1;
-    for (size_t i = 0; i < n_streams && plan->hot; i++)
-        plan->hot = rows[i].mode == ROW_LERP && rows[i].c_in == 1 && rows[i].uni.from <= rows[i].uni.to;
+    for (size_t i = 0; i < n_streams && plan->hot; i++) {
+        const FusedRow& r = rows[i];
+        const bool window_fits = (uint64_t)TT * r.uni.from / r.uni.to + 8 <= (uint64_t)WSTRIDE;
+        plan->hot = r.c_in == 1 && (r.mode == ROW_DIRECT || r.mode == ROW_PASS || (r.mode == ROW_LERP && window_fits));
+    }
     // rows per CTA: one balanced wave over the SMs (k CTAs per SM when the batch is large)
     uint32_t S = (uint32_t)n_streams;
     uint32_t max_g = plan->hot ? HOT_MAX_ROWS : MAX_G;

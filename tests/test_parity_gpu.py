@@ -391,6 +391,9 @@ FUSED_CASES = [
     (500, 2, 48000, (2, 48000), None, True, False),
     (33, 2, 44100, (4, 96000), None, False, True),
     (5, 4, 48000, (2, 48000), "lp", False, False),
+    (64, 1, 48000, (1, 44100), "lp", False, True),      # mild downsampling: HOT kernel window 280 floats
+    (180, 1, 48000, (1, 40000), "hp", False, False),
+    (30, 1, 96000, (1, 48000), "lp", False, True),      # 2:1 -> generic fused kernel
 ]
 
 
