@@ -604,6 +604,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 }
 
 // Index state of (row, tile) -- incremental from the previous tile when that one was a full interior tile.
+// C = channels (source == mixer): positions are flat interleaved samples, i0 / r0 / qT / q32 count FRAMES.
+template <int C>
 __device__ __forceinline__ void hot_tile_setup(const FusedRow& r, uint64_t m0, const HotTile* prev, HotTile& ht) {
     const uint64_t s = r.mix_start, e = r.mix_start + r.out_len;
     const uint64_t lo = m0 > s ? m0 : s, hi = (m0 + TT) < e ? (m0 + TT) : e;
@@ -616,14 +618,15 @@ __device__ __forceinline__ void hot_tile_setup(const FusedRow& r, uint64_t m0, c
         if (rr >= r.uni.to) rr -= r.uni.to, ii += 1;
         ht.r0 = rr, ht.i0 = ii;
     } else {
-        const uint64_t prod = (lo - s) * (uint64_t)r.uni.from;
+        const uint64_t prod = ((lo - s) / C) * (uint64_t)r.uni.from;   // streams join and tiles start on frame boundaries
         ht.i0 = prod / r.uni.to;
         ht.r0 = (uint32_t)(prod - ht.i0 * r.uni.to);
     }
-    ht.woff = (uint32_t)(ht.i0 & 3ull);
+    ht.woff = (uint32_t)((ht.i0 * C) & 3ull);
 }
 
 // Stage L for one (row, tile): arm the stage barrier and launch the bulk copy of the input window.
+template <int C>
 __device__ __forceinline__ void hot_issue_window(const FusedRow& r, const HotTile& ht, float* win, uint64_t* bar) {
     if (ht.lo >= ht.hi) {
         mbar_arrive(bar);
@@ -634,9 +637,9 @@ __device__ __forceinline__ void hot_issue_window(const FusedRow& r, const HotTil
     (void)n;
     uint64_t taps = (uint64_t)r.qT + 3;          // >= floor((r0 + (TT-1)*from)/to) + 2 because r0 < to
     if (ht.i0 + taps > L) taps = L - ht.i0;
-    const uint32_t frames = ht.woff + (uint32_t)taps;
-    const uint32_t bytes = (frames * 4u + 15u) & ~15u;                  // <= 12 bytes into the row's 16-byte tail pad
-    const float* src = (const float*)r.in + (ht.i0 - ht.woff);
+    const uint32_t floats = ht.woff + (uint32_t)taps * C;
+    const uint32_t bytes = (floats * 4u + 15u) & ~15u;                  // <= 12 bytes into the row's 16-byte tail pad
+    const float* src = (const float*)r.in + (ht.i0 * C - ht.woff);
     mbar_arrive_expect_tx(bar, bytes);
     bulk_g2s(win, src, bytes, bar);
 }
@@ -653,7 +656,9 @@ __device__ __forceinline__ void hot_issue_window(const FusedRow& r, const HotTil
 // its 12-cycle dependent chain if it executes nothing but  y = (t - a1*y1) - a2*y2.
 // `row` points at tile position 0; row[-2], row[-1] are pad slots that receive the previous tile's last two
 // x values (`xtail`, kept in registers of lanes 30/31 across tiles) or zeros at the start of the stream.
-template <bool NOGAIN>
+// With C interleaved channels lane l works on channel l % C of frame l / C + (32 / C) * u: the tile position is
+// still lane + 32 * u, taps sit C floats apart, the left neighbours of the feed-forward C and 2C positions back.
+template <bool NOGAIN, int C>
 __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht, uint32_t n_pre, uint32_t n_mid,
                                             uint32_t lane, uint32_t lane_q, uint32_t lane_r, float& xtail,
                                             const float* __restrict__ win, float* __restrict__ row) {
@@ -664,7 +669,7 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
     const float b0 = r.b0, b1 = r.b1, b2 = r.b2;
     const uint64_t remain = r.uni.tail.L - 1 - ht.i0;
     const uint32_t lim = remain > 0x7fffffffull ? 0x7fffffffu : (uint32_t)remain;   // interpolate iff di < lim
-    const float* __restrict__ w = win + ht.woff;
+    const float* __restrict__ w = win + ht.woff + (lane % C);   // this lane's channel
     const float* pre = r.pre;
     const float* mid = r.mid;
     uint32_t num = ht.r0 + lane_r;
@@ -673,7 +678,7 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
     float* __restrict__ out = row + ht.lo + lane;
     // x[n-2], x[n-1] of the first active position: zeros when the stream starts in this tile (ht.lo > 0 or the
     // very first tile), else the previous tile's tail
-    if (lane >= 30) row[(int)ht.lo - 32 + (int)lane] = (ht.i0 == 0 && ht.r0 == 0) ? 0.0f : xtail;
+    if (lane >= 32 - 2 * C) row[(int)ht.lo - 32 + (int)lane] = (ht.i0 == 0 && ht.r0 == 0) ? 0.0f : xtail;
     // warp-uniform: the vote below needs the whole warp on the same side of this branch
     const bool pass = r.mode != ROW_LERP;   // same-rate rows: x[n] = in[n], no interpolation (from = to = 1 in the row)
     const bool interior = !pass && __all_sync(0xffffffffu, n == (uint32_t)TT && (di + (uint32_t)(U - 1) * (q32 + 1) + 1) < lim);
@@ -693,7 +698,7 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
                 if (num >= to) num -= to, di += 1;
             }
 #pragma unroll
-            for (int u = 0; u < H; u++) x0[u] = w[dis[u]], x1[u] = w[dis[u] + 1];
+            for (int u = 0; u < H; u++) x0[u] = w[dis[u] * C], x1[u] = w[(dis[u] + 1) * C];
 #pragma unroll
             for (int u = 0; u < H; u++) {
                 const float a0 = gains<NOGAIN>(x0[u], pre, n_pre), a1 = gains<NOGAIN>(x1[u], pre, n_pre);
@@ -711,11 +716,11 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
             __syncwarp();
             float xm1[U], xm2[U];
 #pragma unroll
-            for (int u = 0; u < U; u++) xm1[u] = out[32 * u - 1], xm2[u] = out[32 * u - 2];
+            for (int u = 0; u < U; u++) xm1[u] = out[32 * u - C], xm2[u] = out[32 * u - 2 * C];
             __syncwarp();
 #pragma unroll
             for (int u = 0; u < U; u++) out[32 * u] = biquad_ff(b0, b1, b2, xv[u], xm1[u], xm2[u]);
-            if (lane >= 30) xtail = xv[U - 1];     // positions TT-2 (lane 30) and TT-1 (lane 31)
+            if (lane >= 32 - 2 * C) xtail = xv[U - 1];     // the last two frames of the tile
             done = true;
         } else {
             di = di0, num = num0;   // some operand was denormal / huge / NaN: redo this row-tile with IEEE divisions
@@ -726,8 +731,8 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
 #pragma unroll 1
     for (int u = 0; u < U; u++) {
         if (lane + 32u * (uint32_t)u < n) {
-            float v = gains<NOGAIN>(w[di], pre, n_pre);
-            if (!pass && di < lim) v = lerp_f(v, gains<NOGAIN>(w[di + 1], pre, n_pre), __uint2float_rn(num), den_f);
+            float v = gains<NOGAIN>(w[di * C], pre, n_pre);
+            if (!pass && di < lim) v = lerp_f(v, gains<NOGAIN>(w[(di + 1) * C], pre, n_pre), __uint2float_rn(num), den_f);
             out[32 * u] = gains<NOGAIN>(v, mid, n_mid);
         }
         num += r32, di += q32;
@@ -738,12 +743,11 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
 #pragma unroll
     for (int u = 0; u < U; u++) {
         xv[u] = xm1[u] = xm2[u] = 0.0f;
-        if (lane + 32u * (uint32_t)u < n) xv[u] = out[32 * u], xm1[u] = out[32 * u - 1], xm2[u] = out[32 * u - 2];
+        if (lane + 32u * (uint32_t)u < n) xv[u] = out[32 * u], xm1[u] = out[32 * u - C], xm2[u] = out[32 * u - 2 * C];
     }
     // new tail = x at the last two active positions (n == 1: shift the old tail)
-    const float t_hi1 = row[(int)ht.hi - 1], t_hi2 = row[(int)ht.hi - 2];   // hi-2 >= lo-1 >= -1: inside the padded row
-    if (lane == 30) xtail = t_hi2;
-    if (lane == 31) xtail = t_hi1;
+    const float t_tail = row[(int)ht.hi - 32 + (int)lane];   // lanes >= 32-2C: positions hi-2C .. hi-1 (>= lo-C: inside the padded row)
+    if (lane >= 32 - 2 * C) xtail = t_tail;
     __syncwarp();
 #pragma unroll
     for (int u = 0; u < U; u++)
@@ -764,6 +768,7 @@ __device__ __forceinline__ int hot_row_slot(uint32_t warp) {
 }
 constexpr uint32_t HOT_ROW_WARPS = 24;
 constexpr uint32_t HOT_MAX_ROWS = 28;   // 24 slots + 4 second rows
+constexpr uint32_t HOT_MAX_ROWS_STEREO = 16;   // 32 chains in the recurrence warp
 constexpr uint32_t HOT_REC_WARP = 31, HOT_LOAD_WARP = 27;
 // second row of a slot (rows beyond 24), or -1
 __device__ __forceinline__ int hot_second_row(int slot) {
@@ -779,6 +784,10 @@ __device__ __forceinline__ int hot_mix_block(int slot) {
     }
 }
 
+// C == 2 (stereo source into a stereo mixer): a row carries two recurrence chains, so a CTA owns at most 16 rows
+// and the recurrence warp's lane is (row, channel) = (lane / 2, lane % 2); the eight stage-C blocks move to the
+// row-less slots 16..23.
+template <int C>
 __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(16) FusedRow s_rows[MAX_G];
@@ -812,22 +821,23 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
     // (lane * from) divmod to for the rows this warp owns (first row in registers, wrapped rows recomputed)
     uint32_t lane_q0 = 0, lane_r0 = 0;
     if (slot >= 0 && (uint32_t)slot < G) {
-        const uint32_t p = lane * s_rows[slot].uni.from;
+        const uint32_t p = (lane / C) * s_rows[slot].uni.from;
         lane_q0 = p / s_rows[slot].uni.to;
         lane_r0 = p - lane_q0 * s_rows[slot].uni.to;
     }
 
-    const bool chain_on = is_rec && lane < G;
+    const uint32_t rec_row = lane / C, rec_ch = lane % C;
+    const bool chain_on = is_rec && rec_row < G;
     float y1 = 0.f, y2 = 0.f, a1 = 0.f, a2 = 0.f;
-    if (chain_on) a1 = s_rows[lane].a1, a2 = s_rows[lane].a2;
+    if (chain_on) a1 = s_rows[rec_row].a1, a2 = s_rows[rec_row].a2;
     float xtail0 = 0.f, xtail1 = 0.f;   // lanes 30/31: x at the last two positions of the previous tile, per owned row
 
     // prologue: the loader warp (lane = row) fetches the windows of tiles 0 and 1
     if (is_loader && lane < G) {
         for (uint32_t kt = 0; kt < 2 && kt < n_tiles; kt++) {
             HotTile& ht = s_ht[kt % NHT][lane];
-            hot_tile_setup(s_rows[lane], m_begin + (uint64_t)kt * TT, kt ? &s_ht[(kt - 1) % NHT][lane] : nullptr, ht);
-            hot_issue_window(s_rows[lane], ht, wins + (kt % NWIN) * win_sz + lane * WSTRIDE, &s_full[kt % NWIN]);
+            hot_tile_setup<C>(s_rows[lane], m_begin + (uint64_t)kt * TT, kt ? &s_ht[(kt - 1) % NHT][lane] : nullptr, ht);
+            hot_issue_window<C>(s_rows[lane], ht, wins + (kt % NWIN) * win_sz + lane * WSTRIDE, &s_full[kt % NWIN]);
         }
     }
     __syncthreads();
@@ -838,40 +848,67 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
             const uint32_t kt = it + 2;
             if (lane < G && kt < n_tiles) {
                 HotTile& ht = s_ht[kt % NHT][lane];
-                hot_tile_setup(s_rows[lane], m_begin + (uint64_t)kt * TT, &s_ht[(kt - 1) % NHT][lane], ht);
-                hot_issue_window(s_rows[lane], ht, wins + (kt % NWIN) * win_sz + lane * WSTRIDE, &s_full[kt % NWIN]);
+                hot_tile_setup<C>(s_rows[lane], m_begin + (uint64_t)kt * TT, &s_ht[(kt - 1) % NHT][lane], ht);
+                hot_issue_window<C>(s_rows[lane], ht, wins + (kt % NWIN) * win_sz + lane * WSTRIDE, &s_full[kt % NWIN]);
             }
         } else if (is_rec) {
-            // ---- stage B on tile it-1 (lane = row): nothing but y = (t - a1*y1) - a2*y2 ----
+            // ---- stage B on tile it-1 (lane = chain): nothing but y = (t - a1*y1) - a2*y2 ----
             if (it >= 1 && it <= n_tiles && chain_on) {
                 const uint32_t kt = it - 1;
-                float* row = tiles + (kt % NBUF) * tile_sz + lane * ROW_STRIDE + HOT_PAD;
-                const uint2 act = *reinterpret_cast<const uint2*>(&s_ht[kt % NHT][lane].lo);
+                float* row = tiles + (kt % NBUF) * tile_sz + rec_row * ROW_STRIDE + HOT_PAD;
+                const uint2 act = *reinterpret_cast<const uint2*>(&s_ht[kt % NHT][rec_row].lo);
                 uint32_t t = act.x;
                 const uint32_t hi_t = act.y;
-                for (; t < hi_t && (t & 3); t++) {
-                    const float y = biquad_fb(a1, a2, row[t], y1, y2);
-                    y2 = y1, y1 = y;
-                    row[t] = y;
-                }
-                float4 nx = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (t + 4 <= hi_t) nx = *reinterpret_cast<const float4*>(row + t);
+                if constexpr (C == 1) {
+                    for (; t < hi_t && (t & 3); t++) {
+                        const float y = biquad_fb(a1, a2, row[t], y1, y2);
+                        y2 = y1, y1 = y;
+                        row[t] = y;
+                    }
+                    float4 nx = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (t + 4 <= hi_t) nx = *reinterpret_cast<const float4*>(row + t);
 #pragma unroll 2
-                for (; t + 4 <= hi_t; t += 4) {
-                    const float4 f = nx;
-                    if (t + 8 <= hi_t) nx = *reinterpret_cast<const float4*>(row + t + 4);
-                    float4 yv;
-                    yv.x = biquad_fb(a1, a2, f.x, y1, y2);
-                    yv.y = biquad_fb(a1, a2, f.y, yv.x, y1);
-                    yv.z = biquad_fb(a1, a2, f.z, yv.y, yv.x);
-                    yv.w = biquad_fb(a1, a2, f.w, yv.z, yv.y);
-                    y2 = yv.z, y1 = yv.w;
-                    *reinterpret_cast<float4*>(row + t) = yv;
-                }
-                for (; t < hi_t; t++) {
-                    const float y = biquad_fb(a1, a2, row[t], y1, y2);
-                    y2 = y1, y1 = y;
-                    row[t] = y;
+                    for (; t + 4 <= hi_t; t += 4) {
+                        const float4 f = nx;
+                        if (t + 8 <= hi_t) nx = *reinterpret_cast<const float4*>(row + t + 4);
+                        float4 yv;
+                        yv.x = biquad_fb(a1, a2, f.x, y1, y2);
+                        yv.y = biquad_fb(a1, a2, f.y, yv.x, y1);
+                        yv.z = biquad_fb(a1, a2, f.z, yv.y, yv.x);
+                        yv.w = biquad_fb(a1, a2, f.w, yv.z, yv.y);
+                        y2 = yv.z, y1 = yv.w;
+                        *reinterpret_cast<float4*>(row + t) = yv;
+                    }
+                    for (; t < hi_t; t++) {
+                        const float y = biquad_fb(a1, a2, row[t], y1, y2);
+                        y2 = y1, y1 = y;
+                        row[t] = y;
+                    }
+                } else {
+                    // interleaved frames: lo / hi are even, this lane owns positions t + rec_ch
+                    float* rc = row + rec_ch;
+                    if (t < hi_t && (t & 3)) {
+                        const float y = biquad_fb(a1, a2, rc[t], y1, y2);
+                        y2 = y1, y1 = y;
+                        rc[t] = y;
+                        t += 2;
+                    }
+                    float4 nx = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (t + 4 <= hi_t) nx = *reinterpret_cast<const float4*>(row + t);
+#pragma unroll 2
+                    for (; t + 4 <= hi_t; t += 4) {
+                        const float4 f = nx;
+                        if (t + 8 <= hi_t) nx = *reinterpret_cast<const float4*>(row + t + 4);
+                        const float ya = biquad_fb(a1, a2, rec_ch ? f.y : f.x, y1, y2);
+                        const float yb = biquad_fb(a1, a2, rec_ch ? f.w : f.z, ya, y1);
+                        y2 = ya, y1 = yb;
+                        rc[t] = ya, rc[t + 2] = yb;
+                    }
+                    if (t < hi_t) {
+                        const float y = biquad_fb(a1, a2, rc[t], y1, y2);
+                        y2 = y1, y1 = y;
+                        rc[t] = y;
+                    }
                 }
             }
         } else if (slot >= 0) {
@@ -888,18 +925,18 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
                     if (ht.lo >= ht.hi) continue;
                     uint32_t lq = lane_q0, lr = lane_r0;
                     if (g != (uint32_t)slot) {
-                        const uint32_t p = lane * s_rows[g].uni.from;
+                        const uint32_t p = (lane / C) * s_rows[g].uni.from;
                         lq = p / s_rows[g].uni.to;
                         lr = p - lq * s_rows[g].uni.to;
                     }
                     float& xt = (g == (uint32_t)slot) ? xtail0 : xtail1;
                     float* row = tile + g * ROW_STRIDE + HOT_PAD;
-                    if (nogain) hot_stage_a<true>(s_rows[g], ht, a.n_pre, a.n_mid, lane, lq, lr, xt, win + g * WSTRIDE, row);
-                    else hot_stage_a<false>(s_rows[g], ht, a.n_pre, a.n_mid, lane, lq, lr, xt, win + g * WSTRIDE, row);
+                    if (nogain) hot_stage_a<true, C>(s_rows[g], ht, a.n_pre, a.n_mid, lane, lq, lr, xt, win + g * WSTRIDE, row);
+                    else hot_stage_a<false, C>(s_rows[g], ht, a.n_pre, a.n_mid, lane, lq, lr, xt, win + g * WSTRIDE, row);
                 }
             }
             // ---- stage C on tile it-2: eight warps take 32 positions each ----
-            const int mix_block = hot_mix_block(slot);
+            const int mix_block = C == 1 ? hot_mix_block(slot) : slot - 16;
             if (it >= 2 && mix_block >= 0) {
                 const uint32_t kt = it - 2;
                 const uint64_t m0 = m_begin + (uint64_t)kt * TT;
@@ -1048,15 +1085,29 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     auto plan = new rb_fused_plan;
     plan->all_f32 = true;
     for (size_t i = 0; i < n_streams; i++) plan->all_f32 = plan->all_f32 && streams[i].fmt == RB_FMT_F32;
-    plan->hot = has_b && plan->all_f32 && mixer_channels == 1;
+    const uint32_t C = mixer_channels;
+    plan->hot = has_b && plan->all_f32 && (C == 1 || C == 2);
     for (size_t i = 0; i < n_streams && plan->hot; i++) {
-        const FusedRow& r = rows[i];
-        const bool window_fits = (uint64_t)TT * r.uni.from / r.uni.to + 8 <= (uint64_t)WSTRIDE;
-        plan->hot = r.c_in == 1 && (r.mode == ROW_DIRECT || r.mode == ROW_PASS || (r.mode == ROW_LERP && window_fits));
+        FusedRow& r = rows[i];
+        // the HOT kernel counts the index state in frames: C interleaved channels share one (i0, r0)
+        const uint64_t qT = (uint64_t)(TT / C) * r.uni.from / r.uni.to;
+        const bool window_fits = 3 + (qT + 3) * C <= (uint64_t)WSTRIDE;
+        const bool whole_frames = r.n_in % C == 0 && r.out_len % C == 0 && r.mix_start % C == 0;
+        plan->hot = r.c_in == C && whole_frames &&
+                    (r.mode == ROW_DIRECT || r.mode == ROW_PASS || (r.mode == ROW_LERP && window_fits));
+    }
+    if (plan->hot && C == 2) {
+        for (size_t i = 0; i < n_streams; i++) {
+            FusedRow& r = rows[i];
+            r.q32 = (uint32_t)((uint64_t)(32 / C) * r.uni.from / r.uni.to);
+            r.r32 = (uint32_t)((uint64_t)(32 / C) * r.uni.from % r.uni.to);
+            r.qT = (uint32_t)((uint64_t)(TT / C) * r.uni.from / r.uni.to);
+            r.rT = (uint32_t)((uint64_t)(TT / C) * r.uni.from % r.uni.to);
+        }
     }
     // rows per CTA: one balanced wave over the SMs (k CTAs per SM when the batch is large)
     uint32_t S = (uint32_t)n_streams;
-    uint32_t max_g = plan->hot ? HOT_MAX_ROWS : MAX_G;
+    uint32_t max_g = plan->hot ? (C == 2 ? HOT_MAX_ROWS_STEREO : HOT_MAX_ROWS) : MAX_G;
     if (has_b) {
         while (max_g > 1 && max_g * mixer_channels > 128) max_g--;   // at most 4 recurrence warps
     }
@@ -1084,7 +1135,8 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused_biquad<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
         plan->hot_smem = ((size_t)NBUF * ROW_STRIDE + (size_t)NWIN * WSTRIDE) * G * sizeof(float);
         if (e == cudaSuccess && plan->hot)
-            e = cudaFuncSetAttribute(k_fused_hot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->hot_smem);
+            e = C == 2 ? cudaFuncSetAttribute(k_fused_hot<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->hot_smem)
+                       : cudaFuncSetAttribute(k_fused_hot<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->hot_smem);
     }
     if (e != cudaSuccess) {
         rb_fused_destroy(plan);
@@ -1109,7 +1161,8 @@ cudaError_t rb_fused_run(rb_fused_plan* p, cudaStream_t st) {
     if (a.has_biquad) {
         const uint32_t threads = 512;
         const bool mono = a.c_mix == 1;
-        if (p->hot) k_fused_hot<<<p->n_ctas, 1024, p->hot_smem, st>>>(a);
+        if (p->hot && mono) k_fused_hot<1><<<p->n_ctas, 1024, p->hot_smem, st>>>(a);
+        else if (p->hot) k_fused_hot<2><<<p->n_ctas, 1024, p->hot_smem, st>>>(a);
         else if (p->all_f32 && mono) k_fused_biquad<true, 1><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
         else if (p->all_f32) k_fused_biquad<true, 0><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
         else if (mono) k_fused_biquad<false, 1><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);

@@ -394,6 +394,10 @@ FUSED_CASES = [
     (64, 1, 48000, (1, 44100), "lp", False, True),      # mild downsampling: HOT kernel window 280 floats
     (180, 1, 48000, (1, 40000), "hp", False, False),
     (30, 1, 96000, (1, 48000), "lp", False, True),      # 2:1 -> generic fused kernel
+    (300, 2, 44100, (2, 48000), "lp", False, True),     # stereo HOT kernel, several rows per CTA
+    (40, 2, 48000, (2, 48000), "hp", False, True),      # stereo, same rate
+    (100, 2, 48000, (2, 44100), "lp", False, False),    # stereo, mild downsampling
+    (2400, 2, 44100, (2, 48000), "hp", False, True),    # stereo, 16 rows per CTA and two CTAs per SM
 ]
 
 
@@ -415,6 +419,27 @@ def test_fused_shapes_match_oracle(ctx, case):
         assert_bit_exact(got, want, f"fused case {case}")
     else:
         assert_close_peak(got, want, 1e-5, f"fused case {case}")
+
+
+def test_fused_ragged_batch_stereo(ctx):
+    """Stereo HOT kernel: empty, one-frame, tile-boundary and long streams, S above and below one row per CTA."""
+    rng = np.random.default_rng(4343)
+    for lens in ([0, 2, 4, 6, 510, 512, 514, 1022, 1026, 2000, 8820] * 12, [0, 2, 4, 512, 2002] * 8):
+        srcs, starts = [], []
+        for i, n in enumerate(lens):
+            src = rb.UniformSourceIterator(rb.TestSource(noise(n, 7100 + i), 2, 44100), 2, 48000).high_pass(90 + i)
+            srcs.append(src.amplify(0.7))
+            starts.append(0 if i % 3 else int(rng.integers(0, 900)))
+        starts = sorted(starts)
+        want = oracle.mixer([to_oracle(s, st) for s, st in zip(srcs, starts)], 2, 48000)
+        with rb.Batch(srcs, 2, 48000, mix_starts=starts, ctx=ctx) as b:
+            b.upload_all()
+            got = b.render_mix()
+            assert b.launches_per_render <= 2
+        if len(lens) <= 148:
+            assert_bit_exact(got, want, "ragged stereo fused batch")
+        else:
+            assert_close_peak(got, want, 1e-5, "ragged stereo fused batch")
 
 
 def test_fused_ragged_batch(ctx):

@@ -61,7 +61,7 @@ def main():
         S, frames = 2048, 44100 * 2
         srcs = [rb.UniformSourceIterator(rb.TestSource(z(2 * frames), 2, 44100), 2, 48000).low_pass(200).amplify(1.2)
                 for _ in range(S)]
-        time_batch("cfg3 shape, 2048 STEREO streams x 2s (generic fused kernel)", srcs, (2, 48000))
+        time_batch("cfg3 shape, 2048 STEREO streams x 2s (stereo HOT kernel)", srcs, (2, 48000))
         srcs = [rb.UniformSourceIterator(rb.TestSource(z(44100 * 2), 1, 44100), 1, 48000).low_pass(200).amplify(1.2)
                 for _ in range(4096)]
         time_batch("cfg3 4096 mono x 2s, general path (RB_NO_FUSION)", srcs, (1, 48000), flags=rb.capi.RB_NO_FUSION, steps=3)
