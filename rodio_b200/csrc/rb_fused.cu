@@ -582,6 +582,8 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// CTA-wide barrier reached from the role-specialised loops (every warp executes the same number of them)
+__device__ __forceinline__ void cta_bar() { asm volatile("bar.sync 0;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -645,89 +647,113 @@ __device__ __forceinline__ void hot_issue_window(const FusedRow& r, const HotTil
 }
 
 // Stage A for one (row, tile) out of the shared-memory window.
-// (lane_q, lane_r) = divmod(lane * from, to), computed once per kernel by the row's warp.
-// The exact-division fast path is used optimistically: a per-lane flag collects "operand outside the
-// guarded range" and ONE warp vote per row-tile decides whether the tile is redone with IEEE divisions.
-//
-// The feed-forward half of the biquad, t[n] = (b0*x[n] + b1*x[n-1]) + b2*x[n-2], is computed HERE (same
-// three roundings as the reference, it does not depend on y): x goes to the tile row, the warp syncs,
-// every lane reads its two left neighbours, the warp syncs again and overwrites x with t in place.
-// A single warp issues roughly one instruction every two cycles, so the recurrence warp can only stay on
-// its 12-cycle dependent chain if it executes nothing but  y = (t - a1*y1) - a2*y2.
-// `row` points at tile position 0; row[-2], row[-1] are pad slots that receive the previous tile's last two
-// x values (`xtail`, kept in registers of lanes 30/31 across tiles) or zeros at the start of the stream.
-// With C interleaved channels lane l works on channel l % C of frame l / C + (32 / C) * u: the tile position is
-// still lane + 32 * u, taps sit C floats apart, the left neighbours of the feed-forward C and 2C positions back.
+// Full interior tiles use a BLOCKED layout: lane l owns the P = TT/32 consecutive positions P*l .. P*l+P-1
+// (P/C frames), so that
+//   * the index state advances by ONE frame per step -- kept as a float numerator (exact, < 2^24) and a word
+//     offset into the window: FADD, FSETP, two predicated adds per frame;
+//   * the feed-forward half of the biquad, t[n] = (b0*x[n] + b1*x[n-1]) + b2*x[n-2] (same three roundings as the
+//     reference; it does not depend on y), finds its left neighbours in the lane's own registers -- only the
+//     first 2C positions take them from lane l-1 by shuffle, and lane 0 from `xtail`, the previous tile's last 2C
+//     x values (replicated in every lane);
+//   * t leaves with two 16-byte stores.  x itself never touches shared memory.
+// (lane_q, lane_r) = divmod(lane * (P/C) * from, to), computed once per kernel by the row's warp; r.q32 / r.r32 =
+// divmod(from, to), the per-frame step.
+// The exact-division fast path is used optimistically: a per-lane flag collects "operand outside the guarded
+// range" and ONE warp vote per row-tile decides whether the tile is redone with IEEE divisions.
+// A single warp issues roughly one instruction every two cycles, so the recurrence warp can only stay on its
+// 12-cycle dependent chain if it executes nothing but  y = (t - a1*y1) - a2*y2  -- hence t, not x, in the row.
+// Partial tiles (stream start / end, same-rate rows, the IEEE redo) take the strided path below: lane l works on
+// positions l + 32u, x goes through the row in shared memory, `row[-2C..-1]` are pad slots for the tail.
 template <bool NOGAIN, int C>
 __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht, uint32_t n_pre, uint32_t n_mid,
-                                            uint32_t lane, uint32_t lane_q, uint32_t lane_r, float& xtail,
+                                            uint32_t lane, uint32_t lane_q, uint32_t lane_r, float (&xtail)[2 * C],
                                             const float* __restrict__ win, float* __restrict__ row) {
-    constexpr int U = TT / 32, H = 4;
+    constexpr int U = TT / 32, P = TT / 32, F = P / C;
     const uint32_t n = ht.hi - ht.lo;
-    const uint32_t to = r.uni.to, q32 = r.q32, r32 = r.r32;
+    const uint32_t to = r.uni.to;
     const float den_f = r.den_f, rcp_den = r.rcp_den;
     const float b0 = r.b0, b1 = r.b1, b2 = r.b2;
     const uint64_t remain = r.uni.tail.L - 1 - ht.i0;
     const uint32_t lim = remain > 0x7fffffffull ? 0x7fffffffu : (uint32_t)remain;   // interpolate iff di < lim
-    const float* __restrict__ w = win + ht.woff + (lane % C);   // this lane's channel
     const float* pre = r.pre;
     const float* mid = r.mid;
-    uint32_t num = ht.r0 + lane_r;
-    uint32_t di = lane_q;
-    if (num >= to) num -= to, di += 1;
-    float* __restrict__ out = row + ht.lo + lane;
-    // x[n-2], x[n-1] of the first active position: zeros when the stream starts in this tile (ht.lo > 0 or the
-    // very first tile), else the previous tile's tail
-    if (lane >= 32 - 2 * C) row[(int)ht.lo - 32 + (int)lane] = (ht.i0 == 0 && ht.r0 == 0) ? 0.0f : xtail;
-    // warp-uniform: the vote below needs the whole warp on the same side of this branch
     const bool pass = r.mode != ROW_LERP;   // same-rate rows: x[n] = in[n], no interpolation (from = to = 1 in the row)
-    const bool interior = !pass && __all_sync(0xffffffffu, n == (uint32_t)TT && (di + (uint32_t)(U - 1) * (q32 + 1) + 1) < lim);
     bool done = false;
-    if (interior) {
-        const uint32_t di0 = di, num0 = num;
-        bool bad = false;
-        float xv[U];
+    {
+        uint32_t num = ht.r0 + lane_r;
+        uint32_t di = lane_q;
+        if (num >= to) num -= to, di += 1;
+        // warp-uniform: the votes below need the whole warp on the same side of this branch
+        const bool interior = !pass && __all_sync(0xffffffffu, n == (uint32_t)TT && (di + (uint32_t)(F - 1) * (r.q32 + 1) + 1) < lim);
+        if (interior) {
+            const float* __restrict__ w = win + ht.woff + di * C;
+            const uint32_t step_w = r.q32 * C;            // whole frames per output frame, in words
+            const float r1f = __uint2float_rn(r.r32);
+            float nf = __uint2float_rn(num);
+            bool bad = false;
+            float xv[P];
 #pragma unroll
-        for (int h = 0; h < U; h += H) {
-            uint32_t dis[H];
-            float nf[H], x0[H], x1[H];
+            for (int f = 0; f < F; f++) {
+                float x0[C], x1[C];
 #pragma unroll
-            for (int u = 0; u < H; u++) {
-                dis[u] = di, nf[u] = __uint2float_rn(num);
-                num += r32, di += q32;
-                if (num >= to) num -= to, di += 1;
+                for (int c = 0; c < C; c++) x0[c] = w[c], x1[c] = w[C + c];
+                const float nfc = nf;
+                nf = add(nf, r1f);
+                w += step_w;
+                if (nf >= den_f) nf = sub(nf, den_f), w += C;
+#pragma unroll
+                for (int c = 0; c < C; c++) {
+                    const float a0 = gains<NOGAIN>(x0[c], pre, n_pre), a1 = gains<NOGAIN>(x1[c], pre, n_pre);
+                    const float m = mul(sub(a1, a0), nfc);
+                    const float q0 = mul(m, rcp_den);
+                    const float q = __fmaf_rn(__fmaf_rn(-q0, den_f, m), rcp_den, q0);
+                    // guarded range as one unsigned compare on the exponent field: 2^-100 <= |m| < 2^100; m == 0
+                    // (also outside) yields q = m = +-0 exactly as the division would
+                    const uint32_t e = __float_as_uint(m) & 0x7fffffffu;
+                    const bool in_range = e - 0x0d800000u < 0x64000000u;
+                    bad |= !in_range && e != 0u;
+                    xv[f * C + c] = gains<NOGAIN>(add(a0, in_range ? q : m), mid, n_mid);
+                }
             }
+            if (!__any_sync(0xffffffffu, bad)) {
+                float pv[2 * C];
 #pragma unroll
-            for (int u = 0; u < H; u++) x0[u] = w[dis[u] * C], x1[u] = w[(dis[u] + 1) * C];
+                for (int j = 0; j < 2 * C; j++) {
+                    const float up = __shfl_up_sync(0xffffffffu, xv[P - 2 * C + j], 1);
+                    pv[j] = lane == 0 ? xtail[j] : up;
+                }
 #pragma unroll
-            for (int u = 0; u < H; u++) {
-                const float a0 = gains<NOGAIN>(x0[u], pre, n_pre), a1 = gains<NOGAIN>(x1[u], pre, n_pre);
-                const float m = mul(sub(a1, a0), nf[u]);
-                const float q0 = mul(m, rcp_den);
-                float q = __fmaf_rn(__fmaf_rn(-q0, den_f, m), rcp_den, q0);
-                q = (m == 0.0f) ? m : q;
-                // guarded range as one unsigned compare on the exponent field: 2^-100 <= |m| < 2^100 (or m == 0)
-                bad |= ((__float_as_uint(m) & 0x7fffffffu) - 0x0d800000u >= 0x64000000u) && (m != 0.0f);
-                xv[h + u] = gains<NOGAIN>(add(a0, q), mid, n_mid);
-                out[32 * (h + u)] = xv[h + u];
+                for (int j = 0; j < 2 * C; j++) xtail[j] = __shfl_sync(0xffffffffu, xv[P - 2 * C + j], 31);
+                float tv[P];
+#pragma unroll
+                for (int u = 0; u < P; u++) {
+                    const float xm1 = u >= C ? xv[u >= C ? u - C : 0] : pv[C + u < 2 * C ? C + u : 0];
+                    const float xm2 = u >= 2 * C ? xv[u >= 2 * C ? u - 2 * C : 0] : pv[u < 2 * C ? u : 0];
+                    tv[u] = biquad_ff(b0, b1, b2, xv[u], xm1, xm2);
+                }
+                float4* o = reinterpret_cast<float4*>(row + P * lane);
+#pragma unroll
+                for (int u = 0; u < P; u += 4) o[u / 4] = make_float4(tv[u], tv[u + 1], tv[u + 2], tv[u + 3]);
+                done = true;
             }
-        }
-        if (!__any_sync(0xffffffffu, bad)) {
-            __syncwarp();
-            float xm1[U], xm2[U];
-#pragma unroll
-            for (int u = 0; u < U; u++) xm1[u] = out[32 * u - C], xm2[u] = out[32 * u - 2 * C];
-            __syncwarp();
-#pragma unroll
-            for (int u = 0; u < U; u++) out[32 * u] = biquad_ff(b0, b1, b2, xv[u], xm1[u], xm2[u]);
-            if (lane >= 32 - 2 * C) xtail = xv[U - 1];     // the last two frames of the tile
-            done = true;
-        } else {
-            di = di0, num = num0;   // some operand was denormal / huge / NaN: redo this row-tile with IEEE divisions
+            // else: some operand was denormal / huge / NaN: redo this row-tile with IEEE divisions
         }
     }
     if (done) return;
-    // general path: partial tiles, end of stream, or the rare IEEE-division redo
+    // strided path: partial tiles, end of stream, same-rate rows, or the rare IEEE-division redo
+    const uint32_t fs = (32u / C) * r.uni.from;            // frames step of 32 positions
+    const uint32_t q32 = fs / to, r32 = fs - q32 * to;
+    const uint32_t pl = (lane / C) * r.uni.from;
+    uint32_t di = pl / to;
+    uint32_t num = ht.r0 + (pl - di * to);
+    if (num >= to) num -= to, di += 1;
+    const float* __restrict__ w = win + ht.woff + (lane % C);   // this lane's channel
+    float* __restrict__ out = row + ht.lo + lane;
+    // x of the 2C positions before the first active one: zeros when the stream starts in this tile, else the tail
+    const bool first = ht.i0 == 0 && ht.r0 == 0;
+#pragma unroll
+    for (int j = 0; j < 2 * C; j++)
+        if (lane == (uint32_t)j) row[(int)ht.lo - 2 * C + j] = first ? 0.0f : xtail[j];
 #pragma unroll 1
     for (int u = 0; u < U; u++) {
         if (lane + 32u * (uint32_t)u < n) {
@@ -745,9 +771,9 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
         xv[u] = xm1[u] = xm2[u] = 0.0f;
         if (lane + 32u * (uint32_t)u < n) xv[u] = out[32 * u], xm1[u] = out[32 * u - C], xm2[u] = out[32 * u - 2 * C];
     }
-    // new tail = x at the last two active positions (n == 1: shift the old tail)
-    const float t_tail = row[(int)ht.hi - 32 + (int)lane];   // lanes >= 32-2C: positions hi-2C .. hi-1 (>= lo-C: inside the padded row)
-    if (lane >= 32 - 2 * C) xtail = t_tail;
+    // new tail = x at the last 2C active positions (a one-frame tile shifts the old tail in from the pad slots)
+#pragma unroll
+    for (int j = 0; j < 2 * C; j++) xtail[j] = row[(int)ht.hi - 2 * C + j];
     __syncwarp();
 #pragma unroll
     for (int u = 0; u < U; u++)
@@ -818,20 +844,6 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
     const bool is_rec = warp == HOT_REC_WARP, is_loader = warp == HOT_LOAD_WARP;
     const int slot = hot_row_slot(warp);
     const bool nogain = a.n_pre == 0 && a.n_mid == 0;
-    // (lane * from) divmod to for the rows this warp owns (first row in registers, wrapped rows recomputed)
-    uint32_t lane_q0 = 0, lane_r0 = 0;
-    if (slot >= 0 && (uint32_t)slot < G) {
-        const uint32_t p = (lane / C) * s_rows[slot].uni.from;
-        lane_q0 = p / s_rows[slot].uni.to;
-        lane_r0 = p - lane_q0 * s_rows[slot].uni.to;
-    }
-
-    const uint32_t rec_row = lane / C, rec_ch = lane % C;
-    const bool chain_on = is_rec && rec_row < G;
-    float y1 = 0.f, y2 = 0.f, a1 = 0.f, a2 = 0.f;
-    if (chain_on) a1 = s_rows[rec_row].a1, a2 = s_rows[rec_row].a2;
-    float xtail0 = 0.f, xtail1 = 0.f;   // lanes 30/31: x at the last two positions of the previous tile, per owned row
-
     // prologue: the loader warp (lane = row) fetches the windows of tiles 0 and 1
     if (is_loader && lane < G) {
         for (uint32_t kt = 0; kt < 2 && kt < n_tiles; kt++) {
@@ -842,21 +854,38 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
     }
     __syncthreads();
 
-    for (uint32_t it = 0; it < n_tiles + 2; it++) {
-        if (is_loader) {
-            // ---- stage L on tile it+2: lane g plans and fetches row g's window ----
+    // One loop per role, n_tiles + 2 iterations each, joined by the CTA barrier at the end of every iteration.
+    // Ring positions (tile % NBUF, % NWIN, % NHT) are carried incrementally: the role bodies are short enough
+    // that a handful of modulo / dispatch instructions per warp and iteration showed up as a third of all issue slots.
+    const uint32_t n_iter = n_tiles + 2;
+    if (is_loader) {
+        // ---- stage L on tile it+2: lane g plans and fetches row g's window ----
+        uint32_t kw = 2 % NWIN, kh = 2 % NHT, khp = 1;
+        for (uint32_t it = 0; it < n_iter; it++) {
             const uint32_t kt = it + 2;
             if (lane < G && kt < n_tiles) {
-                HotTile& ht = s_ht[kt % NHT][lane];
-                hot_tile_setup<C>(s_rows[lane], m_begin + (uint64_t)kt * TT, &s_ht[(kt - 1) % NHT][lane], ht);
-                hot_issue_window<C>(s_rows[lane], ht, wins + (kt % NWIN) * win_sz + lane * WSTRIDE, &s_full[kt % NWIN]);
+                HotTile& ht = s_ht[kh][lane];
+                hot_tile_setup<C>(s_rows[lane], m_begin + (uint64_t)kt * TT, &s_ht[khp][lane], ht);
+                hot_issue_window<C>(s_rows[lane], ht, wins + kw * win_sz + lane * WSTRIDE, &s_full[kw]);
             }
-        } else if (is_rec) {
-            // ---- stage B on tile it-1 (lane = chain): nothing but y = (t - a1*y1) - a2*y2 ----
-            if (it >= 1 && it <= n_tiles && chain_on) {
-                const uint32_t kt = it - 1;
-                float* row = tiles + (kt % NBUF) * tile_sz + rec_row * ROW_STRIDE + HOT_PAD;
-                const uint2 act = *reinterpret_cast<const uint2*>(&s_ht[kt % NHT][rec_row].lo);
+            khp = kh;
+            kh = kh + 1 == NHT ? 0 : kh + 1;
+            kw = kw + 1 == NWIN ? 0 : kw + 1;
+            cta_bar();
+        }
+    } else if (is_rec) {
+        // ---- stage B on tile it-1 (lane = chain): nothing but y = (t - a1*y1) - a2*y2 ----
+        const uint32_t rec_row = lane / C, rec_ch = lane % C;
+        const bool chain_on = rec_row < G;
+        float y1 = 0.f, y2 = 0.f, a1 = 0.f, a2 = 0.f;
+        if (chain_on) a1 = s_rows[rec_row].a1, a2 = s_rows[rec_row].a2;
+        float* rbase = tiles + rec_row * ROW_STRIDE + HOT_PAD;
+        uint32_t kb = 0, kh = 0;
+        cta_bar();   // it == 0: nothing to do yet
+        for (uint32_t it = 1; it < n_iter; it++) {
+            if (it <= n_tiles && chain_on) {
+                float* row = rbase + kb * tile_sz;
+                const uint2 act = *reinterpret_cast<const uint2*>(&s_ht[kh][rec_row].lo);
                 uint32_t t = act.x;
                 const uint32_t hi_t = act.y;
                 if constexpr (C == 1) {
@@ -865,19 +894,40 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
                         y2 = y1, y1 = y;
                         row[t] = y;
                     }
-                    float4 nx = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (t + 4 <= hi_t) nx = *reinterpret_cast<const float4*>(row + t);
-#pragma unroll 2
-                    for (; t + 4 <= hi_t; t += 4) {
-                        const float4 f = nx;
-                        if (t + 8 <= hi_t) nx = *reinterpret_cast<const float4*>(row + t + 4);
-                        float4 yv;
-                        yv.x = biquad_fb(a1, a2, f.x, y1, y2);
-                        yv.y = biquad_fb(a1, a2, f.y, yv.x, y1);
-                        yv.z = biquad_fb(a1, a2, f.z, yv.y, yv.x);
-                        yv.w = biquad_fb(a1, a2, f.w, yv.z, yv.y);
-                        y2 = yv.z, y1 = yv.w;
-                        *reinterpret_cast<float4*>(row + t) = yv;
+                    float4* p4 = reinterpret_cast<float4*>(row + t);
+                    const uint32_t n4 = hi_t > t ? (hi_t - t) >> 2 : 0;
+                    float4* const e4 = p4 + (n4 & ~1u);
+                    float4 fa = make_float4(0.f, 0.f, 0.f, 0.f), fb;
+                    if (n4) fa = p4[0];
+                    // two groups of four per trip, the next group's load issued before the dependent chain
+                    while (p4 != e4) {
+                        fb = p4[1];
+                        float4 ya;
+                        ya.x = biquad_fb(a1, a2, fa.x, y1, y2);
+                        ya.y = biquad_fb(a1, a2, fa.y, ya.x, y1);
+                        ya.z = biquad_fb(a1, a2, fa.z, ya.y, ya.x);
+                        ya.w = biquad_fb(a1, a2, fa.w, ya.z, ya.y);
+                        p4[0] = ya;
+                        fa = p4[2];   // at most 16 bytes past the active span: still inside the row (tile ring + windows follow)
+                        float4 yb;
+                        yb.x = biquad_fb(a1, a2, fb.x, ya.w, ya.z);
+                        yb.y = biquad_fb(a1, a2, fb.y, yb.x, ya.w);
+                        yb.z = biquad_fb(a1, a2, fb.z, yb.y, yb.x);
+                        yb.w = biquad_fb(a1, a2, fb.w, yb.z, yb.y);
+                        p4[1] = yb;
+                        y2 = yb.z, y1 = yb.w;
+                        p4 += 2;
+                    }
+                    t += (n4 & ~1u) << 2;
+                    if (n4 & 1u) {
+                        float4 ya;
+                        ya.x = biquad_fb(a1, a2, fa.x, y1, y2);
+                        ya.y = biquad_fb(a1, a2, fa.y, ya.x, y1);
+                        ya.z = biquad_fb(a1, a2, fa.z, ya.y, ya.x);
+                        ya.w = biquad_fb(a1, a2, fa.w, ya.z, ya.y);
+                        p4[0] = ya;
+                        y2 = ya.z, y1 = ya.w;
+                        t += 4;
                     }
                     for (; t < hi_t; t++) {
                         const float y = biquad_fb(a1, a2, row[t], y1, y2);
@@ -910,44 +960,79 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
                         rc[t] = y;
                     }
                 }
+                kb = kb + 1 == NBUF ? 0 : kb + 1;
+                kh = kh + 1 == NHT ? 0 : kh + 1;
             }
-        } else if (slot >= 0) {
-            // ---- stage A on tile it ----
-            if (it < n_tiles) {
-                mbar_wait(&s_full[it % NWIN], (it / NWIN) & 1u);
-                float* tile = tiles + (it % NBUF) * tile_sz;
-                const float* win = wins + (it % NWIN) * win_sz;
-                for (int pass = 0; pass < 2; pass++) {
-                    const int gi = pass == 0 ? slot : hot_second_row(slot);
-                    if (gi < 0 || (uint32_t)gi >= G) continue;
-                    const uint32_t g = (uint32_t)gi;
-                    const HotTile& ht = s_ht[it % NHT][g];
-                    if (ht.lo >= ht.hi) continue;
-                    uint32_t lq = lane_q0, lr = lane_r0;
-                    if (g != (uint32_t)slot) {
-                        const uint32_t p = (lane / C) * s_rows[g].uni.from;
-                        lq = p / s_rows[g].uni.to;
-                        lr = p - lq * s_rows[g].uni.to;
-                    }
-                    float& xt = (g == (uint32_t)slot) ? xtail0 : xtail1;
-                    float* row = tile + g * ROW_STRIDE + HOT_PAD;
-                    if (nogain) hot_stage_a<true, C>(s_rows[g], ht, a.n_pre, a.n_mid, lane, lq, lr, xt, win + g * WSTRIDE, row);
-                    else hot_stage_a<false, C>(s_rows[g], ht, a.n_pre, a.n_mid, lane, lq, lr, xt, win + g * WSTRIDE, row);
-                }
-            }
-            // ---- stage C on tile it-2: eight warps take 32 positions each ----
-            const int mix_block = C == 1 ? hot_mix_block(slot) : slot - 16;
-            if (it >= 2 && mix_block >= 0) {
-                const uint32_t kt = it - 2;
-                const uint64_t m0 = m_begin + (uint64_t)kt * TT;
-                const uint32_t t = (uint32_t)mix_block * 32 + lane;
-                if (m0 + t < a.mix_len) {
-                    const bool full = m0 >= f_lo && m0 + TT <= f_hi;
-                    partial[m0 + t] = mix_rows(tiles + (kt % NBUF) * tile_sz + HOT_PAD, s_ht[kt % NHT], s_rows, G, a.n_post, t, full);
-                }
-            }
+            cta_bar();
         }
-        __syncthreads();
+    } else if (slot >= 0) {
+        // ---- stage A on tile it, stage C on tile it-2 ----
+        const bool has_first = (uint32_t)slot < G;
+        const int second = C == 1 ? hot_second_row(slot) : -1;
+        const bool has_second = second >= 0 && (uint32_t)second < G;
+        const int mix_block = C == 1 ? hot_mix_block(slot) : slot - 16;
+        // (lane's first frame * from) divmod to for the rows this warp owns
+        uint32_t lane_q0 = 0, lane_r0 = 0, lane_q1 = 0, lane_r1 = 0;
+        if (has_first) {
+            const uint32_t p = lane * (uint32_t)(TT / 32 / C) * s_rows[slot].uni.from;
+            lane_q0 = p / s_rows[slot].uni.to;
+            lane_r0 = p - lane_q0 * s_rows[slot].uni.to;
+        }
+        if (has_second) {
+            const uint32_t p = lane * (uint32_t)(TT / 32 / C) * s_rows[second].uni.from;
+            lane_q1 = p / s_rows[second].uni.to;
+            lane_r1 = p - lane_q1 * s_rows[second].uni.to;
+        }
+        float xtail0[2 * C], xtail1[2 * C];   // x at the last two frames of the previous tile, per owned row
+#pragma unroll
+        for (int j = 0; j < 2 * C; j++) xtail0[j] = xtail1[j] = 0.f;
+        const FusedRow& rowA = s_rows[has_first ? slot : 0];
+        const FusedRow& rowB = s_rows[has_second ? second : 0];
+        uint32_t kw = 0, kb = 0, kh = 0, phase = 0;   // tile it
+        uint32_t cb = 0, ch = 0;                      // tile it-2
+        const uint32_t mix_t = (uint32_t)(mix_block < 0 ? 0 : mix_block) * 32 + lane;
+        for (uint32_t it = 0; it < n_iter; it++) {
+            if (it < n_tiles) {
+                if (has_first) {
+                    mbar_wait(&s_full[kw], phase);
+                    float* tile = tiles + kb * tile_sz + HOT_PAD;
+                    const float* win = wins + kw * win_sz;
+                    {
+                        const HotTile& ht = s_ht[kh][slot];
+                        if (ht.lo < ht.hi) {
+                            if (nogain) hot_stage_a<true, C>(rowA, ht, a.n_pre, a.n_mid, lane, lane_q0, lane_r0, xtail0, win + slot * WSTRIDE, tile + slot * ROW_STRIDE);
+                            else hot_stage_a<false, C>(rowA, ht, a.n_pre, a.n_mid, lane, lane_q0, lane_r0, xtail0, win + slot * WSTRIDE, tile + slot * ROW_STRIDE);
+                        }
+                    }
+                    if (has_second) {
+                        const HotTile& ht = s_ht[kh][second];
+                        if (ht.lo < ht.hi) {
+                            if (nogain) hot_stage_a<true, C>(rowB, ht, a.n_pre, a.n_mid, lane, lane_q1, lane_r1, xtail1, win + second * WSTRIDE, tile + second * ROW_STRIDE);
+                            else hot_stage_a<false, C>(rowB, ht, a.n_pre, a.n_mid, lane, lane_q1, lane_r1, xtail1, win + second * WSTRIDE, tile + second * ROW_STRIDE);
+                        }
+                    }
+                }
+                kw = kw + 1 == NWIN ? 0 : kw + 1;
+                phase ^= kw == 0;
+                kb = kb + 1 == NBUF ? 0 : kb + 1;
+                kh = kh + 1 == NHT ? 0 : kh + 1;
+            }
+            if (it >= 2) {
+                // ---- stage C: eight warps take 32 positions each ----
+                if (mix_block >= 0) {
+                    const uint64_t m0 = m_begin + (uint64_t)(it - 2) * TT;
+                    if (m0 + mix_t < a.mix_len) {
+                        const bool full = m0 >= f_lo && m0 + TT <= f_hi;
+                        partial[m0 + mix_t] = mix_rows(tiles + cb * tile_sz + HOT_PAD, s_ht[ch], s_rows, G, a.n_post, mix_t, full);
+                    }
+                }
+                cb = cb + 1 == NBUF ? 0 : cb + 1;
+                ch = ch + 1 == NHT ? 0 : ch + 1;
+            }
+            cta_bar();
+        }
+    } else {
+        for (uint32_t it = 0; it < n_iter; it++) cta_bar();
     }
 }
 
@@ -1096,11 +1181,11 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
         plan->hot = r.c_in == C && whole_frames &&
                     (r.mode == ROW_DIRECT || r.mode == ROW_PASS || (r.mode == ROW_LERP && window_fits));
     }
-    if (plan->hot && C == 2) {
+    if (plan->hot) {
         for (size_t i = 0; i < n_streams; i++) {
             FusedRow& r = rows[i];
-            r.q32 = (uint32_t)((uint64_t)(32 / C) * r.uni.from / r.uni.to);
-            r.r32 = (uint32_t)((uint64_t)(32 / C) * r.uni.from % r.uni.to);
+            r.q32 = r.uni.from / r.uni.to;          // HOT rows: the per-frame step
+            r.r32 = r.uni.from % r.uni.to;
             r.qT = (uint32_t)((uint64_t)(TT / C) * r.uni.from / r.uni.to);
             r.rT = (uint32_t)((uint64_t)(TT / C) * r.uni.from % r.uni.to);
         }

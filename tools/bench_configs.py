@@ -65,6 +65,34 @@ def main():
         srcs = [rb.UniformSourceIterator(rb.TestSource(z(44100 * 2), 1, 44100), 1, 48000).low_pass(200).amplify(1.2)
                 for _ in range(4096)]
         time_batch("cfg3 4096 mono x 2s, general path (RB_NO_FUSION)", srcs, (1, 48000), flags=rb.capi.RB_NO_FUSION, steps=3)
+    if "cfg5" in which:
+        # HBM sweep: the cfg3 pipeline at 1 s of 44.1 kHz mono per stream, S from 1 to 65536
+        for S in [1, 4, 16, 64, 256, 1024, 4096, 16384, 65536]:
+            one = z(44100)
+            srcs = [rb.UniformSourceIterator(rb.TestSource(one, 1, 44100), 1, 48000).low_pass(200).amplify(1.2)
+                    for _ in range(S)]
+            time_batch(f"cfg5 sweep S={S}: 44.1k mono x 1s -> uniform(1,48k) -> low_pass(200) -> amplify -> mix", srcs,
+                       (1, 48000), steps=5 if S >= 16384 else 10)
+    if "cpu" in which:
+        # C++ restatement of rodio's CPU path on this box's host cores: one audio thread (what rodio itself runs)
+        # and all cores with a final partial-mix reduction; dynamic dispatch (Box<dyn Source>) and monomorphised.
+        import oracle
+
+        def to_oracle_stream(x):
+            src = rb.UniformSourceIterator(rb.TestSource(x, 1, 44100), 1, 48000).low_pass(200).amplify(1.2)
+            return oracle.Stream(pcm=src.pcm, channels=src.base_channels, sample_rate=src.base_rate, effects=src.effects,
+                                 span_len=src.span_len, mix_start=0)
+
+        rng = np.random.default_rng(5)
+        ncpu = os.cpu_count() or 1
+        for threads, S in [(1, 64), (ncpu, 64 * min(ncpu, 64))]:
+            xs = [rng.uniform(-1, 1, 44100).astype(np.float32) for _ in range(min(S, 256))]
+            streams = [to_oracle_stream(xs[i % len(xs)]) for i in range(S)]
+            for static in (False, True):
+                _, secs = oracle.mixer_mt(streams, 1, 48000, threads, 48000, static_dispatch=static)
+                print(json.dumps({"case": f"cpu cfg3 pipeline, {threads} thread(s), {'static' if static else 'dyn'} dispatch",
+                                  "streams": S, "seconds": round(secs, 4),
+                                  "Msamples_s": round(S * 48000 / secs / 1e6, 1), "cores": threads}), flush=True)
 
 
 if __name__ == "__main__":
