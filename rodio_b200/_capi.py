@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librodio_b200.so")
+# RODIO_B200_LIB: an instrumented build of the same library (tools/hot_timing.py); never a different implementation
+LIB_PATH = os.environ.get("RODIO_B200_LIB") or os.path.join(HERE, "librodio_b200.so")
 
 RB_OK = 0
 RB_ERR_INVALID_ARGUMENT = 1

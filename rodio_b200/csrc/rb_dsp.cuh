@@ -45,6 +45,12 @@ __device__ __forceinline__ float biquad_ff(float b0, float b1, float b2, float x
 __device__ __forceinline__ float biquad_fb(float a1, float a2, float t, float y1, float y2) {
     return sub(sub(t, mul(a1, y1)), mul(a2, y2));
 }
+// The same value with the two subtractions written as fma(p, -1, t) = RN(t - p): p * -1 is exact, so each step
+// still rounds exactly once, but all three dependent operations now run on the FMA pipe.  An FMUL feeding an FADD
+// crosses pipes (5 instead of 4 cycles each way): 18 cycles per sample for the serial chain instead of 12.
+__device__ __forceinline__ float biquad_fb_chain(float a1, float a2, float t, float y1, float y2, float neg1) {
+    return __fmaf_rn(mul(a2, y2), neg1, __fmaf_rn(mul(a1, y1), neg1, t));
+}
 
 // src/conversions/channels.rs:57-85 as a pure map: which input channel feeds output channel j
 // (-1 = literal 0.0).

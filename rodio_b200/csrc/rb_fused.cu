@@ -584,6 +584,43 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 // CTA-wide barrier reached from the role-specialised loops (every warp executes the same number of them)
 __device__ __forceinline__ void cta_bar() { asm volatile("bar.sync 0;" ::: "memory"); }
+#ifdef RB_HOT_TIMING
+// Instrumented build (tools/hot_timing.py): cycles each warp spends working / waiting at the tile barrier.
+__device__ unsigned long long g_hot_timing[32][4];   // work, barrier, window wait, -
+__device__ int g_hot_skip;   // bit 0: no stage A, bit 1: no recurrence, bit 2: no stage C, bit 3: no second rows (results are wrong)
+#define HOT_SKIP(bit) (g_hot_skip_v & (bit))
+#define HOT_TIMING_DECL long long tw_ = 0, tb_ = 0, tm_ = 0, tt0_ = clock64(), tt1_ = 0; const int g_hot_skip_v = g_hot_skip;
+#define HOT_MBAR_WAIT(bar_, ph_) do { const long long m0_ = clock64(); mbar_wait(bar_, ph_); tm_ += clock64() - m0_; } while (0)
+// BAR.SYNC.DEFER_BLOCKING lets the warp run on past the barrier until its next shared-memory access, so the wait is
+// made visible with a dependent branch on a volatile shared load (always zero) before the clock is read again.
+__device__ __forceinline__ void hot_timing_fence() {
+    uint32_t d;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(d) : "r"(0u) : "memory");
+    if (d == 0xdeadbeefu) __trap();
+}
+#define HOT_BAR()                      \
+    do {                               \
+        hot_timing_fence();            \
+        tt1_ = clock64();              \
+        cta_bar();                     \
+        hot_timing_fence();            \
+        const long long t2_ = clock64(); \
+        tw_ += tt1_ - tt0_, tb_ += t2_ - tt1_, tt0_ = t2_; \
+    } while (0)
+#define HOT_TIMING_END                                                        \
+    if ((threadIdx.x & 31) == 0) {                                            \
+        atomicAdd(&g_hot_timing[threadIdx.x >> 5][0], (unsigned long long)tw_); \
+        atomicAdd(&g_hot_timing[threadIdx.x >> 5][1], (unsigned long long)tb_); \
+        atomicAdd(&g_hot_timing[threadIdx.x >> 5][2], (unsigned long long)tm_); \
+    }
+#else
+#define HOT_SKIP(bit) false
+#define HOT_MBAR_WAIT(bar_, ph_) mbar_wait(bar_, ph_)
+#define HOT_TIMING_DECL
+#define HOT_BAR() cta_bar()
+#define HOT_TIMING_END
+#endif
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -687,6 +724,9 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
         const bool interior = !pass && __all_sync(0xffffffffu, n == (uint32_t)TT && (di + (uint32_t)(F - 1) * (r.q32 + 1) + 1) < lim);
         if (interior) {
             const float* __restrict__ w = win + ht.woff + di * C;
+#ifdef RB_HOT_TIMING
+            if (g_hot_skip & 16) w = win + lane;          // ablation: conflict-free (wrong) window addresses
+#endif
             const uint32_t step_w = r.q32 * C;            // whole frames per output frame, in words
             const float r1f = __uint2float_rn(r.r32);
             float nf = __uint2float_rn(num);
@@ -711,6 +751,9 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
                     // (also outside) yields q = m = +-0 exactly as the division would
                     const uint32_t e = __float_as_uint(m) & 0x7fffffffu;
                     const bool in_range = e - 0x0d800000u < 0x64000000u;
+#ifdef RB_HOT_TIMING
+                    if (!(g_hot_skip & 32))               // ablation: no range check
+#endif
                     bad |= !in_range && e != 0u;
                     xv[f * C + c] = gains<NOGAIN>(add(a0, in_range ? q : m), mid, n_mid);
                 }
@@ -858,6 +901,7 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
     // Ring positions (tile % NBUF, % NWIN, % NHT) are carried incrementally: the role bodies are short enough
     // that a handful of modulo / dispatch instructions per warp and iteration showed up as a third of all issue slots.
     const uint32_t n_iter = n_tiles + 2;
+    HOT_TIMING_DECL
     if (is_loader) {
         // ---- stage L on tile it+2: lane g plans and fetches row g's window ----
         uint32_t kw = 2 % NWIN, kh = 2 % NHT, khp = 1;
@@ -871,7 +915,7 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
             khp = kh;
             kh = kh + 1 == NHT ? 0 : kh + 1;
             kw = kw + 1 == NWIN ? 0 : kw + 1;
-            cta_bar();
+            HOT_BAR();
         }
     } else if (is_rec) {
         // ---- stage B on tile it-1 (lane = chain): nothing but y = (t - a1*y1) - a2*y2 ----
@@ -879,58 +923,69 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
         const bool chain_on = rec_row < G;
         float y1 = 0.f, y2 = 0.f, a1 = 0.f, a2 = 0.f;
         if (chain_on) a1 = s_rows[rec_row].a1, a2 = s_rows[rec_row].a2;
+        // -1.0 as a run-time value (ptxas would turn fma(p, -1.0, t) back into an FADD)
+        const float neg1 = -s_rows[0].den_f / s_rows[0].den_f;
+#define FB(t_, y1_, y2_) biquad_fb_chain(a1, a2, t_, y1_, y2_, neg1)
         float* rbase = tiles + rec_row * ROW_STRIDE + HOT_PAD;
         uint32_t kb = 0, kh = 0;
-        cta_bar();   // it == 0: nothing to do yet
+        HOT_BAR();   // it == 0: nothing to do yet
         for (uint32_t it = 1; it < n_iter; it++) {
-            if (it <= n_tiles && chain_on) {
+            if (it <= n_tiles && chain_on && !HOT_SKIP(2)) {
                 float* row = rbase + kb * tile_sz;
                 const uint2 act = *reinterpret_cast<const uint2*>(&s_ht[kh][rec_row].lo);
                 uint32_t t = act.x;
                 const uint32_t hi_t = act.y;
                 if constexpr (C == 1) {
                     for (; t < hi_t && (t & 3); t++) {
-                        const float y = biquad_fb(a1, a2, row[t], y1, y2);
+                        const float y = FB(row[t], y1, y2);
                         y2 = y1, y1 = y;
                         row[t] = y;
                     }
                     float4* p4 = reinterpret_cast<float4*>(row + t);
-                    const uint32_t n4 = hi_t > t ? (hi_t - t) >> 2 : 0;
-                    float4* const e4 = p4 + (n4 & ~1u);
-                    float4 fa = make_float4(0.f, 0.f, 0.f, 0.f), fb;
-                    if (n4) fa = p4[0];
-                    // two groups of four per trip, the next group's load issued before the dependent chain
-                    while (p4 != e4) {
-                        fb = p4[1];
-                        float4 ya;
-                        ya.x = biquad_fb(a1, a2, fa.x, y1, y2);
-                        ya.y = biquad_fb(a1, a2, fa.y, ya.x, y1);
-                        ya.z = biquad_fb(a1, a2, fa.z, ya.y, ya.x);
-                        ya.w = biquad_fb(a1, a2, fa.w, ya.z, ya.y);
-                        p4[0] = ya;
-                        fa = p4[2];   // at most 16 bytes past the active span: still inside the row (tile ring + windows follow)
-                        float4 yb;
-                        yb.x = biquad_fb(a1, a2, fb.x, ya.w, ya.z);
-                        yb.y = biquad_fb(a1, a2, fb.y, yb.x, ya.w);
-                        yb.z = biquad_fb(a1, a2, fb.z, yb.y, yb.x);
-                        yb.w = biquad_fb(a1, a2, fb.w, yb.z, yb.y);
-                        p4[1] = yb;
-                        y2 = yb.z, y1 = yb.w;
-                        p4 += 2;
+                    uint32_t n4 = hi_t > t ? (hi_t - t) >> 2 : 0;
+                    t += n4 << 2;
+                    // 16 samples per step, the next step's four loads issued a whole step (~200 cycles) ahead of their
+                    // use: the serial chain never waits on shared memory.  The look-ahead reads at most 64 bytes past
+                    // the active span -- the next row, or the window ring that follows the last row.
+#define FB4(v_, o_)                          \
+    o_.x = FB(v_.x, y1, y2);                 \
+    o_.y = FB(v_.y, o_.x, y1);               \
+    o_.z = FB(v_.z, o_.y, o_.x);             \
+    o_.w = FB(v_.w, o_.z, o_.y);             \
+    y2 = o_.z, y1 = o_.w;
+                    if (n4 >= 4) {
+                        float4 c0 = p4[0], c1 = p4[1], c2 = p4[2], c3 = p4[3];
+                        while (n4 >= 8) {
+                            const float4 d0 = p4[4], d1 = p4[5], d2 = p4[6], d3 = p4[7];
+                            float4 o;
+                            FB4(c0, o) p4[0] = o;
+                            FB4(c1, o) p4[1] = o;
+                            FB4(c2, o) p4[2] = o;
+                            FB4(c3, o) p4[3] = o;
+                            c0 = p4[8], c1 = p4[9], c2 = p4[10], c3 = p4[11];
+                            FB4(d0, o) p4[4] = o;
+                            FB4(d1, o) p4[5] = o;
+                            FB4(d2, o) p4[6] = o;
+                            FB4(d3, o) p4[7] = o;
+                            p4 += 8, n4 -= 8;
+                        }
+                        if (n4 >= 4) {
+                            float4 o;
+                            FB4(c0, o) p4[0] = o;
+                            FB4(c1, o) p4[1] = o;
+                            FB4(c2, o) p4[2] = o;
+                            FB4(c3, o) p4[3] = o;
+                            p4 += 4, n4 -= 4;
+                        }
                     }
-                    t += (n4 & ~1u) << 2;
-                    if (n4 & 1u) {
-                        float4 ya;
-                        ya.x = biquad_fb(a1, a2, fa.x, y1, y2);
-                        ya.y = biquad_fb(a1, a2, fa.y, ya.x, y1);
-                        ya.z = biquad_fb(a1, a2, fa.z, ya.y, ya.x);
-                        ya.w = biquad_fb(a1, a2, fa.w, ya.z, ya.y);
-                        p4[0] = ya;
-                        y2 = ya.z, y1 = ya.w;
-                        t += 4;
+                    for (; n4; n4--, p4++) {
+                        const float4 v = p4[0];
+                        float4 o;
+                        FB4(v, o) p4[0] = o;
                     }
+#undef FB4
                     for (; t < hi_t; t++) {
-                        const float y = biquad_fb(a1, a2, row[t], y1, y2);
+                        const float y = FB(row[t], y1, y2);
                         y2 = y1, y1 = y;
                         row[t] = y;
                     }
@@ -938,7 +993,7 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
                     // interleaved frames: lo / hi are even, this lane owns positions t + rec_ch
                     float* rc = row + rec_ch;
                     if (t < hi_t && (t & 3)) {
-                        const float y = biquad_fb(a1, a2, rc[t], y1, y2);
+                        const float y = FB(rc[t], y1, y2);
                         y2 = y1, y1 = y;
                         rc[t] = y;
                         t += 2;
@@ -949,13 +1004,13 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
                     for (; t + 4 <= hi_t; t += 4) {
                         const float4 f = nx;
                         if (t + 8 <= hi_t) nx = *reinterpret_cast<const float4*>(row + t + 4);
-                        const float ya = biquad_fb(a1, a2, rec_ch ? f.y : f.x, y1, y2);
-                        const float yb = biquad_fb(a1, a2, rec_ch ? f.w : f.z, ya, y1);
+                        const float ya = FB(rec_ch ? f.y : f.x, y1, y2);
+                        const float yb = FB(rec_ch ? f.w : f.z, ya, y1);
                         y2 = ya, y1 = yb;
                         rc[t] = ya, rc[t + 2] = yb;
                     }
                     if (t < hi_t) {
-                        const float y = biquad_fb(a1, a2, rc[t], y1, y2);
+                        const float y = FB(rc[t], y1, y2);
                         y2 = y1, y1 = y;
                         rc[t] = y;
                     }
@@ -963,8 +1018,9 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
                 kb = kb + 1 == NBUF ? 0 : kb + 1;
                 kh = kh + 1 == NHT ? 0 : kh + 1;
             }
-            cta_bar();
+            HOT_BAR();
         }
+#undef FB
     } else if (slot >= 0) {
         // ---- stage A on tile it, stage C on tile it-2 ----
         const bool has_first = (uint32_t)slot < G;
@@ -993,8 +1049,8 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
         const uint32_t mix_t = (uint32_t)(mix_block < 0 ? 0 : mix_block) * 32 + lane;
         for (uint32_t it = 0; it < n_iter; it++) {
             if (it < n_tiles) {
-                if (has_first) {
-                    mbar_wait(&s_full[kw], phase);
+                if (has_first && !HOT_SKIP(1)) {
+                    HOT_MBAR_WAIT(&s_full[kw], phase);
                     float* tile = tiles + kb * tile_sz + HOT_PAD;
                     const float* win = wins + kw * win_sz;
                     {
@@ -1004,7 +1060,7 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
                             else hot_stage_a<false, C>(rowA, ht, a.n_pre, a.n_mid, lane, lane_q0, lane_r0, xtail0, win + slot * WSTRIDE, tile + slot * ROW_STRIDE);
                         }
                     }
-                    if (has_second) {
+                    if (has_second && !HOT_SKIP(8)) {
                         const HotTile& ht = s_ht[kh][second];
                         if (ht.lo < ht.hi) {
                             if (nogain) hot_stage_a<true, C>(rowB, ht, a.n_pre, a.n_mid, lane, lane_q1, lane_r1, xtail1, win + second * WSTRIDE, tile + second * ROW_STRIDE);
@@ -1019,7 +1075,7 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
             }
             if (it >= 2) {
                 // ---- stage C: eight warps take 32 positions each ----
-                if (mix_block >= 0) {
+                if (mix_block >= 0 && !HOT_SKIP(4)) {
                     const uint64_t m0 = m_begin + (uint64_t)(it - 2) * TT;
                     if (m0 + mix_t < a.mix_len) {
                         const bool full = m0 >= f_lo && m0 + TT <= f_hi;
@@ -1029,11 +1085,12 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
                 cb = cb + 1 == NBUF ? 0 : cb + 1;
                 ch = ch + 1 == NHT ? 0 : ch + 1;
             }
-            cta_bar();
+            HOT_BAR();
         }
     } else {
-        for (uint32_t it = 0; it < n_iter; it++) cta_bar();
+        for (uint32_t it = 0; it < n_iter; it++) HOT_BAR();
     }
+    HOT_TIMING_END
 }
 
 // ordered sum of the per-CTA partial rows
@@ -1275,3 +1332,15 @@ void rb_fused_destroy(rb_fused_plan* p) {
 }
 
 uint32_t rb_fused_launch_count(const rb_fused_plan* p) { return p->single_cta_direct ? 1u : 2u; }
+
+#ifdef RB_HOT_TIMING
+extern "C" int rb_debug_hot_skip(int mask) { return (int)cudaMemcpyToSymbol(g_hot_skip, &mask, sizeof(int)); }
+extern "C" int rb_debug_hot_timing(unsigned long long* out, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_hot_timing, sizeof(unsigned long long) * 128);
+    if (e == cudaSuccess && reset) {
+        unsigned long long z[128] = {0};
+        e = cudaMemcpyToSymbol(g_hot_timing, z, sizeof(z));
+    }
+    return (int)e;
+}
+#endif
