@@ -570,6 +570,8 @@ struct HotTile {
     uint32_t r0;           // (n0 * from) mod to at position lo
     uint32_t woff;         // i0 & 3: offset of frame i0 inside the 16-byte aligned window
     uint64_t i0;           // left input frame of position lo
+    uint32_t lim;          // frames (relative to i0) that still have a right neighbour: interpolate iff di < lim
+    uint32_t interior;     // full tile of an interpolated row, every tap inside the stream: blocked fast path
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -648,7 +650,7 @@ template <int C>
 __device__ __forceinline__ void hot_tile_setup(const FusedRow& r, uint64_t m0, const HotTile* prev, HotTile& ht) {
     const uint64_t s = r.mix_start, e = r.mix_start + r.out_len;
     const uint64_t lo = m0 > s ? m0 : s, hi = (m0 + TT) < e ? (m0 + TT) : e;
-    ht.lo = ht.hi = 0, ht.r0 = 0, ht.woff = 0, ht.i0 = 0;
+    ht.lo = ht.hi = 0, ht.r0 = 0, ht.woff = 0, ht.i0 = 0, ht.lim = 0, ht.interior = 0;
     if (lo >= hi) return;
     ht.lo = (uint32_t)(lo - m0), ht.hi = (uint32_t)(hi - m0);
     if (prev && prev->lo == 0 && prev->hi == (uint32_t)TT && ht.lo == 0) {
@@ -662,6 +664,10 @@ __device__ __forceinline__ void hot_tile_setup(const FusedRow& r, uint64_t m0, c
         ht.r0 = (uint32_t)(prod - ht.i0 * r.uni.to);
     }
     ht.woff = (uint32_t)((ht.i0 * C) & 3ull);
+    const uint64_t remain = r.uni.tail.L - 1 - ht.i0;
+    ht.lim = remain > 0x7fffffffull ? 0x7fffffffu : (uint32_t)remain;
+    // the last frame a full tile touches is i0 + floor((r0 + (TT/C - 1) * from) / to) <= i0 + qT + 1
+    ht.interior = r.mode == ROW_LERP && ht.hi - ht.lo == (uint32_t)TT && r.qT + 2 < ht.lim;
 }
 
 // Stage L for one (row, tile): arm the stage barrier and launch the bulk copy of the input window.
@@ -710,8 +716,7 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
     const uint32_t to = r.uni.to;
     const float den_f = r.den_f, rcp_den = r.rcp_den;
     const float b0 = r.b0, b1 = r.b1, b2 = r.b2;
-    const uint64_t remain = r.uni.tail.L - 1 - ht.i0;
-    const uint32_t lim = remain > 0x7fffffffull ? 0x7fffffffu : (uint32_t)remain;   // interpolate iff di < lim
+    const uint32_t lim = ht.lim;
     const float* pre = r.pre;
     const float* mid = r.mid;
     const bool pass = r.mode != ROW_LERP;   // same-rate rows: x[n] = in[n], no interpolation (from = to = 1 in the row)
@@ -720,8 +725,7 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
         uint32_t num = ht.r0 + lane_r;
         uint32_t di = lane_q;
         if (num >= to) num -= to, di += 1;
-        // warp-uniform: the votes below need the whole warp on the same side of this branch
-        const bool interior = !pass && __all_sync(0xffffffffu, n == (uint32_t)TT && (di + (uint32_t)(F - 1) * (r.q32 + 1) + 1) < lim);
+        const bool interior = ht.interior != 0;   // warp-uniform (planned by the loader): the vote below needs the whole warp
         if (interior) {
             const float* __restrict__ w = win + ht.woff + di * C;
 #ifdef RB_HOT_TIMING
@@ -824,32 +828,66 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
 }
 
 // Warp roles (32 warps; sub-partition = warp % 4).  Measured: the recurrence warp must have its sub-partition
-// to itself -- co-resident throughput warps (even with lower warp ids) hold the issue port greedily and the
-// 12-cycle dependent chain doubles in length.
-//   warp 31                  recurrence (stage B)
-//   warp 27                  loader (stage L, lane = row), ~100 instructions per tile
-//   warps 3,7,..,23          idle
-//   the 24 warps with warp % 4 != 3: stage A, slot = (warp/4)*3 + warp%4 owns row `slot`; rows 24..27 go to
-//   slots {0,1,2,5} and the eight stage-C warps are chosen so that the three sub-partitions carry equal work.
-__device__ __forceinline__ int hot_row_slot(uint32_t warp) {
-    if ((warp & 3u) == 3u) return -1;
-    return (int)((warp >> 2) * 3u + (warp & 3u));   // 0..23
-}
-constexpr uint32_t HOT_ROW_WARPS = 24;
-constexpr uint32_t HOT_MAX_ROWS = 28;   // 24 slots + 4 second rows
+// to itself.  Its dependent chain (FMUL -> FFMA -> FFMA, 12.9 cycles per sample when alone) needs every issue slot
+// on time: with the loader as its neighbour it ran at 16.4 cycles per sample, with stage-A warps at twice that.
+//   warp 31                  recurrence (stage B), alone on sub-partition 3 (warps 3,7,..,27 idle)
+//   warp 30                  loader (stage L, lane = row)
+//   the other 23 warps with warp % 4 != 3: stage A, slot = (warp/4)*3 + warp%4 owns row `slot`; rows 23..27 are the
+//   second rows of slots {0,3 | 1 | 2,5} and stage C runs on slots {6, 7}: the three sub-partitions carry about
+//   equal instruction counts (the loader sits where one row fewer does).
+constexpr uint32_t HOT_MAX_ROWS = 28;          // 23 slots + 5 second rows
 constexpr uint32_t HOT_MAX_ROWS_STEREO = 16;   // 32 chains in the recurrence warp
-constexpr uint32_t HOT_REC_WARP = 31, HOT_LOAD_WARP = 27;
-// second row of a slot (rows beyond 24), or -1
-__device__ __forceinline__ int hot_second_row(int slot) {
-    return slot == 0 ? 24 : slot == 1 ? 25 : slot == 2 ? 26 : slot == 5 ? 27 : -1;
+constexpr uint32_t HOT_REC_WARP = 31, HOT_LOAD_WARP = 30;
+__device__ __forceinline__ int hot_row_slot(uint32_t warp) {
+    if ((warp & 3u) == 3u || warp == HOT_LOAD_WARP) return -1;
+    return (int)((warp >> 2) * 3u + (warp & 3u));   // 0..22
 }
-// stage-C block (32 tile positions) handled by a slot, or -1
-__device__ __forceinline__ int hot_mix_block(int slot) {
-    switch (slot) {
-        case 3: return 0; case 6: return 1; case 9: return 2; case 12: return 3;   // sub-partition 0
-        case 4: return 4; case 7: return 5; case 10: return 6;                      // sub-partition 1
-        case 8: return 7;                                                           // sub-partition 2
-        default: return -1;
+// second row of a slot (rows beyond the 23 slots), or -1
+__device__ __forceinline__ int hot_second_row(int slot) {
+    return slot == 0 ? 23 : slot == 3 ? 24 : slot == 1 ? 25 : slot == 2 ? 26 : slot == 5 ? 27 : -1;
+}
+// Stage C of the HOT kernel: one thread sums FOUR consecutive tile positions over the CTA's rows (row order =
+// the mixer's insertion order), 16-byte loads of y, the post-gain applied on the fly.  64 threads cover a tile.
+template <int NPOST>
+__device__ __forceinline__ float4 hot_mix4_full(const float* tile, const FusedRow* s_rows, uint32_t G, uint32_t n_post, uint32_t t4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (uint32_t g = 0; g < G; g++) {
+        float4 v = *reinterpret_cast<const float4*>(tile + g * ROW_STRIDE + t4);
+        if (NPOST == 1) {
+            const float pg = s_rows[g].post[0];
+            v.x = mul(v.x, pg), v.y = mul(v.y, pg), v.z = mul(v.z, pg), v.w = mul(v.w, pg);
+        } else if (NPOST < 0) {
+            v.x = apply_gains(v.x, s_rows[g].post, n_post), v.y = apply_gains(v.y, s_rows[g].post, n_post);
+            v.z = apply_gains(v.z, s_rows[g].post, n_post), v.w = apply_gains(v.w, s_rows[g].post, n_post);
+        }
+        acc.x = add(acc.x, v.x), acc.y = add(acc.y, v.y), acc.z = add(acc.z, v.z), acc.w = add(acc.w, v.w);
+    }
+    return acc;
+}
+__device__ __forceinline__ void hot_mix4(const float* tile, const HotTile* hts, const FusedRow* s_rows, uint32_t G,
+                                         uint32_t n_post, uint32_t t4, bool full, uint64_t m0, uint64_t mix_len,
+                                         float* __restrict__ partial) {
+    if (m0 + t4 >= mix_len) return;
+    float4 acc;
+    if (full) {
+        acc = n_post == 0 ? hot_mix4_full<0>(tile, s_rows, G, n_post, t4)
+              : n_post == 1 ? hot_mix4_full<1>(tile, s_rows, G, n_post, t4)
+                            : hot_mix4_full<-1>(tile, s_rows, G, n_post, t4);
+    } else {
+        acc.x = mix_rows(tile, hts, s_rows, G, n_post, t4, false);
+        acc.y = mix_rows(tile, hts, s_rows, G, n_post, t4 + 1, false);
+        acc.z = mix_rows(tile, hts, s_rows, G, n_post, t4 + 2, false);
+        acc.w = mix_rows(tile, hts, s_rows, G, n_post, t4 + 3, false);
+    }
+    float* o = partial + m0 + t4;
+    if (m0 + t4 + 4 <= mix_len && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+        *reinterpret_cast<float4*>(o) = acc;
+    } else {
+        o[0] = acc.x;
+        if (m0 + t4 + 1 < mix_len) o[1] = acc.y;
+        if (m0 + t4 + 2 < mix_len) o[2] = acc.z;
+        if (m0 + t4 + 3 < mix_len) o[3] = acc.w;
     }
 }
 
@@ -1026,7 +1064,8 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
         const bool has_first = (uint32_t)slot < G;
         const int second = C == 1 ? hot_second_row(slot) : -1;
         const bool has_second = second >= 0 && (uint32_t)second < G;
-        const int mix_block = C == 1 ? hot_mix_block(slot) : slot - 16;
+        // stage C: two warps, 4 positions per thread (slots without a second row, on different sub-partitions)
+        const int mix_block = C == 1 ? (slot == 6 ? 0 : slot == 7 ? 1 : -1) : (slot == 16 ? 0 : slot == 17 ? 1 : -1);
         // (lane's first frame * from) divmod to for the rows this warp owns
         uint32_t lane_q0 = 0, lane_r0 = 0, lane_q1 = 0, lane_r1 = 0;
         if (has_first) {
@@ -1046,7 +1085,7 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
         const FusedRow& rowB = s_rows[has_second ? second : 0];
         uint32_t kw = 0, kb = 0, kh = 0, phase = 0;   // tile it
         uint32_t cb = 0, ch = 0;                      // tile it-2
-        const uint32_t mix_t = (uint32_t)(mix_block < 0 ? 0 : mix_block) * 32 + lane;
+        const uint32_t mix_t = ((uint32_t)(mix_block < 0 ? 0 : mix_block) * 32 + lane) * 4;
         for (uint32_t it = 0; it < n_iter; it++) {
             if (it < n_tiles) {
                 if (has_first && !HOT_SKIP(1)) {
@@ -1074,13 +1113,11 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
                 kh = kh + 1 == NHT ? 0 : kh + 1;
             }
             if (it >= 2) {
-                // ---- stage C: eight warps take 32 positions each ----
+                // ---- stage C ----
                 if (mix_block >= 0 && !HOT_SKIP(4)) {
                     const uint64_t m0 = m_begin + (uint64_t)(it - 2) * TT;
-                    if (m0 + mix_t < a.mix_len) {
-                        const bool full = m0 >= f_lo && m0 + TT <= f_hi;
-                        partial[m0 + mix_t] = mix_rows(tiles + cb * tile_sz + HOT_PAD, s_ht[ch], s_rows, G, a.n_post, mix_t, full);
-                    }
+                    const bool full = m0 >= f_lo && m0 + TT <= f_hi;
+                    hot_mix4(tiles + cb * tile_sz + HOT_PAD, s_ht[ch], s_rows, G, a.n_post, mix_t, full, m0, a.mix_len, partial);
                 }
                 cb = cb + 1 == NBUF ? 0 : cb + 1;
                 ch = ch + 1 == NHT ? 0 : ch + 1;

@@ -274,6 +274,158 @@ __global__ void __launch_bounds__(32) k_agc_seq_pass(const rb_node_dev* __restri
         }
     }
 }
+// Passes A and C as a warp-specialised pipeline (the shape of the fused mixer kernel): a CTA owns 32 streams,
+// SIX mover warps stream tiles of AT samples per stream between HBM and shared memory with 16-byte accesses
+// (stage L on tile k+1, stage S on tile k-1) while ONE chain warp (lane = stream, alone on its SM sub-partition)
+// walks tile k in place.  A single warp issues about one instruction every two cycles, so the chain warp executes
+// nothing but the recurrences: the movers also apply y = x * gain on the way out.
+//   A  sum[n]  = (sum - x[n-8192]^2) + x[n]^2                       (agc.rs:157; ring of 8192 squares)
+//      peak[n] = |x| > peak ? |x| : peak * release + |x| * (1 - release)
+//         (agc.rs:397-408 with coeff = 0 spelled out: peak * 0 = +0 and |x| * (1 - 0) = |x| exactly, peak >= +0)
+//   C  k = desired > gain ? attack : release;  gain = clamp(gain * k + desired * (1 - k), 0.1, max_gain)
+//         (agc.rs:474-491; desired is never NaN -- pass B builds it with fmin / fmax -- so min/max is the clamp)
+constexpr int AT = 128;              // samples per stream and tile
+constexpr int ATS = AT + 4;          // padded row, (AT + 4) / 4 odd: 16-byte accesses of 8 lanes hit 8 bank groups
+constexpr int ANB = 3;               // tile ring: loading k+1, chain on k, storing k-1
+constexpr int AGC_CHAIN_WARP = 3;    // 7 warps: warps 0,1,2,4,5,6 move data, warp 3 is alone on sub-partition 3
+constexpr int AGC_THREADS = 7 * 32;
+constexpr size_t AGC_SMEM = (size_t)ANB * 2 * 32 * ATS * sizeof(float);
+
+template <int PASS>   // 0 = A, 2 = C
+__global__ void __launch_bounds__(AGC_THREADS) k_agc_pipe(const rb_node_dev* __restrict__ nodes, uint32_t n_nodes) {
+    extern __shared__ __align__(16) float agc_sm[];   // [ANB][2][32][ATS]
+    __shared__ const float* s_in0[32];
+    __shared__ const float* s_in1[32];
+    __shared__ float* s_out0[32];
+    __shared__ float* s_out1[32];
+    __shared__ uint64_t s_n[32];
+    __shared__ uint64_t s_max_n;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t s0 = blockIdx.x * 32;
+    const uint32_t cnt_rows = min(32u, n_nodes - s0);
+    const rb_node_dev* nds = nodes + s0;
+    if (threadIdx.x < 32) {
+        uint64_t n = 0;
+        if (lane < cnt_rows) {
+            const rb_node_dev& nd = nds[lane];
+            n = nd.n_in;
+            s_in0[lane] = (const float*)nd.src;
+            s_in1[lane] = PASS == 0 ? (const float*)nd.src - 8192 : nd.aux0;   // A: x[n-8192] (tiles below 8192 skip it), C: desired[n]
+            s_out0[lane] = PASS == 0 ? nd.aux0 : nd.dst;
+            s_out1[lane] = nd.aux1;
+        }
+        s_n[lane] = n;
+        for (int o = 16; o; o >>= 1) n = max(n, __shfl_xor_sync(0xffffffffu, n, o));
+        if (lane == 0) s_max_n = n;
+    }
+    __syncthreads();
+    const uint64_t max_n = s_max_n;
+    const uint32_t n_tiles = (uint32_t)((max_n + AT - 1) / AT);
+    const bool is_chain = warp == AGC_CHAIN_WARP;
+    const uint32_t mv = warp < AGC_CHAIN_WARP ? warp : warp - 1;   // mover index 0..5
+    constexpr size_t ARR = (size_t)32 * ATS, BUF = 2 * ARR;
+
+    // chain state (lane = stream)
+    float gain = 1.0f, peak = 0.0f, sum = 0.0f;
+    float attack = 0.f, release = 0.f, max_gain = 0.f, oma = 0.f, omr = 0.f;
+    uint64_t my_n = 0;
+    if (is_chain && lane < cnt_rows) {
+        const rb_node_dev& nd = nds[lane];
+        my_n = nd.n_in;
+        max_gain = nd.p.agc.max_gain, attack = nd.p.agc.attack, release = nd.p.agc.release;
+        oma = sub(1.0f, attack), omr = sub(1.0f, release);
+    }
+
+    uint32_t lb = 0, cb = 0, sb = 0;   // ring slots of the tile being loaded / walked / stored
+    for (uint32_t it = 0; it < n_tiles + 2; it++) {
+        if (!is_chain) {
+            if (it < n_tiles) {
+                // ---- stage L: tile `it`, rows mv, mv+6, ..: one 16-byte load per lane covers a row of AT samples ----
+                const uint64_t n = (uint64_t)it * AT + 4 * lane;
+                const bool second_on = PASS != 0 || (uint64_t)it * AT >= 8192;
+                float* base = agc_sm + lb * BUF;
+                for (uint32_t r = mv; r < 32; r += 6) {
+                    const uint64_t nr = s_n[r];
+                    float4 vx = make_float4(0.f, 0.f, 0.f, 0.f), vo = vx;
+                    if (n + 4 <= nr) {
+                        vx = __ldg(reinterpret_cast<const float4*>(s_in0[r] + n));
+                        if (second_on) vo = PASS == 0 ? __ldg(reinterpret_cast<const float4*>(s_in1[r] + n))
+                                                      : *reinterpret_cast<const float4*>(s_in1[r] + n);
+                    } else if (n < nr) {
+                        float ax[4] = {0.f, 0.f, 0.f, 0.f}, ao[4] = {0.f, 0.f, 0.f, 0.f};
+                        for (int j = 0; j < 4; j++)
+                            if (n + j < nr) {
+                                ax[j] = s_in0[r][n + j];
+                                if (second_on) ao[j] = s_in1[r][n + j];
+                            }
+                        vx = make_float4(ax[0], ax[1], ax[2], ax[3]), vo = make_float4(ao[0], ao[1], ao[2], ao[3]);
+                    }
+                    *reinterpret_cast<float4*>(base + r * ATS + 4 * lane) = vx;
+                    *reinterpret_cast<float4*>(base + ARR + r * ATS + 4 * lane) = vo;
+                }
+            }
+            if (it >= 2) {
+                // ---- stage S: tile `it - 2` ----
+                const uint64_t n = (uint64_t)(it - 2) * AT + 4 * lane;
+                const float* base = agc_sm + sb * BUF;
+                for (uint32_t r = mv; r < 32; r += 6) {
+                    const uint64_t nr = s_n[r];
+                    if (n >= nr) continue;
+                    float4 a = *reinterpret_cast<const float4*>(base + r * ATS + 4 * lane);
+                    const float4 b = *reinterpret_cast<const float4*>(base + ARR + r * ATS + 4 * lane);
+                    if (PASS == 2) a.x = mul(a.x, b.x), a.y = mul(a.y, b.y), a.z = mul(a.z, b.z), a.w = mul(a.w, b.w);   // y = x * gain
+                    if (n + 4 <= nr) {
+                        *reinterpret_cast<float4*>(s_out0[r] + n) = a;
+                        if (PASS == 0) *reinterpret_cast<float4*>(s_out1[r] + n) = b;
+                    } else {
+                        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+                        for (int j = 0; j < 4; j++)
+                            if (n + j < nr) {
+                                s_out0[r][n + j] = av[j];
+                                if (PASS == 0) s_out1[r][n + j] = bv[j];
+                            }
+                    }
+                }
+            }
+        } else if (it >= 1 && it <= n_tiles) {
+            // ---- chain: tile `it - 1`, lane = stream; whole groups of four (positions past the end are never stored) ----
+            const uint64_t n0 = (uint64_t)(it - 1) * AT;
+            const int cnt = (int)min((uint64_t)AT, my_n > n0 ? my_n - n0 : 0);
+            float4* px = reinterpret_cast<float4*>(agc_sm + cb * BUF + lane * ATS);
+            float4* po = reinterpret_cast<float4*>(agc_sm + cb * BUF + ARR + lane * ATS);
+#pragma unroll 2
+            for (int k4 = 0; k4 * 4 < cnt; k4++) {
+                const float4 a = px[k4], b = po[k4];
+                const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+                float r0[4], r1[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (PASS == 0) {
+                        const float v = fabsf(av[j]), ov = fabsf(bv[j]);
+                        const float decayed = add(mul(peak, release), mul(v, omr));
+                        peak = (v > peak) ? v : decayed;
+                        sum = add(sub(sum, mul(ov, ov)), mul(v, v));
+                        r0[j] = sum, r1[j] = peak;
+                    } else {
+                        const float desired = bv[j];
+                        const bool up = desired > gain;
+                        const float kk = up ? attack : release, omk = up ? oma : omr;
+                        gain = add(mul(gain, kk), mul(desired, omk));
+                        gain = fminf(fmaxf(gain, 0.1f), max_gain);
+                        r1[j] = gain;
+                    }
+                }
+                if (PASS == 0) px[k4] = make_float4(r0[0], r0[1], r0[2], r0[3]);
+                po[k4] = make_float4(r1[0], r1[1], r1[2], r1[3]);
+            }
+        }
+        if (it < n_tiles) lb = lb + 1 == ANB ? 0 : lb + 1;
+        if (it >= 1 && it <= n_tiles) cb = cb + 1 == ANB ? 0 : cb + 1;
+        if (it >= 2) sb = sb + 1 == ANB ? 0 : sb + 1;
+        __syncthreads();
+    }
+}
+
 // pass B: desired gain per sample, fully parallel (grid convention of the time-parallel kernels)
 __global__ void __launch_bounds__(TPB) k_agc_desired(const rb_node_dev* __restrict__ nodes) {
     const rb_node_dev& nd = nodes[blockIdx.x];
@@ -475,11 +627,15 @@ cudaError_t rb_launch_nodes(uint32_t kind, const rb_node_dev* d_nodes, uint32_t 
             k_biquad_seq<<<(threads + 127) / 128, 128, 0, st>>>(d_nodes, n_nodes, max_channels);
             break;
         }
-        case RB_N_AGC:
-            k_agc_seq_pass<0><<<(n_nodes + 31) / 32, 32, 0, st>>>(d_nodes, n_nodes);
+        case RB_N_AGC: {
+            cudaError_t e = cudaFuncSetAttribute(k_agc_pipe<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AGC_SMEM);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_agc_pipe<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AGC_SMEM);
+            if (e != cudaSuccess) return e;
+            k_agc_pipe<0><<<(n_nodes + 31) / 32, AGC_THREADS, AGC_SMEM, st>>>(d_nodes, n_nodes);
             k_agc_desired<<<grid, TPB, 0, st>>>(d_nodes);
-            k_agc_seq_pass<2><<<(n_nodes + 31) / 32, 32, 0, st>>>(d_nodes, n_nodes);
+            k_agc_pipe<2><<<(n_nodes + 31) / 32, AGC_THREADS, AGC_SMEM, st>>>(d_nodes, n_nodes);
             break;
+        }
         case RB_N_LIMIT: k_limit_tile<<<(n_nodes + 31) / 32, 32, 0, st>>>(d_nodes, n_nodes); break;
         default: return cudaErrorInvalidValue;
     }
