@@ -344,24 +344,34 @@ __global__ void __launch_bounds__(AGC_THREADS) k_agc_pipe(const rb_node_dev* __r
                 const uint64_t n = (uint64_t)it * AT + 4 * lane;
                 const bool second_on = PASS != 0 || (uint64_t)it * AT >= 8192;
                 float* base = agc_sm + lb * BUF;
-                for (uint32_t r = mv; r < 32; r += 6) {
+                // all of this warp's loads go out before the first one is consumed (HBM latency is paid once per tile)
+                float4 vx[6], vo[6];
+#pragma unroll
+                for (int j = 0; j < 6; j++) {
+                    const uint32_t r = mv + 6 * j;
+                    vx[j] = make_float4(0.f, 0.f, 0.f, 0.f), vo[j] = vx[j];
+                    if (r >= 32) continue;
                     const uint64_t nr = s_n[r];
-                    float4 vx = make_float4(0.f, 0.f, 0.f, 0.f), vo = vx;
                     if (n + 4 <= nr) {
-                        vx = __ldg(reinterpret_cast<const float4*>(s_in0[r] + n));
-                        if (second_on) vo = PASS == 0 ? __ldg(reinterpret_cast<const float4*>(s_in1[r] + n))
-                                                      : *reinterpret_cast<const float4*>(s_in1[r] + n);
+                        vx[j] = __ldg(reinterpret_cast<const float4*>(s_in0[r] + n));
+                        if (second_on) vo[j] = PASS == 0 ? __ldg(reinterpret_cast<const float4*>(s_in1[r] + n))
+                                                         : *reinterpret_cast<const float4*>(s_in1[r] + n);
                     } else if (n < nr) {
                         float ax[4] = {0.f, 0.f, 0.f, 0.f}, ao[4] = {0.f, 0.f, 0.f, 0.f};
-                        for (int j = 0; j < 4; j++)
-                            if (n + j < nr) {
-                                ax[j] = s_in0[r][n + j];
-                                if (second_on) ao[j] = s_in1[r][n + j];
+                        for (int k = 0; k < 4; k++)
+                            if (n + k < nr) {
+                                ax[k] = s_in0[r][n + k];
+                                if (second_on) ao[k] = s_in1[r][n + k];
                             }
-                        vx = make_float4(ax[0], ax[1], ax[2], ax[3]), vo = make_float4(ao[0], ao[1], ao[2], ao[3]);
+                        vx[j] = make_float4(ax[0], ax[1], ax[2], ax[3]), vo[j] = make_float4(ao[0], ao[1], ao[2], ao[3]);
                     }
-                    *reinterpret_cast<float4*>(base + r * ATS + 4 * lane) = vx;
-                    *reinterpret_cast<float4*>(base + ARR + r * ATS + 4 * lane) = vo;
+                }
+#pragma unroll
+                for (int j = 0; j < 6; j++) {
+                    const uint32_t r = mv + 6 * j;
+                    if (r >= 32) continue;
+                    *reinterpret_cast<float4*>(base + r * ATS + 4 * lane) = vx[j];
+                    *reinterpret_cast<float4*>(base + ARR + r * ATS + 4 * lane) = vo[j];
                 }
             }
             if (it >= 2) {

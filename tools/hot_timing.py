@@ -44,7 +44,7 @@ def main():
         torch.cuda.synchronize()
         skips = [0, 1, 2, 4, 8, 1 | 4 | 8, 2 | 4, 1 | 2 | 4] if "--skips" in sys.argv else [0]
         if "--ablate" in sys.argv:
-            skips = [0, 2 | 4]
+            skips = [0, 1 | 4 | 8, 2 | 4, 2]
         names = {1: "no stage A", 2: "no recurrence", 4: "no stage C", 8: "no second rows", 16: "conflict-free window reads", 32: "no range check"}
         for skip in skips:
             lib.rb_debug_hot_skip(skip)
