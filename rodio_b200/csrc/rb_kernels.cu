@@ -178,7 +178,6 @@ __global__ void __launch_bounds__(128) k_biquad_seq(const rb_node_dev* __restric
 // and leave with coalesced stores.
 constexpr int RT = 32;            // samples per tile (one 128-byte line per stream)
 constexpr int RTS = RT + 1;       // padded row: lane r reading column k hits bank (r*33 + k) % 32 -> conflict-free
-constexpr int RTV = RT + 4;       // padded row for 16-byte accesses: (r*36/4 + j) % 8 distinct per quarter-warp
 
 // AGC: state shared across interleaved channels (src/source/agc.rs:524-557 applies it to the flat stream).
 // The reference's per-sample step splits into three passes with identical arithmetic (agc.rs:433-504):
@@ -186,99 +185,13 @@ constexpr int RTV = RT + 4;       // padded row for 16-byte accesses: (r*36/4 + 
 //   B (time-parallel)      rms = sqrt(sum/8192); rms_gain; peak_gain; desired[n]     -> aux0 = desired[n]
 //   C (sequential, cheap)  gain smoother + clamp, y = x * gain
 // so the sqrt and the three IEEE divisions (≈ 500 cycles of dependent latency per sample in one thread)
-// leave the sequential chains.  A and C use the warp-transposed tiles above (lane = stream).
-template <int PASS>   // 0 = A, 2 = C
-__global__ void __launch_bounds__(32) k_agc_seq_pass(const rb_node_dev* __restrict__ nodes, uint32_t n_nodes) {
-    __shared__ __align__(16) float t_x[32 * RTV], t_y[32 * RTV];
-    __shared__ const float* s_in0[32];
-    __shared__ const float* s_in1[32];
-    __shared__ float* s_out0[32];
-    __shared__ float* s_out1[32];
-    __shared__ uint64_t s_n[32];
-    const uint32_t lane = threadIdx.x;
-    const uint32_t s0 = blockIdx.x * 32;
-    const uint32_t cnt_rows = min(32u, n_nodes - s0);
-    const rb_node_dev* nds = nodes + s0;
-    uint64_t my_n = 0;
-    float max_gain = 0.f, attack = 0.f, release = 0.f;
-    s_n[lane] = 0;
-    if (lane < cnt_rows) {
-        const rb_node_dev& nd = nds[lane];
-        my_n = nd.n_in;
-        max_gain = nd.p.agc.max_gain, attack = nd.p.agc.attack, release = nd.p.agc.release;
-        s_n[lane] = nd.n_in;
-        s_in0[lane] = (const float*)nd.src;
-        s_in1[lane] = PASS == 0 ? (const float*)nd.src - 8192 : nd.aux0;   // A: x[n-8192] (guarded by n >= 8192), C: desired[n]
-        s_out0[lane] = PASS == 0 ? nd.aux0 : nd.dst;
-        s_out1[lane] = nd.aux1;
-    }
-    uint64_t max_n = my_n;
-    for (int o = 16; o; o >>= 1) max_n = max(max_n, __shfl_xor_sync(0xffffffffu, max_n, o));
-    __syncwarp();
-    float gain = 1.0f, peak = 0.0f, sum = 0.0f;
-    float rx[32], ro[32];   // PASS A: x[n], x[n-8192] ; PASS C: x[n], desired[n]
-    auto load_tile = [&](uint64_t n0) {
-        const uint64_t n = n0 + lane;
-#pragma unroll
-        for (int r = 0; r < 32; r++) {
-            rx[r] = 0.0f, ro[r] = 0.0f;
-            if (n < s_n[r]) {
-                rx[r] = __ldg(s_in0[r] + n);
-                if (PASS != 0 || n >= 8192) ro[r] = PASS == 0 ? __ldg(s_in1[r] + n) : s_in1[r][n];
-            }
-        }
-    };
-    load_tile(0);
-    for (uint64_t n0 = 0; n0 < max_n; n0 += RT) {
-        __syncwarp();
-#pragma unroll
-        for (int r = 0; r < 32; r++) t_x[r * RTV + lane] = rx[r], t_y[r * RTV + lane] = ro[r];
-        __syncwarp();
-        if (n0 + RT < max_n) load_tile(n0 + RT);                    // prefetch the next tile
-        const int cnt = (int)min((uint64_t)RT, my_n > n0 ? my_n - n0 : 0);
-        float4* mx4 = reinterpret_cast<float4*>(t_x + lane * RTV);
-        float4* my4 = reinterpret_cast<float4*>(t_y + lane * RTV);
-        // whole float4 groups; positions >= cnt hold zeros / stale values and are never stored
-#pragma unroll 2
-        for (int k4 = 0; k4 * 4 < cnt; k4++) {
-            float4 a = mx4[k4], b = my4[k4];
-            float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (PASS == 0) {
-                    float v = fabsf(av[j]), ov = fabsf(bv[j]);
-                    float coeff = (v > peak) ? 0.0f : release;             // agc.rs:397-408
-                    peak = add(mul(peak, coeff), mul(v, sub(1.0f, coeff)));
-                    sum = add(sub(sum, mul(ov, ov)), mul(v, v));           // agc.rs:157
-                    av[j] = sum, bv[j] = peak;
-                } else if (k4 * 4 + j < cnt) {
-                    const float desired = bv[j];
-                    float kk = (desired > gain) ? attack : release;
-                    gain = add(mul(gain, kk), mul(desired, sub(1.0f, kk)));
-                    if (gain < 0.1f) gain = 0.1f;                          // f32::clamp(0.1, max)
-                    if (gain > max_gain) gain = max_gain;
-                    av[j] = mul(av[j], gain);
-                }
-            }
-            mx4[k4] = make_float4(av[0], av[1], av[2], av[3]);
-            if (PASS == 0) my4[k4] = make_float4(bv[0], bv[1], bv[2], bv[3]);
-        }
-        __syncwarp();
-        const uint64_t n = n0 + lane;
-#pragma unroll
-        for (int r = 0; r < 32; r++) {
-            if (n < s_n[r]) {
-                s_out0[r][n] = t_x[r * RTV + lane];
-                if (PASS == 0) s_out1[r][n] = t_y[r * RTV + lane];
-            }
-        }
-    }
-}
+// leave the sequential chains.
 // Passes A and C as a warp-specialised pipeline (the shape of the fused mixer kernel): a CTA owns 32 streams,
-// SIX mover warps stream tiles of AT samples per stream between HBM and shared memory with 16-byte accesses
-// (stage L on tile k+1, stage S on tile k-1) while ONE chain warp (lane = stream, alone on its SM sub-partition)
-// walks tile k in place.  A single warp issues about one instruction every two cycles, so the chain warp executes
-// nothing but the recurrences: the movers also apply y = x * gain on the way out.
+// the mover warps stream tiles of AT samples per stream between HBM and shared memory with 16-byte accesses
+// (stage L on tile k+1, stage S on tile k-1) while the chain warps (lane = stream) walk tile k.
+// A single warp issues about one instruction every 3.5 cycles when every instruction hangs on a dependent chain,
+// so the chain warps execute nothing but the recurrences: pass A runs its two independent chains on two warps
+// (different SM sub-partitions), the movers apply y = x * gain on the way out of pass C.
 //   A  sum[n]  = (sum - x[n-8192]^2) + x[n]^2                       (agc.rs:157; ring of 8192 squares)
 //      peak[n] = |x| > peak ? |x| : peak * release + |x| * (1 - release)
 //         (agc.rs:397-408 with coeff = 0 spelled out: peak * 0 = +0 and |x| * (1 - 0) = |x| exactly, peak >= +0)
@@ -286,14 +199,15 @@ __global__ void __launch_bounds__(32) k_agc_seq_pass(const rb_node_dev* __restri
 //         (agc.rs:474-491; desired is never NaN -- pass B builds it with fmin / fmax -- so min/max is the clamp)
 constexpr int AT = 128;              // samples per stream and tile
 constexpr int ATS = AT + 4;          // padded row, (AT + 4) / 4 odd: 16-byte accesses of 8 lanes hit 8 bank groups
-constexpr int ANB = 3;               // tile ring: loading k+1, chain on k, storing k-1
-constexpr int AGC_CHAIN_WARP = 3;    // 7 warps: warps 0,1,2,4,5,6 move data, warp 3 is alone on sub-partition 3
-constexpr int AGC_THREADS = 7 * 32;
-constexpr size_t AGC_SMEM = (size_t)ANB * 2 * 32 * ATS * sizeof(float);
+constexpr int ANB = 3;               // tile ring: loading k+1, chains on k, storing k-1
+constexpr int AGC_THREADS = 7 * 32;  // warps 3 (sub-partition 3) and, in pass A, 6 (sub-partition 2) are chain warps
+constexpr size_t AGC_ARR = (size_t)32 * ATS;          // one array of a tile: [32 streams][ATS]
+constexpr size_t AGC_BUF = 3 * AGC_ARR;               // x | x[n-8192] -> sum, or desired -> gain | peak
+constexpr size_t AGC_SMEM = (size_t)ANB * AGC_BUF * sizeof(float);
 
 template <int PASS>   // 0 = A, 2 = C
 __global__ void __launch_bounds__(AGC_THREADS) k_agc_pipe(const rb_node_dev* __restrict__ nodes, uint32_t n_nodes) {
-    extern __shared__ __align__(16) float agc_sm[];   // [ANB][2][32][ATS]
+    extern __shared__ __align__(16) float agc_sm[];   // [ANB][3][32][ATS]
     __shared__ const float* s_in0[32];
     __shared__ const float* s_in1[32];
     __shared__ float* s_out0[32];
@@ -321,15 +235,16 @@ __global__ void __launch_bounds__(AGC_THREADS) k_agc_pipe(const rb_node_dev* __r
     __syncthreads();
     const uint64_t max_n = s_max_n;
     const uint32_t n_tiles = (uint32_t)((max_n + AT - 1) / AT);
-    const bool is_chain = warp == AGC_CHAIN_WARP;
-    const uint32_t mv = warp < AGC_CHAIN_WARP ? warp : warp - 1;   // mover index 0..5
-    constexpr size_t ARR = (size_t)32 * ATS, BUF = 2 * ARR;
+    const bool chain_sum = warp == 3;                       // pass C: the gain chain
+    const bool chain_peak = PASS == 0 && warp == 6;
+    constexpr uint32_t NMOV = PASS == 0 ? 5 : 6;
+    const uint32_t mv = warp < 3 ? warp : warp - 1;         // mover index among warps {0,1,2,4,5(,6)}
 
     // chain state (lane = stream)
     float gain = 1.0f, peak = 0.0f, sum = 0.0f;
     float attack = 0.f, release = 0.f, max_gain = 0.f, oma = 0.f, omr = 0.f;
     uint64_t my_n = 0;
-    if (is_chain && lane < cnt_rows) {
+    if ((chain_sum || chain_peak) && lane < cnt_rows) {
         const rb_node_dev& nd = nds[lane];
         my_n = nd.n_in;
         max_gain = nd.p.agc.max_gain, attack = nd.p.agc.attack, release = nd.p.agc.release;
@@ -338,17 +253,18 @@ __global__ void __launch_bounds__(AGC_THREADS) k_agc_pipe(const rb_node_dev* __r
 
     uint32_t lb = 0, cb = 0, sb = 0;   // ring slots of the tile being loaded / walked / stored
     for (uint32_t it = 0; it < n_tiles + 2; it++) {
-        if (!is_chain) {
+        if (!chain_sum && !chain_peak) {
             if (it < n_tiles) {
-                // ---- stage L: tile `it`, rows mv, mv+6, ..: one 16-byte load per lane covers a row of AT samples ----
+                // ---- stage L: tile `it`, rows mv, mv+NMOV, ..: one 16-byte load per lane covers a row of AT samples ----
                 const uint64_t n = (uint64_t)it * AT + 4 * lane;
                 const bool second_on = PASS != 0 || (uint64_t)it * AT >= 8192;
-                float* base = agc_sm + lb * BUF;
+                float* base = agc_sm + lb * AGC_BUF;
                 // all of this warp's loads go out before the first one is consumed (HBM latency is paid once per tile)
-                float4 vx[6], vo[6];
+                constexpr int NR = (32 + NMOV - 1) / NMOV;
+                float4 vx[NR], vo[NR];
 #pragma unroll
-                for (int j = 0; j < 6; j++) {
-                    const uint32_t r = mv + 6 * j;
+                for (int j = 0; j < NR; j++) {
+                    const uint32_t r = mv + NMOV * j;
                     vx[j] = make_float4(0.f, 0.f, 0.f, 0.f), vo[j] = vx[j];
                     if (r >= 32) continue;
                     const uint64_t nr = s_n[r];
@@ -367,23 +283,24 @@ __global__ void __launch_bounds__(AGC_THREADS) k_agc_pipe(const rb_node_dev* __r
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 6; j++) {
-                    const uint32_t r = mv + 6 * j;
+                for (int j = 0; j < NR; j++) {
+                    const uint32_t r = mv + NMOV * j;
                     if (r >= 32) continue;
                     *reinterpret_cast<float4*>(base + r * ATS + 4 * lane) = vx[j];
-                    *reinterpret_cast<float4*>(base + ARR + r * ATS + 4 * lane) = vo[j];
+                    *reinterpret_cast<float4*>(base + AGC_ARR + r * ATS + 4 * lane) = vo[j];
                 }
             }
             if (it >= 2) {
                 // ---- stage S: tile `it - 2` ----
                 const uint64_t n = (uint64_t)(it - 2) * AT + 4 * lane;
-                const float* base = agc_sm + sb * BUF;
-                for (uint32_t r = mv; r < 32; r += 6) {
+                const float* base = agc_sm + sb * AGC_BUF;
+                for (uint32_t r = mv; r < 32; r += NMOV) {
                     const uint64_t nr = s_n[r];
                     if (n >= nr) continue;
-                    float4 a = *reinterpret_cast<const float4*>(base + r * ATS + 4 * lane);
-                    const float4 b = *reinterpret_cast<const float4*>(base + ARR + r * ATS + 4 * lane);
-                    if (PASS == 2) a.x = mul(a.x, b.x), a.y = mul(a.y, b.y), a.z = mul(a.z, b.z), a.w = mul(a.w, b.w);   // y = x * gain
+                    // pass A: sum (second array) -> aux0, peak (third array) -> aux1; pass C: x * gain -> dst
+                    float4 a = *reinterpret_cast<const float4*>(base + (PASS == 0 ? AGC_ARR : 0) + r * ATS + 4 * lane);
+                    const float4 b = *reinterpret_cast<const float4*>(base + (PASS == 0 ? 2 * AGC_ARR : AGC_ARR) + r * ATS + 4 * lane);
+                    if (PASS == 2) a.x = mul(a.x, b.x), a.y = mul(a.y, b.y), a.z = mul(a.z, b.z), a.w = mul(a.w, b.w);
                     if (n + 4 <= nr) {
                         *reinterpret_cast<float4*>(s_out0[r] + n) = a;
                         if (PASS == 0) *reinterpret_cast<float4*>(s_out1[r] + n) = b;
@@ -398,25 +315,46 @@ __global__ void __launch_bounds__(AGC_THREADS) k_agc_pipe(const rb_node_dev* __r
                 }
             }
         } else if (it >= 1 && it <= n_tiles) {
-            // ---- chain: tile `it - 1`, lane = stream; whole groups of four (positions past the end are never stored) ----
+            // ---- chains: tile `it - 1`, lane = stream; whole groups of four (positions past the end are never stored) ----
             const uint64_t n0 = (uint64_t)(it - 1) * AT;
             const int cnt = (int)min((uint64_t)AT, my_n > n0 ? my_n - n0 : 0);
-            float4* px = reinterpret_cast<float4*>(agc_sm + cb * BUF + lane * ATS);
-            float4* po = reinterpret_cast<float4*>(agc_sm + cb * BUF + ARR + lane * ATS);
+            const float4* px = reinterpret_cast<const float4*>(agc_sm + cb * AGC_BUF + lane * ATS);
+            float4* po = reinterpret_cast<float4*>(agc_sm + cb * AGC_BUF + AGC_ARR + lane * ATS);
+            float4* pp = reinterpret_cast<float4*>(agc_sm + cb * AGC_BUF + 2 * AGC_ARR + lane * ATS);
+            if (PASS == 0 && chain_sum) {
 #pragma unroll 2
-            for (int k4 = 0; k4 * 4 < cnt; k4++) {
-                const float4 a = px[k4], b = po[k4];
-                const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-                float r0[4], r1[4];
+                for (int k4 = 0; k4 * 4 < cnt; k4++) {
+                    const float4 a = px[k4], b = po[k4];
+                    float4 o;
+                    sum = add(sub(sum, mul(b.x, b.x)), mul(a.x, a.x)), o.x = sum;
+                    sum = add(sub(sum, mul(b.y, b.y)), mul(a.y, a.y)), o.y = sum;
+                    sum = add(sub(sum, mul(b.z, b.z)), mul(a.z, a.z)), o.z = sum;
+                    sum = add(sub(sum, mul(b.w, b.w)), mul(a.w, a.w)), o.w = sum;
+                    po[k4] = o;
+                }
+            } else if (PASS == 0) {
+#pragma unroll 2
+                for (int k4 = 0; k4 * 4 < cnt; k4++) {
+                    const float4 a = px[k4];
+                    const float av[4] = {a.x, a.y, a.z, a.w};
+                    float r1[4];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    if (PASS == 0) {
-                        const float v = fabsf(av[j]), ov = fabsf(bv[j]);
+                    for (int j = 0; j < 4; j++) {
+                        const float v = fabsf(av[j]);
                         const float decayed = add(mul(peak, release), mul(v, omr));
                         peak = (v > peak) ? v : decayed;
-                        sum = add(sub(sum, mul(ov, ov)), mul(v, v));
-                        r0[j] = sum, r1[j] = peak;
-                    } else {
+                        r1[j] = peak;
+                    }
+                    pp[k4] = make_float4(r1[0], r1[1], r1[2], r1[3]);
+                }
+            } else {
+#pragma unroll 2
+                for (int k4 = 0; k4 * 4 < cnt; k4++) {
+                    const float4 b = po[k4];
+                    const float bv[4] = {b.x, b.y, b.z, b.w};
+                    float r1[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
                         const float desired = bv[j];
                         const bool up = desired > gain;
                         const float kk = up ? attack : release, omk = up ? oma : omr;
@@ -424,9 +362,8 @@ __global__ void __launch_bounds__(AGC_THREADS) k_agc_pipe(const rb_node_dev* __r
                         gain = fminf(fmaxf(gain, 0.1f), max_gain);
                         r1[j] = gain;
                     }
+                    po[k4] = make_float4(r1[0], r1[1], r1[2], r1[3]);
                 }
-                if (PASS == 0) px[k4] = make_float4(r0[0], r0[1], r0[2], r0[3]);
-                po[k4] = make_float4(r1[0], r1[1], r1[2], r1[3]);
             }
         }
         if (it < n_tiles) lb = lb + 1 == ANB ? 0 : lb + 1;
