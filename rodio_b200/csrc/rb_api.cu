@@ -509,6 +509,8 @@ struct rb_batch {
     size_t buf_floats = 0;
     rb_node_dev* d_nodes = nullptr;
     rb_mix_src* d_mix = nullptr;
+    float* d_mix_partial = nullptr;   // [mix_groups][mix_len] when the source list is summed in concurrent runs
+    uint32_t mix_groups = 1;
     float* d_out = nullptr;
     std::vector<LaunchGroup> groups;
     rb_fused_plan* fused = nullptr;   // non-null when the fused path serves this batch
@@ -531,6 +533,7 @@ extern "C" rb_status rb_batch_destroy(rb_batch* b) {
     cudaFree(b->d_aux[1]);
     cudaFree(b->d_nodes);
     cudaFree(b->d_mix);
+    cudaFree(b->d_mix_partial);
     cudaFree(b->d_out);
     delete b;
     return RB_OK;
@@ -659,10 +662,23 @@ extern "C" rb_status rb_batch_create(rb_context* ctx, uint16_t mixer_ch, uint32_
         RB_CUDA(cudaMalloc(&b->d_mix, std::max<size_t>(n_streams * sizeof(rb_mix_src), 256)));
         if (n_streams)
             RB_CUDA(cudaMemcpy(b->d_mix, mix.data(), n_streams * sizeof(rb_mix_src), cudaMemcpyHostToDevice));
+        // Few output samples, many sources (short blocks of a big mixer): one thread per four outputs leaves most SMs
+        // idle.  Unless the caller pinned the summation order, cut the source list into runs summed concurrently.
+        const uint64_t mix_blocks = ((mix_len + 3) / 4 + 255) / 256;
+        const uint64_t want_blocks = 2ull * (uint64_t)ctx->sm_count;
+        if (!(flags & RB_MIX_EXACT_ORDER) && mix_len && n_streams >= 256 && mix_blocks < want_blocks) {
+            uint64_t g = (want_blocks + mix_blocks - 1) / mix_blocks;
+            g = std::min<uint64_t>(g, n_streams / 64);
+            g = std::min<uint64_t>(g, 64);
+            if (g > 1) {
+                RB_CUDA(cudaMalloc(&b->d_mix_partial, (size_t)g * ((mix_len + 3) & ~3ull) * sizeof(float)));
+                b->mix_groups = (uint32_t)g;
+            }
+        }
     }
     uint32_t general_launches = 0;
     for (const LaunchGroup& g : b->groups) general_launches += (g.kind == RB_N_AGC) ? 3u : 1u;
-    b->launches = b->fused ? rb_fused_launch_count(b->fused) : general_launches + (mix_len ? 1u : 0u);
+    b->launches = b->fused ? rb_fused_launch_count(b->fused) : general_launches + (mix_len ? (b->mix_groups > 1 ? 2u : 1u) : 0u);
     if (b->fused && (flags & RB_KEEP_STREAM_OUTPUTS)) b->launches += general_launches;
     *out = b.release();
     return RB_OK;
@@ -759,7 +775,8 @@ static rb_status run_general(rb_batch* b, bool with_mix) {
     cudaStream_t st = b->ctx->stream;
     for (const LaunchGroup& g : b->groups)
         RB_CUDA(rb_launch_nodes(g.kind, b->d_nodes + g.first, g.count, g.max_n_out, g.max_channels, st));
-    if (with_mix) RB_CUDA(rb_launch_mix(b->d_mix, (uint32_t)b->streams.size(), b->d_out, b->mix_len, st));
+    if (with_mix)
+        RB_CUDA(rb_launch_mix(b->d_mix, (uint32_t)b->streams.size(), b->d_out, b->mix_len, st, b->d_mix_partial, b->mix_groups));
     return RB_OK;
 }
 

@@ -84,6 +84,9 @@ struct rb_mix_src {
 // ---- launchers implemented in rb_kernels.cu (all asynchronous on `st`) ----
 cudaError_t rb_launch_nodes(uint32_t kind, const rb_node_dev* d_nodes, uint32_t n_nodes, uint64_t max_n_out,
                             uint32_t max_channels, cudaStream_t st);
-cudaError_t rb_launch_mix(const rb_mix_src* d_srcs, uint32_t n_srcs, float* d_out, uint64_t out_len, cudaStream_t st);
+// n_groups > 1: the source list is cut into n_groups contiguous runs summed concurrently into d_partial
+// ([n_groups][out_len]) and the runs are added in order -- more bytes in flight when there are few output samples.
+cudaError_t rb_launch_mix(const rb_mix_src* d_srcs, uint32_t n_srcs, float* d_out, uint64_t out_len, cudaStream_t st,
+                          float* d_partial = nullptr, uint32_t n_groups = 1);
 cudaError_t rb_launch_convert(const void* d_in, uint32_t in_fmt, void* d_out, uint32_t out_fmt, uint64_t n,
                               cudaStream_t st);

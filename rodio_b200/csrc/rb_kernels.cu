@@ -484,6 +484,12 @@ template <int U>
 __global__ void __launch_bounds__(256) k_mix_ordered(const rb_mix_src* __restrict__ srcs, uint32_t n_srcs,
                                                      float* __restrict__ out, uint64_t out_len) {
     __shared__ rb_mix_src s_src[MIX_CHUNK];
+    if (gridDim.y > 1) {   // run blockIdx.y of the source list -> its own partial row
+        const uint32_t per = (n_srcs + gridDim.y - 1) / gridDim.y;
+        const uint32_t first = min(n_srcs, blockIdx.y * per);
+        srcs += first, n_srcs = min(per, n_srcs - first);
+        out += (uint64_t)blockIdx.y * ((out_len + 3) & ~3ull);   // row pitch keeps the 16-byte stores aligned
+    }
     const uint64_t n_quads = (out_len + 3) / 4;
     const uint64_t qd = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;   // grid covers every quad exactly once
     const bool live = qd < n_quads;
@@ -589,8 +595,28 @@ cudaError_t rb_launch_nodes(uint32_t kind, const rb_node_dev* d_nodes, uint32_t 
     return cudaGetLastError();
 }
 
-cudaError_t rb_launch_mix(const rb_mix_src* d_srcs, uint32_t n_srcs, float* d_out, uint64_t out_len, cudaStream_t st) {
+// ordered sum of the partial rows of the source runs
+__global__ void __launch_bounds__(256) k_mix_sum_runs(const float* __restrict__ partial, uint32_t n_groups, uint64_t out_len,
+                                                      float* __restrict__ out) {
+    const uint64_t pitch = (out_len + 3) & ~3ull;
+    for (uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; m < out_len; m += (uint64_t)gridDim.x * blockDim.x) {
+        float acc = partial[m];
+        for (uint32_t g = 1; g < n_groups; g++) acc = add(acc, partial[(uint64_t)g * pitch + m]);
+        out[m] = acc;
+    }
+}
+
+cudaError_t rb_launch_mix(const rb_mix_src* d_srcs, uint32_t n_srcs, float* d_out, uint64_t out_len, cudaStream_t st,
+                          float* d_partial, uint32_t n_groups) {
     if (out_len == 0) return cudaSuccess;
+    if (d_partial && n_groups > 1) {
+        const uint64_t nq = (out_len + 3) / 4;
+        const dim3 grid((uint32_t)((nq + 255) / 256), n_groups);
+        k_mix_ordered<16><<<grid, 256, 0, st>>>(d_srcs, n_srcs, d_partial, out_len);
+        const uint64_t sb = (out_len + 255) / 256;
+        k_mix_sum_runs<<<(uint32_t)(sb < 1184 ? sb : 1184), 256, 0, st>>>(d_partial, n_groups, out_len, d_out);
+        return cudaGetLastError();
+    }
     // one thread per 4 outputs; the fewer threads there are, the more 16-byte loads each keeps in flight
     const uint64_t n_quads = (out_len + 3) / 4;
     const uint64_t blocks = (n_quads + 255) / 256;

@@ -275,6 +275,24 @@ def test_cfg2_mixer_of_sines(ctx):
         assert_close_peak(b.render_mix(), want, 1e-5, "cfg2 default")
 
 
+def test_wide_short_mixer(ctx):
+    """Many sources, few output samples (a 10 ms block of a big mixer): the default mode sums the source list in
+    concurrent runs (1e-5 * peak), the exact-order mode keeps the reference's sequential sum bit for bit."""
+    rng = np.random.default_rng(77)
+    n = 700
+    srcs = [rb.TestSource(noise(int(rng.integers(1, 481)), 5000 + s, 0.5), 1, 48000) for s in range(n)]
+    starts = sorted(int(rng.integers(0, 200)) * (s % 5 == 0) for s in range(n))
+    want = oracle.mixer([to_oracle(s, st) for s, st in zip(srcs, starts)], 1, 48000)
+    with rb.Batch(srcs, 1, 48000, mix_starts=starts, ctx=ctx) as b:
+        b.upload_all()
+        got = b.render_mix()
+        assert b.launches_per_render == 2, "expected the run-split mix"
+    assert_close_peak(got, want, 1e-5, "wide short mixer, default")
+    with rb.Batch(srcs, 1, 48000, flags=capi.RB_MIX_EXACT_ORDER, mix_starts=starts, ctx=ctx) as b:
+        b.upload_all()
+        assert_bit_exact(b.render_mix(), want, "wide short mixer, exact order")
+
+
 def test_cfg4_effect_chain(ctx):
     """cfg4 shape: spatial -> reverb(50 ms, 0.3) -> AGC(default) -> mix(2 ch)."""
     n, frames = 12, 12000

@@ -50,6 +50,11 @@ def main():
         for S, secs in [(1024, 10), (4096, 2), (16384, 1)]:
             srcs = [rb.TestSource(z(48000 * secs), 1, 48000) for _ in range(S)]
             time_batch(f"cfg2 mixer of {S} mono 48k sources x {secs}s (fused)", srcs, (1, 48000))
+        for S in (1024, 16384):
+            srcs = [rb.TestSource(z(480), 1, 48000) for _ in range(S)]
+            time_batch(f"cfg2 mixer of {S} sources x 10 ms block (concurrent source runs)", srcs, (1, 48000), steps=20)
+            time_batch(f"cfg2 mixer of {S} sources x 10 ms block, exact order", srcs, (1, 48000), steps=20,
+                       flags=rb.capi.RB_MIX_EXACT_ORDER)
         srcs = [rb.TestSource(z(48000 * 10), 1, 48000) for _ in range(1024)]
         time_batch("cfg2 1024 x 10s exact-order general path", srcs, (1, 48000), flags=rb.capi.RB_MIX_EXACT_ORDER)
     if "cfg4" in which:
