@@ -707,7 +707,8 @@ __device__ __forceinline__ void hot_issue_window(const FusedRow& r, const HotTil
 // 12-cycle dependent chain if it executes nothing but  y = (t - a1*y1) - a2*y2  -- hence t, not x, in the row.
 // Partial tiles (stream start / end, same-rate rows, the IEEE redo) take the strided path below: lane l works on
 // positions l + 32u, x goes through the row in shared memory, `row[-2C..-1]` are pad slots for the tail.
-template <bool NOGAIN, int C>
+// HASB = false (no filter in the chain: resample -> gains -> mix): the row receives x itself, there is no tail.
+template <bool NOGAIN, int C, bool HASB>
 __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht, uint32_t n_pre, uint32_t n_mid,
                                             uint32_t lane, uint32_t lane_q, uint32_t lane_r, float (&xtail)[2 * C],
                                             const float* __restrict__ win, float* __restrict__ row) {
@@ -763,20 +764,25 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
                 }
             }
             if (!__any_sync(0xffffffffu, bad)) {
-                float pv[2 * C];
-#pragma unroll
-                for (int j = 0; j < 2 * C; j++) {
-                    const float up = __shfl_up_sync(0xffffffffu, xv[P - 2 * C + j], 1);
-                    pv[j] = lane == 0 ? xtail[j] : up;
-                }
-#pragma unroll
-                for (int j = 0; j < 2 * C; j++) xtail[j] = __shfl_sync(0xffffffffu, xv[P - 2 * C + j], 31);
                 float tv[P];
+                if constexpr (HASB) {
+                    float pv[2 * C];
 #pragma unroll
-                for (int u = 0; u < P; u++) {
-                    const float xm1 = u >= C ? xv[u >= C ? u - C : 0] : pv[C + u < 2 * C ? C + u : 0];
-                    const float xm2 = u >= 2 * C ? xv[u >= 2 * C ? u - 2 * C : 0] : pv[u < 2 * C ? u : 0];
-                    tv[u] = biquad_ff(b0, b1, b2, xv[u], xm1, xm2);
+                    for (int j = 0; j < 2 * C; j++) {
+                        const float up = __shfl_up_sync(0xffffffffu, xv[P - 2 * C + j], 1);
+                        pv[j] = lane == 0 ? xtail[j] : up;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 2 * C; j++) xtail[j] = __shfl_sync(0xffffffffu, xv[P - 2 * C + j], 31);
+#pragma unroll
+                    for (int u = 0; u < P; u++) {
+                        const float xm1 = u >= C ? xv[u >= C ? u - C : 0] : pv[C + u < 2 * C ? C + u : 0];
+                        const float xm2 = u >= 2 * C ? xv[u >= 2 * C ? u - 2 * C : 0] : pv[u < 2 * C ? u : 0];
+                        tv[u] = biquad_ff(b0, b1, b2, xv[u], xm1, xm2);
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < P; u++) tv[u] = xv[u];
                 }
                 float4* o = reinterpret_cast<float4*>(row + P * lane);
 #pragma unroll
@@ -798,9 +804,11 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
     float* __restrict__ out = row + ht.lo + lane;
     // x of the 2C positions before the first active one: zeros when the stream starts in this tile, else the tail
     const bool first = ht.i0 == 0 && ht.r0 == 0;
+    if constexpr (HASB) {
 #pragma unroll
-    for (int j = 0; j < 2 * C; j++)
-        if (lane == (uint32_t)j) row[(int)ht.lo - 2 * C + j] = first ? 0.0f : xtail[j];
+        for (int j = 0; j < 2 * C; j++)
+            if (lane == (uint32_t)j) row[(int)ht.lo - 2 * C + j] = first ? 0.0f : xtail[j];
+    }
 #pragma unroll 1
     for (int u = 0; u < U; u++) {
         if (lane + 32u * (uint32_t)u < n) {
@@ -811,6 +819,7 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
         num += r32, di += q32;
         if (num >= to) num -= to, di += 1;
     }
+    if constexpr (!HASB) return;
     __syncwarp();
     float xv[U], xm1[U], xm2[U];
 #pragma unroll
@@ -894,7 +903,7 @@ __device__ __forceinline__ void hot_mix4(const float* tile, const HotTile* hts, 
 // C == 2 (stereo source into a stereo mixer): a row carries two recurrence chains, so a CTA owns at most 16 rows
 // and the recurrence warp's lane is (row, channel) = (lane / 2, lane % 2); the eight stage-C blocks move to the
 // row-less slots 16..23.
-template <int C>
+template <int C, bool HASB>
 __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(16) FusedRow s_rows[MAX_G];
@@ -916,8 +925,15 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
     uint64_t lo, hi;
     cta_span(s_rows, G, a, lo, hi);
     if (lo >= hi) return;
-    const uint64_t m_begin = lo / TT * TT;
-    const uint32_t n_tiles = (uint32_t)((hi - m_begin + TT - 1) / TT);
+    uint64_t m_begin = lo / TT * TT;
+    uint32_t n_tiles = (uint32_t)((hi - m_begin + TT - 1) / TT);
+    if (!HASB && gridDim.y > 1) {
+        // no recurrence, no state: the timeline of the row group is cut into gridDim.y independent slices
+        const uint32_t t0 = (uint32_t)((uint64_t)n_tiles * blockIdx.y / gridDim.y);
+        const uint32_t t1 = (uint32_t)((uint64_t)n_tiles * (blockIdx.y + 1) / gridDim.y);
+        if (t0 >= t1) return;
+        m_begin += (uint64_t)t0 * TT, n_tiles = t1 - t0;
+    }
     uint64_t f_lo, f_hi;
     cta_full_span(s_rows, G, f_lo, f_hi);
 
@@ -968,7 +984,7 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
         uint32_t kb = 0, kh = 0;
         HOT_BAR();   // it == 0: nothing to do yet
         for (uint32_t it = 1; it < n_iter; it++) {
-            if (it <= n_tiles && chain_on && !HOT_SKIP(2)) {
+            if (HASB && it <= n_tiles && chain_on && !HOT_SKIP(2)) {
                 float* row = rbase + kb * tile_sz;
                 const uint2 act = *reinterpret_cast<const uint2*>(&s_ht[kh][rec_row].lo);
                 uint32_t t = act.x;
@@ -1095,15 +1111,15 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
                     {
                         const HotTile& ht = s_ht[kh][slot];
                         if (ht.lo < ht.hi) {
-                            if (nogain) hot_stage_a<true, C>(rowA, ht, a.n_pre, a.n_mid, lane, lane_q0, lane_r0, xtail0, win + slot * WSTRIDE, tile + slot * ROW_STRIDE);
-                            else hot_stage_a<false, C>(rowA, ht, a.n_pre, a.n_mid, lane, lane_q0, lane_r0, xtail0, win + slot * WSTRIDE, tile + slot * ROW_STRIDE);
+                            if (nogain) hot_stage_a<true, C, HASB>(rowA, ht, a.n_pre, a.n_mid, lane, lane_q0, lane_r0, xtail0, win + slot * WSTRIDE, tile + slot * ROW_STRIDE);
+                            else hot_stage_a<false, C, HASB>(rowA, ht, a.n_pre, a.n_mid, lane, lane_q0, lane_r0, xtail0, win + slot * WSTRIDE, tile + slot * ROW_STRIDE);
                         }
                     }
                     if (has_second && !HOT_SKIP(8)) {
                         const HotTile& ht = s_ht[kh][second];
                         if (ht.lo < ht.hi) {
-                            if (nogain) hot_stage_a<true, C>(rowB, ht, a.n_pre, a.n_mid, lane, lane_q1, lane_r1, xtail1, win + second * WSTRIDE, tile + second * ROW_STRIDE);
-                            else hot_stage_a<false, C>(rowB, ht, a.n_pre, a.n_mid, lane, lane_q1, lane_r1, xtail1, win + second * WSTRIDE, tile + second * ROW_STRIDE);
+                            if (nogain) hot_stage_a<true, C, HASB>(rowB, ht, a.n_pre, a.n_mid, lane, lane_q1, lane_r1, xtail1, win + second * WSTRIDE, tile + second * ROW_STRIDE);
+                            else hot_stage_a<false, C, HASB>(rowB, ht, a.n_pre, a.n_mid, lane, lane_q1, lane_r1, xtail1, win + second * WSTRIDE, tile + second * ROW_STRIDE);
                         }
                     }
                 }
@@ -1265,7 +1281,7 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     plan->all_f32 = true;
     for (size_t i = 0; i < n_streams; i++) plan->all_f32 = plan->all_f32 && streams[i].fmt == RB_FMT_F32;
     const uint32_t C = mixer_channels;
-    plan->hot = has_b && plan->all_f32 && (C == 1 || C == 2);
+    plan->hot = (has_b || has_u) && plan->all_f32 && (C == 1 || C == 2);
     for (size_t i = 0; i < n_streams && plan->hot; i++) {
         FusedRow& r = rows[i];
         // the HOT kernel counts the index state in frames: C interleaved channels share one (i0, r0)
@@ -1274,6 +1290,18 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
         const bool whole_frames = r.n_in % C == 0 && r.out_len % C == 0 && r.mix_start % C == 0;
         plan->hot = r.c_in == C && whole_frames &&
                     (r.mode == ROW_DIRECT || r.mode == ROW_PASS || (r.mode == ROW_LERP && window_fits));
+        // without a filter only rows that really interpolate take the HOT pipeline (the time axis is parallel as
+        // well there: small batches are spread over the machine in time slices, see grid_y below)
+        if (!has_b) plan->hot = plan->hot && r.mode == ROW_LERP;
+    }
+    if (plan->hot && !has_b && n_post == 0) {
+        // no filter: the gains behind the resampler are the last thing before the sum -- apply them in stage C
+        // (same single rounding per gain, same place in the chain) and keep stage A on its gain-free fast path
+        for (size_t i = 0; i < n_streams; i++) {
+            FusedRow& r = rows[i];
+            for (uint32_t k = 0; k < n_mid; k++) r.post[k] = r.mid[k], r.mid[k] = 0.0f;
+        }
+        n_post = n_mid, n_mid = 0;
     }
     if (plan->hot) {
         for (size_t i = 0; i < n_streams; i++) {
@@ -1292,6 +1320,12 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     }
     uint32_t k = (S + (uint32_t)sm_count * max_g - 1) / ((uint32_t)sm_count * max_g);
     uint32_t G = (S + (uint32_t)sm_count * k - 1) / ((uint32_t)sm_count * k);
+    if (plan->hot && !has_b && S > (uint32_t)sm_count) {
+        // full CTAs (every stage-A warp has a row); the machine is filled along the time axis instead.
+        // (Up to one stream per SM the rule above gives G = 1: the sum stays in the reference's sequential order.)
+        const uint32_t nx = (S + max_g - 1) / max_g;
+        G = (S + nx - 1) / nx;
+    }
     if (G > max_g) G = max_g;
     if (G < 1) G = 1;
     uint32_t n_ctas = (S + G - 1) / G;
@@ -1306,16 +1340,20 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     plan->single_cta_direct = (n_ctas == 1);
     if (e == cudaSuccess && !plan->single_cta_direct) e = cudaMalloc(&plan->d_partial, (size_t)n_ctas * mix_len * sizeof(float));
     if (e == cudaSuccess && !plan->single_cta_direct) e = cudaMemsetAsync(plan->d_partial, 0, (size_t)n_ctas * mix_len * sizeof(float), st);
+    plan->hot_smem = ((size_t)NBUF * ROW_STRIDE + (size_t)NWIN * WSTRIDE) * G * sizeof(float);
+    if (e == cudaSuccess && plan->hot) {
+        const int hs = (int)plan->hot_smem;
+        e = C == 2 ? (has_b ? cudaFuncSetAttribute(k_fused_hot<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hs)
+                            : cudaFuncSetAttribute(k_fused_hot<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hs))
+                   : (has_b ? cudaFuncSetAttribute(k_fused_hot<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hs)
+                            : cudaFuncSetAttribute(k_fused_hot<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hs));
+    }
     if (e == cudaSuccess && has_b) {
         const int sb = (int)plan->smem_bytes;
         e = cudaFuncSetAttribute(k_fused_biquad<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused_biquad<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused_biquad<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused_biquad<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb);
-        plan->hot_smem = ((size_t)NBUF * ROW_STRIDE + (size_t)NWIN * WSTRIDE) * G * sizeof(float);
-        if (e == cudaSuccess && plan->hot)
-            e = C == 2 ? cudaFuncSetAttribute(k_fused_hot<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->hot_smem)
-                       : cudaFuncSetAttribute(k_fused_hot<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->hot_smem);
     }
     if (e != cudaSuccess) {
         rb_fused_destroy(plan);
@@ -1330,6 +1368,7 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     // no-biquad variant: spread the timeline of each CTA over blockIdx.y so small batches still fill the GPU
     uint64_t tiles = (mix_len + TT - 1) / TT;
     uint64_t want_y = ((uint64_t)sm_count * 8 + n_ctas - 1) / n_ctas;
+    if (plan->hot) want_y = has_b ? 1 : std::min<uint64_t>(((uint64_t)sm_count + n_ctas - 1) / n_ctas, std::max<uint64_t>(1, tiles / 8));
     plan->grid_y = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(tiles, want_y), 65535));
     *out = plan;
     return cudaSuccess;
@@ -1337,12 +1376,18 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
 
 cudaError_t rb_fused_run(rb_fused_plan* p, cudaStream_t st) {
     const FusedArgs& a = p->args;
-    if (a.has_biquad) {
+    if (p->hot) {
+        if (a.c_mix == 1) {
+            if (a.has_biquad) k_fused_hot<1, true><<<p->n_ctas, 1024, p->hot_smem, st>>>(a);
+            else k_fused_hot<1, false><<<dim3(p->n_ctas, p->grid_y), 1024, p->hot_smem, st>>>(a);
+        } else {
+            if (a.has_biquad) k_fused_hot<2, true><<<p->n_ctas, 1024, p->hot_smem, st>>>(a);
+            else k_fused_hot<2, false><<<dim3(p->n_ctas, p->grid_y), 1024, p->hot_smem, st>>>(a);
+        }
+    } else if (a.has_biquad) {
         const uint32_t threads = 512;
         const bool mono = a.c_mix == 1;
-        if (p->hot && mono) k_fused_hot<1><<<p->n_ctas, 1024, p->hot_smem, st>>>(a);
-        else if (p->hot) k_fused_hot<2><<<p->n_ctas, 1024, p->hot_smem, st>>>(a);
-        else if (p->all_f32 && mono) k_fused_biquad<true, 1><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
+        if (p->all_f32 && mono) k_fused_biquad<true, 1><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
         else if (p->all_f32) k_fused_biquad<true, 0><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
         else if (mono) k_fused_biquad<false, 1><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);
         else k_fused_biquad<false, 0><<<p->n_ctas, threads, p->smem_bytes, st>>>(a, p->n_rec_warps);

@@ -416,6 +416,8 @@ FUSED_CASES = [
     (40, 2, 48000, (2, 48000), "hp", False, True),      # stereo, same rate
     (100, 2, 48000, (2, 44100), "lp", False, False),    # stereo, mild downsampling
     (2400, 2, 44100, (2, 48000), "hp", False, True),    # stereo, 16 rows per CTA and two CTAs per SM
+    (1300, 1, 44100, (1, 48000), None, False, True),    # no filter, batch large enough for the HOT pipeline
+    (1250, 2, 44100, (2, 48000), None, False, False),   # same, stereo
 ]
 
 

@@ -62,6 +62,12 @@ def main():
         srcs = [rb.Spatial(rb.TestSource(z(2 * frames), 2, 48000), [float(s % 7 - 3), 1.0, 0.0], [-1, 0, 0], [1, 0, 0])
                 .reverb(rb.Duration.from_millis(50), 0.3).automatic_gain_control() for s in range(S)]
         time_batch("cfg4 512 stereo: spatial -> reverb -> agc -> mix (general path)", srcs, (2, 48000), steps=3)
+    if "nofilter" in which:
+        for ch, S in ((1, 4096), (2, 2048)):
+            srcs = [rb.UniformSourceIterator(rb.TestSource(z(44100 * 2 * ch), ch, 44100), ch, 48000).amplify(0.8)
+                    for _ in range(S)]
+            time_batch(f"resample 44.1k->48k -> amplify -> mix, {S} streams x {ch} ch x 2s (HOT pipeline, no filter)", srcs, (ch, 48000))
+            time_batch(f"same, {S // 8} streams (generic fused kernel, timeline split over CTAs)", srcs[: S // 8], (ch, 48000))
     if "cfg3_stereo" in which:
         S, frames = 2048, 44100 * 2
         srcs = [rb.UniformSourceIterator(rb.TestSource(z(2 * frames), 2, 44100), 2, 48000).low_pass(200).amplify(1.2)
