@@ -554,12 +554,14 @@ __global__ void __launch_bounds__(512, 1) k_fused_biquad(FusedArgs a, uint32_t n
 }
 
 // ---------------------------------------------------------------------------------------------------
-// HOT variant (BASELINE cfg3): every row is a mono f32 source, linear interpolation with from <= to,
-// mono mixer, one biquad.  Same three-stage pipeline, plus a fourth, asynchronous stage in front:
-//   L  tile k+2 : each row's input window (<= TT+8 floats) is fetched by the bulk-copy engine
+// HOT variant (BASELINE cfg3 and its relatives): every row is an f32 source with the mixer's channel count
+// (mono or stereo), same rate or linear interpolation with from/to <= 1.2, at most one biquad.
+// Same three-stage pipeline, plus a fourth, asynchronous stage in front:
+//   L  tile k+2 : each row's input window (<= TT*from/to + 3 frames) is fetched by the bulk-copy engine
 //                 (cp.async.bulk global -> shared, completion counted on an mbarrier), two tiles ahead,
 //                 so stage A never touches global memory and never waits for HBM latency.
-// 1024 threads: one stage-A warp per row, the recurrence warp has the highest warp id.
+// 1024 threads, one loop per role: 23 stage-A warps (one row each, five take a second row), the loader warp,
+// the recurrence warp alone on its SM sub-partition, stage C on two of the stage-A warps.
 // ---------------------------------------------------------------------------------------------------
 constexpr int NWIN = 3;                 // input-window ring (tile k .. k+2)
 constexpr int WSTRIDE = 320;            // floats per row window (>= 3 + TT*from/to + 3, multiple of 4): from/to <= 1.2
