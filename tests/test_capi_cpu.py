@@ -148,7 +148,7 @@ def test_source_metadata_follows_the_trait():
 
 # ---- planner closed forms vs the literal pull iterator (host only) --------------------------
 from chains import CHAINS, LIMIT_CHAINS  # noqa: E402
-from helpers import to_oracle  # noqa: E402
+from helpers import noise, to_oracle  # noqa: E402
 
 
 @pytest.mark.parametrize("name", sorted(CHAINS) + sorted(LIMIT_CHAINS))
@@ -186,6 +186,24 @@ def test_planner_random_uniform_lengths(built):
             assert e.status in (capi.RB_ERR_UNSUPPORTED,), e
             continue
         assert got == oracle.chain_uniform(to_oracle(src), *mix).size, (i, kind, c, n, mix)
+
+
+def test_planner_cfg1_shape(built):
+    """BASELINE cfg1 (benches/resampler.rs): 12 s of s16 stereo 44.1 kHz -> take_duration(10 s) ->
+    UniformSourceIterator(2 ch, 48 kHz), at full size, against the literal iterators of the oracle.
+    take.rs:65-69 truncates the per-sample duration to 11 337 ns: the take yields 882 067 samples plus one of
+    frame padding (882 068) -- and the padding is never pulled through the UniformSourceIterator,
+    whose span-limited Take stops at the 882 067 the source reports (take.rs:171-196, uniform.rs:50-68)."""
+    x = (noise(2 * 44100 * 12, 31, 0.9) * 30000).astype(np.int16)
+    src = rb.TestSource(x, 2, 44100).take_duration(rb.Duration.from_secs(10))
+    chain, ch, rate = oracle.chain(to_oracle(src))
+    assert (chain.size, ch, rate) == (882_068, 2, 44100)
+    n, pch, prate, cn = rb.plan(src, 2, 48000)
+    assert (pch, prate, cn) == (2, 44100, 882_068)
+    want = oracle.chain_uniform(to_oracle(src), 2, 48000)
+    assert n == want.size == 960_076
+    for to_rate in (8000, 44100, 96000, 192000):
+        assert rb.plan(src, 2, to_rate)[0] == oracle.chain_uniform(to_oracle(src), 2, to_rate).size
 
 
 def test_planner_take_ramp_distortion_lengths(built):

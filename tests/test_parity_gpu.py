@@ -371,6 +371,19 @@ def test_full_size_properties(ctx):
     assert np.isfinite(y1).all() and np.max(np.abs(y1)) > 0
 
 
+def test_cfg1_full_size(ctx):
+    """BASELINE cfg1 at full size: 10 s of s16 stereo 44.1 kHz (take_duration) -> UniformSourceIterator(2, 48 kHz),
+    bit-exact against the literal iterators, through the general path and through the fused path."""
+    x = (noise(2 * 44100 * 12, 31, 0.9) * 30000).astype(np.int16)
+    src = rb.TestSource(x, 2, 44100).take_duration(rb.Duration.from_secs(10))
+    want = oracle.chain_uniform(to_oracle(src), 2, 48000)
+    assert want.size == 960_076
+    assert_bit_exact(run_chain(src, ctx, mixer=(2, 48000)), want, "cfg1 general path")
+    with rb.Batch([src], 2, 48000, ctx=ctx) as b:
+        b.upload_all()
+        assert_bit_exact(b.render_mix(), want, "cfg1 default path")
+
+
 # ------------------------------------------------------------------ fused kernel shapes (default flags)
 def _fused_case(rng, i, S, c_in, rate_in, mix, biquad, fmt16, late):
     srcs, starts = [], []
