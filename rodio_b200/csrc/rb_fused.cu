@@ -847,7 +847,8 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
 //   second rows of slots {0,3 | 1 | 2,5} and stage C runs on slots {6, 7}: the three sub-partitions carry about
 //   equal instruction counts (the loader sits where one row fewer does).
 constexpr uint32_t HOT_MAX_ROWS = 28;          // 23 slots + 5 second rows
-constexpr uint32_t HOT_MAX_ROWS_STEREO = 16;   // 32 chains in the recurrence warp
+constexpr uint32_t HOT_MAX_ROWS_STEREO = 28;   // 56 chains: a second recurrence warp (27, same sub-partition) takes rows 16..27
+constexpr uint32_t HOT_REC_WARP2 = 27;
 constexpr uint32_t HOT_REC_WARP = 31, HOT_LOAD_WARP = 30;
 __device__ __forceinline__ int hot_row_slot(uint32_t warp) {
     if ((warp & 3u) == 3u || warp == HOT_LOAD_WARP) return -1;
@@ -902,9 +903,8 @@ __device__ __forceinline__ void hot_mix4(const float* tile, const HotTile* hts, 
     }
 }
 
-// C == 2 (stereo source into a stereo mixer): a row carries two recurrence chains, so a CTA owns at most 16 rows
-// and the recurrence warp's lane is (row, channel) = (lane / 2, lane % 2); the eight stage-C blocks move to the
-// row-less slots 16..23.
+// C == 2 (stereo source into a stereo mixer): a row carries two recurrence chains; the recurrence lane is
+// (row, channel) and a second recurrence warp on the same sub-partition takes the chains of rows 16..27.
 template <int C, bool HASB>
 __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
     extern __shared__ __align__(16) float smem[];
@@ -940,7 +940,7 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
     cta_full_span(s_rows, G, f_lo, f_hi);
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool is_rec = warp == HOT_REC_WARP, is_loader = warp == HOT_LOAD_WARP;
+    const bool is_rec = warp == HOT_REC_WARP || (C == 2 && warp == HOT_REC_WARP2), is_loader = warp == HOT_LOAD_WARP;
     const int slot = hot_row_slot(warp);
     const bool nogain = a.n_pre == 0 && a.n_mid == 0;
     // prologue: the loader warp (lane = row) fetches the windows of tiles 0 and 1
@@ -975,7 +975,9 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
         }
     } else if (is_rec) {
         // ---- stage B on tile it-1 (lane = chain): nothing but y = (t - a1*y1) - a2*y2 ----
-        const uint32_t rec_row = lane / C, rec_ch = lane % C;
+        // two latency-bound warps interleave on one sub-partition without slowing each other much
+        const uint32_t chain = (warp == HOT_REC_WARP ? 0u : 32u) + lane;
+        const uint32_t rec_row = chain / C, rec_ch = chain % C;
         const bool chain_on = rec_row < G;
         float y1 = 0.f, y2 = 0.f, a1 = 0.f, a2 = 0.f;
         if (chain_on) a1 = s_rows[rec_row].a1, a2 = s_rows[rec_row].a2;
@@ -1080,10 +1082,10 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
     } else if (slot >= 0) {
         // ---- stage A on tile it, stage C on tile it-2 ----
         const bool has_first = (uint32_t)slot < G;
-        const int second = C == 1 ? hot_second_row(slot) : -1;
+        const int second = hot_second_row(slot);
         const bool has_second = second >= 0 && (uint32_t)second < G;
         // stage C: two warps, 4 positions per thread (slots without a second row, on different sub-partitions)
-        const int mix_block = C == 1 ? (slot == 6 ? 0 : slot == 7 ? 1 : -1) : (slot == 16 ? 0 : slot == 17 ? 1 : -1);
+        const int mix_block = slot == 6 ? 0 : slot == 7 ? 1 : -1;
         // (lane's first frame * from) divmod to for the rows this warp owns
         uint32_t lane_q0 = 0, lane_r0 = 0, lane_q1 = 0, lane_r1 = 0;
         if (has_first) {

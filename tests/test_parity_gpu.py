@@ -397,7 +397,7 @@ def _fused_case(rng, i, S, c_in, rate_in, mix, biquad, fmt16, late):
             src = rb.UniformSourceIterator(src, mix[0], mix[1])
         src = src.amplify(1.1)
         if biquad == "lp":
-            src = src.low_pass(300 + 10 * s)
+            src = src.low_pass(300 + 10 * (s % 300))
         elif biquad == "hp":
             src = src.high_pass(150 + s)
         src = src.amplify(1.2).amplify(0.5)
@@ -429,6 +429,7 @@ FUSED_CASES = [
     (40, 2, 48000, (2, 48000), "hp", False, True),      # stereo, same rate
     (100, 2, 48000, (2, 44100), "lp", False, False),    # stereo, mild downsampling
     (2400, 2, 44100, (2, 48000), "hp", False, True),    # stereo, 16 rows per CTA and two CTAs per SM
+    (4100, 2, 44100, (2, 48000), "lp", False, True),    # stereo, 28 rows per CTA: both recurrence warps
     (1300, 1, 44100, (1, 48000), None, False, True),    # no filter, batch large enough for the HOT pipeline
     (1250, 2, 44100, (2, 48000), None, False, False),   # same, stereo
 ]
