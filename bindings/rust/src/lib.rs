@@ -56,7 +56,12 @@ pub const RB_FX_REVERB: u32 = 5;
 pub const RB_FX_AGC: u32 = 6;
 pub const RB_FX_LIMIT: u32 = 7;
 pub const RB_FX_SPATIAL: u32 = 8;
+pub const RB_FX_CHANNEL_VOLUME: u32 = 9;
 pub const RB_FX_UNIFORM: u32 = 10;
+pub const RB_FX_DELAY: u32 = 11;
+pub const RB_FX_DISTORTION: u32 = 12;
+pub const RB_FX_LINEAR_RAMP: u32 = 13;
+pub const RB_FX_TAKE_DURATION: u32 = 14;
 
 /// An in-memory source plus the adapters recorded on it (what `SamplesBuffer::new(..).amplify(..)` builds).
 pub struct GpuSource {
@@ -95,6 +100,26 @@ impl GpuSource {
     /// `Source::reverb` (src/source/mod.rs:628-634)
     pub fn reverb(self, duration: Duration, amplitude: f32) -> Self {
         self.push(RB_FX_REVERB, [0; 3], &[amplitude], [duration.as_nanos() as u64, 0])
+    }
+    /// `Source::delay` (src/source/delay.rs:19-29)
+    pub fn delay(self, duration: Duration) -> Self { self.push(RB_FX_DELAY, [0; 3], &[], [duration.as_nanos() as u64, 0]) }
+    /// `Source::distortion` (src/source/mod.rs:726-731)
+    pub fn distortion(self, gain: f32, threshold: f32) -> Self { self.push(RB_FX_DISTORTION, [0; 3], &[gain, threshold], [0; 2]) }
+    /// `Source::linear_gain_ramp` (src/source/mod.rs:534-546); `fade_in` / `fade_out` are the (0,1,false) / (1,0,true) cases
+    pub fn linear_gain_ramp(self, duration: Duration, start: f32, end: f32, clamp_end: bool) -> Self {
+        self.push(RB_FX_LINEAR_RAMP, [clamp_end as u32, 0, 0], &[start, end], [duration.as_nanos() as u64, 0])
+    }
+    /// `Source::take_duration` (src/source/take.rs:9-26); `fadeout` = `TakeDuration::set_filter_fadeout`
+    pub fn take_duration(self, duration: Duration, fadeout: bool) -> Self {
+        self.push(RB_FX_TAKE_DURATION, [fadeout as u32, 0, 0], &[], [duration.as_nanos() as u64, 0])
+    }
+    /// `Source::automatic_gain_control` (src/source/mod.rs:415-446): target, max gain, floor; attack / release times
+    pub fn automatic_gain_control(self, target: f32, attack: Duration, release: Duration, max_gain: f32) -> Self {
+        self.push(RB_FX_AGC, [0; 3], &[target, max_gain, 0.0], [attack.as_nanos() as u64, release.as_nanos() as u64])
+    }
+    /// `Source::limit` (src/source/limit.rs:94-130): threshold dB, knee dB, attack, release
+    pub fn limit(self, threshold: f32, knee_width: f32, attack: Duration, release: Duration) -> Self {
+        self.push(RB_FX_LIMIT, [0; 3], &[threshold, knee_width], [attack.as_nanos() as u64, release.as_nanos() as u64])
     }
 }
 

@@ -58,8 +58,10 @@ def main():
             ms = e0.elapsed_time(e1)
             what = " + ".join(v for k, v in names.items() if skip & k) or "full kernel"
             print(json.dumps({"streams": S, "channels": ch, "ms": round(ms, 4), "variant": what}))
-            groups = {"rows 2x (w0,1,2,6)": [0, 1, 2, 6], "row+mix": [4, 5, 8, 9, 10, 12, 13, 16],
-                      "row only": [14, 17, 18, 20, 21, 22, 24, 25, 26, 28, 29, 30], "loader": [27], "recurrence": [31]}
+            # warp roles of k_fused_hot (rb_fused.cu: hot_row_slot / hot_second_row / stage C on slots 6, 7)
+            groups = {"two rows (w0,1,2,4,6)": [0, 1, 2, 4, 6], "row + stage C (w8,9)": [8, 9],
+                      "one row": [5, 10, 12, 13, 14, 16, 17, 18, 20, 21, 22, 24, 25, 26, 28, 29], "loader": [30],
+                      "recurrence": [31] + ([27] if ch == 2 else [])}
             n_cta = (S + 27) // 28 if ch == 1 else (S + 15) // 16
             for g, ws in groups.items():
                 work = sum(buf[4 * w] for w in ws) / len(ws) / n_cta
