@@ -371,6 +371,21 @@ def test_full_size_properties(ctx):
     assert np.isfinite(y1).all() and np.max(np.abs(y1)) > 0
 
 
+@pytest.mark.parametrize("channels", [1, 2])
+def test_few_streams_resample_default_path(ctx, channels):
+    """The everyday case: one or a few f32 files at 44.1 kHz played into a 48 kHz mixer with a volume, default flags.
+    One stream per CTA, the timeline cut into slices over the SMs, the mix written in place: bit-exact."""
+    for S in (1, 2, 5):
+        srcs = [rb.TestSource(noise(channels * (30000 + 777 * s), 400 + s, 0.7), channels, 44100).amplify(0.5 + 0.1 * s)
+                for s in range(S)]
+        starts = [0] + [channels * 1000 * s for s in range(1, S)]
+        want = oracle.mixer([to_oracle(s, st) for s, st in zip(srcs, starts)], channels, 48000)
+        with rb.Batch(srcs, channels, 48000, mix_starts=starts, ctx=ctx) as b:
+            b.upload_all()
+            assert b.launches_per_render <= 2
+            assert_bit_exact(b.render_mix(), want, f"{S} stream(s), {channels} ch")
+
+
 def test_cfg1_full_size(ctx):
     """BASELINE cfg1 at full size: 10 s of s16 stereo 44.1 kHz (take_duration) -> UniformSourceIterator(2, 48 kHz),
     bit-exact against the literal iterators, through the general path and through the fused path."""
