@@ -127,10 +127,12 @@ typedef struct rb_batch rb_batch;
 /* rb_batch_create flags */
 enum {
     RB_MIX_EXACT_ORDER = 1u << 0,   /* mixer sum strictly sequential in insertion order (bit-exact with
-                                       src/mixer.rs:185-198 on one GPU); default = per-group ordered partial
-                                       sums combined in group order (deterministic, <= 1e-5 * peak)          */
+                                       src/mixer.rs:185-198 on one GPU); default = ordered partial sums over
+                                       contiguous groups of sources (rows of a fused CTA; runs of a short, wide
+                                       mix of >= 256 sources) combined in group order: deterministic,
+                                       <= 1e-5 * peak, and still the sequential sum for <= 148 fused streams  */
     RB_NO_FUSION = 1u << 1,         /* run one kernel per adapter (debug / cross-check path)                  */
-    RB_BIQUAD_TIME_PARALLEL = 1u << 2, /* chunked-scan biquad: not bit-exact, tolerance-checked; off by default */
+    RB_BIQUAD_TIME_PARALLEL = 1u << 2, /* reserved (chunked-scan biquad, not bit-exact): accepted, served by the exact path */
     RB_KEEP_STREAM_OUTPUTS = 1u << 3   /* also keep every stream's post-chain (pre-mix) samples in HBM so
                                           rb_batch_read_stream can return them                                */
 };
