@@ -133,8 +133,15 @@ enum {
                                        <= 1e-5 * peak, and still the sequential sum for <= 148 fused streams  */
     RB_NO_FUSION = 1u << 1,         /* run one kernel per adapter (debug / cross-check path)                  */
     RB_BIQUAD_TIME_PARALLEL = 1u << 2, /* reserved (chunked-scan biquad, not bit-exact): accepted, served by the exact path */
-    RB_KEEP_STREAM_OUTPUTS = 1u << 3   /* also keep every stream's post-chain (pre-mix) samples in HBM so
+    RB_KEEP_STREAM_OUTPUTS = 1u << 3,  /* also keep every stream's post-chain (pre-mix) samples in HBM so
                                           rb_batch_read_stream can return them                                */
+    RB_FUSED_LANES = 1u << 4           /* opt-in (large batches): serve resample -> [low/high_pass] -> [amplify] -> mix
+                                          of mono f32 sources that share one rate pair (from < to) with the
+                                          lane-per-stream kernel: every stream's samples are bit-identical to the
+                                          default path, the mixer sum is a fixed tree over groups of 32 sources
+                                          (<= 1e-5 * peak like the default grouping).  Ignored when the batch has
+                                          another shape.  Inputs are classified when uploaded: writers through
+                                          rb_batch_input_device_ptr ask for the pointer again after rewriting. */
 };
 
 const char* rb_status_string(rb_status s);
@@ -175,6 +182,9 @@ rb_status rb_batch_stream_out_len(rb_batch* b, size_t stream, uint64_t* n_sample
 rb_status rb_batch_mix_len(rb_batch* b, uint64_t* n_samples);
 /* Number of kernels one rb_batch_render_mix_device enqueues (bench "gpu_launches"). */
 rb_status rb_batch_launches_per_render(rb_batch* b, uint32_t* n);
+/* Which kernel family serves the batch: -1 = one kernel per adapter (general path), 0 = k_fused_biquad /
+ * k_fused_nobiquad, 1 = k_fused_hot, 2 = k_fused_lanes (RB_FUSED_LANES).  For tests and bench labels. */
+rb_status rb_batch_kernel_family(rb_batch* b, int* family);
 /* Algorithmic bytes of one render: 4*sum(in_samples)(or format size) + 4*mix_len. */
 rb_status rb_batch_algorithmic_bytes(rb_batch* b, uint64_t* bytes);
 

@@ -34,6 +34,7 @@ RB_MIX_EXACT_ORDER = 1 << 0
 RB_NO_FUSION = 1 << 1
 RB_BIQUAD_TIME_PARALLEL = 1 << 2
 RB_KEEP_STREAM_OUTPUTS = 1 << 3
+RB_FUSED_LANES = 1 << 4
 
 
 class rb_effect(C.Structure):
@@ -78,6 +79,7 @@ SYMBOLS = {
     "rb_batch_stream_out_len": (C.c_int32, [C.c_void_p, C.c_size_t, _u64p]),
     "rb_batch_mix_len": (C.c_int32, [C.c_void_p, _u64p]),
     "rb_batch_launches_per_render": (C.c_int32, [C.c_void_p, C.POINTER(C.c_uint32)]),
+    "rb_batch_kernel_family": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int)]),
     "rb_batch_algorithmic_bytes": (C.c_int32, [C.c_void_p, _u64p]),
     "rb_batch_render_mix_device": (C.c_int32, [C.c_void_p]),
     "rb_batch_mix_device_ptr": (C.c_int32, [C.c_void_p, _vpp]),

@@ -701,6 +701,7 @@ extern "C" rb_status rb_batch_upload(rb_batch* b, size_t stream, const void* pcm
         RB_CUDA(cudaMemcpyAsync(b->d_in + ps.in_off, pcm, n_samples * fmt_size(ps.desc.format), cudaMemcpyHostToDevice,
                                 b->ctx->stream));
     b->uploaded[stream] = 1;
+    rb_fused_inputs_changed(b->fused);
     return RB_OK;
 }
 
@@ -734,6 +735,7 @@ extern "C" rb_status rb_batch_upload_packed(rb_batch* b, const void* pcm, uint64
         for (size_t k = i; k < j; k++) b->uploaded[k] = 1;
         i = j;
     }
+    rb_fused_inputs_changed(b->fused);
     return RB_OK;
 }
 
@@ -745,6 +747,7 @@ extern "C" rb_status rb_batch_input_device_ptr(rb_batch* b, size_t stream, void*
     *dptr = b->d_in + ps.in_off;
     if (capacity) *capacity = ps.desc.n_samples;
     b->uploaded[stream] = 1;   // the caller takes responsibility for the contents
+    rb_fused_inputs_changed(b->fused);   // ... and asks for the pointer again after rewriting them
     return RB_OK;
 }
 
@@ -763,6 +766,11 @@ extern "C" rb_status rb_batch_mix_len(rb_batch* b, uint64_t* n) {
 extern "C" rb_status rb_batch_launches_per_render(rb_batch* b, uint32_t* n) {
     if (!b || !n) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
     *n = b->launches;
+    return RB_OK;
+}
+extern "C" rb_status rb_batch_kernel_family(rb_batch* b, int* family) {
+    if (!b || !family) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
+    *family = b->fused ? rb_fused_kind(b->fused) : -1;
     return RB_OK;
 }
 extern "C" rb_status rb_batch_algorithmic_bytes(rb_batch* b, uint64_t* bytes) {

@@ -31,6 +31,7 @@
 
 #include "rb_dsp.cuh"
 #include "rb_fused.h"
+#include "rb_lanes.h"
 
 using namespace rbd;
 
@@ -1179,6 +1180,7 @@ struct rb_fused_plan {
     bool all_f32 = true;
     bool hot = false;
     size_t hot_smem = 0;
+    rb_lanes_plan* lanes = nullptr;   // RB_FUSED_LANES: the lane-per-stream kernel serves the batch (rb_lanes.cu)
 };
 
 static const rb_node_dev& node_at(const rb_fused_stream& s, uint32_t i) {
@@ -1284,6 +1286,33 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     auto plan = new rb_fused_plan;
     plan->all_f32 = true;
     for (size_t i = 0; i < n_streams; i++) plan->all_f32 = plan->all_f32 && streams[i].fmt == RB_FMT_F32;
+    if ((flags & RB_FUSED_LANES) && mixer_channels == 1 && plan->all_f32 && has_u && n_pre == 0) {
+        // Lane-per-stream kernel (opt-in): mono f32 streams that all interpolate with ONE reduced ratio from < to,
+        // optional biquad, at most one gain and that one directly in front of the sum.
+        bool ok = has_b ? (n_mid == 0 && n_post <= 1) : (n_mid + n_post <= 1);
+        const uint32_t from = rows[0].uni.from, to = rows[0].uni.to;
+        std::vector<rb_lanes_stream> ls(ok ? n_streams : 0);
+        for (size_t i = 0; i < n_streams && ok; i++) {
+            const FusedRow& r = rows[i];
+            ok = r.mode == ROW_LERP && r.c_in == 1 && r.uni.from == from && r.uni.to == to;
+            rb_lanes_stream& l = ls[i];
+            l.in = (const float*)r.in, l.n_frames = r.uni.tail.L, l.out_len = r.out_len, l.mix_start = r.mix_start;
+            l.b0 = r.b0, l.b1 = r.b1, l.b2 = r.b2, l.a1 = r.a1, l.a2 = r.a2;
+            l.post = n_post ? r.post[0] : (n_mid ? r.mid[0] : 1.0f);
+        }
+        if (ok) {
+            cudaError_t e = rb_lanes_try_create(ls.data(), n_streams, from, to, has_b != 0, (n_mid + n_post) != 0, d_out, mix_len,
+                                                sm_count, st, &plan->lanes);
+            if (e != cudaSuccess) {
+                delete plan;
+                return e;
+            }
+            if (plan->lanes) {
+                *out = plan;
+                return cudaSuccess;
+            }
+        }
+    }
     const uint32_t C = mixer_channels;
     plan->hot = (has_b || has_u) && plan->all_f32 && (C == 1 || C == 2);
     for (size_t i = 0; i < n_streams && plan->hot; i++) {
@@ -1378,7 +1407,12 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     return cudaSuccess;
 }
 
+void rb_fused_inputs_changed(rb_fused_plan* p) {
+    if (p && p->lanes) rb_lanes_inputs_changed(p->lanes);
+}
+
 cudaError_t rb_fused_run(rb_fused_plan* p, cudaStream_t st) {
+    if (p->lanes) return rb_lanes_run(p->lanes, st);
     const FusedArgs& a = p->args;
     if (p->hot) {
         if (a.c_mix == 1) {
@@ -1412,12 +1446,17 @@ cudaError_t rb_fused_run(rb_fused_plan* p, cudaStream_t st) {
 
 void rb_fused_destroy(rb_fused_plan* p) {
     if (!p) return;
+    rb_lanes_destroy(p->lanes);
     cudaFree(p->d_rows);
     cudaFree(p->d_partial);
     delete p;
 }
 
-uint32_t rb_fused_launch_count(const rb_fused_plan* p) { return p->single_cta_direct ? 1u : 2u; }
+uint32_t rb_fused_launch_count(const rb_fused_plan* p) {
+    if (p->lanes) return rb_lanes_launch_count(p->lanes);
+    return p->single_cta_direct ? 1u : 2u;
+}
+int rb_fused_kind(const rb_fused_plan* p) { return p->lanes ? 2 : (p->hot ? 1 : 0); }
 
 #ifdef RB_HOT_TIMING
 extern "C" int rb_debug_hot_skip(int mask) { return (int)cudaMemcpyToSymbol(g_hot_skip, &mask, sizeof(int)); }

@@ -29,3 +29,7 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
 cudaError_t rb_fused_run(rb_fused_plan* plan, cudaStream_t st);
 void rb_fused_destroy(rb_fused_plan* plan);
 uint32_t rb_fused_launch_count(const rb_fused_plan* plan);
+// The input PCM of the batch was (re)written: plans that keep per-stream facts about it refresh them at the next run.
+void rb_fused_inputs_changed(rb_fused_plan* plan);
+// Which kernel family serves the plan: 0 = k_fused_biquad / k_fused_nobiquad, 1 = k_fused_hot, 2 = k_fused_lanes.
+int rb_fused_kind(const rb_fused_plan* plan);

@@ -1,0 +1,287 @@
+// rb_lanes_core.h — the lane-per-stream fused kernel: resample (linear interpolation, from < to) -> [biquad] ->
+// [one gain] -> mixer sum, for LARGE batches of mono f32 streams that share one reduced rate ratio.
+//
+// Why a second kernel next to k_fused_hot (rb_fused.cu).  The exact biquad is a serial chain per stream (bit
+// parity with src/source/blt.rs:558-560 forbids re-association), so a stream can never run faster than one sample
+// per ~13 cycles.  k_fused_hot answers that for a few thousand streams: one warp per SM runs nothing but the
+// recurrences while the other warps do the time-parallel work for it -- the right shape at 28 streams per SM, but
+// beyond that its throughput is flat (~33 issue slots per sample on three of the four SM sub-partitions, 25 % of
+// the HBM roofline at 16 384 and 65 536 streams).  With hundreds of streams per SM the parallelism is across
+// streams, so here EVERY lane owns one stream and walks it serially in time:
+//   * no cross-lane traffic for the resampler or the filter: both taps, the numerator, the filter state live in
+//     the lane's registers; about 21 issue slots per sample in the steady state (index 6, interpolation with its
+//     exact division 6, feed-forward 3-5, recurrence 4, gain 1, sum 0.15), spread over all four sub-partitions;
+//   * a warp = 32 consecutive streams (insertion order) in lock step on the mixer timeline, TILE = 8 samples per
+//     loop iteration (one basic block: the loads and index arithmetic of all 8 steps are hoisted above the
+//     recurrence chain by the compiler);
+//   * the mixer sum is a transposing warp-shuffle reduction (7 + 2 shuffles per 8 x 32 samples): lane 4p ends up
+//     with the sum of timeline position p over the warp's 32 streams and stores it -- one partial row per warp,
+//     added in warp order by k_sum_groups.  (Summation order differs from the reference's sequential order: the
+//     tolerance class of the fused path, <= 1e-5 * peak, tested; RB_MIX_EXACT_ORDER keeps the bit-exact path.)
+//   * inputs reach the lanes through a per-lane ring in shared memory filled by 16-byte cp.async (LDGSTS) in
+//     CHUNK-frame chunks, two chunks ahead; the copies of a chunk are distributed so that 4 consecutive lanes fetch
+//     64 contiguous bytes of one stream (coalesced sectors), whatever stream the copying lane itself owns.
+//     Every input byte is read from HBM once; there are no intermediates in HBM.
+// Streams that start late / end early / end in the "last frame raw" rule (sample_rate.rs:187-199) are handled by
+// run management: the timeline is cut into FAST runs (every lane either fully interior or idle -- idle lanes walk
+// a buffer of zeros) and single SLOW tiles (per-lane closed form with 64-bit index math, IEEE division, global
+// loads), so the hot loop carries no per-lane activity predicates at all.
+//
+// Exact division.  The reference computes a + ((b-a)*num)/den with an IEEE division (src/math.rs:24-26).  The fast
+// tile uses q0 = m*r, q = fma(fma(-q0, den, m), r, q0) with r = RN(1/den) -- correctly rounded whenever the
+// residual is exact, i.e. for every m that is 0 or in [2^-100, 2^100) (verified against `/` on 136 M cases
+// including every den <= 4000).  Instead of guarding every sample, streams are classified ONCE when their PCM is
+// uploaded (k_classify_inputs: all non-zero |x| inside [2^-70, 2^60]); a stream outside that class never takes the
+// fast path (its warp stays on slow tiles, which divide with __fdiv_rn).  Within the class (b-a)*num is 0 or at
+// least 2^-94, so the quotient is exact.  The only visible difference is the sign of a zero quotient
+// ((-0)/den = -0, here +0): it can flip the sign of an exactly-zero stream sample, never a non-zero one, and the
+// mixer adds +0.0 last, as the reference's accumulator starts from it (src/mixer.rs:185-198).
+//
+// This header is compiled twice: by nvcc into k_fused_lanes (rb_lanes.cu) and by g++ into the CPU emulator of
+// tests/emu/ (RB_SIMT_EMULATE), which runs the same warp program on 32 host threads against the oracle.
+#pragma once
+#include <cstdint>
+
+#include "rb_simt.h"
+
+namespace lanes {
+
+constexpr int TILE = 8;                 // timeline samples per loop iteration
+constexpr int CHUNK = 16;               // input frames per ring chunk (one cp.async group)
+constexpr int NSLOT = 4;                // ring slots: chunk c-1 (draining), c, c+1 (in flight), c+2 (just issued)
+constexpr int RING = CHUNK * NSLOT;     // 64 words
+constexpr int MIRROR = CHUNK;           // ring words [RING, RING + MIRROR) repeat [0, MIRROR): a tile never wraps
+constexpr int RS = RING + MIRROR + 4;   // 84 words per lane; RS / 4 odd: LDS of 8 consecutive lanes hits 8 bank quads
+constexpr int QPC = CHUNK / 4;          // 16-byte quads per chunk and stream
+constexpr int RPI = 32 / QPC;           // streams served by one cp.async warp instruction
+constexpr uint32_t RUN_CAP = 1u << 30;
+constexpr uint32_t MIN_RUN = 4 * TILE;  // shortest fast run worth priming the ring for
+static_assert(MIRROR >= TILE && MIRROR <= CHUNK && (RS / 4) % 2 == 1 && RUN_CAP % TILE == 0, "ring geometry");
+constexpr uint32_t ROW_UNSAFE = 1u;     // Row::flags: some sample outside the exact-reciprocal class
+
+struct Row {                 // one stream
+    const float* in;         // mono f32 frames, 16-byte aligned, readable up to a 16-byte tail pad
+    uint64_t L;              // input frames
+    uint64_t out_len;        // samples on the mixer timeline
+    uint64_t mix_start;
+    uint64_t n_int;          // outputs [0, n_int) interpolate between two frames (left frame <= L-2)
+    float b0, b1, b2, a1, a2;
+    float ffk;               // FF2 variant: b1 == ffk * b0 (ffk = +-2) and b2 == b0
+    float post;              // the one gain behind the chain (NPOST == 1)
+    uint32_t flags;
+};
+
+struct Args {
+    const Row* rows;
+    uint32_t n_rows, n_groups;
+    uint32_t from, to;       // reduced ratio, from < to <= 2^20
+    uint32_t q8, r8;         // divmod(TILE * from, to)
+    float den_f, rcp_den, from_f;
+    float neg1;              // -1.0f as a run-time value (keeps fma(p, -1, t) an FFMA: the chain stays on one pipe)
+    uint64_t mix_len;
+    uint64_t pstride;        // floats per partial row: mix_len rounded up to TILE
+    float* partial;          // [n_groups][pstride], zero outside the span each group writes
+    const float* zeros;      // CHUNK zeros, 16-byte aligned: the source of idle lanes
+};
+
+// (t - a1*y1) - a2*y2, each product and each difference rounded once (src/source/blt.rs:558-560)
+SIMT_FN float fb(float a1, float a2, float t, float y1, float y2, float neg1) {
+    return simt::ffma(simt::fmul(a2, y2), neg1, simt::ffma(simt::fmul(a1, y1), neg1, t));
+}
+
+// Sum of v[u] over the 32 lanes for the 8 tile positions u; lane 4p receives position p.  Fixed tree.
+SIMT_FN float reduce_tile(const float (&v)[TILE], uint32_t ln) {
+    const bool b4 = ln & 16u, b3 = ln & 8u, b2 = ln & 4u;
+    float w[4], z[2];
+#pragma unroll
+    for (int j = 0; j < 4; j++) w[j] = simt::fadd(b4 ? v[j + 4] : v[j], simt::shfl_xor(b4 ? v[j] : v[j + 4], 16));
+#pragma unroll
+    for (int j = 0; j < 2; j++) z[j] = simt::fadd(b3 ? w[j + 2] : w[j], simt::shfl_xor(b3 ? w[j] : w[j + 2], 8));
+    float s = simt::fadd(b2 ? z[1] : z[0], simt::shfl_xor(b2 ? z[0] : z[1], 4));
+    s = simt::fadd(s, simt::shfl_xor(s, 1));
+    s = simt::fadd(s, simt::shfl_xor(s, 2));
+    return simt::fadd(s, 0.0f);   // the reference's accumulator starts from +0.0: an all-(-0) column sums to +0
+}
+
+template <bool HASB, bool FF2, int NPOST>
+SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
+    const uint32_t ln = simt::lane();
+    const uint32_t r = group * 32u + ln;
+    const bool has = r < a.n_rows;
+    Row row;
+    if (has) {
+        row = a.rows[r];
+    } else {
+        row.in = a.zeros, row.L = 0, row.out_len = 0, row.mix_start = 0, row.n_int = 0;
+        row.b0 = row.b1 = row.b2 = row.a1 = row.a2 = row.ffk = row.post = 0.0f, row.flags = 0;
+    }
+    const uint64_t ms = row.mix_start, end = row.mix_start + row.out_len;
+    const bool safe = has && !(row.flags & ROW_UNSAFE);
+    const bool live = has && row.out_len != 0;
+    const uint64_t t_lo = simt::reduce_min64(live ? ms : ~0ull), t_hi = simt::reduce_max64(live ? end : 0ull);
+    if (t_lo >= t_hi) return;
+    const uint64_t t_end = (t_hi + TILE - 1) / TILE * TILE;
+    uint64_t t = t_lo / TILE * TILE;
+    float* const ringl = ring_warp + ln * RS;
+    float* const prow = a.partial + (uint64_t)group * a.pstride;
+    const float den = a.den_f, rcp = a.rcp_den, from_f = a.from_f, neg1 = a.neg1;
+    const float b0 = row.b0, b1 = row.b1, b2 = row.b2, a1 = row.a1, a2 = row.a2, ffk = row.ffk, post = row.post;
+    const uint32_t from = a.from, to = a.to;
+    float xh1 = 0.f, xh2 = 0.f, y1 = 0.f, y2 = 0.f;   // canonical filter state: x[n-1], x[n-2], y[n-1], y[n-2]
+    const uint32_t cq = ln % QPC;                      // the quad of a chunk this lane copies ...
+    const uint32_t cr = ln / QPC;                      // ... for stream cr + RPI * j of the warp
+
+    while (t < t_end) {
+        // ---- how long does every lane stay "interior or idle" from t on? ----
+        uint32_t d;
+        if (!has || t >= end) {
+            d = RUN_CAP;
+            xh1 = xh2 = y1 = y2 = 0.f;                  // a finished stream contributes nothing, its filter stops
+        } else if (t < ms) {
+            const uint64_t g = (ms - t) / TILE * TILE;  // idle until the tile the stream starts in
+            d = g > RUN_CAP ? RUN_CAP : (uint32_t)g;
+        } else {
+            const uint64_t o = t - ms;
+            d = 0;
+            if (safe && o + TILE <= row.n_int) {
+                const uint64_t g = (row.n_int - o) / TILE * TILE;
+                d = g > RUN_CAP ? RUN_CAP : (uint32_t)g;
+            }
+        }
+        const uint64_t left = t_end - t;
+        const uint32_t cap = left > RUN_CAP ? RUN_CAP : (uint32_t)left;
+        const uint32_t run = simt::reduce_min(d < cap ? d : cap);
+
+        if (run >= MIN_RUN) {
+            // =================================== FAST RUN: `run` timeline samples ===================================
+            const bool act = has && t >= ms && t < end;
+            uint32_t num = 0, k0 = 0, maxq = QPC - 1;
+            const float* src = a.zeros;
+            if (act) {
+                const uint64_t prod = (t - ms) * (uint64_t)from;
+                const uint64_t i = prod / to;
+                num = (uint32_t)(prod - i * to);
+                const uint64_t ibase = i & ~3ull;
+                k0 = (uint32_t)(i - ibase);
+                src = row.in + ibase;
+                const uint64_t mq = ((row.L - 1) >> 2) - (ibase >> 2);   // last quad (relative) that holds a frame
+                maxq = mq > 0x7fffffffull ? 0x7fffffffu : (uint32_t)mq;
+            }
+            // the streams this lane copies for: source pointer and clamp of stream cr + RPI * j
+            uint64_t sq[QPC];
+            uint32_t mq[QPC];
+#pragma unroll
+            for (int j = 0; j < QPC; j++) {
+                sq[j] = simt::shfl_idx64((uint64_t)(uintptr_t)src, cr + RPI * j);
+                mq[j] = simt::shfl_idx(maxq, cr + RPI * j);
+            }
+            auto issue = [&](uint32_t c) {
+                const uint32_t slot = c % NSLOT;
+                const uint32_t want = c * QPC + cq;
+#pragma unroll
+                for (int j = 0; j < QPC; j++) {
+                    const uint32_t off = want < mq[j] ? want : mq[j];
+                    const float* s = (const float*)(uintptr_t)sq[j] + 4ull * off;
+                    float* dst = ring_warp + (cr + RPI * j) * RS + slot * CHUNK + cq * 4;
+                    simt::cp16(dst, s);
+                    if (slot == 0 && (int)(cq * 4) < MIRROR) simt::cp16(dst + RING, s);
+                }
+                simt::cp_commit();
+            };
+            issue(0);
+            issue(1);
+            simt::cp_wait<1>();   // chunk 0 has landed
+            simt::syncwarp();
+            issue(2);
+            uint32_t c_ready = 1;   // chunks [0, c_ready) are readable; c_ready and c_ready + 1 are in flight
+            const simt::sptr ring_end = simt::sptr_of(ringl + RING);
+            simt::sptr p = simt::sptr_of(ringl + k0);
+            float x0 = simt::lds(p), x1 = simt::lds(simt::sptr_add(p, 1));
+            p = simt::sptr_add(p, 2);
+            float nf = simt::u2f(num);
+            // upper bound of any lane's next ring index after the coming tile: the lane with the largest phase
+            uint32_t kb = 5, kbn = to - 1;
+            float p1 = 0.f, p2 = 0.f;
+            if (HASB && FF2) p1 = simt::fmul(b0, xh1), p2 = simt::fmul(b0, xh2);
+
+            for (uint32_t done = 0; done < run; done += TILE) {
+                kb += a.q8, kbn += a.r8;
+                if (kbn >= to) kbn -= to, kb += 1;
+                if ((kb - 1) / CHUNK >= c_ready) {
+                    simt::cp_wait<1>();      // chunk c_ready has landed (c_ready + 1 may still be in flight)
+                    simt::syncwarp();        // ... for every lane, and nobody reads chunk c_ready - 2 any more
+                    issue(c_ready + 2);      // into the slot of chunk c_ready - 2
+                    c_ready += 1;
+                    simt::emu_count(2, 1);
+                }
+                if (simt::sptr_ge(p, ring_end)) p = simt::sptr_add(p, -RING);
+                float v[TILE];
+#pragma unroll
+                for (int u = 0; u < TILE; u++) {
+                    // src/math.rs:24-26: first + (second - first) * num / den, the division as an exact reciprocal step
+                    const float m = simt::fmul(simt::fsub(x1, x0), nf);
+                    const float q0 = simt::fmul(m, rcp);
+                    const float q = simt::ffma(simt::ffma(-q0, den, m), rcp, q0);
+                    const float x = simt::fadd(x0, q);
+                    // next output frame: numerator += from (mod to); a carry moves one input frame on
+                    simt::lerp_advance(nf, x0, x1, p, from_f, den);
+                    float y = x;
+                    if (HASB) {
+                        float tt;
+                        if (FF2) {
+                            // b1*x1 = ffk*(b0*x1) and b2*x2 = b0*x2 exactly: one product per sample, same roundings
+                            const float pz = simt::fmul(b0, x);
+                            tt = simt::fadd(simt::ffma(p1, ffk, pz), p2);
+                            p2 = p1, p1 = pz;
+                        } else {
+                            tt = simt::fadd(simt::fadd(simt::fmul(b0, x), simt::fmul(b1, xh1)), simt::fmul(b2, xh2));
+                        }
+                        xh2 = xh1, xh1 = x;
+                        y = fb(a1, a2, tt, y1, y2, neg1);
+                        y2 = y1, y1 = y;
+                    }
+                    v[u] = NPOST ? simt::fmul(y, post) : y;
+                }
+                const float s = reduce_tile(v, ln);
+                if ((ln & 3u) == 0) prow[t + done + (ln >> 2)] = s;
+            }
+            simt::cp_wait<0>();
+            simt::syncwarp();
+            simt::emu_count(0, run / TILE);
+            t += run;
+        } else {
+            // =================================== SLOW TILE: per-lane closed form ===================================
+            float v[TILE];
+#pragma unroll 1
+            for (int u = 0; u < TILE; u++) {
+                const uint64_t tt = t + (uint64_t)u;
+                float val = 0.0f;
+                if (has && tt >= ms && tt < end) {
+                    const uint64_t prod = (tt - ms) * (uint64_t)from;
+                    const uint64_t i = prod / to;
+                    const uint32_t num = (uint32_t)(prod - i * to);
+                    const float xa = simt::ldg(row.in + i);
+                    float x = xa;
+                    if (i + 1 < row.L)
+                        x = simt::fadd(xa, simt::fdiv(simt::fmul(simt::fsub(simt::ldg(row.in + i + 1), xa), simt::u2f(num)), den));
+                    float y = x;
+                    if (HASB) {
+                        const float f = simt::fadd(simt::fadd(simt::fmul(b0, x), simt::fmul(b1, xh1)), simt::fmul(b2, xh2));
+                        y = fb(a1, a2, f, y1, y2, neg1);
+                        xh2 = xh1, xh1 = x, y2 = y1, y1 = y;
+                    }
+                    val = NPOST ? simt::fmul(y, post) : y;
+                } else if (has && tt >= end) {
+                    xh1 = xh2 = y1 = y2 = 0.f;
+                }
+                v[u] = val;
+            }
+            const float s = reduce_tile(v, ln);
+            if ((ln & 3u) == 0) prow[t + (ln >> 2)] = s;
+            simt::emu_count(1, 1);
+            t += TILE;
+        }
+    }
+}
+
+}  // namespace lanes

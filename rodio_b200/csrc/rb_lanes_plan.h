@@ -1,0 +1,55 @@
+// rb_lanes_plan.h — host-side arithmetic of the lane-per-stream kernel's plan (plain C++: shared by rb_lanes.cu and
+// by the CPU emulator under tests/emu/ so that both fill lanes::Row / lanes::Args identically).
+#pragma once
+#include <cstdint>
+#include <cstring>
+
+#include "rb_lanes_core.h"
+
+namespace lanes {
+
+// Outputs [0, n) of a converter run over L frames whose left frame is <= L-2, i.e. that interpolate:
+// n = ceil((L-1) * to / from), clipped to the stream's length (src/conversions/sample_rate.rs:157-199: the last
+// frame is emitted raw, once).
+inline uint64_t n_interp(uint64_t L, uint32_t from, uint32_t to, uint64_t out_len) {
+    if (L < 2) return 0;
+    const uint64_t n = ((L - 1) * (uint64_t)to + from - 1) / from;
+    return n < out_len ? n : out_len;
+}
+
+// b1 == +-2*b0 and b2 == b0 (low_pass / high_pass of src/source/blt.rs:504-541: b0 = b1/2 resp. b1 = -(2*b0),
+// b2 = b0, all three divided by the same a0 -- halving and doubling commute with a correctly rounded division).
+// b0 must be far enough from the subnormals that b0*x is normal for every x the classified inputs produce.
+inline bool ff2_coeffs(float b0, float b1, float b2, float* ffk) {
+    uint32_t u0, u2;
+    std::memcpy(&u0, &b0, 4), std::memcpy(&u2, &b2, 4);
+    if (u0 != u2) return false;
+    const float a0 = b0 < 0 ? -b0 : b0;
+    if (!(a0 >= 9.3132257e-10f && a0 <= 1.0737418e9f)) return false;   // [2^-30, 2^30]
+    if (b1 == 2.0f * b0) *ffk = 2.0f;
+    else if (b1 == -2.0f * b0) *ffk = -2.0f;
+    else return false;
+    return true;
+}
+
+inline void fill_ratio(Args& a, uint32_t from, uint32_t to) {
+    a.from = from, a.to = to;
+    a.q8 = (uint32_t)(((uint64_t)TILE * from) / to);
+    a.r8 = (uint32_t)(((uint64_t)TILE * from) % to);
+    a.den_f = (float)to;
+    a.rcp_den = 1.0f / a.den_f;
+    a.from_f = (float)from;
+    a.neg1 = -1.0f;
+}
+
+inline uint64_t round_up_tile(uint64_t n) { return (n + TILE - 1) / TILE * TILE; }
+
+// Input classification for the exact-reciprocal division: every non-zero |x| inside [2^-70, 2^60].
+inline bool sample_in_class(float x) {
+    uint32_t u;
+    std::memcpy(&u, &x, 4);
+    u &= 0x7fffffffu;
+    return u == 0 || (u >= 0x1c800000u && u < 0x5d800000u);   // 2^-70 = 0x1c800000, 2^60 = 0x5d800000
+}
+
+}  // namespace lanes

@@ -1,0 +1,239 @@
+// rb_simt.h — the handful of warp-level primitives the lane-per-stream kernel (rb_lanes_core.h) is written
+// against, with two implementations:
+//   * device (nvcc, default): thin wrappers over the CUDA intrinsics / PTX they name;
+//   * RB_SIMT_EMULATE (g++, tests/emu/): every lane is a host thread, collectives meet at a std::barrier,
+//     cp.async is a queue of pending 16-byte copies that only land at the matching wait_group and whose
+//     destination is poisoned with NaN the moment the copy is issued -- so a read that the device code could
+//     only get right by luck (too short a look-ahead, a slot refilled while still in use) reads NaN in the
+//     emulator.  The emulator is test infrastructure: it lets the CPU suite run the kernel's index / ring / run
+//     logic bit for bit against the oracle without a GPU.  The product never links it.
+// Every float operation is an explicitly rounded single operation on both sides (no contraction: the device TU is
+// built --fmad=false, the emulator -ffp-contract=off).
+#pragma once
+#include <cstdint>
+
+#if defined(RB_SIMT_EMULATE)
+#include <barrier>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <limits>
+#include <utility>
+#include <vector>
+#define SIMT_FN inline
+#else
+#include <cuda_runtime.h>
+#define SIMT_FN __device__ __forceinline__
+#endif
+
+namespace simt {
+
+#if defined(RB_SIMT_EMULATE)
+// ------------------------------------------------------------------------------------------ emulator
+struct WarpEmu {
+    std::barrier<> bar{32};
+    uint32_t xu[32];
+    uint64_t xl[32];
+    float xf[32];
+    // address ranges cp16 / ldg may read (the harness registers every input row with its 16-byte tail pad)
+    std::vector<std::pair<const char*, const char*>> readable;
+    bool ok_read(const void* p, size_t n) const {
+        for (auto& r : readable)
+            if ((const char*)p >= r.first && (const char*)p + n <= r.second) return true;
+        return false;
+    }
+};
+struct LaneEmu {
+    WarpEmu* w = nullptr;
+    uint32_t lane = 0;
+    struct Copy { float* dst; const float* src; };
+    std::vector<Copy> open;                 // copies issued since the last commit
+    std::deque<std::vector<Copy>> groups;   // committed, not yet landed
+    uint64_t n_instr_hint = 0;
+};
+inline thread_local LaneEmu g_lane;
+
+[[noreturn]] inline void emu_fail(const char* what) {
+    std::fprintf(stderr, "simt emulator: %s (lane %u)\n", what, g_lane.lane);
+    std::abort();
+}
+SIMT_FN uint32_t lane() { return g_lane.lane; }
+// coverage counters of the emulator (0: fast tiles, 1: slow tiles, 2: ring refills), counted by lane 0
+inline uint64_t g_emu_count[4] = {0, 0, 0, 0};
+SIMT_FN void emu_count(int which, uint64_t n) {
+    if (g_lane.lane == 0) g_emu_count[which] += n;
+}
+SIMT_FN float fmul(float a, float b) { return a * b; }
+SIMT_FN float fadd(float a, float b) { return a + b; }
+SIMT_FN float fsub(float a, float b) { return a - b; }
+SIMT_FN float fdiv(float a, float b) { return a / b; }
+SIMT_FN float ffma(float a, float b, float c) { return std::fmaf(a, b, c); }
+SIMT_FN float u2f(uint32_t v) { return (float)v; }
+SIMT_FN float ldg(const float* p) {
+    if (!g_lane.w->ok_read(p, 4)) emu_fail("ldg outside the registered input rows");
+    return *p;
+}
+SIMT_FN void sync() { g_lane.w->bar.arrive_and_wait(); }
+SIMT_FN void syncwarp() { sync(); }
+SIMT_FN float shfl_xor(float v, int m) {
+    WarpEmu* w = g_lane.w;
+    w->xf[g_lane.lane] = v;
+    sync();
+    const float r = w->xf[g_lane.lane ^ (uint32_t)m];
+    sync();
+    return r;
+}
+SIMT_FN uint32_t shfl_idx(uint32_t v, uint32_t src) {
+    WarpEmu* w = g_lane.w;
+    w->xu[g_lane.lane] = v;
+    sync();
+    const uint32_t r = w->xu[src & 31u];
+    sync();
+    return r;
+}
+SIMT_FN uint64_t shfl_idx64(uint64_t v, uint32_t src) {
+    WarpEmu* w = g_lane.w;
+    w->xl[g_lane.lane] = v;
+    sync();
+    const uint64_t r = w->xl[src & 31u];
+    sync();
+    return r;
+}
+SIMT_FN uint32_t reduce_min(uint32_t v) {
+    WarpEmu* w = g_lane.w;
+    w->xu[g_lane.lane] = v;
+    sync();
+    uint32_t r = w->xu[0];
+    for (int i = 1; i < 32; i++) r = w->xu[i] < r ? w->xu[i] : r;
+    sync();
+    return r;
+}
+SIMT_FN uint64_t reduce_min64(uint64_t v) {
+    WarpEmu* w = g_lane.w;
+    w->xl[g_lane.lane] = v;
+    sync();
+    uint64_t r = w->xl[0];
+    for (int i = 1; i < 32; i++) r = w->xl[i] < r ? w->xl[i] : r;
+    sync();
+    return r;
+}
+SIMT_FN uint64_t reduce_max64(uint64_t v) {
+    WarpEmu* w = g_lane.w;
+    w->xl[g_lane.lane] = v;
+    sync();
+    uint64_t r = w->xl[0];
+    for (int i = 1; i < 32; i++) r = w->xl[i] > r ? w->xl[i] : r;
+    sync();
+    return r;
+}
+// Shared-memory cursor of a lane (the device keeps a 32-bit shared-window address).
+using sptr = const float*;
+SIMT_FN sptr sptr_of(const float* p) { return p; }
+SIMT_FN sptr sptr_add(sptr p, int words) { return p + words; }
+SIMT_FN bool sptr_ge(sptr a, sptr b) { return a >= b; }
+SIMT_FN float lds(sptr p) { return *p; }
+// One index step of the resampler: numerator += from (mod den); on a carry the right tap becomes the left one and
+// the next ring word is fetched.  (Six instructions on the device, see below.)
+SIMT_FN void lerp_advance(float& nf, float& x0, float& x1, sptr& p, float from_f, float den) {
+    const float nf2 = nf + from_f;
+    if (nf2 >= den) {
+        nf = nf2 - den;
+        x0 = x1;
+        x1 = *p;
+        p += 1;
+    } else {
+        nf = nf2;
+    }
+}
+// 16-byte asynchronous copy global -> shared (cp.async.cg.shared.global): lands at the matching cp_wait.
+SIMT_FN void cp16(float* smem_dst, const float* gsrc) {
+    if (((uintptr_t)smem_dst & 15) || ((uintptr_t)gsrc & 15)) emu_fail("cp16: operands must be 16-byte aligned");
+    if (!g_lane.w->ok_read(gsrc, 16)) emu_fail("cp16 source outside the registered input rows");
+    const float nan = std::numeric_limits<float>::quiet_NaN();
+    for (int i = 0; i < 4; i++) smem_dst[i] = nan;   // the engine may overwrite the slot any time from now on
+    g_lane.open.push_back({smem_dst, gsrc});
+}
+SIMT_FN void cp_commit() {
+    g_lane.groups.push_back(std::move(g_lane.open));
+    g_lane.open.clear();
+}
+template <int N>
+SIMT_FN void cp_wait() {
+    while ((int)g_lane.groups.size() > N) {
+        for (auto& c : g_lane.groups.front()) std::memcpy(c.dst, c.src, 16);
+        g_lane.groups.pop_front();
+    }
+}
+#else
+// ------------------------------------------------------------------------------------------ device
+SIMT_FN uint32_t lane() { return threadIdx.x & 31u; }
+SIMT_FN void emu_count(int, uint64_t) {}
+SIMT_FN float fmul(float a, float b) { return __fmul_rn(a, b); }
+SIMT_FN float fadd(float a, float b) { return __fadd_rn(a, b); }
+SIMT_FN float fsub(float a, float b) { return __fsub_rn(a, b); }
+SIMT_FN float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+SIMT_FN float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+SIMT_FN float u2f(uint32_t v) { return __uint2float_rn(v); }
+SIMT_FN float ldg(const float* p) { return __ldg(p); }
+SIMT_FN void syncwarp() { __syncwarp(); }
+SIMT_FN float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+SIMT_FN uint32_t shfl_idx(uint32_t v, uint32_t src) { return __shfl_sync(0xffffffffu, v, (int)src); }
+SIMT_FN uint64_t shfl_idx64(uint64_t v, uint32_t src) {
+    const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, (int)src);
+    const uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), (int)src);
+    return ((uint64_t)hi << 32) | lo;
+}
+SIMT_FN uint32_t reduce_min(uint32_t v) { return __reduce_min_sync(0xffffffffu, v); }
+SIMT_FN uint64_t reduce_min64(uint64_t v) {
+    // high words first, then the low words of the lanes that hold the minimal high word
+    const uint32_t hi = __reduce_min_sync(0xffffffffu, (uint32_t)(v >> 32));
+    const uint32_t lo = __reduce_min_sync(0xffffffffu, (uint32_t)(v >> 32) == hi ? (uint32_t)v : 0xffffffffu);
+    return ((uint64_t)hi << 32) | lo;
+}
+SIMT_FN uint64_t reduce_max64(uint64_t v) {
+    const uint32_t hi = __reduce_max_sync(0xffffffffu, (uint32_t)(v >> 32));
+    const uint32_t lo = __reduce_max_sync(0xffffffffu, (uint32_t)(v >> 32) == hi ? (uint32_t)v : 0u);
+    return ((uint64_t)hi << 32) | lo;
+}
+using sptr = uint32_t;   // address in the shared window
+SIMT_FN sptr sptr_of(const float* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+SIMT_FN sptr sptr_add(sptr p, int words) { return p + (uint32_t)(words * 4); }
+SIMT_FN bool sptr_ge(sptr a, sptr b) { return a >= b; }
+SIMT_FN float lds(sptr p) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(p) : "memory");
+    return v;
+}
+// FADD, FSETP, then four predicated instructions: numerator wrap, tap move, tap load, cursor increment.  Written in
+// PTX because nvcc otherwise keeps a second cursor and copies the taps through temporaries (3 extra moves per step).
+SIMT_FN void lerp_advance(float& nf, float& x0, float& x1, sptr& p, float from_f, float den) {
+    asm volatile(
+        "{\n"
+        ".reg .pred c;\n"
+        ".reg .f32 t;\n"
+        "add.rn.f32 t, %0, %4;\n"
+        "setp.ge.f32 c, t, %5;\n"
+        "@c sub.rn.f32 t, t, %5;\n"
+        "mov.f32 %0, t;\n"
+        "@c mov.f32 %1, %2;\n"
+        "@c ld.shared.f32 %2, [%3];\n"
+        "@c add.u32 %3, %3, 4;\n"
+        "}\n"
+        : "+f"(nf), "+f"(x0), "+f"(x1), "+r"(p)
+        : "f"(from_f), "f"(den)
+        : "memory");
+}
+SIMT_FN void cp16(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
+SIMT_FN void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+SIMT_FN void cp_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+#endif
+
+}  // namespace simt

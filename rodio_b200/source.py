@@ -429,6 +429,13 @@ class Batch:
         return n.value
 
     @property
+    def kernel_family(self) -> int:
+        """-1 general path, 0 k_fused_biquad / k_fused_nobiquad, 1 k_fused_hot, 2 k_fused_lanes."""
+        n = C.c_int()
+        check(lib().rb_batch_kernel_family(self._h, C.byref(n)), "rb_batch_kernel_family")
+        return n.value
+
+    @property
     def algorithmic_bytes(self) -> int:
         n = C.c_uint64()
         check(lib().rb_batch_algorithmic_bytes(self._h, C.byref(n)), "rb_batch_algorithmic_bytes")

@@ -1,0 +1,98 @@
+// CPU emulator of k_fused_lanes (test infrastructure): runs rodio_b200/csrc/rb_lanes_core.h -- the very source the
+// device kernel is compiled from -- on 32 host threads per warp (see rb_simt.h, RB_SIMT_EMULATE) and adds the
+// per-warp partial rows in warp order like k_sum_groups.  Built and loaded by tests/test_lanes_emulator.py.
+#define RB_SIMT_EMULATE 1
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <thread>
+#include <vector>
+
+#include "../../rodio_b200/csrc/rb_lanes_plan.h"
+
+namespace {
+template <bool HASB, bool FF2, int NPOST>
+void run_warp(const lanes::Args& a, uint32_t group, simt::WarpEmu* w, float* ring) {
+    std::vector<std::thread> th;
+    for (uint32_t l = 0; l < 32; l++)
+        th.emplace_back([&, l] {
+            simt::g_lane = simt::LaneEmu{};
+            simt::g_lane.w = w, simt::g_lane.lane = l;
+            lanes::warp_main<HASB, FF2, NPOST>(a, group, ring);
+        });
+    for (auto& t : th) t.join();
+}
+}  // namespace
+
+// coverage of the last runs: [0] fast tiles, [1] slow tiles, [2] ring refills; reset = 1 clears the counters
+extern "C" void rb_lanes_emu_counters(uint64_t* out, int reset) {
+    for (int i = 0; i < 4; i++) out[i] = simt::g_emu_count[i];
+    if (reset)
+        for (int i = 0; i < 4; i++) simt::g_emu_count[i] = 0;
+}
+
+extern "C" int rb_lanes_emulate(const float* const* pcm, const uint64_t* n_frames, const uint64_t* out_len,
+                                const uint64_t* mix_start, const float* coefs /* [n][5] b0 b1 b2 a1 a2 */,
+                                const float* post, uint32_t n_rows, uint32_t from, uint32_t to, uint64_t mix_len, int hasb,
+                                int want_ff2, int npost, float* out_mix, float* out_partials /* may be NULL */,
+                                int* used_ff2, uint32_t* n_unsafe) {
+    using namespace lanes;
+    if (!(from < to) || to > (1u << 20) || n_rows == 0) return 1;
+    const float nan = std::numeric_limits<float>::quiet_NaN();
+    simt::WarpEmu warp;
+    // inputs: 16-byte aligned copies with a 16-byte tail pad of NaN (reading the pad as data would show)
+    std::vector<std::vector<float>> store(n_rows);
+    std::vector<Row> rows(n_rows);
+    bool ff2 = want_ff2 && hasb;
+    *n_unsafe = 0;
+    for (uint32_t r = 0; r < n_rows; r++) {
+        store[r].assign(n_frames[r] + 4 + 4, nan);
+        float* base = store[r].data();
+        while ((uintptr_t)base & 15) base++;
+        if (n_frames[r]) std::memcpy(base, pcm[r], n_frames[r] * 4);
+        warp.readable.push_back({(const char*)base, (const char*)(base + n_frames[r] + 4)});
+        Row& row = rows[r];
+        std::memset(&row, 0, sizeof(row));
+        row.in = base, row.L = n_frames[r], row.out_len = out_len[r], row.mix_start = mix_start[r];
+        row.n_int = n_interp(row.L, from, to, row.out_len);
+        if (hasb) {
+            const float* c = coefs + 5 * r;
+            row.b0 = c[0], row.b1 = c[1], row.b2 = c[2], row.a1 = c[3], row.a2 = c[4];
+            float k = 0;
+            if (ff2_coeffs(row.b0, row.b1, row.b2, &k)) row.ffk = k;
+            else ff2 = false;
+        }
+        row.post = npost ? post[r] : 1.0f;
+        bool ok = true;
+        for (uint64_t i = 0; i < n_frames[r] && ok; i++) ok = sample_in_class(pcm[r][i]);
+        if (!ok) row.flags |= ROW_UNSAFE, (*n_unsafe)++;
+    }
+    *used_ff2 = ff2;
+    alignas(16) static float zeros[CHUNK] = {0};
+    warp.readable.push_back({(const char*)zeros, (const char*)(zeros + CHUNK)});
+    Args a{};
+    a.rows = rows.data(), a.n_rows = n_rows, a.n_groups = (n_rows + 31) / 32;
+    fill_ratio(a, from, to);
+    a.mix_len = mix_len, a.pstride = round_up_tile(mix_len);
+    std::vector<float> partial((size_t)a.n_groups * a.pstride, 0.0f);
+    a.partial = partial.data(), a.zeros = zeros;
+    std::vector<float> ring_store(32 * RS + 4, nan);
+    float* ring = ring_store.data();
+    while ((uintptr_t)ring & 15) ring++;
+    for (uint32_t g = 0; g < a.n_groups; g++) {
+        for (int i = 0; i < 32 * RS; i++) ring[i] = nan;
+        if (hasb && ff2 && npost) run_warp<true, true, 1>(a, g, &warp, ring);
+        else if (hasb && ff2) run_warp<true, true, 0>(a, g, &warp, ring);
+        else if (hasb && npost) run_warp<true, false, 1>(a, g, &warp, ring);
+        else if (hasb) run_warp<true, false, 0>(a, g, &warp, ring);
+        else if (npost) run_warp<false, false, 1>(a, g, &warp, ring);
+        else run_warp<false, false, 0>(a, g, &warp, ring);
+    }
+    for (uint64_t m = 0; m < mix_len; m++) {
+        float acc = 0.0f;
+        for (uint32_t g = 0; g < a.n_groups; g++) acc = acc + partial[(size_t)g * a.pstride + m];
+        out_mix[m] = acc;
+    }
+    if (out_partials) std::memcpy(out_partials, partial.data(), partial.size() * 4);
+    return 0;
+}

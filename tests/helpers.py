@@ -44,3 +44,24 @@ def assert_close_peak(got: np.ndarray, want: np.ndarray, tol: float = 1e-5, what
 def noise(n: int, seed: int, amp: float = 1.0) -> np.ndarray:
     rng = np.random.default_rng(seed)
     return (rng.uniform(-1.0, 1.0, n) * amp).astype(np.float32)
+
+
+def lanes_tree_sum(rows) -> np.ndarray:
+    """The reduction tree of k_fused_lanes over the 32 lanes of a warp (rb_lanes_core.h reduce_tile), in float32."""
+    y = np.asarray(rows, dtype=np.float32)
+    a = y[:16] + y[16:]
+    b = a[:8] + a[8:]
+    c = b[:4] + b[4:]
+    return ((c[0] + c[1]) + (c[2] + c[3])) + np.float32(0.0)
+
+
+def lanes_expected_mix(per_stream, starts, mix_len: int) -> np.ndarray:
+    """Mixer output of the lane-per-stream kernel given every stream's exact samples: groups of 32 streams (insertion
+    order) summed with the tree, the groups added in order from +0.0."""
+    acc = np.zeros(mix_len, dtype=np.float32)
+    for g in range(0, len(per_stream), 32):
+        lanes_ = np.zeros((32, mix_len), dtype=np.float32)
+        for l, (y, s) in enumerate(zip(per_stream[g:g + 32], starts[g:g + 32])):
+            lanes_[l, s:s + y.size] = y
+        acc = acc + lanes_tree_sum(lanes_)
+    return acc

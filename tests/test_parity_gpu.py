@@ -558,3 +558,113 @@ def test_player_volume_speed_and_queueing(ctx):
     # the mixer adds +0.0 before every sample (mixer.rs:186-189): -0.0 becomes +0.0, everything else is unchanged
     want = np.concatenate([first, second]) + np.float32(0.0)
     assert_bit_exact(got, want, "player queue")
+
+
+# ------------------------------------------------------------------ lane-per-stream kernel (RB_FUSED_LANES, rb_lanes.cu)
+# Written in the round without GPU minutes left: the warp program is verified on the CPU emulator
+# (tests/test_lanes_emulator.py, same source), these are its on-device counterparts.  They run when
+# RB_TEST_LANES=1 until the first GPU pass has confirmed them (then the gate goes).
+import os
+
+from helpers import lanes_expected_mix
+
+lanes_gate = pytest.mark.skipif(os.environ.get("RB_TEST_LANES") != "1", reason="set RB_TEST_LANES=1 (first GPU pass pending)")
+LANES = capi.RB_FUSED_LANES
+
+
+def _lanes_case(ctx, pcms, starts, in_rate=44100, mix_rate=48000, lp=None, hp=None, q=0.5, gain=None, expect_family=2):
+    srcs = []
+    for p in pcms:
+        s = rb.UniformSourceIterator(rb.TestSource(p, 1, in_rate), 1, mix_rate)
+        if lp is not None:
+            s = s.low_pass_with_q(lp, q)
+        if hp is not None:
+            s = s.high_pass_with_q(hp, q)
+        if gain is not None:
+            s = s.amplify(gain)
+        srcs.append(s)
+    with rb.Batch(srcs, 1, mix_rate, flags=LANES, ctx=ctx, mix_starts=starts) as b:
+        assert b.kernel_family == expect_family
+        b.upload_all()
+        got = b.render_mix()
+        again = b.render_mix()
+    assert np.array_equal(got.view(np.uint32), again.view(np.uint32)), "render is not idempotent"
+    per_stream = [oracle.chain_uniform(to_oracle(s), 1, mix_rate) for s in srcs]
+    ref = oracle.mixer([to_oracle(s, mix_start=st) for s, st in zip(srcs, starts)], 1, mix_rate)
+    assert got.shape == ref.shape
+    assert_close_peak(got, ref, 1e-5, "lanes kernel vs the reference's sequential mixer")          # north-star tolerance
+    if expect_family == 2:
+        assert_bit_exact(got, lanes_expected_mix(per_stream, starts, ref.size), "lanes kernel vs oracle streams + its tree")
+    return got
+
+
+@lanes_gate
+def test_lanes_single_stream_is_the_reference_stream(ctx):
+    pcm = noise(6000, 1)
+    got = _lanes_case(ctx, [pcm], [0], lp=200, gain=1.2)
+    want = oracle.chain_uniform(to_oracle(rb.UniformSourceIterator(rb.TestSource(pcm, 1, 44100), 1, 48000).low_pass(200).amplify(1.2)), 1, 48000)
+    assert_bit_exact(got, want, "one stream through k_fused_lanes")
+
+
+@lanes_gate
+@pytest.mark.parametrize("kw", [dict(lp=200, gain=1.2), dict(lp=1000, q=0.707), dict(hp=300, gain=0.5), dict(gain=1.2), dict()])
+def test_lanes_cfg3_shapes(ctx, kw):
+    pcms = [noise(5000 + 13 * i, 100 + i) for i in range(150)]
+    _lanes_case(ctx, pcms, [0] * len(pcms), **kw)
+
+
+@lanes_gate
+def test_lanes_ragged(ctx):
+    rng = np.random.default_rng(5)
+    lens = [4000, 37, 1, 0, 2, 2500, 4000, 999, 16, 17] + [int(v) for v in rng.integers(3, 6000, 90)]
+    starts = sorted([0, 100, 5, 9, 3000, 1234, 8, 16, 4001, 7] + [int(v) for v in rng.integers(0, 5000, 90)])
+    pcms = [noise(n, 300 + i) for i, n in enumerate(lens)]
+    _lanes_case(ctx, pcms, starts, lp=1000, gain=0.7)
+
+
+@lanes_gate
+@pytest.mark.parametrize("rates", [(8000, 48000), (22050, 48000), (32000, 44100), (47999, 48000), (11025, 96000)])
+def test_lanes_other_ratios(ctx, rates):
+    pcms = [noise(1500 + 11 * i, 900 + i) for i in range(70)]
+    _lanes_case(ctx, pcms, [0] * 70, in_rate=rates[0], mix_rate=rates[1], lp=400, gain=1.1)
+
+
+@lanes_gate
+def test_lanes_unsafe_inputs_stay_exact(ctx):
+    pcms = [noise(3000, 40 + i) for i in range(70)]
+    pcms[3][100:110] = np.float32(1e-41)
+    pcms[3][500] = np.float32(3e-30)
+    pcms[40][7] = np.float32(1e25)
+    _lanes_case(ctx, pcms, [0] * 70, lp=800, gain=1.2)
+
+
+@lanes_gate
+def test_lanes_falls_back_when_the_shape_differs(ctx):
+    """Two rate pairs in one batch, or a down-sampling pair: the flag is ignored, the default fused kernels serve."""
+    a = rb.UniformSourceIterator(rb.TestSource(noise(2000, 1), 1, 44100), 1, 48000).low_pass(200)
+    b_ = rb.UniformSourceIterator(rb.TestSource(noise(2000, 2), 1, 32000), 1, 48000).low_pass(200)
+    with rb.Batch([a, b_], 1, 48000, flags=LANES, ctx=ctx) as b:
+        assert b.kernel_family != 2
+        b.upload_all()
+        got = b.render_mix()
+    assert_close_peak(got, oracle.mixer([to_oracle(a), to_oracle(b_)], 1, 48000), 1e-5, "fallback")
+    d = rb.UniformSourceIterator(rb.TestSource(noise(2000, 3), 1, 48000), 1, 44100).low_pass(200)
+    with rb.Batch([d], 1, 44100, flags=LANES, ctx=ctx) as b:
+        assert b.kernel_family != 2
+
+
+@lanes_gate
+def test_lanes_full_size_properties(ctx):
+    """BASELINE cfg5 size per stream (1 s of 44.1 kHz), 2048 streams: matches the default fused path within the
+    tolerance, is idempotent, and a re-upload re-classifies."""
+    rng = np.random.default_rng(9)
+    base = [rng.uniform(-1, 1, 44100).astype(np.float32) for _ in range(8)]
+    mk = lambda: [rb.UniformSourceIterator(rb.TestSource(base[i % 8], 1, 44100), 1, 48000).low_pass(200).amplify(1.2) for i in range(2048)]
+    with rb.Batch(mk(), 1, 48000, flags=LANES, ctx=ctx) as b:
+        assert b.kernel_family == 2
+        b.upload_all()
+        got = b.render_mix()
+    with rb.Batch(mk(), 1, 48000, ctx=ctx) as b:
+        b.upload_all()
+        ref = b.render_mix()
+    assert_close_peak(got, ref, 1e-5, "lanes vs default fused path at full size")

@@ -39,7 +39,7 @@ def time_batch(name, srcs, mixer, flags=0, steps=10, fill="uniform"):
         samples = sum(b.stream_out_len(i) for i in range(S))
         out = {"case": name, "streams": S, "ms": round(ms, 4), "Msamples_s": round(samples / ms / 1e3, 1),
                "algo_GBs": round(b.algorithmic_bytes / ms / 1e6, 1), "frac_6570": round(b.algorithmic_bytes / ms / 1e6 / 6570, 4),
-               "launches": b.launches_per_render}
+               "launches": b.launches_per_render, "kernel_family": b.kernel_family}
         print(json.dumps(out), flush=True)
 
 
@@ -84,6 +84,18 @@ def main():
                     for _ in range(S)]
             time_batch(f"cfg5 sweep S={S}: 44.1k mono x 1s -> uniform(1,48k) -> low_pass(200) -> amplify -> mix", srcs,
                        (1, 48000), steps=5 if S >= 16384 else 10)
+    if "lanes" in which:
+        # the lane-per-stream kernel (RB_FUSED_LANES) beside the default fused kernel on the large end of the sweep,
+        # at the bench's low_pass(200), at low_pass(1000), and without a filter
+        for S in [4096, 16384, 65536]:
+            one = z(44100)
+            for label, mk in (("low_pass(200) -> amplify", lambda s: s.low_pass(200).amplify(1.2)),
+                              ("low_pass(1000) -> amplify", lambda s: s.low_pass(1000).amplify(1.2)),
+                              ("amplify (no filter)", lambda s: s.amplify(1.2))):
+                srcs = [mk(rb.UniformSourceIterator(rb.TestSource(one, 1, 44100), 1, 48000)) for _ in range(S)]
+                for fl, nm in ((rb.capi.RB_FUSED_LANES, "k_fused_lanes"), (0, "default")):
+                    time_batch(f"lanes sweep S={S}: 44.1k mono x 1s -> uniform(1,48k) -> {label} -> mix [{nm}]", srcs,
+                               (1, 48000), flags=fl, steps=5)
     if "cpu" in which:
         # C++ restatement of rodio's CPU path on this box's host cores: one audio thread (what rodio itself runs)
         # and all cores with a final partial-mix reduction; dynamic dispatch (Box<dyn Source>) and monomorphised.
