@@ -58,13 +58,18 @@ constexpr uint32_t RUN_CAP = 1u << 30;
 constexpr uint32_t MIN_RUN = 4 * TILE;  // shortest fast run worth priming the ring for
 static_assert(MIRROR >= TILE && MIRROR <= CHUNK && (RS / 4) % 2 == 1 && RUN_CAP % TILE == 0, "ring geometry");
 constexpr uint32_t ROW_UNSAFE = 1u;     // Row::flags: some sample outside the exact-reciprocal class
+constexpr uint32_t ROW_CONTINUES = 2u;  // Row::flags: the stream goes on in the next block -- keep the filter state past `end`
 
-struct Row {                 // one stream
+struct Row {                 // one stream (whole, or the part of it one block of a streaming session renders)
     const float* in;         // mono f32 frames, 16-byte aligned, readable up to a 16-byte tail pad
-    uint64_t L;              // input frames
-    uint64_t out_len;        // samples on the mixer timeline
-    uint64_t mix_start;
+    uint64_t L;              // input frames at `in`
+    uint64_t out_len;        // samples on the (block's) mixer timeline
+    uint64_t mix_start;      // timeline position of the first of them
     uint64_t n_int;          // outputs [0, n_int) interpolate between two frames (left frame <= L-2)
+    uint64_t o0;             // streaming: stream-absolute index of the first output of the block (0 for whole streams)
+    uint64_t i0;             // streaming: stream-absolute index of the frame at in[0]; (o0 * from) / to >= i0
+    float* state;            // streaming: {x[n-1], x[n-2], y[n-1], y[n-2]} read at the start, written at the end
+                             // (16-byte aligned); NULL: start from zeros, keep nothing
     float b0, b1, b2, a1, a2;
     float ffk;               // FF2 variant: b1 == ffk * b0 (ffk = +-2) and b2 == b0
     float post;              // the one gain behind the chain (NPOST == 1)
@@ -112,11 +117,12 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
     if (has) {
         row = a.rows[r];
     } else {
-        row.in = a.zeros, row.L = 0, row.out_len = 0, row.mix_start = 0, row.n_int = 0;
+        row.in = a.zeros, row.L = 0, row.out_len = 0, row.mix_start = 0, row.n_int = 0, row.o0 = 0, row.i0 = 0, row.state = nullptr;
         row.b0 = row.b1 = row.b2 = row.a1 = row.a2 = row.ffk = row.post = 0.0f, row.flags = 0;
     }
     const uint64_t ms = row.mix_start, end = row.mix_start + row.out_len;
     const bool safe = has && !(row.flags & ROW_UNSAFE);
+    const bool stops = !(row.flags & ROW_CONTINUES);   // the stream ends inside this block (or is a whole stream)
     const bool live = has && row.out_len != 0;
     const uint64_t t_lo = simt::reduce_min64(live ? ms : ~0ull), t_hi = simt::reduce_max64(live ? end : 0ull);
     if (t_lo >= t_hi) return;
@@ -128,6 +134,10 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
     const float b0 = row.b0, b1 = row.b1, b2 = row.b2, a1 = row.a1, a2 = row.a2, ffk = row.ffk, post = row.post;
     const uint32_t from = a.from, to = a.to;
     float xh1 = 0.f, xh2 = 0.f, y1 = 0.f, y2 = 0.f;   // canonical filter state: x[n-1], x[n-2], y[n-1], y[n-2]
+    if (HASB && row.state) xh1 = row.state[0], xh2 = row.state[1], y1 = row.state[2], y2 = row.state[3];
+    // stream-absolute numerator of local output o is (o0 + o) * from; the frame it falls on, relative to in[0],
+    // is that / to - i0.  Both offsets are zero for whole streams.
+    const uint64_t o0 = row.o0, i0 = row.i0;
     const uint32_t cq = ln % QPC;                      // the quad of a chunk this lane copies ...
     const uint32_t cr = ln / QPC;                      // ... for stream cr + RPI * j of the warp
 
@@ -136,7 +146,7 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
         uint32_t d;
         if (!has || t >= end) {
             d = RUN_CAP;
-            xh1 = xh2 = y1 = y2 = 0.f;                  // a finished stream contributes nothing, its filter stops
+            if (stops) xh1 = xh2 = y1 = y2 = 0.f;       // a finished stream contributes nothing, its filter stops
         } else if (t < ms) {
             const uint64_t g = (ms - t) / TILE * TILE;  // idle until the tile the stream starts in
             d = g > RUN_CAP ? RUN_CAP : (uint32_t)g;
@@ -158,9 +168,10 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
             uint32_t num = 0, k0 = 0, maxq = QPC - 1;
             const float* src = a.zeros;
             if (act) {
-                const uint64_t prod = (t - ms) * (uint64_t)from;
-                const uint64_t i = prod / to;
-                num = (uint32_t)(prod - i * to);
+                const uint64_t prod = (o0 + (t - ms)) * (uint64_t)from;
+                const uint64_t ia = prod / to;
+                num = (uint32_t)(prod - ia * to);
+                const uint64_t i = ia - i0;
                 const uint64_t ibase = i & ~3ull;
                 k0 = (uint32_t)(i - ibase);
                 src = row.in + ibase;
@@ -257,9 +268,10 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                 const uint64_t tt = t + (uint64_t)u;
                 float val = 0.0f;
                 if (has && tt >= ms && tt < end) {
-                    const uint64_t prod = (tt - ms) * (uint64_t)from;
-                    const uint64_t i = prod / to;
-                    const uint32_t num = (uint32_t)(prod - i * to);
+                    const uint64_t prod = (o0 + (tt - ms)) * (uint64_t)from;
+                    const uint64_t ia = prod / to;
+                    const uint32_t num = (uint32_t)(prod - ia * to);
+                    const uint64_t i = ia - i0;
                     const float xa = simt::ldg(row.in + i);
                     float x = xa;
                     if (i + 1 < row.L)
@@ -271,7 +283,7 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                         xh2 = xh1, xh1 = x, y2 = y1, y1 = y;
                     }
                     val = NPOST ? simt::fmul(y, post) : y;
-                } else if (has && tt >= end) {
+                } else if (has && tt >= end && stops) {
                     xh1 = xh2 = y1 = y2 = 0.f;
                 }
                 v[u] = val;
@@ -282,6 +294,7 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
             t += TILE;
         }
     }
+    if (HASB && row.state) row.state[0] = xh1, row.state[1] = xh2, row.state[2] = y1, row.state[3] = y2;
 }
 
 }  // namespace lanes

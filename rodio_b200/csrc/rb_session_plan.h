@@ -1,0 +1,99 @@
+// rb_session_plan.h — host-side bookkeeping of a streaming session (plain C++, no CUDA): which mixer frames the next
+// render can produce from the PCM pushed so far, which part of every stream's FIFO the block reads, and what is left
+// for the next block.  Shared by rb_session.cu and by the CPU emulator under tests/emu/, so the whole block logic is
+// exercised on the CPU against whole-stream renders.
+//
+// What it replaces: rodio pulls one sample at a time through MixerSource::next (src/mixer.rs:120-136) ->
+// UniformSourceIterator::next (src/source/uniform.rs:78-97) -> SampleRateConverter::next
+// (src/conversions/sample_rate.rs:131-201); every adapter keeps its state between calls.  A block render must carry
+// exactly that state from block to block:
+//   * resampler: the stream-absolute index of the next output frame (its numerator and left frame follow from it:
+//     (o * from) mod to and floor(o * from / to)) and the input frames from that left frame on -- they stay in the
+//     stream's FIFO; an output is only rendered once its right neighbour has arrived, or the stream has ended (the
+//     last frame is then emitted raw, sample_rate.rs:187-199);
+//   * biquad: x[n-1], x[n-2], y[n-1], y[n-2] (src/source/blt.rs:397-410) -- four floats per stream on the device.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <vector>
+
+namespace session {
+
+struct Stream {
+    uint64_t mix_start = 0;    // mixer frame the stream joins at (frame aligned, src/mixer.rs:175-183)
+    uint64_t pushed = 0;       // input frames received so far
+    uint64_t out_done = 0;     // output frames rendered so far (= stream-absolute index of the next one)
+    uint64_t i0 = 0;           // stream-absolute index of the frame at the front of the FIFO (multiple of 4)
+    bool eof = false;          // no more input will come
+    uint64_t fill() const { return pushed - i0; }   // frames in the FIFO
+};
+
+// SampleRateConverter output length for L input frames on the reduced grid from:to, from != to
+// (closed form of src/conversions/sample_rate.rs:157-199; rb_sample_rate_out_len in the C ABI is the same formula).
+inline uint64_t out_total(uint64_t L, uint32_t from, uint32_t to) {
+    if (L == 0) return 0;
+    if (L == 1) return 1;
+    const uint64_t ns = ((L - 1) * (uint64_t)to + from - 1) / from;   // first output whose left frame is L-1
+    return ns + ((ns * (uint64_t)from < L * (uint64_t)to) ? 1 : 0);
+}
+// Outputs [0, n) whose right neighbour exists among L frames: n = ceil((L-1) * to / from).
+inline uint64_t out_interp(uint64_t L, uint32_t from, uint32_t to) {
+    return L < 2 ? 0 : ((L - 1) * (uint64_t)to + from - 1) / from;
+}
+// Output frames of stream `s` that exist so far (renderable): everything once it has ended, else the interpolated ones.
+inline uint64_t out_ready(const Stream& s, uint32_t from, uint32_t to) {
+    return s.eof ? out_total(s.pushed, from, to) : out_interp(s.pushed, from, to);
+}
+inline bool finished(const Stream& s, uint32_t from, uint32_t to) {
+    return s.eof && s.out_done >= out_total(s.pushed, from, to);
+}
+
+// How many mixer frames [T, T + n) can be rendered now (every unfinished stream must be able to supply its part).
+// Returns 0 with *ended = true when no stream is left (MixerSource::next returns None, src/mixer.rs:129-135).
+inline uint64_t renderable(const std::vector<Stream>& st, uint64_t T, uint32_t from, uint32_t to, uint64_t max_frames,
+                           bool* ended) {
+    uint64_t n = max_frames;
+    bool any = false;
+    for (const Stream& s : st) {
+        if (finished(s, from, to)) continue;
+        any = true;
+        const uint64_t upto = s.mix_start + out_ready(s, from, to);   // the stream can cover the timeline up to here
+        n = std::min(n, upto > T ? upto - T : 0);
+    }
+    *ended = !any;
+    return any ? n : 0;
+}
+
+// One stream's part of the block [T, T + n).
+struct Part {
+    uint64_t mix_start = 0;   // block-local timeline position of its first output
+    uint64_t out_len = 0;     // outputs it contributes
+    uint64_t o0 = 0;          // stream-absolute index of the first of them
+    uint64_t n_int = 0;       // how many of them interpolate (the rest is the raw last frame)
+    bool continues = false;   // more outputs will follow in later blocks
+};
+inline Part part_of(const Stream& s, uint64_t T, uint64_t n, uint32_t from, uint32_t to) {
+    Part p;
+    const uint64_t ready = out_ready(s, from, to);
+    const uint64_t lo = std::max(T, s.mix_start + s.out_done), hi = std::min(T + n, s.mix_start + ready);
+    if (lo >= hi) {
+        p.continues = !finished(s, from, to);
+        return p;
+    }
+    p.mix_start = lo - T, p.out_len = hi - lo, p.o0 = lo - s.mix_start;
+    const uint64_t ni = out_interp(s.pushed, from, to);
+    p.n_int = ni > p.o0 ? std::min(p.out_len, ni - p.o0) : 0;
+    p.continues = !(s.eof && p.o0 + p.out_len >= out_total(s.pushed, from, to));
+    return p;
+}
+// After the block: advance the stream and tell how many FIFO frames (from the front) are dead.
+inline uint64_t advance(Stream& s, const Part& p, uint32_t from, uint32_t to) {
+    s.out_done = p.out_len ? p.o0 + p.out_len : s.out_done;
+    const uint64_t left = std::min((s.out_done * (uint64_t)from) / to, s.pushed);   // left frame of the next output
+    const uint64_t keep_from = left & ~3ull;                                        // FIFO front stays 16-byte aligned
+    const uint64_t drop = keep_from > s.i0 ? keep_from - s.i0 : 0;
+    s.i0 += drop;
+    return drop;
+}
+
+}  // namespace session

@@ -96,3 +96,126 @@ extern "C" int rb_lanes_emulate(const float* const* pcm, const uint64_t* n_frame
     if (out_partials) std::memcpy(out_partials, partial.data(), partial.size() * 4);
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Streaming session on the emulator: the bookkeeping of rodio_b200/csrc/rb_session_plan.h driving the same warp
+// program block by block.  ops: triples (kind, stream, count) -- kind 0: push `count` more frames of the stream's PCM
+// (the stream ends when all of it has been pushed, or on kind 2), kind 1: render up to `count` mixer frames,
+// kind 2: mark the stream ended now (whatever was pushed is all there is).  After the last op everything is ended and
+// drained.  Returns the number of mixer frames written to out (capacity out_cap), or -1.
+#include "../../rodio_b200/csrc/rb_session_plan.h"
+
+extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t* n_frames, const uint64_t* mix_start,
+                                        const float* coefs, const float* post, uint32_t n_rows, uint32_t from, uint32_t to,
+                                        int hasb, int npost, const uint64_t* ops, uint64_t n_ops, float* out,
+                                        uint64_t out_cap, uint64_t* n_renders, uint64_t* pushed_total /* [n_rows] */) {
+    using namespace lanes;
+    if (!(from < to) || to > (1u << 20) || n_rows == 0) return -1;
+    const float nan = std::numeric_limits<float>::quiet_NaN();
+    simt::WarpEmu warp;
+    std::vector<session::Stream> st(n_rows);
+    std::vector<std::vector<float>> fifo_store(n_rows);
+    std::vector<float*> fifo(n_rows);
+    std::vector<uint8_t> unsafe(n_rows, 0);
+    std::vector<float> state_store(4 * n_rows + 4, 0.0f);
+    float* state = state_store.data();
+    while ((uintptr_t)state & 15) state++;
+    bool ff2 = hasb;
+    std::vector<float> ffk(n_rows, 0.0f);
+    for (uint32_t r = 0; r < n_rows; r++) {
+        fifo_store[r].assign(n_frames[r] + 16, nan);
+        fifo[r] = fifo_store[r].data();
+        while ((uintptr_t)fifo[r] & 15) fifo[r]++;
+        warp.readable.push_back({(const char*)fifo[r], (const char*)(fifo[r] + n_frames[r] + 8)});
+        st[r].mix_start = mix_start[r];
+        if (hasb) {
+            const float* c = coefs + 5 * r;
+            if (!ff2_coeffs(c[0], c[1], c[2], &ffk[r])) ff2 = false;
+        }
+    }
+    alignas(16) static float zeros[CHUNK] = {0};
+    warp.readable.push_back({(const char*)zeros, (const char*)(zeros + CHUNK)});
+    std::vector<float> ring_store(32 * RS + 4, nan);
+    float* ring = ring_store.data();
+    while ((uintptr_t)ring & 15) ring++;
+    uint64_t T = 0, written = 0;
+    *n_renders = 0;
+
+    auto push = [&](uint32_t r, uint64_t n) {
+        session::Stream& s = st[r];
+        n = std::min(n, n_frames[r] - s.pushed);
+        for (uint64_t k = 0; k < n; k++) {
+            const float v = pcm[r][s.pushed + k];
+            fifo[r][s.fill() + k] = v;
+            if (!sample_in_class(v)) unsafe[r] = 1;
+        }
+        s.pushed += n;
+        if (s.pushed == n_frames[r]) s.eof = true;
+    };
+    auto render = [&](uint64_t max_frames) -> bool {   // false: session ended
+        bool ended = false;
+        const uint64_t n = session::renderable(st, T, from, to, max_frames, &ended);
+        if (ended) return false;
+        if (n == 0) return true;
+        if (written + n > out_cap) std::abort();
+        std::vector<Row> rows(n_rows);
+        std::vector<session::Part> parts(n_rows);
+        for (uint32_t r = 0; r < n_rows; r++) {
+            parts[r] = session::part_of(st[r], T, n, from, to);
+            Row& row = rows[r];
+            std::memset(&row, 0, sizeof(row));
+            row.in = fifo[r], row.L = st[r].fill(), row.out_len = parts[r].out_len, row.mix_start = parts[r].mix_start;
+            row.n_int = parts[r].n_int, row.o0 = parts[r].o0, row.i0 = st[r].i0, row.state = state + 4 * r;
+            if (hasb) {
+                const float* c = coefs + 5 * r;
+                row.b0 = c[0], row.b1 = c[1], row.b2 = c[2], row.a1 = c[3], row.a2 = c[4], row.ffk = ffk[r];
+            }
+            row.post = npost ? post[r] : 1.0f;
+            row.flags = (unsafe[r] ? ROW_UNSAFE : 0u) | (parts[r].continues ? ROW_CONTINUES : 0u);
+        }
+        Args a{};
+        a.rows = rows.data(), a.n_rows = n_rows, a.n_groups = (n_rows + 31) / 32;
+        fill_ratio(a, from, to);
+        a.mix_len = n, a.pstride = round_up_tile(n);
+        std::vector<float> partial((size_t)a.n_groups * a.pstride, 0.0f);
+        a.partial = partial.data(), a.zeros = zeros;
+        for (uint32_t g = 0; g < a.n_groups; g++) {
+            for (int i = 0; i < 32 * RS; i++) ring[i] = nan;
+            if (hasb && ff2 && npost) run_warp<true, true, 1>(a, g, &warp, ring);
+            else if (hasb && ff2) run_warp<true, true, 0>(a, g, &warp, ring);
+            else if (hasb && npost) run_warp<true, false, 1>(a, g, &warp, ring);
+            else if (hasb) run_warp<true, false, 0>(a, g, &warp, ring);
+            else if (npost) run_warp<false, false, 1>(a, g, &warp, ring);
+            else run_warp<false, false, 0>(a, g, &warp, ring);
+        }
+        for (uint64_t m = 0; m < n; m++) {
+            float acc = 0.0f;
+            for (uint32_t g = 0; g < a.n_groups; g++) acc = acc + partial[(size_t)g * a.pstride + m];
+            out[written + m] = acc;
+        }
+        written += n, T += n, (*n_renders)++;
+        for (uint32_t r = 0; r < n_rows; r++) {
+            const uint64_t fill_before = st[r].fill();
+            const uint64_t drop = session::advance(st[r], parts[r], from, to);
+            if (drop) {
+                std::memmove(fifo[r], fifo[r] + drop, (fill_before - drop) * sizeof(float));
+                for (uint64_t k = fill_before - drop; k < fill_before; k++) fifo[r][k] = nan;
+            }
+        }
+        return true;
+    };
+
+    for (uint64_t k = 0; k < n_ops; k++) {
+        const uint64_t kind = ops[3 * k], r = ops[3 * k + 1], cnt = ops[3 * k + 2];
+        if (kind == 0) push((uint32_t)r, cnt);
+        else if (kind == 1) render(cnt);
+        else st[r].eof = true;
+    }
+    for (uint32_t r = 0; r < n_rows; r++) st[r].eof = true;   // whatever was pushed is all there is
+    for (uint32_t r = 0; r < n_rows; r++) pushed_total[r] = st[r].pushed;
+    while (render(1ull << 20)) {
+        bool ended = false;
+        if (session::renderable(st, T, from, to, 1, &ended) == 0 && !ended) std::abort();   // no progress
+    }
+    return (long long)written;
+}

@@ -160,3 +160,85 @@ def test_silence_and_negative_zero(emu):
     pcms[2][200:300] = 0.0
     check(emu, pcms, 44100, 48000, [0, 0, 0], gain=-1.0)
     check(emu, pcms[:2], 44100, 48000, [0, 0], lp=300, gain=-1.0)
+
+
+# ------------------------------------------------------------------------------------------------- streaming sessions
+def run_session(emu, pcms, starts, coefs, posts, from_, to, hasb, npost, ops, out_cap):
+    n = len(pcms)
+    pcms = [np.ascontiguousarray(p, dtype=np.float32) for p in pcms]
+    ptrs = (C.POINTER(C.c_float) * n)(*[p.ctypes.data_as(C.POINTER(C.c_float)) for p in pcms])
+    u64 = lambda v: (C.c_uint64 * len(v))(*[int(x) for x in v])
+    co = np.ascontiguousarray(coefs, dtype=np.float32).reshape(-1)
+    po = np.ascontiguousarray(posts, dtype=np.float32)
+    flat = [int(x) for op in ops for x in op]
+    out = np.full(out_cap, np.nan, dtype=np.float32)
+    renders = C.c_uint64(0)
+    pushed = (C.c_uint64 * n)()
+    emu.rb_session_emulate.restype = C.c_longlong
+    w = emu.rb_session_emulate(ptrs, u64([p.size for p in pcms]), u64(starts), co.ctypes.data_as(C.POINTER(C.c_float)),
+                               po.ctypes.data_as(C.POINTER(C.c_float)), C.c_uint32(n), C.c_uint32(from_), C.c_uint32(to),
+                               int(hasb), int(npost), u64(flat), C.c_uint64(len(ops)), out.ctypes.data_as(C.POINTER(C.c_float)),
+                               C.c_uint64(out_cap), C.byref(renders), pushed)
+    assert w >= 0
+    return out[:w], renders.value, [int(v) for v in pushed]
+
+
+def session_case(emu, pcms, starts, ops, in_rate=44100, mix_rate=48000, lp=None, gain=None):
+    """Any split of the streams into pushed blocks and of the mixer output into rendered blocks gives the bytes of the
+    whole-stream render (tests/test_block_state_spec.py is the numpy form of the same contract)."""
+    c = make_case(pcms, in_rate, mix_rate, starts, lp=lp, gain=gain)
+    got, renders, pushed = run_session(emu, pcms, starts, c["coefs"], c["posts"], c["from_"], c["to"], c["hasb"], c["npost"], ops,
+                                       c["mix_len"] + 64)
+    assert pushed == [p.size for p in pcms]
+    want = expected_mix(c["per_stream"], starts, c["mix_len"])
+    assert_bit_exact(got, want, "session blocks vs whole-stream render")
+    return renders
+
+
+def test_session_any_split_is_the_whole(emu):
+    rng = np.random.default_rng(11)
+    pcms = [noise(int(n), 60 + i) for i, n in enumerate(rng.integers(400, 2600, 37))]
+    starts = [0] * 37
+    ops = []
+    left = [p.size for p in pcms]
+    while any(left):                      # random interleaving of pushes (1..700 frames) and renders (1..900 frames)
+        for r in rng.permutation(37):
+            n = min(left[r], int(rng.integers(1, 700)))
+            if n and rng.random() < 0.8:
+                ops.append((0, r, n))
+                left[r] -= n
+        ops.append((1, 0, int(rng.integers(1, 900))))
+    renders = session_case(emu, pcms, starts, ops, lp=200, gain=1.2)
+    assert renders > 5
+
+
+def test_session_tiny_blocks_and_late_joiners(emu):
+    """10 ms style blocks (and blocks of 1..7 frames, shorter than the kernel's tile), streams that join later."""
+    pcms = [noise(900 + 50 * i, 80 + i) for i in range(5)]
+    starts = [0, 0, 480, 481, 1000]
+    ops = []
+    for step in range(200):
+        for r in range(5):
+            ops.append((0, r, 97 + r))
+        ops.append((1, 0, [441, 1, 7, 3, 480, 5][step % 6]))
+    session_case(emu, pcms, starts, ops, lp=1000, gain=0.9)
+
+
+def test_session_without_filter_and_starved_render(emu):
+    """A render with nothing new pushed produces nothing and leaves the state alone."""
+    pcms = [noise(1500, 90 + i) for i in range(3)]
+    ops = [(0, 0, 500), (0, 1, 500), (0, 2, 10), (1, 0, 10000), (1, 0, 10000), (1, 0, 10000),
+           (0, 2, 1490), (1, 0, 100), (0, 0, 1000), (0, 1, 1000)]
+    session_case(emu, pcms, [0, 0, 0], ops, gain=1.2)
+
+
+def test_session_early_end_of_stream(emu):
+    """A stream that is cut short (eof before all of its PCM was pushed) renders like the shorter whole stream."""
+    pcms = [noise(2000, 95 + i) for i in range(4)]
+    ops = [(0, r, 700) for r in range(4)] + [(1, 0, 300), (2, 1, 0), (0, 0, 1300), (0, 2, 1300), (0, 3, 1300), (1, 0, 5000)]
+    c_full = make_case(pcms, 44100, 48000, [0] * 4, lp=300, gain=1.1)
+    got, _, pushed = run_session(emu, pcms, [0] * 4, c_full["coefs"], c_full["posts"], 147, 160, True, True, ops, 4000)
+    assert pushed == [2000, 700, 2000, 2000]
+    cut = [pcms[0], pcms[1][:700], pcms[2], pcms[3]]
+    c = make_case(cut, 44100, 48000, [0] * 4, lp=300, gain=1.1)
+    assert_bit_exact(got, expected_mix(c["per_stream"], [0] * 4, c["mix_len"]), "cut stream")
