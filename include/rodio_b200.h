@@ -213,6 +213,40 @@ rb_status rb_batch_read_mix(rb_batch* b, uint64_t offset, float* out_host, uint6
 rb_status rb_batch_read_stream(rb_batch* b, size_t stream, float* out_host, uint64_t max_samples,
                                uint64_t* written);
 
+/* ---- Streaming sessions: sources whose length is not known when they are added --------------------------------
+ * rodio pulls MixerSource one sample at a time while decoders produce their sources incrementally
+ * (src/mixer.rs:120-136 -> src/source/uniform.rs:78-97 -> src/conversions/sample_rate.rs:131-201 ->
+ * src/source/blt.rs:397-410); every adapter keeps its state between pulls.  A session is the block form of that pull:
+ * PCM is pushed per source as it arrives, the mixer output is pulled in blocks; the resampler position, the input
+ * frames still needed and the filter state carry over from block to block, so ANY split into pushes and renders gives
+ * the bytes of a whole-stream rb_batch render with RB_FUSED_LANES (tests/test_lanes_emulator.py::test_session_*).
+ * Shape served (RB_ERR_UNSUPPORTED otherwise): mono f32 sources that share one sample rate below the mixer's, a mono
+ * mixer, effects = UNIFORM(1, mixer rate) [LOW_PASS | HIGH_PASS] [AMPLIFY] -- the chain of BASELINE cfg3;
+ * desc.n_samples / span_len are ignored, desc.mix_start is the mixer frame the source joins at.
+ * One caller per session; every call returns with the work done (the caller may reuse its buffers). */
+typedef struct rb_session rb_session;
+/* fifo_frames: input frames a source can hold between renders (>= 64); max_block_frames: largest render. */
+rb_status rb_session_create(rb_context* ctx, uint32_t mixer_sample_rate, const rb_stream_desc* descs, size_t n_streams,
+                            uint32_t fifo_frames, uint32_t max_block_frames, rb_session** out);
+rb_status rb_session_destroy(rb_session* s);
+/* n_frames more frames of source `stream` have arrived; end_of_stream != 0: the source's Iterator::next would return
+ * None after them.  RB_ERR_BUFFER_TOO_SMALL when its FIFO cannot take them (render first). */
+rb_status rb_session_push(rb_session* s, size_t stream, const float* pcm, uint64_t n_frames, int end_of_stream);
+/* The same for every source at once: pcm holds n_frames[0] frames of source 0, then n_frames[1] of source 1, ...;
+ * end_of_stream may be NULL.  One host->device copy and one kernel for the whole session. */
+rb_status rb_session_push_packed(rb_session* s, const float* pcm, const uint64_t* n_frames, const uint8_t* end_of_stream);
+/* Mixer frames the next render can produce from what has been pushed (an output frame exists once its right input
+ * neighbour has arrived, or its source has ended: sample_rate.rs:187-199).  *ended != 0: every source is exhausted
+ * and drained -- MixerSource::next() returns None (src/mixer.rs:129-135). */
+rb_status rb_session_available(rb_session* s, uint64_t* frames, int* ended);
+/* Pull up to max_frames (<= max_block_frames per call) mixer frames into out_host. */
+rb_status rb_session_render(rb_session* s, float* out_host, uint64_t max_frames, uint64_t* written, int* ended);
+/* Block-to-block state as an opaque blob -- resampler positions, pending input frames, filter state (the
+ * rb_batch_get_state / rb_batch_set_state of SURVEY.md 8b): a session of the same shape restored from it, on any
+ * context, continues bit-identically.  buf == NULL: only *size is returned. */
+rb_status rb_session_get_state(rb_session* s, void* buf, uint64_t cap, uint64_t* size);
+rb_status rb_session_set_state(rb_session* s, const void* buf, uint64_t size);
+
 /* Stand-alone conversions (rows a1..a3 of SURVEY.md §8) on host buffers: H2D, one kernel, D2H.
  *   rb_convert_sample_rate   = SampleRateConverter::new(input, from, to, channels).collect()
  *                              (src/conversions/sample_rate.rs:52-201)

@@ -9,11 +9,11 @@ from . import _capi as capi
 from ._capi import RodioB200Error, lib
 from .source import (AutomaticGainControlSettings, Batch, ChannelCountConverter, ChannelVolume, Context, Duration,
                      Effect, LimitSettings, Mixer, MixerSource, Player, SampleRateConverter, SamplesBuffer,
-                     SampleTypeConverter, Source, Spatial, TestSource, UniformSourceIterator, default_context, mixer, plan)
+                     SampleTypeConverter, Session, Source, Spatial, TestSource, UniformSourceIterator, default_context, mixer, plan)
 
 __all__ = [
     "capi", "lib", "RodioB200Error", "AutomaticGainControlSettings", "Batch", "ChannelCountConverter",
     "ChannelVolume", "Context", "Duration", "Effect", "LimitSettings", "Mixer", "MixerSource", "Player",
-    "SampleRateConverter", "SamplesBuffer", "SampleTypeConverter", "Source", "Spatial", "TestSource",
+    "SampleRateConverter", "SamplesBuffer", "SampleTypeConverter", "Session", "Source", "Spatial", "TestSource",
     "UniformSourceIterator", "default_context", "mixer", "plan",
 ]

@@ -16,6 +16,9 @@
 
 #include "rb_internal.h"
 #include "rb_fused.h"
+#include "rb_lanes.h"
+#include "rb_lanes_plan.h"
+#include "rb_session_plan.h"
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -936,5 +939,318 @@ extern "C" rb_status rb_convert_samples(rb_context* ctx, const void* in, rb_samp
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(d_in), cudaFree(d_out);
     if (e != cudaSuccess) return fail(RB_ERR_CUDA, cudaGetErrorString(e));
+    return RB_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// streaming sessions (block form of MixerSource::next for sources that arrive incrementally)
+// ------------------------------------------------------------------------------------------------
+// Bookkeeping: rb_session_plan.h (plain host code, also run by the CPU emulator of tests/emu/);
+// kernel: k_fused_lanes over per-block rows (rb_lanes_core.h: o0 / i0 / state / ROW_CONTINUES).
+struct rb_session {
+    rb_context* ctx = nullptr;
+    uint32_t mixer_rate = 0, from = 0, to = 0;
+    bool has_biquad = false, ff2 = false, has_post = false;
+    std::vector<session::Stream> st;
+    std::vector<float> coef;      // 5 per stream
+    std::vector<float> ffk, post;
+    uint64_t T = 0;               // mixer frames rendered so far
+    uint32_t fifo_cap = 0, max_block = 0;
+    uint64_t stride = 0;          // floats per stream in a FIFO arena
+    float* d_fifo[2] = {nullptr, nullptr};
+    int cur = 0;
+    float *d_state = nullptr, *d_zeros = nullptr, *d_partial = nullptr, *d_out = nullptr;
+    uint32_t* d_flags = nullptr;  // sticky: a pushed frame was outside the exact-reciprocal class
+    lanes::Row* d_rows = nullptr;
+    uint32_t* d_u32 = nullptr;    // [2][n]: drop, keep (render) / count, fill (packed push)
+    uint64_t* d_off = nullptr;    // [n]: packed push offsets
+    float* d_stage = nullptr;     // packed push staging, [n * fifo_cap]
+    uint64_t* h_off = nullptr;
+    // pinned host mirrors, reused by every call (each call ends with a stream synchronisation)
+    lanes::Row* h_rows = nullptr;
+    uint32_t* h_u32 = nullptr;
+    float* h_out = nullptr;
+};
+
+extern "C" rb_status rb_session_destroy(rb_session* s) {
+    if (!s) return RB_OK;
+    if (s->ctx) cudaSetDevice(s->ctx->device);
+    cudaFree(s->d_fifo[0]), cudaFree(s->d_fifo[1]), cudaFree(s->d_state), cudaFree(s->d_zeros), cudaFree(s->d_partial);
+    cudaFree(s->d_out), cudaFree(s->d_flags), cudaFree(s->d_rows), cudaFree(s->d_u32), cudaFree(s->d_off), cudaFree(s->d_stage);
+    cudaFreeHost(s->h_rows), cudaFreeHost(s->h_u32), cudaFreeHost(s->h_out), cudaFreeHost(s->h_off);
+    delete s;
+    return RB_OK;
+}
+
+extern "C" rb_status rb_session_create(rb_context* ctx, uint32_t mixer_rate, const rb_stream_desc* descs, size_t n_streams,
+                                       uint32_t fifo_frames, uint32_t max_block_frames, rb_session** out) {
+    if (!ctx || !out || !descs) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (mixer_rate == 0 || n_streams == 0 || n_streams > 0x7FFFFFFFull) return fail(RB_ERR_INVALID_ARGUMENT, "zero mixer rate or no streams");
+    if (fifo_frames < 64 || max_block_frames == 0) return fail(RB_ERR_INVALID_ARGUMENT, "fifo_frames < 64 or max_block_frames == 0");
+    std::unique_ptr<rb_session, rb_status (*)(rb_session*)> s(new (std::nothrow) rb_session, rb_session_destroy);
+    if (!s) return fail(RB_ERR_OUT_OF_MEMORY, "host allocation failed");
+    s->ctx = ctx, s->mixer_rate = mixer_rate, s->fifo_cap = fifo_frames, s->max_block = max_block_frames;
+    const size_t n = n_streams;
+    s->st.resize(n), s->coef.assign(5 * n, 0.0f), s->ffk.assign(n, 0.0f), s->post.assign(n, 1.0f);
+    bool any_biquad = false, all_biquad = true, ff2 = true;
+    for (size_t i = 0; i < n; i++) {
+        const rb_stream_desc& d = descs[i];
+        const std::string where = "stream " + std::to_string(i) + ": ";
+        if (d.sample_rate == 0 || d.channels == 0) return fail(RB_ERR_INVALID_ARGUMENT, where + "zero sample rate or channels");
+        if (d.channels != 1 || d.format != RB_FMT_F32) return fail(RB_ERR_UNSUPPORTED, where + "sessions take mono f32 sources");
+        if (d.n_effects && !d.effects) return fail(RB_ERR_INVALID_ARGUMENT, where + "effects is NULL");
+        uint32_t k = 0;
+        if (k >= d.n_effects || d.effects[k].kind != RB_FX_UNIFORM || d.effects[k].u32[0] != 1 || d.effects[k].u32[1] != mixer_rate)
+            return fail(RB_ERR_UNSUPPORTED, where + "the chain must start with UNIFORM(1, mixer rate)");
+        k++;
+        const uint32_t g = std::gcd(d.sample_rate, mixer_rate);
+        const uint32_t from = d.sample_rate / g, to = mixer_rate / g;
+        if (!(from < to) || to > (1u << 20)) return fail(RB_ERR_UNSUPPORTED, where + "the source rate must be below the mixer rate (reduced ratio < 2^20)");
+        if (i == 0) s->from = from, s->to = to;
+        else if (from != s->from || to != s->to) return fail(RB_ERR_UNSUPPORTED, where + "all sources of a session share one sample rate");
+        bool biq = false;
+        if (k < d.n_effects && (d.effects[k].kind == RB_FX_LOW_PASS || d.effects[k].kind == RB_FX_HIGH_PASS)) {
+            const rb_effect& e = d.effects[k];
+            if (e.u32[0] == 0 || !(e.f32[0] > 0.0f)) return fail(RB_ERR_INVALID_ARGUMENT, where + "filter frequency and q must be positive");
+            const hostmath::Blt c = hostmath::blt(e.kind == RB_FX_HIGH_PASS, e.u32[0], e.f32[0], mixer_rate);
+            float* co = &s->coef[5 * i];
+            co[0] = c.b0, co[1] = c.b1, co[2] = c.b2, co[3] = c.a1, co[4] = c.a2;
+            if (!lanes::ff2_coeffs(c.b0, c.b1, c.b2, &s->ffk[i])) ff2 = false;
+            biq = true, k++;
+        }
+        any_biquad |= biq, all_biquad &= biq;
+        if (k < d.n_effects && d.effects[k].kind == RB_FX_AMPLIFY) s->post[i] = d.effects[k].f32[0], s->has_post = true, k++;
+        if (k != d.n_effects) return fail(RB_ERR_UNSUPPORTED, where + "chain shape: UNIFORM [LOW_PASS | HIGH_PASS] [AMPLIFY]");
+        s->st[i].mix_start = d.mix_start;
+    }
+    if (any_biquad && !all_biquad) return fail(RB_ERR_UNSUPPORTED, "either every source of a session has a filter or none has");
+    s->has_biquad = any_biquad, s->ff2 = any_biquad && ff2;
+    RB_CUDA(cudaSetDevice(ctx->device));
+    s->stride = align_up((size_t)fifo_frames + 16, 32);
+    const size_t arena = n * s->stride * sizeof(float);
+    const uint32_t n_groups = (uint32_t)((n + 31) / 32);
+    const uint64_t pstride = lanes::round_up_tile(max_block_frames);
+    RB_CUDA(cudaMalloc(&s->d_fifo[0], arena));
+    RB_CUDA(cudaMalloc(&s->d_fifo[1], arena));
+    RB_CUDA(cudaMalloc(&s->d_state, n * 4 * sizeof(float)));
+    RB_CUDA(cudaMalloc(&s->d_zeros, 256));
+    RB_CUDA(cudaMalloc(&s->d_partial, (size_t)n_groups * pstride * sizeof(float)));
+    RB_CUDA(cudaMalloc(&s->d_out, pstride * sizeof(float)));
+    RB_CUDA(cudaMalloc(&s->d_flags, n * sizeof(uint32_t)));
+    RB_CUDA(cudaMalloc(&s->d_rows, n * sizeof(lanes::Row)));
+    RB_CUDA(cudaMalloc(&s->d_u32, 2 * n * sizeof(uint32_t)));
+    RB_CUDA(cudaMalloc(&s->d_off, n * sizeof(uint64_t)));
+    RB_CUDA(cudaMallocHost(&s->h_off, n * sizeof(uint64_t)));
+    RB_CUDA(cudaMallocHost(&s->h_rows, n * sizeof(lanes::Row)));
+    RB_CUDA(cudaMallocHost(&s->h_u32, 2 * n * sizeof(uint32_t)));
+    RB_CUDA(cudaMallocHost(&s->h_out, pstride * sizeof(float)));
+    RB_CUDA(cudaMemsetAsync(s->d_fifo[0], 0, arena, ctx->stream));
+    RB_CUDA(cudaMemsetAsync(s->d_fifo[1], 0, arena, ctx->stream));
+    RB_CUDA(cudaMemsetAsync(s->d_state, 0, n * 4 * sizeof(float), ctx->stream));
+    RB_CUDA(cudaMemsetAsync(s->d_zeros, 0, 256, ctx->stream));
+    RB_CUDA(cudaMemsetAsync(s->d_flags, 0, n * sizeof(uint32_t), ctx->stream));
+    RB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = s.release();
+    return RB_OK;
+}
+
+extern "C" rb_status rb_session_push(rb_session* s, size_t stream, const float* pcm, uint64_t n_frames, int end_of_stream) {
+    if (!s || (!pcm && n_frames)) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (stream >= s->st.size()) return fail(RB_ERR_INVALID_ARGUMENT, "stream index out of range");
+    session::Stream& st = s->st[stream];
+    if (st.eof) return n_frames ? fail(RB_ERR_STATE, "push after end_of_stream") : RB_OK;
+    if (st.fill() + n_frames > s->fifo_cap) return fail(RB_ERR_BUFFER_TOO_SMALL, "the stream's FIFO is full: render first");
+    RB_CUDA(cudaSetDevice(s->ctx->device));
+    if (n_frames) {
+        // one stream: straight into the FIFO tail, classified in place (count = n for this stream only)
+        float* dst = s->d_fifo[s->cur] + stream * s->stride + st.fill();
+        RB_CUDA(cudaMemcpyAsync(dst, pcm, n_frames * sizeof(float), cudaMemcpyHostToDevice, s->ctx->stream));
+        RB_CUDA(rb_lanes_classify_range(dst, n_frames, s->d_flags + stream, s->ctx->stream));
+        RB_CUDA(cudaStreamSynchronize(s->ctx->stream));   // the caller may reuse `pcm` as soon as we return
+        st.pushed += n_frames;
+    }
+    if (end_of_stream) st.eof = true;
+    return RB_OK;
+}
+
+extern "C" rb_status rb_session_push_packed(rb_session* s, const float* pcm, const uint64_t* n_frames, const uint8_t* end_of_stream) {
+    if (!s || !n_frames) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
+    const size_t ns = s->st.size();
+    uint64_t total = 0;
+    for (size_t r = 0; r < ns; r++) {
+        const session::Stream& st = s->st[r];
+        if (st.eof && n_frames[r]) return fail(RB_ERR_STATE, "stream " + std::to_string(r) + ": push after end_of_stream");
+        if (st.fill() + n_frames[r] > s->fifo_cap) return fail(RB_ERR_BUFFER_TOO_SMALL, "stream " + std::to_string(r) + ": FIFO full, render first");
+        total += n_frames[r];
+    }
+    if (total && !pcm) return fail(RB_ERR_INVALID_ARGUMENT, "pcm is NULL");
+    RB_CUDA(cudaSetDevice(s->ctx->device));
+    if (total) {
+        if (!s->d_stage) RB_CUDA(cudaMalloc(&s->d_stage, ns * (size_t)s->fifo_cap * sizeof(float)));
+        uint64_t off = 0;
+        for (size_t r = 0; r < ns; r++) {
+            s->h_off[r] = off, s->h_u32[r] = (uint32_t)n_frames[r], s->h_u32[ns + r] = (uint32_t)s->st[r].fill();
+            off += n_frames[r];
+        }
+        cudaStream_t stq = s->ctx->stream;
+        RB_CUDA(cudaMemcpyAsync(s->d_stage, pcm, total * sizeof(float), cudaMemcpyHostToDevice, stq));
+        RB_CUDA(cudaMemcpyAsync(s->d_off, s->h_off, ns * sizeof(uint64_t), cudaMemcpyHostToDevice, stq));
+        RB_CUDA(cudaMemcpyAsync(s->d_u32, s->h_u32, 2 * ns * sizeof(uint32_t), cudaMemcpyHostToDevice, stq));
+        RB_CUDA(rb_lanes_fifo_append(s->d_stage, s->d_off, s->d_u32, s->d_u32 + ns, s->d_fifo[s->cur], s->stride, s->d_flags, (uint32_t)ns, stq));
+        RB_CUDA(cudaStreamSynchronize(stq));
+    }
+    for (size_t r = 0; r < ns; r++) {
+        s->st[r].pushed += n_frames[r];
+        if (end_of_stream && end_of_stream[r]) s->st[r].eof = true;
+    }
+    return RB_OK;
+}
+
+extern "C" rb_status rb_session_available(rb_session* s, uint64_t* frames, int* ended) {
+    if (!s || !frames) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
+    bool e = false;
+    *frames = session::renderable(s->st, s->T, s->from, s->to, ~0ull >> 1, &e);
+    if (ended) *ended = e ? 1 : 0;
+    return RB_OK;
+}
+
+extern "C" rb_status rb_session_render(rb_session* s, float* out_host, uint64_t max_frames, uint64_t* written, int* ended) {
+    if (!s || !written) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
+    *written = 0;
+    bool e = false;
+    const uint64_t n = session::renderable(s->st, s->T, s->from, s->to, std::min<uint64_t>(max_frames, s->max_block), &e);
+    if (ended) *ended = e ? 1 : 0;
+    if (n == 0) return RB_OK;
+    if (!out_host) return fail(RB_ERR_INVALID_ARGUMENT, "out_host is NULL");
+    RB_CUDA(cudaSetDevice(s->ctx->device));
+    cudaStream_t stq = s->ctx->stream;
+    const size_t ns = s->st.size();
+    std::vector<session::Part> parts(ns);
+    float* fifo = s->d_fifo[s->cur];
+    for (size_t r = 0; r < ns; r++) {
+        const session::Part p = parts[r] = session::part_of(s->st[r], s->T, n, s->from, s->to);
+        lanes::Row& row = s->h_rows[r];
+        memset(&row, 0, sizeof(row));
+        row.in = fifo + r * s->stride, row.L = s->st[r].fill(), row.out_len = p.out_len, row.mix_start = p.mix_start;
+        row.n_int = p.n_int, row.o0 = p.o0, row.i0 = s->st[r].i0, row.state = s->d_state + 4 * r;
+        const float* co = &s->coef[5 * r];
+        row.b0 = co[0], row.b1 = co[1], row.b2 = co[2], row.a1 = co[3], row.a2 = co[4], row.ffk = s->ffk[r];
+        row.post = s->post[r];
+        row.flags = p.continues ? lanes::ROW_CONTINUES : 0u;
+    }
+    RB_CUDA(cudaMemcpyAsync(s->d_rows, s->h_rows, ns * sizeof(lanes::Row), cudaMemcpyHostToDevice, stq));
+    lanes::Args a{};
+    a.rows = s->d_rows, a.n_rows = (uint32_t)ns, a.n_groups = (uint32_t)((ns + 31) / 32);
+    lanes::fill_ratio(a, s->from, s->to);
+    a.mix_len = n, a.pstride = lanes::round_up_tile(s->max_block);
+    a.partial = s->d_partial, a.zeros = s->d_zeros, a.unsafe = s->d_flags;
+    // rows of the partial buffer are only written inside each warp's span: clear what this block may read
+    RB_CUDA(cudaMemsetAsync(s->d_partial, 0, (size_t)a.n_groups * a.pstride * sizeof(float), stq));
+    RB_CUDA(rb_lanes_launch_block(a, s->has_biquad, s->ff2, s->has_post, s->d_out, stq));
+    // the host already knows what every stream consumed: compact the FIFOs into the other arena behind the kernel
+    for (size_t r = 0; r < ns; r++) {
+        const uint64_t fill_before = s->st[r].fill();
+        const uint64_t drop = session::advance(s->st[r], parts[r], s->from, s->to);
+        s->h_u32[r] = (uint32_t)drop, s->h_u32[ns + r] = (uint32_t)(fill_before - drop);
+    }
+    RB_CUDA(cudaMemcpyAsync(s->d_u32, s->h_u32, 2 * ns * sizeof(uint32_t), cudaMemcpyHostToDevice, stq));
+    RB_CUDA(rb_lanes_fifo_compact(fifo, s->d_fifo[s->cur ^ 1], s->stride, s->d_u32, s->d_u32 + ns, (uint32_t)ns, stq));
+    s->cur ^= 1;
+    RB_CUDA(cudaMemcpyAsync(s->h_out, s->d_out, n * sizeof(float), cudaMemcpyDeviceToHost, stq));
+    RB_CUDA(cudaStreamSynchronize(stq));
+    memcpy(out_host, s->h_out, n * sizeof(float));
+    s->T += n;
+    *written = n;
+    if (ended) {
+        bool e2 = false;
+        session::renderable(s->st, s->T, s->from, s->to, 1, &e2);
+        *ended = e2 ? 1 : 0;
+    }
+    return RB_OK;
+}
+
+// ---- block-to-block state as a blob ----
+namespace {
+struct SessionBlobHeader {
+    uint32_t magic, version, n_streams, from, to, has_biquad;
+    uint64_t T;
+};
+struct SessionBlobStream {
+    uint64_t mix_start, pushed, out_done, i0;
+    uint32_t eof, unsafe, fill, pad_;
+    float state[4];
+};
+constexpr uint32_t SESSION_MAGIC = 0x52425353u;   // "RBSS"
+}  // namespace
+
+extern "C" rb_status rb_session_get_state(rb_session* s, void* buf, uint64_t cap, uint64_t* size) {
+    if (!s || !size) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
+    const size_t ns = s->st.size();
+    uint64_t need = sizeof(SessionBlobHeader) + ns * sizeof(SessionBlobStream);
+    for (auto& st : s->st) need += st.fill() * sizeof(float);
+    *size = need;
+    if (!buf) return RB_OK;
+    if (cap < need) return fail(RB_ERR_BUFFER_TOO_SMALL, "state buffer too small");
+    RB_CUDA(cudaSetDevice(s->ctx->device));
+    std::vector<float> state(4 * ns);
+    std::vector<uint32_t> flags(ns);
+    RB_CUDA(cudaMemcpyAsync(state.data(), s->d_state, 4 * ns * sizeof(float), cudaMemcpyDeviceToHost, s->ctx->stream));
+    RB_CUDA(cudaMemcpyAsync(flags.data(), s->d_flags, ns * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->ctx->stream));
+    uint8_t* p = (uint8_t*)buf;
+    SessionBlobHeader h{SESSION_MAGIC, 1u, (uint32_t)ns, s->from, s->to, s->has_biquad ? 1u : 0u, s->T};
+    memcpy(p, &h, sizeof(h)), p += sizeof(h);
+    uint8_t* recs = p;
+    p += ns * sizeof(SessionBlobStream);
+    for (size_t r = 0; r < ns; r++) {
+        const uint64_t fill = s->st[r].fill();
+        if (fill) RB_CUDA(cudaMemcpyAsync(p, s->d_fifo[s->cur] + r * s->stride, fill * sizeof(float), cudaMemcpyDeviceToHost, s->ctx->stream));
+        p += fill * sizeof(float);
+    }
+    RB_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    for (size_t r = 0; r < ns; r++) {
+        const session::Stream& st = s->st[r];
+        SessionBlobStream b{st.mix_start, st.pushed, st.out_done, st.i0, st.eof ? 1u : 0u, flags[r], (uint32_t)st.fill(), 0u,
+                            {state[4 * r], state[4 * r + 1], state[4 * r + 2], state[4 * r + 3]}};
+        memcpy(recs + r * sizeof(b), &b, sizeof(b));
+    }
+    return RB_OK;
+}
+
+extern "C" rb_status rb_session_set_state(rb_session* s, const void* buf, uint64_t size) {
+    if (!s || !buf) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
+    const size_t ns = s->st.size();
+    const uint8_t* p = (const uint8_t*)buf;
+    SessionBlobHeader h;
+    if (size < sizeof(h)) return fail(RB_ERR_INVALID_ARGUMENT, "state blob truncated");
+    memcpy(&h, p, sizeof(h)), p += sizeof(h);
+    if (h.magic != SESSION_MAGIC || h.version != 1u) return fail(RB_ERR_INVALID_ARGUMENT, "not a session state blob");
+    if (h.n_streams != ns || h.from != s->from || h.to != s->to || h.has_biquad != (s->has_biquad ? 1u : 0u))
+        return fail(RB_ERR_INVALID_ARGUMENT, "state blob belongs to a session of another shape");
+    if (size < sizeof(h) + ns * sizeof(SessionBlobStream)) return fail(RB_ERR_INVALID_ARGUMENT, "state blob truncated");
+    std::vector<SessionBlobStream> recs(ns);
+    memcpy(recs.data(), p, ns * sizeof(SessionBlobStream)), p += ns * sizeof(SessionBlobStream);
+    uint64_t need = sizeof(h) + ns * sizeof(SessionBlobStream);
+    for (auto& b : recs) {
+        if (b.fill > s->fifo_cap || b.pushed - b.i0 != b.fill || (b.i0 & 3u)) return fail(RB_ERR_INVALID_ARGUMENT, "state blob: FIFO record out of range");
+        need += (uint64_t)b.fill * sizeof(float);
+    }
+    if (size < need) return fail(RB_ERR_INVALID_ARGUMENT, "state blob truncated");
+    RB_CUDA(cudaSetDevice(s->ctx->device));
+    std::vector<float> state(4 * ns);
+    std::vector<uint32_t> flags(ns);
+    for (size_t r = 0; r < ns; r++) {
+        const SessionBlobStream& b = recs[r];
+        session::Stream& st = s->st[r];
+        st.mix_start = b.mix_start, st.pushed = b.pushed, st.out_done = b.out_done, st.i0 = b.i0, st.eof = b.eof != 0;
+        flags[r] = b.unsafe;
+        for (int k = 0; k < 4; k++) state[4 * r + k] = b.state[k];
+        if (b.fill) RB_CUDA(cudaMemcpyAsync(s->d_fifo[s->cur] + r * s->stride, p, (size_t)b.fill * sizeof(float), cudaMemcpyHostToDevice, s->ctx->stream));
+        p += (size_t)b.fill * sizeof(float);
+    }
+    RB_CUDA(cudaMemcpyAsync(s->d_state, state.data(), 4 * ns * sizeof(float), cudaMemcpyHostToDevice, s->ctx->stream));
+    RB_CUDA(cudaMemcpyAsync(s->d_flags, flags.data(), ns * sizeof(uint32_t), cudaMemcpyHostToDevice, s->ctx->stream));
+    RB_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    s->T = h.T;
     return RB_OK;
 }

@@ -54,7 +54,95 @@ __global__ void __launch_bounds__(256) k_sum_groups(const float* __restrict__ pa
     }
 }
 
+// FIFO append + sticky classification, one CTA per stream
+__global__ void __launch_bounds__(128) k_fifo_append(const float* __restrict__ staging, const uint64_t* __restrict__ offset,
+                                                     const uint32_t* __restrict__ count, const uint32_t* __restrict__ fill,
+                                                     float* __restrict__ fifo, uint64_t stride, uint32_t* __restrict__ flags) {
+    const uint32_t r = blockIdx.x, n = count[r];
+    if (n == 0) return;
+    const float* __restrict__ src = staging + offset[r];
+    float* __restrict__ dst = fifo + (uint64_t)r * stride + fill[r];
+    bool bad = false;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = src[i];
+        const uint32_t u = __float_as_uint(v) & 0x7fffffffu;
+        bad |= u != 0u && (u - 0x1c800000u) >= (0x5d800000u - 0x1c800000u);
+        dst[i] = v;
+    }
+    if (__syncthreads_or(bad ? 1 : 0) && threadIdx.x == 0) flags[r] = 1u;
+}
+
+__global__ void __launch_bounds__(128) k_fifo_compact(const float* __restrict__ src, float* __restrict__ dst, uint64_t stride,
+                                                      const uint32_t* __restrict__ drop, const uint32_t* __restrict__ keep) {
+    const uint32_t r = blockIdx.x, n = keep[r];
+    const float* __restrict__ s = src + (uint64_t)r * stride + drop[r];   // drop is a multiple of 4: both sides 16-byte aligned
+    float* __restrict__ d = dst + (uint64_t)r * stride;
+    const uint32_t n4 = n / 4;
+    for (uint32_t i = threadIdx.x; i < n4; i += blockDim.x)
+        reinterpret_cast<float4*>(d)[i] = reinterpret_cast<const float4*>(s)[i];
+    for (uint32_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+}
+
+__global__ void __launch_bounds__(256) k_classify_range(const float* __restrict__ x, uint64_t n, uint32_t* __restrict__ flag) {
+    bool bad = false;
+    for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t u = __float_as_uint(x[i]) & 0x7fffffffu;
+        bad |= u != 0u && (u - 0x1c800000u) >= (0x5d800000u - 0x1c800000u);
+    }
+    if (__syncthreads_or(bad ? 1 : 0) && threadIdx.x == 0) *flag = 1u;
+}
+
+template <bool HASB, bool FF2, int NPOST>
+static void launch_lanes(const lanes::Args& a, cudaStream_t st) {
+    const uint32_t n_ctas = (a.n_groups + LANES_WARPS - 1) / LANES_WARPS;
+    k_fused_lanes<HASB, FF2, NPOST><<<n_ctas, LANES_THREADS, LANES_SMEM, st>>>(a);
+}
+
 }  // namespace
+
+static cudaError_t launch_lanes_any(const lanes::Args& a, bool has_biquad, bool ff2, bool has_post, cudaStream_t st) {
+    if (has_biquad) {
+        if (ff2) has_post ? launch_lanes<true, true, 1>(a, st) : launch_lanes<true, true, 0>(a, st);
+        else has_post ? launch_lanes<true, false, 1>(a, st) : launch_lanes<true, false, 0>(a, st);
+    } else {
+        has_post ? launch_lanes<false, false, 1>(a, st) : launch_lanes<false, false, 0>(a, st);
+    }
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_sum_groups(const lanes::Args& a, float* d_out, cudaStream_t st) {
+    uint64_t blocks = (a.mix_len + 255) / 256;
+    if (blocks > 148ull * 8) blocks = 148ull * 8;
+    k_sum_groups<<<(uint32_t)blocks, 256, 0, st>>>(a.partial, a.n_groups, a.pstride, a.mix_len, d_out);
+    return cudaGetLastError();
+}
+
+cudaError_t rb_lanes_launch_block(const lanes::Args& a, bool has_biquad, bool ff2, bool has_post, float* d_out, cudaStream_t st) {
+    if (a.mix_len == 0 || a.n_groups == 0) return cudaSuccess;
+    cudaError_t e = launch_lanes_any(a, has_biquad, ff2, has_post, st);
+    if (e != cudaSuccess) return e;
+    return launch_sum_groups(a, d_out, st);
+}
+
+cudaError_t rb_lanes_fifo_append(const float* d_staging, const uint64_t* d_offset, const uint32_t* d_count, const uint32_t* d_fill,
+                                 float* d_fifo, uint64_t stride, uint32_t* d_flags, uint32_t n_streams, cudaStream_t st) {
+    if (n_streams == 0) return cudaSuccess;
+    k_fifo_append<<<n_streams, 128, 0, st>>>(d_staging, d_offset, d_count, d_fill, d_fifo, stride, d_flags);
+    return cudaGetLastError();
+}
+
+cudaError_t rb_lanes_classify_range(const float* d_ptr, uint64_t n, uint32_t* d_flag, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_classify_range<<<1, 256, 0, st>>>(d_ptr, n, d_flag);
+    return cudaGetLastError();
+}
+
+cudaError_t rb_lanes_fifo_compact(const float* d_src, float* d_dst, uint64_t stride, const uint32_t* d_drop, const uint32_t* d_keep,
+                                  uint32_t n_streams, cudaStream_t st) {
+    if (n_streams == 0) return cudaSuccess;
+    k_fifo_compact<<<n_streams, 128, 0, st>>>(d_src, d_dst, stride, d_drop, d_keep);
+    return cudaGetLastError();
+}
 
 struct rb_lanes_plan {
     lanes::Args args{};
@@ -124,25 +212,9 @@ cudaError_t rb_lanes_run(rb_lanes_plan* p, cudaStream_t st) {
         if (e != cudaSuccess) return e;
         p->classified = true;
     }
-    const dim3 grid(p->n_ctas), block(LANES_THREADS);
-    if (p->has_biquad) {
-        if (p->ff2) {
-            if (p->has_post) k_fused_lanes<true, true, 1><<<grid, block, LANES_SMEM, st>>>(a);
-            else k_fused_lanes<true, true, 0><<<grid, block, LANES_SMEM, st>>>(a);
-        } else {
-            if (p->has_post) k_fused_lanes<true, false, 1><<<grid, block, LANES_SMEM, st>>>(a);
-            else k_fused_lanes<true, false, 0><<<grid, block, LANES_SMEM, st>>>(a);
-        }
-    } else {
-        if (p->has_post) k_fused_lanes<false, false, 1><<<grid, block, LANES_SMEM, st>>>(a);
-        else k_fused_lanes<false, false, 0><<<grid, block, LANES_SMEM, st>>>(a);
-    }
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_lanes_any(a, p->has_biquad, p->ff2, p->has_post, st);
     if (e != cudaSuccess) return e;
-    uint64_t blocks = (a.mix_len + 255) / 256;
-    if (blocks > 148ull * 8) blocks = 148ull * 8;
-    k_sum_groups<<<(uint32_t)blocks, 256, 0, st>>>(p->d_partial, a.n_groups, a.pstride, a.mix_len, p->d_out);
-    return cudaGetLastError();
+    return launch_sum_groups(a, p->d_out, st);
 }
 
 uint32_t rb_lanes_launch_count(const rb_lanes_plan*) { return 2u; }

@@ -4,6 +4,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "rb_lanes_core.h"
+
 // One stream of a batch that fits the lane kernel's shape:
 //   f32 mono source -> UniformSourceIterator(1 ch, to) with reduced from < to -> [biquad] -> [one gain] -> mixer(1 ch)
 struct rb_lanes_stream {
@@ -26,3 +28,16 @@ void rb_lanes_inputs_changed(rb_lanes_plan* p);
 cudaError_t rb_lanes_run(rb_lanes_plan* p, cudaStream_t st);
 uint32_t rb_lanes_launch_count(const rb_lanes_plan* p);
 void rb_lanes_destroy(rb_lanes_plan* p);
+
+// ---- streaming blocks (rb_session_* in rb_api.cu): the caller owns every buffer and fills lanes::Args itself ----
+// One block: k_fused_lanes over a.rows, then the ordered sum of the per-warp partial rows into d_out[0, a.mix_len).
+cudaError_t rb_lanes_launch_block(const lanes::Args& a, bool has_biquad, bool ff2, bool has_post, float* d_out, cudaStream_t st);
+// FIFO append: stream r receives count[r] frames, taken from staging + offset[r], behind its fill[r] frames in
+// fifo + r * stride; flags[r] becomes non-zero (and stays so) when a new frame lies outside the exact-reciprocal class.
+cudaError_t rb_lanes_fifo_append(const float* d_staging, const uint64_t* d_offset, const uint32_t* d_count, const uint32_t* d_fill,
+                                 float* d_fifo, uint64_t stride, uint32_t* d_flags, uint32_t n_streams, cudaStream_t st);
+// FIFO compaction into the other arena: dst[r][0, keep[r]) = src[r][drop[r], drop[r] + keep[r]).
+cudaError_t rb_lanes_fifo_compact(const float* d_src, float* d_dst, uint64_t stride, const uint32_t* d_drop, const uint32_t* d_keep,
+                                  uint32_t n_streams, cudaStream_t st);
+// Sticky classification of n freshly written floats at d_ptr: *d_flag = 1 when one lies outside the class.
+cudaError_t rb_lanes_classify_range(const float* d_ptr, uint64_t n, uint32_t* d_flag, cudaStream_t st);

@@ -87,6 +87,7 @@ struct Args {
     uint64_t pstride;        // floats per partial row: mix_len rounded up to TILE
     float* partial;          // [n_groups][pstride], zero outside the span each group writes
     const float* zeros;      // CHUNK zeros, 16-byte aligned: the source of idle lanes
+    const uint32_t* unsafe;  // optional [n_rows]: non-zero = as if ROW_UNSAFE were set (streaming: kept on the device)
 };
 
 // (t - a1*y1) - a2*y2, each product and each difference rounded once (src/source/blt.rs:558-560)
@@ -121,7 +122,7 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
         row.b0 = row.b1 = row.b2 = row.a1 = row.a2 = row.ffk = row.post = 0.0f, row.flags = 0;
     }
     const uint64_t ms = row.mix_start, end = row.mix_start + row.out_len;
-    const bool safe = has && !(row.flags & ROW_UNSAFE);
+    const bool safe = has && !(row.flags & ROW_UNSAFE) && !(a.unsafe && a.unsafe[r]);
     const bool stops = !(row.flags & ROW_CONTINUES);   // the stream ends inside this block (or is a whole stream)
     const bool live = has && row.out_len != 0;
     const uint64_t t_lo = simt::reduce_min64(live ? ms : ~0ull), t_hi = simt::reduce_max64(live ? end : 0ull);

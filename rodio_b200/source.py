@@ -483,6 +483,71 @@ class Batch:
 # ---------------------------------------------------------------------------------------------
 # mixer::mixer(channels, sample_rate) -> (Mixer, MixerSource)   src/mixer.rs:25-43
 # ---------------------------------------------------------------------------------------------
+class Session:
+    """Streaming mixer: sources whose PCM arrives block by block (decoders, live input), the mixer output pulled block by
+    block -- the block form of MixerSource::next (src/mixer.rs:120-136).  Any split into pushes and renders gives the
+    bytes of the whole-stream Batch render with RB_FUSED_LANES.  `sources` describe the chains
+    (UniformSourceIterator(src, 1, rate)[.low_pass / .high_pass][.amplify]); their pcm is ignored."""
+
+    def __init__(self, sources: Sequence[Source], mixer_rate: int, fifo_frames: int = 8192, max_block_frames: int = 4096,
+                 mix_starts: Optional[Sequence[int]] = None, ctx: Optional[Context] = None):
+        self.ctx = ctx or default_context()
+        self.sources = list(sources)
+        self.max_block_frames = max_block_frames
+        self._descs, self._keep = pack_descs(self.sources, mix_starts)
+        self._h = C.c_void_p()
+        check(lib().rb_session_create(self.ctx._h, mixer_rate, self._descs, len(self.sources), fifo_frames, max_block_frames,
+                                      C.byref(self._h)), "rb_session_create")
+
+    def close(self):
+        if self._h:
+            lib().rb_session_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def push(self, stream: int, pcm, end_of_stream: bool = False):
+        a = np.ascontiguousarray(pcm, dtype=np.float32)
+        check(lib().rb_session_push(self._h, stream, a.ctypes.data_as(C.c_void_p), a.size, int(end_of_stream)), "rb_session_push")
+
+    def push_packed(self, blocks: Sequence[np.ndarray], end_of_stream: Optional[Sequence[bool]] = None):
+        """One block per source (possibly empty), pushed with one copy and one kernel."""
+        assert len(blocks) == len(self.sources)
+        blocks = [np.ascontiguousarray(b, dtype=np.float32) for b in blocks]
+        flat = np.concatenate(blocks) if blocks else np.zeros(0, np.float32)
+        n = (C.c_uint64 * len(blocks))(*[b.size for b in blocks])
+        eos = (C.c_uint8 * len(blocks))(*[int(bool(e)) for e in end_of_stream]) if end_of_stream is not None else None
+        check(lib().rb_session_push_packed(self._h, flat.ctypes.data_as(C.c_void_p), n, eos), "rb_session_push_packed")
+
+    def available(self) -> Tuple[int, bool]:
+        n, e = C.c_uint64(), C.c_int()
+        check(lib().rb_session_available(self._h, C.byref(n), C.byref(e)), "rb_session_available")
+        return n.value, bool(e.value)
+
+    def render(self, max_frames: Optional[int] = None) -> Tuple[np.ndarray, bool]:
+        """Up to max_frames mixer frames; (samples, ended) -- ended: MixerSource::next() would return None from here on."""
+        cap = self.max_block_frames if max_frames is None else min(int(max_frames), self.max_block_frames)
+        out = np.empty(cap, dtype=np.float32)
+        n, e = C.c_uint64(), C.c_int()
+        check(lib().rb_session_render(self._h, out.ctypes.data_as(C.c_void_p), cap, C.byref(n), C.byref(e)), "rb_session_render")
+        return out[: n.value].copy(), bool(e.value)
+
+    def get_state(self) -> bytes:
+        n = C.c_uint64()
+        check(lib().rb_session_get_state(self._h, None, 0, C.byref(n)), "rb_session_get_state")
+        buf = (C.c_uint8 * n.value)()
+        check(lib().rb_session_get_state(self._h, buf, n.value, C.byref(n)), "rb_session_get_state")
+        return bytes(buf)
+
+    def set_state(self, blob: bytes):
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        check(lib().rb_session_set_state(self._h, buf, len(blob)), "rb_session_set_state")
+
+
 class _MixerShared:
     def __init__(self, channels, rate, flags, ctx):
         self.channels, self.rate, self.flags, self.ctx = channels, rate, flags, ctx

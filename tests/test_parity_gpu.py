@@ -668,3 +668,99 @@ def test_lanes_full_size_properties(ctx):
         b.upload_all()
         ref = b.render_mix()
     assert_close_peak(got, ref, 1e-5, "lanes vs default fused path at full size")
+
+
+# ------------------------------------------------------------------ streaming sessions (rb_session_*), same gate
+def _session_sources(n, lp=200, gain=1.2):
+    mk = lambda: rb.UniformSourceIterator(rb.TestSource(np.zeros(0, np.float32), 1, 44100), 1, 48000)
+    out = []
+    for _ in range(n):
+        s = mk()
+        if lp is not None:
+            s = s.low_pass(lp)
+        if gain is not None:
+            s = s.amplify(gain)
+        out.append(s)
+    return out
+
+
+def _whole_render(ctx, pcms, starts, lp=200, gain=1.2):
+    srcs = []
+    for p in pcms:
+        s = rb.UniformSourceIterator(rb.TestSource(p, 1, 44100), 1, 48000)
+        if lp is not None:
+            s = s.low_pass(lp)
+        if gain is not None:
+            s = s.amplify(gain)
+        srcs.append(s)
+    with rb.Batch(srcs, 1, 48000, flags=LANES, ctx=ctx, mix_starts=starts) as b:
+        assert b.kernel_family == 2
+        b.upload_all()
+        return b.render_mix(), srcs
+
+
+@lanes_gate
+def test_session_any_split_is_the_whole_render(ctx):
+    rng = np.random.default_rng(11)
+    pcms = [noise(int(n), 60 + i) for i, n in enumerate(rng.integers(2000, 9000, 70))]
+    want, srcs = _whole_render(ctx, pcms, [0] * 70)
+    got = []
+    with rb.Session(_session_sources(70), 48000, fifo_frames=4096, max_block_frames=2048, ctx=ctx) as s:
+        left = [0] * 70
+        ended = False
+        while not ended:
+            for r in rng.permutation(70):
+                room = 4096 - 1100       # stay below the FIFO capacity whatever the renders leave behind
+                n = min(pcms[r].size - left[r], int(rng.integers(0, 700)))
+                if n and rng.random() < 0.8 and n < room:
+                    try:
+                        s.push(int(r), pcms[r][left[r]:left[r] + n], end_of_stream=(left[r] + n == pcms[r].size))
+                        left[r] += n
+                    except rb.RodioB200Error:
+                        pass                 # FIFO full: render first
+            block, ended = s.render(int(rng.integers(1, 2048)))
+            got.append(block)
+    got = np.concatenate(got)
+    assert_bit_exact(got, want, "session blocks vs the whole-stream render")
+    ref = oracle.mixer([to_oracle(x) for x in srcs], 1, 48000)
+    assert_close_peak(got, ref, 1e-5, "session vs the reference's mixer")
+
+
+@lanes_gate
+def test_session_packed_push_10ms_blocks_and_state_blob(ctx):
+    """10 ms blocks pushed for all sources at once; half-way the state moves into a fresh session that carries on."""
+    n_src, frames = 40, 44100 // 2
+    pcms = [noise(frames, 200 + i) for i in range(n_src)]
+    want, _ = _whole_render(ctx, pcms, [0] * n_src, lp=1000, gain=0.8)
+    got, pos, blob = [], 0, None
+    sa = rb.Session(_session_sources(n_src, lp=1000, gain=0.8), 48000, fifo_frames=2048, max_block_frames=480, ctx=ctx)
+    sb = rb.Session(_session_sources(n_src, lp=1000, gain=0.8), 48000, fifo_frames=2048, max_block_frames=480, ctx=ctx)
+    cur, ended = sa, False
+    while not ended:
+        n = min(441, frames - pos)
+        cur.push_packed([p[pos:pos + n] for p in pcms], [pos + n == frames] * n_src)
+        pos += n
+        while True:
+            block, ended = cur.render(480)
+            got.append(block)
+            if block.size == 0 or ended:
+                break
+        if blob is None and pos >= frames // 2:
+            blob = cur.get_state()
+            sb.set_state(blob)
+            cur = sb
+    sa.close(), sb.close()
+    assert_bit_exact(np.concatenate(got), want, "10 ms blocks with a state hand-over vs the whole-stream render")
+
+
+@lanes_gate
+def test_session_rejects_other_shapes(ctx):
+    stereo = rb.UniformSourceIterator(rb.TestSource(np.zeros(0, np.float32), 2, 44100), 1, 48000)
+    with pytest.raises(rb.RodioB200Error):
+        rb.Session([stereo], 48000, ctx=ctx)
+    down = rb.UniformSourceIterator(rb.TestSource(np.zeros(0, np.float32), 1, 96000), 1, 48000)
+    with pytest.raises(rb.RodioB200Error):
+        rb.Session([down], 48000, ctx=ctx)
+    agc = rb.UniformSourceIterator(rb.TestSource(np.zeros(0, np.float32), 1, 44100), 1, 48000).automatic_gain_control()
+    with pytest.raises(rb.RodioB200Error):
+        rb.Session([agc], 48000, ctx=ctx)
