@@ -195,3 +195,87 @@ impl Source for GpuMixerSource {
         Err(SeekError::NotSupported { underlying_source: std::any::type_name::<Self>() })
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Streaming: live `Source`s (decoders, microphones) pulled into a GPU session block by block.
+// `rb_session_*` is the block form of MixerSource::next (reference src/mixer.rs:120-136): the shim pulls a block of
+// samples from every inner rodio `Source` (the only place their per-sample iterators are driven), pushes the blocks,
+// and hands the rendered mixer frames out one by one.  State (resampler position, pending frames, filter state) lives
+// in the session, so the block size is free -- 10 ms blocks for a cpal callback, whole seconds for offline renders.
+pub enum rb_session {}
+
+extern "C" {
+    fn rb_session_create(ctx: *mut rb_context, mixer_rate: u32, descs: *const rb_stream_desc, n: usize, fifo_frames: u32,
+                         max_block_frames: u32, out: *mut *mut rb_session) -> i32;
+    fn rb_session_destroy(s: *mut rb_session) -> i32;
+    fn rb_session_push_packed(s: *mut rb_session, pcm: *const f32, n_frames: *const u64, end_of_stream: *const u8) -> i32;
+    fn rb_session_render(s: *mut rb_session, out: *mut f32, max_frames: u64, written: *mut u64, ended: *mut i32) -> i32;
+    fn rb_session_get_state(s: *mut rb_session, buf: *mut c_void, cap: u64, size: *mut u64) -> i32;
+    fn rb_session_set_state(s: *mut rb_session, buf: *const c_void, size: u64) -> i32;
+}
+
+/// `mixer::mixer(1, rate)` whose inputs are arbitrary mono rodio sources of one sample rate, each followed by
+/// `UniformSourceIterator::new(_, 1, rate)[.low_pass(f)][.amplify(g)]` on the GPU.
+pub struct GpuLiveMixer {
+    session: *mut rb_session,
+    inputs: Vec<Box<dyn Source + Send>>,   // the sources being pulled (decoders ...)
+    done: Vec<bool>,
+    block: Vec<f32>,                       // rendered mixer frames not yet handed out
+    at: usize,
+    pull_frames: usize,                    // input frames pulled per source and refill
+    sample_rate: SampleRate,
+    ended: bool,
+}
+
+impl GpuLiveMixer {
+    fn refill(&mut self) {
+        // pull up to `pull_frames` samples from every live source -- packed: source 0's block, then source 1's, ...
+        let mut pcm: Vec<f32> = Vec::with_capacity(self.inputs.len() * self.pull_frames);
+        let mut n = vec![0u64; self.inputs.len()];
+        let mut eos = vec![0u8; self.inputs.len()];
+        for (i, src) in self.inputs.iter_mut().enumerate() {
+            if self.done[i] { continue; }
+            for _ in 0..self.pull_frames {
+                match src.next() {
+                    Some(s) => { pcm.push(s); n[i] += 1; }
+                    None => { self.done[i] = true; eos[i] = 1; break; }
+                }
+            }
+        }
+        self.block.resize(4096, 0.0);
+        let (mut written, mut ended) = (0u64, 0i32);
+        unsafe {
+            rb_session_push_packed(self.session, pcm.as_ptr(), n.as_ptr(), eos.as_ptr());
+            rb_session_render(self.session, self.block.as_mut_ptr(), 4096, &mut written, &mut ended);
+        }
+        self.block.truncate(written as usize);
+        self.at = 0;
+        self.ended = ended != 0;
+    }
+}
+
+impl Iterator for GpuLiveMixer {
+    type Item = Sample;
+    fn next(&mut self) -> Option<Sample> {
+        while self.at == self.block.len() {
+            if self.ended { return None; }                                  // src/mixer.rs:129-135
+            self.refill();
+        }
+        self.at += 1;
+        Some(self.block[self.at - 1])
+    }
+}
+
+impl Source for GpuLiveMixer {
+    fn current_span_len(&self) -> Option<usize> { None }
+    fn channels(&self) -> ChannelCount { NonZero::new(1).unwrap() }
+    fn sample_rate(&self) -> SampleRate { self.sample_rate }
+    fn total_duration(&self) -> Option<Duration> { None }
+    fn try_seek(&mut self, _: Duration) -> Result<(), SeekError> {
+        Err(SeekError::NotSupported { underlying_source: std::any::type_name::<Self>() })
+    }
+}
+
+impl Drop for GpuLiveMixer {
+    fn drop(&mut self) { unsafe { rb_session_destroy(self.session); } }
+}
