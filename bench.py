@@ -205,6 +205,12 @@ def run_ours(args):
     samples_per_step = S * out_frames * world
     algo_bytes = batch.algorithmic_bytes
     launches = batch.launches_per_render
+    try:
+        family = batch.kernel_family
+    except Exception:   # an older library without the query: the default plan is the HOT kernel
+        family = 1
+    kernel_label = {2: "k_fused_lanes + k_sum_groups (2 launches per step)",
+                    1: "k_fused_hot + k_sum_partials (2 launches per step)"}.get(family, "kernel family %d" % family)
 
     # ---- inputs resident in HBM before the timed region (seeded, distinct per rank) ----
     p0, _ = batch.input_device_ptr(0)
@@ -353,7 +359,7 @@ def run_ours(args):
                        "flags": args.flags},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "kernel_ms": ms_kernel, "kernel": "k_fused_hot + k_sum_partials (2 launches per step)",
+                         "kernel_ms": ms_kernel, "kernel": kernel_label,
                          "algorithmic_bytes_per_step": algo_bytes,
                          "note": "whole render (all launches of one step) timed with CUDA events on the launch stream"},
             "cpu_baseline": cpu,
