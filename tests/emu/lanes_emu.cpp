@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstring>
 #include <limits>
+#include <numeric>
 #include <thread>
 #include <vector>
 
@@ -218,4 +219,77 @@ extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t*
         if (session::renderable(st, T, from, to, 1, &ended) == 0 && !ended) std::abort();   // no progress
     }
     return (long long)written;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Plan-only fuzz of rb_session_plan.h (no kernel): random pushes / renders / early ends on random rate pairs; checks
+// the invariants the device code relies on.  Returns 0, or a line number of the violated check.
+extern "C" int rb_session_plan_fuzz(uint64_t seed, uint32_t n_cases) {
+    uint64_t x = seed * 0x9E3779B97F4A7C15ull + 1;
+    auto rnd = [&](uint64_t n) { x ^= x << 13, x ^= x >> 7, x ^= x << 17; return n ? x % n : 0; };
+#define CHECK(c) do { if (!(c)) return __LINE__; } while (0)
+    for (uint32_t cs = 0; cs < n_cases; cs++) {
+        uint32_t to = 2 + (uint32_t)rnd(400), from = 1 + (uint32_t)rnd(to - 1);
+        uint32_t g = std::gcd(from, to);
+        from /= g, to /= g;
+        const uint32_t ns = 1 + (uint32_t)rnd(5);
+        const uint64_t cap = 64 + rnd(3000);
+        std::vector<session::Stream> st(ns);
+        std::vector<uint64_t> total(ns), rendered(ns, 0);
+        for (uint32_t r = 0; r < ns; r++) st[r].mix_start = rnd(3) ? 0 : rnd(500), total[r] = rnd(6000);
+        uint64_t T = 0;
+        for (int step = 0; step < 4000; step++) {
+            const uint32_t r = (uint32_t)rnd(ns);
+            if (!st[r].eof) {
+                uint64_t n = std::min<uint64_t>(rnd(900), total[r] - st[r].pushed);
+                n = std::min<uint64_t>(n, cap - st[r].fill());            // the device refuses more than the FIFO takes
+                st[r].pushed += n;
+                if (st[r].pushed == total[r] || rnd(400) == 0) st[r].eof = true;
+            }
+            if (rnd(3) == 0) continue;
+            bool ended = false;
+            const uint64_t n = session::renderable(st, T, from, to, 1 + rnd(1500), &ended);
+            if (ended) break;
+            for (uint32_t q = 0; q < ns; q++) {
+                const session::Part p = session::part_of(st[q], T, n, from, to);
+                CHECK(p.mix_start + p.out_len <= n);
+                if (p.out_len) {
+                    CHECK(p.o0 == st[q].out_done);                                   // no output skipped or repeated
+                    CHECK(p.mix_start + T == st[q].mix_start + p.o0);                // it sits where the timeline says
+                    const uint64_t first = (p.o0 * (uint64_t)from) / to, last = ((p.o0 + p.out_len - 1) * (uint64_t)from) / to;
+                    CHECK(first >= st[q].i0 && last < st[q].pushed);                  // taps inside the FIFO ...
+                    CHECK(p.n_int <= p.out_len);
+                    if (p.n_int) CHECK(((p.o0 + p.n_int - 1) * (uint64_t)from) / to + 1 < st[q].pushed);   // ... right taps too
+                    if (p.n_int < p.out_len) CHECK(st[q].eof && p.out_len - p.n_int == 1);                  // only the raw last frame
+                    if (!session::finished(st[q], from, to) && st[q].mix_start + st[q].out_done <= T) CHECK(p.mix_start == 0);
+                } else {
+                    CHECK(session::finished(st[q], from, to) || st[q].mix_start >= T + n || n == 0);
+                }
+                const uint64_t fill = st[q].fill();
+                const uint64_t drop = session::advance(st[q], p, from, to);
+                rendered[q] += p.out_len;
+                CHECK(drop <= fill && (st[q].i0 & 3) == 0);
+                CHECK(st[q].eof || (st[q].out_done * (uint64_t)from) / to >= st[q].i0);
+                // what stays in the FIFO is bounded: an unfinished stream keeps at most the frames not yet usable + 4
+                CHECK(p.continues == !session::finished(st[q], from, to) || p.out_len == 0);
+            }
+            T += n;
+        }
+        for (uint32_t r = 0; r < ns; r++) st[r].eof = true;
+        for (int guard = 0; guard < 100000; guard++) {
+            bool ended = false;
+            const uint64_t n = session::renderable(st, T, from, to, 1 + rnd(5000), &ended);
+            if (ended) break;
+            CHECK(n > 0);
+            for (uint32_t q = 0; q < ns; q++) {
+                const session::Part p = session::part_of(st[q], T, n, from, to);
+                rendered[q] += p.out_len;
+                session::advance(st[q], p, from, to);
+            }
+            T += n;
+        }
+        for (uint32_t r = 0; r < ns; r++) CHECK(rendered[r] == session::out_total(st[r].pushed, from, to));
+    }
+#undef CHECK
+    return 0;
 }

@@ -242,3 +242,12 @@ def test_session_early_end_of_stream(emu):
     cut = [pcms[0], pcms[1][:700], pcms[2], pcms[3]]
     c = make_case(cut, 44100, 48000, [0] * 4, lp=300, gain=1.1)
     assert_bit_exact(got, expected_mix(c["per_stream"], [0] * 4, c["mix_len"]), "cut stream")
+
+
+def test_session_plan_fuzz(emu):
+    """rb_session_plan.h alone (no kernel): 3000 random sessions on random rate pairs -- every output rendered exactly
+    once and where the timeline says, taps always inside the FIFO, FIFO front aligned, totals equal the closed form."""
+    emu.rb_session_plan_fuzz.restype = C.c_int
+    for seed in range(6):
+        line = emu.rb_session_plan_fuzz(C.c_uint64(seed), C.c_uint32(500))
+        assert line == 0, f"invariant at tests/emu/lanes_emu.cpp:{line} violated (seed {seed})"
