@@ -951,6 +951,7 @@ extern "C" rb_status rb_convert_samples(rb_context* ctx, const void* in, rb_samp
 struct rb_session {
     rb_context* ctx = nullptr;
     uint32_t mixer_rate = 0, from = 0, to = 0;
+    uint32_t channels = 1;        // of every source and of the mixer (1 or 2)
     bool has_biquad = false, ff2 = false, has_post = false;
     std::vector<session::Stream> st;
     std::vector<float> coef;      // 5 per stream
@@ -998,11 +999,13 @@ extern "C" rb_status rb_session_create(rb_context* ctx, uint32_t mixer_rate, con
         const rb_stream_desc& d = descs[i];
         const std::string where = "stream " + std::to_string(i) + ": ";
         if (d.sample_rate == 0 || d.channels == 0) return fail(RB_ERR_INVALID_ARGUMENT, where + "zero sample rate or channels");
-        if (d.channels != 1 || d.format != RB_FMT_F32) return fail(RB_ERR_UNSUPPORTED, where + "sessions take mono f32 sources");
+        if ((d.channels != 1 && d.channels != 2) || d.format != RB_FMT_F32) return fail(RB_ERR_UNSUPPORTED, where + "sessions take mono or stereo f32 sources");
+        if (i == 0) s->channels = d.channels;
+        else if (d.channels != s->channels) return fail(RB_ERR_UNSUPPORTED, where + "all sources of a session have the same channel count");
         if (d.n_effects && !d.effects) return fail(RB_ERR_INVALID_ARGUMENT, where + "effects is NULL");
         uint32_t k = 0;
-        if (k >= d.n_effects || d.effects[k].kind != RB_FX_UNIFORM || d.effects[k].u32[0] != 1 || d.effects[k].u32[1] != mixer_rate)
-            return fail(RB_ERR_UNSUPPORTED, where + "the chain must start with UNIFORM(1, mixer rate)");
+        if (k >= d.n_effects || d.effects[k].kind != RB_FX_UNIFORM || d.effects[k].u32[0] != d.channels || d.effects[k].u32[1] != mixer_rate)
+            return fail(RB_ERR_UNSUPPORTED, where + "the chain must start with UNIFORM(source channels, mixer rate)");
         k++;
         const uint32_t g = std::gcd(d.sample_rate, mixer_rate);
         const uint32_t from = d.sample_rate / g, to = mixer_rate / g;
@@ -1027,13 +1030,14 @@ extern "C" rb_status rb_session_create(rb_context* ctx, uint32_t mixer_rate, con
     if (any_biquad && !all_biquad) return fail(RB_ERR_UNSUPPORTED, "either every source of a session has a filter or none has");
     s->has_biquad = any_biquad, s->ff2 = any_biquad && ff2;
     RB_CUDA(cudaSetDevice(ctx->device));
-    s->stride = align_up((size_t)fifo_frames + 16, 32);
+    const uint32_t C = s->channels;
+    s->stride = align_up((size_t)fifo_frames * C + 16, 32);
     const size_t arena = n * s->stride * sizeof(float);
     const uint32_t n_groups = (uint32_t)((n + 31) / 32);
-    const uint64_t pstride = lanes::round_up_tile(max_block_frames);
+    const uint64_t pstride = lanes::round_up_tile((uint64_t)max_block_frames * C);
     RB_CUDA(cudaMalloc(&s->d_fifo[0], arena));
     RB_CUDA(cudaMalloc(&s->d_fifo[1], arena));
-    RB_CUDA(cudaMalloc(&s->d_state, n * 4 * sizeof(float)));
+    RB_CUDA(cudaMalloc(&s->d_state, n * 4 * C * sizeof(float)));
     RB_CUDA(cudaMalloc(&s->d_zeros, 256));
     RB_CUDA(cudaMalloc(&s->d_partial, (size_t)n_groups * pstride * sizeof(float)));
     RB_CUDA(cudaMalloc(&s->d_out, pstride * sizeof(float)));
@@ -1047,7 +1051,7 @@ extern "C" rb_status rb_session_create(rb_context* ctx, uint32_t mixer_rate, con
     RB_CUDA(cudaMallocHost(&s->h_out, pstride * sizeof(float)));
     RB_CUDA(cudaMemsetAsync(s->d_fifo[0], 0, arena, ctx->stream));
     RB_CUDA(cudaMemsetAsync(s->d_fifo[1], 0, arena, ctx->stream));
-    RB_CUDA(cudaMemsetAsync(s->d_state, 0, n * 4 * sizeof(float), ctx->stream));
+    RB_CUDA(cudaMemsetAsync(s->d_state, 0, n * 4 * C * sizeof(float), ctx->stream));
     RB_CUDA(cudaMemsetAsync(s->d_zeros, 0, 256, ctx->stream));
     RB_CUDA(cudaMemsetAsync(s->d_flags, 0, n * sizeof(uint32_t), ctx->stream));
     RB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1064,9 +1068,10 @@ extern "C" rb_status rb_session_push(rb_session* s, size_t stream, const float* 
     RB_CUDA(cudaSetDevice(s->ctx->device));
     if (n_frames) {
         // one stream: straight into the FIFO tail, classified in place (count = n for this stream only)
-        float* dst = s->d_fifo[s->cur] + stream * s->stride + st.fill();
-        RB_CUDA(cudaMemcpyAsync(dst, pcm, n_frames * sizeof(float), cudaMemcpyHostToDevice, s->ctx->stream));
-        RB_CUDA(rb_lanes_classify_range(dst, n_frames, s->d_flags + stream, s->ctx->stream));
+        const uint32_t C = s->channels;
+        float* dst = s->d_fifo[s->cur] + stream * s->stride + st.fill() * C;
+        RB_CUDA(cudaMemcpyAsync(dst, pcm, n_frames * C * sizeof(float), cudaMemcpyHostToDevice, s->ctx->stream));
+        RB_CUDA(rb_lanes_classify_range(dst, n_frames * C, s->d_flags + stream, s->ctx->stream));
         RB_CUDA(cudaStreamSynchronize(s->ctx->stream));   // the caller may reuse `pcm` as soon as we return
         st.pushed += n_frames;
     }
@@ -1087,14 +1092,15 @@ extern "C" rb_status rb_session_push_packed(rb_session* s, const float* pcm, con
     if (total && !pcm) return fail(RB_ERR_INVALID_ARGUMENT, "pcm is NULL");
     RB_CUDA(cudaSetDevice(s->ctx->device));
     if (total) {
-        if (!s->d_stage) RB_CUDA(cudaMalloc(&s->d_stage, ns * (size_t)s->fifo_cap * sizeof(float)));
+        const uint32_t C = s->channels;   // the kernel counts floats
+        if (!s->d_stage) RB_CUDA(cudaMalloc(&s->d_stage, ns * (size_t)s->fifo_cap * C * sizeof(float)));
         uint64_t off = 0;
         for (size_t r = 0; r < ns; r++) {
-            s->h_off[r] = off, s->h_u32[r] = (uint32_t)n_frames[r], s->h_u32[ns + r] = (uint32_t)s->st[r].fill();
-            off += n_frames[r];
+            s->h_off[r] = off, s->h_u32[r] = (uint32_t)(n_frames[r] * C), s->h_u32[ns + r] = (uint32_t)(s->st[r].fill() * C);
+            off += n_frames[r] * C;
         }
         cudaStream_t stq = s->ctx->stream;
-        RB_CUDA(cudaMemcpyAsync(s->d_stage, pcm, total * sizeof(float), cudaMemcpyHostToDevice, stq));
+        RB_CUDA(cudaMemcpyAsync(s->d_stage, pcm, total * C * sizeof(float), cudaMemcpyHostToDevice, stq));
         RB_CUDA(cudaMemcpyAsync(s->d_off, s->h_off, ns * sizeof(uint64_t), cudaMemcpyHostToDevice, stq));
         RB_CUDA(cudaMemcpyAsync(s->d_u32, s->h_u32, 2 * ns * sizeof(uint32_t), cudaMemcpyHostToDevice, stq));
         RB_CUDA(rb_lanes_fifo_append(s->d_stage, s->d_off, s->d_u32, s->d_u32 + ns, s->d_fifo[s->cur], s->stride, s->d_flags, (uint32_t)ns, stq));
@@ -1126,6 +1132,7 @@ extern "C" rb_status rb_session_render(rb_session* s, float* out_host, uint64_t 
     RB_CUDA(cudaSetDevice(s->ctx->device));
     cudaStream_t stq = s->ctx->stream;
     const size_t ns = s->st.size();
+    const uint32_t C = s->channels;
     std::vector<session::Part> parts(ns);
     float* fifo = s->d_fifo[s->cur];
     for (size_t r = 0; r < ns; r++) {
@@ -1133,7 +1140,7 @@ extern "C" rb_status rb_session_render(rb_session* s, float* out_host, uint64_t 
         lanes::Row& row = s->h_rows[r];
         memset(&row, 0, sizeof(row));
         row.in = fifo + r * s->stride, row.L = s->st[r].fill(), row.out_len = p.out_len, row.mix_start = p.mix_start;
-        row.n_int = p.n_int, row.o0 = p.o0, row.i0 = s->st[r].i0, row.state = s->d_state + 4 * r;
+        row.n_int = p.n_int, row.o0 = p.o0, row.i0 = s->st[r].i0, row.state = s->d_state + 4 * C * r;
         const float* co = &s->coef[5 * r];
         row.b0 = co[0], row.b1 = co[1], row.b2 = co[2], row.a1 = co[3], row.a2 = co[4], row.ffk = s->ffk[r];
         row.post = s->post[r];
@@ -1142,24 +1149,24 @@ extern "C" rb_status rb_session_render(rb_session* s, float* out_host, uint64_t 
     RB_CUDA(cudaMemcpyAsync(s->d_rows, s->h_rows, ns * sizeof(lanes::Row), cudaMemcpyHostToDevice, stq));
     lanes::Args a{};
     a.rows = s->d_rows, a.n_rows = (uint32_t)ns, a.n_groups = (uint32_t)((ns + 31) / 32);
-    lanes::fill_ratio(a, s->from, s->to);
-    a.mix_len = n, a.pstride = lanes::round_up_tile(s->max_block);
+    lanes::fill_ratio(a, s->from, s->to, C);
+    a.mix_len = n, a.pstride = lanes::round_up_tile((uint64_t)s->max_block * C);
     a.partial = s->d_partial, a.zeros = s->d_zeros, a.unsafe = s->d_flags;
     // rows of the partial buffer are only written inside each warp's span: clear what this block may read
     RB_CUDA(cudaMemsetAsync(s->d_partial, 0, (size_t)a.n_groups * a.pstride * sizeof(float), stq));
-    RB_CUDA(rb_lanes_launch_block(a, s->has_biquad, s->ff2, s->has_post, s->d_out, stq));
+    RB_CUDA(rb_lanes_launch_block(a, C, s->has_biquad, s->ff2, s->has_post, s->d_out, stq));
     // the host already knows what every stream consumed: compact the FIFOs into the other arena behind the kernel
     for (size_t r = 0; r < ns; r++) {
         const uint64_t fill_before = s->st[r].fill();
         const uint64_t drop = session::advance(s->st[r], parts[r], s->from, s->to);
-        s->h_u32[r] = (uint32_t)drop, s->h_u32[ns + r] = (uint32_t)(fill_before - drop);
+        s->h_u32[r] = (uint32_t)(drop * C), s->h_u32[ns + r] = (uint32_t)((fill_before - drop) * C);   // floats
     }
     RB_CUDA(cudaMemcpyAsync(s->d_u32, s->h_u32, 2 * ns * sizeof(uint32_t), cudaMemcpyHostToDevice, stq));
     RB_CUDA(rb_lanes_fifo_compact(fifo, s->d_fifo[s->cur ^ 1], s->stride, s->d_u32, s->d_u32 + ns, (uint32_t)ns, stq));
     s->cur ^= 1;
-    RB_CUDA(cudaMemcpyAsync(s->h_out, s->d_out, n * sizeof(float), cudaMemcpyDeviceToHost, stq));
+    RB_CUDA(cudaMemcpyAsync(s->h_out, s->d_out, n * C * sizeof(float), cudaMemcpyDeviceToHost, stq));
     RB_CUDA(cudaStreamSynchronize(stq));
-    memcpy(out_host, s->h_out, n * sizeof(float));
+    memcpy(out_host, s->h_out, n * C * sizeof(float));
     s->T += n;
     *written = n;
     if (ended) {
@@ -1173,13 +1180,13 @@ extern "C" rb_status rb_session_render(rb_session* s, float* out_host, uint64_t 
 // ---- block-to-block state as a blob ----
 namespace {
 struct SessionBlobHeader {
-    uint32_t magic, version, n_streams, from, to, has_biquad;
+    uint32_t magic, version, n_streams, from, to, has_biquad, channels, pad_;
     uint64_t T;
 };
 struct SessionBlobStream {
     uint64_t mix_start, pushed, out_done, i0;
-    uint32_t eof, unsafe, fill, pad_;
-    float state[4];
+    uint32_t eof, unsafe, fill, pad_;   // fill in frames
+    float state[8];                      // 4 per channel
 };
 constexpr uint32_t SESSION_MAGIC = 0x52425353u;   // "RBSS"
 }  // namespace
@@ -1188,30 +1195,31 @@ extern "C" rb_status rb_session_get_state(rb_session* s, void* buf, uint64_t cap
     if (!s || !size) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
     const size_t ns = s->st.size();
     uint64_t need = sizeof(SessionBlobHeader) + ns * sizeof(SessionBlobStream);
-    for (auto& st : s->st) need += st.fill() * sizeof(float);
+    const uint32_t C = s->channels;
+    for (auto& st : s->st) need += st.fill() * C * sizeof(float);
     *size = need;
     if (!buf) return RB_OK;
     if (cap < need) return fail(RB_ERR_BUFFER_TOO_SMALL, "state buffer too small");
     RB_CUDA(cudaSetDevice(s->ctx->device));
-    std::vector<float> state(4 * ns);
+    std::vector<float> state(4 * C * ns);
     std::vector<uint32_t> flags(ns);
-    RB_CUDA(cudaMemcpyAsync(state.data(), s->d_state, 4 * ns * sizeof(float), cudaMemcpyDeviceToHost, s->ctx->stream));
+    RB_CUDA(cudaMemcpyAsync(state.data(), s->d_state, 4 * C * ns * sizeof(float), cudaMemcpyDeviceToHost, s->ctx->stream));
     RB_CUDA(cudaMemcpyAsync(flags.data(), s->d_flags, ns * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->ctx->stream));
     uint8_t* p = (uint8_t*)buf;
-    SessionBlobHeader h{SESSION_MAGIC, 1u, (uint32_t)ns, s->from, s->to, s->has_biquad ? 1u : 0u, s->T};
+    SessionBlobHeader h{SESSION_MAGIC, 2u, (uint32_t)ns, s->from, s->to, s->has_biquad ? 1u : 0u, C, 0u, s->T};
     memcpy(p, &h, sizeof(h)), p += sizeof(h);
     uint8_t* recs = p;
     p += ns * sizeof(SessionBlobStream);
     for (size_t r = 0; r < ns; r++) {
-        const uint64_t fill = s->st[r].fill();
+        const uint64_t fill = s->st[r].fill() * C;   // floats
         if (fill) RB_CUDA(cudaMemcpyAsync(p, s->d_fifo[s->cur] + r * s->stride, fill * sizeof(float), cudaMemcpyDeviceToHost, s->ctx->stream));
         p += fill * sizeof(float);
     }
     RB_CUDA(cudaStreamSynchronize(s->ctx->stream));
     for (size_t r = 0; r < ns; r++) {
         const session::Stream& st = s->st[r];
-        SessionBlobStream b{st.mix_start, st.pushed, st.out_done, st.i0, st.eof ? 1u : 0u, flags[r], (uint32_t)st.fill(), 0u,
-                            {state[4 * r], state[4 * r + 1], state[4 * r + 2], state[4 * r + 3]}};
+        SessionBlobStream b{st.mix_start, st.pushed, st.out_done, st.i0, st.eof ? 1u : 0u, flags[r], (uint32_t)st.fill(), 0u, {0}};
+        for (uint32_t k = 0; k < 4 * C; k++) b.state[k] = state[4 * C * r + k];
         memcpy(recs + r * sizeof(b), &b, sizeof(b));
     }
     return RB_OK;
@@ -1224,8 +1232,9 @@ extern "C" rb_status rb_session_set_state(rb_session* s, const void* buf, uint64
     SessionBlobHeader h;
     if (size < sizeof(h)) return fail(RB_ERR_INVALID_ARGUMENT, "state blob truncated");
     memcpy(&h, p, sizeof(h)), p += sizeof(h);
-    if (h.magic != SESSION_MAGIC || h.version != 1u) return fail(RB_ERR_INVALID_ARGUMENT, "not a session state blob");
-    if (h.n_streams != ns || h.from != s->from || h.to != s->to || h.has_biquad != (s->has_biquad ? 1u : 0u))
+    const uint32_t C = s->channels;
+    if (h.magic != SESSION_MAGIC || h.version != 2u) return fail(RB_ERR_INVALID_ARGUMENT, "not a session state blob");
+    if (h.n_streams != ns || h.from != s->from || h.to != s->to || h.has_biquad != (s->has_biquad ? 1u : 0u) || h.channels != C)
         return fail(RB_ERR_INVALID_ARGUMENT, "state blob belongs to a session of another shape");
     if (size < sizeof(h) + ns * sizeof(SessionBlobStream)) return fail(RB_ERR_INVALID_ARGUMENT, "state blob truncated");
     std::vector<SessionBlobStream> recs(ns);
@@ -1233,22 +1242,22 @@ extern "C" rb_status rb_session_set_state(rb_session* s, const void* buf, uint64
     uint64_t need = sizeof(h) + ns * sizeof(SessionBlobStream);
     for (auto& b : recs) {
         if (b.fill > s->fifo_cap || b.pushed - b.i0 != b.fill || (b.i0 & 3u)) return fail(RB_ERR_INVALID_ARGUMENT, "state blob: FIFO record out of range");
-        need += (uint64_t)b.fill * sizeof(float);
+        need += (uint64_t)b.fill * C * sizeof(float);
     }
     if (size < need) return fail(RB_ERR_INVALID_ARGUMENT, "state blob truncated");
     RB_CUDA(cudaSetDevice(s->ctx->device));
-    std::vector<float> state(4 * ns);
+    std::vector<float> state(4 * C * ns);
     std::vector<uint32_t> flags(ns);
     for (size_t r = 0; r < ns; r++) {
         const SessionBlobStream& b = recs[r];
         session::Stream& st = s->st[r];
         st.mix_start = b.mix_start, st.pushed = b.pushed, st.out_done = b.out_done, st.i0 = b.i0, st.eof = b.eof != 0;
         flags[r] = b.unsafe;
-        for (int k = 0; k < 4; k++) state[4 * r + k] = b.state[k];
-        if (b.fill) RB_CUDA(cudaMemcpyAsync(s->d_fifo[s->cur] + r * s->stride, p, (size_t)b.fill * sizeof(float), cudaMemcpyHostToDevice, s->ctx->stream));
-        p += (size_t)b.fill * sizeof(float);
+        for (uint32_t k = 0; k < 4 * C; k++) state[4 * C * r + k] = b.state[k];
+        if (b.fill) RB_CUDA(cudaMemcpyAsync(s->d_fifo[s->cur] + r * s->stride, p, (size_t)b.fill * C * sizeof(float), cudaMemcpyHostToDevice, s->ctx->stream));
+        p += (size_t)b.fill * C * sizeof(float);
     }
-    RB_CUDA(cudaMemcpyAsync(s->d_state, state.data(), 4 * ns * sizeof(float), cudaMemcpyHostToDevice, s->ctx->stream));
+    RB_CUDA(cudaMemcpyAsync(s->d_state, state.data(), 4 * C * ns * sizeof(float), cudaMemcpyHostToDevice, s->ctx->stream));
     RB_CUDA(cudaMemcpyAsync(s->d_flags, flags.data(), ns * sizeof(uint32_t), cudaMemcpyHostToDevice, s->ctx->stream));
     RB_CUDA(cudaStreamSynchronize(s->ctx->stream));
     s->T = h.T;

@@ -11,23 +11,24 @@ namespace {
 
 constexpr int LANES_WARPS = 2;                      // warps per CTA: every warp is independent, small CTAs pack the SM
 constexpr int LANES_THREADS = 32 * LANES_WARPS;
-constexpr size_t LANES_SMEM = (size_t)LANES_WARPS * 32 * lanes::RS * sizeof(float);
+template <int C>
+constexpr size_t lanes_smem_bytes() { return (size_t)LANES_WARPS * 32 * lanes::Geo<C>::RS * sizeof(float); }   // 21.0 / 41.0 KB
 
-template <bool HASB, bool FF2, int NPOST>
+template <int C, bool HASB, bool FF2, int NPOST>
 __global__ void __launch_bounds__(LANES_THREADS) k_fused_lanes(lanes::Args a) {
     extern __shared__ __align__(16) float lanes_smem[];
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t group = blockIdx.x * LANES_WARPS + warp;
     if (group >= a.n_groups) return;   // whole warps leave: the warp program only synchronises within a warp
-    lanes::warp_main<HASB, FF2, NPOST>(a, group, lanes_smem + (size_t)warp * 32 * lanes::RS);
+    lanes::warp_main<C, HASB, FF2, NPOST>(a, group, lanes_smem + (size_t)warp * 32 * lanes::Geo<C>::RS);
 }
 
 // One CTA per stream: does every non-zero |x| lie inside [2^-70, 2^60]?  (rb_lanes_core.h, "Exact division".)
-__global__ void __launch_bounds__(256) k_classify_inputs(lanes::Row* rows, uint32_t n_rows) {
+__global__ void __launch_bounds__(256) k_classify_inputs(lanes::Row* rows, uint32_t n_rows, uint32_t channels) {
     const uint32_t r = blockIdx.x;
     if (r >= n_rows) return;
     const float* __restrict__ x = rows[r].in;
-    const uint64_t L = rows[r].L;
+    const uint64_t L = rows[r].L * channels;   // floats
     bool bad = false;
     const uint64_t n4 = L / 4;
     const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
@@ -92,36 +93,43 @@ __global__ void __launch_bounds__(256) k_classify_range(const float* __restrict_
     if (__syncthreads_or(bad ? 1 : 0) && threadIdx.x == 0) *flag = 1u;
 }
 
-template <bool HASB, bool FF2, int NPOST>
+template <int C, bool HASB, bool FF2, int NPOST>
 static void launch_lanes(const lanes::Args& a, cudaStream_t st) {
     const uint32_t n_ctas = (a.n_groups + LANES_WARPS - 1) / LANES_WARPS;
-    k_fused_lanes<HASB, FF2, NPOST><<<n_ctas, LANES_THREADS, LANES_SMEM, st>>>(a);
+    k_fused_lanes<C, HASB, FF2, NPOST><<<n_ctas, LANES_THREADS, lanes_smem_bytes<C>(), st>>>(a);   // < 48 KB: no opt-in needed
+}
+template <int C>
+static void launch_lanes_c(const lanes::Args& a, bool has_biquad, bool ff2, bool has_post, cudaStream_t st) {
+    if (has_biquad) {
+        if (ff2) has_post ? launch_lanes<C, true, true, 1>(a, st) : launch_lanes<C, true, true, 0>(a, st);
+        else has_post ? launch_lanes<C, true, false, 1>(a, st) : launch_lanes<C, true, false, 0>(a, st);
+    } else {
+        has_post ? launch_lanes<C, false, false, 1>(a, st) : launch_lanes<C, false, false, 0>(a, st);
+    }
 }
 
 }  // namespace
 
-static cudaError_t launch_lanes_any(const lanes::Args& a, bool has_biquad, bool ff2, bool has_post, cudaStream_t st) {
-    if (has_biquad) {
-        if (ff2) has_post ? launch_lanes<true, true, 1>(a, st) : launch_lanes<true, true, 0>(a, st);
-        else has_post ? launch_lanes<true, false, 1>(a, st) : launch_lanes<true, false, 0>(a, st);
-    } else {
-        has_post ? launch_lanes<false, false, 1>(a, st) : launch_lanes<false, false, 0>(a, st);
-    }
+static cudaError_t launch_lanes_any(const lanes::Args& a, uint32_t channels, bool has_biquad, bool ff2, bool has_post, cudaStream_t st) {
+    if (channels == 2) launch_lanes_c<2>(a, has_biquad, ff2, has_post, st);
+    else launch_lanes_c<1>(a, has_biquad, ff2, has_post, st);
     return cudaGetLastError();
 }
 
-static cudaError_t launch_sum_groups(const lanes::Args& a, float* d_out, cudaStream_t st) {
-    uint64_t blocks = (a.mix_len + 255) / 256;
+static cudaError_t launch_sum_groups(const lanes::Args& a, uint32_t channels, float* d_out, cudaStream_t st) {
+    const uint64_t n = a.mix_len * channels;   // floats
+    uint64_t blocks = (n + 255) / 256;
     if (blocks > 148ull * 8) blocks = 148ull * 8;
-    k_sum_groups<<<(uint32_t)blocks, 256, 0, st>>>(a.partial, a.n_groups, a.pstride, a.mix_len, d_out);
+    k_sum_groups<<<(uint32_t)blocks, 256, 0, st>>>(a.partial, a.n_groups, a.pstride, n, d_out);
     return cudaGetLastError();
 }
 
-cudaError_t rb_lanes_launch_block(const lanes::Args& a, bool has_biquad, bool ff2, bool has_post, float* d_out, cudaStream_t st) {
-    if (a.mix_len == 0 || a.n_groups == 0) return cudaSuccess;
-    cudaError_t e = launch_lanes_any(a, has_biquad, ff2, has_post, st);
+cudaError_t rb_lanes_launch_block(const lanes::Args& a, uint32_t channels, bool has_biquad, bool ff2, bool has_post, float* d_out,
+                                  cudaStream_t st) {
+    if (a.mix_len == 0 || a.n_groups == 0 || (channels != 1 && channels != 2)) return cudaSuccess;
+    cudaError_t e = launch_lanes_any(a, channels, has_biquad, ff2, has_post, st);
     if (e != cudaSuccess) return e;
-    return launch_sum_groups(a, d_out, st);
+    return launch_sum_groups(a, channels, d_out, st);
 }
 
 cudaError_t rb_lanes_fifo_append(const float* d_staging, const uint64_t* d_offset, const uint32_t* d_count, const uint32_t* d_fill,
@@ -152,15 +160,15 @@ struct rb_lanes_plan {
     float* d_out = nullptr;
     bool has_biquad = false, ff2 = false, has_post = false;
     bool classified = false;
-    uint32_t n_ctas = 0;
+    uint32_t channels = 1;
 };
 
-cudaError_t rb_lanes_try_create(const rb_lanes_stream* streams, size_t n_streams, uint32_t from, uint32_t to, bool has_biquad,
-                                bool has_post, float* d_out, uint64_t mix_len, int sm_count, cudaStream_t st,
+cudaError_t rb_lanes_try_create(const rb_lanes_stream* streams, size_t n_streams, uint32_t channels, uint32_t from, uint32_t to,
+                                bool has_biquad, bool has_post, float* d_out, uint64_t mix_len, int sm_count, cudaStream_t st,
                                 rb_lanes_plan** out) {
     (void)sm_count;
     *out = nullptr;
-    if (n_streams == 0 || mix_len == 0 || !(from < to) || to > (1u << 20)) return cudaSuccess;
+    if (n_streams == 0 || mix_len == 0 || !(from < to) || to > (1u << 20) || (channels != 1 && channels != 2)) return cudaSuccess;
     std::vector<lanes::Row> rows(n_streams);
     bool ff2 = has_biquad;
     for (size_t i = 0; i < n_streams; i++) {
@@ -178,12 +186,11 @@ cudaError_t rb_lanes_try_create(const rb_lanes_stream* streams, size_t n_streams
         else ff2 = false;
     }
     auto p = new rb_lanes_plan;
-    p->has_biquad = has_biquad, p->ff2 = ff2, p->has_post = has_post, p->d_out = d_out;
+    p->has_biquad = has_biquad, p->ff2 = ff2, p->has_post = has_post, p->d_out = d_out, p->channels = channels;
     lanes::Args& a = p->args;
     a.n_rows = (uint32_t)n_streams, a.n_groups = (uint32_t)((n_streams + 31) / 32);
-    lanes::fill_ratio(a, from, to);
-    a.mix_len = mix_len, a.pstride = lanes::round_up_tile(mix_len);
-    p->n_ctas = (a.n_groups + LANES_WARPS - 1) / LANES_WARPS;
+    lanes::fill_ratio(a, from, to, channels);
+    a.mix_len = mix_len, a.pstride = lanes::round_up_tile(mix_len * channels);
     cudaError_t e = cudaMalloc(&p->d_rows, n_streams * sizeof(lanes::Row));
     if (e == cudaSuccess) e = cudaMalloc(&p->d_partial, (size_t)a.n_groups * a.pstride * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&p->d_zeros, 256);
@@ -207,14 +214,14 @@ void rb_lanes_inputs_changed(rb_lanes_plan* p) {
 cudaError_t rb_lanes_run(rb_lanes_plan* p, cudaStream_t st) {
     const lanes::Args& a = p->args;
     if (!p->classified) {
-        k_classify_inputs<<<a.n_rows, 256, 0, st>>>(p->d_rows, a.n_rows);
+        k_classify_inputs<<<a.n_rows, 256, 0, st>>>(p->d_rows, a.n_rows, p->channels);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         p->classified = true;
     }
-    cudaError_t e = launch_lanes_any(a, p->has_biquad, p->ff2, p->has_post, st);
+    cudaError_t e = launch_lanes_any(a, p->channels, p->has_biquad, p->ff2, p->has_post, st);
     if (e != cudaSuccess) return e;
-    return launch_sum_groups(a, p->d_out, st);
+    return launch_sum_groups(a, p->channels, p->d_out, st);
 }
 
 uint32_t rb_lanes_launch_count(const rb_lanes_plan*) { return 2u; }

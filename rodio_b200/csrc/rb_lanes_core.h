@@ -46,30 +46,37 @@
 
 namespace lanes {
 
-constexpr int TILE = 8;                 // timeline samples per loop iteration
+constexpr int TILE = 8;                 // timeline SAMPLES per loop iteration (TILE / C frames)
 constexpr int CHUNK = 16;               // input frames per ring chunk (one cp.async group)
 constexpr int NSLOT = 4;                // ring slots: chunk c-1 (draining), c, c+1 (in flight), c+2 (just issued)
-constexpr int RING = CHUNK * NSLOT;     // 64 words
-constexpr int MIRROR = CHUNK;           // ring words [RING, RING + MIRROR) repeat [0, MIRROR): a tile never wraps
-constexpr int RS = RING + MIRROR + 4;   // 84 words per lane; RS / 4 odd: LDS of 8 consecutive lanes hits 8 bank quads
-constexpr int QPC = CHUNK / 4;          // 16-byte quads per chunk and stream
-constexpr int RPI = 32 / QPC;           // streams served by one cp.async warp instruction
-constexpr uint32_t RUN_CAP = 1u << 30;
-constexpr uint32_t MIN_RUN = 4 * TILE;  // shortest fast run worth priming the ring for
-static_assert(MIRROR >= TILE && MIRROR <= CHUNK && (RS / 4) % 2 == 1 && RUN_CAP % TILE == 0, "ring geometry");
+constexpr uint32_t RUN_CAP = 1u << 30;  // frames
+constexpr int MIN_RUN_TILES = 4;        // shortest fast run worth priming the ring for
+// Per-lane ring geometry for C interleaved channels (C = 1 mono, 2 stereo); sizes in 32-bit words.
+template <int C>
+struct Geo {
+    static constexpr int TF = TILE / C;            // frames per tile
+    static constexpr int CHW = CHUNK * C;          // words per chunk
+    static constexpr int RING = CHW * NSLOT;       // 64 / 128
+    static constexpr int MIRROR = CHW;             // ring words [RING, RING + MIRROR) repeat [0, MIRROR): a tile never wraps
+    static constexpr int RS = RING + MIRROR + 4;   // 84 / 164 words per lane; RS / 4 odd: 8 lanes hit 8 bank quads
+    static constexpr int QPC = CHW / 4;            // 16-byte quads per chunk and stream
+    static constexpr int RPI = 32 / QPC;           // streams served by one cp.async warp instruction
+    static_assert(TILE % C == 0 && MIRROR >= TILE && (RS / 4) % 2 == 1 && 32 % QPC == 0, "ring geometry");
+};
+static_assert(RUN_CAP % TILE == 0, "run cap");
 constexpr uint32_t ROW_UNSAFE = 1u;     // Row::flags: some sample outside the exact-reciprocal class
 constexpr uint32_t ROW_CONTINUES = 2u;  // Row::flags: the stream goes on in the next block -- keep the filter state past `end`
 
 struct Row {                 // one stream (whole, or the part of it one block of a streaming session renders)
-    const float* in;         // mono f32 frames, 16-byte aligned, readable up to a 16-byte tail pad
+    const float* in;         // f32 frames (C interleaved channels), 16-byte aligned, readable up to a 16-byte tail pad
     uint64_t L;              // input frames at `in`
-    uint64_t out_len;        // samples on the (block's) mixer timeline
-    uint64_t mix_start;      // timeline position of the first of them
+    uint64_t out_len;        // FRAMES on the (block's) mixer timeline
+    uint64_t mix_start;      // timeline frame of the first of them
     uint64_t n_int;          // outputs [0, n_int) interpolate between two frames (left frame <= L-2)
     uint64_t o0;             // streaming: stream-absolute index of the first output of the block (0 for whole streams)
     uint64_t i0;             // streaming: stream-absolute index of the frame at in[0]; (o0 * from) / to >= i0
-    float* state;            // streaming: {x[n-1], x[n-2], y[n-1], y[n-2]} read at the start, written at the end
-                             // (16-byte aligned); NULL: start from zeros, keep nothing
+    float* state;            // streaming: per channel {x[n-1], x[n-2], y[n-1], y[n-2]} (4*C floats) read at the start,
+                             // written at the end; NULL: start from zeros, keep nothing
     float b0, b1, b2, a1, a2;
     float ffk;               // FF2 variant: b1 == ffk * b0 (ffk = +-2) and b2 == b0
     float post;              // the one gain behind the chain (NPOST == 1)
@@ -80,13 +87,13 @@ struct Args {
     const Row* rows;
     uint32_t n_rows, n_groups;
     uint32_t from, to;       // reduced ratio, from < to <= 2^20
-    uint32_t q8, r8;         // divmod(TILE * from, to)
+    uint32_t q8, r8;         // divmod((TILE / C) * from, to): frames a tile advances
     float den_f, rcp_den, from_f;
     float neg1;              // -1.0f as a run-time value (keeps fma(p, -1, t) an FFMA: the chain stays on one pipe)
-    uint64_t mix_len;
-    uint64_t pstride;        // floats per partial row: mix_len rounded up to TILE
+    uint64_t mix_len;        // mixer timeline, frames
+    uint64_t pstride;        // floats per partial row: mix_len * C rounded up to TILE
     float* partial;          // [n_groups][pstride], zero outside the span each group writes
-    const float* zeros;      // CHUNK zeros, 16-byte aligned: the source of idle lanes
+    const float* zeros;      // CHUNK * C zeros, 16-byte aligned: the source of idle lanes
     const uint32_t* unsafe;  // optional [n_rows]: non-zero = as if ROW_UNSAFE were set (streaming: kept on the device)
 };
 
@@ -109,8 +116,10 @@ SIMT_FN float reduce_tile(const float (&v)[TILE], uint32_t ln) {
     return simt::fadd(s, 0.0f);   // the reference's accumulator starts from +0.0: an all-(-0) column sums to +0
 }
 
-template <bool HASB, bool FF2, int NPOST>
+template <int C, bool HASB, bool FF2, int NPOST>
 SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
+    using G = Geo<C>;
+    constexpr int TF = G::TF, RS = G::RS, QPC = G::QPC, RPI = G::RPI, RING = G::RING, MIRROR = G::MIRROR, CHW = G::CHW;
     const uint32_t ln = simt::lane();
     const uint32_t r = group * 32u + ln;
     const bool has = r < a.n_rows;
@@ -121,23 +130,28 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
         row.in = a.zeros, row.L = 0, row.out_len = 0, row.mix_start = 0, row.n_int = 0, row.o0 = 0, row.i0 = 0, row.state = nullptr;
         row.b0 = row.b1 = row.b2 = row.a1 = row.a2 = row.ffk = row.post = 0.0f, row.flags = 0;
     }
-    const uint64_t ms = row.mix_start, end = row.mix_start + row.out_len;
+    const uint64_t ms = row.mix_start, end = row.mix_start + row.out_len;   // frames
     const bool safe = has && !(row.flags & ROW_UNSAFE) && !(a.unsafe && a.unsafe[r]);
     const bool stops = !(row.flags & ROW_CONTINUES);   // the stream ends inside this block (or is a whole stream)
     const bool live = has && row.out_len != 0;
     const uint64_t t_lo = simt::reduce_min64(live ? ms : ~0ull), t_hi = simt::reduce_max64(live ? end : 0ull);
     if (t_lo >= t_hi) return;
-    const uint64_t t_end = (t_hi + TILE - 1) / TILE * TILE;
-    uint64_t t = t_lo / TILE * TILE;
+    const uint64_t t_end = (t_hi + TF - 1) / TF * TF;
+    uint64_t t = t_lo / TF * TF;                        // timeline position in frames, a multiple of TF
     float* const ringl = ring_warp + ln * RS;
     float* const prow = a.partial + (uint64_t)group * a.pstride;
     const float den = a.den_f, rcp = a.rcp_den, from_f = a.from_f, neg1 = a.neg1;
     const float b0 = row.b0, b1 = row.b1, b2 = row.b2, a1 = row.a1, a2 = row.a2, ffk = row.ffk, post = row.post;
     const uint32_t from = a.from, to = a.to;
-    float xh1 = 0.f, xh2 = 0.f, y1 = 0.f, y2 = 0.f;   // canonical filter state: x[n-1], x[n-2], y[n-1], y[n-2]
-    if (HASB && row.state) xh1 = row.state[0], xh2 = row.state[1], y1 = row.state[2], y2 = row.state[3];
-    // stream-absolute numerator of local output o is (o0 + o) * from; the frame it falls on, relative to in[0],
-    // is that / to - i0.  Both offsets are zero for whole streams.
+    // canonical filter state per channel: x[n-1], x[n-2], y[n-1], y[n-2]
+    float xh1[C], xh2[C], y1[C], y2[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        xh1[c] = xh2[c] = y1[c] = y2[c] = 0.f;
+        if (HASB && row.state) xh1[c] = row.state[4 * c], xh2[c] = row.state[4 * c + 1], y1[c] = row.state[4 * c + 2], y2[c] = row.state[4 * c + 3];
+    }
+    // stream-absolute numerator of local output frame o is (o0 + o) * from; the input frame it falls on, relative to
+    // in[0], is that / to - i0.  Both offsets are zero for whole streams.
     const uint64_t o0 = row.o0, i0 = row.i0;
     const uint32_t cq = ln % QPC;                      // the quad of a chunk this lane copies ...
     const uint32_t cr = ln / QPC;                      // ... for stream cr + RPI * j of the warp
@@ -147,24 +161,27 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
         uint32_t d;
         if (!has || t >= end) {
             d = RUN_CAP;
-            if (stops) xh1 = xh2 = y1 = y2 = 0.f;       // a finished stream contributes nothing, its filter stops
+            if (stops) {                                // a finished stream contributes nothing, its filter stops
+#pragma unroll
+                for (int c = 0; c < C; c++) xh1[c] = xh2[c] = y1[c] = y2[c] = 0.f;
+            }
         } else if (t < ms) {
-            const uint64_t g = (ms - t) / TILE * TILE;  // idle until the tile the stream starts in
+            const uint64_t g = (ms - t) / TF * TF;      // idle until the tile the stream starts in
             d = g > RUN_CAP ? RUN_CAP : (uint32_t)g;
         } else {
             const uint64_t o = t - ms;
             d = 0;
-            if (safe && o + TILE <= row.n_int) {
-                const uint64_t g = (row.n_int - o) / TILE * TILE;
+            if (safe && o + TF <= row.n_int) {
+                const uint64_t g = (row.n_int - o) / TF * TF;
                 d = g > RUN_CAP ? RUN_CAP : (uint32_t)g;
             }
         }
         const uint64_t left = t_end - t;
         const uint32_t cap = left > RUN_CAP ? RUN_CAP : (uint32_t)left;
-        const uint32_t run = simt::reduce_min(d < cap ? d : cap);
+        const uint32_t run = simt::reduce_min(d < cap ? d : cap);   // frames, a multiple of TF
 
-        if (run >= MIN_RUN) {
-            // =================================== FAST RUN: `run` timeline samples ===================================
+        if (run >= (uint32_t)(MIN_RUN_TILES * TF)) {
+            // =================================== FAST RUN: `run` timeline frames ===================================
             const bool act = has && t >= ms && t < end;
             uint32_t num = 0, k0 = 0, maxq = QPC - 1;
             const float* src = a.zeros;
@@ -173,10 +190,10 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                 const uint64_t ia = prod / to;
                 num = (uint32_t)(prod - ia * to);
                 const uint64_t i = ia - i0;
-                const uint64_t ibase = i & ~3ull;
+                const uint64_t ibase = i & ~3ull;       // a multiple of 4 frames: 16-byte aligned for either C
                 k0 = (uint32_t)(i - ibase);
-                src = row.in + ibase;
-                const uint64_t mq = ((row.L - 1) >> 2) - (ibase >> 2);   // last quad (relative) that holds a frame
+                src = row.in + ibase * C;
+                const uint64_t mq = ((row.L * C - 1) >> 2) - ((ibase * C) >> 2);   // last quad (relative) that holds a frame
                 maxq = mq > 0x7fffffffull ? 0x7fffffffu : (uint32_t)mq;
             }
             // the streams this lane copies for: source pointer and clamp of stream cr + RPI * j
@@ -194,7 +211,7 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                 for (int j = 0; j < QPC; j++) {
                     const uint32_t off = want < mq[j] ? want : mq[j];
                     const float* s = (const float*)(uintptr_t)sq[j] + 4ull * off;
-                    float* dst = ring_warp + (cr + RPI * j) * RS + slot * CHUNK + cq * 4;
+                    float* dst = ring_warp + (cr + RPI * j) * RS + slot * CHW + cq * 4;
                     simt::cp16(dst, s);
                     if (slot == 0 && (int)(cq * 4) < MIRROR) simt::cp16(dst + RING, s);
                 }
@@ -207,16 +224,22 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
             issue(2);
             uint32_t c_ready = 1;   // chunks [0, c_ready) are readable; c_ready and c_ready + 1 are in flight
             const simt::sptr ring_end = simt::sptr_of(ringl + RING);
-            simt::sptr p = simt::sptr_of(ringl + k0);
-            float x0 = simt::lds(p), x1 = simt::lds(simt::sptr_add(p, 1));
-            p = simt::sptr_add(p, 2);
+            simt::sptr p = simt::sptr_of(ringl + k0 * C);
+            float x0[C], x1[C];
+#pragma unroll
+            for (int c = 0; c < C; c++) x0[c] = simt::lds(simt::sptr_add(p, c)), x1[c] = simt::lds(simt::sptr_add(p, C + c));
+            p = simt::sptr_add(p, 2 * C);
             float nf = simt::u2f(num);
-            // upper bound of any lane's next ring index after the coming tile: the lane with the largest phase
+            // upper bound (in frames) of any lane's next ring frame after the coming tile: the lane with the largest phase
             uint32_t kb = 5, kbn = to - 1;
-            float p1 = 0.f, p2 = 0.f;
-            if (HASB && FF2) p1 = simt::fmul(b0, xh1), p2 = simt::fmul(b0, xh2);
+            float p1[C], p2[C];
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                p1[c] = p2[c] = 0.f;
+                if (HASB && FF2) p1[c] = simt::fmul(b0, xh1[c]), p2[c] = simt::fmul(b0, xh2[c]);
+            }
 
-            for (uint32_t done = 0; done < run; done += TILE) {
+            for (uint32_t done = 0; done < run; done += TF) {
                 kb += a.q8, kbn += a.r8;
                 if (kbn >= to) kbn -= to, kb += 1;
                 if ((kb - 1) / CHUNK >= c_ready) {
@@ -229,73 +252,92 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                 if (simt::sptr_ge(p, ring_end)) p = simt::sptr_add(p, -RING);
                 float v[TILE];
 #pragma unroll
-                for (int u = 0; u < TILE; u++) {
-                    // src/math.rs:24-26: first + (second - first) * num / den, the division as an exact reciprocal step
-                    const float m = simt::fmul(simt::fsub(x1, x0), nf);
-                    const float q0 = simt::fmul(m, rcp);
-                    const float q = simt::ffma(simt::ffma(-q0, den, m), rcp, q0);
-                    const float x = simt::fadd(x0, q);
-                    // next output frame: numerator += from (mod to); a carry moves one input frame on
-                    simt::lerp_advance(nf, x0, x1, p, from_f, den);
-                    float y = x;
-                    if (HASB) {
-                        float tt;
-                        if (FF2) {
-                            // b1*x1 = ffk*(b0*x1) and b2*x2 = b0*x2 exactly: one product per sample, same roundings
-                            const float pz = simt::fmul(b0, x);
-                            tt = simt::fadd(simt::ffma(p1, ffk, pz), p2);
-                            p2 = p1, p1 = pz;
-                        } else {
-                            tt = simt::fadd(simt::fadd(simt::fmul(b0, x), simt::fmul(b1, xh1)), simt::fmul(b2, xh2));
-                        }
-                        xh2 = xh1, xh1 = x;
-                        y = fb(a1, a2, tt, y1, y2, neg1);
-                        y2 = y1, y1 = y;
+                for (int f = 0; f < TF; f++) {
+                    float x[C];
+#pragma unroll
+                    for (int c = 0; c < C; c++) {
+                        // src/math.rs:24-26: first + (second - first) * num / den, the division as an exact reciprocal step
+                        const float m = simt::fmul(simt::fsub(x1[c], x0[c]), nf);
+                        const float q0 = simt::fmul(m, rcp);
+                        const float q = simt::ffma(simt::ffma(-q0, den, m), rcp, q0);
+                        x[c] = simt::fadd(x0[c], q);
                     }
-                    v[u] = NPOST ? simt::fmul(y, post) : y;
+                    // next output frame: numerator += from (mod to); a carry moves one input frame on
+                    simt::lerp_advance<C>(nf, x0, x1, p, from_f, den);
+#pragma unroll
+                    for (int c = 0; c < C; c++) {
+                        float y = x[c];
+                        if (HASB) {
+                            float tt;
+                            if (FF2) {
+                                // b1*x1 = ffk*(b0*x1) and b2*x2 = b0*x2 exactly: one product per sample, same roundings
+                                const float pz = simt::fmul(b0, x[c]);
+                                tt = simt::fadd(simt::ffma(p1[c], ffk, pz), p2[c]);
+                                p2[c] = p1[c], p1[c] = pz;
+                            } else {
+                                tt = simt::fadd(simt::fadd(simt::fmul(b0, x[c]), simt::fmul(b1, xh1[c])), simt::fmul(b2, xh2[c]));
+                            }
+                            xh2[c] = xh1[c], xh1[c] = x[c];
+                            y = fb(a1, a2, tt, y1[c], y2[c], neg1);
+                            y2[c] = y1[c], y1[c] = y;
+                        }
+                        v[f * C + c] = NPOST ? simt::fmul(y, post) : y;
+                    }
                 }
                 const float s = reduce_tile(v, ln);
-                if ((ln & 3u) == 0) prow[t + done + (ln >> 2)] = s;
+                if ((ln & 3u) == 0) prow[(t + done) * C + (ln >> 2)] = s;
             }
             simt::cp_wait<0>();
             simt::syncwarp();
-            simt::emu_count(0, run / TILE);
+            simt::emu_count(0, run / TF);
             t += run;
         } else {
             // =================================== SLOW TILE: per-lane closed form ===================================
             float v[TILE];
 #pragma unroll 1
-            for (int u = 0; u < TILE; u++) {
-                const uint64_t tt = t + (uint64_t)u;
-                float val = 0.0f;
-                if (has && tt >= ms && tt < end) {
+            for (int f = 0; f < TF; f++) {
+                const uint64_t tt = t + (uint64_t)f;
+                const bool on = has && tt >= ms && tt < end;
+                uint64_t i = 0;
+                uint32_t num = 0;
+                if (on) {
                     const uint64_t prod = (o0 + (tt - ms)) * (uint64_t)from;
                     const uint64_t ia = prod / to;
-                    const uint32_t num = (uint32_t)(prod - ia * to);
-                    const uint64_t i = ia - i0;
-                    const float xa = simt::ldg(row.in + i);
-                    float x = xa;
-                    if (i + 1 < row.L)
-                        x = simt::fadd(xa, simt::fdiv(simt::fmul(simt::fsub(simt::ldg(row.in + i + 1), xa), simt::u2f(num)), den));
-                    float y = x;
-                    if (HASB) {
-                        const float f = simt::fadd(simt::fadd(simt::fmul(b0, x), simt::fmul(b1, xh1)), simt::fmul(b2, xh2));
-                        y = fb(a1, a2, f, y1, y2, neg1);
-                        xh2 = xh1, xh1 = x, y2 = y1, y1 = y;
-                    }
-                    val = NPOST ? simt::fmul(y, post) : y;
+                    num = (uint32_t)(prod - ia * to);
+                    i = ia - i0;
                 } else if (has && tt >= end && stops) {
-                    xh1 = xh2 = y1 = y2 = 0.f;
+#pragma unroll
+                    for (int c = 0; c < C; c++) xh1[c] = xh2[c] = y1[c] = y2[c] = 0.f;
                 }
-                v[u] = val;
+#pragma unroll
+                for (int c = 0; c < C; c++) {
+                    float val = 0.0f;
+                    if (on) {
+                        const float xa = simt::ldg(row.in + i * C + c);
+                        float x = xa;
+                        if (i + 1 < row.L)
+                            x = simt::fadd(xa, simt::fdiv(simt::fmul(simt::fsub(simt::ldg(row.in + (i + 1) * C + c), xa), simt::u2f(num)), den));
+                        float y = x;
+                        if (HASB) {
+                            const float ff = simt::fadd(simt::fadd(simt::fmul(b0, x), simt::fmul(b1, xh1[c])), simt::fmul(b2, xh2[c]));
+                            y = fb(a1, a2, ff, y1[c], y2[c], neg1);
+                            xh2[c] = xh1[c], xh1[c] = x, y2[c] = y1[c], y1[c] = y;
+                        }
+                        val = NPOST ? simt::fmul(y, post) : y;
+                    }
+                    v[f * C + c] = val;
+                }
             }
             const float s = reduce_tile(v, ln);
-            if ((ln & 3u) == 0) prow[t + (ln >> 2)] = s;
+            if ((ln & 3u) == 0) prow[t * C + (ln >> 2)] = s;
             simt::emu_count(1, 1);
-            t += TILE;
+            t += TF;
         }
     }
-    if (HASB && row.state) row.state[0] = xh1, row.state[1] = xh2, row.state[2] = y1, row.state[3] = y2;
+    if (HASB && row.state) {
+#pragma unroll
+        for (int c = 0; c < C; c++) row.state[4 * c] = xh1[c], row.state[4 * c + 1] = xh2[c], row.state[4 * c + 2] = y1[c], row.state[4 * c + 3] = y2[c];
+    }
 }
 
 }  // namespace lanes

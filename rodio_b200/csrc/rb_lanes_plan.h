@@ -32,17 +32,18 @@ inline bool ff2_coeffs(float b0, float b1, float b2, float* ffk) {
     return true;
 }
 
-inline void fill_ratio(Args& a, uint32_t from, uint32_t to) {
+inline void fill_ratio(Args& a, uint32_t from, uint32_t to, uint32_t channels) {
     a.from = from, a.to = to;
-    a.q8 = (uint32_t)(((uint64_t)TILE * from) / to);
-    a.r8 = (uint32_t)(((uint64_t)TILE * from) % to);
+    const uint64_t tf = TILE / channels;   // frames per tile
+    a.q8 = (uint32_t)((tf * from) / to);
+    a.r8 = (uint32_t)((tf * from) % to);
     a.den_f = (float)to;
     a.rcp_den = 1.0f / a.den_f;
     a.from_f = (float)from;
     a.neg1 = -1.0f;
 }
 
-inline uint64_t round_up_tile(uint64_t n) { return (n + TILE - 1) / TILE * TILE; }
+inline uint64_t round_up_tile(uint64_t n) { return (n + TILE - 1) / TILE * TILE; }   // n in floats (frames * channels)
 
 // Input classification for the exact-reciprocal division: every non-zero |x| inside [2^-70, 2^60].
 inline bool sample_in_class(float x) {

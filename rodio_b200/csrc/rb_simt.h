@@ -134,15 +134,15 @@ SIMT_FN sptr sptr_of(const float* p) { return p; }
 SIMT_FN sptr sptr_add(sptr p, int words) { return p + words; }
 SIMT_FN bool sptr_ge(sptr a, sptr b) { return a >= b; }
 SIMT_FN float lds(sptr p) { return *p; }
-// One index step of the resampler: numerator += from (mod den); on a carry the right tap becomes the left one and
-// the next ring word is fetched.  (Six instructions on the device, see below.)
-SIMT_FN void lerp_advance(float& nf, float& x0, float& x1, sptr& p, float from_f, float den) {
+// One index step of the resampler for a frame of C channels: numerator += from (mod den); on a carry the right taps
+// become the left ones and the next ring frame is fetched.  (Six / eight instructions on the device, see below.)
+template <int C>
+SIMT_FN void lerp_advance(float& nf, float (&x0)[C], float (&x1)[C], sptr& p, float from_f, float den) {
     const float nf2 = nf + from_f;
     if (nf2 >= den) {
         nf = nf2 - den;
-        x0 = x1;
-        x1 = *p;
-        p += 1;
+        for (int c = 0; c < C; c++) x0[c] = x1[c], x1[c] = p[c];
+        p += C;
     } else {
         nf = nf2;
     }
@@ -206,24 +206,46 @@ SIMT_FN float lds(sptr p) {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(p) : "memory");
     return v;
 }
-// FADD, FSETP, then four predicated instructions: numerator wrap, tap move, tap load, cursor increment.  Written in
-// PTX because nvcc otherwise keeps a second cursor and copies the taps through temporaries (3 extra moves per step).
-SIMT_FN void lerp_advance(float& nf, float& x0, float& x1, sptr& p, float from_f, float den) {
-    asm volatile(
-        "{\n"
-        ".reg .pred c;\n"
-        ".reg .f32 t;\n"
-        "add.rn.f32 t, %0, %4;\n"
-        "setp.ge.f32 c, t, %5;\n"
-        "@c sub.rn.f32 t, t, %5;\n"
-        "mov.f32 %0, t;\n"
-        "@c mov.f32 %1, %2;\n"
-        "@c ld.shared.f32 %2, [%3];\n"
-        "@c add.u32 %3, %3, 4;\n"
-        "}\n"
-        : "+f"(nf), "+f"(x0), "+f"(x1), "+r"(p)
-        : "f"(from_f), "f"(den)
-        : "memory");
+// FADD, FSETP, then predicated instructions: numerator wrap, tap move(s), tap load (one LDS / LDS.64), cursor increment.
+// Written in PTX because nvcc otherwise keeps a second cursor and copies the taps through temporaries (3 extra moves
+// per step).
+template <int C>
+SIMT_FN void lerp_advance(float& nf, float (&x0)[C], float (&x1)[C], sptr& p, float from_f, float den) {
+    static_assert(C == 1 || C == 2, "mono or stereo");
+    if constexpr (C == 1) {
+        asm volatile(
+            "{\n"
+            ".reg .pred c;\n"
+            ".reg .f32 t;\n"
+            "add.rn.f32 t, %0, %4;\n"
+            "setp.ge.f32 c, t, %5;\n"
+            "@c sub.rn.f32 t, t, %5;\n"
+            "mov.f32 %0, t;\n"
+            "@c mov.f32 %1, %2;\n"
+            "@c ld.shared.f32 %2, [%3];\n"
+            "@c add.u32 %3, %3, 4;\n"
+            "}\n"
+            : "+f"(nf), "+f"(x0[0]), "+f"(x1[0]), "+r"(p)
+            : "f"(from_f), "f"(den)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n"
+            ".reg .pred c;\n"
+            ".reg .f32 t;\n"
+            "add.rn.f32 t, %0, %6;\n"
+            "setp.ge.f32 c, t, %7;\n"
+            "@c sub.rn.f32 t, t, %7;\n"
+            "mov.f32 %0, t;\n"
+            "@c mov.f32 %1, %3;\n"
+            "@c mov.f32 %2, %4;\n"
+            "@c ld.shared.v2.f32 {%3, %4}, [%5];\n"
+            "@c add.u32 %5, %5, 8;\n"
+            "}\n"
+            : "+f"(nf), "+f"(x0[0]), "+f"(x0[1]), "+f"(x1[0]), "+f"(x1[1]), "+r"(p)
+            : "f"(from_f), "f"(den)
+            : "memory");
+    }
 }
 SIMT_FN void cp16(float* smem_dst, const float* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)

@@ -494,6 +494,7 @@ class Session:
         self.ctx = ctx or default_context()
         self.sources = list(sources)
         self.max_block_frames = max_block_frames
+        self.channels = self.sources[0].channels() if self.sources else 1   # of every source and of the mixer
         self._descs, self._keep = pack_descs(self.sources, mix_starts)
         self._h = C.c_void_p()
         check(lib().rb_session_create(self.ctx._h, mixer_rate, self._descs, len(self.sources), fifo_frames, max_block_frames,
@@ -512,14 +513,16 @@ class Session:
 
     def push(self, stream: int, pcm, end_of_stream: bool = False):
         a = np.ascontiguousarray(pcm, dtype=np.float32)
-        check(lib().rb_session_push(self._h, stream, a.ctypes.data_as(C.c_void_p), a.size, int(end_of_stream)), "rb_session_push")
+        assert a.size % self.channels == 0, "whole frames"
+        check(lib().rb_session_push(self._h, stream, a.ctypes.data_as(C.c_void_p), a.size // self.channels, int(end_of_stream)),
+              "rb_session_push")
 
     def push_packed(self, blocks: Sequence[np.ndarray], end_of_stream: Optional[Sequence[bool]] = None):
         """One block per source (possibly empty), pushed with one copy and one kernel."""
         assert len(blocks) == len(self.sources)
         blocks = [np.ascontiguousarray(b, dtype=np.float32) for b in blocks]
         flat = np.concatenate(blocks) if blocks else np.zeros(0, np.float32)
-        n = (C.c_uint64 * len(blocks))(*[b.size for b in blocks])
+        n = (C.c_uint64 * len(blocks))(*[b.size // self.channels for b in blocks])
         eos = (C.c_uint8 * len(blocks))(*[int(bool(e)) for e in end_of_stream]) if end_of_stream is not None else None
         check(lib().rb_session_push_packed(self._h, flat.ctypes.data_as(C.c_void_p), n, eos), "rb_session_push_packed")
 
@@ -529,12 +532,13 @@ class Session:
         return n.value, bool(e.value)
 
     def render(self, max_frames: Optional[int] = None) -> Tuple[np.ndarray, bool]:
-        """Up to max_frames mixer frames; (samples, ended) -- ended: MixerSource::next() would return None from here on."""
+        """Up to max_frames mixer frames; (interleaved samples, ended) -- ended: MixerSource::next() would return None from
+        here on."""
         cap = self.max_block_frames if max_frames is None else min(int(max_frames), self.max_block_frames)
-        out = np.empty(cap, dtype=np.float32)
+        out = np.empty(cap * self.channels, dtype=np.float32)
         n, e = C.c_uint64(), C.c_int()
         check(lib().rb_session_render(self._h, out.ctypes.data_as(C.c_void_p), cap, C.byref(n), C.byref(e)), "rb_session_render")
-        return out[: n.value].copy(), bool(e.value)
+        return out[: n.value * self.channels].copy(), bool(e.value)
 
     def get_state(self) -> bytes:
         n = C.c_uint64()

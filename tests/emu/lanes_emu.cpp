@@ -12,17 +12,31 @@
 #include "../../rodio_b200/csrc/rb_lanes_plan.h"
 
 namespace {
-template <bool HASB, bool FF2, int NPOST>
-void run_warp(const lanes::Args& a, uint32_t group, simt::WarpEmu* w, float* ring) {
+template <int C, bool HASB, bool FF2, int NPOST>
+void run_warp_c(const lanes::Args& a, uint32_t group, simt::WarpEmu* w, float* ring) {
     std::vector<std::thread> th;
     for (uint32_t l = 0; l < 32; l++)
         th.emplace_back([&, l] {
             simt::g_lane = simt::LaneEmu{};
             simt::g_lane.w = w, simt::g_lane.lane = l;
-            lanes::warp_main<HASB, FF2, NPOST>(a, group, ring);
+            lanes::warp_main<C, HASB, FF2, NPOST>(a, group, ring);
         });
     for (auto& t : th) t.join();
 }
+template <int C>
+void run_group(const lanes::Args& a, uint32_t g, simt::WarpEmu* w, float* ring, bool hasb, bool ff2, bool npost) {
+    if (hasb && ff2 && npost) run_warp_c<C, true, true, 1>(a, g, w, ring);
+    else if (hasb && ff2) run_warp_c<C, true, true, 0>(a, g, w, ring);
+    else if (hasb && npost) run_warp_c<C, true, false, 1>(a, g, w, ring);
+    else if (hasb) run_warp_c<C, true, false, 0>(a, g, w, ring);
+    else if (npost) run_warp_c<C, false, false, 1>(a, g, w, ring);
+    else run_warp_c<C, false, false, 0>(a, g, w, ring);
+}
+void run_group_any(uint32_t channels, const lanes::Args& a, uint32_t g, simt::WarpEmu* w, float* ring, bool hasb, bool ff2, bool npost) {
+    if (channels == 2) run_group<2>(a, g, w, ring, hasb, ff2, npost);
+    else run_group<1>(a, g, w, ring, hasb, ff2, npost);
+}
+constexpr int MAX_RS = lanes::Geo<2>::RS;
 }  // namespace
 
 // coverage of the last runs: [0] fast tiles, [1] slow tiles, [2] ring refills; reset = 1 clears the counters
@@ -34,11 +48,12 @@ extern "C" void rb_lanes_emu_counters(uint64_t* out, int reset) {
 
 extern "C" int rb_lanes_emulate(const float* const* pcm, const uint64_t* n_frames, const uint64_t* out_len,
                                 const uint64_t* mix_start, const float* coefs /* [n][5] b0 b1 b2 a1 a2 */,
-                                const float* post, uint32_t n_rows, uint32_t from, uint32_t to, uint64_t mix_len, int hasb,
+                                const float* post, uint32_t n_rows, uint32_t channels, uint32_t from, uint32_t to, uint64_t mix_len, int hasb,
                                 int want_ff2, int npost, float* out_mix, float* out_partials /* may be NULL */,
                                 int* used_ff2, uint32_t* n_unsafe) {
     using namespace lanes;
-    if (!(from < to) || to > (1u << 20) || n_rows == 0) return 1;
+    if (!(from < to) || to > (1u << 20) || n_rows == 0 || (channels != 1 && channels != 2)) return 1;
+    const uint32_t C = channels;   // n_frames / out_len / mix_start / mix_len count FRAMES; pcm and out_mix hold frames * C floats
     const float nan = std::numeric_limits<float>::quiet_NaN();
     simt::WarpEmu warp;
     // inputs: 16-byte aligned copies with a 16-byte tail pad of NaN (reading the pad as data would show)
@@ -47,11 +62,11 @@ extern "C" int rb_lanes_emulate(const float* const* pcm, const uint64_t* n_frame
     bool ff2 = want_ff2 && hasb;
     *n_unsafe = 0;
     for (uint32_t r = 0; r < n_rows; r++) {
-        store[r].assign(n_frames[r] + 4 + 4, nan);
+        store[r].assign(n_frames[r] * C + 4 + 4, nan);
         float* base = store[r].data();
         while ((uintptr_t)base & 15) base++;
-        if (n_frames[r]) std::memcpy(base, pcm[r], n_frames[r] * 4);
-        warp.readable.push_back({(const char*)base, (const char*)(base + n_frames[r] + 4)});
+        if (n_frames[r]) std::memcpy(base, pcm[r], n_frames[r] * C * 4);
+        warp.readable.push_back({(const char*)base, (const char*)(base + n_frames[r] * C + 4)});
         Row& row = rows[r];
         std::memset(&row, 0, sizeof(row));
         row.in = base, row.L = n_frames[r], row.out_len = out_len[r], row.mix_start = mix_start[r];
@@ -65,31 +80,26 @@ extern "C" int rb_lanes_emulate(const float* const* pcm, const uint64_t* n_frame
         }
         row.post = npost ? post[r] : 1.0f;
         bool ok = true;
-        for (uint64_t i = 0; i < n_frames[r] && ok; i++) ok = sample_in_class(pcm[r][i]);
+        for (uint64_t i = 0; i < n_frames[r] * C && ok; i++) ok = sample_in_class(pcm[r][i]);
         if (!ok) row.flags |= ROW_UNSAFE, (*n_unsafe)++;
     }
     *used_ff2 = ff2;
-    alignas(16) static float zeros[CHUNK] = {0};
-    warp.readable.push_back({(const char*)zeros, (const char*)(zeros + CHUNK)});
+    alignas(16) static float zeros[CHUNK * 2] = {0};
+    warp.readable.push_back({(const char*)zeros, (const char*)(zeros + CHUNK * C)});
     Args a{};
     a.rows = rows.data(), a.n_rows = n_rows, a.n_groups = (n_rows + 31) / 32;
-    fill_ratio(a, from, to);
-    a.mix_len = mix_len, a.pstride = round_up_tile(mix_len);
+    fill_ratio(a, from, to, C);
+    a.mix_len = mix_len, a.pstride = round_up_tile(mix_len * C);
     std::vector<float> partial((size_t)a.n_groups * a.pstride, 0.0f);
     a.partial = partial.data(), a.zeros = zeros;
-    std::vector<float> ring_store(32 * RS + 4, nan);
+    std::vector<float> ring_store(32 * MAX_RS + 4, nan);
     float* ring = ring_store.data();
     while ((uintptr_t)ring & 15) ring++;
     for (uint32_t g = 0; g < a.n_groups; g++) {
-        for (int i = 0; i < 32 * RS; i++) ring[i] = nan;
-        if (hasb && ff2 && npost) run_warp<true, true, 1>(a, g, &warp, ring);
-        else if (hasb && ff2) run_warp<true, true, 0>(a, g, &warp, ring);
-        else if (hasb && npost) run_warp<true, false, 1>(a, g, &warp, ring);
-        else if (hasb) run_warp<true, false, 0>(a, g, &warp, ring);
-        else if (npost) run_warp<false, false, 1>(a, g, &warp, ring);
-        else run_warp<false, false, 0>(a, g, &warp, ring);
+        for (int i = 0; i < 32 * MAX_RS; i++) ring[i] = nan;
+        run_group_any(channels, a, g, &warp, ring, hasb, ff2, npost);
     }
-    for (uint64_t m = 0; m < mix_len; m++) {
+    for (uint64_t m = 0; m < mix_len * C; m++) {
         float acc = 0.0f;
         for (uint32_t g = 0; g < a.n_groups; g++) acc = acc + partial[(size_t)g * a.pstride + m];
         out_mix[m] = acc;
@@ -107,36 +117,37 @@ extern "C" int rb_lanes_emulate(const float* const* pcm, const uint64_t* n_frame
 #include "../../rodio_b200/csrc/rb_session_plan.h"
 
 extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t* n_frames, const uint64_t* mix_start,
-                                        const float* coefs, const float* post, uint32_t n_rows, uint32_t from, uint32_t to,
-                                        int hasb, int npost, const uint64_t* ops, uint64_t n_ops, float* out,
+                                        const float* coefs, const float* post, uint32_t n_rows, uint32_t channels, uint32_t from,
+                                        uint32_t to, int hasb, int npost, const uint64_t* ops, uint64_t n_ops, float* out,
                                         uint64_t out_cap, uint64_t* n_renders, uint64_t* pushed_total /* [n_rows] */) {
     using namespace lanes;
-    if (!(from < to) || to > (1u << 20) || n_rows == 0) return -1;
+    if (!(from < to) || to > (1u << 20) || n_rows == 0 || (channels != 1 && channels != 2)) return -1;
+    const uint32_t C = channels;   // frames everywhere; pcm / FIFOs / out hold frames * C floats
     const float nan = std::numeric_limits<float>::quiet_NaN();
     simt::WarpEmu warp;
     std::vector<session::Stream> st(n_rows);
     std::vector<std::vector<float>> fifo_store(n_rows);
     std::vector<float*> fifo(n_rows);
     std::vector<uint8_t> unsafe(n_rows, 0);
-    std::vector<float> state_store(4 * n_rows + 4, 0.0f);
+    std::vector<float> state_store(4 * C * n_rows + 4, 0.0f);
     float* state = state_store.data();
     while ((uintptr_t)state & 15) state++;
     bool ff2 = hasb;
     std::vector<float> ffk(n_rows, 0.0f);
     for (uint32_t r = 0; r < n_rows; r++) {
-        fifo_store[r].assign(n_frames[r] + 16, nan);
+        fifo_store[r].assign(n_frames[r] * C + 16, nan);
         fifo[r] = fifo_store[r].data();
         while ((uintptr_t)fifo[r] & 15) fifo[r]++;
-        warp.readable.push_back({(const char*)fifo[r], (const char*)(fifo[r] + n_frames[r] + 8)});
+        warp.readable.push_back({(const char*)fifo[r], (const char*)(fifo[r] + n_frames[r] * C + 8)});
         st[r].mix_start = mix_start[r];
         if (hasb) {
             const float* c = coefs + 5 * r;
             if (!ff2_coeffs(c[0], c[1], c[2], &ffk[r])) ff2 = false;
         }
     }
-    alignas(16) static float zeros[CHUNK] = {0};
-    warp.readable.push_back({(const char*)zeros, (const char*)(zeros + CHUNK)});
-    std::vector<float> ring_store(32 * RS + 4, nan);
+    alignas(16) static float zeros[CHUNK * 2] = {0};
+    warp.readable.push_back({(const char*)zeros, (const char*)(zeros + CHUNK * C)});
+    std::vector<float> ring_store(32 * MAX_RS + 4, nan);
     float* ring = ring_store.data();
     while ((uintptr_t)ring & 15) ring++;
     uint64_t T = 0, written = 0;
@@ -145,9 +156,9 @@ extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t*
     auto push = [&](uint32_t r, uint64_t n) {
         session::Stream& s = st[r];
         n = std::min(n, n_frames[r] - s.pushed);
-        for (uint64_t k = 0; k < n; k++) {
-            const float v = pcm[r][s.pushed + k];
-            fifo[r][s.fill() + k] = v;
+        for (uint64_t k = 0; k < n * C; k++) {
+            const float v = pcm[r][s.pushed * C + k];
+            fifo[r][s.fill() * C + k] = v;
             if (!sample_in_class(v)) unsafe[r] = 1;
         }
         s.pushed += n;
@@ -158,7 +169,7 @@ extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t*
         const uint64_t n = session::renderable(st, T, from, to, max_frames, &ended);
         if (ended) return false;
         if (n == 0) return true;
-        if (written + n > out_cap) std::abort();
+        if ((written + n) * C > out_cap) std::abort();
         std::vector<Row> rows(n_rows);
         std::vector<session::Part> parts(n_rows);
         for (uint32_t r = 0; r < n_rows; r++) {
@@ -166,7 +177,7 @@ extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t*
             Row& row = rows[r];
             std::memset(&row, 0, sizeof(row));
             row.in = fifo[r], row.L = st[r].fill(), row.out_len = parts[r].out_len, row.mix_start = parts[r].mix_start;
-            row.n_int = parts[r].n_int, row.o0 = parts[r].o0, row.i0 = st[r].i0, row.state = state + 4 * r;
+            row.n_int = parts[r].n_int, row.o0 = parts[r].o0, row.i0 = st[r].i0, row.state = state + 4 * C * r;
             if (hasb) {
                 const float* c = coefs + 5 * r;
                 row.b0 = c[0], row.b1 = c[1], row.b2 = c[2], row.a1 = c[3], row.a2 = c[4], row.ffk = ffk[r];
@@ -176,31 +187,26 @@ extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t*
         }
         Args a{};
         a.rows = rows.data(), a.n_rows = n_rows, a.n_groups = (n_rows + 31) / 32;
-        fill_ratio(a, from, to);
-        a.mix_len = n, a.pstride = round_up_tile(n);
+        fill_ratio(a, from, to, C);
+        a.mix_len = n, a.pstride = round_up_tile(n * C);
         std::vector<float> partial((size_t)a.n_groups * a.pstride, 0.0f);
         a.partial = partial.data(), a.zeros = zeros;
         for (uint32_t g = 0; g < a.n_groups; g++) {
-            for (int i = 0; i < 32 * RS; i++) ring[i] = nan;
-            if (hasb && ff2 && npost) run_warp<true, true, 1>(a, g, &warp, ring);
-            else if (hasb && ff2) run_warp<true, true, 0>(a, g, &warp, ring);
-            else if (hasb && npost) run_warp<true, false, 1>(a, g, &warp, ring);
-            else if (hasb) run_warp<true, false, 0>(a, g, &warp, ring);
-            else if (npost) run_warp<false, false, 1>(a, g, &warp, ring);
-            else run_warp<false, false, 0>(a, g, &warp, ring);
+            for (int i = 0; i < 32 * MAX_RS; i++) ring[i] = nan;
+            run_group_any(channels, a, g, &warp, ring, hasb, ff2, npost);
         }
-        for (uint64_t m = 0; m < n; m++) {
+        for (uint64_t m = 0; m < n * C; m++) {
             float acc = 0.0f;
             for (uint32_t g = 0; g < a.n_groups; g++) acc = acc + partial[(size_t)g * a.pstride + m];
-            out[written + m] = acc;
+            out[written * C + m] = acc;
         }
         written += n, T += n, (*n_renders)++;
         for (uint32_t r = 0; r < n_rows; r++) {
             const uint64_t fill_before = st[r].fill();
             const uint64_t drop = session::advance(st[r], parts[r], from, to);
             if (drop) {
-                std::memmove(fifo[r], fifo[r] + drop, (fill_before - drop) * sizeof(float));
-                for (uint64_t k = fill_before - drop; k < fill_before; k++) fifo[r][k] = nan;
+                std::memmove(fifo[r], fifo[r] + drop * C, (fill_before - drop) * C * sizeof(float));
+                for (uint64_t k = (fill_before - drop) * C; k < fill_before * C; k++) fifo[r][k] = nan;
             }
         }
         return true;

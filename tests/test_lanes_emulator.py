@@ -38,28 +38,30 @@ def counters(emu, reset=True):
     return {"fast": out[0], "slow": out[1], "refills": out[2]}
 
 
-def run_emu(emu, pcms, outs_len, starts, coefs, posts, from_, to, mix_len, hasb, ff2, npost):
+def run_emu(emu, pcms, outs_len, starts, coefs, posts, from_, to, mix_len, hasb, ff2, npost, channels=1):
+    """Frames everywhere (outs_len, starts, mix_len); pcms and the result hold frames * channels floats."""
     n = len(pcms)
     pcms = [np.ascontiguousarray(p, dtype=np.float32) for p in pcms]
     ptrs = (C.POINTER(C.c_float) * n)(*[p.ctypes.data_as(C.POINTER(C.c_float)) for p in pcms])
     u64 = lambda v: (C.c_uint64 * n)(*[int(x) for x in v])
     co = np.ascontiguousarray(coefs, dtype=np.float32).reshape(-1)
     po = np.ascontiguousarray(posts, dtype=np.float32)
-    out = np.full(mix_len, np.nan, dtype=np.float32)
+    out = np.full(mix_len * channels, np.nan, dtype=np.float32)
     used, unsafe = C.c_int(0), C.c_uint32(0)
-    rc = emu.rb_lanes_emulate(ptrs, u64([p.size for p in pcms]), u64(outs_len), u64(starts),
+    rc = emu.rb_lanes_emulate(ptrs, u64([p.size // channels for p in pcms]), u64(outs_len), u64(starts),
                               co.ctypes.data_as(C.POINTER(C.c_float)), po.ctypes.data_as(C.POINTER(C.c_float)),
-                              C.c_uint32(n), C.c_uint32(from_), C.c_uint32(to), C.c_uint64(mix_len), int(hasb), int(ff2),
+                              C.c_uint32(n), C.c_uint32(channels), C.c_uint32(from_), C.c_uint32(to), C.c_uint64(mix_len), int(hasb), int(ff2),
                               int(npost), out.ctypes.data_as(C.POINTER(C.c_float)), None, C.byref(used), C.byref(unsafe))
     assert rc == 0
     return out, bool(used.value), unsafe.value
 
 
-def make_case(pcms, in_rate, mix_rate, starts, lp=None, hp=None, q=0.5, gain=None):
-    """Sources as a rodio user writes them + everything the emulator needs, the expectation from the oracle."""
+def make_case(pcms, in_rate, mix_rate, starts, lp=None, hp=None, q=0.5, gain=None, channels=1):
+    """Sources as a rodio user writes them + everything the emulator needs, the expectation from the oracle.
+    `starts` and the lengths in the result are frames."""
     srcs, per_stream = [], []
     for p in pcms:
-        s = rb.UniformSourceIterator(rb.TestSource(p, 1, in_rate), 1, mix_rate)
+        s = rb.UniformSourceIterator(rb.TestSource(p, channels, in_rate), channels, mix_rate)
         if lp is not None:
             s = s.low_pass_with_q(lp, q)
         if hp is not None:
@@ -67,27 +69,28 @@ def make_case(pcms, in_rate, mix_rate, starts, lp=None, hp=None, q=0.5, gain=Non
         if gain is not None:
             s = s.amplify(gain)
         srcs.append(s)
-        per_stream.append(oracle.chain_uniform(to_oracle(s), 1, mix_rate))
+        per_stream.append(oracle.chain_uniform(to_oracle(s), channels, mix_rate))
     g = math.gcd(in_rate, mix_rate)
     hasb = lp is not None or hp is not None
     co = oracle.blt_coeffs(hp is not None, lp if lp is not None else (hp or 1), q, mix_rate) if hasb else np.zeros(5, np.float32)
     coefs = np.tile(co, (len(pcms), 1))
-    mix_len = max([s + y.size for s, y in zip(starts, per_stream)] + [0])
-    return dict(per_stream=per_stream, outs_len=[y.size for y in per_stream], coefs=coefs,
+    mix_len = max([s + y.size // channels for s, y in zip(starts, per_stream)] + [0])
+    return dict(per_stream=per_stream, outs_len=[y.size // channels for y in per_stream], coefs=coefs, channels=channels,
                 posts=np.full(len(pcms), gain if gain is not None else 1.0, np.float32), from_=in_rate // g, to=mix_rate // g,
                 mix_len=mix_len, hasb=hasb, npost=gain is not None, srcs=srcs)
 
 
 def check(emu, pcms, in_rate, mix_rate, starts, ff2=True, expect_ff2=None, **kw):
     c = make_case(pcms, in_rate, mix_rate, starts, **kw)
+    ch = c["channels"]
     got, used_ff2, unsafe = run_emu(emu, pcms, c["outs_len"], starts, c["coefs"], c["posts"], c["from_"], c["to"], c["mix_len"],
-                                    c["hasb"], ff2, c["npost"])
+                                    c["hasb"], ff2, c["npost"], channels=ch)
     if expect_ff2 is not None:
         assert used_ff2 == expect_ff2
-    want = expected_mix(c["per_stream"], starts, c["mix_len"])
+    want = expected_mix(c["per_stream"], [st * ch for st in starts], c["mix_len"] * ch)
     assert_bit_exact(got, want, "emulated kernel vs oracle streams summed with the kernel's tree")
     # and the north-star tolerance against the reference's sequential mixer
-    ref = oracle.mixer([to_oracle(s, mix_start=st) for s, st in zip(c["srcs"], starts)], 1, mix_rate)
+    ref = oracle.mixer([to_oracle(s, mix_start=st * ch) for s, st in zip(c["srcs"], starts)], ch, mix_rate)
     assert_close_peak(got, ref, 1e-5, "emulated kernel vs the reference's sequential mixer sum")
     return unsafe
 
@@ -163,7 +166,7 @@ def test_silence_and_negative_zero(emu):
 
 
 # ------------------------------------------------------------------------------------------------- streaming sessions
-def run_session(emu, pcms, starts, coefs, posts, from_, to, hasb, npost, ops, out_cap):
+def run_session(emu, pcms, starts, coefs, posts, from_, to, hasb, npost, ops, out_cap, channels=1):
     n = len(pcms)
     pcms = [np.ascontiguousarray(p, dtype=np.float32) for p in pcms]
     ptrs = (C.POINTER(C.c_float) * n)(*[p.ctypes.data_as(C.POINTER(C.c_float)) for p in pcms])
@@ -175,22 +178,22 @@ def run_session(emu, pcms, starts, coefs, posts, from_, to, hasb, npost, ops, ou
     renders = C.c_uint64(0)
     pushed = (C.c_uint64 * n)()
     emu.rb_session_emulate.restype = C.c_longlong
-    w = emu.rb_session_emulate(ptrs, u64([p.size for p in pcms]), u64(starts), co.ctypes.data_as(C.POINTER(C.c_float)),
-                               po.ctypes.data_as(C.POINTER(C.c_float)), C.c_uint32(n), C.c_uint32(from_), C.c_uint32(to),
+    w = emu.rb_session_emulate(ptrs, u64([p.size // channels for p in pcms]), u64(starts), co.ctypes.data_as(C.POINTER(C.c_float)),
+                               po.ctypes.data_as(C.POINTER(C.c_float)), C.c_uint32(n), C.c_uint32(channels), C.c_uint32(from_), C.c_uint32(to),
                                int(hasb), int(npost), u64(flat), C.c_uint64(len(ops)), out.ctypes.data_as(C.POINTER(C.c_float)),
                                C.c_uint64(out_cap), C.byref(renders), pushed)
     assert w >= 0
-    return out[:w], renders.value, [int(v) for v in pushed]
+    return out[:w * channels], renders.value, [int(v) for v in pushed]
 
 
-def session_case(emu, pcms, starts, ops, in_rate=44100, mix_rate=48000, lp=None, gain=None):
+def session_case(emu, pcms, starts, ops, in_rate=44100, mix_rate=48000, lp=None, gain=None, channels=1):
     """Any split of the streams into pushed blocks and of the mixer output into rendered blocks gives the bytes of the
     whole-stream render (tests/test_block_state_spec.py is the numpy form of the same contract)."""
-    c = make_case(pcms, in_rate, mix_rate, starts, lp=lp, gain=gain)
+    c = make_case(pcms, in_rate, mix_rate, starts, lp=lp, gain=gain, channels=channels)
     got, renders, pushed = run_session(emu, pcms, starts, c["coefs"], c["posts"], c["from_"], c["to"], c["hasb"], c["npost"], ops,
-                                       c["mix_len"] + 64)
-    assert pushed == [p.size for p in pcms]
-    want = expected_mix(c["per_stream"], starts, c["mix_len"])
+                                       (c["mix_len"] + 64) * channels, channels=channels)
+    assert pushed == [p.size // channels for p in pcms]
+    want = expected_mix(c["per_stream"], [st * channels for st in starts], c["mix_len"] * channels)
     assert_bit_exact(got, want, "session blocks vs whole-stream render")
     return renders
 
@@ -251,3 +254,38 @@ def test_session_plan_fuzz(emu):
     for seed in range(6):
         line = emu.rb_session_plan_fuzz(C.c_uint64(seed), C.c_uint32(500))
         assert line == 0, f"invariant at tests/emu/lanes_emu.cpp:{line} violated (seed {seed})"
+
+
+# ------------------------------------------------------------------------------------------------- stereo (C = 2)
+def test_stereo_cfg3_shape(emu):
+    """Interleaved stereo sources into a stereo mixer: one lane carries both channels (shared index state, two filters)."""
+    pcms = [noise(2 * (2000 + 9 * i), 400 + i, 0.9) for i in range(40)]
+    counters(emu)
+    check(emu, pcms, 44100, 48000, [0] * 40, lp=200, gain=1.2, channels=2, expect_ff2=True)
+    c = counters(emu)
+    assert c["fast"] > 800 and c["refills"] > 200, c
+    check(emu, pcms[:33], 44100, 48000, [0] * 33, ff2=False, hp=300, channels=2, expect_ff2=False)
+
+
+def test_stereo_ragged_and_no_filter(emu):
+    rng = np.random.default_rng(6)
+    lens = [1500, 3, 1, 0, 2, 900] + [int(v) for v in rng.integers(3, 1500, 30)]
+    starts = [0, 10, 5, 9, 700, 123] + [int(v) for v in rng.integers(0, 900, 30)]
+    pcms = [noise(2 * n, 600 + i) for i, n in enumerate(lens)]
+    check(emu, pcms, 32000, 44100, starts, lp=900, gain=0.6, channels=2)
+    check(emu, pcms[:12], 22050, 48000, starts[:12], gain=1.3, channels=2)
+
+
+def test_stereo_session_any_split(emu):
+    rng = np.random.default_rng(12)
+    pcms = [noise(2 * int(n), 700 + i) for i, n in enumerate(rng.integers(300, 1800, 9))]
+    starts = [0, 0, 0, 100, 0, 37, 0, 0, 512]
+    ops, left = [], [p.size // 2 for p in pcms]
+    while any(left):
+        for r in rng.permutation(9):
+            n = min(left[r], int(rng.integers(1, 500)))
+            if n and rng.random() < 0.8:
+                ops.append((0, r, n))
+                left[r] -= n
+        ops.append((1, 0, int(rng.integers(1, 600))))
+    session_case(emu, pcms, starts, ops, lp=300, gain=1.1, channels=2)
