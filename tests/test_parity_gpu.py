@@ -572,10 +572,11 @@ lanes_gate = pytest.mark.skipif(os.environ.get("RB_TEST_LANES") != "1", reason="
 LANES = capi.RB_FUSED_LANES
 
 
-def _lanes_case(ctx, pcms, starts, in_rate=44100, mix_rate=48000, lp=None, hp=None, q=0.5, gain=None, expect_family=2):
+def _lanes_case(ctx, pcms, starts, in_rate=44100, mix_rate=48000, lp=None, hp=None, q=0.5, gain=None, expect_family=2, ch=1):
+    """`starts` in frames; pcms interleaved."""
     srcs = []
     for p in pcms:
-        s = rb.UniformSourceIterator(rb.TestSource(p, 1, in_rate), 1, mix_rate)
+        s = rb.UniformSourceIterator(rb.TestSource(p, ch, in_rate), ch, mix_rate)
         if lp is not None:
             s = s.low_pass_with_q(lp, q)
         if hp is not None:
@@ -583,14 +584,15 @@ def _lanes_case(ctx, pcms, starts, in_rate=44100, mix_rate=48000, lp=None, hp=No
         if gain is not None:
             s = s.amplify(gain)
         srcs.append(s)
-    with rb.Batch(srcs, 1, mix_rate, flags=LANES, ctx=ctx, mix_starts=starts) as b:
+    starts = [st * ch for st in starts]           # the batch API counts interleaved samples
+    with rb.Batch(srcs, ch, mix_rate, flags=LANES, ctx=ctx, mix_starts=starts) as b:
         assert b.kernel_family == expect_family
         b.upload_all()
         got = b.render_mix()
         again = b.render_mix()
     assert np.array_equal(got.view(np.uint32), again.view(np.uint32)), "render is not idempotent"
-    per_stream = [oracle.chain_uniform(to_oracle(s), 1, mix_rate) for s in srcs]
-    ref = oracle.mixer([to_oracle(s, mix_start=st) for s, st in zip(srcs, starts)], 1, mix_rate)
+    per_stream = [oracle.chain_uniform(to_oracle(s), ch, mix_rate) for s in srcs]
+    ref = oracle.mixer([to_oracle(s, mix_start=st) for s, st in zip(srcs, starts)], ch, mix_rate)
     assert got.shape == ref.shape
     assert_close_peak(got, ref, 1e-5, "lanes kernel vs the reference's sequential mixer")          # north-star tolerance
     if expect_family == 2:
@@ -627,6 +629,17 @@ def test_lanes_ragged(ctx):
 def test_lanes_other_ratios(ctx, rates):
     pcms = [noise(1500 + 11 * i, 900 + i) for i in range(70)]
     _lanes_case(ctx, pcms, [0] * 70, in_rate=rates[0], mix_rate=rates[1], lp=400, gain=1.1)
+
+
+@lanes_gate
+@pytest.mark.parametrize("kw", [dict(lp=200, gain=1.2), dict(hp=300), dict(gain=0.8)])
+def test_lanes_stereo(ctx, kw):
+    """Interleaved stereo sources into a stereo mixer: one lane carries both channels."""
+    pcms = [noise(2 * (3000 + 9 * i), 400 + i, 0.9) for i in range(100)]
+    _lanes_case(ctx, pcms, [0] * 100, ch=2, **kw)
+    rng = np.random.default_rng(6)
+    starts = sorted(int(v) for v in rng.integers(0, 2000, 100))
+    _lanes_case(ctx, pcms, starts, ch=2, **kw)
 
 
 @lanes_gate
@@ -764,3 +777,32 @@ def test_session_rejects_other_shapes(ctx):
     agc = rb.UniformSourceIterator(rb.TestSource(np.zeros(0, np.float32), 1, 44100), 1, 48000).automatic_gain_control()
     with pytest.raises(rb.RodioB200Error):
         rb.Session([agc], 48000, ctx=ctx)
+
+
+@lanes_gate
+def test_session_stereo_any_split(ctx):
+    rng = np.random.default_rng(12)
+    pcms = [noise(2 * int(n), 700 + i) for i, n in enumerate(rng.integers(3000, 9000, 40))]
+    srcs = [rb.UniformSourceIterator(rb.TestSource(p, 2, 44100), 2, 48000).low_pass(300).amplify(1.1) for p in pcms]
+    with rb.Batch(srcs, 2, 48000, flags=LANES, ctx=ctx) as b:
+        assert b.kernel_family == 2
+        b.upload_all()
+        want = b.render_mix()
+    chains = [rb.UniformSourceIterator(rb.TestSource(np.zeros(0, np.float32), 2, 44100), 2, 48000).low_pass(300).amplify(1.1)
+              for _ in pcms]
+    got, left, ended = [], [0] * 40, False
+    with rb.Session(chains, 48000, fifo_frames=4096, max_block_frames=1024, ctx=ctx) as s:
+        while not ended:
+            blocks, eos = [], []
+            for r in range(40):
+                n = min(pcms[r].size // 2 - left[r], int(rng.integers(0, 600)))
+                blocks.append(pcms[r][2 * left[r]: 2 * (left[r] + n)])
+                left[r] += n
+                eos.append(left[r] == pcms[r].size // 2)
+            s.push_packed(blocks, eos)
+            while True:
+                block, ended = s.render(int(rng.integers(1, 1024)))
+                got.append(block)
+                if block.size == 0 or ended:
+                    break
+    assert_bit_exact(np.concatenate(got), want, "stereo session vs the whole-stream render")
