@@ -1,5 +1,7 @@
 // rb_lanes_core.h — the lane-per-stream fused kernel: resample (linear interpolation, from < to) -> [biquad] ->
-// [one gain] -> mixer sum, for LARGE batches of mono f32 streams that share one reduced rate ratio.
+// [one gain] -> mixer sum, for LARGE batches of mono or interleaved-stereo f32 streams that share one reduced rate ratio
+// (template parameter C = channels of every stream and of the mixer; a stereo lane carries both channels of its stream:
+// one index state, one 8-byte tap fetch per input frame, two filters).
 //
 // Why a second kernel next to k_fused_hot (rb_fused.cu).  The exact biquad is a serial chain per stream (bit
 // parity with src/source/blt.rs:558-560 forbids re-association), so a stream can never run faster than one sample
@@ -9,8 +11,9 @@
 // the HBM roofline at 16 384 and 65 536 streams).  With hundreds of streams per SM the parallelism is across
 // streams, so here EVERY lane owns one stream and walks it serially in time:
 //   * no cross-lane traffic for the resampler or the filter: both taps, the numerator, the filter state live in
-//     the lane's registers; about 21 issue slots per sample in the steady state (index 6, interpolation with its
-//     exact division 6, feed-forward 3-5, recurrence 4, gain 1, sum 0.15), spread over all four sub-partitions;
+//     the lane's registers; 28.4 (mono) / 26.0 (stereo) issue slots per sample in the steady state by static count
+//     (tools/sass_loop_count.py: index 6, interpolation with its exact division 6, feed-forward 3-5, recurrence 4,
+//     gain 1, mixer sum 4, bookkeeping 3), spread over all four sub-partitions;
 //   * a warp = 32 consecutive streams (insertion order) in lock step on the mixer timeline, TILE = 8 samples per
 //     loop iteration (one basic block: the loads and index arithmetic of all 8 steps are hoisted above the
 //     recurrence chain by the compiler);
