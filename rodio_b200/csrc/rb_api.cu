@@ -1113,6 +1113,14 @@ extern "C" rb_status rb_session_push_packed(rb_session* s, const float* pcm, con
     return RB_OK;
 }
 
+extern "C" rb_status rb_session_set_amplify(rb_session* s, size_t stream, float factor) {
+    if (!s) return fail(RB_ERR_INVALID_ARGUMENT, "session is NULL");
+    if (stream >= s->st.size()) return fail(RB_ERR_INVALID_ARGUMENT, "stream index out of range");
+    s->post[stream] = factor;
+    s->has_post = true;   // sources without an AMPLIFY keep the factor 1.0: x * 1.0 is exact
+    return RB_OK;
+}
+
 extern "C" rb_status rb_session_available(rb_session* s, uint64_t* frames, int* ended) {
     if (!s || !frames) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
     bool e = false;

@@ -526,6 +526,10 @@ class Session:
         eos = (C.c_uint8 * len(blocks))(*[int(bool(e)) for e in end_of_stream]) if end_of_stream is not None else None
         check(lib().rb_session_push_packed(self._h, flat.ctypes.data_as(C.c_void_p), n, eos), "rb_session_push_packed")
 
+    def set_amplify(self, stream: int, factor: float):
+        """Amplify::set_factor / Player::set_volume on a live source: applies from the next rendered block on."""
+        check(lib().rb_session_set_amplify(self._h, stream, float(factor)), "rb_session_set_amplify")
+
     def available(self) -> Tuple[int, bool]:
         n, e = C.c_uint64(), C.c_int()
         check(lib().rb_session_available(self._h, C.byref(n), C.byref(e)), "rb_session_available")

@@ -112,7 +112,8 @@ extern "C" int rb_lanes_emulate(const float* const* pcm, const uint64_t* n_frame
 // Streaming session on the emulator: the bookkeeping of rodio_b200/csrc/rb_session_plan.h driving the same warp
 // program block by block.  ops: triples (kind, stream, count) -- kind 0: push `count` more frames of the stream's PCM
 // (the stream ends when all of it has been pushed, or on kind 2), kind 1: render up to `count` mixer frames,
-// kind 2: mark the stream ended now (whatever was pushed is all there is).  After the last op everything is ended and
+// kind 2: mark the stream ended now (whatever was pushed is all there is), kind 3: the stream's gain becomes the float
+// whose bits are `count` from the next block on (rb_session_set_amplify).  After the last op everything is ended and
 // drained.  Returns the number of mixer frames written to out (capacity out_cap), or -1.
 #include "../../rodio_b200/csrc/rb_session_plan.h"
 
@@ -134,7 +135,9 @@ extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t*
     while ((uintptr_t)state & 15) state++;
     bool ff2 = hasb;
     std::vector<float> ffk(n_rows, 0.0f);
+    std::vector<float> gain(n_rows, 1.0f);
     for (uint32_t r = 0; r < n_rows; r++) {
+        if (npost) gain[r] = post[r];
         fifo_store[r].assign(n_frames[r] * C + 16, nan);
         fifo[r] = fifo_store[r].data();
         while ((uintptr_t)fifo[r] & 15) fifo[r]++;
@@ -182,7 +185,7 @@ extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t*
                 const float* c = coefs + 5 * r;
                 row.b0 = c[0], row.b1 = c[1], row.b2 = c[2], row.a1 = c[3], row.a2 = c[4], row.ffk = ffk[r];
             }
-            row.post = npost ? post[r] : 1.0f;
+            row.post = gain[r];
             row.flags = (unsafe[r] ? ROW_UNSAFE : 0u) | (parts[r].continues ? ROW_CONTINUES : 0u);
         }
         Args a{};
@@ -216,7 +219,11 @@ extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t*
         const uint64_t kind = ops[3 * k], r = ops[3 * k + 1], cnt = ops[3 * k + 2];
         if (kind == 0) push((uint32_t)r, cnt);
         else if (kind == 1) render(cnt);
-        else st[r].eof = true;
+        else if (kind == 2) st[r].eof = true;
+        else {
+            const uint32_t bits = (uint32_t)cnt;
+            std::memcpy(&gain[r], &bits, 4);
+        }
     }
     for (uint32_t r = 0; r < n_rows; r++) st[r].eof = true;   // whatever was pushed is all there is
     for (uint32_t r = 0; r < n_rows; r++) pushed_total[r] = st[r].pushed;

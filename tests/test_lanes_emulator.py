@@ -289,3 +289,27 @@ def test_stereo_session_any_split(emu):
                 left[r] -= n
         ops.append((1, 0, int(rng.integers(1, 600))))
     session_case(emu, pcms, starts, ops, lp=300, gain=1.1, channels=2)
+
+
+def test_session_gain_changes_between_blocks(emu):
+    """rb_session_set_amplify: the gain of a live source changes from one rendered block to the next (Player::set_volume
+    through its 5 ms periodic access, src/player.rs:138-166); inside a block it is constant."""
+    pcms = [noise(1500, 800 + i) for i in range(3)]
+    c = make_case(pcms, 44100, 48000, [0] * 3, lp=500, gain=1.0)        # oracle streams with gain 1.0: y * 1.0 = y
+    ops = [(0, r, 1500) for r in range(3)]
+    gains, block = [], 240                                               # 5 ms at 48 kHz
+    n_blocks = -(-c["mix_len"] // block)
+    rng = np.random.default_rng(3)
+    for k in range(n_blocks):
+        g = [np.float32(v) for v in rng.uniform(0.0, 1.5, 3)]
+        gains.append(g)
+        ops += [(3, r, int(np.float32(g[r]).view(np.uint32))) for r in range(3)] + [(1, 0, block)]
+    got, renders, _ = run_session(emu, pcms, [0] * 3, c["coefs"], c["posts"], 147, 160, True, True, ops, c["mix_len"] + 64)
+    assert renders == n_blocks
+    scaled = []
+    for r in range(3):
+        y = c["per_stream"][r].copy()
+        for k in range(n_blocks):
+            y[k * block:(k + 1) * block] = y[k * block:(k + 1) * block] * gains[k][r]     # one f32 rounding, like Amplify::next
+        scaled.append(y)
+    assert_bit_exact(got, expected_mix(scaled, [0] * 3, c["mix_len"]), "per-block gains")
