@@ -96,6 +96,28 @@ def main():
                 for fl, nm in ((rb.capi.RB_FUSED_LANES, "k_fused_lanes"), (0, "default")):
                     time_batch(f"lanes sweep S={S}: 44.1k mono x 1s -> uniform(1,48k) -> {label} -> mix [{nm}]", srcs,
                                (1, 48000), flags=fl, steps=5)
+    if "session" in which:
+        # streaming sessions: every source receives 10 ms of 44.1 kHz PCM per step (one packed push), the mixer output is
+        # pulled as it becomes available; wall clock per step through the public calls (host -> device -> host included)
+        import time
+        for S, ch in [(256, 1), (4096, 1), (1024, 2), (16384, 1)]:
+            chains = [rb.UniformSourceIterator(rb.TestSource(z(0), ch, 44100), ch, 48000).low_pass(200).amplify(1.2) for _ in range(S)]
+            rng = np.random.default_rng(1)
+            block = [rng.uniform(-0.5, 0.5, 441 * ch).astype(np.float32) for _ in range(min(S, 64))]
+            blocks = [block[i % len(block)] for i in range(S)]
+            with rb.Session(chains, 48000, fifo_frames=2048, max_block_frames=1024, ctx=rb.default_context(0)) as sess:
+                for _ in range(20):                       # warm-up
+                    sess.push_packed(blocks)
+                    sess.render(1024)
+                t0, frames, steps = time.perf_counter(), 0, 200
+                for _ in range(steps):
+                    sess.push_packed(blocks)
+                    out, _ = sess.render(1024)
+                    frames += out.size // ch
+                dt = time.perf_counter() - t0
+            print(json.dumps({"case": f"session: {S} x {ch} ch sources, 10 ms pushes -> low_pass(200) -> amplify -> mix", "streams": S,
+                              "ms_per_10ms_block": round(1e3 * dt / steps, 3), "realtime_factor": round(frames / 48000 / dt, 2),
+                              "Msamples_s": round(S * frames * ch / dt / 1e6, 1)}), flush=True)
     if "cpu" in which:
         # C++ restatement of rodio's CPU path on this box's host cores: one audio thread (what rodio itself runs)
         # and all cores with a final partial-mix reduction; dynamic dispatch (Box<dyn Source>) and monomorphised.
