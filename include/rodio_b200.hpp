@@ -267,6 +267,52 @@ inline std::pair<Mixer, MixerSource> mixer(uint16_t channels, uint32_t sample_ra
     return {Mixer(s), MixerSource(s)};
 }
 
+// Streaming counterpart (rb_session_*): sources that arrive block by block -- decoders, capture -- behind one
+// MixerSource-like pull.  `chains` describe the sources (channels, rate, adapters: .uniform(ch, rate)[.low_pass / .high_pass]
+// [.amplify]); their PCM is pushed later.  next() hands out the mixer samples one at a time like Iterator::next
+// (src/mixer.rs:120-136); std::nullopt while nothing can be rendered yet, `ended()` once every source is exhausted.
+class LiveMixer {
+  public:
+    LiveMixer(const std::vector<Source>& chains, uint32_t sample_rate, uint32_t fifo_frames = 8192, uint32_t block_frames = 1024)
+        : channels_(chains.empty() ? 1 : chains[0].channels()), rate_(sample_rate), block_frames_(block_frames) {
+        std::vector<rb_stream_desc> descs;
+        for (const Source& c : chains) descs.push_back(c.desc(0));
+        check(rb_session_create(Context::get(), sample_rate, descs.data(), descs.size(), fifo_frames, block_frames, &h_), "rb_session_create");
+    }
+    LiveMixer(const LiveMixer&) = delete;
+    LiveMixer& operator=(const LiveMixer&) = delete;
+    ~LiveMixer() { rb_session_destroy(h_); }
+    uint16_t channels() const { return channels_; }
+    uint32_t sample_rate() const { return rate_; }
+    // more interleaved samples of source `i`; end_of_stream: its Iterator::next would return None after them
+    void push(size_t i, const std::vector<Sample>& pcm, bool end_of_stream = false) {
+        check(rb_session_push(h_, i, pcm.data(), pcm.size() / channels_, end_of_stream ? 1 : 0), "rb_session_push");
+    }
+    void set_volume(size_t i, float factor) { check(rb_session_set_amplify(h_, i, factor), "rb_session_set_amplify"); }   // player.rs:138-166
+    bool ended() const { return ended_ && at_ == block_.size(); }
+    std::optional<Sample> next() {
+        if (at_ == block_.size()) {
+            if (ended_) return std::nullopt;
+            block_.resize((size_t)block_frames_ * channels_);
+            uint64_t written = 0;
+            int e = 0;
+            check(rb_session_render(h_, block_.data(), block_frames_, &written, &e), "rb_session_render");
+            block_.resize((size_t)written * channels_);
+            at_ = 0, ended_ = e != 0;
+            if (block_.empty()) return std::nullopt;   // starved (or ended): nothing renderable right now
+        }
+        return block_[at_++];
+    }
+
+  private:
+    rb_session* h_ = nullptr;
+    uint16_t channels_;
+    uint32_t rate_, block_frames_;
+    std::vector<Sample> block_;
+    size_t at_ = 0;
+    bool ended_ = false;
+};
+
 }  // namespace mixer
 
 namespace conversions {

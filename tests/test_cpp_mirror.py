@@ -10,9 +10,13 @@ SRC = os.path.join(ROOT, "tests", "cpp", "test_reference_api.cpp")
 EXE = os.path.join(ROOT, "tests", "cpp", "test_reference_api.bin")
 
 
-def _build():
+SRC_SESSION = os.path.join(ROOT, "tests", "cpp", "test_session_api.cpp")
+EXE_SESSION = os.path.join(ROOT, "tests", "cpp", "test_session_api.bin")
+
+
+def _build(src=SRC, exe=EXE):
     lib_dir = os.path.join(ROOT, "rodio_b200")
-    cmd = ["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), SRC, "-o", EXE,
+    cmd = ["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
            "-L", lib_dir, "-l:librodio_b200.so", f"-Wl,-rpath,{lib_dir}"]
     subprocess.run(cmd, check=True, capture_output=True)
 
@@ -29,3 +33,18 @@ def test_cpp_mirror_runs_reference_tests(built):
     r = subprocess.run([EXE], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "all reference API tests passed" in r.stdout
+
+
+def test_cpp_session_mirror_compiles_and_links(built):
+    _build(SRC_SESSION, EXE_SESSION)
+    assert os.path.exists(EXE_SESSION)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("RB_TEST_LANES") != "1", reason="set RB_TEST_LANES=1 (first GPU pass of the lane kernel pending)")
+def test_cpp_session_mirror_streams_like_the_whole_render(built):
+    if not os.path.exists(EXE_SESSION):
+        _build(SRC_SESSION, EXE_SESSION)
+    r = subprocess.run([EXE_SESSION], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all session API tests passed" in r.stdout
