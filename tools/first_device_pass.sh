@@ -1,0 +1,37 @@
+#!/usr/bin/env bash
+# First run of k_fused_lanes / rb_session_* on a B200 (they were written without GPU access).
+# One gpurun call:   gpurun --timeout 1500 -- 'bash tools/first_device_pass.sh'
+# Everything lands in gpurun_out/lanes_first/; every step is bounded by `timeout` so a hang cannot eat the box.
+set -u
+cd "$(dirname "$0")/.."
+OUT=gpurun_out/lanes_first
+mkdir -p "$OUT"
+export RB_TEST_LANES=1
+
+# 1. memory errors first, on the smallest cases (compute-sanitizer is slow: keep it to a handful of tests)
+timeout 420 compute-sanitizer --tool memcheck --error-exitcode 9 \
+    python -m pytest tests/test_parity_gpu.py -x -q -m gpu -k "lanes_single or lanes_ragged or session_rejects" \
+    > "$OUT/memcheck.log" 2>&1
+echo "memcheck exit $?" | tee -a "$OUT/summary.txt"
+
+# 2. the gated parity tests (bit-exact against the oracle streams + the kernel's tree, sessions vs whole renders)
+timeout 600 python -m pytest tests -q -m gpu -k "lanes or session" > "$OUT/pytest_lanes.log" 2>&1
+echo "pytest lanes/session exit $?" | tee -a "$OUT/summary.txt"
+tail -5 "$OUT/pytest_lanes.log" >> "$OUT/summary.txt"
+
+# 3. throughput: large end of the cfg5 sweep with and without the flag, then the streaming case
+timeout 600 python tools/bench_configs.py lanes > "$OUT/lanes_sweep.jsonl" 2> "$OUT/lanes_sweep.err"
+echo "lanes sweep exit $?" | tee -a "$OUT/summary.txt"
+timeout 300 python tools/bench_configs.py session > "$OUT/session.jsonl" 2> "$OUT/session.err"
+echo "session bench exit $?" | tee -a "$OUT/summary.txt"
+timeout 300 python bench.py --streams 65536 --seconds 1 --flags 16 --steps 5 --warmup 3 --no-cpu-baseline \
+    > "$OUT/bench_65536_lanes.json" 2> "$OUT/bench_65536_lanes.err"
+echo "bench 65536 lanes exit $?" | tee -a "$OUT/summary.txt"
+
+# 4. launch list and one full capture of the new kernel (numbers printed under ncu are never bench values)
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file "$OUT/launches_lanes.csv" \
+    python bench.py --streams 16384 --seconds 1 --flags 16 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2>&1
+timeout 500 ncu --set full --clock-control none --import-source on -k regex:k_fused_lanes -s 3 -c 1 -o "$OUT/lanes_full" \
+    python bench.py --streams 16384 --seconds 1 --flags 16 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2>&1
+echo "ncu done" | tee -a "$OUT/summary.txt"
+cat "$OUT/summary.txt"
