@@ -65,13 +65,14 @@ def main():
     same = got.size == whole.size and bool(np.array_equal(got.view(np.uint32), whole.view(np.uint32)))
     print(f"session, 10 ms blocks: {got.size} samples, identical to the whole render: {same}", flush=True)
     ok &= same
-    if ok and "--time" in sys.argv:
-        S = 16384
+    sizes = ([16384] if "--time" in sys.argv else []) + ([65536] if "--time-big" in sys.argv else [])
+    for S in (sizes if ok else []):
         one = np.zeros(44100, np.float32)
-        for flags, nm in ((LANES, "k_fused_lanes"), (0, "default")):
+        for flags, nm in ((LANES, "k_fused_lanes"),) + (() if "--lanes-only" in sys.argv else ((0, "default"),)):
             srcs = [rb.UniformSourceIterator(rb.TestSource(one, 1, 44100), 1, 48000).low_pass(200).amplify(1.2) for _ in range(S)]
             with rb.Batch(srcs, 1, 48000, flags=flags, ctx=ctx) as b:
-                b.upload_all()                      # silence: classified safe, same arithmetic cost as any normal input
+                for i in range(S):                  # silence: classified safe, same arithmetic cost as any normal input
+                    b.upload(i, one)
                 b.render_mix_device()
                 ctx.sync()
                 t0 = time.perf_counter()
