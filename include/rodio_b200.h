@@ -135,7 +135,7 @@ enum {
     RB_BIQUAD_TIME_PARALLEL = 1u << 2, /* reserved (chunked-scan biquad, not bit-exact): accepted, served by the exact path */
     RB_KEEP_STREAM_OUTPUTS = 1u << 3,  /* also keep every stream's post-chain (pre-mix) samples in HBM so
                                           rb_batch_read_stream can return them                                */
-    RB_FUSED_LANES = 1u << 4           /* opt-in (large batches): serve resample -> [low/high_pass] -> [amplify] -> mix
+    RB_FUSED_LANES = 1u << 4           /* large batches (chosen automatically from ~277 sources per SM on): serve resample -> [low/high_pass] -> [amplify] -> mix
                                           of mono (or stereo, into a stereo mixer) f32 sources that share one rate pair (from < to) with the
                                           lane-per-stream kernel: every stream's samples are bit-identical to the
                                           default path, the mixer sum is a fixed tree over groups of 32 sources
