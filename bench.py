@@ -332,6 +332,38 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": b2.algorithmic_bytes / (ms2 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": b2.algorithmic_bytes / (ms2 * 1e-3) / 1e9 / peak, "kernel": "k_mix_ordered"}}}
         b2.close()
+        # ---- the large end of BASELINE configs[4] (HBM sweep) beside it: 65 536 streams x 1 s through the same chain;
+        # the planner serves it with the lane-per-stream kernel.  Guarded: a failure here is reported, never fatal.
+        try:
+            n3, frames3 = 65536, IN_RATE
+            b3 = rb.Batch(make_sources(rb, n3, frames3), MIX_CH, MIX_RATE, flags=args.flags, ctx=ctx)
+            r0, _ = b3.input_device_ptr(0)
+            pitch3 = (b3.input_device_ptr(1)[0] - r0) // 4
+            for i in range(n3):
+                b3.input_device_ptr(i)
+            with torch.cuda.stream(ext):
+                torch.as_tensor(rbd.DeviceArray(r0, pitch3 * (n3 - 1) + frames3), device=dev).uniform_(-1.0, 1.0, generator=gen)
+            for _ in range(3):
+                b3.render_mix_device()
+            torch.cuda.synchronize(dev)
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            steps3 = max(3, min(args.steps, 10))
+            h0.record(ext)
+            for _ in range(steps3):
+                b3.render_mix_device()
+            h1.record(ext)
+            torch.cuda.synchronize(dev)
+            ms3 = h0.elapsed_time(h1) / steps3
+            fam3 = b3.kernel_family
+            also["cfg5_65536_streams"] = {
+                "workload": "65536 mono streams x 1 s, 44.1 -> 48 kHz -> low_pass(200) -> amplify(1.2) -> mix, inputs 11.6 GB resident",
+                "value": n3 * b3.stream_out_len(0) / (ms3 * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms3, "steps": steps3,
+                "roofline": {"bound": "hbm", "achieved": b3.algorithmic_bytes / (ms3 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": b3.algorithmic_bytes / (ms3 * 1e-3) / 1e9 / peak,
+                             "kernel": {2: "k_fused_lanes + k_sum_groups", 1: "k_fused_hot + k_sum_partials"}.get(fam3, str(fam3))}}
+            b3.close()
+        except Exception as exc:   # noqa: BLE001 -- the headline line must survive whatever happens here
+            also["cfg5_65536_streams"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     clocks = sampler.stop()   # sampled over the timed region, the kernel-only loop and the end-to-end loop
 
