@@ -136,7 +136,7 @@ enum {
     RB_KEEP_STREAM_OUTPUTS = 1u << 3,  /* also keep every stream's post-chain (pre-mix) samples in HBM so
                                           rb_batch_read_stream can return them                                */
     RB_FUSED_LANES = 1u << 4           /* large batches (chosen automatically from ~277 sources per SM on): serve resample -> [low/high_pass] -> [amplify] -> mix
-                                          of mono (or stereo, into a stereo mixer) f32 sources that share one rate pair (from < to) with the
+                                          of mono (or stereo, into a stereo mixer) f32 sources at or below the mixer's rate with the
                                           lane-per-stream kernel: every stream's samples are bit-identical to the
                                           default path, the mixer sum is a fixed tree over groups of 32 sources
                                           (<= 1e-5 * peak like the default grouping).  Ignored when the batch has
@@ -221,8 +221,9 @@ rb_status rb_batch_read_stream(rb_batch* b, size_t stream, float* out_host, uint
  * frames still needed and the filter state carry over from block to block, so ANY split into pushes and renders gives
  * the bytes of a whole-stream rb_batch render with RB_FUSED_LANES (tests/test_lanes_emulator.py::test_session_*).
  * Shape served (RB_ERR_UNSUPPORTED otherwise): mono or stereo f32 sources (all the same; the mixer has that channel
- * count) that share one sample rate below the mixer's, effects = UNIFORM(channels, mixer rate)
- * [LOW_PASS | HIGH_PASS] [AMPLIFY] -- the chain of BASELINE cfg3; desc.n_samples / span_len are ignored,
+ * count), each at a sample rate at or below the mixer's (44.1 kHz, 22.05 kHz and 48 kHz sources in one 48 kHz mixer
+ * are fine: one kernel launch per rate pair), effects = UNIFORM(channels, mixer rate) [LOW_PASS | HIGH_PASS] [AMPLIFY]
+ * -- the chain of BASELINE cfg3; desc.n_samples / span_len are ignored,
  * desc.mix_start is the mixer FRAME the source joins at.  Everything below counts frames; PCM is interleaved.
  * One caller per session; every call returns with the work done (the caller may reuse its buffers). */
 typedef struct rb_session rb_session;

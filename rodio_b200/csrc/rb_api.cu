@@ -950,9 +950,17 @@ extern "C" rb_status rb_convert_samples(rb_context* ctx, const void* in, rb_samp
 // kernel: k_fused_lanes over per-block rows (rb_lanes_core.h: o0 / i0 / state / ROW_CONTINUES).
 struct rb_session {
     rb_context* ctx = nullptr;
-    uint32_t mixer_rate = 0, from = 0, to = 0;
+    uint32_t mixer_rate = 0;
     uint32_t channels = 1;        // of every source and of the mixer (1 or 2)
-    bool has_biquad = false, ff2 = false, has_post = false;
+    bool has_biquad = false, has_post = false;
+    // Sources may have different rates (each at or below the mixer's): one kernel launch per reduced rate pair.  All
+    // per-source arrays below are in CLASS ORDER (stable partition by rate pair); pos[] maps the caller's index to it.
+    struct Class {
+        uint32_t first = 0, count = 0;
+        bool ff2 = false;
+    };
+    std::vector<Class> classes;
+    std::vector<uint32_t> pos;
     std::vector<session::Stream> st;
     std::vector<float> coef;      // 5 per stream
     std::vector<float> ffk, post;
@@ -993,8 +1001,8 @@ extern "C" rb_status rb_session_create(rb_context* ctx, uint32_t mixer_rate, con
     if (!s) return fail(RB_ERR_OUT_OF_MEMORY, "host allocation failed");
     s->ctx = ctx, s->mixer_rate = mixer_rate, s->fifo_cap = fifo_frames, s->max_block = max_block_frames;
     const size_t n = n_streams;
-    s->st.resize(n), s->coef.assign(5 * n, 0.0f), s->ffk.assign(n, 0.0f), s->post.assign(n, 1.0f);
-    bool any_biquad = false, all_biquad = true, ff2 = true;
+    // pass 1: validate, find every source's reduced rate pair -> classes
+    std::vector<uint32_t> from(n), to(n);
     for (size_t i = 0; i < n; i++) {
         const rb_stream_desc& d = descs[i];
         const std::string where = "stream " + std::to_string(i) + ": ";
@@ -1003,37 +1011,58 @@ extern "C" rb_status rb_session_create(rb_context* ctx, uint32_t mixer_rate, con
         if (i == 0) s->channels = d.channels;
         else if (d.channels != s->channels) return fail(RB_ERR_UNSUPPORTED, where + "all sources of a session have the same channel count");
         if (d.n_effects && !d.effects) return fail(RB_ERR_INVALID_ARGUMENT, where + "effects is NULL");
-        uint32_t k = 0;
-        if (k >= d.n_effects || d.effects[k].kind != RB_FX_UNIFORM || d.effects[k].u32[0] != d.channels || d.effects[k].u32[1] != mixer_rate)
+        if (d.n_effects == 0 || d.effects[0].kind != RB_FX_UNIFORM || d.effects[0].u32[0] != d.channels || d.effects[0].u32[1] != mixer_rate)
             return fail(RB_ERR_UNSUPPORTED, where + "the chain must start with UNIFORM(source channels, mixer rate)");
-        k++;
         const uint32_t g = std::gcd(d.sample_rate, mixer_rate);
-        const uint32_t from = d.sample_rate / g, to = mixer_rate / g;
-        if (!(from < to) || to > (1u << 20)) return fail(RB_ERR_UNSUPPORTED, where + "the source rate must be below the mixer rate (reduced ratio < 2^20)");
-        if (i == 0) s->from = from, s->to = to;
-        else if (from != s->from || to != s->to) return fail(RB_ERR_UNSUPPORTED, where + "all sources of a session share one sample rate");
+        from[i] = d.sample_rate / g, to[i] = mixer_rate / g;
+        if (!(from[i] <= to[i]) || to[i] > (1u << 20))
+            return fail(RB_ERR_UNSUPPORTED, where + "the source rate must not exceed the mixer rate (reduced ratio < 2^20)");
+    }
+    const auto classes = lanes::classes_by_ratio(from.data(), to.data(), (uint32_t)n);
+    s->pos.assign(n, 0);
+    std::vector<uint32_t> order;   // class order -> caller's index
+    for (const auto& cls : classes) {
+        rb_session::Class c;
+        c.first = (uint32_t)order.size(), c.count = (uint32_t)cls.size();
+        for (uint32_t i : cls) s->pos[i] = (uint32_t)order.size(), order.push_back(i);
+        s->classes.push_back(c);
+    }
+    // pass 2: chains, in class order
+    s->st.resize(n), s->coef.assign(5 * n, 0.0f), s->ffk.assign(n, 0.0f), s->post.assign(n, 1.0f);
+    bool any_biquad = false, all_biquad = true;
+    std::vector<uint8_t> row_ff2(n, 1);
+    for (size_t r = 0; r < n; r++) {
+        const size_t i = order[r];
+        const rb_stream_desc& d = descs[i];
+        const std::string where = "stream " + std::to_string(i) + ": ";
+        uint32_t k = 1;
         bool biq = false;
         if (k < d.n_effects && (d.effects[k].kind == RB_FX_LOW_PASS || d.effects[k].kind == RB_FX_HIGH_PASS)) {
             const rb_effect& e = d.effects[k];
             if (e.u32[0] == 0 || !(e.f32[0] > 0.0f)) return fail(RB_ERR_INVALID_ARGUMENT, where + "filter frequency and q must be positive");
             const hostmath::Blt c = hostmath::blt(e.kind == RB_FX_HIGH_PASS, e.u32[0], e.f32[0], mixer_rate);
-            float* co = &s->coef[5 * i];
+            float* co = &s->coef[5 * r];
             co[0] = c.b0, co[1] = c.b1, co[2] = c.b2, co[3] = c.a1, co[4] = c.a2;
-            if (!lanes::ff2_coeffs(c.b0, c.b1, c.b2, &s->ffk[i])) ff2 = false;
+            if (!lanes::ff2_coeffs(c.b0, c.b1, c.b2, &s->ffk[r])) row_ff2[r] = 0;
             biq = true, k++;
         }
         any_biquad |= biq, all_biquad &= biq;
-        if (k < d.n_effects && d.effects[k].kind == RB_FX_AMPLIFY) s->post[i] = d.effects[k].f32[0], s->has_post = true, k++;
+        if (k < d.n_effects && d.effects[k].kind == RB_FX_AMPLIFY) s->post[r] = d.effects[k].f32[0], s->has_post = true, k++;
         if (k != d.n_effects) return fail(RB_ERR_UNSUPPORTED, where + "chain shape: UNIFORM [LOW_PASS | HIGH_PASS] [AMPLIFY]");
-        s->st[i].mix_start = d.mix_start;
+        s->st[r].mix_start = d.mix_start, s->st[r].from = from[i], s->st[r].to = to[i];
     }
     if (any_biquad && !all_biquad) return fail(RB_ERR_UNSUPPORTED, "either every source of a session has a filter or none has");
-    s->has_biquad = any_biquad, s->ff2 = any_biquad && ff2;
+    s->has_biquad = any_biquad;
+    for (auto& c : s->classes) {
+        c.ff2 = any_biquad;
+        for (uint32_t r = c.first; r < c.first + c.count; r++) c.ff2 = c.ff2 && row_ff2[r];
+    }
     RB_CUDA(cudaSetDevice(ctx->device));
     const uint32_t C = s->channels;
     s->stride = align_up((size_t)fifo_frames * C + 16, 32);
     const size_t arena = n * s->stride * sizeof(float);
-    const uint32_t n_groups = (uint32_t)((n + 31) / 32);
+    uint32_t n_groups = 0;   // partial rows: one per warp, every class rounds up on its own
+    for (const auto& c : s->classes) n_groups += (c.count + 31) / 32;
     const uint64_t pstride = lanes::round_up_tile((uint64_t)max_block_frames * C);
     RB_CUDA(cudaMalloc(&s->d_fifo[0], arena));
     RB_CUDA(cudaMalloc(&s->d_fifo[1], arena));
@@ -1062,6 +1091,7 @@ extern "C" rb_status rb_session_create(rb_context* ctx, uint32_t mixer_rate, con
 extern "C" rb_status rb_session_push(rb_session* s, size_t stream, const float* pcm, uint64_t n_frames, int end_of_stream) {
     if (!s || (!pcm && n_frames)) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
     if (stream >= s->st.size()) return fail(RB_ERR_INVALID_ARGUMENT, "stream index out of range");
+    stream = s->pos[stream];   // class order from here on
     session::Stream& st = s->st[stream];
     if (st.eof) return n_frames ? fail(RB_ERR_STATE, "push after end_of_stream") : RB_OK;
     if (st.fill() + n_frames > s->fifo_cap) return fail(RB_ERR_BUFFER_TOO_SMALL, "the stream's FIFO is full: render first");
@@ -1083,11 +1113,11 @@ extern "C" rb_status rb_session_push_packed(rb_session* s, const float* pcm, con
     if (!s || !n_frames) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
     const size_t ns = s->st.size();
     uint64_t total = 0;
-    for (size_t r = 0; r < ns; r++) {
-        const session::Stream& st = s->st[r];
-        if (st.eof && n_frames[r]) return fail(RB_ERR_STATE, "stream " + std::to_string(r) + ": push after end_of_stream");
-        if (st.fill() + n_frames[r] > s->fifo_cap) return fail(RB_ERR_BUFFER_TOO_SMALL, "stream " + std::to_string(r) + ": FIFO full, render first");
-        total += n_frames[r];
+    for (size_t i = 0; i < ns; i++) {   // i: the caller's index, pos[i]: class order
+        const session::Stream& st = s->st[s->pos[i]];
+        if (st.eof && n_frames[i]) return fail(RB_ERR_STATE, "stream " + std::to_string(i) + ": push after end_of_stream");
+        if (st.fill() + n_frames[i] > s->fifo_cap) return fail(RB_ERR_BUFFER_TOO_SMALL, "stream " + std::to_string(i) + ": FIFO full, render first");
+        total += n_frames[i];
     }
     if (total && !pcm) return fail(RB_ERR_INVALID_ARGUMENT, "pcm is NULL");
     RB_CUDA(cudaSetDevice(s->ctx->device));
@@ -1095,9 +1125,10 @@ extern "C" rb_status rb_session_push_packed(rb_session* s, const float* pcm, con
         const uint32_t C = s->channels;   // the kernel counts floats
         if (!s->d_stage) RB_CUDA(cudaMalloc(&s->d_stage, ns * (size_t)s->fifo_cap * C * sizeof(float)));
         uint64_t off = 0;
-        for (size_t r = 0; r < ns; r++) {
-            s->h_off[r] = off, s->h_u32[r] = (uint32_t)(n_frames[r] * C), s->h_u32[ns + r] = (uint32_t)(s->st[r].fill() * C);
-            off += n_frames[r] * C;
+        for (size_t i = 0; i < ns; i++) {
+            const size_t r = s->pos[i];
+            s->h_off[r] = off, s->h_u32[r] = (uint32_t)(n_frames[i] * C), s->h_u32[ns + r] = (uint32_t)(s->st[r].fill() * C);
+            off += n_frames[i] * C;
         }
         cudaStream_t stq = s->ctx->stream;
         RB_CUDA(cudaMemcpyAsync(s->d_stage, pcm, total * C * sizeof(float), cudaMemcpyHostToDevice, stq));
@@ -1106,9 +1137,9 @@ extern "C" rb_status rb_session_push_packed(rb_session* s, const float* pcm, con
         RB_CUDA(rb_lanes_fifo_append(s->d_stage, s->d_off, s->d_u32, s->d_u32 + ns, s->d_fifo[s->cur], s->stride, s->d_flags, (uint32_t)ns, stq));
         RB_CUDA(cudaStreamSynchronize(stq));
     }
-    for (size_t r = 0; r < ns; r++) {
-        s->st[r].pushed += n_frames[r];
-        if (end_of_stream && end_of_stream[r]) s->st[r].eof = true;
+    for (size_t i = 0; i < ns; i++) {
+        s->st[s->pos[i]].pushed += n_frames[i];
+        if (end_of_stream && end_of_stream[i]) s->st[s->pos[i]].eof = true;
     }
     return RB_OK;
 }
@@ -1116,7 +1147,7 @@ extern "C" rb_status rb_session_push_packed(rb_session* s, const float* pcm, con
 extern "C" rb_status rb_session_set_amplify(rb_session* s, size_t stream, float factor) {
     if (!s) return fail(RB_ERR_INVALID_ARGUMENT, "session is NULL");
     if (stream >= s->st.size()) return fail(RB_ERR_INVALID_ARGUMENT, "stream index out of range");
-    s->post[stream] = factor;
+    s->post[s->pos[stream]] = factor;
     s->has_post = true;   // sources without an AMPLIFY keep the factor 1.0: x * 1.0 is exact
     return RB_OK;
 }
@@ -1124,7 +1155,7 @@ extern "C" rb_status rb_session_set_amplify(rb_session* s, size_t stream, float 
 extern "C" rb_status rb_session_available(rb_session* s, uint64_t* frames, int* ended) {
     if (!s || !frames) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
     bool e = false;
-    *frames = session::renderable(s->st, s->T, s->from, s->to, ~0ull >> 1, &e);
+    *frames = session::renderable(s->st, s->T, ~0ull >> 1, &e);
     if (ended) *ended = e ? 1 : 0;
     return RB_OK;
 }
@@ -1133,7 +1164,7 @@ extern "C" rb_status rb_session_render(rb_session* s, float* out_host, uint64_t 
     if (!s || !written) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
     *written = 0;
     bool e = false;
-    const uint64_t n = session::renderable(s->st, s->T, s->from, s->to, std::min<uint64_t>(max_frames, s->max_block), &e);
+    const uint64_t n = session::renderable(s->st, s->T, std::min<uint64_t>(max_frames, s->max_block), &e);
     if (ended) *ended = e ? 1 : 0;
     if (n == 0) return RB_OK;
     if (!out_host) return fail(RB_ERR_INVALID_ARGUMENT, "out_host is NULL");
@@ -1144,7 +1175,7 @@ extern "C" rb_status rb_session_render(rb_session* s, float* out_host, uint64_t 
     std::vector<session::Part> parts(ns);
     float* fifo = s->d_fifo[s->cur];
     for (size_t r = 0; r < ns; r++) {
-        const session::Part p = parts[r] = session::part_of(s->st[r], s->T, n, s->from, s->to);
+        const session::Part p = parts[r] = session::part_of(s->st[r], s->T, n);
         lanes::Row& row = s->h_rows[r];
         memset(&row, 0, sizeof(row));
         row.in = fifo + r * s->stride, row.L = s->st[r].fill(), row.out_len = p.out_len, row.mix_start = p.mix_start;
@@ -1155,18 +1186,25 @@ extern "C" rb_status rb_session_render(rb_session* s, float* out_host, uint64_t 
         row.flags = p.continues ? lanes::ROW_CONTINUES : 0u;
     }
     RB_CUDA(cudaMemcpyAsync(s->d_rows, s->h_rows, ns * sizeof(lanes::Row), cudaMemcpyHostToDevice, stq));
-    lanes::Args a{};
-    a.rows = s->d_rows, a.n_rows = (uint32_t)ns, a.n_groups = (uint32_t)((ns + 31) / 32);
-    lanes::fill_ratio(a, s->from, s->to, C);
-    a.mix_len = n, a.pstride = lanes::round_up_tile((uint64_t)s->max_block * C);
-    a.partial = s->d_partial, a.zeros = s->d_zeros, a.unsafe = s->d_flags;
+    const uint64_t pstride = lanes::round_up_tile((uint64_t)s->max_block * C);
+    const uint32_t n_groups_total = [&] { uint32_t g = 0; for (auto& c : s->classes) g += (c.count + 31) / 32; return g; }();
     // rows of the partial buffer are only written inside each warp's span: clear what this block may read
-    RB_CUDA(cudaMemsetAsync(s->d_partial, 0, (size_t)a.n_groups * a.pstride * sizeof(float), stq));
-    RB_CUDA(rb_lanes_launch_block(a, C, s->has_biquad, s->ff2, s->has_post, s->d_out, stq));
+    RB_CUDA(cudaMemsetAsync(s->d_partial, 0, (size_t)n_groups_total * pstride * sizeof(float), stq));
+    uint32_t g0 = 0;
+    for (const auto& c : s->classes) {   // one launch per rate pair over its rows and its partial rows
+        lanes::Args a{};
+        a.rows = s->d_rows + c.first, a.n_rows = c.count, a.n_groups = (c.count + 31) / 32;
+        lanes::fill_ratio(a, s->st[c.first].from, s->st[c.first].to, C);
+        a.mix_len = n, a.pstride = pstride;
+        a.partial = s->d_partial + (size_t)g0 * pstride, a.zeros = s->d_zeros, a.unsafe = s->d_flags + c.first;
+        RB_CUDA(rb_lanes_launch_kernel(a, C, s->has_biquad, c.ff2, s->has_post, stq));
+        g0 += a.n_groups;
+    }
+    RB_CUDA(rb_lanes_launch_sum(s->d_partial, n_groups_total, pstride, n * C, s->d_out, stq));
     // the host already knows what every stream consumed: compact the FIFOs into the other arena behind the kernel
     for (size_t r = 0; r < ns; r++) {
         const uint64_t fill_before = s->st[r].fill();
-        const uint64_t drop = session::advance(s->st[r], parts[r], s->from, s->to);
+        const uint64_t drop = session::advance(s->st[r], parts[r]);
         s->h_u32[r] = (uint32_t)(drop * C), s->h_u32[ns + r] = (uint32_t)((fill_before - drop) * C);   // floats
     }
     RB_CUDA(cudaMemcpyAsync(s->d_u32, s->h_u32, 2 * ns * sizeof(uint32_t), cudaMemcpyHostToDevice, stq));
@@ -1179,7 +1217,7 @@ extern "C" rb_status rb_session_render(rb_session* s, float* out_host, uint64_t 
     *written = n;
     if (ended) {
         bool e2 = false;
-        session::renderable(s->st, s->T, s->from, s->to, 1, &e2);
+        session::renderable(s->st, s->T, 1, &e2);
         *ended = e2 ? 1 : 0;
     }
     return RB_OK;
@@ -1188,11 +1226,12 @@ extern "C" rb_status rb_session_render(rb_session* s, float* out_host, uint64_t 
 // ---- block-to-block state as a blob ----
 namespace {
 struct SessionBlobHeader {
-    uint32_t magic, version, n_streams, from, to, has_biquad, channels, pad_;
+    uint32_t magic, version, n_streams, has_biquad, channels, pad_;
     uint64_t T;
 };
-struct SessionBlobStream {
+struct SessionBlobStream {   // in class order (the same descriptors give the same order)
     uint64_t mix_start, pushed, out_done, i0;
+    uint32_t from, to;
     uint32_t eof, unsafe, fill, pad_;   // fill in frames
     float state[8];                      // 4 per channel
 };
@@ -1214,7 +1253,7 @@ extern "C" rb_status rb_session_get_state(rb_session* s, void* buf, uint64_t cap
     RB_CUDA(cudaMemcpyAsync(state.data(), s->d_state, 4 * C * ns * sizeof(float), cudaMemcpyDeviceToHost, s->ctx->stream));
     RB_CUDA(cudaMemcpyAsync(flags.data(), s->d_flags, ns * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->ctx->stream));
     uint8_t* p = (uint8_t*)buf;
-    SessionBlobHeader h{SESSION_MAGIC, 2u, (uint32_t)ns, s->from, s->to, s->has_biquad ? 1u : 0u, C, 0u, s->T};
+    SessionBlobHeader h{SESSION_MAGIC, 3u, (uint32_t)ns, s->has_biquad ? 1u : 0u, C, 0u, s->T};
     memcpy(p, &h, sizeof(h)), p += sizeof(h);
     uint8_t* recs = p;
     p += ns * sizeof(SessionBlobStream);
@@ -1226,7 +1265,7 @@ extern "C" rb_status rb_session_get_state(rb_session* s, void* buf, uint64_t cap
     RB_CUDA(cudaStreamSynchronize(s->ctx->stream));
     for (size_t r = 0; r < ns; r++) {
         const session::Stream& st = s->st[r];
-        SessionBlobStream b{st.mix_start, st.pushed, st.out_done, st.i0, st.eof ? 1u : 0u, flags[r], (uint32_t)st.fill(), 0u, {0}};
+        SessionBlobStream b{st.mix_start, st.pushed, st.out_done, st.i0, st.from, st.to, st.eof ? 1u : 0u, flags[r], (uint32_t)st.fill(), 0u, {0}};
         for (uint32_t k = 0; k < 4 * C; k++) b.state[k] = state[4 * C * r + k];
         memcpy(recs + r * sizeof(b), &b, sizeof(b));
     }
@@ -1241,14 +1280,16 @@ extern "C" rb_status rb_session_set_state(rb_session* s, const void* buf, uint64
     if (size < sizeof(h)) return fail(RB_ERR_INVALID_ARGUMENT, "state blob truncated");
     memcpy(&h, p, sizeof(h)), p += sizeof(h);
     const uint32_t C = s->channels;
-    if (h.magic != SESSION_MAGIC || h.version != 2u) return fail(RB_ERR_INVALID_ARGUMENT, "not a session state blob");
-    if (h.n_streams != ns || h.from != s->from || h.to != s->to || h.has_biquad != (s->has_biquad ? 1u : 0u) || h.channels != C)
+    if (h.magic != SESSION_MAGIC || h.version != 3u) return fail(RB_ERR_INVALID_ARGUMENT, "not a session state blob");
+    if (h.n_streams != ns || h.has_biquad != (s->has_biquad ? 1u : 0u) || h.channels != C)
         return fail(RB_ERR_INVALID_ARGUMENT, "state blob belongs to a session of another shape");
     if (size < sizeof(h) + ns * sizeof(SessionBlobStream)) return fail(RB_ERR_INVALID_ARGUMENT, "state blob truncated");
     std::vector<SessionBlobStream> recs(ns);
     memcpy(recs.data(), p, ns * sizeof(SessionBlobStream)), p += ns * sizeof(SessionBlobStream);
     uint64_t need = sizeof(h) + ns * sizeof(SessionBlobStream);
-    for (auto& b : recs) {
+    for (size_t r = 0; r < ns; r++) {
+        const SessionBlobStream& b = recs[r];
+        if (b.from != s->st[r].from || b.to != s->st[r].to) return fail(RB_ERR_INVALID_ARGUMENT, "state blob belongs to a session of another shape");
         if (b.fill > s->fifo_cap || b.pushed - b.i0 != b.fill || (b.i0 & 3u)) return fail(RB_ERR_INVALID_ARGUMENT, "state blob: FIFO record out of range");
         need += (uint64_t)b.fill * C * sizeof(float);
     }

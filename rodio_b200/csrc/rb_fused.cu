@@ -1294,22 +1294,25 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
         // interpolate with ONE reduced ratio from < to, optional biquad, at most one gain directly in front of the sum.
         const uint32_t C = mixer_channels;
         bool ok = has_b ? (n_mid == 0 && n_post <= 1) : (n_mid + n_post <= 1);
-        const uint32_t from = rows[0].uni.from, to = rows[0].uni.to;
         std::vector<rb_lanes_stream> ls(ok ? n_streams : 0);
         for (size_t i = 0; i < n_streams && ok; i++) {
             const FusedRow& r = rows[i];
-            ok = r.mode == ROW_LERP && r.c_in == C && r.uni.from == from && r.uni.to == to && r.out_len % C == 0 &&
-                 r.mix_start % C == 0 && r.n_in % C == 0;
+            // every stream interpolates upwards on its own reduced grid (several rate pairs are served class by class),
+            // or is at the mixer's rate already (UniformSourceIterator hands it through)
+            const bool lerp_up = r.mode == ROW_LERP && r.uni.from < r.uni.to;
+            const bool pass = r.mode == ROW_PASS;
+            ok = (lerp_up || pass) && r.c_in == C && r.out_len % C == 0 && r.mix_start % C == 0 && r.n_in % C == 0;
             rb_lanes_stream& l = ls[i];
             l.in = (const float*)r.in, l.n_frames = r.uni.tail.L, l.out_len = r.out_len / C, l.mix_start = r.mix_start / C;
+            l.from = pass ? 1u : r.uni.from, l.to = pass ? 1u : r.uni.to;
             l.b0 = r.b0, l.b1 = r.b1, l.b2 = r.b2, l.a1 = r.a1, l.a2 = r.a2;
             l.post = n_post ? r.post[0] : (n_mid ? r.mid[0] : 1.0f);
         }
         if (ok) {
             cudaError_t e = cudaSuccess;
             if (mix_len % C == 0)
-                e = rb_lanes_try_create(ls.data(), n_streams, C, from, to, has_b != 0, (n_mid + n_post) != 0, d_out, mix_len / C,
-                                        sm_count, st, &plan->lanes);
+                e = rb_lanes_try_create(ls.data(), n_streams, C, has_b != 0, (n_mid + n_post) != 0, d_out, mix_len / C, sm_count, st,
+                                        &plan->lanes);
             if (e != cudaSuccess) {
                 delete plan;
                 return e;

@@ -14,13 +14,13 @@ constexpr int LANES_THREADS = 32 * LANES_WARPS;
 template <int C>
 constexpr size_t lanes_smem_bytes() { return (size_t)LANES_WARPS * 32 * lanes::Geo<C>::RS * sizeof(float); }   // 21.0 / 41.0 KB
 
-template <int C, bool HASB, bool FF2, int NPOST>
+template <int C, bool HASB, bool FF2, int NPOST, bool PASS>
 __global__ void __launch_bounds__(LANES_THREADS) k_fused_lanes(lanes::Args a) {
     extern __shared__ __align__(16) float lanes_smem[];
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t group = blockIdx.x * LANES_WARPS + warp;
     if (group >= a.n_groups) return;   // whole warps leave: the warp program only synchronises within a warp
-    lanes::warp_main<C, HASB, FF2, NPOST>(a, group, lanes_smem + (size_t)warp * 32 * lanes::Geo<C>::RS);
+    lanes::warp_main<C, HASB, FF2, NPOST, PASS>(a, group, lanes_smem + (size_t)warp * 32 * lanes::Geo<C>::RS);
 }
 
 // One CTA per stream: does every non-zero |x| lie inside [2^-70, 2^60]?  (rb_lanes_core.h, "Exact division".)
@@ -93,43 +93,38 @@ __global__ void __launch_bounds__(256) k_classify_range(const float* __restrict_
     if (__syncthreads_or(bad ? 1 : 0) && threadIdx.x == 0) *flag = 1u;
 }
 
-template <int C, bool HASB, bool FF2, int NPOST>
+template <int C, bool HASB, bool FF2, int NPOST, bool PASS>
 static void launch_lanes(const lanes::Args& a, cudaStream_t st) {
     const uint32_t n_ctas = (a.n_groups + LANES_WARPS - 1) / LANES_WARPS;
-    k_fused_lanes<C, HASB, FF2, NPOST><<<n_ctas, LANES_THREADS, lanes_smem_bytes<C>(), st>>>(a);   // < 48 KB: no opt-in needed
+    k_fused_lanes<C, HASB, FF2, NPOST, PASS><<<n_ctas, LANES_THREADS, lanes_smem_bytes<C>(), st>>>(a);   // < 48 KB: no opt-in needed
 }
-template <int C>
+template <int C, bool PASS>
 static void launch_lanes_c(const lanes::Args& a, bool has_biquad, bool ff2, bool has_post, cudaStream_t st) {
     if (has_biquad) {
-        if (ff2) has_post ? launch_lanes<C, true, true, 1>(a, st) : launch_lanes<C, true, true, 0>(a, st);
-        else has_post ? launch_lanes<C, true, false, 1>(a, st) : launch_lanes<C, true, false, 0>(a, st);
+        if (ff2) has_post ? launch_lanes<C, true, true, 1, PASS>(a, st) : launch_lanes<C, true, true, 0, PASS>(a, st);
+        else has_post ? launch_lanes<C, true, false, 1, PASS>(a, st) : launch_lanes<C, true, false, 0, PASS>(a, st);
     } else {
-        has_post ? launch_lanes<C, false, false, 1>(a, st) : launch_lanes<C, false, false, 0>(a, st);
+        has_post ? launch_lanes<C, false, false, 1, PASS>(a, st) : launch_lanes<C, false, false, 0, PASS>(a, st);
     }
 }
 
 }  // namespace
 
-static cudaError_t launch_lanes_any(const lanes::Args& a, uint32_t channels, bool has_biquad, bool ff2, bool has_post, cudaStream_t st) {
-    if (channels == 2) launch_lanes_c<2>(a, has_biquad, ff2, has_post, st);
-    else launch_lanes_c<1>(a, has_biquad, ff2, has_post, st);
-    return cudaGetLastError();
-}
-
-static cudaError_t launch_sum_groups(const lanes::Args& a, uint32_t channels, float* d_out, cudaStream_t st) {
-    const uint64_t n = a.mix_len * channels;   // floats
-    uint64_t blocks = (n + 255) / 256;
-    if (blocks > 148ull * 8) blocks = 148ull * 8;
-    k_sum_groups<<<(uint32_t)blocks, 256, 0, st>>>(a.partial, a.n_groups, a.pstride, n, d_out);
-    return cudaGetLastError();
-}
-
-cudaError_t rb_lanes_launch_block(const lanes::Args& a, uint32_t channels, bool has_biquad, bool ff2, bool has_post, float* d_out,
-                                  cudaStream_t st) {
+cudaError_t rb_lanes_launch_kernel(const lanes::Args& a, uint32_t channels, bool has_biquad, bool ff2, bool has_post, cudaStream_t st) {
     if (a.mix_len == 0 || a.n_groups == 0 || (channels != 1 && channels != 2)) return cudaSuccess;
-    cudaError_t e = launch_lanes_any(a, channels, has_biquad, ff2, has_post, st);
-    if (e != cudaSuccess) return e;
-    return launch_sum_groups(a, channels, d_out, st);
+    const bool pass = a.from == a.to;   // sources at the mixer's rate: taps used raw
+    if (channels == 2) pass ? launch_lanes_c<2, true>(a, has_biquad, ff2, has_post, st) : launch_lanes_c<2, false>(a, has_biquad, ff2, has_post, st);
+    else pass ? launch_lanes_c<1, true>(a, has_biquad, ff2, has_post, st) : launch_lanes_c<1, false>(a, has_biquad, ff2, has_post, st);
+    return cudaGetLastError();
+}
+
+cudaError_t rb_lanes_launch_sum(const float* d_partial, uint32_t n_groups, uint64_t pstride, uint64_t n_floats, float* d_out,
+                                cudaStream_t st) {
+    if (n_floats == 0) return cudaSuccess;
+    uint64_t blocks = (n_floats + 255) / 256;
+    if (blocks > 148ull * 8) blocks = 148ull * 8;
+    k_sum_groups<<<(uint32_t)blocks, 256, 0, st>>>(d_partial, n_groups, pstride, n_floats, d_out);
+    return cudaGetLastError();
 }
 
 cudaError_t rb_lanes_fifo_append(const float* d_staging, const uint64_t* d_offset, const uint32_t* d_count, const uint32_t* d_fill,
@@ -153,48 +148,69 @@ cudaError_t rb_lanes_fifo_compact(const float* d_src, float* d_dst, uint64_t str
 }
 
 struct rb_lanes_plan {
-    lanes::Args args{};
-    lanes::Row* d_rows = nullptr;
-    float* d_partial = nullptr;
+    struct Class {
+        lanes::Args args{};
+        bool ff2 = false;
+    };
+    std::vector<Class> classes;      // one launch per reduced rate pair
+    lanes::Row* d_rows = nullptr;    // class after class
+    float* d_partial = nullptr;      // [n_groups_total][pstride]
     float* d_zeros = nullptr;
     float* d_out = nullptr;
-    bool has_biquad = false, ff2 = false, has_post = false;
+    uint32_t n_rows = 0, n_groups_total = 0, channels = 1;
+    uint64_t pstride = 0, mix_len = 0;
+    bool has_biquad = false, has_post = false;
     bool classified = false;
-    uint32_t channels = 1;
 };
 
-cudaError_t rb_lanes_try_create(const rb_lanes_stream* streams, size_t n_streams, uint32_t channels, uint32_t from, uint32_t to,
-                                bool has_biquad, bool has_post, float* d_out, uint64_t mix_len, int sm_count, cudaStream_t st,
-                                rb_lanes_plan** out) {
+cudaError_t rb_lanes_try_create(const rb_lanes_stream* streams, size_t n_streams, uint32_t channels, bool has_biquad, bool has_post,
+                                float* d_out, uint64_t mix_len, int sm_count, cudaStream_t st, rb_lanes_plan** out) {
     (void)sm_count;
     *out = nullptr;
-    if (n_streams == 0 || mix_len == 0 || !(from < to) || to > (1u << 20) || (channels != 1 && channels != 2)) return cudaSuccess;
-    std::vector<lanes::Row> rows(n_streams);
-    bool ff2 = has_biquad;
+    if (n_streams == 0 || n_streams > 0x7fffffffull || mix_len == 0 || (channels != 1 && channels != 2)) return cudaSuccess;
+    std::vector<uint32_t> from(n_streams), to(n_streams);
     for (size_t i = 0; i < n_streams; i++) {
-        const rb_lanes_stream& s = streams[i];
-        if (reinterpret_cast<uintptr_t>(s.in) & 15u) return cudaSuccess;
-        lanes::Row& r = rows[i];
-        memset(&r, 0, sizeof(r));
-        r.in = s.in, r.L = s.n_frames, r.out_len = s.out_len, r.mix_start = s.mix_start;
-        r.n_int = lanes::n_interp(r.L, from, to, r.out_len);
-        r.b0 = s.b0, r.b1 = s.b1, r.b2 = s.b2, r.a1 = s.a1, r.a2 = s.a2;
-        r.post = has_post ? s.post : 1.0f;
-        r.flags = lanes::ROW_UNSAFE;   // until classified
-        float k = 0.0f;
-        if (has_biquad && lanes::ff2_coeffs(r.b0, r.b1, r.b2, &k)) r.ffk = k;
-        else ff2 = false;
+        from[i] = streams[i].from, to[i] = streams[i].to;
+        if (!(from[i] <= to[i]) || from[i] == 0 || to[i] > (1u << 20)) return cudaSuccess;
+        if (reinterpret_cast<uintptr_t>(streams[i].in) & 15u) return cudaSuccess;
     }
+    const auto classes = lanes::classes_by_ratio(from.data(), to.data(), (uint32_t)n_streams);
     auto p = new rb_lanes_plan;
-    p->has_biquad = has_biquad, p->ff2 = ff2, p->has_post = has_post, p->d_out = d_out, p->channels = channels;
-    lanes::Args& a = p->args;
-    a.n_rows = (uint32_t)n_streams, a.n_groups = (uint32_t)((n_streams + 31) / 32);
-    lanes::fill_ratio(a, from, to, channels);
-    a.mix_len = mix_len, a.pstride = lanes::round_up_tile(mix_len * channels);
+    p->has_biquad = has_biquad, p->has_post = has_post, p->d_out = d_out, p->channels = channels;
+    p->n_rows = (uint32_t)n_streams, p->mix_len = mix_len, p->pstride = lanes::round_up_tile(mix_len * channels);
+    std::vector<lanes::Row> rows;
+    rows.reserve(n_streams);
+    std::vector<size_t> first_row;
+    for (const auto& cls : classes) {
+        rb_lanes_plan::Class c;
+        lanes::Args& a = c.args;
+        a.n_rows = (uint32_t)cls.size(), a.n_groups = (a.n_rows + 31) / 32;
+        lanes::fill_ratio(a, from[cls[0]], to[cls[0]], channels);
+        a.mix_len = mix_len, a.pstride = p->pstride;
+        c.ff2 = has_biquad;
+        first_row.push_back(rows.size());
+        for (uint32_t i : cls) {
+            const rb_lanes_stream& s = streams[i];
+            lanes::Row r;
+            memset(&r, 0, sizeof(r));
+            r.in = s.in, r.L = s.n_frames, r.out_len = s.out_len, r.mix_start = s.mix_start;
+            r.n_int = lanes::n_interp(r.L, s.from, s.to, r.out_len);
+            r.b0 = s.b0, r.b1 = s.b1, r.b2 = s.b2, r.a1 = s.a1, r.a2 = s.a2;
+            r.post = has_post ? s.post : 1.0f;
+            r.flags = lanes::ROW_UNSAFE;   // until classified
+            float k = 0.0f;
+            if (has_biquad && lanes::ff2_coeffs(r.b0, r.b1, r.b2, &k)) r.ffk = k;
+            else c.ff2 = false;
+            rows.push_back(r);
+        }
+        p->n_groups_total += a.n_groups;
+        p->classes.push_back(c);
+    }
+    const size_t partial_bytes = (size_t)p->n_groups_total * p->pstride * sizeof(float);
     cudaError_t e = cudaMalloc(&p->d_rows, n_streams * sizeof(lanes::Row));
-    if (e == cudaSuccess) e = cudaMalloc(&p->d_partial, (size_t)a.n_groups * a.pstride * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_partial, partial_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&p->d_zeros, 256);
-    if (e == cudaSuccess) e = cudaMemsetAsync(p->d_partial, 0, (size_t)a.n_groups * a.pstride * sizeof(float), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(p->d_partial, 0, partial_bytes, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(p->d_zeros, 0, 256, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_rows, rows.data(), n_streams * sizeof(lanes::Row), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -202,7 +218,12 @@ cudaError_t rb_lanes_try_create(const rb_lanes_stream* streams, size_t n_streams
         rb_lanes_destroy(p);
         return e;
     }
-    a.rows = p->d_rows, a.partial = p->d_partial, a.zeros = p->d_zeros;
+    uint32_t g0 = 0;
+    for (size_t k = 0; k < p->classes.size(); k++) {
+        lanes::Args& a = p->classes[k].args;
+        a.rows = p->d_rows + first_row[k], a.partial = p->d_partial + (size_t)g0 * p->pstride, a.zeros = p->d_zeros;
+        g0 += a.n_groups;
+    }
     *out = p;
     return cudaSuccess;
 }
@@ -212,19 +233,20 @@ void rb_lanes_inputs_changed(rb_lanes_plan* p) {
 }
 
 cudaError_t rb_lanes_run(rb_lanes_plan* p, cudaStream_t st) {
-    const lanes::Args& a = p->args;
     if (!p->classified) {
-        k_classify_inputs<<<a.n_rows, 256, 0, st>>>(p->d_rows, a.n_rows, p->channels);
+        k_classify_inputs<<<p->n_rows, 256, 0, st>>>(p->d_rows, p->n_rows, p->channels);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         p->classified = true;
     }
-    cudaError_t e = launch_lanes_any(a, p->channels, p->has_biquad, p->ff2, p->has_post, st);
-    if (e != cudaSuccess) return e;
-    return launch_sum_groups(a, p->channels, p->d_out, st);
+    for (const auto& c : p->classes) {
+        cudaError_t e = rb_lanes_launch_kernel(c.args, p->channels, p->has_biquad, c.ff2, p->has_post, st);
+        if (e != cudaSuccess) return e;
+    }
+    return rb_lanes_launch_sum(p->d_partial, p->n_groups_total, p->pstride, p->mix_len * p->channels, p->d_out, st);
 }
 
-uint32_t rb_lanes_launch_count(const rb_lanes_plan*) { return 2u; }
+uint32_t rb_lanes_launch_count(const rb_lanes_plan* p) { return (uint32_t)p->classes.size() + 1u; }
 
 void rb_lanes_destroy(rb_lanes_plan* p) {
     if (!p) return;

@@ -13,6 +13,7 @@ struct rb_lanes_stream {
     uint64_t n_frames;
     uint64_t out_len;      // frames
     uint64_t mix_start;    // frames
+    uint32_t from, to;     // reduced rate pair of this stream, from <= to (1:1 = already at the mixer's rate)
     float b0, b1, b2, a1, a2;
     float post;
 };
@@ -20,10 +21,10 @@ struct rb_lanes_stream {
 struct rb_lanes_plan;
 
 // *out stays NULL when the shape is not covered.  `d_out` is the mixer output ([mix_len] f32).
-// mix_len in frames; `d_out` holds mix_len * channels floats.
-cudaError_t rb_lanes_try_create(const rb_lanes_stream* streams, size_t n_streams, uint32_t channels, uint32_t from, uint32_t to,
-                                bool has_biquad, bool has_post, float* d_out, uint64_t mix_len, int sm_count, cudaStream_t st,
-                                rb_lanes_plan** out);
+// mix_len in frames; `d_out` holds mix_len * channels floats.  Streams with different rate pairs are served class by
+// class (rb_lanes_plan.h classes_by_ratio): the mixer sum then groups by class first.
+cudaError_t rb_lanes_try_create(const rb_lanes_stream* streams, size_t n_streams, uint32_t channels, bool has_biquad, bool has_post,
+                                float* d_out, uint64_t mix_len, int sm_count, cudaStream_t st, rb_lanes_plan** out);
 // Inputs were (re)written: classify them again before the next render.
 void rb_lanes_inputs_changed(rb_lanes_plan* p);
 cudaError_t rb_lanes_run(rb_lanes_plan* p, cudaStream_t st);
@@ -31,9 +32,11 @@ uint32_t rb_lanes_launch_count(const rb_lanes_plan* p);
 void rb_lanes_destroy(rb_lanes_plan* p);
 
 // ---- streaming blocks (rb_session_* in rb_api.cu): the caller owns every buffer and fills lanes::Args itself ----
-// One block: k_fused_lanes over a.rows, then the ordered sum of the per-warp partial rows into d_out[0, a.mix_len * channels).
-cudaError_t rb_lanes_launch_block(const lanes::Args& a, uint32_t channels, bool has_biquad, bool ff2, bool has_post, float* d_out,
-                                  cudaStream_t st);
+// k_fused_lanes over a.rows (one rate pair; a.from == a.to selects the pass-through variant) ...
+cudaError_t rb_lanes_launch_kernel(const lanes::Args& a, uint32_t channels, bool has_biquad, bool ff2, bool has_post, cudaStream_t st);
+// ... and the ordered sum of n_groups partial rows (all classes) into d_out[0, n_floats).
+cudaError_t rb_lanes_launch_sum(const float* d_partial, uint32_t n_groups, uint64_t pstride, uint64_t n_floats, float* d_out,
+                                cudaStream_t st);
 // FIFO append: stream r receives count[r] frames, taken from staging + offset[r], behind its fill[r] frames in
 // fifo + r * stride; flags[r] becomes non-zero (and stays so) when a new frame lies outside the exact-reciprocal class.
 cudaError_t rb_lanes_fifo_append(const float* d_staging, const uint64_t* d_offset, const uint32_t* d_count, const uint32_t* d_fill,

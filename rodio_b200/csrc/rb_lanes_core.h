@@ -119,7 +119,11 @@ SIMT_FN float reduce_tile(const float (&v)[TILE], uint32_t ln) {
     return simt::fadd(s, 0.0f);   // the reference's accumulator starts from +0.0: an all-(-0) column sums to +0
 }
 
-template <int C, bool HASB, bool FF2, int NPOST>
+// PASS: the streams are at the mixer's rate already (reduced ratio 1:1): SampleRateConverter hands its input through
+// untouched (src/conversions/sample_rate.rs:131-136), so the taps are used raw -- no interpolation, no division, and no
+// input class to respect; everything else (ring, runs, "an output needs its successor or the end of the stream") is the
+// same code with from = to = 1.
+template <int C, bool HASB, bool FF2, int NPOST, bool PASS = false>
 SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
     using G = Geo<C>;
     constexpr int TF = G::TF, RS = G::RS, QPC = G::QPC, RPI = G::RPI, RING = G::RING, MIRROR = G::MIRROR, CHW = G::CHW;
@@ -134,7 +138,7 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
         row.b0 = row.b1 = row.b2 = row.a1 = row.a2 = row.ffk = row.post = 0.0f, row.flags = 0;
     }
     const uint64_t ms = row.mix_start, end = row.mix_start + row.out_len;   // frames
-    const bool safe = has && !(row.flags & ROW_UNSAFE) && !(a.unsafe && a.unsafe[r]);
+    const bool safe = has && (PASS || (!(row.flags & ROW_UNSAFE) && !(a.unsafe && a.unsafe[r])));
     const bool stops = !(row.flags & ROW_CONTINUES);   // the stream ends inside this block (or is a whole stream)
     const bool live = has && row.out_len != 0;
     const uint64_t t_lo = simt::reduce_min64(live ? ms : ~0ull), t_hi = simt::reduce_max64(live ? end : 0ull);
@@ -259,11 +263,15 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                     float x[C];
 #pragma unroll
                     for (int c = 0; c < C; c++) {
-                        // src/math.rs:24-26: first + (second - first) * num / den, the division as an exact reciprocal step
-                        const float m = simt::fmul(simt::fsub(x1[c], x0[c]), nf);
-                        const float q0 = simt::fmul(m, rcp);
-                        const float q = simt::ffma(simt::ffma(-q0, den, m), rcp, q0);
-                        x[c] = simt::fadd(x0[c], q);
+                        if (PASS) {
+                            x[c] = x0[c];
+                        } else {
+                            // src/math.rs:24-26: first + (second - first) * num / den, the division as an exact reciprocal step
+                            const float m = simt::fmul(simt::fsub(x1[c], x0[c]), nf);
+                            const float q0 = simt::fmul(m, rcp);
+                            const float q = simt::ffma(simt::ffma(-q0, den, m), rcp, q0);
+                            x[c] = simt::fadd(x0[c], q);
+                        }
                     }
                     // next output frame: numerator += from (mod to); a carry moves one input frame on
                     simt::lerp_advance<C>(nf, x0, x1, p, from_f, den);
@@ -318,7 +326,7 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                     if (on) {
                         const float xa = simt::ldg(row.in + i * C + c);
                         float x = xa;
-                        if (i + 1 < row.L)
+                        if (!PASS && i + 1 < row.L)
                             x = simt::fadd(xa, simt::fdiv(simt::fmul(simt::fsub(simt::ldg(row.in + (i + 1) * C + c), xa), simt::u2f(num)), den));
                         float y = x;
                         if (HASB) {

@@ -3,6 +3,8 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <utility>
+#include <vector>
 
 #include "rb_lanes_core.h"
 
@@ -41,6 +43,21 @@ inline void fill_ratio(Args& a, uint32_t from, uint32_t to, uint32_t channels) {
     a.rcp_den = 1.0f / a.den_f;
     a.from_f = (float)from;
     a.neg1 = -1.0f;
+}
+
+// Streams of one kernel launch share a reduced rate pair.  A batch / session with several pairs (44.1 kHz and 48 kHz
+// sources in one mixer) is served class by class: stable partition by (from, to) in order of first appearance; every
+// class gets its own launch over its own rows and its own partial rows, k_sum_groups adds all partial rows in order.
+inline std::vector<std::vector<uint32_t>> classes_by_ratio(const uint32_t* from, const uint32_t* to, uint32_t n) {
+    std::vector<std::pair<uint32_t, uint32_t>> keys;
+    std::vector<std::vector<uint32_t>> out;
+    for (uint32_t i = 0; i < n; i++) {
+        size_t k = 0;
+        while (k < keys.size() && !(keys[k].first == from[i] && keys[k].second == to[i])) k++;
+        if (k == keys.size()) keys.push_back({from[i], to[i]}), out.emplace_back();
+        out[k].push_back(i);
+    }
+    return out;
 }
 
 inline uint64_t round_up_tile(uint64_t n) { return (n + TILE - 1) / TILE * TILE; }   // n in floats (frames * channels)

@@ -20,6 +20,7 @@
 namespace session {
 
 struct Stream {
+    uint32_t from = 1, to = 1; // the source's rate pair, reduced (from <= to; 1:1 = already at the mixer's rate)
     uint64_t mix_start = 0;    // mixer frame the stream joins at (frame aligned, src/mixer.rs:175-183)
     uint64_t pushed = 0;       // input frames received so far
     uint64_t out_done = 0;     // output frames rendered so far (= stream-absolute index of the next one)
@@ -41,23 +42,20 @@ inline uint64_t out_interp(uint64_t L, uint32_t from, uint32_t to) {
     return L < 2 ? 0 : ((L - 1) * (uint64_t)to + from - 1) / from;
 }
 // Output frames of stream `s` that exist so far (renderable): everything once it has ended, else the interpolated ones.
-inline uint64_t out_ready(const Stream& s, uint32_t from, uint32_t to) {
-    return s.eof ? out_total(s.pushed, from, to) : out_interp(s.pushed, from, to);
+inline uint64_t out_ready(const Stream& s) {
+    return s.eof ? out_total(s.pushed, s.from, s.to) : out_interp(s.pushed, s.from, s.to);
 }
-inline bool finished(const Stream& s, uint32_t from, uint32_t to) {
-    return s.eof && s.out_done >= out_total(s.pushed, from, to);
-}
+inline bool finished(const Stream& s) { return s.eof && s.out_done >= out_total(s.pushed, s.from, s.to); }
 
 // How many mixer frames [T, T + n) can be rendered now (every unfinished stream must be able to supply its part).
 // Returns 0 with *ended = true when no stream is left (MixerSource::next returns None, src/mixer.rs:129-135).
-inline uint64_t renderable(const std::vector<Stream>& st, uint64_t T, uint32_t from, uint32_t to, uint64_t max_frames,
-                           bool* ended) {
+inline uint64_t renderable(const std::vector<Stream>& st, uint64_t T, uint64_t max_frames, bool* ended) {
     uint64_t n = max_frames;
     bool any = false;
     for (const Stream& s : st) {
-        if (finished(s, from, to)) continue;
+        if (finished(s)) continue;
         any = true;
-        const uint64_t upto = s.mix_start + out_ready(s, from, to);   // the stream can cover the timeline up to here
+        const uint64_t upto = s.mix_start + out_ready(s);   // the stream can cover the timeline up to here
         n = std::min(n, upto > T ? upto - T : 0);
     }
     *ended = !any;
@@ -72,12 +70,13 @@ struct Part {
     uint64_t n_int = 0;       // how many of them interpolate (the rest is the raw last frame)
     bool continues = false;   // more outputs will follow in later blocks
 };
-inline Part part_of(const Stream& s, uint64_t T, uint64_t n, uint32_t from, uint32_t to) {
+inline Part part_of(const Stream& s, uint64_t T, uint64_t n) {
     Part p;
-    const uint64_t ready = out_ready(s, from, to);
+    const uint32_t from = s.from, to = s.to;
+    const uint64_t ready = out_ready(s);
     const uint64_t lo = std::max(T, s.mix_start + s.out_done), hi = std::min(T + n, s.mix_start + ready);
     if (lo >= hi) {
-        p.continues = !finished(s, from, to);
+        p.continues = !finished(s);
         return p;
     }
     p.mix_start = lo - T, p.out_len = hi - lo, p.o0 = lo - s.mix_start;
@@ -87,9 +86,9 @@ inline Part part_of(const Stream& s, uint64_t T, uint64_t n, uint32_t from, uint
     return p;
 }
 // After the block: advance the stream and tell how many FIFO frames (from the front) are dead.
-inline uint64_t advance(Stream& s, const Part& p, uint32_t from, uint32_t to) {
+inline uint64_t advance(Stream& s, const Part& p) {
     s.out_done = p.out_len ? p.o0 + p.out_len : s.out_done;
-    const uint64_t left = std::min((s.out_done * (uint64_t)from) / to, s.pushed);   // left frame of the next output
+    const uint64_t left = std::min((s.out_done * (uint64_t)s.from) / s.to, s.pushed);   // left frame of the next output
     const uint64_t keep_from = left & ~3ull;                                        // FIFO front stays 16-byte aligned
     const uint64_t drop = keep_from > s.i0 ? keep_from - s.i0 : 0;
     s.i0 += drop;

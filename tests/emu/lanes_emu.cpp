@@ -12,29 +12,31 @@
 #include "../../rodio_b200/csrc/rb_lanes_plan.h"
 
 namespace {
-template <int C, bool HASB, bool FF2, int NPOST>
+template <int C, bool HASB, bool FF2, int NPOST, bool PASS>
 void run_warp_c(const lanes::Args& a, uint32_t group, simt::WarpEmu* w, float* ring) {
     std::vector<std::thread> th;
     for (uint32_t l = 0; l < 32; l++)
         th.emplace_back([&, l] {
             simt::g_lane = simt::LaneEmu{};
             simt::g_lane.w = w, simt::g_lane.lane = l;
-            lanes::warp_main<C, HASB, FF2, NPOST>(a, group, ring);
+            lanes::warp_main<C, HASB, FF2, NPOST, PASS>(a, group, ring);
         });
     for (auto& t : th) t.join();
 }
-template <int C>
+template <int C, bool PASS>
 void run_group(const lanes::Args& a, uint32_t g, simt::WarpEmu* w, float* ring, bool hasb, bool ff2, bool npost) {
-    if (hasb && ff2 && npost) run_warp_c<C, true, true, 1>(a, g, w, ring);
-    else if (hasb && ff2) run_warp_c<C, true, true, 0>(a, g, w, ring);
-    else if (hasb && npost) run_warp_c<C, true, false, 1>(a, g, w, ring);
-    else if (hasb) run_warp_c<C, true, false, 0>(a, g, w, ring);
-    else if (npost) run_warp_c<C, false, false, 1>(a, g, w, ring);
-    else run_warp_c<C, false, false, 0>(a, g, w, ring);
+    if (hasb && ff2 && npost) run_warp_c<C, true, true, 1, PASS>(a, g, w, ring);
+    else if (hasb && ff2) run_warp_c<C, true, true, 0, PASS>(a, g, w, ring);
+    else if (hasb && npost) run_warp_c<C, true, false, 1, PASS>(a, g, w, ring);
+    else if (hasb) run_warp_c<C, true, false, 0, PASS>(a, g, w, ring);
+    else if (npost) run_warp_c<C, false, false, 1, PASS>(a, g, w, ring);
+    else run_warp_c<C, false, false, 0, PASS>(a, g, w, ring);
 }
+// the ratio of the class decides PASS (from == to) -- like the device launcher
 void run_group_any(uint32_t channels, const lanes::Args& a, uint32_t g, simt::WarpEmu* w, float* ring, bool hasb, bool ff2, bool npost) {
-    if (channels == 2) run_group<2>(a, g, w, ring, hasb, ff2, npost);
-    else run_group<1>(a, g, w, ring, hasb, ff2, npost);
+    const bool pass = a.from == a.to;
+    if (channels == 2) pass ? run_group<2, true>(a, g, w, ring, hasb, ff2, npost) : run_group<2, false>(a, g, w, ring, hasb, ff2, npost);
+    else pass ? run_group<1, true>(a, g, w, ring, hasb, ff2, npost) : run_group<1, false>(a, g, w, ring, hasb, ff2, npost);
 }
 constexpr int MAX_RS = lanes::Geo<2>::RS;
 }  // namespace
@@ -48,17 +50,19 @@ extern "C" void rb_lanes_emu_counters(uint64_t* out, int reset) {
 
 extern "C" int rb_lanes_emulate(const float* const* pcm, const uint64_t* n_frames, const uint64_t* out_len,
                                 const uint64_t* mix_start, const float* coefs /* [n][5] b0 b1 b2 a1 a2 */,
-                                const float* post, uint32_t n_rows, uint32_t channels, uint32_t from, uint32_t to, uint64_t mix_len, int hasb,
-                                int want_ff2, int npost, float* out_mix, float* out_partials /* may be NULL */,
+                                const float* post, uint32_t n_rows, uint32_t channels, const uint32_t* from, const uint32_t* to,
+                                uint64_t mix_len, int hasb, int want_ff2, int npost, float* out_mix, float* out_partials /* may be NULL */,
                                 int* used_ff2, uint32_t* n_unsafe) {
     using namespace lanes;
-    if (!(from < to) || to > (1u << 20) || n_rows == 0 || (channels != 1 && channels != 2)) return 1;
+    if (n_rows == 0 || (channels != 1 && channels != 2)) return 1;
+    for (uint32_t r = 0; r < n_rows; r++)
+        if (!(from[r] <= to[r]) || to[r] > (1u << 20)) return 1;
     const uint32_t C = channels;   // n_frames / out_len / mix_start / mix_len count FRAMES; pcm and out_mix hold frames * C floats
     const float nan = std::numeric_limits<float>::quiet_NaN();
     simt::WarpEmu warp;
     // inputs: 16-byte aligned copies with a 16-byte tail pad of NaN (reading the pad as data would show)
     std::vector<std::vector<float>> store(n_rows);
-    std::vector<Row> rows(n_rows);
+    std::vector<Row> all(n_rows);
     bool ff2 = want_ff2 && hasb;
     *n_unsafe = 0;
     for (uint32_t r = 0; r < n_rows; r++) {
@@ -67,10 +71,10 @@ extern "C" int rb_lanes_emulate(const float* const* pcm, const uint64_t* n_frame
         while ((uintptr_t)base & 15) base++;
         if (n_frames[r]) std::memcpy(base, pcm[r], n_frames[r] * C * 4);
         warp.readable.push_back({(const char*)base, (const char*)(base + n_frames[r] * C + 4)});
-        Row& row = rows[r];
+        Row& row = all[r];
         std::memset(&row, 0, sizeof(row));
         row.in = base, row.L = n_frames[r], row.out_len = out_len[r], row.mix_start = mix_start[r];
-        row.n_int = n_interp(row.L, from, to, row.out_len);
+        row.n_int = n_interp(row.L, from[r], to[r], row.out_len);
         if (hasb) {
             const float* c = coefs + 5 * r;
             row.b0 = c[0], row.b1 = c[1], row.b2 = c[2], row.a1 = c[3], row.a2 = c[4];
@@ -86,22 +90,37 @@ extern "C" int rb_lanes_emulate(const float* const* pcm, const uint64_t* n_frame
     *used_ff2 = ff2;
     alignas(16) static float zeros[CHUNK * 2] = {0};
     warp.readable.push_back({(const char*)zeros, (const char*)(zeros + CHUNK * C)});
-    Args a{};
-    a.rows = rows.data(), a.n_rows = n_rows, a.n_groups = (n_rows + 31) / 32;
-    fill_ratio(a, from, to, C);
-    a.mix_len = mix_len, a.pstride = round_up_tile(mix_len * C);
-    std::vector<float> partial((size_t)a.n_groups * a.pstride, 0.0f);
-    a.partial = partial.data(), a.zeros = zeros;
+    // one launch per rate pair over its own rows and partial rows
+    const auto classes = classes_by_ratio(from, to, n_rows);
+    std::vector<Row> rows;
+    std::vector<Args> launches;
+    uint32_t n_groups_total = 0;
+    const uint64_t pstride = round_up_tile(mix_len * C);
+    for (const auto& cls : classes) {
+        Args a{};
+        a.n_rows = (uint32_t)cls.size(), a.n_groups = (a.n_rows + 31) / 32;
+        fill_ratio(a, from[cls[0]], to[cls[0]], C);
+        a.mix_len = mix_len, a.pstride = pstride;
+        a.rows = (const Row*)(uintptr_t)rows.size();        // offsets until the vectors stop growing
+        a.partial = (float*)(uintptr_t)n_groups_total;
+        for (uint32_t i : cls) rows.push_back(all[i]);
+        n_groups_total += a.n_groups;
+        launches.push_back(a);
+    }
+    std::vector<float> partial((size_t)n_groups_total * pstride, 0.0f);
     std::vector<float> ring_store(32 * MAX_RS + 4, nan);
     float* ring = ring_store.data();
     while ((uintptr_t)ring & 15) ring++;
-    for (uint32_t g = 0; g < a.n_groups; g++) {
-        for (int i = 0; i < 32 * MAX_RS; i++) ring[i] = nan;
-        run_group_any(channels, a, g, &warp, ring, hasb, ff2, npost);
+    for (Args& a : launches) {
+        a.rows = rows.data() + (uintptr_t)a.rows, a.partial = partial.data() + (uintptr_t)a.partial * pstride, a.zeros = zeros;
+        for (uint32_t g = 0; g < a.n_groups; g++) {
+            for (int i = 0; i < 32 * MAX_RS; i++) ring[i] = nan;
+            run_group_any(channels, a, g, &warp, ring, hasb, ff2, npost);
+        }
     }
     for (uint64_t m = 0; m < mix_len * C; m++) {
         float acc = 0.0f;
-        for (uint32_t g = 0; g < a.n_groups; g++) acc = acc + partial[(size_t)g * a.pstride + m];
+        for (uint32_t g = 0; g < n_groups_total; g++) acc = acc + partial[(size_t)g * pstride + m];
         out_mix[m] = acc;
     }
     if (out_partials) std::memcpy(out_partials, partial.data(), partial.size() * 4);
@@ -118,11 +137,15 @@ extern "C" int rb_lanes_emulate(const float* const* pcm, const uint64_t* n_frame
 #include "../../rodio_b200/csrc/rb_session_plan.h"
 
 extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t* n_frames, const uint64_t* mix_start,
-                                        const float* coefs, const float* post, uint32_t n_rows, uint32_t channels, uint32_t from,
-                                        uint32_t to, int hasb, int npost, const uint64_t* ops, uint64_t n_ops, float* out,
-                                        uint64_t out_cap, uint64_t* n_renders, uint64_t* pushed_total /* [n_rows] */) {
+                                        const float* coefs, const float* post, uint32_t n_rows, uint32_t channels,
+                                        const uint32_t* from, const uint32_t* to, int hasb, int npost, const uint64_t* ops,
+                                        uint64_t n_ops, float* out, uint64_t out_cap, uint64_t* n_renders,
+                                        uint64_t* pushed_total /* [n_rows] */) {
     using namespace lanes;
-    if (!(from < to) || to > (1u << 20) || n_rows == 0 || (channels != 1 && channels != 2)) return -1;
+    if (n_rows == 0 || (channels != 1 && channels != 2)) return -1;
+    for (uint32_t r = 0; r < n_rows; r++)
+        if (!(from[r] <= to[r]) || to[r] > (1u << 20)) return -1;
+    const auto classes = classes_by_ratio(from, to, n_rows);   // fixed for the session: rows are laid out class by class
     const uint32_t C = channels;   // frames everywhere; pcm / FIFOs / out hold frames * C floats
     const float nan = std::numeric_limits<float>::quiet_NaN();
     simt::WarpEmu warp;
@@ -142,7 +165,7 @@ extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t*
         fifo[r] = fifo_store[r].data();
         while ((uintptr_t)fifo[r] & 15) fifo[r]++;
         warp.readable.push_back({(const char*)fifo[r], (const char*)(fifo[r] + n_frames[r] * C + 8)});
-        st[r].mix_start = mix_start[r];
+        st[r].mix_start = mix_start[r], st[r].from = from[r], st[r].to = to[r];
         if (hasb) {
             const float* c = coefs + 5 * r;
             if (!ff2_coeffs(c[0], c[1], c[2], &ffk[r])) ff2 = false;
@@ -169,15 +192,15 @@ extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t*
     };
     auto render = [&](uint64_t max_frames) -> bool {   // false: session ended
         bool ended = false;
-        const uint64_t n = session::renderable(st, T, from, to, max_frames, &ended);
+        const uint64_t n = session::renderable(st, T, max_frames, &ended);
         if (ended) return false;
         if (n == 0) return true;
         if ((written + n) * C > out_cap) std::abort();
-        std::vector<Row> rows(n_rows);
+        std::vector<Row> all(n_rows);
         std::vector<session::Part> parts(n_rows);
         for (uint32_t r = 0; r < n_rows; r++) {
-            parts[r] = session::part_of(st[r], T, n, from, to);
-            Row& row = rows[r];
+            parts[r] = session::part_of(st[r], T, n);
+            Row& row = all[r];
             std::memset(&row, 0, sizeof(row));
             row.in = fifo[r], row.L = st[r].fill(), row.out_len = parts[r].out_len, row.mix_start = parts[r].mix_start;
             row.n_int = parts[r].n_int, row.o0 = parts[r].o0, row.i0 = st[r].i0, row.state = state + 4 * C * r;
@@ -188,25 +211,36 @@ extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t*
             row.post = gain[r];
             row.flags = (unsafe[r] ? ROW_UNSAFE : 0u) | (parts[r].continues ? ROW_CONTINUES : 0u);
         }
-        Args a{};
-        a.rows = rows.data(), a.n_rows = n_rows, a.n_groups = (n_rows + 31) / 32;
-        fill_ratio(a, from, to, C);
-        a.mix_len = n, a.pstride = round_up_tile(n * C);
-        std::vector<float> partial((size_t)a.n_groups * a.pstride, 0.0f);
-        a.partial = partial.data(), a.zeros = zeros;
-        for (uint32_t g = 0; g < a.n_groups; g++) {
-            for (int i = 0; i < 32 * MAX_RS; i++) ring[i] = nan;
-            run_group_any(channels, a, g, &warp, ring, hasb, ff2, npost);
+        const uint64_t pstride = round_up_tile(n * C);
+        uint32_t n_groups_total = 0;
+        for (const auto& cls : classes) n_groups_total += ((uint32_t)cls.size() + 31) / 32;
+        std::vector<float> partial((size_t)n_groups_total * pstride, 0.0f);
+        std::vector<Row> rows;
+        rows.reserve(n_rows);
+        uint32_t g0 = 0;
+        for (const auto& cls : classes) {           // one launch per rate pair
+            Args a{};
+            a.n_rows = (uint32_t)cls.size(), a.n_groups = (a.n_rows + 31) / 32;
+            fill_ratio(a, from[cls[0]], to[cls[0]], C);
+            a.mix_len = n, a.pstride = pstride;
+            const size_t first = rows.size();
+            for (uint32_t i : cls) rows.push_back(all[i]);
+            a.rows = rows.data() + first, a.partial = partial.data() + (size_t)g0 * pstride, a.zeros = zeros;
+            for (uint32_t g = 0; g < a.n_groups; g++) {
+                for (int i = 0; i < 32 * MAX_RS; i++) ring[i] = nan;
+                run_group_any(channels, a, g, &warp, ring, hasb, ff2, npost);
+            }
+            g0 += a.n_groups;
         }
         for (uint64_t m = 0; m < n * C; m++) {
             float acc = 0.0f;
-            for (uint32_t g = 0; g < a.n_groups; g++) acc = acc + partial[(size_t)g * a.pstride + m];
+            for (uint32_t g = 0; g < n_groups_total; g++) acc = acc + partial[(size_t)g * pstride + m];
             out[written * C + m] = acc;
         }
         written += n, T += n, (*n_renders)++;
         for (uint32_t r = 0; r < n_rows; r++) {
             const uint64_t fill_before = st[r].fill();
-            const uint64_t drop = session::advance(st[r], parts[r], from, to);
+            const uint64_t drop = session::advance(st[r], parts[r]);
             if (drop) {
                 std::memmove(fifo[r], fifo[r] + drop * C, (fill_before - drop) * C * sizeof(float));
                 for (uint64_t k = (fill_before - drop) * C; k < fill_before * C; k++) fifo[r][k] = nan;
@@ -229,7 +263,7 @@ extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t*
     for (uint32_t r = 0; r < n_rows; r++) pushed_total[r] = st[r].pushed;
     while (render(1ull << 20)) {
         bool ended = false;
-        if (session::renderable(st, T, from, to, 1, &ended) == 0 && !ended) std::abort();   // no progress
+        if (session::renderable(st, T, 1, &ended) == 0 && !ended) std::abort();   // no progress
     }
     return (long long)written;
 }
@@ -242,14 +276,16 @@ extern "C" int rb_session_plan_fuzz(uint64_t seed, uint32_t n_cases) {
     auto rnd = [&](uint64_t n) { x ^= x << 13, x ^= x >> 7, x ^= x << 17; return n ? x % n : 0; };
 #define CHECK(c) do { if (!(c)) return __LINE__; } while (0)
     for (uint32_t cs = 0; cs < n_cases; cs++) {
-        uint32_t to = 2 + (uint32_t)rnd(400), from = 1 + (uint32_t)rnd(to - 1);
-        uint32_t g = std::gcd(from, to);
-        from /= g, to /= g;
         const uint32_t ns = 1 + (uint32_t)rnd(5);
         const uint64_t cap = 64 + rnd(3000);
         std::vector<session::Stream> st(ns);
         std::vector<uint64_t> total(ns), rendered(ns, 0);
-        for (uint32_t r = 0; r < ns; r++) st[r].mix_start = rnd(3) ? 0 : rnd(500), total[r] = rnd(6000);
+        for (uint32_t r = 0; r < ns; r++) {
+            uint32_t to = 1 + (uint32_t)rnd(400), from = 1 + (uint32_t)rnd(to);   // from <= to, 1:1 included
+            const uint32_t g = std::gcd(from, to);
+            st[r].from = from / g, st[r].to = to / g;
+            st[r].mix_start = rnd(3) ? 0 : rnd(500), total[r] = rnd(6000);
+        }
         uint64_t T = 0;
         for (int step = 0; step < 4000; step++) {
             const uint32_t r = (uint32_t)rnd(ns);
@@ -261,10 +297,11 @@ extern "C" int rb_session_plan_fuzz(uint64_t seed, uint32_t n_cases) {
             }
             if (rnd(3) == 0) continue;
             bool ended = false;
-            const uint64_t n = session::renderable(st, T, from, to, 1 + rnd(1500), &ended);
+            const uint64_t n = session::renderable(st, T, 1 + rnd(1500), &ended);
             if (ended) break;
             for (uint32_t q = 0; q < ns; q++) {
-                const session::Part p = session::part_of(st[q], T, n, from, to);
+                const uint32_t from = st[q].from, to = st[q].to;
+                const session::Part p = session::part_of(st[q], T, n);
                 CHECK(p.mix_start + p.out_len <= n);
                 if (p.out_len) {
                     CHECK(p.o0 == st[q].out_done);                                   // no output skipped or repeated
@@ -274,34 +311,34 @@ extern "C" int rb_session_plan_fuzz(uint64_t seed, uint32_t n_cases) {
                     CHECK(p.n_int <= p.out_len);
                     if (p.n_int) CHECK(((p.o0 + p.n_int - 1) * (uint64_t)from) / to + 1 < st[q].pushed);   // ... right taps too
                     if (p.n_int < p.out_len) CHECK(st[q].eof && p.out_len - p.n_int == 1);                  // only the raw last frame
-                    if (!session::finished(st[q], from, to) && st[q].mix_start + st[q].out_done <= T) CHECK(p.mix_start == 0);
+                    if (!session::finished(st[q]) && st[q].mix_start + st[q].out_done <= T) CHECK(p.mix_start == 0);
                 } else {
-                    CHECK(session::finished(st[q], from, to) || st[q].mix_start >= T + n || n == 0);
+                    CHECK(session::finished(st[q]) || st[q].mix_start >= T + n || n == 0);
                 }
                 const uint64_t fill = st[q].fill();
-                const uint64_t drop = session::advance(st[q], p, from, to);
+                const uint64_t drop = session::advance(st[q], p);
                 rendered[q] += p.out_len;
                 CHECK(drop <= fill && (st[q].i0 & 3) == 0);
                 CHECK(st[q].eof || (st[q].out_done * (uint64_t)from) / to >= st[q].i0);
                 // what stays in the FIFO is bounded: an unfinished stream keeps at most the frames not yet usable + 4
-                CHECK(p.continues == !session::finished(st[q], from, to) || p.out_len == 0);
+                CHECK(p.continues == !session::finished(st[q]) || p.out_len == 0);
             }
             T += n;
         }
         for (uint32_t r = 0; r < ns; r++) st[r].eof = true;
         for (int guard = 0; guard < 100000; guard++) {
             bool ended = false;
-            const uint64_t n = session::renderable(st, T, from, to, 1 + rnd(5000), &ended);
+            const uint64_t n = session::renderable(st, T, 1 + rnd(5000), &ended);
             if (ended) break;
             CHECK(n > 0);
             for (uint32_t q = 0; q < ns; q++) {
-                const session::Part p = session::part_of(st[q], T, n, from, to);
+                const session::Part p = session::part_of(st[q], T, n);
                 rendered[q] += p.out_len;
-                session::advance(st[q], p, from, to);
+                session::advance(st[q], p);
             }
             T += n;
         }
-        for (uint32_t r = 0; r < ns; r++) CHECK(rendered[r] == session::out_total(st[r].pushed, from, to));
+        for (uint32_t r = 0; r < ns; r++) CHECK(rendered[r] == session::out_total(st[r].pushed, st[r].from, st[r].to));
     }
 #undef CHECK
     return 0;

@@ -38,6 +38,33 @@ def counters(emu, reset=True):
     return {"fast": out[0], "slow": out[1], "refills": out[2]}
 
 
+def _u32(v, n):
+    v = list(v) if isinstance(v, (list, tuple, np.ndarray)) else [v] * n
+    return (C.c_uint32 * n)(*[int(x) for x in v]), v
+
+
+def expected_mix_classes(per_stream, starts, mix_len, froms, tos):
+    """Streams with several rate pairs are served class by class (rb_lanes_plan.h classes_by_ratio): per class, groups of
+    32 in stream order summed with the tree; all groups added in class order from +0.0."""
+    keys, classes = [], []
+    for i, k in enumerate(zip(froms, tos)):
+        if k not in keys:
+            keys.append(k)
+            classes.append([])
+        classes[keys.index(k)].append(i)
+    acc = np.zeros(mix_len, dtype=np.float32)
+    for cls in classes:
+        for g in range(0, len(cls), 32):
+            rows = np.zeros((32, mix_len), dtype=np.float32)
+            for l, i in enumerate(cls[g:g + 32]):
+                rows[l, starts[i]:starts[i] + per_stream[i].size] = per_stream[i]
+            a = rows[:16] + rows[16:]
+            b = a[:8] + a[8:]
+            c = b[:4] + b[4:]
+            acc = acc + (((c[0] + c[1]) + (c[2] + c[3])) + np.float32(0.0))
+    return acc
+
+
 def run_emu(emu, pcms, outs_len, starts, coefs, posts, from_, to, mix_len, hasb, ff2, npost, channels=1):
     """Frames everywhere (outs_len, starts, mix_len); pcms and the result hold frames * channels floats."""
     n = len(pcms)
@@ -50,7 +77,7 @@ def run_emu(emu, pcms, outs_len, starts, coefs, posts, from_, to, mix_len, hasb,
     used, unsafe = C.c_int(0), C.c_uint32(0)
     rc = emu.rb_lanes_emulate(ptrs, u64([p.size // channels for p in pcms]), u64(outs_len), u64(starts),
                               co.ctypes.data_as(C.POINTER(C.c_float)), po.ctypes.data_as(C.POINTER(C.c_float)),
-                              C.c_uint32(n), C.c_uint32(channels), C.c_uint32(from_), C.c_uint32(to), C.c_uint64(mix_len), int(hasb), int(ff2),
+                              C.c_uint32(n), C.c_uint32(channels), _u32(from_, n)[0], _u32(to, n)[0], C.c_uint64(mix_len), int(hasb), int(ff2),
                               int(npost), out.ctypes.data_as(C.POINTER(C.c_float)), None, C.byref(used), C.byref(unsafe))
     assert rc == 0
     return out, bool(used.value), unsafe.value
@@ -60,8 +87,9 @@ def make_case(pcms, in_rate, mix_rate, starts, lp=None, hp=None, q=0.5, gain=Non
     """Sources as a rodio user writes them + everything the emulator needs, the expectation from the oracle.
     `starts` and the lengths in the result are frames."""
     srcs, per_stream = [], []
-    for p in pcms:
-        s = rb.UniformSourceIterator(rb.TestSource(p, channels, in_rate), channels, mix_rate)
+    in_rates = list(in_rate) if isinstance(in_rate, (list, tuple)) else [in_rate] * len(pcms)
+    for p, rate in zip(pcms, in_rates):
+        s = rb.UniformSourceIterator(rb.TestSource(p, channels, rate), channels, mix_rate)
         if lp is not None:
             s = s.low_pass_with_q(lp, q)
         if hp is not None:
@@ -70,13 +98,14 @@ def make_case(pcms, in_rate, mix_rate, starts, lp=None, hp=None, q=0.5, gain=Non
             s = s.amplify(gain)
         srcs.append(s)
         per_stream.append(oracle.chain_uniform(to_oracle(s), channels, mix_rate))
-    g = math.gcd(in_rate, mix_rate)
+    froms = [r // math.gcd(r, mix_rate) for r in in_rates]
+    tos = [mix_rate // math.gcd(r, mix_rate) for r in in_rates]
     hasb = lp is not None or hp is not None
     co = oracle.blt_coeffs(hp is not None, lp if lp is not None else (hp or 1), q, mix_rate) if hasb else np.zeros(5, np.float32)
     coefs = np.tile(co, (len(pcms), 1))
     mix_len = max([s + y.size // channels for s, y in zip(starts, per_stream)] + [0])
     return dict(per_stream=per_stream, outs_len=[y.size // channels for y in per_stream], coefs=coefs, channels=channels,
-                posts=np.full(len(pcms), gain if gain is not None else 1.0, np.float32), from_=in_rate // g, to=mix_rate // g,
+                posts=np.full(len(pcms), gain if gain is not None else 1.0, np.float32), from_=froms, to=tos,
                 mix_len=mix_len, hasb=hasb, npost=gain is not None, srcs=srcs)
 
 
@@ -87,7 +116,7 @@ def check(emu, pcms, in_rate, mix_rate, starts, ff2=True, expect_ff2=None, **kw)
                                     c["hasb"], ff2, c["npost"], channels=ch)
     if expect_ff2 is not None:
         assert used_ff2 == expect_ff2
-    want = expected_mix(c["per_stream"], [st * ch for st in starts], c["mix_len"] * ch)
+    want = expected_mix_classes(c["per_stream"], [st * ch for st in starts], c["mix_len"] * ch, c["from_"], c["to"])
     assert_bit_exact(got, want, "emulated kernel vs oracle streams summed with the kernel's tree")
     # and the north-star tolerance against the reference's sequential mixer
     ref = oracle.mixer([to_oracle(s, mix_start=st * ch) for s, st in zip(c["srcs"], starts)], ch, mix_rate)
@@ -179,7 +208,7 @@ def run_session(emu, pcms, starts, coefs, posts, from_, to, hasb, npost, ops, ou
     pushed = (C.c_uint64 * n)()
     emu.rb_session_emulate.restype = C.c_longlong
     w = emu.rb_session_emulate(ptrs, u64([p.size // channels for p in pcms]), u64(starts), co.ctypes.data_as(C.POINTER(C.c_float)),
-                               po.ctypes.data_as(C.POINTER(C.c_float)), C.c_uint32(n), C.c_uint32(channels), C.c_uint32(from_), C.c_uint32(to),
+                               po.ctypes.data_as(C.POINTER(C.c_float)), C.c_uint32(n), C.c_uint32(channels), _u32(from_, n)[0], _u32(to, n)[0],
                                int(hasb), int(npost), u64(flat), C.c_uint64(len(ops)), out.ctypes.data_as(C.POINTER(C.c_float)),
                                C.c_uint64(out_cap), C.byref(renders), pushed)
     assert w >= 0
@@ -193,7 +222,7 @@ def session_case(emu, pcms, starts, ops, in_rate=44100, mix_rate=48000, lp=None,
     got, renders, pushed = run_session(emu, pcms, starts, c["coefs"], c["posts"], c["from_"], c["to"], c["hasb"], c["npost"], ops,
                                        (c["mix_len"] + 64) * channels, channels=channels)
     assert pushed == [p.size // channels for p in pcms]
-    want = expected_mix(c["per_stream"], [st * channels for st in starts], c["mix_len"] * channels)
+    want = expected_mix_classes(c["per_stream"], [st * channels for st in starts], c["mix_len"] * channels, c["from_"], c["to"])
     assert_bit_exact(got, want, "session blocks vs whole-stream render")
     return renders
 
@@ -313,3 +342,48 @@ def test_session_gain_changes_between_blocks(emu):
             y[k * block:(k + 1) * block] = y[k * block:(k + 1) * block] * gains[k][r]     # one f32 rounding, like Amplify::next
         scaled.append(y)
     assert_bit_exact(got, expected_mix(scaled, [0] * 3, c["mix_len"]), "per-block gains")
+
+
+# ------------------------------------------------------------------------------------------------- same-rate sources
+def test_same_rate_sources_pass_through(emu):
+    """Sources already at the mixer's rate (SampleRateConverter hands them through, sample_rate.rs:131-136): raw taps,
+    every bit kept -- denormals, huge values and signed zeros included, no input class needed."""
+    pcms = [noise(900 + 13 * i, 30 + i) for i in range(35)]
+    pcms[2][10:20] = np.float32(1e-41)
+    pcms[5][7] = np.float32(1e30)
+    pcms[6][:50] = -0.0
+    counters(emu)
+    unsafe = check(emu, pcms, 48000, 48000, [i % 3 for i in range(35)], lp=250, gain=1.2)
+    c = counters(emu)
+    assert c["fast"] > 150, c            # the streams outside the class still take the fast path: nothing is divided
+    check(emu, pcms[:9], 44100, 44100, [0] * 9, gain=0.5)
+    stereo = [noise(2 * (400 + i), 70 + i) for i in range(8)]
+    check(emu, stereo, 48000, 48000, [0] * 8, hp=300, channels=2)
+
+
+def test_same_rate_session(emu):
+    pcms = [noise(1200 + 31 * i, 130 + i) for i in range(6)]
+    ops = []
+    for step in range(40):
+        ops += [(0, r, 100 + 7 * r) for r in range(6)] + [(1, 0, 97)]
+    session_case(emu, pcms, [0, 0, 5, 0, 300, 0], ops, in_rate=48000, mix_rate=48000, lp=400, gain=0.9)
+
+
+# ------------------------------------------------------------------------------------------------- several rate pairs
+def test_mixed_rates_in_one_mixer(emu):
+    """44.1 kHz, 48 kHz (pass-through), 22.05 kHz and 32 kHz sources in one 48 kHz mixer: one launch per rate pair over its
+    own rows, all partial rows added in order."""
+    rates = [44100, 48000, 22050, 44100, 32000, 48000, 44100] * 6
+    pcms = [noise(700 + 17 * i, 500 + i) for i in range(len(rates))]
+    starts = [(5 * i) % 97 for i in range(len(rates))]
+    check(emu, pcms, rates, 48000, starts, lp=600, gain=1.1)
+    check(emu, pcms[:10], rates[:10], 48000, [0] * 10)
+
+
+def test_mixed_rates_session(emu):
+    rates = [44100, 48000, 22050, 48000, 44100]
+    pcms = [noise(int(1.0 * r / 40) + 11 * i, 900 + i) for i, r in enumerate(rates)]      # about 25 ms each
+    ops = []
+    for step in range(60):
+        ops += [(0, r, int(rates[r] / 1000) + r) for r in range(5)] + [(1, 0, 45 + step % 7)]
+    session_case(emu, pcms, [0, 0, 0, 100, 3], ops, in_rate=rates, mix_rate=48000, lp=700, gain=0.8)

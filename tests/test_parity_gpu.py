@@ -649,18 +649,30 @@ def test_lanes_unsafe_inputs_stay_exact(ctx):
 
 
 @lanes_gate
-def test_lanes_falls_back_when_the_shape_differs(ctx):
-    """Two rate pairs in one batch, or a down-sampling pair: the flag is ignored, the default fused kernels serve."""
-    a = rb.UniformSourceIterator(rb.TestSource(noise(2000, 1), 1, 44100), 1, 48000).low_pass(200)
-    b_ = rb.UniformSourceIterator(rb.TestSource(noise(2000, 2), 1, 32000), 1, 48000).low_pass(200)
-    with rb.Batch([a, b_], 1, 48000, flags=LANES, ctx=ctx) as b:
-        assert b.kernel_family != 2
+def test_lanes_mixed_rate_pairs_and_fallback(ctx):
+    """Several rate pairs in one mixer (44.1 kHz, 48 kHz pass-through, 32 kHz) are served class by class; a down-sampling
+    source is outside the kernel's shape: the flag is ignored there and the default fused kernels serve the batch."""
+    rates = [44100, 48000, 32000, 44100, 48000, 22050] * 8
+    pcms = [noise(1500 + 13 * i, 40 + i) for i in range(len(rates))]
+    srcs = [rb.UniformSourceIterator(rb.TestSource(p, 1, r), 1, 48000).low_pass(500).amplify(0.9) for p, r in zip(pcms, rates)]
+    with rb.Batch(srcs, 1, 48000, flags=LANES, ctx=ctx) as b:
+        assert b.kernel_family == 2
         b.upload_all()
         got = b.render_mix()
-    assert_close_peak(got, oracle.mixer([to_oracle(a), to_oracle(b_)], 1, 48000), 1e-5, "fallback")
+    ref = oracle.mixer([to_oracle(s) for s in srcs], 1, 48000)
+    assert_close_peak(got, ref, 1e-5, "mixed rate pairs vs the reference's mixer")
+    # bit-exact against the oracle streams summed class by class with the kernel's tree
+    per_stream = [oracle.chain_uniform(to_oracle(s), 1, 48000) for s in srcs]
+    acc = np.zeros(ref.size, np.float32)
+    for rate in dict.fromkeys(rates):                       # classes in order of first appearance
+        idx = [i for i, r in enumerate(rates) if r == rate]
+        acc = acc + (lanes_expected_mix([per_stream[i] for i in idx], [0] * len(idx), ref.size) - np.float32(0.0))
+    assert_bit_exact(got, acc, "mixed rate pairs vs oracle streams + class-wise tree")
     d = rb.UniformSourceIterator(rb.TestSource(noise(2000, 3), 1, 48000), 1, 44100).low_pass(200)
     with rb.Batch([d], 1, 44100, flags=LANES, ctx=ctx) as b:
         assert b.kernel_family != 2
+        b.upload_all()
+        assert_close_peak(b.render_mix(), oracle.mixer([to_oracle(d)], 1, 44100), 1e-5, "fallback")
 
 
 @lanes_gate
