@@ -205,8 +205,8 @@ impl Source for GpuMixerSource {
 pub enum rb_session {}
 
 extern "C" {
-    fn rb_session_create(ctx: *mut rb_context, mixer_rate: u32, descs: *const rb_stream_desc, n: usize, fifo_frames: u32,
-                         max_block_frames: u32, out: *mut *mut rb_session) -> i32;
+    fn rb_session_create(ctx: *mut rb_context, mixer_channels: u16, mixer_rate: u32, descs: *const rb_stream_desc, n: usize,
+                         fifo_frames: u32, max_block_frames: u32, out: *mut *mut rb_session) -> i32;
     fn rb_session_destroy(s: *mut rb_session) -> i32;
     fn rb_session_push_packed(s: *mut rb_session, pcm: *const f32, n_frames: *const u64, end_of_stream: *const u8) -> i32;
     fn rb_session_render(s: *mut rb_session, out: *mut f32, max_frames: u64, written: *mut u64, ended: *mut i32) -> i32;

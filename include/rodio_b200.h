@@ -220,16 +220,17 @@ rb_status rb_batch_read_stream(rb_batch* b, size_t stream, float* out_host, uint
  * PCM is pushed per source as it arrives, the mixer output is pulled in blocks; the resampler position, the input
  * frames still needed and the filter state carry over from block to block, so ANY split into pushes and renders gives
  * the bytes of a whole-stream rb_batch render with RB_FUSED_LANES (tests/test_lanes_emulator.py::test_session_*).
- * Shape served (RB_ERR_UNSUPPORTED otherwise): mono or stereo f32 sources (all the same; the mixer has that channel
- * count), each at a sample rate at or below the mixer's (44.1 kHz, 22.05 kHz and 48 kHz sources in one 48 kHz mixer
- * are fine: one kernel launch per rate pair), effects = UNIFORM(channels, mixer rate) [LOW_PASS | HIGH_PASS] [AMPLIFY]
- * -- the chain of BASELINE cfg3; desc.n_samples / span_len are ignored,
+ * Shape served (RB_ERR_UNSUPPORTED otherwise): a mono or stereo mixer = mixer(channels, rate) of src/mixer.rs:25-43; f32
+ * sources with the mixer's channel count or mono sources in a stereo mixer (repeated on both channels like
+ * ChannelCountConverter, src/conversions/channels.rs:57-85), each at a sample rate at or below the mixer's (44.1 kHz, 22.05 kHz and 48 kHz sources in one 48 kHz mixer
+ * are fine: one kernel launch per rate pair), effects = UNIFORM(mixer channels, mixer rate) [LOW_PASS | HIGH_PASS]
+ * [AMPLIFY] -- the chain of BASELINE cfg3; desc.n_samples / span_len are ignored,
  * desc.mix_start is the mixer FRAME the source joins at.  Everything below counts frames; PCM is interleaved.
  * One caller per session; every call returns with the work done (the caller may reuse its buffers). */
 typedef struct rb_session rb_session;
 /* fifo_frames: input frames a source can hold between renders (>= 64); max_block_frames: largest render. */
-rb_status rb_session_create(rb_context* ctx, uint32_t mixer_sample_rate, const rb_stream_desc* descs, size_t n_streams,
-                            uint32_t fifo_frames, uint32_t max_block_frames, rb_session** out);
+rb_status rb_session_create(rb_context* ctx, uint16_t mixer_channels, uint32_t mixer_sample_rate, const rb_stream_desc* descs,
+                            size_t n_streams, uint32_t fifo_frames, uint32_t max_block_frames, rb_session** out);
 rb_status rb_session_destroy(rb_session* s);
 /* n_frames more frames of source `stream` have arrived; end_of_stream != 0: the source's Iterator::next would return
  * None after them.  RB_ERR_BUFFER_TOO_SMALL when its FIFO cannot take them (render first). */

@@ -273,11 +273,14 @@ inline std::pair<Mixer, MixerSource> mixer(uint16_t channels, uint32_t sample_ra
 // (src/mixer.rs:120-136); std::nullopt while nothing can be rendered yet, `ended()` once every source is exhausted.
 class LiveMixer {
   public:
-    LiveMixer(const std::vector<Source>& chains, uint32_t sample_rate, uint32_t fifo_frames = 8192, uint32_t block_frames = 1024)
-        : channels_(chains.empty() ? 1 : chains[0].channels()), rate_(sample_rate), block_frames_(block_frames) {
+    // mixer::mixer(channels, sample_rate) whose inputs arrive later: chains[i] ends in .uniform(channels, sample_rate)...
+    LiveMixer(const std::vector<Source>& chains, uint16_t channels, uint32_t sample_rate, uint32_t fifo_frames = 8192,
+              uint32_t block_frames = 1024)
+        : channels_(channels), rate_(sample_rate), block_frames_(block_frames) {
         std::vector<rb_stream_desc> descs;
-        for (const Source& c : chains) descs.push_back(c.desc(0));
-        check(rb_session_create(Context::get(), sample_rate, descs.data(), descs.size(), fifo_frames, block_frames, &h_), "rb_session_create");
+        for (const Source& c : chains) descs.push_back(c.desc(0)), src_channels_.push_back(descs.back().channels);
+        check(rb_session_create(Context::get(), channels, sample_rate, descs.data(), descs.size(), fifo_frames, block_frames, &h_),
+              "rb_session_create");
     }
     LiveMixer(const LiveMixer&) = delete;
     LiveMixer& operator=(const LiveMixer&) = delete;
@@ -286,7 +289,7 @@ class LiveMixer {
     uint32_t sample_rate() const { return rate_; }
     // more interleaved samples of source `i`; end_of_stream: its Iterator::next would return None after them
     void push(size_t i, const std::vector<Sample>& pcm, bool end_of_stream = false) {
-        check(rb_session_push(h_, i, pcm.data(), pcm.size() / channels_, end_of_stream ? 1 : 0), "rb_session_push");
+        check(rb_session_push(h_, i, pcm.data(), pcm.size() / src_channels_.at(i), end_of_stream ? 1 : 0), "rb_session_push");
     }
     void set_volume(size_t i, float factor) { check(rb_session_set_amplify(h_, i, factor), "rb_session_set_amplify"); }   // player.rs:138-166
     bool ended() const { return ended_ && at_ == block_.size(); }
@@ -307,6 +310,7 @@ class LiveMixer {
   private:
     rb_session* h_ = nullptr;
     uint16_t channels_;
+    std::vector<uint16_t> src_channels_;   // the sources' own interleaving (a mono source in a stereo mixer pushes mono)
     uint32_t rate_, block_frames_;
     std::vector<Sample> block_;
     size_t at_ = 0;

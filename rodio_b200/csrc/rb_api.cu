@@ -951,12 +951,13 @@ extern "C" rb_status rb_convert_samples(rb_context* ctx, const void* in, rb_samp
 struct rb_session {
     rb_context* ctx = nullptr;
     uint32_t mixer_rate = 0;
-    uint32_t channels = 1;        // of every source and of the mixer (1 or 2)
+    uint32_t channels = 1;        // of the mixer (1 or 2); a source has the same count, or is mono in a stereo mixer
+    std::vector<uint8_t> src_ch;  // per source (class order): its own channel count
     bool has_biquad = false, has_post = false;
     // Sources may have different rates (each at or below the mixer's): one kernel launch per reduced rate pair.  All
     // per-source arrays below are in CLASS ORDER (stable partition by rate pair); pos[] maps the caller's index to it.
     struct Class {
-        uint32_t first = 0, count = 0;
+        uint32_t first = 0, count = 0, ch_in = 1;
         bool ff2 = false;
     };
     std::vector<Class> classes;
@@ -992,43 +993,46 @@ extern "C" rb_status rb_session_destroy(rb_session* s) {
     return RB_OK;
 }
 
-extern "C" rb_status rb_session_create(rb_context* ctx, uint32_t mixer_rate, const rb_stream_desc* descs, size_t n_streams,
-                                       uint32_t fifo_frames, uint32_t max_block_frames, rb_session** out) {
+extern "C" rb_status rb_session_create(rb_context* ctx, uint16_t mixer_channels, uint32_t mixer_rate, const rb_stream_desc* descs,
+                                       size_t n_streams, uint32_t fifo_frames, uint32_t max_block_frames, rb_session** out) {
     if (!ctx || !out || !descs) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
-    if (mixer_rate == 0 || n_streams == 0 || n_streams > 0x7FFFFFFFull) return fail(RB_ERR_INVALID_ARGUMENT, "zero mixer rate or no streams");
+    if (mixer_rate == 0 || mixer_channels == 0 || n_streams == 0 || n_streams > 0x7FFFFFFFull)
+        return fail(RB_ERR_INVALID_ARGUMENT, "zero mixer rate / channels or no streams");
+    if (mixer_channels > 2) return fail(RB_ERR_UNSUPPORTED, "sessions serve mono and stereo mixers");
     if (fifo_frames < 64 || max_block_frames == 0) return fail(RB_ERR_INVALID_ARGUMENT, "fifo_frames < 64 or max_block_frames == 0");
     std::unique_ptr<rb_session, rb_status (*)(rb_session*)> s(new (std::nothrow) rb_session, rb_session_destroy);
     if (!s) return fail(RB_ERR_OUT_OF_MEMORY, "host allocation failed");
-    s->ctx = ctx, s->mixer_rate = mixer_rate, s->fifo_cap = fifo_frames, s->max_block = max_block_frames;
+    s->ctx = ctx, s->mixer_rate = mixer_rate, s->channels = mixer_channels, s->fifo_cap = fifo_frames, s->max_block = max_block_frames;
     const size_t n = n_streams;
     // pass 1: validate, find every source's reduced rate pair -> classes
-    std::vector<uint32_t> from(n), to(n);
+    std::vector<uint32_t> from(n), to(n), chs(n);
     for (size_t i = 0; i < n; i++) {
         const rb_stream_desc& d = descs[i];
         const std::string where = "stream " + std::to_string(i) + ": ";
         if (d.sample_rate == 0 || d.channels == 0) return fail(RB_ERR_INVALID_ARGUMENT, where + "zero sample rate or channels");
-        if ((d.channels != 1 && d.channels != 2) || d.format != RB_FMT_F32) return fail(RB_ERR_UNSUPPORTED, where + "sessions take mono or stereo f32 sources");
-        if (i == 0) s->channels = d.channels;
-        else if (d.channels != s->channels) return fail(RB_ERR_UNSUPPORTED, where + "all sources of a session have the same channel count");
+        if (d.format != RB_FMT_F32) return fail(RB_ERR_UNSUPPORTED, where + "sessions take f32 sources");
+        if (!(d.channels == mixer_channels || (d.channels == 1 && mixer_channels == 2)))
+            return fail(RB_ERR_UNSUPPORTED, where + "a source has the mixer's channel count, or is mono in a stereo mixer");
+        chs[i] = d.channels;
         if (d.n_effects && !d.effects) return fail(RB_ERR_INVALID_ARGUMENT, where + "effects is NULL");
-        if (d.n_effects == 0 || d.effects[0].kind != RB_FX_UNIFORM || d.effects[0].u32[0] != d.channels || d.effects[0].u32[1] != mixer_rate)
-            return fail(RB_ERR_UNSUPPORTED, where + "the chain must start with UNIFORM(source channels, mixer rate)");
+        if (d.n_effects == 0 || d.effects[0].kind != RB_FX_UNIFORM || d.effects[0].u32[0] != mixer_channels || d.effects[0].u32[1] != mixer_rate)
+            return fail(RB_ERR_UNSUPPORTED, where + "the chain must start with UNIFORM(mixer channels, mixer rate)");
         const uint32_t g = std::gcd(d.sample_rate, mixer_rate);
         from[i] = d.sample_rate / g, to[i] = mixer_rate / g;
         if (!(from[i] <= to[i]) || to[i] > (1u << 20))
             return fail(RB_ERR_UNSUPPORTED, where + "the source rate must not exceed the mixer rate (reduced ratio < 2^20)");
     }
-    const auto classes = lanes::classes_by_ratio(from.data(), to.data(), (uint32_t)n);
+    const auto classes = lanes::classes_by_ratio(from.data(), to.data(), chs.data(), (uint32_t)n);
     s->pos.assign(n, 0);
     std::vector<uint32_t> order;   // class order -> caller's index
     for (const auto& cls : classes) {
         rb_session::Class c;
-        c.first = (uint32_t)order.size(), c.count = (uint32_t)cls.size();
+        c.first = (uint32_t)order.size(), c.count = (uint32_t)cls.size(), c.ch_in = chs[cls[0]];
         for (uint32_t i : cls) s->pos[i] = (uint32_t)order.size(), order.push_back(i);
         s->classes.push_back(c);
     }
     // pass 2: chains, in class order
-    s->st.resize(n), s->coef.assign(5 * n, 0.0f), s->ffk.assign(n, 0.0f), s->post.assign(n, 1.0f);
+    s->st.resize(n), s->coef.assign(5 * n, 0.0f), s->ffk.assign(n, 0.0f), s->post.assign(n, 1.0f), s->src_ch.assign(n, 1);
     bool any_biquad = false, all_biquad = true;
     std::vector<uint8_t> row_ff2(n, 1);
     for (size_t r = 0; r < n; r++) {
@@ -1050,6 +1054,7 @@ extern "C" rb_status rb_session_create(rb_context* ctx, uint32_t mixer_rate, con
         if (k < d.n_effects && d.effects[k].kind == RB_FX_AMPLIFY) s->post[r] = d.effects[k].f32[0], s->has_post = true, k++;
         if (k != d.n_effects) return fail(RB_ERR_UNSUPPORTED, where + "chain shape: UNIFORM [LOW_PASS | HIGH_PASS] [AMPLIFY]");
         s->st[r].mix_start = d.mix_start, s->st[r].from = from[i], s->st[r].to = to[i];
+        s->src_ch[r] = (uint8_t)d.channels;
     }
     if (any_biquad && !all_biquad) return fail(RB_ERR_UNSUPPORTED, "either every source of a session has a filter or none has");
     s->has_biquad = any_biquad;
@@ -1098,7 +1103,7 @@ extern "C" rb_status rb_session_push(rb_session* s, size_t stream, const float* 
     RB_CUDA(cudaSetDevice(s->ctx->device));
     if (n_frames) {
         // one stream: straight into the FIFO tail, classified in place (count = n for this stream only)
-        const uint32_t C = s->channels;
+        const uint32_t C = s->src_ch[stream];   // this source's interleaved channels
         float* dst = s->d_fifo[s->cur] + stream * s->stride + st.fill() * C;
         RB_CUDA(cudaMemcpyAsync(dst, pcm, n_frames * C * sizeof(float), cudaMemcpyHostToDevice, s->ctx->stream));
         RB_CUDA(rb_lanes_classify_range(dst, n_frames * C, s->d_flags + stream, s->ctx->stream));
@@ -1122,16 +1127,16 @@ extern "C" rb_status rb_session_push_packed(rb_session* s, const float* pcm, con
     if (total && !pcm) return fail(RB_ERR_INVALID_ARGUMENT, "pcm is NULL");
     RB_CUDA(cudaSetDevice(s->ctx->device));
     if (total) {
-        const uint32_t C = s->channels;   // the kernel counts floats
-        if (!s->d_stage) RB_CUDA(cudaMalloc(&s->d_stage, ns * (size_t)s->fifo_cap * C * sizeof(float)));
-        uint64_t off = 0;
+        if (!s->d_stage) RB_CUDA(cudaMalloc(&s->d_stage, ns * (size_t)s->fifo_cap * s->channels * sizeof(float)));
+        uint64_t off = 0;   // floats: every source counts its own channels
         for (size_t i = 0; i < ns; i++) {
             const size_t r = s->pos[i];
+            const uint32_t C = s->src_ch[r];
             s->h_off[r] = off, s->h_u32[r] = (uint32_t)(n_frames[i] * C), s->h_u32[ns + r] = (uint32_t)(s->st[r].fill() * C);
             off += n_frames[i] * C;
         }
         cudaStream_t stq = s->ctx->stream;
-        RB_CUDA(cudaMemcpyAsync(s->d_stage, pcm, total * C * sizeof(float), cudaMemcpyHostToDevice, stq));
+        RB_CUDA(cudaMemcpyAsync(s->d_stage, pcm, off * sizeof(float), cudaMemcpyHostToDevice, stq));
         RB_CUDA(cudaMemcpyAsync(s->d_off, s->h_off, ns * sizeof(uint64_t), cudaMemcpyHostToDevice, stq));
         RB_CUDA(cudaMemcpyAsync(s->d_u32, s->h_u32, 2 * ns * sizeof(uint32_t), cudaMemcpyHostToDevice, stq));
         RB_CUDA(rb_lanes_fifo_append(s->d_stage, s->d_off, s->d_u32, s->d_u32 + ns, s->d_fifo[s->cur], s->stride, s->d_flags, (uint32_t)ns, stq));
@@ -1197,7 +1202,7 @@ extern "C" rb_status rb_session_render(rb_session* s, float* out_host, uint64_t 
         lanes::fill_ratio(a, s->st[c.first].from, s->st[c.first].to, C);
         a.mix_len = n, a.pstride = pstride;
         a.partial = s->d_partial + (size_t)g0 * pstride, a.zeros = s->d_zeros, a.unsafe = s->d_flags + c.first;
-        RB_CUDA(rb_lanes_launch_kernel(a, C, s->has_biquad, c.ff2, s->has_post, stq));
+        RB_CUDA(rb_lanes_launch_kernel(a, c.ch_in, C, s->has_biquad, c.ff2, s->has_post, stq));
         g0 += a.n_groups;
     }
     RB_CUDA(rb_lanes_launch_sum(s->d_partial, n_groups_total, pstride, n * C, s->d_out, stq));
@@ -1205,7 +1210,7 @@ extern "C" rb_status rb_session_render(rb_session* s, float* out_host, uint64_t 
     for (size_t r = 0; r < ns; r++) {
         const uint64_t fill_before = s->st[r].fill();
         const uint64_t drop = session::advance(s->st[r], parts[r]);
-        s->h_u32[r] = (uint32_t)(drop * C), s->h_u32[ns + r] = (uint32_t)((fill_before - drop) * C);   // floats
+        s->h_u32[r] = (uint32_t)(drop * s->src_ch[r]), s->h_u32[ns + r] = (uint32_t)((fill_before - drop) * s->src_ch[r]);   // floats
     }
     RB_CUDA(cudaMemcpyAsync(s->d_u32, s->h_u32, 2 * ns * sizeof(uint32_t), cudaMemcpyHostToDevice, stq));
     RB_CUDA(rb_lanes_fifo_compact(fifo, s->d_fifo[s->cur ^ 1], s->stride, s->d_u32, s->d_u32 + ns, (uint32_t)ns, stq));
@@ -1243,7 +1248,7 @@ extern "C" rb_status rb_session_get_state(rb_session* s, void* buf, uint64_t cap
     const size_t ns = s->st.size();
     uint64_t need = sizeof(SessionBlobHeader) + ns * sizeof(SessionBlobStream);
     const uint32_t C = s->channels;
-    for (auto& st : s->st) need += st.fill() * C * sizeof(float);
+    for (size_t r = 0; r < ns; r++) need += s->st[r].fill() * s->src_ch[r] * sizeof(float);
     *size = need;
     if (!buf) return RB_OK;
     if (cap < need) return fail(RB_ERR_BUFFER_TOO_SMALL, "state buffer too small");
@@ -1258,7 +1263,7 @@ extern "C" rb_status rb_session_get_state(rb_session* s, void* buf, uint64_t cap
     uint8_t* recs = p;
     p += ns * sizeof(SessionBlobStream);
     for (size_t r = 0; r < ns; r++) {
-        const uint64_t fill = s->st[r].fill() * C;   // floats
+        const uint64_t fill = s->st[r].fill() * s->src_ch[r];   // floats
         if (fill) RB_CUDA(cudaMemcpyAsync(p, s->d_fifo[s->cur] + r * s->stride, fill * sizeof(float), cudaMemcpyDeviceToHost, s->ctx->stream));
         p += fill * sizeof(float);
     }
@@ -1291,7 +1296,7 @@ extern "C" rb_status rb_session_set_state(rb_session* s, const void* buf, uint64
         const SessionBlobStream& b = recs[r];
         if (b.from != s->st[r].from || b.to != s->st[r].to) return fail(RB_ERR_INVALID_ARGUMENT, "state blob belongs to a session of another shape");
         if (b.fill > s->fifo_cap || b.pushed - b.i0 != b.fill || (b.i0 & 3u)) return fail(RB_ERR_INVALID_ARGUMENT, "state blob: FIFO record out of range");
-        need += (uint64_t)b.fill * C * sizeof(float);
+        need += (uint64_t)b.fill * s->src_ch[r] * sizeof(float);
     }
     if (size < need) return fail(RB_ERR_INVALID_ARGUMENT, "state blob truncated");
     RB_CUDA(cudaSetDevice(s->ctx->device));
@@ -1303,8 +1308,9 @@ extern "C" rb_status rb_session_set_state(rb_session* s, const void* buf, uint64
         st.mix_start = b.mix_start, st.pushed = b.pushed, st.out_done = b.out_done, st.i0 = b.i0, st.eof = b.eof != 0;
         flags[r] = b.unsafe;
         for (uint32_t k = 0; k < 4 * C; k++) state[4 * C * r + k] = b.state[k];
-        if (b.fill) RB_CUDA(cudaMemcpyAsync(s->d_fifo[s->cur] + r * s->stride, p, (size_t)b.fill * C * sizeof(float), cudaMemcpyHostToDevice, s->ctx->stream));
-        p += (size_t)b.fill * C * sizeof(float);
+        const size_t fill_floats = (size_t)b.fill * s->src_ch[r];
+        if (b.fill) RB_CUDA(cudaMemcpyAsync(s->d_fifo[s->cur] + r * s->stride, p, fill_floats * sizeof(float), cudaMemcpyHostToDevice, s->ctx->stream));
+        p += fill_floats * sizeof(float);
     }
     RB_CUDA(cudaMemcpyAsync(s->d_state, state.data(), 4 * C * ns * sizeof(float), cudaMemcpyHostToDevice, s->ctx->stream));
     RB_CUDA(cudaMemcpyAsync(s->d_flags, flags.data(), ns * sizeof(uint32_t), cudaMemcpyHostToDevice, s->ctx->stream));

@@ -1301,8 +1301,11 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
             // or is at the mixer's rate already (UniformSourceIterator hands it through)
             const bool lerp_up = r.mode == ROW_LERP && r.uni.from < r.uni.to;
             const bool pass = r.mode == ROW_PASS;
-            ok = (lerp_up || pass) && r.c_in == C && r.out_len % C == 0 && r.mix_start % C == 0 && r.n_in % C == 0;
+            // the stream has the mixer's channels, or is mono in a stereo mixer (repeated on both channels, channels.rs:57-85)
+            ok = (lerp_up || pass) && (r.c_in == C || (r.c_in == 1 && C == 2)) && r.out_len % C == 0 && r.mix_start % C == 0 &&
+                 r.n_in % r.c_in == 0;
             rb_lanes_stream& l = ls[i];
+            l.channels = r.c_in;
             l.in = (const float*)r.in, l.n_frames = r.uni.tail.L, l.out_len = r.out_len / C, l.mix_start = r.mix_start / C;
             l.from = pass ? 1u : r.uni.from, l.to = pass ? 1u : r.uni.to;
             l.b0 = r.b0, l.b1 = r.b1, l.b2 = r.b2, l.a1 = r.a1, l.a2 = r.a2;

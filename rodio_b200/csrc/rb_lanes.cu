@@ -14,21 +14,22 @@ constexpr int LANES_THREADS = 32 * LANES_WARPS;
 template <int C>
 constexpr size_t lanes_smem_bytes() { return (size_t)LANES_WARPS * 32 * lanes::Geo<C>::RS * sizeof(float); }   // 21.0 / 41.0 KB
 
-template <int C, bool HASB, bool FF2, int NPOST, bool PASS>
+template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS>
 __global__ void __launch_bounds__(LANES_THREADS) k_fused_lanes(lanes::Args a) {
     extern __shared__ __align__(16) float lanes_smem[];
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t group = blockIdx.x * LANES_WARPS + warp;
     if (group >= a.n_groups) return;   // whole warps leave: the warp program only synchronises within a warp
-    lanes::warp_main<C, HASB, FF2, NPOST, PASS>(a, group, lanes_smem + (size_t)warp * 32 * lanes::Geo<C>::RS);
+    lanes::warp_main<CI, CO, HASB, FF2, NPOST, PASS>(a, group, lanes_smem + (size_t)warp * 32 * lanes::Geo<CI>::RS);
 }
 
 // One CTA per stream: does every non-zero |x| lie inside [2^-70, 2^60]?  (rb_lanes_core.h, "Exact division".)
-__global__ void __launch_bounds__(256) k_classify_inputs(lanes::Row* rows, uint32_t n_rows, uint32_t channels) {
+// channels[r]: interleaved channels of stream r.
+__global__ void __launch_bounds__(256) k_classify_inputs(lanes::Row* rows, uint32_t n_rows, const uint8_t* __restrict__ channels) {
     const uint32_t r = blockIdx.x;
     if (r >= n_rows) return;
     const float* __restrict__ x = rows[r].in;
-    const uint64_t L = rows[r].L * channels;   // floats
+    const uint64_t L = rows[r].L * channels[r];   // floats
     bool bad = false;
     const uint64_t n4 = L / 4;
     const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
@@ -93,28 +94,31 @@ __global__ void __launch_bounds__(256) k_classify_range(const float* __restrict_
     if (__syncthreads_or(bad ? 1 : 0) && threadIdx.x == 0) *flag = 1u;
 }
 
-template <int C, bool HASB, bool FF2, int NPOST, bool PASS>
+template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS>
 static void launch_lanes(const lanes::Args& a, cudaStream_t st) {
     const uint32_t n_ctas = (a.n_groups + LANES_WARPS - 1) / LANES_WARPS;
-    k_fused_lanes<C, HASB, FF2, NPOST, PASS><<<n_ctas, LANES_THREADS, lanes_smem_bytes<C>(), st>>>(a);   // < 48 KB: no opt-in needed
+    k_fused_lanes<CI, CO, HASB, FF2, NPOST, PASS><<<n_ctas, LANES_THREADS, lanes_smem_bytes<CI>(), st>>>(a);   // < 48 KB: no opt-in needed
 }
-template <int C, bool PASS>
+template <int CI, int CO, bool PASS>
 static void launch_lanes_c(const lanes::Args& a, bool has_biquad, bool ff2, bool has_post, cudaStream_t st) {
     if (has_biquad) {
-        if (ff2) has_post ? launch_lanes<C, true, true, 1, PASS>(a, st) : launch_lanes<C, true, true, 0, PASS>(a, st);
-        else has_post ? launch_lanes<C, true, false, 1, PASS>(a, st) : launch_lanes<C, true, false, 0, PASS>(a, st);
+        if (ff2) has_post ? launch_lanes<CI, CO, true, true, 1, PASS>(a, st) : launch_lanes<CI, CO, true, true, 0, PASS>(a, st);
+        else has_post ? launch_lanes<CI, CO, true, false, 1, PASS>(a, st) : launch_lanes<CI, CO, true, false, 0, PASS>(a, st);
     } else {
-        has_post ? launch_lanes<C, false, false, 1, PASS>(a, st) : launch_lanes<C, false, false, 0, PASS>(a, st);
+        has_post ? launch_lanes<CI, CO, false, false, 1, PASS>(a, st) : launch_lanes<CI, CO, false, false, 0, PASS>(a, st);
     }
 }
 
 }  // namespace
 
-cudaError_t rb_lanes_launch_kernel(const lanes::Args& a, uint32_t channels, bool has_biquad, bool ff2, bool has_post, cudaStream_t st) {
-    if (a.mix_len == 0 || a.n_groups == 0 || (channels != 1 && channels != 2)) return cudaSuccess;
+cudaError_t rb_lanes_launch_kernel(const lanes::Args& a, uint32_t ch_in, uint32_t ch_out, bool has_biquad, bool ff2, bool has_post,
+                                   cudaStream_t st) {
+    if (a.mix_len == 0 || a.n_groups == 0) return cudaSuccess;
+    if (!((ch_in == 1 || ch_in == 2) && (ch_in == ch_out || (ch_in == 1 && ch_out == 2)))) return cudaErrorInvalidValue;
     const bool pass = a.from == a.to;   // sources at the mixer's rate: taps used raw
-    if (channels == 2) pass ? launch_lanes_c<2, true>(a, has_biquad, ff2, has_post, st) : launch_lanes_c<2, false>(a, has_biquad, ff2, has_post, st);
-    else pass ? launch_lanes_c<1, true>(a, has_biquad, ff2, has_post, st) : launch_lanes_c<1, false>(a, has_biquad, ff2, has_post, st);
+    if (ch_in == 2) pass ? launch_lanes_c<2, 2, true>(a, has_biquad, ff2, has_post, st) : launch_lanes_c<2, 2, false>(a, has_biquad, ff2, has_post, st);
+    else if (ch_out == 2) pass ? launch_lanes_c<1, 2, true>(a, has_biquad, ff2, has_post, st) : launch_lanes_c<1, 2, false>(a, has_biquad, ff2, has_post, st);
+    else pass ? launch_lanes_c<1, 1, true>(a, has_biquad, ff2, has_post, st) : launch_lanes_c<1, 1, false>(a, has_biquad, ff2, has_post, st);
     return cudaGetLastError();
 }
 
@@ -151,13 +155,15 @@ struct rb_lanes_plan {
     struct Class {
         lanes::Args args{};
         bool ff2 = false;
+        uint32_t ch_in = 1;
     };
     std::vector<Class> classes;      // one launch per reduced rate pair
     lanes::Row* d_rows = nullptr;    // class after class
     float* d_partial = nullptr;      // [n_groups_total][pstride]
     float* d_zeros = nullptr;
     float* d_out = nullptr;
-    uint32_t n_rows = 0, n_groups_total = 0, channels = 1;
+    uint8_t* d_row_channels = nullptr;   // [n_rows], class order: interleaved channels of every stream
+    uint32_t n_rows = 0, n_groups_total = 0, channels = 1;   // channels: of the mixer
     uint64_t pstride = 0, mix_len = 0;
     bool has_biquad = false, has_post = false;
     bool classified = false;
@@ -168,21 +174,24 @@ cudaError_t rb_lanes_try_create(const rb_lanes_stream* streams, size_t n_streams
     (void)sm_count;
     *out = nullptr;
     if (n_streams == 0 || n_streams > 0x7fffffffull || mix_len == 0 || (channels != 1 && channels != 2)) return cudaSuccess;
-    std::vector<uint32_t> from(n_streams), to(n_streams);
+    std::vector<uint32_t> from(n_streams), to(n_streams), chs(n_streams);
     for (size_t i = 0; i < n_streams; i++) {
-        from[i] = streams[i].from, to[i] = streams[i].to;
+        from[i] = streams[i].from, to[i] = streams[i].to, chs[i] = streams[i].channels;
         if (!(from[i] <= to[i]) || from[i] == 0 || to[i] > (1u << 20)) return cudaSuccess;
+        if (!(chs[i] == channels || (chs[i] == 1 && channels == 2))) return cudaSuccess;
         if (reinterpret_cast<uintptr_t>(streams[i].in) & 15u) return cudaSuccess;
     }
-    const auto classes = lanes::classes_by_ratio(from.data(), to.data(), (uint32_t)n_streams);
+    const auto classes = lanes::classes_by_ratio(from.data(), to.data(), chs.data(), (uint32_t)n_streams);
     auto p = new rb_lanes_plan;
     p->has_biquad = has_biquad, p->has_post = has_post, p->d_out = d_out, p->channels = channels;
     p->n_rows = (uint32_t)n_streams, p->mix_len = mix_len, p->pstride = lanes::round_up_tile(mix_len * channels);
     std::vector<lanes::Row> rows;
     rows.reserve(n_streams);
+    std::vector<uint8_t> row_channels;
     std::vector<size_t> first_row;
     for (const auto& cls : classes) {
         rb_lanes_plan::Class c;
+        c.ch_in = chs[cls[0]];
         lanes::Args& a = c.args;
         a.n_rows = (uint32_t)cls.size(), a.n_groups = (a.n_rows + 31) / 32;
         lanes::fill_ratio(a, from[cls[0]], to[cls[0]], channels);
@@ -202,6 +211,7 @@ cudaError_t rb_lanes_try_create(const rb_lanes_stream* streams, size_t n_streams
             if (has_biquad && lanes::ff2_coeffs(r.b0, r.b1, r.b2, &k)) r.ffk = k;
             else c.ff2 = false;
             rows.push_back(r);
+            row_channels.push_back((uint8_t)s.channels);
         }
         p->n_groups_total += a.n_groups;
         p->classes.push_back(c);
@@ -210,6 +220,8 @@ cudaError_t rb_lanes_try_create(const rb_lanes_stream* streams, size_t n_streams
     cudaError_t e = cudaMalloc(&p->d_rows, n_streams * sizeof(lanes::Row));
     if (e == cudaSuccess) e = cudaMalloc(&p->d_partial, partial_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&p->d_zeros, 256);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_row_channels, n_streams);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_row_channels, row_channels.data(), n_streams, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(p->d_partial, 0, partial_bytes, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(p->d_zeros, 0, 256, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_rows, rows.data(), n_streams * sizeof(lanes::Row), cudaMemcpyHostToDevice, st);
@@ -234,13 +246,13 @@ void rb_lanes_inputs_changed(rb_lanes_plan* p) {
 
 cudaError_t rb_lanes_run(rb_lanes_plan* p, cudaStream_t st) {
     if (!p->classified) {
-        k_classify_inputs<<<p->n_rows, 256, 0, st>>>(p->d_rows, p->n_rows, p->channels);
+        k_classify_inputs<<<p->n_rows, 256, 0, st>>>(p->d_rows, p->n_rows, p->d_row_channels);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         p->classified = true;
     }
     for (const auto& c : p->classes) {
-        cudaError_t e = rb_lanes_launch_kernel(c.args, p->channels, p->has_biquad, c.ff2, p->has_post, st);
+        cudaError_t e = rb_lanes_launch_kernel(c.args, c.ch_in, p->channels, p->has_biquad, c.ff2, p->has_post, st);
         if (e != cudaSuccess) return e;
     }
     return rb_lanes_launch_sum(p->d_partial, p->n_groups_total, p->pstride, p->mix_len * p->channels, p->d_out, st);
@@ -253,5 +265,6 @@ void rb_lanes_destroy(rb_lanes_plan* p) {
     cudaFree(p->d_rows);
     cudaFree(p->d_partial);
     cudaFree(p->d_zeros);
+    cudaFree(p->d_row_channels);
     delete p;
 }

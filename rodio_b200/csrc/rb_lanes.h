@@ -14,6 +14,7 @@ struct rb_lanes_stream {
     uint64_t out_len;      // frames
     uint64_t mix_start;    // frames
     uint32_t from, to;     // reduced rate pair of this stream, from <= to (1:1 = already at the mixer's rate)
+    uint32_t channels;     // of this stream: the mixer's, or 1 in a stereo mixer (the sample is repeated on both channels)
     float b0, b1, b2, a1, a2;
     float post;
 };
@@ -32,8 +33,10 @@ uint32_t rb_lanes_launch_count(const rb_lanes_plan* p);
 void rb_lanes_destroy(rb_lanes_plan* p);
 
 // ---- streaming blocks (rb_session_* in rb_api.cu): the caller owns every buffer and fills lanes::Args itself ----
-// k_fused_lanes over a.rows (one rate pair; a.from == a.to selects the pass-through variant) ...
-cudaError_t rb_lanes_launch_kernel(const lanes::Args& a, uint32_t channels, bool has_biquad, bool ff2, bool has_post, cudaStream_t st);
+// k_fused_lanes over a.rows (one class: one rate pair -- a.from == a.to selects the pass-through variant --, ch_in channels
+// per stream, ch_out channels in the mixer) ...
+cudaError_t rb_lanes_launch_kernel(const lanes::Args& a, uint32_t ch_in, uint32_t ch_out, bool has_biquad, bool ff2, bool has_post,
+                                   cudaStream_t st);
 // ... and the ordered sum of n_groups partial rows (all classes) into d_out[0, n_floats).
 cudaError_t rb_lanes_launch_sum(const float* d_partial, uint32_t n_groups, uint64_t pstride, uint64_t n_floats, float* d_out,
                                 cudaStream_t st);

@@ -90,11 +90,11 @@ struct Args {
     const Row* rows;
     uint32_t n_rows, n_groups;
     uint32_t from, to;       // reduced ratio, from < to <= 2^20
-    uint32_t q8, r8;         // divmod((TILE / C) * from, to): frames a tile advances
+    uint32_t q8, r8;         // divmod((TILE / CO) * from, to): input frames a tile advances (CO = mixer channels)
     float den_f, rcp_den, from_f;
     float neg1;              // -1.0f as a run-time value (keeps fma(p, -1, t) an FFMA: the chain stays on one pipe)
     uint64_t mix_len;        // mixer timeline, frames
-    uint64_t pstride;        // floats per partial row: mix_len * C rounded up to TILE
+    uint64_t pstride;        // floats per partial row: mix_len * CO rounded up to TILE
     float* partial;          // [n_groups][pstride], zero outside the span each group writes
     const float* zeros;      // CHUNK * C zeros, 16-byte aligned: the source of idle lanes
     const uint32_t* unsafe;  // optional [n_rows]: non-zero = as if ROW_UNSAFE were set (streaming: kept on the device)
@@ -123,10 +123,17 @@ SIMT_FN float reduce_tile(const float (&v)[TILE], uint32_t ln) {
 // untouched (src/conversions/sample_rate.rs:131-136), so the taps are used raw -- no interpolation, no division, and no
 // input class to respect; everything else (ring, runs, "an output needs its successor or the end of the stream") is the
 // same code with from = to = 1.
-template <int C, bool HASB, bool FF2, int NPOST, bool PASS = false>
+// CI / CO: channels of the streams of this launch / of the mixer.  CI == CO (mono into mono, stereo into stereo), or
+// CI = 1, CO = 2: a mono source in a stereo mixer -- ChannelCountConverter repeats the sample on both channels
+// (src/conversions/channels.rs:57-85) and the two filter channels see the same input, so the lane computes the frame once
+// and emits it twice.
+template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS = false>
 SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
-    using G = Geo<C>;
-    constexpr int TF = G::TF, RS = G::RS, QPC = G::QPC, RPI = G::RPI, RING = G::RING, MIRROR = G::MIRROR, CHW = G::CHW;
+    static_assert(CI == CO || (CI == 1 && CO == 2), "channel layouts served");
+    using G = Geo<CI>;
+    constexpr int C = CI;               // taps, ring and filter state follow the source's channels
+    constexpr int TF = TILE / CO;       // frames per tile: the mixer timeline has CO samples per frame
+    constexpr int RS = G::RS, QPC = G::QPC, RPI = G::RPI, RING = G::RING, MIRROR = G::MIRROR, CHW = G::CHW;
     const uint32_t ln = simt::lane();
     const uint32_t r = group * 32u + ln;
     const bool has = r < a.n_rows;
@@ -275,6 +282,7 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                     }
                     // next output frame: numerator += from (mod to); a carry moves one input frame on
                     simt::lerp_advance<C>(nf, x0, x1, p, from_f, den);
+                    float val[C];
 #pragma unroll
                     for (int c = 0; c < C; c++) {
                         float y = x[c];
@@ -292,11 +300,13 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                             y = fb(a1, a2, tt, y1[c], y2[c], neg1);
                             y2[c] = y1[c], y1[c] = y;
                         }
-                        v[f * C + c] = NPOST ? simt::fmul(y, post) : y;
+                        val[c] = NPOST ? simt::fmul(y, post) : y;
                     }
+#pragma unroll
+                    for (int co = 0; co < CO; co++) v[f * CO + co] = val[co < C ? co : 0];
                 }
                 const float s = reduce_tile(v, ln);
-                if ((ln & 3u) == 0) prow[(t + done) * C + (ln >> 2)] = s;
+                if ((ln & 3u) == 0) prow[(t + done) * CO + (ln >> 2)] = s;
             }
             simt::cp_wait<0>();
             simt::syncwarp();
@@ -320,9 +330,10 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
 #pragma unroll
                     for (int c = 0; c < C; c++) xh1[c] = xh2[c] = y1[c] = y2[c] = 0.f;
                 }
+                float val[C];
 #pragma unroll
                 for (int c = 0; c < C; c++) {
-                    float val = 0.0f;
+                    val[c] = 0.0f;
                     if (on) {
                         const float xa = simt::ldg(row.in + i * C + c);
                         float x = xa;
@@ -334,13 +345,14 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                             y = fb(a1, a2, ff, y1[c], y2[c], neg1);
                             xh2[c] = xh1[c], xh1[c] = x, y2[c] = y1[c], y1[c] = y;
                         }
-                        val = NPOST ? simt::fmul(y, post) : y;
+                        val[c] = NPOST ? simt::fmul(y, post) : y;
                     }
-                    v[f * C + c] = val;
                 }
+#pragma unroll
+                for (int co = 0; co < CO; co++) v[f * CO + co] = val[co < C ? co : 0];
             }
             const float s = reduce_tile(v, ln);
-            if ((ln & 3u) == 0) prow[t * C + (ln >> 2)] = s;
+            if ((ln & 3u) == 0) prow[t * CO + (ln >> 2)] = s;
             simt::emu_count(1, 1);
             t += TF;
         }

@@ -48,13 +48,17 @@ inline void fill_ratio(Args& a, uint32_t from, uint32_t to, uint32_t channels) {
 // Streams of one kernel launch share a reduced rate pair.  A batch / session with several pairs (44.1 kHz and 48 kHz
 // sources in one mixer) is served class by class: stable partition by (from, to) in order of first appearance; every
 // class gets its own launch over its own rows and its own partial rows, k_sum_groups adds all partial rows in order.
-inline std::vector<std::vector<uint32_t>> classes_by_ratio(const uint32_t* from, const uint32_t* to, uint32_t n) {
-    std::vector<std::pair<uint32_t, uint32_t>> keys;
+// Mono sources in a stereo mixer form classes of their own (the CI = 1, CO = 2 instantiation).
+// `ch` (source channels per stream) may be NULL when all streams have the mixer's channel count.
+inline std::vector<std::vector<uint32_t>> classes_by_ratio(const uint32_t* from, const uint32_t* to, const uint32_t* ch, uint32_t n) {
+    struct Key { uint32_t from, to, ch; };
+    std::vector<Key> keys;
     std::vector<std::vector<uint32_t>> out;
     for (uint32_t i = 0; i < n; i++) {
+        const uint32_t c = ch ? ch[i] : 0;
         size_t k = 0;
-        while (k < keys.size() && !(keys[k].first == from[i] && keys[k].second == to[i])) k++;
-        if (k == keys.size()) keys.push_back({from[i], to[i]}), out.emplace_back();
+        while (k < keys.size() && !(keys[k].from == from[i] && keys[k].to == to[i] && keys[k].ch == c)) k++;
+        if (k == keys.size()) keys.push_back({from[i], to[i], c}), out.emplace_back();
         out[k].push_back(i);
     }
     return out;

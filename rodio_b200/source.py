@@ -490,15 +490,17 @@ class Session:
     (UniformSourceIterator(src, 1, rate)[.low_pass / .high_pass][.amplify]); their pcm is ignored."""
 
     def __init__(self, sources: Sequence[Source], mixer_rate: int, fifo_frames: int = 8192, max_block_frames: int = 4096,
-                 mix_starts: Optional[Sequence[int]] = None, ctx: Optional[Context] = None):
+                 mix_starts: Optional[Sequence[int]] = None, ctx: Optional[Context] = None, mixer_channels: Optional[int] = None):
         self.ctx = ctx or default_context()
         self.sources = list(sources)
         self.max_block_frames = max_block_frames
-        self.channels = self.sources[0].channels() if self.sources else 1   # of every source and of the mixer
+        # mixer(channels, rate): the chains end in UniformSourceIterator(_, channels, rate), so they report the mixer's count
+        self.channels = mixer_channels or (self.sources[0].channels() if self.sources else 1)
+        self.src_channels = [s.base_channels for s in self.sources]       # what is pushed: the source's own interleaving
         self._descs, self._keep = pack_descs(self.sources, mix_starts)
         self._h = C.c_void_p()
-        check(lib().rb_session_create(self.ctx._h, mixer_rate, self._descs, len(self.sources), fifo_frames, max_block_frames,
-                                      C.byref(self._h)), "rb_session_create")
+        check(lib().rb_session_create(self.ctx._h, self.channels, mixer_rate, self._descs, len(self.sources), fifo_frames,
+                                      max_block_frames, C.byref(self._h)), "rb_session_create")
 
     def close(self):
         if self._h:
@@ -513,16 +515,16 @@ class Session:
 
     def push(self, stream: int, pcm, end_of_stream: bool = False):
         a = np.ascontiguousarray(pcm, dtype=np.float32)
-        assert a.size % self.channels == 0, "whole frames"
-        check(lib().rb_session_push(self._h, stream, a.ctypes.data_as(C.c_void_p), a.size // self.channels, int(end_of_stream)),
-              "rb_session_push")
+        ch = self.src_channels[stream]
+        assert a.size % ch == 0, "whole frames"
+        check(lib().rb_session_push(self._h, stream, a.ctypes.data_as(C.c_void_p), a.size // ch, int(end_of_stream)), "rb_session_push")
 
     def push_packed(self, blocks: Sequence[np.ndarray], end_of_stream: Optional[Sequence[bool]] = None):
         """One block per source (possibly empty), pushed with one copy and one kernel."""
         assert len(blocks) == len(self.sources)
         blocks = [np.ascontiguousarray(b, dtype=np.float32) for b in blocks]
         flat = np.concatenate(blocks) if blocks else np.zeros(0, np.float32)
-        n = (C.c_uint64 * len(blocks))(*[b.size // self.channels for b in blocks])
+        n = (C.c_uint64 * len(blocks))(*[b.size // ch for b, ch in zip(blocks, self.src_channels)])
         eos = (C.c_uint8 * len(blocks))(*[int(bool(e)) for e in end_of_stream]) if end_of_stream is not None else None
         check(lib().rb_session_push_packed(self._h, flat.ctypes.data_as(C.c_void_p), n, eos), "rb_session_push_packed")
 

@@ -47,7 +47,7 @@ int main() {
         check(rb_batch_render_mix(b, want.data(), n, &w), "rb_batch_render_mix");
         rb_batch_destroy(b);
 
-        mixer::LiveMixer live(chains, 48000, 4096, 500);
+        mixer::LiveMixer live(chains, ch, 48000, 4096, 500);
         std::vector<size_t> at(n_src, 0);
         std::vector<Sample> got;
         while (!live.ended()) {

@@ -12,31 +12,32 @@
 #include "../../rodio_b200/csrc/rb_lanes_plan.h"
 
 namespace {
-template <int C, bool HASB, bool FF2, int NPOST, bool PASS>
+template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS>
 void run_warp_c(const lanes::Args& a, uint32_t group, simt::WarpEmu* w, float* ring) {
     std::vector<std::thread> th;
     for (uint32_t l = 0; l < 32; l++)
         th.emplace_back([&, l] {
             simt::g_lane = simt::LaneEmu{};
             simt::g_lane.w = w, simt::g_lane.lane = l;
-            lanes::warp_main<C, HASB, FF2, NPOST, PASS>(a, group, ring);
+            lanes::warp_main<CI, CO, HASB, FF2, NPOST, PASS>(a, group, ring);
         });
     for (auto& t : th) t.join();
 }
-template <int C, bool PASS>
+template <int CI, int CO, bool PASS>
 void run_group(const lanes::Args& a, uint32_t g, simt::WarpEmu* w, float* ring, bool hasb, bool ff2, bool npost) {
-    if (hasb && ff2 && npost) run_warp_c<C, true, true, 1, PASS>(a, g, w, ring);
-    else if (hasb && ff2) run_warp_c<C, true, true, 0, PASS>(a, g, w, ring);
-    else if (hasb && npost) run_warp_c<C, true, false, 1, PASS>(a, g, w, ring);
-    else if (hasb) run_warp_c<C, true, false, 0, PASS>(a, g, w, ring);
-    else if (npost) run_warp_c<C, false, false, 1, PASS>(a, g, w, ring);
-    else run_warp_c<C, false, false, 0, PASS>(a, g, w, ring);
+    if (hasb && ff2 && npost) run_warp_c<CI, CO, true, true, 1, PASS>(a, g, w, ring);
+    else if (hasb && ff2) run_warp_c<CI, CO, true, true, 0, PASS>(a, g, w, ring);
+    else if (hasb && npost) run_warp_c<CI, CO, true, false, 1, PASS>(a, g, w, ring);
+    else if (hasb) run_warp_c<CI, CO, true, false, 0, PASS>(a, g, w, ring);
+    else if (npost) run_warp_c<CI, CO, false, false, 1, PASS>(a, g, w, ring);
+    else run_warp_c<CI, CO, false, false, 0, PASS>(a, g, w, ring);
 }
-// the ratio of the class decides PASS (from == to) -- like the device launcher
-void run_group_any(uint32_t channels, const lanes::Args& a, uint32_t g, simt::WarpEmu* w, float* ring, bool hasb, bool ff2, bool npost) {
+// the class decides the instantiation -- source channels ci, mixer channels co, PASS when from == to -- like the device launcher
+void run_group_any(uint32_t ci, uint32_t co, const lanes::Args& a, uint32_t g, simt::WarpEmu* w, float* ring, bool hasb, bool ff2, bool npost) {
     const bool pass = a.from == a.to;
-    if (channels == 2) pass ? run_group<2, true>(a, g, w, ring, hasb, ff2, npost) : run_group<2, false>(a, g, w, ring, hasb, ff2, npost);
-    else pass ? run_group<1, true>(a, g, w, ring, hasb, ff2, npost) : run_group<1, false>(a, g, w, ring, hasb, ff2, npost);
+    if (ci == 2) pass ? run_group<2, 2, true>(a, g, w, ring, hasb, ff2, npost) : run_group<2, 2, false>(a, g, w, ring, hasb, ff2, npost);
+    else if (co == 2) pass ? run_group<1, 2, true>(a, g, w, ring, hasb, ff2, npost) : run_group<1, 2, false>(a, g, w, ring, hasb, ff2, npost);
+    else pass ? run_group<1, 1, true>(a, g, w, ring, hasb, ff2, npost) : run_group<1, 1, false>(a, g, w, ring, hasb, ff2, npost);
 }
 constexpr int MAX_RS = lanes::Geo<2>::RS;
 }  // namespace
@@ -50,14 +51,15 @@ extern "C" void rb_lanes_emu_counters(uint64_t* out, int reset) {
 
 extern "C" int rb_lanes_emulate(const float* const* pcm, const uint64_t* n_frames, const uint64_t* out_len,
                                 const uint64_t* mix_start, const float* coefs /* [n][5] b0 b1 b2 a1 a2 */,
-                                const float* post, uint32_t n_rows, uint32_t channels, const uint32_t* from, const uint32_t* to,
-                                uint64_t mix_len, int hasb, int want_ff2, int npost, float* out_mix, float* out_partials /* may be NULL */,
+                                const float* post, uint32_t n_rows, uint32_t channels /* mixer */, const uint32_t* ch_in /* per stream */,
+                                const uint32_t* from, const uint32_t* to, uint64_t mix_len, int hasb, int want_ff2, int npost, float* out_mix, float* out_partials /* may be NULL */,
                                 int* used_ff2, uint32_t* n_unsafe) {
     using namespace lanes;
     if (n_rows == 0 || (channels != 1 && channels != 2)) return 1;
     for (uint32_t r = 0; r < n_rows; r++)
-        if (!(from[r] <= to[r]) || to[r] > (1u << 20)) return 1;
-    const uint32_t C = channels;   // n_frames / out_len / mix_start / mix_len count FRAMES; pcm and out_mix hold frames * C floats
+        if (!(from[r] <= to[r]) || to[r] > (1u << 20) || !(ch_in[r] == channels || (ch_in[r] == 1 && channels == 2))) return 1;
+    const uint32_t C = channels;   // n_frames / out_len / mix_start / mix_len count FRAMES; out_mix holds frames * C floats,
+                                   // pcm[r] frames * ch_in[r] floats
     const float nan = std::numeric_limits<float>::quiet_NaN();
     simt::WarpEmu warp;
     // inputs: 16-byte aligned copies with a 16-byte tail pad of NaN (reading the pad as data would show)
@@ -66,11 +68,12 @@ extern "C" int rb_lanes_emulate(const float* const* pcm, const uint64_t* n_frame
     bool ff2 = want_ff2 && hasb;
     *n_unsafe = 0;
     for (uint32_t r = 0; r < n_rows; r++) {
-        store[r].assign(n_frames[r] * C + 4 + 4, nan);
+        const uint32_t ci = ch_in[r];
+        store[r].assign(n_frames[r] * ci + 4 + 4, nan);
         float* base = store[r].data();
         while ((uintptr_t)base & 15) base++;
-        if (n_frames[r]) std::memcpy(base, pcm[r], n_frames[r] * C * 4);
-        warp.readable.push_back({(const char*)base, (const char*)(base + n_frames[r] * C + 4)});
+        if (n_frames[r]) std::memcpy(base, pcm[r], n_frames[r] * ci * 4);
+        warp.readable.push_back({(const char*)base, (const char*)(base + n_frames[r] * ci + 4)});
         Row& row = all[r];
         std::memset(&row, 0, sizeof(row));
         row.in = base, row.L = n_frames[r], row.out_len = out_len[r], row.mix_start = mix_start[r];
@@ -84,16 +87,17 @@ extern "C" int rb_lanes_emulate(const float* const* pcm, const uint64_t* n_frame
         }
         row.post = npost ? post[r] : 1.0f;
         bool ok = true;
-        for (uint64_t i = 0; i < n_frames[r] * C && ok; i++) ok = sample_in_class(pcm[r][i]);
+        for (uint64_t i = 0; i < n_frames[r] * ci && ok; i++) ok = sample_in_class(pcm[r][i]);
         if (!ok) row.flags |= ROW_UNSAFE, (*n_unsafe)++;
     }
     *used_ff2 = ff2;
     alignas(16) static float zeros[CHUNK * 2] = {0};
     warp.readable.push_back({(const char*)zeros, (const char*)(zeros + CHUNK * C)});
     // one launch per rate pair over its own rows and partial rows
-    const auto classes = classes_by_ratio(from, to, n_rows);
+    const auto classes = classes_by_ratio(from, to, ch_in, n_rows);
     std::vector<Row> rows;
     std::vector<Args> launches;
+    std::vector<uint32_t> launch_ci;
     uint32_t n_groups_total = 0;
     const uint64_t pstride = round_up_tile(mix_len * C);
     for (const auto& cls : classes) {
@@ -106,16 +110,18 @@ extern "C" int rb_lanes_emulate(const float* const* pcm, const uint64_t* n_frame
         for (uint32_t i : cls) rows.push_back(all[i]);
         n_groups_total += a.n_groups;
         launches.push_back(a);
+        launch_ci.push_back(ch_in[cls[0]]);
     }
     std::vector<float> partial((size_t)n_groups_total * pstride, 0.0f);
     std::vector<float> ring_store(32 * MAX_RS + 4, nan);
     float* ring = ring_store.data();
     while ((uintptr_t)ring & 15) ring++;
-    for (Args& a : launches) {
+    for (size_t k = 0; k < launches.size(); k++) {
+        Args& a = launches[k];
         a.rows = rows.data() + (uintptr_t)a.rows, a.partial = partial.data() + (uintptr_t)a.partial * pstride, a.zeros = zeros;
         for (uint32_t g = 0; g < a.n_groups; g++) {
             for (int i = 0; i < 32 * MAX_RS; i++) ring[i] = nan;
-            run_group_any(channels, a, g, &warp, ring, hasb, ff2, npost);
+            run_group_any(launch_ci[k], channels, a, g, &warp, ring, hasb, ff2, npost);
         }
     }
     for (uint64_t m = 0; m < mix_len * C; m++) {
@@ -137,16 +143,16 @@ extern "C" int rb_lanes_emulate(const float* const* pcm, const uint64_t* n_frame
 #include "../../rodio_b200/csrc/rb_session_plan.h"
 
 extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t* n_frames, const uint64_t* mix_start,
-                                        const float* coefs, const float* post, uint32_t n_rows, uint32_t channels,
-                                        const uint32_t* from, const uint32_t* to, int hasb, int npost, const uint64_t* ops,
+                                        const float* coefs, const float* post, uint32_t n_rows, uint32_t channels /* mixer */,
+                                        const uint32_t* ch_in, const uint32_t* from, const uint32_t* to, int hasb, int npost, const uint64_t* ops,
                                         uint64_t n_ops, float* out, uint64_t out_cap, uint64_t* n_renders,
                                         uint64_t* pushed_total /* [n_rows] */) {
     using namespace lanes;
     if (n_rows == 0 || (channels != 1 && channels != 2)) return -1;
     for (uint32_t r = 0; r < n_rows; r++)
-        if (!(from[r] <= to[r]) || to[r] > (1u << 20)) return -1;
-    const auto classes = classes_by_ratio(from, to, n_rows);   // fixed for the session: rows are laid out class by class
-    const uint32_t C = channels;   // frames everywhere; pcm / FIFOs / out hold frames * C floats
+        if (!(from[r] <= to[r]) || to[r] > (1u << 20) || !(ch_in[r] == channels || (ch_in[r] == 1 && channels == 2))) return -1;
+    const auto classes = classes_by_ratio(from, to, ch_in, n_rows);   // fixed for the session: rows are laid out class by class
+    const uint32_t C = channels;   // frames everywhere; out holds frames * C floats, pcm[r] / FIFO r frames * ch_in[r] floats
     const float nan = std::numeric_limits<float>::quiet_NaN();
     simt::WarpEmu warp;
     std::vector<session::Stream> st(n_rows);
@@ -161,10 +167,10 @@ extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t*
     std::vector<float> gain(n_rows, 1.0f);
     for (uint32_t r = 0; r < n_rows; r++) {
         if (npost) gain[r] = post[r];
-        fifo_store[r].assign(n_frames[r] * C + 16, nan);
+        fifo_store[r].assign(n_frames[r] * ch_in[r] + 16, nan);
         fifo[r] = fifo_store[r].data();
         while ((uintptr_t)fifo[r] & 15) fifo[r]++;
-        warp.readable.push_back({(const char*)fifo[r], (const char*)(fifo[r] + n_frames[r] * C + 8)});
+        warp.readable.push_back({(const char*)fifo[r], (const char*)(fifo[r] + n_frames[r] * ch_in[r] + 8)});
         st[r].mix_start = mix_start[r], st[r].from = from[r], st[r].to = to[r];
         if (hasb) {
             const float* c = coefs + 5 * r;
@@ -182,9 +188,10 @@ extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t*
     auto push = [&](uint32_t r, uint64_t n) {
         session::Stream& s = st[r];
         n = std::min(n, n_frames[r] - s.pushed);
-        for (uint64_t k = 0; k < n * C; k++) {
-            const float v = pcm[r][s.pushed * C + k];
-            fifo[r][s.fill() * C + k] = v;
+        const uint32_t ci = ch_in[r];
+        for (uint64_t k = 0; k < n * ci; k++) {
+            const float v = pcm[r][s.pushed * ci + k];
+            fifo[r][s.fill() * ci + k] = v;
             if (!sample_in_class(v)) unsafe[r] = 1;
         }
         s.pushed += n;
@@ -228,7 +235,7 @@ extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t*
             a.rows = rows.data() + first, a.partial = partial.data() + (size_t)g0 * pstride, a.zeros = zeros;
             for (uint32_t g = 0; g < a.n_groups; g++) {
                 for (int i = 0; i < 32 * MAX_RS; i++) ring[i] = nan;
-                run_group_any(channels, a, g, &warp, ring, hasb, ff2, npost);
+                run_group_any(ch_in[cls[0]], channels, a, g, &warp, ring, hasb, ff2, npost);
             }
             g0 += a.n_groups;
         }
@@ -242,8 +249,9 @@ extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t*
             const uint64_t fill_before = st[r].fill();
             const uint64_t drop = session::advance(st[r], parts[r]);
             if (drop) {
-                std::memmove(fifo[r], fifo[r] + drop * C, (fill_before - drop) * C * sizeof(float));
-                for (uint64_t k = (fill_before - drop) * C; k < fill_before * C; k++) fifo[r][k] = nan;
+                const uint32_t ci = ch_in[r];
+                std::memmove(fifo[r], fifo[r] + drop * ci, (fill_before - drop) * ci * sizeof(float));
+                for (uint64_t k = (fill_before - drop) * ci; k < fill_before * ci; k++) fifo[r][k] = nan;
             }
         }
         return true;

@@ -65,8 +65,9 @@ def expected_mix_classes(per_stream, starts, mix_len, froms, tos):
     return acc
 
 
-def run_emu(emu, pcms, outs_len, starts, coefs, posts, from_, to, mix_len, hasb, ff2, npost, channels=1):
-    """Frames everywhere (outs_len, starts, mix_len); pcms and the result hold frames * channels floats."""
+def run_emu(emu, pcms, outs_len, starts, coefs, posts, from_, to, mix_len, hasb, ff2, npost, channels=1, ch_in=None):
+    """Frames everywhere (outs_len, starts, mix_len); the result holds frames * channels floats, pcms[r] frames * ch_in[r]."""
+    ch_in = [channels] * len(pcms) if ch_in is None else list(ch_in)
     n = len(pcms)
     pcms = [np.ascontiguousarray(p, dtype=np.float32) for p in pcms]
     ptrs = (C.POINTER(C.c_float) * n)(*[p.ctypes.data_as(C.POINTER(C.c_float)) for p in pcms])
@@ -75,21 +76,22 @@ def run_emu(emu, pcms, outs_len, starts, coefs, posts, from_, to, mix_len, hasb,
     po = np.ascontiguousarray(posts, dtype=np.float32)
     out = np.full(mix_len * channels, np.nan, dtype=np.float32)
     used, unsafe = C.c_int(0), C.c_uint32(0)
-    rc = emu.rb_lanes_emulate(ptrs, u64([p.size // channels for p in pcms]), u64(outs_len), u64(starts),
+    rc = emu.rb_lanes_emulate(ptrs, u64([p.size // c for p, c in zip(pcms, ch_in)]), u64(outs_len), u64(starts),
                               co.ctypes.data_as(C.POINTER(C.c_float)), po.ctypes.data_as(C.POINTER(C.c_float)),
-                              C.c_uint32(n), C.c_uint32(channels), _u32(from_, n)[0], _u32(to, n)[0], C.c_uint64(mix_len), int(hasb), int(ff2),
+                              C.c_uint32(n), C.c_uint32(channels), _u32(ch_in, n)[0], _u32(from_, n)[0], _u32(to, n)[0], C.c_uint64(mix_len), int(hasb), int(ff2),
                               int(npost), out.ctypes.data_as(C.POINTER(C.c_float)), None, C.byref(used), C.byref(unsafe))
     assert rc == 0
     return out, bool(used.value), unsafe.value
 
 
-def make_case(pcms, in_rate, mix_rate, starts, lp=None, hp=None, q=0.5, gain=None, channels=1):
+def make_case(pcms, in_rate, mix_rate, starts, lp=None, hp=None, q=0.5, gain=None, channels=1, ch_in=None):
     """Sources as a rodio user writes them + everything the emulator needs, the expectation from the oracle.
     `starts` and the lengths in the result are frames."""
     srcs, per_stream = [], []
     in_rates = list(in_rate) if isinstance(in_rate, (list, tuple)) else [in_rate] * len(pcms)
-    for p, rate in zip(pcms, in_rates):
-        s = rb.UniformSourceIterator(rb.TestSource(p, channels, rate), channels, mix_rate)
+    ch_in = [channels] * len(pcms) if ch_in is None else list(ch_in)
+    for p, rate, ci in zip(pcms, in_rates, ch_in):
+        s = rb.UniformSourceIterator(rb.TestSource(p, ci, rate), channels, mix_rate)
         if lp is not None:
             s = s.low_pass_with_q(lp, q)
         if hp is not None:
@@ -104,7 +106,7 @@ def make_case(pcms, in_rate, mix_rate, starts, lp=None, hp=None, q=0.5, gain=Non
     co = oracle.blt_coeffs(hp is not None, lp if lp is not None else (hp or 1), q, mix_rate) if hasb else np.zeros(5, np.float32)
     coefs = np.tile(co, (len(pcms), 1))
     mix_len = max([s + y.size // channels for s, y in zip(starts, per_stream)] + [0])
-    return dict(per_stream=per_stream, outs_len=[y.size // channels for y in per_stream], coefs=coefs, channels=channels,
+    return dict(per_stream=per_stream, outs_len=[y.size // channels for y in per_stream], coefs=coefs, channels=channels, ch_in=ch_in,
                 posts=np.full(len(pcms), gain if gain is not None else 1.0, np.float32), from_=froms, to=tos,
                 mix_len=mix_len, hasb=hasb, npost=gain is not None, srcs=srcs)
 
@@ -113,10 +115,10 @@ def check(emu, pcms, in_rate, mix_rate, starts, ff2=True, expect_ff2=None, **kw)
     c = make_case(pcms, in_rate, mix_rate, starts, **kw)
     ch = c["channels"]
     got, used_ff2, unsafe = run_emu(emu, pcms, c["outs_len"], starts, c["coefs"], c["posts"], c["from_"], c["to"], c["mix_len"],
-                                    c["hasb"], ff2, c["npost"], channels=ch)
+                                    c["hasb"], ff2, c["npost"], channels=ch, ch_in=c["ch_in"])
     if expect_ff2 is not None:
         assert used_ff2 == expect_ff2
-    want = expected_mix_classes(c["per_stream"], [st * ch for st in starts], c["mix_len"] * ch, c["from_"], c["to"])
+    want = expected_mix_classes(c["per_stream"], [st * ch for st in starts], c["mix_len"] * ch, c["from_"], list(zip(c["to"], c["ch_in"])))
     assert_bit_exact(got, want, "emulated kernel vs oracle streams summed with the kernel's tree")
     # and the north-star tolerance against the reference's sequential mixer
     ref = oracle.mixer([to_oracle(s, mix_start=st * ch) for s, st in zip(c["srcs"], starts)], ch, mix_rate)
@@ -195,7 +197,8 @@ def test_silence_and_negative_zero(emu):
 
 
 # ------------------------------------------------------------------------------------------------- streaming sessions
-def run_session(emu, pcms, starts, coefs, posts, from_, to, hasb, npost, ops, out_cap, channels=1):
+def run_session(emu, pcms, starts, coefs, posts, from_, to, hasb, npost, ops, out_cap, channels=1, ch_in=None):
+    ch_in = [channels] * len(pcms) if ch_in is None else list(ch_in)
     n = len(pcms)
     pcms = [np.ascontiguousarray(p, dtype=np.float32) for p in pcms]
     ptrs = (C.POINTER(C.c_float) * n)(*[p.ctypes.data_as(C.POINTER(C.c_float)) for p in pcms])
@@ -207,22 +210,23 @@ def run_session(emu, pcms, starts, coefs, posts, from_, to, hasb, npost, ops, ou
     renders = C.c_uint64(0)
     pushed = (C.c_uint64 * n)()
     emu.rb_session_emulate.restype = C.c_longlong
-    w = emu.rb_session_emulate(ptrs, u64([p.size // channels for p in pcms]), u64(starts), co.ctypes.data_as(C.POINTER(C.c_float)),
-                               po.ctypes.data_as(C.POINTER(C.c_float)), C.c_uint32(n), C.c_uint32(channels), _u32(from_, n)[0], _u32(to, n)[0],
+    w = emu.rb_session_emulate(ptrs, u64([p.size // c for p, c in zip(pcms, ch_in)]), u64(starts), co.ctypes.data_as(C.POINTER(C.c_float)),
+                               po.ctypes.data_as(C.POINTER(C.c_float)), C.c_uint32(n), C.c_uint32(channels), _u32(ch_in, n)[0], _u32(from_, n)[0], _u32(to, n)[0],
                                int(hasb), int(npost), u64(flat), C.c_uint64(len(ops)), out.ctypes.data_as(C.POINTER(C.c_float)),
                                C.c_uint64(out_cap), C.byref(renders), pushed)
     assert w >= 0
     return out[:w * channels], renders.value, [int(v) for v in pushed]
 
 
-def session_case(emu, pcms, starts, ops, in_rate=44100, mix_rate=48000, lp=None, gain=None, channels=1):
+def session_case(emu, pcms, starts, ops, in_rate=44100, mix_rate=48000, lp=None, gain=None, channels=1, ch_in=None):
     """Any split of the streams into pushed blocks and of the mixer output into rendered blocks gives the bytes of the
     whole-stream render (tests/test_block_state_spec.py is the numpy form of the same contract)."""
-    c = make_case(pcms, in_rate, mix_rate, starts, lp=lp, gain=gain, channels=channels)
+    c = make_case(pcms, in_rate, mix_rate, starts, lp=lp, gain=gain, channels=channels, ch_in=ch_in)
     got, renders, pushed = run_session(emu, pcms, starts, c["coefs"], c["posts"], c["from_"], c["to"], c["hasb"], c["npost"], ops,
-                                       (c["mix_len"] + 64) * channels, channels=channels)
-    assert pushed == [p.size // channels for p in pcms]
-    want = expected_mix_classes(c["per_stream"], [st * channels for st in starts], c["mix_len"] * channels, c["from_"], c["to"])
+                                       (c["mix_len"] + 64) * channels, channels=channels, ch_in=c["ch_in"])
+    assert pushed == [p.size // ci for p, ci in zip(pcms, c["ch_in"])]
+    want = expected_mix_classes(c["per_stream"], [st * channels for st in starts], c["mix_len"] * channels, c["from_"],
+                                list(zip(c["to"], c["ch_in"])))
     assert_bit_exact(got, want, "session blocks vs whole-stream render")
     return renders
 
@@ -387,3 +391,25 @@ def test_mixed_rates_session(emu):
     for step in range(60):
         ops += [(0, r, int(rates[r] / 1000) + r) for r in range(5)] + [(1, 0, 45 + step % 7)]
     session_case(emu, pcms, [0, 0, 0, 100, 3], ops, in_rate=rates, mix_rate=48000, lp=700, gain=0.8)
+
+
+# ------------------------------------------------------------------------------------------------- mono sources, stereo mixer
+def test_mono_and_stereo_sources_in_a_stereo_mixer(emu):
+    """ChannelCountConverter repeats a mono source on both channels (src/conversions/channels.rs:57-85); the lane computes
+    the frame once and emits it twice.  Mono and stereo sources, two rates, one stereo mixer."""
+    ch_in = [1, 2, 1, 1, 2, 1, 2, 1] * 5
+    rates = [44100, 44100, 48000, 22050, 48000, 44100, 44100, 48000] * 5
+    pcms = [noise(ci * (600 + 11 * i), 1500 + i) for i, ci in enumerate(ch_in)]
+    starts = [(7 * i) % 50 for i in range(len(ch_in))]
+    check(emu, pcms, rates, 48000, starts, lp=800, gain=0.7, channels=2, ch_in=ch_in)
+    check(emu, pcms[:6], rates[:6], 48000, [0] * 6, channels=2, ch_in=ch_in[:6])
+
+
+def test_mono_and_stereo_session(emu):
+    ch_in = [1, 2, 1, 2]
+    rates = [44100, 48000, 48000, 44100]
+    pcms = [noise(ci * (1100 + 13 * i), 1700 + i) for i, ci in enumerate(ch_in)]
+    ops = []
+    for step in range(50):
+        ops += [(0, r, 40 + 3 * r) for r in range(4)] + [(1, 0, 41 + step % 5)]
+    session_case(emu, pcms, [0, 0, 10, 0], ops, in_rate=rates, mix_rate=48000, lp=900, gain=1.05, channels=2, ch_in=ch_in)

@@ -800,7 +800,7 @@ def test_session_stereo_any_split(ctx):
     chains = [rb.UniformSourceIterator(rb.TestSource(np.zeros(0, np.float32), 2, 44100), 2, 48000).low_pass(300).amplify(1.1)
               for _ in pcms]
     got, left, ended = [], [0] * 40, False
-    with rb.Session(chains, 48000, fifo_frames=4096, max_block_frames=1024, ctx=ctx) as s:
+    with rb.Session(chains, 48000, fifo_frames=4096, max_block_frames=1024, ctx=ctx, mixer_channels=2) as s:
         while not ended:
             blocks, eos = [], []
             for r in range(40):
@@ -815,3 +815,37 @@ def test_session_stereo_any_split(ctx):
                 if block.size == 0 or ended:
                     break
     assert_bit_exact(np.concatenate(got), want, "stereo session vs the whole-stream render")
+
+
+@lanes_gate
+def test_session_mono_and_stereo_sources_mixed_rates(ctx):
+    """A stereo 48 kHz mixer fed by mono and stereo sources at 44.1, 22.05 and 48 kHz (classes of their own), pushed in
+    10 ms blocks: the bytes of the whole-stream batch render."""
+    ch_in = [1, 2, 1, 1, 2, 1, 2, 1] * 3
+    rates = [44100, 44100, 48000, 22050, 48000, 44100, 44100, 48000] * 3
+    pcms = [noise(ci * int(0.2 * r), 1500 + i, 0.8) for i, (ci, r) in enumerate(zip(ch_in, rates))]      # 200 ms each
+    srcs = [rb.UniformSourceIterator(rb.TestSource(p, ci, r), 2, 48000).low_pass(800).amplify(0.7) for p, ci, r in zip(pcms, ch_in, rates)]
+    with rb.Batch(srcs, 2, 48000, flags=LANES, ctx=ctx) as b:
+        assert b.kernel_family == 2
+        b.upload_all()
+        want = b.render_mix()
+    ref = oracle.mixer([to_oracle(s) for s in srcs], 2, 48000)
+    assert_close_peak(want, ref, 1e-5, "mono + stereo, three rates vs the reference's mixer")
+    chains = [rb.UniformSourceIterator(rb.TestSource(np.zeros(0, np.float32), ci, r), 2, 48000).low_pass(800).amplify(0.7)
+              for ci, r in zip(ch_in, rates)]
+    got, pos, ended = [], [0] * len(pcms), False
+    with rb.Session(chains, 48000, fifo_frames=2048, max_block_frames=480, ctx=ctx, mixer_channels=2) as s:
+        while not ended:
+            blocks, eos = [], []
+            for i, (p, ci, r) in enumerate(zip(pcms, ch_in, rates)):
+                n = min(r // 100, p.size // ci - pos[i])
+                blocks.append(p[ci * pos[i]: ci * (pos[i] + n)])
+                pos[i] += n
+                eos.append(pos[i] == p.size // ci)
+            s.push_packed(blocks, eos)
+            while True:
+                block, ended = s.render(480)
+                got.append(block)
+                if block.size == 0 or ended:
+                    break
+    assert_bit_exact(np.concatenate(got), want, "session vs whole-stream render, mono + stereo sources at three rates")
