@@ -1019,8 +1019,8 @@ extern "C" rb_status rb_session_create(rb_context* ctx, uint16_t mixer_channels,
             return fail(RB_ERR_UNSUPPORTED, where + "the chain must start with UNIFORM(mixer channels, mixer rate)");
         const uint32_t g = std::gcd(d.sample_rate, mixer_rate);
         from[i] = d.sample_rate / g, to[i] = mixer_rate / g;
-        if (!(from[i] <= to[i]) || to[i] > (1u << 20))
-            return fail(RB_ERR_UNSUPPORTED, where + "the source rate must not exceed the mixer rate (reduced ratio < 2^20)");
+        if (from[i] > (1u << 20) || to[i] > (1u << 20))
+            return fail(RB_ERR_RATIO_OVERFLOW, where + "reduced rate pair beyond 2^20");
     }
     const auto classes = lanes::classes_by_ratio(from.data(), to.data(), chs.data(), (uint32_t)n);
     s->pos.assign(n, 0);

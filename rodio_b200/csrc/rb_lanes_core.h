@@ -145,7 +145,9 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
         row.b0 = row.b1 = row.b2 = row.a1 = row.a2 = row.ffk = row.post = 0.0f, row.flags = 0;
     }
     const uint64_t ms = row.mix_start, end = row.mix_start + row.out_len;   // frames
-    const bool safe = has && (PASS || (!(row.flags & ROW_UNSAFE) && !(a.unsafe && a.unsafe[r])));
+    // Down-sampling classes (from > to: more than one input frame per output) are served by the slow tiles only -- exact,
+    // general, not fast; the fast run below assumes at most one new frame per step.
+    const bool safe = has && a.from <= a.to && (PASS || (!(row.flags & ROW_UNSAFE) && !(a.unsafe && a.unsafe[r])));
     const bool stops = !(row.flags & ROW_CONTINUES);   // the stream ends inside this block (or is a whole stream)
     const bool live = has && row.out_len != 0;
     const uint64_t t_lo = simt::reduce_min64(live ? ms : ~0ull), t_hi = simt::reduce_max64(live ? end : 0ull);

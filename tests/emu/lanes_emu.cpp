@@ -57,7 +57,7 @@ extern "C" int rb_lanes_emulate(const float* const* pcm, const uint64_t* n_frame
     using namespace lanes;
     if (n_rows == 0 || (channels != 1 && channels != 2)) return 1;
     for (uint32_t r = 0; r < n_rows; r++)
-        if (!(from[r] <= to[r]) || to[r] > (1u << 20) || !(ch_in[r] == channels || (ch_in[r] == 1 && channels == 2))) return 1;
+        if (from[r] == 0 || from[r] > (1u << 20) || to[r] > (1u << 20) || !(ch_in[r] == channels || (ch_in[r] == 1 && channels == 2))) return 1;
     const uint32_t C = channels;   // n_frames / out_len / mix_start / mix_len count FRAMES; out_mix holds frames * C floats,
                                    // pcm[r] frames * ch_in[r] floats
     const float nan = std::numeric_limits<float>::quiet_NaN();
@@ -150,7 +150,7 @@ extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t*
     using namespace lanes;
     if (n_rows == 0 || (channels != 1 && channels != 2)) return -1;
     for (uint32_t r = 0; r < n_rows; r++)
-        if (!(from[r] <= to[r]) || to[r] > (1u << 20) || !(ch_in[r] == channels || (ch_in[r] == 1 && channels == 2))) return -1;
+        if (from[r] == 0 || from[r] > (1u << 20) || to[r] > (1u << 20) || !(ch_in[r] == channels || (ch_in[r] == 1 && channels == 2))) return -1;
     const auto classes = classes_by_ratio(from, to, ch_in, n_rows);   // fixed for the session: rows are laid out class by class
     const uint32_t C = channels;   // frames everywhere; out holds frames * C floats, pcm[r] / FIFO r frames * ch_in[r] floats
     const float nan = std::numeric_limits<float>::quiet_NaN();
@@ -289,7 +289,7 @@ extern "C" int rb_session_plan_fuzz(uint64_t seed, uint32_t n_cases) {
         std::vector<session::Stream> st(ns);
         std::vector<uint64_t> total(ns), rendered(ns, 0);
         for (uint32_t r = 0; r < ns; r++) {
-            uint32_t to = 1 + (uint32_t)rnd(400), from = 1 + (uint32_t)rnd(to);   // from <= to, 1:1 included
+            uint32_t to = 1 + (uint32_t)rnd(400), from = rnd(4) ? 1 + (uint32_t)rnd(to) : 1 + (uint32_t)rnd(3 * to);   // mostly from <= to (1:1 included), some down-sampling
             const uint32_t g = std::gcd(from, to);
             st[r].from = from / g, st[r].to = to / g;
             st[r].mix_start = rnd(3) ? 0 : rnd(500), total[r] = rnd(6000);

@@ -413,3 +413,17 @@ def test_mono_and_stereo_session(emu):
     for step in range(50):
         ops += [(0, r, 40 + 3 * r) for r in range(4)] + [(1, 0, 41 + step % 5)]
     session_case(emu, pcms, [0, 0, 10, 0], ops, in_rate=rates, mix_rate=48000, lp=900, gain=1.05, channels=2, ch_in=ch_in)
+
+
+def test_session_with_sources_above_the_mixer_rate(emu):
+    """48 kHz and 96 kHz sources in a 44.1 kHz mixer: down-sampling classes run on the kernel's slow tiles (closed form, IEEE
+    division) -- exact, block-split invariant like everything else, just not fast."""
+    rates = [48000, 96000, 44100, 22050, 48000]
+    pcms = [noise(int(0.02 * r) + 7 * i, 2100 + i) for i, r in enumerate(rates)]       # about 20 ms each
+    ops = []
+    for step in range(40):
+        ops += [(0, r, int(rates[r] / 1500) + r) for r in range(5)] + [(1, 0, 30 + step % 9)]
+    counters(emu)
+    session_case(emu, pcms, [0, 0, 0, 50, 3], ops, in_rate=rates, mix_rate=44100, lp=500, gain=0.9)
+    c = counters(emu)
+    assert c["slow"] > 50, c
