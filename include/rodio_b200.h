@@ -238,9 +238,11 @@ rb_status rb_session_push(rb_session* s, size_t stream, const float* pcm, uint64
 /* The same for every source at once: pcm holds n_frames[0] frames of source 0, then n_frames[1] of source 1, ...;
  * end_of_stream may be NULL.  One host->device copy and one kernel for the whole session. */
 rb_status rb_session_push_packed(rb_session* s, const float* pcm, const uint64_t* n_frames, const uint8_t* end_of_stream);
-/* Amplify::set_factor (src/source/amplify.rs:25-29) on a live source -- what Player::set_volume does through its
- * periodic access every 5 ms of audio (src/player.rs:138-166): the source's gain is `factor` from the next rendered
- * block on (a source without an AMPLIFY in its chain behaves as amplify(1.0), like Player's own chain). */
+/* Amplify::set_factor (src/source/amplify.rs:25-29) on the AMPLIFY of a live source's chain: the gain is `factor` from the
+ * next rendered block on (a source without an AMPLIFY behaves as amplify(1.0)).  Player::set_volume does the same to its
+ * own Amplify every 5 ms of audio (src/player.rs:138-166) -- but that one sits in FRONT of the mixer's resampler
+ * (src/player.rs:120-128), while the session's chain amplifies behind it: equal up to the rounding of one multiplication
+ * per sample, not bit for bit; an exact Player mirror needs a gain on the taps (not in the session shape yet). */
 rb_status rb_session_set_amplify(rb_session* s, size_t stream, float factor);
 /* Mixer frames the next render can produce from what has been pushed (an output frame exists once its right input
  * neighbour has arrived, or its source has ended: sample_rate.rs:187-199).  *ended != 0: every source is exhausted

@@ -529,7 +529,7 @@ class Session:
         check(lib().rb_session_push_packed(self._h, flat.ctypes.data_as(C.c_void_p), n, eos), "rb_session_push_packed")
 
     def set_amplify(self, stream: int, factor: float):
-        """Amplify::set_factor / Player::set_volume on a live source: applies from the next rendered block on."""
+        """Amplify::set_factor on the chain's AMPLIFY of a live source: applies from the next rendered block on."""
         check(lib().rb_session_set_amplify(self._h, stream, float(factor)), "rb_session_set_amplify")
 
     def available(self) -> Tuple[int, bool]:
