@@ -255,7 +255,10 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                 if (HASB && FF2) p1[c] = simt::fmul(b0, xh1[c]), p2[c] = simt::fmul(b0, xh2[c]);
             }
 
-            for (uint32_t done = 0; done < run; done += TF) {
+            // One tile: ring bookkeeping, then TF frames per lane into v[].  The mixer sum of a tile (five dependent shuffle
+            // levels, nothing in the tile left to overlap them) is issued one tile late, inside the next tile's basic block,
+            // so that the scheduler can hide its latency behind that tile's loads and arithmetic.
+            auto tile = [&](float (&v)[TILE]) {
                 kb += a.q8, kbn += a.r8;
                 if (kbn >= to) kbn -= to, kb += 1;
                 if ((kb - 1) / CHUNK >= c_ready) {
@@ -266,7 +269,6 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                     simt::emu_count(2, 1);
                 }
                 if (simt::sptr_ge(p, ring_end)) p = simt::sptr_add(p, -RING);
-                float v[TILE];
 #pragma unroll
                 for (int f = 0; f < TF; f++) {
                     float x[C];
@@ -307,8 +309,20 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
 #pragma unroll
                     for (int co = 0; co < CO; co++) v[f * CO + co] = val[co < C ? co : 0];
                 }
-                const float s = reduce_tile(v, ln);
-                if ((ln & 3u) == 0) prow[(t + done) * CO + (ln >> 2)] = s;
+            };
+            float vp[TILE];
+            tile(vp);
+            for (uint32_t done = TF; done < run; done += TF) {
+                float v[TILE];
+                tile(v);
+                const float s = reduce_tile(vp, ln);                              // the previous tile's sum
+                if ((ln & 3u) == 0) prow[(t + done - TF) * CO + (ln >> 2)] = s;
+#pragma unroll
+                for (int u = 0; u < TILE; u++) vp[u] = v[u];
+            }
+            {
+                const float s = reduce_tile(vp, ln);
+                if ((ln & 3u) == 0) prow[(t + run - TF) * CO + (ln >> 2)] = s;
             }
             simt::cp_wait<0>();
             simt::syncwarp();

@@ -3,7 +3,8 @@
 steady-state loop of the <biquad, FF2, one gain> instantiation (the backward branch whose body holds the butterfly
 shuffles of the mixer sum) and print its instruction mix per tile of 8 samples x 32 lanes.  The refill block (LDGSTS)
 sits inside the loop but is branched over on most iterations; it is listed separately.
-    python tools/sass_loop_count.py [mangled-name-fragment, default ILb1ELb1ELi1]"""
+    python tools/sass_loop_count.py [mangled-name-fragment]
+    default ILi1ELi1ELb1ELb1ELi1ELb0E = <CI 1, CO 1, biquad, FF2, one gain, interpolating>; stereo: ILi2ELi2ELb1ELb1ELi1ELb0E"""
 import collections
 import os
 import re
@@ -18,7 +19,7 @@ FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-li
 
 
 def main():
-    frag = sys.argv[1] if len(sys.argv) > 1 else "ILb1ELb1ELi1"
+    frag = sys.argv[1] if len(sys.argv) > 1 else "ILi1ELi1ELb1ELb1ELi1ELb0E"
     with tempfile.TemporaryDirectory() as td:
         obj = os.path.join(td, "rb_lanes.o")
         r = subprocess.run(["nvcc"] + FLAGS + ["-Xptxas", "-v", "-c", SRC, "-o", obj], capture_output=True, text=True, check=True)
