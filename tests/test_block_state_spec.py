@@ -1,8 +1,10 @@
 """Executable specification of block-to-block state for the fused family:
     [amplify]* -> UniformSourceIterator (same channels) -> biquad -> [amplify]*
 rendered block by block with explicit carried state, against the whole-stream oracle, bit for bit.
-This is the contract the CUDA state carry of the next round has to meet (rb_batch_get_state / set_state);
-it is CPU-only and uses numpy float32 scalars (one rounding per operation, like the kernels)."""
+This is the contract of the CUDA state carry: rb_session_* (include/rodio_b200.h) implements it for the
+uniform -> biquad -> amplify shape and is held to it by tests/test_lanes_emulator.py::test_session_* (CPU emulator) and
+tests/test_parity_gpu.py::test_session_* (device); the pre-gain, AGC and reverb forms below are still specification only.
+CPU-only, numpy float32 scalars (one rounding per operation, like the kernels)."""
 from dataclasses import dataclass, field
 from math import gcd
 
