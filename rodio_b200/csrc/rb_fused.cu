@@ -1290,8 +1290,8 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     // (measured: 65 536 x 1 s in 4.26 ms against 7.0 ms for k_fused_hot, 16 384 x 1 s in 2.46 ms against 1.74 ms).
     const bool want_lanes = (flags & RB_FUSED_LANES) || n_streams >= (size_t)277 * (size_t)(sm_count > 0 ? sm_count : 148);
     if (want_lanes && (mixer_channels == 1 || mixer_channels == 2) && plan->all_f32 && has_u && n_pre == 0) {
-        // Lane-per-stream kernel (opt-in): mono or stereo f32 streams (same channel count as the mixer) that all
-        // interpolate with ONE reduced ratio from < to, optional biquad, at most one gain directly in front of the sum.
+        // Lane-per-stream kernel: f32 streams with the mixer's channel count (or mono in a stereo mixer), each at or
+        // below the mixer's rate (classes per rate pair), optional biquad, at most one gain directly in front of the sum.
         const uint32_t C = mixer_channels;
         bool ok = has_b ? (n_mid == 0 && n_post <= 1) : (n_mid + n_post <= 1);
         std::vector<rb_lanes_stream> ls(ok ? n_streams : 0);

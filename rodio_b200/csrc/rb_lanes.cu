@@ -1,6 +1,8 @@
 // rb_lanes.cu — k_fused_lanes: the lane-per-stream fused kernel for large uniform batches (the warp program lives in
 // rb_lanes_core.h, shared with the CPU emulator of tests/emu/), its input classification, the ordered sum of the
-// per-warp partial rows, and the host-side plan.  Opt-in through RB_FUSED_LANES (include/rodio_b200.h).
+// per-warp partial rows, and the host-side plan (one launch per class of streams: rate pair x source channels).
+// Chosen by the fused planner for very large batches or on RB_FUSED_LANES (include/rodio_b200.h); also renders the blocks
+// of the streaming sessions (rb_session_* in rb_api.cu).
 #include <algorithm>
 #include <vector>
 

@@ -1,5 +1,6 @@
 #!/usr/bin/env bash
-# First run of k_fused_lanes / rb_session_* on a B200 (they were written without GPU access).
+# Measurement pass for k_fused_lanes / rb_session_* on a B200 (round 1 only had two ten-second runs:
+# all parity checks green, two wall-clock timings).
 # One gpurun call:   gpurun --timeout 1500 -- 'bash tools/first_device_pass.sh'
 # Everything lands in gpurun_out/lanes_first/; every step is bounded by `timeout` so a hang cannot eat the box.
 set -u
@@ -14,7 +15,7 @@ timeout 420 compute-sanitizer --tool memcheck --error-exitcode 9 \
     > "$OUT/memcheck.log" 2>&1
 echo "memcheck exit $?" | tee -a "$OUT/summary.txt"
 
-# 2. the gated parity tests (bit-exact against the oracle streams + the kernel's tree, sessions vs whole renders)
+# 2. the parity tests of the kernel and the sessions (+ the still gated C++ session binary)
 timeout 600 python -m pytest tests -q -m gpu -k "lanes or session" > "$OUT/pytest_lanes.log" 2>&1
 echo "pytest lanes/session exit $?" | tee -a "$OUT/summary.txt"
 tail -5 "$OUT/pytest_lanes.log" >> "$OUT/summary.txt"

@@ -24,7 +24,8 @@ timeout 120 python tools/hot_timing.py 4096 --skips > gpurun_out/r1_hot_timing.t
 #   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531 \
 #       bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/r1_bench_2gpu.json
 
-# --- first device pass of k_fused_lanes / sessions (not run in round 1: no GPU minutes left) ---
+# --- k_fused_lanes / sessions: round 1 had two ten-second runs (profiles/r1_lanes_*.log: python tools/lanes_quick_check.py
+#     --time, --time-big --lanes-only, and the pytest line below); the full measurement plan is tools/first_device_pass.sh ---
 # RB_TEST_LANES=1 python -m pytest tests -m gpu -x -q -k "lanes or session"
 # python tools/bench_configs.py lanes > gpurun_out/lanes_sweep.jsonl
 # ncu --set full --clock-control none --import-source on -k regex:k_fused_lanes -s 3 -c 1 -o gpurun_out/lanes_full python tools/bench_configs.py lanes
