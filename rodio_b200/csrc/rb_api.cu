@@ -1005,7 +1005,7 @@ extern "C" rb_status rb_session_create(rb_context* ctx, uint16_t mixer_channels,
     s->ctx = ctx, s->mixer_rate = mixer_rate, s->channels = mixer_channels, s->fifo_cap = fifo_frames, s->max_block = max_block_frames;
     const size_t n = n_streams;
     // pass 1: validate, find every source's reduced rate pair -> classes
-    std::vector<uint32_t> from(n), to(n), chs(n);
+    std::vector<uint32_t> from(n), to(n), chs(n), first_fx(n);
     for (size_t i = 0; i < n; i++) {
         const rb_stream_desc& d = descs[i];
         const std::string where = "stream " + std::to_string(i) + ": ";
@@ -1015,10 +1015,14 @@ extern "C" rb_status rb_session_create(rb_context* ctx, uint16_t mixer_channels,
             return fail(RB_ERR_UNSUPPORTED, where + "a source has the mixer's channel count, or is mono in a stereo mixer");
         chs[i] = d.channels;
         if (d.n_effects && !d.effects) return fail(RB_ERR_INVALID_ARGUMENT, where + "effects is NULL");
-        if (d.n_effects == 0 || d.effects[0].kind != RB_FX_UNIFORM || d.effects[0].u32[0] != mixer_channels || d.effects[0].u32[1] != mixer_rate)
-            return fail(RB_ERR_UNSUPPORTED, where + "the chain must start with UNIFORM(mixer channels, mixer rate)");
-        const uint32_t g = std::gcd(d.sample_rate, mixer_rate);
-        from[i] = d.sample_rate / g, to[i] = mixer_rate / g;
+        // Source::speed in front of the conversion only changes the rate the source reports (src/source/speed.rs:130-133)
+        uint32_t k0 = 0, rate = d.sample_rate;
+        while (k0 < d.n_effects && d.effects[k0].kind == RB_FX_SPEED) rate = rb_speed_sample_rate(rate, d.effects[k0].f32[0]), k0++;
+        first_fx[i] = k0;
+        if (k0 >= d.n_effects || d.effects[k0].kind != RB_FX_UNIFORM || d.effects[k0].u32[0] != mixer_channels || d.effects[k0].u32[1] != mixer_rate)
+            return fail(RB_ERR_UNSUPPORTED, where + "the chain must be [SPEED] UNIFORM(mixer channels, mixer rate) ...");
+        const uint32_t g = std::gcd(rate, mixer_rate);
+        from[i] = rate / g, to[i] = mixer_rate / g;
         if (from[i] > (1u << 20) || to[i] > (1u << 20))
             return fail(RB_ERR_RATIO_OVERFLOW, where + "reduced rate pair beyond 2^20");
     }
@@ -1039,7 +1043,7 @@ extern "C" rb_status rb_session_create(rb_context* ctx, uint16_t mixer_channels,
         const size_t i = order[r];
         const rb_stream_desc& d = descs[i];
         const std::string where = "stream " + std::to_string(i) + ": ";
-        uint32_t k = 1;
+        uint32_t k = first_fx[i] + 1;   // behind [SPEED] UNIFORM
         bool biq = false;
         if (k < d.n_effects && (d.effects[k].kind == RB_FX_LOW_PASS || d.effects[k].kind == RB_FX_HIGH_PASS)) {
             const rb_effect& e = d.effects[k];
@@ -1052,7 +1056,7 @@ extern "C" rb_status rb_session_create(rb_context* ctx, uint16_t mixer_channels,
         }
         any_biquad |= biq, all_biquad &= biq;
         if (k < d.n_effects && d.effects[k].kind == RB_FX_AMPLIFY) s->post[r] = d.effects[k].f32[0], s->has_post = true, k++;
-        if (k != d.n_effects) return fail(RB_ERR_UNSUPPORTED, where + "chain shape: UNIFORM [LOW_PASS | HIGH_PASS] [AMPLIFY]");
+        if (k != d.n_effects) return fail(RB_ERR_UNSUPPORTED, where + "chain shape: [SPEED] UNIFORM [LOW_PASS | HIGH_PASS] [AMPLIFY]");
         s->st[r].mix_start = d.mix_start, s->st[r].from = from[i], s->st[r].to = to[i];
         s->src_ch[r] = (uint8_t)d.channels;
     }

@@ -849,3 +849,22 @@ def test_session_mono_and_stereo_sources_mixed_rates(ctx):
                 if block.size == 0 or ended:
                     break
     assert_bit_exact(np.concatenate(got), want, "session vs whole-stream render, mono + stereo sources at three rates")
+
+
+@lanes_gate
+def test_session_speed_changes_the_rate_pair(ctx):
+    """source.speed(0.9) in front of the conversion: 44 100 Hz is reported as 39 690 Hz (speed.rs:130-133), nothing else."""
+    pcms = [noise(6000 + 100 * i, 2300 + i) for i in range(6)]
+    mk = lambda p: rb.UniformSourceIterator(rb.TestSource(p, 1, 44100).speed(0.9), 1, 48000).low_pass(400)
+    want = oracle.mixer([to_oracle(mk(p)) for p in pcms], 1, 48000)
+    got, pos, ended = [], 0, False
+    with rb.Session([mk(np.zeros(0, np.float32)) for _ in pcms], 48000, fifo_frames=2048, max_block_frames=512, ctx=ctx) as s:
+        while not ended:
+            s.push_packed([p[pos:pos + 400] for p in pcms], [pos + 400 >= p.size for p in pcms])
+            pos += 400
+            while True:
+                block, ended = s.render(512)
+                got.append(block)
+                if block.size == 0 or ended:
+                    break
+    assert_close_peak(np.concatenate(got), want, 1e-5, "session with speed() vs the reference's mixer")
