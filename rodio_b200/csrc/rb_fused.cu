@@ -1289,7 +1289,7 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     // RB_FUSED_LANES asks for it; from about 277 streams per SM on (10 warps of 32 streams) it is the faster kernel anyway
     // (measured: 65 536 x 1 s in 4.26 ms against 7.0 ms for k_fused_hot, 16 384 x 1 s in 2.46 ms against 1.74 ms).
     const bool want_lanes = (flags & RB_FUSED_LANES) || n_streams >= (size_t)277 * (size_t)(sm_count > 0 ? sm_count : 148);
-    if (want_lanes && (mixer_channels == 1 || mixer_channels == 2) && plan->all_f32 && has_u && n_pre == 0) {
+    if (want_lanes && (mixer_channels == 1 || mixer_channels == 2) && plan->all_f32 && (has_u || has_b) && n_pre == 0) {
         // Lane-per-stream kernel: f32 streams with the mixer's channel count (or mono in a stereo mixer), each at or
         // below the mixer's rate (classes per rate pair), optional biquad, at most one gain directly in front of the sum.
         const uint32_t C = mixer_channels;
@@ -1300,7 +1300,7 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
             // every stream interpolates upwards on its own reduced grid (several rate pairs are served class by class),
             // or is at the mixer's rate already (UniformSourceIterator hands it through)
             const bool lerp_up = r.mode == ROW_LERP && r.uni.from < r.uni.to;
-            const bool pass = r.mode == ROW_PASS;
+            const bool pass = r.mode == ROW_PASS || r.mode == ROW_DIRECT;   // no conversion needed / none in the chain
             // the stream has the mixer's channels, or is mono in a stereo mixer (repeated on both channels, channels.rs:57-85)
             ok = (lerp_up || pass) && (r.c_in == C || (r.c_in == 1 && C == 2)) && r.out_len % C == 0 && r.mix_start % C == 0 &&
                  r.n_in % r.c_in == 0;

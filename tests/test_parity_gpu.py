@@ -868,3 +868,16 @@ def test_session_speed_changes_the_rate_pair(ctx):
                 if block.size == 0 or ended:
                     break
     assert_close_peak(np.concatenate(got), want, 1e-5, "session with speed() vs the reference's mixer")
+
+
+@lanes_gate
+def test_lanes_sources_without_a_conversion(ctx):
+    """Sources at the mixer's format with a filter and a gain, no UniformSourceIterator in the chain."""
+    pcms = [noise(4000 + 7 * i, 2500 + i) for i in range(70)]
+    srcs = [rb.TestSource(p, 1, 48000).low_pass(300).amplify(0.6) for p in pcms]
+    with rb.Batch(srcs, 1, 48000, flags=LANES, ctx=ctx) as b:
+        assert b.kernel_family == 2
+        b.upload_all()
+        got = b.render_mix()
+    per_stream = [oracle.chain_uniform(to_oracle(s), 1, 48000) for s in srcs]
+    assert_bit_exact(got, lanes_expected_mix(per_stream, [0] * 70, got.size), "filter + gain on same-rate sources")
