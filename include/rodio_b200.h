@@ -228,6 +228,9 @@ rb_status rb_batch_read_stream(rb_batch* b, size_t stream, float* out_host, uint
  * desc.mix_start is the mixer FRAME the source joins at.  Everything below counts frames; PCM is interleaved.
  * One caller per session; every call returns with the work done (the caller may reuse its buffers). */
 typedef struct rb_session rb_session;
+/* desc.mix_start of a source that is declared now but handed to the mixer later -- Mixer::add while the mixer is playing
+ * (src/mixer.rs:58-66): the source takes pushes at once, renders nothing and holds nobody up until rb_session_start. */
+#define RB_SESSION_HELD UINT64_MAX
 /* fifo_frames: input frames a source can hold between renders (>= 64); max_block_frames: largest render. */
 rb_status rb_session_create(rb_context* ctx, uint16_t mixer_channels, uint32_t mixer_sample_rate, const rb_stream_desc* descs,
                             size_t n_streams, uint32_t fifo_frames, uint32_t max_block_frames, rb_session** out);
@@ -238,6 +241,10 @@ rb_status rb_session_push(rb_session* s, size_t stream, const float* pcm, uint64
 /* The same for every source at once: pcm holds n_frames[0] frames of source 0, then n_frames[1] of source 1, ...;
  * end_of_stream may be NULL.  One host->device copy and one kernel for the whole session. */
 rb_status rb_session_push_packed(rb_session* s, const float* pcm, const uint64_t* n_frames, const uint8_t* end_of_stream);
+/* Mixer::add for a source declared with RB_SESSION_HELD: it joins at the mixer frame rendered next (sources join on a frame
+ * boundary, src/mixer.rs:175-183).  While no source is playing the session renders nothing and its timeline stands still,
+ * as MixerSource::next() returns None (src/mixer.rs:129-135); `ended` stays 0 as long as a held source may still come. */
+rb_status rb_session_start(rb_session* s, size_t stream);
 /* Amplify::set_factor (src/source/amplify.rs:25-29) on the AMPLIFY of a live source's chain: the gain is `factor` from the
  * next rendered block on (a source without an AMPLIFY behaves as amplify(1.0)).  Player::set_volume does the same to its
  * own Amplify every 5 ms of audio (src/player.rs:138-166) -- but that one sits in FRONT of the mixer's resampler

@@ -291,6 +291,8 @@ class LiveMixer {
     void push(size_t i, const std::vector<Sample>& pcm, bool end_of_stream = false) {
         check(rb_session_push(h_, i, pcm.data(), pcm.size() / src_channels_.at(i), end_of_stream ? 1 : 0), "rb_session_push");
     }
+    // Mixer::add (mixer.rs:58-66) for a source that was declared held (its desc().mix_start == RB_SESSION_HELD)
+    void add(size_t i) { check(rb_session_start(h_, i), "rb_session_start"); }
     // Amplify::set_factor on the chain's .amplify() (amplify.rs:25-29); Player::set_volume's Amplify sits before the resampler
     void set_amplify(size_t i, float factor) { check(rb_session_set_amplify(h_, i, factor), "rb_session_set_amplify"); }
     bool ended() const { return ended_ && at_ == block_.size(); }

@@ -35,6 +35,7 @@ RB_NO_FUSION = 1 << 1
 RB_BIQUAD_TIME_PARALLEL = 1 << 2
 RB_KEEP_STREAM_OUTPUTS = 1 << 3
 RB_FUSED_LANES = 1 << 4
+RB_SESSION_HELD = (1 << 64) - 1
 
 
 class rb_effect(C.Structure):
@@ -84,6 +85,7 @@ SYMBOLS = {
     "rb_session_destroy": (C.c_int32, [C.c_void_p]),
     "rb_session_push": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint64, C.c_int]),
     "rb_session_push_packed": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rb_session_start": (C.c_int32, [C.c_void_p, C.c_size_t]),
     "rb_session_set_amplify": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_float]),
     "rb_session_available": (C.c_int32, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
     "rb_session_render": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),

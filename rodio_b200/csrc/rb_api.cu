@@ -1058,6 +1058,7 @@ extern "C" rb_status rb_session_create(rb_context* ctx, uint16_t mixer_channels,
         if (k < d.n_effects && d.effects[k].kind == RB_FX_AMPLIFY) s->post[r] = d.effects[k].f32[0], s->has_post = true, k++;
         if (k != d.n_effects) return fail(RB_ERR_UNSUPPORTED, where + "chain shape: [SPEED] UNIFORM [LOW_PASS | HIGH_PASS] [AMPLIFY]");
         s->st[r].mix_start = d.mix_start, s->st[r].from = from[i], s->st[r].to = to[i];
+        if (d.mix_start == RB_SESSION_HELD) s->st[r].held = true, s->st[r].mix_start = 0;   // Mixer::add comes later (rb_session_start)
         s->src_ch[r] = (uint8_t)d.channels;
     }
     if (any_biquad && !all_biquad) return fail(RB_ERR_UNSUPPORTED, "either every source of a session has a filter or none has");
@@ -1150,6 +1151,13 @@ extern "C" rb_status rb_session_push_packed(rb_session* s, const float* pcm, con
         s->st[s->pos[i]].pushed += n_frames[i];
         if (end_of_stream && end_of_stream[i]) s->st[s->pos[i]].eof = true;
     }
+    return RB_OK;
+}
+
+extern "C" rb_status rb_session_start(rb_session* s, size_t stream) {
+    if (!s) return fail(RB_ERR_INVALID_ARGUMENT, "session is NULL");
+    if (stream >= s->st.size()) return fail(RB_ERR_INVALID_ARGUMENT, "stream index out of range");
+    session::start(s->st[s->pos[stream]], s->T);   // joins at the frame rendered next; no-op when it is playing already
     return RB_OK;
 }
 

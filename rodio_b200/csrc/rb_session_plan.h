@@ -26,6 +26,8 @@ struct Stream {
     uint64_t out_done = 0;     // output frames rendered so far (= stream-absolute index of the next one)
     uint64_t i0 = 0;           // stream-absolute index of the frame at the front of the FIFO (multiple of 4)
     bool eof = false;          // no more input will come
+    bool held = false;         // declared when the session was created but not handed to the mixer yet (Mixer::add comes
+                               // later): it takes pushes, renders nothing and holds nobody up until it is started
     uint64_t fill() const { return pushed - i0; }   // frames in the FIFO
 };
 
@@ -51,15 +53,19 @@ inline bool finished(const Stream& s) { return s.eof && s.out_done >= out_total(
 // Returns 0 with *ended = true when no stream is left (MixerSource::next returns None, src/mixer.rs:129-135).
 inline uint64_t renderable(const std::vector<Stream>& st, uint64_t T, uint64_t max_frames, bool* ended) {
     uint64_t n = max_frames;
-    bool any = false;
+    bool active = false, waiting = false;
     for (const Stream& s : st) {
+        if (s.held) {             // may still be added: keeps the session alive, holds nobody up
+            waiting = true;
+            continue;
+        }
         if (finished(s)) continue;
-        any = true;
+        active = true;
         const uint64_t upto = s.mix_start + out_ready(s);   // the stream can cover the timeline up to here
         n = std::min(n, upto > T ? upto - T : 0);
     }
-    *ended = !any;
-    return any ? n : 0;
+    *ended = !active && !waiting;
+    return active ? n : 0;        // nothing is playing: MixerSource::next() is None, the timeline stands still (mixer.rs:129-135)
 }
 
 // One stream's part of the block [T, T + n).
@@ -72,6 +78,10 @@ struct Part {
 };
 inline Part part_of(const Stream& s, uint64_t T, uint64_t n) {
     Part p;
+    if (s.held) {
+        p.continues = true;
+        return p;
+    }
     const uint32_t from = s.from, to = s.to;
     const uint64_t ready = out_ready(s);
     const uint64_t lo = std::max(T, s.mix_start + s.out_done), hi = std::min(T + n, s.mix_start + ready);
@@ -85,6 +95,11 @@ inline Part part_of(const Stream& s, uint64_t T, uint64_t n) {
     p.continues = !(s.eof && p.o0 + p.out_len >= out_total(s.pushed, from, to));
     return p;
 }
+// Mixer::add for a held source while the mixer has rendered T frames: it joins at the next frame (src/mixer.rs:175-183).
+inline void start(Stream& s, uint64_t T) {
+    if (s.held) s.held = false, s.mix_start = T;
+}
+
 // After the block: advance the stream and tell how many FIFO frames (from the front) are dead.
 inline uint64_t advance(Stream& s, const Part& p) {
     s.out_done = p.out_len ? p.o0 + p.out_len : s.out_done;

@@ -528,6 +528,10 @@ class Session:
         eos = (C.c_uint8 * len(blocks))(*[int(bool(e)) for e in end_of_stream]) if end_of_stream is not None else None
         check(lib().rb_session_push_packed(self._h, flat.ctypes.data_as(C.c_void_p), n, eos), "rb_session_push_packed")
 
+    def start(self, stream: int):
+        """Mixer::add for a source created with mix_start = capi.RB_SESSION_HELD: joins at the frame rendered next."""
+        check(lib().rb_session_start(self._h, stream), "rb_session_start")
+
     def set_amplify(self, stream: int, factor: float):
         """Amplify::set_factor on the chain's AMPLIFY of a live source: applies from the next rendered block on."""
         check(lib().rb_session_set_amplify(self._h, stream, float(factor)), "rb_session_set_amplify")

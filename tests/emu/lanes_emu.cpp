@@ -138,15 +138,16 @@ extern "C" int rb_lanes_emulate(const float* const* pcm, const uint64_t* n_frame
 // program block by block.  ops: triples (kind, stream, count) -- kind 0: push `count` more frames of the stream's PCM
 // (the stream ends when all of it has been pushed, or on kind 2), kind 1: render up to `count` mixer frames,
 // kind 2: mark the stream ended now (whatever was pushed is all there is), kind 3: the stream's gain becomes the float
-// whose bits are `count` from the next block on (rb_session_set_amplify).  After the last op everything is ended and
-// drained.  Returns the number of mixer frames written to out (capacity out_cap), or -1.
+// whose bits are `count` from the next block on (rb_session_set_amplify), kind 4: Mixer::add of a source that was declared
+// held (mix_start == ~0 in the arguments): it joins at the frame rendered next.  After the last op everything is ended and
+// drained (sources still held are dropped).  Returns the number of mixer frames written to out (capacity out_cap), or -1.
 #include "../../rodio_b200/csrc/rb_session_plan.h"
 
 extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t* n_frames, const uint64_t* mix_start,
                                         const float* coefs, const float* post, uint32_t n_rows, uint32_t channels /* mixer */,
                                         const uint32_t* ch_in, const uint32_t* from, const uint32_t* to, int hasb, int npost, const uint64_t* ops,
                                         uint64_t n_ops, float* out, uint64_t out_cap, uint64_t* n_renders,
-                                        uint64_t* pushed_total /* [n_rows] */) {
+                                        uint64_t* pushed_total /* [n_rows] */, uint64_t* joined_at /* [n_rows]: mixer frame, ~0 = never */) {
     using namespace lanes;
     if (n_rows == 0 || (channels != 1 && channels != 2)) return -1;
     for (uint32_t r = 0; r < n_rows; r++)
@@ -172,6 +173,7 @@ extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t*
         while ((uintptr_t)fifo[r] & 15) fifo[r]++;
         warp.readable.push_back({(const char*)fifo[r], (const char*)(fifo[r] + n_frames[r] * ch_in[r] + 8)});
         st[r].mix_start = mix_start[r], st[r].from = from[r], st[r].to = to[r];
+        if (mix_start[r] == ~0ull) st[r].held = true, st[r].mix_start = 0;
         if (hasb) {
             const float* c = coefs + 5 * r;
             if (!ff2_coeffs(c[0], c[1], c[2], &ffk[r])) ff2 = false;
@@ -262,6 +264,7 @@ extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t*
         if (kind == 0) push((uint32_t)r, cnt);
         else if (kind == 1) render(cnt);
         else if (kind == 2) st[r].eof = true;
+        else if (kind == 4) session::start(st[r], T);
         else {
             const uint32_t bits = (uint32_t)cnt;
             std::memcpy(&gain[r], &bits, 4);
@@ -269,6 +272,10 @@ extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t*
     }
     for (uint32_t r = 0; r < n_rows; r++) st[r].eof = true;   // whatever was pushed is all there is
     for (uint32_t r = 0; r < n_rows; r++) pushed_total[r] = st[r].pushed;
+    for (uint32_t r = 0; r < n_rows; r++) {
+        joined_at[r] = st[r].held ? ~0ull : st[r].mix_start;
+        if (st[r].held) st[r].held = false, st[r].pushed = st[r].i0 = 0, st[r].out_done = 0;   // never added: contributes nothing
+    }
     while (render(1ull << 20)) {
         bool ended = false;
         if (session::renderable(st, T, 1, &ended) == 0 && !ended) std::abort();   // no progress
@@ -293,10 +300,12 @@ extern "C" int rb_session_plan_fuzz(uint64_t seed, uint32_t n_cases) {
             const uint32_t g = std::gcd(from, to);
             st[r].from = from / g, st[r].to = to / g;
             st[r].mix_start = rnd(3) ? 0 : rnd(500), total[r] = rnd(6000);
+            if (rnd(4) == 0) st[r].held = true, st[r].mix_start = 0;     // Mixer::add comes later
         }
         uint64_t T = 0;
         for (int step = 0; step < 4000; step++) {
             const uint32_t r = (uint32_t)rnd(ns);
+            if (st[r].held && rnd(12) == 0) session::start(st[r], T);
             if (!st[r].eof) {
                 uint64_t n = std::min<uint64_t>(rnd(900), total[r] - st[r].pushed);
                 n = std::min<uint64_t>(n, cap - st[r].fill());            // the device refuses more than the FIFO takes
@@ -321,7 +330,7 @@ extern "C" int rb_session_plan_fuzz(uint64_t seed, uint32_t n_cases) {
                     if (p.n_int < p.out_len) CHECK(st[q].eof && p.out_len - p.n_int == 1);                  // only the raw last frame
                     if (!session::finished(st[q]) && st[q].mix_start + st[q].out_done <= T) CHECK(p.mix_start == 0);
                 } else {
-                    CHECK(session::finished(st[q]) || st[q].mix_start >= T + n || n == 0);
+                    CHECK(session::finished(st[q]) || st[q].held || st[q].mix_start >= T + n || n == 0);
                 }
                 const uint64_t fill = st[q].fill();
                 const uint64_t drop = session::advance(st[q], p);
@@ -330,15 +339,20 @@ extern "C" int rb_session_plan_fuzz(uint64_t seed, uint32_t n_cases) {
                 CHECK(st[q].eof || (st[q].out_done * (uint64_t)from) / to >= st[q].i0);
                 // what stays in the FIFO is bounded: an unfinished stream keeps at most the frames not yet usable + 4
                 CHECK(p.continues == !session::finished(st[q]) || p.out_len == 0);
+                if (st[q].held) CHECK(p.out_len == 0 && drop == 0 && st[q].out_done == 0);
             }
             T += n;
         }
         for (uint32_t r = 0; r < ns; r++) st[r].eof = true;
         for (int guard = 0; guard < 100000; guard++) {
+            for (uint32_t r = 0; r < ns; r++)
+                if (st[r].held && rnd(3) == 0) session::start(st[r], T);        // the held ones join as the others drain
             bool ended = false;
             const uint64_t n = session::renderable(st, T, 1 + rnd(5000), &ended);
             if (ended) break;
-            CHECK(n > 0);
+            bool waiting = false;
+            for (uint32_t r = 0; r < ns; r++) waiting = waiting || st[r].held;
+            CHECK(n > 0 || waiting);                                             // only a held source may stall the drain
             for (uint32_t q = 0; q < ns; q++) {
                 const session::Part p = session::part_of(st[q], T, n);
                 rendered[q] += p.out_len;

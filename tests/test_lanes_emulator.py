@@ -209,12 +209,14 @@ def run_session(emu, pcms, starts, coefs, posts, from_, to, hasb, npost, ops, ou
     out = np.full(out_cap, np.nan, dtype=np.float32)
     renders = C.c_uint64(0)
     pushed = (C.c_uint64 * n)()
+    joined = (C.c_uint64 * n)()
     emu.rb_session_emulate.restype = C.c_longlong
     w = emu.rb_session_emulate(ptrs, u64([p.size // c for p, c in zip(pcms, ch_in)]), u64(starts), co.ctypes.data_as(C.POINTER(C.c_float)),
                                po.ctypes.data_as(C.POINTER(C.c_float)), C.c_uint32(n), C.c_uint32(channels), _u32(ch_in, n)[0], _u32(from_, n)[0], _u32(to, n)[0],
                                int(hasb), int(npost), u64(flat), C.c_uint64(len(ops)), out.ctypes.data_as(C.POINTER(C.c_float)),
-                               C.c_uint64(out_cap), C.byref(renders), pushed)
+                               C.c_uint64(out_cap), C.byref(renders), pushed, joined)
     assert w >= 0
+    run_session.joined_at = [int(v) for v in joined]
     return out[:w * channels], renders.value, [int(v) for v in pushed]
 
 
@@ -427,3 +429,27 @@ def test_session_with_sources_above_the_mixer_rate(emu):
     session_case(emu, pcms, [0, 0, 0, 50, 3], ops, in_rate=rates, mix_rate=44100, lp=500, gain=0.9)
     c = counters(emu)
     assert c["slow"] > 50, c
+
+
+def test_session_sources_added_while_it_runs(emu):
+    """Sources declared when the session is created but handed to the mixer later (Mixer::add during playback,
+    src/mixer.rs:58-66,:175-183): they join at the frame rendered next -- the bytes of a session in which they had that
+    mix_start from the beginning; a source that is never added contributes nothing; while nothing plays the timeline stands
+    still."""
+    HELD = (1 << 64) - 1
+    pcms = [noise(1200 + 50 * i, 3100 + i) for i in range(5)]
+    starts = [0, HELD, 0, HELD, HELD]
+    ops = [(0, r, pcms[r].size) for r in range(5)]                 # everything is decoded already
+    ops += [(1, 0, 300), (4, 1, 0), (1, 0, 211)]                  # source 1 joins at frame 300
+    ops += [(1, 0, 5000)] * 5                                      # a render stops where a source ends: play the three out
+    ops += [(1, 0, 100), (4, 3, 0), (1, 0, 5000)]                  # nothing plays: no frames; source 3 joins where the timeline stopped
+    c = make_case(pcms, 44100, 48000, [0] * 5, lp=600, gain=0.9)
+    got, renders, pushed = run_session(emu, pcms, starts, c["coefs"], c["posts"], 147, 160, True, True, ops, 20000)
+    joined = run_session.joined_at
+    assert joined[0] == 0 and joined[1] == 300 and joined[2] == 0 and joined[4] == HELD
+    end_of_first_three = max(joined[i] + c["per_stream"][i].size for i in (0, 1, 2))
+    assert joined[3] == end_of_first_three                        # the timeline did not move while nothing was playing
+    keep = [0, 1, 2, 3]
+    want = expected_mix_classes([c["per_stream"][i] if i in keep else np.zeros(0, np.float32) for i in range(5)],
+                                [joined[i] if i in keep else 0 for i in range(5)], got.size, c["from_"], list(zip(c["to"], c["ch_in"])))
+    assert_bit_exact(got, want, "sources added during playback")

@@ -881,3 +881,34 @@ def test_lanes_sources_without_a_conversion(ctx):
         got = b.render_mix()
     per_stream = [oracle.chain_uniform(to_oracle(s), 1, 48000) for s in srcs]
     assert_bit_exact(got, lanes_expected_mix(per_stream, [0] * 70, got.size), "filter + gain on same-rate sources")
+
+
+@lanes_gate
+def test_session_sources_added_while_it_runs(ctx):
+    """Mixer::add during playback: a held source joins at the frame rendered next -- the bytes of a batch in which it has that
+    mix_start."""
+    pcms = [noise(5000 + 300 * i, 3100 + i) for i in range(4)]
+    mk = lambda p: rb.UniformSourceIterator(rb.TestSource(p, 1, 44100), 1, 48000).low_pass(600).amplify(0.9)
+    held = [0, capi.RB_SESSION_HELD, 0, capi.RB_SESSION_HELD]
+    got = []
+    with rb.Session([mk(np.zeros(0, np.float32)) for _ in pcms], 48000, fifo_frames=8192, max_block_frames=1024, ctx=ctx, mix_starts=held) as s:
+        for i, p in enumerate(pcms):
+            s.push(i, p, end_of_stream=True)
+        got.append(s.render(700)[0])
+        s.start(1)                                   # joins at frame 700
+        got.append(s.render(333)[0])
+        s.start(3)                                   # joins at frame 1033
+        ended = False
+        while not ended:
+            block, ended = s.render(1024)
+            got.append(block)
+    got = np.concatenate(got)
+    with rb.Batch([mk(p) for p in pcms], 1, 48000, flags=LANES, ctx=ctx, mix_starts=[0, 700, 0, 1033]) as b:
+        b.upload_all()
+        want = b.render_mix()
+    # the batch orders its sources by mix_start (0, 0, 700, 1033), the session keeps the declared order: same set of lanes in one
+    # warp, idle lanes add +0.0 -> the sums agree up to the tree's lane order, i.e. within the mixer tolerance
+    assert got.size == want.size
+    assert_close_peak(got, want, 1e-5, "sources added during playback vs the batch with those mix_starts")
+    ref = oracle.mixer([to_oracle(mk(p), mix_start=m) for p, m in zip(pcms, [0, 700, 0, 1033])], 1, 48000)
+    assert_close_peak(got, ref, 1e-5, "... and vs the reference's mixer")
