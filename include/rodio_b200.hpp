@@ -293,6 +293,8 @@ class LiveMixer {
     }
     // Mixer::add (mixer.rs:58-66) for a source that was declared held (its desc().mix_start == RB_SESSION_HELD)
     void add(size_t i) { check(rb_session_start(h_, i), "rb_session_start"); }
+    // queue a held source behind another one: Player::append / queue.rs:128-192
+    void append_after(size_t i, size_t predecessor) { check(rb_session_follow(h_, i, predecessor), "rb_session_follow"); }
     // Amplify::set_factor on the chain's .amplify() (amplify.rs:25-29); Player::set_volume's Amplify sits before the resampler
     void set_amplify(size_t i, float factor) { check(rb_session_set_amplify(h_, i, factor), "rb_session_set_amplify"); }
     bool ended() const { return ended_ && at_ == block_.size(); }

@@ -1161,6 +1161,16 @@ extern "C" rb_status rb_session_start(rb_session* s, size_t stream) {
     return RB_OK;
 }
 
+extern "C" rb_status rb_session_follow(rb_session* s, size_t stream, size_t predecessor) {
+    if (!s) return fail(RB_ERR_INVALID_ARGUMENT, "session is NULL");
+    if (stream >= s->st.size() || predecessor >= s->st.size() || stream == predecessor)
+        return fail(RB_ERR_INVALID_ARGUMENT, "stream index out of range");
+    session::Stream& st = s->st[s->pos[stream]];
+    if (!st.held) return fail(RB_ERR_STATE, "only a source declared with RB_SESSION_HELD can be queued");
+    st.follows = (int64_t)s->pos[predecessor];
+    return RB_OK;
+}
+
 extern "C" rb_status rb_session_set_amplify(rb_session* s, size_t stream, float factor) {
     if (!s) return fail(RB_ERR_INVALID_ARGUMENT, "session is NULL");
     if (stream >= s->st.size()) return fail(RB_ERR_INVALID_ARGUMENT, "stream index out of range");
@@ -1172,6 +1182,7 @@ extern "C" rb_status rb_session_set_amplify(rb_session* s, size_t stream, float 
 extern "C" rb_status rb_session_available(rb_session* s, uint64_t* frames, int* ended) {
     if (!s || !frames) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
     bool e = false;
+    session::resolve_queue(s->st);
     *frames = session::renderable(s->st, s->T, ~0ull >> 1, &e);
     if (ended) *ended = e ? 1 : 0;
     return RB_OK;
@@ -1181,6 +1192,7 @@ extern "C" rb_status rb_session_render(rb_session* s, float* out_host, uint64_t 
     if (!s || !written) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
     *written = 0;
     bool e = false;
+    session::resolve_queue(s->st);   // queued sources whose predecessor's end is known by now get their place on the timeline
     const uint64_t n = session::renderable(s->st, s->T, std::min<uint64_t>(max_frames, s->max_block), &e);
     if (ended) *ended = e ? 1 : 0;
     if (n == 0) return RB_OK;

@@ -28,6 +28,8 @@ struct Stream {
     bool eof = false;          // no more input will come
     bool held = false;         // declared when the session was created but not handed to the mixer yet (Mixer::add comes
                                // later): it takes pushes, renders nothing and holds nobody up until it is started
+    int64_t follows = -1;      // held source that starts on the frame after source `follows` has played out -- the
+                               // sources of a queue (src/queue.rs:128-192: the next sound begins where the current one ends)
     uint64_t fill() const { return pushed - i0; }   // frames in the FIFO
 };
 
@@ -51,6 +53,21 @@ inline bool finished(const Stream& s) { return s.eof && s.out_done >= out_total(
 
 // How many mixer frames [T, T + n) can be rendered now (every unfinished stream must be able to supply its part).
 // Returns 0 with *ended = true when no stream is left (MixerSource::next returns None, src/mixer.rs:129-135).
+// A queued source can be scheduled as soon as the end of its predecessor is known, i.e. once that one has received all
+// of its input: its first frame follows the predecessor's last.  (Chains resolve front to back.)
+inline void resolve_queue(std::vector<Stream>& st) {
+    for (bool again = true; again;) {
+        again = false;
+        for (Stream& s : st) {
+            if (!s.held || s.follows < 0) continue;
+            const Stream& p = st[(size_t)s.follows];
+            if (p.held || !p.eof) continue;
+            s.mix_start = p.mix_start + out_total(p.pushed, p.from, p.to);
+            s.held = false, again = true;
+        }
+    }
+}
+
 inline uint64_t renderable(const std::vector<Stream>& st, uint64_t T, uint64_t max_frames, bool* ended) {
     uint64_t n = max_frames;
     bool active = false, waiting = false;

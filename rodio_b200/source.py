@@ -532,6 +532,10 @@ class Session:
         """Mixer::add for a source created with mix_start = capi.RB_SESSION_HELD: joins at the frame rendered next."""
         check(lib().rb_session_start(self._h, stream), "rb_session_start")
 
+    def follow(self, stream: int, predecessor: int):
+        """Queue a held source behind another one (Player::append): it starts on the frame after that one has played out."""
+        check(lib().rb_session_follow(self._h, stream, predecessor), "rb_session_follow")
+
     def set_amplify(self, stream: int, factor: float):
         """Amplify::set_factor on the chain's AMPLIFY of a live source: applies from the next rendered block on."""
         check(lib().rb_session_set_amplify(self._h, stream, float(factor)), "rb_session_set_amplify")

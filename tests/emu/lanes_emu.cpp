@@ -200,6 +200,7 @@ extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t*
         if (s.pushed == n_frames[r]) s.eof = true;
     };
     auto render = [&](uint64_t max_frames) -> bool {   // false: session ended
+        session::resolve_queue(st);
         bool ended = false;
         const uint64_t n = session::renderable(st, T, max_frames, &ended);
         if (ended) return false;
@@ -265,12 +266,14 @@ extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t*
         else if (kind == 1) render(cnt);
         else if (kind == 2) st[r].eof = true;
         else if (kind == 4) session::start(st[r], T);
+        else if (kind == 5) st[r].follows = (int64_t)cnt;
         else {
             const uint32_t bits = (uint32_t)cnt;
             std::memcpy(&gain[r], &bits, 4);
         }
     }
     for (uint32_t r = 0; r < n_rows; r++) st[r].eof = true;   // whatever was pushed is all there is
+    session::resolve_queue(st);
     for (uint32_t r = 0; r < n_rows; r++) pushed_total[r] = st[r].pushed;
     for (uint32_t r = 0; r < n_rows; r++) {
         joined_at[r] = st[r].held ? ~0ull : st[r].mix_start;

@@ -453,3 +453,32 @@ def test_session_sources_added_while_it_runs(emu):
     want = expected_mix_classes([c["per_stream"][i] if i in keep else np.zeros(0, np.float32) for i in range(5)],
                                 [joined[i] if i in keep else 0 for i in range(5)], got.size, c["from_"], list(zip(c["to"], c["ch_in"])))
     assert_bit_exact(got, want, "sources added during playback")
+
+
+def test_session_queue_of_sources(emu):
+    """Sources queued one behind the other (Player::append -> queue, src/queue.rs:128-192): the next one starts on the frame
+    after the current one has played out -- known as soon as the current one has all of its input --, different rates and
+    a second, independent voice beside the queue."""
+    HELD = (1 << 64) - 1
+    rates = [44100, 48000, 22050, 44100]
+    pcms = [noise(int(0.03 * r) + 17 * i, 3300 + i) for i, r in enumerate(rates)]
+    starts = [0, HELD, HELD, 40]                       # 0 -> 1 -> 2 is the queue, 3 plays beside it
+    ops = [(5, 1, 0), (5, 2, 1)]
+    left = [p.size for p in pcms]
+    step = 0
+    while any(left):
+        for r in range(4):
+            n = min(left[r], 90 + 20 * r)
+            if n:
+                ops.append((0, r, n))
+                left[r] -= n
+        ops.append((1, 0, 77 + step % 13))
+        step += 1
+    c = make_case(pcms, rates, 48000, [0] * 4, lp=900, gain=0.8)
+    got, renders, pushed = run_session(emu, pcms, starts, c["coefs"], c["posts"], c["from_"], c["to"], True, True, ops, 20000)
+    joined = run_session.joined_at
+    assert joined[0] == 0 and joined[3] == 40
+    assert joined[1] == c["per_stream"][0].size and joined[2] == joined[1] + c["per_stream"][1].size
+    want = expected_mix_classes(c["per_stream"], joined, got.size, c["from_"], list(zip(c["to"], c["ch_in"])))
+    assert got.size == max(j + y.size for j, y in zip(joined, c["per_stream"]))
+    assert_bit_exact(got, want, "queued sources")

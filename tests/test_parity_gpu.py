@@ -912,3 +912,36 @@ def test_session_sources_added_while_it_runs(ctx):
     assert_close_peak(got, want, 1e-5, "sources added during playback vs the batch with those mix_starts")
     ref = oracle.mixer([to_oracle(mk(p), mix_start=m) for p, m in zip(pcms, [0, 700, 0, 1033])], 1, 48000)
     assert_close_peak(got, ref, 1e-5, "... and vs the reference's mixer")
+
+
+@lanes_gate
+def test_session_queue_of_sources(ctx):
+    """Player::append: sources of different rates played one after the other, an independent voice beside them."""
+    rates = [44100, 48000, 22050, 44100]
+    pcms = [noise(int(0.1 * r) + 17 * i, 3300 + i) for i, r in enumerate(rates)]
+    mk = lambda p, r: rb.UniformSourceIterator(rb.TestSource(p, 1, r), 1, 48000).low_pass(900).amplify(0.8)
+    held = capi.RB_SESSION_HELD
+    got, pos, ended = [], [0] * 4, False
+    with rb.Session([mk(np.zeros(0, np.float32), r) for r in rates], 48000, fifo_frames=4096, max_block_frames=480, ctx=ctx,
+                    mix_starts=[0, held, held, 40]) as s:
+        s.follow(1, 0)
+        s.follow(2, 1)
+        while not ended:
+            blocks, eos = [], []
+            for i, (p, r) in enumerate(zip(pcms, rates)):
+                n = min(r // 100, p.size - pos[i])
+                blocks.append(p[pos[i]:pos[i] + n])
+                pos[i] += n
+                eos.append(pos[i] == p.size)
+            s.push_packed(blocks, eos)
+            while True:
+                block, ended = s.render(480)
+                got.append(block)
+                if block.size == 0 or ended:
+                    break
+    got = np.concatenate(got)
+    lens = [oracle.chain_uniform(to_oracle(mk(p, r)), 1, 48000).size for p, r in zip(pcms, rates)]
+    starts = [0, lens[0], lens[0] + lens[1], 40]
+    ref = oracle.mixer([to_oracle(mk(p, r), mix_start=m) for p, r, m in zip(pcms, rates, starts)], 1, 48000)
+    assert got.size == ref.size
+    assert_close_peak(got, ref, 1e-5, "queued sources vs the reference's mixer with the same starts")
