@@ -247,7 +247,8 @@ rb_status rb_session_push_packed(rb_session* s, const float* pcm, const uint64_t
 rb_status rb_session_start(rb_session* s, size_t stream);
 /* Queue the held source `stream` behind `predecessor` -- Player::append / queue::queue (src/queue.rs:128-192): it starts on
  * the mixer frame after the predecessor's last, which is known as soon as the predecessor has received its end_of_stream.
- * Each source keeps its own chain and rate pair (the queue's sounds need not share a format). */
+ * Each source keeps its own chain and rate pair (the queue's sounds need not share a format).  Sources end on whole frames
+ * here, so the queue's padding of a sound that ends mid-frame and its keep-alive silence do not arise. */
 rb_status rb_session_follow(rb_session* s, size_t stream, size_t predecessor);
 /* Amplify::set_factor (src/source/amplify.rs:25-29) on the AMPLIFY of a live source's chain: the gain is `factor` from the
  * next rendered block on (a source without an AMPLIFY behaves as amplify(1.0)).  Player::set_volume does the same to its
