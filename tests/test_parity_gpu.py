@@ -922,7 +922,8 @@ def test_session_queue_of_sources(ctx):
     mk = lambda p, r: rb.UniformSourceIterator(rb.TestSource(p, 1, r), 1, 48000).low_pass(900).amplify(0.8)
     held = capi.RB_SESSION_HELD
     got, pos, ended = [], [0] * 4, False
-    with rb.Session([mk(np.zeros(0, np.float32), r) for r in rates], 48000, fifo_frames=4096, max_block_frames=480, ctx=ctx,
+    # the queued sources are decoded ahead while they wait: their FIFOs hold them whole
+    with rb.Session([mk(np.zeros(0, np.float32), r) for r in rates], 48000, fifo_frames=16384, max_block_frames=480, ctx=ctx,
                     mix_starts=[0, held, held, 40]) as s:
         s.follow(1, 0)
         s.follow(2, 1)
