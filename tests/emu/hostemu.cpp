@@ -1,0 +1,122 @@
+// librodio_b200_hostemu.so (test infrastructure): the library's real host code -- rodio_b200/csrc/rb_api.cu, compiled as C++
+// against tests/emu/mockcuda/cuda_runtime.h -- with the lane kernel's launchers replaced by the SIMT emulator.  It exports the
+// C ABI of include/rodio_b200.h, so the Python mirror (rodio_b200.Session ...) drives it unchanged: the session bookkeeping of
+// rb_api.cu (class order, packed pushes, FIFO compaction, state blobs) runs on the CPU exactly as it runs in front of the GPU.
+// Only the streaming sessions are served: batches need the kernels of rb_kernels.cu / rb_fused.cu and fail loudly here.
+#define RB_SIMT_EMULATE 1
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "../../rodio_b200/csrc/rb_fused.h"
+#include "../../rodio_b200/csrc/rb_lanes.h"
+#include "../../rodio_b200/csrc/rb_lanes_plan.h"
+
+// ---- allocation registry of the mock runtime ----
+static std::map<void*, size_t> g_allocs;
+static std::mutex g_alloc_mutex;
+extern "C" void mock_cuda_register(void* p, size_t n) {
+    std::lock_guard<std::mutex> l(g_alloc_mutex);
+    g_allocs[p] = n;
+}
+extern "C" void mock_cuda_unregister(void* p) {
+    std::lock_guard<std::mutex> l(g_alloc_mutex);
+    g_allocs.erase(p);
+}
+
+// ---- the lane kernel on 32 host threads per warp ----
+namespace {
+template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS>
+void run_warp(const lanes::Args& a, uint32_t group, simt::WarpEmu* w, float* ring) {
+    std::vector<std::thread> th;
+    for (uint32_t l = 0; l < 32; l++)
+        th.emplace_back([&, l] {
+            simt::g_lane = simt::LaneEmu{};
+            simt::g_lane.w = w, simt::g_lane.lane = l;
+            lanes::warp_main<CI, CO, HASB, FF2, NPOST, PASS>(a, group, ring);
+        });
+    for (auto& t : th) t.join();
+}
+template <int CI, int CO, bool PASS>
+void run_variant(const lanes::Args& a, uint32_t g, simt::WarpEmu* w, float* ring, bool hasb, bool ff2, bool npost) {
+    if (hasb && ff2 && npost) run_warp<CI, CO, true, true, 1, PASS>(a, g, w, ring);
+    else if (hasb && ff2) run_warp<CI, CO, true, true, 0, PASS>(a, g, w, ring);
+    else if (hasb && npost) run_warp<CI, CO, true, false, 1, PASS>(a, g, w, ring);
+    else if (hasb) run_warp<CI, CO, true, false, 0, PASS>(a, g, w, ring);
+    else if (npost) run_warp<CI, CO, false, false, 1, PASS>(a, g, w, ring);
+    else run_warp<CI, CO, false, false, 0, PASS>(a, g, w, ring);
+}
+}  // namespace
+
+cudaError_t rb_lanes_launch_kernel(const lanes::Args& a, uint32_t ch_in, uint32_t ch_out, bool has_biquad, bool ff2, bool has_post,
+                                   cudaStream_t) {
+    if (a.mix_len == 0 || a.n_groups == 0) return cudaSuccess;
+    if (!((ch_in == 1 || ch_in == 2) && (ch_in == ch_out || (ch_in == 1 && ch_out == 2)))) return cudaErrorInvalidValue;
+    simt::WarpEmu warp;
+    {
+        std::lock_guard<std::mutex> l(g_alloc_mutex);
+        for (auto& kv : g_allocs) warp.readable.push_back({(const char*)kv.first, (const char*)kv.first + kv.second});
+    }
+    const float nan = std::numeric_limits<float>::quiet_NaN();
+    constexpr int MAX_RS = lanes::Geo<2>::RS;
+    std::vector<float> ring_store(32 * MAX_RS + 4, nan);
+    float* ring = ring_store.data();
+    while ((uintptr_t)ring & 15) ring++;
+    const bool pass = a.from == a.to;
+    for (uint32_t g = 0; g < a.n_groups; g++) {
+        for (int i = 0; i < 32 * MAX_RS; i++) ring[i] = nan;
+        if (ch_in == 2) pass ? run_variant<2, 2, true>(a, g, &warp, ring, has_biquad, ff2, has_post) : run_variant<2, 2, false>(a, g, &warp, ring, has_biquad, ff2, has_post);
+        else if (ch_out == 2) pass ? run_variant<1, 2, true>(a, g, &warp, ring, has_biquad, ff2, has_post) : run_variant<1, 2, false>(a, g, &warp, ring, has_biquad, ff2, has_post);
+        else pass ? run_variant<1, 1, true>(a, g, &warp, ring, has_biquad, ff2, has_post) : run_variant<1, 1, false>(a, g, &warp, ring, has_biquad, ff2, has_post);
+    }
+    return cudaSuccess;
+}
+
+cudaError_t rb_lanes_launch_sum(const float* partial, uint32_t n_groups, uint64_t pstride, uint64_t n_floats, float* out, cudaStream_t) {
+    for (uint64_t m = 0; m < n_floats; m++) {
+        float acc = 0.0f;
+        for (uint32_t g = 0; g < n_groups; g++) acc = acc + partial[(uint64_t)g * pstride + m];
+        out[m] = acc;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t rb_lanes_classify_range(const float* p, uint64_t n, uint32_t* flag, cudaStream_t) {
+    for (uint64_t i = 0; i < n; i++)
+        if (!lanes::sample_in_class(p[i])) *flag = 1u;
+    return cudaSuccess;
+}
+
+cudaError_t rb_lanes_fifo_append(const float* staging, const uint64_t* offset, const uint32_t* count, const uint32_t* fill, float* fifo,
+                                 uint64_t stride, uint32_t* flags, uint32_t n_streams, cudaStream_t) {
+    for (uint32_t r = 0; r < n_streams; r++)
+        for (uint32_t i = 0; i < count[r]; i++) {
+            const float v = staging[offset[r] + i];
+            if (!lanes::sample_in_class(v)) flags[r] = 1u;
+            fifo[(uint64_t)r * stride + fill[r] + i] = v;
+        }
+    return cudaSuccess;
+}
+
+cudaError_t rb_lanes_fifo_compact(const float* src, float* dst, uint64_t stride, const uint32_t* drop, const uint32_t* keep,
+                                  uint32_t n_streams, cudaStream_t) {
+    for (uint32_t r = 0; r < n_streams; r++)
+        for (uint32_t i = 0; i < keep[r]; i++) dst[(uint64_t)r * stride + i] = src[(uint64_t)r * stride + drop[r] + i];
+    return cudaSuccess;
+}
+
+// ---- everything else the host code links against: not available without the real kernels ----
+cudaError_t rb_fused_try_create(const rb_fused_stream*, size_t, uint16_t, float*, uint64_t, uint32_t, int, cudaStream_t, rb_fused_plan** out) {
+    *out = nullptr;
+    return cudaSuccess;
+}
+cudaError_t rb_fused_run(rb_fused_plan*, cudaStream_t) { return cudaErrorInvalidValue; }
+void rb_fused_destroy(rb_fused_plan*) {}
+uint32_t rb_fused_launch_count(const rb_fused_plan*) { return 0; }
+void rb_fused_inputs_changed(rb_fused_plan*) {}
+int rb_fused_kind(const rb_fused_plan*) { return -1; }
+cudaError_t rb_launch_nodes(uint32_t, const rb_node_dev*, uint32_t, uint64_t, uint32_t, cudaStream_t) { return cudaErrorInvalidValue; }
+cudaError_t rb_launch_mix(const rb_mix_src*, uint32_t, float*, uint64_t, cudaStream_t, float*, uint32_t) { return cudaErrorInvalidValue; }
+cudaError_t rb_launch_convert(const void*, uint32_t, void*, uint32_t, uint64_t, cudaStream_t) { return cudaErrorInvalidValue; }

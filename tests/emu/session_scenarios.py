@@ -1,0 +1,183 @@
+"""Scenarios for tests/test_session_hostemu.py, run in a subprocess: the Python mirror (rodio_b200.Session) on top of
+tests/emu/librodio_b200_hostemu.so -- the library's real host code (rb_api.cu) over the mock CUDA runtime, kernels on the SIMT
+emulator.  The library path is swapped HERE, in the test process only; the product loader knows nothing of it.
+    python tests/emu/session_scenarios.py <scenario> ...        exit code 0 = every scenario held bit for bit"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+import rodio_b200._capi as capi                       # noqa: E402
+capi.LIB_PATH = os.path.join(HERE, "librodio_b200_hostemu.so")
+import oracle                                         # noqa: E402
+import rodio_b200 as rb                               # noqa: E402
+from helpers import assert_bit_exact, assert_close_peak, noise, to_oracle     # noqa: E402
+from test_lanes_emulator import expected_mix_classes                          # noqa: E402
+import math                                           # noqa: E402
+
+HELD = capi.RB_SESSION_HELD
+
+
+def chain(pcm, ch_in, rate, mix_ch, mix_rate, lp, gain, speed=None):
+    s = rb.TestSource(pcm, ch_in, rate)
+    if speed:
+        s = s.speed(speed)
+    s = rb.UniformSourceIterator(s, mix_ch, mix_rate)
+    if lp:
+        s = s.low_pass(lp)
+    if gain is not None:
+        s = s.amplify(gain)
+    return s
+
+
+def expected(pcms, ch_in, rates, mix_ch, mix_rate, joined, lp, gain, speeds=None):
+    speeds = speeds or [None] * len(pcms)
+    srcs = [chain(p, ci, r, mix_ch, mix_rate, lp, gain, sp) for p, ci, r, sp in zip(pcms, ch_in, rates, speeds)]
+    per = [oracle.chain_uniform(to_oracle(s), mix_ch, mix_rate) for s in srcs]
+    eff = [s.base_rate if sp is None else rb.capi.lib().rb_speed_sample_rate(r, sp) for s, r, sp in zip(srcs, rates, speeds)]
+    froms = [r // math.gcd(r, mix_rate) for r in eff]
+    tos = [mix_rate // math.gcd(r, mix_rate) for r in eff]
+    n = max(j * mix_ch + y.size for j, y in zip(joined, per))
+    return expected_mix_classes(per, [j * mix_ch for j in joined], n, froms, list(zip(tos, ch_in)))
+
+
+def drive(sess, pcms, ch_in, block_frames, render_frames, rng=None, packed=True, hooks=None):
+    """Push `block_frames[i]` frames of every source per round, render until nothing comes; hooks: {round: callable(sess)}."""
+    pos, got, ended, rnd = [0] * len(pcms), [], False, 0
+    while not ended:
+        if hooks and rnd in hooks:
+            r = hooks[rnd](sess)
+            if r is not None:
+                sess = r
+        blocks, eos = [], []
+        for i, (p, ci) in enumerate(zip(pcms, ch_in)):
+            k = block_frames[i] if rng is None else int(rng.integers(0, 2 * block_frames[i] + 1))
+            k = min(k, p.size // ci - pos[i])
+            blocks.append(p[ci * pos[i]: ci * (pos[i] + k)])
+            pos[i] += k
+            eos.append(pos[i] == p.size // ci)
+        if packed:
+            sess.push_packed(blocks, eos)
+        else:
+            for i, (b, e) in enumerate(zip(blocks, eos)):
+                if b.size or e:
+                    sess.push(i, b, end_of_stream=e)
+        while True:
+            n = render_frames if rng is None else int(rng.integers(1, render_frames + 1))
+            block, ended = sess.render(n)
+            got.append(block)
+            if block.size == 0 or ended:
+                break
+        rnd += 1
+        assert rnd < 100000
+    return np.concatenate(got), sess
+
+
+def s_mono_random_split():
+    rng = np.random.default_rng(1)
+    pcms = [noise(int(n), 60 + i) for i, n in enumerate(rng.integers(300, 1500, 37))]
+    ch = [1] * 37
+    with rb.Session([chain(np.zeros(0, np.float32), 1, 44100, 1, 48000, 200, 1.2) for _ in pcms], 48000, fifo_frames=2048,
+                    max_block_frames=500) as s:
+        got, _ = drive(s, pcms, ch, [120] * 37, 500, rng=rng, packed=False)
+    assert_bit_exact(got, expected(pcms, ch, [44100] * 37, 1, 48000, [0] * 37, 200, 1.2), "mono random split, single pushes")
+
+
+def s_mixed_everything_with_state_blob():
+    """Mono and stereo sources at three rates in a stereo mixer, packed 10 ms pushes, the state handed to a fresh session
+    half-way (rb_session_get_state / set_state)."""
+    ch_in = [1, 2, 1, 1, 2, 1, 2, 1] * 5
+    rates = [44100, 44100, 48000, 22050, 48000, 44100, 44100, 48000] * 5
+    pcms = [noise(ci * (int(0.05 * r) + 3 * i), 1500 + i, 0.8) for i, (ci, r) in enumerate(zip(ch_in, rates))]
+    mk = lambda: [chain(np.zeros(0, np.float32), ci, r, 2, 48000, 800, 0.7) for ci, r in zip(ch_in, rates)]
+    sa = rb.Session(mk(), 48000, fifo_frames=1024, max_block_frames=480, mixer_channels=2)
+    sb = rb.Session(mk(), 48000, fifo_frames=1024, max_block_frames=480, mixer_channels=2)
+
+    def hand_over(s):
+        sb.set_state(s.get_state())
+        return sb
+    got, _ = drive(sa, pcms, ch_in, [r // 100 for r in rates], 480, hooks={3: hand_over})
+    sa.close(), sb.close()
+    assert_bit_exact(got, expected(pcms, ch_in, rates, 2, 48000, [0] * len(pcms), 800, 0.7), "mixed sources, blob hand-over")
+
+
+def s_held_queue_gain_speed():
+    """A queue of three sounds (one of them with speed(0.9)), a voice added later, a gain change, late mix_start."""
+    rates = [44100, 48000, 22050, 44100, 32000]
+    speeds = [None, None, 0.9, None, None]
+    pcms = [noise(int(0.04 * r) + 7 * i, 3300 + i) for i, r in enumerate(rates)]
+    ch = [1] * 5
+    srcs = [chain(np.zeros(0, np.float32), 1, r, 1, 48000, 900, 0.8, sp) for r, sp in zip(rates, speeds)]
+    starts = [0, HELD, HELD, HELD, 333]                      # 0 -> 1 -> 2 queue; 3 is added by hand; 4 is scheduled
+    marks = {}
+    with rb.Session(srcs, 48000, fifo_frames=8192, max_block_frames=256, mix_starts=starts) as s:
+        s.follow(1, 0)
+        s.follow(2, 1)
+
+        def add_voice(sess):
+            marks["T3"] = sum(b.size for b in marks["got"])   # frames rendered so far = where source 3 joins
+            sess.start(3)
+        pos, got, ended, rnd = [0] * 5, [], False, 0
+        marks["got"] = got
+        while not ended:
+            if rnd == 4:
+                add_voice(s)
+            blocks, eos = [], []
+            for i, p in enumerate(pcms):
+                k = min(rates[i] // 100, p.size - pos[i])
+                blocks.append(p[pos[i]:pos[i] + k])
+                pos[i] += k
+                eos.append(pos[i] == p.size)
+            s.push_packed(blocks, eos)
+            while True:
+                block, ended = s.render(256)
+                got.append(block)
+                if block.size == 0 or ended:
+                    break
+            rnd += 1
+    got = np.concatenate(got)
+    lens = [oracle.chain_uniform(to_oracle(chain(p, 1, r, 1, 48000, 900, 0.8, sp)), 1, 48000).size for p, r, sp in zip(pcms, rates, speeds)]
+    joined = [0, lens[0], lens[0] + lens[1], marks["T3"], 333]
+    assert_bit_exact(got, expected(pcms, ch, rates, 1, 48000, joined, 900, 0.8, speeds), "queue + added voice + scheduled source")
+
+
+def s_errors():
+    mk = lambda ci, r, mc: chain(np.zeros(0, np.float32), ci, r, mc, 48000, 200, None)
+    for bad in (lambda: rb.Session([mk(2, 44100, 1)], 48000, mixer_channels=1),                       # stereo source, mono mixer
+                lambda: rb.Session([rb.UniformSourceIterator(rb.TestSource(np.zeros(0, np.float32), 1, 44100), 1, 48000)
+                                    .automatic_gain_control()], 48000),                                 # adapter outside the shape
+                lambda: rb.Session([rb.TestSource(np.zeros(0, np.float32), 1, 44100).low_pass(100)], 48000)):   # no UNIFORM
+        try:
+            bad()
+        except rb.RodioB200Error:
+            continue
+        raise AssertionError("a session outside the served shape was accepted")
+    with rb.Session([mk(1, 44100, 1)], 48000, fifo_frames=64, max_block_frames=64) as s:
+        s.push(0, noise(64, 1))
+        try:
+            s.push(0, noise(1, 2))
+        except rb.RodioB200Error as e:
+            assert "FIFO" in str(e) or "full" in str(e).lower(), str(e)
+        else:
+            raise AssertionError("a push beyond the FIFO was accepted")
+        out, ended = s.render(64)
+        assert out.size > 0 and not ended
+        s.push(0, noise(10, 3), end_of_stream=True)
+        try:
+            s.push(0, noise(1, 4))
+        except rb.RodioB200Error:
+            pass
+        else:
+            raise AssertionError("a push after end_of_stream was accepted")
+
+
+SCENARIOS = {"mono_random_split": s_mono_random_split, "mixed_with_state_blob": s_mixed_everything_with_state_blob,
+             "held_queue_gain_speed": s_held_queue_gain_speed, "errors": s_errors}
+
+if __name__ == "__main__":
+    for name in (sys.argv[1:] or list(SCENARIOS)):
+        SCENARIOS[name]()
+        print("ok", name, flush=True)
