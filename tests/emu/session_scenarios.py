@@ -174,10 +174,38 @@ def s_errors():
             raise AssertionError("a push after end_of_stream was accepted")
 
 
+def s_random(seed=0, cases=6):
+    """Randomised sessions through the real host code (not part of the suite: python tests/emu/session_scenarios.py random:SEED)."""
+    rng = np.random.default_rng(seed)
+    for case in range(cases):
+        mix_rate = int(rng.choice([48000, 44100]))
+        mix_ch = int(rng.choice([1, 2]))
+        n = int(rng.integers(1, 45))
+        rates = [int(rng.choice([44100, 22050, 48000, 32000, 96000, 8000])) for _ in range(n)]
+        ch_in = [mix_ch if (mix_ch == 1 or rng.random() < 0.6) else 1 for _ in range(n)]
+        lens = [int(rng.integers(0, 1200)) for _ in range(n)]
+        pcms = [noise(ci * L, 991 * case + i + 7 * seed) for i, (ci, L) in enumerate(zip(ch_in, lens))]
+        starts = [0 if rng.random() < 0.6 else int(rng.integers(0, 500)) for _ in range(n)]
+        lp, gain = [(300, 0.8), (None, 1.1), (2000, None), (None, None)][int(rng.integers(4))]
+        srcs = [chain(np.zeros(0, np.float32), ci, r, mix_ch, mix_rate, lp, gain) for ci, r in zip(ch_in, rates)]
+        with rb.Session(srcs, mix_rate, fifo_frames=4096, max_block_frames=int(rng.choice([64, 333, 1024])), mix_starts=starts,
+                        mixer_channels=mix_ch) as s:
+            got, _ = drive(s, pcms, ch_in, [max(1, r // 150) for r in rates], 700, rng=rng, packed=bool(rng.integers(2)))
+        want = expected(pcms, ch_in, rates, mix_ch, mix_rate, starts, lp, gain)
+        if not any(lens):
+            assert got.size == 0
+            continue
+        assert_bit_exact(got, want[:got.size], f"random session {seed}/{case}")
+        assert got.size == want.size or not np.any(want[got.size:]), "tail"
+
+
 SCENARIOS = {"mono_random_split": s_mono_random_split, "mixed_with_state_blob": s_mixed_everything_with_state_blob,
              "held_queue_gain_speed": s_held_queue_gain_speed, "errors": s_errors}
 
 if __name__ == "__main__":
     for name in (sys.argv[1:] or list(SCENARIOS)):
-        SCENARIOS[name]()
+        if name.startswith("random"):
+            s_random(int(name.split(":")[1]) if ":" in name else 0)
+        else:
+            SCENARIOS[name]()
         print("ok", name, flush=True)
