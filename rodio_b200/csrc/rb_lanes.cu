@@ -1,6 +1,7 @@
 // rb_lanes.cu — k_fused_lanes: the lane-per-stream fused kernel for large uniform batches (the warp program lives in
 // rb_lanes_core.h, shared with the CPU emulator of tests/emu/), its input classification, the ordered sum of the
-// per-warp partial rows, and the host-side plan (one launch per class of streams: rate pair x source channels).
+// per-warp partial rows, the FIFO kernels of the sessions, and the launchers; the host-side plan of a whole batch is
+// rb_lanes_batch.cu (no device syntax there, so that the CPU suite can run it).
 // Chosen by the fused planner for very large batches or on RB_FUSED_LANES (include/rodio_b200.h); also renders the blocks
 // of the streaming sessions (rb_session_* in rb_api.cu).
 #include <algorithm>
@@ -153,120 +154,8 @@ cudaError_t rb_lanes_fifo_compact(const float* d_src, float* d_dst, uint64_t str
     return cudaGetLastError();
 }
 
-struct rb_lanes_plan {
-    struct Class {
-        lanes::Args args{};
-        bool ff2 = false;
-        uint32_t ch_in = 1;
-    };
-    std::vector<Class> classes;      // one launch per reduced rate pair
-    lanes::Row* d_rows = nullptr;    // class after class
-    float* d_partial = nullptr;      // [n_groups_total][pstride]
-    float* d_zeros = nullptr;
-    float* d_out = nullptr;
-    uint8_t* d_row_channels = nullptr;   // [n_rows], class order: interleaved channels of every stream
-    uint32_t n_rows = 0, n_groups_total = 0, channels = 1;   // channels: of the mixer
-    uint64_t pstride = 0, mix_len = 0;
-    bool has_biquad = false, has_post = false;
-    bool classified = false;
-};
-
-cudaError_t rb_lanes_try_create(const rb_lanes_stream* streams, size_t n_streams, uint32_t channels, bool has_biquad, bool has_post,
-                                float* d_out, uint64_t mix_len, int sm_count, cudaStream_t st, rb_lanes_plan** out) {
-    (void)sm_count;
-    *out = nullptr;
-    if (n_streams == 0 || n_streams > 0x7fffffffull || mix_len == 0 || (channels != 1 && channels != 2)) return cudaSuccess;
-    std::vector<uint32_t> from(n_streams), to(n_streams), chs(n_streams);
-    for (size_t i = 0; i < n_streams; i++) {
-        from[i] = streams[i].from, to[i] = streams[i].to, chs[i] = streams[i].channels;
-        if (!(from[i] <= to[i]) || from[i] == 0 || to[i] > (1u << 20)) return cudaSuccess;
-        if (!(chs[i] == channels || (chs[i] == 1 && channels == 2))) return cudaSuccess;
-        if (reinterpret_cast<uintptr_t>(streams[i].in) & 15u) return cudaSuccess;
-    }
-    const auto classes = lanes::classes_by_ratio(from.data(), to.data(), chs.data(), (uint32_t)n_streams);
-    auto p = new rb_lanes_plan;
-    p->has_biquad = has_biquad, p->has_post = has_post, p->d_out = d_out, p->channels = channels;
-    p->n_rows = (uint32_t)n_streams, p->mix_len = mix_len, p->pstride = lanes::round_up_tile(mix_len * channels);
-    std::vector<lanes::Row> rows;
-    rows.reserve(n_streams);
-    std::vector<uint8_t> row_channels;
-    std::vector<size_t> first_row;
-    for (const auto& cls : classes) {
-        rb_lanes_plan::Class c;
-        c.ch_in = chs[cls[0]];
-        lanes::Args& a = c.args;
-        a.n_rows = (uint32_t)cls.size(), a.n_groups = (a.n_rows + 31) / 32;
-        lanes::fill_ratio(a, from[cls[0]], to[cls[0]], channels);
-        a.mix_len = mix_len, a.pstride = p->pstride;
-        c.ff2 = has_biquad;
-        first_row.push_back(rows.size());
-        for (uint32_t i : cls) {
-            const rb_lanes_stream& s = streams[i];
-            lanes::Row r;
-            memset(&r, 0, sizeof(r));
-            r.in = s.in, r.L = s.n_frames, r.out_len = s.out_len, r.mix_start = s.mix_start;
-            r.n_int = lanes::n_interp(r.L, s.from, s.to, r.out_len);
-            r.b0 = s.b0, r.b1 = s.b1, r.b2 = s.b2, r.a1 = s.a1, r.a2 = s.a2;
-            r.post = has_post ? s.post : 1.0f;
-            r.flags = lanes::ROW_UNSAFE;   // until classified
-            float k = 0.0f;
-            if (has_biquad && lanes::ff2_coeffs(r.b0, r.b1, r.b2, &k)) r.ffk = k;
-            else c.ff2 = false;
-            rows.push_back(r);
-            row_channels.push_back((uint8_t)s.channels);
-        }
-        p->n_groups_total += a.n_groups;
-        p->classes.push_back(c);
-    }
-    const size_t partial_bytes = (size_t)p->n_groups_total * p->pstride * sizeof(float);
-    cudaError_t e = cudaMalloc(&p->d_rows, n_streams * sizeof(lanes::Row));
-    if (e == cudaSuccess) e = cudaMalloc(&p->d_partial, partial_bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&p->d_zeros, 256);
-    if (e == cudaSuccess) e = cudaMalloc(&p->d_row_channels, n_streams);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_row_channels, row_channels.data(), n_streams, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(p->d_partial, 0, partial_bytes, st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(p->d_zeros, 0, 256, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_rows, rows.data(), n_streams * sizeof(lanes::Row), cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) {
-        rb_lanes_destroy(p);
-        return e;
-    }
-    uint32_t g0 = 0;
-    for (size_t k = 0; k < p->classes.size(); k++) {
-        lanes::Args& a = p->classes[k].args;
-        a.rows = p->d_rows + first_row[k], a.partial = p->d_partial + (size_t)g0 * p->pstride, a.zeros = p->d_zeros;
-        g0 += a.n_groups;
-    }
-    *out = p;
-    return cudaSuccess;
-}
-
-void rb_lanes_inputs_changed(rb_lanes_plan* p) {
-    if (p) p->classified = false;
-}
-
-cudaError_t rb_lanes_run(rb_lanes_plan* p, cudaStream_t st) {
-    if (!p->classified) {
-        k_classify_inputs<<<p->n_rows, 256, 0, st>>>(p->d_rows, p->n_rows, p->d_row_channels);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        p->classified = true;
-    }
-    for (const auto& c : p->classes) {
-        cudaError_t e = rb_lanes_launch_kernel(c.args, c.ch_in, p->channels, p->has_biquad, c.ff2, p->has_post, st);
-        if (e != cudaSuccess) return e;
-    }
-    return rb_lanes_launch_sum(p->d_partial, p->n_groups_total, p->pstride, p->mix_len * p->channels, p->d_out, st);
-}
-
-uint32_t rb_lanes_launch_count(const rb_lanes_plan* p) { return (uint32_t)p->classes.size() + 1u; }
-
-void rb_lanes_destroy(rb_lanes_plan* p) {
-    if (!p) return;
-    cudaFree(p->d_rows);
-    cudaFree(p->d_partial);
-    cudaFree(p->d_zeros);
-    cudaFree(p->d_row_channels);
-    delete p;
+cudaError_t rb_lanes_launch_classify(lanes::Row* d_rows, uint32_t n_rows, const uint8_t* d_row_channels, cudaStream_t st) {
+    if (n_rows == 0) return cudaSuccess;
+    k_classify_inputs<<<n_rows, 256, 0, st>>>(d_rows, n_rows, d_row_channels);
+    return cudaGetLastError();
 }

@@ -49,3 +49,5 @@ cudaError_t rb_lanes_fifo_compact(const float* d_src, float* d_dst, uint64_t str
                                   uint32_t n_streams, cudaStream_t st);
 // Sticky classification of n freshly written floats at d_ptr: *d_flag = 1 when one lies outside the class.
 cudaError_t rb_lanes_classify_range(const float* d_ptr, uint64_t n, uint32_t* d_flag, cudaStream_t st);
+// One CTA per stream of d_rows: Row::flags = ROW_UNSAFE when a sample lies outside the exact-reciprocal class.
+cudaError_t rb_lanes_launch_classify(lanes::Row* d_rows, uint32_t n_rows, const uint8_t* d_row_channels, cudaStream_t st);

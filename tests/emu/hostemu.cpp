@@ -89,6 +89,15 @@ cudaError_t rb_lanes_classify_range(const float* p, uint64_t n, uint32_t* flag, 
     return cudaSuccess;
 }
 
+cudaError_t rb_lanes_launch_classify(lanes::Row* rows, uint32_t n_rows, const uint8_t* channels, cudaStream_t) {
+    for (uint32_t r = 0; r < n_rows; r++) {
+        bool ok = true;
+        for (uint64_t i = 0; i < rows[r].L * channels[r] && ok; i++) ok = lanes::sample_in_class(rows[r].in[i]);
+        rows[r].flags = ok ? 0u : lanes::ROW_UNSAFE;
+    }
+    return cudaSuccess;
+}
+
 cudaError_t rb_lanes_fifo_append(const float* staging, const uint64_t* offset, const uint32_t* count, const uint32_t* fill, float* fifo,
                                  uint64_t stride, uint32_t* flags, uint32_t n_streams, cudaStream_t) {
     for (uint32_t r = 0; r < n_streams; r++)
@@ -120,3 +129,34 @@ int rb_fused_kind(const rb_fused_plan*) { return -1; }
 cudaError_t rb_launch_nodes(uint32_t, const rb_node_dev*, uint32_t, uint64_t, uint32_t, cudaStream_t) { return cudaErrorInvalidValue; }
 cudaError_t rb_launch_mix(const rb_mix_src*, uint32_t, float*, uint64_t, cudaStream_t, float*, uint32_t) { return cudaErrorInvalidValue; }
 cudaError_t rb_launch_convert(const void*, uint32_t, void*, uint32_t, uint64_t, cudaStream_t) { return cudaErrorInvalidValue; }
+
+
+// ---- test entry: the batch plan of the lane kernel (rb_lanes_batch.cu: classes, row order, partial-row offsets) ----
+// pcm[r] holds n_frames[r] * ch_in[r] floats; out_len / mix_start / mix_len in frames; out receives mix_len * channels floats.
+extern "C" int hostemu_lanes_batch(const float* const* pcm, const uint64_t* n_frames, const uint64_t* out_len, const uint64_t* mix_start,
+                                   const float* coefs, const float* post, uint32_t n, uint32_t channels, const uint32_t* ch_in,
+                                   const uint32_t* from, const uint32_t* to, uint64_t mix_len, int hasb, int npost, float* out,
+                                   uint32_t* n_launches) {
+    std::vector<float*> d_in(n, nullptr);
+    std::vector<rb_lanes_stream> st(n);
+    for (uint32_t r = 0; r < n; r++) {
+        if (cudaMalloc(&d_in[r], (n_frames[r] * ch_in[r] + 4) * sizeof(float)) != cudaSuccess) return 1;
+        std::memcpy(d_in[r], pcm[r], n_frames[r] * ch_in[r] * sizeof(float));
+        rb_lanes_stream& s = st[r];
+        s.in = d_in[r], s.n_frames = n_frames[r], s.out_len = out_len[r], s.mix_start = mix_start[r];
+        s.from = from[r], s.to = to[r], s.channels = ch_in[r];
+        const float* c = coefs + 5 * r;
+        s.b0 = c[0], s.b1 = c[1], s.b2 = c[2], s.a1 = c[3], s.a2 = c[4], s.post = post[r];
+    }
+    float* d_out = nullptr;
+    if (cudaMalloc(&d_out, (mix_len * channels + 8) * sizeof(float)) != cudaSuccess) return 1;
+    rb_lanes_plan* plan = nullptr;
+    int rc = 0;
+    if (rb_lanes_try_create(st.data(), n, channels, hasb != 0, npost != 0, d_out, mix_len, 148, nullptr, &plan) != cudaSuccess || !plan) rc = 2;
+    if (!rc && (rb_lanes_run(plan, nullptr) != cudaSuccess || rb_lanes_run(plan, nullptr) != cudaSuccess)) rc = 3;   // twice: idempotent
+    if (!rc) std::memcpy(out, d_out, mix_len * channels * sizeof(float)), *n_launches = rb_lanes_launch_count(plan);
+    rb_lanes_destroy(plan);
+    cudaFree(d_out);
+    for (float* p : d_in) cudaFree(p);
+    return rc;
+}

@@ -16,7 +16,8 @@ ROOT = os.path.dirname(HERE)
 EMU = os.path.join(HERE, "emu")
 LIB = os.path.join(EMU, "librodio_b200_hostemu.so")
 CSRC = os.path.join(ROOT, "rodio_b200", "csrc")
-DEPS = [os.path.join(EMU, "hostemu.cpp"), os.path.join(EMU, "mockcuda", "cuda_runtime.h"), os.path.join(CSRC, "rb_api.cu")] + \
+DEPS = [os.path.join(EMU, "hostemu.cpp"), os.path.join(EMU, "mockcuda", "cuda_runtime.h"), os.path.join(CSRC, "rb_api.cu"),
+        os.path.join(CSRC, "rb_lanes_batch.cu")] + \
        [os.path.join(CSRC, f) for f in ("rb_lanes_core.h", "rb_lanes_plan.h", "rb_session_plan.h", "rb_simt.h", "rb_lanes.h", "rb_fused.h",
                                          "rb_internal.h")] + [os.path.join(ROOT, "include", "rodio_b200.h")]
 
@@ -26,7 +27,7 @@ def hostemu(built):
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in DEPS):
         subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC",
                                "-DRB_SIMT_EMULATE=1", "-I", os.path.join(EMU, "mockcuda"), "-x", "c++", os.path.join(CSRC, "rb_api.cu"),
-                               os.path.join(EMU, "hostemu.cpp"), "-o", LIB])
+                               os.path.join(CSRC, "rb_lanes_batch.cu"), os.path.join(EMU, "hostemu.cpp"), "-o", LIB])
     return LIB
 
 
@@ -36,3 +37,41 @@ def test_session_host_code_on_the_emulator(hostemu, scenario):
     r = subprocess.run([sys.executable, os.path.join(EMU, "session_scenarios.py"), scenario], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and f"ok {scenario}" in r.stdout, (r.stdout + r.stderr)[-3000:]
     print(f"{scenario}: {time.time() - t0:.1f} s")
+
+
+def test_lanes_batch_plan_on_the_emulator(hostemu):
+    """rb_lanes_batch.cu (classes by rate pair and source channels, class-ordered rows, partial-row offsets, classification)
+    compiled against the mock runtime: mono and stereo sources at four rates in a stereo mixer, one stream outside the input
+    class -- bit for bit against the oracle streams summed class by class."""
+    import ctypes as C
+
+    import numpy as np
+
+    sys.path[:0] = [HERE]
+    import test_lanes_emulator as T
+    from helpers import assert_bit_exact, noise
+
+    ch_in = [1, 2, 1, 1, 2, 1, 2, 1] * 6
+    rates = [44100, 44100, 48000, 22050, 48000, 44100, 32000, 48000] * 6
+    pcms = [noise(ci * (500 + 9 * i), 4100 + i) for i, ci in enumerate(ch_in)]
+    pcms[5][40:50] = np.float32(1e-41)
+    starts = [(11 * i) % 70 for i in range(len(ch_in))]
+    c = T.make_case(pcms, rates, 48000, starts, lp=700, gain=0.9, channels=2, ch_in=ch_in)
+    lib = C.CDLL(hostemu)
+    n = len(pcms)
+    arrs = [np.ascontiguousarray(p, dtype=np.float32) for p in pcms]
+    ptrs = (C.POINTER(C.c_float) * n)(*[a.ctypes.data_as(C.POINTER(C.c_float)) for a in arrs])
+    u64 = lambda v: (C.c_uint64 * n)(*[int(x) for x in v])
+    u32 = lambda v: (C.c_uint32 * n)(*[int(x) for x in v])
+    co = np.ascontiguousarray(c["coefs"], np.float32).reshape(-1)
+    po = np.ascontiguousarray(c["posts"], np.float32)
+    out = np.full(c["mix_len"] * 2, np.nan, np.float32)
+    launches = C.c_uint32(0)
+    rc = lib.hostemu_lanes_batch(ptrs, u64([a.size // ci for a, ci in zip(arrs, ch_in)]), u64(c["outs_len"]), u64(starts),
+                                 co.ctypes.data_as(C.POINTER(C.c_float)), po.ctypes.data_as(C.POINTER(C.c_float)), C.c_uint32(n),
+                                 C.c_uint32(2), u32(ch_in), u32(c["from_"]), u32(c["to"]), C.c_uint64(c["mix_len"]), 1, 1,
+                                 out.ctypes.data_as(C.POINTER(C.c_float)), C.byref(launches))
+    assert rc == 0
+    assert launches.value == 6 + 1            # six classes (rate pair x source channels) and the sum
+    want = T.expected_mix_classes(c["per_stream"], [s * 2 for s in starts], c["mix_len"] * 2, c["from_"], list(zip(c["to"], ch_in)))
+    assert_bit_exact(out, want, "batch plan of the lane kernel")
