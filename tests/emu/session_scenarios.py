@@ -144,6 +144,36 @@ def s_held_queue_gain_speed():
     assert_bit_exact(got, expected(pcms, ch, rates, 1, 48000, joined, 900, 0.8, speeds), "queue + added voice + scheduled source")
 
 
+def s_gain_changes():
+    """rb_session_set_amplify between 5 ms blocks, rb_session_available in step with what render delivers."""
+    pcms = [noise(1500, 800 + i) for i in range(3)]
+    srcs = [chain(np.zeros(0, np.float32), 1, 44100, 1, 48000, 500, 1.0) for _ in pcms]
+    per = [oracle.chain_uniform(to_oracle(chain(p, 1, 44100, 1, 48000, 500, 1.0)), 1, 48000) for p in pcms]
+    rng = np.random.default_rng(3)
+    got, gains, block = [], [], 240
+    with rb.Session(srcs, 48000, fifo_frames=4096, max_block_frames=block) as s:
+        for i, p in enumerate(pcms):
+            s.push(i, p, end_of_stream=True)
+        ended = False
+        while not ended:
+            g = [np.float32(v) for v in rng.uniform(0.0, 1.5, 3)]
+            for i in range(3):
+                s.set_amplify(i, float(g[i]))
+            avail, _ = s.available()
+            out, ended = s.render(block)
+            assert out.size == min(avail, block)
+            if out.size:
+                got.append(out), gains.append(g)
+    got = np.concatenate(got)
+    scaled = []
+    for r in range(3):
+        y = per[r].copy()
+        for k, g in enumerate(gains):
+            y[k * block:(k + 1) * block] = y[k * block:(k + 1) * block] * g[r]
+        scaled.append(y)
+    assert_bit_exact(got, expected_mix_classes(scaled, [0] * 3, got.size, [147] * 3, [(160, 1)] * 3), "per-block gains")
+
+
 def s_errors():
     mk = lambda ci, r, mc: chain(np.zeros(0, np.float32), ci, r, mc, 48000, 200, None)
     for bad in (lambda: rb.Session([mk(2, 44100, 1)], 48000, mixer_channels=1),                       # stereo source, mono mixer
@@ -200,7 +230,7 @@ def s_random(seed=0, cases=6):
 
 
 SCENARIOS = {"mono_random_split": s_mono_random_split, "mixed_with_state_blob": s_mixed_everything_with_state_blob,
-             "held_queue_gain_speed": s_held_queue_gain_speed, "errors": s_errors}
+             "held_queue_gain_speed": s_held_queue_gain_speed, "gain_changes": s_gain_changes, "errors": s_errors}
 
 if __name__ == "__main__":
     for name in (sys.argv[1:] or list(SCENARIOS)):

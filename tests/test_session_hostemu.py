@@ -31,7 +31,7 @@ def hostemu(built):
     return LIB
 
 
-@pytest.mark.parametrize("scenario", ["errors", "mono_random_split", "mixed_with_state_blob", "held_queue_gain_speed"])
+@pytest.mark.parametrize("scenario", ["errors", "mono_random_split", "mixed_with_state_blob", "held_queue_gain_speed", "gain_changes"])
 def test_session_host_code_on_the_emulator(hostemu, scenario):
     t0 = time.time()
     r = subprocess.run([sys.executable, os.path.join(EMU, "session_scenarios.py"), scenario], capture_output=True, text=True, timeout=900)
