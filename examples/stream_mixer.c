@@ -21,7 +21,8 @@
         }                                                                                    \
     } while (0)
 
-int main(void) {
+int main(int argc, char** argv) {
+    const int blocks = argc > 1 ? atoi(argv[1]) : 100;   /* 10 ms each: one second by default */
     rb_context* ctx = NULL;
     CHECK(rb_context_create(0, &ctx));
 
@@ -40,20 +41,20 @@ int main(void) {
     rb_session* mixer = NULL;
     CHECK(rb_session_create(ctx, 2, 48000, descs, 2, /* fifo_frames */ 4096, /* max_block_frames */ 480, &mixer));
 
-    enum { MUSIC_BLOCK = 441, VOICE_BLOCK = 480, BLOCKS = 100 };   /* 10 ms each, one second in all */
+    enum { MUSIC_BLOCK = 441, VOICE_BLOCK = 480 };
     float music[MUSIC_BLOCK * 2], voice[VOICE_BLOCK], out[480 * 2];
     double peak = 0.0;
     uint64_t total = 0;
     int ended = 0;
     for (int b = 0; !ended; b++) {
-        if (b < BLOCKS) {   /* "decode" the next 10 ms of both sources */
+        if (b < blocks) {   /* "decode" the next 10 ms of both sources */
             for (int i = 0; i < MUSIC_BLOCK; i++) {
                 const double t = (b * MUSIC_BLOCK + i) / 44100.0;
                 music[2 * i] = (float)(0.5 * sin(2 * M_PI * 110.0 * t)), music[2 * i + 1] = (float)(0.5 * sin(2 * M_PI * 165.0 * t));
             }
             for (int i = 0; i < VOICE_BLOCK; i++) voice[i] = (float)(0.25 * sin(2 * M_PI * 440.0 * (b * VOICE_BLOCK + i) / 48000.0));
-            CHECK(rb_session_push(mixer, 0, music, MUSIC_BLOCK, b == BLOCKS - 1));
-            CHECK(rb_session_push(mixer, 1, voice, VOICE_BLOCK, b == BLOCKS - 1));
+            CHECK(rb_session_push(mixer, 0, music, MUSIC_BLOCK, b == blocks - 1));
+            CHECK(rb_session_push(mixer, 1, voice, VOICE_BLOCK, b == blocks - 1));
         }
         for (;;) {   /* hand the mixer output on (to a device callback, a file ...) as it becomes available */
             uint64_t n = 0;

@@ -958,7 +958,7 @@ struct rb_session {
     // per-source arrays below are in CLASS ORDER (stable partition by rate pair); pos[] maps the caller's index to it.
     struct Class {
         uint32_t first = 0, count = 0, ch_in = 1;
-        bool ff2 = false;
+        bool has_biquad = false, ff2 = false;
     };
     std::vector<Class> classes;
     std::vector<uint32_t> pos;
@@ -1005,7 +1005,7 @@ extern "C" rb_status rb_session_create(rb_context* ctx, uint16_t mixer_channels,
     s->ctx = ctx, s->mixer_rate = mixer_rate, s->channels = mixer_channels, s->fifo_cap = fifo_frames, s->max_block = max_block_frames;
     const size_t n = n_streams;
     // pass 1: validate, find every source's reduced rate pair -> classes
-    std::vector<uint32_t> from(n), to(n), chs(n), first_fx(n);
+    std::vector<uint32_t> from(n), to(n), chs(n), first_fx(n), key(n);
     for (size_t i = 0; i < n; i++) {
         const rb_stream_desc& d = descs[i];
         const std::string where = "stream " + std::to_string(i) + ": ";
@@ -1023,21 +1023,24 @@ extern "C" rb_status rb_session_create(rb_context* ctx, uint16_t mixer_channels,
             return fail(RB_ERR_UNSUPPORTED, where + "the chain must be [SPEED] UNIFORM(mixer channels, mixer rate) ...");
         const uint32_t g = std::gcd(rate, mixer_rate);
         from[i] = rate / g, to[i] = mixer_rate / g;
+        const bool filtered = k0 + 1 < d.n_effects && (d.effects[k0 + 1].kind == RB_FX_LOW_PASS || d.effects[k0 + 1].kind == RB_FX_HIGH_PASS);
+        key[i] = d.channels | (filtered ? 0x100u : 0u);   // filtered and unfiltered sources are classes of their own
         if (from[i] > (1u << 20) || to[i] > (1u << 20))
             return fail(RB_ERR_RATIO_OVERFLOW, where + "reduced rate pair beyond 2^20");
     }
-    const auto classes = lanes::classes_by_ratio(from.data(), to.data(), chs.data(), (uint32_t)n);
+    const auto classes = lanes::classes_by_ratio(from.data(), to.data(), key.data(), (uint32_t)n);
     s->pos.assign(n, 0);
     std::vector<uint32_t> order;   // class order -> caller's index
     for (const auto& cls : classes) {
         rb_session::Class c;
         c.first = (uint32_t)order.size(), c.count = (uint32_t)cls.size(), c.ch_in = chs[cls[0]];
+        c.has_biquad = (key[cls[0]] & 0x100u) != 0;
         for (uint32_t i : cls) s->pos[i] = (uint32_t)order.size(), order.push_back(i);
         s->classes.push_back(c);
     }
     // pass 2: chains, in class order
     s->st.resize(n), s->coef.assign(5 * n, 0.0f), s->ffk.assign(n, 0.0f), s->post.assign(n, 1.0f), s->src_ch.assign(n, 1);
-    bool any_biquad = false, all_biquad = true;
+    bool any_biquad = false;
     std::vector<uint8_t> row_ff2(n, 1);
     for (size_t r = 0; r < n; r++) {
         const size_t i = order[r];
@@ -1054,17 +1057,16 @@ extern "C" rb_status rb_session_create(rb_context* ctx, uint16_t mixer_channels,
             if (!lanes::ff2_coeffs(c.b0, c.b1, c.b2, &s->ffk[r])) row_ff2[r] = 0;
             biq = true, k++;
         }
-        any_biquad |= biq, all_biquad &= biq;
+        any_biquad |= biq;
         if (k < d.n_effects && d.effects[k].kind == RB_FX_AMPLIFY) s->post[r] = d.effects[k].f32[0], s->has_post = true, k++;
         if (k != d.n_effects) return fail(RB_ERR_UNSUPPORTED, where + "chain shape: [SPEED] UNIFORM [LOW_PASS | HIGH_PASS] [AMPLIFY]");
         s->st[r].mix_start = d.mix_start, s->st[r].from = from[i], s->st[r].to = to[i];
         if (d.mix_start == RB_SESSION_HELD) s->st[r].held = true, s->st[r].mix_start = 0;   // Mixer::add comes later (rb_session_start)
         s->src_ch[r] = (uint8_t)d.channels;
     }
-    if (any_biquad && !all_biquad) return fail(RB_ERR_UNSUPPORTED, "either every source of a session has a filter or none has");
     s->has_biquad = any_biquad;
     for (auto& c : s->classes) {
-        c.ff2 = any_biquad;
+        c.ff2 = c.has_biquad;
         for (uint32_t r = c.first; r < c.first + c.count; r++) c.ff2 = c.ff2 && row_ff2[r];
     }
     RB_CUDA(cudaSetDevice(ctx->device));
@@ -1226,7 +1228,7 @@ extern "C" rb_status rb_session_render(rb_session* s, float* out_host, uint64_t 
         lanes::fill_ratio(a, s->st[c.first].from, s->st[c.first].to, C);
         a.mix_len = n, a.pstride = pstride;
         a.partial = s->d_partial + (size_t)g0 * pstride, a.zeros = s->d_zeros, a.unsafe = s->d_flags + c.first;
-        RB_CUDA(rb_lanes_launch_kernel(a, c.ch_in, C, s->has_biquad, c.ff2, s->has_post, stq));
+        RB_CUDA(rb_lanes_launch_kernel(a, c.ch_in, C, c.has_biquad, c.ff2, s->has_post, stq));
         g0 += a.n_groups;
     }
     RB_CUDA(rb_lanes_launch_sum(s->d_partial, n_groups_total, pstride, n * C, s->d_out, stq));

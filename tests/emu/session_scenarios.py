@@ -144,6 +144,28 @@ def s_held_queue_gain_speed():
     assert_bit_exact(got, expected(pcms, ch, rates, 1, 48000, joined, 900, 0.8, speeds), "queue + added voice + scheduled source")
 
 
+def s_filtered_and_plain_sources():
+    """A low-passed source beside an untouched one (examples/stream_mixer.c): classes of their own, two launches."""
+    pcms = [noise(2 * 900, 51), noise(1000, 52), noise(2 * 700, 53), noise(800, 54)]
+    ch_in, rates = [2, 1, 2, 1], [44100, 48000, 48000, 22050]
+    srcs = [chain(np.zeros(0, np.float32), 2, 44100, 2, 48000, 200, 0.8), chain(np.zeros(0, np.float32), 1, 48000, 2, 48000, None, None),
+            chain(np.zeros(0, np.float32), 2, 48000, 2, 48000, None, 0.5), chain(np.zeros(0, np.float32), 1, 22050, 2, 48000, 300, None)]
+    with rb.Session(srcs, 48000, fifo_frames=2048, max_block_frames=480, mixer_channels=2) as s:
+        got, _ = drive(s, pcms, ch_in, [r // 100 for r in rates], 480)
+    real = [chain(pcms[0], 2, 44100, 2, 48000, 200, 0.8), chain(pcms[1], 1, 48000, 2, 48000, None, None),
+            chain(pcms[2], 2, 48000, 2, 48000, None, 0.5), chain(pcms[3], 1, 22050, 2, 48000, 300, None)]
+    per = [oracle.chain_uniform(to_oracle(x), 2, 48000) for x in real]
+    # every source is a class of its own here (rate pair x channels x filtered): the mix is the plain sum in source order
+    acc = np.zeros(max(y.size for y in per), np.float32)
+    for y in per:
+        row = np.zeros(acc.size, np.float32)
+        row[:y.size] = y
+        acc = acc + (row + np.float32(0.0))
+    assert_bit_exact(got, acc, "filtered beside plain sources")
+    ref = oracle.mixer([to_oracle(x) for x in real], 2, 48000)
+    assert_close_peak(got, ref, 1e-5, "... and the reference's mixer")
+
+
 def s_gain_changes():
     """rb_session_set_amplify between 5 ms blocks, rb_session_available in step with what render delivers."""
     pcms = [noise(1500, 800 + i) for i in range(3)]
@@ -230,7 +252,7 @@ def s_random(seed=0, cases=6):
 
 
 SCENARIOS = {"mono_random_split": s_mono_random_split, "mixed_with_state_blob": s_mixed_everything_with_state_blob,
-             "held_queue_gain_speed": s_held_queue_gain_speed, "gain_changes": s_gain_changes, "errors": s_errors}
+             "held_queue_gain_speed": s_held_queue_gain_speed, "gain_changes": s_gain_changes, "filtered_and_plain": s_filtered_and_plain_sources, "errors": s_errors}
 
 if __name__ == "__main__":
     for name in (sys.argv[1:] or list(SCENARIOS)):

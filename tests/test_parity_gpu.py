@@ -781,11 +781,13 @@ def test_session_rejects_other_shapes(ctx):
     with pytest.raises(rb.RodioB200Error):
         rb.Session([stereo], 48000, ctx=ctx)
     down = rb.UniformSourceIterator(rb.TestSource(np.zeros(0, np.float32), 1, 96000), 1, 48000)
-    with pytest.raises(rb.RodioB200Error):
-        rb.Session([down], 48000, ctx=ctx)
+    rb.Session([down], 48000, ctx=ctx).close()          # above the mixer's rate: served (general per-sample path), not rejected
     agc = rb.UniformSourceIterator(rb.TestSource(np.zeros(0, np.float32), 1, 44100), 1, 48000).automatic_gain_control()
     with pytest.raises(rb.RodioB200Error):
         rb.Session([agc], 48000, ctx=ctx)
+    no_uniform = rb.TestSource(np.zeros(0, np.float32), 1, 44100).low_pass(100)
+    with pytest.raises(rb.RodioB200Error):
+        rb.Session([no_uniform], 48000, ctx=ctx)
 
 
 @lanes_gate

@@ -31,7 +31,8 @@ def hostemu(built):
     return LIB
 
 
-@pytest.mark.parametrize("scenario", ["errors", "mono_random_split", "mixed_with_state_blob", "held_queue_gain_speed", "gain_changes"])
+@pytest.mark.parametrize("scenario", ["errors", "mono_random_split", "mixed_with_state_blob", "held_queue_gain_speed", "gain_changes",
+                                      "filtered_and_plain"])
 def test_session_host_code_on_the_emulator(hostemu, scenario):
     t0 = time.time()
     r = subprocess.run([sys.executable, os.path.join(EMU, "session_scenarios.py"), scenario], capture_output=True, text=True, timeout=900)
@@ -75,3 +76,15 @@ def test_lanes_batch_plan_on_the_emulator(hostemu):
     assert launches.value == 6 + 1            # six classes (rate pair x source channels) and the sum
     want = T.expected_mix_classes(c["per_stream"], [s * 2 for s in starts], c["mix_len"] * 2, c["from_"], list(zip(c["to"], ch_in)))
     assert_bit_exact(out, want, "batch plan of the lane kernel")
+
+
+def test_plain_c_example_runs_on_the_emulator(hostemu):
+    """examples/stream_mixer.c linked against the host-emulated library: 200 ms of a filtered stereo 44.1 kHz source and a
+    plain mono 48 kHz one through a stereo session, from C."""
+    exe = os.path.join(HERE, "cpp", "stream_mixer_emu.bin")
+    subprocess.run(["gcc", "-std=c11", "-D_GNU_SOURCE", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "stream_mixer.c"),
+                    "-o", exe, "-L", EMU, "-l:librodio_b200_hostemu.so", f"-Wl,-rpath,{EMU}", "-lm"], check=True, capture_output=True)
+    r = subprocess.run([exe, "20"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    frames, peak = int(r.stdout.split()[0]), float(r.stdout.split()[-1])
+    assert frames == 9600 and 0.3 < peak < 0.9, r.stdout      # 20 x 10 ms at 48 kHz; 0.8 * 0.5 low-passed music + 0.25 voice
