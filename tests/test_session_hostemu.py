@@ -88,3 +88,14 @@ def test_plain_c_example_runs_on_the_emulator(hostemu):
     assert r.returncode == 0, r.stdout + r.stderr
     frames, peak = int(r.stdout.split()[0]), float(r.stdout.split()[-1])
     assert frames == 9600 and 0.3 < peak < 0.9, r.stdout      # 20 x 10 ms at 48 kHz; 0.8 * 0.5 low-passed music + 0.25 voice
+
+
+def test_oracle_only_gpu_session_tests_hold_on_the_emulator(hostemu):
+    """The GPU session tests that need nothing but the session and the oracle, run unchanged against the host-emulated library
+    (their expectations are then known to be right before they meet a device)."""
+    code = ("import os, sys; sys.path[:0] = [%r, %r]; import rodio_b200._capi as c; c.LIB_PATH = %r; import pytest; "
+            "sys.exit(pytest.main([%r, '-q', '-m', 'gpu', '-x', '-p', 'no:cacheprovider', '-k', "
+            "'test_session_rejects or test_session_speed or test_session_queue_of_sources']))"
+            % (ROOT, HERE, hostemu, os.path.join(HERE, "test_parity_gpu.py")))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0 and "3 passed" in r.stdout, (r.stdout + r.stderr)[-3000:]
