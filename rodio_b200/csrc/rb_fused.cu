@@ -32,42 +32,16 @@
 #include "rb_dsp.cuh"
 #include "rb_fused.h"
 #include "rb_lanes.h"
+#include "rb_fused_rows.h"   // FusedRow, ROW_*, TT, MAX_GAINS, parse_row, fused_lanes_hook (host-visible: also run by the CPU suite)
 
 using namespace rbd;
 
 namespace {
 
-constexpr int TT = 256;            // mixer-timeline samples per tile
 constexpr int ROW_STRIDE = TT + 4; // words; (TT+4)/4 odd -> LDS.128 by 8 lanes hits 8 distinct bank groups
 constexpr int HOT_PAD = 4;          // k_fused_hot: tile position 0 sits at word 4 of its row; words 2,3 hold x[-2], x[-1]
 constexpr int MAX_G = 32;          // rows per CTA
 constexpr int NBUF = 3;
-constexpr int MAX_GAINS = 4;
-
-struct FusedRow {                  // one stream, device side
-    const void* in;
-    uint64_t n_in;
-    uint64_t out_len;              // samples on the mixer timeline
-    uint64_t mix_start;
-    uint32_t fmt, c_in;
-    uint32_t has_uniform;
-    uint32_t mode;                 // row-wide fast mode, see ROW_*
-    rb_uniform_params uni;
-    uint32_t q32, r32;             // divmod(32 * from, to): index advance for a lane stride of 32 output frames
-    uint32_t qT, rT;               // divmod(TT * from, to): index advance from one full tile to the next
-    float den_f, rcp_den;          // (f32)to and RN(1 / (f32)to)
-    float pre[MAX_GAINS];          // gains applied to raw input samples (before interpolation)
-    float mid[MAX_GAINS];          // gains between the uniform conversion and the biquad
-    float post[MAX_GAINS];         // gains after the biquad
-    float b0, b1, b2, a1, a2;
-    uint32_t pad_[1];
-};
-enum : uint32_t {
-    ROW_GENERIC = 0,   // exact closed form per sample (span chunks, trailing partial frames, huge ratios)
-    ROW_DIRECT = 1,    // no conversion at all: out[o] = in[o]
-    ROW_PASS = 2,      // same rate, channel map only
-    ROW_LERP = 3       // linear interpolation on the reduced grid, one segment, whole frames
-};
 
 struct FusedArgs {
     const FusedRow* rows;
@@ -1183,83 +1157,6 @@ struct rb_fused_plan {
     rb_lanes_plan* lanes = nullptr;   // RB_FUSED_LANES: the lane-per-stream kernel serves the batch (rb_lanes.cu)
 };
 
-static const rb_node_dev& node_at(const rb_fused_stream& s, uint32_t i) {
-    return *reinterpret_cast<const rb_node_dev*>(reinterpret_cast<const char*>(s.nodes) + (size_t)i * s.node_stride);
-}
-
-// Parse one stream into a FusedRow; returns false when its chain is outside the fused shape.
-static bool parse_row(const rb_fused_stream& s, uint16_t mixer_ch, FusedRow& r, uint32_t& n_pre, uint32_t& n_mid,
-                      uint32_t& n_post, uint32_t& has_uniform, uint32_t& has_biquad) {
-    memset(&r, 0, sizeof(r));
-    r.in = s.in, r.n_in = s.n_in, r.out_len = s.out_len, r.mix_start = s.mix_start;
-    r.fmt = s.fmt, r.c_in = s.c_in;
-    n_pre = n_mid = n_post = has_uniform = has_biquad = 0;
-    uint32_t cur_c = s.c_in;
-    for (uint32_t i = 0; i < s.n_nodes; i++) {
-        const rb_node_dev& nd = node_at(s, i);
-        switch (nd.kind) {
-            case RB_N_CONVERT:
-                if (i != 0) return false;
-                break;   // the format is applied at load time
-            case RB_N_AMPLIFY:
-                if (has_biquad) {
-                    if (n_post >= MAX_GAINS) return false;
-                    r.post[n_post++] = nd.p.amp.factor;
-                } else if (has_uniform) {
-                    if (n_mid >= MAX_GAINS) return false;
-                    r.mid[n_mid++] = nd.p.amp.factor;
-                } else {
-                    if (n_pre >= MAX_GAINS) return false;
-                    r.pre[n_pre++] = nd.p.amp.factor;
-                }
-                break;
-            case RB_N_UNIFORM:
-                if (has_uniform || has_biquad) return false;
-                has_uniform = 1;
-                r.uni = nd.p.uni;
-                if (nd.c_in != s.c_in) return false;
-                cur_c = nd.c_out;
-                break;
-            case RB_N_BIQUAD:
-                if (has_biquad) return false;
-                has_biquad = 1;
-                r.b0 = nd.p.blt.b0, r.b1 = nd.p.blt.b1, r.b2 = nd.p.blt.b2, r.a1 = nd.p.blt.a1, r.a2 = nd.p.blt.a2;
-                break;
-            default: return false;
-        }
-    }
-    if (cur_c != mixer_ch) return false;
-    if (!has_uniform) {
-        // gains before a (missing) uniform were collected as `pre`; keep that, n_mid stays 0
-    }
-    r.has_uniform = has_uniform;
-    r.mode = ROW_GENERIC;
-    if (!has_uniform) {
-        r.mode = ROW_DIRECT;
-        // the HOT kernel walks same-rate rows as a 1:1 "ratio"
-        r.uni.from = r.uni.to = 1, r.uni.tail.L = s.n_in / (s.c_in ? s.c_in : 1);
-        r.q32 = 32, r.r32 = 0, r.qT = TT, r.rT = 0, r.den_f = 1.0f, r.rcp_den = 1.0f;
-    } else {
-        const rb_uniform_params& u = r.uni;
-        r.den_f = (float)u.to;
-        r.rcp_den = 1.0f / r.den_f;
-        if (u.from == u.to) {
-            if (u.tail.p == 0 && (u.chunk_samples == 0 || u.chunk_samples % s.c_in == 0)) {
-                r.mode = ROW_PASS;
-                r.uni.tail.L = r.n_in / (s.c_in ? s.c_in : 1);   // chunks are irrelevant for a whole-frame pass-through
-                r.q32 = 32, r.r32 = 0, r.qT = TT, r.rT = 0;
-            }
-        } else if (u.chunk_samples == 0 && u.tail.p == 0 && u.from <= (1u << 20) && u.to <= (1u << 20)) {
-            r.mode = ROW_LERP;
-            r.q32 = (uint32_t)((32ull * u.from) / u.to);
-            r.r32 = (uint32_t)((32ull * u.from) % u.to);
-            r.qT = (uint32_t)(((uint64_t)TT * u.from) / u.to);
-            r.rT = (uint32_t)(((uint64_t)TT * u.from) % u.to);
-        }
-    }
-    return true;
-}
-
 cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams, uint16_t mixer_channels, float* d_out,
                                 uint64_t mix_len, uint32_t flags, int sm_count, cudaStream_t st, rb_fused_plan** out) {
     *out = nullptr;
@@ -1267,13 +1164,8 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     if (flags & (RB_MIX_EXACT_ORDER | RB_BIQUAD_TIME_PARALLEL)) return cudaSuccess;   // served by the general path
     std::vector<FusedRow> rows(n_streams);
     uint32_t n_pre = 0, n_mid = 0, n_post = 0, has_u = 0, has_b = 0;
-    for (size_t i = 0; i < n_streams; i++) {
-        uint32_t p, m, q, u, b;
-        if (!parse_row(streams[i], mixer_channels, rows[i], p, m, q, u, b)) return cudaSuccess;
-        // a biquad directly on the input (no uniform) sees the `pre` gains as its input gains: move them
-        if (i == 0) n_pre = p, n_mid = m, n_post = q, has_u = u, has_b = b;
-        else if (p != n_pre || m != n_mid || q != n_post || u != has_u || b != has_b) return cudaSuccess;
-    }
+    bool mixed_u = false;   // some rows lost an identity conversion: only the lane kernel may take such a batch
+    if (!fused_parse_rows(streams, n_streams, mixer_channels, rows, n_pre, n_mid, n_post, has_u, has_b, mixed_u)) return cudaSuccess;
     if (has_b && (uint32_t)mixer_channels * 1u > 32u) return cudaSuccess;
 
     // Plain mixer of f32 sources at the mixer's own rate/channels (BASELINE cfg2): nothing to fuse -- the ordered
@@ -1286,44 +1178,20 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     auto plan = new rb_fused_plan;
     plan->all_f32 = true;
     for (size_t i = 0; i < n_streams; i++) plan->all_f32 = plan->all_f32 && streams[i].fmt == RB_FMT_F32;
-    // RB_FUSED_LANES asks for it; from about 277 streams per SM on (10 warps of 32 streams) it is the faster kernel anyway
-    // (measured: 65 536 x 1 s in 4.26 ms against 7.0 ms for k_fused_hot, 16 384 x 1 s in 2.46 ms against 1.74 ms).
-    const bool want_lanes = (flags & RB_FUSED_LANES) || n_streams >= (size_t)277 * (size_t)(sm_count > 0 ? sm_count : 148);
-    if (want_lanes && (mixer_channels == 1 || mixer_channels == 2) && plan->all_f32 && (has_u || has_b) && n_pre == 0) {
-        // Lane-per-stream kernel: f32 streams with the mixer's channel count (or mono in a stereo mixer), each at or
-        // below the mixer's rate (classes per rate pair), optional biquad, at most one gain directly in front of the sum.
-        const uint32_t C = mixer_channels;
-        bool ok = has_b ? (n_mid == 0 && n_post <= 1) : (n_mid + n_post <= 1);
-        std::vector<rb_lanes_stream> ls(ok ? n_streams : 0);
-        for (size_t i = 0; i < n_streams && ok; i++) {
-            const FusedRow& r = rows[i];
-            // every stream interpolates upwards on its own reduced grid (several rate pairs are served class by class),
-            // or is at the mixer's rate already (UniformSourceIterator hands it through)
-            const bool lerp_up = r.mode == ROW_LERP && r.uni.from < r.uni.to;
-            const bool pass = r.mode == ROW_PASS || r.mode == ROW_DIRECT;   // no conversion needed / none in the chain
-            // the stream has the mixer's channels, or is mono in a stereo mixer (repeated on both channels, channels.rs:57-85)
-            ok = (lerp_up || pass) && (r.c_in == C || (r.c_in == 1 && C == 2)) && r.out_len % C == 0 && r.mix_start % C == 0 &&
-                 r.n_in % r.c_in == 0;
-            rb_lanes_stream& l = ls[i];
-            l.channels = r.c_in;
-            l.in = (const float*)r.in, l.n_frames = r.uni.tail.L, l.out_len = r.out_len / C, l.mix_start = r.mix_start / C;
-            l.from = pass ? 1u : r.uni.from, l.to = pass ? 1u : r.uni.to;
-            l.b0 = r.b0, l.b1 = r.b1, l.b2 = r.b2, l.a1 = r.a1, l.a2 = r.a2;
-            l.post = n_post ? r.post[0] : (n_mid ? r.mid[0] : 1.0f);
+    {
+        cudaError_t e = fused_lanes_hook(rows, n_streams, mixer_channels, plan->all_f32, n_pre, n_mid, n_post, has_u, has_b, flags, sm_count,
+                                         d_out, mix_len, st, &plan->lanes);
+        if (e != cudaSuccess) {
+            delete plan;
+            return e;
         }
-        if (ok) {
-            cudaError_t e = cudaSuccess;
-            if (mix_len % C == 0)
-                e = rb_lanes_try_create(ls.data(), n_streams, C, has_b != 0, (n_mid + n_post) != 0, d_out, mix_len / C, sm_count, st,
-                                        &plan->lanes);
-            if (e != cudaSuccess) {
-                delete plan;
-                return e;
-            }
-            if (plan->lanes) {
-                *out = plan;
-                return cudaSuccess;
-            }
+        if (plan->lanes) {
+            *out = plan;
+            return cudaSuccess;
+        }
+        if (mixed_u) {   // the other fused kernels keep their one-shape rule: general path, as before
+            delete plan;
+            return cudaSuccess;
         }
     }
     const uint32_t C = mixer_channels;

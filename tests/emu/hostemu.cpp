@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../rodio_b200/csrc/rb_fused.h"
+#include "../../rodio_b200/csrc/rb_fused_rows.h"
 #include "../../rodio_b200/csrc/rb_lanes.h"
 #include "../../rodio_b200/csrc/rb_lanes_plan.h"
 
@@ -117,15 +118,36 @@ cudaError_t rb_lanes_fifo_compact(const float* src, float* dst, uint64_t stride,
 }
 
 // ---- everything else the host code links against: not available without the real kernels ----
-cudaError_t rb_fused_try_create(const rb_fused_stream*, size_t, uint16_t, float*, uint64_t, uint32_t, int, cudaStream_t, rb_fused_plan** out) {
+// The fused planner as far as the CPU can follow it: the product's own parser and hand-over to the lane kernel
+// (rb_fused_rows.h); batches the lane kernel does not take have no kernels here and fall to the (absent) general path.
+struct rb_fused_plan {
+    rb_lanes_plan* lanes = nullptr;
+};
+cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams, uint16_t mixer_channels, float* d_out, uint64_t mix_len,
+                                uint32_t flags, int sm_count, cudaStream_t st, rb_fused_plan** out) {
     *out = nullptr;
+    if (n_streams == 0 || mix_len == 0 || (flags & (RB_MIX_EXACT_ORDER | RB_BIQUAD_TIME_PARALLEL))) return cudaSuccess;
+    std::vector<FusedRow> rows(n_streams);
+    uint32_t n_pre = 0, n_mid = 0, n_post = 0, has_u = 0, has_b = 0;
+    bool mixed_u = false, all_f32 = true;
+    if (!fused_parse_rows(streams, n_streams, mixer_channels, rows, n_pre, n_mid, n_post, has_u, has_b, mixed_u)) return cudaSuccess;
+    for (size_t i = 0; i < n_streams; i++) all_f32 = all_f32 && streams[i].fmt == RB_FMT_F32;
+    rb_lanes_plan* lanes = nullptr;
+    cudaError_t e = fused_lanes_hook(rows, n_streams, mixer_channels, all_f32, n_pre, n_mid, n_post, has_u, has_b, flags, sm_count, d_out,
+                                     mix_len, st, &lanes);
+    if (e != cudaSuccess || !lanes) return e;
+    *out = new rb_fused_plan{lanes};
     return cudaSuccess;
 }
-cudaError_t rb_fused_run(rb_fused_plan*, cudaStream_t) { return cudaErrorInvalidValue; }
-void rb_fused_destroy(rb_fused_plan*) {}
-uint32_t rb_fused_launch_count(const rb_fused_plan*) { return 0; }
-void rb_fused_inputs_changed(rb_fused_plan*) {}
-int rb_fused_kind(const rb_fused_plan*) { return -1; }
+cudaError_t rb_fused_run(rb_fused_plan* p, cudaStream_t st) { return rb_lanes_run(p->lanes, st); }
+void rb_fused_destroy(rb_fused_plan* p) {
+    if (p) rb_lanes_destroy(p->lanes), delete p;
+}
+uint32_t rb_fused_launch_count(const rb_fused_plan* p) { return rb_lanes_launch_count(p->lanes); }
+void rb_fused_inputs_changed(rb_fused_plan* p) {
+    if (p) rb_lanes_inputs_changed(p->lanes);
+}
+int rb_fused_kind(const rb_fused_plan*) { return 2; }
 cudaError_t rb_launch_nodes(uint32_t, const rb_node_dev*, uint32_t, uint64_t, uint32_t, cudaStream_t) { return cudaErrorInvalidValue; }
 cudaError_t rb_launch_mix(const rb_mix_src*, uint32_t, float*, uint64_t, cudaStream_t, float*, uint32_t) { return cudaErrorInvalidValue; }
 cudaError_t rb_launch_convert(const void*, uint32_t, void*, uint32_t, uint64_t, cudaStream_t) { return cudaErrorInvalidValue; }

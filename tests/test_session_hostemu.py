@@ -19,7 +19,7 @@ CSRC = os.path.join(ROOT, "rodio_b200", "csrc")
 DEPS = [os.path.join(EMU, "hostemu.cpp"), os.path.join(EMU, "mockcuda", "cuda_runtime.h"), os.path.join(CSRC, "rb_api.cu"),
         os.path.join(CSRC, "rb_lanes_batch.cu")] + \
        [os.path.join(CSRC, f) for f in ("rb_lanes_core.h", "rb_lanes_plan.h", "rb_session_plan.h", "rb_simt.h", "rb_lanes.h", "rb_fused.h",
-                                         "rb_internal.h")] + [os.path.join(ROOT, "include", "rodio_b200.h")]
+                                         "rb_fused_rows.h", "rb_internal.h")] + [os.path.join(ROOT, "include", "rodio_b200.h")]
 
 
 @pytest.fixture(scope="module")
@@ -32,7 +32,7 @@ def hostemu(built):
 
 
 @pytest.mark.parametrize("scenario", ["errors", "mono_random_split", "mixed_with_state_blob", "held_queue_gain_speed", "gain_changes",
-                                      "filtered_and_plain"])
+                                      "filtered_and_plain", "batch_with_identity_conversions"])
 def test_session_host_code_on_the_emulator(hostemu, scenario):
     t0 = time.time()
     r = subprocess.run([sys.executable, os.path.join(EMU, "session_scenarios.py"), scenario], capture_output=True, text=True, timeout=900)
