@@ -91,7 +91,7 @@ def s_mixed_everything_with_state_blob():
     half-way (rb_session_get_state / set_state)."""
     ch_in = [1, 2, 1, 1, 2, 1, 2, 1] * 5
     rates = [44100, 44100, 48000, 22050, 48000, 44100, 44100, 48000] * 5
-    pcms = [noise(ci * (int(0.05 * r) + 3 * i), 1500 + i, 0.8) for i, (ci, r) in enumerate(zip(ch_in, rates))]
+    pcms = [noise(ci * (int(0.025 * r) + 3 * i), 1500 + i, 0.8) for i, (ci, r) in enumerate(zip(ch_in, rates))]
     mk = lambda: [chain(np.zeros(0, np.float32), ci, r, 2, 48000, 800, 0.7) for ci, r in zip(ch_in, rates)]
     sa = rb.Session(mk(), 48000, fifo_frames=1024, max_block_frames=480, mixer_channels=2)
     sb = rb.Session(mk(), 48000, fifo_frames=1024, max_block_frames=480, mixer_channels=2)
@@ -99,7 +99,7 @@ def s_mixed_everything_with_state_blob():
     def hand_over(s):
         sb.set_state(s.get_state())
         return sb
-    got, _ = drive(sa, pcms, ch_in, [r // 100 for r in rates], 480, hooks={3: hand_over})
+    got, _ = drive(sa, pcms, ch_in, [r // 100 for r in rates], 480, hooks={2: hand_over})
     sa.close(), sb.close()
     assert_bit_exact(got, expected(pcms, ch_in, rates, 2, 48000, [0] * len(pcms), 800, 0.7), "mixed sources, blob hand-over")
 

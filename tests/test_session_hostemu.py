@@ -52,9 +52,9 @@ def test_lanes_batch_plan_on_the_emulator(hostemu):
     import test_lanes_emulator as T
     from helpers import assert_bit_exact, noise
 
-    ch_in = [1, 2, 1, 1, 2, 1, 2, 1] * 6
-    rates = [44100, 44100, 48000, 22050, 48000, 44100, 32000, 48000] * 6
-    pcms = [noise(ci * (500 + 9 * i), 4100 + i) for i, ci in enumerate(ch_in)]
+    ch_in = [1, 2, 1, 1, 2, 1, 2, 1] * 5
+    rates = [44100, 44100, 48000, 22050, 48000, 44100, 32000, 48000] * 5
+    pcms = [noise(ci * (250 + 5 * i), 4100 + i) for i, ci in enumerate(ch_in)]
     pcms[5][40:50] = np.float32(1e-41)
     starts = [(11 * i) % 70 for i in range(len(ch_in))]
     c = T.make_case(pcms, rates, 48000, starts, lp=700, gain=0.9, channels=2, ch_in=ch_in)
@@ -79,15 +79,15 @@ def test_lanes_batch_plan_on_the_emulator(hostemu):
 
 
 def test_plain_c_example_runs_on_the_emulator(hostemu):
-    """examples/stream_mixer.c linked against the host-emulated library: 200 ms of a filtered stereo 44.1 kHz source and a
+    """examples/stream_mixer.c linked against the host-emulated library: 60 ms of a filtered stereo 44.1 kHz source and a
     plain mono 48 kHz one through a stereo session, from C."""
     exe = os.path.join(HERE, "cpp", "stream_mixer_emu.bin")
     subprocess.run(["gcc", "-std=c11", "-D_GNU_SOURCE", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "stream_mixer.c"),
                     "-o", exe, "-L", EMU, "-l:librodio_b200_hostemu.so", f"-Wl,-rpath,{EMU}", "-lm"], check=True, capture_output=True)
-    r = subprocess.run([exe, "20"], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([exe, "6"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     frames, peak = int(r.stdout.split()[0]), float(r.stdout.split()[-1])
-    assert frames == 9600 and 0.3 < peak < 0.9, r.stdout      # 20 x 10 ms at 48 kHz; 0.8 * 0.5 low-passed music + 0.25 voice
+    assert frames == 2880 and 0.3 < peak < 0.9, r.stdout      # 6 x 10 ms at 48 kHz; 0.8 * 0.5 low-passed music + 0.25 voice
 
 
 def test_oracle_only_gpu_session_tests_hold_on_the_emulator(hostemu):
