@@ -41,7 +41,6 @@ def test_cpp_session_mirror_compiles_and_links(built):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("RB_TEST_LANES") != "1", reason="set RB_TEST_LANES=1 (this C++ binary has not run on a device yet; the Python session tests have)")
 def test_cpp_session_mirror_streams_like_the_whole_render(built):
     if not os.path.exists(EXE_SESSION):
         _build(SRC_SESSION, EXE_SESSION)

@@ -99,3 +99,13 @@ def test_oracle_only_gpu_session_tests_hold_on_the_emulator(hostemu):
             % (ROOT, HERE, hostemu, os.path.join(HERE, "test_parity_gpu.py")))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0 and "3 passed" in r.stdout, (r.stdout + r.stderr)[-3000:]
+
+
+def test_cpp_live_mixer_on_the_emulator(hostemu):
+    """tests/cpp/test_session_api.cpp (rodio::mixer::LiveMixer of include/rodio_b200.hpp: uneven pushes, sample-by-sample pull,
+    mono and stereo, against the whole-stream lane render) linked against the host-emulated library."""
+    exe = os.path.join(HERE, "cpp", "test_session_api_emu.bin")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(HERE, "cpp", "test_session_api.cpp"), "-o", exe,
+                    "-L", EMU, "-l:librodio_b200_hostemu.so", f"-Wl,-rpath,{EMU}"], check=True, capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "all session API tests passed" in r.stdout, r.stdout + r.stderr
