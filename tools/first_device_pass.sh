@@ -7,7 +7,7 @@ set -u
 cd "$(dirname "$0")/.."
 OUT=gpurun_out/lanes_first
 mkdir -p "$OUT"
-export RB_TEST_LANES=1
+# (the tests of the kernel and the sessions are part of the normal -m gpu suite since the first device pass)
 
 # 1. memory errors first, on the smallest cases (compute-sanitizer is slow: keep it to a handful of tests)
 timeout 420 compute-sanitizer --tool memcheck --error-exitcode 9 \
@@ -15,7 +15,7 @@ timeout 420 compute-sanitizer --tool memcheck --error-exitcode 9 \
     > "$OUT/memcheck.log" 2>&1
 echo "memcheck exit $?" | tee -a "$OUT/summary.txt"
 
-# 2. the parity tests of the kernel and the sessions (+ the still gated C++ session binary)
+# 2. the parity tests of the kernel and the sessions
 timeout 600 python -m pytest tests -q -m gpu -k "lanes or session" > "$OUT/pytest_lanes.log" 2>&1
 echo "pytest lanes/session exit $?" | tee -a "$OUT/summary.txt"
 tail -5 "$OUT/pytest_lanes.log" >> "$OUT/summary.txt"

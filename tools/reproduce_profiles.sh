@@ -26,6 +26,6 @@ timeout 120 python tools/hot_timing.py 4096 --skips > gpurun_out/r1_hot_timing.t
 
 # --- k_fused_lanes / sessions: round 1 had two ten-second runs (profiles/r1_lanes_*.log: python tools/lanes_quick_check.py
 #     --time, --time-big --lanes-only, and the pytest line below); the full measurement plan is tools/first_device_pass.sh ---
-# RB_TEST_LANES=1 python -m pytest tests -m gpu -x -q -k "lanes or session"
+# python -m pytest tests -m gpu -x -q -k "lanes or session"      (round 1: with RB_TEST_LANES=1, the gate of the time)
 # python tools/bench_configs.py lanes > gpurun_out/lanes_sweep.jsonl
 # ncu --set full --clock-control none --import-source on -k regex:k_fused_lanes -s 3 -c 1 -o gpurun_out/lanes_full python tools/bench_configs.py lanes
