@@ -186,6 +186,26 @@ def s_batch_with_identity_conversions():
         assert b.kernel_family != 2
 
 
+def s_batch_unsorted_starts():
+    """Mixer::add calls in arbitrary timeline order: the batch orders its sources by mix_start (stable) -- that order is the
+    lane order; the rendered mix is also served in blocks (rb_batch_read_mix)."""
+    from helpers import lanes_expected_mix
+    rng = np.random.default_rng(4)
+    n = 40
+    pcms = [noise(300 + 11 * i, 7000 + i) for i in range(n)]
+    starts = [int(v) for v in rng.integers(0, 400, n)]
+    srcs = [chain(p, 1, 44100, 1, 48000, 700, 0.9) for p in pcms]
+    with rb.Batch(srcs, 1, 48000, flags=capi.RB_FUSED_LANES, mix_starts=starts) as b:
+        assert b.kernel_family == 2
+        b.upload_all()
+        got = b.render_mix()
+        blocks = np.concatenate([b.read_mix(o, 100) for o in range(0, got.size, 100)])
+    assert np.array_equal(blocks.view(np.uint32), got.view(np.uint32))
+    order = sorted(range(n), key=lambda i: starts[i])
+    per = [oracle.chain_uniform(to_oracle(srcs[i]), 1, 48000) for i in order]
+    assert_bit_exact(got, lanes_expected_mix(per, [starts[i] for i in order], got.size), "unsorted mix_starts")
+
+
 def s_gain_changes():
     """rb_session_set_amplify between 5 ms blocks, rb_session_available in step with what render delivers."""
     pcms = [noise(1500, 800 + i) for i in range(3)]
@@ -273,7 +293,7 @@ def s_random(seed=0, cases=6):
 
 SCENARIOS = {"mono_random_split": s_mono_random_split, "mixed_with_state_blob": s_mixed_everything_with_state_blob,
              "held_queue_gain_speed": s_held_queue_gain_speed, "gain_changes": s_gain_changes, "filtered_and_plain": s_filtered_and_plain_sources,
-             "batch_with_identity_conversions": s_batch_with_identity_conversions, "errors": s_errors}
+             "batch_with_identity_conversions": s_batch_with_identity_conversions, "batch_unsorted_starts": s_batch_unsorted_starts, "errors": s_errors}
 
 if __name__ == "__main__":
     for name in (sys.argv[1:] or list(SCENARIOS)):
