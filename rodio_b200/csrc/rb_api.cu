@@ -958,13 +958,13 @@ struct rb_session {
     // per-source arrays below are in CLASS ORDER (stable partition by rate pair); pos[] maps the caller's index to it.
     struct Class {
         uint32_t first = 0, count = 0, ch_in = 1;
-        bool has_biquad = false, ff2 = false;
+        bool has_biquad = false, ff2 = false, has_pre = false;
     };
     std::vector<Class> classes;
     std::vector<uint32_t> pos;
     std::vector<session::Stream> st;
     std::vector<float> coef;      // 5 per stream
-    std::vector<float> ffk, post;
+    std::vector<float> ffk, post, pre;
     uint64_t T = 0;               // mixer frames rendered so far
     uint32_t fifo_cap = 0, max_block = 0;
     uint64_t stride = 0;          // floats per stream in a FIFO arena
@@ -1006,6 +1006,7 @@ extern "C" rb_status rb_session_create(rb_context* ctx, uint16_t mixer_channels,
     const size_t n = n_streams;
     // pass 1: validate, find every source's reduced rate pair -> classes
     std::vector<uint32_t> from(n), to(n), chs(n), first_fx(n), key(n);
+    std::vector<float> pre_of(n, 1.0f);
     for (size_t i = 0; i < n; i++) {
         const rb_stream_desc& d = descs[i];
         const std::string where = "stream " + std::to_string(i) + ": ";
@@ -1015,16 +1016,25 @@ extern "C" rb_status rb_session_create(rb_context* ctx, uint16_t mixer_channels,
             return fail(RB_ERR_UNSUPPORTED, where + "a source has the mixer's channel count, or is mono in a stereo mixer");
         chs[i] = d.channels;
         if (d.n_effects && !d.effects) return fail(RB_ERR_INVALID_ARGUMENT, where + "effects is NULL");
-        // Source::speed in front of the conversion only changes the rate the source reports (src/source/speed.rs:130-133)
+        // Source::speed in front of the conversion only changes the rate the source reports (src/source/speed.rs:130-133);
+        // one Source::amplify there -- `source.amplify(v)` handed to Mixer::add -- scales every frame before it is interpolated
+        // (src/source/amplify.rs:91-95).  The two commute: one touches the samples, the other the reported rate.
         uint32_t k0 = 0, rate = d.sample_rate;
-        while (k0 < d.n_effects && d.effects[k0].kind == RB_FX_SPEED) rate = rb_speed_sample_rate(rate, d.effects[k0].f32[0]), k0++;
+        bool has_pre = false;
+        while (k0 < d.n_effects) {
+            if (d.effects[k0].kind == RB_FX_SPEED) rate = rb_speed_sample_rate(rate, d.effects[k0].f32[0]);
+            else if (d.effects[k0].kind == RB_FX_AMPLIFY && !has_pre) has_pre = true, pre_of[i] = d.effects[k0].f32[0];
+            else break;
+            k0++;
+        }
         first_fx[i] = k0;
         if (k0 >= d.n_effects || d.effects[k0].kind != RB_FX_UNIFORM || d.effects[k0].u32[0] != mixer_channels || d.effects[k0].u32[1] != mixer_rate)
-            return fail(RB_ERR_UNSUPPORTED, where + "the chain must be [SPEED] UNIFORM(mixer channels, mixer rate) ...");
+            return fail(RB_ERR_UNSUPPORTED, where + "the chain must be [SPEED | one AMPLIFY] UNIFORM(mixer channels, mixer rate) ...");
         const uint32_t g = std::gcd(rate, mixer_rate);
         from[i] = rate / g, to[i] = mixer_rate / g;
         const bool filtered = k0 + 1 < d.n_effects && (d.effects[k0 + 1].kind == RB_FX_LOW_PASS || d.effects[k0 + 1].kind == RB_FX_HIGH_PASS);
-        key[i] = d.channels | (filtered ? 0x100u : 0u);   // filtered and unfiltered sources are classes of their own
+        // filtered / unfiltered sources and sources with / without a gain in front are classes of their own
+        key[i] = d.channels | (filtered ? 0x100u : 0u) | (has_pre ? 0x200u : 0u);
         if (from[i] > (1u << 20) || to[i] > (1u << 20))
             return fail(RB_ERR_RATIO_OVERFLOW, where + "reduced rate pair beyond 2^20");
     }
@@ -1034,19 +1044,20 @@ extern "C" rb_status rb_session_create(rb_context* ctx, uint16_t mixer_channels,
     for (const auto& cls : classes) {
         rb_session::Class c;
         c.first = (uint32_t)order.size(), c.count = (uint32_t)cls.size(), c.ch_in = chs[cls[0]];
-        c.has_biquad = (key[cls[0]] & 0x100u) != 0;
+        c.has_biquad = (key[cls[0]] & 0x100u) != 0, c.has_pre = (key[cls[0]] & 0x200u) != 0;
         for (uint32_t i : cls) s->pos[i] = (uint32_t)order.size(), order.push_back(i);
         s->classes.push_back(c);
     }
     // pass 2: chains, in class order
-    s->st.resize(n), s->coef.assign(5 * n, 0.0f), s->ffk.assign(n, 0.0f), s->post.assign(n, 1.0f), s->src_ch.assign(n, 1);
+    s->st.resize(n), s->coef.assign(5 * n, 0.0f), s->ffk.assign(n, 0.0f), s->post.assign(n, 1.0f), s->pre.assign(n, 1.0f), s->src_ch.assign(n, 1);
     bool any_biquad = false;
     std::vector<uint8_t> row_ff2(n, 1);
     for (size_t r = 0; r < n; r++) {
         const size_t i = order[r];
         const rb_stream_desc& d = descs[i];
         const std::string where = "stream " + std::to_string(i) + ": ";
-        uint32_t k = first_fx[i] + 1;   // behind [SPEED] UNIFORM
+        uint32_t k = first_fx[i] + 1;   // behind [SPEED | AMPLIFY] UNIFORM
+        s->pre[r] = pre_of[i];
         bool biq = false;
         if (k < d.n_effects && (d.effects[k].kind == RB_FX_LOW_PASS || d.effects[k].kind == RB_FX_HIGH_PASS)) {
             const rb_effect& e = d.effects[k];
@@ -1059,7 +1070,7 @@ extern "C" rb_status rb_session_create(rb_context* ctx, uint16_t mixer_channels,
         }
         any_biquad |= biq;
         if (k < d.n_effects && d.effects[k].kind == RB_FX_AMPLIFY) s->post[r] = d.effects[k].f32[0], s->has_post = true, k++;
-        if (k != d.n_effects) return fail(RB_ERR_UNSUPPORTED, where + "chain shape: [SPEED] UNIFORM [LOW_PASS | HIGH_PASS] [AMPLIFY]");
+        if (k != d.n_effects) return fail(RB_ERR_UNSUPPORTED, where + "chain shape: [SPEED | one AMPLIFY] UNIFORM [LOW_PASS | HIGH_PASS] [AMPLIFY]");
         s->st[r].mix_start = d.mix_start, s->st[r].from = from[i], s->st[r].to = to[i];
         if (d.mix_start == RB_SESSION_HELD) s->st[r].held = true, s->st[r].mix_start = 0;   // Mixer::add comes later (rb_session_start)
         s->src_ch[r] = (uint8_t)d.channels;
@@ -1213,8 +1224,9 @@ extern "C" rb_status rb_session_render(rb_session* s, float* out_host, uint64_t 
         row.n_int = p.n_int, row.o0 = p.o0, row.i0 = s->st[r].i0, row.state = s->d_state + 4 * C * r;
         const float* co = &s->coef[5 * r];
         row.b0 = co[0], row.b1 = co[1], row.b2 = co[2], row.a1 = co[3], row.a2 = co[4], row.ffk = s->ffk[r];
-        row.post = s->post[r];
+        row.post = s->post[r], row.pre = s->pre[r];
         row.flags = p.continues ? lanes::ROW_CONTINUES : 0u;
+        if (!lanes::pre_gain_keeps_class(row.pre)) row.flags |= lanes::ROW_FORCE_SLOW;
     }
     RB_CUDA(cudaMemcpyAsync(s->d_rows, s->h_rows, ns * sizeof(lanes::Row), cudaMemcpyHostToDevice, stq));
     const uint64_t pstride = lanes::round_up_tile((uint64_t)s->max_block * C);
@@ -1228,7 +1240,7 @@ extern "C" rb_status rb_session_render(rb_session* s, float* out_host, uint64_t 
         lanes::fill_ratio(a, s->st[c.first].from, s->st[c.first].to, C);
         a.mix_len = n, a.pstride = pstride;
         a.partial = s->d_partial + (size_t)g0 * pstride, a.zeros = s->d_zeros, a.unsafe = s->d_flags + c.first;
-        RB_CUDA(rb_lanes_launch_kernel(a, c.ch_in, C, c.has_biquad, c.ff2, s->has_post, stq));
+        RB_CUDA(rb_lanes_launch_kernel(a, c.ch_in, C, c.has_biquad, c.ff2, s->has_post, c.has_pre, stq));
         g0 += a.n_groups;
     }
     RB_CUDA(rb_lanes_launch_sum(s->d_partial, n_groups_total, pstride, n * C, s->d_out, stq));

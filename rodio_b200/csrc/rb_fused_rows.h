@@ -146,9 +146,10 @@ static cudaError_t fused_lanes_hook(const std::vector<FusedRow>& rows, size_t n_
                                     int sm_count, float* d_out, uint64_t mix_len, cudaStream_t st, rb_lanes_plan** lanes) {
     *lanes = nullptr;
     const bool want_lanes = (flags & RB_FUSED_LANES) || n_streams >= (size_t)277 * (size_t)(sm_count > 0 ? sm_count : 148);
-    if (!(want_lanes && (mixer_channels == 1 || mixer_channels == 2) && all_f32 && (has_u || has_b) && n_pre == 0)) return cudaSuccess;
+    if (!(want_lanes && (mixer_channels == 1 || mixer_channels == 2) && all_f32 && (has_u || has_b) && n_pre <= 1)) return cudaSuccess;
     // f32 streams with the mixer's channel count (or mono in a stereo mixer), each at or below the mixer's rate (classes per
-    // rate pair), optional biquad, at most one gain directly in front of the sum.
+    // rate pair), at most one gain in front of the conversion (source.amplify(v) handed to the mixer), optional biquad, at most
+    // one gain directly in front of the sum.
     const uint32_t C = mixer_channels;
     const bool shape = has_b ? (n_mid == 0 && n_post <= 1) : (n_mid + n_post <= 1);
     if (!shape || mix_len % C != 0) return cudaSuccess;
@@ -169,6 +170,8 @@ static cudaError_t fused_lanes_hook(const std::vector<FusedRow>& rows, size_t n_
         l.from = pass ? 1u : r.uni.from, l.to = pass ? 1u : r.uni.to;
         l.b0 = r.b0, l.b1 = r.b1, l.b2 = r.b2, l.a1 = r.a1, l.a2 = r.a2;
         l.post = n_post ? r.post[0] : (n_mid ? r.mid[0] : 1.0f);
+        l.pre = n_pre ? r.pre[0] : 1.0f;
     }
-    return rb_lanes_try_create(ls.data(), n_streams, C, has_b != 0, (n_mid + n_post) != 0, d_out, mix_len / C, sm_count, st, lanes);
+    return rb_lanes_try_create(ls.data(), n_streams, C, has_b != 0, (n_mid + n_post) != 0, n_pre != 0, d_out, mix_len / C, sm_count, st,
+                               lanes);
 }

@@ -17,13 +17,13 @@ constexpr int LANES_THREADS = 32 * LANES_WARPS;
 template <int C>
 constexpr size_t lanes_smem_bytes() { return (size_t)LANES_WARPS * 32 * lanes::Geo<C>::RS * sizeof(float); }   // 21.0 / 41.0 KB
 
-template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS>
+template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS, bool PRE>
 __global__ void __launch_bounds__(LANES_THREADS) k_fused_lanes(lanes::Args a) {
     extern __shared__ __align__(16) float lanes_smem[];
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t group = blockIdx.x * LANES_WARPS + warp;
     if (group >= a.n_groups) return;   // whole warps leave: the warp program only synchronises within a warp
-    lanes::warp_main<CI, CO, HASB, FF2, NPOST, PASS>(a, group, lanes_smem + (size_t)warp * 32 * lanes::Geo<CI>::RS);
+    lanes::warp_main<CI, CO, HASB, FF2, NPOST, PASS, PRE>(a, group, lanes_smem + (size_t)warp * 32 * lanes::Geo<CI>::RS);
 }
 
 // One CTA per stream: does every non-zero |x| lie inside [2^-70, 2^60]?  (rb_lanes_core.h, "Exact division".)
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) k_classify_inputs(lanes::Row* rows, uint3
     }
     for (uint64_t i = n4 * 4 + threadIdx.x; i < L; i += blockDim.x) bad |= out_of_class(__ldg(x + i));
     const int any = __syncthreads_or(bad ? 1 : 0);
-    if (threadIdx.x == 0) rows[r].flags = any ? lanes::ROW_UNSAFE : 0u;
+    if (threadIdx.x == 0) rows[r].flags = (rows[r].flags & ~lanes::ROW_UNSAFE) | (any ? lanes::ROW_UNSAFE : 0u);
 }
 
 // out[m] = +0.0 + partial[0][m] + partial[1][m] + ...  (warp order = insertion order of the streams)
@@ -97,31 +97,36 @@ __global__ void __launch_bounds__(256) k_classify_range(const float* __restrict_
     if (__syncthreads_or(bad ? 1 : 0) && threadIdx.x == 0) *flag = 1u;
 }
 
-template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS>
+template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS, bool PRE>
 static void launch_lanes(const lanes::Args& a, cudaStream_t st) {
     const uint32_t n_ctas = (a.n_groups + LANES_WARPS - 1) / LANES_WARPS;
-    k_fused_lanes<CI, CO, HASB, FF2, NPOST, PASS><<<n_ctas, LANES_THREADS, lanes_smem_bytes<CI>(), st>>>(a);   // < 48 KB: no opt-in needed
+    k_fused_lanes<CI, CO, HASB, FF2, NPOST, PASS, PRE><<<n_ctas, LANES_THREADS, lanes_smem_bytes<CI>(), st>>>(a);   // < 48 KB: no opt-in needed
 }
-template <int CI, int CO, bool PASS>
+template <int CI, int CO, bool PASS, bool PRE>
 static void launch_lanes_c(const lanes::Args& a, bool has_biquad, bool ff2, bool has_post, cudaStream_t st) {
     if (has_biquad) {
-        if (ff2) has_post ? launch_lanes<CI, CO, true, true, 1, PASS>(a, st) : launch_lanes<CI, CO, true, true, 0, PASS>(a, st);
-        else has_post ? launch_lanes<CI, CO, true, false, 1, PASS>(a, st) : launch_lanes<CI, CO, true, false, 0, PASS>(a, st);
+        if (ff2) has_post ? launch_lanes<CI, CO, true, true, 1, PASS, PRE>(a, st) : launch_lanes<CI, CO, true, true, 0, PASS, PRE>(a, st);
+        else has_post ? launch_lanes<CI, CO, true, false, 1, PASS, PRE>(a, st) : launch_lanes<CI, CO, true, false, 0, PASS, PRE>(a, st);
     } else {
-        has_post ? launch_lanes<CI, CO, false, false, 1, PASS>(a, st) : launch_lanes<CI, CO, false, false, 0, PASS>(a, st);
+        has_post ? launch_lanes<CI, CO, false, false, 1, PASS, PRE>(a, st) : launch_lanes<CI, CO, false, false, 0, PASS, PRE>(a, st);
     }
+}
+template <int CI, int CO>
+static void launch_lanes_cc(const lanes::Args& a, bool has_biquad, bool ff2, bool has_post, bool has_pre, cudaStream_t st) {
+    const bool pass = a.from == a.to;   // sources at the mixer's rate: taps used raw
+    if (pass) has_pre ? launch_lanes_c<CI, CO, true, true>(a, has_biquad, ff2, has_post, st) : launch_lanes_c<CI, CO, true, false>(a, has_biquad, ff2, has_post, st);
+    else has_pre ? launch_lanes_c<CI, CO, false, true>(a, has_biquad, ff2, has_post, st) : launch_lanes_c<CI, CO, false, false>(a, has_biquad, ff2, has_post, st);
 }
 
 }  // namespace
 
 cudaError_t rb_lanes_launch_kernel(const lanes::Args& a, uint32_t ch_in, uint32_t ch_out, bool has_biquad, bool ff2, bool has_post,
-                                   cudaStream_t st) {
+                                   bool has_pre, cudaStream_t st) {
     if (a.mix_len == 0 || a.n_groups == 0) return cudaSuccess;
     if (!((ch_in == 1 || ch_in == 2) && (ch_in == ch_out || (ch_in == 1 && ch_out == 2)))) return cudaErrorInvalidValue;
-    const bool pass = a.from == a.to;   // sources at the mixer's rate: taps used raw
-    if (ch_in == 2) pass ? launch_lanes_c<2, 2, true>(a, has_biquad, ff2, has_post, st) : launch_lanes_c<2, 2, false>(a, has_biquad, ff2, has_post, st);
-    else if (ch_out == 2) pass ? launch_lanes_c<1, 2, true>(a, has_biquad, ff2, has_post, st) : launch_lanes_c<1, 2, false>(a, has_biquad, ff2, has_post, st);
-    else pass ? launch_lanes_c<1, 1, true>(a, has_biquad, ff2, has_post, st) : launch_lanes_c<1, 1, false>(a, has_biquad, ff2, has_post, st);
+    if (ch_in == 2) launch_lanes_cc<2, 2>(a, has_biquad, ff2, has_post, has_pre, st);
+    else if (ch_out == 2) launch_lanes_cc<1, 2>(a, has_biquad, ff2, has_post, has_pre, st);
+    else launch_lanes_cc<1, 1>(a, has_biquad, ff2, has_post, has_pre, st);
     return cudaGetLastError();
 }
 

@@ -69,6 +69,7 @@ struct Geo {
 static_assert(RUN_CAP % TILE == 0, "run cap");
 constexpr uint32_t ROW_UNSAFE = 1u;     // Row::flags: some sample outside the exact-reciprocal class
 constexpr uint32_t ROW_CONTINUES = 2u;  // Row::flags: the stream goes on in the next block -- keep the filter state past `end`
+constexpr uint32_t ROW_FORCE_SLOW = 4u; // Row::flags: set by the host (a gain in front of the conversion outside [2^-6, 2^6]): slow tiles only
 
 struct Row {                 // one stream (whole, or the part of it one block of a streaming session renders)
     const float* in;         // f32 frames (C interleaved channels), 16-byte aligned, readable up to a 16-byte tail pad
@@ -83,6 +84,8 @@ struct Row {                 // one stream (whole, or the part of it one block o
     float b0, b1, b2, a1, a2;
     float ffk;               // FF2 variant: b1 == ffk * b0 (ffk = +-2) and b2 == b0
     float post;              // the one gain behind the chain (NPOST == 1)
+    float pre;               // PRE: the one gain in front of the conversion -- source.amplify(v) handed to the mixer, the
+                             // usual rodio idiom -- applied to every input frame once, when it is fetched
     uint32_t flags;
 };
 
@@ -127,7 +130,7 @@ SIMT_FN float reduce_tile(const float (&v)[TILE], uint32_t ln) {
 // CI = 1, CO = 2: a mono source in a stereo mixer -- ChannelCountConverter repeats the sample on both channels
 // (src/conversions/channels.rs:57-85) and the two filter channels see the same input, so the lane computes the frame once
 // and emits it twice.
-template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS = false>
+template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS = false, bool PRE = false>
 SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
     static_assert(CI == CO || (CI == 1 && CO == 2), "channel layouts served");
     using G = Geo<CI>;
@@ -142,12 +145,13 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
         row = a.rows[r];
     } else {
         row.in = a.zeros, row.L = 0, row.out_len = 0, row.mix_start = 0, row.n_int = 0, row.o0 = 0, row.i0 = 0, row.state = nullptr;
-        row.b0 = row.b1 = row.b2 = row.a1 = row.a2 = row.ffk = row.post = 0.0f, row.flags = 0;
+        row.b0 = row.b1 = row.b2 = row.a1 = row.a2 = row.ffk = row.post = row.pre = 0.0f, row.flags = 0;
     }
     const uint64_t ms = row.mix_start, end = row.mix_start + row.out_len;   // frames
     // Down-sampling classes (from > to: more than one input frame per output) are served by the slow tiles only -- exact,
     // general, not fast; the fast run below assumes at most one new frame per step.
-    const bool safe = has && a.from <= a.to && (PASS || (!(row.flags & ROW_UNSAFE) && !(a.unsafe && a.unsafe[r])));
+    const bool safe = has && a.from <= a.to && !(row.flags & ROW_FORCE_SLOW) &&
+                      (PASS || (!(row.flags & ROW_UNSAFE) && !(a.unsafe && a.unsafe[r])));
     const bool stops = !(row.flags & ROW_CONTINUES);   // the stream ends inside this block (or is a whole stream)
     const bool live = has && row.out_len != 0;
     const uint64_t t_lo = simt::reduce_min64(live ? ms : ~0ull), t_hi = simt::reduce_max64(live ? end : 0ull);
@@ -157,7 +161,7 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
     float* const ringl = ring_warp + ln * RS;
     float* const prow = a.partial + (uint64_t)group * a.pstride;
     const float den = a.den_f, rcp = a.rcp_den, from_f = a.from_f, neg1 = a.neg1;
-    const float b0 = row.b0, b1 = row.b1, b2 = row.b2, a1 = row.a1, a2 = row.a2, ffk = row.ffk, post = row.post;
+    const float b0 = row.b0, b1 = row.b1, b2 = row.b2, a1 = row.a1, a2 = row.a2, ffk = row.ffk, post = row.post, gpre = row.pre;
     const uint32_t from = a.from, to = a.to;
     // canonical filter state per channel: x[n-1], x[n-2], y[n-1], y[n-2]
     float xh1[C], xh2[C], y1[C], y2[C];
@@ -243,7 +247,10 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
             simt::sptr p = simt::sptr_of(ringl + k0 * C);
             float x0[C], x1[C];
 #pragma unroll
-            for (int c = 0; c < C; c++) x0[c] = simt::lds(simt::sptr_add(p, c)), x1[c] = simt::lds(simt::sptr_add(p, C + c));
+            for (int c = 0; c < C; c++) {
+                x0[c] = simt::lds(simt::sptr_add(p, c)), x1[c] = simt::lds(simt::sptr_add(p, C + c));
+                if (PRE) x0[c] = simt::fmul(x0[c], gpre), x1[c] = simt::fmul(x1[c], gpre);
+            }
             p = simt::sptr_add(p, 2 * C);
             float nf = simt::u2f(num);
             // upper bound (in frames) of any lane's next ring frame after the coming tile: the lane with the largest phase
@@ -285,7 +292,7 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                         }
                     }
                     // next output frame: numerator += from (mod to); a carry moves one input frame on
-                    simt::lerp_advance<C>(nf, x0, x1, p, from_f, den);
+                    simt::lerp_advance<C, PRE>(nf, x0, x1, p, from_f, den, gpre);
                     float val[C];
 #pragma unroll
                     for (int c = 0; c < C; c++) {
@@ -351,10 +358,14 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                 for (int c = 0; c < C; c++) {
                     val[c] = 0.0f;
                     if (on) {
-                        const float xa = simt::ldg(row.in + i * C + c);
+                        float xa = simt::ldg(row.in + i * C + c);
+                        if (PRE) xa = simt::fmul(xa, gpre);
                         float x = xa;
-                        if (!PASS && i + 1 < row.L)
-                            x = simt::fadd(xa, simt::fdiv(simt::fmul(simt::fsub(simt::ldg(row.in + (i + 1) * C + c), xa), simt::u2f(num)), den));
+                        if (!PASS && i + 1 < row.L) {
+                            float xb = simt::ldg(row.in + (i + 1) * C + c);
+                            if (PRE) xb = simt::fmul(xb, gpre);
+                            x = simt::fadd(xa, simt::fdiv(simt::fmul(simt::fsub(xb, xa), simt::u2f(num)), den));
+                        }
                         float y = x;
                         if (HASB) {
                             const float ff = simt::fadd(simt::fadd(simt::fmul(b0, x), simt::fmul(b1, xh1[c])), simt::fmul(b2, xh2[c]));

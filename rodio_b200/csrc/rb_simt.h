@@ -136,12 +136,13 @@ SIMT_FN bool sptr_ge(sptr a, sptr b) { return a >= b; }
 SIMT_FN float lds(sptr p) { return *p; }
 // One index step of the resampler for a frame of C channels: numerator += from (mod den); on a carry the right taps
 // become the left ones and the next ring frame is fetched.  (Six / eight instructions on the device, see below.)
-template <int C>
-SIMT_FN void lerp_advance(float& nf, float (&x0)[C], float (&x1)[C], sptr& p, float from_f, float den) {
+// PRE: the fetched frame is multiplied by `gpre` (an Amplify in front of the conversion, one rounding like Amplify::next).
+template <int C, bool PRE = false>
+SIMT_FN void lerp_advance(float& nf, float (&x0)[C], float (&x1)[C], sptr& p, float from_f, float den, float gpre = 1.0f) {
     const float nf2 = nf + from_f;
     if (nf2 >= den) {
         nf = nf2 - den;
-        for (int c = 0; c < C; c++) x0[c] = x1[c], x1[c] = p[c];
+        for (int c = 0; c < C; c++) x0[c] = x1[c], x1[c] = PRE ? p[c] * gpre : p[c];
         p += C;
     } else {
         nf = nf2;
@@ -209,10 +210,10 @@ SIMT_FN float lds(sptr p) {
 // FADD, FSETP, then predicated instructions: numerator wrap, tap move(s), tap load (one LDS / LDS.64), cursor increment.
 // Written in PTX because nvcc otherwise keeps a second cursor and copies the taps through temporaries (3 extra moves
 // per step).
-template <int C>
-SIMT_FN void lerp_advance(float& nf, float (&x0)[C], float (&x1)[C], sptr& p, float from_f, float den) {
+template <int C, bool PRE = false>
+SIMT_FN void lerp_advance(float& nf, float (&x0)[C], float (&x1)[C], sptr& p, float from_f, float den, float gpre = 1.0f) {
     static_assert(C == 1 || C == 2, "mono or stereo");
-    if constexpr (C == 1) {
+    if constexpr (C == 1 && !PRE) {
         asm volatile(
             "{\n"
             ".reg .pred c;\n"
@@ -228,7 +229,24 @@ SIMT_FN void lerp_advance(float& nf, float (&x0)[C], float (&x1)[C], sptr& p, fl
             : "+f"(nf), "+f"(x0[0]), "+f"(x1[0]), "+r"(p)
             : "f"(from_f), "f"(den)
             : "memory");
-    } else {
+    } else if constexpr (C == 1 && PRE) {
+        asm volatile(
+            "{\n"
+            ".reg .pred c;\n"
+            ".reg .f32 t;\n"
+            "add.rn.f32 t, %0, %4;\n"
+            "setp.ge.f32 c, t, %5;\n"
+            "@c sub.rn.f32 t, t, %5;\n"
+            "mov.f32 %0, t;\n"
+            "@c mov.f32 %1, %2;\n"
+            "@c ld.shared.f32 %2, [%3];\n"
+            "@c mul.rn.f32 %2, %2, %6;\n"          // the gain in front of the conversion, applied once to the fetched frame
+            "@c add.u32 %3, %3, 4;\n"
+            "}\n"
+            : "+f"(nf), "+f"(x0[0]), "+f"(x1[0]), "+r"(p)
+            : "f"(from_f), "f"(den), "f"(gpre)
+            : "memory");
+    } else if constexpr (C == 2 && !PRE) {
         asm volatile(
             "{\n"
             ".reg .pred c;\n"
@@ -244,6 +262,25 @@ SIMT_FN void lerp_advance(float& nf, float (&x0)[C], float (&x1)[C], sptr& p, fl
             "}\n"
             : "+f"(nf), "+f"(x0[0]), "+f"(x0[1]), "+f"(x1[0]), "+f"(x1[1]), "+r"(p)
             : "f"(from_f), "f"(den)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n"
+            ".reg .pred c;\n"
+            ".reg .f32 t;\n"
+            "add.rn.f32 t, %0, %6;\n"
+            "setp.ge.f32 c, t, %7;\n"
+            "@c sub.rn.f32 t, t, %7;\n"
+            "mov.f32 %0, t;\n"
+            "@c mov.f32 %1, %3;\n"
+            "@c mov.f32 %2, %4;\n"
+            "@c ld.shared.v2.f32 {%3, %4}, [%5];\n"
+            "@c mul.rn.f32 %3, %3, %8;\n"
+            "@c mul.rn.f32 %4, %4, %8;\n"
+            "@c add.u32 %5, %5, 8;\n"
+            "}\n"
+            : "+f"(nf), "+f"(x0[0]), "+f"(x0[1]), "+f"(x1[0]), "+f"(x1[1]), "+r"(p)
+            : "f"(from_f), "f"(den), "f"(gpre)
             : "memory");
     }
 }

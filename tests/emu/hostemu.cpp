@@ -29,30 +29,36 @@ extern "C" void mock_cuda_unregister(void* p) {
 
 // ---- the lane kernel on 32 host threads per warp ----
 namespace {
-template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS>
+template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS, bool PRE>
 void run_warp(const lanes::Args& a, uint32_t group, simt::WarpEmu* w, float* ring) {
     std::vector<std::thread> th;
     for (uint32_t l = 0; l < 32; l++)
         th.emplace_back([&, l] {
             simt::g_lane = simt::LaneEmu{};
             simt::g_lane.w = w, simt::g_lane.lane = l;
-            lanes::warp_main<CI, CO, HASB, FF2, NPOST, PASS>(a, group, ring);
+            lanes::warp_main<CI, CO, HASB, FF2, NPOST, PASS, PRE>(a, group, ring);
         });
     for (auto& t : th) t.join();
 }
-template <int CI, int CO, bool PASS>
-void run_variant(const lanes::Args& a, uint32_t g, simt::WarpEmu* w, float* ring, bool hasb, bool ff2, bool npost) {
-    if (hasb && ff2 && npost) run_warp<CI, CO, true, true, 1, PASS>(a, g, w, ring);
-    else if (hasb && ff2) run_warp<CI, CO, true, true, 0, PASS>(a, g, w, ring);
-    else if (hasb && npost) run_warp<CI, CO, true, false, 1, PASS>(a, g, w, ring);
-    else if (hasb) run_warp<CI, CO, true, false, 0, PASS>(a, g, w, ring);
-    else if (npost) run_warp<CI, CO, false, false, 1, PASS>(a, g, w, ring);
-    else run_warp<CI, CO, false, false, 0, PASS>(a, g, w, ring);
+template <int CI, int CO, bool PASS, bool PRE>
+void run_variant_p(const lanes::Args& a, uint32_t g, simt::WarpEmu* w, float* ring, bool hasb, bool ff2, bool npost) {
+    if (hasb && ff2 && npost) run_warp<CI, CO, true, true, 1, PASS, PRE>(a, g, w, ring);
+    else if (hasb && ff2) run_warp<CI, CO, true, true, 0, PASS, PRE>(a, g, w, ring);
+    else if (hasb && npost) run_warp<CI, CO, true, false, 1, PASS, PRE>(a, g, w, ring);
+    else if (hasb) run_warp<CI, CO, true, false, 0, PASS, PRE>(a, g, w, ring);
+    else if (npost) run_warp<CI, CO, false, false, 1, PASS, PRE>(a, g, w, ring);
+    else run_warp<CI, CO, false, false, 0, PASS, PRE>(a, g, w, ring);
+}
+template <int CI, int CO>
+void run_variant(const lanes::Args& a, uint32_t g, simt::WarpEmu* w, float* ring, bool hasb, bool ff2, bool npost, bool pre) {
+    const bool pass = a.from == a.to;
+    if (pass) pre ? run_variant_p<CI, CO, true, true>(a, g, w, ring, hasb, ff2, npost) : run_variant_p<CI, CO, true, false>(a, g, w, ring, hasb, ff2, npost);
+    else pre ? run_variant_p<CI, CO, false, true>(a, g, w, ring, hasb, ff2, npost) : run_variant_p<CI, CO, false, false>(a, g, w, ring, hasb, ff2, npost);
 }
 }  // namespace
 
 cudaError_t rb_lanes_launch_kernel(const lanes::Args& a, uint32_t ch_in, uint32_t ch_out, bool has_biquad, bool ff2, bool has_post,
-                                   cudaStream_t) {
+                                   bool has_pre, cudaStream_t) {
     if (a.mix_len == 0 || a.n_groups == 0) return cudaSuccess;
     if (!((ch_in == 1 || ch_in == 2) && (ch_in == ch_out || (ch_in == 1 && ch_out == 2)))) return cudaErrorInvalidValue;
     simt::WarpEmu warp;
@@ -65,12 +71,11 @@ cudaError_t rb_lanes_launch_kernel(const lanes::Args& a, uint32_t ch_in, uint32_
     std::vector<float> ring_store(32 * MAX_RS + 4, nan);
     float* ring = ring_store.data();
     while ((uintptr_t)ring & 15) ring++;
-    const bool pass = a.from == a.to;
     for (uint32_t g = 0; g < a.n_groups; g++) {
         for (int i = 0; i < 32 * MAX_RS; i++) ring[i] = nan;
-        if (ch_in == 2) pass ? run_variant<2, 2, true>(a, g, &warp, ring, has_biquad, ff2, has_post) : run_variant<2, 2, false>(a, g, &warp, ring, has_biquad, ff2, has_post);
-        else if (ch_out == 2) pass ? run_variant<1, 2, true>(a, g, &warp, ring, has_biquad, ff2, has_post) : run_variant<1, 2, false>(a, g, &warp, ring, has_biquad, ff2, has_post);
-        else pass ? run_variant<1, 1, true>(a, g, &warp, ring, has_biquad, ff2, has_post) : run_variant<1, 1, false>(a, g, &warp, ring, has_biquad, ff2, has_post);
+        if (ch_in == 2) run_variant<2, 2>(a, g, &warp, ring, has_biquad, ff2, has_post, has_pre);
+        else if (ch_out == 2) run_variant<1, 2>(a, g, &warp, ring, has_biquad, ff2, has_post, has_pre);
+        else run_variant<1, 1>(a, g, &warp, ring, has_biquad, ff2, has_post, has_pre);
     }
     return cudaSuccess;
 }
@@ -156,9 +161,9 @@ cudaError_t rb_launch_convert(const void*, uint32_t, void*, uint32_t, uint64_t, 
 // ---- test entry: the batch plan of the lane kernel (rb_lanes_batch.cu: classes, row order, partial-row offsets) ----
 // pcm[r] holds n_frames[r] * ch_in[r] floats; out_len / mix_start / mix_len in frames; out receives mix_len * channels floats.
 extern "C" int hostemu_lanes_batch(const float* const* pcm, const uint64_t* n_frames, const uint64_t* out_len, const uint64_t* mix_start,
-                                   const float* coefs, const float* post, uint32_t n, uint32_t channels, const uint32_t* ch_in,
-                                   const uint32_t* from, const uint32_t* to, uint64_t mix_len, int hasb, int npost, float* out,
-                                   uint32_t* n_launches) {
+                                   const float* coefs, const float* post, const float* pre, uint32_t n, uint32_t channels,
+                                   const uint32_t* ch_in, const uint32_t* from, const uint32_t* to, uint64_t mix_len, int hasb, int npost,
+                                   int npre, float* out, uint32_t* n_launches) {
     std::vector<float*> d_in(n, nullptr);
     std::vector<rb_lanes_stream> st(n);
     for (uint32_t r = 0; r < n; r++) {
@@ -168,13 +173,13 @@ extern "C" int hostemu_lanes_batch(const float* const* pcm, const uint64_t* n_fr
         s.in = d_in[r], s.n_frames = n_frames[r], s.out_len = out_len[r], s.mix_start = mix_start[r];
         s.from = from[r], s.to = to[r], s.channels = ch_in[r];
         const float* c = coefs + 5 * r;
-        s.b0 = c[0], s.b1 = c[1], s.b2 = c[2], s.a1 = c[3], s.a2 = c[4], s.post = post[r];
+        s.b0 = c[0], s.b1 = c[1], s.b2 = c[2], s.a1 = c[3], s.a2 = c[4], s.post = post[r], s.pre = pre[r];
     }
     float* d_out = nullptr;
     if (cudaMalloc(&d_out, (mix_len * channels + 8) * sizeof(float)) != cudaSuccess) return 1;
     rb_lanes_plan* plan = nullptr;
     int rc = 0;
-    if (rb_lanes_try_create(st.data(), n, channels, hasb != 0, npost != 0, d_out, mix_len, 148, nullptr, &plan) != cudaSuccess || !plan) rc = 2;
+    if (rb_lanes_try_create(st.data(), n, channels, hasb != 0, npost != 0, npre != 0, d_out, mix_len, 148, nullptr, &plan) != cudaSuccess || !plan) rc = 2;
     if (!rc && (rb_lanes_run(plan, nullptr) != cudaSuccess || rb_lanes_run(plan, nullptr) != cudaSuccess)) rc = 3;   // twice: idempotent
     if (!rc) std::memcpy(out, d_out, mix_len * channels * sizeof(float)), *n_launches = rb_lanes_launch_count(plan);
     rb_lanes_destroy(plan);

@@ -12,32 +12,38 @@
 #include "../../rodio_b200/csrc/rb_lanes_plan.h"
 
 namespace {
-template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS>
+template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS, bool PRE>
 void run_warp_c(const lanes::Args& a, uint32_t group, simt::WarpEmu* w, float* ring) {
     std::vector<std::thread> th;
     for (uint32_t l = 0; l < 32; l++)
         th.emplace_back([&, l] {
             simt::g_lane = simt::LaneEmu{};
             simt::g_lane.w = w, simt::g_lane.lane = l;
-            lanes::warp_main<CI, CO, HASB, FF2, NPOST, PASS>(a, group, ring);
+            lanes::warp_main<CI, CO, HASB, FF2, NPOST, PASS, PRE>(a, group, ring);
         });
     for (auto& t : th) t.join();
 }
-template <int CI, int CO, bool PASS>
+template <int CI, int CO, bool PASS, bool PRE>
 void run_group(const lanes::Args& a, uint32_t g, simt::WarpEmu* w, float* ring, bool hasb, bool ff2, bool npost) {
-    if (hasb && ff2 && npost) run_warp_c<CI, CO, true, true, 1, PASS>(a, g, w, ring);
-    else if (hasb && ff2) run_warp_c<CI, CO, true, true, 0, PASS>(a, g, w, ring);
-    else if (hasb && npost) run_warp_c<CI, CO, true, false, 1, PASS>(a, g, w, ring);
-    else if (hasb) run_warp_c<CI, CO, true, false, 0, PASS>(a, g, w, ring);
-    else if (npost) run_warp_c<CI, CO, false, false, 1, PASS>(a, g, w, ring);
-    else run_warp_c<CI, CO, false, false, 0, PASS>(a, g, w, ring);
+    if (hasb && ff2 && npost) run_warp_c<CI, CO, true, true, 1, PASS, PRE>(a, g, w, ring);
+    else if (hasb && ff2) run_warp_c<CI, CO, true, true, 0, PASS, PRE>(a, g, w, ring);
+    else if (hasb && npost) run_warp_c<CI, CO, true, false, 1, PASS, PRE>(a, g, w, ring);
+    else if (hasb) run_warp_c<CI, CO, true, false, 0, PASS, PRE>(a, g, w, ring);
+    else if (npost) run_warp_c<CI, CO, false, false, 1, PASS, PRE>(a, g, w, ring);
+    else run_warp_c<CI, CO, false, false, 0, PASS, PRE>(a, g, w, ring);
+}
+template <int CI, int CO>
+void run_group_c(const lanes::Args& a, uint32_t g, simt::WarpEmu* w, float* ring, bool hasb, bool ff2, bool npost, bool pre) {
+    const bool pass = a.from == a.to;
+    if (pass) pre ? run_group<CI, CO, true, true>(a, g, w, ring, hasb, ff2, npost) : run_group<CI, CO, true, false>(a, g, w, ring, hasb, ff2, npost);
+    else pre ? run_group<CI, CO, false, true>(a, g, w, ring, hasb, ff2, npost) : run_group<CI, CO, false, false>(a, g, w, ring, hasb, ff2, npost);
 }
 // the class decides the instantiation -- source channels ci, mixer channels co, PASS when from == to -- like the device launcher
-void run_group_any(uint32_t ci, uint32_t co, const lanes::Args& a, uint32_t g, simt::WarpEmu* w, float* ring, bool hasb, bool ff2, bool npost) {
-    const bool pass = a.from == a.to;
-    if (ci == 2) pass ? run_group<2, 2, true>(a, g, w, ring, hasb, ff2, npost) : run_group<2, 2, false>(a, g, w, ring, hasb, ff2, npost);
-    else if (co == 2) pass ? run_group<1, 2, true>(a, g, w, ring, hasb, ff2, npost) : run_group<1, 2, false>(a, g, w, ring, hasb, ff2, npost);
-    else pass ? run_group<1, 1, true>(a, g, w, ring, hasb, ff2, npost) : run_group<1, 1, false>(a, g, w, ring, hasb, ff2, npost);
+void run_group_any(uint32_t ci, uint32_t co, const lanes::Args& a, uint32_t g, simt::WarpEmu* w, float* ring, bool hasb, bool ff2, bool npost,
+                   bool pre = false) {
+    if (ci == 2) run_group_c<2, 2>(a, g, w, ring, hasb, ff2, npost, pre);
+    else if (co == 2) run_group_c<1, 2>(a, g, w, ring, hasb, ff2, npost, pre);
+    else run_group_c<1, 1>(a, g, w, ring, hasb, ff2, npost, pre);
 }
 constexpr int MAX_RS = lanes::Geo<2>::RS;
 }  // namespace
@@ -53,7 +59,7 @@ extern "C" int rb_lanes_emulate(const float* const* pcm, const uint64_t* n_frame
                                 const uint64_t* mix_start, const float* coefs /* [n][5] b0 b1 b2 a1 a2 */,
                                 const float* post, uint32_t n_rows, uint32_t channels /* mixer */, const uint32_t* ch_in /* per stream */,
                                 const uint32_t* from, const uint32_t* to, uint64_t mix_len, int hasb, int want_ff2, int npost, float* out_mix, float* out_partials /* may be NULL */,
-                                int* used_ff2, uint32_t* n_unsafe) {
+                                int* used_ff2, uint32_t* n_unsafe, const float* pre /* NULL: no gain in front of the conversion */) {
     using namespace lanes;
     if (n_rows == 0 || (channels != 1 && channels != 2)) return 1;
     for (uint32_t r = 0; r < n_rows; r++)
@@ -86,6 +92,8 @@ extern "C" int rb_lanes_emulate(const float* const* pcm, const uint64_t* n_frame
             else ff2 = false;
         }
         row.post = npost ? post[r] : 1.0f;
+        row.pre = pre ? pre[r] : 1.0f;
+        if (pre && !pre_gain_keeps_class(row.pre)) row.flags |= ROW_FORCE_SLOW;
         bool ok = true;
         for (uint64_t i = 0; i < n_frames[r] * ci && ok; i++) ok = sample_in_class(pcm[r][i]);
         if (!ok) row.flags |= ROW_UNSAFE, (*n_unsafe)++;
@@ -121,7 +129,7 @@ extern "C" int rb_lanes_emulate(const float* const* pcm, const uint64_t* n_frame
         a.rows = rows.data() + (uintptr_t)a.rows, a.partial = partial.data() + (uintptr_t)a.partial * pstride, a.zeros = zeros;
         for (uint32_t g = 0; g < a.n_groups; g++) {
             for (int i = 0; i < 32 * MAX_RS; i++) ring[i] = nan;
-            run_group_any(launch_ci[k], channels, a, g, &warp, ring, hasb, ff2, npost);
+            run_group_any(launch_ci[k], channels, a, g, &warp, ring, hasb, ff2, npost, pre != nullptr);
         }
     }
     for (uint64_t m = 0; m < mix_len * C; m++) {

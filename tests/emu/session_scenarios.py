@@ -21,8 +21,10 @@ import math                                           # noqa: E402
 HELD = capi.RB_SESSION_HELD
 
 
-def chain(pcm, ch_in, rate, mix_ch, mix_rate, lp, gain, speed=None):
+def chain(pcm, ch_in, rate, mix_ch, mix_rate, lp, gain, speed=None, pre=None):
     s = rb.TestSource(pcm, ch_in, rate)
+    if pre is not None:
+        s = s.amplify(pre)           # source.amplify(v), then handed to the mixer: the gain is in front of the conversion
     if speed:
         s = s.speed(speed)
     s = rb.UniformSourceIterator(s, mix_ch, mix_rate)
@@ -33,9 +35,10 @@ def chain(pcm, ch_in, rate, mix_ch, mix_rate, lp, gain, speed=None):
     return s
 
 
-def expected(pcms, ch_in, rates, mix_ch, mix_rate, joined, lp, gain, speeds=None):
+def expected(pcms, ch_in, rates, mix_ch, mix_rate, joined, lp, gain, speeds=None, pres=None):
     speeds = speeds or [None] * len(pcms)
-    srcs = [chain(p, ci, r, mix_ch, mix_rate, lp, gain, sp) for p, ci, r, sp in zip(pcms, ch_in, rates, speeds)]
+    pres = pres or [None] * len(pcms)
+    srcs = [chain(p, ci, r, mix_ch, mix_rate, lp, gain, sp, pr) for p, ci, r, sp, pr in zip(pcms, ch_in, rates, speeds, pres)]
     per = [oracle.chain_uniform(to_oracle(s), mix_ch, mix_rate) for s in srcs]
     eff = [s.base_rate if sp is None else rb.capi.lib().rb_speed_sample_rate(r, sp) for s, r, sp in zip(srcs, rates, speeds)]
     froms = [r // math.gcd(r, mix_rate) for r in eff]
@@ -166,6 +169,41 @@ def s_filtered_and_plain_sources():
     assert_close_peak(got, ref, 1e-5, "... and the reference's mixer")
 
 
+def s_gain_in_front_of_the_conversion():
+    """`source.amplify(v)` handed to the mixer -- the usual rodio idiom -- in a session (random split, one source sped up, one
+    gain outside the range of the fast tiles) and in a batch on the lane kernel."""
+    rng = np.random.default_rng(9)
+    n = 36
+    rates = [44100, 48000, 22050, 44100] * 9
+    ch_in = [2, 1, 1, 2] * 9
+    pres = [float(np.float32(v)) for v in rng.uniform(0.1, 1.2, n)]
+    pres[3], pres[10] = 0.004, -0.7
+    speeds = [None] * n
+    speeds[6] = 1.25
+    pcms = [noise(ci * (500 + 17 * i), 8100 + i) for i, ci in enumerate(ch_in)]
+    starts = [0 if i % 3 else 20 * i for i in range(n)]
+    srcs = [chain(np.zeros(0, np.float32), ci, r, 2, 48000, 400, 0.9, sp, pr) for ci, r, sp, pr in zip(ch_in, rates, speeds, pres)]
+    with rb.Session(srcs, 48000, fifo_frames=2048, max_block_frames=256, mix_starts=starts, mixer_channels=2) as s:
+        got, _ = drive(s, pcms, ch_in, [r // 200 for r in rates], 256, rng=rng)
+    want = expected(pcms, ch_in, rates, 2, 48000, starts, 400, 0.9, speeds, pres)
+    assert_bit_exact(got, want[:got.size], "session with gains in front of the conversion")
+    assert got.size == want.size or not np.any(want[got.size:])
+    # sources with and without such a gain in one session: classes of their own, summed in class order
+    mixed = [chain(np.zeros(0, np.float32), 1, 44100, 1, 48000, None, None, None, 0.5), chain(np.zeros(0, np.float32), 1, 44100, 1, 48000, None, None)]
+    with rb.Session(mixed, 48000, fifo_frames=1024, max_block_frames=128, mixer_channels=1) as s:
+        got, _ = drive(s, [pcms[1][:500], pcms[2][:500]], [1, 1], [100, 100], 128)
+    a = oracle.chain_uniform(to_oracle(chain(pcms[1][:500], 1, 44100, 1, 48000, None, None, None, 0.5)), 1, 48000)
+    b = oracle.chain_uniform(to_oracle(chain(pcms[2][:500], 1, 44100, 1, 48000, None, None)), 1, 48000)
+    assert_bit_exact(got, (a + np.float32(0.0)) + (b + np.float32(0.0)), "with and without a gain in front")
+    # the same shape as a batch: rb_batch_create -> fused parser -> lane plan
+    real = [chain(p, ci, r, 2, 48000, 400, 0.9, None, pr) for p, ci, r, pr in zip(pcms, ch_in, [44100, 22050] * 18, pres)]
+    with rb.Batch(real, 2, 48000, flags=capi.RB_FUSED_LANES) as b:
+        assert b.kernel_family == 2
+        b.upload_all()
+        got = b.render_mix()
+    assert_bit_exact(got, expected(pcms, ch_in, [44100, 22050] * 18, 2, 48000, [0] * n, 400, 0.9, None, pres), "batch with gains in front")
+
+
 def s_batch_with_identity_conversions():
     """rb_batch_create -> fused parser -> lane plan on the CPU: 44.1 kHz sources beside 48 kHz ones (whose conversion is the
     identity and is dropped by the planner) and mono beside stereo -- the batch still goes to the lane kernel, class by class."""
@@ -279,11 +317,13 @@ def s_random(seed=0, cases=6):
         pcms = [noise(ci * L, 991 * case + i + 7 * seed) for i, (ci, L) in enumerate(zip(ch_in, lens))]
         starts = [0 if rng.random() < 0.6 else int(rng.integers(0, 500)) for _ in range(n)]
         lp, gain = [(300, 0.8), (None, 1.1), (2000, None), (None, None)][int(rng.integers(4))]
-        srcs = [chain(np.zeros(0, np.float32), ci, r, mix_ch, mix_rate, lp, gain) for ci, r in zip(ch_in, rates)]
+        pres = [float(np.float32(rng.choice([0.002, -0.4, rng.uniform(0.05, 1.5)]))) for _ in range(n)] if rng.random() < 0.4 else None
+        srcs = [chain(np.zeros(0, np.float32), ci, r, mix_ch, mix_rate, lp, gain, None, None if pres is None else pres[i])
+                for i, (ci, r) in enumerate(zip(ch_in, rates))]
         with rb.Session(srcs, mix_rate, fifo_frames=4096, max_block_frames=int(rng.choice([64, 333, 1024])), mix_starts=starts,
                         mixer_channels=mix_ch) as s:
             got, _ = drive(s, pcms, ch_in, [max(1, r // 150) for r in rates], 700, rng=rng, packed=bool(rng.integers(2)))
-        want = expected(pcms, ch_in, rates, mix_ch, mix_rate, starts, lp, gain)
+        want = expected(pcms, ch_in, rates, mix_ch, mix_rate, starts, lp, gain, None, pres)
         if not any(lens):
             assert got.size == 0
             continue
@@ -293,7 +333,8 @@ def s_random(seed=0, cases=6):
 
 SCENARIOS = {"mono_random_split": s_mono_random_split, "mixed_with_state_blob": s_mixed_everything_with_state_blob,
              "held_queue_gain_speed": s_held_queue_gain_speed, "gain_changes": s_gain_changes, "filtered_and_plain": s_filtered_and_plain_sources,
-             "batch_with_identity_conversions": s_batch_with_identity_conversions, "batch_unsorted_starts": s_batch_unsorted_starts, "errors": s_errors}
+             "batch_with_identity_conversions": s_batch_with_identity_conversions, "batch_unsorted_starts": s_batch_unsorted_starts, "errors": s_errors,
+             "gain_in_front": s_gain_in_front_of_the_conversion}
 
 if __name__ == "__main__":
     for name in (sys.argv[1:] or list(SCENARIOS)):

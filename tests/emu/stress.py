@@ -33,6 +33,8 @@ def batches(seed, cases):
         pcms = [noise(ci * L, 10000 * case + i) for i, (ci, L) in enumerate(zip(ch_in, lens))]
         kind = rng.integers(4)
         kw = [dict(lp=int(rng.choice([200, 1000, 3000])), gain=float(np.float32(rng.uniform(0.2, 1.5)))), dict(hp=300), dict(gain=1.2), dict()][kind]
+        if rng.random() < 0.4:   # source.amplify(v) in front of the mixer's conversion; a few outside the fast-path gain range
+            kw = dict(kw, pre=[float(np.float32(rng.choice([0.001, -0.5, 100.0, rng.uniform(0.05, 2.0)]))) for _ in range(n)])
         try:
             T.check(emu, pcms, rates, mix_rate, starts, channels=ch, ch_in=ch_in, **kw)
         except AssertionError as e:

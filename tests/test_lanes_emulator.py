@@ -65,7 +65,7 @@ def expected_mix_classes(per_stream, starts, mix_len, froms, tos):
     return acc
 
 
-def run_emu(emu, pcms, outs_len, starts, coefs, posts, from_, to, mix_len, hasb, ff2, npost, channels=1, ch_in=None):
+def run_emu(emu, pcms, outs_len, starts, coefs, posts, from_, to, mix_len, hasb, ff2, npost, channels=1, ch_in=None, pres=None):
     """Frames everywhere (outs_len, starts, mix_len); the result holds frames * channels floats, pcms[r] frames * ch_in[r]."""
     ch_in = [channels] * len(pcms) if ch_in is None else list(ch_in)
     n = len(pcms)
@@ -76,22 +76,28 @@ def run_emu(emu, pcms, outs_len, starts, coefs, posts, from_, to, mix_len, hasb,
     po = np.ascontiguousarray(posts, dtype=np.float32)
     out = np.full(mix_len * channels, np.nan, dtype=np.float32)
     used, unsafe = C.c_int(0), C.c_uint32(0)
+    pr = None if pres is None else np.ascontiguousarray(pres, dtype=np.float32)
     rc = emu.rb_lanes_emulate(ptrs, u64([p.size // c for p, c in zip(pcms, ch_in)]), u64(outs_len), u64(starts),
                               co.ctypes.data_as(C.POINTER(C.c_float)), po.ctypes.data_as(C.POINTER(C.c_float)),
                               C.c_uint32(n), C.c_uint32(channels), _u32(ch_in, n)[0], _u32(from_, n)[0], _u32(to, n)[0], C.c_uint64(mix_len), int(hasb), int(ff2),
-                              int(npost), out.ctypes.data_as(C.POINTER(C.c_float)), None, C.byref(used), C.byref(unsafe))
+                              int(npost), out.ctypes.data_as(C.POINTER(C.c_float)), None, C.byref(used), C.byref(unsafe),
+                              None if pr is None else pr.ctypes.data_as(C.POINTER(C.c_float)))
     assert rc == 0
     return out, bool(used.value), unsafe.value
 
 
-def make_case(pcms, in_rate, mix_rate, starts, lp=None, hp=None, q=0.5, gain=None, channels=1, ch_in=None):
+def make_case(pcms, in_rate, mix_rate, starts, lp=None, hp=None, q=0.5, gain=None, channels=1, ch_in=None, pre=None):
     """Sources as a rodio user writes them + everything the emulator needs, the expectation from the oracle.
     `starts` and the lengths in the result are frames."""
     srcs, per_stream = [], []
     in_rates = list(in_rate) if isinstance(in_rate, (list, tuple)) else [in_rate] * len(pcms)
     ch_in = [channels] * len(pcms) if ch_in is None else list(ch_in)
-    for p, rate, ci in zip(pcms, in_rates, ch_in):
-        s = rb.UniformSourceIterator(rb.TestSource(p, ci, rate), channels, mix_rate)
+    pres = None if pre is None else (list(pre) if isinstance(pre, (list, tuple, np.ndarray)) else [pre] * len(pcms))
+    for k, (p, rate, ci) in enumerate(zip(pcms, in_rates, ch_in)):
+        s = rb.TestSource(p, ci, rate)
+        if pres is not None:
+            s = s.amplify(float(pres[k]))       # source.amplify(v) handed to the mixer: the gain sits in front of the conversion
+        s = rb.UniformSourceIterator(s, channels, mix_rate)
         if lp is not None:
             s = s.low_pass_with_q(lp, q)
         if hp is not None:
@@ -108,14 +114,14 @@ def make_case(pcms, in_rate, mix_rate, starts, lp=None, hp=None, q=0.5, gain=Non
     mix_len = max([s + y.size // channels for s, y in zip(starts, per_stream)] + [0])
     return dict(per_stream=per_stream, outs_len=[y.size // channels for y in per_stream], coefs=coefs, channels=channels, ch_in=ch_in,
                 posts=np.full(len(pcms), gain if gain is not None else 1.0, np.float32), from_=froms, to=tos,
-                mix_len=mix_len, hasb=hasb, npost=gain is not None, srcs=srcs)
+                mix_len=mix_len, hasb=hasb, npost=gain is not None, srcs=srcs, pres=pres)
 
 
 def check(emu, pcms, in_rate, mix_rate, starts, ff2=True, expect_ff2=None, **kw):
     c = make_case(pcms, in_rate, mix_rate, starts, **kw)
     ch = c["channels"]
     got, used_ff2, unsafe = run_emu(emu, pcms, c["outs_len"], starts, c["coefs"], c["posts"], c["from_"], c["to"], c["mix_len"],
-                                    c["hasb"], ff2, c["npost"], channels=ch, ch_in=c["ch_in"])
+                                    c["hasb"], ff2, c["npost"], channels=ch, ch_in=c["ch_in"], pres=c["pres"])
     if expect_ff2 is not None:
         assert used_ff2 == expect_ff2
     want = expected_mix_classes(c["per_stream"], [st * ch for st in starts], c["mix_len"] * ch, c["from_"], list(zip(c["to"], c["ch_in"])))
@@ -482,3 +488,25 @@ def test_session_queue_of_sources(emu):
     want = expected_mix_classes(c["per_stream"], joined, got.size, c["from_"], list(zip(c["to"], c["ch_in"])))
     assert got.size == max(j + y.size for j, y in zip(joined, c["per_stream"]))
     assert_bit_exact(got, want, "queued sources")
+
+
+def test_gain_in_front_of_the_conversion(emu):
+    """`source.amplify(v)` handed to the mixer: the gain multiplies every input frame before the interpolation
+    (src/source/amplify.rs:91-95 in front of src/source/uniform.rs).  Per-stream gains; 0.001 and 100 lie outside the range
+    the fast tiles accept and run on the slow tiles; -0.5 and 0.8 stay on the fast path."""
+    n = 40
+    pcms = [noise(1500 + 13 * i, 900 + i) for i in range(n)]
+    pres = [[0.8, -0.5, 1.0, 0.3][i % 4] for i in range(n)]
+    counters(emu)
+    check(emu, pcms, 44100, 48000, [0] * n, lp=200, gain=0.7, pre=pres, expect_ff2=True)
+    c = counters(emu)
+    assert c["fast"] > 4 * c["slow"]
+    pres[5], pres[33] = 0.001, 100.0
+    check(emu, pcms, 44100, 48000, [7 * (i % 5) for i in range(n)], lp=200, gain=0.7, pre=pres)
+    c = counters(emu)
+    assert c["slow"] > 100          # the two groups holding a far gain never leave the slow tiles
+    # no filter, stereo and mono-in-stereo sources, sources at the mixer's rate (taps used raw, times the gain)
+    ch_in = [2 if i % 3 else 1 for i in range(12)]
+    pcms = [noise(ci * (700 + 9 * i), 950 + i) for i, ci in enumerate(ch_in)]
+    check(emu, pcms, [44100, 48000, 22050] * 4, 48000, [0] * 12, channels=2, ch_in=ch_in, pre=[0.5 + 0.1 * i for i in range(12)])
+    check(emu, pcms, 48000, 48000, [3 * i for i in range(12)], hp=300, channels=2, ch_in=ch_in, pre=0.9)

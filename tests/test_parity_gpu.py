@@ -948,3 +948,36 @@ def test_session_queue_of_sources(ctx):
     ref = oracle.mixer([to_oracle(mk(p, r), mix_start=m) for p, r, m in zip(pcms, rates, starts)], 1, 48000)
     assert got.size == ref.size
     assert_close_peak(got, ref, 1e-5, "queued sources vs the reference's mixer with the same starts")
+
+
+@lanes_gate
+def test_lanes_and_session_gain_in_front_of_the_conversion(ctx):
+    """`source.amplify(v)` handed to the mixer -- the gain multiplies every frame BEFORE it is interpolated (amplify.rs:91-95 in
+    front of uniform.rs) -- as a batch on the lane kernel and as a session; 0.004 lies outside the gain range of the fast tiles
+    (rb_lanes_plan.h pre_gain_keeps_class) and goes through the slow ones, same bytes."""
+    n = 70
+    pcms = [noise(3000 + 41 * i, 4700 + i) for i in range(n)]
+    pres = [float(np.float32(0.2 + 0.013 * i)) for i in range(n)]
+    pres[9], pres[40] = 0.004, -0.6
+    mk = lambda p, g: rb.UniformSourceIterator(rb.TestSource(p, 1, 44100).amplify(g), 1, 48000).low_pass(250).amplify(0.8)
+    srcs = [mk(p, g) for p, g in zip(pcms, pres)]
+    per_stream = [oracle.chain_uniform(to_oracle(s), 1, 48000) for s in srcs]
+    with rb.Batch(srcs, 1, 48000, flags=LANES, ctx=ctx) as b:
+        assert b.kernel_family == 2
+        b.upload_all()
+        whole = b.render_mix()
+    assert_bit_exact(whole, lanes_expected_mix(per_stream, [0] * n, whole.size), "gain -> conversion -> low_pass -> gain on the lane kernel")
+    assert_close_peak(whole, oracle.mixer([to_oracle(s) for s in srcs], 1, 48000), 1e-5, "... and the reference's sequential mixer")
+    got, pos, ended = [], 0, False
+    with rb.Session([mk(np.zeros(0, np.float32), g) for g in pres], 48000, fifo_frames=2048, max_block_frames=480, ctx=ctx) as s:
+        while not ended:
+            s.push_packed([p[pos:pos + 441] for p in pcms], [pos + 441 >= p.size for p in pcms])
+            pos += 441
+            while True:
+                block, ended = s.render(480)
+                got.append(block)
+                if block.size == 0 or ended:
+                    break
+    got = np.concatenate(got)
+    assert_bit_exact(got, whole[:got.size], "the session in 10 ms blocks vs the whole-stream render")
+    assert got.size == whole.size or not np.any(whole[got.size:])

@@ -33,7 +33,7 @@ def hostemu(built):
 
 @pytest.mark.parametrize("scenario", ["errors", "mono_random_split", "mixed_with_state_blob", "held_queue_gain_speed", "gain_changes",
                                       "filtered_and_plain", "batch_with_identity_conversions",
-                                      "batch_unsorted_starts"])
+                                      "batch_unsorted_starts", "gain_in_front"])
 def test_session_host_code_on_the_emulator(hostemu, scenario):
     t0 = time.time()
     r = subprocess.run([sys.executable, os.path.join(EMU, "session_scenarios.py"), scenario], capture_output=True, text=True, timeout=900)
@@ -58,7 +58,9 @@ def test_lanes_batch_plan_on_the_emulator(hostemu):
     pcms = [noise(ci * (250 + 5 * i), 4100 + i) for i, ci in enumerate(ch_in)]
     pcms[5][40:50] = np.float32(1e-41)
     starts = [(11 * i) % 70 for i in range(len(ch_in))]
-    c = T.make_case(pcms, rates, 48000, starts, lp=700, gain=0.9, channels=2, ch_in=ch_in)
+    pres = [0.5 + 0.02 * i for i in range(len(ch_in))]
+    pres[7] = 1000.0                                      # outside the fast tiles' gain range: slow tiles for its group
+    c = T.make_case(pcms, rates, 48000, starts, lp=700, gain=0.9, channels=2, ch_in=ch_in, pre=pres)
     lib = C.CDLL(hostemu)
     n = len(pcms)
     arrs = [np.ascontiguousarray(p, dtype=np.float32) for p in pcms]
@@ -67,11 +69,12 @@ def test_lanes_batch_plan_on_the_emulator(hostemu):
     u32 = lambda v: (C.c_uint32 * n)(*[int(x) for x in v])
     co = np.ascontiguousarray(c["coefs"], np.float32).reshape(-1)
     po = np.ascontiguousarray(c["posts"], np.float32)
+    pr = np.ascontiguousarray(pres, np.float32)
     out = np.full(c["mix_len"] * 2, np.nan, np.float32)
     launches = C.c_uint32(0)
     rc = lib.hostemu_lanes_batch(ptrs, u64([a.size // ci for a, ci in zip(arrs, ch_in)]), u64(c["outs_len"]), u64(starts),
-                                 co.ctypes.data_as(C.POINTER(C.c_float)), po.ctypes.data_as(C.POINTER(C.c_float)), C.c_uint32(n),
-                                 C.c_uint32(2), u32(ch_in), u32(c["from_"]), u32(c["to"]), C.c_uint64(c["mix_len"]), 1, 1,
+                                 co.ctypes.data_as(C.POINTER(C.c_float)), po.ctypes.data_as(C.POINTER(C.c_float)), pr.ctypes.data_as(C.POINTER(C.c_float)),
+                                 C.c_uint32(n), C.c_uint32(2), u32(ch_in), u32(c["from_"]), u32(c["to"]), C.c_uint64(c["mix_len"]), 1, 1, 1,
                                  out.ctypes.data_as(C.POINTER(C.c_float)), C.byref(launches))
     assert rc == 0
     assert launches.value == 6 + 1            # six classes (rate pair x source channels) and the sum
