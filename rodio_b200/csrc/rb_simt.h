@@ -14,6 +14,8 @@
 
 #if defined(RB_SIMT_EMULATE)
 #include <barrier>
+#include <functional>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -32,8 +34,16 @@ namespace simt {
 
 #if defined(RB_SIMT_EMULATE)
 // ------------------------------------------------------------------------------------------ emulator
+struct WarpEmu;
+struct LaneEmu {
+    WarpEmu* w = nullptr;
+    uint32_t lane = 0;
+    struct Copy { float* dst; const float* src; };
+    std::vector<Copy> open;                 // copies issued since the last commit
+    std::deque<std::vector<Copy>> groups;   // committed, not yet landed
+    uint64_t n_instr_hint = 0;
+};
 struct WarpEmu {
-    std::barrier<> bar{32};
     uint32_t xu[32];
     uint64_t xl[32];
     float xf[32];
@@ -44,26 +54,61 @@ struct WarpEmu {
             if ((const char*)p >= r.first && (const char*)p + n <= r.second) return true;
         return false;
     }
+#if defined(__x86_64__)
+    // The 32 lanes are fibers of ONE host thread (run_warp below): a collective is a counter, and a lane that has to wait
+    // hands the processor to the scheduler, which resumes the others in an order that changes from pass to pass.
+    uint32_t epoch = 0, arrived = 0, order_seed = 12345u;
+    void* main_sp = nullptr;
+    void* sp[32] = {};
+    bool done[32] = {};
+    LaneEmu lanes[32];
+    std::function<void()> body;
+#else
+    std::barrier<> bar{32};
+#endif
 };
-struct LaneEmu {
-    WarpEmu* w = nullptr;
-    uint32_t lane = 0;
-    struct Copy { float* dst; const float* src; };
-    std::vector<Copy> open;                 // copies issued since the last commit
-    std::deque<std::vector<Copy>> groups;   // committed, not yet landed
-    uint64_t n_instr_hint = 0;
-};
+
+#if defined(__x86_64__)
+// Context switch between fibers: callee-saved registers on the old stack, stack pointers exchanged (System V x86-64).
+extern "C" void rb_fiber_switch(void** save_sp, void* load_sp);
+asm(R"(
+.text
+.weak rb_fiber_switch
+.type rb_fiber_switch,@function
+rb_fiber_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size rb_fiber_switch,.-rb_fiber_switch
+)");
+inline thread_local LaneEmu* g_cur = nullptr;
+inline LaneEmu& cur() { return *g_cur; }
+#else
 inline thread_local LaneEmu g_lane;
+inline LaneEmu& cur() { return g_lane; }
+#endif
 
 [[noreturn]] inline void emu_fail(const char* what) {
-    std::fprintf(stderr, "simt emulator: %s (lane %u)\n", what, g_lane.lane);
+    std::fprintf(stderr, "simt emulator: %s (lane %u)\n", what, cur().lane);
     std::abort();
 }
-SIMT_FN uint32_t lane() { return g_lane.lane; }
+SIMT_FN uint32_t lane() { return cur().lane; }
 // coverage counters of the emulator (0: fast tiles, 1: slow tiles, 2: ring refills), counted by lane 0
 inline uint64_t g_emu_count[4] = {0, 0, 0, 0};
 SIMT_FN void emu_count(int which, uint64_t n) {
-    if (g_lane.lane == 0) g_emu_count[which] += n;
+    if (cur().lane == 0) g_emu_count[which] += n;
 }
 SIMT_FN float fmul(float a, float b) { return a * b; }
 SIMT_FN float fadd(float a, float b) { return a + b; }
@@ -72,38 +117,110 @@ SIMT_FN float fdiv(float a, float b) { return a / b; }
 SIMT_FN float ffma(float a, float b, float c) { return std::fmaf(a, b, c); }
 SIMT_FN float u2f(uint32_t v) { return (float)v; }
 SIMT_FN float ldg(const float* p) {
-    if (!g_lane.w->ok_read(p, 4)) emu_fail("ldg outside the registered input rows");
+    if (!cur().w->ok_read(p, 4)) emu_fail("ldg outside the registered input rows");
     return *p;
 }
-SIMT_FN void sync() { g_lane.w->bar.arrive_and_wait(); }
+#if defined(__x86_64__)
+SIMT_FN void sync() {
+    LaneEmu* me = g_cur;
+    WarpEmu* w = me->w;
+    const uint32_t e = w->epoch;
+    if (++w->arrived == 32) {   // the last lane to arrive releases the others and runs on
+        w->arrived = 0, w->epoch = e + 1;
+        return;
+    }
+    while (w->epoch == e) {
+        rb_fiber_switch(&w->sp[me->lane], w->main_sp);
+        g_cur = me;
+    }
+}
+[[noreturn]] inline void fiber_entry() {
+    LaneEmu* me = g_cur;
+    WarpEmu* w = me->w;
+    w->body();
+    w->done[me->lane] = true;
+    rb_fiber_switch(&w->sp[me->lane], w->main_sp);
+    std::abort();   // a finished lane is never resumed
+}
+// Run `body` as the 32 lanes of warp `w` (every lane executes it; simt::lane() tells them apart).
+template <class F>
+void run_warp(WarpEmu* w, F&& body) {
+    constexpr size_t STACK = 256 * 1024;
+    static thread_local std::vector<char> stacks(32 * STACK + 64);
+    w->body = body, w->epoch = 0, w->arrived = 0;
+    for (uint32_t l = 0; l < 32; l++) {
+        w->lanes[l] = LaneEmu{};
+        w->lanes[l].w = w, w->lanes[l].lane = l, w->done[l] = false;
+        uintptr_t top = ((uintptr_t)stacks.data() + (l + 1) * STACK) & ~(uintptr_t)15;
+        void** q = (void**)top;
+        *--q = nullptr;                 // the frame fiber_entry "returns" to (never used); entry sees rsp % 16 == 8
+        *--q = (void*)&fiber_entry;     // popped by the `ret` of the first switch
+        for (int i = 0; i < 6; i++) *--q = nullptr;   // rbp rbx r12 r13 r14 r15
+        w->sp[l] = q;
+    }
+    uint32_t left = 32;
+    while (left) {
+        // a different lane order every pass: what lockstep execution would hide (a lane touching another lane's ring slot
+        // on the wrong side of a syncwarp) must not be hidden by a fixed order either
+        w->order_seed = w->order_seed * 1664525u + 1013904223u;
+        const uint32_t first = w->order_seed >> 27, step = ((w->order_seed >> 20) & 30u) | 1u;   // odd step: a permutation of 0..31
+        const uint32_t before = left, epoch = w->epoch;
+        for (uint32_t k = 0; k < 32; k++) {
+            const uint32_t l = (first + k * step) & 31u;
+            if (w->done[l]) continue;
+            g_cur = &w->lanes[l];
+            rb_fiber_switch(&w->main_sp, w->sp[l]);
+            if (w->done[l]) left--;
+        }
+        if (left && left == before && w->epoch == epoch) {   // every live lane waits, and nobody is left to release them
+            std::fprintf(stderr, "simt emulator: collective reached by %u of %u live lanes\n", w->arrived, left);
+            std::abort();
+        }
+    }
+    g_cur = nullptr;
+}
+#else
+SIMT_FN void sync() { cur().w->bar.arrive_and_wait(); }
+template <class F>
+void run_warp(WarpEmu* w, F&& body) {
+    std::vector<std::thread> th;
+    for (uint32_t l = 0; l < 32; l++)
+        th.emplace_back([&, l] {
+            g_lane = LaneEmu{};
+            g_lane.w = w, g_lane.lane = l;
+            body();
+        });
+    for (auto& t : th) t.join();
+}
+#endif
 SIMT_FN void syncwarp() { sync(); }
 SIMT_FN float shfl_xor(float v, int m) {
-    WarpEmu* w = g_lane.w;
-    w->xf[g_lane.lane] = v;
+    WarpEmu* w = cur().w;
+    w->xf[cur().lane] = v;
     sync();
-    const float r = w->xf[g_lane.lane ^ (uint32_t)m];
+    const float r = w->xf[cur().lane ^ (uint32_t)m];
     sync();
     return r;
 }
 SIMT_FN uint32_t shfl_idx(uint32_t v, uint32_t src) {
-    WarpEmu* w = g_lane.w;
-    w->xu[g_lane.lane] = v;
+    WarpEmu* w = cur().w;
+    w->xu[cur().lane] = v;
     sync();
     const uint32_t r = w->xu[src & 31u];
     sync();
     return r;
 }
 SIMT_FN uint64_t shfl_idx64(uint64_t v, uint32_t src) {
-    WarpEmu* w = g_lane.w;
-    w->xl[g_lane.lane] = v;
+    WarpEmu* w = cur().w;
+    w->xl[cur().lane] = v;
     sync();
     const uint64_t r = w->xl[src & 31u];
     sync();
     return r;
 }
 SIMT_FN uint32_t reduce_min(uint32_t v) {
-    WarpEmu* w = g_lane.w;
-    w->xu[g_lane.lane] = v;
+    WarpEmu* w = cur().w;
+    w->xu[cur().lane] = v;
     sync();
     uint32_t r = w->xu[0];
     for (int i = 1; i < 32; i++) r = w->xu[i] < r ? w->xu[i] : r;
@@ -111,8 +228,8 @@ SIMT_FN uint32_t reduce_min(uint32_t v) {
     return r;
 }
 SIMT_FN uint64_t reduce_min64(uint64_t v) {
-    WarpEmu* w = g_lane.w;
-    w->xl[g_lane.lane] = v;
+    WarpEmu* w = cur().w;
+    w->xl[cur().lane] = v;
     sync();
     uint64_t r = w->xl[0];
     for (int i = 1; i < 32; i++) r = w->xl[i] < r ? w->xl[i] : r;
@@ -120,8 +237,8 @@ SIMT_FN uint64_t reduce_min64(uint64_t v) {
     return r;
 }
 SIMT_FN uint64_t reduce_max64(uint64_t v) {
-    WarpEmu* w = g_lane.w;
-    w->xl[g_lane.lane] = v;
+    WarpEmu* w = cur().w;
+    w->xl[cur().lane] = v;
     sync();
     uint64_t r = w->xl[0];
     for (int i = 1; i < 32; i++) r = w->xl[i] > r ? w->xl[i] : r;
@@ -151,20 +268,20 @@ SIMT_FN void lerp_advance(float& nf, float (&x0)[C], float (&x1)[C], sptr& p, fl
 // 16-byte asynchronous copy global -> shared (cp.async.cg.shared.global): lands at the matching cp_wait.
 SIMT_FN void cp16(float* smem_dst, const float* gsrc) {
     if (((uintptr_t)smem_dst & 15) || ((uintptr_t)gsrc & 15)) emu_fail("cp16: operands must be 16-byte aligned");
-    if (!g_lane.w->ok_read(gsrc, 16)) emu_fail("cp16 source outside the registered input rows");
+    if (!cur().w->ok_read(gsrc, 16)) emu_fail("cp16 source outside the registered input rows");
     const float nan = std::numeric_limits<float>::quiet_NaN();
     for (int i = 0; i < 4; i++) smem_dst[i] = nan;   // the engine may overwrite the slot any time from now on
-    g_lane.open.push_back({smem_dst, gsrc});
+    cur().open.push_back({smem_dst, gsrc});
 }
 SIMT_FN void cp_commit() {
-    g_lane.groups.push_back(std::move(g_lane.open));
-    g_lane.open.clear();
+    cur().groups.push_back(std::move(cur().open));
+    cur().open.clear();
 }
 template <int N>
 SIMT_FN void cp_wait() {
-    while ((int)g_lane.groups.size() > N) {
-        for (auto& c : g_lane.groups.front()) std::memcpy(c.dst, c.src, 16);
-        g_lane.groups.pop_front();
+    while ((int)cur().groups.size() > N) {
+        for (auto& c : cur().groups.front()) std::memcpy(c.dst, c.src, 16);
+        cur().groups.pop_front();
     }
 }
 #else

@@ -3,13 +3,13 @@
 // C ABI of include/rodio_b200.h, so the Python mirror (rodio_b200.Session ...) drives it unchanged: the session bookkeeping of
 // rb_api.cu (class order, packed pushes, FIFO compaction, state blobs) runs on the CPU exactly as it runs in front of the GPU.
 // Only the streaming sessions are served: batches need the kernels of rb_kernels.cu / rb_fused.cu and fail loudly here.
-#define RB_SIMT_EMULATE 1
 #include <cstdio>
 #include <map>
 #include <mutex>
 #include <thread>
 #include <vector>
 
+#include "warp_variants.h"
 #include "../../rodio_b200/csrc/rb_fused.h"
 #include "../../rodio_b200/csrc/rb_fused_rows.h"
 #include "../../rodio_b200/csrc/rb_lanes.h"
@@ -27,36 +27,7 @@ extern "C" void mock_cuda_unregister(void* p) {
     g_allocs.erase(p);
 }
 
-// ---- the lane kernel on 32 host threads per warp ----
-namespace {
-template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS, bool PRE>
-void run_warp(const lanes::Args& a, uint32_t group, simt::WarpEmu* w, float* ring) {
-    std::vector<std::thread> th;
-    for (uint32_t l = 0; l < 32; l++)
-        th.emplace_back([&, l] {
-            simt::g_lane = simt::LaneEmu{};
-            simt::g_lane.w = w, simt::g_lane.lane = l;
-            lanes::warp_main<CI, CO, HASB, FF2, NPOST, PASS, PRE>(a, group, ring);
-        });
-    for (auto& t : th) t.join();
-}
-template <int CI, int CO, bool PASS, bool PRE>
-void run_variant_p(const lanes::Args& a, uint32_t g, simt::WarpEmu* w, float* ring, bool hasb, bool ff2, bool npost) {
-    if (hasb && ff2 && npost) run_warp<CI, CO, true, true, 1, PASS, PRE>(a, g, w, ring);
-    else if (hasb && ff2) run_warp<CI, CO, true, true, 0, PASS, PRE>(a, g, w, ring);
-    else if (hasb && npost) run_warp<CI, CO, true, false, 1, PASS, PRE>(a, g, w, ring);
-    else if (hasb) run_warp<CI, CO, true, false, 0, PASS, PRE>(a, g, w, ring);
-    else if (npost) run_warp<CI, CO, false, false, 1, PASS, PRE>(a, g, w, ring);
-    else run_warp<CI, CO, false, false, 0, PASS, PRE>(a, g, w, ring);
-}
-template <int CI, int CO>
-void run_variant(const lanes::Args& a, uint32_t g, simt::WarpEmu* w, float* ring, bool hasb, bool ff2, bool npost, bool pre) {
-    const bool pass = a.from == a.to;
-    if (pass) pre ? run_variant_p<CI, CO, true, true>(a, g, w, ring, hasb, ff2, npost) : run_variant_p<CI, CO, true, false>(a, g, w, ring, hasb, ff2, npost);
-    else pre ? run_variant_p<CI, CO, false, true>(a, g, w, ring, hasb, ff2, npost) : run_variant_p<CI, CO, false, false>(a, g, w, ring, hasb, ff2, npost);
-}
-}  // namespace
-
+// ---- the lane kernel on the SIMT emulator (warp_variants.cpp) ----
 cudaError_t rb_lanes_launch_kernel(const lanes::Args& a, uint32_t ch_in, uint32_t ch_out, bool has_biquad, bool ff2, bool has_post,
                                    bool has_pre, cudaStream_t) {
     if (a.mix_len == 0 || a.n_groups == 0) return cudaSuccess;
@@ -73,9 +44,7 @@ cudaError_t rb_lanes_launch_kernel(const lanes::Args& a, uint32_t ch_in, uint32_
     while ((uintptr_t)ring & 15) ring++;
     for (uint32_t g = 0; g < a.n_groups; g++) {
         for (int i = 0; i < 32 * MAX_RS; i++) ring[i] = nan;
-        if (ch_in == 2) run_variant<2, 2>(a, g, &warp, ring, has_biquad, ff2, has_post, has_pre);
-        else if (ch_out == 2) run_variant<1, 2>(a, g, &warp, ring, has_biquad, ff2, has_post, has_pre);
-        else run_variant<1, 1>(a, g, &warp, ring, has_biquad, ff2, has_post, has_pre);
+        emu_run_group(ch_in, ch_out, a, g, &warp, ring, has_biquad, ff2, has_post, has_pre);
     }
     return cudaSuccess;
 }

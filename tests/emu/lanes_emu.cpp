@@ -1,7 +1,6 @@
 // CPU emulator of k_fused_lanes (test infrastructure): runs rodio_b200/csrc/rb_lanes_core.h -- the very source the
 // device kernel is compiled from -- on 32 host threads per warp (see rb_simt.h, RB_SIMT_EMULATE) and adds the
 // per-warp partial rows in warp order like k_sum_groups.  Built and loaded by tests/test_lanes_emulator.py.
-#define RB_SIMT_EMULATE 1
 #include <cstdint>
 #include <cstring>
 #include <limits>
@@ -9,41 +8,14 @@
 #include <thread>
 #include <vector>
 
+#include "warp_variants.h"
 #include "../../rodio_b200/csrc/rb_lanes_plan.h"
 
 namespace {
-template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS, bool PRE>
-void run_warp_c(const lanes::Args& a, uint32_t group, simt::WarpEmu* w, float* ring) {
-    std::vector<std::thread> th;
-    for (uint32_t l = 0; l < 32; l++)
-        th.emplace_back([&, l] {
-            simt::g_lane = simt::LaneEmu{};
-            simt::g_lane.w = w, simt::g_lane.lane = l;
-            lanes::warp_main<CI, CO, HASB, FF2, NPOST, PASS, PRE>(a, group, ring);
-        });
-    for (auto& t : th) t.join();
-}
-template <int CI, int CO, bool PASS, bool PRE>
-void run_group(const lanes::Args& a, uint32_t g, simt::WarpEmu* w, float* ring, bool hasb, bool ff2, bool npost) {
-    if (hasb && ff2 && npost) run_warp_c<CI, CO, true, true, 1, PASS, PRE>(a, g, w, ring);
-    else if (hasb && ff2) run_warp_c<CI, CO, true, true, 0, PASS, PRE>(a, g, w, ring);
-    else if (hasb && npost) run_warp_c<CI, CO, true, false, 1, PASS, PRE>(a, g, w, ring);
-    else if (hasb) run_warp_c<CI, CO, true, false, 0, PASS, PRE>(a, g, w, ring);
-    else if (npost) run_warp_c<CI, CO, false, false, 1, PASS, PRE>(a, g, w, ring);
-    else run_warp_c<CI, CO, false, false, 0, PASS, PRE>(a, g, w, ring);
-}
-template <int CI, int CO>
-void run_group_c(const lanes::Args& a, uint32_t g, simt::WarpEmu* w, float* ring, bool hasb, bool ff2, bool npost, bool pre) {
-    const bool pass = a.from == a.to;
-    if (pass) pre ? run_group<CI, CO, true, true>(a, g, w, ring, hasb, ff2, npost) : run_group<CI, CO, true, false>(a, g, w, ring, hasb, ff2, npost);
-    else pre ? run_group<CI, CO, false, true>(a, g, w, ring, hasb, ff2, npost) : run_group<CI, CO, false, false>(a, g, w, ring, hasb, ff2, npost);
-}
 // the class decides the instantiation -- source channels ci, mixer channels co, PASS when from == to -- like the device launcher
 void run_group_any(uint32_t ci, uint32_t co, const lanes::Args& a, uint32_t g, simt::WarpEmu* w, float* ring, bool hasb, bool ff2, bool npost,
                    bool pre = false) {
-    if (ci == 2) run_group_c<2, 2>(a, g, w, ring, hasb, ff2, npost, pre);
-    else if (co == 2) run_group_c<1, 2>(a, g, w, ring, hasb, ff2, npost, pre);
-    else run_group_c<1, 1>(a, g, w, ring, hasb, ff2, npost, pre);
+    emu_run_group(ci, co, a, g, w, ring, hasb, ff2, npost, pre);
 }
 constexpr int MAX_RS = lanes::Geo<2>::RS;
 }  // namespace

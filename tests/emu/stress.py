@@ -3,7 +3,7 @@
     python tests/emu/stress.py batches [seed] [cases]     random batches: channels, rate pairs, lengths, starts, chain variants
     python tests/emu/stress.py sessions [seed] [cases]    random sessions: random pushes / renders over random sources
 Every case is held bit for bit against the oracle streams summed with the kernel's tree (tests/test_lanes_emulator.py).
-Needs tests/emu/liblanes_emu.so (built by the emulator tests)."""
+The emulator library is built on demand (tests/emu/build_emu.py)."""
 import ctypes as C
 import os
 import sys
@@ -12,12 +12,13 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path[:0] = [os.path.dirname(os.path.dirname(HERE)), os.path.dirname(HERE)]
+import build_emu                         # noqa: E402
 import test_lanes_emulator as T          # noqa: E402
 from helpers import noise                # noqa: E402
 
 
 def batches(seed, cases):
-    emu = C.CDLL(T.LIB)
+    emu = C.CDLL(build_emu.lanes_lib())
     emu.rb_lanes_emulate.restype = C.c_int
     rng = np.random.default_rng(seed)
     mixers = [(48000, [44100, 22050, 48000, 32000, 8000, 11025, 47999]), (44100, [22050, 44100, 32000, 8000, 11025]), (96000, [44100, 48000, 96000, 88200])]
@@ -45,7 +46,7 @@ def batches(seed, cases):
 
 
 def sessions(seed, cases):
-    emu = C.CDLL(T.LIB)
+    emu = C.CDLL(build_emu.lanes_lib())
     rng = np.random.default_rng(seed)
     bad = 0
     for case in range(cases):

@@ -6,7 +6,7 @@ CPU only -- the GPU counterpart is tests/test_parity_gpu.py::test_lanes_*."""
 import ctypes as C
 import math
 import os
-import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -16,18 +16,14 @@ import rodio_b200 as rb
 from helpers import assert_bit_exact, assert_close_peak, lanes_expected_mix as expected_mix, noise, to_oracle
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-ROOT = os.path.dirname(HERE)
-SRC = os.path.join(HERE, "emu", "lanes_emu.cpp")
-LIB = os.path.join(HERE, "emu", "liblanes_emu.so")
-DEPS = [SRC] + [os.path.join(ROOT, "rodio_b200", "csrc", f) for f in ("rb_lanes_core.h", "rb_lanes_plan.h", "rb_simt.h")]
+LIB = os.path.join(HERE, "emu", "liblanes_emu.so")      # built by tests/emu/build_emu.py
 
 
 @pytest.fixture(scope="module")
 def emu(built):
-    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in DEPS):
-        subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-ffp-contract=off", "-fno-fast-math", "-shared",
-                               "-fPIC", "-o", LIB, SRC])
-    lib = C.CDLL(LIB)
+    sys.path[:0] = [os.path.join(HERE, "emu")]
+    import build_emu
+    lib = C.CDLL(build_emu.lanes_lib())
     lib.rb_lanes_emulate.restype = C.c_int
     return lib
 

@@ -14,21 +14,13 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 EMU = os.path.join(HERE, "emu")
-LIB = os.path.join(EMU, "librodio_b200_hostemu.so")
-CSRC = os.path.join(ROOT, "rodio_b200", "csrc")
-DEPS = [os.path.join(EMU, "hostemu.cpp"), os.path.join(EMU, "mockcuda", "cuda_runtime.h"), os.path.join(CSRC, "rb_api.cu"),
-        os.path.join(CSRC, "rb_lanes_batch.cu")] + \
-       [os.path.join(CSRC, f) for f in ("rb_lanes_core.h", "rb_lanes_plan.h", "rb_session_plan.h", "rb_simt.h", "rb_lanes.h", "rb_fused.h",
-                                         "rb_fused_rows.h", "rb_internal.h")] + [os.path.join(ROOT, "include", "rodio_b200.h")]
 
 
 @pytest.fixture(scope="module")
 def hostemu(built):
-    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in DEPS):
-        subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC",
-                               "-DRB_SIMT_EMULATE=1", "-I", os.path.join(EMU, "mockcuda"), "-x", "c++", os.path.join(CSRC, "rb_api.cu"),
-                               os.path.join(CSRC, "rb_lanes_batch.cu"), os.path.join(EMU, "hostemu.cpp"), "-o", LIB])
-    return LIB
+    sys.path[:0] = [EMU]
+    import build_emu
+    return build_emu.host_lib()
 
 
 @pytest.mark.parametrize("scenario", ["errors", "mono_random_split", "mixed_with_state_blob", "held_queue_gain_speed", "gain_changes",
