@@ -223,9 +223,10 @@ rb_status rb_batch_read_stream(rb_batch* b, size_t stream, float* out_host, uint
  * Shape served (RB_ERR_UNSUPPORTED otherwise): a mono or stereo mixer = mixer(channels, rate) of src/mixer.rs:25-43; f32
  * sources with the mixer's channel count or mono sources in a stereo mixer (repeated on both channels like
  * ChannelCountConverter, src/conversions/channels.rs:57-85), each at its own sample rate (44.1 kHz, 22.05 kHz and 48 kHz sources in one 48 kHz mixer: one kernel launch
- * per rate pair; sources ABOVE the mixer's rate are exact as well but run on the kernel's general per-sample path), effects = [SPEED] UNIFORM(mixer channels, mixer rate)
- * [LOW_PASS | HIGH_PASS] [AMPLIFY] -- the chain of BASELINE cfg3 (a SPEED in front only changes the rate pair; filtered and
- * unfiltered sources may share a session); desc.n_samples / span_len are ignored,
+ * per rate pair; sources ABOVE the mixer's rate are exact as well but run on the kernel's general per-sample path), effects = [SPEED | one AMPLIFY]* UNIFORM(mixer channels, mixer rate)
+ * [LOW_PASS | HIGH_PASS] [AMPLIFY] -- the chain of BASELINE cfg3 (a SPEED in front only changes the rate pair, an AMPLIFY in
+ * front -- source.amplify(v) handed to Mixer::add, src/source/amplify.rs:91-95 -- multiplies every frame before it is
+ * interpolated; filtered and unfiltered sources, and sources with and without a gain in front, may share a session); desc.n_samples / span_len are ignored,
  * desc.mix_start is the mixer FRAME the source joins at.  Everything below counts frames; PCM is interleaved.
  * One caller per session; every call returns with the work done (the caller may reuse its buffers). */
 typedef struct rb_session rb_session;

@@ -1,5 +1,5 @@
 """The lane-per-stream fused kernel (rodio_b200/csrc/rb_lanes_core.h) on the CPU: tests/emu/lanes_emu.cpp compiles
-the kernel's own source against the SIMT emulator of rb_simt.h (32 host threads per warp; cp.async copies land only
+the kernel's own source against the SIMT emulator of rb_simt.h (32 fibers per warp; cp.async copies land only
 at their wait_group and poison their destination when issued) and this file holds it bit for bit against the
 oracle: per-stream outputs from the literal pull iterators, summed with the kernel's documented reduction tree.
 CPU only -- the GPU counterpart is tests/test_parity_gpu.py::test_lanes_*."""
@@ -506,3 +506,13 @@ def test_gain_in_front_of_the_conversion(emu):
     pcms = [noise(ci * (700 + 9 * i), 950 + i) for i, ci in enumerate(ch_in)]
     check(emu, pcms, [44100, 48000, 22050] * 4, 48000, [0] * 12, channels=2, ch_in=ch_in, pre=[0.5 + 0.1 * i for i in range(12)])
     check(emu, pcms, 48000, 48000, [3 * i for i in range(12)], hp=300, channels=2, ch_in=ch_in, pre=0.9)
+
+
+@pytest.mark.parametrize("what,seed,cases", [("batches", 11, 40), ("sessions", 12, 15)])
+def test_randomised_soak(emu, what, seed, cases):
+    """tests/emu/stress.py: random mixers, rate pairs (up and down), mono / stereo / mono-in-stereo sources, ragged lengths and
+    starts, chain variants with and without a gain in front -- every case bit for bit against the oracle.  (Hundreds of cases
+    per seed run in a minute from the command line; the suite keeps one short seed of each kind.)"""
+    sys.path[:0] = [os.path.join(HERE, "emu")]
+    import stress
+    assert getattr(stress, what)(seed, cases) == 0

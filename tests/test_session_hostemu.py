@@ -25,7 +25,7 @@ def hostemu(built):
 
 @pytest.mark.parametrize("scenario", ["errors", "mono_random_split", "mixed_with_state_blob", "held_queue_gain_speed", "gain_changes",
                                       "filtered_and_plain", "batch_with_identity_conversions",
-                                      "batch_unsorted_starts", "gain_in_front"])
+                                      "batch_unsorted_starts", "gain_in_front", "random:5"])
 def test_session_host_code_on_the_emulator(hostemu, scenario):
     t0 = time.time()
     r = subprocess.run([sys.executable, os.path.join(EMU, "session_scenarios.py"), scenario], capture_output=True, text=True, timeout=900)
@@ -86,15 +86,17 @@ def test_plain_c_example_runs_on_the_emulator(hostemu):
     assert frames == 2880 and 0.3 < peak < 0.9, r.stdout      # 6 x 10 ms at 48 kHz; 0.8 * 0.5 low-passed music + 0.25 voice
 
 
-def test_oracle_only_gpu_session_tests_hold_on_the_emulator(hostemu):
-    """The GPU session tests that need nothing but the session and the oracle, run unchanged against the host-emulated library
-    (their expectations are then known to be right before they meet a device)."""
+def test_gpu_lane_and_session_tests_hold_on_the_emulator(hostemu):
+    """Every GPU test of the lane kernel and of the sessions that needs nothing but the C ABI and the oracle, run unchanged
+    against the host-emulated library -- their expectations are known to be right before they meet a device.  (Left out: the
+    two tests that compare with the default kernels, which exist on the device only.)"""
     code = ("import os, sys; sys.path[:0] = [%r, %r]; import rodio_b200._capi as c; c.LIB_PATH = %r; import pytest; "
             "sys.exit(pytest.main([%r, '-q', '-m', 'gpu', '-x', '-p', 'no:cacheprovider', '-k', "
-            "'test_session_rejects or test_session_speed or test_session_queue_of_sources']))"
+            "'(test_lanes or test_session) and not fallback and not full_size']))"
             % (ROOT, HERE, hostemu, os.path.join(HERE, "test_parity_gpu.py")))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, cwd=ROOT)
-    assert r.returncode == 0 and "3 passed" in r.stdout, (r.stdout + r.stderr)[-3000:]
+    assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, (r.stdout + r.stderr)[-3000:]
+    assert int(r.stdout.rsplit(" passed", 1)[0].split()[-1]) >= 26, r.stdout[-500:]
 
 
 def test_cpp_live_mixer_on_the_emulator(hostemu):
