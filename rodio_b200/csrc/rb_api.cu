@@ -958,13 +958,13 @@ struct rb_session {
     // per-source arrays below are in CLASS ORDER (stable partition by rate pair); pos[] maps the caller's index to it.
     struct Class {
         uint32_t first = 0, count = 0, ch_in = 1;
-        bool has_biquad = false, ff2 = false, has_pre = false;
+        bool has_biquad = false, ff2 = false, has_pre = false, front = false;
     };
     std::vector<Class> classes;
     std::vector<uint32_t> pos;
     std::vector<session::Stream> st;
     std::vector<float> coef;      // 5 per stream
-    std::vector<float> ffk, post, pre;
+    std::vector<float> ffk, post, pre, mid;
     uint64_t T = 0;               // mixer frames rendered so far
     uint32_t fifo_cap = 0, max_block = 0;
     uint64_t stride = 0;          // floats per stream in a FIFO arena
@@ -1006,7 +1006,8 @@ extern "C" rb_status rb_session_create(rb_context* ctx, uint16_t mixer_channels,
     const size_t n = n_streams;
     // pass 1: validate, find every source's reduced rate pair -> classes
     std::vector<uint32_t> from(n), to(n), chs(n), first_fx(n), key(n);
-    std::vector<float> pre_of(n, 1.0f);
+    std::vector<float> pre_of(n, 1.0f), mid_of(n, 1.0f);
+    std::vector<uint32_t> front_fx(n, 0xFFFFFFFFu), front_rate(n, 0);
     for (size_t i = 0; i < n; i++) {
         const rb_stream_desc& d = descs[i];
         const std::string where = "stream " + std::to_string(i) + ": ";
@@ -1020,21 +1021,29 @@ extern "C" rb_status rb_session_create(rb_context* ctx, uint16_t mixer_channels,
         // one Source::amplify there -- `source.amplify(v)` handed to Mixer::add -- scales every frame before it is interpolated
         // (src/source/amplify.rs:91-95).  The two commute: one touches the samples, the other the reported rate.
         uint32_t k0 = 0, rate = d.sample_rate;
-        bool has_pre = false;
+        bool has_pre = false, has_mid = false, front = false;
+        // A filter there as well -- `source.low_pass(f)` handed to the mixer, or appended to a Player, which keeps its volume
+        // behind it (src/player.rs:120-128) -- runs at the rate its input reports at that point (src/source/blt.rs:
+        // to_applier(input.sample_rate())), once per input frame; one gain in front of it, one behind.
         while (k0 < d.n_effects) {
-            if (d.effects[k0].kind == RB_FX_SPEED) rate = rb_speed_sample_rate(rate, d.effects[k0].f32[0]);
-            else if (d.effects[k0].kind == RB_FX_AMPLIFY && !has_pre) has_pre = true, pre_of[i] = d.effects[k0].f32[0];
+            const rb_effect& e = d.effects[k0];
+            if (e.kind == RB_FX_SPEED) rate = rb_speed_sample_rate(rate, e.f32[0]);
+            else if (e.kind == RB_FX_AMPLIFY && !front && !has_pre) has_pre = true, pre_of[i] = e.f32[0];
+            else if (e.kind == RB_FX_AMPLIFY && front && !has_mid) has_mid = true, mid_of[i] = e.f32[0];
+            else if ((e.kind == RB_FX_LOW_PASS || e.kind == RB_FX_HIGH_PASS) && !front) front = true, front_fx[i] = k0, front_rate[i] = rate;
             else break;
             k0++;
         }
         first_fx[i] = k0;
         if (k0 >= d.n_effects || d.effects[k0].kind != RB_FX_UNIFORM || d.effects[k0].u32[0] != mixer_channels || d.effects[k0].u32[1] != mixer_rate)
-            return fail(RB_ERR_UNSUPPORTED, where + "the chain must be [SPEED | one AMPLIFY] UNIFORM(mixer channels, mixer rate) ...");
+            return fail(RB_ERR_UNSUPPORTED, where + "the chain must be [SPEED | AMPLIFY | one filter] UNIFORM(mixer channels, mixer rate) ...");
         const uint32_t g = std::gcd(rate, mixer_rate);
         from[i] = rate / g, to[i] = mixer_rate / g;
         const bool filtered = k0 + 1 < d.n_effects && (d.effects[k0 + 1].kind == RB_FX_LOW_PASS || d.effects[k0 + 1].kind == RB_FX_HIGH_PASS);
-        // filtered / unfiltered sources and sources with / without a gain in front are classes of their own
-        key[i] = d.channels | (filtered ? 0x100u : 0u) | (has_pre ? 0x200u : 0u);
+        if (front && filtered) return fail(RB_ERR_UNSUPPORTED, where + "one filter per source: in front of the conversion or behind it");
+        // filtered / unfiltered sources, sources with / without a gain in front and sources whose filter sits in front are
+        // classes of their own (a filter in front always applies the gains around it: no class of its own for those)
+        key[i] = d.channels | (filtered ? 0x100u : 0u) | (has_pre && !front ? 0x200u : 0u) | (front ? 0x400u : 0u);
         if (from[i] > (1u << 20) || to[i] > (1u << 20))
             return fail(RB_ERR_RATIO_OVERFLOW, where + "reduced rate pair beyond 2^20");
     }
@@ -1044,12 +1053,13 @@ extern "C" rb_status rb_session_create(rb_context* ctx, uint16_t mixer_channels,
     for (const auto& cls : classes) {
         rb_session::Class c;
         c.first = (uint32_t)order.size(), c.count = (uint32_t)cls.size(), c.ch_in = chs[cls[0]];
-        c.has_biquad = (key[cls[0]] & 0x100u) != 0, c.has_pre = (key[cls[0]] & 0x200u) != 0;
+        c.front = (key[cls[0]] & 0x400u) != 0;
+        c.has_biquad = (key[cls[0]] & 0x100u) != 0 || c.front, c.has_pre = (key[cls[0]] & 0x200u) != 0;
         for (uint32_t i : cls) s->pos[i] = (uint32_t)order.size(), order.push_back(i);
         s->classes.push_back(c);
     }
     // pass 2: chains, in class order
-    s->st.resize(n), s->coef.assign(5 * n, 0.0f), s->ffk.assign(n, 0.0f), s->post.assign(n, 1.0f), s->pre.assign(n, 1.0f), s->src_ch.assign(n, 1);
+    s->st.resize(n), s->coef.assign(5 * n, 0.0f), s->ffk.assign(n, 0.0f), s->post.assign(n, 1.0f), s->pre.assign(n, 1.0f), s->mid.assign(n, 1.0f), s->src_ch.assign(n, 1);
     bool any_biquad = false;
     std::vector<uint8_t> row_ff2(n, 1);
     for (size_t r = 0; r < n; r++) {
@@ -1057,8 +1067,17 @@ extern "C" rb_status rb_session_create(rb_context* ctx, uint16_t mixer_channels,
         const rb_stream_desc& d = descs[i];
         const std::string where = "stream " + std::to_string(i) + ": ";
         uint32_t k = first_fx[i] + 1;   // behind [SPEED | AMPLIFY] UNIFORM
-        s->pre[r] = pre_of[i];
+        s->pre[r] = pre_of[i], s->mid[r] = mid_of[i];
         bool biq = false;
+        if (front_fx[i] != 0xFFFFFFFFu) {
+            const rb_effect& e = d.effects[front_fx[i]];
+            if (e.u32[0] == 0 || !(e.f32[0] > 0.0f)) return fail(RB_ERR_INVALID_ARGUMENT, where + "filter frequency and q must be positive");
+            const hostmath::Blt c = hostmath::blt(e.kind == RB_FX_HIGH_PASS, e.u32[0], e.f32[0], front_rate[i]);
+            float* co = &s->coef[5 * r];
+            co[0] = c.b0, co[1] = c.b1, co[2] = c.b2, co[3] = c.a1, co[4] = c.a2;
+            row_ff2[r] = 0, biq = true;
+            s->st[r].front = true;
+        }
         if (k < d.n_effects && (d.effects[k].kind == RB_FX_LOW_PASS || d.effects[k].kind == RB_FX_HIGH_PASS)) {
             const rb_effect& e = d.effects[k];
             if (e.u32[0] == 0 || !(e.f32[0] > 0.0f)) return fail(RB_ERR_INVALID_ARGUMENT, where + "filter frequency and q must be positive");
@@ -1070,7 +1089,7 @@ extern "C" rb_status rb_session_create(rb_context* ctx, uint16_t mixer_channels,
         }
         any_biquad |= biq;
         if (k < d.n_effects && d.effects[k].kind == RB_FX_AMPLIFY) s->post[r] = d.effects[k].f32[0], s->has_post = true, k++;
-        if (k != d.n_effects) return fail(RB_ERR_UNSUPPORTED, where + "chain shape: [SPEED | one AMPLIFY] UNIFORM [LOW_PASS | HIGH_PASS] [AMPLIFY]");
+        if (k != d.n_effects) return fail(RB_ERR_UNSUPPORTED, where + "chain shape: [SPEED | AMPLIFY | one filter] UNIFORM [LOW_PASS | HIGH_PASS] [AMPLIFY]");
         s->st[r].mix_start = d.mix_start, s->st[r].from = from[i], s->st[r].to = to[i];
         if (d.mix_start == RB_SESSION_HELD) s->st[r].held = true, s->st[r].mix_start = 0;   // Mixer::add comes later (rb_session_start)
         s->src_ch[r] = (uint8_t)d.channels;
@@ -1224,9 +1243,10 @@ extern "C" rb_status rb_session_render(rb_session* s, float* out_host, uint64_t 
         row.n_int = p.n_int, row.o0 = p.o0, row.i0 = s->st[r].i0, row.state = s->d_state + 4 * C * r;
         const float* co = &s->coef[5 * r];
         row.b0 = co[0], row.b1 = co[1], row.b2 = co[2], row.a1 = co[3], row.a2 = co[4], row.ffk = s->ffk[r];
-        row.post = s->post[r], row.pre = s->pre[r];
+        row.post = s->post[r], row.pre = s->pre[r], row.mid = s->mid[r];
         row.flags = p.continues ? lanes::ROW_CONTINUES : 0u;
-        if (!lanes::pre_gain_keeps_class(row.pre)) row.flags |= lanes::ROW_FORCE_SLOW;
+        if (s->st[r].front) row.f0 = s->st[r].fpos - s->st[r].i0;
+        else if (!lanes::pre_gain_keeps_class(row.pre)) row.flags |= lanes::ROW_FORCE_SLOW;
     }
     RB_CUDA(cudaMemcpyAsync(s->d_rows, s->h_rows, ns * sizeof(lanes::Row), cudaMemcpyHostToDevice, stq));
     const uint64_t pstride = lanes::round_up_tile((uint64_t)s->max_block * C);
@@ -1240,7 +1260,7 @@ extern "C" rb_status rb_session_render(rb_session* s, float* out_host, uint64_t 
         lanes::fill_ratio(a, s->st[c.first].from, s->st[c.first].to, C);
         a.mix_len = n, a.pstride = pstride;
         a.partial = s->d_partial + (size_t)g0 * pstride, a.zeros = s->d_zeros, a.unsafe = s->d_flags + c.first;
-        RB_CUDA(rb_lanes_launch_kernel(a, c.ch_in, C, c.has_biquad, c.ff2, s->has_post, c.has_pre, stq));
+        RB_CUDA(rb_lanes_launch_kernel(a, c.ch_in, C, c.has_biquad, c.ff2, s->has_post, c.has_pre, c.front, stq));
         g0 += a.n_groups;
     }
     RB_CUDA(rb_lanes_launch_sum(s->d_partial, n_groups_total, pstride, n * C, s->d_out, stq));
@@ -1275,7 +1295,7 @@ struct SessionBlobHeader {
 struct SessionBlobStream {   // in class order (the same descriptors give the same order)
     uint64_t mix_start, pushed, out_done, i0;
     uint32_t from, to;
-    uint32_t eof, unsafe, fill, pad_;   // fill in frames
+    uint32_t eof, unsafe, fill, filter_ahead;   // fill in frames; filter_ahead = fpos - i0 of a filter in front of the conversion
     float state[8];                      // 4 per channel
 };
 constexpr uint32_t SESSION_MAGIC = 0x52425353u;   // "RBSS"
@@ -1296,7 +1316,7 @@ extern "C" rb_status rb_session_get_state(rb_session* s, void* buf, uint64_t cap
     RB_CUDA(cudaMemcpyAsync(state.data(), s->d_state, 4 * C * ns * sizeof(float), cudaMemcpyDeviceToHost, s->ctx->stream));
     RB_CUDA(cudaMemcpyAsync(flags.data(), s->d_flags, ns * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->ctx->stream));
     uint8_t* p = (uint8_t*)buf;
-    SessionBlobHeader h{SESSION_MAGIC, 3u, (uint32_t)ns, s->has_biquad ? 1u : 0u, C, 0u, s->T};
+    SessionBlobHeader h{SESSION_MAGIC, 4u, (uint32_t)ns, s->has_biquad ? 1u : 0u, C, 0u, s->T};
     memcpy(p, &h, sizeof(h)), p += sizeof(h);
     uint8_t* recs = p;
     p += ns * sizeof(SessionBlobStream);
@@ -1308,7 +1328,7 @@ extern "C" rb_status rb_session_get_state(rb_session* s, void* buf, uint64_t cap
     RB_CUDA(cudaStreamSynchronize(s->ctx->stream));
     for (size_t r = 0; r < ns; r++) {
         const session::Stream& st = s->st[r];
-        SessionBlobStream b{st.mix_start, st.pushed, st.out_done, st.i0, st.from, st.to, st.eof ? 1u : 0u, flags[r], (uint32_t)st.fill(), 0u, {0}};
+        SessionBlobStream b{st.mix_start, st.pushed, st.out_done, st.i0, st.from, st.to, st.eof ? 1u : 0u, flags[r], (uint32_t)st.fill(), st.front ? (uint32_t)(st.fpos - st.i0) : 0u, {0}};
         for (uint32_t k = 0; k < 4 * C; k++) b.state[k] = state[4 * C * r + k];
         memcpy(recs + r * sizeof(b), &b, sizeof(b));
     }
@@ -1323,7 +1343,7 @@ extern "C" rb_status rb_session_set_state(rb_session* s, const void* buf, uint64
     if (size < sizeof(h)) return fail(RB_ERR_INVALID_ARGUMENT, "state blob truncated");
     memcpy(&h, p, sizeof(h)), p += sizeof(h);
     const uint32_t C = s->channels;
-    if (h.magic != SESSION_MAGIC || h.version != 3u) return fail(RB_ERR_INVALID_ARGUMENT, "not a session state blob");
+    if (h.magic != SESSION_MAGIC || h.version != 4u) return fail(RB_ERR_INVALID_ARGUMENT, "not a session state blob");
     if (h.n_streams != ns || h.has_biquad != (s->has_biquad ? 1u : 0u) || h.channels != C)
         return fail(RB_ERR_INVALID_ARGUMENT, "state blob belongs to a session of another shape");
     if (size < sizeof(h) + ns * sizeof(SessionBlobStream)) return fail(RB_ERR_INVALID_ARGUMENT, "state blob truncated");
@@ -1333,7 +1353,8 @@ extern "C" rb_status rb_session_set_state(rb_session* s, const void* buf, uint64
     for (size_t r = 0; r < ns; r++) {
         const SessionBlobStream& b = recs[r];
         if (b.from != s->st[r].from || b.to != s->st[r].to) return fail(RB_ERR_INVALID_ARGUMENT, "state blob belongs to a session of another shape");
-        if (b.fill > s->fifo_cap || b.pushed - b.i0 != b.fill || (b.i0 & 3u)) return fail(RB_ERR_INVALID_ARGUMENT, "state blob: FIFO record out of range");
+        if (b.fill > s->fifo_cap || b.pushed - b.i0 != b.fill || (b.i0 & 3u) || b.filter_ahead > b.fill)
+            return fail(RB_ERR_INVALID_ARGUMENT, "state blob: FIFO record out of range");
         need += (uint64_t)b.fill * s->src_ch[r] * sizeof(float);
     }
     if (size < need) return fail(RB_ERR_INVALID_ARGUMENT, "state blob truncated");
@@ -1343,7 +1364,7 @@ extern "C" rb_status rb_session_set_state(rb_session* s, const void* buf, uint64
     for (size_t r = 0; r < ns; r++) {
         const SessionBlobStream& b = recs[r];
         session::Stream& st = s->st[r];
-        st.mix_start = b.mix_start, st.pushed = b.pushed, st.out_done = b.out_done, st.i0 = b.i0, st.eof = b.eof != 0;
+        st.mix_start = b.mix_start, st.pushed = b.pushed, st.out_done = b.out_done, st.i0 = b.i0, st.eof = b.eof != 0, st.fpos = b.i0 + b.filter_ahead;
         flags[r] = b.unsafe;
         for (uint32_t k = 0; k < 4 * C; k++) state[4 * C * r + k] = b.state[k];
         const size_t fill_floats = (size_t)b.fill * s->src_ch[r];

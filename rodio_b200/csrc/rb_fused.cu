@@ -1163,9 +1163,9 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     if (n_streams == 0 || mix_len == 0) return cudaSuccess;
     if (flags & (RB_MIX_EXACT_ORDER | RB_BIQUAD_TIME_PARALLEL)) return cudaSuccess;   // served by the general path
     std::vector<FusedRow> rows(n_streams);
-    uint32_t n_pre = 0, n_mid = 0, n_post = 0, has_u = 0, has_b = 0;
+    uint32_t n_pre = 0, n_mid = 0, n_post = 0, has_u = 0, has_b = 0, front = 0;
     bool mixed_u = false;   // some rows lost an identity conversion: only the lane kernel may take such a batch
-    if (!fused_parse_rows(streams, n_streams, mixer_channels, rows, n_pre, n_mid, n_post, has_u, has_b, mixed_u)) return cudaSuccess;
+    if (!fused_parse_rows(streams, n_streams, mixer_channels, rows, n_pre, n_mid, n_post, has_u, has_b, mixed_u, front)) return cudaSuccess;
     if (has_b && (uint32_t)mixer_channels * 1u > 32u) return cudaSuccess;
 
     // Plain mixer of f32 sources at the mixer's own rate/channels (BASELINE cfg2): nothing to fuse -- the ordered
@@ -1179,7 +1179,7 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     plan->all_f32 = true;
     for (size_t i = 0; i < n_streams; i++) plan->all_f32 = plan->all_f32 && streams[i].fmt == RB_FMT_F32;
     {
-        cudaError_t e = fused_lanes_hook(rows, n_streams, mixer_channels, plan->all_f32, n_pre, n_mid, n_post, has_u, has_b, flags, sm_count,
+        cudaError_t e = fused_lanes_hook(rows, n_streams, mixer_channels, plan->all_f32, n_pre, n_mid, n_post, has_u, has_b, front, flags, sm_count,
                                          d_out, mix_len, st, &plan->lanes);
         if (e != cudaSuccess) {
             delete plan;

@@ -46,9 +46,12 @@ static const rb_node_dev& node_at(const rb_fused_stream& s, uint32_t i) {
 }
 
 // Parse one stream into a FusedRow; returns false when its chain is outside the fused shape.
+// front = 1: the biquad sits in front of the conversion (`source.low_pass(f)` handed to the mixer): pre = gains in front of the
+// filter, mid = gains between the filter and the conversion, post = gains behind the conversion.
 static bool parse_row(const rb_fused_stream& s, uint16_t mixer_ch, FusedRow& r, uint32_t& n_pre, uint32_t& n_mid,
-                      uint32_t& n_post, uint32_t& has_uniform, uint32_t& has_biquad) {
+                      uint32_t& n_post, uint32_t& has_uniform, uint32_t& has_biquad, uint32_t& front) {
     memset(&r, 0, sizeof(r));
+    front = 0;
     r.in = s.in, r.n_in = s.n_in, r.out_len = s.out_len, r.mix_start = s.mix_start;
     r.fmt = s.fmt, r.c_in = s.c_in;
     n_pre = n_mid = n_post = has_uniform = has_biquad = 0;
@@ -72,7 +75,12 @@ static bool parse_row(const rb_fused_stream& s, uint16_t mixer_ch, FusedRow& r, 
                 }
                 break;
             case RB_N_UNIFORM:
-                if (has_uniform || has_biquad) return false;
+                if (has_uniform) return false;
+                if (has_biquad) {   // what was collected behind the filter sits between it and the conversion
+                    front = 1;
+                    for (uint32_t g = 0; g < n_post; g++) r.mid[g] = r.post[g], r.post[g] = 0.0f;
+                    n_mid = n_post, n_post = 0;
+                }
                 has_uniform = 1;
                 r.uni = nd.p.uni;
                 if (nd.c_in != s.c_in) return false;
@@ -123,18 +131,37 @@ static bool parse_row(const rb_fused_stream& s, uint16_t mixer_ch, FusedRow& r, 
 // planner, so such a row has no uniform node where its neighbours have one -- `mixed_u` then tells that only kernels
 // which treat rows individually (the lane kernel) may take the batch.  Returns false when the batch is outside the family.
 static bool fused_parse_rows(const rb_fused_stream* streams, size_t n_streams, uint16_t mixer_channels, std::vector<FusedRow>& rows,
-                             uint32_t& n_pre, uint32_t& n_mid, uint32_t& n_post, uint32_t& has_u, uint32_t& has_b, bool& mixed_u) {
-    n_pre = n_mid = n_post = has_u = has_b = 0;
+                             uint32_t& n_pre, uint32_t& n_mid, uint32_t& n_post, uint32_t& has_u, uint32_t& has_b, bool& mixed_u,
+                             uint32_t& front) {
+    n_pre = n_mid = n_post = has_u = has_b = front = 0;
     mixed_u = false;
+    struct Shape { uint32_t p, m, q, u, b, f; };
+    std::vector<Shape> sh(n_streams);
     for (size_t i = 0; i < n_streams; i++) {
-        uint32_t p, m, q, u, b;
-        if (!parse_row(streams[i], mixer_channels, rows[i], p, m, q, u, b)) return false;
-        if (i == 0) n_pre = p, n_mid = m, n_post = q, has_u = u, has_b = b;
-        else if (p != n_pre || m != n_mid || q != n_post || b != has_b) return false;
-        else if (u != has_u) mixed_u = true, has_u = 1;
+        Shape& k = sh[i];
+        if (!parse_row(streams[i], mixer_channels, rows[i], k.p, k.m, k.q, k.u, k.b, k.f)) return false;
+        if (k.f && !front) front = 1, n_mid = k.m;   // n_mid: how many gains the batch has between filter and conversion
+    }
+    const uint32_t m_front = n_mid;
+    for (size_t i = 0; i < n_streams; i++) {
+        Shape& k = sh[i];
+        // a filtered row without a conversion (it is in the mixer's format already) beside rows whose filter sits in front of
+        // theirs: its filter is "in front" just as well -- the first gains behind it file as `mid` like theirs, the rest as `post`
+        if (front && !k.f && !k.u && k.b && k.q >= m_front) {
+            FusedRow& r = rows[i];
+            for (uint32_t g = 0; g < m_front; g++) r.mid[g] = r.post[g];
+            for (uint32_t g = m_front; g < k.q; g++) r.post[g - m_front] = r.post[g];
+            for (uint32_t g = k.q - m_front; g < k.q; g++) r.post[g] = 0.0f;
+            k.m = m_front, k.q -= m_front, k.f = 1;
+        }
+        if (i == 0) n_pre = k.p, n_mid = k.m, n_post = k.q, has_u = k.u, has_b = k.b;
+        else if (k.p != n_pre || k.m != n_mid || k.q != n_post || k.b != has_b) return false;
+        else if (k.u != has_u) mixed_u = true, has_u = 1;
+        if (k.f != front) return false;
     }
     // with gains in front of the biquad the two row kinds file them differently (pre / mid): not the same shape after all
-    if (mixed_u && (n_pre || n_mid)) return false;
+    if (mixed_u && !front && (n_pre || n_mid)) return false;
+    if (front) mixed_u = true;   // only the lane kernel knows a filter in front of the conversion
     return true;
 }
 
@@ -142,8 +169,8 @@ static bool fused_parse_rows(const rb_fused_stream* streams, size_t n_streams, u
 // is the faster kernel anyway (measured: 65 536 x 1 s in 4.26 ms against 7.0 ms for k_fused_hot, 16 384 x 1 s in 2.46 ms
 // against 1.74 ms).  *lanes stays NULL when the shape is not the kernel's.
 static cudaError_t fused_lanes_hook(const std::vector<FusedRow>& rows, size_t n_streams, uint16_t mixer_channels, bool all_f32,
-                                    uint32_t n_pre, uint32_t n_mid, uint32_t n_post, uint32_t has_u, uint32_t has_b, uint32_t flags,
-                                    int sm_count, float* d_out, uint64_t mix_len, cudaStream_t st, rb_lanes_plan** lanes) {
+                                    uint32_t n_pre, uint32_t n_mid, uint32_t n_post, uint32_t has_u, uint32_t has_b, uint32_t front,
+                                    uint32_t flags, int sm_count, float* d_out, uint64_t mix_len, cudaStream_t st, rb_lanes_plan** lanes) {
     *lanes = nullptr;
     const bool want_lanes = (flags & RB_FUSED_LANES) || n_streams >= (size_t)277 * (size_t)(sm_count > 0 ? sm_count : 148);
     if (!(want_lanes && (mixer_channels == 1 || mixer_channels == 2) && all_f32 && (has_u || has_b) && n_pre <= 1)) return cudaSuccess;
@@ -151,7 +178,8 @@ static cudaError_t fused_lanes_hook(const std::vector<FusedRow>& rows, size_t n_
     // rate pair), at most one gain in front of the conversion (source.amplify(v) handed to the mixer), optional biquad, at most
     // one gain directly in front of the sum.
     const uint32_t C = mixer_channels;
-    const bool shape = has_b ? (n_mid == 0 && n_post <= 1) : (n_mid + n_post <= 1);
+    // front: [gain] filter [gain] conversion [gain]
+    const bool shape = front ? (has_b && n_mid <= 1 && n_post <= 1) : (has_b ? (n_mid == 0 && n_post <= 1) : (n_mid + n_post <= 1));
     if (!shape || mix_len % C != 0) return cudaSuccess;
     std::vector<rb_lanes_stream> ls(n_streams);
     for (size_t i = 0; i < n_streams; i++) {
@@ -169,9 +197,10 @@ static cudaError_t fused_lanes_hook(const std::vector<FusedRow>& rows, size_t n_
         l.in = (const float*)r.in, l.n_frames = r.uni.tail.L, l.out_len = r.out_len / C, l.mix_start = r.mix_start / C;
         l.from = pass ? 1u : r.uni.from, l.to = pass ? 1u : r.uni.to;
         l.b0 = r.b0, l.b1 = r.b1, l.b2 = r.b2, l.a1 = r.a1, l.a2 = r.a2;
-        l.post = n_post ? r.post[0] : (n_mid ? r.mid[0] : 1.0f);
+        l.post = n_post ? r.post[0] : (n_mid && !front ? r.mid[0] : 1.0f);
         l.pre = n_pre ? r.pre[0] : 1.0f;
+        l.mid = front && n_mid ? r.mid[0] : 1.0f;
     }
-    return rb_lanes_try_create(ls.data(), n_streams, C, has_b != 0, (n_mid + n_post) != 0, n_pre != 0, d_out, mix_len / C, sm_count, st,
-                               lanes);
+    return rb_lanes_try_create(ls.data(), n_streams, C, has_b != 0, front ? n_post != 0 : (n_mid + n_post) != 0, n_pre != 0, front != 0, d_out,
+                               mix_len / C, sm_count, st, lanes);
 }

@@ -18,6 +18,7 @@ struct rb_lanes_stream {
     float b0, b1, b2, a1, a2;
     float post;
     float pre;             // gain in front of the conversion (has_pre)
+    float mid;             // front: gain between the filter and the conversion
 };
 
 struct rb_lanes_plan;
@@ -26,7 +27,7 @@ struct rb_lanes_plan;
 // mix_len in frames; `d_out` holds mix_len * channels floats.  Streams with different rate pairs are served class by
 // class (rb_lanes_plan.h classes_by_ratio): the mixer sum then groups by class first.
 cudaError_t rb_lanes_try_create(const rb_lanes_stream* streams, size_t n_streams, uint32_t channels, bool has_biquad, bool has_post,
-                                bool has_pre, float* d_out, uint64_t mix_len, int sm_count, cudaStream_t st, rb_lanes_plan** out);
+                                bool has_pre, bool front, float* d_out, uint64_t mix_len, int sm_count, cudaStream_t st, rb_lanes_plan** out);
 // Inputs were (re)written: classify them again before the next render.
 void rb_lanes_inputs_changed(rb_lanes_plan* p);
 cudaError_t rb_lanes_run(rb_lanes_plan* p, cudaStream_t st);
@@ -37,7 +38,7 @@ void rb_lanes_destroy(rb_lanes_plan* p);
 // k_fused_lanes over a.rows (one class: one rate pair -- a.from == a.to selects the pass-through variant --, ch_in channels
 // per stream, ch_out channels in the mixer) ...
 cudaError_t rb_lanes_launch_kernel(const lanes::Args& a, uint32_t ch_in, uint32_t ch_out, bool has_biquad, bool ff2, bool has_post,
-                                   bool has_pre, cudaStream_t st);
+                                   bool has_pre, bool front, cudaStream_t st);
 // ... and the ordered sum of n_groups partial rows (all classes) into d_out[0, n_floats).
 cudaError_t rb_lanes_launch_sum(const float* d_partial, uint32_t n_groups, uint64_t pstride, uint64_t n_floats, float* d_out,
                                 cudaStream_t st);

@@ -22,12 +22,12 @@ struct rb_lanes_plan {
     uint8_t* d_row_channels = nullptr;   // [n_rows], class order: interleaved channels of every stream
     uint32_t n_rows = 0, n_groups_total = 0, channels = 1;   // channels: of the mixer
     uint64_t pstride = 0, mix_len = 0;
-    bool has_biquad = false, has_post = false, has_pre = false;
+    bool has_biquad = false, has_post = false, has_pre = false, front = false;
     bool classified = false;
 };
 
 cudaError_t rb_lanes_try_create(const rb_lanes_stream* streams, size_t n_streams, uint32_t channels, bool has_biquad, bool has_post,
-                                bool has_pre, float* d_out, uint64_t mix_len, int sm_count, cudaStream_t st, rb_lanes_plan** out) {
+                                bool has_pre, bool front, float* d_out, uint64_t mix_len, int sm_count, cudaStream_t st, rb_lanes_plan** out) {
     (void)sm_count;
     *out = nullptr;
     if (n_streams == 0 || n_streams > 0x7fffffffull || mix_len == 0 || (channels != 1 && channels != 2)) return cudaSuccess;
@@ -40,7 +40,7 @@ cudaError_t rb_lanes_try_create(const rb_lanes_stream* streams, size_t n_streams
     }
     const auto classes = lanes::classes_by_ratio(from.data(), to.data(), chs.data(), (uint32_t)n_streams);
     auto p = new rb_lanes_plan;
-    p->has_biquad = has_biquad, p->has_post = has_post, p->has_pre = has_pre, p->d_out = d_out, p->channels = channels;
+    p->has_biquad = has_biquad, p->has_post = has_post, p->has_pre = has_pre, p->front = front, p->d_out = d_out, p->channels = channels;
     p->n_rows = (uint32_t)n_streams, p->mix_len = mix_len, p->pstride = lanes::round_up_tile(mix_len * channels);
     std::vector<lanes::Row> rows;
     rows.reserve(n_streams);
@@ -64,8 +64,9 @@ cudaError_t rb_lanes_try_create(const rb_lanes_stream* streams, size_t n_streams
             r.b0 = s.b0, r.b1 = s.b1, r.b2 = s.b2, r.a1 = s.a1, r.a2 = s.a2;
             r.post = has_post ? s.post : 1.0f;
             r.pre = has_pre ? s.pre : 1.0f;
+            r.mid = front ? s.mid : 1.0f;
             r.flags = lanes::ROW_UNSAFE;   // until classified
-            if (has_pre && !lanes::pre_gain_keeps_class(r.pre)) r.flags |= lanes::ROW_FORCE_SLOW;
+            if (has_pre && !front && !lanes::pre_gain_keeps_class(r.pre)) r.flags |= lanes::ROW_FORCE_SLOW;
             float k = 0.0f;
             if (has_biquad && lanes::ff2_coeffs(r.b0, r.b1, r.b2, &k)) r.ffk = k;
             else c.ff2 = false;
@@ -110,7 +111,7 @@ cudaError_t rb_lanes_run(rb_lanes_plan* p, cudaStream_t st) {
         p->classified = true;
     }
     for (const auto& c : p->classes) {
-        cudaError_t e = rb_lanes_launch_kernel(c.args, c.ch_in, p->channels, p->has_biquad, c.ff2, p->has_post, p->has_pre, st);
+        cudaError_t e = rb_lanes_launch_kernel(c.args, c.ch_in, p->channels, p->has_biquad, c.ff2 && !p->front, p->has_post, p->has_pre, p->front, st);
         if (e != cudaSuccess) return e;
     }
     return rb_lanes_launch_sum(p->d_partial, p->n_groups_total, p->pstride, p->mix_len * p->channels, p->d_out, st);

@@ -86,7 +86,9 @@ struct Row {                 // one stream (whole, or the part of it one block o
     float post;              // the one gain behind the chain (NPOST == 1)
     float pre;               // PRE: the one gain in front of the conversion -- source.amplify(v) handed to the mixer, the
                              // usual rodio idiom -- applied to every input frame once, when it is fetched
+    float mid;               // FRONT: the gain between the filter and the conversion (Player keeps its volume there)
     uint32_t flags;
+    uint64_t f0;             // FRONT: frames of in[] the filter has consumed when the block starts (0 for a whole stream)
 };
 
 struct Args {
@@ -130,9 +132,18 @@ SIMT_FN float reduce_tile(const float (&v)[TILE], uint32_t ln) {
 // CI = 1, CO = 2: a mono source in a stereo mixer -- ChannelCountConverter repeats the sample on both channels
 // (src/conversions/channels.rs:57-85) and the two filter channels see the same input, so the lane computes the frame once
 // and emits it twice.
-template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS = false, bool PRE = false>
+//
+// FRONT: the biquad sits IN FRONT of the conversion -- `source.low_pass(f)` handed to Mixer::add or appended to a Player
+// (src/player.rs:120-128: user source -> pausable -> amplify -> mixer's UniformSourceIterator).  The filter then runs once per
+// INPUT frame, at the source's rate: frame * pre -> biquad -> * mid -> interpolation taps -> [* post].  The lane keeps the
+// filter exactly one frame ahead of the interpolation (it has consumed frames [0, i + 2) when the output with left frame i
+// is formed, or all L of them at the end), so the taps ARE y[n-2], y[n-1] (times `mid`) and no state is added.  Filter
+// outputs cannot be classified in advance, so the division of the fast tile is guarded per sample (|m| inside
+// [2^-100, 2^100) or zero: reciprocal step, else IEEE division).
+template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS = false, bool PRE = false, bool FRONT = false>
 SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
     static_assert(CI == CO || (CI == 1 && CO == 2), "channel layouts served");
+    static_assert(!FRONT || (HASB && !FF2 && !PRE), "FRONT: plain coefficients, the gain in front is always applied");
     using G = Geo<CI>;
     constexpr int C = CI;               // taps, ring and filter state follow the source's channels
     constexpr int TF = TILE / CO;       // frames per tile: the mixer timeline has CO samples per frame
@@ -145,13 +156,13 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
         row = a.rows[r];
     } else {
         row.in = a.zeros, row.L = 0, row.out_len = 0, row.mix_start = 0, row.n_int = 0, row.o0 = 0, row.i0 = 0, row.state = nullptr;
-        row.b0 = row.b1 = row.b2 = row.a1 = row.a2 = row.ffk = row.post = row.pre = 0.0f, row.flags = 0;
+        row.b0 = row.b1 = row.b2 = row.a1 = row.a2 = row.ffk = row.post = row.pre = row.mid = 0.0f, row.flags = 0, row.f0 = 0;
     }
     const uint64_t ms = row.mix_start, end = row.mix_start + row.out_len;   // frames
     // Down-sampling classes (from > to: more than one input frame per output) are served by the slow tiles only -- exact,
     // general, not fast; the fast run below assumes at most one new frame per step.
     const bool safe = has && a.from <= a.to && !(row.flags & ROW_FORCE_SLOW) &&
-                      (PASS || (!(row.flags & ROW_UNSAFE) && !(a.unsafe && a.unsafe[r])));
+                      (PASS || FRONT || (!(row.flags & ROW_UNSAFE) && !(a.unsafe && a.unsafe[r])));
     const bool stops = !(row.flags & ROW_CONTINUES);   // the stream ends inside this block (or is a whole stream)
     const bool live = has && row.out_len != 0;
     const uint64_t t_lo = simt::reduce_min64(live ? ms : ~0ull), t_hi = simt::reduce_max64(live ? end : 0ull);
@@ -161,8 +172,9 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
     float* const ringl = ring_warp + ln * RS;
     float* const prow = a.partial + (uint64_t)group * a.pstride;
     const float den = a.den_f, rcp = a.rcp_den, from_f = a.from_f, neg1 = a.neg1;
-    const float b0 = row.b0, b1 = row.b1, b2 = row.b2, a1 = row.a1, a2 = row.a2, ffk = row.ffk, post = row.post, gpre = row.pre;
+    const float b0 = row.b0, b1 = row.b1, b2 = row.b2, a1 = row.a1, a2 = row.a2, ffk = row.ffk, post = row.post, gpre = row.pre, gmid = row.mid;
     const uint32_t from = a.from, to = a.to;
+    uint64_t fpos = row.f0;   // FRONT: frames of in[] consumed by the filter
     // canonical filter state per channel: x[n-1], x[n-2], y[n-1], y[n-2]
     float xh1[C], xh2[C], y1[C], y2[C];
 #pragma unroll
@@ -175,6 +187,26 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
     const uint64_t o0 = row.o0, i0 = row.i0;
     const uint32_t cq = ln % QPC;                      // the quad of a chunk this lane copies ...
     const uint32_t cr = ln / QPC;                      // ... for stream cr + RPI * j of the warp
+    // FRONT: one step of the filter on input frame `raw` (src/source/blt.rs:397-410 on src/source/amplify.rs:91-95)
+    auto front_step = [&](const float (&raw)[C]) {
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const float x = simt::fmul(raw[c], gpre);
+            const float ff = simt::fadd(simt::fadd(simt::fmul(b0, x), simt::fmul(b1, xh1[c])), simt::fmul(b2, xh2[c]));
+            const float y = fb(a1, a2, ff, y1[c], y2[c], neg1);
+            xh2[c] = xh1[c], xh1[c] = x, y2[c] = y1[c], y1[c] = y;
+        }
+    };
+    // FRONT: let the filter consume in[fpos .. upto) from global memory (run starts, slow tiles)
+    auto front_catch_up = [&](uint64_t upto) {
+        while (fpos < upto) {
+            float raw[C];
+#pragma unroll
+            for (int c = 0; c < C; c++) raw[c] = simt::ldg(row.in + fpos * C + c);
+            front_step(raw);
+            fpos++;
+        }
+    };
 
     while (t < t_end) {
         // ---- how long does every lane stay "interior or idle" from t on? ----
@@ -191,8 +223,11 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
         } else {
             const uint64_t o = t - ms;
             d = 0;
-            if (safe && o + TF <= row.n_int) {
-                const uint64_t g = (row.n_int - o) / TF * TF;
+            // FRONT: the index step behind the last output of a run already feeds the NEXT frame to the filter, so that
+            // output must be an interpolating one as well (its right neighbour exists): the run stops one output short
+            const uint64_t n_fast = FRONT ? (row.n_int ? row.n_int - 1 : 0) : row.n_int;
+            if (safe && o + TF <= n_fast) {
+                const uint64_t g = (n_fast - o) / TF * TF;
                 d = g > RUN_CAP ? RUN_CAP : (uint32_t)g;
             }
         }
@@ -215,6 +250,7 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                 src = row.in + ibase * C;
                 const uint64_t mq = ((row.L * C - 1) >> 2) - ((ibase * C) >> 2);   // last quad (relative) that holds a frame
                 maxq = mq > 0x7fffffffull ? 0x7fffffffu : (uint32_t)mq;
+                if (FRONT) front_catch_up(i + 2);       // interior: i + 1 < L
             }
             // the streams this lane copies for: source pointer and clamp of stream cr + RPI * j
             uint64_t sq[QPC];
@@ -250,6 +286,7 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
             for (int c = 0; c < C; c++) {
                 x0[c] = simt::lds(simt::sptr_add(p, c)), x1[c] = simt::lds(simt::sptr_add(p, C + c));
                 if (PRE) x0[c] = simt::fmul(x0[c], gpre), x1[c] = simt::fmul(x1[c], gpre);
+                if (FRONT) x0[c] = simt::fmul(y2[c], gmid), x1[c] = simt::fmul(y1[c], gmid);   // the filter is one frame ahead
             }
             p = simt::sptr_add(p, 2 * C);
             float nf = simt::u2f(num);
@@ -287,17 +324,27 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                             // src/math.rs:24-26: first + (second - first) * num / den, the division as an exact reciprocal step
                             const float m = simt::fmul(simt::fsub(x1[c], x0[c]), nf);
                             const float q0 = simt::fmul(m, rcp);
-                            const float q = simt::ffma(simt::ffma(-q0, den, m), rcp, q0);
+                            float q = simt::ffma(simt::ffma(-q0, den, m), rcp, q0);
+                            if (FRONT && !simt::in_exact_quotient_class(m)) q = simt::fdiv(m, den), simt::emu_count(3, 1);   // filter tails: denormals
                             x[c] = simt::fadd(x0[c], q);
                         }
                     }
                     // next output frame: numerator += from (mod to); a carry moves one input frame on
-                    simt::lerp_advance<C, PRE>(nf, x0, x1, p, from_f, den, gpre);
+                    if (FRONT) {
+                        float raw[C];
+                        if (simt::lerp_carry<C>(nf, p, from_f, den, raw)) {
+                            front_step(raw);
+#pragma unroll
+                            for (int c = 0; c < C; c++) x0[c] = x1[c], x1[c] = simt::fmul(y1[c], gmid);
+                        }
+                    } else {
+                        simt::lerp_advance<C, PRE>(nf, x0, x1, p, from_f, den, gpre);
+                    }
                     float val[C];
 #pragma unroll
                     for (int c = 0; c < C; c++) {
                         float y = x[c];
-                        if (HASB) {
+                        if (HASB && !FRONT) {
                             float tt;
                             if (FF2) {
                                 // b1*x1 = ffk*(b0*x1) and b2*x2 = b0*x2 exactly: one product per sample, same roundings
@@ -334,6 +381,10 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
             simt::cp_wait<0>();
             simt::syncwarp();
             simt::emu_count(0, run / TF);
+            if (FRONT && act) {   // the taps are those of the output that follows the run: the filter is one frame ahead of them
+                const uint64_t prod = (o0 + (t + run - ms)) * (uint64_t)from;
+                fpos = prod / to - i0 + 2;
+            }
             t += run;
         } else {
             // =================================== SLOW TILE: per-lane closed form ===================================
@@ -353,11 +404,21 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
 #pragma unroll
                     for (int c = 0; c < C; c++) xh1[c] = xh2[c] = y1[c] = y2[c] = 0.f;
                 }
+                if (FRONT && on) front_catch_up(i + 2 < row.L ? i + 2 : row.L);
                 float val[C];
 #pragma unroll
                 for (int c = 0; c < C; c++) {
                     val[c] = 0.0f;
-                    if (on) {
+                    if (FRONT) {
+                        if (on) {
+                            // the filter has consumed frames [0, fpos): y1 = F[fpos - 1], y2 = F[fpos - 2]
+                            const bool two = fpos == i + 2;
+                            const float xa = simt::fmul(two ? y2[c] : y1[c], gmid);
+                            float x = xa;
+                            if (!PASS && two) x = simt::fadd(xa, simt::fdiv(simt::fmul(simt::fsub(simt::fmul(y1[c], gmid), xa), simt::u2f(num)), den));
+                            val[c] = NPOST ? simt::fmul(x, post) : x;
+                        }
+                    } else if (on) {
                         float xa = simt::ldg(row.in + i * C + c);
                         if (PRE) xa = simt::fmul(xa, gpre);
                         float x = xa;

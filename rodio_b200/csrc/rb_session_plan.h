@@ -11,7 +11,9 @@
 //     (o * from) mod to and floor(o * from / to)) and the input frames from that left frame on -- they stay in the
 //     stream's FIFO; an output is only rendered once its right neighbour has arrived, or the stream has ended (the
 //     last frame is then emitted raw, sample_rate.rs:187-199);
-//   * biquad: x[n-1], x[n-2], y[n-1], y[n-2] (src/source/blt.rs:397-410) -- four floats per stream on the device.
+//   * biquad: x[n-1], x[n-2], y[n-1], y[n-2] (src/source/blt.rs:397-410) -- four floats per stream on the device; a filter
+//     in FRONT of the conversion additionally has a position of its own in the input (Stream::fpos): it has consumed the
+//     right neighbour of the last output already, so its two last outputs are the interpolation taps.
 #pragma once
 #include <algorithm>
 #include <cstdint>
@@ -30,6 +32,8 @@ struct Stream {
                                // later): it takes pushes, renders nothing and holds nobody up until it is started
     int64_t follows = -1;      // held source that starts on the frame after source `follows` has played out -- the
                                // sources of a queue (src/queue.rs:128-192: the next sound begins where the current one ends)
+    bool front = false;        // the source's filter sits in front of the conversion and runs once per INPUT frame ...
+    uint64_t fpos = 0;         // ... it has consumed the frames [0, fpos) (stream-absolute): one frame ahead of the interpolation
     uint64_t fill() const { return pushed - i0; }   // frames in the FIFO
 };
 
@@ -119,8 +123,13 @@ inline void start(Stream& s, uint64_t T) {
 
 // After the block: advance the stream and tell how many FIFO frames (from the front) are dead.
 inline uint64_t advance(Stream& s, const Part& p) {
+    if (s.front && p.out_len) {   // the filter stands behind the right neighbour of the block's last output (or at the end)
+        const uint64_t ia = ((p.o0 + p.out_len - 1) * (uint64_t)s.from) / s.to;
+        s.fpos = std::min(ia + 2, s.pushed);
+    }
     s.out_done = p.out_len ? p.o0 + p.out_len : s.out_done;
-    const uint64_t left = std::min((s.out_done * (uint64_t)s.from) / s.to, s.pushed);   // left frame of the next output
+    uint64_t left = std::min((s.out_done * (uint64_t)s.from) / s.to, s.pushed);   // left frame of the next output
+    if (s.front) left = std::min(left, s.fpos);   // more than two input frames per output: the filter still needs the ones between
     const uint64_t keep_from = left & ~3ull;                                        // FIFO front stays 16-byte aligned
     const uint64_t drop = keep_from > s.i0 ? keep_from - s.i0 : 0;
     s.i0 += drop;

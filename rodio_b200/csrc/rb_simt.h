@@ -265,6 +265,26 @@ SIMT_FN void lerp_advance(float& nf, float (&x0)[C], float (&x1)[C], sptr& p, fl
         nf = nf2;
     }
 }
+// FRONT variant of the index step: only the numerator and the cursor; on a carry the next ring frame is returned raw.
+template <int C>
+SIMT_FN bool lerp_carry(float& nf, sptr& p, float from_f, float den, float (&raw)[C]) {
+    const float nf2 = nf + from_f;
+    const bool carry = nf2 >= den;
+    nf = carry ? nf2 - den : nf2;
+    if (carry) {
+        for (int c = 0; c < C; c++) raw[c] = p[c];
+        p += C;
+    }
+    return carry;
+}
+// m is zero or 2^-100 <= |m| < 2^100: the range in which q0 = m*r, q = fma(fma(-q0, den, m), r, q0) is the correctly
+// rounded m / den (rb_lanes_core.h, "Exact division")
+SIMT_FN bool in_exact_quotient_class(float m) {
+    uint32_t u;
+    std::memcpy(&u, &m, 4);
+    u &= 0x7fffffffu;
+    return u == 0u || (u - 0x0d800000u) < 0x64000000u;
+}
 // 16-byte asynchronous copy global -> shared (cp.async.cg.shared.global): lands at the matching cp_wait.
 SIMT_FN void cp16(float* smem_dst, const float* gsrc) {
     if (((uintptr_t)smem_dst & 15) || ((uintptr_t)gsrc & 15)) emu_fail("cp16: operands must be 16-byte aligned");
@@ -400,6 +420,22 @@ SIMT_FN void lerp_advance(float& nf, float (&x0)[C], float (&x1)[C], sptr& p, fl
             : "f"(from_f), "f"(den), "f"(gpre)
             : "memory");
     }
+}
+template <int C>
+SIMT_FN bool lerp_carry(float& nf, sptr& p, float from_f, float den, float (&raw)[C]) {
+    const float nf2 = __fadd_rn(nf, from_f);
+    const bool carry = nf2 >= den;
+    nf = carry ? __fsub_rn(nf2, den) : nf2;
+    if (carry) {
+#pragma unroll
+        for (int c = 0; c < C; c++) raw[c] = lds(sptr_add(p, c));
+        p = sptr_add(p, C);
+    }
+    return carry;
+}
+SIMT_FN bool in_exact_quotient_class(float m) {
+    const uint32_t u = __float_as_uint(m) & 0x7fffffffu;
+    return u == 0u || (u - 0x0d800000u) < 0x64000000u;
 }
 SIMT_FN void cp16(float* smem_dst, const float* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)

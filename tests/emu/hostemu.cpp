@@ -29,7 +29,7 @@ extern "C" void mock_cuda_unregister(void* p) {
 
 // ---- the lane kernel on the SIMT emulator (warp_variants.cpp) ----
 cudaError_t rb_lanes_launch_kernel(const lanes::Args& a, uint32_t ch_in, uint32_t ch_out, bool has_biquad, bool ff2, bool has_post,
-                                   bool has_pre, cudaStream_t) {
+                                   bool has_pre, bool front, cudaStream_t) {
     if (a.mix_len == 0 || a.n_groups == 0) return cudaSuccess;
     if (!((ch_in == 1 || ch_in == 2) && (ch_in == ch_out || (ch_in == 1 && ch_out == 2)))) return cudaErrorInvalidValue;
     simt::WarpEmu warp;
@@ -44,7 +44,7 @@ cudaError_t rb_lanes_launch_kernel(const lanes::Args& a, uint32_t ch_in, uint32_
     while ((uintptr_t)ring & 15) ring++;
     for (uint32_t g = 0; g < a.n_groups; g++) {
         for (int i = 0; i < 32 * MAX_RS; i++) ring[i] = nan;
-        emu_run_group(ch_in, ch_out, a, g, &warp, ring, has_biquad, ff2, has_post, has_pre);
+        emu_run_group(ch_in, ch_out, a, g, &warp, ring, has_biquad, ff2, has_post, has_pre, front);
     }
     return cudaSuccess;
 }
@@ -102,12 +102,12 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     *out = nullptr;
     if (n_streams == 0 || mix_len == 0 || (flags & (RB_MIX_EXACT_ORDER | RB_BIQUAD_TIME_PARALLEL))) return cudaSuccess;
     std::vector<FusedRow> rows(n_streams);
-    uint32_t n_pre = 0, n_mid = 0, n_post = 0, has_u = 0, has_b = 0;
+    uint32_t n_pre = 0, n_mid = 0, n_post = 0, has_u = 0, has_b = 0, front = 0;
     bool mixed_u = false, all_f32 = true;
-    if (!fused_parse_rows(streams, n_streams, mixer_channels, rows, n_pre, n_mid, n_post, has_u, has_b, mixed_u)) return cudaSuccess;
+    if (!fused_parse_rows(streams, n_streams, mixer_channels, rows, n_pre, n_mid, n_post, has_u, has_b, mixed_u, front)) return cudaSuccess;
     for (size_t i = 0; i < n_streams; i++) all_f32 = all_f32 && streams[i].fmt == RB_FMT_F32;
     rb_lanes_plan* lanes = nullptr;
-    cudaError_t e = fused_lanes_hook(rows, n_streams, mixer_channels, all_f32, n_pre, n_mid, n_post, has_u, has_b, flags, sm_count, d_out,
+    cudaError_t e = fused_lanes_hook(rows, n_streams, mixer_channels, all_f32, n_pre, n_mid, n_post, has_u, has_b, front, flags, sm_count, d_out,
                                      mix_len, st, &lanes);
     if (e != cudaSuccess || !lanes) return e;
     *out = new rb_fused_plan{lanes};
@@ -142,13 +142,13 @@ extern "C" int hostemu_lanes_batch(const float* const* pcm, const uint64_t* n_fr
         s.in = d_in[r], s.n_frames = n_frames[r], s.out_len = out_len[r], s.mix_start = mix_start[r];
         s.from = from[r], s.to = to[r], s.channels = ch_in[r];
         const float* c = coefs + 5 * r;
-        s.b0 = c[0], s.b1 = c[1], s.b2 = c[2], s.a1 = c[3], s.a2 = c[4], s.post = post[r], s.pre = pre[r];
+        s.b0 = c[0], s.b1 = c[1], s.b2 = c[2], s.a1 = c[3], s.a2 = c[4], s.post = post[r], s.pre = pre[r], s.mid = 1.0f;
     }
     float* d_out = nullptr;
     if (cudaMalloc(&d_out, (mix_len * channels + 8) * sizeof(float)) != cudaSuccess) return 1;
     rb_lanes_plan* plan = nullptr;
     int rc = 0;
-    if (rb_lanes_try_create(st.data(), n, channels, hasb != 0, npost != 0, npre != 0, d_out, mix_len, 148, nullptr, &plan) != cudaSuccess || !plan) rc = 2;
+    if (rb_lanes_try_create(st.data(), n, channels, hasb != 0, npost != 0, npre != 0, false, d_out, mix_len, 148, nullptr, &plan) != cudaSuccess || !plan) rc = 2;
     if (!rc && (rb_lanes_run(plan, nullptr) != cudaSuccess || rb_lanes_run(plan, nullptr) != cudaSuccess)) rc = 3;   // twice: idempotent
     if (!rc) std::memcpy(out, d_out, mix_len * channels * sizeof(float)), *n_launches = rb_lanes_launch_count(plan);
     rb_lanes_destroy(plan);

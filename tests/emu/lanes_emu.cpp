@@ -14,8 +14,8 @@
 namespace {
 // the class decides the instantiation -- source channels ci, mixer channels co, PASS when from == to -- like the device launcher
 void run_group_any(uint32_t ci, uint32_t co, const lanes::Args& a, uint32_t g, simt::WarpEmu* w, float* ring, bool hasb, bool ff2, bool npost,
-                   bool pre = false) {
-    emu_run_group(ci, co, a, g, w, ring, hasb, ff2, npost, pre);
+                   bool pre = false, bool front = false) {
+    emu_run_group(ci, co, a, g, w, ring, hasb, ff2, npost, pre, front);
 }
 constexpr int MAX_RS = lanes::Geo<2>::RS;
 }  // namespace
@@ -31,7 +31,8 @@ extern "C" int rb_lanes_emulate(const float* const* pcm, const uint64_t* n_frame
                                 const uint64_t* mix_start, const float* coefs /* [n][5] b0 b1 b2 a1 a2 */,
                                 const float* post, uint32_t n_rows, uint32_t channels /* mixer */, const uint32_t* ch_in /* per stream */,
                                 const uint32_t* from, const uint32_t* to, uint64_t mix_len, int hasb, int want_ff2, int npost, float* out_mix, float* out_partials /* may be NULL */,
-                                int* used_ff2, uint32_t* n_unsafe, const float* pre /* NULL: no gain in front of the conversion */) {
+                                int* used_ff2, uint32_t* n_unsafe, const float* pre /* NULL: no gain in front of the conversion */,
+                                int front /* the filter sits in front of the conversion */, const float* mid /* front: gain behind the filter, may be NULL */) {
     using namespace lanes;
     if (n_rows == 0 || (channels != 1 && channels != 2)) return 1;
     for (uint32_t r = 0; r < n_rows; r++)
@@ -43,7 +44,7 @@ extern "C" int rb_lanes_emulate(const float* const* pcm, const uint64_t* n_frame
     // inputs: 16-byte aligned copies with a 16-byte tail pad of NaN (reading the pad as data would show)
     std::vector<std::vector<float>> store(n_rows);
     std::vector<Row> all(n_rows);
-    bool ff2 = want_ff2 && hasb;
+    bool ff2 = want_ff2 && hasb && !front;
     *n_unsafe = 0;
     for (uint32_t r = 0; r < n_rows; r++) {
         const uint32_t ci = ch_in[r];
@@ -65,7 +66,8 @@ extern "C" int rb_lanes_emulate(const float* const* pcm, const uint64_t* n_frame
         }
         row.post = npost ? post[r] : 1.0f;
         row.pre = pre ? pre[r] : 1.0f;
-        if (pre && !pre_gain_keeps_class(row.pre)) row.flags |= ROW_FORCE_SLOW;
+        row.mid = mid ? mid[r] : 1.0f;
+        if (pre && !front && !pre_gain_keeps_class(row.pre)) row.flags |= ROW_FORCE_SLOW;
         bool ok = true;
         for (uint64_t i = 0; i < n_frames[r] * ci && ok; i++) ok = sample_in_class(pcm[r][i]);
         if (!ok) row.flags |= ROW_UNSAFE, (*n_unsafe)++;
@@ -101,7 +103,7 @@ extern "C" int rb_lanes_emulate(const float* const* pcm, const uint64_t* n_frame
         a.rows = rows.data() + (uintptr_t)a.rows, a.partial = partial.data() + (uintptr_t)a.partial * pstride, a.zeros = zeros;
         for (uint32_t g = 0; g < a.n_groups; g++) {
             for (int i = 0; i < 32 * MAX_RS; i++) ring[i] = nan;
-            run_group_any(launch_ci[k], channels, a, g, &warp, ring, hasb, ff2, npost, pre != nullptr);
+            run_group_any(launch_ci[k], channels, a, g, &warp, ring, hasb, ff2, npost, pre != nullptr, front != 0);
         }
     }
     for (uint64_t m = 0; m < mix_len * C; m++) {

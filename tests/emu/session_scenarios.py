@@ -204,6 +204,76 @@ def s_gain_in_front_of_the_conversion():
     assert_bit_exact(got, expected(pcms, ch_in, [44100, 22050] * 18, 2, 48000, [0] * n, 400, 0.9, None, pres), "batch with gains in front")
 
 
+def front_chain(pcm, ch_in, rate, mix_ch, mix_rate, lp, pre=None, mid=None, gain=None, speed=None):
+    """A Player's chain with a user filter: source [.speed] [.amplify(pre)] .low_pass(lp) [.amplify(mid)] -> mixer conversion [-> amplify]."""
+    s = rb.TestSource(pcm, ch_in, rate)
+    if speed:
+        s = s.speed(speed)
+    if pre is not None:
+        s = s.amplify(pre)
+    s = s.low_pass(lp)
+    if mid is not None:
+        s = s.amplify(mid)
+    s = rb.UniformSourceIterator(s, mix_ch, mix_rate)
+    if gain is not None:
+        s = s.amplify(gain)
+    return s
+
+
+def s_filter_in_front_of_the_conversion():
+    """`source.low_pass(f)` handed to the mixer / appended to a Player (player.rs:120-128: the volume sits behind it): the filter
+    runs at the source's rate.  A session with random splits (up- and down-sampling sources, one sped up, mono in stereo), its
+    state handed to a second session half way, and the same shape as a batch on the lane kernel."""
+    rng = np.random.default_rng(21)
+    n = 30
+    rates = [44100, 48000, 22050, 96000, 44100, 32000] * 5
+    ch_in = [2, 1, 1, 2, 1, 2] * 5
+    mids = [float(np.float32(v)) for v in rng.uniform(0.2, 1.1, n)]
+    speeds = [None] * n
+    speeds[4] = 1.1
+    pcms = [noise(ci * (600 + 23 * i), 9100 + i) for i, ci in enumerate(ch_in)]
+    starts = [0 if i % 4 else 15 * i for i in range(n)]
+    mk = lambda p, i: front_chain(p, ch_in[i], rates[i], 2, 48000, 350, 0.9, mids[i], 0.8, speeds[i])
+    srcs = [mk(np.zeros(0, np.float32), i) for i in range(n)]
+    real = [mk(pcms[i], i) for i in range(n)]
+    per = [oracle.chain_uniform(to_oracle(x), 2, 48000) for x in real]
+    eff = [rates[i] if speeds[i] is None else rb.capi.lib().rb_speed_sample_rate(rates[i], speeds[i]) for i in range(n)]
+    froms = [r // math.gcd(r, 48000) for r in eff]
+    tos = [48000 // math.gcd(r, 48000) for r in eff]
+    want = expected_mix_classes(per, [2 * j for j in starts], max(2 * j + y.size for j, y in zip(starts, per)), froms, list(zip(tos, ch_in)))
+
+    def hand_over(s):
+        blob = s.get_state()
+        t = rb.Session(srcs, 48000, fifo_frames=4096, max_block_frames=256, mix_starts=starts, mixer_channels=2)
+        t.set_state(blob)
+        s.close()
+        return t
+    s = rb.Session(srcs, 48000, fifo_frames=4096, max_block_frames=256, mix_starts=starts, mixer_channels=2)
+    got, s = drive(s, pcms, ch_in, [r // 200 for r in rates], 256, rng=rng, hooks={3: hand_over})
+    s.close()
+    assert_bit_exact(got, want[:got.size], "session with the filter in front of the conversion")
+    assert got.size == want.size or not np.any(want[got.size:])
+    # the same as a batch (up-sampling and same-rate sources: the planner drops the identity conversion of the 48 kHz ones)
+    rates_b = [44100, 48000, 22050] * 10
+    real = [front_chain(pcms[i], ch_in[i], rates_b[i], 2, 48000, 350, 0.9, mids[i], 0.8) for i in range(n)]
+    with rb.Batch(real, 2, 48000, flags=capi.RB_FUSED_LANES) as b:
+        assert b.kernel_family == 2
+        b.upload_all()
+        got = b.render_mix()
+    per = [oracle.chain_uniform(to_oracle(x), 2, 48000) for x in real]
+    froms = [r // math.gcd(r, 48000) for r in rates_b]
+    tos = [48000 // math.gcd(r, 48000) for r in rates_b]
+    assert_bit_exact(got, expected_mix_classes(per, [0] * n, max(y.size for y in per), froms, list(zip(tos, ch_in))), "batch with the filter in front")
+    # a filter in front AND one behind: not a session shape
+    both = rb.UniformSourceIterator(rb.TestSource(np.zeros(0, np.float32), 1, 44100).low_pass(300), 1, 48000).low_pass(500)
+    try:
+        rb.Session([both], 48000, mixer_channels=1)
+    except capi.RodioB200Error as e:
+        assert e.status == capi.RB_ERR_UNSUPPORTED
+    else:
+        raise AssertionError("two filters were accepted")
+
+
 def s_batch_with_identity_conversions():
     """rb_batch_create -> fused parser -> lane plan on the CPU: 44.1 kHz sources beside 48 kHz ones (whose conversion is the
     identity and is dropped by the planner) and mono beside stereo -- the batch still goes to the lane kernel, class by class."""
@@ -318,6 +388,23 @@ def s_random(seed=0, cases=6):
         starts = [0 if rng.random() < 0.6 else int(rng.integers(0, 500)) for _ in range(n)]
         lp, gain = [(300, 0.8), (None, 1.1), (2000, None), (None, None)][int(rng.integers(4))]
         pres = [float(np.float32(rng.choice([0.002, -0.4, rng.uniform(0.05, 1.5)]))) for _ in range(n)] if rng.random() < 0.4 else None
+        front = lp is not None and rng.random() < 0.5
+        if front:     # the filter in front of the conversion, the Player's volume behind it
+            mids = [float(np.float32(rng.uniform(0.2, 1.2))) for _ in range(n)]
+            mk = lambda p, i: front_chain(p, ch_in[i], rates[i], mix_ch, mix_rate, lp, None if pres is None else pres[i], mids[i], gain)
+            srcs = [mk(np.zeros(0, np.float32), i) for i in range(n)]
+            with rb.Session(srcs, mix_rate, fifo_frames=4096, max_block_frames=int(rng.choice([64, 333, 1024])), mix_starts=starts,
+                            mixer_channels=mix_ch) as s:
+                got, _ = drive(s, pcms, ch_in, [max(1, r // 150) for r in rates], 700, rng=rng, packed=bool(rng.integers(2)))
+            per = [oracle.chain_uniform(to_oracle(mk(pcms[i], i)), mix_ch, mix_rate) for i in range(n)]
+            froms = [r // math.gcd(r, mix_rate) for r in rates]
+            tos = [mix_rate // math.gcd(r, mix_rate) for r in rates]
+            want = expected_mix_classes(per, [j * mix_ch for j in starts], max(j * mix_ch + y.size for j, y in zip(starts, per)), froms,
+                                        list(zip(tos, ch_in)))
+            if any(lens):
+                assert_bit_exact(got, want[:got.size], f"random session {seed}/{case} (filter in front)")
+                assert got.size == want.size or not np.any(want[got.size:]), "tail"
+            continue
         srcs = [chain(np.zeros(0, np.float32), ci, r, mix_ch, mix_rate, lp, gain, None, None if pres is None else pres[i])
                 for i, (ci, r) in enumerate(zip(ch_in, rates))]
         with rb.Session(srcs, mix_rate, fifo_frames=4096, max_block_frames=int(rng.choice([64, 333, 1024])), mix_starts=starts,
@@ -334,7 +421,7 @@ def s_random(seed=0, cases=6):
 SCENARIOS = {"mono_random_split": s_mono_random_split, "mixed_with_state_blob": s_mixed_everything_with_state_blob,
              "held_queue_gain_speed": s_held_queue_gain_speed, "gain_changes": s_gain_changes, "filtered_and_plain": s_filtered_and_plain_sources,
              "batch_with_identity_conversions": s_batch_with_identity_conversions, "batch_unsorted_starts": s_batch_unsorted_starts, "errors": s_errors,
-             "gain_in_front": s_gain_in_front_of_the_conversion}
+             "gain_in_front": s_gain_in_front_of_the_conversion, "filter_in_front": s_filter_in_front_of_the_conversion}
 
 if __name__ == "__main__":
     for name in (sys.argv[1:] or list(SCENARIOS)):

@@ -34,6 +34,10 @@ def batches(seed, cases):
         pcms = [noise(ci * L, 10000 * case + i) for i, (ci, L) in enumerate(zip(ch_in, lens))]
         kind = rng.integers(4)
         kw = [dict(lp=int(rng.choice([200, 1000, 3000])), gain=float(np.float32(rng.uniform(0.2, 1.5)))), dict(hp=300), dict(gain=1.2), dict()][kind]
+        if kind < 2 and rng.random() < 0.35:   # the filter in front of the conversion, at the source's rate, gains around it
+            kw = dict(kw, front=True)
+            if rng.random() < 0.6:
+                kw["mid"] = [float(np.float32(rng.uniform(0.1, 1.3))) for _ in range(n)]
         if rng.random() < 0.4:   # source.amplify(v) in front of the mixer's conversion; a few outside the fast-path gain range
             kw = dict(kw, pre=[float(np.float32(rng.choice([0.001, -0.5, 100.0, rng.uniform(0.05, 2.0)]))) for _ in range(n)])
         try:

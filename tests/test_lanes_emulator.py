@@ -61,7 +61,8 @@ def expected_mix_classes(per_stream, starts, mix_len, froms, tos):
     return acc
 
 
-def run_emu(emu, pcms, outs_len, starts, coefs, posts, from_, to, mix_len, hasb, ff2, npost, channels=1, ch_in=None, pres=None):
+def run_emu(emu, pcms, outs_len, starts, coefs, posts, from_, to, mix_len, hasb, ff2, npost, channels=1, ch_in=None, pres=None, front=False,
+            mids=None):
     """Frames everywhere (outs_len, starts, mix_len); the result holds frames * channels floats, pcms[r] frames * ch_in[r]."""
     ch_in = [channels] * len(pcms) if ch_in is None else list(ch_in)
     n = len(pcms)
@@ -73,30 +74,39 @@ def run_emu(emu, pcms, outs_len, starts, coefs, posts, from_, to, mix_len, hasb,
     out = np.full(mix_len * channels, np.nan, dtype=np.float32)
     used, unsafe = C.c_int(0), C.c_uint32(0)
     pr = None if pres is None else np.ascontiguousarray(pres, dtype=np.float32)
+    mi = None if mids is None else np.ascontiguousarray(mids, dtype=np.float32)
     rc = emu.rb_lanes_emulate(ptrs, u64([p.size // c for p, c in zip(pcms, ch_in)]), u64(outs_len), u64(starts),
                               co.ctypes.data_as(C.POINTER(C.c_float)), po.ctypes.data_as(C.POINTER(C.c_float)),
                               C.c_uint32(n), C.c_uint32(channels), _u32(ch_in, n)[0], _u32(from_, n)[0], _u32(to, n)[0], C.c_uint64(mix_len), int(hasb), int(ff2),
                               int(npost), out.ctypes.data_as(C.POINTER(C.c_float)), None, C.byref(used), C.byref(unsafe),
-                              None if pr is None else pr.ctypes.data_as(C.POINTER(C.c_float)))
+                              None if pr is None else pr.ctypes.data_as(C.POINTER(C.c_float)), int(front),
+                              None if mi is None else mi.ctypes.data_as(C.POINTER(C.c_float)))
     assert rc == 0
     return out, bool(used.value), unsafe.value
 
 
-def make_case(pcms, in_rate, mix_rate, starts, lp=None, hp=None, q=0.5, gain=None, channels=1, ch_in=None, pre=None):
+def make_case(pcms, in_rate, mix_rate, starts, lp=None, hp=None, q=0.5, gain=None, channels=1, ch_in=None, pre=None, front=False, mid=None):
     """Sources as a rodio user writes them + everything the emulator needs, the expectation from the oracle.
     `starts` and the lengths in the result are frames."""
     srcs, per_stream = [], []
     in_rates = list(in_rate) if isinstance(in_rate, (list, tuple)) else [in_rate] * len(pcms)
     ch_in = [channels] * len(pcms) if ch_in is None else list(ch_in)
     pres = None if pre is None else (list(pre) if isinstance(pre, (list, tuple, np.ndarray)) else [pre] * len(pcms))
+    mids = None if mid is None else (list(mid) if isinstance(mid, (list, tuple, np.ndarray)) else [mid] * len(pcms))
     for k, (p, rate, ci) in enumerate(zip(pcms, in_rates, ch_in)):
         s = rb.TestSource(p, ci, rate)
         if pres is not None:
             s = s.amplify(float(pres[k]))       # source.amplify(v) handed to the mixer: the gain sits in front of the conversion
+        if front:                               # source.low_pass(f) [.amplify(v)] handed to the mixer: the filter runs at the source's rate
+            s = s.low_pass_with_q(lp, q) if lp is not None else s.high_pass_with_q(hp, q)
+            if mids is not None:
+                s = s.amplify(float(mids[k]))
         s = rb.UniformSourceIterator(s, channels, mix_rate)
-        if lp is not None:
+        if front:
+            pass
+        elif lp is not None:
             s = s.low_pass_with_q(lp, q)
-        if hp is not None:
+        if hp is not None and not front:
             s = s.high_pass_with_q(hp, q)
         if gain is not None:
             s = s.amplify(gain)
@@ -105,19 +115,20 @@ def make_case(pcms, in_rate, mix_rate, starts, lp=None, hp=None, q=0.5, gain=Non
     froms = [r // math.gcd(r, mix_rate) for r in in_rates]
     tos = [mix_rate // math.gcd(r, mix_rate) for r in in_rates]
     hasb = lp is not None or hp is not None
-    co = oracle.blt_coeffs(hp is not None, lp if lp is not None else (hp or 1), q, mix_rate) if hasb else np.zeros(5, np.float32)
-    coefs = np.tile(co, (len(pcms), 1))
+    # the filter's coefficients follow the rate of the stream it sees (blt.rs: to_applier(input.sample_rate()))
+    coef_at = lambda rate: oracle.blt_coeffs(hp is not None, lp if lp is not None else (hp or 1), q, rate) if hasb else np.zeros(5, np.float32)
+    coefs = np.stack([coef_at(r if front else mix_rate) for r in in_rates])
     mix_len = max([s + y.size // channels for s, y in zip(starts, per_stream)] + [0])
     return dict(per_stream=per_stream, outs_len=[y.size // channels for y in per_stream], coefs=coefs, channels=channels, ch_in=ch_in,
                 posts=np.full(len(pcms), gain if gain is not None else 1.0, np.float32), from_=froms, to=tos,
-                mix_len=mix_len, hasb=hasb, npost=gain is not None, srcs=srcs, pres=pres)
+                mix_len=mix_len, hasb=hasb, npost=gain is not None, srcs=srcs, pres=pres, front=front, mids=mids)
 
 
 def check(emu, pcms, in_rate, mix_rate, starts, ff2=True, expect_ff2=None, **kw):
     c = make_case(pcms, in_rate, mix_rate, starts, **kw)
     ch = c["channels"]
     got, used_ff2, unsafe = run_emu(emu, pcms, c["outs_len"], starts, c["coefs"], c["posts"], c["from_"], c["to"], c["mix_len"],
-                                    c["hasb"], ff2, c["npost"], channels=ch, ch_in=c["ch_in"], pres=c["pres"])
+                                    c["hasb"], ff2, c["npost"], channels=ch, ch_in=c["ch_in"], pres=c["pres"], front=c["front"], mids=c["mids"])
     if expect_ff2 is not None:
         assert used_ff2 == expect_ff2
     want = expected_mix_classes(c["per_stream"], [st * ch for st in starts], c["mix_len"] * ch, c["from_"], list(zip(c["to"], c["ch_in"])))
@@ -516,3 +527,26 @@ def test_randomised_soak(emu, what, seed, cases):
     sys.path[:0] = [os.path.join(HERE, "emu")]
     import stress
     assert getattr(stress, what)(seed, cases) == 0
+
+
+def test_filter_in_front_of_the_conversion(emu):
+    """`source.low_pass(f)` handed to the mixer (or appended to a Player, whose volume then sits behind it, player.rs:120-128):
+    the filter runs at the SOURCE's rate on every input frame, the interpolation reads its outputs.  Up-sampling on the fast
+    tiles, down-sampling and ragged edges on the slow ones, same-rate sources, mono / stereo / mono-in-stereo."""
+    n = 40
+    pcms = [noise(1800 + 13 * i, 1300 + i) for i in range(n)]
+    counters(emu)
+    check(emu, pcms, 44100, 48000, [0] * n, lp=300, front=True, pre=0.9, mid=[0.5 + 0.01 * i for i in range(n)], gain=0.8)
+    c = counters(emu)
+    assert c["fast"] > 4 * c["slow"]
+    check(emu, pcms, [44100, 22050, 48000, 32000] * 10, 48000, [5 * (i % 7) for i in range(n)], hp=500, front=True)
+    check(emu, pcms[:8], 48000, 44100, [0] * 8, lp=1000, front=True, mid=0.7)            # down-sampling: slow tiles
+    check(emu, pcms[:8], 96000, 44100, [3 * i for i in range(8)], lp=1000, front=True)    # more than two input frames per output
+    ch_in = [2 if i % 3 else 1 for i in range(12)]
+    st = [noise(ci * (900 + 9 * i), 1400 + i) for i, ci in enumerate(ch_in)]
+    check(emu, st, [44100, 48000, 22050] * 4, 48000, [0] * 12, channels=2, ch_in=ch_in, lp=400, front=True, mid=0.6, gain=1.1)
+    # a filter that rings down into denormals behind a burst: the guarded division of the fast tiles
+    quiet = [np.concatenate([noise(200, 1500 + i) * np.float32(1e-30), np.zeros(4000, np.float32)]) for i in range(4)]
+    check(emu, quiet, 44100, 48000, [0] * 4, lp=4000, front=True)
+    # tiny streams
+    check(emu, [noise(k, 1600 + k) for k in (0, 1, 2, 3, 5)], 44100, 48000, [0, 1, 2, 3, 4], lp=300, front=True, mid=0.5)

@@ -981,3 +981,58 @@ def test_lanes_and_session_gain_in_front_of_the_conversion(ctx):
     got = np.concatenate(got)
     assert_bit_exact(got, whole[:got.size], "the session in 10 ms blocks vs the whole-stream render")
     assert got.size == whole.size or not np.any(whole[got.size:])
+
+
+@lanes_gate
+def test_lanes_and_session_filter_in_front_of_the_conversion(ctx):
+    """`source.low_pass(f)` handed to the mixer, or appended to a Player whose volume then sits behind it (player.rs:120-128):
+    the filter runs once per INPUT frame at the source's rate (blt.rs: to_applier(input.sample_rate())), the interpolation reads
+    its outputs.  As a batch on the lane kernel (up-sampling and same-rate sources) and as a session in 10 ms blocks, both
+    against the oracle's literal iterators; a down-sampling source alone in a session."""
+    n = 66
+    rates = [44100, 48000, 22050, 44100, 32000, 44100] * 11
+    pcms = [noise(2500 + 37 * i, 5200 + i) for i in range(n)]
+    mids = [float(np.float32(0.3 + 0.01 * i)) for i in range(n)]
+    mk = lambda p, r, g: rb.UniformSourceIterator(rb.TestSource(p, 1, r).amplify(0.9).low_pass(300).amplify(g), 1, 48000).amplify(0.8)
+    srcs = [mk(p, r, g) for p, r, g in zip(pcms, rates, mids)]
+    per_stream = [oracle.chain_uniform(to_oracle(s), 1, 48000) for s in srcs]
+    ref = oracle.mixer([to_oracle(s) for s in srcs], 1, 48000)
+    with rb.Batch(srcs, 1, 48000, flags=LANES, ctx=ctx) as b:
+        assert b.kernel_family == 2
+        b.upload_all()
+        whole = b.render_mix()
+    assert_close_peak(whole, ref, 1e-5, "filter in front, lane kernel vs the reference's sequential mixer")
+    # one stream alone: the tree adds zeros only -- the kernel output IS the reference stream
+    for k in (0, 2, 4):
+        with rb.Batch([srcs[k]], 1, 48000, flags=LANES, ctx=ctx) as b:
+            assert b.kernel_family == 2
+            b.upload_all()
+            assert_bit_exact(b.render_mix(), per_stream[k] + np.float32(0.0), f"filter in front, one {rates[k]} Hz stream")
+    got, pos, ended = [], 0, False
+    blocks = [r // 100 for r in rates]
+    with rb.Session([mk(np.zeros(0, np.float32), r, g) for r, g in zip(rates, mids)], 48000, fifo_frames=4096, max_block_frames=480, ctx=ctx) as s:
+        while not ended:
+            s.push_packed([p[pos * k:(pos + 1) * k] for p, k in zip(pcms, blocks)], [(pos + 1) * k >= p.size for p, k in zip(pcms, blocks)])
+            pos += 1
+            while True:
+                block, ended = s.render(480)
+                got.append(block)
+                if block.size == 0 or ended:
+                    break
+    got = np.concatenate(got)
+    assert_bit_exact(got, whole[:got.size], "the session in 10 ms blocks vs the whole-stream render")
+    assert got.size == whole.size or not np.any(whole[got.size:])
+    # 96 kHz into 48 kHz: two input frames per output, the filter consumes both
+    down = mk(pcms[0], 96000, 0.5)
+    want = oracle.chain_uniform(to_oracle(down), 1, 48000)
+    got, pos, ended = [], 0, False
+    with rb.Session([mk(np.zeros(0, np.float32), 96000, 0.5)], 48000, fifo_frames=4096, max_block_frames=480, ctx=ctx) as s:
+        while not ended:
+            s.push(0, pcms[0][pos:pos + 700], end_of_stream=pos + 700 >= pcms[0].size)
+            pos += 700
+            while True:
+                block, ended = s.render(333)
+                got.append(block)
+                if block.size == 0 or ended:
+                    break
+    assert_bit_exact(np.concatenate(got), want + np.float32(0.0), "down-sampling source with the filter in front, alone in a session")
