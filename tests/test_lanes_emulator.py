@@ -31,7 +31,7 @@ def emu(built):
 def counters(emu, reset=True):
     out = (C.c_uint64 * 4)()
     emu.rb_lanes_emu_counters(out, int(reset))
-    return {"fast": out[0], "slow": out[1], "refills": out[2]}
+    return {"fast": out[0], "slow": out[1], "refills": out[2], "divided": out[3]}
 
 
 def _u32(v, n):
@@ -547,6 +547,8 @@ def test_filter_in_front_of_the_conversion(emu):
     check(emu, st, [44100, 48000, 22050] * 4, 48000, [0] * 12, channels=2, ch_in=ch_in, lp=400, front=True, mid=0.6, gain=1.1)
     # a filter that rings down into denormals behind a burst: the guarded division of the fast tiles
     quiet = [np.concatenate([noise(200, 1500 + i) * np.float32(1e-30), np.zeros(4000, np.float32)]) for i in range(4)]
+    counters(emu)
     check(emu, quiet, 44100, 48000, [0] * 4, lp=4000, front=True)
+    assert counters(emu)["divided"] > 0        # lane 0 met quotients outside the reciprocal's exact range and divided
     # tiny streams
     check(emu, [noise(k, 1600 + k) for k in (0, 1, 2, 3, 5)], 44100, 48000, [0, 1, 2, 3, 4], lp=300, front=True, mid=0.5)
