@@ -1136,7 +1136,7 @@ extern "C" rb_status rb_session_push(rb_session* s, size_t stream, const float* 
     stream = s->pos[stream];   // class order from here on
     session::Stream& st = s->st[stream];
     if (st.eof) return n_frames ? fail(RB_ERR_STATE, "push after end_of_stream") : RB_OK;
-    if (st.fill() + n_frames > s->fifo_cap) return fail(RB_ERR_BUFFER_TOO_SMALL, "the stream's FIFO is full: render first");
+    if (n_frames > s->fifo_cap - st.fill()) return fail(RB_ERR_BUFFER_TOO_SMALL, "the stream's FIFO is full: render first");
     RB_CUDA(cudaSetDevice(s->ctx->device));
     if (n_frames) {
         // one stream: straight into the FIFO tail, classified in place (count = n for this stream only)
@@ -1158,7 +1158,7 @@ extern "C" rb_status rb_session_push_packed(rb_session* s, const float* pcm, con
     for (size_t i = 0; i < ns; i++) {   // i: the caller's index, pos[i]: class order
         const session::Stream& st = s->st[s->pos[i]];
         if (st.eof && n_frames[i]) return fail(RB_ERR_STATE, "stream " + std::to_string(i) + ": push after end_of_stream");
-        if (st.fill() + n_frames[i] > s->fifo_cap) return fail(RB_ERR_BUFFER_TOO_SMALL, "stream " + std::to_string(i) + ": FIFO full, render first");
+        if (n_frames[i] > s->fifo_cap - st.fill()) return fail(RB_ERR_BUFFER_TOO_SMALL, "stream " + std::to_string(i) + ": FIFO full, render first");
         total += n_frames[i];
     }
     if (total && !pcm) return fail(RB_ERR_INVALID_ARGUMENT, "pcm is NULL");
