@@ -22,7 +22,7 @@
 //     added in warp order by k_sum_groups.  (Summation order differs from the reference's sequential order: the
 //     tolerance class of the fused path, <= 1e-5 * peak, tested; RB_MIX_EXACT_ORDER keeps the bit-exact path.)
 //   * inputs reach the lanes through a per-lane ring in shared memory filled by 16-byte cp.async (LDGSTS) in
-//     CHUNK-frame chunks, two chunks ahead; the copies of a chunk are distributed so that 4 consecutive lanes fetch
+//     64-byte chunks (16 mono / 8 stereo frames), two chunks ahead; the copies of a chunk are distributed so that 4 consecutive lanes fetch
 //     64 contiguous bytes of one stream (coalesced sectors), whatever stream the copying lane itself owns.
 //     Every input byte is read from HBM once; there are no intermediates in HBM.
 // Streams that start late / end early / end in the "last frame raw" rule (sample_rate.rs:187-199) are handled by
@@ -50,7 +50,10 @@
 namespace lanes {
 
 constexpr int TILE = 8;                 // timeline SAMPLES per loop iteration (TILE / C frames)
-constexpr int CHUNK = 16;               // input frames per ring chunk (one cp.async group)
+#ifndef RB_LANES_STEREO_CHW
+#define RB_LANES_STEREO_CHW 16
+#endif
+constexpr int CHUNK = 16;               // 32-bit words per ring chunk and lane (one cp.async group): 16 mono / 8 stereo frames
 constexpr int NSLOT = 4;                // ring slots: chunk c-1 (draining), c, c+1 (in flight), c+2 (just issued)
 constexpr uint32_t RUN_CAP = 1u << 30;  // frames
 constexpr int MIN_RUN_TILES = 4;        // shortest fast run worth priming the ring for
@@ -58,13 +61,17 @@ constexpr int MIN_RUN_TILES = 4;        // shortest fast run worth priming the r
 template <int C>
 struct Geo {
     static constexpr int TF = TILE / C;            // frames per tile
-    static constexpr int CHW = CHUNK * C;          // words per chunk
-    static constexpr int RING = CHW * NSLOT;       // 64 / 128
+    // words per chunk: 64 bytes per lane for either layout.  (Stereo lanes had 16-frame chunks when the kernel first ran on
+    // a device: 41 KB per CTA, 10 warps per SM.  Halved afterwards, not timed yet: -DRB_LANES_STEREO_CHW=32 rebuilds the
+    // old geometry for an A/B run.)
+    static constexpr int CHW = C == 2 ? RB_LANES_STEREO_CHW : CHUNK;
+    static constexpr int CHF = CHW / C;            // frames per chunk
+    static constexpr int RING = CHW * NSLOT;       // 64 words
     static constexpr int MIRROR = CHW;             // ring words [RING, RING + MIRROR) repeat [0, MIRROR): a tile never wraps
-    static constexpr int RS = RING + MIRROR + 4;   // 84 / 164 words per lane; RS / 4 odd: 8 lanes hit 8 bank quads
+    static constexpr int RS = RING + MIRROR + 4;   // 84 words per lane; RS / 4 odd: 8 lanes hit 8 bank quads
     static constexpr int QPC = CHW / 4;            // 16-byte quads per chunk and stream
     static constexpr int RPI = 32 / QPC;           // streams served by one cp.async warp instruction
-    static_assert(TILE % C == 0 && MIRROR >= TILE && (RS / 4) % 2 == 1 && 32 % QPC == 0, "ring geometry");
+    static_assert(TILE % C == 0 && MIRROR >= TILE && (RS / 4) % 2 == 1 && 32 % QPC == 0 && CHW % (4 * C) == 0 && CHF >= 2 * (TILE / C), "ring geometry");
 };
 static_assert(RUN_CAP % TILE == 0, "run cap");
 constexpr uint32_t ROW_UNSAFE = 1u;     // Row::flags: some sample outside the exact-reciprocal class
@@ -101,7 +108,7 @@ struct Args {
     uint64_t mix_len;        // mixer timeline, frames
     uint64_t pstride;        // floats per partial row: mix_len * CO rounded up to TILE
     float* partial;          // [n_groups][pstride], zero outside the span each group writes
-    const float* zeros;      // CHUNK * C zeros, 16-byte aligned: the source of idle lanes
+    const float* zeros;      // CHUNK zeros, 16-byte aligned: the source of idle lanes
     const uint32_t* unsafe;  // optional [n_rows]: non-zero = as if ROW_UNSAFE were set (streaming: kept on the device)
 };
 
@@ -147,7 +154,7 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
     using G = Geo<CI>;
     constexpr int C = CI;               // taps, ring and filter state follow the source's channels
     constexpr int TF = TILE / CO;       // frames per tile: the mixer timeline has CO samples per frame
-    constexpr int RS = G::RS, QPC = G::QPC, RPI = G::RPI, RING = G::RING, MIRROR = G::MIRROR, CHW = G::CHW;
+    constexpr int RS = G::RS, QPC = G::QPC, RPI = G::RPI, RING = G::RING, MIRROR = G::MIRROR, CHW = G::CHW, CHF = G::CHF;
     const uint32_t ln = simt::lane();
     const uint32_t r = group * 32u + ln;
     const bool has = r < a.n_rows;
@@ -305,7 +312,7 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
             auto tile = [&](float (&v)[TILE]) {
                 kb += a.q8, kbn += a.r8;
                 if (kbn >= to) kbn -= to, kb += 1;
-                if ((kb - 1) / CHUNK >= c_ready) {
+                if ((kb - 1) / CHF >= c_ready) {
                     simt::cp_wait<1>();      // chunk c_ready has landed (c_ready + 1 may still be in flight)
                     simt::syncwarp();        // ... for every lane, and nobody reads chunk c_ready - 2 any more
                     issue(c_ready + 2);      // into the slot of chunk c_ready - 2

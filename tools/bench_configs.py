@@ -96,6 +96,22 @@ def main():
                 for fl, nm in ((rb.capi.RB_FUSED_LANES, "k_fused_lanes"), (0, "default")):
                     time_batch(f"lanes sweep S={S}: 44.1k mono x 1s -> uniform(1,48k) -> {label} -> mix [{nm}]", srcs,
                                (1, 48000), flags=fl, steps=5)
+    if "lanes_shapes" in which:
+        # the lane kernel on the shapes added after its first device runs: stereo (ring geometry: see RB_LANES_STEREO_CHW in
+        # rb_lanes_core.h, A/B via RODIO_B200_LIB), mono sources in a stereo mixer, and the chain the way rodio users write it
+        # (gain / filter in front of the mixer's conversion)
+        S = 16384
+        mono, stereo = z(44100), z(2 * 44100)
+        shapes = [
+            ("stereo: uniform -> low_pass(200) -> amplify", 2, lambda: rb.UniformSourceIterator(rb.TestSource(stereo, 2, 44100), 2, 48000).low_pass(200).amplify(1.2)),
+            ("mono in a stereo mixer: uniform -> low_pass(200) -> amplify", 2, lambda: rb.UniformSourceIterator(rb.TestSource(mono, 1, 44100), 2, 48000).low_pass(200).amplify(1.2)),
+            ("mono: amplify -> uniform -> low_pass(200) -> amplify", 1, lambda: rb.UniformSourceIterator(rb.TestSource(mono, 1, 44100).amplify(0.9), 1, 48000).low_pass(200).amplify(1.2)),
+            ("mono: low_pass(200) -> amplify -> uniform (filter in front)", 1, lambda: rb.UniformSourceIterator(rb.TestSource(mono, 1, 44100).low_pass(200).amplify(0.9), 1, 48000)),
+            ("stereo: low_pass(200) -> amplify -> uniform (filter in front)", 2, lambda: rb.UniformSourceIterator(rb.TestSource(stereo, 2, 44100).low_pass(200).amplify(0.9), 2, 48000)),
+        ]
+        for label, ch, mk in shapes:
+            srcs = [mk() for _ in range(S)]
+            time_batch(f"lanes shapes S={S} x 1s: {label} [k_fused_lanes]", srcs, (ch, 48000), flags=rb.capi.RB_FUSED_LANES, steps=5)
     if "session" in which:
         # streaming sessions: every source receives 10 ms of 44.1 kHz PCM per step (one packed push), the mixer output is
         # pulled as it becomes available; wall clock per step through the public calls (host -> device -> host included)

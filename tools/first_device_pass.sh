@@ -29,6 +29,15 @@ timeout 300 python bench.py --streams 65536 --seconds 1 --flags 16 --steps 5 --w
     > "$OUT/bench_65536_lanes.json" 2> "$OUT/bench_65536_lanes.err"
 echo "bench 65536 lanes exit $?" | tee -a "$OUT/summary.txt"
 
+# 3b. the shapes added after the first device runs, and the stereo ring geometry A/B (64-byte against 128-byte chunks per lane)
+timeout 400 python tools/bench_configs.py lanes_shapes > "$OUT/lanes_shapes.jsonl" 2> "$OUT/lanes_shapes.err"
+echo "lanes shapes exit $?" | tee -a "$OUT/summary.txt"
+timeout 300 python -c "from rodio_b200 import build; build.build(force=True, extra_flags=['-DRB_LANES_STEREO_CHW=32'], out='rodio_b200/librodio_b200_chw32.so')" \
+    > "$OUT/build_chw32.log" 2>&1 && \
+RODIO_B200_LIB="$PWD/rodio_b200/librodio_b200_chw32.so" timeout 400 python tools/bench_configs.py lanes_shapes \
+    > "$OUT/lanes_shapes_chw32.jsonl" 2> "$OUT/lanes_shapes_chw32.err"
+echo "lanes shapes (128-byte stereo chunks) exit $?" | tee -a "$OUT/summary.txt"
+
 # 4. launch list and one full capture of the new kernel (numbers printed under ncu are never bench values)
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file "$OUT/launches_lanes.csv" \
     python bench.py --streams 16384 --seconds 1 --flags 16 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2>&1
