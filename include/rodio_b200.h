@@ -260,6 +260,12 @@ rb_status rb_session_follow(rb_session* s, size_t stream, size_t predecessor);
  * (src/player.rs:120-128), while the session's chain amplifies behind it: equal up to the rounding of one multiplication
  * per sample, not bit for bit; an exact Player mirror needs a gain on the taps (not in the session shape yet). */
 rb_status rb_session_set_amplify(rb_session* s, size_t stream, float factor);
+/* Player::set_volume (src/player.rs:180-186): the Player's Amplify sits IN FRONT of the mixer's conversion, behind the user's
+ * source and its filters (src/player.rs:120-128).  Changes that AMPLIFY of the source's chain -- the one in front of the
+ * conversion, behind a filter in front if there is one -- for every input frame the converter pulls from the next render on;
+ * the (at most two) frames it has pulled already keep the factor they were multiplied with, like Amplify::next
+ * (src/source/amplify.rs:91-95).  RB_ERR_STATE when the source was declared without that AMPLIFY. */
+rb_status rb_session_set_volume(rb_session* s, size_t stream, float factor);
 /* Mixer frames the next render can produce from what has been pushed (an output frame exists once its right input
  * neighbour has arrived, or its source has ended: sample_rate.rs:187-199).  *ended != 0: every source is exhausted
  * and drained -- MixerSource::next() returns None (src/mixer.rs:129-135). */

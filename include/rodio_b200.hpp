@@ -297,6 +297,8 @@ class LiveMixer {
     void append_after(size_t i, size_t predecessor) { check(rb_session_follow(h_, i, predecessor), "rb_session_follow"); }
     // Amplify::set_factor on the chain's .amplify() (amplify.rs:25-29); Player::set_volume's Amplify sits before the resampler
     void set_amplify(size_t i, float factor) { check(rb_session_set_amplify(h_, i, factor), "rb_session_set_amplify"); }
+    // Player::set_volume: the AMPLIFY in front of the mixer's conversion (src/player.rs:120-128, :180-186)
+    void set_volume(size_t i, float factor) { check(rb_session_set_volume(h_, i, factor), "rb_session_set_volume"); }
     bool ended() const { return ended_ && at_ == block_.size(); }
     std::optional<Sample> next() {
         if (at_ == block_.size()) {

@@ -965,6 +965,7 @@ struct rb_session {
     std::vector<session::Stream> st;
     std::vector<float> coef;      // 5 per stream
     std::vector<float> ffk, post, pre, mid;
+    std::vector<float> vol_a, vol_b;   // the factor the two frames in front of Stream::fpos were pulled with (rb_session_set_volume)
     uint64_t T = 0;               // mixer frames rendered so far
     uint32_t fifo_cap = 0, max_block = 0;
     uint64_t stride = 0;          // floats per stream in a FIFO arena
@@ -1060,6 +1061,7 @@ extern "C" rb_status rb_session_create(rb_context* ctx, uint16_t mixer_channels,
     }
     // pass 2: chains, in class order
     s->st.resize(n), s->coef.assign(5 * n, 0.0f), s->ffk.assign(n, 0.0f), s->post.assign(n, 1.0f), s->pre.assign(n, 1.0f), s->mid.assign(n, 1.0f), s->src_ch.assign(n, 1);
+    s->vol_a.assign(n, 1.0f), s->vol_b.assign(n, 1.0f);
     bool any_biquad = false;
     std::vector<uint8_t> row_ff2(n, 1);
     for (size_t r = 0; r < n; r++) {
@@ -1068,6 +1070,7 @@ extern "C" rb_status rb_session_create(rb_context* ctx, uint16_t mixer_channels,
         const std::string where = "stream " + std::to_string(i) + ": ";
         uint32_t k = first_fx[i] + 1;   // behind [SPEED | AMPLIFY] UNIFORM
         s->pre[r] = pre_of[i], s->mid[r] = mid_of[i];
+        s->vol_a[r] = s->vol_b[r] = front_fx[i] != 0xFFFFFFFFu ? mid_of[i] : pre_of[i];
         bool biq = false;
         if (front_fx[i] != 0xFFFFFFFFu) {
             const rb_effect& e = d.effects[front_fx[i]];
@@ -1211,6 +1214,21 @@ extern "C" rb_status rb_session_set_amplify(rb_session* s, size_t stream, float 
     return RB_OK;
 }
 
+extern "C" rb_status rb_session_set_volume(rb_session* s, size_t stream, float factor) {
+    if (!s) return fail(RB_ERR_INVALID_ARGUMENT, "session is NULL");
+    if (stream >= s->st.size()) return fail(RB_ERR_INVALID_ARGUMENT, "stream index out of range");
+    const size_t r = s->pos[stream];
+    if (s->st[r].front) {
+        s->mid[r] = factor;   // the gain behind a filter in front is always applied
+        return RB_OK;
+    }
+    for (const auto& c : s->classes)
+        if (r >= c.first && r < c.first + c.count && !c.has_pre)
+            return fail(RB_ERR_STATE, "the source was declared without an AMPLIFY in front of the conversion (declare one with factor 1.0)");
+    s->pre[r] = factor;
+    return RB_OK;
+}
+
 extern "C" rb_status rb_session_available(rb_session* s, uint64_t* frames, int* ended) {
     if (!s || !frames) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
     bool e = false;
@@ -1245,8 +1263,9 @@ extern "C" rb_status rb_session_render(rb_session* s, float* out_host, uint64_t 
         row.b0 = co[0], row.b1 = co[1], row.b2 = co[2], row.a1 = co[3], row.a2 = co[4], row.ffk = s->ffk[r];
         row.post = s->post[r], row.pre = s->pre[r], row.mid = s->mid[r];
         row.flags = p.continues ? lanes::ROW_CONTINUES : 0u;
-        if (s->st[r].front) row.f0 = s->st[r].fpos - s->st[r].i0;
-        else if (!lanes::pre_gain_keeps_class(row.pre)) row.flags |= lanes::ROW_FORCE_SLOW;
+        row.f0 = s->st[r].fpos - s->st[r].i0, row.ga = s->vol_a[r], row.gb = s->vol_b[r];
+        if (!s->st[r].front && !(lanes::pre_gain_keeps_class(row.pre) && lanes::pre_gain_keeps_class(row.ga) && lanes::pre_gain_keeps_class(row.gb)))
+            row.flags |= lanes::ROW_FORCE_SLOW;
     }
     RB_CUDA(cudaMemcpyAsync(s->d_rows, s->h_rows, ns * sizeof(lanes::Row), cudaMemcpyHostToDevice, stq));
     const uint64_t pstride = lanes::round_up_tile((uint64_t)s->max_block * C);
@@ -1266,8 +1285,13 @@ extern "C" rb_status rb_session_render(rb_session* s, float* out_host, uint64_t 
     RB_CUDA(rb_lanes_launch_sum(s->d_partial, n_groups_total, pstride, n * C, s->d_out, stq));
     // the host already knows what every stream consumed: compact the FIFOs into the other arena behind the kernel
     for (size_t r = 0; r < ns; r++) {
-        const uint64_t fill_before = s->st[r].fill();
+        const uint64_t fill_before = s->st[r].fill(), pulled_before = s->st[r].fpos;
         const uint64_t drop = session::advance(s->st[r], parts[r]);
+        // the frames the converter pulled in this block carry the block's factor from now on
+        const float vol = s->st[r].front ? s->mid[r] : s->pre[r];
+        const uint64_t pulled = s->st[r].fpos - pulled_before;
+        if (pulled >= 2) s->vol_a[r] = s->vol_b[r] = vol;
+        else if (pulled == 1) s->vol_a[r] = s->vol_b[r], s->vol_b[r] = vol;
         s->h_u32[r] = (uint32_t)(drop * s->src_ch[r]), s->h_u32[ns + r] = (uint32_t)((fill_before - drop) * s->src_ch[r]);   // floats
     }
     RB_CUDA(cudaMemcpyAsync(s->d_u32, s->h_u32, 2 * ns * sizeof(uint32_t), cudaMemcpyHostToDevice, stq));
@@ -1297,6 +1321,8 @@ struct SessionBlobStream {   // in class order (the same descriptors give the sa
     uint32_t from, to;
     uint32_t eof, unsafe, fill, filter_ahead;   // fill in frames; filter_ahead = fpos - i0 of a filter in front of the conversion
     float state[8];                      // 4 per channel
+    float vol_a, vol_b;                  // factor of the two frames in front of fpos (rb_session_set_volume)
+    float vol, post;                     // the current factors: rb_session_set_volume / rb_session_set_amplify
 };
 constexpr uint32_t SESSION_MAGIC = 0x52425353u;   // "RBSS"
 }  // namespace
@@ -1328,7 +1354,8 @@ extern "C" rb_status rb_session_get_state(rb_session* s, void* buf, uint64_t cap
     RB_CUDA(cudaStreamSynchronize(s->ctx->stream));
     for (size_t r = 0; r < ns; r++) {
         const session::Stream& st = s->st[r];
-        SessionBlobStream b{st.mix_start, st.pushed, st.out_done, st.i0, st.from, st.to, st.eof ? 1u : 0u, flags[r], (uint32_t)st.fill(), st.front ? (uint32_t)(st.fpos - st.i0) : 0u, {0}};
+        SessionBlobStream b{st.mix_start, st.pushed, st.out_done, st.i0, st.from, st.to, st.eof ? 1u : 0u, flags[r], (uint32_t)st.fill(), (uint32_t)(st.fpos - st.i0), {0}, s->vol_a[r], s->vol_b[r],
+                            st.front ? s->mid[r] : s->pre[r], s->post[r]};
         for (uint32_t k = 0; k < 4 * C; k++) b.state[k] = state[4 * C * r + k];
         memcpy(recs + r * sizeof(b), &b, sizeof(b));
     }
@@ -1364,7 +1391,9 @@ extern "C" rb_status rb_session_set_state(rb_session* s, const void* buf, uint64
     for (size_t r = 0; r < ns; r++) {
         const SessionBlobStream& b = recs[r];
         session::Stream& st = s->st[r];
-        st.mix_start = b.mix_start, st.pushed = b.pushed, st.out_done = b.out_done, st.i0 = b.i0, st.eof = b.eof != 0, st.fpos = b.i0 + b.filter_ahead;
+        st.mix_start = b.mix_start, st.pushed = b.pushed, st.out_done = b.out_done, st.i0 = b.i0, st.eof = b.eof != 0, st.fpos = b.i0 + b.filter_ahead, s->vol_a[r] = b.vol_a, s->vol_b[r] = b.vol_b;
+        (st.front ? s->mid[r] : s->pre[r]) = b.vol;
+        if (b.post != s->post[r]) s->post[r] = b.post, s->has_post = true;
         flags[r] = b.unsafe;
         for (uint32_t k = 0; k < 4 * C; k++) state[4 * C * r + k] = b.state[k];
         const size_t fill_floats = (size_t)b.fill * s->src_ch[r];

@@ -95,7 +95,10 @@ struct Row {                 // one stream (whole, or the part of it one block o
                              // usual rodio idiom -- applied to every input frame once, when it is fetched
     float mid;               // FRONT: the gain between the filter and the conversion (Player keeps its volume there)
     uint32_t flags;
-    uint64_t f0;             // FRONT: frames of in[] the filter has consumed when the block starts (0 for a whole stream)
+    uint64_t f0;             // frames of in[] the converter had pulled when the block starts (0 for a whole stream): a FRONT filter
+                             // has consumed them; the gain in front (PRE: pre, FRONT: mid) applies to frames >= f0 only ...
+    float ga, gb;            // ... frame f0 - 2 was pulled with gain ga, frame f0 - 1 with gb (Player::set_volume between blocks:
+                             // a frame keeps the factor it was multiplied with when Amplify::next pulled it)
 };
 
 struct Args {
@@ -163,7 +166,7 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
         row = a.rows[r];
     } else {
         row.in = a.zeros, row.L = 0, row.out_len = 0, row.mix_start = 0, row.n_int = 0, row.o0 = 0, row.i0 = 0, row.state = nullptr;
-        row.b0 = row.b1 = row.b2 = row.a1 = row.a2 = row.ffk = row.post = row.pre = row.mid = 0.0f, row.flags = 0, row.f0 = 0;
+        row.b0 = row.b1 = row.b2 = row.a1 = row.a2 = row.ffk = row.post = row.pre = row.mid = row.ga = row.gb = 0.0f, row.flags = 0, row.f0 = 0;
     }
     const uint64_t ms = row.mix_start, end = row.mix_start + row.out_len;   // frames
     // Down-sampling classes (from > to: more than one input frame per output) are served by the slow tiles only -- exact,
@@ -182,6 +185,9 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
     const float b0 = row.b0, b1 = row.b1, b2 = row.b2, a1 = row.a1, a2 = row.a2, ffk = row.ffk, post = row.post, gpre = row.pre, gmid = row.mid;
     const uint32_t from = a.from, to = a.to;
     uint64_t fpos = row.f0;   // FRONT: frames of in[] consumed by the filter
+    // the gain in front for input frame k (relative to in[0]): frames the converter pulled in earlier blocks keep their factor
+    const float gcur = FRONT ? gmid : gpre;
+    auto gain_of = [&](uint64_t k) { return k >= row.f0 ? gcur : (k + 1 == row.f0 ? row.gb : row.ga); };
     // canonical filter state per channel: x[n-1], x[n-2], y[n-1], y[n-2]
     float xh1[C], xh2[C], y1[C], y2[C];
 #pragma unroll
@@ -246,6 +252,7 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
             // =================================== FAST RUN: `run` timeline frames ===================================
             const bool act = has && t >= ms && t < end;
             uint32_t num = 0, k0 = 0, maxq = QPC - 1;
+            float g_tap0 = gcur, g_tap1 = gcur;          // the first two taps may have been pulled in an earlier block
             const float* src = a.zeros;
             if (act) {
                 const uint64_t prod = (o0 + (t - ms)) * (uint64_t)from;
@@ -258,6 +265,7 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                 const uint64_t mq = ((row.L * C - 1) >> 2) - ((ibase * C) >> 2);   // last quad (relative) that holds a frame
                 maxq = mq > 0x7fffffffull ? 0x7fffffffu : (uint32_t)mq;
                 if (FRONT) front_catch_up(i + 2);       // interior: i + 1 < L
+                if (PRE || FRONT) g_tap0 = gain_of(i), g_tap1 = gain_of(i + 1);
             }
             // the streams this lane copies for: source pointer and clamp of stream cr + RPI * j
             uint64_t sq[QPC];
@@ -292,8 +300,8 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
 #pragma unroll
             for (int c = 0; c < C; c++) {
                 x0[c] = simt::lds(simt::sptr_add(p, c)), x1[c] = simt::lds(simt::sptr_add(p, C + c));
-                if (PRE) x0[c] = simt::fmul(x0[c], gpre), x1[c] = simt::fmul(x1[c], gpre);
-                if (FRONT) x0[c] = simt::fmul(y2[c], gmid), x1[c] = simt::fmul(y1[c], gmid);   // the filter is one frame ahead
+                if (PRE) x0[c] = simt::fmul(x0[c], g_tap0), x1[c] = simt::fmul(x1[c], g_tap1);
+                if (FRONT) x0[c] = simt::fmul(y2[c], g_tap0), x1[c] = simt::fmul(y1[c], g_tap1);   // the filter is one frame ahead
             }
             p = simt::sptr_add(p, 2 * C);
             float nf = simt::u2f(num);
@@ -420,18 +428,18 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                         if (on) {
                             // the filter has consumed frames [0, fpos): y1 = F[fpos - 1], y2 = F[fpos - 2]
                             const bool two = fpos == i + 2;
-                            const float xa = simt::fmul(two ? y2[c] : y1[c], gmid);
+                            const float xa = simt::fmul(two ? y2[c] : y1[c], gain_of(i));
                             float x = xa;
-                            if (!PASS && two) x = simt::fadd(xa, simt::fdiv(simt::fmul(simt::fsub(simt::fmul(y1[c], gmid), xa), simt::u2f(num)), den));
+                            if (!PASS && two) x = simt::fadd(xa, simt::fdiv(simt::fmul(simt::fsub(simt::fmul(y1[c], gain_of(i + 1)), xa), simt::u2f(num)), den));
                             val[c] = NPOST ? simt::fmul(x, post) : x;
                         }
                     } else if (on) {
                         float xa = simt::ldg(row.in + i * C + c);
-                        if (PRE) xa = simt::fmul(xa, gpre);
+                        if (PRE) xa = simt::fmul(xa, gain_of(i));
                         float x = xa;
                         if (!PASS && i + 1 < row.L) {
                             float xb = simt::ldg(row.in + (i + 1) * C + c);
-                            if (PRE) xb = simt::fmul(xb, gpre);
+                            if (PRE) xb = simt::fmul(xb, gain_of(i + 1));
                             x = simt::fadd(xa, simt::fdiv(simt::fmul(simt::fsub(xb, xa), simt::u2f(num)), den));
                         }
                         float y = x;

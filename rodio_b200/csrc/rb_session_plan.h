@@ -32,8 +32,10 @@ struct Stream {
                                // later): it takes pushes, renders nothing and holds nobody up until it is started
     int64_t follows = -1;      // held source that starts on the frame after source `follows` has played out -- the
                                // sources of a queue (src/queue.rs:128-192: the next sound begins where the current one ends)
-    bool front = false;        // the source's filter sits in front of the conversion and runs once per INPUT frame ...
-    uint64_t fpos = 0;         // ... it has consumed the frames [0, fpos) (stream-absolute): one frame ahead of the interpolation
+    uint64_t fpos = 0;         // input frames [0, fpos) have been pulled by the converter (stream-absolute): up to the right
+                               // neighbour of the last output -- a gain in front of the conversion is final for them
+    bool front = false;        // the source's filter sits in front of the conversion, runs once per INPUT frame and has
+                               // consumed exactly those frames: the FIFO must keep everything from fpos on
     uint64_t fill() const { return pushed - i0; }   // frames in the FIFO
 };
 
@@ -123,7 +125,7 @@ inline void start(Stream& s, uint64_t T) {
 
 // After the block: advance the stream and tell how many FIFO frames (from the front) are dead.
 inline uint64_t advance(Stream& s, const Part& p) {
-    if (s.front && p.out_len) {   // the filter stands behind the right neighbour of the block's last output (or at the end)
+    if (p.out_len) {   // the converter (and a filter in front of it) stands behind the right neighbour of the block's last output
         const uint64_t ia = ((p.o0 + p.out_len - 1) * (uint64_t)s.from) / s.to;
         s.fpos = std::min(ia + 2, s.pushed);
     }

@@ -540,6 +540,11 @@ class Session:
         """Amplify::set_factor on the chain's AMPLIFY of a live source: applies from the next rendered block on."""
         check(lib().rb_session_set_amplify(self._h, stream, float(factor)), "rb_session_set_amplify")
 
+    def set_volume(self, stream: int, factor: float):
+        """Player::set_volume (src/player.rs:180-186): the AMPLIFY in FRONT of the mixer's conversion (behind a filter in front
+        of it, where the Player keeps its own, src/player.rs:120-128), for every frame the converter pulls from now on."""
+        check(lib().rb_session_set_volume(self._h, stream, float(factor)), "rb_session_set_volume")
+
     def available(self) -> Tuple[int, bool]:
         n, e = C.c_uint64(), C.c_int()
         check(lib().rb_session_available(self._h, C.byref(n), C.byref(e)), "rb_session_available")

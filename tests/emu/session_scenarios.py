@@ -274,6 +274,85 @@ def s_filter_in_front_of_the_conversion():
         raise AssertionError("two filters were accepted")
 
 
+def s_player_volume_changes():
+    """Player::set_volume while playing (rb_session_set_volume): the Player's Amplify sits in front of the mixer's conversion
+    (behind the user's filter), so a frame keeps the factor it had when the converter pulled it -- frames pulled in a block
+    carry that block's factor, the two look-ahead frames of the converter included.  Expectation: the oracle's literal chain
+    over an input that was multiplied frame by frame with exactly those factors."""
+    rates = [44100, 22050, 48000, 96000]
+    front = [False, True, False, True]
+    L = [6000, 3000, 6600, 13000]
+    pcms = [noise(n, 8800 + i) for i, n in enumerate(L)]
+    mk_plain = lambda p, r, g: rb.UniformSourceIterator(rb.TestSource(p, 1, r).amplify(g), 1, 48000).low_pass(500).amplify(0.9)
+    mk_front = lambda p, r, g: rb.UniformSourceIterator(rb.TestSource(p, 1, r).amplify(0.8).low_pass(400).amplify(g), 1, 48000)
+    srcs = [(mk_front if f else mk_plain)(np.zeros(0, np.float32), r, 1.0) for r, f in zip(rates, front)]
+    plan = {2: (0, 0.5), 3: (1, 0.25), 5: (0, 1.5), 6: (3, 0.1), 7: (2, 0.7), 9: (1, 1.0), 10: (3, 0.9)}   # round -> (stream, volume)
+    vol = [1.0] * 4
+    gains = [np.ones(n, np.float32) for n in L]       # factor of every input frame
+    pulled, pushed, done = [0] * 4, [0] * 4, [0] * 4
+    total = [int(rb.plan((mk_front if f else mk_plain)(p, r, 1.0), 1, 48000)[0]) for p, r, f in zip(pcms, rates, front)]
+    got, ended, rnd = [], False, 0
+    with rb.Session(srcs, 48000, fifo_frames=4096, max_block_frames=240, mixer_channels=1) as s:
+        while not ended:
+            if rnd == 4:      # hand the session over: the blob carries the factors and those of the look-ahead frames
+                t = rb.Session(srcs, 48000, fifo_frames=4096, max_block_frames=240, mixer_channels=1)
+                t.set_state(s.get_state())
+                s.close()
+                s = t
+            if rnd in plan:
+                i, v = plan[rnd]
+                s.set_volume(i, v)
+                vol[i] = v
+            blocks, eos = [], []
+            for i, (p, r) in enumerate(zip(pcms, rates)):
+                k = min(r // 100, L[i] - pushed[i])
+                blocks.append(p[pushed[i]:pushed[i] + k])
+                pushed[i] += k
+                eos.append(pushed[i] == L[i])
+            s.push_packed(blocks, eos)
+            while True:
+                block, ended = s.render(240)
+                got.append(block)
+                if block.size == 0:
+                    break
+                for i, r in enumerate(rates):          # what the converter of every source pulled in this block
+                    o = min(done[i] + block.size, total[i])
+                    if o > done[i]:
+                        g = math.gcd(r, 48000)
+                        p_new = min(((o - 1) * (r // g)) // (48000 // g) + 2, pushed[i])
+                        gains[i][pulled[i]:p_new] = np.float32(vol[i])
+                        pulled[i], done[i] = p_new, o
+                if ended:
+                    break
+            rnd += 1
+            assert rnd < 1000
+        s.close()         # the session that took over
+    got = np.concatenate(got)
+    per = []
+    for i, (p, r, f) in enumerate(zip(pcms, rates, front)):
+        if f:     # amplify(0.8) -> low_pass at the source's rate, then the Player's factor on every filter output
+            y = oracle.chain_uniform(to_oracle(rb.TestSource(p, 1, r).amplify(0.8).low_pass(400)), 1, r)
+            per.append(oracle.chain_uniform(to_oracle(rb.UniformSourceIterator(rb.TestSource(y * gains[i], 1, r), 1, 48000)), 1, 48000))
+        else:
+            x = rb.UniformSourceIterator(rb.TestSource(p * gains[i], 1, r), 1, 48000).low_pass(500).amplify(0.9)
+            per.append(oracle.chain_uniform(to_oracle(x), 1, 48000))
+    acc = np.zeros(max(y.size for y in per), np.float32)
+    for y in per:                                      # every source is a class of its own: the plain sum in source order
+        row = np.zeros(acc.size, np.float32)
+        row[:y.size] = y
+        acc = acc + (row + np.float32(0.0))
+    assert all(np.unique(g).size > 1 for g in gains), "every source saw a volume change"
+    assert_bit_exact(got, acc, "volume changes in front of the conversion")
+    # a source declared without an AMPLIFY in front cannot get one later
+    with rb.Session([rb.UniformSourceIterator(rb.TestSource(np.zeros(0, np.float32), 1, 44100), 1, 48000)], 48000, mixer_channels=1) as s:
+        try:
+            s.set_volume(0, 0.5)
+        except capi.RodioB200Error as e:
+            assert e.status == capi.RB_ERR_STATE
+        else:
+            raise AssertionError("set_volume without an AMPLIFY in front was accepted")
+
+
 def s_batch_with_identity_conversions():
     """rb_batch_create -> fused parser -> lane plan on the CPU: 44.1 kHz sources beside 48 kHz ones (whose conversion is the
     identity and is dropped by the planner) and mono beside stereo -- the batch still goes to the lane kernel, class by class."""
@@ -421,7 +500,7 @@ def s_random(seed=0, cases=6):
 SCENARIOS = {"mono_random_split": s_mono_random_split, "mixed_with_state_blob": s_mixed_everything_with_state_blob,
              "held_queue_gain_speed": s_held_queue_gain_speed, "gain_changes": s_gain_changes, "filtered_and_plain": s_filtered_and_plain_sources,
              "batch_with_identity_conversions": s_batch_with_identity_conversions, "batch_unsorted_starts": s_batch_unsorted_starts, "errors": s_errors,
-             "gain_in_front": s_gain_in_front_of_the_conversion, "filter_in_front": s_filter_in_front_of_the_conversion}
+             "gain_in_front": s_gain_in_front_of_the_conversion, "filter_in_front": s_filter_in_front_of_the_conversion, "player_volume": s_player_volume_changes}
 
 if __name__ == "__main__":
     for name in (sys.argv[1:] or list(SCENARIOS)):

@@ -1036,3 +1036,42 @@ def test_lanes_and_session_filter_in_front_of_the_conversion(ctx):
                 if block.size == 0 or ended:
                     break
     assert_bit_exact(np.concatenate(got), want + np.float32(0.0), "down-sampling source with the filter in front, alone in a session")
+
+
+@lanes_gate
+def test_session_player_volume_changes(ctx):
+    """Player::set_volume while playing (rb_session_set_volume): the Player's Amplify sits in front of the mixer's conversion
+    (src/player.rs:120-128), so every input frame keeps the factor it had when the converter pulled it.  One 44.1 kHz source,
+    5 ms blocks, four volume changes; the expectation is the oracle's literal chain over an input multiplied frame by frame with
+    the factor of the block that pulled it (the converter stands two frames behind the left neighbour of the last output)."""
+    L, rate = 9000, 44100
+    pcm = noise(L, 6100)
+    mk = lambda p: rb.UniformSourceIterator(rb.TestSource(p, 1, rate).amplify(1.0), 1, 48000).low_pass(500).amplify(0.9)
+    total = int(rb.plan(mk(pcm), 1, 48000)[0])
+    plan_ = {1: 0.5, 4: 1.5, 9: 0.05, 14: 0.8}
+    gains = np.ones(L, np.float32)
+    vol, pulled, pushed, done, got, ended, rnd = 1.0, 0, 0, 0, [], False, 0
+    with rb.Session([mk(np.zeros(0, np.float32))], 48000, fifo_frames=4096, max_block_frames=240, ctx=ctx) as s:
+        while not ended:
+            if rnd in plan_:
+                vol = plan_[rnd]
+                s.set_volume(0, vol)
+            k = min(441, L - pushed)
+            s.push(0, pcm[pushed:pushed + k], end_of_stream=pushed + k == L)
+            pushed += k
+            while True:
+                block, ended = s.render(240)
+                got.append(block)
+                if block.size == 0:
+                    break
+                o = min(done + block.size, total)
+                p_new = min(((o - 1) * 147) // 160 + 2, pushed)
+                gains[pulled:p_new] = np.float32(vol)
+                pulled, done = p_new, o
+                if ended:
+                    break
+            rnd += 1
+            assert rnd < 1000
+    assert np.unique(gains).size == 5
+    want = oracle.chain_uniform(to_oracle(rb.UniformSourceIterator(rb.TestSource(pcm * gains, 1, rate), 1, 48000).low_pass(500).amplify(0.9)), 1, 48000)
+    assert_bit_exact(np.concatenate(got), want + np.float32(0.0), "volume changes in front of the conversion")

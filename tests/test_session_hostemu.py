@@ -25,7 +25,7 @@ def hostemu(built):
 
 @pytest.mark.parametrize("scenario", ["errors", "mono_random_split", "mixed_with_state_blob", "held_queue_gain_speed", "gain_changes",
                                       "filtered_and_plain", "batch_with_identity_conversions",
-                                      "batch_unsorted_starts", "gain_in_front", "filter_in_front", "random:5"])
+                                      "batch_unsorted_starts", "gain_in_front", "filter_in_front", "player_volume", "random:5"])
 def test_session_host_code_on_the_emulator(hostemu, scenario):
     t0 = time.time()
     r = subprocess.run([sys.executable, os.path.join(EMU, "session_scenarios.py"), scenario], capture_output=True, text=True, timeout=900)
