@@ -210,6 +210,8 @@ extern "C" {
     fn rb_session_destroy(s: *mut rb_session) -> i32;
     fn rb_session_push_packed(s: *mut rb_session, pcm: *const f32, n_frames: *const u64, end_of_stream: *const u8) -> i32;
     fn rb_session_render(s: *mut rb_session, out: *mut f32, max_frames: u64, written: *mut u64, ended: *mut i32) -> i32;
+    fn rb_session_follow(s: *mut rb_session, stream: usize, predecessor: usize) -> i32;
+    fn rb_session_set_volume(s: *mut rb_session, stream: usize, factor: f32) -> i32;
     fn rb_session_get_state(s: *mut rb_session, buf: *mut c_void, cap: u64, size: *mut u64) -> i32;
     fn rb_session_set_state(s: *mut rb_session, buf: *const c_void, size: u64) -> i32;
 }
@@ -278,4 +280,35 @@ impl Source for GpuLiveMixer {
 
 impl Drop for GpuLiveMixer {
     fn drop(&mut self) { unsafe { rb_session_destroy(self.session); } }
+}
+
+/// The controls of `Player` (reference src/player.rs) on a session.  rodio builds, per appended sound,
+/// `speed -> track_position -> pausable -> amplify(volume) -> skippable -> stoppable -> periodic_access(5 ms)` and lets the
+/// mixer convert the result (src/player.rs:120-166).  On a session that chain is declared when the sound's slot is created
+/// -- `[SPEED] [user effects: AMPLIFY, LOW_PASS ...] AMPLIFY(volume) UNIFORM(mixer)` with `mix_start = RB_SESSION_HELD` -- and
+/// the controls become:
+///   append      rb_session_follow(slot, previous slot)     the sound starts on the frame after its predecessor's last
+///   set_volume  rb_session_set_volume(slot, v)             the Amplify in front of the conversion; frames the converter has
+///                                                          pulled already keep their factor, like Amplify::next
+///   pause/play  the shim pushes zero frames instead of pulling the source while paused (Pausable emits whole frames of
+///               zeros in front of the converter, src/source/pausable.rs:85-97)
+///   stop/skip   end_of_stream for the slot (Stoppable / Skippable end the inner iterator, the queue moves on)
+///   set_speed   read when the sound is appended (Speed only changes the rate the source reports, src/source/speed.rs:130-133)
+pub struct GpuPlayer<'a> {
+    mixer: &'a mut GpuLiveMixer,
+    slots: Vec<usize>,         // session slots of the sounds appended so far, in order
+    paused: bool,
+}
+
+impl<'a> GpuPlayer<'a> {
+    pub fn append_slot(&mut self, slot: usize) {
+        if let Some(&prev) = self.slots.last() { unsafe { rb_session_follow(self.mixer.session, slot, prev); } }
+        self.slots.push(slot);
+    }
+    pub fn set_volume(&mut self, value: f32) {
+        for &slot in &self.slots { unsafe { rb_session_set_volume(self.mixer.session, slot, value); } }
+    }
+    pub fn pause(&mut self) { self.paused = true; }     // GpuLiveMixer::refill pushes zeros for these slots while set
+    pub fn play(&mut self) { self.paused = false; }
+    pub fn is_paused(&self) -> bool { self.paused }
 }
