@@ -49,10 +49,11 @@ def test_cpp_session_mirror_streams_like_the_whole_render(built):
     assert "all session API tests passed" in r.stdout
 
 
-def test_plain_c_example_compiles_against_the_header(built):
-    """examples/stream_mixer.c: the boundary is usable from C (plain pointers and sizes, no C++ in the header)."""
-    src = os.path.join(ROOT, "examples", "stream_mixer.c")
-    exe = os.path.join(ROOT, "tests", "cpp", "stream_mixer.bin")
+@pytest.mark.parametrize("name", ["stream_mixer", "live_player"])
+def test_plain_c_example_compiles_against_the_header(built, name):
+    """examples/*.c: the boundary is usable from C (plain pointers and sizes, no C++ in the header)."""
+    src = os.path.join(ROOT, "examples", name + ".c")
+    exe = os.path.join(ROOT, "tests", "cpp", name + ".bin")
     lib_dir = os.path.join(ROOT, "rodio_b200")
     subprocess.run(["gcc", "-std=c11", "-D_GNU_SOURCE", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
                     "-L", lib_dir, "-l:librodio_b200.so", f"-Wl,-rpath,{lib_dir}", "-lm"], check=True, capture_output=True)

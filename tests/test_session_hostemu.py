@@ -86,6 +86,20 @@ def test_plain_c_example_runs_on_the_emulator(hostemu):
     assert frames == 2880 and 0.3 < peak < 0.9, r.stdout      # 6 x 10 ms at 48 kHz; 0.8 * 0.5 low-passed music + 0.25 voice
 
 
+def test_live_player_example_runs_on_the_emulator(hostemu):
+    """examples/live_player.c: a queue of two sounds (the first low-passed at its own rate), a pause, a volume change -- the
+    Player controls on a session, from C, against the host-emulated library."""
+    exe = os.path.join(HERE, "cpp", "live_player_emu.bin")
+    subprocess.run(["gcc", "-std=c11", "-D_GNU_SOURCE", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "live_player.c"),
+                    "-o", exe, "-L", EMU, "-l:librodio_b200_hostemu.so", f"-Wl,-rpath,{EMU}", "-lm"], check=True, capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    w = r.stdout.replace(",", " ").split()
+    frames, silent, loud, quiet = int(w[0]), int(w[2]), float(w[5]), float(w[7])
+    # 4400 frames of 22.05 kHz (9578 at 48 kHz), then (30 + 5) x 441 frames of 44.1 kHz (16800); 5 x 10 ms of pause; 0.6 -> 0.6 * 0.25
+    assert frames == 9578 + 16800 and 2400 <= silent <= 2420 and abs(loud - 0.6) < 0.01 and abs(quiet - 0.15) < 0.005, r.stdout
+
+
 def test_gpu_lane_and_session_tests_hold_on_the_emulator(hostemu):
     """Every GPU test of the lane kernel and of the sessions that needs nothing but the C ABI and the oracle, run unchanged
     against the host-emulated library -- their expectations are known to be right before they meet a device.  (Left out: the
