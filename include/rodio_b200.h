@@ -223,7 +223,7 @@ rb_status rb_batch_read_stream(rb_batch* b, size_t stream, float* out_host, uint
  * Shape served (RB_ERR_UNSUPPORTED otherwise): a mono or stereo mixer = mixer(channels, rate) of src/mixer.rs:25-43; f32
  * sources with the mixer's channel count or mono sources in a stereo mixer (repeated on both channels like
  * ChannelCountConverter, src/conversions/channels.rs:57-85), each at its own sample rate (44.1 kHz, 22.05 kHz and 48 kHz sources in one 48 kHz mixer: one kernel launch
- * per rate pair; sources ABOVE the mixer's rate are exact as well but run on the kernel's general per-sample path), effects = [SPEED | AMPLIFY | one LOW_PASS / HIGH_PASS]* UNIFORM(mixer channels, mixer rate)
+ * per rate pair; sources ABOVE the mixer's rate have fast tiles of their own up to a factor of two, the kernel's general per-sample path beyond), effects = [SPEED | AMPLIFY | one LOW_PASS / HIGH_PASS]* UNIFORM(mixer channels, mixer rate)
  * [LOW_PASS | HIGH_PASS] [AMPLIFY] -- the chain of BASELINE cfg3 behind the conversion, and in front of it what a rodio user
  * hands to Mixer::add or appends to a Player (src/player.rs:120-128): any SPEED (it only changes the rate pair), one filter
  * -- it then runs once per INPUT frame with coefficients for the rate its input reports (src/source/blt.rs to_applier) --,

@@ -186,7 +186,10 @@ static cudaError_t fused_lanes_hook(const std::vector<FusedRow>& rows, size_t n_
         const FusedRow& r = rows[i];
         // every stream interpolates upwards on its own reduced grid (several rate pairs are served class by class),
         // or is at the mixer's rate already (UniformSourceIterator hands it through / there is no conversion in the chain)
-        const bool lerp_up = r.mode == ROW_LERP && r.uni.from < r.uni.to;
+        // ... or downwards by at most a factor of two (fast tiles of their own, untimed so far: only on request)
+        const bool lerp_up = r.mode == ROW_LERP && (r.uni.from < r.uni.to ||
+                                                    ((flags & RB_FUSED_LANES) && !front && r.uni.from > r.uni.to &&
+                                                     (uint64_t)r.uni.from <= 2ull * r.uni.to));   // = lanes::ratio_runs_down
         const bool pass = r.mode == ROW_PASS || r.mode == ROW_DIRECT;
         // the stream has the mixer's channels, or is mono in a stereo mixer (repeated on both channels, channels.rs:57-85)
         if (!((lerp_up || pass) && (r.c_in == C || (r.c_in == 1 && C == 2)) && r.out_len % C == 0 && r.mix_start % C == 0 &&

@@ -17,13 +17,13 @@ constexpr int LANES_THREADS = 32 * LANES_WARPS;
 template <int C>
 constexpr size_t lanes_smem_bytes() { return (size_t)LANES_WARPS * 32 * lanes::Geo<C>::RS * sizeof(float); }   // 21.0 KB
 
-template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS, bool PRE, bool FRONT>
+template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS, bool PRE, bool FRONT, bool DOWN>
 __global__ void __launch_bounds__(LANES_THREADS) k_fused_lanes(lanes::Args a) {
     extern __shared__ __align__(16) float lanes_smem[];
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t group = blockIdx.x * LANES_WARPS + warp;
     if (group >= a.n_groups) return;   // whole warps leave: the warp program only synchronises within a warp
-    lanes::warp_main<CI, CO, HASB, FF2, NPOST, PASS, PRE, FRONT>(a, group, lanes_smem + (size_t)warp * 32 * lanes::Geo<CI>::RS);
+    lanes::warp_main<CI, CO, HASB, FF2, NPOST, PASS, PRE, FRONT, DOWN>(a, group, lanes_smem + (size_t)warp * 32 * lanes::Geo<CI>::RS);
 }
 
 // One CTA per stream: does every non-zero |x| lie inside [2^-70, 2^60]?  (rb_lanes_core.h, "Exact division".)
@@ -97,10 +97,10 @@ __global__ void __launch_bounds__(256) k_classify_range(const float* __restrict_
     if (__syncthreads_or(bad ? 1 : 0) && threadIdx.x == 0) *flag = 1u;
 }
 
-template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS, bool PRE, bool FRONT = false>
+template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS, bool PRE, bool FRONT = false, bool DOWN = false>
 static void launch_lanes(const lanes::Args& a, cudaStream_t st) {
     const uint32_t n_ctas = (a.n_groups + LANES_WARPS - 1) / LANES_WARPS;
-    k_fused_lanes<CI, CO, HASB, FF2, NPOST, PASS, PRE, FRONT><<<n_ctas, LANES_THREADS, lanes_smem_bytes<CI>(), st>>>(a);   // < 48 KB: no opt-in needed
+    k_fused_lanes<CI, CO, HASB, FF2, NPOST, PASS, PRE, FRONT, DOWN><<<n_ctas, LANES_THREADS, lanes_smem_bytes<CI>(), st>>>(a);   // < 48 KB: no opt-in needed
 }
 template <int CI, int CO, bool PASS, bool PRE>
 static void launch_lanes_c(const lanes::Args& a, bool has_biquad, bool ff2, bool has_post, cudaStream_t st) {
@@ -117,6 +117,15 @@ static void launch_lanes_cc(const lanes::Args& a, bool has_biquad, bool ff2, boo
     if (front) {                        // the filter in front of the conversion: plain coefficients, Row::pre always applied
         if (pass) has_post ? launch_lanes<CI, CO, true, false, 1, true, false, true>(a, st) : launch_lanes<CI, CO, true, false, 0, true, false, true>(a, st);
         else has_post ? launch_lanes<CI, CO, true, false, 1, false, false, true>(a, st) : launch_lanes<CI, CO, true, false, 0, false, false, true>(a, st);
+        return;
+    }
+    if (lanes::ratio_runs_down(a.from, a.to)) {   // above the mixer's rate, up to twice: fast tiles of their own, Row::pre always applied
+        if (has_biquad) {
+            if (ff2) has_post ? launch_lanes<CI, CO, true, true, 1, false, false, false, true>(a, st) : launch_lanes<CI, CO, true, true, 0, false, false, false, true>(a, st);
+            else has_post ? launch_lanes<CI, CO, true, false, 1, false, false, false, true>(a, st) : launch_lanes<CI, CO, true, false, 0, false, false, false, true>(a, st);
+        } else {
+            has_post ? launch_lanes<CI, CO, false, false, 1, false, false, false, true>(a, st) : launch_lanes<CI, CO, false, false, 0, false, false, false, true>(a, st);
+        }
         return;
     }
     if (pass) has_pre ? launch_lanes_c<CI, CO, true, true>(a, has_biquad, ff2, has_post, st) : launch_lanes_c<CI, CO, true, false>(a, has_biquad, ff2, has_post, st);

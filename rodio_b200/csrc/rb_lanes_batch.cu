@@ -34,7 +34,8 @@ cudaError_t rb_lanes_try_create(const rb_lanes_stream* streams, size_t n_streams
     std::vector<uint32_t> from(n_streams), to(n_streams), chs(n_streams);
     for (size_t i = 0; i < n_streams; i++) {
         from[i] = streams[i].from, to[i] = streams[i].to, chs[i] = streams[i].channels;
-        if (!(from[i] <= to[i]) || from[i] == 0 || to[i] > (1u << 20)) return cudaSuccess;
+        // at or below the mixer's rate, or above it by at most a factor of two (the DOWN tiles)
+        if (!(from[i] <= to[i] || lanes::ratio_runs_down(from[i], to[i])) || from[i] == 0 || from[i] > (1u << 20) || to[i] > (1u << 20)) return cudaSuccess;
         if (!(chs[i] == channels || (chs[i] == 1 && channels == 2))) return cudaSuccess;
         if (reinterpret_cast<uintptr_t>(streams[i].in) & 15u) return cudaSuccess;
     }

@@ -107,6 +107,8 @@ struct Args {
     uint32_t from, to;       // reduced ratio, from < to <= 2^20
     uint32_t q8, r8;         // divmod((TILE / CO) * from, to): input frames a tile advances (CO = mixer channels)
     float den_f, rcp_den, from_f;
+    uint32_t adv_q;          // DOWN: from / to, whole input frames per output (1 or 2) ...
+    float rem_f;             // ... and from % to, what the numerator gains per output on top of them
     float neg1;              // -1.0f as a run-time value (keeps fma(p, -1, t) an FFMA: the chain stays on one pipe)
     uint64_t mix_len;        // mixer timeline, frames
     uint64_t pstride;        // floats per partial row: mix_len * CO rounded up to TILE
@@ -150,9 +152,15 @@ SIMT_FN float reduce_tile(const float (&v)[TILE], uint32_t ln) {
 // is formed, or all L of them at the end), so the taps ARE y[n-2], y[n-1] (times `mid`) and no state is added.  Filter
 // outputs cannot be classified in advance, so the division of the fast tile is guarded per sample (|m| inside
 // [2^-100, 2^100) or zero: reciprocal step, else IEEE division).
-template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS = false, bool PRE = false, bool FRONT = false>
+//
+// DOWN: sources above the mixer's rate, up to twice (48 kHz in a 44.1 kHz mixer, 96 kHz in a 48 kHz one) on fast tiles: every
+// output moves on q = from / to whole frames (1 or 2) plus one more on a numerator carry, and reloads both taps from the
+// ring; a tile consumes at most one chunk, so the refill logic is the one of the up-sampling tile.  Row::pre is always
+// applied (no PRE twin).  Larger ratios stay on the slow tiles.
+template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS = false, bool PRE = false, bool FRONT = false, bool DOWN = false>
 SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
     static_assert(CI == CO || (CI == 1 && CO == 2), "channel layouts served");
+    static_assert(!DOWN || (!PASS && !PRE && !FRONT), "DOWN: interpolating, the gain in front always applied, filter behind");
     static_assert(!FRONT || (HASB && !FF2 && !PRE), "FRONT: plain coefficients, the gain in front is always applied");
     using G = Geo<CI>;
     constexpr int C = CI;               // taps, ring and filter state follow the source's channels
@@ -171,7 +179,7 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
     const uint64_t ms = row.mix_start, end = row.mix_start + row.out_len;   // frames
     // Down-sampling classes (from > to: more than one input frame per output) are served by the slow tiles only -- exact,
     // general, not fast; the fast run below assumes at most one new frame per step.
-    const bool safe = has && a.from <= a.to && !(row.flags & ROW_FORCE_SLOW) &&
+    const bool safe = has && (a.from <= a.to || (DOWN && a.from <= 2 * a.to)) && !(row.flags & ROW_FORCE_SLOW) &&
                       (PASS || FRONT || (!(row.flags & ROW_UNSAFE) && !(a.unsafe && a.unsafe[r])));
     const bool stops = !(row.flags & ROW_CONTINUES);   // the stream ends inside this block (or is a whole stream)
     const bool live = has && row.out_len != 0;
@@ -187,6 +195,8 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
     uint64_t fpos = row.f0;   // FRONT: frames of in[] consumed by the filter
     // the gain in front for input frame k (relative to in[0]): frames the converter pulled in earlier blocks keep their factor
     const float gcur = FRONT ? gmid : gpre;
+    const float rem_f = a.rem_f;
+    const int adv_w0 = (int)a.adv_q * C, adv_w1 = adv_w0 + C;   // DOWN: ring words per output without / with a carry
     auto gain_of = [&](uint64_t k) { return k >= row.f0 ? gcur : (k + 1 == row.f0 ? row.gb : row.ga); };
     // canonical filter state per channel: x[n-1], x[n-2], y[n-1], y[n-2]
     float xh1[C], xh2[C], y1[C], y2[C];
@@ -265,7 +275,7 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                 const uint64_t mq = ((row.L * C - 1) >> 2) - ((ibase * C) >> 2);   // last quad (relative) that holds a frame
                 maxq = mq > 0x7fffffffull ? 0x7fffffffu : (uint32_t)mq;
                 if (FRONT) front_catch_up(i + 2);       // interior: i + 1 < L
-                if (PRE || FRONT) g_tap0 = gain_of(i), g_tap1 = gain_of(i + 1);
+                if (PRE || FRONT || DOWN) g_tap0 = gain_of(i), g_tap1 = gain_of(i + 1);
             }
             // the streams this lane copies for: source pointer and clamp of stream cr + RPI * j
             uint64_t sq[QPC];
@@ -292,18 +302,20 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
             issue(1);
             simt::cp_wait<1>();   // chunk 0 has landed
             simt::syncwarp();
-            issue(2);
-            uint32_t c_ready = 1;   // chunks [0, c_ready) are readable; c_ready and c_ready + 1 are in flight
+            // DOWN looks one chunk ahead instead of two: a tile may consume a whole chunk, so the slowest lane can still be
+            // reading chunk c_ready - 2 when chunk c_ready is waited for -- the new copy then goes into the slot of c_ready - 3
+            if (!DOWN) issue(2);
+            uint32_t c_ready = 1;   // chunks [0, c_ready) are readable; c_ready and (not DOWN) c_ready + 1 are in flight
             const simt::sptr ring_end = simt::sptr_of(ringl + RING);
             simt::sptr p = simt::sptr_of(ringl + k0 * C);
             float x0[C], x1[C];
 #pragma unroll
             for (int c = 0; c < C; c++) {
                 x0[c] = simt::lds(simt::sptr_add(p, c)), x1[c] = simt::lds(simt::sptr_add(p, C + c));
-                if (PRE) x0[c] = simt::fmul(x0[c], g_tap0), x1[c] = simt::fmul(x1[c], g_tap1);
+                if (PRE || DOWN) x0[c] = simt::fmul(x0[c], g_tap0), x1[c] = simt::fmul(x1[c], g_tap1);
                 if (FRONT) x0[c] = simt::fmul(y2[c], g_tap0), x1[c] = simt::fmul(y1[c], g_tap1);   // the filter is one frame ahead
             }
-            p = simt::sptr_add(p, 2 * C);
+            if (!DOWN) p = simt::sptr_add(p, 2 * C);   // the next frame to fetch; DOWN keeps the cursor on the left tap
             float nf = simt::u2f(num);
             // upper bound (in frames) of any lane's next ring frame after the coming tile: the lane with the largest phase
             uint32_t kb = 5, kbn = to - 1;
@@ -321,9 +333,15 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                 kb += a.q8, kbn += a.r8;
                 if (kbn >= to) kbn -= to, kb += 1;
                 if ((kb - 1) / CHF >= c_ready) {
-                    simt::cp_wait<1>();      // chunk c_ready has landed (c_ready + 1 may still be in flight)
-                    simt::syncwarp();        // ... for every lane, and nobody reads chunk c_ready - 2 any more
-                    issue(c_ready + 2);      // into the slot of chunk c_ready - 2
+                    if (DOWN) {
+                        simt::cp_wait<0>();      // chunk c_ready has landed
+                        simt::syncwarp();        // ... for every lane, and nobody reads chunk c_ready - 3 any more
+                        issue(c_ready + 1);      // into the slot of chunk c_ready - 3
+                    } else {
+                        simt::cp_wait<1>();      // chunk c_ready has landed (c_ready + 1 may still be in flight)
+                        simt::syncwarp();        // ... for every lane, and nobody reads chunk c_ready - 2 any more
+                        issue(c_ready + 2);      // into the slot of chunk c_ready - 2
+                    }
                     c_ready += 1;
                     simt::emu_count(2, 1);
                 }
@@ -345,7 +363,18 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                         }
                     }
                     // next output frame: numerator += from (mod to); a carry moves one input frame on
-                    if (FRONT) {
+                    if (DOWN) {
+                        const float nf2 = simt::fadd(nf, rem_f);
+                        const bool carry = nf2 >= den;
+                        nf = carry ? simt::fsub(nf2, den) : nf2;
+                        p = simt::sptr_add(p, carry ? adv_w1 : adv_w0);
+                        if (simt::sptr_ge(p, ring_end)) p = simt::sptr_add(p, -RING);
+#pragma unroll
+                        for (int c = 0; c < C; c++) {
+                            x0[c] = simt::fmul(simt::lds(simt::sptr_add(p, c)), gpre);
+                            x1[c] = simt::fmul(simt::lds(simt::sptr_add(p, C + c)), gpre);
+                        }
+                    } else if (FRONT) {
                         float raw[C];
                         if (simt::lerp_carry<C>(nf, p, from_f, den, raw)) {
                             front_step(raw);
@@ -435,11 +464,11 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                         }
                     } else if (on) {
                         float xa = simt::ldg(row.in + i * C + c);
-                        if (PRE) xa = simt::fmul(xa, gain_of(i));
+                        if (PRE || DOWN) xa = simt::fmul(xa, gain_of(i));
                         float x = xa;
                         if (!PASS && i + 1 < row.L) {
                             float xb = simt::ldg(row.in + (i + 1) * C + c);
-                            if (PRE) xb = simt::fmul(xb, gain_of(i + 1));
+                            if (PRE || DOWN) xb = simt::fmul(xb, gain_of(i + 1));
                             x = simt::fadd(xa, simt::fdiv(simt::fmul(simt::fsub(xb, xa), simt::u2f(num)), den));
                         }
                         float y = x;

@@ -43,6 +43,9 @@ inline bool pre_gain_keeps_class(float g) {
     return a >= 0.015625f && a <= 64.0f;   // false for NaN too
 }
 
+// A class above the mixer's rate, up to twice, runs on the DOWN instantiation (fast tiles); beyond that on the slow tiles.
+inline bool ratio_runs_down(uint32_t from, uint32_t to) { return from > to && (uint64_t)from <= 2ull * to; }
+
 inline void fill_ratio(Args& a, uint32_t from, uint32_t to, uint32_t channels) {
     a.from = from, a.to = to;
     const uint64_t tf = TILE / channels;   // frames per tile
@@ -51,6 +54,7 @@ inline void fill_ratio(Args& a, uint32_t from, uint32_t to, uint32_t channels) {
     a.den_f = (float)to;
     a.rcp_den = 1.0f / a.den_f;
     a.from_f = (float)from;
+    a.adv_q = from / to, a.rem_f = (float)(from % to);
     a.neg1 = -1.0f;
 }
 

@@ -200,7 +200,7 @@ extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t*
                 const float* c = coefs + 5 * r;
                 row.b0 = c[0], row.b1 = c[1], row.b2 = c[2], row.a1 = c[3], row.a2 = c[4], row.ffk = ffk[r];
             }
-            row.post = gain[r];
+            row.post = gain[r], row.pre = 1.0f, row.mid = 1.0f;   // no gain in front (the DOWN variants always apply Row::pre)
             row.flags = (unsafe[r] ? ROW_UNSAFE : 0u) | (parts[r].continues ? ROW_CONTINUES : 0u);
         }
         const uint64_t pstride = round_up_tile(n * C);

@@ -552,3 +552,25 @@ def test_filter_in_front_of_the_conversion(emu):
     assert counters(emu)["divided"] > 0        # lane 0 met quotients outside the reciprocal's exact range and divided
     # tiny streams
     check(emu, [noise(k, 1600 + k) for k in (0, 1, 2, 3, 5)], 44100, 48000, [0, 1, 2, 3, 4], lp=300, front=True, mid=0.5)
+
+
+def test_sources_above_the_mixers_rate_on_fast_tiles(emu):
+    """48 kHz sources in a 44.1 kHz mixer, 96 kHz in a 48 kHz one (exactly two frames per output), 88.2 kHz in 48 kHz: up to
+    twice the mixer's rate the lane kernel has fast tiles of its own (DOWN: one or two frames per output plus the carry, both
+    taps reloaded); beyond that (96 kHz into 44.1 kHz) the slow tiles."""
+    n = 40
+    pcms = [noise(4000 + 29 * i, 1700 + i) for i in range(n)]
+    for in_rate, mix_rate, kw in ((48000, 44100, dict(lp=300, gain=0.8)), (96000, 48000, dict(lp=300, gain=0.8)), (88200, 48000, dict(hp=400)),
+                                  (48000, 44100, dict(gain=1.1)), (48000, 44100, dict(lp=300, gain=0.8, pre=[0.3 + 0.01 * i for i in range(n)]))):
+        counters(emu)
+        check(emu, pcms, in_rate, mix_rate, [3 * (i % 5) for i in range(n)], **kw)
+        c = counters(emu)
+        assert c["fast"] > 4 * c["slow"] and c["refills"] > 20, (in_rate, mix_rate, c)
+    counters(emu)
+    check(emu, pcms[:8], 96000, 44100, [0] * 8, lp=300, gain=0.8)
+    assert counters(emu)["fast"] == 0
+    ch_in = [2 if i % 3 else 1 for i in range(12)]
+    st = [noise(ci * (2500 + 9 * i), 1800 + i) for i, ci in enumerate(ch_in)]
+    counters(emu)
+    check(emu, st, [48000, 44100, 88200] * 4, 44100, [0] * 12, channels=2, ch_in=ch_in, lp=400, gain=1.1)
+    assert counters(emu)["fast"] > 100

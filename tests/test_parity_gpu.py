@@ -650,8 +650,8 @@ def test_lanes_unsafe_inputs_stay_exact(ctx):
 
 @lanes_gate
 def test_lanes_mixed_rate_pairs_and_fallback(ctx):
-    """Several rate pairs in one mixer (44.1 kHz, 48 kHz pass-through, 32 kHz) are served class by class; a down-sampling
-    source is outside the kernel's shape: the flag is ignored there and the default fused kernels serve the batch."""
+    """Several rate pairs in one mixer (44.1 kHz, 48 kHz pass-through, 32 kHz) are served class by class; a source at more than
+    twice the mixer's rate is outside the kernel's batch shape: the flag is ignored there and the other kernels serve the batch."""
     rates = [44100, 48000, 32000, 44100, 48000, 22050] * 8
     pcms = [noise(1500 + 13 * i, 40 + i) for i in range(len(rates))]
     srcs = [rb.UniformSourceIterator(rb.TestSource(p, 1, r), 1, 48000).low_pass(500).amplify(0.9) for p, r in zip(pcms, rates)]
@@ -668,7 +668,7 @@ def test_lanes_mixed_rate_pairs_and_fallback(ctx):
         idx = [i for i, r in enumerate(rates) if r == rate]
         acc = acc + (lanes_expected_mix([per_stream[i] for i in idx], [0] * len(idx), ref.size) - np.float32(0.0))
     assert_bit_exact(got, acc, "mixed rate pairs vs oracle streams + class-wise tree")
-    d = rb.UniformSourceIterator(rb.TestSource(noise(2000, 3), 1, 48000), 1, 44100).low_pass(200)
+    d = rb.UniformSourceIterator(rb.TestSource(noise(2000, 3), 1, 96000), 1, 44100).low_pass(200)
     with rb.Batch([d], 1, 44100, flags=LANES, ctx=ctx) as b:
         assert b.kernel_family != 2
         b.upload_all()
@@ -1075,3 +1075,37 @@ def test_session_player_volume_changes(ctx):
     assert np.unique(gains).size == 5
     want = oracle.chain_uniform(to_oracle(rb.UniformSourceIterator(rb.TestSource(pcm * gains, 1, rate), 1, 48000).low_pass(500).amplify(0.9)), 1, 48000)
     assert_bit_exact(np.concatenate(got), want + np.float32(0.0), "volume changes in front of the conversion")
+
+
+@lanes_gate
+@pytest.mark.parametrize("rate,mix", [(48000, 44100), (96000, 48000), (88200, 48000)])
+def test_lanes_and_session_sources_above_the_mixers_rate(ctx, rate, mix):
+    """Sources above the mixer's rate, up to twice: fast tiles of their own in the lane kernel (one or two input frames per
+    output plus the carry).  Batch on request (RB_FUSED_LANES; without the flag the default kernels keep such batches) and
+    session, both bit for bit against the oracle streams summed with the kernel's tree."""
+    n = 70
+    pcms = [noise(5000 + 31 * i, 6400 + i) for i in range(n)]
+    mk = lambda p: rb.UniformSourceIterator(rb.TestSource(p, 1, rate), 1, mix).low_pass(300).amplify(0.9)
+    srcs = [mk(p) for p in pcms]
+    per_stream = [oracle.chain_uniform(to_oracle(s), 1, mix) for s in srcs]
+    with rb.Batch(srcs, 1, mix, flags=LANES, ctx=ctx) as b:
+        assert b.kernel_family == 2
+        b.upload_all()
+        whole = b.render_mix()
+    assert_bit_exact(whole, lanes_expected_mix(per_stream, [0] * n, whole.size), "down-sampling batch on the lane kernel")
+    assert_close_peak(whole, oracle.mixer([to_oracle(s) for s in srcs], 1, mix), 1e-5, "... and the reference's sequential mixer")
+    with rb.Batch(srcs, 1, mix, ctx=ctx) as b:
+        assert b.kernel_family != 2                      # not chosen automatically
+    got, pos, ended, k = [], 0, False, rate // 100
+    with rb.Session([mk(np.zeros(0, np.float32)) for _ in pcms], mix, fifo_frames=4096, max_block_frames=480, ctx=ctx) as s:
+        while not ended:
+            s.push_packed([p[pos:pos + k] for p in pcms], [pos + k >= p.size for p in pcms])
+            pos += k
+            while True:
+                block, ended = s.render(480)
+                got.append(block)
+                if block.size == 0 or ended:
+                    break
+    got = np.concatenate(got)
+    assert_bit_exact(got, whole[:got.size], "the session in 10 ms blocks vs the whole-stream render")
+    assert got.size == whole.size or not np.any(whole[got.size:])

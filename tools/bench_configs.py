@@ -108,6 +108,7 @@ def main():
             ("mono: amplify -> uniform -> low_pass(200) -> amplify", 1, lambda: rb.UniformSourceIterator(rb.TestSource(mono, 1, 44100).amplify(0.9), 1, 48000).low_pass(200).amplify(1.2)),
             ("mono: low_pass(200) -> amplify -> uniform (filter in front)", 1, lambda: rb.UniformSourceIterator(rb.TestSource(mono, 1, 44100).low_pass(200).amplify(0.9), 1, 48000)),
             ("stereo: low_pass(200) -> amplify -> uniform (filter in front)", 2, lambda: rb.UniformSourceIterator(rb.TestSource(stereo, 2, 44100).low_pass(200).amplify(0.9), 2, 48000)),
+            ("mono 96 kHz into 48 kHz (DOWN tiles): uniform -> low_pass(200) -> amplify", 1, lambda: rb.UniformSourceIterator(rb.TestSource(z(96000), 1, 96000), 1, 48000).low_pass(200).amplify(1.2)),
         ]
         for label, ch, mk in shapes:
             srcs = [mk() for _ in range(S)]
