@@ -115,7 +115,9 @@ template <int CI, int CO>
 static void launch_lanes_cc(const lanes::Args& a, bool has_biquad, bool ff2, bool has_post, bool has_pre, bool front, cudaStream_t st) {
     const bool pass = a.from == a.to;   // sources at the mixer's rate: taps used raw
     if (front) {                        // the filter in front of the conversion: plain coefficients, Row::pre always applied
-        if (pass) has_post ? launch_lanes<CI, CO, true, false, 1, true, false, true>(a, st) : launch_lanes<CI, CO, true, false, 0, true, false, true>(a, st);
+        if (lanes::ratio_runs_down(a.from, a.to))
+            has_post ? launch_lanes<CI, CO, true, false, 1, false, false, true, true>(a, st) : launch_lanes<CI, CO, true, false, 0, false, false, true, true>(a, st);
+        else if (pass) has_post ? launch_lanes<CI, CO, true, false, 1, true, false, true>(a, st) : launch_lanes<CI, CO, true, false, 0, true, false, true>(a, st);
         else has_post ? launch_lanes<CI, CO, true, false, 1, false, false, true>(a, st) : launch_lanes<CI, CO, true, false, 0, false, false, true>(a, st);
         return;
     }

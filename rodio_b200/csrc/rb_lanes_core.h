@@ -156,11 +156,12 @@ SIMT_FN float reduce_tile(const float (&v)[TILE], uint32_t ln) {
 // DOWN: sources above the mixer's rate, up to twice (48 kHz in a 44.1 kHz mixer, 96 kHz in a 48 kHz one) on fast tiles: every
 // output moves on q = from / to whole frames (1 or 2) plus one more on a numerator carry, and reloads both taps from the
 // ring; a tile consumes at most one chunk, so the refill logic is the one of the up-sampling tile.  Row::pre is always
-// applied (no PRE twin).  Larger ratios stay on the slow tiles.
+// applied (no PRE twin).  Larger ratios stay on the slow tiles.  With FRONT the one or two frames an output moves on are
+// one or two steps of the filter.
 template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS = false, bool PRE = false, bool FRONT = false, bool DOWN = false>
 SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
     static_assert(CI == CO || (CI == 1 && CO == 2), "channel layouts served");
-    static_assert(!DOWN || (!PASS && !PRE && !FRONT), "DOWN: interpolating, the gain in front always applied, filter behind");
+    static_assert(!DOWN || (!PASS && !PRE), "DOWN: interpolating, the gain in front always applied");
     static_assert(!FRONT || (HASB && !FF2 && !PRE), "FRONT: plain coefficients, the gain in front is always applied");
     using G = Geo<CI>;
     constexpr int C = CI;               // taps, ring and filter state follow the source's channels
@@ -312,10 +313,10 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
 #pragma unroll
             for (int c = 0; c < C; c++) {
                 x0[c] = simt::lds(simt::sptr_add(p, c)), x1[c] = simt::lds(simt::sptr_add(p, C + c));
-                if (PRE || DOWN) x0[c] = simt::fmul(x0[c], g_tap0), x1[c] = simt::fmul(x1[c], g_tap1);
+                if (PRE || (DOWN && !FRONT)) x0[c] = simt::fmul(x0[c], g_tap0), x1[c] = simt::fmul(x1[c], g_tap1);
                 if (FRONT) x0[c] = simt::fmul(y2[c], g_tap0), x1[c] = simt::fmul(y1[c], g_tap1);   // the filter is one frame ahead
             }
-            if (!DOWN) p = simt::sptr_add(p, 2 * C);   // the next frame to fetch; DOWN keeps the cursor on the left tap
+            if (!DOWN || FRONT) p = simt::sptr_add(p, 2 * C);   // the next frame to fetch; DOWN (without FRONT) keeps the cursor on the left tap
             float nf = simt::u2f(num);
             // upper bound (in frames) of any lane's next ring frame after the coming tile: the lane with the largest phase
             uint32_t kb = 5, kbn = to - 1;
@@ -363,7 +364,22 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                         }
                     }
                     // next output frame: numerator += from (mod to); a carry moves one input frame on
-                    if (DOWN) {
+                    if (DOWN && FRONT) {
+                        const float nf2 = simt::fadd(nf, rem_f);
+                        const bool carry = nf2 >= den;
+                        nf = carry ? simt::fsub(nf2, den) : nf2;
+                        const int adv = (int)a.adv_q + (carry ? 1 : 0);   // 1 or 2 frames: as many filter steps
+                        for (int k = 0; k < adv; k++) {
+                            float raw[C];
+#pragma unroll
+                            for (int c = 0; c < C; c++) raw[c] = simt::lds(simt::sptr_add(p, c));
+                            p = simt::sptr_add(p, C);
+                            if (simt::sptr_ge(p, ring_end)) p = simt::sptr_add(p, -RING);
+                            front_step(raw);
+                        }
+#pragma unroll
+                        for (int c = 0; c < C; c++) x0[c] = simt::fmul(y2[c], gmid), x1[c] = simt::fmul(y1[c], gmid);
+                    } else if (DOWN) {
                         const float nf2 = simt::fadd(nf, rem_f);
                         const bool carry = nf2 >= den;
                         nf = carry ? simt::fsub(nf2, den) : nf2;

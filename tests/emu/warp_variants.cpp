@@ -23,6 +23,12 @@ void run(const lanes::Args& a, uint32_t group, simt::WarpEmu* w, float* ring) {
 void RB_EMU_CAT(emu_run_part_, RB_EMU_PART)(const lanes::Args& a, uint32_t g, simt::WarpEmu* w, float* ring, bool hasb, bool ff2, bool npost, bool front) {
     if constexpr (!PRE) {   // the filter in front of the conversion: plain coefficients, the gain in front always applied
         if (front) {
+            if constexpr (!PASS) {
+                if (lanes::ratio_runs_down(a.from, a.to)) {
+                    npost ? run<true, false, 1, true, true>(a, g, w, ring) : run<true, false, 0, true, true>(a, g, w, ring);
+                    return;
+                }
+            }
             npost ? run<true, false, 1, true>(a, g, w, ring) : run<true, false, 0, true>(a, g, w, ring);
             return;
         }

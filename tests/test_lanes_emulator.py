@@ -540,8 +540,14 @@ def test_filter_in_front_of_the_conversion(emu):
     c = counters(emu)
     assert c["fast"] > 4 * c["slow"]
     check(emu, pcms, [44100, 22050, 48000, 32000] * 10, 48000, [5 * (i % 7) for i in range(n)], hp=500, front=True)
-    check(emu, pcms[:8], 48000, 44100, [0] * 8, lp=1000, front=True, mid=0.7)            # down-sampling: slow tiles
-    check(emu, pcms[:8], 96000, 44100, [3 * i for i in range(8)], lp=1000, front=True)    # more than two input frames per output
+    counters(emu)
+    check(emu, pcms, 48000, 44100, [0] * n, lp=1000, front=True, mid=0.7)                 # above the mixer's rate: one or two
+    check(emu, pcms, 96000, 48000, [2 * (i % 3) for i in range(n)], lp=1000, front=True, gain=0.9)   # filter steps per output
+    c = counters(emu)
+    assert c["fast"] > 4 * c["slow"]
+    counters(emu)
+    check(emu, pcms[:8], 96000, 44100, [3 * i for i in range(8)], lp=1000, front=True)    # more than two input frames per output:
+    assert counters(emu)["fast"] == 0                                                      # slow tiles
     ch_in = [2 if i % 3 else 1 for i in range(12)]
     st = [noise(ci * (900 + 9 * i), 1400 + i) for i, ci in enumerate(ch_in)]
     check(emu, st, [44100, 48000, 22050] * 4, 48000, [0] * 12, channels=2, ch_in=ch_in, lp=400, front=True, mid=0.6, gain=1.1)
