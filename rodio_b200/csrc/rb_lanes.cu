@@ -14,8 +14,10 @@ namespace {
 
 constexpr int LANES_WARPS = 2;                      // warps per CTA: every warp is independent, small CTAs pack the SM
 constexpr int LANES_THREADS = 32 * LANES_WARPS;
-template <int C>
-constexpr size_t lanes_smem_bytes() { return (size_t)LANES_WARPS * 32 * lanes::Geo<C>::RS * sizeof(float); }   // 21.0 KB
+template <int C, bool DOWN>
+constexpr int lanes_rs() { return lanes::Geo<C, DOWN ? lanes::NSLOT_DOWN : RB_LANES_UP_SLOTS>::RS; }
+template <int C, bool DOWN>
+constexpr size_t lanes_smem_bytes() { return (size_t)LANES_WARPS * 32 * lanes_rs<C, DOWN>() * sizeof(float); }   // 21.0 KB
 
 template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS, bool PRE, bool FRONT, bool DOWN>
 __global__ void __launch_bounds__(LANES_THREADS) k_fused_lanes(lanes::Args a) {
@@ -23,7 +25,7 @@ __global__ void __launch_bounds__(LANES_THREADS) k_fused_lanes(lanes::Args a) {
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t group = blockIdx.x * LANES_WARPS + warp;
     if (group >= a.n_groups) return;   // whole warps leave: the warp program only synchronises within a warp
-    lanes::warp_main<CI, CO, HASB, FF2, NPOST, PASS, PRE, FRONT, DOWN>(a, group, lanes_smem + (size_t)warp * 32 * lanes::Geo<CI>::RS);
+    lanes::warp_main<CI, CO, HASB, FF2, NPOST, PASS, PRE, FRONT, DOWN>(a, group, lanes_smem + (size_t)warp * 32 * lanes::Geo<CI, DOWN ? lanes::NSLOT_DOWN : RB_LANES_UP_SLOTS>::RS);
 }
 
 // One CTA per stream: does every non-zero |x| lie inside [2^-70, 2^60]?  (rb_lanes_core.h, "Exact division".)
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(256) k_classify_range(const float* __restrict_
 template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS, bool PRE, bool FRONT = false, bool DOWN = false>
 static void launch_lanes(const lanes::Args& a, cudaStream_t st) {
     const uint32_t n_ctas = (a.n_groups + LANES_WARPS - 1) / LANES_WARPS;
-    k_fused_lanes<CI, CO, HASB, FF2, NPOST, PASS, PRE, FRONT, DOWN><<<n_ctas, LANES_THREADS, lanes_smem_bytes<CI>(), st>>>(a);   // < 48 KB: no opt-in needed
+    k_fused_lanes<CI, CO, HASB, FF2, NPOST, PASS, PRE, FRONT, DOWN><<<n_ctas, LANES_THREADS, lanes_smem_bytes<CI, DOWN>(), st>>>(a);   // < 48 KB: no opt-in needed
 }
 template <int CI, int CO, bool PASS, bool PRE>
 static void launch_lanes_c(const lanes::Args& a, bool has_biquad, bool ff2, bool has_post, cudaStream_t st) {

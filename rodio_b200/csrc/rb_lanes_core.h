@@ -54,11 +54,20 @@ constexpr int TILE = 8;                 // timeline SAMPLES per loop iteration (
 #define RB_LANES_STEREO_CHW 16
 #endif
 constexpr int CHUNK = 16;               // 32-bit words per ring chunk and lane (one cp.async group): 16 mono / 8 stereo frames
-constexpr int NSLOT = 4;                // ring slots: chunk c-1 (draining), c, c+1 (in flight), c+2 (just issued)
+// Ring slots of the up-sampling / same-rate tiles.  4 (the measured geometry): chunk c-1 (draining), c, c+1 (in flight),
+// c+2 (just issued) -- two chunks of look-ahead.  -DRB_LANES_UP_SLOTS=3 builds them with ONE chunk of look-ahead (a chunk is
+// two tiles of work, several HBM latencies at the measured issue rate) and 68 instead of 84 words per lane: 24 instead of 20
+// warps per SM.  Verified on the emulator, never timed: an A/B knob for the next device pass.  The DOWN tiles always have
+// 4 slots and one chunk of look-ahead (see there).
+#ifndef RB_LANES_UP_SLOTS
+#define RB_LANES_UP_SLOTS 4
+#endif
+static_assert(RB_LANES_UP_SLOTS == 3 || RB_LANES_UP_SLOTS == 4, "3 (one chunk ahead) or 4 (two chunks ahead)");
+constexpr int NSLOT_DOWN = 4;
 constexpr uint32_t RUN_CAP = 1u << 30;  // frames
 constexpr int MIN_RUN_TILES = 4;        // shortest fast run worth priming the ring for
 // Per-lane ring geometry for C interleaved channels (C = 1 mono, 2 stereo); sizes in 32-bit words.
-template <int C>
+template <int C, int NSLOT = RB_LANES_UP_SLOTS>
 struct Geo {
     static constexpr int TF = TILE / C;            // frames per tile
     // words per chunk: 64 bytes per lane for either layout.  (Stereo lanes had 16-frame chunks when the kernel first ran on
@@ -163,7 +172,9 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
     static_assert(CI == CO || (CI == 1 && CO == 2), "channel layouts served");
     static_assert(!DOWN || (!PASS && !PRE), "DOWN: interpolating, the gain in front always applied");
     static_assert(!FRONT || (HASB && !FF2 && !PRE), "FRONT: plain coefficients, the gain in front is always applied");
-    using G = Geo<CI>;
+    constexpr int NSLOT = DOWN ? NSLOT_DOWN : RB_LANES_UP_SLOTS;
+    constexpr bool ONE_AHEAD = DOWN || RB_LANES_UP_SLOTS == 3;   // one chunk of look-ahead instead of two
+    using G = Geo<CI, NSLOT>;
     constexpr int C = CI;               // taps, ring and filter state follow the source's channels
     constexpr int TF = TILE / CO;       // frames per tile: the mixer timeline has CO samples per frame
     constexpr int RS = G::RS, QPC = G::QPC, RPI = G::RPI, RING = G::RING, MIRROR = G::MIRROR, CHW = G::CHW, CHF = G::CHF;
@@ -305,8 +316,8 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
             simt::syncwarp();
             // DOWN looks one chunk ahead instead of two: a tile may consume a whole chunk, so the slowest lane can still be
             // reading chunk c_ready - 2 when chunk c_ready is waited for -- the new copy then goes into the slot of c_ready - 3
-            if (!DOWN) issue(2);
-            uint32_t c_ready = 1;   // chunks [0, c_ready) are readable; c_ready and (not DOWN) c_ready + 1 are in flight
+            if (!ONE_AHEAD) issue(2);
+            uint32_t c_ready = 1;   // chunks [0, c_ready) are readable; c_ready and (two ahead) c_ready + 1 are in flight
             const simt::sptr ring_end = simt::sptr_of(ringl + RING);
             simt::sptr p = simt::sptr_of(ringl + k0 * C);
             float x0[C], x1[C];
@@ -334,10 +345,10 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                 kb += a.q8, kbn += a.r8;
                 if (kbn >= to) kbn -= to, kb += 1;
                 if ((kb - 1) / CHF >= c_ready) {
-                    if (DOWN) {
+                    if (ONE_AHEAD) {
                         simt::cp_wait<0>();      // chunk c_ready has landed
-                        simt::syncwarp();        // ... for every lane, and nobody reads chunk c_ready - 3 any more
-                        issue(c_ready + 1);      // into the slot of chunk c_ready - 3
+                        simt::syncwarp();        // ... for every lane, and nobody reads chunk c_ready + 1 - NSLOT any more
+                        issue(c_ready + 1);      // into the slot of chunk c_ready + 1 - NSLOT (DOWN: c - 3, 3 slots: c - 2)
                     } else {
                         simt::cp_wait<1>();      // chunk c_ready has landed (c_ready + 1 may still be in flight)
                         simt::syncwarp();        // ... for every lane, and nobody reads chunk c_ready - 2 any more

@@ -38,7 +38,7 @@ cudaError_t rb_lanes_launch_kernel(const lanes::Args& a, uint32_t ch_in, uint32_
         for (auto& kv : g_allocs) warp.readable.push_back({(const char*)kv.first, (const char*)kv.first + kv.second});
     }
     const float nan = std::numeric_limits<float>::quiet_NaN();
-    constexpr int MAX_RS = lanes::Geo<2>::RS;
+    constexpr int MAX_RS = lanes::Geo<2, 4>::RS;   // the largest ring of any variant
     std::vector<float> ring_store(32 * MAX_RS + 4, nan);
     float* ring = ring_store.data();
     while ((uintptr_t)ring & 15) ring++;

@@ -17,7 +17,7 @@ void run_group_any(uint32_t ci, uint32_t co, const lanes::Args& a, uint32_t g, s
                    bool pre = false, bool front = false) {
     emu_run_group(ci, co, a, g, w, ring, hasb, ff2, npost, pre, front);
 }
-constexpr int MAX_RS = lanes::Geo<2>::RS;
+constexpr int MAX_RS = lanes::Geo<2, 4>::RS;   // the largest ring of any variant
 }  // namespace
 
 // coverage of the last runs: [0] fast tiles, [1] slow tiles, [2] ring refills; reset = 1 clears the counters

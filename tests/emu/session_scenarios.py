@@ -9,9 +9,10 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), HERE]
+import build_emu                                      # noqa: E402
 import rodio_b200._capi as capi                       # noqa: E402
-capi.LIB_PATH = os.path.join(HERE, "librodio_b200_hostemu.so")
+capi.LIB_PATH = build_emu.HOST_LIB                    # RB_EMU_VARIANT picks a geometry variant of the kernel
 import oracle                                         # noqa: E402
 import rodio_b200 as rb                               # noqa: E402
 from helpers import assert_bit_exact, assert_close_peak, noise, to_oracle     # noqa: E402

@@ -79,7 +79,7 @@ def test_plain_c_example_runs_on_the_emulator(hostemu):
     plain mono 48 kHz one through a stereo session, from C."""
     exe = os.path.join(HERE, "cpp", "stream_mixer_emu.bin")
     subprocess.run(["gcc", "-std=c11", "-D_GNU_SOURCE", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "stream_mixer.c"),
-                    "-o", exe, "-L", EMU, "-l:librodio_b200_hostemu.so", f"-Wl,-rpath,{EMU}", "-lm"], check=True, capture_output=True)
+                    "-o", exe, "-L", EMU, "-l:" + os.path.basename(hostemu), f"-Wl,-rpath,{EMU}", "-lm"], check=True, capture_output=True)
     r = subprocess.run([exe, "6"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     frames, peak = int(r.stdout.split()[0]), float(r.stdout.split()[-1])
@@ -91,7 +91,7 @@ def test_live_player_example_runs_on_the_emulator(hostemu):
     Player controls on a session, from C, against the host-emulated library."""
     exe = os.path.join(HERE, "cpp", "live_player_emu.bin")
     subprocess.run(["gcc", "-std=c11", "-D_GNU_SOURCE", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "live_player.c"),
-                    "-o", exe, "-L", EMU, "-l:librodio_b200_hostemu.so", f"-Wl,-rpath,{EMU}", "-lm"], check=True, capture_output=True)
+                    "-o", exe, "-L", EMU, "-l:" + os.path.basename(hostemu), f"-Wl,-rpath,{EMU}", "-lm"], check=True, capture_output=True)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     w = r.stdout.replace(",", " ").split()
@@ -118,6 +118,6 @@ def test_cpp_live_mixer_on_the_emulator(hostemu):
     mono and stereo, against the whole-stream lane render) linked against the host-emulated library."""
     exe = os.path.join(HERE, "cpp", "test_session_api_emu.bin")
     subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(HERE, "cpp", "test_session_api.cpp"), "-o", exe,
-                    "-L", EMU, "-l:librodio_b200_hostemu.so", f"-Wl,-rpath,{EMU}"], check=True, capture_output=True)
+                    "-L", EMU, "-l:" + os.path.basename(hostemu), f"-Wl,-rpath,{EMU}"], check=True, capture_output=True)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "all session API tests passed" in r.stdout, r.stdout + r.stderr

@@ -38,6 +38,13 @@ RODIO_B200_LIB="$PWD/rodio_b200/librodio_b200_chw32.so" timeout 400 python tools
     > "$OUT/lanes_shapes_chw32.jsonl" 2> "$OUT/lanes_shapes_chw32.err"
 echo "lanes shapes (128-byte stereo chunks) exit $?" | tee -a "$OUT/summary.txt"
 
+# 3c. ring with three slots and one chunk of look-ahead (68 instead of 84 words per lane: 24 instead of 20 warps per SM)
+timeout 300 python -c "from rodio_b200 import build; build.build(force=True, extra_flags=['-DRB_LANES_UP_SLOTS=3'], out='rodio_b200/librodio_b200_slots3.so')" \
+    > "$OUT/build_slots3.log" 2>&1 && \
+RODIO_B200_LIB="$PWD/rodio_b200/librodio_b200_slots3.so" timeout 600 python tools/bench_configs.py lanes lanes_shapes \
+    > "$OUT/lanes_slots3.jsonl" 2> "$OUT/lanes_slots3.err"
+echo "lanes sweep + shapes (3 ring slots) exit $?" | tee -a "$OUT/summary.txt"
+
 # 4. launch list and one full capture of the new kernel (numbers printed under ncu are never bench values)
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file "$OUT/launches_lanes.csv" \
     python bench.py --streams 16384 --seconds 1 --flags 16 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2>&1
