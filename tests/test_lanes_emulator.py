@@ -6,6 +6,7 @@ CPU only -- the GPU counterpart is tests/test_parity_gpu.py::test_lanes_*."""
 import ctypes as C
 import math
 import os
+import subprocess
 import sys
 
 import numpy as np
@@ -580,3 +581,13 @@ def test_sources_above_the_mixers_rate_on_fast_tiles(emu):
     counters(emu)
     check(emu, st, [48000, 44100, 88200] * 4, 44100, [0] * 12, channels=2, ch_in=ch_in, lp=400, gain=1.1)
     assert counters(emu)["fast"] > 100
+
+
+def test_three_slot_ring_variant(built):
+    """The A/B knob -DRB_LANES_UP_SLOTS=3 (three ring slots, one chunk of look-ahead: rb_lanes_core.h) stays correct: a subset of
+    this file against an emulator library built with it (RB_EMU_VARIANT=slots3 runs everything)."""
+    env = dict(os.environ, RB_EMU_VARIANT="slots3")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-p", "no:cacheprovider", "-k",
+                        "cfg3 or stereo_ragged or mixed_rates or gain_in_front or filter_in_front or any_split"],
+                       capture_output=True, text=True, env=env, timeout=1200, cwd=os.path.dirname(HERE))
+    assert r.returncode == 0 and " passed" in r.stdout, (r.stdout + r.stderr)[-3000:]
