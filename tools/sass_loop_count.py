@@ -4,7 +4,9 @@ steady-state loop of the <biquad, FF2, one gain> instantiation (the backward bra
 shuffles of the mixer sum) and print its instruction mix per tile of 8 samples x 32 lanes.  The refill block (LDGSTS)
 sits inside the loop but is branched over on most iterations; it is listed separately.
     python tools/sass_loop_count.py [mangled-name-fragment]
-    default ILi1ELi1ELb1ELb1ELi1ELb0E = <CI 1, CO 1, biquad, FF2, one gain, interpolating>; stereo: ILi2ELi2ELb1ELb1ELi1ELb0E"""
+    default ILi1ELi1ELb1ELb1ELi1ELb0E = <CI 1, CO 1, biquad, FF2, one gain, interpolating> (the first match is the variant
+    without PRE / FRONT / DOWN: ...Lb0ELb0ELb0E); stereo: ILi2ELi2ELb1ELb1ELi1ELb0E; gain in front: ...Lb0ELb1ELb0ELb0E; filter in
+    front: ILi1ELi1ELb1ELb0ELi1ELb0ELb0ELb1ELb0E; sources above the mixer's rate: ILi1ELi1ELb1ELb1ELi1ELb0ELb0ELb0ELb1E"""
 import collections
 import os
 import re
