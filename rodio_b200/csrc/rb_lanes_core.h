@@ -370,7 +370,7 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                             const float m = simt::fmul(simt::fsub(x1[c], x0[c]), nf);
                             const float q0 = simt::fmul(m, rcp);
                             float q = simt::ffma(simt::ffma(-q0, den, m), rcp, q0);
-                            if (FRONT && !simt::in_exact_quotient_class(m)) q = simt::fdiv(m, den), simt::emu_count(3, 1);   // filter tails: denormals
+                            if (FRONT && !simt::in_exact_quotient_class(m)) q = simt::fdiv_cold(m, den), simt::emu_count(3, 1);   // filter tails: denormals
                             x[c] = simt::fadd(x0[c], q);
                         }
                     }
@@ -402,12 +402,23 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                             x1[c] = simt::fmul(simt::lds(simt::sptr_add(p, C + c)), gpre);
                         }
                     } else if (FRONT) {
-                        float raw[C];
-                        if (simt::lerp_carry<C>(nf, p, from_f, den, raw)) {
-                            front_step(raw);
+                        // The filter step sits on the carry of the index step (0.92 of the steps at 44.1 -> 48 kHz): computed
+                        // on every step from the frame under the cursor and committed by selects -- no divergent branch; a
+                        // frame that is not consumed (no carry) may not even have landed yet, its result is dropped.
+                        const float nf2 = simt::fadd(nf, from_f);
+                        const bool carry = nf2 >= den;
+                        nf = carry ? simt::fsub(nf2, den) : nf2;
 #pragma unroll
-                            for (int c = 0; c < C; c++) x0[c] = x1[c], x1[c] = simt::fmul(y1[c], gmid);
+                        for (int c = 0; c < C; c++) {
+                            const float xin = simt::fmul(simt::lds(simt::sptr_add(p, c)), gpre);
+                            const float ff = simt::fadd(simt::fadd(simt::fmul(b0, xin), simt::fmul(b1, xh1[c])), simt::fmul(b2, xh2[c]));
+                            const float yn = fb(a1, a2, ff, y1[c], y2[c], neg1);
+                            const float tap = simt::fmul(yn, gmid);
+                            xh2[c] = carry ? xh1[c] : xh2[c], xh1[c] = carry ? xin : xh1[c];
+                            y2[c] = carry ? y1[c] : y2[c], y1[c] = carry ? yn : y1[c];
+                            x0[c] = carry ? x1[c] : x0[c], x1[c] = carry ? tap : x1[c];
                         }
+                        p = simt::sptr_add(p, carry ? C : 0);
                     } else {
                         simt::lerp_advance<C, PRE>(nf, x0, x1, p, from_f, den, gpre);
                     }

@@ -114,6 +114,7 @@ SIMT_FN float fmul(float a, float b) { return a * b; }
 SIMT_FN float fadd(float a, float b) { return a + b; }
 SIMT_FN float fsub(float a, float b) { return a - b; }
 SIMT_FN float fdiv(float a, float b) { return a / b; }
+SIMT_FN float fdiv_cold(float a, float b) { return a / b; }   // the same division, kept out of line on the device
 SIMT_FN float ffma(float a, float b, float c) { return std::fmaf(a, b, c); }
 SIMT_FN float u2f(uint32_t v) { return (float)v; }
 SIMT_FN float ldg(const float* p) {
@@ -265,18 +266,6 @@ SIMT_FN void lerp_advance(float& nf, float (&x0)[C], float (&x1)[C], sptr& p, fl
         nf = nf2;
     }
 }
-// FRONT variant of the index step: only the numerator and the cursor; on a carry the next ring frame is returned raw.
-template <int C>
-SIMT_FN bool lerp_carry(float& nf, sptr& p, float from_f, float den, float (&raw)[C]) {
-    const float nf2 = nf + from_f;
-    const bool carry = nf2 >= den;
-    nf = carry ? nf2 - den : nf2;
-    if (carry) {
-        for (int c = 0; c < C; c++) raw[c] = p[c];
-        p += C;
-    }
-    return carry;
-}
 // m is zero or 2^-100 <= |m| < 2^100: the range in which q0 = m*r, q = fma(fma(-q0, den, m), r, q0) is the correctly
 // rounded m / den (rb_lanes_core.h, "Exact division")
 SIMT_FN bool in_exact_quotient_class(float m) {
@@ -312,6 +301,8 @@ SIMT_FN float fmul(float a, float b) { return __fmul_rn(a, b); }
 SIMT_FN float fadd(float a, float b) { return __fadd_rn(a, b); }
 SIMT_FN float fsub(float a, float b) { return __fsub_rn(a, b); }
 SIMT_FN float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+// the same division for paths that are taken once in a blue moon: one copy per kernel instead of one per call site
+static __device__ __noinline__ float fdiv_cold(float a, float b) { return __fdiv_rn(a, b); }
 SIMT_FN float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 SIMT_FN float u2f(uint32_t v) { return __uint2float_rn(v); }
 SIMT_FN float ldg(const float* p) { return __ldg(p); }
@@ -420,18 +411,6 @@ SIMT_FN void lerp_advance(float& nf, float (&x0)[C], float (&x1)[C], sptr& p, fl
             : "f"(from_f), "f"(den), "f"(gpre)
             : "memory");
     }
-}
-template <int C>
-SIMT_FN bool lerp_carry(float& nf, sptr& p, float from_f, float den, float (&raw)[C]) {
-    const float nf2 = __fadd_rn(nf, from_f);
-    const bool carry = nf2 >= den;
-    nf = carry ? __fsub_rn(nf2, den) : nf2;
-    if (carry) {
-#pragma unroll
-        for (int c = 0; c < C; c++) raw[c] = lds(sptr_add(p, c));
-        p = sptr_add(p, C);
-    }
-    return carry;
 }
 SIMT_FN bool in_exact_quotient_class(float m) {
     const uint32_t u = __float_as_uint(m) & 0x7fffffffu;
