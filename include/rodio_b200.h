@@ -135,9 +135,13 @@ enum {
     RB_BIQUAD_TIME_PARALLEL = 1u << 2, /* reserved (chunked-scan biquad, not bit-exact): accepted, served by the exact path */
     RB_KEEP_STREAM_OUTPUTS = 1u << 3,  /* also keep every stream's post-chain (pre-mix) samples in HBM so
                                           rb_batch_read_stream can return them                                */
-    RB_FUSED_LANES = 1u << 4           /* large batches (chosen automatically from ~277 sources per SM on): serve resample -> [low/high_pass] -> [amplify] -> mix
-                                          of mono (or stereo, into a stereo mixer) f32 sources at or below the mixer's rate with the
-                                          lane-per-stream kernel: every stream's samples are bit-identical to the
+    RB_FUSED_LANES = 1u << 4           /* large batches (chosen automatically from ~277 sources per SM on): serve
+                                          [amplify] -> resample -> [low/high_pass] -> [amplify] -> mix, or the chain with the
+                                          filter in front of the conversion ([amplify] -> low/high_pass -> [amplify] ->
+                                          resample -> [amplify] -> mix: chosen automatically from 32 sources per SM on, no
+                                          other fused kernel serves it), of mono (or stereo, into a stereo mixer) f32
+                                          sources at or below the mixer's rate -- with the flag also above it, up to twice --
+                                          with the lane-per-stream kernel: every stream's samples are bit-identical to the
                                           default path, the mixer sum is a fixed tree over groups of 32 sources
                                           (<= 1e-5 * peak like the default grouping).  Ignored when the batch has
                                           another shape.  Inputs are classified when uploaded: writers through
