@@ -117,8 +117,13 @@ def main():
         # streaming sessions: every source receives 10 ms of 44.1 kHz PCM per step (one packed push), the mixer output is
         # pulled as it becomes available; wall clock per step through the public calls (host -> device -> host included)
         import time
-        for S, ch in [(256, 1), (4096, 1), (1024, 2), (16384, 1)]:
-            chains = [rb.UniformSourceIterator(rb.TestSource(z(0), ch, 44100), ch, 48000).low_pass(200).amplify(1.2) for _ in range(S)]
+        shapes = {"uniform -> low_pass(200) -> amplify": lambda ch: rb.UniformSourceIterator(rb.TestSource(z(0), ch, 44100), ch, 48000).low_pass(200).amplify(1.2),
+                  # the chain of a Player with a user filter: both in front of the mixer's conversion (src/player.rs:120-128)
+                  "low_pass(200) -> amplify(volume) -> uniform [Player]": lambda ch: rb.UniformSourceIterator(rb.TestSource(z(0), ch, 44100).low_pass(200).amplify(0.8), ch, 48000)}
+        names = list(shapes)
+        for S, ch, k in [(256, 1, 0), (4096, 1, 0), (1024, 2, 0), (16384, 1, 0), (4096, 1, 1), (1024, 2, 1)]:
+            label, mk = names[k], shapes[names[k]]
+            chains = [mk(ch) for _ in range(S)]
             rng = np.random.default_rng(1)
             block = [rng.uniform(-0.5, 0.5, 441 * ch).astype(np.float32) for _ in range(min(S, 64))]
             blocks = [block[i % len(block)] for i in range(S)]
@@ -127,12 +132,14 @@ def main():
                     sess.push_packed(blocks)
                     sess.render(1024)
                 t0, frames, steps = time.perf_counter(), 0, 200
-                for _ in range(steps):
+                for k in range(steps):
+                    if "Player" in label and k % 10 == 0:
+                        sess.set_volume(k % S, 0.5 + 0.001 * (k % 100))   # Player::set_volume now and then
                     sess.push_packed(blocks)
                     out, _ = sess.render(1024)
                     frames += out.size // ch
                 dt = time.perf_counter() - t0
-            print(json.dumps({"case": f"session: {S} x {ch} ch sources, 10 ms pushes -> low_pass(200) -> amplify -> mix", "streams": S,
+            print(json.dumps({"case": f"session: {S} x {ch} ch sources, 10 ms pushes -> {label} -> mix", "streams": S,
                               "ms_per_10ms_block": round(1e3 * dt / steps, 3), "realtime_factor": round(frames / 48000 / dt, 2),
                               "Msamples_s": round(S * frames * ch / dt / 1e6, 1)}), flush=True)
     if "cpu" in which:
