@@ -287,7 +287,8 @@ def s_player_volume_changes():
     mk_plain = lambda p, r, g: rb.UniformSourceIterator(rb.TestSource(p, 1, r).amplify(g), 1, 48000).low_pass(500).amplify(0.9)
     mk_front = lambda p, r, g: rb.UniformSourceIterator(rb.TestSource(p, 1, r).amplify(0.8).low_pass(400).amplify(g), 1, 48000)
     srcs = [(mk_front if f else mk_plain)(np.zeros(0, np.float32), r, 1.0) for r, f in zip(rates, front)]
-    plan = {2: (0, 0.5), 3: (1, 0.25), 5: (0, 1.5), 6: (3, 0.1), 7: (2, 0.7), 9: (1, 1.0), 10: (3, 0.9)}   # round -> (stream, volume)
+    plan = {2: (0, 0.5), 3: (1, 0.25), 5: (0, 1.5), 6: (3, 0.1), 7: (2, 0.7), 8: (0, 0.0), 9: (1, 1.0), 10: (3, 0.9), 11: (0, 0.6),
+            12: (1, 0.0)}   # round -> (stream, volume); 0.0 = muted
     vol = [1.0] * 4
     gains = [np.ones(n, np.float32) for n in L]       # factor of every input frame
     pulled, pushed, done = [0] * 4, [0] * 4, [0] * 4
