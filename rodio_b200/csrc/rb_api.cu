@@ -1252,6 +1252,7 @@ extern "C" rb_status rb_session_render(rb_session* s, float* out_host, uint64_t 
     const size_t ns = s->st.size();
     const uint32_t C = s->channels;
     std::vector<session::Part> parts(ns);
+    std::vector<uint8_t> quiet(ns, 0);
     float* fifo = s->d_fifo[s->cur];
     for (size_t r = 0; r < ns; r++) {
         const session::Part p = parts[r] = session::part_of(s->st[r], s->T, n);
@@ -1265,7 +1266,7 @@ extern "C" rb_status rb_session_render(rb_session* s, float* out_host, uint64_t 
         row.flags = p.continues ? lanes::ROW_CONTINUES : 0u;
         row.f0 = s->st[r].fpos - s->st[r].i0, row.ga = s->vol_a[r], row.gb = s->vol_b[r];
         if (!s->st[r].front && !(lanes::pre_gain_keeps_class(row.pre) && lanes::pre_gain_keeps_class(row.ga) && lanes::pre_gain_keeps_class(row.gb)))
-            row.flags |= lanes::ROW_FORCE_SLOW;
+            row.flags |= lanes::ROW_FORCE_SLOW, quiet[r] = 1;   // its class runs the guarded tile in this block (or, DOWN, slow tiles)
     }
     RB_CUDA(cudaMemcpyAsync(s->d_rows, s->h_rows, ns * sizeof(lanes::Row), cudaMemcpyHostToDevice, stq));
     const uint64_t pstride = lanes::round_up_tile((uint64_t)s->max_block * C);
@@ -1279,7 +1280,9 @@ extern "C" rb_status rb_session_render(rb_session* s, float* out_host, uint64_t 
         lanes::fill_ratio(a, s->st[c.first].from, s->st[c.first].to, C);
         a.mix_len = n, a.pstride = pstride;
         a.partial = s->d_partial + (size_t)g0 * pstride, a.zeros = s->d_zeros, a.unsafe = s->d_flags + c.first;
-        RB_CUDA(rb_lanes_launch_kernel(a, c.ch_in, C, c.has_biquad, c.ff2, s->has_post, c.has_pre, c.front, stq));
+        bool guard = false;
+        for (uint32_t r = c.first; r < c.first + c.count; r++) guard = guard || quiet[r];
+        RB_CUDA(rb_lanes_launch_kernel(a, c.ch_in, C, c.has_biquad, c.ff2, s->has_post, c.has_pre, c.front, guard, stq));
         g0 += a.n_groups;
     }
     RB_CUDA(rb_lanes_launch_sum(s->d_partial, n_groups_total, pstride, n * C, s->d_out, stq));

@@ -19,13 +19,13 @@ constexpr int lanes_rs() { return lanes::Geo<C, DOWN ? lanes::NSLOT_DOWN : RB_LA
 template <int C, bool DOWN>
 constexpr size_t lanes_smem_bytes() { return (size_t)LANES_WARPS * 32 * lanes_rs<C, DOWN>() * sizeof(float); }   // 21.0 KB
 
-template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS, bool PRE, bool FRONT, bool DOWN>
+template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS, bool PRE, bool FRONT, bool DOWN, bool GUARD>
 __global__ void __launch_bounds__(LANES_THREADS) k_fused_lanes(lanes::Args a) {
     extern __shared__ __align__(16) float lanes_smem[];
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t group = blockIdx.x * LANES_WARPS + warp;
     if (group >= a.n_groups) return;   // whole warps leave: the warp program only synchronises within a warp
-    lanes::warp_main<CI, CO, HASB, FF2, NPOST, PASS, PRE, FRONT, DOWN>(a, group, lanes_smem + (size_t)warp * 32 * lanes::Geo<CI, DOWN ? lanes::NSLOT_DOWN : RB_LANES_UP_SLOTS>::RS);
+    lanes::warp_main<CI, CO, HASB, FF2, NPOST, PASS, PRE, FRONT, DOWN, GUARD>(a, group, lanes_smem + (size_t)warp * 32 * lanes::Geo<CI, DOWN ? lanes::NSLOT_DOWN : RB_LANES_UP_SLOTS>::RS);
 }
 
 // One CTA per stream: does every non-zero |x| lie inside [2^-70, 2^60]?  (rb_lanes_core.h, "Exact division".)
@@ -99,22 +99,22 @@ __global__ void __launch_bounds__(256) k_classify_range(const float* __restrict_
     if (__syncthreads_or(bad ? 1 : 0) && threadIdx.x == 0) *flag = 1u;
 }
 
-template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS, bool PRE, bool FRONT = false, bool DOWN = false>
+template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS, bool PRE, bool FRONT = false, bool DOWN = false, bool GUARD = false>
 static void launch_lanes(const lanes::Args& a, cudaStream_t st) {
     const uint32_t n_ctas = (a.n_groups + LANES_WARPS - 1) / LANES_WARPS;
-    k_fused_lanes<CI, CO, HASB, FF2, NPOST, PASS, PRE, FRONT, DOWN><<<n_ctas, LANES_THREADS, lanes_smem_bytes<CI, DOWN>(), st>>>(a);   // < 48 KB: no opt-in needed
+    k_fused_lanes<CI, CO, HASB, FF2, NPOST, PASS, PRE, FRONT, DOWN, GUARD><<<n_ctas, LANES_THREADS, lanes_smem_bytes<CI, DOWN>(), st>>>(a);   // < 48 KB: no opt-in needed
 }
-template <int CI, int CO, bool PASS, bool PRE>
+template <int CI, int CO, bool PASS, bool PRE, bool GUARD = false>
 static void launch_lanes_c(const lanes::Args& a, bool has_biquad, bool ff2, bool has_post, cudaStream_t st) {
     if (has_biquad) {
-        if (ff2) has_post ? launch_lanes<CI, CO, true, true, 1, PASS, PRE>(a, st) : launch_lanes<CI, CO, true, true, 0, PASS, PRE>(a, st);
-        else has_post ? launch_lanes<CI, CO, true, false, 1, PASS, PRE>(a, st) : launch_lanes<CI, CO, true, false, 0, PASS, PRE>(a, st);
+        if (ff2) has_post ? launch_lanes<CI, CO, true, true, 1, PASS, PRE, false, false, GUARD>(a, st) : launch_lanes<CI, CO, true, true, 0, PASS, PRE, false, false, GUARD>(a, st);
+        else has_post ? launch_lanes<CI, CO, true, false, 1, PASS, PRE, false, false, GUARD>(a, st) : launch_lanes<CI, CO, true, false, 0, PASS, PRE, false, false, GUARD>(a, st);
     } else {
-        has_post ? launch_lanes<CI, CO, false, false, 1, PASS, PRE>(a, st) : launch_lanes<CI, CO, false, false, 0, PASS, PRE>(a, st);
+        has_post ? launch_lanes<CI, CO, false, false, 1, PASS, PRE, false, false, GUARD>(a, st) : launch_lanes<CI, CO, false, false, 0, PASS, PRE, false, false, GUARD>(a, st);
     }
 }
 template <int CI, int CO>
-static void launch_lanes_cc(const lanes::Args& a, bool has_biquad, bool ff2, bool has_post, bool has_pre, bool front, cudaStream_t st) {
+static void launch_lanes_cc(const lanes::Args& a, bool has_biquad, bool ff2, bool has_post, bool has_pre, bool front, bool guard, cudaStream_t st) {
     const bool pass = a.from == a.to;   // sources at the mixer's rate: taps used raw
     if (front) {                        // the filter in front of the conversion: plain coefficients, Row::pre always applied
         if (lanes::ratio_runs_down(a.from, a.to))
@@ -133,19 +133,20 @@ static void launch_lanes_cc(const lanes::Args& a, bool has_biquad, bool ff2, boo
         return;
     }
     if (pass) has_pre ? launch_lanes_c<CI, CO, true, true>(a, has_biquad, ff2, has_post, st) : launch_lanes_c<CI, CO, true, false>(a, has_biquad, ff2, has_post, st);
+    else if (has_pre && guard) launch_lanes_c<CI, CO, false, true, true>(a, has_biquad, ff2, has_post, st);   // a gain in front out of range
     else has_pre ? launch_lanes_c<CI, CO, false, true>(a, has_biquad, ff2, has_post, st) : launch_lanes_c<CI, CO, false, false>(a, has_biquad, ff2, has_post, st);
 }
 
 }  // namespace
 
 cudaError_t rb_lanes_launch_kernel(const lanes::Args& a, uint32_t ch_in, uint32_t ch_out, bool has_biquad, bool ff2, bool has_post,
-                                   bool has_pre, bool front, cudaStream_t st) {
+                                   bool has_pre, bool front, bool guard, cudaStream_t st) {
     if (a.mix_len == 0 || a.n_groups == 0) return cudaSuccess;
     if (front && !has_biquad) return cudaErrorInvalidValue;
     if (!((ch_in == 1 || ch_in == 2) && (ch_in == ch_out || (ch_in == 1 && ch_out == 2)))) return cudaErrorInvalidValue;
-    if (ch_in == 2) launch_lanes_cc<2, 2>(a, has_biquad, ff2, has_post, has_pre, front, st);
-    else if (ch_out == 2) launch_lanes_cc<1, 2>(a, has_biquad, ff2, has_post, has_pre, front, st);
-    else launch_lanes_cc<1, 1>(a, has_biquad, ff2, has_post, has_pre, front, st);
+    if (ch_in == 2) launch_lanes_cc<2, 2>(a, has_biquad, ff2, has_post, has_pre, front, guard, st);
+    else if (ch_out == 2) launch_lanes_cc<1, 2>(a, has_biquad, ff2, has_post, has_pre, front, guard, st);
+    else launch_lanes_cc<1, 1>(a, has_biquad, ff2, has_post, has_pre, front, guard, st);
     return cudaGetLastError();
 }
 

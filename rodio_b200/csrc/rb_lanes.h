@@ -38,7 +38,7 @@ void rb_lanes_destroy(rb_lanes_plan* p);
 // k_fused_lanes over a.rows (one class: one rate pair -- a.from == a.to selects the pass-through variant --, ch_in channels
 // per stream, ch_out channels in the mixer) ...
 cudaError_t rb_lanes_launch_kernel(const lanes::Args& a, uint32_t ch_in, uint32_t ch_out, bool has_biquad, bool ff2, bool has_post,
-                                   bool has_pre, bool front, cudaStream_t st);
+                                   bool has_pre, bool front, bool guard, cudaStream_t st);
 // ... and the ordered sum of n_groups partial rows (all classes) into d_out[0, n_floats).
 cudaError_t rb_lanes_launch_sum(const float* d_partial, uint32_t n_groups, uint64_t pstride, uint64_t n_floats, float* d_out,
                                 cudaStream_t st);

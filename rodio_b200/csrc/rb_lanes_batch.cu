@@ -12,6 +12,7 @@ struct rb_lanes_plan {
     struct Class {
         lanes::Args args{};
         bool ff2 = false;
+        bool guard = false;   // some row's gain in front is outside the range of the unguarded tile
         uint32_t ch_in = 1;
     };
     std::vector<Class> classes;      // one launch per reduced rate pair
@@ -67,7 +68,7 @@ cudaError_t rb_lanes_try_create(const rb_lanes_stream* streams, size_t n_streams
             r.pre = has_pre ? s.pre : 1.0f;
             r.mid = front ? s.mid : 1.0f;
             r.flags = lanes::ROW_UNSAFE;   // until classified
-            if (has_pre && !front && !lanes::pre_gain_keeps_class(r.pre)) r.flags |= lanes::ROW_FORCE_SLOW;
+            if (has_pre && !front && !lanes::pre_gain_keeps_class(r.pre)) r.flags |= lanes::ROW_FORCE_SLOW, c.guard = true;
             float k = 0.0f;
             if (has_biquad && lanes::ff2_coeffs(r.b0, r.b1, r.b2, &k)) r.ffk = k;
             else c.ff2 = false;
@@ -112,7 +113,7 @@ cudaError_t rb_lanes_run(rb_lanes_plan* p, cudaStream_t st) {
         p->classified = true;
     }
     for (const auto& c : p->classes) {
-        cudaError_t e = rb_lanes_launch_kernel(c.args, c.ch_in, p->channels, p->has_biquad, c.ff2 && !p->front, p->has_post, p->has_pre, p->front, st);
+        cudaError_t e = rb_lanes_launch_kernel(c.args, c.ch_in, p->channels, p->has_biquad, c.ff2 && !p->front, p->has_post, p->has_pre, p->front, c.guard, st);
         if (e != cudaSuccess) return e;
     }
     return rb_lanes_launch_sum(p->d_partial, p->n_groups_total, p->pstride, p->mix_len * p->channels, p->d_out, st);

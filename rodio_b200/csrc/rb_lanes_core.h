@@ -85,7 +85,8 @@ struct Geo {
 static_assert(RUN_CAP % TILE == 0, "run cap");
 constexpr uint32_t ROW_UNSAFE = 1u;     // Row::flags: some sample outside the exact-reciprocal class
 constexpr uint32_t ROW_CONTINUES = 2u;  // Row::flags: the stream goes on in the next block -- keep the filter state past `end`
-constexpr uint32_t ROW_FORCE_SLOW = 4u; // Row::flags: set by the host (a gain in front of the conversion outside [2^-6, 2^6]): slow tiles only
+constexpr uint32_t ROW_FORCE_SLOW = 4u; // Row::flags: set by the host (a gain in front of the conversion outside [2^-6, 2^6]): not on an
+                                        // unguarded interpolating tile -- the host launches the GUARD twin for the class, or (DOWN) slow tiles
 
 struct Row {                 // one stream (whole, or the part of it one block of a streaming session renders)
     const float* in;         // f32 frames (C interleaved channels), 16-byte aligned, readable up to a 16-byte tail pad
@@ -167,8 +168,15 @@ SIMT_FN float reduce_tile(const float (&v)[TILE], uint32_t ln) {
 // ring; a tile consumes at most one chunk, so the refill logic is the one of the up-sampling tile.  Row::pre is always
 // applied (no PRE twin).  Larger ratios stay on the slow tiles.  With FRONT the one or two frames an output moves on are
 // one or two steps of the filter.
-template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS = false, bool PRE = false, bool FRONT = false, bool DOWN = false>
+//
+// GUARD (with PRE): some stream of the class has a gain in front outside [2^-6, 2^6] (a Player at -40 dB): its scaled taps may
+// leave the range in which the reciprocal division is exact, so the tile checks every quotient like FRONT does and the
+// stream stays on the fast tiles.  The host picks the variant per launch; rows and their order are the same, and so are the
+// bits of every stream whose quotients were in range anyway.
+template <int CI, int CO, bool HASB, bool FF2, int NPOST, bool PASS = false, bool PRE = false, bool FRONT = false, bool DOWN = false,
+          bool GUARD = false>
 SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
+    static_assert(!GUARD || (PRE && !PASS), "GUARD: the guarded twin of the interpolating PRE variant");
     static_assert(CI == CO || (CI == 1 && CO == 2), "channel layouts served");
     static_assert(!DOWN || (!PASS && !PRE), "DOWN: interpolating, the gain in front always applied");
     static_assert(!FRONT || (HASB && !FF2 && !PRE), "FRONT: plain coefficients, the gain in front is always applied");
@@ -191,7 +199,8 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
     const uint64_t ms = row.mix_start, end = row.mix_start + row.out_len;   // frames
     // Down-sampling classes (from > to: more than one input frame per output) are served by the slow tiles only -- exact,
     // general, not fast; the fast run below assumes at most one new frame per step.
-    const bool safe = has && (a.from <= a.to || (DOWN && a.from <= 2 * a.to)) && !(row.flags & ROW_FORCE_SLOW) &&
+    // (a same-rate stream never divides, a guarded tile checks every quotient: ROW_FORCE_SLOW means nothing to them)
+    const bool safe = has && (a.from <= a.to || (DOWN && a.from <= 2 * a.to)) && (PASS || GUARD || !(row.flags & ROW_FORCE_SLOW)) &&
                       (PASS || FRONT || (!(row.flags & ROW_UNSAFE) && !(a.unsafe && a.unsafe[r])));
     const bool stops = !(row.flags & ROW_CONTINUES);   // the stream ends inside this block (or is a whole stream)
     const bool live = has && row.out_len != 0;
@@ -370,7 +379,7 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                             const float m = simt::fmul(simt::fsub(x1[c], x0[c]), nf);
                             const float q0 = simt::fmul(m, rcp);
                             float q = simt::ffma(simt::ffma(-q0, den, m), rcp, q0);
-                            if (FRONT && !simt::in_exact_quotient_class(m)) q = simt::fdiv_cold(m, den), simt::emu_count(3, 1);   // filter tails: denormals
+                            if ((FRONT || GUARD) && !simt::in_exact_quotient_class(m)) q = simt::fdiv_cold(m, den), simt::emu_count(3, 1);   // filter tails: denormals
                             x[c] = simt::fadd(x0[c], q);
                         }
                     }

@@ -36,8 +36,8 @@ inline bool ff2_coeffs(float b0, float b1, float b2, float* ffk) {
 
 // A gain in front of the conversion scales what the exact-reciprocal class was measured on.  For |g| in [2^-6, 2^6] the scaled
 // taps are 0 or in [2^-76, 2^66): their difference is 0 or at least one ulp of the smaller tap (>= 2^-99), times num >= 1, and
-// below 2^67 * 2^20 -- inside [2^-100, 2^100) where the reciprocal step is exact (rb_lanes_core.h).  Any other gain sends the
-// stream to the slow tiles, which divide.  (Zero -- Player::set_volume(0.0) -- makes every tap zero: exact.)
+// below 2^67 * 2^20 -- inside [2^-100, 2^100) where the reciprocal step is exact (rb_lanes_core.h).  Any other gain makes the
+// class run the guarded tile (GUARD: every quotient checked), or, above the mixer's rate, sends the stream to the slow tiles.  (Zero -- Player::set_volume(0.0) -- makes every tap zero: exact.)
 inline bool pre_gain_keeps_class(float g) {
     const float a = g < 0 ? -g : g;
     return a == 0.0f || (a >= 0.015625f && a <= 64.0f);   // a muted source (all taps zero) is exact as well; false for NaN

@@ -29,7 +29,7 @@ extern "C" void mock_cuda_unregister(void* p) {
 
 // ---- the lane kernel on the SIMT emulator (warp_variants.cpp) ----
 cudaError_t rb_lanes_launch_kernel(const lanes::Args& a, uint32_t ch_in, uint32_t ch_out, bool has_biquad, bool ff2, bool has_post,
-                                   bool has_pre, bool front, cudaStream_t) {
+                                   bool has_pre, bool front, bool guard, cudaStream_t) {
     if (a.mix_len == 0 || a.n_groups == 0) return cudaSuccess;
     if (!((ch_in == 1 || ch_in == 2) && (ch_in == ch_out || (ch_in == 1 && ch_out == 2)))) return cudaErrorInvalidValue;
     simt::WarpEmu warp;
@@ -44,7 +44,7 @@ cudaError_t rb_lanes_launch_kernel(const lanes::Args& a, uint32_t ch_in, uint32_
     while ((uintptr_t)ring & 15) ring++;
     for (uint32_t g = 0; g < a.n_groups; g++) {
         for (int i = 0; i < 32 * MAX_RS; i++) ring[i] = nan;
-        emu_run_group(ch_in, ch_out, a, g, &warp, ring, has_biquad, ff2, has_post, has_pre, front);
+        emu_run_group(ch_in, ch_out, a, g, &warp, ring, has_biquad, ff2, has_post, has_pre, front, guard);
     }
     return cudaSuccess;
 }

@@ -14,8 +14,8 @@
 namespace {
 // the class decides the instantiation -- source channels ci, mixer channels co, PASS when from == to -- like the device launcher
 void run_group_any(uint32_t ci, uint32_t co, const lanes::Args& a, uint32_t g, simt::WarpEmu* w, float* ring, bool hasb, bool ff2, bool npost,
-                   bool pre = false, bool front = false) {
-    emu_run_group(ci, co, a, g, w, ring, hasb, ff2, npost, pre, front);
+                   bool pre = false, bool front = false, bool guard = false) {
+    emu_run_group(ci, co, a, g, w, ring, hasb, ff2, npost, pre, front, guard);
 }
 constexpr int MAX_RS = lanes::Geo<2, 4>::RS;   // the largest ring of any variant
 }  // namespace
@@ -80,6 +80,7 @@ extern "C" int rb_lanes_emulate(const float* const* pcm, const uint64_t* n_frame
     std::vector<Row> rows;
     std::vector<Args> launches;
     std::vector<uint32_t> launch_ci;
+    std::vector<uint8_t> launch_guard;   // the class holds a row whose gain in front is out of the unguarded tile's range
     uint32_t n_groups_total = 0;
     const uint64_t pstride = round_up_tile(mix_len * C);
     for (const auto& cls : classes) {
@@ -93,6 +94,9 @@ extern "C" int rb_lanes_emulate(const float* const* pcm, const uint64_t* n_frame
         n_groups_total += a.n_groups;
         launches.push_back(a);
         launch_ci.push_back(ch_in[cls[0]]);
+        bool guard = false;
+        for (uint32_t i : cls) guard = guard || (all[i].flags & ROW_FORCE_SLOW);
+        launch_guard.push_back(guard);
     }
     std::vector<float> partial((size_t)n_groups_total * pstride, 0.0f);
     std::vector<float> ring_store(32 * MAX_RS + 4, nan);
@@ -103,7 +107,7 @@ extern "C" int rb_lanes_emulate(const float* const* pcm, const uint64_t* n_frame
         a.rows = rows.data() + (uintptr_t)a.rows, a.partial = partial.data() + (uintptr_t)a.partial * pstride, a.zeros = zeros;
         for (uint32_t g = 0; g < a.n_groups; g++) {
             for (int i = 0; i < 32 * MAX_RS; i++) ring[i] = nan;
-            run_group_any(launch_ci[k], channels, a, g, &warp, ring, hasb, ff2, npost, pre != nullptr, front != 0);
+            run_group_any(launch_ci[k], channels, a, g, &warp, ring, hasb, ff2, npost, pre != nullptr, front != 0, launch_guard[k] != 0);
         }
     }
     for (uint64_t m = 0; m < mix_len * C; m++) {

@@ -501,7 +501,8 @@ def test_session_queue_of_sources(emu):
 def test_gain_in_front_of_the_conversion(emu):
     """`source.amplify(v)` handed to the mixer: the gain multiplies every input frame before the interpolation
     (src/source/amplify.rs:91-95 in front of src/source/uniform.rs).  Per-stream gains; 0.001 and 100 lie outside the range
-    the fast tiles accept and run on the slow tiles; -0.5 and 0.8 stay on the fast path."""
+    the unguarded tile accepts: their class runs the guarded twin (every quotient checked like with a filter in front), still on
+    fast tiles."""
     n = 40
     pcms = [noise(1500 + 13 * i, 900 + i) for i in range(n)]
     pres = [[0.8, -0.5, 1.0, 0.3][i % 4] for i in range(n)]
@@ -512,7 +513,13 @@ def test_gain_in_front_of_the_conversion(emu):
     pres[5], pres[33], pres[20] = 0.001, 100.0, 0.0      # ... and a muted source (zero taps are exact: fast tiles)
     check(emu, pcms, 44100, 48000, [7 * (i % 5) for i in range(n)], lp=200, gain=0.7, pre=pres)
     c = counters(emu)
-    assert c["slow"] > 100          # the two groups holding a far gain never leave the slow tiles
+    assert c["fast"] > 4 * c["slow"]   # a gain out of range does not cost the fast tiles: the class runs the guarded twin
+    # tiny taps (2^-116) behind an absurdly small gain: quotients below the reciprocal's exact range, divided instead
+    quiet = [noise(1500, 990 + i) * np.float32(1e-15) for i in range(4)]
+    counters(emu)
+    check(emu, quiet, 44100, 48000, [0] * 4, lp=200, pre=[1e-20, 1.0, 0.5, 1e-20])
+    c = counters(emu)
+    assert c["divided"] > 0 and c["fast"] > 4 * c["slow"]
     # no filter, stereo and mono-in-stereo sources, sources at the mixer's rate (taps used raw, times the gain)
     ch_in = [2 if i % 3 else 1 for i in range(12)]
     pcms = [noise(ci * (700 + 9 * i), 950 + i) for i, ci in enumerate(ch_in)]
