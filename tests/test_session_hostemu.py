@@ -110,7 +110,7 @@ def test_gpu_lane_and_session_tests_hold_on_the_emulator(hostemu):
             % (ROOT, HERE, hostemu, os.path.join(HERE, "test_parity_gpu.py")))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, (r.stdout + r.stderr)[-3000:]
-    assert int(r.stdout.rsplit(" passed", 1)[0].split()[-1]) >= 26, r.stdout[-500:]
+    assert int(r.stdout.rsplit(" passed", 1)[0].split()[-1]) >= 31, r.stdout[-500:]
 
 
 def test_cpp_live_mixer_on_the_emulator(hostemu):
