@@ -682,8 +682,10 @@ class Player:
     stoppable (src/player.rs:122-166) and samples the controls every 5 ms of audio.  On blocks the controls are
     read when a source is appended: its chain becomes `source.speed(speed).amplify(volume)` and it is queued
     behind the sources appended before it (src/queue.rs: one source after the other, each converted to the
-    mixer's format on its own).  Pausing / skipping / seeking mid-playback are control-plane features of the
-    real-time callback and are out of scope."""
+    mixer's format on its own).  This class renders offline; the controls WHILE playing live on a `Session`: `follow` (append),
+    `set_volume` (the Amplify in front of the mixer's conversion, per pulled frame), pausing = pushing zero frames, stop / skip =
+    end_of_stream (examples/live_player.c).  Seeking is a control-plane feature of the decoders and out of
+    scope."""
 
     def __init__(self, mixer: "Mixer"):
         self._mixer = mixer
