@@ -1105,6 +1105,9 @@ extern "C" rb_status rb_session_create(rb_context* ctx, uint16_t mixer_channels,
     RB_CUDA(cudaSetDevice(ctx->device));
     const uint32_t C = s->channels;
     s->stride = align_up((size_t)fifo_frames * C + 16, 32);
+    // every product below stays far inside 64 bits: n < 2^31, stride < 2^34 floats, max_block_frames < 2^32
+    if ((uint64_t)n * s->stride > (1ull << 40) || (uint64_t)max_block_frames * C * ((n + 31) / 32 + 1) > (1ull << 40))
+        return fail(RB_ERR_OUT_OF_MEMORY, "session of this size (sources x fifo_frames, or max_block_frames) exceeds 4 TB of device memory");
     const size_t arena = n * s->stride * sizeof(float);
     uint32_t n_groups = 0;   // partial rows: one per warp, every class rounds up on its own
     for (const auto& c : s->classes) n_groups += (c.count + 31) / 32;

@@ -453,6 +453,14 @@ def s_errors():
             pass
         else:
             raise AssertionError("a push after end_of_stream was accepted")
+    # a session whose FIFOs could not exist is refused before any allocation (no size_t wrap-around)
+    big = [chain(np.zeros(0, np.float32), 1, 44100, 1, 48000, None, None) for _ in range(2000)]
+    try:
+        rb.Session(big, 48000, fifo_frames=2 ** 32 - 1, max_block_frames=480, mixer_channels=1)
+    except capi.RodioB200Error as e:
+        assert e.status == capi.RB_ERR_OUT_OF_MEMORY
+    else:
+        raise AssertionError("a 32 TB session was accepted")
 
 
 def s_random(seed=0, cases=6):
