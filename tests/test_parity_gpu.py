@@ -650,8 +650,8 @@ def test_lanes_unsafe_inputs_stay_exact(ctx):
 
 @lanes_gate
 def test_lanes_mixed_rate_pairs_and_fallback(ctx):
-    """Several rate pairs in one mixer (44.1 kHz, 48 kHz pass-through, 32 kHz) are served class by class; a source at more than
-    twice the mixer's rate is outside the kernel's batch shape: the flag is ignored there and the other kernels serve the batch."""
+    """Several rate pairs in one mixer (44.1 kHz, 48 kHz pass-through, 32 kHz) are served class by class; a three-channel
+    mixer is outside the kernel's shape: the flag is ignored there and the other kernels serve the batch."""
     rates = [44100, 48000, 32000, 44100, 48000, 22050] * 8
     pcms = [noise(1500 + 13 * i, 40 + i) for i in range(len(rates))]
     srcs = [rb.UniformSourceIterator(rb.TestSource(p, 1, r), 1, 48000).low_pass(500).amplify(0.9) for p, r in zip(pcms, rates)]
@@ -668,11 +668,11 @@ def test_lanes_mixed_rate_pairs_and_fallback(ctx):
         idx = [i for i, r in enumerate(rates) if r == rate]
         acc = acc + (lanes_expected_mix([per_stream[i] for i in idx], [0] * len(idx), ref.size) - np.float32(0.0))
     assert_bit_exact(got, acc, "mixed rate pairs vs oracle streams + class-wise tree")
-    d = rb.UniformSourceIterator(rb.TestSource(noise(2000, 3), 1, 96000), 1, 44100).low_pass(200)
-    with rb.Batch([d], 1, 44100, flags=LANES, ctx=ctx) as b:
+    d = rb.UniformSourceIterator(rb.TestSource(noise(3 * 2000, 3), 3, 32000), 3, 48000).low_pass(200)
+    with rb.Batch([d], 3, 48000, flags=LANES, ctx=ctx) as b:     # three channels: the shape of FUSED_CASES[7], not the lane kernel's
         assert b.kernel_family != 2
         b.upload_all()
-        assert_close_peak(b.render_mix(), oracle.mixer([to_oracle(d)], 1, 44100), 1e-5, "fallback")
+        assert_close_peak(b.render_mix(), oracle.mixer([to_oracle(d)], 3, 48000), 1e-5, "fallback")
 
 
 @lanes_gate
