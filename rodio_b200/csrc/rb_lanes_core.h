@@ -388,17 +388,25 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                         const float nf2 = simt::fadd(nf, rem_f);
                         const bool carry = nf2 >= den;
                         nf = carry ? simt::fsub(nf2, den) : nf2;
-                        const int adv = (int)a.adv_q + (carry ? 1 : 0);   // 1 or 2 frames: as many filter steps
-                        for (int k = 0; k < adv; k++) {
-                            float raw[C];
+                        // one or two frames per output = one or two filter steps: the first always, the second (a whole
+                        // second frame per output at a ratio of two, else the carry) computed and committed by selects
+                        const bool second = carry || a.adv_q == 2u;
 #pragma unroll
-                            for (int c = 0; c < C; c++) raw[c] = simt::lds(simt::sptr_add(p, c));
-                            p = simt::sptr_add(p, C);
+                        for (int k = 0; k < 2; k++) {
+                            const bool take = k == 0 || second;
+#pragma unroll
+                            for (int c = 0; c < C; c++) {
+                                const float xin = simt::fmul(simt::lds(simt::sptr_add(p, c)), gpre);
+                                const float ff = simt::fadd(simt::fadd(simt::fmul(b0, xin), simt::fmul(b1, xh1[c])), simt::fmul(b2, xh2[c]));
+                                const float yn = fb(a1, a2, ff, y1[c], y2[c], neg1);
+                                const float tap = simt::fmul(yn, gmid);
+                                xh2[c] = take ? xh1[c] : xh2[c], xh1[c] = take ? xin : xh1[c];
+                                y2[c] = take ? y1[c] : y2[c], y1[c] = take ? yn : y1[c];
+                                x0[c] = take ? x1[c] : x0[c], x1[c] = take ? tap : x1[c];   // a tap keeps the factor it was pulled with
+                            }
+                            p = simt::sptr_add(p, take ? C : 0);
                             if (simt::sptr_ge(p, ring_end)) p = simt::sptr_add(p, -RING);
-                            front_step(raw);
                         }
-#pragma unroll
-                        for (int c = 0; c < C; c++) x0[c] = simt::fmul(y2[c], gmid), x1[c] = simt::fmul(y1[c], gmid);
                     } else if (DOWN) {
                         const float nf2 = simt::fadd(nf, rem_f);
                         const bool carry = nf2 >= den;

@@ -280,18 +280,20 @@ def s_player_volume_changes():
     (behind the user's filter), so a frame keeps the factor it had when the converter pulled it -- frames pulled in a block
     carry that block's factor, the two look-ahead frames of the converter included.  Expectation: the oracle's literal chain
     over an input that was multiplied frame by frame with exactly those factors."""
-    rates = [44100, 22050, 48000, 96000]
-    front = [False, True, False, True]
-    L = [6000, 3000, 6600, 13000]
+    rates = [44100, 22050, 48000, 96000, 88200, 88200]
+    front = [False, True, False, True, True, False]
+    L = [6000, 3000, 6600, 13000, 40000, 12100]
     pcms = [noise(n, 8800 + i) for i, n in enumerate(L)]
     mk_plain = lambda p, r, g: rb.UniformSourceIterator(rb.TestSource(p, 1, r).amplify(g), 1, 48000).low_pass(500).amplify(0.9)
     mk_front = lambda p, r, g: rb.UniformSourceIterator(rb.TestSource(p, 1, r).amplify(0.8).low_pass(400).amplify(g), 1, 48000)
     srcs = [(mk_front if f else mk_plain)(np.zeros(0, np.float32), r, 1.0) for r, f in zip(rates, front)]
     plan = {2: (0, 0.5), 3: (1, 0.25), 5: (0, 1.5), 6: (3, 0.1), 7: (2, 0.7), 8: (0, 0.0), 9: (1, 1.0), 10: (3, 0.9), 11: (0, 0.6),
-            12: (1, 0.0)}   # round -> (stream, volume); 0.0 = muted
-    vol = [1.0] * 4
+            12: (1, 0.0), 4: (4, 0.3), 13: (4, 1.2), 1: (5, 0.45), 14: (5, 0.9)}   # round -> (stream, volume); 0.0 = muted
+    vol = [1.0] * len(rates)
+    busy = {r: (4, 0.3 + 0.04 * r) for r in range(15, 40)}      # and one source whose volume moves in every round for a while
+    plan = {**busy, **plan}
     gains = [np.ones(n, np.float32) for n in L]       # factor of every input frame
-    pulled, pushed, done = [0] * 4, [0] * 4, [0] * 4
+    pulled, pushed, done = [0] * len(rates), [0] * len(rates), [0] * len(rates)
     total = [int(rb.plan((mk_front if f else mk_plain)(p, r, 1.0), 1, 48000)[0]) for p, r, f in zip(pcms, rates, front)]
     got, ended, rnd = [], False, 0
     with rb.Session(srcs, 48000, fifo_frames=4096, max_block_frames=240, mixer_channels=1) as s:
