@@ -189,6 +189,12 @@ rb_status rb_batch_launches_per_render(rb_batch* b, uint32_t* n);
 /* Which kernel family serves the batch: -1 = one kernel per adapter (general path), 0 = k_fused_biquad /
  * k_fused_nobiquad, 1 = k_fused_hot, 2 = k_fused_lanes (RB_FUSED_LANES).  For tests and bench labels. */
 rb_status rb_batch_kernel_family(rb_batch* b, int* family);
+/* Summation geometry of the fused mixer sum (src/mixer.rs:185-198 adds the sources sequentially): `rows` consecutive
+ * streams (insertion order) form one partial sum -- sequential from +0.0 in k_fused_hot / k_fused_biquad, the fixed
+ * 32-lane tree in k_fused_lanes -- and the partial sums are added in order.  0 = the whole mix is one sequential sum
+ * (general path, RB_MIX_EXACT_ORDER).  For the parity tests, which rebuild the kernel's documented order from the
+ * oracle's per-stream outputs. */
+rb_status rb_batch_mix_group(rb_batch* b, uint32_t* rows);
 /* Algorithmic bytes of one render: 4*sum(in_samples)(or format size) + 4*mix_len. */
 rb_status rb_batch_algorithmic_bytes(rb_batch* b, uint64_t* bytes);
 

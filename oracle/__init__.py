@@ -89,6 +89,24 @@ class Stream:
     mix_start: int = 0
 
 
+@dataclass
+class Fx:
+    """One adapter of a chain in the oracle's own terms (same layout as the 80-byte effect record of the C side), so that
+    callers which must not touch the product package (bench.py --impl reference) can build chains."""
+    kind: int
+    u32: Sequence = (0, 0, 0)
+    f32: Sequence = (0.0,) * 12
+    ns: Sequence = (0, 0)
+
+
+FX_AMPLIFY, FX_LOW_PASS, FX_HIGH_PASS, FX_UNIFORM = 1, 3, 4, 10     # rodio_oracle_capi.cpp, enum of adapter kinds
+
+
+def fx(kind: int, u32=(), f32=(), ns=()) -> Fx:
+    return Fx(kind, tuple(int(v) for v in u32) + (0,) * (3 - len(u32)), tuple(float(v) for v in f32) + (0.0,) * (12 - len(f32)),
+              tuple(int(v) for v in ns) + (0,) * (2 - len(ns)))
+
+
 def _fptr(a: np.ndarray):
     return a.ctypes.data_as(C.POINTER(C.c_float))
 

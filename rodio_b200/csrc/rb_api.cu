@@ -776,6 +776,11 @@ extern "C" rb_status rb_batch_kernel_family(rb_batch* b, int* family) {
     *family = b->fused ? rb_fused_kind(b->fused) : -1;
     return RB_OK;
 }
+extern "C" rb_status rb_batch_mix_group(rb_batch* b, uint32_t* rows) {
+    if (!b || !rows) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
+    *rows = b->fused ? rb_fused_mix_group(b->fused) : 0u;
+    return RB_OK;
+}
 extern "C" rb_status rb_batch_algorithmic_bytes(rb_batch* b, uint64_t* bytes) {
     if (!b || !bytes) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
     *bytes = b->algo_bytes;
@@ -1235,7 +1240,7 @@ extern "C" rb_status rb_session_set_volume(rb_session* s, size_t stream, float f
 extern "C" rb_status rb_session_available(rb_session* s, uint64_t* frames, int* ended) {
     if (!s || !frames) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
     bool e = false;
-    session::resolve_queue(s->st);
+    session::resolve_queue(s->st, s->T);
     *frames = session::renderable(s->st, s->T, ~0ull >> 1, &e);
     if (ended) *ended = e ? 1 : 0;
     return RB_OK;
@@ -1245,7 +1250,7 @@ extern "C" rb_status rb_session_render(rb_session* s, float* out_host, uint64_t 
     if (!s || !written) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
     *written = 0;
     bool e = false;
-    session::resolve_queue(s->st);   // queued sources whose predecessor's end is known by now get their place on the timeline
+    session::resolve_queue(s->st, s->T);   // queued sources whose predecessor's end is known by now get their place on the timeline
     const uint64_t n = session::renderable(s->st, s->T, std::min<uint64_t>(max_frames, s->max_block), &e);
     if (ended) *ended = e ? 1 : 0;
     if (n == 0) return RB_OK;
@@ -1329,6 +1334,8 @@ struct SessionBlobStream {   // in class order (the same descriptors give the sa
     float state[8];                      // 4 per channel
     float vol_a, vol_b;                  // factor of the two frames in front of fpos (rb_session_set_volume)
     float vol, post;                     // the current factors: rb_session_set_volume / rb_session_set_amplify
+    uint32_t held;                       // still waiting for rb_session_start / its predecessor (RB_SESSION_HELD)
+    int32_t follows;                     // class-order index of the source it is queued behind (rb_session_follow), -1: none
 };
 constexpr uint32_t SESSION_MAGIC = 0x52425353u;   // "RBSS"
 }  // namespace
@@ -1348,7 +1355,7 @@ extern "C" rb_status rb_session_get_state(rb_session* s, void* buf, uint64_t cap
     RB_CUDA(cudaMemcpyAsync(state.data(), s->d_state, 4 * C * ns * sizeof(float), cudaMemcpyDeviceToHost, s->ctx->stream));
     RB_CUDA(cudaMemcpyAsync(flags.data(), s->d_flags, ns * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->ctx->stream));
     uint8_t* p = (uint8_t*)buf;
-    SessionBlobHeader h{SESSION_MAGIC, 4u, (uint32_t)ns, s->has_biquad ? 1u : 0u, C, 0u, s->T};
+    SessionBlobHeader h{SESSION_MAGIC, 5u, (uint32_t)ns, s->has_biquad ? 1u : 0u, C, 0u, s->T};
     memcpy(p, &h, sizeof(h)), p += sizeof(h);
     uint8_t* recs = p;
     p += ns * sizeof(SessionBlobStream);
@@ -1361,7 +1368,7 @@ extern "C" rb_status rb_session_get_state(rb_session* s, void* buf, uint64_t cap
     for (size_t r = 0; r < ns; r++) {
         const session::Stream& st = s->st[r];
         SessionBlobStream b{st.mix_start, st.pushed, st.out_done, st.i0, st.from, st.to, st.eof ? 1u : 0u, flags[r], (uint32_t)st.fill(), (uint32_t)(st.fpos - st.i0), {0}, s->vol_a[r], s->vol_b[r],
-                            st.front ? s->mid[r] : s->pre[r], s->post[r]};
+                            st.front ? s->mid[r] : s->pre[r], s->post[r], st.held ? 1u : 0u, (int32_t)st.follows};
         for (uint32_t k = 0; k < 4 * C; k++) b.state[k] = state[4 * C * r + k];
         memcpy(recs + r * sizeof(b), &b, sizeof(b));
     }
@@ -1376,7 +1383,7 @@ extern "C" rb_status rb_session_set_state(rb_session* s, const void* buf, uint64
     if (size < sizeof(h)) return fail(RB_ERR_INVALID_ARGUMENT, "state blob truncated");
     memcpy(&h, p, sizeof(h)), p += sizeof(h);
     const uint32_t C = s->channels;
-    if (h.magic != SESSION_MAGIC || h.version != 4u) return fail(RB_ERR_INVALID_ARGUMENT, "not a session state blob");
+    if (h.magic != SESSION_MAGIC || h.version != 5u) return fail(RB_ERR_INVALID_ARGUMENT, "not a session state blob");
     if (h.n_streams != ns || h.has_biquad != (s->has_biquad ? 1u : 0u) || h.channels != C)
         return fail(RB_ERR_INVALID_ARGUMENT, "state blob belongs to a session of another shape");
     if (size < sizeof(h) + ns * sizeof(SessionBlobStream)) return fail(RB_ERR_INVALID_ARGUMENT, "state blob truncated");
@@ -1388,6 +1395,10 @@ extern "C" rb_status rb_session_set_state(rb_session* s, const void* buf, uint64
         if (b.from != s->st[r].from || b.to != s->st[r].to) return fail(RB_ERR_INVALID_ARGUMENT, "state blob belongs to a session of another shape");
         if (b.fill > s->fifo_cap || b.pushed - b.i0 != b.fill || (b.i0 & 3u) || b.filter_ahead > b.fill)
             return fail(RB_ERR_INVALID_ARGUMENT, "state blob: FIFO record out of range");
+        if (b.follows < -1 || (b.follows >= 0 && ((size_t)b.follows >= ns || (size_t)b.follows == r)))
+            return fail(RB_ERR_INVALID_ARGUMENT, "state blob: queue record out of range");
+        if (b.out_done > session::out_total(b.pushed, b.from, b.to))
+            return fail(RB_ERR_INVALID_ARGUMENT, "state blob: more outputs rendered than the pushed input holds");
         need += (uint64_t)b.fill * s->src_ch[r] * sizeof(float);
     }
     if (size < need) return fail(RB_ERR_INVALID_ARGUMENT, "state blob truncated");
@@ -1398,6 +1409,7 @@ extern "C" rb_status rb_session_set_state(rb_session* s, const void* buf, uint64
         const SessionBlobStream& b = recs[r];
         session::Stream& st = s->st[r];
         st.mix_start = b.mix_start, st.pushed = b.pushed, st.out_done = b.out_done, st.i0 = b.i0, st.eof = b.eof != 0, st.fpos = b.i0 + b.filter_ahead, s->vol_a[r] = b.vol_a, s->vol_b[r] = b.vol_b;
+        st.held = b.held != 0, st.follows = b.follows;
         (st.front ? s->mid[r] : s->pre[r]) = b.vol;
         if (b.post != s->post[r]) s->post[r] = b.post, s->has_post = true;
         flags[r] = b.unsafe;

@@ -1338,6 +1338,7 @@ uint32_t rb_fused_launch_count(const rb_fused_plan* p) {
     return p->single_cta_direct ? 1u : 2u;
 }
 int rb_fused_kind(const rb_fused_plan* p) { return p->lanes ? 2 : (p->hot ? 1 : 0); }
+uint32_t rb_fused_mix_group(const rb_fused_plan* p) { return p->lanes ? 32u : p->args.rows_per_cta; }
 
 #ifdef RB_HOT_TIMING
 extern "C" int rb_debug_hot_skip(int mask) { return (int)cudaMemcpyToSymbol(g_hot_skip, &mask, sizeof(int)); }

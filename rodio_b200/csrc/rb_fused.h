@@ -33,3 +33,5 @@ uint32_t rb_fused_launch_count(const rb_fused_plan* plan);
 void rb_fused_inputs_changed(rb_fused_plan* plan);
 // Which kernel family serves the plan: 0 = k_fused_biquad / k_fused_nobiquad, 1 = k_fused_hot, 2 = k_fused_lanes.
 int rb_fused_kind(const rb_fused_plan* plan);
+// streams per partial sum of the mixer (rows per CTA; 32 for the lane kernel)
+uint32_t rb_fused_mix_group(const rb_fused_plan* plan);

@@ -61,14 +61,17 @@ inline bool finished(const Stream& s) { return s.eof && s.out_done >= out_total(
 // Returns 0 with *ended = true when no stream is left (MixerSource::next returns None, src/mixer.rs:129-135).
 // A queued source can be scheduled as soon as the end of its predecessor is known, i.e. once that one has received all
 // of its input: its first frame follows the predecessor's last.  (Chains resolve front to back.)
-inline void resolve_queue(std::vector<Stream>& st) {
+// A predecessor that has played out before the successor was queued (Player::append on a player whose queue has run dry:
+// the sound starts at the current position) hands over at T, the frame rendered next -- never behind the timeline, where the
+// successor could neither render its head nor let the session move on.
+inline void resolve_queue(std::vector<Stream>& st, uint64_t T) {
     for (bool again = true; again;) {
         again = false;
         for (Stream& s : st) {
             if (!s.held || s.follows < 0) continue;
             const Stream& p = st[(size_t)s.follows];
             if (p.held || !p.eof) continue;
-            s.mix_start = p.mix_start + out_total(p.pushed, p.from, p.to);
+            s.mix_start = std::max(T, p.mix_start + out_total(p.pushed, p.from, p.to));
             s.held = false, again = true;
         }
     }

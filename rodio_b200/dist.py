@@ -42,9 +42,8 @@ def init_process_group(backend: str = "nccl"):
         kw = {}
         if backend == "nccl":
             import torch
-            # NCCL prints its version banner (level VERSION and above) on STDOUT; the bench contract is one JSON line
-            # there, so the log goes to stderr (measured on the box, which exports NCCL_DEBUG=VERSION)
-            os.environ["NCCL_DEBUG"] = os.environ.get("RB_NCCL_DEBUG", "WARN")
+            # NCCL prints its log (version banner included) on STDOUT; the bench contract is one JSON line there, so the
+            # log goes to stderr.  The level is the caller's (NCCL_DEBUG=INFO shows the communicator's ranks and NVLS).
             os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
             kw["device_id"] = torch.device("cuda", local_rank)
         dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)

@@ -436,6 +436,13 @@ class Batch:
         return n.value
 
     @property
+    def mix_group(self) -> int:
+        """Streams per partial sum of the fused mixer sum (0: one sequential sum), see rb_batch_mix_group."""
+        n = C.c_uint32()
+        check(lib().rb_batch_mix_group(self._h, C.byref(n)), "rb_batch_mix_group")
+        return n.value
+
+    @property
     def algorithmic_bytes(self) -> int:
         n = C.c_uint64()
         check(lib().rb_batch_algorithmic_bytes(self._h, C.byref(n)), "rb_batch_algorithmic_bytes")

@@ -122,6 +122,7 @@ void rb_fused_inputs_changed(rb_fused_plan* p) {
     if (p) rb_lanes_inputs_changed(p->lanes);
 }
 int rb_fused_kind(const rb_fused_plan*) { return 2; }
+uint32_t rb_fused_mix_group(const rb_fused_plan*) { return 32u; }
 cudaError_t rb_launch_nodes(uint32_t, const rb_node_dev*, uint32_t, uint64_t, uint32_t, cudaStream_t) { return cudaErrorInvalidValue; }
 cudaError_t rb_launch_mix(const rb_mix_src*, uint32_t, float*, uint64_t, cudaStream_t, float*, uint32_t) { return cudaErrorInvalidValue; }
 cudaError_t rb_launch_convert(const void*, uint32_t, void*, uint32_t, uint64_t, cudaStream_t) { return cudaErrorInvalidValue; }

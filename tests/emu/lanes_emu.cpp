@@ -186,7 +186,7 @@ extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t*
         if (s.pushed == n_frames[r]) s.eof = true;
     };
     auto render = [&](uint64_t max_frames) -> bool {   // false: session ended
-        session::resolve_queue(st);
+        session::resolve_queue(st, T);
         bool ended = false;
         const uint64_t n = session::renderable(st, T, max_frames, &ended);
         if (ended) return false;
@@ -259,7 +259,7 @@ extern "C" long long rb_session_emulate(const float* const* pcm, const uint64_t*
         }
     }
     for (uint32_t r = 0; r < n_rows; r++) st[r].eof = true;   // whatever was pushed is all there is
-    session::resolve_queue(st);
+    session::resolve_queue(st, T);
     for (uint32_t r = 0; r < n_rows; r++) pushed_total[r] = st[r].pushed;
     for (uint32_t r = 0; r < n_rows; r++) {
         joined_at[r] = st[r].held ? ~0ull : st[r].mix_start;

@@ -148,6 +148,80 @@ def s_held_queue_gain_speed():
     assert_bit_exact(got, expected(pcms, ch, rates, 1, 48000, joined, 900, 0.8, speeds), "queue + added voice + scheduled source")
 
 
+def s_follow_after_predecessor_played_out():
+    """Player::append on a player whose queue has run dry while another voice keeps the timeline moving: the sound starts at the
+    current position (the frame rendered next), it neither stalls the session nor loses its head."""
+    rates = [44100, 44100, 48000]
+    pcms = [noise(100, 4100), noise(6000, 4101), noise(900, 4102)]
+    ch = [1, 1, 1]
+    srcs = [chain(np.zeros(0, np.float32), 1, r, 1, 48000, 700, 0.9) for r in rates]
+    with rb.Session(srcs, 48000, fifo_frames=8192, max_block_frames=256, mix_starts=[0, 0, HELD]) as s:
+        got = []
+        s.push(0, pcms[0], end_of_stream=True)
+        s.push(1, pcms[1][:1500])
+        while True:
+            block, ended = s.render(256)
+            if block.size == 0:
+                break
+            got.append(block)
+        T = sum(b.size for b in got)
+        assert T > 200, T                      # source 0 (about 109 frames) has played out long ago
+        s.follow(2, 0)
+        s.push(2, pcms[2], end_of_stream=True)
+        s.push(1, pcms[1][1500:], end_of_stream=True)
+        frames, ended = s.available()
+        assert frames > 0 and not ended, (frames, ended)
+        while True:
+            block, ended = s.render(256)
+            got.append(block)
+            if block.size == 0 or ended:
+                break
+    got = np.concatenate(got)
+    assert_bit_exact(got, expected(pcms, ch, rates, 1, 48000, [0, 0, T], 700, 0.9), "follow after the predecessor has played out")
+
+
+def s_held_and_queued_across_state_blob():
+    """get_state / set_state carries `held` and `follows`: a started source keeps playing, a queued one keeps its place, a
+    source that is still held stays held."""
+    rates = [44100, 48000, 44100, 22050]
+    pcms = [noise(1800 + 100 * i, 4200 + i) for i in range(4)]
+    ch = [1] * 4
+    mk = lambda: [chain(np.zeros(0, np.float32), 1, r, 1, 48000, 500, 1.1) for r in rates]
+    starts = [0, HELD, HELD, HELD]            # 1 follows 0; 2 is started by hand before the hand-over; 3 after it
+    sa = rb.Session(mk(), 48000, fifo_frames=8192, max_block_frames=200, mix_starts=starts)
+    sb = rb.Session(mk(), 48000, fifo_frames=8192, max_block_frames=200, mix_starts=starts)
+    sa.follow(1, 0)
+    marks, got, pos, sess, rnd, ended = {}, [], [0] * 4, sa, 0, False
+    while not ended:
+        if rnd == 2:
+            marks[2] = sum(b.size for b in got)
+            sess.start(2)
+        if rnd == 3:
+            sb.set_state(sess.get_state())
+            sess = sb
+        if rnd == 5:
+            marks[3] = sum(b.size for b in got)
+            sess.start(3)
+        blocks, eos = [], []
+        for i, p in enumerate(pcms):
+            k = min(rates[i] // 100, p.size - pos[i])
+            blocks.append(p[pos[i]:pos[i] + k])
+            pos[i] += k
+            eos.append(pos[i] == p.size)
+        sess.push_packed(blocks, eos)
+        while True:
+            block, ended = sess.render(200)
+            got.append(block)
+            if block.size == 0 or ended:
+                break
+        rnd += 1
+        assert rnd < 10000
+    sa.close(), sb.close()
+    got = np.concatenate(got)
+    len0 = oracle.chain_uniform(to_oracle(chain(pcms[0], 1, rates[0], 1, 48000, 500, 1.1)), 1, 48000).size
+    assert_bit_exact(got, expected(pcms, ch, rates, 1, 48000, [0, len0, marks[2], marks[3]], 500, 1.1), "held / queued sources across a hand-over")
+
+
 def s_filtered_and_plain_sources():
     """A low-passed source beside an untouched one (examples/stream_mixer.c): classes of their own, two launches."""
     pcms = [noise(2 * 900, 51), noise(1000, 52), noise(2 * 700, 53), noise(800, 54)]
@@ -510,7 +584,8 @@ def s_random(seed=0, cases=6):
 
 
 SCENARIOS = {"mono_random_split": s_mono_random_split, "mixed_with_state_blob": s_mixed_everything_with_state_blob,
-             "held_queue_gain_speed": s_held_queue_gain_speed, "gain_changes": s_gain_changes, "filtered_and_plain": s_filtered_and_plain_sources,
+             "held_queue_gain_speed": s_held_queue_gain_speed, "follow_after_played_out": s_follow_after_predecessor_played_out,
+             "held_across_state_blob": s_held_and_queued_across_state_blob, "gain_changes": s_gain_changes, "filtered_and_plain": s_filtered_and_plain_sources,
              "batch_with_identity_conversions": s_batch_with_identity_conversions, "batch_unsorted_starts": s_batch_unsorted_starts, "errors": s_errors,
              "gain_in_front": s_gain_in_front_of_the_conversion, "filter_in_front": s_filter_in_front_of_the_conversion, "player_volume": s_player_volume_changes}
 

@@ -1,0 +1,140 @@
+"""Parity at the launch geometries the bench lines are quoted on ("parity gaps" 1, 2, 4):
+cfg3 with 4096 mono streams (k_fused_hot, 28 rows per CTA incl. the second-row warps), its stereo and filter-free
+twins, the automatically selected lane kernel at >= 277 streams per SM, cfg2 at 1024 sources, cfg4 at 512 streams.
+Streams are short (the oracle finishes in seconds); the launch configuration is the one of the full-length run
+because it depends on the number of streams only.
+
+Two bars per fused case: <= 1e-5 * peak against the reference's sequential mixer (src/mixer.rs:185-198) -- the
+north-star tolerance -- and BIT-EXACT against the oracle's per-stream outputs added in the kernel's documented
+order (rb_batch_mix_group)."""
+import numpy as np
+import pytest
+
+import oracle
+import rodio_b200 as rb
+from helpers import assert_bit_exact, assert_close_peak, lanes_expected_mix, noise, to_oracle
+from rodio_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+GENERAL = capi.RB_KEEP_STREAM_OUTPUTS | capi.RB_NO_FUSION | capi.RB_MIX_EXACT_ORDER
+
+
+def grouped_expected_mix(per_stream, starts, mix_len, group):
+    """Per-CTA sequential sums from +0.0 over `group` consecutive streams (only where a stream is active), the partial
+    rows added in CTA order starting from the first (k_fused_hot stage C + k_sum_partials)."""
+    total = None
+    for g in range(0, len(per_stream), group):
+        acc = np.zeros(mix_len, dtype=np.float32)
+        for y, s in zip(per_stream[g:g + group], starts[g:g + group]):
+            acc[s:s + y.size] = acc[s:s + y.size] + y
+        total = acc if total is None else total + acc
+    return total
+
+
+def _cfg3(n, frames, ch=1, lp=200, gain=1.2, seed=31000):
+    srcs = []
+    for s in range(n):
+        src = rb.UniformSourceIterator(rb.TestSource(noise(frames * ch, seed + s), ch, 44100), ch, 48000)
+        if lp:
+            src = src.low_pass(lp)
+        srcs.append(src.amplify(gain))
+    return srcs
+
+
+def _check_fused(ctx, srcs, ch, family, group=None, flags=0):
+    with rb.Batch(srcs, ch, 48000, flags=flags, ctx=ctx) as b:
+        assert b.kernel_family == family, f"kernel family {b.kernel_family}, expected {family}"
+        if group is not None:
+            assert b.mix_group == group, f"rows per partial sum {b.mix_group}, expected {group}"
+        group = b.mix_group
+        b.upload_all()
+        got = b.render_mix()
+        again = b.render_mix()
+    assert np.array_equal(got.view(np.uint32), again.view(np.uint32)), "render is not idempotent"
+    streams = [to_oracle(s) for s in srcs]
+    ref = oracle.mixer(streams, ch, 48000)
+    assert got.shape == ref.shape
+    assert_close_peak(got, ref, 1e-5, "fused kernel vs the reference's sequential mixer")
+    per_stream = [oracle.chain_uniform(s, ch, 48000) for s in streams]
+    starts = [0] * len(srcs)
+    want = lanes_expected_mix(per_stream, starts, ref.size) if family == 2 else grouped_expected_mix(per_stream, starts, ref.size, group)
+    assert_bit_exact(got, want, "fused kernel vs oracle streams added in the kernel's documented order")
+
+
+def test_cfg3_bench_geometry_mono_4096(ctx):
+    """The headline launch: 4096 mono streams, default flags -> k_fused_hot<1, true>, 147 CTAs x 28 rows."""
+    _check_fused(ctx, _cfg3(4096, 4410), 1, family=1, group=28)
+
+
+def test_cfg3_bench_geometry_mono_4096_low_pass_1000(ctx):
+    _check_fused(ctx, _cfg3(4096, 2000, lp=1000, seed=32000), 1, family=1, group=28)
+
+
+def test_cfg3_bench_geometry_stereo_2048(ctx):
+    """profiles' cfg3_stereo line: 2048 stereo streams -> k_fused_hot<2, true>."""
+    _check_fused(ctx, _cfg3(2048, 2205, ch=2, seed=33000), 2, family=1)
+
+
+def test_nofilter_bench_geometry_mono_4096(ctx):
+    """resample -> amplify -> mix at 4096 streams -> k_fused_hot<1, false> with full CTAs."""
+    _check_fused(ctx, _cfg3(4096, 4410, lp=None, seed=34000), 1, family=1)
+
+
+def test_cfg5_auto_selected_large_batch(ctx):
+    """No flag, 41 000 streams (>= 277 per SM): the planner hands the batch to the lane kernel on its own."""
+    _check_fused(ctx, _cfg3(41000, 600, seed=35000), 1, family=2)
+
+
+def test_cfg5_large_batch_16384(ctx):
+    """16 384 streams, whatever kernel the planner picks at that size."""
+    srcs = _cfg3(16384, 900, seed=36000)
+    with rb.Batch(srcs, 1, 48000, ctx=ctx) as b:
+        family = b.kernel_family
+    assert family in (1, 2)
+    _check_fused(ctx, srcs, 1, family=family)
+
+
+def test_cfg2_1024_sources(ctx):
+    """BASELINE cfg2 stream count: mixer(1, 48000) of 1024 SineWave sources, exact order and default."""
+    n, frames = 1024, 4800
+    srcs = [rb.TestSource(oracle.sine_wave(min(55.0 + 19.3 * s, 19900.0), frames), 1, 48000) for s in range(n)]
+    want = oracle.mixer([to_oracle(s) for s in srcs], 1, 48000)
+    with rb.Batch(srcs, 1, 48000, flags=capi.RB_MIX_EXACT_ORDER, ctx=ctx) as b:
+        b.upload_all()
+        assert_bit_exact(b.render_mix(), want, "cfg2 1024 sources, exact order")
+    with rb.Batch(srcs, 1, 48000, ctx=ctx) as b:     # the bench's launch (default flags)
+        b.upload_all()
+        got = b.render_mix()
+    assert_close_peak(got, want, 1e-5, "cfg2 1024 sources, default")
+
+
+def cfg4_sources(n, frames, seed=700):
+    srcs = []
+    t = np.arange(frames, dtype=np.float32)
+    for s in range(n):
+        l = np.sin(t * np.float32(0.02 + 0.00001 * s)).astype(np.float32) * np.float32(0.4)
+        r = np.sin(t * np.float32(0.021 + 0.00001 * s)).astype(np.float32) * np.float32(0.4)
+        x = np.stack([l, r], 1).reshape(-1) + noise(2 * frames, seed + s, 0.1)
+        srcs.append(rb.Spatial(rb.TestSource(x, 2, 48000), [float(s % 7 - 3), 1.0, 0.0], [-1, 0, 0], [1, 0, 0])
+                    .reverb(rb.Duration.from_millis(50), 0.3).automatic_gain_control())
+    return srcs
+
+
+def test_cfg4_512_streams(ctx):
+    """BASELINE cfg4 stream count: 512 stereo sources, spatial -> reverb(50 ms, 0.3) -> AGC -> mix(2 ch): the default
+    launch within the tolerance, the exact-order launch and its per-stream outputs bit for bit."""
+    n, frames = 512, 2400 + 2400     # the echo starts after 2400 frames
+    srcs = cfg4_sources(n, frames)
+    streams = [to_oracle(s) for s in srcs]
+    want = oracle.mixer(streams, 2, 48000)
+    with rb.Batch(srcs, 2, 48000, flags=GENERAL, ctx=ctx) as b:
+        b.upload_all()
+        got = b.render_mix()
+        for i in (0, 255, n - 1):
+            assert_bit_exact(b.read_stream(i), oracle.chain_uniform(streams[i], 2, 48000), f"cfg4 stream {i}")
+    assert_bit_exact(got, want, "cfg4 512 streams, exact order")
+    with rb.Batch(srcs, 2, 48000, ctx=ctx) as b:
+        b.upload_all()
+        got = b.render_mix()
+    assert_close_peak(got, want, 1e-5, "cfg4 512 streams, default launch")
