@@ -132,10 +132,17 @@ enum {
                                        mix of >= 256 sources) combined in group order: deterministic,
                                        <= 1e-5 * peak, and still the sequential sum for <= 148 fused streams  */
     RB_NO_FUSION = 1u << 1,         /* run one kernel per adapter (debug / cross-check path)                  */
-    RB_BIQUAD_TIME_PARALLEL = 1u << 2, /* reserved (chunked-scan biquad, not bit-exact): accepted, served by the exact path */
+    RB_BIQUAD_TIME_PARALLEL = 1u << 2, /* low/high_pass of a resample -> filter -> [amplify] -> mix batch of mono f32 sources
+                                          run time-parallel: the mixer timeline is cut into segments, every source contributes
+                                          one row per segment that starts a warm-up in front of it from zero filter state
+                                          (arithmetic per sample = the reference's, src/source/blt.rs:558-560).  Taken only for
+                                          filters whose f32 rounding noise leaves the 1e-5 * peak tolerance a margin
+                                          (noise gain <= 400: cut-offs from about 700 Hz at q = 0.5; most segments are then
+                                          bit-identical to the serial run); every other batch is served as without the flag
+                                          (exact serial recurrence).  rb_batch_kernel_family tells which: 4 = time-parallel */
     RB_KEEP_STREAM_OUTPUTS = 1u << 3,  /* also keep every stream's post-chain (pre-mix) samples in HBM so
                                           rb_batch_read_stream can return them                                */
-    RB_FUSED_LANES = 1u << 4           /* large batches (chosen automatically from ~277 sources per SM on): serve
+    RB_FUSED_LANES = 1u << 4,          /* large batches (chosen automatically from ~277 sources per SM on): serve
                                           [amplify] -> resample -> [low/high_pass] -> [amplify] -> mix, or the chain with the
                                           filter in front of the conversion ([amplify] -> low/high_pass -> [amplify] ->
                                           resample -> [amplify] -> mix: chosen automatically from 32 sources per SM on, no
@@ -146,6 +153,11 @@ enum {
                                           (<= 1e-5 * peak like the default grouping).  Ignored when the batch has
                                           another shape.  Inputs are classified when uploaded: writers through
                                           rb_batch_input_device_ptr ask for the pointer again after rewriting. */
+    RB_FUSED_DUO = 1u << 5             /* the large-batch kernels whatever the batch size, the lane-PAIR kernel where the
+                                          batch allows it (mono sources below the mixer's rate, neighbours starting in phase:
+                                          two sources per lane, packed f32x2 arithmetic, mixer sum = pairs, then the tree over
+                                          groups of 64), k_fused_lanes elsewhere.  This is what very large batches get without
+                                          any flag. */
 };
 
 const char* rb_status_string(rb_status s);
@@ -187,7 +199,8 @@ rb_status rb_batch_mix_len(rb_batch* b, uint64_t* n_samples);
 /* Number of kernels one rb_batch_render_mix_device enqueues (bench "gpu_launches"). */
 rb_status rb_batch_launches_per_render(rb_batch* b, uint32_t* n);
 /* Which kernel family serves the batch: -1 = one kernel per adapter (general path), 0 = k_fused_biquad /
- * k_fused_nobiquad, 1 = k_fused_hot, 2 = k_fused_lanes (RB_FUSED_LANES).  For tests and bench labels. */
+ * k_fused_nobiquad, 1 = k_fused_hot, 2 = k_fused_lanes (RB_FUSED_LANES), 3 = k_fused_duo (lane-pair kernel),
+ * 4 = time-parallel plan on k_fused_duo (RB_BIQUAD_TIME_PARALLEL).  For tests and bench labels. */
 rb_status rb_batch_kernel_family(rb_batch* b, int* family);
 /* Summation geometry of the fused mixer sum (src/mixer.rs:185-198 adds the sources sequentially): `rows` consecutive
  * streams (insertion order) form one partial sum -- sequential from +0.0 in k_fused_hot / k_fused_biquad, the fixed

@@ -35,6 +35,7 @@ RB_NO_FUSION = 1 << 1
 RB_BIQUAD_TIME_PARALLEL = 1 << 2
 RB_KEEP_STREAM_OUTPUTS = 1 << 3
 RB_FUSED_LANES = 1 << 4
+RB_FUSED_DUO = 1 << 5
 RB_SESSION_HELD = (1 << 64) - 1
 
 

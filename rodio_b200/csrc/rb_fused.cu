@@ -1161,7 +1161,7 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
                                 uint64_t mix_len, uint32_t flags, int sm_count, cudaStream_t st, rb_fused_plan** out) {
     *out = nullptr;
     if (n_streams == 0 || mix_len == 0) return cudaSuccess;
-    if (flags & (RB_MIX_EXACT_ORDER | RB_BIQUAD_TIME_PARALLEL)) return cudaSuccess;   // served by the general path
+    if (flags & RB_MIX_EXACT_ORDER) return cudaSuccess;   // served by the general path
     std::vector<FusedRow> rows(n_streams);
     uint32_t n_pre = 0, n_mid = 0, n_post = 0, has_u = 0, has_b = 0, front = 0;
     bool mixed_u = false;   // some rows lost an identity conversion: only the lane kernel may take such a batch
@@ -1337,8 +1337,8 @@ uint32_t rb_fused_launch_count(const rb_fused_plan* p) {
     if (p->lanes) return rb_lanes_launch_count(p->lanes);
     return p->single_cta_direct ? 1u : 2u;
 }
-int rb_fused_kind(const rb_fused_plan* p) { return p->lanes ? 2 : (p->hot ? 1 : 0); }
-uint32_t rb_fused_mix_group(const rb_fused_plan* p) { return p->lanes ? 32u : p->args.rows_per_cta; }
+int rb_fused_kind(const rb_fused_plan* p) { return p->lanes ? rb_lanes_kind(p->lanes) : (p->hot ? 1 : 0); }
+uint32_t rb_fused_mix_group(const rb_fused_plan* p) { return p->lanes ? rb_lanes_mix_group(p->lanes) : p->args.rows_per_cta; }
 
 #ifdef RB_HOT_TIMING
 extern "C" int rb_debug_hot_skip(int mask) { return (int)cudaMemcpyToSymbol(g_hot_skip, &mask, sizeof(int)); }

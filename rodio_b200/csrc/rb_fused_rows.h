@@ -175,8 +175,11 @@ static cudaError_t fused_lanes_hook(const std::vector<FusedRow>& rows, size_t n_
     // A filter in front of the conversion has no other fused kernel: the alternative is the general path (one kernel per adapter,
     // intermediates in HBM: 24.5 ms against 0.85 ms on cfg3), so the lane kernel takes such a batch as soon as every SM gets a warp.
     const size_t sms = (size_t)(sm_count > 0 ? sm_count : 148);
-    const bool want_lanes = (flags & RB_FUSED_LANES) || n_streams >= 277 * sms || (front && n_streams >= 32 * sms);
-    if (!(want_lanes && (mixer_channels == 1 || mixer_channels == 2) && all_f32 && (has_u || has_b) && n_pre <= 1)) return cudaSuccess;
+    const bool want_lanes = (flags & (RB_FUSED_LANES | RB_FUSED_DUO)) || n_streams >= 277 * sms || (front && n_streams >= 32 * sms);
+    // RB_BIQUAD_TIME_PARALLEL: the lane kernels serve the batch cut into timeline segments when it qualifies (rb_lanes_batch.cu);
+    // when it does not, the flag changes nothing
+    const bool want_tp = (flags & RB_BIQUAD_TIME_PARALLEL) && has_b && !front && mixer_channels == 1;
+    if (!((want_lanes || want_tp) && (mixer_channels == 1 || mixer_channels == 2) && all_f32 && (has_u || has_b) && n_pre <= 1)) return cudaSuccess;
     // f32 streams with the mixer's channel count (or mono in a stereo mixer), each at or below the mixer's rate (classes per
     // rate pair), at most one gain in front of the conversion (source.amplify(v) handed to the mixer), optional biquad, at most
     // one gain directly in front of the sum.
@@ -207,6 +210,12 @@ static cudaError_t fused_lanes_hook(const std::vector<FusedRow>& rows, size_t n_
         l.pre = n_pre ? r.pre[0] : 1.0f;
         l.mid = front && n_mid ? r.mid[0] : 1.0f;
     }
-    return rb_lanes_try_create(ls.data(), n_streams, C, has_b != 0, front ? n_post != 0 : (n_mid + n_post) != 0, n_pre != 0, front != 0, d_out,
-                               mix_len / C, sm_count, st, lanes);
+    cudaError_t e = rb_lanes_try_create(ls.data(), n_streams, C, has_b != 0, front ? n_post != 0 : (n_mid + n_post) != 0, n_pre != 0, front != 0, d_out,
+                                        mix_len / C, sm_count, st, lanes,
+                                        (want_tp ? LANES_TIME_PARALLEL : 0u) | ((flags & RB_FUSED_LANES) ? LANES_NO_DUO : 0u));   // RB_FUSED_LANES names k_fused_lanes itself
+    if (e == cudaSuccess && *lanes && !want_lanes && rb_lanes_kind(*lanes) != 4) {   // asked for the time-parallel plan only, and it was not built
+        rb_lanes_destroy(*lanes);
+        *lanes = nullptr;
+    }
+    return e;
 }

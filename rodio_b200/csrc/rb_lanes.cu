@@ -9,6 +9,7 @@
 
 #include "rb_lanes.h"
 #include "rb_lanes_plan.h"
+#include "rb_duo_core.h"
 
 namespace {
 
@@ -26,6 +27,18 @@ __global__ void __launch_bounds__(LANES_THREADS) k_fused_lanes(lanes::Args a) {
     const uint32_t group = blockIdx.x * LANES_WARPS + warp;
     if (group >= a.n_groups) return;   // whole warps leave: the warp program only synchronises within a warp
     lanes::warp_main<CI, CO, HASB, FF2, NPOST, PASS, PRE, FRONT, DOWN, GUARD>(a, group, lanes_smem + (size_t)warp * 32 * lanes::Geo<CI, DOWN ? lanes::NSLOT_DOWN : RB_LANES_UP_SLOTS>::RS);
+}
+
+// The lane-pair kernel (rb_duo_core.h): a warp = 64 mono streams, packed f32x2 arithmetic.
+constexpr int DUO_WARPS = 2;
+constexpr size_t DUO_SMEM = (size_t)DUO_WARPS * duo::WARP_WORDS * sizeof(float);   // 42.0 KB: no opt-in needed
+template <bool HASB, bool FF2, int NPOST>
+__global__ void __launch_bounds__(32 * DUO_WARPS) k_fused_duo(lanes::Args a) {
+    extern __shared__ __align__(16) float lanes_smem[];
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t group = blockIdx.x * DUO_WARPS + warp;
+    if (group >= a.n_groups) return;
+    duo::warp_main<HASB, FF2, NPOST>(a, group, lanes_smem + (size_t)warp * duo::WARP_WORDS);
 }
 
 // One CTA per stream: does every non-zero |x| lie inside [2^-70, 2^60]?  (rb_lanes_core.h, "Exact division".)
@@ -49,6 +62,15 @@ __global__ void __launch_bounds__(256) k_classify_inputs(lanes::Row* rows, uint3
     for (uint64_t i = n4 * 4 + threadIdx.x; i < L; i += blockDim.x) bad |= out_of_class(__ldg(x + i));
     const int any = __syncthreads_or(bad ? 1 : 0);
     if (threadIdx.x == 0) rows[r].flags = (rows[r].flags & ~lanes::ROW_UNSAFE) | (any ? lanes::ROW_UNSAFE : 0u);
+}
+
+__global__ void __launch_bounds__(256) k_spread_flags(lanes::Row* rows, uint32_t n_rows, const uint32_t* __restrict__ row_stream,
+                                                      const lanes::Row* __restrict__ stream_rows) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const uint32_t s = row_stream[r];
+    const uint32_t bad = s == ~0u ? 0u : (stream_rows[s].flags & lanes::ROW_UNSAFE);
+    rows[r].flags = (rows[r].flags & ~lanes::ROW_UNSAFE) | bad;
 }
 
 // out[m] = +0.0 + partial[0][m] + partial[1][m] + ...  (warp order = insertion order of the streams)
@@ -150,6 +172,20 @@ cudaError_t rb_lanes_launch_kernel(const lanes::Args& a, uint32_t ch_in, uint32_
     return cudaGetLastError();
 }
 
+// k_fused_duo over a.rows: a.n_groups counts groups of 64 rows
+cudaError_t rb_duo_launch_kernel(const lanes::Args& a, bool has_biquad, bool ff2, bool has_post, cudaStream_t st) {
+    if (a.mix_len == 0 || a.n_groups == 0) return cudaSuccess;
+    const uint32_t n_ctas = (a.n_groups + DUO_WARPS - 1) / DUO_WARPS;
+    const dim3 g(n_ctas), b(32 * DUO_WARPS);
+    if (has_biquad) {
+        if (ff2) has_post ? k_fused_duo<true, true, 1><<<g, b, DUO_SMEM, st>>>(a) : k_fused_duo<true, true, 0><<<g, b, DUO_SMEM, st>>>(a);
+        else has_post ? k_fused_duo<true, false, 1><<<g, b, DUO_SMEM, st>>>(a) : k_fused_duo<true, false, 0><<<g, b, DUO_SMEM, st>>>(a);
+    } else {
+        has_post ? k_fused_duo<false, false, 1><<<g, b, DUO_SMEM, st>>>(a) : k_fused_duo<false, false, 0><<<g, b, DUO_SMEM, st>>>(a);
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t rb_lanes_launch_sum(const float* d_partial, uint32_t n_groups, uint64_t pstride, uint64_t n_floats, float* d_out,
                                 cudaStream_t st) {
     if (n_floats == 0) return cudaSuccess;
@@ -176,6 +212,12 @@ cudaError_t rb_lanes_fifo_compact(const float* d_src, float* d_dst, uint64_t str
                                   uint32_t n_streams, cudaStream_t st) {
     if (n_streams == 0) return cudaSuccess;
     k_fifo_compact<<<n_streams, 128, 0, st>>>(d_src, d_dst, stride, d_drop, d_keep);
+    return cudaGetLastError();
+}
+
+cudaError_t rb_lanes_spread_flags(lanes::Row* d_rows, uint32_t n_rows, const uint32_t* d_row_stream, const lanes::Row* d_stream_rows, cudaStream_t st) {
+    if (n_rows == 0) return cudaSuccess;
+    k_spread_flags<<<(n_rows + 255) / 256, 256, 0, st>>>(d_rows, n_rows, d_row_stream, d_stream_rows);
     return cudaGetLastError();
 }
 

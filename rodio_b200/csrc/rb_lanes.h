@@ -26,8 +26,18 @@ struct rb_lanes_plan;
 // *out stays NULL when the shape is not covered.  `d_out` is the mixer output ([mix_len] f32).
 // mix_len in frames; `d_out` holds mix_len * channels floats.  Streams with different rate pairs are served class by
 // class (rb_lanes_plan.h classes_by_ratio): the mixer sum then groups by class first.
+// mode: LANES_TIME_PARALLEL asks for the time-parallel biquad plan (built only when the batch qualifies: rb_lanes_batch.cu),
+// LANES_NO_DUO keeps every class on k_fused_lanes (A/B runs; the environment variable RB_NO_DUO does the same).
+enum : uint32_t { LANES_TIME_PARALLEL = 1u, LANES_NO_DUO = 2u };
 cudaError_t rb_lanes_try_create(const rb_lanes_stream* streams, size_t n_streams, uint32_t channels, bool has_biquad, bool has_post,
-                                bool has_pre, bool front, float* d_out, uint64_t mix_len, int sm_count, cudaStream_t st, rb_lanes_plan** out);
+                                bool has_pre, bool front, float* d_out, uint64_t mix_len, int sm_count, cudaStream_t st, rb_lanes_plan** out,
+                                uint32_t mode = 0);
+// 2: k_fused_lanes, 3: every class on k_fused_duo, 4: the time-parallel plan (k_fused_duo over segment rows)
+int rb_lanes_kind(const rb_lanes_plan* p);
+// streams per partial sum of the mixer: 32 (k_fused_lanes) or 64 (k_fused_duo: lane = even row + odd row, then the same tree)
+uint32_t rb_lanes_mix_group(const rb_lanes_plan* p);
+// time-parallel plan: number of timeline segments, their length and the warm-up in front of each (frames); zeros otherwise
+void rb_lanes_tp_geometry(const rb_lanes_plan* p, uint32_t* segments, uint32_t* seg_len, uint32_t* warmup);
 // Inputs were (re)written: classify them again before the next render.
 void rb_lanes_inputs_changed(rb_lanes_plan* p);
 cudaError_t rb_lanes_run(rb_lanes_plan* p, cudaStream_t st);
@@ -39,6 +49,8 @@ void rb_lanes_destroy(rb_lanes_plan* p);
 // per stream, ch_out channels in the mixer) ...
 cudaError_t rb_lanes_launch_kernel(const lanes::Args& a, uint32_t ch_in, uint32_t ch_out, bool has_biquad, bool ff2, bool has_post,
                                    bool has_pre, bool front, bool guard, cudaStream_t st);
+// k_fused_duo (rb_duo_core.h) over a.rows: mono sources below the mixer's rate, two rows per lane, a.n_groups groups of 64
+cudaError_t rb_duo_launch_kernel(const lanes::Args& a, bool has_biquad, bool ff2, bool has_post, cudaStream_t st);
 // ... and the ordered sum of n_groups partial rows (all classes) into d_out[0, n_floats).
 cudaError_t rb_lanes_launch_sum(const float* d_partial, uint32_t n_groups, uint64_t pstride, uint64_t n_floats, float* d_out,
                                 cudaStream_t st);
@@ -51,5 +63,8 @@ cudaError_t rb_lanes_fifo_compact(const float* d_src, float* d_dst, uint64_t str
                                   uint32_t n_streams, cudaStream_t st);
 // Sticky classification of n freshly written floats at d_ptr: *d_flag = 1 when one lies outside the class.
 cudaError_t rb_lanes_classify_range(const float* d_ptr, uint64_t n, uint32_t* d_flag, cudaStream_t st);
+// rows[r].flags takes the ROW_UNSAFE bit of stream_rows[row_stream[r]] (time-parallel plan: a stream is classified once, its
+// segment rows inherit the verdict); row_stream[r] == ~0u (padding) clears it.
+cudaError_t rb_lanes_spread_flags(lanes::Row* d_rows, uint32_t n_rows, const uint32_t* d_row_stream, const lanes::Row* d_stream_rows, cudaStream_t st);
 // One CTA per stream of d_rows: Row::flags = ROW_UNSAFE when a sample lies outside the exact-reciprocal class.
 cudaError_t rb_lanes_launch_classify(lanes::Row* d_rows, uint32_t n_rows, const uint8_t* d_row_channels, cudaStream_t st);

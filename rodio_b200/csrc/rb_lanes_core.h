@@ -111,6 +111,13 @@ struct Row {                 // one stream (whole, or the part of it one block o
                              // a frame keeps the factor it was multiplied with when Amplify::next pulled it)
 };
 
+// Optional per-group record (duo kernel, time-parallel plan): which partial row the group adds into, and from which timeline
+// frame on its tiles are stored (what lies in front is the warm-up of a segment: computed, never stored).
+struct GroupSpan {
+    uint64_t store_lo;   // a multiple of TILE
+    uint32_t slot, pad_;
+};
+
 struct Args {
     const Row* rows;
     uint32_t n_rows, n_groups;
@@ -125,6 +132,7 @@ struct Args {
     float* partial;          // [n_groups][pstride], zero outside the span each group writes
     const float* zeros;      // CHUNK zeros, 16-byte aligned: the source of idle lanes
     const uint32_t* unsafe;  // optional [n_rows]: non-zero = as if ROW_UNSAFE were set (streaming: kept on the device)
+    const GroupSpan* spans;  // optional [n_groups] (rb_duo_core.h)
 };
 
 // (t - a1*y1) - a2*y2, each product and each difference rounded once (src/source/blt.rs:558-560)

@@ -1,6 +1,7 @@
 // rb_lanes_plan.h — host-side arithmetic of the lane-per-stream kernel's plan (plain C++: shared by rb_lanes.cu and
 // by the CPU emulator under tests/emu/ so that both fill lanes::Row / lanes::Args identically).
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <utility>
@@ -75,6 +76,58 @@ inline std::vector<std::vector<uint32_t>> classes_by_ratio(const uint32_t* from,
         out[k].push_back(i);
     }
     return out;
+}
+
+// ---- the lane-pair kernel (rb_duo_core.h) ----
+// Two rows may share a lane when they are in phase on the mixer timeline: (o0 - mix_start) congruent modulo 4 * to -- the
+// same numerator and the same offset of the left frame inside its 16-byte quad at every timeline frame.
+inline bool duo_in_phase(const Row& a, const Row& b, uint32_t to) {
+    const uint64_t m = 4ull * to;
+    const uint64_t pa = (a.o0 % m + m - a.mix_start % m) % m, pb = (b.o0 % m + m - b.mix_start % m) % m;
+    return pa == pb;
+}
+// A class goes to the lane-pair kernel when every lane's two rows are in phase (rows 2l, 2l + 1 of every group of 64).
+inline bool duo_compatible(const Row* rows, size_t n, uint32_t to) {
+    for (size_t i = 0; i + 1 < n; i += 2)
+        if (rows[i].out_len && rows[i + 1].out_len && !duo_in_phase(rows[i], rows[i + 1], to)) return false;
+    return true;
+}
+
+// ---- the time-parallel biquad plan (RB_BIQUAD_TIME_PARALLEL) ----
+// Largest pole magnitude and noise gain (sum of squares of the impulse response of 1 / (1 + a1 z^-1 + a2 z^-2)) of a filter.
+// The f32 recurrence of the reference (src/source/blt.rs:558-560) carries rounding noise of about 2.1e-7 * sqrt(gain) * peak
+// (measured against an f64 run for 200 Hz ... 5 kHz, white noise; up to twice that for sines).  Two f32 trajectories of the
+// same filter on the same input that start from different states differ by at most that much until they merge bit for
+// bit, which they do within a few hundred samples above ~700 Hz and practically never at 200 Hz (tools/microbench/
+// biquad_merge.cpp).  The plan is therefore taken only when 3.5e-7 * sqrt(gain) <= 7e-6 (gain <= 400: a cut-off of >= ~700 Hz
+// at q = 0.5), leaving the north-star tolerance of 1e-5 * peak a margin; other filters keep the exact serial path.
+inline bool tp_filter_ok(float a1, float a2, double* radius, double* gain) {
+    const double A1 = a1, A2 = a2;
+    const double disc = A1 * A1 - 4.0 * A2;
+    double r;
+    if (disc < 0) r = A2 > 0 ? std::sqrt(A2) : 2.0;
+    else {
+        const double s = std::sqrt(disc), r1 = (-A1 + s) / 2, r2 = (-A1 - s) / 2;
+        r = (r1 < 0 ? -r1 : r1) > (r2 < 0 ? -r2 : r2) ? (r1 < 0 ? -r1 : r1) : (r2 < 0 ? -r2 : r2);
+    }
+    *radius = r, *gain = 1e300;
+    if (!(r < 0.985)) return false;
+    double h1 = 0, h2 = 0, g = 0;                 // h[n] = delta[n] - a1 h[n-1] - a2 h[n-2]
+    for (int n = 0; n < 200000; n++) {
+        const double h = (n == 0 ? 1.0 : 0.0) - A1 * h1 - A2 * h2;
+        g += h * h, h2 = h1, h1 = h;
+        if (n > 16 && h * h + h2 * h2 < 1e-24 * g) break;
+    }
+    *gain = g;
+    return g <= 400.0;
+}
+// Warm-up in front of a segment: 60 time constants of the slowest pole -- the zero-state start has decayed far below an ulp
+// long before, the length is chosen so that most segments have MERGED with the exact trajectory bit for bit when they
+// begin to count (measured: 3 of 4 segments at 1 kHz; the rest stay within the rounding noise above).
+inline uint32_t tp_warmup(double radius) {
+    const double w = 60.0 / (1.0 - radius);
+    uint32_t W = w > 16000.0 ? 16000u : (uint32_t)w + 1u;
+    return (W + TILE - 1) / TILE * TILE;
 }
 
 inline uint64_t round_up_tile(uint64_t n) { return (n + TILE - 1) / TILE * TILE; }   // n in floats (frames * channels)

@@ -110,6 +110,9 @@ inline uint64_t g_emu_count[4] = {0, 0, 0, 0};
 SIMT_FN void emu_count(int which, uint64_t n) {
     if (cur().lane == 0) g_emu_count[which] += n;
 }
+SIMT_FN void emu_assert(bool ok, const char* what) {
+    if (!ok) emu_fail(what);
+}
 SIMT_FN float fmul(float a, float b) { return a * b; }
 SIMT_FN float fadd(float a, float b) { return a + b; }
 SIMT_FN float fsub(float a, float b) { return a - b; }
@@ -274,6 +277,29 @@ SIMT_FN bool in_exact_quotient_class(float m) {
     u &= 0x7fffffffu;
     return u == 0u || (u - 0x0d800000u) < 0x64000000u;
 }
+// ---- packed pairs (two independent f32 values per lane; the device uses the f32x2 instructions of sm_100) ----
+struct f2 { float lo, hi; };
+SIMT_FN f2 pack2(float lo, float hi) { return f2{lo, hi}; }
+SIMT_FN float lo2(f2 v) { return v.lo; }
+SIMT_FN float hi2(f2 v) { return v.hi; }
+SIMT_FN f2 add2(f2 a, f2 b) { return f2{a.lo + b.lo, a.hi + b.hi}; }
+SIMT_FN f2 sub2(f2 a, f2 b) { return f2{a.lo - b.lo, a.hi - b.hi}; }
+SIMT_FN f2 mul2(f2 a, f2 b) { return f2{a.lo * b.lo, a.hi * b.hi}; }
+SIMT_FN f2 fma2(f2 a, f2 b, f2 c) { return f2{std::fmaf(a.lo, b.lo, c.lo), std::fmaf(a.hi, b.hi, c.hi)}; }
+// One index step of the resampler for the TWO streams of a lane that share their phase: numerator += from (mod den); on a
+// carry the right taps become the left ones and the next ring frame of either stream is fetched (ring B lies `B_OFF` words
+// behind ring A).  The numerator is one scalar for both (the packed multiply takes it as a broadcast operand).
+template <int B_OFF>
+SIMT_FN void lerp_advance2(float& nf, f2& x0, f2& x1, sptr& p, float from_f, float den) {
+    const float t = nf + from_f;
+    if (t >= den) {
+        nf = t - den;
+        x0 = x1, x1 = f2{p[0], p[B_OFF]};
+        p += 1;
+    } else {
+        nf = t;
+    }
+}
 // 16-byte asynchronous copy global -> shared (cp.async.cg.shared.global): lands at the matching cp_wait.
 SIMT_FN void cp16(float* smem_dst, const float* gsrc) {
     if (((uintptr_t)smem_dst & 15) || ((uintptr_t)gsrc & 15)) emu_fail("cp16: operands must be 16-byte aligned");
@@ -297,6 +323,7 @@ SIMT_FN void cp_wait() {
 // ------------------------------------------------------------------------------------------ device
 SIMT_FN uint32_t lane() { return threadIdx.x & 31u; }
 SIMT_FN void emu_count(int, uint64_t) {}
+SIMT_FN void emu_assert(bool, const char*) {}
 SIMT_FN float fmul(float a, float b) { return __fmul_rn(a, b); }
 SIMT_FN float fadd(float a, float b) { return __fadd_rn(a, b); }
 SIMT_FN float fsub(float a, float b) { return __fsub_rn(a, b); }
@@ -411,6 +438,72 @@ SIMT_FN void lerp_advance(float& nf, float (&x0)[C], float (&x1)[C], sptr& p, fl
             : "f"(from_f), "f"(den), "f"(gpre)
             : "memory");
     }
+}
+// ---- packed pairs: add/mul/fma.rn.f32x2 (SASS FADD2 / FMUL2 / FFMA2): one issue slot for two lanes' worth of arithmetic.
+// NOTE ptxas (12.9) contracts a mul.rn.f32x2 whose only use is an add/sub.rn.f32x2 into FFMA2 (it never does that to the
+// scalar forms): code that needs the rounded product must not feed it to add2 / sub2 directly -- the kernels use
+// fma2(p, +-1, t) with the constant in a register, which keeps both roundings (tools/sass_loop_count.py checks the counts).
+using f2 = unsigned long long;
+SIMT_FN f2 pack2(float lo, float hi) {
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+SIMT_FN float lo2(f2 v) {
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return a;
+}
+SIMT_FN float hi2(f2 v) {
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return b;
+}
+SIMT_FN f2 add2(f2 a, f2 b) {
+    f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+SIMT_FN f2 sub2(f2 a, f2 b) {
+    f2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+SIMT_FN f2 mul2(f2 a, f2 b) {
+    f2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+SIMT_FN f2 fma2(f2 a, f2 b, f2 c) {
+    f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// FADD, FSETP, then predicated: numerator wrap, tap moves, two tap loads (ring A at p, ring B B_OFF words behind it: an
+// immediate offset), cursor increment.  The taps are handed over as separate halves so that the loads land in place.
+template <int B_OFF>
+SIMT_FN void lerp_advance2(float& nf, f2& x0, f2& x1, sptr& p, float from_f, float den) {
+    asm volatile(
+        "{\n"
+        ".reg .pred c;\n"
+        ".reg .f32 t, a, b, u, v;\n"
+        "add.rn.f32 t, %0, %4;\n"
+        "setp.ge.f32 c, t, %5;\n"
+        "@c sub.rn.f32 t, t, %5;\n"
+        "mov.f32 %0, t;\n"
+        "mov.b64 {u, v}, %1;\n"
+        "mov.b64 {a, b}, %2;\n"
+        "@c mov.f32 u, a;\n"
+        "@c mov.f32 v, b;\n"
+        "@c ld.shared.f32 a, [%3];\n"
+        "@c ld.shared.f32 b, [%3 + %6];\n"
+        "mov.b64 %1, {u, v};\n"
+        "mov.b64 %2, {a, b};\n"
+        "@c add.u32 %3, %3, 4;\n"
+        "}\n"
+        : "+f"(nf), "+l"(x0), "+l"(x1), "+r"(p)
+        : "f"(from_f), "f"(den), "n"(B_OFF * 4)
+        : "memory");
 }
 SIMT_FN bool in_exact_quotient_class(float m) {
     const uint32_t u = __float_as_uint(m) & 0x7fffffffu;

@@ -18,7 +18,7 @@ VARIANTS = {"": [], "slots3": ["-DRB_LANES_UP_SLOTS=3"], "stereo32": ["-DRB_LANE
 VARIANT = os.environ.get("RB_EMU_VARIANT", "")
 CXX += VARIANTS[VARIANT]
 _SFX = ("_" + VARIANT) if VARIANT else ""
-KERNEL_DEPS = [os.path.join(CSRC, f) for f in ("rb_lanes_core.h", "rb_lanes_plan.h", "rb_simt.h")]
+KERNEL_DEPS = [os.path.join(CSRC, f) for f in ("rb_lanes_core.h", "rb_duo_core.h", "rb_lanes_plan.h", "rb_simt.h")]
 VARIANT_DEPS = KERNEL_DEPS + [os.path.join(EMU, "warp_variants.cpp"), os.path.join(EMU, "warp_variants.h")]
 LANES_LIB = os.path.join(EMU, f"liblanes_emu{_SFX}.so")
 HOST_LIB = os.path.join(EMU, f"librodio_b200_hostemu{_SFX}.so")

@@ -14,6 +14,7 @@
 #include "../../rodio_b200/csrc/rb_fused_rows.h"
 #include "../../rodio_b200/csrc/rb_lanes.h"
 #include "../../rodio_b200/csrc/rb_lanes_plan.h"
+#include "../../rodio_b200/csrc/rb_duo_core.h"
 
 // ---- allocation registry of the mock runtime ----
 static std::map<void*, size_t> g_allocs;
@@ -45,6 +46,41 @@ cudaError_t rb_lanes_launch_kernel(const lanes::Args& a, uint32_t ch_in, uint32_
     for (uint32_t g = 0; g < a.n_groups; g++) {
         for (int i = 0; i < 32 * MAX_RS; i++) ring[i] = nan;
         emu_run_group(ch_in, ch_out, a, g, &warp, ring, has_biquad, ff2, has_post, has_pre, front, guard);
+    }
+    return cudaSuccess;
+}
+
+// ---- the lane-pair kernel (rb_duo_core.h) on the same emulator ----
+template <bool HASB, bool FF2, int NPOST>
+static void duo_run(const lanes::Args& a, uint32_t g, simt::WarpEmu* w, float* ring) {
+    simt::run_warp(w, [&] { duo::warp_main<HASB, FF2, NPOST>(a, g, ring); });
+}
+cudaError_t rb_duo_launch_kernel(const lanes::Args& a, bool has_biquad, bool ff2, bool has_post, cudaStream_t) {
+    if (a.mix_len == 0 || a.n_groups == 0) return cudaSuccess;
+    simt::WarpEmu warp;
+    {
+        std::lock_guard<std::mutex> l(g_alloc_mutex);
+        for (auto& kv : g_allocs) warp.readable.push_back({(const char*)kv.first, (const char*)kv.first + kv.second});
+    }
+    const float nan = std::numeric_limits<float>::quiet_NaN();
+    std::vector<float> ring_store(duo::WARP_WORDS + 4, nan);
+    float* ring = ring_store.data();
+    while ((uintptr_t)ring & 15) ring++;
+    for (uint32_t g = 0; g < a.n_groups; g++) {
+        for (int i = 0; i < duo::WARP_WORDS; i++) ring[i] = nan;
+        if (has_biquad) {
+            if (ff2) has_post ? duo_run<true, true, 1>(a, g, &warp, ring) : duo_run<true, true, 0>(a, g, &warp, ring);
+            else has_post ? duo_run<true, false, 1>(a, g, &warp, ring) : duo_run<true, false, 0>(a, g, &warp, ring);
+        } else {
+            has_post ? duo_run<false, false, 1>(a, g, &warp, ring) : duo_run<false, false, 0>(a, g, &warp, ring);
+        }
+    }
+    return cudaSuccess;
+}
+cudaError_t rb_lanes_spread_flags(lanes::Row* rows, uint32_t n_rows, const uint32_t* row_stream, const lanes::Row* stream_rows, cudaStream_t) {
+    for (uint32_t r = 0; r < n_rows; r++) {
+        const uint32_t bad = row_stream[r] == ~0u ? 0u : (stream_rows[row_stream[r]].flags & lanes::ROW_UNSAFE);
+        rows[r].flags = (rows[r].flags & ~lanes::ROW_UNSAFE) | bad;
     }
     return cudaSuccess;
 }
@@ -100,7 +136,7 @@ struct rb_fused_plan {
 cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams, uint16_t mixer_channels, float* d_out, uint64_t mix_len,
                                 uint32_t flags, int sm_count, cudaStream_t st, rb_fused_plan** out) {
     *out = nullptr;
-    if (n_streams == 0 || mix_len == 0 || (flags & (RB_MIX_EXACT_ORDER | RB_BIQUAD_TIME_PARALLEL))) return cudaSuccess;
+    if (n_streams == 0 || mix_len == 0 || (flags & RB_MIX_EXACT_ORDER)) return cudaSuccess;
     std::vector<FusedRow> rows(n_streams);
     uint32_t n_pre = 0, n_mid = 0, n_post = 0, has_u = 0, has_b = 0, front = 0;
     bool mixed_u = false, all_f32 = true;
@@ -121,8 +157,8 @@ uint32_t rb_fused_launch_count(const rb_fused_plan* p) { return rb_lanes_launch_
 void rb_fused_inputs_changed(rb_fused_plan* p) {
     if (p) rb_lanes_inputs_changed(p->lanes);
 }
-int rb_fused_kind(const rb_fused_plan*) { return 2; }
-uint32_t rb_fused_mix_group(const rb_fused_plan*) { return 32u; }
+int rb_fused_kind(const rb_fused_plan* p) { return rb_lanes_kind(p->lanes); }
+uint32_t rb_fused_mix_group(const rb_fused_plan* p) { return rb_lanes_mix_group(p->lanes); }
 cudaError_t rb_launch_nodes(uint32_t, const rb_node_dev*, uint32_t, uint64_t, uint32_t, cudaStream_t) { return cudaErrorInvalidValue; }
 cudaError_t rb_launch_mix(const rb_mix_src*, uint32_t, float*, uint64_t, cudaStream_t, float*, uint32_t) { return cudaErrorInvalidValue; }
 cudaError_t rb_launch_convert(const void*, uint32_t, void*, uint32_t, uint64_t, cudaStream_t) { return cudaErrorInvalidValue; }

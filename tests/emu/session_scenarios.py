@@ -501,6 +501,97 @@ def s_gain_changes():
     assert_bit_exact(got, expected_mix_classes(scaled, [0] * 3, got.size, [147] * 3, [(160, 1)] * 3), "per-block gains")
 
 
+def s_duo_batches():
+    """The lane-pair kernel (rb_duo_core.h, RB_FUSED_DUO) through the library's own planner: bit for bit against the oracle's
+    streams added in the kernel's documented order (pairs, then the tree over 64), within the tolerance of the sequential sum."""
+    from helpers import duo_expected_mix, lanes_expected_mix
+
+    def run(srcs, starts, family, what):
+        with rb.Batch(srcs, 1, 48000, flags=capi.RB_FUSED_DUO, mix_starts=starts) as b:
+            assert b.kernel_family == family, (what, b.kernel_family)
+            assert b.mix_group == (64 if family == 3 else 32)
+            b.upload_all()
+            got = b.render_mix()
+            again = b.render_mix()
+        assert np.array_equal(got.view(np.uint32), again.view(np.uint32)), what
+        per = [oracle.chain_uniform(to_oracle(x), 1, 48000) for x in srcs]
+        ref = oracle.mixer([to_oracle(x, st) for x, st in zip(srcs, starts)], 1, 48000)
+        assert_close_peak(got, ref, 1e-5, what + ": vs the sequential mixer")
+        want = (duo_expected_mix if family == 3 else lanes_expected_mix)(per, starts, ref.size)
+        assert_bit_exact(got, want, what)
+    rng = np.random.default_rng(77)
+    # cfg3 shape, more than one group, an odd number of streams (the last lane has one row, the last group is partial)
+    pcms = [noise(1500 + 7 * i, 8000 + i) for i in range(131)]
+    run([chain(p, 1, 44100, 1, 48000, 200, 1.2) for p in pcms], [0] * 131, 3, "cfg3 shape")
+    # ragged lengths (empty, one frame, shorter than a tile), starts that differ by multiples of 4 * to = 640 frames
+    lens = [0, 1, 2, 7, 37, 900, 2500, 16, 17, 640, 641, 3000] + [int(v) for v in rng.integers(3, 2500, 40)]
+    starts = sorted(640 * int(v) for v in rng.integers(0, 4, len(lens)))
+    run([chain(noise(n, 8200 + i), 1, 44100, 1, 48000, 1000, 0.7) for i, n in enumerate(lens)], starts, 3, "ragged, starts in phase")
+    # high_pass (ffk = -2), no gain; then no filter at all
+    run([rb.UniformSourceIterator(rb.TestSource(noise(1200 + i, 8300 + i), 1, 22050), 1, 48000).high_pass(300) for i in range(70)], [0] * 70, 3, "high_pass, 22.05 kHz")
+    run([chain(noise(1000 + 3 * i, 8400 + i), 1, 44100, 1, 48000, None, 0.8) for i in range(66)], [0] * 66, 3, "no filter")
+    run([chain(noise(1000 + 3 * i, 8500 + i), 1, 32000, 1, 48000, None, None) for i in range(10)], [0] * 10, 3, "nothing but the conversion")
+    # inputs outside the exact-reciprocal class keep their lane on the slow tiles
+    bad = [noise(900, 8600 + i) for i in range(40)]
+    bad[3][100] = 1e-42
+    bad[17][5] = 1e25
+    bad[18][6] = -0.0
+    run([chain(p, 1, 44100, 1, 48000, 500, 1.1) for p in bad], [0] * 40, 3, "unsafe inputs")
+    # neighbours out of phase: the class stays on k_fused_lanes
+    starts = sorted(int(v) for v in rng.integers(0, 300, 50))
+    run([chain(noise(800 + i, 8700 + i), 1, 44100, 1, 48000, 200, 1.2) for i in range(50)], starts, 2, "starts out of phase")
+    # several rate pairs: classes of their own, each on the pair kernel
+    rates = [44100, 22050, 32000] * 30
+    srcs = [chain(noise(700 + 5 * i, 8800 + i), 1, r, 1, 48000, 600, 0.9) for i, r in enumerate(rates)]
+    with rb.Batch(srcs, 1, 48000, flags=capi.RB_FUSED_DUO) as b:
+        assert b.kernel_family == 3
+        b.upload_all()
+        got = b.render_mix()
+    per = [oracle.chain_uniform(to_oracle(x), 1, 48000) for x in srcs]
+    acc = np.zeros(got.size, np.float32)
+    for r in (44100, 22050, 32000):
+        idx = [i for i, q in enumerate(rates) if q == r]
+        acc = acc + (duo_expected_mix([per[i] for i in idx], [0] * len(idx), got.size) - np.float32(0.0))
+    assert_bit_exact(got, acc, "three rate pairs on the pair kernel")
+
+
+def s_time_parallel_plan():
+    """RB_BIQUAD_TIME_PARALLEL: low_pass(1000) batches run as timeline segments with a warm-up (family 4), within the north-star
+    tolerance of the reference and no further from an f64 run of the same filter than the reference itself; low_pass(200) is
+    refused by the accuracy gate and served exactly."""
+    os.environ["RB_TP_SEGMENTS"] = "5"
+    n, frames = 70, 9000
+    pcms = [noise(frames - 40 * (i % 9), 9300 + i) for i in range(n)]
+    starts = [0] * n
+    starts[5], starts[6], starts[40] = 640, 1280, 3200     # late joiners, in phase (multiples of 4 * to)
+    starts = sorted(starts)
+    for lp, q, want_family in ((1000, 0.5, 4), (3000, 0.707, 4), (200, 0.5, 3)):
+        srcs = [rb.UniformSourceIterator(rb.TestSource(p, 1, 44100), 1, 48000).low_pass_with_q(lp, q).amplify(1.2) for p in pcms]
+        with rb.Batch(srcs, 1, 48000, flags=capi.RB_BIQUAD_TIME_PARALLEL | capi.RB_FUSED_DUO, mix_starts=starts) as b:
+            assert b.kernel_family == want_family, (lp, b.kernel_family)
+            b.upload_all()
+            got = b.render_mix()
+            again = b.render_mix()
+        assert np.array_equal(got.view(np.uint32), again.view(np.uint32))
+        ref = oracle.mixer([to_oracle(x, st) for x, st in zip(srcs, starts)], 1, 48000)
+        assert_close_peak(got, ref, 1e-5, f"time-parallel low_pass({lp}) vs the reference")
+        if want_family == 4:
+            per = [oracle.chain_uniform(to_oracle(x), 1, 48000) for x in srcs]
+            from helpers import duo_expected_mix
+            exact = duo_expected_mix(per, starts, ref.size)
+            same = float(np.mean(got.view(np.uint32) == exact.view(np.uint32)))
+            print(f"low_pass({lp}, q={q}): {100 * same:.1f} % of the mix bit-identical to the serial run in the same order")
+            assert same > 0.5
+    # without the duo flag and below the automatic threshold the flag alone selects the plan
+    srcs = [rb.UniformSourceIterator(rb.TestSource(p, 1, 44100), 1, 48000).low_pass(2000) for p in pcms]
+    with rb.Batch(srcs, 1, 48000, flags=capi.RB_BIQUAD_TIME_PARALLEL) as b:
+        assert b.kernel_family == 4
+        b.upload_all()
+        got = b.render_mix()
+    assert_close_peak(got, oracle.mixer([to_oracle(x) for x in srcs], 1, 48000), 1e-5, "time-parallel, no gain")
+    del os.environ["RB_TP_SEGMENTS"]
+
+
 def s_errors():
     mk = lambda ci, r, mc: chain(np.zeros(0, np.float32), ci, r, mc, 48000, 200, None)
     for bad in (lambda: rb.Session([mk(2, 44100, 1)], 48000, mixer_channels=1),                       # stereo source, mono mixer
@@ -585,7 +676,7 @@ def s_random(seed=0, cases=6):
 
 SCENARIOS = {"mono_random_split": s_mono_random_split, "mixed_with_state_blob": s_mixed_everything_with_state_blob,
              "held_queue_gain_speed": s_held_queue_gain_speed, "follow_after_played_out": s_follow_after_predecessor_played_out,
-             "held_across_state_blob": s_held_and_queued_across_state_blob, "gain_changes": s_gain_changes, "filtered_and_plain": s_filtered_and_plain_sources,
+             "held_across_state_blob": s_held_and_queued_across_state_blob, "duo_batches": s_duo_batches, "time_parallel_plan": s_time_parallel_plan, "gain_changes": s_gain_changes, "filtered_and_plain": s_filtered_and_plain_sources,
              "batch_with_identity_conversions": s_batch_with_identity_conversions, "batch_unsorted_starts": s_batch_unsorted_starts, "errors": s_errors,
              "gain_in_front": s_gain_in_front_of_the_conversion, "filter_in_front": s_filter_in_front_of_the_conversion, "player_volume": s_player_volume_changes}
 

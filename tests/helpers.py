@@ -65,3 +65,21 @@ def lanes_expected_mix(per_stream, starts, mix_len: int) -> np.ndarray:
             lanes_[l, s:s + y.size] = y
         acc = acc + lanes_tree_sum(lanes_)
     return acc
+
+
+def duo_expected_mix(per_stream, starts, mix_len: int) -> np.ndarray:
+    """Mixer output of the lane-pair kernel (rb_duo_core.h) given every stream's exact samples: groups of 64 streams
+    (insertion order); lane l = stream 2l + stream 2l+1 (an absent or silent one counts +0.0), the 32 lane values summed with
+    the tree of k_fused_lanes, the groups added in order from +0.0."""
+    acc = np.zeros(mix_len, dtype=np.float32)
+    for g in range(0, len(per_stream), 64):
+        halves = np.zeros((64, mix_len), dtype=np.float32)
+        for l, (y, s) in enumerate(zip(per_stream[g:g + 64], starts[g:g + 64])):
+            halves[l, s:s + y.size] = y
+        acc = acc + lanes_tree_sum(halves[0::2] + halves[1::2])
+    return acc
+
+
+def fused_expected_mix(family: int, per_stream, starts, mix_len: int) -> np.ndarray:
+    """The documented order of kernel family 2 (k_fused_lanes) or 3 (k_fused_duo)."""
+    return (duo_expected_mix if family == 3 else lanes_expected_mix)(per_stream, starts, mix_len)

@@ -12,7 +12,7 @@ import pytest
 
 import oracle
 import rodio_b200 as rb
-from helpers import assert_bit_exact, assert_close_peak, lanes_expected_mix, noise, to_oracle
+from helpers import assert_bit_exact, assert_close_peak, fused_expected_mix, noise, to_oracle
 from rodio_b200 import capi
 
 pytestmark = pytest.mark.gpu
@@ -44,6 +44,9 @@ def _cfg3(n, frames, ch=1, lp=200, gain=1.2, seed=31000):
 
 def _check_fused(ctx, srcs, ch, family, group=None, flags=0):
     with rb.Batch(srcs, ch, 48000, flags=flags, ctx=ctx) as b:
+        if isinstance(family, tuple):
+            assert b.kernel_family in family, f"kernel family {b.kernel_family}, expected one of {family}"
+            family = b.kernel_family
         assert b.kernel_family == family, f"kernel family {b.kernel_family}, expected {family}"
         if group is not None:
             assert b.mix_group == group, f"rows per partial sum {b.mix_group}, expected {group}"
@@ -58,7 +61,7 @@ def _check_fused(ctx, srcs, ch, family, group=None, flags=0):
     assert_close_peak(got, ref, 1e-5, "fused kernel vs the reference's sequential mixer")
     per_stream = [oracle.chain_uniform(s, ch, 48000) for s in streams]
     starts = [0] * len(srcs)
-    want = lanes_expected_mix(per_stream, starts, ref.size) if family == 2 else grouped_expected_mix(per_stream, starts, ref.size, group)
+    want = fused_expected_mix(family, per_stream, starts, ref.size) if family >= 2 else grouped_expected_mix(per_stream, starts, ref.size, group)
     assert_bit_exact(got, want, "fused kernel vs oracle streams added in the kernel's documented order")
 
 
@@ -82,8 +85,9 @@ def test_nofilter_bench_geometry_mono_4096(ctx):
 
 
 def test_cfg5_auto_selected_large_batch(ctx):
-    """No flag, 41 000 streams (>= 277 per SM): the planner hands the batch to the lane kernel on its own."""
-    _check_fused(ctx, _cfg3(41000, 600, seed=35000), 1, family=2)
+    """No flag, 41 000 streams (>= 277 per SM): the planner hands the batch to the large-batch kernels on its own (mono
+    sources that start together: the lane-pair kernel)."""
+    _check_fused(ctx, _cfg3(41000, 600, seed=35000), 1, family=3)
 
 
 def test_cfg5_large_batch_16384(ctx):
@@ -91,7 +95,7 @@ def test_cfg5_large_batch_16384(ctx):
     srcs = _cfg3(16384, 900, seed=36000)
     with rb.Batch(srcs, 1, 48000, ctx=ctx) as b:
         family = b.kernel_family
-    assert family in (1, 2)
+    assert family in (1, 2, 3)
     _check_fused(ctx, srcs, 1, family=family)
 
 
@@ -138,3 +142,91 @@ def test_cfg4_512_streams(ctx):
         b.upload_all()
         got = b.render_mix()
     assert_close_peak(got, want, 1e-5, "cfg4 512 streams, default launch")
+
+
+# ------------------------------------------------------------------ the lane-pair kernel and the time-parallel plan
+def test_duo_kernel_by_flag(ctx):
+    """RB_FUSED_DUO on a batch far below the automatic threshold: k_fused_duo, several CTAs, ragged lengths, late joiners in
+    phase (multiples of 4 * to = 640 frames)."""
+    rng = np.random.default_rng(5)
+    n = 1500
+    lens = [int(v) for v in rng.integers(1, 3000, n)]
+    lens[:6] = [0, 1, 2, 9, 640, 641]
+    starts = sorted(640 * int(v) for v in rng.integers(0, 3, n))
+    srcs = [rb.UniformSourceIterator(rb.TestSource(noise(L, 41000 + i), 1, 44100), 1, 48000).low_pass(200 + (i % 50) * 40).amplify(1.2)
+            for i, L in enumerate(lens)]
+    with rb.Batch(srcs, 1, 48000, flags=capi.RB_FUSED_DUO, mix_starts=starts, ctx=ctx) as b:
+        assert b.kernel_family == 3 and b.mix_group == 64
+        b.upload_all()
+        got = b.render_mix()
+    streams = [to_oracle(s, st) for s, st in zip(srcs, starts)]
+    ref = oracle.mixer(streams, 1, 48000)
+    assert_close_peak(got, ref, 1e-5, "k_fused_duo vs the sequential mixer")
+    per = [oracle.chain_uniform(to_oracle(s), 1, 48000) for s in srcs]
+    assert_bit_exact(got, fused_expected_mix(3, per, starts, ref.size), "k_fused_duo vs oracle streams in its documented order")
+
+
+@pytest.mark.parametrize("chain", ["no_filter", "high_pass", "other_ratio"])
+def test_duo_kernel_shapes(ctx, chain):
+    n = 700
+    mk = {"no_filter": lambda x: rb.UniformSourceIterator(rb.TestSource(x, 1, 44100), 1, 48000).amplify(0.8),
+          "high_pass": lambda x: rb.UniformSourceIterator(rb.TestSource(x, 1, 44100), 1, 48000).high_pass(300),
+          "other_ratio": lambda x: rb.UniformSourceIterator(rb.TestSource(x, 1, 22050), 1, 48000).low_pass(1500).amplify(0.5)}[chain]
+    srcs = [mk(noise(900 + 3 * (i % 200), 42000 + i)) for i in range(n)]
+    with rb.Batch(srcs, 1, 48000, flags=capi.RB_FUSED_DUO, ctx=ctx) as b:
+        assert b.kernel_family == 3
+        b.upload_all()
+        got = b.render_mix()
+    per = [oracle.chain_uniform(to_oracle(s), 1, 48000) for s in srcs]
+    assert_bit_exact(got, fused_expected_mix(3, per, [0] * n, got.size), f"k_fused_duo, {chain}")
+
+
+def test_duo_falls_back_when_neighbours_are_out_of_phase(ctx):
+    rng = np.random.default_rng(6)
+    n = 300
+    starts = sorted(int(v) for v in rng.integers(0, 500, n))
+    srcs = _cfg3(n, 1500, seed=43000)
+    with rb.Batch(srcs, 1, 48000, flags=capi.RB_FUSED_DUO, mix_starts=starts, ctx=ctx) as b:
+        assert b.kernel_family == 2
+        b.upload_all()
+        got = b.render_mix()
+    per = [oracle.chain_uniform(to_oracle(s), 1, 48000) for s in srcs]
+    assert_bit_exact(got, fused_expected_mix(2, per, starts, got.size), "out of phase: k_fused_lanes")
+
+
+def _f64_truth(srcs, lp, q, gain):
+    """The same chain with the biquad's recurrence carried in f64 (coefficients and input as the f32 reference has them)."""
+    total = None
+    for s in srcs:
+        x = oracle.chain_uniform(oracle.Stream(s.pcm, 1, 44100, [e for e in to_oracle(s).effects if e.kind == capi.RB_FX_UNIFORM], 0), 1, 48000).astype(np.float64)
+        b0, b1, b2, a1, a2 = (float(v) for v in oracle.blt_coeffs(False, lp, q, 48000))
+        import scipy.signal
+        y = scipy.signal.lfilter([b0, b1, b2], [1.0, a1, a2], x) * float(np.float32(gain))
+        total = y if total is None else total + y
+    return total
+
+
+@pytest.mark.parametrize("lp,q,family", [(1000, 0.5, 4), (2500, 0.707, 4), (200, 0.5, 1)])
+def test_time_parallel_plan_4096_streams(ctx, lp, q, family):
+    """RB_BIQUAD_TIME_PARALLEL at the bench's stream count: taken for filters inside the accuracy gate (<= 1e-5 * peak against
+    the f32 reference AND no further from an f64 run of the same filter than the reference itself, times 1.5), refused for
+    low_pass(200), which is then served by the exact default kernel."""
+    n, frames = 4096, 11025
+    srcs = [rb.UniformSourceIterator(rb.TestSource(noise(frames, 44000 + i), 1, 44100), 1, 48000).low_pass_with_q(lp, q).amplify(1.2)
+            for i in range(n)]
+    with rb.Batch(srcs, 1, 48000, flags=capi.RB_BIQUAD_TIME_PARALLEL, ctx=ctx) as b:
+        assert b.kernel_family == family, b.kernel_family
+        b.upload_all()
+        got = b.render_mix()
+    ref = oracle.mixer([to_oracle(s) for s in srcs], 1, 48000)
+    assert_close_peak(got, ref, 1e-5, f"time-parallel low_pass({lp}) vs the f32 reference")
+    if family == 4:
+        truth = _f64_truth(srcs[:256], lp, q, 1.2)
+        with rb.Batch(srcs[:256], 1, 48000, flags=capi.RB_BIQUAD_TIME_PARALLEL, ctx=ctx) as b:
+            assert b.kernel_family == 4
+            b.upload_all()
+            got256 = b.render_mix()
+        ref256 = oracle.mixer([to_oracle(s) for s in srcs[:256]], 1, 48000)
+        e_ref = float(np.max(np.abs(ref256 - truth)))
+        e_tp = float(np.max(np.abs(got256 - truth)))
+        assert e_tp <= 1.5 * e_ref + 1e-7 * float(np.max(np.abs(truth))), (e_tp, e_ref)

@@ -96,6 +96,23 @@ def main():
                 for fl, nm in ((rb.capi.RB_FUSED_LANES, "k_fused_lanes"), (0, "default")):
                     time_batch(f"lanes sweep S={S}: 44.1k mono x 1s -> uniform(1,48k) -> {label} -> mix [{nm}]", srcs,
                                (1, 48000), flags=fl, steps=5)
+    if "duo" in which:
+        # the lane-pair kernel and the time-parallel plan beside k_fused_lanes and the default planner, over the batch sizes
+        # where the planner's thresholds lie; 1 s of 44.1 kHz per stream except the 4096-stream points (2 s: the bench config)
+        one = z(44100)
+        for S, secs in [(2048, 2), (4096, 2), (8192, 1), (16384, 1), (32768, 1), (65536, 1)]:
+            x = z(44100 * secs)
+            for label, mk in (("low_pass(200) -> amplify", lambda s: s.low_pass(200).amplify(1.2)),
+                              ("low_pass(1000) -> amplify", lambda s: s.low_pass(1000).amplify(1.2)),
+                              ("amplify (no filter)", lambda s: s.amplify(1.2))):
+                srcs = [mk(rb.UniformSourceIterator(rb.TestSource(x, 1, 44100), 1, 48000)) for _ in range(S)]
+                kinds = [(0, "default"), (rb.capi.RB_FUSED_LANES, "k_fused_lanes"), (rb.capi.RB_FUSED_DUO, "k_fused_duo")]
+                if "1000" in label:
+                    kinds.append((rb.capi.RB_BIQUAD_TIME_PARALLEL, "time-parallel"))
+                for fl, nm in kinds:
+                    if nm == "k_fused_lanes" and S < 8192:
+                        continue
+                    time_batch(f"duo sweep S={S} x {secs}s: uniform(1,48k) -> {label} -> mix [{nm}]", srcs, (1, 48000), flags=fl, steps=5)
     if "lanes_shapes" in which:
         # the lane kernel on the shapes added after its first device runs: stereo (ring geometry: see RB_LANES_STEREO_CHW in
         # rb_lanes_core.h, A/B via RODIO_B200_LIB), mono sources in a stereo mixer, and the chain the way rodio users write it

@@ -22,13 +22,15 @@ FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-li
 
 def main():
     frag = sys.argv[1] if len(sys.argv) > 1 else "ILi1ELi1ELb1ELb1ELi1ELb0E"
+    kernel = sys.argv[2] if len(sys.argv) > 2 else "k_fused_lanes"   # k_fused_duo ILb1ELb1ELi1E: the lane-pair kernel
+    per = 16 if kernel == "k_fused_duo" else 8                       # samples per lane and tile
     with tempfile.TemporaryDirectory() as td:
         obj = os.path.join(td, "rb_lanes.o")
         r = subprocess.run(["nvcc"] + FLAGS + ["-Xptxas", "-v", "-c", SRC, "-o", obj], capture_output=True, text=True, check=True)
         regs = [l for l in (r.stdout + r.stderr).splitlines() if "registers" in l or "Compiling entry" in l]
         sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True, check=True).stdout
     funcs = re.split(r"\n\s*Function : ", sass)
-    body = next(f for f in funcs if "k_fused_lanes" in f.split("\n", 1)[0] and frag in f.split("\n", 1)[0])
+    body = next(f for f in funcs if kernel in f.split("\n", 1)[0] and frag in f.split("\n", 1)[0])
     ins = []   # (address, predicate, opcode, text)
     for line in body.splitlines():
         m = re.match(r"\s*/\*([0-9a-f]{4})\*/\s+(@!?U?P\w+\s+)?([A-Z0-9_.]+)(.*?);", line)
@@ -56,10 +58,10 @@ def main():
     for l in regs:
         if frag in l or "registers" in l:
             pass
-    print(f"k_fused_lanes<{frag}>: loop of {len(best)} instructions, {len(refill)} of them in the ring-refill block")
-    print(f"steady state: {n} warp instructions per tile of 8 steps = {n / 8:.1f} issue slots per sample and lane")
+    print(f"{kernel}<{frag}>: loop of {len(best)} instructions, {len(refill)} of them in the ring-refill block")
+    print(f"steady state: {n} warp instructions per tile of 8 steps = {n / per:.1f} issue slots per sample and lane")
     for op, c in hist.most_common():
-        print(f"  {op:10s} {c:4d}  {c / 8:5.2f} / sample")
+        print(f"  {op:10s} {c:4d}  {c / per:5.2f} / sample")
     print("(static count; the measured issue rate decides what fraction of 4 x 1 warp-instruction/clk/SM it reaches)")
 
 
