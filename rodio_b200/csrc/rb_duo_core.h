@@ -194,7 +194,14 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
             f2 P1 = XH1, P2 = XH2;
             if (HASB && FF2) P1 = simt::mul2(B0, XH1), P2 = simt::mul2(B0, XH2);
 
-            auto tile = [&](float (&v)[TILE]) {
+            // The run is a software pipeline of three stages, one tile apart, so that a warp always has three independent
+            // instruction streams to issue from (measured on the first version, one stage after the other: 0.3 instructions per
+            // clock for a lone warp -- the tap loads, the interpolation, the recurrence and the five shuffle levels of the mixer
+            // sum each waited for the one before):
+            //   A(k + 1)  ring bookkeeping, index steps, tap loads, interpolation, feed-forward half  -> T' (tt per step)
+            //   B(k)      the recurrence on T, gain, the two halves added                               -> v
+            //   C(k - 1)  the transposing tree over the 32 lanes (lanes::reduce_tile, stage by stage), store
+            auto refill = [&]() {
                 kb += a.q8, kbn += a.r8;
                 if (kbn >= to) kbn -= to, kb += 1;
                 if ((kb - 1) / CHF >= c_ready) {
@@ -205,51 +212,98 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                     simt::emu_count(2, 1);
                 }
                 if (simt::sptr_ge(p, ring_end)) p = simt::sptr_add(p, -RING);
-#pragma unroll
-                for (int f = 0; f < TF; f++) {
-                    // src/math.rs:24-26: first + (second - first) * num / den, the division as an exact reciprocal step
-                    const f2 m = simt::mul2(simt::sub2(X1, X0), simt::pack2(nf, nf));
-                    const f2 q0 = simt::mul2(m, RCP);
-                    const f2 q = simt::fma2(simt::fma2(q0, NDEN, m), RCP, q0);
-                    const f2 x = simt::add2(X0, q);
-                    simt::lerp_advance2<HALF_WORDS>(nf, X0, X1, p, from_f, den);
-                    f2 y = x;
-                    if (HASB) {
-                        f2 tt;
-                        if (FF2) {
-                            const f2 pz = simt::mul2(B0, x);
-                            tt = simt::fma2(P2, ONE, simt::fma2(P1, FFK, pz));   // (.. ) + p2 with one rounding; p2 stays a multiplicand (rb_simt.h)
-                            P2 = P1, P1 = pz;
-                        } else {
-                            // (b0*x + b1*x1) + b2*x2: every product rounded, then added (fma(p, 1, s) = p + s, one rounding)
-                            const f2 s01 = simt::fma2(simt::mul2(B1, XH1), ONE, simt::mul2(B0, x));
-                            tt = simt::fma2(simt::mul2(B2, XH2), ONE, s01);
-                        }
-                        XH2 = XH1, XH1 = x;
-                        // (t - a1*y1) - a2*y2, src/source/blt.rs:558-560
-                        y = simt::fma2(simt::mul2(A2, Y2), NEG1, simt::fma2(simt::mul2(A1, Y1), NEG1, tt));
-                        Y2 = Y1, Y1 = y;
+            };
+            auto step_a = [&](f2& out) {
+                // src/math.rs:24-26: first + (second - first) * num / den, the division as an exact reciprocal step
+                const f2 m = simt::mul2(simt::sub2(X1, X0), simt::pack2(nf, nf));
+                const f2 q0 = simt::mul2(m, RCP);
+                const f2 q = simt::fma2(simt::fma2(q0, NDEN, m), RCP, q0);
+                const f2 x = simt::add2(X0, q);
+                simt::lerp_advance2<HALF_WORDS>(nf, X0, X1, p, from_f, den);
+                out = x;
+                if (HASB) {
+                    if (FF2) {
+                        const f2 pz = simt::mul2(B0, x);
+                        out = simt::fma2(P2, ONE, simt::fma2(P1, FFK, pz));   // (.. ) + p2 with one rounding; p2 stays a multiplicand (rb_simt.h)
+                        P2 = P1, P1 = pz;
+                    } else {
+                        // (b0*x + b1*x1) + b2*x2: every product rounded, then added (fma(p, 1, s) = p + s, one rounding)
+                        const f2 s01 = simt::fma2(simt::mul2(B1, XH1), ONE, simt::mul2(B0, x));
+                        out = simt::fma2(simt::mul2(B2, XH2), ONE, s01);
                     }
-                    const f2 val = NPOST ? simt::mul2(y, POST) : y;
-                    v[f] = simt::fadd(simt::lo2(val), simt::hi2(val));
+                    XH2 = XH1, XH1 = x;
                 }
             };
-            float vp[TILE];
-            tile(vp);
-            for (uint32_t done = TF; done < run; done += TF) {
-                float v[TILE];
-                tile(v);
-                if (t + done - TF >= st_lo) {
-                    const float s = lanes::reduce_tile(vp, ln);
-                    if ((ln & 3u) == 0) prow[t + done - TF + (ln >> 2)] = s;
+            auto step_b = [&](f2 tt, float& v) {
+                f2 y = tt;
+                if (HASB) {
+                    // (t - a1*y1) - a2*y2, src/source/blt.rs:558-560
+                    y = simt::fma2(simt::mul2(A2, Y2), NEG1, simt::fma2(simt::mul2(A1, Y1), NEG1, tt));
+                    Y2 = Y1, Y1 = y;
                 }
+                const f2 val = NPOST ? simt::mul2(y, POST) : y;
+                v = simt::fadd(simt::lo2(val), simt::hi2(val));
+            };
+            // lanes::reduce_tile in five stages (the same operations in the same order)
+            const bool rb4 = ln & 16u, rb3 = ln & 8u, rb2 = ln & 4u;
+            float rw[4], rz[2], rs = 0.f;
+            auto stage_c = [&](int stage, const float (&vv)[TILE], uint64_t pos) {
+                if (stage == 0) {
 #pragma unroll
-                for (int u = 0; u < TILE; u++) vp[u] = v[u];
+                    for (int j = 0; j < 4; j++) rw[j] = simt::fadd(rb4 ? vv[j + 4] : vv[j], simt::shfl_xor(rb4 ? vv[j] : vv[j + 4], 16));
+                } else if (stage == 1) {
+#pragma unroll
+                    for (int j = 0; j < 2; j++) rz[j] = simt::fadd(rb3 ? rw[j + 2] : rw[j], simt::shfl_xor(rb3 ? rw[j] : rw[j + 2], 8));
+                } else if (stage == 2) {
+                    rs = simt::fadd(rb2 ? rz[1] : rz[0], simt::shfl_xor(rb2 ? rz[0] : rz[1], 4));
+                } else if (stage == 3) {
+                    rs = simt::fadd(rs, simt::shfl_xor(rs, 1));
+                } else if (stage == 4) {
+                    rs = simt::fadd(rs, simt::shfl_xor(rs, 2));
+                    rs = simt::fadd(rs, 0.0f);
+                } else if (stage == 5) {
+                    if (pos >= st_lo && (ln & 3u) == 0) prow[pos + (ln >> 2)] = rs;
+                }
+            };
+            auto all_c = [&](const float (&vv)[TILE], uint64_t pos) {
+#pragma unroll
+                for (int st = 0; st < 6; st++) stage_c(st, vv, pos);
+            };
+            const uint32_t n_tiles = run / TF;     // >= MIN_RUN_TILES
+            f2 T[TILE], Tn[TILE];
+            float v[TILE], vp[TILE];
+            refill();
+#pragma unroll
+            for (int f = 0; f < TF; f++) step_a(T[f]);                       // A(0)
+            refill();
+#pragma unroll
+            for (int f = 0; f < TF; f++) step_a(Tn[f]), step_b(T[f], vp[f]);   // A(1), B(0)
+#pragma unroll
+            for (int f = 0; f < TF; f++) T[f] = Tn[f];
+            // steady state, two tiles per trip so that the tile buffers alternate instead of being copied
+            auto body = [&](const f2 (&tin)[TILE], f2 (&tout)[TILE], const float (&vred)[TILE], float (&vout)[TILE], uint64_t pos) {
+                refill();
+#pragma unroll
+                for (int f = 0; f < TF; f++) {
+                    step_a(tout[f]);
+                    step_b(tin[f], vout[f]);
+                    stage_c(f == 0 ? 0 : f == 2 ? 1 : f == 4 ? 2 : f == 5 ? 3 : f == 6 ? 4 : f == 7 ? 5 : -1, vred, pos);
+                }
+            };
+            uint32_t k = 2;                                                  // A(k), B(k - 1), C(k - 2)
+            for (; k + 1 < n_tiles; k += 2) {
+                body(T, Tn, vp, v, t + (uint64_t)(k - 2) * TF);
+                body(Tn, T, v, vp, t + (uint64_t)(k - 1) * TF);
             }
-            if (t + run - TF >= st_lo) {
-                const float s = lanes::reduce_tile(vp, ln);
-                if ((ln & 3u) == 0) prow[t + run - TF + (ln >> 2)] = s;
+            if (k < n_tiles) {
+                body(T, Tn, vp, v, t + (uint64_t)(k - 2) * TF);
+#pragma unroll
+                for (int f = 0; f < TF; f++) T[f] = Tn[f], vp[f] = v[f];
             }
+#pragma unroll
+            for (int f = 0; f < TF; f++) step_b(T[f], v[f]);                 // B(n - 1)
+            all_c(vp, t + (uint64_t)(n_tiles - 2) * TF);                     // C(n - 2)
+            all_c(v, t + (uint64_t)(n_tiles - 1) * TF);                      // C(n - 1)
             simt::cp_wait<0>();
             simt::syncwarp();
             simt::emu_count(0, run / TF);

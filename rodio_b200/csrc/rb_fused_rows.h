@@ -3,6 +3,7 @@
 // No device syntax: included by rb_fused.cu (product) and by the host-emulated library of the CPU suite
 // (tests/emu/hostemu.cpp), so that rb_batch_create -> parse -> lane plan runs on the CPU as it runs in front of the GPU.
 #pragma once
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -178,7 +179,12 @@ static cudaError_t fused_lanes_hook(const std::vector<FusedRow>& rows, size_t n_
     const bool want_lanes = (flags & (RB_FUSED_LANES | RB_FUSED_DUO)) || n_streams >= 277 * sms || (front && n_streams >= 32 * sms);
     // RB_BIQUAD_TIME_PARALLEL: the lane kernels serve the batch cut into timeline segments when it qualifies (rb_lanes_batch.cu);
     // when it does not, the flag changes nothing
-    const bool want_tp = (flags & RB_BIQUAD_TIME_PARALLEL) && has_b && !front && mixer_channels == 1;
+    bool want_tp = (flags & RB_BIQUAD_TIME_PARALLEL) && has_b && !front && mixer_channels == 1;
+    // a chain without a filter carries nothing from sample to sample: cut into timeline segments it is still the serial run bit
+    // for bit, and a batch of a few thousand mono streams fills the machine that way (measured against k_fused_hot<1, false>)
+    size_t seg_min = 1024;
+    if (const char* e = getenv("RB_SEGMENTS_FROM")) seg_min = (size_t)atoll(e);
+    if (!has_b && has_u && !front && mixer_channels == 1 && n_streams >= seg_min && !(flags & RB_FUSED_LANES)) want_tp = true;
     if (!((want_lanes || want_tp) && (mixer_channels == 1 || mixer_channels == 2) && all_f32 && (has_u || has_b) && n_pre <= 1)) return cudaSuccess;
     // f32 streams with the mixer's channel count (or mono in a stereo mixer), each at or below the mixer's rate (classes per
     // rate pair), at most one gain in front of the conversion (source.amplify(v) handed to the mixer), optional biquad, at most

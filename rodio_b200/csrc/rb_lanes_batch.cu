@@ -6,6 +6,8 @@
 //     contributes one row per segment that starts a warm-up in front of the segment from zero filter state, and the rows of
 //     one segment form warps of their own -- a 4096-stream batch then runs as 60 000 rows.  Taken only for filters that
 //     pass lanes::tp_filter_ok (the result stays within the tolerance of the exact path); otherwise the exact plan is built.
+//     A chain WITHOUT a filter has no state at all: its segments need no warm-up and reproduce the serial run bit for bit,
+//     so the fused planner asks for this plan by itself (rb_fused_rows.h) when the batch alone cannot fill the machine.
 // No device syntax in this file: besides nvcc (product) it is compiled as plain C++ against tests/emu/mockcuda by the CPU
 // suite, with the launchers of rb_lanes.cu replaced by the SIMT emulator (tests/test_session_hostemu.py).
 #include <algorithm>
@@ -57,7 +59,9 @@ void fill_row(lanes::Row& r, const rb_lanes_stream& s, bool has_biquad, bool has
 
 // The time-parallel plan of one class (mono, below the mixer's rate, whole streams that are pairwise in phase, every filter
 // within the accuracy gate).  Returns false when the class does not qualify.
-bool plan_time_parallel(const rb_lanes_stream* streams, const std::vector<uint32_t>& cls, uint64_t mix_len, int sm_count, bool has_post,
+// Without a filter (has_biquad false) nothing is carried from sample to sample: the segments need no warm-up and every output
+// is the bit the serial run produces -- the plan is then simply the way a few thousand streams fill the machine.
+bool plan_time_parallel(const rb_lanes_stream* streams, const std::vector<uint32_t>& cls, uint64_t mix_len, int sm_count, bool has_biquad, bool has_post,
                         std::vector<lanes::Row>& rows, std::vector<uint32_t>& row_stream, std::vector<lanes::GroupSpan>& spans,
                         uint32_t* n_slots, uint32_t* warmup, uint32_t* seg_len, bool* ff2) {
     const uint32_t S = (uint32_t)cls.size();
@@ -65,17 +69,19 @@ bool plan_time_parallel(const rb_lanes_stream* streams, const std::vector<uint32
     double rmax = 0.0;
     for (uint32_t i : cls) {
         double r = 0, g = 0;
+        if (!has_biquad) break;
         if (!lanes::tp_filter_ok(streams[i].a1, streams[i].a2, &r, &g)) return false;
         rmax = std::max(rmax, r);
     }
     const uint32_t to = streams[cls[0]].to;
     for (size_t k = 0; k + 1 < cls.size(); k++)   // every stream in phase with its neighbour: any two may share a lane
         if ((streams[cls[k]].mix_start % (4ull * to)) != (streams[cls[k + 1]].mix_start % (4ull * to))) return false;
-    const uint32_t W = lanes::tp_warmup(rmax);
+    const uint32_t W = has_biquad ? lanes::tp_warmup(rmax) : 0u;
     // segments: enough rows to fill the machine (about 7 warps of 64 rows per SM), but never shorter than 8 warm-ups
+    // (2048 frames without a filter: a run has to be worth priming the rings for)
     const uint64_t want_rows = 64ull * (uint64_t)(sm_count > 0 ? sm_count : 148) * 7ull;
     uint64_t K = (want_rows + S - 1) / S;
-    const uint64_t max_k = std::max<uint64_t>(1, mix_len / (8ull * W));
+    const uint64_t max_k = std::max<uint64_t>(1, mix_len / (has_biquad ? 8ull * W : 2048ull));
     K = std::max<uint64_t>(1, std::min<uint64_t>(K, max_k));
     if (const char* e = getenv("RB_TP_SEGMENTS")) K = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)atoll(e), std::max<uint64_t>(1, mix_len / lanes::TILE)));
     if (K < 2) return false;   // nothing to gain
@@ -91,14 +97,14 @@ bool plan_time_parallel(const rb_lanes_stream* streams, const std::vector<uint32
             const uint64_t s_end = s.mix_start + s.out_len;
             if (s.out_len == 0 || s.mix_start >= hi || s_end <= lo) continue;      // not active inside the segment
             lanes::Row r;
-            fill_row(r, s, true, has_post, false, false);
+            fill_row(r, s, has_biquad, has_post, false, false);
             const uint64_t n_int_stream = r.n_int;
             r.mix_start = std::max(s.mix_start, from_t);
             r.o0 = r.mix_start - s.mix_start;
             r.out_len = std::min(s_end, hi) - r.mix_start;
             r.n_int = n_int_stream > r.o0 ? std::min<uint64_t>(r.out_len, n_int_stream - r.o0) : 0;
             float k = 0.0f;
-            if (lanes::ff2_coeffs(r.b0, r.b1, r.b2, &k)) r.ffk = k;
+            if (has_biquad && lanes::ff2_coeffs(r.b0, r.b1, r.b2, &k)) r.ffk = k;
             else *ff2 = false;
             rows.push_back(r);
             row_stream.push_back(i);
@@ -144,14 +150,14 @@ cudaError_t rb_lanes_try_create(const rb_lanes_stream* streams, size_t n_streams
     uint32_t n_slots_total = 0;
 
     // ---- the time-parallel plan: one class of mono sources, a filter, nothing in front of the conversion ----
-    if ((mode & LANES_TIME_PARALLEL) && duo_shape && has_biquad && classes.size() == 1 && from[0] < to[0]) {
+    if ((mode & LANES_TIME_PARALLEL) && duo_shape && classes.size() == 1 && from[0] < to[0]) {
         uint32_t n_slots = 0;
         bool ff2 = false;
         const bool force_post = true;   // (y * 1.0 is exact: the plan always runs the instantiation with a gain)
         std::vector<rb_lanes_stream> ls(streams, streams + n_streams);
         if (!has_post)
             for (auto& s : ls) s.post = 1.0f;
-        if (plan_time_parallel(ls.data(), classes[0], mix_len, sm_count, force_post, rows, row_stream, spans, &n_slots, &p->tp_warmup, &p->tp_seg_len, &ff2)) {
+        if (plan_time_parallel(ls.data(), classes[0], mix_len, sm_count, has_biquad, force_post, rows, row_stream, spans, &n_slots, &p->tp_warmup, &p->tp_seg_len, &ff2)) {
             rb_lanes_plan::Class c;
             c.ch_in = 1, c.duo = true, c.ff2 = ff2;
             c.args.n_rows = (uint32_t)rows.size(), c.args.n_groups = (uint32_t)(rows.size() / 64);
