@@ -228,7 +228,8 @@ def run_ours(args):
         family = batch.kernel_family
     except Exception:   # an older library without the query: the default plan is the HOT kernel
         family = 1
-    kernel_label = {2: "k_fused_lanes + k_sum_groups (2 launches per step)",
+    kernel_label = {2: "k_fused_lanes + k_sum_groups (2 launches per step)", 3: "k_fused_duo + k_sum_groups (2 launches per step)",
+                    4: "k_fused_duo over timeline segments + k_sum_groups (2 launches per step)",
                     1: "k_fused_hot + k_sum_partials (2 launches per step)"}.get(family, "kernel family %d" % family)
 
     # ---- inputs resident in HBM before the timed region (seeded, distinct per rank) ----
@@ -323,66 +324,77 @@ def run_ours(args):
                "h2d_bytes_per_step": S * frames * 4, "d2h_bytes_per_step": mix_len * 4, "ms_per_step": e2e_ms,
                "steps": e2e_steps, "note": "pinned host PCM -> rb_batch_upload_packed -> render -> host mix, per step"}
 
-    # ---- BASELINE configs[1] beside it: DynamicMixer, 1024 mono 48 kHz sources summed (N=1 only) ----
+    # ---- the other BASELINE configurations beside it (N=1 only): every entry is one render of resident inputs, CUDA events on
+    # the render stream, its own algorithmic bytes and roofline fraction; a failure is reported in place, never fatal ----
     also = None
     if world == 1 and not args.no_e2e:
-        n2, frames2 = 1024, 48000 * 10
-        srcs2 = [rb.TestSource(np.zeros(frames2, np.float32), 1, MIX_RATE) for _ in range(n2)]
-        b2 = rb.Batch(srcs2, MIX_CH, MIX_RATE, flags=args.flags, ctx=ctx)
-        q0, _ = b2.input_device_ptr(0)
-        pitch2 = (b2.input_device_ptr(1)[0] - q0) // 4
-        for i in range(n2):
-            b2.input_device_ptr(i)
-        with torch.cuda.stream(ext):
-            torch.as_tensor(rbd.DeviceArray(q0, pitch2 * (n2 - 1) + frames2), device=dev).uniform_(-1.0, 1.0, generator=gen)
-        for _ in range(3):
-            b2.render_mix_device()
-        torch.cuda.synchronize(dev)
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record(ext)
-        for _ in range(args.steps):
-            b2.render_mix_device()
-        g1.record(ext)
-        torch.cuda.synchronize(dev)
-        ms2 = g0.elapsed_time(g1) / args.steps
-        also = {"cfg2_dynamic_mixer": {
-            "workload": "mixer(1, 48000) of 1024 mono 48 kHz f32 sources x 10 s, summed in insertion order (bit-exact)",
-            "value": n2 * frames2 / (ms2 * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms2,
-            "roofline": {"bound": "hbm", "achieved": b2.algorithmic_bytes / (ms2 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": b2.algorithmic_bytes / (ms2 * 1e-3) / 1e9 / peak, "kernel": "k_mix_ordered"}}}
-        b2.close()
-        # ---- the large end of BASELINE configs[4] (HBM sweep) beside it: 65 536 streams x 1 s through the same chain;
-        # the planner serves it with the lane-per-stream kernel.  Guarded: a failure here is reported, never fatal.
-        try:
-            n3, frames3 = 65536, IN_RATE
-            b3 = rb.Batch(make_sources(rb, n3, frames3), MIX_CH, MIX_RATE, flags=args.flags, ctx=ctx)
-            r0, _ = b3.input_device_ptr(0)
-            pitch3 = (b3.input_device_ptr(1)[0] - r0) // 4
-            for i in range(n3):
-                b3.input_device_ptr(i)
-            with torch.cuda.stream(ext):
-                torch.as_tensor(rbd.DeviceArray(r0, pitch3 * (n3 - 1) + frames3), device=dev).uniform_(-1.0, 1.0, generator=gen)
-            for _ in range(3):
-                b3.render_mix_device()
-            torch.cuda.synchronize(dev)
-            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            steps3 = max(3, min(args.steps, 10))
-            h0.record(ext)
-            for _ in range(steps3):
-                b3.render_mix_device()
-            h1.record(ext)
-            torch.cuda.synchronize(dev)
-            ms3 = h0.elapsed_time(h1) / steps3
-            fam3 = b3.kernel_family
-            also["cfg5_65536_streams"] = {
-                "workload": "65536 mono streams x 1 s, 44.1 -> 48 kHz -> low_pass(200) -> amplify(1.2) -> mix, inputs 11.6 GB resident",
-                "value": n3 * b3.stream_out_len(0) / (ms3 * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms3, "steps": steps3,
-                "roofline": {"bound": "hbm", "achieved": b3.algorithmic_bytes / (ms3 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                             "frac": b3.algorithmic_bytes / (ms3 * 1e-3) / 1e9 / peak,
-                             "kernel": {2: "k_fused_lanes + k_sum_groups", 1: "k_fused_hot + k_sum_partials"}.get(fam3, str(fam3))}}
-            b3.close()
-        except Exception as exc:   # noqa: BLE001 -- the headline line must survive whatever happens here
-            also["cfg5_65536_streams"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        also = {}
+
+        def timed(name, workload, srcs, mixer_ch, flags, steps, kernel_names):
+            try:
+                b2 = rb.Batch(srcs, mixer_ch, MIX_RATE, flags=flags, ctx=ctx)
+                n2 = len(srcs)
+                q0, cap0 = b2.input_device_ptr(0)
+                pitch2 = (b2.input_device_ptr(1)[0] - q0) // 4 if n2 > 1 else cap0
+                for i in range(n2):
+                    b2.input_device_ptr(i)
+                with torch.cuda.stream(ext):
+                    torch.as_tensor(rbd.DeviceArray(q0, pitch2 * (n2 - 1) + cap0), device=dev).uniform_(-0.5, 0.5, generator=gen)
+                for _ in range(3):
+                    b2.render_mix_device()
+                torch.cuda.synchronize(dev)
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record(ext)
+                for _ in range(steps):
+                    b2.render_mix_device()
+                g1.record(ext)
+                torch.cuda.synchronize(dev)
+                ms2 = g0.elapsed_time(g1) / steps
+                fam = b2.kernel_family
+                samples2 = n2 * b2.stream_out_len(0)      # every stream of these configurations has the same shape
+                gbs = b2.algorithmic_bytes / (ms2 * 1e-3) / 1e9
+                also[name] = {"workload": workload, "value": samples2 / (ms2 * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms2,
+                              "steps": steps, "launches": b2.launches_per_render,
+                              "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                                           "kernel": kernel_names.get(fam, "kernel family %d" % fam)}}
+                b2.close()
+            except Exception as exc:   # noqa: BLE001 -- the headline line must survive whatever happens here
+                also[name] = {"workload": workload, "error": f"{type(exc).__name__}: {exc}"[:300]}
+
+        FAM = {-1: "general path (one kernel per adapter)", 0: "k_fused_biquad", 1: "k_fused_hot + k_sum_partials", 2: "k_fused_lanes + k_sum_groups",
+               3: "k_fused_duo + k_sum_groups", 4: "k_fused_duo over timeline segments + k_sum_groups", 5: "k_fused_fx + k_fx_sum_partials"}
+        z = lambda n: np.zeros(n, np.float32)
+        steps2 = max(3, min(args.steps, 10))
+        timed("cfg2_dynamic_mixer", "mixer(1, 48000) of 1024 mono 48 kHz f32 sources x 10 s, summed in insertion order (bit-exact)",
+              [rb.TestSource(z(48000 * 10), 1, MIX_RATE) for _ in range(1024)], 1, args.flags, args.steps, {-1: "k_mix_ordered"})
+        one2 = z(2 * IN_RATE)
+        timed("cfg3_low_pass_1000_time_parallel",
+              "cfg3 shape at low_pass(1000) with RB_BIQUAD_TIME_PARALLEL (SURVEY 8d cfg3: the scan variant beside the exact one): 4096 mono "
+              "streams x 2 s, timeline segments with a warm-up; <= 1e-5 * peak of the reference (tests), most segments bit-identical",
+              [rb.UniformSourceIterator(rb.TestSource(one2, 1, IN_RATE), 1, MIX_RATE).low_pass(1000).amplify(AMPLIFY) for _ in range(4096)],
+              1, rb.capi.RB_BIQUAD_TIME_PARALLEL, steps2, FAM)
+        timed("cfg3_no_filter", "4096 mono streams x 2 s, 44.1 -> 48 kHz -> amplify(1.2) -> mix (bit-exact per stream)",
+              [rb.UniformSourceIterator(rb.TestSource(one2, 1, IN_RATE), 1, MIX_RATE).amplify(AMPLIFY) for _ in range(4096)], 1, 0, steps2, FAM)
+        timed("cfg4_effect_chain", "512 stereo 48 kHz sources x 1 s: Spatial -> reverb(50 ms, 0.3) -> automatic_gain_control -> mix(2 ch); "
+              "latency-bound: three serial recurrences per stream, 100 800 steps of >= 22 cycles",
+              [rb.Spatial(rb.TestSource(z(2 * 48000), 2, MIX_RATE), [float(s % 7 - 3), 1.0, 0.0], [-1, 0, 0], [1, 0, 0])
+               .reverb(rb.Duration.from_millis(50), 0.3).automatic_gain_control() for s in range(512)], 2, 0, 3, FAM)
+        one1 = z(IN_RATE)
+        sweep = {}
+        for n3 in (1, 16, 256, 1024, 4096, 16384, 65536):
+            timed("_sweep", f"{n3} mono streams x 1 s, 44.1 -> 48 kHz -> low_pass(200) -> amplify(1.2) -> mix",
+                  [rb.UniformSourceIterator(rb.TestSource(one1, 1, IN_RATE), 1, MIX_RATE).low_pass(LOW_PASS_HZ).amplify(AMPLIFY) for _ in range(n3)],
+                  1, args.flags, 5 if n3 >= 16384 else steps2, FAM)
+            r = also.pop("_sweep")
+            sweep[str(n3)] = {"ms": r.get("ms_per_step"), "Msamples_s": r.get("value"), "frac": (r.get("roofline") or {}).get("frac"),
+                              "kernel": (r.get("roofline") or {}).get("kernel"), **({"error": r["error"]} if "error" in r else {})}
+        also["cfg5_sweep"] = {"workload": "BASELINE configs[4]: batch 1 -> 65536 x 1 s@44.1 kHz f32 through the fused pipeline (exact biquad), default planner",
+                              "streams": sweep}
+        if "65536" in sweep and sweep["65536"].get("frac") is not None:
+            also["cfg5_65536_streams"] = {"workload": "65536 mono streams x 1 s, 44.1 -> 48 kHz -> low_pass(200) -> amplify(1.2) -> mix, inputs 11.6 GB resident",
+                                          "value": sweep["65536"]["Msamples_s"], "unit": "Msamples/s", "ms_per_step": sweep["65536"]["ms"],
+                                          "roofline": {"bound": "hbm", "achieved": sweep["65536"]["frac"] * peak, "peak": peak, "unit": "GB/s",
+                                                       "frac": sweep["65536"]["frac"], "kernel": sweep["65536"]["kernel"]}}
 
     clocks = sampler.stop()   # sampled over the timed region, the kernel-only loop and the end-to-end loop
 

@@ -44,7 +44,15 @@ using lanes::TILE;
 using lanes::RUN_CAP;
 using lanes::MIN_RUN_TILES;
 
-constexpr int NSLOT = 4;                    // ring slots per stream: chunk c-1 (draining), c, c+1, c+2 (in flight)
+// Ring slots per stream.  4: chunk c-1 (draining), c, c+1, c+2 (in flight) -- two chunks of look-ahead.  3 (default): ONE chunk
+// of look-ahead (a chunk is two tiles of work, several HBM latencies at the measured pace) and 68 instead of 84 words per
+// stream: 12 instead of 10 warps per SM -- the kernel is bound by the latency of its warps, not by HBM (profiles/README.md).
+#ifndef RB_DUO_SLOTS
+#define RB_DUO_SLOTS 3
+#endif
+static_assert(RB_DUO_SLOTS == 3 || RB_DUO_SLOTS == 4, "3 (one chunk ahead) or 4 (two chunks ahead)");
+constexpr int NSLOT = RB_DUO_SLOTS;
+constexpr bool ONE_AHEAD = RB_DUO_SLOTS == 3;
 constexpr int CHW = lanes::CHUNK;           // words (= mono frames) per chunk
 constexpr int CHF = CHW;
 constexpr int RING = CHW * NSLOT;
@@ -54,7 +62,7 @@ constexpr int QPC = CHW / 4;                // 16-byte quads per chunk and strea
 constexpr int SPI = 32 / QPC;               // streams served by one cp.async warp instruction (8)
 constexpr int NCOPY = 64 / SPI;             // cp.async instructions per chunk of the 64 streams
 constexpr int HALF_WORDS = 32 * RS;         // ring of the odd row lies this many words behind the ring of the even row
-constexpr int WARP_WORDS = 64 * RS;         // 21.0 KB per warp
+constexpr int WARP_WORDS = 64 * RS;         // 17.0 KB per warp (3 slots)
 constexpr int TF = TILE;                    // frames per tile (mono)
 static_assert((RS / 4) % 2 == 1 && MIRROR >= TILE && CHF >= 2 * TF, "ring geometry");
 
@@ -179,8 +187,8 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
             issue(1);
             simt::cp_wait<1>();
             simt::syncwarp();
-            issue(2);
-            uint32_t c_ready = 1;
+            if (!ONE_AHEAD) issue(2);
+            uint32_t c_ready = 1;   // chunks [0, c_ready) are readable; c_ready (and, two ahead, c_ready + 1) are in flight
             float* const ringl = ring_warp + ln * RS;
             const simt::sptr ring_end = simt::sptr_of(ringl + RING);
             simt::sptr p = simt::sptr_of(ringl + k0);
@@ -205,9 +213,15 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                 kb += a.q8, kbn += a.r8;
                 if (kbn >= to) kbn -= to, kb += 1;
                 if ((kb - 1) / CHF >= c_ready) {
-                    simt::cp_wait<1>();      // chunk c_ready has landed (c_ready + 1 may still be in flight)
-                    simt::syncwarp();        // ... for every lane, and nobody reads chunk c_ready - 2 any more
-                    issue(c_ready + 2);
+                    if (ONE_AHEAD) {
+                        simt::cp_wait<0>();      // chunk c_ready has landed
+                        simt::syncwarp();        // ... for every lane, and nobody reads chunk c_ready - 2 any more
+                        issue(c_ready + 1);      // into the slot of chunk c_ready - 2
+                    } else {
+                        simt::cp_wait<1>();      // chunk c_ready has landed (c_ready + 1 may still be in flight)
+                        simt::syncwarp();        // ... for every lane, and nobody reads chunk c_ready - 2 any more
+                        issue(c_ready + 2);
+                    }
                     c_ready += 1;
                     simt::emu_count(2, 1);
                 }

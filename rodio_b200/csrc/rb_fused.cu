@@ -1155,6 +1155,7 @@ struct rb_fused_plan {
     bool hot = false;
     size_t hot_smem = 0;
     rb_lanes_plan* lanes = nullptr;   // RB_FUSED_LANES: the lane-per-stream kernel serves the batch (rb_lanes.cu)
+    rb_fx_plan* fx = nullptr;         // the effect-chain kernel serves the batch (rb_fx.cu)
 };
 
 cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams, uint16_t mixer_channels, float* d_out,
@@ -1162,6 +1163,17 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     *out = nullptr;
     if (n_streams == 0 || mix_len == 0) return cudaSuccess;
     if (flags & RB_MIX_EXACT_ORDER) return cudaSuccess;   // served by the general path
+    {   // spatial / reverb / AGC chains have a kernel of their own
+        rb_fx_plan* fx = nullptr;
+        cudaError_t e = rb_fx_try_create(streams, n_streams, mixer_channels, d_out, mix_len, flags, st, &fx);
+        if (e != cudaSuccess) return e;
+        if (fx) {
+            auto plan = new rb_fused_plan;
+            plan->fx = fx;
+            *out = plan;
+            return cudaSuccess;
+        }
+    }
     std::vector<FusedRow> rows(n_streams);
     uint32_t n_pre = 0, n_mid = 0, n_post = 0, has_u = 0, has_b = 0, front = 0;
     bool mixed_u = false;   // some rows lost an identity conversion: only the lane kernel may take such a batch
@@ -1293,6 +1305,7 @@ void rb_fused_inputs_changed(rb_fused_plan* p) {
 }
 
 cudaError_t rb_fused_run(rb_fused_plan* p, cudaStream_t st) {
+    if (p->fx) return rb_fx_run(p->fx, st);
     if (p->lanes) return rb_lanes_run(p->lanes, st);
     const FusedArgs& a = p->args;
     if (p->hot) {
@@ -1328,17 +1341,19 @@ cudaError_t rb_fused_run(rb_fused_plan* p, cudaStream_t st) {
 void rb_fused_destroy(rb_fused_plan* p) {
     if (!p) return;
     rb_lanes_destroy(p->lanes);
+    rb_fx_destroy(p->fx);
     cudaFree(p->d_rows);
     cudaFree(p->d_partial);
     delete p;
 }
 
 uint32_t rb_fused_launch_count(const rb_fused_plan* p) {
+    if (p->fx) return 2u;
     if (p->lanes) return rb_lanes_launch_count(p->lanes);
     return p->single_cta_direct ? 1u : 2u;
 }
-int rb_fused_kind(const rb_fused_plan* p) { return p->lanes ? rb_lanes_kind(p->lanes) : (p->hot ? 1 : 0); }
-uint32_t rb_fused_mix_group(const rb_fused_plan* p) { return p->lanes ? rb_lanes_mix_group(p->lanes) : p->args.rows_per_cta; }
+int rb_fused_kind(const rb_fused_plan* p) { return p->fx ? 5 : p->lanes ? rb_lanes_kind(p->lanes) : (p->hot ? 1 : 0); }
+uint32_t rb_fused_mix_group(const rb_fused_plan* p) { return p->fx ? 4u : p->lanes ? rb_lanes_mix_group(p->lanes) : p->args.rows_per_cta; }
 
 #ifdef RB_HOT_TIMING
 extern "C" int rb_debug_hot_skip(int mask) { return (int)cudaMemcpyToSymbol(g_hot_skip, &mask, sizeof(int)); }

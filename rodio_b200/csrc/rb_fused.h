@@ -31,7 +31,16 @@ void rb_fused_destroy(rb_fused_plan* plan);
 uint32_t rb_fused_launch_count(const rb_fused_plan* plan);
 // The input PCM of the batch was (re)written: plans that keep per-stream facts about it refresh them at the next run.
 void rb_fused_inputs_changed(rb_fused_plan* plan);
-// Which kernel family serves the plan: 0 = k_fused_biquad / k_fused_nobiquad, 1 = k_fused_hot, 2 = k_fused_lanes.
+// Which kernel family serves the plan: 0 = k_fused_biquad / k_fused_nobiquad, 1 = k_fused_hot, 2 = k_fused_lanes,
+// 3 = k_fused_duo, 4 = the time-parallel plan on k_fused_duo, 5 = k_fused_fx (effect chain).
 int rb_fused_kind(const rb_fused_plan* plan);
 // streams per partial sum of the mixer (rows per CTA; 32 for the lane kernel)
 uint32_t rb_fused_mix_group(const rb_fused_plan* plan);
+
+// ---- the effect-chain kernel (rb_fx.cu): [Spatial / ChannelVolume] -> [reverb] -> automatic_gain_control -> mix in one launch ----
+struct rb_fx_plan;
+// *out stays NULL when the batch has another shape (see rb_fx.cu).
+cudaError_t rb_fx_try_create(const rb_fused_stream* streams, size_t n_streams, uint16_t mixer_channels, float* d_out, uint64_t mix_len,
+                             uint32_t flags, cudaStream_t st, rb_fx_plan** out);
+cudaError_t rb_fx_run(rb_fx_plan* plan, cudaStream_t st);
+void rb_fx_destroy(rb_fx_plan* plan);

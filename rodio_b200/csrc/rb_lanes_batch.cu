@@ -77,9 +77,11 @@ bool plan_time_parallel(const rb_lanes_stream* streams, const std::vector<uint32
     for (size_t k = 0; k + 1 < cls.size(); k++)   // every stream in phase with its neighbour: any two may share a lane
         if ((streams[cls[k]].mix_start % (4ull * to)) != (streams[cls[k + 1]].mix_start % (4ull * to))) return false;
     const uint32_t W = has_biquad ? lanes::tp_warmup(rmax) : 0u;
-    // segments: enough rows to fill the machine (about 7 warps of 64 rows per SM), but never shorter than 8 warm-ups
+    // segments: enough rows to fill the machine (12 warps of 64 rows per SM), but never shorter than 8 warm-ups
     // (2048 frames without a filter: a run has to be worth priming the rings for)
-    const uint64_t want_rows = 64ull * (uint64_t)(sm_count > 0 ? sm_count : 148) * 7ull;
+    uint64_t warps_per_sm = 12;      // what the rings of k_fused_duo leave room for; the kernel lives on the number of resident warps
+    if (const char* e = getenv("RB_TP_WARPS_PER_SM")) warps_per_sm = std::max<uint64_t>(1, (uint64_t)atoll(e));
+    const uint64_t want_rows = 64ull * (uint64_t)(sm_count > 0 ? sm_count : 148) * warps_per_sm;
     uint64_t K = (want_rows + S - 1) / S;
     const uint64_t max_k = std::max<uint64_t>(1, mix_len / (has_biquad ? 8ull * W : 2048ull));
     K = std::max<uint64_t>(1, std::min<uint64_t>(K, max_k));

@@ -138,10 +138,44 @@ def test_cfg4_512_streams(ctx):
         for i in (0, 255, n - 1):
             assert_bit_exact(b.read_stream(i), oracle.chain_uniform(streams[i], 2, 48000), f"cfg4 stream {i}")
     assert_bit_exact(got, want, "cfg4 512 streams, exact order")
-    with rb.Batch(srcs, 2, 48000, ctx=ctx) as b:
+    with rb.Batch(srcs, 2, 48000, ctx=ctx) as b:     # the default launch: k_fused_fx, 4 streams per CTA
+        assert b.kernel_family == 5 and b.mix_group == 4 and b.launches_per_render == 2
         b.upload_all()
         got = b.render_mix()
+        again = b.render_mix()
+    assert np.array_equal(got.view(np.uint32), again.view(np.uint32))
     assert_close_peak(got, want, 1e-5, "cfg4 512 streams, default launch")
+    per = [oracle.chain_uniform(s, 2, 48000) for s in streams]
+    assert_bit_exact(got, grouped_expected_mix(per, [0] * n, want.size, 4), "k_fused_fx vs oracle streams in its documented order")
+
+
+@pytest.mark.parametrize("shape", ["mono_agc_only", "stereo_reverb_agc", "stereo_spatial_agc", "ragged"])
+def test_fx_kernel_shapes(ctx, shape):
+    """The other shapes k_fused_fx serves: without the channel volumes, without the echo, mono, streams of different lengths,
+    odd echo delays, custom AGC settings, a number of streams that is not a multiple of four."""
+    rng = np.random.default_rng(17)
+    ch = 1 if shape == "mono_agc_only" else 2
+    n = 37
+    srcs = []
+    for s in range(n):
+        frames = 9000 + (int(rng.integers(0, 4000)) if shape == "ragged" else 0)
+        src = rb.TestSource(noise(frames * ch, 51000 + s, 0.3), ch, 48000)
+        if shape in ("stereo_spatial_agc", "ragged"):
+            src = rb.Spatial(src, [float(s % 5 - 2), 1.0, 0.5], [-1, 0, 0], [1, 0, 0])
+        if shape in ("stereo_reverb_agc", "ragged"):
+            src = src.reverb(rb.Duration.from_micros(20000 + 137 * s), 0.4)
+        settings = rb.AutomaticGainControlSettings(target_level=0.8, attack_time=rb.Duration.from_millis(200 + s),
+                                                   release_time=rb.Duration.from_millis(50), absolute_max_gain=5.0) if s % 2 else rb.AutomaticGainControlSettings()
+        srcs.append(src.automatic_gain_control(settings))
+    streams = [to_oracle(s) for s in srcs]
+    want = oracle.mixer(streams, ch, 48000)
+    with rb.Batch(srcs, ch, 48000, ctx=ctx) as b:
+        assert b.kernel_family == 5
+        b.upload_all()
+        got = b.render_mix()
+    assert_close_peak(got, want, 1e-5, f"k_fused_fx {shape}")
+    per = [oracle.chain_uniform(s, ch, 48000) for s in streams]
+    assert_bit_exact(got, grouped_expected_mix(per, [0] * n, want.size, 4), f"k_fused_fx {shape}: documented order")
 
 
 # ------------------------------------------------------------------ the lane-pair kernel and the time-parallel plan
