@@ -208,6 +208,21 @@ rb_status rb_batch_kernel_family(rb_batch* b, int* family);
  * (general path, RB_MIX_EXACT_ORDER).  For the parity tests, which rebuild the kernel's documented order from the
  * oracle's per-stream outputs. */
 rb_status rb_batch_mix_group(rb_batch* b, uint32_t* rows);
+/* ---- multi-GPU: shard the sources over GPUs, one all-reduce for the cross-shard mixer sum (src/mixer.rs:185-198 is the sum
+ * being distributed).  NCCL over NVLink, loaded at first use (dlopen libnccl.so.2); RB_ERR_UNSUPPORTED when
+ * the box has none.  One process per GPU: rank 0 calls rb_comm_unique_id, hands the 128 bytes to the other ranks by whatever
+ * channel the host has, every rank calls rb_comm_init_rank.  One process driving several GPUs: rb_comm_init_all over its
+ * contexts.  rb_batch_render_mix_allreduce renders the batch of every LOCAL rank (one per context of the communicator, in
+ * order) and sums the mixes over all ranks in place, on the contexts' streams; shards keep the insertion order inside a GPU,
+ * the cross-shard association differs from the sequential sum: the fused kernels' tolerance class (<= 1e-5 * peak). ---- */
+typedef struct rb_comm rb_comm;
+typedef struct { char bytes[128]; } rb_comm_id;
+rb_status rb_comm_unique_id(rb_comm_id* id);
+rb_status rb_comm_init_rank(rb_context* ctx, int n_ranks, int rank, const rb_comm_id* id, rb_comm** out);
+rb_status rb_comm_init_all(rb_context** ctxs, int n_gpus, rb_comm** out);
+rb_status rb_comm_destroy(rb_comm* comm);
+rb_status rb_batch_render_mix_allreduce(rb_batch** batches, int n_local, rb_comm* comm);
+
 /* Algorithmic bytes of one render: 4*sum(in_samples)(or format size) + 4*mix_len. */
 rb_status rb_batch_algorithmic_bytes(rb_batch* b, uint64_t* bytes);
 

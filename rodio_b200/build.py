@@ -21,6 +21,7 @@ NVCC_FLAGS = [
     "-cudart", "static",
     "--shared",
     "--threads", "0",          # the translation units compile side by side
+    "-ldl",                    # libnccl is loaded at first use (rb_comm_*)
 ]
 
 

@@ -815,6 +815,146 @@ extern "C" rb_status rb_batch_render_mix_device(rb_batch* b) {
     b->rendered = true;
     return RB_OK;
 }
+// ----------------------------------------------------------------------------------------------------
+// Multi-GPU: the cross-shard mixer sum.  Streams are independent until the mixer adds them
+// (src/mixer.rs:185-198), so every GPU renders the partial mix of its own shard and ONE all-reduce(sum, f32, mix_len)
+// gives every rank the MixerSource output.  The collective is NCCL's (over NVLink / NVSwitch on a B200 node), called
+// from here on the context's stream, so a Rust / C host needs no NCCL binding of its own.  The library is loaded on first
+// use (dlopen "libnccl.so.2": a process that already holds NCCL -- torch -- shares that copy); a build without NCCL on the
+// box fails the call loudly, nothing falls back to the host.
+// ----------------------------------------------------------------------------------------------------
+#include <dlfcn.h>
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, rb_comm_id, int) = nullptr;
+    int (*CommInitAll)(void**, int, const int*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi* nccl_api(std::string* why) {
+    static NcclApi api;
+    static bool tried = false;
+    static std::string err;
+    if (!tried) {
+        tried = true;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
+        }
+        if (!api.lib) err = std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "?");
+        else {
+            auto sym = [&](const char* n) {
+                void* p = dlsym(api.lib, n);
+                if (!p && err.empty()) err = std::string("libnccl lacks ") + n;
+                return p;
+            };
+            api.GetUniqueId = (int (*)(void*))sym("ncclGetUniqueId");
+            api.CommInitRank = (int (*)(void**, int, rb_comm_id, int))sym("ncclCommInitRank");
+            api.CommInitAll = (int (*)(void**, int, const int*))sym("ncclCommInitAll");
+            api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))sym("ncclAllReduce");
+            api.CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
+            api.GroupStart = (int (*)())sym("ncclGroupStart");
+            api.GroupEnd = (int (*)())sym("ncclGroupEnd");
+            api.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+        }
+    }
+    if (!err.empty()) {
+        if (why) *why = err;
+        return nullptr;
+    }
+    return &api;
+}
+constexpr int NCCL_FLOAT32 = 7, NCCL_SUM = 0;   // ncclFloat32, ncclSum (nccl.h)
+}  // namespace
+
+struct rb_comm {
+    std::vector<void*> comms;           // one per local rank (one entry for the process-per-GPU form)
+    std::vector<rb_context*> ctxs;
+    int n_ranks = 0;
+};
+
+#define RB_NCCL(call, api)                                                                             \
+    do {                                                                                               \
+        const int r_ = (call);                                                                         \
+        if (r_ != 0) return fail(RB_ERR_CUDA, std::string("NCCL: ") + (api)->GetErrorString(r_));      \
+    } while (0)
+
+extern "C" rb_status rb_comm_unique_id(rb_comm_id* id) {
+    if (!id) return fail(RB_ERR_INVALID_ARGUMENT, "id is NULL");
+    std::string why;
+    NcclApi* api = nccl_api(&why);
+    if (!api) return fail(RB_ERR_UNSUPPORTED, why);
+    RB_NCCL(api->GetUniqueId(id), api);
+    return RB_OK;
+}
+
+extern "C" rb_status rb_comm_init_rank(rb_context* ctx, int n_ranks, int rank, const rb_comm_id* id, rb_comm** out) {
+    if (!ctx || !id || !out || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(RB_ERR_INVALID_ARGUMENT, "bad communicator arguments");
+    std::string why;
+    NcclApi* api = nccl_api(&why);
+    if (!api) return fail(RB_ERR_UNSUPPORTED, why);
+    RB_CUDA(cudaSetDevice(ctx->device));
+    auto c = std::make_unique<rb_comm>();
+    c->comms.resize(1), c->ctxs = {ctx}, c->n_ranks = n_ranks;
+    RB_NCCL(api->CommInitRank(&c->comms[0], n_ranks, *id, rank), api);
+    *out = c.release();
+    return RB_OK;
+}
+
+extern "C" rb_status rb_comm_init_all(rb_context** ctxs, int n_gpus, rb_comm** out) {
+    if (!ctxs || !out || n_gpus < 1) return fail(RB_ERR_INVALID_ARGUMENT, "bad communicator arguments");
+    std::string why;
+    NcclApi* api = nccl_api(&why);
+    if (!api) return fail(RB_ERR_UNSUPPORTED, why);
+    auto c = std::make_unique<rb_comm>();
+    std::vector<int> devs(n_gpus);
+    for (int i = 0; i < n_gpus; i++) {
+        if (!ctxs[i]) return fail(RB_ERR_INVALID_ARGUMENT, "context is NULL");
+        devs[i] = ctxs[i]->device, c->ctxs.push_back(ctxs[i]);
+    }
+    c->comms.resize(n_gpus), c->n_ranks = n_gpus;
+    RB_NCCL(api->CommInitAll(c->comms.data(), n_gpus, devs.data()), api);
+    *out = c.release();
+    return RB_OK;
+}
+
+extern "C" rb_status rb_comm_destroy(rb_comm* c) {
+    if (!c) return RB_OK;
+    NcclApi* api = nccl_api(nullptr);
+    if (api)
+        for (void* k : c->comms)
+            if (k) api->CommDestroy(k);
+    delete c;
+    return RB_OK;
+}
+
+// Render every batch (one per local rank of the communicator, in rank order) and all-reduce the mixes in place: afterwards
+// each rb_batch_mix_device_ptr holds the sum over ALL ranks.  Asynchronous on the contexts' streams like a render.
+extern "C" rb_status rb_batch_render_mix_allreduce(rb_batch** batches, int n_local, rb_comm* c) {
+    if (!batches || !c || n_local != (int)c->comms.size()) return fail(RB_ERR_INVALID_ARGUMENT, "one batch per local rank of the communicator");
+    NcclApi* api = nccl_api(nullptr);
+    if (!api) return fail(RB_ERR_UNSUPPORTED, "NCCL is not loaded");
+    for (int i = 0; i < n_local; i++) {
+        if (!batches[i] || batches[i]->ctx != c->ctxs[i]) return fail(RB_ERR_INVALID_ARGUMENT, "batch i must live on the context of local rank i");
+        if (batches[i]->mix_len != batches[0]->mix_len) return fail(RB_ERR_INVALID_ARGUMENT, "the shards must share the mixer timeline (equal mix_len)");
+        rb_status s = rb_batch_render_mix_device(batches[i]);
+        if (s != RB_OK) return s;
+    }
+    if (c->n_ranks == 1 || batches[0]->mix_len == 0) return RB_OK;
+    if (n_local > 1) RB_NCCL(api->GroupStart(), api);
+    for (int i = 0; i < n_local; i++) {
+        RB_CUDA(cudaSetDevice(c->ctxs[i]->device));
+        RB_NCCL(api->AllReduce(batches[i]->d_out, batches[i]->d_out, (size_t)batches[i]->mix_len, NCCL_FLOAT32, NCCL_SUM, c->comms[i], c->ctxs[i]->stream), api);
+    }
+    if (n_local > 1) RB_NCCL(api->GroupEnd(), api);
+    return RB_OK;
+}
+
 extern "C" rb_status rb_batch_mix_device_ptr(rb_batch* b, float** dptr) {
     if (!b || !dptr) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
     *dptr = b->d_out;

@@ -66,9 +66,16 @@ constexpr int WARP_WORDS = 64 * RS;         // 17.0 KB per warp (3 slots)
 constexpr int TF = TILE;                    // frames per tile (mono)
 static_assert((RS / 4) % 2 == 1 && MIRROR >= TILE && CHF >= 2 * TF, "ring geometry");
 
-template <bool HASB, bool FF2, int NPOST>
-SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
+// ROLE 0: one warp does everything.  ROLE 1 / 2: the group is served by a PAIR of warps of one CTA (k_fused_duo_split):
+// warp A (1) owns the rings and produces the interpolated samples of a tile, warp B (2) takes them from `handoff`
+// ([2][TILE][32] packed pairs in shared memory, one CTA barrier per tile) and runs the filter, the gain and the mixer tree.
+// Both warps walk the same sequence of runs (each derives it from the rows), B alone computes the slow tiles.  Twice the
+// warps per stream, half the instructions per warp: the single-warp form is bound by the latency of its warps
+// (profiles/README.md: 0.33 instructions per clock and warp at 1.7 warps per sub-partition).
+template <bool HASB, bool FF2, int NPOST, int ROLE = 0>
+SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp, simt::f2* handoff = nullptr) {
     using simt::f2;
+    constexpr bool DO_A = ROLE != 2, DO_B = ROLE != 1;
     const uint32_t ln = simt::lane();
     Row row[2];
     bool has[2], safe[2], live[2];
@@ -183,17 +190,22 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                 }
                 simt::cp_commit();
             };
-            issue(0);
-            issue(1);
-            simt::cp_wait<1>();
-            simt::syncwarp();
-            if (!ONE_AHEAD) issue(2);
+            if (DO_A) {
+                issue(0);
+                issue(1);
+                simt::cp_wait<1>();
+                simt::syncwarp();
+                if (!ONE_AHEAD) issue(2);
+            }
             uint32_t c_ready = 1;   // chunks [0, c_ready) are readable; c_ready (and, two ahead, c_ready + 1) are in flight
             float* const ringl = ring_warp + ln * RS;
             const simt::sptr ring_end = simt::sptr_of(ringl + RING);
             simt::sptr p = simt::sptr_of(ringl + k0);
-            f2 X0 = simt::pack2(simt::lds(p), simt::lds(simt::sptr_add(p, HALF_WORDS)));
-            f2 X1 = simt::pack2(simt::lds(simt::sptr_add(p, 1)), simt::lds(simt::sptr_add(p, HALF_WORDS + 1)));
+            f2 X0 = simt::pack2(0.f, 0.f), X1 = X0;
+            if (DO_A) {
+                X0 = simt::pack2(simt::lds(p), simt::lds(simt::sptr_add(p, HALF_WORDS)));
+                X1 = simt::pack2(simt::lds(simt::sptr_add(p, 1)), simt::lds(simt::sptr_add(p, HALF_WORDS + 1)));
+            }
             p = simt::sptr_add(p, 2);
             float nf = simt::u2f(num);
             uint32_t kb = 5, kbn = to - 1;
@@ -235,7 +247,7 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                 const f2 x = simt::add2(X0, q);
                 simt::lerp_advance2<HALF_WORDS>(nf, X0, X1, p, from_f, den);
                 out = x;
-                if (HASB) {
+                if (HASB && ROLE == 0) {
                     if (FF2) {
                         const f2 pz = simt::mul2(B0, x);
                         out = simt::fma2(P2, ONE, simt::fma2(P1, FFK, pz));   // (.. ) + p2 with one rounding; p2 stays a multiplicand (rb_simt.h)
@@ -249,6 +261,18 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                 }
             };
             auto step_b = [&](f2 tt, float& v) {
+                if (HASB && ROLE == 2) {   // the feed-forward half runs here when the warps are split: tt arrives as x
+                    const f2 x = tt;
+                    if (FF2) {
+                        const f2 pz = simt::mul2(B0, x);
+                        tt = simt::fma2(P2, ONE, simt::fma2(P1, FFK, pz));
+                        P2 = P1, P1 = pz;
+                    } else {
+                        const f2 s01 = simt::fma2(simt::mul2(B1, XH1), ONE, simt::mul2(B0, x));
+                        tt = simt::fma2(simt::mul2(B2, XH2), ONE, s01);
+                    }
+                    XH2 = XH1, XH1 = x;
+                }
                 f2 y = tt;
                 if (HASB) {
                     // (t - a1*y1) - a2*y2, src/source/blt.rs:558-560
@@ -284,6 +308,46 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
                 for (int st = 0; st < 6; st++) stage_c(st, vv, pos);
             };
             const uint32_t n_tiles = run / TF;     // >= MIN_RUN_TILES
+            if (ROLE == 1) {
+                // ---- warp A of a split pair: produce tile k into handoff[k & 1], one barrier per tile, one at the end of the run
+                // (B may still be reading the last tile when the next run starts to write) ----
+                for (uint32_t k = 0; k < n_tiles; k++) {
+                    f2 X[TILE];
+                    refill();
+#pragma unroll
+                    for (int f = 0; f < TF; f++) step_a(X[f]);
+                    f2* dst = handoff + (k & 1u) * (TILE * 32) + ln;
+#pragma unroll
+                    for (int f = 0; f < TF; f++) simt::sts2(dst + f * 32, X[f]);
+                    simt::cta_sync();
+                }
+                simt::cta_sync();
+            } else if (ROLE == 2) {
+                // ---- warp B: consume tile j (feed-forward, recurrence, gain), the mixer tree of tile j - 1 interleaved ----
+                float v[TILE], vp[TILE];
+                for (uint32_t j = 0; j < n_tiles; j++) {
+                    simt::cta_sync();      // tile j has been written
+                    f2 X[TILE];
+                    const f2* srcx = handoff + (j & 1u) * (TILE * 32) + ln;
+#pragma unroll
+                    for (int f = 0; f < TF; f++) X[f] = simt::lds2(srcx + f * 32);
+                    const uint64_t pos = t + (uint64_t)(j - 1) * TF;
+                    if (j == 0) {
+#pragma unroll
+                        for (int f = 0; f < TF; f++) step_b(X[f], vp[f]);
+                    } else {
+#pragma unroll
+                        for (int f = 0; f < TF; f++) {
+                            step_b(X[f], v[f]);
+                            stage_c(f == 0 ? 0 : f == 2 ? 1 : f == 4 ? 2 : f == 5 ? 3 : f == 6 ? 4 : f == 7 ? 5 : -1, vp, pos);
+                        }
+#pragma unroll
+                        for (int f = 0; f < TF; f++) vp[f] = v[f];
+                    }
+                }
+                all_c(vp, t + (uint64_t)(n_tiles - 1) * TF);
+                simt::cta_sync();
+            } else {
             f2 T[TILE], Tn[TILE];
             float v[TILE], vp[TILE];
             refill();
@@ -318,14 +382,21 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp) {
             for (int f = 0; f < TF; f++) step_b(T[f], v[f]);                 // B(n - 1)
             all_c(vp, t + (uint64_t)(n_tiles - 2) * TF);                     // C(n - 2)
             all_c(v, t + (uint64_t)(n_tiles - 1) * TF);                      // C(n - 1)
-            simt::cp_wait<0>();
-            simt::syncwarp();
+            }
+            if (DO_A) {
+                simt::cp_wait<0>();
+                simt::syncwarp();
+            }
             simt::emu_count(0, run / TF);
             xh1[0] = simt::lo2(XH1), xh1[1] = simt::hi2(XH1), xh2[0] = simt::lo2(XH2), xh2[1] = simt::hi2(XH2);
             y1[0] = simt::lo2(Y1), y1[1] = simt::hi2(Y1), y2[0] = simt::lo2(Y2), y2[1] = simt::hi2(Y2);
             t += run;
         } else {
             // =================================== SLOW TILE: per-half closed form ===================================
+            if (!DO_B) {     // warp A of a split pair has no part in it
+                t += TF;
+                continue;
+            }
             float v[TILE];
 #pragma unroll 1
             for (int f = 0; f < TF; f++) {

@@ -5,6 +5,7 @@
 // Chosen by the fused planner for very large batches or on RB_FUSED_LANES (include/rodio_b200.h); also renders the blocks
 // of the streaming sessions (rb_session_* in rb_api.cu).
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "rb_lanes.h"
@@ -39,6 +40,18 @@ __global__ void __launch_bounds__(32 * DUO_WARPS) k_fused_duo(lanes::Args a) {
     const uint32_t group = blockIdx.x * DUO_WARPS + warp;
     if (group >= a.n_groups) return;
     duo::warp_main<HASB, FF2, NPOST>(a, group, lanes_smem + (size_t)warp * duo::WARP_WORDS);
+}
+
+// The same program on a PAIR of warps per group (rb_duo_core.h, ROLE): warp 0 feeds, warp 1 filters and sums.
+constexpr size_t DUO_SPLIT_SMEM = (size_t)duo::WARP_WORDS * sizeof(float) + 2 * lanes::TILE * 32 * sizeof(simt::f2);   // 17.0 + 4 KB
+template <bool HASB, bool FF2, int NPOST>
+__global__ void __launch_bounds__(64) k_fused_duo_split(lanes::Args a) {
+    extern __shared__ __align__(16) float lanes_smem[];
+    const uint32_t group = blockIdx.x;
+    if (group >= a.n_groups) return;
+    simt::f2* handoff = reinterpret_cast<simt::f2*>(lanes_smem + duo::WARP_WORDS);
+    if ((threadIdx.x >> 5) == 0) duo::warp_main<HASB, FF2, NPOST, 1>(a, group, lanes_smem, handoff);
+    else duo::warp_main<HASB, FF2, NPOST, 2>(a, group, lanes_smem, handoff);
 }
 
 // One CTA per stream: does every non-zero |x| lie inside [2^-70, 2^60]?  (rb_lanes_core.h, "Exact division".)
@@ -175,6 +188,17 @@ cudaError_t rb_lanes_launch_kernel(const lanes::Args& a, uint32_t ch_in, uint32_
 // k_fused_duo over a.rows: a.n_groups counts groups of 64 rows
 cudaError_t rb_duo_launch_kernel(const lanes::Args& a, bool has_biquad, bool ff2, bool has_post, cudaStream_t st) {
     if (a.mix_len == 0 || a.n_groups == 0) return cudaSuccess;
+    static const bool split = []() { const char* e = getenv("RB_DUO_SPLIT"); return e ? atoi(e) != 0 : true; }();
+    if (split) {
+        const dim3 g(a.n_groups), b(64);
+        if (has_biquad) {
+            if (ff2) has_post ? k_fused_duo_split<true, true, 1><<<g, b, DUO_SPLIT_SMEM, st>>>(a) : k_fused_duo_split<true, true, 0><<<g, b, DUO_SPLIT_SMEM, st>>>(a);
+            else has_post ? k_fused_duo_split<true, false, 1><<<g, b, DUO_SPLIT_SMEM, st>>>(a) : k_fused_duo_split<true, false, 0><<<g, b, DUO_SPLIT_SMEM, st>>>(a);
+        } else {
+            has_post ? k_fused_duo_split<false, false, 1><<<g, b, DUO_SPLIT_SMEM, st>>>(a) : k_fused_duo_split<false, false, 0><<<g, b, DUO_SPLIT_SMEM, st>>>(a);
+        }
+        return cudaGetLastError();
+    }
     const uint32_t n_ctas = (a.n_groups + DUO_WARPS - 1) / DUO_WARPS;
     const dim3 g(n_ctas), b(32 * DUO_WARPS);
     if (has_biquad) {

@@ -286,6 +286,10 @@ SIMT_FN f2 add2(f2 a, f2 b) { return f2{a.lo + b.lo, a.hi + b.hi}; }
 SIMT_FN f2 sub2(f2 a, f2 b) { return f2{a.lo - b.lo, a.hi - b.hi}; }
 SIMT_FN f2 mul2(f2 a, f2 b) { return f2{a.lo * b.lo, a.hi * b.hi}; }
 SIMT_FN f2 fma2(f2 a, f2 b, f2 c) { return f2{std::fmaf(a.lo, b.lo, c.lo), std::fmaf(a.hi, b.hi, c.hi)}; }
+// split warps (k_fused_duo_split) exist on the device only: the emulator runs one warp at a time
+SIMT_FN void cta_sync() { emu_fail("cta_sync: the split-warp variant is not emulated"); }
+SIMT_FN void sts2(f2* p, f2 v) { *p = v; }
+SIMT_FN f2 lds2(const f2* p) { return *p; }
 // One index step of the resampler for the TWO streams of a lane that share their phase: numerator += from (mod den); on a
 // carry the right taps become the left ones and the next ring frame of either stream is fetched (ring B lies `B_OFF` words
 // behind ring A).  The numerator is one scalar for both (the packed multiply takes it as a broadcast operand).
@@ -479,6 +483,9 @@ SIMT_FN f2 fma2(f2 a, f2 b, f2 c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
     return r;
 }
+SIMT_FN void cta_sync() { __syncthreads(); }
+SIMT_FN void sts2(f2* p, f2 v) { *p = v; }    // STS.64 / LDS.64 of a packed pair
+SIMT_FN f2 lds2(const f2* p) { return *p; }
 // FADD, FSETP, then predicated: numerator wrap, tap moves, two tap loads (ring A at p, ring B B_OFF words behind it: an
 // immediate offset), cursor increment.  The taps are handed over as separate halves so that the loads land in place.
 template <int B_OFF>
