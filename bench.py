@@ -209,11 +209,17 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: rodio_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        rbd.init_process_group("nccl")
     dev = torch.device("cuda", local_rank)
     ctx = rb.Context(local_rank)
     ext = torch.cuda.ExternalStream(ctx.cuda_stream, device=dev)
+    comm = None
+    if world > 1:
+        # torch.distributed is the plumbing (barrier, max over ranks, handing out the communicator id); the data-path
+        # collective is the library's own: rb_batch_render_mix_allreduce = render + ncclAllReduce on the context's stream
+        rbd.init_process_group("nccl")
+        ids = [rb.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        comm = rb.Comm(ctx, world, rank, ids[0])
 
     S = args.streams
     frames = int(round(args.seconds * IN_RATE))
@@ -245,10 +251,10 @@ def run_ours(args):
     mix = torch.as_tensor(rbd.DeviceArray(batch.mix_device_ptr, max(1, mix_len)), device=dev)
 
     def step():
-        batch.render_mix_device()
-        if world > 1:
-            with torch.cuda.stream(ext):
-                dist.all_reduce(mix, op=dist.ReduceOp.SUM)
+        if comm is not None:
+            comm.render_mix_allreduce(batch)
+        else:
+            batch.render_mix_device()
 
     def fence():
         if world > 1:
@@ -299,9 +305,8 @@ def run_ours(args):
         def e2e_step():
             batch.upload_packed(host_in.data_ptr(), S * frames)
             if world > 1:
-                batch.render_mix_device()
+                comm.render_mix_allreduce(batch)
                 with torch.cuda.stream(ext):
-                    dist.all_reduce(mix, op=dist.ReduceOp.SUM)
                     host_out.copy_(mix, non_blocking=True)
                 ctx.sync()
             else:
@@ -323,6 +328,48 @@ def run_ours(args):
         e2e = {"value": samples_per_step / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s",
                "h2d_bytes_per_step": S * frames * 4, "d2h_bytes_per_step": mix_len * 4, "ms_per_step": e2e_ms,
                "steps": e2e_steps, "note": "pinned host PCM -> rb_batch_upload_packed -> render -> host mix, per step"}
+        # the same through s16 host PCM (what rodio's decoders yield: src/decoder/wav.rs:119-151, converted by
+        # SampleTypeConverter, src/conversions/sample.rs:42-44): half the bytes over PCIe, converted on the device at upload
+        try:
+            srcs16 = [rb.UniformSourceIterator(rb.TestSource(np.zeros(frames, np.int16), 1, IN_RATE), MIX_CH, MIX_RATE)
+                      .low_pass(LOW_PASS_HZ).amplify(AMPLIFY) for _ in range(S)]
+            batch16 = rb.Batch(srcs16, MIX_CH, MIX_RATE, flags=args.flags, ctx=ctx)
+            host16 = torch.empty(S * frames, dtype=torch.int16, pin_memory=True)
+            with torch.cuda.stream(ext):
+                tmp = torch.empty(S * frames, dtype=torch.float32, device=dev)
+                tmp.uniform_(-30000.0, 30000.0, generator=gen)
+                host16.copy_(tmp.to(torch.int16), non_blocking=False)
+            del tmp
+            mix16 = torch.as_tensor(rbd.DeviceArray(batch16.mix_device_ptr, max(1, mix_len)), device=dev)
+
+            def e2e16_step():
+                batch16.upload_packed(host16.data_ptr(), S * frames)
+                if world > 1:
+                    comm.render_mix_allreduce(batch16)
+                    with torch.cuda.stream(ext):
+                        host_out.copy_(mix16, non_blocking=True)
+                    ctx.sync()
+                else:
+                    batch16.render_mix_into(host_out.data_ptr(), mix_len)
+            for _ in range(2):
+                e2e16_step()
+            fence()
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0.record(ext)
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                e2e16_step()
+            h1.record(ext)
+            fence()
+            wall16 = (time.perf_counter() - t0) * 1e3
+            ms16 = rbd.max_over_ranks(max(h0.elapsed_time(h1), wall16) / e2e_steps, dev)
+            e2e["s16_input"] = {"value": samples_per_step / (ms16 * 1e-3) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": S * frames * 2,
+                                "d2h_bytes_per_step": mix_len * 4, "ms_per_step": ms16, "kernel_family": batch16.kernel_family,
+                                "note": "pinned host s16 PCM -> rb_batch_upload_packed -> k_convert (device) -> render -> host mix, per step"}
+            batch16.close()
+            del host16
+        except Exception as exc:   # noqa: BLE001
+            e2e["s16_input"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     # ---- the other BASELINE configurations beside it (N=1 only): every entry is one render of resident inputs, CUDA events on
     # the render stream, its own algorithmic bytes and roofline fraction; a failure is reported in place, never fatal ----
@@ -396,6 +443,50 @@ def run_ours(args):
                                           "roofline": {"bound": "hbm", "achieved": sweep["65536"]["frac"] * peak, "peak": peak, "unit": "GB/s",
                                                        "frac": sweep["65536"]["frac"], "kernel": sweep["65536"]["kernel"]}}
 
+    # ---- strong scaling beside the weak-scaling headline: a FIXED total batch sharded over the ranks (SURVEY 8d cfg3 is 4096
+    # streams in total on 8 GPUs; cfg5's large end 65 536).  Exact biquad, all-reduce inside the timed region, max over ranks. ----
+    strong = None
+    if not args.no_e2e:
+        strong = {}
+        for total, secs in ((4096, args.seconds), (65536, 1.0)):
+            try:
+                lo, hi = rbd.shard_range(total, rank, world)
+                fr = int(round(secs * IN_RATE))
+                bs = rb.Batch(make_sources(rb, hi - lo, fr), MIX_CH, MIX_RATE, flags=args.flags, ctx=ctx)
+                s0, cap0 = bs.input_device_ptr(0)
+                pitch_s = (bs.input_device_ptr(1)[0] - s0) // 4 if hi - lo > 1 else cap0
+                for i in range(hi - lo):
+                    bs.input_device_ptr(i)
+                with torch.cuda.stream(ext):
+                    torch.as_tensor(rbd.DeviceArray(s0, pitch_s * (hi - lo - 1) + cap0), device=dev).uniform_(-1.0, 1.0, generator=gen)
+                run = (lambda: comm.render_mix_allreduce(bs)) if comm is not None else bs.render_mix_device
+                for _ in range(3):
+                    run()
+                fence()
+                st = max(3, min(args.steps, 10))
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record(ext)
+                for _ in range(st):
+                    run()
+                t1.record(ext)
+                fence()
+                ms_s = rbd.max_over_ranks(t0.elapsed_time(t1) / st, dev)
+                r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                r0.record(ext)
+                for _ in range(st):
+                    bs.render_mix_device()
+                r1.record(ext)
+                fence()
+                ms_r = rbd.max_over_ranks(r0.elapsed_time(r1) / st, dev)
+                strong[f"{total}_streams_total"] = {
+                    "streams_per_gpu": hi - lo, "seconds": secs, "ms_per_step": ms_s, "render_only_ms": ms_r, "allreduce_ms": max(0.0, ms_s - ms_r),
+                    "value": total * bs.stream_out_len(0) / (ms_s * 1e-3) / 1e6, "unit": "Msamples/s", "kernel_family": bs.kernel_family,
+                    "limiter": ("recurrence latency: a stream of %d samples is a serial chain of >= 13 cycles per sample whatever the shard size" % bs.stream_out_len(0))
+                               if bs.kernel_family == 1 and hi - lo <= 4096 else "see roofline of the shard size"}
+                bs.close()
+            except Exception as exc:   # noqa: BLE001
+                strong[f"{total}_streams_total"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
     clocks = sampler.stop()   # sampled over the timed region, the kernel-only loop and the end-to-end loop
 
     # ---- CPU baseline beside it (rank 0, N=1): bounded sample of the same workload ----
@@ -430,6 +521,9 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "e2e": e2e,
             "also": also,
+            "strong_scaling": strong,
+            "allreduce": None if world == 1 else {"impl": "rb_batch_render_mix_allreduce (ncclAllReduce sum f32 on the render stream)", "floats": mix_len,
+                                                  "ms": max(0.0, ms_step - ms_kernel)},
             "gpu_launches": launches * args.steps,
             "clocks": clocks,
         }
@@ -437,6 +531,7 @@ def run_ours(args):
     batch.close()
     if world > 1:
         dist.barrier()
+        comm.close()
         dist.destroy_process_group()
 
 

@@ -7,13 +7,13 @@ the first call that needs a device fails loudly.
 """
 from . import _capi as capi
 from ._capi import RodioB200Error, lib
-from .source import (AutomaticGainControlSettings, Batch, ChannelCountConverter, ChannelVolume, Context, Duration,
+from .source import (AutomaticGainControlSettings, Batch, ChannelCountConverter, ChannelVolume, Comm, Context, Duration,
                      Effect, LimitSettings, Mixer, MixerSource, Player, SampleRateConverter, SamplesBuffer,
                      SampleTypeConverter, Session, Source, Spatial, TestSource, UniformSourceIterator, default_context, mixer, plan)
 
 __all__ = [
     "capi", "lib", "RodioB200Error", "AutomaticGainControlSettings", "Batch", "ChannelCountConverter",
-    "ChannelVolume", "Context", "Duration", "Effect", "LimitSettings", "Mixer", "MixerSource", "Player",
+    "ChannelVolume", "Comm", "Context", "Duration", "Effect", "LimitSettings", "Mixer", "MixerSource", "Player",
     "SampleRateConverter", "SamplesBuffer", "SampleTypeConverter", "Session", "Source", "Spatial", "TestSource",
     "UniformSourceIterator", "default_context", "mixer", "plan",
 ]

@@ -517,6 +517,13 @@ struct rb_batch {
     float* d_out = nullptr;
     std::vector<LaunchGroup> groups;
     rb_fused_plan* fused = nullptr;   // non-null when the fused path serves this batch
+    // Integer PCM (what decoders yield: src/decoder/wav.rs:119-151) in front of a fused plan: the batch keeps an f32 copy of the
+    // inputs resident (SampleTypeConverter, src/conversions/sample.rs:42-44, applied once per upload by k_convert), the fused
+    // kernels read that -- the host -> device copy moves 2 bytes per sample instead of 4.
+    float* d_in_f32 = nullptr;
+    rb_node_dev* d_conv_nodes = nullptr;   // one RB_N_CONVERT record per stream: raw arena -> f32 arena
+    uint64_t conv_max_n = 0;
+    bool conv_dirty = false;               // raw inputs were (re)written since the last conversion
     uint32_t launches = 0;
     bool rendered = false;
     std::vector<uint8_t> uploaded;
@@ -530,6 +537,8 @@ extern "C" rb_status rb_batch_destroy(rb_batch* b) {
     cudaStreamSynchronize(b->ctx->stream);
     if (b->fused) rb_fused_destroy(b->fused);
     cudaFree(b->d_in);
+    cudaFree(b->d_in_f32);
+    cudaFree(b->d_conv_nodes);
     cudaFree(b->d_buf[0]);
     cudaFree(b->d_buf[1]);
     cudaFree(b->d_aux[0]);
@@ -598,12 +607,22 @@ extern "C" rb_status rb_batch_create(rb_context* ctx, uint16_t mixer_ch, uint32_
     if (!(flags & RB_NO_FUSION)) {
         std::vector<rb_fused_stream> fs(n_streams);
         bool ok = true;
+        // every stream integer PCM: plan the fused kernels on a resident f32 copy (converted once per upload)
+        bool all_int = n_streams > 0;
+        for (size_t i = 0; i < n_streams; i++) all_int = all_int && b->streams[i].desc.format != RB_FMT_F32 && !b->streams[i].nodes.empty();
+        std::vector<size_t> f32_off(n_streams, 0);
+        if (all_int) {
+            size_t floats = 0;
+            for (size_t i = 0; i < n_streams; i++) f32_off[i] = floats, floats += align_up((size_t)b->streams[i].desc.n_samples + 4, 32);
+            RB_CUDA(cudaMalloc(&b->d_in_f32, std::max<size_t>(floats * sizeof(float), 256)));
+            RB_CUDA(cudaMemsetAsync(b->d_in_f32, 0, std::max<size_t>(floats * sizeof(float), 256), ctx->stream));
+        }
         for (size_t i = 0; i < n_streams && ok; i++) {
             PlanStream& ps = b->streams[order[i]];
-            fs[i].in = b->d_in + ps.in_off;
-            fs[i].fmt = ps.desc.format;
-            fs[i].n_nodes = (uint32_t)ps.nodes.size();
-            fs[i].nodes = ps.nodes.empty() ? nullptr : &ps.nodes[0].d;
+            fs[i].in = all_int ? (const void*)(b->d_in_f32 + f32_off[order[i]]) : (const void*)(b->d_in + ps.in_off);
+            fs[i].fmt = all_int ? (uint32_t)RB_FMT_F32 : ps.desc.format;
+            fs[i].n_nodes = (uint32_t)ps.nodes.size() - (all_int ? 1u : 0u);
+            fs[i].nodes = fs[i].n_nodes == 0 ? nullptr : &ps.nodes[all_int ? 1 : 0].d;
             fs[i].node_stride = sizeof(PlanNode);
             fs[i].out_len = ps.out_len;
             fs[i].mix_start = ps.mix_start;
@@ -616,6 +635,32 @@ extern "C" rb_status rb_batch_create(rb_context* ctx, uint16_t mixer_ch, uint32_
                                                 ctx->sm_count, ctx->stream, &fp);
             if (e != cudaSuccess) return fail(RB_ERR_CUDA, std::string("fused plan: ") + cudaGetErrorString(e));
             b->fused = fp;   // may be null: shape not covered -> general path
+        }
+        if (all_int && b->fused) {
+            std::vector<rb_node_dev> conv(n_streams);
+            for (size_t i = 0; i < n_streams; i++) {
+                const PlanStream& ps = b->streams[i];
+                rb_node_dev nd = ps.nodes[0].d;          // the RB_N_CONVERT the planner put in front
+                nd.src = b->d_in + ps.in_off, nd.dst = b->d_in_f32 + f32_off[i];
+                conv[i] = nd;
+                b->conv_max_n = std::max(b->conv_max_n, nd.n_out);
+            }
+            RB_CUDA(cudaMalloc(&b->d_conv_nodes, n_streams * sizeof(rb_node_dev)));
+            RB_CUDA(cudaMemcpy(b->d_conv_nodes, conv.data(), n_streams * sizeof(rb_node_dev), cudaMemcpyHostToDevice));
+            b->conv_dirty = true;
+        } else if (all_int) {
+            cudaFree(b->d_in_f32);
+            b->d_in_f32 = nullptr;
+            // no fused kernel took the f32 view: plan again on the raw format (the generic fused kernels convert at load time)
+            for (size_t i = 0; i < n_streams; i++) {
+                PlanStream& ps = b->streams[order[i]];
+                fs[i].in = b->d_in + ps.in_off, fs[i].fmt = ps.desc.format;
+                fs[i].n_nodes = (uint32_t)ps.nodes.size(), fs[i].nodes = &ps.nodes[0].d;
+            }
+            rb_fused_plan* fp = nullptr;
+            cudaError_t e = rb_fused_try_create(fs.data(), n_streams, mixer_ch, b->d_out, mix_len, flags, ctx->sm_count, ctx->stream, &fp);
+            if (e != cudaSuccess) return fail(RB_ERR_CUDA, std::string("fused plan: ") + cudaGetErrorString(e));
+            b->fused = fp;
         }
     }
 
@@ -704,6 +749,7 @@ extern "C" rb_status rb_batch_upload(rb_batch* b, size_t stream, const void* pcm
         RB_CUDA(cudaMemcpyAsync(b->d_in + ps.in_off, pcm, n_samples * fmt_size(ps.desc.format), cudaMemcpyHostToDevice,
                                 b->ctx->stream));
     b->uploaded[stream] = 1;
+    b->conv_dirty = true;
     rb_fused_inputs_changed(b->fused);
     return RB_OK;
 }
@@ -738,6 +784,7 @@ extern "C" rb_status rb_batch_upload_packed(rb_batch* b, const void* pcm, uint64
         for (size_t k = i; k < j; k++) b->uploaded[k] = 1;
         i = j;
     }
+    b->conv_dirty = true;
     rb_fused_inputs_changed(b->fused);
     return RB_OK;
 }
@@ -750,6 +797,7 @@ extern "C" rb_status rb_batch_input_device_ptr(rb_batch* b, size_t stream, void*
     *dptr = b->d_in + ps.in_off;
     if (capacity) *capacity = ps.desc.n_samples;
     b->uploaded[stream] = 1;   // the caller takes responsibility for the contents
+    b->conv_dirty = true;
     rb_fused_inputs_changed(b->fused);   // ... and asks for the pointer again after rewriting them
     return RB_OK;
 }
@@ -803,6 +851,10 @@ extern "C" rb_status rb_batch_render_mix_device(rb_batch* b) {
             return fail(RB_ERR_STATE, "stream " + std::to_string(i) + " was never uploaded");
     RB_CUDA(cudaSetDevice(b->ctx->device));
     if (b->fused) {
+        if (b->d_conv_nodes && b->conv_dirty) {   // integer PCM was uploaded: refresh the resident f32 copy
+            RB_CUDA(rb_launch_nodes(RB_N_CONVERT, b->d_conv_nodes, (uint32_t)b->streams.size(), b->conv_max_n, 1, b->ctx->stream));
+            b->conv_dirty = false;
+        }
         RB_CUDA(rb_fused_run(b->fused, b->ctx->stream));
         if (b->flags & RB_KEEP_STREAM_OUTPUTS) {
             rb_status s = run_general(b, false);

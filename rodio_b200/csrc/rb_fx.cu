@@ -21,6 +21,8 @@
 //     tile it-3    warp G    gain[n]  = clamp(gain*k + desired*(1-k), 0.1, max_gain), k = desired > gain ? attack : release
 //                                       both candidates computed, one selected: FMUL, FADD, SEL, FMNMX, FMNMX on the chain
 //     tile it-4    workers   y = e * gain, summed over the CTA's streams in insertion order -> one partial row per CTA
+// (eight worker warps, two per stream; the three chain warps share one SM sub-partition -- each of them issues an instruction
+// every four or five cycles.)
 //
 // A CTA owns FX_R = 4 consecutive streams (lane = stream in the chain warps), so that 512 streams spread over 128 SMs: the
 // chains are latency-bound and gain nothing from sharing an SM, the parallel stages need the SMs.  The 8192-entry ring of
@@ -45,7 +47,8 @@ constexpr int FX_SLOTS = 5;                // tiles in flight: front | P,S | des
 constexpr int FX_ARR = FX_R * FX_TS;       // one array of a tile
 constexpr int FX_SLOT = 4 * FX_ARR;        // e | v -> peak | sq -> sum -> desired -> gain | old sq
 constexpr size_t FX_SMEM = (size_t)FX_SLOTS * FX_SLOT * sizeof(float);
-constexpr int FX_THREADS = 7 * 32;         // warps 0, 1, 4, 5 workers (stream = worker index); 2 peak, 6 sum, 3 gain
+constexpr int FX_THREADS = 12 * 32;        // warps 3, 7, 11 (one sub-partition): the peak, sum and gain chains; the other eight are workers,
+                                           // two per stream (a half tile each)
 constexpr uint32_t RMS_WINDOW = 8192;
 
 struct FxRow {
@@ -74,13 +77,15 @@ template <int C>
 __device__ __forceinline__ float fx_cv(const FxRow& r, bool has_cv, uint64_t m) {
     // ChannelVolume over C input channels (channel_volume.rs:75-88): mono = ((0 + s0) + s1) / C, out[ch] = mono * vol[ch]
     if (!has_cv) return __ldg(r.in + m);
-    if (C == 1) return mul(divf(add(0.0f, __ldg(r.in + m)), 1.0f), r.vol[0]);
+    // (x / 1 == x and x / 2 == x * 0.5 for every x, subnormal results included: both are one rounding of the same real number)
+    if (C == 1) return mul(add(0.0f, __ldg(r.in + m)), r.vol[0]);
     const float2 fr = __ldg(reinterpret_cast<const float2*>(r.in) + (m >> 1));
-    return mul(divf(add(add(0.0f, fr.x), fr.y), 2.0f), r.vol[m & 1]);
+    return mul(mul(add(add(0.0f, fr.x), fr.y), 0.5f), (m & 1) ? r.vol[1] : r.vol[0]);
 }
-template <int C>
+template <int C, bool INTERIOR = false>   // INTERIOR: the sample and its echo tap both exist (no range checks)
 __device__ __forceinline__ float fx_e(const FxRow& r, bool has_cv, bool has_echo, uint64_t n) {
     if (!has_echo) return fx_cv<C>(r, has_cv, n);
+    if (INTERIOR) return add(fx_cv<C>(r, has_cv, n), mul(fx_cv<C>(r, has_cv, n - r.delay), r.amp));
     const float s2 = n < r.delay ? 0.0f : mul(fx_cv<C>(r, has_cv, n - r.delay), r.amp);   // Delay emits literal 0.0 first
     return n < r.n_in ? add(fx_cv<C>(r, has_cv, n), s2) : s2;
 }
@@ -108,8 +113,8 @@ __global__ void __launch_bounds__(FX_THREADS) k_fused_fx(FxArgs a) {
     __syncthreads();
     const uint32_t n_tiles = (uint32_t)((s_max_n + FX_T - 1) / FX_T);
     const bool has_cv = a.has_cv != 0, has_echo = a.has_echo != 0;
-    const int worker = warp == 0 ? 0 : warp == 1 ? 1 : warp == 4 ? 2 : warp == 5 ? 3 : -1;
-    const bool chain_p = warp == 2, chain_s = warp == 6, chain_g = warp == 3;
+    const int worker = (warp & 3u) == 3u ? -1 : (int)(warp - (warp >> 2));   // 0..8 minus the chain warps: 0,1,2,4,5,6,8,9 -> 0..7
+    const bool chain_p = warp == 3, chain_s = warp == 7, chain_g = warp == 11;
     const uint64_t mix_start = s_rows[0].mix_start;      // equal for the CTA's streams (planner)
     float* const prow = a.partial + (uint64_t)blockIdx.x * a.mix_len + mix_start;
 
@@ -121,71 +126,77 @@ __global__ void __launch_bounds__(FX_THREADS) k_fused_fx(FxArgs a) {
     const float oma = sub(1.0f, attack), omr = sub(1.0f, release);
 
     for (uint32_t it = 0; it < n_tiles + 4; it++) {
-        if (worker >= 0) {
-            // ---- front, tile `it`: stream `worker`, 8 consecutive samples per lane ----
-            if (it < n_tiles && (uint32_t)worker < cnt) {
-                const FxRow& r = s_rows[worker];
-                float* base = fx_sm + (it % FX_SLOTS) * FX_SLOT + worker * FX_TS + 8 * lane;
-                const uint64_t n0 = (uint64_t)it * FX_T + 8 * lane;
-                float e[8], v[8], q[8], o[8];
+        if (worker >= 0 && worker < 8) {   // (warp 10 is spare: it only keeps the barrier count)
+            // ---- front, tile `it`: stream worker / 2, half tile worker % 2, 4 consecutive samples per lane ----
+            const uint32_t ws = (uint32_t)worker >> 1, wo = ((uint32_t)worker & 1u) * (FX_T / 2) + 4 * lane;
+            if (it < n_tiles && ws < cnt) {
+                const FxRow& r = s_rows[ws];
+                float* base = fx_sm + (it % FX_SLOTS) * FX_SLOT + ws * FX_TS + wo;
+                const uint64_t n0 = (uint64_t)it * FX_T + wo;
+                float e[4], v[4], q[4], o[4];
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const uint64_t n = n0 + j;
-                    e[j] = v[j] = q[j] = o[j] = 0.0f;
-                    if (n < r.n_out) {
-                        e[j] = fx_e<C>(r, has_cv, has_echo, n);
-                        v[j] = fabsf(e[j]);
-                        q[j] = mul(v[j], v[j]);
-                        if (n >= RMS_WINDOW) {
-                            const float w = fabsf(fx_e<C>(r, has_cv, has_echo, n - RMS_WINDOW));
+                for (int j = 0; j < 4; j++) e[j] = v[j] = q[j] = o[j] = 0.0f;
+                if (n0 < r.n_out) {
+                    const bool interior = n0 + 4 <= r.n_in && n0 >= r.delay + RMS_WINDOW;   // every tap of every sample exists
+                    if (interior) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            e[j] = fx_e<C, true>(r, has_cv, has_echo, n0 + j);
+                            v[j] = fabsf(e[j]);
+                            q[j] = mul(v[j], v[j]);
+                            const float w = fabsf(fx_e<C, true>(r, has_cv, has_echo, n0 + j - RMS_WINDOW));
                             o[j] = mul(w, w);
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int j = 0; j < 4; j++) {
+                            const uint64_t n = n0 + j;
+                            if (n < r.n_out) {
+                                e[j] = fx_e<C>(r, has_cv, has_echo, n);
+                                v[j] = fabsf(e[j]);
+                                q[j] = mul(v[j], v[j]);
+                                if (n >= RMS_WINDOW) {
+                                    const float w = fabsf(fx_e<C>(r, has_cv, has_echo, n - RMS_WINDOW));
+                                    o[j] = mul(w, w);
+                                }
+                            }
                         }
                     }
                 }
                 *reinterpret_cast<float4*>(base) = make_float4(e[0], e[1], e[2], e[3]);
-                *reinterpret_cast<float4*>(base + 4) = make_float4(e[4], e[5], e[6], e[7]);
                 *reinterpret_cast<float4*>(base + FX_ARR) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4*>(base + FX_ARR + 4) = make_float4(v[4], v[5], v[6], v[7]);
                 *reinterpret_cast<float4*>(base + 2 * FX_ARR) = make_float4(q[0], q[1], q[2], q[3]);
-                *reinterpret_cast<float4*>(base + 2 * FX_ARR + 4) = make_float4(q[4], q[5], q[6], q[7]);
                 *reinterpret_cast<float4*>(base + 3 * FX_ARR) = make_float4(o[0], o[1], o[2], o[3]);
-                *reinterpret_cast<float4*>(base + 3 * FX_ARR + 4) = make_float4(o[4], o[5], o[6], o[7]);
             }
             // ---- desired gain, tile `it - 2` (agc.rs:413-431, :466-470): sum -> desired in place ----
-            if (it >= 2 && it - 2 < n_tiles && (uint32_t)worker < cnt) {
-                const FxRow& r = s_rows[worker];
-                float* base = fx_sm + ((it - 2) % FX_SLOTS) * FX_SLOT + worker * FX_TS + 8 * lane;
-                const float4 p0 = *reinterpret_cast<const float4*>(base + FX_ARR), p1 = *reinterpret_cast<const float4*>(base + FX_ARR + 4);
-                const float4 u0 = *reinterpret_cast<const float4*>(base + 2 * FX_ARR), u1 = *reinterpret_cast<const float4*>(base + 2 * FX_ARR + 4);
-                const float pk[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-                const float sm[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-                float d[8];
+            if (it >= 2 && it - 2 < n_tiles && ws < cnt) {
+                const FxRow& r = s_rows[ws];
+                float* base = fx_sm + ((it - 2) % FX_SLOTS) * FX_SLOT + ws * FX_TS + wo;
+                const float4 p0 = *reinterpret_cast<const float4*>(base + FX_ARR);
+                const float4 u0 = *reinterpret_cast<const float4*>(base + 2 * FX_ARR);
+                const float pk[4] = {p0.x, p0.y, p0.z, p0.w};
+                const float sm[4] = {u0.x, u0.y, u0.z, u0.w};
+                const float target = r.target, mg = r.max_gain, fl = r.floor;
+                float d[4];
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const float rms = __fsqrt_rn(divf(sm[j], 8192.0f));
-                    const float rms_gain = (rms > 0.0f) ? divf(r.target, rms) : r.max_gain;
-                    const float peak_gain = (pk[j] > 0.0f) ? fminf(divf(r.target, pk[j]), r.max_gain) : r.max_gain;
-                    d[j] = fmaxf(fminf(rms_gain, peak_gain), r.floor);
+                for (int j = 0; j < 4; j++) {
+                    const float rms = __fsqrt_rn(mul(sm[j], 1.0f / 8192.0f));     // sum / 8192: a power of two, the product is the quotient
+                    const float rms_gain = (rms > 0.0f) ? divf(target, rms) : mg;
+                    const float peak_gain = (pk[j] > 0.0f) ? fminf(divf(target, pk[j]), mg) : mg;
+                    d[j] = fmaxf(fminf(rms_gain, peak_gain), fl);
                 }
                 *reinterpret_cast<float4*>(base + 2 * FX_ARR) = make_float4(d[0], d[1], d[2], d[3]);
-                *reinterpret_cast<float4*>(base + 2 * FX_ARR + 4) = make_float4(d[4], d[5], d[6], d[7]);
             }
-            // ---- out, tile `it - 4`: y = e * gain, summed over the CTA's streams; worker w takes positions [64 w, 64 w + 64) ----
+            // ---- out, tile `it - 4`: y = e * gain, summed over the CTA's streams; one position per worker lane ----
             if (it >= 4) {
                 const float* base = fx_sm + ((it - 4) % FX_SLOTS) * FX_SLOT;
-                const uint32_t pos = 64 * worker + 2 * lane;
+                const uint32_t pos = 32 * (uint32_t)worker + lane;
                 const uint64_t n = (uint64_t)(it - 4) * FX_T + pos;
-                float acc0 = 0.0f, acc1 = 0.0f;
-                bool any0 = false, any1 = false;
-                for (uint32_t s = 0; s < cnt; s++) {
-                    const uint64_t no = s_rows[s].n_out;
-                    const float2 ev = *reinterpret_cast<const float2*>(base + s * FX_TS + pos);
-                    const float2 gv = *reinterpret_cast<const float2*>(base + 2 * FX_ARR + s * FX_TS + pos);
-                    if (n < no) acc0 = add(acc0, mul(ev.x, gv.x)), any0 = true;
-                    if (n + 1 < no) acc1 = add(acc1, mul(ev.y, gv.y)), any1 = true;
-                }
-                if (any0 && mix_start + n < a.mix_len) prow[n] = acc0;
-                if (any1 && mix_start + n + 1 < a.mix_len) prow[n + 1] = acc1;
+                float acc = 0.0f;
+                bool any = false;
+                for (uint32_t s = 0; s < cnt; s++)
+                    if (n < s_rows[s].n_out) acc = add(acc, mul(base[s * FX_TS + pos], base[2 * FX_ARR + s * FX_TS + pos])), any = true;
+                if (any && mix_start + n < a.mix_len) prow[n] = acc;
             }
         } else if (it >= 1 && it - 1 < n_tiles && (chain_p || chain_s)) {
             // ---- chains P and S, tile `it - 1`, lane = stream ----

@@ -188,7 +188,7 @@ cudaError_t rb_lanes_launch_kernel(const lanes::Args& a, uint32_t ch_in, uint32_
 // k_fused_duo over a.rows: a.n_groups counts groups of 64 rows
 cudaError_t rb_duo_launch_kernel(const lanes::Args& a, bool has_biquad, bool ff2, bool has_post, cudaStream_t st) {
     if (a.mix_len == 0 || a.n_groups == 0) return cudaSuccess;
-    static const bool split = []() { const char* e = getenv("RB_DUO_SPLIT"); return e ? atoi(e) != 0 : true; }();
+    static const bool split = []() { const char* e = getenv("RB_DUO_SPLIT"); return e ? atoi(e) != 0 : false; }();   // measured: the pair is slower (profiles/README.md), kept for A/B runs
     if (split) {
         const dim3 g(a.n_groups), b(64);
         if (has_biquad) {

@@ -326,6 +326,44 @@ class Context:
             self._h = C.c_void_p()
 
 
+class Comm:
+    """The cross-shard mixer sum (include/rodio_b200.h rb_comm_*): NCCL, called by the library on the context's stream.
+    One process per GPU: rank 0 calls Comm.unique_id() and hands the bytes to the others (torchrun: broadcast_object_list),
+    every rank builds Comm(ctx, n_ranks, rank, id).  One process, several GPUs: Comm.all([ctx0, ctx1, ...])."""
+
+    def __init__(self, ctx: Context, n_ranks: int, rank: int, id_bytes: bytes):
+        assert len(id_bytes) == 128
+        self._h = C.c_void_p()
+        self._ctxs = [ctx]
+        buf = (C.c_char * 128).from_buffer_copy(id_bytes)
+        check(lib().rb_comm_init_rank(ctx._h, n_ranks, rank, buf, C.byref(self._h)), "rb_comm_init_rank")
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_char * 128)()
+        check(lib().rb_comm_unique_id(buf), "rb_comm_unique_id")
+        return bytes(buf)
+
+    @classmethod
+    def all(cls, ctxs: Sequence[Context]) -> "Comm":
+        self = cls.__new__(cls)
+        self._h, self._ctxs = C.c_void_p(), list(ctxs)
+        arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+        check(lib().rb_comm_init_all(arr, len(ctxs), C.byref(self._h)), "rb_comm_init_all")
+        return self
+
+    def render_mix_allreduce(self, batches):
+        """Render the batch of every local rank and sum the mixes over all ranks in place (asynchronous like a render)."""
+        batches = [batches] if isinstance(batches, Batch) else list(batches)
+        arr = (C.c_void_p * len(batches))(*[b._h for b in batches])
+        check(lib().rb_batch_render_mix_allreduce(arr, len(batches), self._h), "rb_batch_render_mix_allreduce")
+
+    def close(self):
+        if self._h:
+            lib().rb_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+
 _default_ctx: dict = {}
 
 

@@ -266,3 +266,29 @@ def test_time_parallel_plan_4096_streams(ctx, lp, q, family):
         e_ref = float(np.max(np.abs(ref256 - truth)))
         e_tp = float(np.max(np.abs(got256 - truth)))
         assert e_tp <= 1.5 * e_ref + 1e-7 * float(np.max(np.abs(truth))), (e_tp, e_ref)
+
+
+# ------------------------------------------------------------------ integer PCM in front of the fused kernels
+def test_integer_pcm_keeps_a_resident_f32_copy(ctx):
+    """s16 sources (what decoders yield, src/decoder/wav.rs:119-151) through the cfg3 chain: the batch converts once per upload
+    (SampleTypeConverter, src/conversions/sample.rs:42-44) and the f32 kernels serve it -- same family, same bits as the oracle's
+    conversion + chain; a second upload is converted again."""
+    n, frames = 600, 3000
+    rng = np.random.default_rng(3)
+
+    def make(seed):
+        return [(rng.integers(-30000, 30000, frames)).astype(np.int16) for _ in range(n)]
+    pcm_a, pcm_b = make(1), make(2)
+    mk = lambda pcm: [rb.UniformSourceIterator(rb.TestSource(x, 1, 44100), 1, 48000).low_pass(300).amplify(0.9) for x in pcm]
+    srcs = mk(pcm_a)
+    with rb.Batch(srcs, 1, 48000, ctx=ctx) as b:
+        assert b.kernel_family == 1, b.kernel_family            # k_fused_hot on the f32 copy, not the generic integer kernel
+        group = b.mix_group
+        b.upload_all()
+        got_a = b.render_mix()
+        for i, x in enumerate(pcm_b):                            # upload other PCM into the same batch
+            b.upload(i, x)
+        got_b = b.render_mix()
+    for pcm, got in ((pcm_a, got_a), (pcm_b, got_b)):
+        per = [oracle.chain_uniform(to_oracle(s), 1, 48000) for s in mk(pcm)]
+        assert_bit_exact(got, grouped_expected_mix(per, [0] * n, got.size, group), "s16 input through the f32 kernels")

@@ -113,6 +113,13 @@ def main():
                     if nm == "k_fused_lanes" and S < 8192:
                         continue
                     time_batch(f"duo sweep S={S} x {secs}s: uniform(1,48k) -> {label} -> mix [{nm}]", srcs, (1, 48000), flags=fl, steps=5)
+    if "tp" in which:
+        # the two plans that cut the timeline into segments: time-parallel low_pass(1000) and the filter-free chain, 4096 x 2 s
+        x = z(44100 * 2)
+        srcs = [rb.UniformSourceIterator(rb.TestSource(x, 1, 44100), 1, 48000).low_pass(1000).amplify(1.2) for _ in range(4096)]
+        time_batch("tp: 4096 x 2s low_pass(1000) time-parallel", srcs, (1, 48000), flags=rb.capi.RB_BIQUAD_TIME_PARALLEL, steps=10)
+        srcs = [rb.UniformSourceIterator(rb.TestSource(x, 1, 44100), 1, 48000).amplify(1.2) for _ in range(4096)]
+        time_batch("tp: 4096 x 2s no filter (segments)", srcs, (1, 48000), steps=10)
     if "lanes_shapes" in which:
         # the lane kernel on the shapes added after its first device runs: stereo (ring geometry: see RB_LANES_STEREO_CHW in
         # rb_lanes_core.h, A/B via RODIO_B200_LIB), mono sources in a stereo mixer, and the chain the way rodio users write it
