@@ -58,3 +58,25 @@ def test_plain_c_example_compiles_against_the_header(built, name):
     subprocess.run(["gcc", "-std=c11", "-D_GNU_SOURCE", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
                     "-L", lib_dir, "-l:librodio_b200.so", f"-Wl,-rpath,{lib_dir}", "-lm"], check=True, capture_output=True)
     assert os.path.exists(exe)
+
+
+SRC_COMM = os.path.join(ROOT, "tests", "cpp", "test_comm_two_gpus.cpp")
+EXE_COMM = os.path.join(ROOT, "tests", "cpp", "test_comm_two_gpus.bin")
+
+
+def test_comm_test_compiles_and_links(built):
+    _build(SRC_COMM, EXE_COMM)
+    assert os.path.exists(EXE_COMM)
+
+
+@pytest.mark.gpu
+def test_comm_allreduce_through_the_c_abi(built):
+    """rb_comm_init_all + rb_batch_render_mix_allreduce: two GPUs driven by one process when the box has them (gpurun --gpus 2),
+    a one-rank communicator otherwise (the same entry points, NCCL loaded, no exchange)."""
+    import torch
+    if not os.path.exists(EXE_COMM):
+        _build(SRC_COMM, EXE_COMM)
+    n = 2 if torch.cuda.device_count() >= 2 else 1
+    r = subprocess.run([EXE_COMM, str(n)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all communicator tests passed" in r.stdout
