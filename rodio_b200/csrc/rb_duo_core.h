@@ -44,11 +44,22 @@ using lanes::TILE;
 using lanes::RUN_CAP;
 using lanes::MIN_RUN_TILES;
 
-// Ring slots per stream.  4: chunk c-1 (draining), c, c+1, c+2 (in flight) -- two chunks of look-ahead.  3 (default): ONE chunk
-// of look-ahead (a chunk is two tiles of work, several HBM latencies at the measured pace) and 68 instead of 84 words per
-// stream: 12 instead of 10 warps per SM -- the kernel is bound by the latency of its warps, not by HBM (profiles/README.md).
+// Ring slots per stream.  4 (default): chunk c-1 (draining), c, c+1, c+2 (in flight) -- two chunks of look-ahead.  3: ONE chunk
+// of look-ahead and 68 instead of 84 words per stream (12 instead of 10 warps per SM).  Measured: 3 slots are slower at every
+// batch size (0.526 against 0.544 of the roofline at 65 536 streams, 0.41 against 0.44 on the time-parallel plan): one chunk
+// of look-ahead does not cover the HBM latency under load.
+//
+// Bank conflicts.  Every lane reads its tap at the same ring offset (the streams of a warp are in phase), and the rings of lanes
+// l and l + 8 start a multiple of 32 words apart (RS is a multiple of 4: the cp.async destinations must be 16-byte aligned), so
+// a tap load was a four-way conflict -- 64 of the 93 shared-memory wavefronts of a tile, on a pipe that ncu showed 42 % busy
+// with the warps queueing behind it (short scoreboard ~ 1 stall per issue).  The ring of lane l is therefore ROTATED by
+// l / 8 quads: logical word x lives at physical word (x + 4 (l / 8)) mod RING -- still whole 16-byte quads for the copies,
+// and lanes l, l + 8, l + 16, l + 24 now hit four different banks.
 #ifndef RB_DUO_SLOTS
-#define RB_DUO_SLOTS 3
+#define RB_DUO_SLOTS 4
+#endif
+#ifndef RB_DUO_ROTATE
+#define RB_DUO_ROTATE 0u
 #endif
 static_assert(RB_DUO_SLOTS == 3 || RB_DUO_SLOTS == 4, "3 (one chunk ahead) or 4 (two chunks ahead)");
 constexpr int NSLOT = RB_DUO_SLOTS;
@@ -184,9 +195,12 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp, simt::f2
                 for (int j = 0; j < NCOPY; j++) {
                     const uint32_t off = want < mqc[j] ? want : mqc[j];
                     const float* s = (const float*)(uintptr_t)sq[j] + 4ull * off;
-                    float* dst = ring_warp + chalf * HALF_WORDS + ((cr >> 1) + 4u * (uint32_t)j) * RS + sl * CHW + cq * 4;
+                    const uint32_t tl = (cr >> 1) + 4u * (uint32_t)j;                        // the lane that owns the stream
+                    uint32_t pq = sl * QPC + cq + RB_DUO_ROTATE * (tl >> 3);                 // physical quad: rotated by tl / 8
+                    pq = pq >= (uint32_t)(RING / 4) ? pq - (uint32_t)(RING / 4) : pq;
+                    float* dst = ring_warp + chalf * HALF_WORDS + tl * RS + pq * 4;
                     simt::cp16(dst, s);
-                    if (sl == 0 && (int)(cq * 4) < MIRROR) simt::cp16(dst + RING, s);
+                    if ((int)(pq * 4) < MIRROR) simt::cp16(dst + RING, s);
                 }
                 simt::cp_commit();
             };
@@ -200,7 +214,7 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp, simt::f2
             uint32_t c_ready = 1;   // chunks [0, c_ready) are readable; c_ready (and, two ahead, c_ready + 1) are in flight
             float* const ringl = ring_warp + ln * RS;
             const simt::sptr ring_end = simt::sptr_of(ringl + RING);
-            simt::sptr p = simt::sptr_of(ringl + k0);
+            simt::sptr p = simt::sptr_of(ringl + k0 + RB_DUO_ROTATE * 4u * (ln >> 3));   // the lane's rotation (see "Bank conflicts")
             f2 X0 = simt::pack2(0.f, 0.f), X1 = X0;
             if (DO_A) {
                 X0 = simt::pack2(simt::lds(p), simt::lds(simt::sptr_add(p, HALF_WORDS)));

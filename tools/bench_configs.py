@@ -113,6 +113,11 @@ def main():
                     if nm == "k_fused_lanes" and S < 8192:
                         continue
                     time_batch(f"duo sweep S={S} x {secs}s: uniform(1,48k) -> {label} -> mix [{nm}]", srcs, (1, 48000), flags=fl, steps=5)
+    if "cfg5big" in which:
+        one = z(44100)
+        for S in (16384, 32768, 65536):
+            srcs = [rb.UniformSourceIterator(rb.TestSource(one, 1, 44100), 1, 48000).low_pass(200).amplify(1.2) for _ in range(S)]
+            time_batch(f"cfg5 S={S} x 1s low_pass(200) [RB_FUSED_DUO]", srcs, (1, 48000), flags=rb.capi.RB_FUSED_DUO, steps=5)
     if "tp" in which:
         # the two plans that cut the timeline into segments: time-parallel low_pass(1000) and the filter-free chain, 4096 x 2 s
         x = z(44100 * 2)
