@@ -49,17 +49,12 @@ using lanes::MIN_RUN_TILES;
 // batch size (0.526 against 0.544 of the roofline at 65 536 streams, 0.41 against 0.44 on the time-parallel plan): one chunk
 // of look-ahead does not cover the HBM latency under load.
 //
-// Bank conflicts.  Every lane reads its tap at the same ring offset (the streams of a warp are in phase), and the rings of lanes
-// l and l + 8 start a multiple of 32 words apart (RS is a multiple of 4: the cp.async destinations must be 16-byte aligned), so
-// a tap load was a four-way conflict -- 64 of the 93 shared-memory wavefronts of a tile, on a pipe that ncu showed 42 % busy
-// with the warps queueing behind it (short scoreboard ~ 1 stall per issue).  The ring of lane l is therefore ROTATED by
-// l / 8 quads: logical word x lives at physical word (x + 4 (l / 8)) mod RING -- still whole 16-byte quads for the copies,
-// and lanes l, l + 8, l + 16, l + 24 now hit four different banks.
+// Bank conflicts.  Every lane reads its tap at the same ring offset (the streams of a warp are in phase) and the rings start on
+// 16-byte boundaries (cp.async), so the 32 addresses of a tap load share their residue modulo 4 words: only 8 of the 32 banks can
+// be hit -- a four-way conflict whatever the stride or rotation of the rings (a rotation by l / 8 quads was tried: the same banks,
+// more instructions, 4-10 % slower).  64 of the 93 shared-memory wavefronts of a tile are these loads.
 #ifndef RB_DUO_SLOTS
 #define RB_DUO_SLOTS 4
-#endif
-#ifndef RB_DUO_ROTATE
-#define RB_DUO_ROTATE 0u
 #endif
 static_assert(RB_DUO_SLOTS == 3 || RB_DUO_SLOTS == 4, "3 (one chunk ahead) or 4 (two chunks ahead)");
 constexpr int NSLOT = RB_DUO_SLOTS;
@@ -195,12 +190,9 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp, simt::f2
                 for (int j = 0; j < NCOPY; j++) {
                     const uint32_t off = want < mqc[j] ? want : mqc[j];
                     const float* s = (const float*)(uintptr_t)sq[j] + 4ull * off;
-                    const uint32_t tl = (cr >> 1) + 4u * (uint32_t)j;                        // the lane that owns the stream
-                    uint32_t pq = sl * QPC + cq + RB_DUO_ROTATE * (tl >> 3);                 // physical quad: rotated by tl / 8
-                    pq = pq >= (uint32_t)(RING / 4) ? pq - (uint32_t)(RING / 4) : pq;
-                    float* dst = ring_warp + chalf * HALF_WORDS + tl * RS + pq * 4;
+                    float* dst = ring_warp + chalf * HALF_WORDS + ((cr >> 1) + 4u * (uint32_t)j) * RS + sl * CHW + cq * 4;
                     simt::cp16(dst, s);
-                    if ((int)(pq * 4) < MIRROR) simt::cp16(dst + RING, s);
+                    if (sl == 0 && (int)(cq * 4) < MIRROR) simt::cp16(dst + RING, s);
                 }
                 simt::cp_commit();
             };
@@ -214,7 +206,7 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp, simt::f2
             uint32_t c_ready = 1;   // chunks [0, c_ready) are readable; c_ready (and, two ahead, c_ready + 1) are in flight
             float* const ringl = ring_warp + ln * RS;
             const simt::sptr ring_end = simt::sptr_of(ringl + RING);
-            simt::sptr p = simt::sptr_of(ringl + k0 + RB_DUO_ROTATE * 4u * (ln >> 3));   // the lane's rotation (see "Bank conflicts")
+            simt::sptr p = simt::sptr_of(ringl + k0);
             f2 X0 = simt::pack2(0.f, 0.f), X1 = X0;
             if (DO_A) {
                 X0 = simt::pack2(simt::lds(p), simt::lds(simt::sptr_add(p, HALF_WORDS)));

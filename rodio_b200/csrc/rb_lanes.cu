@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(LANES_THREADS) k_fused_lanes(lanes::Args a) {
 
 // The lane-pair kernel (rb_duo_core.h): a warp = 64 mono streams, packed f32x2 arithmetic.
 #ifndef RB_DUO_WARPS
-#define RB_DUO_WARPS 2
+#define RB_DUO_WARPS 1
 #endif
 constexpr int DUO_WARPS = RB_DUO_WARPS;   // every warp is independent; one per CTA balances 6.9 warps per SM (65 536 streams) as 7 : 6, not 8 : 6
 constexpr size_t DUO_SMEM = (size_t)DUO_WARPS * duo::WARP_WORDS * sizeof(float);   // 17.0 KB

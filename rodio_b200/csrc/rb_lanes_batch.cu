@@ -77,9 +77,9 @@ bool plan_time_parallel(const rb_lanes_stream* streams, const std::vector<uint32
     for (size_t k = 0; k + 1 < cls.size(); k++)   // every stream in phase with its neighbour: any two may share a lane
         if ((streams[cls[k]].mix_start % (4ull * to)) != (streams[cls[k + 1]].mix_start % (4ull * to))) return false;
     const uint32_t W = has_biquad ? lanes::tp_warmup(rmax) : 0u;
-    // segments: enough rows to fill the machine (8 groups of 64 rows per SM), but never shorter than 8 warm-ups
+    // segments: enough rows to fill the machine (7 groups of 64 rows per SM), but never shorter than 8 warm-ups
     // (2048 frames without a filter: a run has to be worth priming the rings for)
-    uint64_t warps_per_sm = 8;       // groups of 64 rows per SM: what the registers of the split pair leave room for (8 CTAs of 2 warps)
+    uint64_t warps_per_sm = 7;       // groups of 64 rows per SM (10 fit: one wave with room to spare); measured best among 7 ... 24
     if (const char* e = getenv("RB_TP_WARPS_PER_SM")) warps_per_sm = std::max<uint64_t>(1, (uint64_t)atoll(e));
     const uint64_t want_rows = 64ull * (uint64_t)(sm_count > 0 ? sm_count : 148) * warps_per_sm;
     uint64_t K = (want_rows + S - 1) / S;
