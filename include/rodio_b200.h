@@ -142,7 +142,7 @@ enum {
                                           (exact serial recurrence).  rb_batch_kernel_family tells which: 4 = time-parallel */
     RB_KEEP_STREAM_OUTPUTS = 1u << 3,  /* also keep every stream's post-chain (pre-mix) samples in HBM so
                                           rb_batch_read_stream can return them                                */
-    RB_FUSED_LANES = 1u << 4,          /* large batches (chosen automatically from ~277 sources per SM on): serve
+    RB_FUSED_LANES = 1u << 4,          /* large batches (chosen automatically from ~128 sources per SM on): serve
                                           [amplify] -> resample -> [low/high_pass] -> [amplify] -> mix, or the chain with the
                                           filter in front of the conversion ([amplify] -> low/high_pass -> [amplify] ->
                                           resample -> [amplify] -> mix: chosen automatically from 32 sources per SM on, no

@@ -56,6 +56,12 @@ using lanes::MIN_RUN_TILES;
 #ifndef RB_DUO_SLOTS
 #define RB_DUO_SLOTS 4
 #endif
+#ifndef RB_DUO_SCALAR_B
+#define RB_DUO_SCALAR_B 0   // A/B knobs of the fast run, see the pipeline below
+#endif
+#ifndef RB_DUO_ORDER
+#define RB_DUO_ORDER 0
+#endif
 static_assert(RB_DUO_SLOTS == 3 || RB_DUO_SLOTS == 4, "3 (one chunk ahead) or 4 (two chunks ahead)");
 constexpr int NSLOT = RB_DUO_SLOTS;
 constexpr bool ONE_AHEAD = RB_DUO_SLOTS == 3;
@@ -280,11 +286,20 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp, simt::f2
                     XH2 = XH1, XH1 = x;
                 }
                 f2 y = tt;
+#if RB_DUO_SCALAR_B
+                if (HASB) {   // A/B knob: the recurrence as two scalar chains (4-cycle dependent issue, 1-cycle pipe) instead of one packed one
+                    const float yl = lanes::fb(simt::lo2(A1), simt::lo2(A2), simt::lo2(tt), simt::lo2(Y1), simt::lo2(Y2), simt::lo2(NEG1));
+                    const float yh = lanes::fb(simt::hi2(A1), simt::hi2(A2), simt::hi2(tt), simt::hi2(Y1), simt::hi2(Y2), simt::hi2(NEG1));
+                    y = simt::pack2(yl, yh);
+                    Y2 = Y1, Y1 = y;
+                }
+#else
                 if (HASB) {
                     // (t - a1*y1) - a2*y2, src/source/blt.rs:558-560
                     y = simt::fma2(simt::mul2(A2, Y2), NEG1, simt::fma2(simt::mul2(A1, Y1), NEG1, tt));
                     Y2 = Y1, Y1 = y;
                 }
+#endif
                 const f2 val = NPOST ? simt::mul2(y, POST) : y;
                 v = simt::fadd(simt::lo2(val), simt::hi2(val));
             };
@@ -369,8 +384,13 @@ SIMT_FN void warp_main(const Args& a, uint32_t group, float* ring_warp, simt::f2
                 refill();
 #pragma unroll
                 for (int f = 0; f < TF; f++) {
+#if RB_DUO_ORDER == 1
+                    step_b(tin[f], vout[f]);
+                    step_a(tout[f]);
+#else
                     step_a(tout[f]);
                     step_b(tin[f], vout[f]);
+#endif
                     stage_c(f == 0 ? 0 : f == 2 ? 1 : f == 4 ? 2 : f == 5 ? 3 : f == 6 ? 4 : f == 7 ? 5 : -1, vred, pos);
                 }
             };

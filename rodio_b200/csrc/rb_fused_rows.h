@@ -166,9 +166,10 @@ static bool fused_parse_rows(const rb_fused_stream* streams, size_t n_streams, u
     return true;
 }
 
-// The lane-per-stream kernel takes the batch when RB_FUSED_LANES asks for it, or from about 277 streams per SM on, where it
-// is the faster kernel anyway (measured: 65 536 x 1 s in 4.26 ms against 7.0 ms for k_fused_hot, 16 384 x 1 s in 2.46 ms
-// against 1.74 ms).  *lanes stays NULL when the shape is not the kernel's.
+// The lane kernels take the batch when RB_FUSED_LANES / RB_FUSED_DUO ask for them, or from 128 streams per SM on (18 944 on a
+// B200), where they are the faster kernels anyway (measured, profiles/README.md round 2: k_fused_duo 1.96 / 2.14 / 3.25 ms at
+// 16 384 / 32 768 / 65 536 streams x 1 s against 1.76 / 3.51 / 7.0 ms for k_fused_hot).  *lanes stays NULL when the shape is not
+// the kernels'.
 static cudaError_t fused_lanes_hook(const std::vector<FusedRow>& rows, size_t n_streams, uint16_t mixer_channels, bool all_f32,
                                     uint32_t n_pre, uint32_t n_mid, uint32_t n_post, uint32_t has_u, uint32_t has_b, uint32_t front,
                                     uint32_t flags, int sm_count, float* d_out, uint64_t mix_len, cudaStream_t st, rb_lanes_plan** lanes) {
@@ -176,7 +177,7 @@ static cudaError_t fused_lanes_hook(const std::vector<FusedRow>& rows, size_t n_
     // A filter in front of the conversion has no other fused kernel: the alternative is the general path (one kernel per adapter,
     // intermediates in HBM: 24.5 ms against 0.85 ms on cfg3), so the lane kernel takes such a batch as soon as every SM gets a warp.
     const size_t sms = (size_t)(sm_count > 0 ? sm_count : 148);
-    const bool want_lanes = (flags & (RB_FUSED_LANES | RB_FUSED_DUO)) || n_streams >= 277 * sms || (front && n_streams >= 32 * sms);
+    const bool want_lanes = (flags & (RB_FUSED_LANES | RB_FUSED_DUO)) || n_streams >= 128 * sms || (front && n_streams >= 32 * sms);
     // RB_BIQUAD_TIME_PARALLEL: the lane kernels serve the batch cut into timeline segments when it qualifies (rb_lanes_batch.cu);
     // when it does not, the flag changes nothing
     bool want_tp = (flags & RB_BIQUAD_TIME_PARALLEL) && has_b && !front && mixer_channels == 1;

@@ -21,8 +21,8 @@
 //     tile it-3    warp G    gain[n]  = clamp(gain*k + desired*(1-k), 0.1, max_gain), k = desired > gain ? attack : release
 //                                       both candidates computed, one selected: FMUL, FADD, SEL, FMNMX, FMNMX on the chain
 //     tile it-4    workers   y = e * gain, summed over the CTA's streams in insertion order -> one partial row per CTA
-// (eight worker warps, two per stream; the three chain warps share one SM sub-partition -- each of them issues an instruction
-// every four or five cycles.)
+// (eight worker warps, two per stream; the gain chain has a sub-partition to itself: sharing one with the other two chains cost it a
+// third of its pace -- 19 instructions per sample from three warps that each want a slot every 4.3 cycles.)
 //
 // A CTA owns FX_R = 4 consecutive streams (lane = stream in the chain warps), so that 512 streams spread over 128 SMs: the
 // chains are latency-bound and gain nothing from sharing an SM, the parallel stages need the SMs.  The 8192-entry ring of
@@ -47,8 +47,8 @@ constexpr int FX_SLOTS = 5;                // tiles in flight: front | P,S | des
 constexpr int FX_ARR = FX_R * FX_TS;       // one array of a tile
 constexpr int FX_SLOT = 4 * FX_ARR;        // e | v -> peak | sq -> sum -> desired -> gain | old sq
 constexpr size_t FX_SMEM = (size_t)FX_SLOTS * FX_SLOT * sizeof(float);
-constexpr int FX_THREADS = 12 * 32;        // warps 3, 7, 11 (one sub-partition): the peak, sum and gain chains; the other eight are workers,
-                                           // two per stream (a half tile each)
+constexpr int FX_THREADS = 15 * 32;        // sub-partition 3: warp 3 = the gain chain, alone (its 5 dependent operations per sample set the pace);
+                                           // sub-partition 2: warps 2, 6 = peak and sum chains beside two workers; 0 and 1: three workers each
 constexpr uint32_t RMS_WINDOW = 8192;
 
 struct FxRow {
@@ -113,8 +113,9 @@ __global__ void __launch_bounds__(FX_THREADS) k_fused_fx(FxArgs a) {
     __syncthreads();
     const uint32_t n_tiles = (uint32_t)((s_max_n + FX_T - 1) / FX_T);
     const bool has_cv = a.has_cv != 0, has_echo = a.has_echo != 0;
-    const int worker = (warp & 3u) == 3u ? -1 : (int)(warp - (warp >> 2));   // 0..8 minus the chain warps: 0,1,2,4,5,6,8,9 -> 0..7
-    const bool chain_p = warp == 3, chain_s = warp == 7, chain_g = warp == 11;
+    // warps 0,4,8 | 1,5,9 | 10,14 are the eight workers; 2 = peak, 6 = sum, 3 = gain; 7, 11, 12, 13 only keep the barrier count
+    const int worker = warp == 0 ? 0 : warp == 4 ? 1 : warp == 8 ? 2 : warp == 1 ? 3 : warp == 5 ? 4 : warp == 9 ? 5 : warp == 10 ? 6 : warp == 14 ? 7 : -1;
+    const bool chain_p = warp == 2, chain_s = warp == 6, chain_g = warp == 3;
     const uint64_t mix_start = s_rows[0].mix_start;      // equal for the CTA's streams (planner)
     float* const prow = a.partial + (uint64_t)blockIdx.x * a.mix_len + mix_start;
 
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(FX_THREADS) k_fused_fx(FxArgs a) {
     const float oma = sub(1.0f, attack), omr = sub(1.0f, release);
 
     for (uint32_t it = 0; it < n_tiles + 4; it++) {
-        if (worker >= 0 && worker < 8) {   // (warp 10 is spare: it only keeps the barrier count)
+        if (worker >= 0) {
             // ---- front, tile `it`: stream worker / 2, half tile worker % 2, 4 consecutive samples per lane ----
             const uint32_t ws = (uint32_t)worker >> 1, wo = ((uint32_t)worker & 1u) * (FX_T / 2) + 4 * lane;
             if (it < n_tiles && ws < cnt) {
@@ -194,8 +195,9 @@ __global__ void __launch_bounds__(FX_THREADS) k_fused_fx(FxArgs a) {
                 const uint64_t n = (uint64_t)(it - 4) * FX_T + pos;
                 float acc = 0.0f;
                 bool any = false;
-                for (uint32_t s = 0; s < cnt; s++)
-                    if (n < s_rows[s].n_out) acc = add(acc, mul(base[s * FX_TS + pos], base[2 * FX_ARR + s * FX_TS + pos])), any = true;
+#pragma unroll
+                for (uint32_t s = 0; s < FX_R; s++)
+                    if (n < s_rows[s].n_out) acc = add(acc, mul(base[s * FX_TS + pos], base[2 * FX_ARR + s * FX_TS + pos])), any = true;   // absent rows: n_out = 0
                 if (any && mix_start + n < a.mix_len) prow[n] = acc;
             }
         } else if (it >= 1 && it - 1 < n_tiles && (chain_p || chain_s)) {

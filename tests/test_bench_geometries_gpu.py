@@ -1,6 +1,6 @@
 """Parity at the launch geometries the bench lines are quoted on ("parity gaps" 1, 2, 4):
 cfg3 with 4096 mono streams (k_fused_hot, 28 rows per CTA incl. the second-row warps), its stereo and filter-free
-twins, the automatically selected lane kernel at >= 277 streams per SM, cfg2 at 1024 sources, cfg4 at 512 streams.
+twins, the automatically selected large-batch kernel (>= 128 streams per SM), cfg2 at 1024 sources, cfg4 at 512 streams.
 Streams are short (the oracle finishes in seconds); the launch configuration is the one of the full-length run
 because it depends on the number of streams only.
 
@@ -87,7 +87,7 @@ def test_nofilter_bench_geometry_mono_4096(ctx):
 
 
 def test_cfg5_auto_selected_large_batch(ctx):
-    """No flag, 41 000 streams (>= 277 per SM): the planner hands the batch to the large-batch kernels on its own (mono
+    """No flag, 41 000 streams (>= 128 per SM): the planner hands the batch to the large-batch kernels on its own (mono
     sources that start together: the lane-pair kernel)."""
     _check_fused(ctx, _cfg3(41000, 600, seed=35000), 1, family=3)
 
