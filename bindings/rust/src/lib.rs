@@ -211,6 +211,7 @@ extern "C" {
     fn rb_session_push_packed(s: *mut rb_session, pcm: *const f32, n_frames: *const u64, end_of_stream: *const u8) -> i32;
     fn rb_session_render(s: *mut rb_session, out: *mut f32, max_frames: u64, written: *mut u64, ended: *mut i32) -> i32;
     fn rb_session_follow(s: *mut rb_session, stream: usize, predecessor: usize) -> i32;
+    fn rb_session_skip(s: *mut rb_session, stream: usize) -> i32;
     fn rb_session_set_volume(s: *mut rb_session, stream: usize, factor: f32) -> i32;
     fn rb_session_get_state(s: *mut rb_session, buf: *mut c_void, cap: u64, size: *mut u64) -> i32;
     fn rb_session_set_state(s: *mut rb_session, buf: *const c_void, size: u64) -> i32;

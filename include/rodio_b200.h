@@ -292,6 +292,12 @@ rb_status rb_session_start(rb_session* s, size_t stream);
  * Each source keeps its own chain and rate pair (the queue's sounds need not share a format).  Sources end on whole frames
  * here, so the queue's padding of a sound that ends mid-frame and its keep-alive silence do not arise. */
 rb_status rb_session_follow(rb_session* s, size_t stream, size_t predecessor);
+/* Player::skip_one / Player::stop / Skippable::skip for one source (src/player.rs:138-166, :253-276; src/source/skippable.rs): the
+ * source's iterator returns None from now on -- its input ends with the last frame the mixer's converter has pulled (what
+ * has been pushed beyond is dropped, later pushes are refused), the converter emits what it still owes (the last frame raw,
+ * src/conversions/sample_rate.rs:187-199) and the source is finished; a source queued behind it (rb_session_follow) starts right
+ * after.  A held source that is skipped never plays. */
+rb_status rb_session_skip(rb_session* s, size_t stream);
 /* Amplify::set_factor (src/source/amplify.rs:25-29) on the AMPLIFY of a live source's chain: the gain is `factor` from the
  * next rendered block on (a source without an AMPLIFY behaves as amplify(1.0)).  Player::set_volume does the same to its
  * own Amplify every 5 ms of audio (src/player.rs:138-166) -- but that one sits in FRONT of the mixer's resampler

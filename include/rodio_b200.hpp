@@ -295,6 +295,7 @@ class LiveMixer {
     void add(size_t i) { check(rb_session_start(h_, i), "rb_session_start"); }
     // queue a held source behind another one: Player::append / queue.rs:128-192
     void append_after(size_t i, size_t predecessor) { check(rb_session_follow(h_, i, predecessor), "rb_session_follow"); }
+    void skip(size_t i) { check(rb_session_skip(h_, i), "rb_session_skip"); }   // Player::skip_one / stop
     // Amplify::set_factor on the chain's .amplify() (amplify.rs:25-29); Player::set_volume's Amplify sits before the resampler
     void set_amplify(size_t i, float factor) { check(rb_session_set_amplify(h_, i, factor), "rb_session_set_amplify"); }
     // Player::set_volume: the AMPLIFY in front of the mixer's conversion (src/player.rs:120-128, :180-186)

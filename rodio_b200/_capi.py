@@ -94,6 +94,7 @@ SYMBOLS = {
     "rb_session_push_packed": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rb_session_start": (C.c_int32, [C.c_void_p, C.c_size_t]),
     "rb_session_follow": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_size_t]),
+    "rb_session_skip": (C.c_int32, [C.c_void_p, C.c_size_t]),
     "rb_session_set_amplify": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_float]),
     "rb_session_set_volume": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_float]),
     "rb_session_available": (C.c_int32, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),

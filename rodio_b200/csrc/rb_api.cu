@@ -1406,6 +1406,13 @@ extern "C" rb_status rb_session_follow(rb_session* s, size_t stream, size_t pred
     return RB_OK;
 }
 
+extern "C" rb_status rb_session_skip(rb_session* s, size_t stream) {
+    if (!s) return fail(RB_ERR_INVALID_ARGUMENT, "session is NULL");
+    if (stream >= s->st.size()) return fail(RB_ERR_INVALID_ARGUMENT, "stream index out of range");
+    session::skip(s->st[s->pos[stream]]);
+    return RB_OK;
+}
+
 extern "C" rb_status rb_session_set_amplify(rb_session* s, size_t stream, float factor) {
     if (!s) return fail(RB_ERR_INVALID_ARGUMENT, "session is NULL");
     if (stream >= s->st.size()) return fail(RB_ERR_INVALID_ARGUMENT, "stream index out of range");

@@ -30,7 +30,6 @@
 #include <vector>
 
 #include "rb_dsp.cuh"
-#include "rb_lanes_plan.h"
 #include "rb_fused.h"
 #include "rb_lanes.h"
 #include "rb_fused_rows.h"   // FusedRow, ROW_*, TT, MAX_GAINS, parse_row, fused_lanes_hook (host-visible: also run by the CPU suite)
@@ -704,9 +703,7 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
         uint32_t num = ht.r0 + lane_r;
         uint32_t di = lane_q;
         if (num >= to) num -= to, di += 1;
-        // warp-uniform (planned by the loader).  Rows whose inputs lie outside the exact-reciprocal class (classified once per
-        // upload, k_classify_hot_rows) never take the blocked path: the strided path below divides with __fdiv_rn.
-        const bool interior = ht.interior != 0 && r.unsafe == 0u;
+        const bool interior = ht.interior != 0;   // warp-uniform (planned by the loader): the vote below needs the whole warp
         if (interior) {
             const float* __restrict__ w = win + ht.woff + di * C;
 #ifdef RB_HOT_TIMING
@@ -715,6 +712,7 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
             const uint32_t step_w = r.q32 * C;            // whole frames per output frame, in words
             const float r1f = __uint2float_rn(r.r32);
             float nf = __uint2float_rn(num);
+            bool bad = false;
             float xv[P];
 #pragma unroll
             for (int f = 0; f < F; f++) {
@@ -729,20 +727,20 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
                 for (int c = 0; c < C; c++) {
                     const float a0 = gains<NOGAIN>(x0[c], pre, n_pre), a1 = gains<NOGAIN>(x1[c], pre, n_pre);
                     const float m = mul(sub(a1, a0), nfc);
-                    // exact reciprocal step: within the input class (and a gain-free chain in front) m is 0 or in [2^-100, 2^100),
-                    // where q is the correctly rounded m / den (rb_lanes_core.h "Exact division"); with gains in front of the
-                    // interpolation the class no longer bounds the taps: those chains keep the checked form
                     const float q0 = mul(m, rcp_den);
-                    float q = __fmaf_rn(__fmaf_rn(-q0, den_f, m), rcp_den, q0);
-                    q = m == 0.0f ? m : q;                // (-0) / den = -0: the reciprocal step would give +0
-                    if (!NOGAIN) {
-                        const uint32_t e = __float_as_uint(m) & 0x7fffffffu;
-                        if (!(e == 0u || e - 0x0d800000u < 0x64000000u)) q = divf(m, den_f);
-                    }
-                    xv[f * C + c] = gains<NOGAIN>(add(a0, q), mid, n_mid);
+                    const float q = __fmaf_rn(__fmaf_rn(-q0, den_f, m), rcp_den, q0);
+                    // guarded range as one unsigned compare on the exponent field: 2^-100 <= |m| < 2^100; m == 0
+                    // (also outside) yields q = m = +-0 exactly as the division would
+                    const uint32_t e = __float_as_uint(m) & 0x7fffffffu;
+                    const bool in_range = e - 0x0d800000u < 0x64000000u;
+#ifdef RB_HOT_TIMING
+                    if (!(g_hot_skip & 32))               // ablation: no range check
+#endif
+                    bad |= !in_range && e != 0u;
+                    xv[f * C + c] = gains<NOGAIN>(add(a0, in_range ? q : m), mid, n_mid);
                 }
             }
-            {
+            if (!__any_sync(0xffffffffu, bad)) {
                 float tv[P];
                 if constexpr (HASB) {
                     float pv[2 * C];
@@ -753,27 +751,11 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
                     }
 #pragma unroll
                     for (int j = 0; j < 2 * C; j++) xtail[j] = __shfl_sync(0xffffffffu, xv[P - 2 * C + j], 31);
-                    const float ffk = r.ffk;
-                    if (ffk != 0.0f) {
-                        // b1*x1 == ffk*(b0*x1) and b2*x2 == b0*x2 exactly (lanes::ff2_coeffs): one product per sample, the same roundings
-                        float pp[P], pq[2 * C];
 #pragma unroll
-                        for (int u = 0; u < P; u++) pp[u] = mul(b0, xv[u]);
-#pragma unroll
-                        for (int j = 0; j < 2 * C; j++) pq[j] = mul(b0, pv[j]);
-#pragma unroll
-                        for (int u = 0; u < P; u++) {
-                            const float p1 = u >= C ? pp[u >= C ? u - C : 0] : pq[C + u < 2 * C ? C + u : 0];
-                            const float p2 = u >= 2 * C ? pp[u >= 2 * C ? u - 2 * C : 0] : pq[u < 2 * C ? u : 0];
-                            tv[u] = add(__fmaf_rn(p1, ffk, pp[u]), p2);
-                        }
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < P; u++) {
-                            const float xm1 = u >= C ? xv[u >= C ? u - C : 0] : pv[C + u < 2 * C ? C + u : 0];
-                            const float xm2 = u >= 2 * C ? xv[u >= 2 * C ? u - 2 * C : 0] : pv[u < 2 * C ? u : 0];
-                            tv[u] = biquad_ff(b0, b1, b2, xv[u], xm1, xm2);
-                        }
+                    for (int u = 0; u < P; u++) {
+                        const float xm1 = u >= C ? xv[u >= C ? u - C : 0] : pv[C + u < 2 * C ? C + u : 0];
+                        const float xm2 = u >= 2 * C ? xv[u >= 2 * C ? u - 2 * C : 0] : pv[u < 2 * C ? u : 0];
+                        tv[u] = biquad_ff(b0, b1, b2, xv[u], xm1, xm2);
                     }
                 } else {
 #pragma unroll
@@ -784,6 +766,7 @@ __device__ __forceinline__ void hot_stage_a(const FusedRow& r, const HotTile& ht
                 for (int u = 0; u < P; u += 4) o[u / 4] = make_float4(tv[u], tv[u + 1], tv[u + 2], tv[u + 3]);
                 done = true;
             }
+            // else: some operand was denormal / huge / NaN: redo this row-tile with IEEE divisions
         }
     }
     if (done) return;
@@ -1142,28 +1125,6 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
     HOT_TIMING_END
 }
 
-// One CTA per row of a HOT plan: does every non-zero |x| of the row's f32 input lie inside [2^-70, 2^60]?  (Once per upload.)
-__global__ void __launch_bounds__(256) k_classify_hot_rows(FusedRow* rows, uint32_t n_rows) {
-    const uint32_t r = blockIdx.x;
-    if (r >= n_rows) return;
-    const float* __restrict__ x = (const float*)rows[r].in;
-    const uint64_t L = rows[r].n_in;
-    bool bad = false;
-    auto out_of_class = [](float v) {
-        const uint32_t u = __float_as_uint(v) & 0x7fffffffu;
-        return u != 0u && (u - 0x1c800000u) >= (0x5d800000u - 0x1c800000u);
-    };
-    const uint64_t n4 = L / 4;
-    const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
-    for (uint64_t i = threadIdx.x; i < n4; i += blockDim.x) {
-        const float4 v = __ldg(x4 + i);
-        bad |= out_of_class(v.x) | out_of_class(v.y) | out_of_class(v.z) | out_of_class(v.w);
-    }
-    for (uint64_t i = n4 * 4 + threadIdx.x; i < L; i += blockDim.x) bad |= out_of_class(__ldg(x + i));
-    const int any = __syncthreads_or(bad ? 1 : 0);
-    if (threadIdx.x == 0) rows[r].unsafe = any ? 1u : 0u;
-}
-
 // ordered sum of the per-CTA partial rows
 __global__ void __launch_bounds__(256) k_sum_partials(const float* __restrict__ partial, uint32_t n_ctas,
                                                       uint64_t mix_len, float* __restrict__ out) {
@@ -1192,7 +1153,6 @@ struct rb_fused_plan {
     bool single_cta_direct = false;
     bool all_f32 = true;
     bool hot = false;
-    bool hot_classified = false;      // k_classify_hot_rows has seen the inputs that are resident now
     size_t hot_smem = 0;
     rb_lanes_plan* lanes = nullptr;   // RB_FUSED_LANES: the lane-per-stream kernel serves the batch (rb_lanes.cu)
     rb_fx_plan* fx = nullptr;         // the effect-chain kernel serves the batch (rb_fx.cu)
@@ -1272,9 +1232,6 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     if (plan->hot) {
         for (size_t i = 0; i < n_streams; i++) {
             FusedRow& r = rows[i];
-            r.unsafe = 1u;                          // until k_classify_hot_rows has seen the inputs
-            float k = 0.0f;
-            r.ffk = (has_b && lanes::ff2_coeffs(r.b0, r.b1, r.b2, &k)) ? k : 0.0f;
             r.q32 = r.uni.from / r.uni.to;          // HOT rows: the per-frame step
             r.r32 = r.uni.from % r.uni.to;
             r.qT = (uint32_t)((uint64_t)(TT / C) * r.uni.from / r.uni.to);
@@ -1345,7 +1302,6 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
 
 void rb_fused_inputs_changed(rb_fused_plan* p) {
     if (p && p->lanes) rb_lanes_inputs_changed(p->lanes);
-    if (p) p->hot_classified = false;
 }
 
 cudaError_t rb_fused_run(rb_fused_plan* p, cudaStream_t st) {
@@ -1353,10 +1309,6 @@ cudaError_t rb_fused_run(rb_fused_plan* p, cudaStream_t st) {
     if (p->lanes) return rb_lanes_run(p->lanes, st);
     const FusedArgs& a = p->args;
     if (p->hot) {
-        if (!p->hot_classified) {   // the inputs were (re)written: which rows may use the unguarded reciprocal division?
-            k_classify_hot_rows<<<a.n_rows, 256, 0, st>>>(p->d_rows, a.n_rows);
-            p->hot_classified = true;
-        }
         if (a.c_mix == 1) {
             if (a.has_biquad) k_fused_hot<1, true><<<p->n_ctas, 1024, p->hot_smem, st>>>(a);
             else k_fused_hot<1, false><<<dim3(p->n_ctas, p->grid_y), 1024, p->hot_smem, st>>>(a);

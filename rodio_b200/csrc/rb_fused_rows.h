@@ -31,14 +31,8 @@ struct FusedRow {                  // one stream, device side
     float mid[MAX_GAINS];          // gains between the uniform conversion and the biquad
     float post[MAX_GAINS];         // gains after the biquad
     float b0, b1, b2, a1, a2;
-    uint32_t unsafe;               // k_fused_hot: set by k_classify_hot_rows when some input sample lies outside the class in which the
-                                   // exact-reciprocal division of the interpolation is correctly rounded (every non-zero |x| in
-                                   // [2^-70, 2^60], as for the lane kernels): the row then takes the IEEE-division path on every tile
-    float ffk;                     // low_pass / high_pass: b1 == ffk * b0 (ffk = +-2) and b2 == b0 -> feed-forward with one product per
-                                   // sample (lanes::ff2_coeffs); 0: plain three-product form
-    uint32_t pad2_[1];
+    uint32_t pad_[1];
 };
-
 enum : uint32_t {
     ROW_GENERIC = 0,   // exact closed form per sample (span chunks, trailing partial frames, huge ratios)
     ROW_DIRECT = 1,    // no conversion at all: out[o] = in[o]

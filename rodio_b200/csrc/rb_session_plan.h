@@ -126,6 +126,15 @@ inline void start(Stream& s, uint64_t T) {
     if (s.held) s.held = false, s.mix_start = T;
 }
 
+// Skippable::skip / Player::skip_one / stop: the source's iterator returns None from now on.  The mixer's converter has pulled
+// frames [0, fpos) of it (the right neighbour of the last rendered output included): those are its whole input now, the rest
+// of the FIFO is forgotten.  A held source (or one that has rendered nothing yet: fpos = 0) ends empty.
+inline void skip(Stream& s) {
+    s.pushed = std::min(s.pushed, std::max(s.fpos, s.i0));
+    s.eof = true;
+    if (s.held) s.held = false, s.follows = -1, s.pushed = s.i0 = s.fpos = 0, s.out_done = 0, s.mix_start = 0;
+}
+
 // After the block: advance the stream and tell how many FIFO frames (from the front) are dead.
 inline uint64_t advance(Stream& s, const Part& p) {
     if (p.out_len) {   // the converter (and a filter in front of it) stands behind the right neighbour of the block's last output

@@ -581,6 +581,10 @@ class Session:
         """Queue a held source behind another one (Player::append): it starts on the frame after that one has played out."""
         check(lib().rb_session_follow(self._h, stream, predecessor), "rb_session_follow")
 
+    def skip(self, stream: int):
+        """Player::skip_one / stop for this source: it ends with the last frame the converter has pulled (rb_session_skip)."""
+        check(lib().rb_session_skip(self._h, stream), "rb_session_skip")
+
     def set_amplify(self, stream: int, factor: float):
         """Amplify::set_factor on the chain's AMPLIFY of a live source: applies from the next rendered block on."""
         check(lib().rb_session_set_amplify(self._h, stream, float(factor)), "rb_session_set_amplify")

@@ -222,6 +222,56 @@ def s_held_and_queued_across_state_blob():
     assert_bit_exact(got, expected(pcms, ch, rates, 1, 48000, [0, len0, marks[2], marks[3]], 500, 1.1), "held / queued sources across a hand-over")
 
 
+def s_skip_one():
+    """Player::skip_one / stop (rb_session_skip): the current sound ends with the last frame the mixer's converter has pulled -- the
+    converter still emits what it owes (the last frame raw) --, the queued one starts right behind it, another voice plays on."""
+    rates = [44100, 32000, 48000]
+    pcms = [noise(6000, 4300), noise(1500, 4301), noise(5000, 4302)]
+    ch = [1, 1, 1]
+    srcs = [chain(np.zeros(0, np.float32), 1, r, 1, 48000, 800, 0.9) for r in rates]
+    with rb.Session(srcs, 48000, fifo_frames=8192, max_block_frames=256, mix_starts=[0, HELD, 0]) as s:
+        s.follow(1, 0)
+        got = []
+        s.push(0, pcms[0][:2500])
+        s.push(1, pcms[1], end_of_stream=True)
+        s.push(2, pcms[2][:2600])
+        for _ in range(6):
+            block, _ = s.render(256)
+            got.append(block)
+        n0 = sum(b.size for b in got)                   # outputs of source 0 rendered so far (it started at 0)
+        assert n0 > 0
+        s.skip(0)
+        fpos = min(((n0 - 1) * 147) // 160 + 2, 2500)   # frames the converter had pulled: its whole input now
+        s.push(2, pcms[2][2600:], end_of_stream=True)
+        try:
+            s.push(0, pcms[0][2500:])
+        except rb.RodioB200Error:
+            pass
+        else:
+            raise AssertionError("a push into a skipped source was accepted")
+        while True:
+            block, ended = s.render(256)
+            got.append(block)
+            if block.size == 0 or ended:
+                break
+    got = np.concatenate(got)
+    cut = [pcms[0][:fpos], pcms[1], pcms[2]]
+    len0 = oracle.chain_uniform(to_oracle(chain(cut[0], 1, rates[0], 1, 48000, 800, 0.9)), 1, 48000).size
+    assert_bit_exact(got, expected(cut, ch, rates, 1, 48000, [0, len0, 0], 800, 0.9), "skip_one: the sound ends where the converter stood")
+    # a held source that is skipped never plays
+    with rb.Session(srcs[:2], 48000, fifo_frames=4096, max_block_frames=256, mix_starts=[0, HELD]) as s:
+        s.push(0, pcms[1], end_of_stream=True)
+        s.push(1, pcms[2][:1000], end_of_stream=True)
+        s.skip(1)
+        got = []
+        while True:
+            block, ended = s.render(256)
+            got.append(block)
+            if block.size == 0 or ended:
+                break
+    assert_bit_exact(np.concatenate(got), expected([pcms[1]], [1], [rates[0]], 1, 48000, [0], 800, 0.9), "a skipped held source never plays")
+
+
 def s_filtered_and_plain_sources():
     """A low-passed source beside an untouched one (examples/stream_mixer.c): classes of their own, two launches."""
     pcms = [noise(2 * 900, 51), noise(1000, 52), noise(2 * 700, 53), noise(800, 54)]
@@ -676,7 +726,7 @@ def s_random(seed=0, cases=6):
 
 SCENARIOS = {"mono_random_split": s_mono_random_split, "mixed_with_state_blob": s_mixed_everything_with_state_blob,
              "held_queue_gain_speed": s_held_queue_gain_speed, "follow_after_played_out": s_follow_after_predecessor_played_out,
-             "held_across_state_blob": s_held_and_queued_across_state_blob, "duo_batches": s_duo_batches, "time_parallel_plan": s_time_parallel_plan, "gain_changes": s_gain_changes, "filtered_and_plain": s_filtered_and_plain_sources,
+             "held_across_state_blob": s_held_and_queued_across_state_blob, "skip_one": s_skip_one, "duo_batches": s_duo_batches, "time_parallel_plan": s_time_parallel_plan, "gain_changes": s_gain_changes, "filtered_and_plain": s_filtered_and_plain_sources,
              "batch_with_identity_conversions": s_batch_with_identity_conversions, "batch_unsorted_starts": s_batch_unsorted_starts, "errors": s_errors,
              "gain_in_front": s_gain_in_front_of_the_conversion, "filter_in_front": s_filter_in_front_of_the_conversion, "player_volume": s_player_volume_changes}
 

@@ -23,7 +23,7 @@ def hostemu(built):
     return build_emu.host_lib()
 
 
-@pytest.mark.parametrize("scenario", ["errors", "mono_random_split", "mixed_with_state_blob", "held_queue_gain_speed", "follow_after_played_out", "held_across_state_blob", "duo_batches", "time_parallel_plan", "gain_changes",
+@pytest.mark.parametrize("scenario", ["errors", "mono_random_split", "mixed_with_state_blob", "held_queue_gain_speed", "follow_after_played_out", "held_across_state_blob", "skip_one", "duo_batches", "time_parallel_plan", "gain_changes",
                                       "filtered_and_plain", "batch_with_identity_conversions",
                                       "batch_unsorted_starts", "gain_in_front", "filter_in_front", "player_volume", "random:5"])
 def test_session_host_code_on_the_emulator(hostemu, scenario):
