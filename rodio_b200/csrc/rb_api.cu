@@ -1198,6 +1198,8 @@ extern "C" rb_status rb_session_create(rb_context* ctx, uint16_t mixer_channels,
         return fail(RB_ERR_INVALID_ARGUMENT, "zero mixer rate / channels or no streams");
     if (mixer_channels > 2) return fail(RB_ERR_UNSUPPORTED, "sessions serve mono and stereo mixers");
     if (fifo_frames < 64 || max_block_frames == 0) return fail(RB_ERR_INVALID_ARGUMENT, "fifo_frames < 64 or max_block_frames == 0");
+    if ((uint64_t)fifo_frames * RB_MAX_CHANNELS >= (1ull << 32))   // per-stream float counts travel as 32-bit words
+        return fail(RB_ERR_OUT_OF_MEMORY, "fifo_frames too large (fifo_frames * channels must stay below 2^32)");
     std::unique_ptr<rb_session, rb_status (*)(rb_session*)> s(new (std::nothrow) rb_session, rb_session_destroy);
     if (!s) return fail(RB_ERR_OUT_OF_MEMORY, "host allocation failed");
     s->ctx = ctx, s->mixer_rate = mixer_rate, s->channels = mixer_channels, s->fifo_cap = fifo_frames, s->max_block = max_block_frames;
@@ -1493,7 +1495,21 @@ extern "C" rb_status rb_session_render(rb_session* s, float* out_host, uint64_t 
         g0 += a.n_groups;
     }
     RB_CUDA(rb_lanes_launch_sum(s->d_partial, n_groups_total, pstride, n * C, s->d_out, stq));
-    // the host already knows what every stream consumed: compact the FIFOs into the other arena behind the kernel
+    // the host already knows what every stream consumed: compact the FIFOs into the other arena behind the kernel.
+    // The bookkeeping is advanced here and committed by the synchronisation below: when a CUDA call in between fails, the
+    // snapshot comes back, so that FIFO positions, volumes and T never run ahead of what the device has done.
+    const std::vector<session::Stream> st_before = s->st;
+    const std::vector<float> va_before = s->vol_a, vb_before = s->vol_b;
+    const uint32_t cur_before = s->cur;
+    auto roll_back = [&]() { s->st = st_before, s->vol_a = va_before, s->vol_b = vb_before, s->cur = cur_before; };
+#define RB_CUDA_TX(call)                                                                              \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            roll_back();                                                                              \
+            return fail(RB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));             \
+        }                                                                                             \
+    } while (0)
     for (size_t r = 0; r < ns; r++) {
         const uint64_t fill_before = s->st[r].fill(), pulled_before = s->st[r].fpos;
         const uint64_t drop = session::advance(s->st[r], parts[r]);
@@ -1504,11 +1520,12 @@ extern "C" rb_status rb_session_render(rb_session* s, float* out_host, uint64_t 
         else if (pulled == 1) s->vol_a[r] = s->vol_b[r], s->vol_b[r] = vol;
         s->h_u32[r] = (uint32_t)(drop * s->src_ch[r]), s->h_u32[ns + r] = (uint32_t)((fill_before - drop) * s->src_ch[r]);   // floats
     }
-    RB_CUDA(cudaMemcpyAsync(s->d_u32, s->h_u32, 2 * ns * sizeof(uint32_t), cudaMemcpyHostToDevice, stq));
-    RB_CUDA(rb_lanes_fifo_compact(fifo, s->d_fifo[s->cur ^ 1], s->stride, s->d_u32, s->d_u32 + ns, (uint32_t)ns, stq));
+    RB_CUDA_TX(cudaMemcpyAsync(s->d_u32, s->h_u32, 2 * ns * sizeof(uint32_t), cudaMemcpyHostToDevice, stq));
+    RB_CUDA_TX(rb_lanes_fifo_compact(fifo, s->d_fifo[s->cur ^ 1], s->stride, s->d_u32, s->d_u32 + ns, (uint32_t)ns, stq));
     s->cur ^= 1;
-    RB_CUDA(cudaMemcpyAsync(s->h_out, s->d_out, n * C * sizeof(float), cudaMemcpyDeviceToHost, stq));
-    RB_CUDA(cudaStreamSynchronize(stq));
+    RB_CUDA_TX(cudaMemcpyAsync(s->h_out, s->d_out, n * C * sizeof(float), cudaMemcpyDeviceToHost, stq));
+    RB_CUDA_TX(cudaStreamSynchronize(stq));
+#undef RB_CUDA_TX
     memcpy(out_host, s->h_out, n * C * sizeof(float));
     s->T += n;
     *written = n;
