@@ -212,6 +212,9 @@ extern "C" {
     fn rb_session_render(s: *mut rb_session, out: *mut f32, max_frames: u64, written: *mut u64, ended: *mut i32) -> i32;
     fn rb_session_follow(s: *mut rb_session, stream: usize, predecessor: usize) -> i32;
     fn rb_session_skip(s: *mut rb_session, stream: usize) -> i32;
+    // WAV ingest: where the samples of a RIFF/WAVE image are and in which rb_sample_format (host only)
+    fn rb_wav_parse(image: *const c_void, image_bytes: u64, out: *mut rb_wav_info) -> i32;
+    fn rb_wav_unpack24(packed: *const c_void, n_samples: u64, out_i24_in_i32: *mut i32);
     fn rb_session_set_volume(s: *mut rb_session, stream: usize, factor: f32) -> i32;
     fn rb_session_get_state(s: *mut rb_session, buf: *mut c_void, cap: u64, size: *mut u64) -> i32;
     fn rb_session_set_state(s: *mut rb_session, buf: *const c_void, size: u64) -> i32;

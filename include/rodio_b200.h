@@ -352,6 +352,27 @@ float rb_linear_to_db(float linear);
 void rb_spatial_volumes(const float emitter[3], const float left_ear[3], const float right_ear[3],
                         float out_volumes[2]);
 
+/* ---- WAV ingest (host only; src/decoder/wav.rs:119-151 reads 8 / 16 / 24 / 32-bit integer and 32-bit float PCM and hands
+ * every sample to dasp's to_sample()): rb_wav_parse finds the format and the sample data inside a RIFF/WAVE image so that the
+ * bytes of an `assets/*.wav` go to HBM as they are (rb_batch_upload with `format`) and are converted on the device by the same
+ * rules (8-bit WAV is unsigned: RB_FMT_U8 = hound's i8 after its -128).  24-bit samples are packed in 3 bytes: `format` is then
+ * RB_FMT_I24_IN_I32 and `packed24` is set -- widen them with rb_wav_unpack24 first. ---- */
+typedef struct rb_wav_info {
+    uint32_t sample_rate;
+    uint16_t channels;
+    uint16_t bits_per_sample;
+    uint16_t format;        /* rb_sample_format of the samples (after rb_wav_unpack24 when packed24) */
+    uint16_t packed24;      /* 1: the data chunk holds 3-byte little-endian samples */
+    uint32_t pad_;
+    uint64_t data_offset;   /* byte offset of the first sample inside the image */
+    uint64_t data_bytes;    /* bytes of sample data present in the image (a truncated file is cut to whole samples) */
+    uint64_t n_samples;     /* interleaved samples */
+} rb_wav_info;
+/* RB_ERR_INVALID_ARGUMENT: not a RIFF/WAVE image or no fmt / data chunk; RB_ERR_UNSUPPORTED: a sample format rodio's decoder
+ * does not read either (compressed tags, float widths other than 32, more than 32 integer bits). */
+rb_status rb_wav_parse(const void* image, uint64_t image_bytes, rb_wav_info* out);
+void rb_wav_unpack24(const void* packed, uint64_t n_samples, int32_t* out_i24_in_i32);
+
 #ifdef __cplusplus
 }
 #endif

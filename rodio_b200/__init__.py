@@ -7,7 +7,7 @@ the first call that needs a device fails loudly.
 """
 from . import _capi as capi
 from ._capi import RodioB200Error, lib
-from .source import (AutomaticGainControlSettings, Batch, ChannelCountConverter, ChannelVolume, Comm, Context, Duration,
+from .source import (AutomaticGainControlSettings, Batch, ChannelCountConverter, ChannelVolume, Comm, Context, Duration, wav_source,
                      Effect, LimitSettings, Mixer, MixerSource, Player, SampleRateConverter, SamplesBuffer,
                      SampleTypeConverter, Session, Source, Spatial, TestSource, UniformSourceIterator, default_context, mixer, plan)
 
@@ -15,5 +15,5 @@ __all__ = [
     "capi", "lib", "RodioB200Error", "AutomaticGainControlSettings", "Batch", "ChannelCountConverter",
     "ChannelVolume", "Comm", "Context", "Duration", "Effect", "LimitSettings", "Mixer", "MixerSource", "Player",
     "SampleRateConverter", "SamplesBuffer", "SampleTypeConverter", "Session", "Source", "Spatial", "TestSource",
-    "UniformSourceIterator", "default_context", "mixer", "plan",
+    "UniformSourceIterator", "default_context", "mixer", "plan", "wav_source",
 ]

@@ -128,6 +128,57 @@ static uint32_t f32_as_u32(float v) {  // Rust `as u32`
 }
 }  // namespace hostmath
 
+// ---- WAV ingest: where the samples are and what they are (src/decoder/wav.rs:119-151 names the formats rodio reads) ----
+extern "C" rb_status rb_wav_parse(const void* image, uint64_t n, rb_wav_info* out) {
+    if (!image || !out) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
+    const uint8_t* p = (const uint8_t*)image;
+    auto u16 = [&](uint64_t o) { return (uint32_t)p[o] | ((uint32_t)p[o + 1] << 8); };
+    auto u32 = [&](uint64_t o) { return u16(o) | (u16(o + 2) << 16); };
+    if (n < 12 || memcmp(p, "RIFF", 4) != 0 || memcmp(p + 8, "WAVE", 4) != 0) return fail(RB_ERR_INVALID_ARGUMENT, "not a RIFF/WAVE image");
+    memset(out, 0, sizeof(*out));
+    bool have_fmt = false, have_data = false;
+    uint32_t tag = 0;
+    for (uint64_t o = 12; o + 8 <= n;) {
+        const uint64_t len = u32(o + 4), body = o + 8;
+        if (memcmp(p + o, "fmt ", 4) == 0) {
+            if (len < 16 || body + 16 > n) return fail(RB_ERR_INVALID_ARGUMENT, "WAV: truncated fmt chunk");
+            tag = u16(body), out->channels = (uint16_t)u16(body + 2), out->sample_rate = u32(body + 4), out->bits_per_sample = (uint16_t)u16(body + 14);
+            if (tag == 0xFFFEu) {   // WAVE_FORMAT_EXTENSIBLE: the real tag is the first two bytes of the sub-format GUID
+                if (len < 40 || body + 40 > n) return fail(RB_ERR_INVALID_ARGUMENT, "WAV: truncated extensible fmt chunk");
+                tag = u16(body + 24);
+            }
+            have_fmt = true;
+        } else if (memcmp(p + o, "data", 4) == 0) {
+            out->data_offset = body;
+            out->data_bytes = body + len <= n ? len : n - body;
+            have_data = true;
+            break;
+        }
+        o = body + len + (len & 1);   // chunks are word aligned
+    }
+    if (!have_fmt || !have_data) return fail(RB_ERR_INVALID_ARGUMENT, "WAV: no fmt or no data chunk");
+    if (out->channels == 0 || out->sample_rate == 0) return fail(RB_ERR_INVALID_ARGUMENT, "WAV: zero channels or sample rate");
+    const uint32_t bits = out->bits_per_sample;
+    if (tag == 3u && bits == 32) out->format = RB_FMT_F32;
+    else if (tag == 1u && bits == 8) out->format = RB_FMT_U8;
+    else if (tag == 1u && bits == 16) out->format = RB_FMT_I16;
+    else if (tag == 1u && bits == 24) out->format = RB_FMT_I24_IN_I32, out->packed24 = 1;
+    else if (tag == 1u && bits == 32) out->format = RB_FMT_I32;
+    else return fail(RB_ERR_UNSUPPORTED, "WAV: a sample format rodio's decoder does not read (tag " + std::to_string(tag) + ", " + std::to_string(bits) + " bits)");
+    const uint64_t bytes_per = bits / 8;
+    out->n_samples = out->data_bytes / bytes_per;
+    out->n_samples -= out->n_samples % out->channels;    // whole frames
+    out->data_bytes = out->n_samples * bytes_per;
+    return RB_OK;
+}
+extern "C" void rb_wav_unpack24(const void* packed, uint64_t n_samples, int32_t* out) {
+    const uint8_t* p = (const uint8_t*)packed;
+    for (uint64_t i = 0; i < n_samples; i++) {
+        const uint32_t v = (uint32_t)p[3 * i] | ((uint32_t)p[3 * i + 1] << 8) | ((uint32_t)p[3 * i + 2] << 16);
+        out[i] = (int32_t)(v << 8) >> 8;   // sign-extend bit 23
+    }
+}
+
 extern "C" uint32_t rb_speed_sample_rate(uint32_t input_rate, float factor) {  // src/source/speed.rs:130-133
     volatile float r = (float)input_rate * factor;
     return hostmath::f32_as_u32(fmaxf(r, 1.0f));

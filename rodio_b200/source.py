@@ -152,6 +152,7 @@ class Source:
         self.effects: List[Effect] = list(effects or [])
         self._channels = int(cur_channels if cur_channels is not None else channels)
         self._rate = int(cur_rate if cur_rate is not None else sample_rate)
+        self.fmt_override: Optional[int] = None     # rb_sample_format the dtype cannot tell (24-bit values in int32)
 
     # -- metadata the trait reports --------------------------------------------------------
     def channels(self) -> int:
@@ -161,9 +162,11 @@ class Source:
         return self._rate
 
     def _with(self, e: Effect, channels=None, rate=None) -> "Source":
-        return Source(self.pcm, self.base_channels, self.base_rate, self.span_len, self.effects + [e],
-                      channels if channels is not None else self._channels,
-                      rate if rate is not None else self._rate)
+        out = Source(self.pcm, self.base_channels, self.base_rate, self.span_len, self.effects + [e],
+                     channels if channels is not None else self._channels,
+                     rate if rate is not None else self._rate)
+        out.fmt_override = self.fmt_override
+        return out
 
     # -- adapters ---------------------------------------------------------------------------
     def amplify(self, value: float) -> "Source":
@@ -272,6 +275,30 @@ class TestSource(Source):
 
     def __init__(self, samples, channels: int, sample_rate: int):
         super().__init__(np.asarray(samples), channels, sample_rate, span_len=0)
+
+
+class WavInfo(C.Structure):
+    _fields_ = [("sample_rate", C.c_uint32), ("channels", C.c_uint16), ("bits_per_sample", C.c_uint16), ("format", C.c_uint16),
+                ("packed24", C.c_uint16), ("pad_", C.c_uint32), ("data_offset", C.c_uint64), ("data_bytes", C.c_uint64),
+                ("n_samples", C.c_uint64)]
+
+
+def wav_source(image: bytes) -> Source:
+    """Decoder::new_wav(..) as far as this path goes (src/decoder/wav.rs:119-151): the samples of a RIFF/WAVE image in their own
+    format -- s16, u8, s32, f32, or 24-bit widened to i24-in-i32 -- as a Source; the conversion to f32 happens on the device by
+    dasp's rules (rb_wav_parse / rb_wav_unpack24)."""
+    info = WavInfo()
+    buf = (C.c_char * len(image)).from_buffer_copy(image)
+    check(lib().rb_wav_parse(buf, len(image), C.byref(info)), "rb_wav_parse")
+    raw = np.frombuffer(image, dtype=np.uint8, count=info.data_bytes, offset=info.data_offset)
+    if info.packed24:
+        out = np.empty(info.n_samples, dtype=np.int32)
+        lib().rb_wav_unpack24(raw.ctypes.data_as(C.c_void_p), info.n_samples, out.ctypes.data_as(C.c_void_p))
+        src = Source(out, info.channels, info.sample_rate, span_len=0)
+        src.fmt_override = capi.RB_FMT_I24_IN_I32
+        return src
+    dt = {capi.RB_FMT_F32: np.float32, capi.RB_FMT_I16: np.int16, capi.RB_FMT_U8: np.uint8, capi.RB_FMT_I32: np.int32}[info.format]
+    return Source(raw.view(dt).copy(), info.channels, info.sample_rate, span_len=0)
 
 
 def ChannelVolume(input: Source, channel_volumes: Sequence[float]) -> Source:
@@ -392,7 +419,7 @@ def pack_descs(sources: Sequence[Source], mix_starts: Optional[Sequence[int]] = 
         d = descs[i]
         d.sample_rate = s.base_rate
         d.channels = s.base_channels
-        d.format = _FMT_OF_NP[s.pcm.dtype]
+        d.format = s.fmt_override if s.fmt_override is not None else _FMT_OF_NP[s.pcm.dtype]
         d.n_samples = s.pcm.size
         d.span_len = s.span_len
         d.n_effects = len(s.effects)

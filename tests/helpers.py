@@ -12,6 +12,8 @@ def to_oracle(src: rb.Source, mix_start: int = 0) -> oracle.Stream:
     if pcm.dtype != np.float32:
         fmt = {np.dtype(np.int16): 1, np.dtype(np.uint16): 2, np.dtype(np.int8): 3, np.dtype(np.uint8): 4,
                np.dtype(np.int32): 5}[pcm.dtype]
+        if getattr(src, "fmt_override", None) is not None:
+            fmt = src.fmt_override
         pcm = oracle.convert(pcm, fmt, 0)
     return oracle.Stream(pcm=pcm, channels=src.base_channels, sample_rate=src.base_rate, effects=src.effects,
                          span_len=src.span_len, mix_start=mix_start)
