@@ -203,6 +203,9 @@ impl Source for GpuMixerSource {
 // and hands the rendered mixer frames out one by one.  State (resampler position, pending frames, filter state) lives
 // in the session, so the block size is free -- 10 ms blocks for a cpal callback, whole seconds for offline renders.
 pub enum rb_session {}
+#[repr(C)]
+pub struct rb_wav_info { pub sample_rate: u32, pub channels: u16, pub bits_per_sample: u16, pub format: u16, pub packed24: u16, pub pad_: u32,
+                         pub data_offset: u64, pub data_bytes: u64, pub n_samples: u64 }
 
 extern "C" {
     fn rb_session_create(ctx: *mut rb_context, mixer_channels: u16, mixer_rate: u32, descs: *const rb_stream_desc, n: usize,
