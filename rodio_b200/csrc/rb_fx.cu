@@ -1,8 +1,9 @@
 // rb_fx.cu — k_fused_fx: the effect chain of BASELINE cfg4 in ONE launch, no intermediates in HBM:
-//     [Spatial / ChannelVolume] -> [reverb] -> automatic_gain_control -> mixer sum
+//     [Spatial / ChannelVolume] -> [reverb] -> [automatic_gain_control] -> [limit] -> mixer sum      (at least one of AGC / limiter)
 // for f32 sources that already have the mixer's rate and channel count (references:
 // src/source/channel_volume.rs:71-88, src/source/spatial.rs:48-69 (the two volumes are computed on the host),
-// src/source/mod.rs:628-634 + mix.rs:43-53 + delay.rs:68-75 (reverb = x + delayed, amplified x), src/source/agc.rs:397-504).
+// src/source/mod.rs:628-634 + mix.rs:43-53 + delay.rs:68-75 (reverb = x + delayed, amplified x), src/source/agc.rs:397-504,
+// src/source/limit.rs:854-988).
 //
 // Where the time goes.  The AGC is three recurrences over the INTERLEAVED sample sequence of a stream (agc.rs keeps one
 // state for all channels): the peak follower, the running sum of the last 8192 squares, and the gain smoother with its clamp.
@@ -21,6 +22,10 @@
 //     tile it-3    warp G    gain[n]  = clamp(gain*k + desired*(1-k), 0.1, max_gain), k = desired > gain ? attack : release
 //                                       both candidates computed, one selected: FMUL, FADD, SEL, FMNMX, FMNMX on the chain
 //     tile it-4    workers   y = e * gain, summed over the CTA's streams in insertion order -> one partial row per CTA
+//   with a limiter behind (or instead of) the AGC the last stage splits in three:
+//     tile it-4    workers   y, and the gain computer's dB for it (log2: within 2 ulp of glibc's, the limiter's 1e-5 * peak class)
+//     tile it-5    warp L    per channel: integrator = max(dB, release-smoothed), peak = attack-smoothed; max over the channels
+//     tile it-6    workers   y * 2^(-max_peak * 0.05 * log2(10)), summed
 // (eight worker warps, two per stream; the gain chain has a sub-partition to itself: sharing one with the other two chains cost it a
 // third of its pace -- 19 instructions per sample from three warps that each want a slot every 4.3 cycles.)
 //
@@ -43,7 +48,7 @@ namespace {
 constexpr int FX_R = 4;                    // streams per CTA
 constexpr int FX_T = 256;                  // samples per stream and tile
 constexpr int FX_TS = FX_T + 4;            // padded row
-constexpr int FX_SLOTS = 5;                // tiles in flight: front | P,S | desired | G | out
+constexpr int FX_SLOTS = 7;                // tiles in flight: front | P,S | desired | G | out, or (with a limiter) y, gain computer | L | out
 constexpr int FX_ARR = FX_R * FX_TS;       // one array of a tile
 constexpr int FX_SLOT = 4 * FX_ARR;        // e | v -> peak | sq -> sum -> desired -> gain | old sq
 constexpr size_t FX_SMEM = (size_t)FX_SLOTS * FX_SLOT * sizeof(float);
@@ -59,15 +64,15 @@ struct FxRow {
     uint64_t delay;       // echo delay in samples (has_echo)
     float amp;            // echo amplitude
     float vol[2];         // channel volumes (has_cv)
-    float target, max_gain, floor, attack, release;
-    uint32_t pad_;
+    float target, max_gain, floor, attack, release;                 // AGC (has_agc)
+    float l_thr, l_knee, l_ik8, l_attack, l_release;                // limiter (has_lim), limit.rs:94-130
 };
 
 struct FxArgs {
     const FxRow* rows;
     uint32_t n_rows;
     uint32_t channels;    // 1 or 2 (source == mixer)
-    uint32_t has_cv, has_echo;
+    uint32_t has_cv, has_echo, has_agc, has_lim;
     float* partial;       // [n_ctas][mix_len]
     uint64_t mix_len;
 };
@@ -112,10 +117,12 @@ __global__ void __launch_bounds__(FX_THREADS) k_fused_fx(FxArgs a) {
     }
     __syncthreads();
     const uint32_t n_tiles = (uint32_t)((s_max_n + FX_T - 1) / FX_T);
-    const bool has_cv = a.has_cv != 0, has_echo = a.has_echo != 0;
-    // warps 0,4,8 | 1,5,9 | 10,14 are the eight workers; 2 = peak, 6 = sum, 3 = gain; 7, 11, 12, 13 only keep the barrier count
-    const int worker = warp == 0 ? 0 : warp == 4 ? 1 : warp == 8 ? 2 : warp == 1 ? 3 : warp == 5 ? 4 : warp == 9 ? 5 : warp == 10 ? 6 : warp == 14 ? 7 : -1;
-    const bool chain_p = warp == 2, chain_s = warp == 6, chain_g = warp == 3;
+    const bool has_cv = a.has_cv != 0, has_echo = a.has_echo != 0, has_agc = a.has_agc != 0, has_lim = a.has_lim != 0;
+    const uint32_t out_lag = has_lim ? 6u : 4u;   // tiles between the front and the mixer sum
+    // warps 0,4,8,12 | 1,5,9 | 10 are the eight workers; 2 = peak, 6 = sum, 14 = limiter envelopes (one sub-partition), 3 = gain;
+    // 7, 11, 13 only keep the barrier count
+    const int worker = warp == 0 ? 0 : warp == 4 ? 1 : warp == 8 ? 2 : warp == 1 ? 3 : warp == 5 ? 4 : warp == 9 ? 5 : warp == 10 ? 6 : warp == 12 ? 7 : -1;
+    const bool chain_p = warp == 2, chain_s = warp == 6, chain_g = warp == 3, chain_l = warp == 14;
     const uint64_t mix_start = s_rows[0].mix_start;      // equal for the CTA's streams (planner)
     float* const prow = a.partial + (uint64_t)blockIdx.x * a.mix_len + mix_start;
 
@@ -125,8 +132,10 @@ __global__ void __launch_bounds__(FX_THREADS) k_fused_fx(FxArgs a) {
     const uint64_t my_n = (lane < cnt) ? my.n_out : 0;
     const float attack = my.attack, release = my.release, max_gain = my.max_gain;
     const float oma = sub(1.0f, attack), omr = sub(1.0f, release);
+    const float l_att = my.l_attack, l_rel = my.l_release, l_oma = sub(1.0f, my.l_attack), l_omr = sub(1.0f, my.l_release);
+    float l_int[2] = {0.0f, 0.0f}, l_pk[2] = {0.0f, 0.0f};   // limiter: integrator and peak per channel (limit.rs:903-916)
 
-    for (uint32_t it = 0; it < n_tiles + 4; it++) {
+    for (uint32_t it = 0; it < n_tiles + out_lag; it++) {
         if (worker >= 0) {
             // ---- front, tile `it`: stream worker / 2, half tile worker % 2, 4 consecutive samples per lane ----
             const uint32_t ws = (uint32_t)worker >> 1, wo = ((uint32_t)worker & 1u) * (FX_T / 2) + 4 * lane;
@@ -139,7 +148,11 @@ __global__ void __launch_bounds__(FX_THREADS) k_fused_fx(FxArgs a) {
                 for (int j = 0; j < 4; j++) e[j] = v[j] = q[j] = o[j] = 0.0f;
                 if (n0 < r.n_out) {
                     const bool interior = n0 + 4 <= r.n_in && n0 >= r.delay + RMS_WINDOW;   // every tap of every sample exists
-                    if (interior) {
+                    if (!has_agc) {
+#pragma unroll 1
+                        for (int j = 0; j < 4; j++)
+                            if (n0 + j < r.n_out) e[j] = fx_e<C>(r, has_cv, has_echo, n0 + j);
+                    } else if (interior) {
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
                             e[j] = fx_e<C, true>(r, has_cv, has_echo, n0 + j);
@@ -170,7 +183,7 @@ __global__ void __launch_bounds__(FX_THREADS) k_fused_fx(FxArgs a) {
                 *reinterpret_cast<float4*>(base + 3 * FX_ARR) = make_float4(o[0], o[1], o[2], o[3]);
             }
             // ---- desired gain, tile `it - 2` (agc.rs:413-431, :466-470): sum -> desired in place ----
-            if (it >= 2 && it - 2 < n_tiles && ws < cnt) {
+            if (has_agc && it >= 2 && it - 2 < n_tiles && ws < cnt) {
                 const FxRow& r = s_rows[ws];
                 float* base = fx_sm + ((it - 2) % FX_SLOTS) * FX_SLOT + ws * FX_TS + wo;
                 const float4 p0 = *reinterpret_cast<const float4*>(base + FX_ARR);
@@ -188,19 +201,37 @@ __global__ void __launch_bounds__(FX_THREADS) k_fused_fx(FxArgs a) {
                 }
                 *reinterpret_cast<float4*>(base + 2 * FX_ARR) = make_float4(d[0], d[1], d[2], d[3]);
             }
-            // ---- out, tile `it - 4`: y = e * gain, summed over the CTA's streams; one position per worker lane ----
-            if (it >= 4) {
-                const float* base = fx_sm + ((it - 4) % FX_SLOTS) * FX_SLOT;
+            // ---- with a limiter, tile `it - 4`: y = e * gain stays in the tile, the gain computer's dB beside it (limit.rs:854-873) ----
+            if (has_lim && it >= 4 && it - 4 < n_tiles && ws < cnt) {
+                const FxRow& r = s_rows[ws];
+                float* base = fx_sm + ((it - 4) % FX_SLOTS) * FX_SLOT + ws * FX_TS + wo;
+                float4 ev = *reinterpret_cast<const float4*>(base);
+                if (has_agc) {
+                    const float4 gv = *reinterpret_cast<const float4*>(base + 2 * FX_ARR);
+                    ev.x = mul(ev.x, gv.x), ev.y = mul(ev.y, gv.y), ev.z = mul(ev.z, gv.z), ev.w = mul(ev.w, gv.w);
+                    *reinterpret_cast<float4*>(base) = ev;
+                }
+                *reinterpret_cast<float4*>(base + FX_ARR) = make_float4(limiter_db(ev.x, r.l_thr, r.l_knee, r.l_ik8), limiter_db(ev.y, r.l_thr, r.l_knee, r.l_ik8),
+                                                                        limiter_db(ev.z, r.l_thr, r.l_knee, r.l_ik8), limiter_db(ev.w, r.l_thr, r.l_knee, r.l_ik8));
+            }
+            // ---- out, tile `it - out_lag`: the last factor, summed over the CTA's streams; one position per worker lane ----
+            if (it >= out_lag) {
+                const float* base = fx_sm + ((it - out_lag) % FX_SLOTS) * FX_SLOT;
                 const uint32_t pos = 32 * (uint32_t)worker + lane;
-                const uint64_t n = (uint64_t)(it - 4) * FX_T + pos;
+                const uint64_t n = (uint64_t)(it - out_lag) * FX_T + pos;
                 float acc = 0.0f;
                 bool any = false;
 #pragma unroll
                 for (uint32_t s = 0; s < FX_R; s++)
-                    if (n < s_rows[s].n_out) acc = add(acc, mul(base[s * FX_TS + pos], base[2 * FX_ARR + s * FX_TS + pos])), any = true;   // absent rows: n_out = 0
+                    if (n < s_rows[s].n_out) {   // absent rows: n_out = 0
+                        float y = base[s * FX_TS + pos];
+                        if (has_lim) y = mul(y, db_to_linear(-base[FX_ARR + s * FX_TS + pos]));                 // limit.rs:927-988
+                        else if (has_agc) y = mul(y, base[2 * FX_ARR + s * FX_TS + pos]);
+                        acc = add(acc, y), any = true;
+                    }
                 if (any && mix_start + n < a.mix_len) prow[n] = acc;
             }
-        } else if (it >= 1 && it - 1 < n_tiles && (chain_p || chain_s)) {
+        } else if (has_agc && it >= 1 && it - 1 < n_tiles && (chain_p || chain_s)) {
             // ---- chains P and S, tile `it - 1`, lane = stream ----
             if (lane < cnt) {
                 const uint64_t nb = (uint64_t)(it - 1) * FX_T;
@@ -239,7 +270,7 @@ __global__ void __launch_bounds__(FX_THREADS) k_fused_fx(FxArgs a) {
                     }
                 }
             }
-        } else if (chain_g && it >= 3 && it - 3 < n_tiles) {
+        } else if (has_agc && chain_g && it >= 3 && it - 3 < n_tiles) {
             // ---- chain G, tile `it - 3` (agc.rs:474-491): desired -> gain in place ----
             if (lane < cnt) {
                 const uint64_t nb = (uint64_t)(it - 3) * FX_T;
@@ -258,6 +289,32 @@ __global__ void __launch_bounds__(FX_THREADS) k_fused_fx(FxArgs a) {
                         const float g = d > gain ? ga : gr;
                         gain = fminf(fmaxf(g, 0.1f), max_gain);
                         r1[j] = gain;
+                    }
+                    pd[k] = make_float4(r1[0], r1[1], r1[2], r1[3]);
+                    cur = nxt;
+                }
+            }
+        } else if (has_lim && chain_l && it >= 5 && it - 5 < n_tiles) {
+            // ---- chain L, tile `it - 5`: per channel integrator (release) and peak (attack) envelopes, the channels coupled by
+            // max(peaks) AFTER the current channel's update (limit.rs:903-916, :946-960): gain-computer dB -> max_peak in place ----
+            if (lane < cnt) {
+                const uint64_t nb = (uint64_t)(it - 5) * FX_T;
+                const int c4 = (int)((min((uint64_t)FX_T, my_n > nb ? my_n - nb : 0) + 3) / 4);
+                float4* pd = reinterpret_cast<float4*>(fx_sm + ((it - 5) % FX_SLOTS) * FX_SLOT + FX_ARR + lane * FX_TS);
+                float4 cur = c4 > 0 ? pd[0] : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k = 0; k < c4; k++) {
+                    const float4 nxt = k + 1 < c4 ? pd[k + 1] : cur;
+                    const float dv[4] = {cur.x, cur.y, cur.z, cur.w};
+                    float r1[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        constexpr int CM = C - 1;
+                        const int c = j & CM;                                   // tiles and groups of four start on channel 0
+                        const float ldb = dv[j];
+                        const float in_c = fmaxf(ldb, add(mul(l_rel, l_int[c]), mul(l_omr, ldb)));
+                        l_int[c] = in_c;
+                        l_pk[c] = add(mul(l_att, l_pk[c]), mul(l_oma, in_c));
+                        r1[j] = C == 1 ? l_pk[0] : fmaxf(l_pk[0], l_pk[1]);
                     }
                     pd[k] = make_float4(r1[0], r1[1], r1[2], r1[3]);
                     cur = nxt;
@@ -287,22 +344,23 @@ struct rb_fx_plan {
     uint32_t n_ctas = 0;
 };
 
-// Shape: every stream f32 with the mixer's channel count (1 or 2) and no conversion, nodes = [CHANVOL]? [ECHO]? AGC, the same
+// Shape: every stream f32 with the mixer's channel count (1 or 2) and no conversion, nodes = [CHANVOL]? [ECHO]? [AGC]? [LIMIT]? with
+// at least one of the last two, the same
 // node kinds for every stream; the streams of a CTA (groups of FX_R in insertion order) share their mix_start.
 cudaError_t rb_fx_try_create(const rb_fused_stream* streams, size_t n_streams, uint16_t mixer_channels, float* d_out, uint64_t mix_len,
                              uint32_t flags, cudaStream_t st, rb_fx_plan** out) {
     *out = nullptr;
     if (n_streams == 0 || mix_len == 0 || (flags & RB_MIX_EXACT_ORDER) || (mixer_channels != 1 && mixer_channels != 2)) return cudaSuccess;
     std::vector<FxRow> rows(n_streams);
-    uint32_t has_cv = 0, has_echo = 0;
+    uint32_t has_cv = 0, has_echo = 0, has_agc = 0, has_lim = 0;
     for (size_t i = 0; i < n_streams; i++) {
         const rb_fused_stream& s = streams[i];
-        if (s.fmt != RB_FMT_F32 || s.c_in != mixer_channels || s.n_nodes == 0 || s.n_nodes > 3) return cudaSuccess;
+        if (s.fmt != RB_FMT_F32 || s.c_in != mixer_channels || s.n_nodes == 0 || s.n_nodes > 4) return cudaSuccess;
         if (s.n_in % mixer_channels || (reinterpret_cast<uintptr_t>(s.in) & 7u)) return cudaSuccess;
         FxRow& r = rows[i];
         memset(&r, 0, sizeof(r));
         r.in = (const float*)s.in, r.n_in = s.n_in, r.n_out = s.out_len, r.mix_start = s.mix_start;
-        uint32_t cv = 0, echo = 0, agc = 0, k = 0;
+        uint32_t cv = 0, echo = 0, agc = 0, lim = 0, k = 0;
         auto node = [&](uint32_t j) -> const rb_node_dev& {
             return *reinterpret_cast<const rb_node_dev*>(reinterpret_cast<const char*>(s.nodes) + (size_t)j * s.node_stride);
         };
@@ -320,10 +378,15 @@ cudaError_t rb_fx_try_create(const rb_fused_stream* streams, size_t n_streams, u
             r.target = nd.p.agc.target, r.max_gain = nd.p.agc.max_gain, r.floor = nd.p.agc.floor, r.attack = nd.p.agc.attack, r.release = nd.p.agc.release;
             agc = 1;
         }
-        if (!agc || k != s.n_nodes) return cudaSuccess;
+        if (k < s.n_nodes && node(k).kind == RB_N_LIMIT) {
+            const rb_node_dev& nd = node(k++);
+            r.l_thr = nd.p.lim.threshold, r.l_knee = nd.p.lim.knee, r.l_ik8 = nd.p.lim.inv_knee_8, r.l_attack = nd.p.lim.attack, r.l_release = nd.p.lim.release;
+            lim = 1;
+        }
+        if (!(agc || lim) || k != s.n_nodes) return cudaSuccess;
         if (r.n_out != r.n_in + (echo ? r.delay : 0)) return cudaSuccess;
-        if (i == 0) has_cv = cv, has_echo = echo;
-        else if (cv != has_cv || echo != has_echo) return cudaSuccess;
+        if (i == 0) has_cv = cv, has_echo = echo, has_agc = agc, has_lim = lim;
+        else if (cv != has_cv || echo != has_echo || agc != has_agc || lim != has_lim) return cudaSuccess;
         if (i % FX_R && r.mix_start != rows[i - 1].mix_start) return cudaSuccess;
     }
     auto p = new rb_fx_plan;
@@ -342,7 +405,7 @@ cudaError_t rb_fx_try_create(const rb_fused_stream* streams, size_t n_streams, u
         return e;
     }
     p->args.rows = p->d_rows, p->args.n_rows = (uint32_t)n_streams, p->args.channels = mixer_channels;
-    p->args.has_cv = has_cv, p->args.has_echo = has_echo, p->args.partial = p->d_partial, p->args.mix_len = mix_len;
+    p->args.has_cv = has_cv, p->args.has_echo = has_echo, p->args.has_agc = has_agc, p->args.has_lim = has_lim, p->args.partial = p->d_partial, p->args.mix_len = mix_len;
     *out = p;
     return cudaSuccess;
 }

@@ -292,3 +292,35 @@ def test_integer_pcm_keeps_a_resident_f32_copy(ctx):
     for pcm, got in ((pcm_a, got_a), (pcm_b, got_b)):
         per = [oracle.chain_uniform(to_oracle(s), 1, 48000) for s in mk(pcm)]
         assert_bit_exact(got, grouped_expected_mix(per, [0] * n, got.size, group), "s16 input through the f32 kernels")
+
+
+@pytest.mark.parametrize("shape", ["limit_only_mono", "reverb_limit_stereo", "spatial_reverb_agc_limit"])
+def test_fx_kernel_with_limiter(ctx, shape):
+    """`limit` behind (or instead of) the AGC inside k_fused_fx: a fourth recurrence warp (per-channel integrator and peak
+    envelopes, the channels coupled through max(peaks), limit.rs:903-988) between the gain computer and the final factor.  The
+    limiter's log2 / exp2 are the device's (within 2 ulp of glibc's): the 1e-5 * peak class of the general-path limiter."""
+    ch = 1 if shape == "limit_only_mono" else 2
+    n, frames = 21, 7000
+    presets = [rb.LimitSettings.default(), rb.LimitSettings.dynamic_content(), rb.LimitSettings.broadcast(), rb.LimitSettings.gaming()]
+    srcs = []
+    for s in range(n):
+        src = rb.TestSource(noise(frames * ch, 61000 + s, 1.5), ch, 48000)     # well above the threshold: the limiter works
+        if shape == "spatial_reverb_agc_limit":
+            src = rb.Spatial(src, [float(s % 5 - 2), 1.0, 0.0], [-1, 0, 0], [1, 0, 0])
+        if shape != "limit_only_mono":
+            src = src.reverb(rb.Duration.from_millis(10 + s), 0.5)
+        if shape == "spatial_reverb_agc_limit":
+            src = src.automatic_gain_control()
+        srcs.append(src.limit(presets[s % 4]))
+    streams = [to_oracle(s) for s in srcs]
+    want = oracle.mixer(streams, ch, 48000)
+    with rb.Batch(srcs, ch, 48000, ctx=ctx) as b:
+        assert b.kernel_family == 5, b.kernel_family
+        b.upload_all()
+        got = b.render_mix()
+    assert_close_peak(got, want, 1e-5, f"k_fused_fx with a limiter, {shape}")
+    with rb.Batch(srcs, ch, 48000, flags=GENERAL, ctx=ctx) as b:       # the general-path limiter uses the same device functions
+        b.upload_all()
+        ref = b.render_mix()
+    per = None
+    assert_close_peak(got, ref, 2e-6, f"k_fused_fx against the general path, {shape}")

@@ -62,6 +62,14 @@ def main():
         srcs = [rb.Spatial(rb.TestSource(z(2 * frames), 2, 48000), [float(s % 7 - 3), 1.0, 0.0], [-1, 0, 0], [1, 0, 0])
                 .reverb(rb.Duration.from_millis(50), 0.3).automatic_gain_control() for s in range(S)]
         time_batch("cfg4 512 stereo: spatial -> reverb -> agc -> mix (general path)", srcs, (2, 48000), steps=3)
+    if "limit" in which:
+        S, frames = 512, 48000
+        srcs = [rb.TestSource(z(2 * frames), 2, 48000).limit() for s in range(S)]
+        time_batch("limit: 512 stereo x 1 s, limit(default) -> mix [k_fused_fx]", srcs, (2, 48000), steps=3)
+        time_batch("limit: the same through the general path (k_limit_tile)", srcs, (2, 48000), steps=3, flags=rb.capi.RB_NO_FUSION)
+        srcs = [rb.Spatial(rb.TestSource(z(2 * frames), 2, 48000), [float(s % 7 - 3), 1.0, 0.0], [-1, 0, 0], [1, 0, 0])
+                .reverb(rb.Duration.from_millis(50), 0.3).automatic_gain_control().limit() for s in range(S)]
+        time_batch("cfg4 + limit: spatial -> reverb -> agc -> limit -> mix [k_fused_fx]", srcs, (2, 48000), steps=3)
     if "nofilter" in which:
         for ch, S in ((1, 4096), (2, 2048)):
             srcs = [rb.UniformSourceIterator(rb.TestSource(z(44100 * 2 * ch), ch, 44100), ch, 48000).amplify(0.8)
