@@ -1162,8 +1162,10 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
                                 uint64_t mix_len, uint32_t flags, int sm_count, cudaStream_t st, rb_fused_plan** out) {
     *out = nullptr;
     if (n_streams == 0 || mix_len == 0) return cudaSuccess;
-    if (flags & RB_MIX_EXACT_ORDER) return cudaSuccess;   // served by the general path
-    {   // spatial / reverb / AGC chains have a kernel of their own
+    // RB_MIX_EXACT_ORDER: the general path, except for filter-free resample -> gain -> mix batches, which k_lerp_mix sums in
+    // one sequential chain per timeline position -- the reference's order (see below)
+    const bool exact_order = (flags & RB_MIX_EXACT_ORDER) != 0;
+    if (!exact_order) {   // spatial / reverb / AGC chains have a kernel of their own
         rb_fx_plan* fx = nullptr;
         cudaError_t e = rb_fx_try_create(streams, n_streams, mixer_channels, d_out, mix_len, flags, st, &fx);
         if (e != cudaSuccess) return e;
@@ -1178,6 +1180,7 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     uint32_t n_pre = 0, n_mid = 0, n_post = 0, has_u = 0, has_b = 0, front = 0;
     bool mixed_u = false;   // some rows lost an identity conversion: only the lane kernel may take such a batch
     if (!fused_parse_rows(streams, n_streams, mixer_channels, rows, n_pre, n_mid, n_post, has_u, has_b, mixed_u, front)) return cudaSuccess;
+    if (exact_order && (has_b || front || !has_u || mixer_channels != 1 || (flags & RB_FUSED_LANES))) return cudaSuccess;
     if (has_b && (uint32_t)mixer_channels * 1u > 32u) return cudaSuccess;
 
     // Plain mixer of f32 sources at the mixer's own rate/channels (BASELINE cfg2): nothing to fuse -- the ordered
@@ -1196,6 +1199,11 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
         if (e != cudaSuccess) {
             delete plan;
             return e;
+        }
+        if (exact_order && (!plan->lanes || rb_lanes_kind(plan->lanes) != 6)) {   // only k_lerp_mix keeps the sequential order
+            rb_lanes_destroy(plan->lanes);
+            delete plan;
+            return cudaSuccess;
         }
         if (plan->lanes) {
             *out = plan;

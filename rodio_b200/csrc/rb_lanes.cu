@@ -57,6 +57,72 @@ __global__ void __launch_bounds__(64) k_fused_duo_split(lanes::Args a) {
     else duo::warp_main<HASB, FF2, NPOST, 2>(a, group, lanes_smem, handoff);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// k_lerp_mix: see rb_lanes.h.  256 threads, LM_U positions per thread (position = tile * 256 * LM_U + u * 256 + thread: consecutive
+// lanes read consecutive input frames), grid (time tiles, stream groups).
+// Arithmetic per sample: a + ((b - a) * num) / den with the division as the exact reciprocal step of the lane kernels for streams
+// whose inputs are inside the class (k_classify_inputs), __fdiv_rn otherwise; (-0) / den keeps its sign.
+// ---------------------------------------------------------------------------------------------------
+constexpr int LM_U = 4;
+template <int NPOST>
+__global__ void __launch_bounds__(256) k_lerp_mix(rb_lerpmix_args a) {
+    const uint64_t tile_lo = (uint64_t)blockIdx.x * (256 * LM_U);
+    if (tile_lo >= a.mix_len) return;
+    const uint64_t tile_hi = min(a.mix_len, tile_lo + 256 * LM_U);
+    const uint32_t g = blockIdx.y;
+    const uint32_t r_lo = g * a.rows_per_group, r_hi = min(a.n_rows, r_lo + a.rows_per_group);
+    uint32_t idx[LM_U], pos[LM_U];
+    float numf[LM_U], acc[LM_U];
+    bool any[LM_U];
+#pragma unroll
+    for (int u = 0; u < LM_U; u++) {
+        const uint64_t n = tile_lo + (uint64_t)u * 256 + threadIdx.x;
+        const uint64_t rel = n - a.origin;                       // origin <= every position that any stream covers
+        const uint64_t prod = rel * (uint64_t)a.from;
+        const uint64_t i = prod / a.to;
+        idx[u] = (uint32_t)i, numf[u] = __uint2float_rn((uint32_t)(prod - i * a.to)), pos[u] = (uint32_t)n;
+        acc[u] = 0.0f, any[u] = false;
+    }
+    const float den = a.den_f, rcp = a.rcp_den;
+    const uint32_t t_lo = (uint32_t)tile_lo, t_hi = (uint32_t)tile_hi;
+    for (uint32_t r = r_lo; r < r_hi; r++) {
+        const rb_lerpmix_row row = a.rows[r];                    // warp-uniform: two 16-byte broadcast loads
+        if (row.hi <= t_lo || row.lo >= t_hi) continue;          // the stream is silent on this tile
+        const bool safe = !(a.lane_rows[row.row].flags & lanes::ROW_UNSAFE);
+        const float* __restrict__ p = row.p;
+        if (safe && row.lo <= t_lo && row.hi_int >= t_hi) {
+            // interior: every position interpolates
+            float xa[LM_U], xb[LM_U];
+#pragma unroll
+            for (int u = 0; u < LM_U; u++) xa[u] = __ldg(p + idx[u]), xb[u] = __ldg(p + idx[u] + 1);
+#pragma unroll
+            for (int u = 0; u < LM_U; u++) {
+                const float m = __fmul_rn(__fsub_rn(xb[u], xa[u]), numf[u]);
+                const float q0 = __fmul_rn(m, rcp);
+                float q = __fmaf_rn(__fmaf_rn(-q0, den, m), rcp, q0);
+                q = m == 0.0f ? m : q;
+                float x = __fadd_rn(xa[u], q);
+                if (NPOST) x = __fmul_rn(x, row.post);
+                acc[u] = __fadd_rn(acc[u], x), any[u] = true;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < LM_U; u++) {
+                if (pos[u] < row.lo || pos[u] >= row.hi || pos[u] >= t_hi) continue;
+                const float xa = __ldg(p + idx[u]);
+                float x = xa;
+                if (pos[u] < row.hi_int) x = __fadd_rn(xa, __fdiv_rn(__fmul_rn(__fsub_rn(__ldg(p + idx[u] + 1), xa), numf[u]), den));
+                if (NPOST) x = __fmul_rn(x, row.post);
+                acc[u] = __fadd_rn(acc[u], x), any[u] = true;
+            }
+        }
+    }
+    float* __restrict__ out = a.out + (uint64_t)g * a.pstride;
+#pragma unroll
+    for (int u = 0; u < LM_U; u++)
+        if (pos[u] < t_hi && (any[u] || a.n_groups == 1)) out[pos[u]] = acc[u];
+}
+
 // One CTA per stream: does every non-zero |x| lie inside [2^-70, 2^60]?  (rb_lanes_core.h, "Exact division".)
 // channels[r]: interleaved channels of stream r.
 __global__ void __launch_bounds__(256) k_classify_inputs(lanes::Row* rows, uint32_t n_rows, const uint8_t* __restrict__ channels) {
@@ -210,6 +276,14 @@ cudaError_t rb_duo_launch_kernel(const lanes::Args& a, bool has_biquad, bool ff2
     } else {
         has_post ? k_fused_duo<false, false, 1><<<g, b, DUO_SMEM, st>>>(a) : k_fused_duo<false, false, 0><<<g, b, DUO_SMEM, st>>>(a);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t rb_lerpmix_launch(const rb_lerpmix_args& a, cudaStream_t st) {
+    if (a.mix_len == 0 || a.n_rows == 0) return cudaSuccess;
+    const dim3 grid((uint32_t)((a.mix_len + 256 * LM_U - 1) / (256 * LM_U)), a.n_groups);
+    if (a.has_post) k_lerp_mix<1><<<grid, 256, 0, st>>>(a);
+    else k_lerp_mix<0><<<grid, 256, 0, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -28,11 +28,13 @@ struct rb_lanes_plan;
 // class (rb_lanes_plan.h classes_by_ratio): the mixer sum then groups by class first.
 // mode: LANES_TIME_PARALLEL asks for the time-parallel biquad plan (built only when the batch qualifies: rb_lanes_batch.cu),
 // LANES_NO_DUO keeps every class on k_fused_lanes (A/B runs; the environment variable RB_NO_DUO does the same).
-enum : uint32_t { LANES_TIME_PARALLEL = 1u, LANES_NO_DUO = 2u };
+enum : uint32_t { LANES_TIME_PARALLEL = 1u, LANES_NO_DUO = 2u, LANES_ONE_GROUP = 4u };   // ONE_GROUP: k_lerp_mix sums all streams in one
+                                                                                       // sequential chain (the reference's order, bit for bit)
 cudaError_t rb_lanes_try_create(const rb_lanes_stream* streams, size_t n_streams, uint32_t channels, bool has_biquad, bool has_post,
                                 bool has_pre, bool front, float* d_out, uint64_t mix_len, int sm_count, cudaStream_t st, rb_lanes_plan** out,
                                 uint32_t mode = 0);
-// 2: k_fused_lanes, 3: every class on k_fused_duo, 4: the time-parallel plan (k_fused_duo over segment rows)
+// 2: k_fused_lanes, 3: every class on k_fused_duo, 4: the time-parallel plan (k_fused_duo over segment rows),
+// 6: k_lerp_mix (filter-free chains, parallel over the timeline)
 int rb_lanes_kind(const rb_lanes_plan* p);
 // streams per partial sum of the mixer: 32 (k_fused_lanes) or 64 (k_fused_duo: lane = even row + odd row, then the same tree)
 uint32_t rb_lanes_mix_group(const rb_lanes_plan* p);
@@ -51,6 +53,31 @@ cudaError_t rb_lanes_launch_kernel(const lanes::Args& a, uint32_t ch_in, uint32_
                                    bool has_pre, bool front, bool guard, cudaStream_t st);
 // k_fused_duo (rb_duo_core.h) over a.rows: mono sources below the mixer's rate, two rows per lane, a.n_groups groups of 64
 cudaError_t rb_duo_launch_kernel(const lanes::Args& a, bool has_biquad, bool ff2, bool has_post, cudaStream_t st);
+// ---- k_lerp_mix (rb_lanes.cu): resample -> [one gain] -> mixer sum for chains WITHOUT a filter, parallel over the timeline ----
+// Nothing is carried from sample to sample in such a chain, so a thread owns timeline positions, walks the streams of its group
+// in insertion order and adds them up in a register: no shared memory, no cross-lane traffic, and the sum inside a group IS the
+// reference's sequential sum (src/mixer.rs:185-198).  All streams of the launch share one reduced rate pair and one phase
+// (mix_start modulo `to`), so the input offset and the numerator of a timeline position are the same for every stream.
+struct rb_lerpmix_row {      // one stream, 32 bytes
+    const float* p;          // input, shifted so that p[idx] is the left tap of the timeline position whose table entry is idx
+    uint32_t lo, hi_int, hi; // timeline frames [lo, hi_int) interpolate, [hi_int, hi) emit the last frame raw
+    float post;              // the one gain (1.0: none)
+    uint32_t row;            // index into the lanes::Row array (classification verdict: Row::flags)
+    uint32_t pad_;
+};
+struct rb_lerpmix_args {
+    const rb_lerpmix_row* rows;
+    const lanes::Row* lane_rows;   // flags (ROW_UNSAFE) per stream
+    uint32_t n_rows, rows_per_group, n_groups;
+    uint32_t from, to;
+    uint64_t origin;               // timeline frame whose numerator is 0 for every stream (the common phase)
+    float den_f, rcp_den;
+    uint64_t mix_len;
+    float* out;                    // [n_groups][pstride] (n_groups == 1: the mixer output itself)
+    uint64_t pstride;
+    uint32_t has_post;
+};
+cudaError_t rb_lerpmix_launch(const rb_lerpmix_args& a, cudaStream_t st);
 // ... and the ordered sum of n_groups partial rows (all classes) into d_out[0, n_floats).
 cudaError_t rb_lanes_launch_sum(const float* d_partial, uint32_t n_groups, uint64_t pstride, uint64_t n_floats, float* d_out,
                                 cudaStream_t st);

@@ -41,6 +41,10 @@ struct rb_lanes_plan {
     bool classified = false;
     bool time_parallel = false;
     uint32_t tp_segments = 0, tp_warmup = 0, tp_seg_len = 0;
+    // filter-free chains: the time-parallel resample -> gain -> mix kernel (k_lerp_mix) serves the batch
+    bool lerpmix = false;
+    rb_lerpmix_args lm{};
+    rb_lerpmix_row* d_lm_rows = nullptr;
 };
 
 namespace {
@@ -151,6 +155,59 @@ cudaError_t rb_lanes_try_create(const rb_lanes_stream* streams, size_t n_streams
     std::vector<size_t> first_row, first_slot;
     uint32_t n_slots_total = 0;
 
+    // ---- chains without a filter: nothing is carried from sample to sample, the whole batch is parallel over the timeline ----
+    if ((mode & LANES_TIME_PARALLEL) && !has_biquad && channels == 1 && !has_pre && !front && classes.size() == 1 && from[0] < to[0] &&
+        mix_len < (1ull << 31) && !getenv("RB_NO_LERPMIX")) {
+        const uint32_t T = to[0];
+        uint64_t origin = ~0ull;
+        bool in_phase = true;
+        for (size_t i = 0; i < n_streams; i++)
+            if (streams[i].out_len) origin = std::min(origin, streams[i].mix_start);
+        for (size_t i = 0; i < n_streams && in_phase; i++)
+            in_phase = streams[i].out_len == 0 || (streams[i].mix_start - origin) % T == 0;
+        if (in_phase && origin != ~0ull) {
+            std::vector<rb_lerpmix_row> lr(n_streams);
+            for (size_t i = 0; i < n_streams; i++) {
+                const rb_lanes_stream& s = streams[i];
+                lanes::Row r;
+                fill_row(r, s, false, has_post, false, false);
+                rows.push_back(r);
+                row_channels.push_back(1);
+                const uint64_t shift = s.out_len ? (s.mix_start - origin) / T * from[0] : 0;
+                lr[i].p = s.in - shift;
+                lr[i].lo = (uint32_t)s.mix_start, lr[i].hi_int = (uint32_t)(s.mix_start + r.n_int), lr[i].hi = (uint32_t)(s.mix_start + s.out_len);
+                lr[i].post = has_post ? s.post : 1.0f, lr[i].row = (uint32_t)i, lr[i].pad_ = 0;
+            }
+            // stream groups: enough CTAs for two waves; a group is summed sequentially in insertion order
+            const uint64_t tiles = (mix_len + 1023) / 1024;
+            uint64_t groups = (2ull * (uint64_t)(sm_count > 0 ? sm_count : 148) + tiles - 1) / tiles;
+            groups = std::max<uint64_t>(1, std::min<uint64_t>(groups, (n_streams + 63) / 64));
+            if (mode & LANES_ONE_GROUP) groups = 1;
+            const uint32_t per = (uint32_t)((n_streams + groups - 1) / groups);
+            groups = (n_streams + per - 1) / per;
+            p->lerpmix = true;
+            p->n_rows = (uint32_t)n_streams, p->n_partial_rows = groups > 1 ? (uint32_t)groups : 0;
+            cudaError_t e = cudaMalloc(&p->d_rows, n_streams * sizeof(lanes::Row));
+            if (e == cudaSuccess) e = cudaMalloc(&p->d_lm_rows, n_streams * sizeof(rb_lerpmix_row));
+            if (e == cudaSuccess) e = cudaMalloc(&p->d_row_channels, n_streams);
+            if (e == cudaSuccess && groups > 1) e = cudaMalloc(&p->d_partial, (size_t)groups * p->pstride * sizeof(float));
+            if (e == cudaSuccess && groups > 1) e = cudaMemsetAsync(p->d_partial, 0, (size_t)groups * p->pstride * sizeof(float), st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_rows, rows.data(), n_streams * sizeof(lanes::Row), cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_lm_rows, lr.data(), n_streams * sizeof(rb_lerpmix_row), cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_row_channels, row_channels.data(), n_streams, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) {
+                rb_lanes_destroy(p);
+                return e;
+            }
+            rb_lerpmix_args& a = p->lm;
+            a.rows = p->d_lm_rows, a.lane_rows = p->d_rows, a.n_rows = (uint32_t)n_streams, a.rows_per_group = per, a.n_groups = (uint32_t)groups;
+            a.from = from[0], a.to = T, a.origin = origin, a.den_f = (float)T, a.rcp_den = 1.0f / (float)T, a.mix_len = mix_len;
+            a.out = groups > 1 ? p->d_partial : d_out, a.pstride = p->pstride, a.has_post = has_post ? 1u : 0u;
+            *out = p;
+            return cudaSuccess;
+        }
+    }
     // ---- the time-parallel plan: one class of mono sources, a filter, nothing in front of the conversion ----
     if ((mode & LANES_TIME_PARALLEL) && duo_shape && classes.size() == 1 && from[0] < to[0]) {
         uint32_t n_slots = 0;
@@ -244,6 +301,16 @@ void rb_lanes_inputs_changed(rb_lanes_plan* p) {
 }
 
 cudaError_t rb_lanes_run(rb_lanes_plan* p, cudaStream_t st) {
+    if (p->lerpmix) {
+        if (!p->classified) {
+            cudaError_t e = rb_lanes_launch_classify(p->d_rows, p->n_rows, p->d_row_channels, st);
+            if (e != cudaSuccess) return e;
+            p->classified = true;
+        }
+        cudaError_t e = rb_lerpmix_launch(p->lm, st);
+        if (e != cudaSuccess || p->lm.n_groups == 1) return e;
+        return rb_lanes_launch_sum(p->d_partial, p->lm.n_groups, p->pstride, p->mix_len, p->d_out, st);
+    }
     if (!p->classified) {
         cudaError_t e;
         if (p->time_parallel) {
@@ -263,15 +330,16 @@ cudaError_t rb_lanes_run(rb_lanes_plan* p, cudaStream_t st) {
     return rb_lanes_launch_sum(p->d_partial, p->n_partial_rows, p->pstride, p->mix_len * p->channels, p->d_out, st);
 }
 
-uint32_t rb_lanes_launch_count(const rb_lanes_plan* p) { return (uint32_t)p->classes.size() + 1u; }
+uint32_t rb_lanes_launch_count(const rb_lanes_plan* p) { return p->lerpmix ? (p->lm.n_groups > 1 ? 2u : 1u) : (uint32_t)p->classes.size() + 1u; }
 // 3: every class on the lane-pair kernel, 4: the time-parallel plan, 2: k_fused_lanes (alone or beside pair classes)
 int rb_lanes_kind(const rb_lanes_plan* p) {
+    if (p->lerpmix) return 6;
     if (p->time_parallel) return 4;
     bool all = !p->classes.empty();
     for (const auto& c : p->classes) all = all && c.duo;
     return all ? 3 : 2;
 }
-uint32_t rb_lanes_mix_group(const rb_lanes_plan* p) { return rb_lanes_kind(p) >= 3 ? 64u : 32u; }
+uint32_t rb_lanes_mix_group(const rb_lanes_plan* p) { return p->lerpmix ? (p->lm.n_groups > 1 ? p->lm.rows_per_group : 0u) : rb_lanes_kind(p) >= 3 ? 64u : 32u; }
 void rb_lanes_tp_geometry(const rb_lanes_plan* p, uint32_t* segments, uint32_t* seg_len, uint32_t* warmup) {
     *segments = p->tp_segments, *seg_len = p->tp_seg_len, *warmup = p->tp_warmup;
 }
@@ -285,5 +353,6 @@ void rb_lanes_destroy(rb_lanes_plan* p) {
     cudaFree(p->d_spans);
     cudaFree(p->d_stream_rows);
     cudaFree(p->d_row_stream);
+    cudaFree(p->d_lm_rows);
     delete p;
 }

@@ -85,6 +85,31 @@ cudaError_t rb_lanes_spread_flags(lanes::Row* rows, uint32_t n_rows, const uint3
     return cudaSuccess;
 }
 
+// k_lerp_mix on the host: the same sums in the same order (plain loops: the kernel has no warp-level structure to emulate)
+cudaError_t rb_lerpmix_launch(const rb_lerpmix_args& a, cudaStream_t) {
+    for (uint32_t g = 0; g < a.n_groups; g++) {
+        float* out = a.out + (uint64_t)g * a.pstride;
+        const uint32_t r_lo = g * a.rows_per_group, r_hi = r_lo + a.rows_per_group < a.n_rows ? r_lo + a.rows_per_group : a.n_rows;
+        for (uint64_t n = 0; n < a.mix_len; n++) {
+            const uint64_t prod = (n - a.origin) * (uint64_t)a.from, i = prod / a.to;
+            const float numf = (float)(uint32_t)(prod - i * a.to);
+            float acc = 0.0f;
+            bool any = false;
+            for (uint32_t r = r_lo; r < r_hi; r++) {
+                const rb_lerpmix_row& row = a.rows[r];
+                if (n < row.lo || n >= row.hi) continue;
+                const float xa = row.p[(uint32_t)i];
+                float x = xa;
+                if (n < row.hi_int) x = xa + ((row.p[(uint32_t)i + 1] - xa) * numf) / a.den_f;
+                if (a.has_post) x = x * row.post;
+                acc = acc + x, any = true;
+            }
+            if (any || a.n_groups == 1) out[n] = acc;
+        }
+    }
+    return cudaSuccess;
+}
+
 cudaError_t rb_lanes_launch_sum(const float* partial, uint32_t n_groups, uint64_t pstride, uint64_t n_floats, float* out, cudaStream_t) {
     for (uint64_t m = 0; m < n_floats; m++) {
         float acc = 0.0f;

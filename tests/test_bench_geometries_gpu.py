@@ -61,7 +61,7 @@ def _check_fused(ctx, srcs, ch, family, group=None, flags=0):
     assert_close_peak(got, ref, 1e-5, "fused kernel vs the reference's sequential mixer")
     per_stream = [oracle.chain_uniform(s, ch, 48000) for s in streams]
     starts = [0] * len(srcs)
-    want = fused_expected_mix(3 if family == 4 else family, per_stream, starts, ref.size) if family >= 2 else grouped_expected_mix(per_stream, starts, ref.size, group)
+    want = grouped_expected_mix(per_stream, starts, ref.size, group or len(srcs)) if family in (0, 1, 5, 6) else fused_expected_mix(3 if family == 4 else family, per_stream, starts, ref.size)
     assert_bit_exact(got, want, "fused kernel vs oracle streams added in the kernel's documented order")
 
 
@@ -83,7 +83,7 @@ def test_nofilter_bench_geometry_mono_4096(ctx):
     """resample -> amplify -> mix at 4096 streams: a chain without a filter carries nothing from sample to sample, so the planner
     cuts the timeline into segments for the lane-pair kernel (family 4) -- still every stream's serial samples bit for bit; with
     RB_FUSED_LANES | ... pinned off (RB_SEGMENTS_FROM) it is k_fused_hot<1, false> with full CTAs."""
-    _check_fused(ctx, _cfg3(4096, 4410, lp=None, seed=34000), 1, family=(1, 4))
+    _check_fused(ctx, _cfg3(4096, 4410, lp=None, seed=34000), 1, family=(1, 4, 6))
 
 
 def test_cfg5_auto_selected_large_batch(ctx):
@@ -324,3 +324,49 @@ def test_fx_kernel_with_limiter(ctx, shape):
         ref = b.render_mix()
     per = None
     assert_close_peak(got, ref, 2e-6, f"k_fused_fx against the general path, {shape}")
+
+
+
+# ------------------------------------------------------------------ k_lerp_mix: filter-free chains, parallel over the timeline
+def test_lerp_mix_kernel_ragged_and_exact_order(ctx):
+    """resample -> [gain] -> mix without a filter: k_lerp_mix (family 6).  Ragged lengths (empty, one frame, shorter than a tile),
+    late joiners in phase (multiples of `to` = 160 frames), inputs outside the exact-reciprocal class, signed zeros; with
+    RB_MIX_EXACT_ORDER the sum is the reference's sequential one, bit for bit."""
+    rng = np.random.default_rng(8)
+    n = 900
+    lens = [int(v) for v in rng.integers(1, 6000, n)]
+    lens[:6] = [0, 1, 2, 147, 148, 5999]
+    starts = sorted(160 * int(v) for v in rng.integers(0, 12, n))
+    pcms = [noise(L, 71000 + i) for i, L in enumerate(lens)]
+    pcms[7][3:9] = [1e-42, -0.0, 0.0, 1e25, -1e-41, 5.0]
+    pcms[8][:] = 0.0
+    srcs = [rb.UniformSourceIterator(rb.TestSource(p, 1, 44100), 1, 48000).amplify(0.7 + 0.001 * i) for i, p in enumerate(pcms)]
+    streams = [to_oracle(s, st) for s, st in zip(srcs, starts)]
+    ref = oracle.mixer(streams, 1, 48000)
+    per = [oracle.chain_uniform(to_oracle(s), 1, 48000) for s in srcs]
+    with rb.Batch(srcs, 1, 48000, mix_starts=starts, ctx=ctx) as b:
+        assert b.kernel_family == 6, b.kernel_family
+        group = b.mix_group
+        b.upload_all()
+        got = b.render_mix()
+    assert_close_peak(got, ref, 1e-5, "k_lerp_mix vs the sequential mixer")
+    assert_bit_exact(got, grouped_expected_mix(per, starts, ref.size, group or n), "k_lerp_mix vs oracle streams in its documented order")
+    with rb.Batch(srcs, 1, 48000, mix_starts=starts, flags=capi.RB_MIX_EXACT_ORDER, ctx=ctx) as b:
+        assert b.kernel_family == 6 and b.mix_group == 0 and b.launches_per_render == 1
+        b.upload_all()
+        assert_bit_exact(b.render_mix(), ref, "k_lerp_mix, RB_MIX_EXACT_ORDER: the reference's order")
+
+
+def test_lerp_mix_other_ratio_no_gain_and_out_of_phase_fallback(ctx):
+    srcs = [rb.UniformSourceIterator(rb.TestSource(noise(2000 + i, 72000 + i), 1, 22050), 1, 48000) for i in range(200)]
+    ref = oracle.mixer([to_oracle(s) for s in srcs], 1, 48000)
+    with rb.Batch(srcs, 1, 48000, flags=capi.RB_MIX_EXACT_ORDER, ctx=ctx) as b:
+        assert b.kernel_family == 6
+        b.upload_all()
+        assert_bit_exact(b.render_mix(), ref, "22.05 -> 48 kHz, no gain, exact order")
+    starts = sorted(int(v) for v in np.random.default_rng(9).integers(0, 999, 200))     # not in phase: another kernel serves it
+    with rb.Batch(srcs, 1, 48000, mix_starts=starts, ctx=ctx) as b:
+        assert b.kernel_family != 6
+        b.upload_all()
+        got = b.render_mix()
+    assert_close_peak(got, oracle.mixer([to_oracle(s, st) for s, st in zip(srcs, starts)], 1, 48000), 1e-5, "out of phase")
