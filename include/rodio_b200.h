@@ -354,7 +354,7 @@ void rb_spatial_volumes(const float emitter[3], const float left_ear[3], const f
 
 /* ---- WAV ingest (host only; src/decoder/wav.rs:119-151 reads 8 / 16 / 24 / 32-bit integer and 32-bit float PCM and hands
  * every sample to dasp's to_sample()): rb_wav_parse finds the format and the sample data inside a RIFF/WAVE image so that the
- * bytes of an `assets/*.wav` go to HBM as they are (rb_batch_upload with `format`) and are converted on the device by the same
+ * bytes of the `.wav` files under assets/ go to HBM as they are (rb_batch_upload with `format`) and are converted on the device by the same
  * rules (8-bit WAV is unsigned: RB_FMT_U8 = hound's i8 after its -128).  24-bit samples are packed in 3 bytes: `format` is then
  * RB_FMT_I24_IN_I32 and `packed24` is set -- widen them with rb_wav_unpack24 first. ---- */
 typedef struct rb_wav_info {
