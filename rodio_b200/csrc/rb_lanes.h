@@ -28,7 +28,7 @@ struct rb_lanes_plan;
 // class (rb_lanes_plan.h classes_by_ratio): the mixer sum then groups by class first.
 // mode: LANES_TIME_PARALLEL asks for the time-parallel biquad plan (built only when the batch qualifies: rb_lanes_batch.cu),
 // LANES_NO_DUO keeps every class on k_fused_lanes (A/B runs; the environment variable RB_NO_DUO does the same).
-enum : uint32_t { LANES_TIME_PARALLEL = 1u, LANES_NO_DUO = 2u, LANES_ONE_GROUP = 4u };   // ONE_GROUP: k_lerp_mix sums all streams in one
+enum : uint32_t { LANES_TIME_PARALLEL = 1u, LANES_NO_DUO = 2u, LANES_ONE_GROUP = 4u, LANES_NO_LERPMIX = 8u };   // ONE_GROUP: k_lerp_mix sums all streams in one
                                                                                        // sequential chain (the reference's order, bit for bit)
 cudaError_t rb_lanes_try_create(const rb_lanes_stream* streams, size_t n_streams, uint32_t channels, bool has_biquad, bool has_post,
                                 bool has_pre, bool front, float* d_out, uint64_t mix_len, int sm_count, cudaStream_t st, rb_lanes_plan** out,

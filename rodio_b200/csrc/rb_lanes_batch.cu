@@ -157,7 +157,7 @@ cudaError_t rb_lanes_try_create(const rb_lanes_stream* streams, size_t n_streams
 
     // ---- chains without a filter: nothing is carried from sample to sample, the whole batch is parallel over the timeline ----
     if ((mode & LANES_TIME_PARALLEL) && !has_biquad && channels == 1 && !has_pre && !front && classes.size() == 1 && from[0] < to[0] &&
-        mix_len < (1ull << 31) && !getenv("RB_NO_LERPMIX")) {
+        mix_len < (1ull << 31) && !(mode & LANES_NO_LERPMIX) && !getenv("RB_NO_LERPMIX")) {
         const uint32_t T = to[0];
         uint64_t origin = ~0ull;
         bool in_phase = true;
