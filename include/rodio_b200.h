@@ -91,9 +91,19 @@ typedef enum {
                                  also fade_in(d) = ramp(d, 0, 1, false) (fadein.rs:8-15) and
                                  fade_out(d) = ramp(d, 1, 0, true) (fadeout.rs:8-15)
                                  ns[0] = duration (> 0), f32[0] = start_gain, f32[1] = end_gain, u32[0] = clamp_end */
-    RB_FX_TAKE_DURATION = 14  /* Source::take_duration(duration) [+ set_filter_fadeout] src/source/take.rs:9-26,:34-41,:107-148
+    RB_FX_TAKE_DURATION = 14, /* Source::take_duration(duration) [+ set_filter_fadeout] src/source/take.rs:9-26,:34-41,:107-148
                                  ns[0] = duration, u32[0] = 1 when the fade-out filter is set                */
+    RB_FX_SIGNAL = 15         /* SignalGenerator::new(sample_rate, frequency, function).take(n) src/source/signal_generator.rs:107-135
+                                 (SineWave / SquareWave / TriangleWave / SawtoothWave = the same at 48 kHz, src/source/sine.rs:23-27):
+                                 the SOURCE of the stream instead of uploaded PCM -- only as effects[0] of a descriptor with
+                                 n_samples = 0, channels = 1, format f32, span_len = 0 (the generator reports None); generated on
+                                 the device: f32 phase accumulation `phase = (phase + 1/(rate/freq)).rem_euclid(1.0)` and, for the
+                                 sine, glibc's sinf bit for bit (double-precision polynomial, restated in rb_kernels.cu).
+                                 u32[0] = rb_signal_function, f32[0] = frequency (> 0 and finite: the reference asserts),
+                                 ns[0] = n, the number of samples taken from the endless generator             */
 } rb_effect_kind;
+typedef enum { RB_SIGNAL_SINE = 0, RB_SIGNAL_TRIANGLE = 1, RB_SIGNAL_SQUARE = 2, RB_SIGNAL_SAWTOOTH = 3 } rb_signal_function;
+                              /* src/source/signal_generator.rs:40-69 */
 
 typedef struct rb_effect {
     uint32_t kind;     /* rb_effect_kind */

@@ -30,7 +30,7 @@ struct ro_stream {
     const float* pcm;
 };
 enum { FX_AMPLIFY = 1, FX_SPEED, FX_LOW_PASS, FX_HIGH_PASS, FX_REVERB, FX_AGC, FX_LIMIT, FX_SPATIAL,
-       FX_CHANNEL_VOLUME, FX_UNIFORM, FX_DELAY, FX_DISTORTION, FX_LINEAR_RAMP, FX_TAKE_DURATION };
+       FX_CHANNEL_VOLUME, FX_UNIFORM, FX_DELAY, FX_DISTORTION, FX_LINEAR_RAMP, FX_TAKE_DURATION, FX_SIGNAL };
 
 float ro_lerp(float a, float b, uint32_t num, uint32_t den) { return lerp(a, b, num, den); }
 float ro_db_to_linear(float d) { return db_to_linear(d); }
@@ -83,7 +83,15 @@ static Src apply_effects(Src src, const ro_effect* fx, uint32_t n) {
     }
     return src;
 }
-static Src build(const ro_stream& s) { return apply_effects(make_input(s), s.effects, s.n_effects); }
+static Src build(const ro_stream& s) {
+    // effects[0] == FX_SIGNAL: the stream's source is SignalGenerator::new(rate, f32[0], u32[0]).take(ns[0]) instead of PCM
+    if (s.n_effects && s.effects[0].kind == FX_SIGNAL) {
+        const ro_effect& e = s.effects[0];
+        Src gen = std::make_unique<TakeN>(std::make_unique<SignalGenerator>(s.sample_rate, e.f32[0], (SignalGenerator::Fn)e.u32[0]), (size_t)e.ns[0]);
+        return apply_effects(std::move(gen), s.effects + 1, s.n_effects - 1);
+    }
+    return apply_effects(make_input(s), s.effects, s.n_effects);
+}
 
 static int drain(Source& src, float* out, uint64_t cap, uint64_t* n_out) {
     uint64_t n = 0;

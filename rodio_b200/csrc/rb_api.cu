@@ -374,11 +374,26 @@ static rb_status plan_stream(PlanStream& ps, uint16_t mixer_ch, uint32_t mixer_r
         nd.rate_out = rate, nd.span_out = span;
         ps.nodes.push_back(nd);
     }
+    bool first_fx = true;
     for (const rb_effect& e : ps.fx) {
         PlanNode nd;
         nd.d.c_in = nd.d.c_out = c, nd.d.n_in = nd.d.n_out = n;
         nd.rate_out = rate, nd.span_out = span;
+        const bool is_first = first_fx;
+        first_fx = false;
         switch (e.kind) {
+            case RB_FX_SIGNAL: {
+                // SignalGenerator::with_function (signal_generator.rs:107-128): mono, span-less, endless; `.take(n)` bounds it
+                if (!is_first || d.n_samples != 0 || d.channels != 1 || d.format != RB_FMT_F32 || d.span_len != 0)
+                    return fail(RB_ERR_INVALID_ARGUMENT, "signal generator: only as effects[0] of an empty mono f32 span-less descriptor");
+                if (e.u32[0] > RB_SIGNAL_SAWTOOTH) return fail(RB_ERR_INVALID_ARGUMENT, "signal generator: unknown function");
+                if (!(e.f32[0] > 0.0f)) return fail(RB_ERR_INVALID_ARGUMENT, "signal generator: frequency must be greater than zero");
+                if (!std::isfinite(e.f32[0])) return fail(RB_ERR_UNSUPPORTED, "signal generator: infinite frequency");
+                volatile float period = (float)rate / e.f32[0];          // :118
+                nd.d.kind = RB_N_SIGNAL, nd.d.p.sig.step = 1.0f / period, nd.d.p.sig.fn = e.u32[0];   // :119
+                nd.d.n_in = 0, nd.d.n_out = e.ns[0];
+                break;
+            }
             case RB_FX_AMPLIFY:
                 nd.d.kind = RB_N_AMPLIFY, nd.d.p.amp.factor = e.f32[0];
                 break;

@@ -24,7 +24,8 @@ enum rb_node_kind : uint32_t {
     RB_N_DISTORT = 9,   // src/source/distortion.rs:66-72
     RB_N_RAMP = 10,     // src/source/linear_ramp.rs:79-104 (also fade_in / fade_out)
     RB_N_TAKE = 11,     // src/source/take.rs:107-148 (+ fade-out filter :34-41)
-    RB_N_KINDS = 12
+    RB_N_SIGNAL = 12,   // src/source/signal_generator.rs:107-135 (a source: no input)
+    RB_N_KINDS = 13
 };
 
 // Closed-form description of one UniformSourceIterator application.
@@ -70,6 +71,7 @@ struct alignas(16) rb_node_dev {
         struct { float gain, threshold; } dist;
         struct { uint64_t total_ns, dt_ns; float start, end; uint32_t clamp_end; } ramp;
         struct { uint64_t total_ns, dps_ns, count; float total_ms_f; uint32_t fadeout; } take;
+        struct { float step; uint32_t fn; } sig;
         rb_uniform_params uni;
     } p;
 };

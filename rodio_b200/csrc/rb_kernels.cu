@@ -59,6 +59,104 @@ __global__ void __launch_bounds__(TPB) k_delay(const rb_node_dev* __restrict__ n
     for_each_out(nd, [&](uint64_t o) { nd.dst[o] = (o < D) ? 0.0f : x[o - D]; });
 }
 
+// ---------------------------------------------------------------- signal generators (a source, src/source/signal_generator.rs)
+// glibc's sinf for arguments in [0, 2*pi] -- what `(TAU * phase).sin()` (signal_generator.rs:51-53) resolves to on linux-gnu:
+// the argument widened to double, one multiply-subtract of range reduction into [-pi/4, pi/4] with the quadrant, a degree-7
+// (sine) or degree-8 (cosine) polynomial in double, one rounding to float.  The coefficients are the published ones of glibc
+// >= 2.28 (sysdeps/ieee754/flt-32/sincosf_data.c); the restatement was held against the libm of this image on every float of
+// [0, 0x40c90fdb] (tools/microbench/sinf_exhaustive.cpp: 1 086 918 620 arguments, 0 mismatches, with and without contraction of
+// the double multiply-adds -- so the ifunc variant libm picks on the host does not matter).  FP64 here is IEEE: bit for bit.
+__device__ __forceinline__ float sinf_glibc_0_tau(float y) {
+    const double x = (double)y;
+    const uint32_t top = (__float_as_uint(y) >> 20) & 0x7ffu;
+    double xr, x2, sgn = 1.0;
+    int n = 0;
+    if (top < 0x3f4u) {                      // |y| < pi/4 (abstop12 of 0x1.921FB6p-1f)
+        if (top < 0x398u) return y;          // |y| < 2^-12
+        xr = x, x2 = __dmul_rn(x, x);
+    } else {
+        const double r = __dmul_rn(x, 0x1.45F306DC9C883p+23);               // 2/pi * 2^24
+        n = (__double2int_rz(r) + 0x800000) >> 24;
+        xr = __dsub_rn(x, __dmul_rn((double)n, 0x1.921FB54442D18p0));       // pi/2
+        sgn = (n & 3) == 1 || (n & 3) == 2 ? -1.0 : 1.0;                     // sign[n & 3] = {1, -1, -1, 1}
+        x2 = __dmul_rn(xr, xr);
+        xr = __dmul_rn(xr, sgn);
+    }
+    const bool neg = (n & 2) != 0;           // second table: the cosine coefficients negated
+    if ((n & 1) == 0) {
+        const double s1c = -0x1.555545995a603p-3, s2c = 0x1.1107605230bc4p-7, s3c = -0x1.994eb3774cf24p-13;
+        const double x3 = __dmul_rn(xr, x2);
+        const double s1 = __dadd_rn(s2c, __dmul_rn(x2, s3c));
+        const double x7 = __dmul_rn(x3, x2);
+        const double s = __dadd_rn(xr, __dmul_rn(x3, s1c));
+        return __double2float_rn(__dadd_rn(s, __dmul_rn(x7, s1)));
+    }
+    const double k = neg ? -1.0 : 1.0;
+    const double c0 = k, c1 = k * -0x1.ffffffd0c621cp-2, c2k = k * 0x1.55553e1068f19p-5, c3 = k * -0x1.6c087e89a359dp-10,
+                 c4 = k * 0x1.99343027bf8c3p-16;
+    const double x4 = __dmul_rn(x2, x2);
+    const double c2 = __dadd_rn(c3, __dmul_rn(x2, c4));
+    const double c1v = __dadd_rn(c0, __dmul_rn(x2, c1));
+    const double x6 = __dmul_rn(x4, x2);
+    const double c = __dadd_rn(c1v, __dmul_rn(x4, c2k));
+    return __double2float_rn(__dadd_rn(c, __dmul_rn(x6, c2)));
+}
+__device__ __forceinline__ float signal_value(uint32_t fn, float phase) {   // signal_generator.rs:51-69
+    switch (fn) {
+        case RB_SIGNAL_SINE: return sinf_glibc_0_tau(mul(6.2831855f, phase));
+        case RB_SIGNAL_TRIANGLE: return sub(mul(4.0f, fabsf(sub(phase, floorf(add(phase, 0.5f))))), 1.0f);
+        case RB_SIGNAL_SQUARE: return phase < 0.5f ? 1.0f : -1.0f;           // phase % 1.0 == phase inside [0, 1)
+        default: return mul(2.0f, sub(phase, floorf(add(phase, 0.5f))));
+    }
+}
+// A CTA owns 32 generators.  The phase is a serial f32 recurrence per generator (`phase = (phase + step).rem_euclid(1.0)`,
+// signal_generator.rs:133: it drifts by design, so it cannot be computed from the sample index): warp 0, lane = generator, walks
+// it a tile ahead into shared memory; the other seven warps evaluate the waveform of the previous tile and store it with
+// consecutive threads on consecutive samples.  Latency-bound by the recurrence (3 dependent operations per sample) -- input
+// generation, outside every timed region.
+constexpr int SIG_TILE = 128, SIG_THREADS = 256, SIG_PITCH = SIG_TILE + 1;
+__global__ void __launch_bounds__(SIG_THREADS) k_siggen(const rb_node_dev* __restrict__ nodes, uint32_t n_nodes) {
+    __shared__ float s_phase[2][32 * SIG_PITCH];
+    const uint32_t g0 = blockIdx.x * 32, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t n_g = min(32u, n_nodes - g0);
+    uint64_t max_n = 0;
+    for (uint32_t g = 0; g < n_g; g++) max_n = max(max_n, nodes[g0 + g].n_out);
+    const uint64_t n_tiles = (max_n + SIG_TILE - 1) / SIG_TILE;
+    float phase = 0.0f, step = 0.0f;
+    if (warp == 0 && lane < n_g) step = nodes[g0 + lane].p.sig.step;
+    for (uint64_t it = 0; it <= n_tiles; it++) {
+        if (warp == 0) {
+            if (it < n_tiles && lane < n_g) {
+                float* row = &s_phase[it & 1][lane * SIG_PITCH];
+                if (step < 1.0f) {
+#pragma unroll 8
+                    for (int t = 0; t < SIG_TILE; t++) {
+                        row[t] = phase;
+                        const float q = add(phase, step);            // < 2: q % 1.0 is q or q - 1, both exact
+                        phase = q >= 1.0f ? sub(q, 1.0f) : q;
+                    }
+                } else {
+                    for (int t = 0; t < SIG_TILE; t++) {
+                        row[t] = phase;
+                        const float q = add(phase, step);
+                        phase = sub(q, floorf(q));                    // q >= 0: fmodf(q, 1.0f) exactly
+                    }
+                }
+            }
+        } else if (it > 0) {
+            const uint64_t base = (it - 1) * SIG_TILE;
+            for (uint32_t g = 0; g < n_g; g++) {
+                const rb_node_dev& nd = nodes[g0 + g];
+                const uint32_t fn = nd.p.sig.fn;
+                const float* row = &s_phase[(it - 1) & 1][g * SIG_PITCH];
+                for (uint32_t t = threadIdx.x - 32; t < SIG_TILE; t += SIG_THREADS - 32)
+                    if (base + t < nd.n_out) nd.dst[base + t] = signal_value(fn, row[t]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // Distortion — src/source/distortion.rs:66-72 : (x * gain).clamp(-t, t)   (f32::clamp: NaN passes through)
 __global__ void __launch_bounds__(TPB) k_distort(const rb_node_dev* __restrict__ nodes) {
     const rb_node_dev& nd = nodes[blockIdx.x];
@@ -590,6 +688,7 @@ cudaError_t rb_launch_nodes(uint32_t kind, const rb_node_dev* d_nodes, uint32_t 
             break;
         }
         case RB_N_LIMIT: k_limit_tile<<<(n_nodes + 31) / 32, 32, 0, st>>>(d_nodes, n_nodes); break;
+        case RB_N_SIGNAL: k_siggen<<<(n_nodes + 31) / 32, SIG_THREADS, 0, st>>>(d_nodes, n_nodes); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

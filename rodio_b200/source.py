@@ -277,6 +277,49 @@ class TestSource(Source):
         super().__init__(np.asarray(samples), channels, sample_rate, span_len=0)
 
 
+class Function:
+    """source::Function -- src/source/signal_generator.rs:40-49."""
+    Sine, Triangle, Square, Sawtooth = capi.RB_SIGNAL_SINE, capi.RB_SIGNAL_TRIANGLE, capi.RB_SIGNAL_SQUARE, capi.RB_SIGNAL_SAWTOOTH
+
+
+class SignalGenerator:
+    """source::SignalGenerator::new(sample_rate, frequency, function) -- src/source/signal_generator.rs:85-99: an endless mono
+    source; `.take(n)` (Iterator::take, what the reference's tests and examples bound it with) gives the Source that is handed
+    to the mixer.  The samples are generated on the device (RB_FX_SIGNAL): nothing is uploaded."""
+
+    def __init__(self, sample_rate: int, frequency: float, f: int = Function.Sine):
+        if not float(np.float32(frequency)) > 0.0:
+            raise ValueError("frequency must be greater than zero (signal_generator.rs:112)")
+        self.rate, self.frequency, self.function = int(sample_rate), float(np.float32(frequency)), int(f)
+
+    def channels(self) -> int:
+        return 1
+
+    def sample_rate(self) -> int:
+        return self.rate
+
+    def take(self, n: int) -> Source:
+        e = Effect.make(capi.RB_FX_SIGNAL, u32=[self.function], f32=[self.frequency], ns=[int(n)])
+        return Source(np.zeros(0, dtype=np.float32), 1, self.rate, 0, [e])
+
+
+def SineWave(freq: float) -> SignalGenerator:
+    """source::SineWave::new(freq): 48 kHz mono -- src/source/sine.rs:23-27."""
+    return SignalGenerator(48000, freq, Function.Sine)
+
+
+def SquareWave(freq: float) -> SignalGenerator:
+    return SignalGenerator(48000, freq, Function.Square)
+
+
+def TriangleWave(freq: float) -> SignalGenerator:
+    return SignalGenerator(48000, freq, Function.Triangle)
+
+
+def SawtoothWave(freq: float) -> SignalGenerator:
+    return SignalGenerator(48000, freq, Function.Sawtooth)
+
+
 class WavInfo(C.Structure):
     _fields_ = [("sample_rate", C.c_uint32), ("channels", C.c_uint16), ("bits_per_sample", C.c_uint16), ("format", C.c_uint16),
                 ("packed24", C.c_uint16), ("pad_", C.c_uint32), ("data_offset", C.c_uint64), ("data_bytes", C.c_uint64),
