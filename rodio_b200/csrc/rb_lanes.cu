@@ -63,9 +63,12 @@ __global__ void __launch_bounds__(64) k_fused_duo_split(lanes::Args a) {
 // Arithmetic per sample: a + ((b - a) * num) / den with the division as the exact reciprocal step of the lane kernels for streams
 // whose inputs are inside the class (k_classify_inputs), __fdiv_rn otherwise; (-0) / den keeps its sign.
 // ---------------------------------------------------------------------------------------------------
-constexpr int LM_U = 4;
+constexpr int LM_U = 4;        // positions per thread
+constexpr int LM_R = 4;        // rows whose loads are in flight together (2 * LM_U * LM_R independent loads per thread)
+constexpr int LM_STAGE = 64;   // row descriptors staged in shared memory at a time
 template <int NPOST>
 __global__ void __launch_bounds__(256) k_lerp_mix(rb_lerpmix_args a) {
+    __shared__ rb_lerpmix_row s_rows[LM_STAGE];
     const uint64_t tile_lo = (uint64_t)blockIdx.x * (256 * LM_U);
     if (tile_lo >= a.mix_len) return;
     const uint64_t tile_hi = min(a.mix_len, tile_lo + 256 * LM_U);
@@ -85,35 +88,71 @@ __global__ void __launch_bounds__(256) k_lerp_mix(rb_lerpmix_args a) {
     }
     const float den = a.den_f, rcp = a.rcp_den;
     const uint32_t t_lo = (uint32_t)tile_lo, t_hi = (uint32_t)tile_hi;
-    for (uint32_t r = r_lo; r < r_hi; r++) {
-        const rb_lerpmix_row row = a.rows[r];                    // warp-uniform: two 16-byte broadcast loads
-        if (row.hi <= t_lo || row.lo >= t_hi) continue;          // the stream is silent on this tile
-        const bool safe = !(a.lane_rows[row.row].flags & lanes::ROW_UNSAFE);
-        const float* __restrict__ p = row.p;
-        if (safe && row.lo <= t_lo && row.hi_int >= t_hi) {
-            // interior: every position interpolates
-            float xa[LM_U], xb[LM_U];
+    for (uint32_t rs = r_lo; rs < r_hi; rs += LM_STAGE) {
+        // stage the next descriptors (and the classification verdict of their streams) once per CTA: the row loop below then
+        // issues its input loads without a dependent global load in front of them
+        const uint32_t n_st = min((uint32_t)LM_STAGE, r_hi - rs);
+        __syncthreads();
+        if (threadIdx.x < n_st) {
+            rb_lerpmix_row row = a.rows[rs + threadIdx.x];
+            row.pad_ = (a.lane_rows[row.row].flags & lanes::ROW_UNSAFE) ? 1u : 0u;
+            s_rows[threadIdx.x] = row;
+        }
+        __syncthreads();
+        for (uint32_t r0 = 0; r0 < n_st; r0 += LM_R) {
+            // a run of LM_R rows that all interpolate on the whole tile: every load first, then the sums in row order
+            bool fast = r0 + LM_R <= n_st;
 #pragma unroll
-            for (int u = 0; u < LM_U; u++) xa[u] = __ldg(p + idx[u]), xb[u] = __ldg(p + idx[u] + 1);
-#pragma unroll
-            for (int u = 0; u < LM_U; u++) {
-                const float m = __fmul_rn(__fsub_rn(xb[u], xa[u]), numf[u]);
-                const float q0 = __fmul_rn(m, rcp);
-                float q = __fmaf_rn(__fmaf_rn(-q0, den, m), rcp, q0);
-                q = m == 0.0f ? m : q;
-                float x = __fadd_rn(xa[u], q);
-                if (NPOST) x = __fmul_rn(x, row.post);
-                acc[u] = __fadd_rn(acc[u], x), any[u] = true;
+            for (int j = 0; j < LM_R; j++) {
+                const rb_lerpmix_row& row = s_rows[min(r0 + j, n_st - 1)];
+                fast = fast && !row.pad_ && row.lo <= t_lo && row.hi_int >= t_hi;
             }
-        } else {
+            if (fast) {
+                float xa[LM_R][LM_U], xb[LM_R][LM_U];
 #pragma unroll
-            for (int u = 0; u < LM_U; u++) {
-                if (pos[u] < row.lo || pos[u] >= row.hi || pos[u] >= t_hi) continue;
-                const float xa = __ldg(p + idx[u]);
-                float x = xa;
-                if (pos[u] < row.hi_int) x = __fadd_rn(xa, __fdiv_rn(__fmul_rn(__fsub_rn(__ldg(p + idx[u] + 1), xa), numf[u]), den));
-                if (NPOST) x = __fmul_rn(x, row.post);
-                acc[u] = __fadd_rn(acc[u], x), any[u] = true;
+                for (int j = 0; j < LM_R; j++) {
+                    const float* __restrict__ p = s_rows[r0 + j].p;
+#pragma unroll
+                    for (int u = 0; u < LM_U; u++) xa[j][u] = __ldg(p + idx[u]), xb[j][u] = __ldg(p + idx[u] + 1);
+                }
+#pragma unroll
+                for (int j = 0; j < LM_R; j++) {
+                    const float post = s_rows[r0 + j].post;
+#pragma unroll
+                    for (int u = 0; u < LM_U; u++) {
+                        const float m = __fmul_rn(__fsub_rn(xb[j][u], xa[j][u]), numf[u]);
+                        const float q0 = __fmul_rn(m, rcp);
+                        float q = __fmaf_rn(__fmaf_rn(-q0, den, m), rcp, q0);
+                        q = m == 0.0f ? m : q;
+                        float x = __fadd_rn(xa[j][u], q);
+                        if (NPOST) x = __fmul_rn(x, post);
+                        acc[u] = __fadd_rn(acc[u], x), any[u] = true;
+                    }
+                }
+                continue;
+            }
+            for (uint32_t j = r0; j < min(r0 + LM_R, n_st); j++) {
+                const rb_lerpmix_row row = s_rows[j];
+                if (row.hi <= t_lo || row.lo >= t_hi) continue;          // the stream is silent on this tile
+                const float* __restrict__ p = row.p;
+#pragma unroll
+                for (int u = 0; u < LM_U; u++) {
+                    if (pos[u] < row.lo || pos[u] >= row.hi || pos[u] >= t_hi) continue;
+                    const float xa = __ldg(p + idx[u]);
+                    float x = xa;
+                    if (pos[u] < row.hi_int) {
+                        const float m = __fmul_rn(__fsub_rn(__ldg(p + idx[u] + 1), xa), numf[u]);
+                        float q = __fdiv_rn(m, den);
+                        if (!row.pad_) {
+                            const float q0 = __fmul_rn(m, rcp);
+                            q = __fmaf_rn(__fmaf_rn(-q0, den, m), rcp, q0);
+                            q = m == 0.0f ? m : q;
+                        }
+                        x = __fadd_rn(xa, q);
+                    }
+                    if (NPOST) x = __fmul_rn(x, row.post);
+                    acc[u] = __fadd_rn(acc[u], x), any[u] = true;
+                }
             }
         }
     }

@@ -178,10 +178,12 @@ cudaError_t rb_lanes_try_create(const rb_lanes_stream* streams, size_t n_streams
                 lr[i].lo = (uint32_t)s.mix_start, lr[i].hi_int = (uint32_t)(s.mix_start + r.n_int), lr[i].hi = (uint32_t)(s.mix_start + s.out_len);
                 lr[i].post = has_post ? s.post : 1.0f, lr[i].row = (uint32_t)i, lr[i].pad_ = 0;
             }
-            // stream groups: enough CTAs for two waves; a group is summed sequentially in insertion order
+            // stream groups: a group is summed sequentially in insertion order by one CTA per tile of 1024 frames.  64 streams per
+            // group keep the partial rows at 3 % of the input bytes; fewer (down to 16) when that leaves the machine short of CTAs
             const uint64_t tiles = (mix_len + 1023) / 1024;
-            uint64_t groups = (2ull * (uint64_t)(sm_count > 0 ? sm_count : 148) + tiles - 1) / tiles;
-            groups = std::max<uint64_t>(1, std::min<uint64_t>(groups, (n_streams + 63) / 64));
+            const uint64_t two_waves = 2ull * (uint64_t)(sm_count > 0 ? sm_count : 148);
+            uint64_t groups = std::max<uint64_t>((two_waves + tiles - 1) / tiles, (n_streams + 63) / 64);
+            groups = std::max<uint64_t>(1, std::min<uint64_t>(groups, (n_streams + 15) / 16));
             if (mode & LANES_ONE_GROUP) groups = 1;
             const uint32_t per = (uint32_t)((n_streams + groups - 1) / groups);
             groups = (n_streams + per - 1) / per;
