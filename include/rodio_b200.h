@@ -93,6 +93,13 @@ typedef enum {
                                  ns[0] = duration (> 0), f32[0] = start_gain, f32[1] = end_gain, u32[0] = clamp_end */
     RB_FX_TAKE_DURATION = 14, /* Source::take_duration(duration) [+ set_filter_fadeout] src/source/take.rs:9-26,:34-41,:107-148
                                  ns[0] = duration, u32[0] = 1 when the fade-out filter is set                */
+    RB_FX_MIX = 16,           /* Source::mix(other) src/source/mod.rs:253-261, mix.rs:10-53 -- and with it crossfade.rs:10-23:
+                                 take_crossfade_with(other, d) = self.take_duration(d) [fade-out filter set] .mix(
+                                 other.take_duration(d).fade_in(d)).  u32[0] = index, in the descriptor array of the same
+                                 rb_batch_create call, of the SECOND input: a descriptor of its own (PCM or generator, its own
+                                 adapters) whose mix_start is RB_MIX_START_CONSUMED -- it is not added to the mixer, one MIX
+                                 consumes it.  Both inputs go through UniformSourceIterator::new(_, channels, rate) of the
+                                 FIRST input (mix.rs:16-21); s1 + s2 while both run, then whichever is left (mix.rs:43-53).  */
     RB_FX_SIGNAL = 15         /* SignalGenerator::new(sample_rate, frequency, function).take(n) src/source/signal_generator.rs:107-135
                                  (SineWave / SquareWave / TriangleWave / SawtoothWave = the same at 48 kHz, src/source/sine.rs:23-27):
                                  the SOURCE of the stream instead of uploaded PCM -- only as effects[0] of a descriptor with
@@ -130,6 +137,9 @@ typedef struct rb_stream_desc {
                                the next frame boundary like src/mixer.rs:175-183.  The mixer sums in the
                                order of the add calls: increasing mix_start, ties in array order. */
 } rb_stream_desc;
+
+/* mix_start of a descriptor that is the second input of another descriptor's RB_FX_MIX */
+#define RB_MIX_START_CONSUMED UINT64_MAX
 
 typedef struct rb_context rb_context;
 typedef struct rb_batch rb_batch;

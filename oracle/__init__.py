@@ -97,9 +97,11 @@ class Fx:
     u32: Sequence = (0, 0, 0)
     f32: Sequence = (0.0,) * 12
     ns: Sequence = (0, 0)
+    other: Optional["Stream"] = None     # FX_MIX: the second input of Source::mix (a Stream of its own)
 
 
-FX_AMPLIFY, FX_LOW_PASS, FX_HIGH_PASS, FX_UNIFORM = 1, 3, 4, 10     # rodio_oracle_capi.cpp, enum of adapter kinds
+FX_AMPLIFY, FX_LOW_PASS, FX_HIGH_PASS, FX_UNIFORM, FX_SIGNAL, FX_MIX = 1, 3, 4, 10, 15, 16     # rodio_oracle_capi.cpp, enum of adapter kinds
+MIX_START_CONSUMED = 0xFFFFFFFFFFFFFFFF
 
 
 def fx(kind: int, u32=(), f32=(), ns=()) -> Fx:
@@ -112,9 +114,20 @@ def _fptr(a: np.ndarray):
 
 
 def _pack(streams: Sequence[Stream]):
+    """The ro_stream array of `streams`, followed by the second inputs of their FX_MIX adapters (entries of their own, marked
+    consumed: the mixer skips them; the adapter finds its second input through the entry's address in u32[1] / u32[2])."""
+    flat = list(streams)
+    i = 0
+    while i < len(flat):
+        for e in flat[i].effects:
+            o = getattr(e, "other", None)
+            if int(e.kind) == FX_MIX and o is not None and not any(o is f for f in flat):
+                flat.append(o)
+        i += 1
     keep = []
-    arr = (_Stream * max(1, len(streams)))()
-    for i, s in enumerate(streams):
+    arr = (_Stream * max(1, len(flat)))()
+    base = C.addressof(arr)
+    for i, s in enumerate(flat):
         pcm = np.ascontiguousarray(s.pcm, dtype=np.float32)
         fx = (_Effect * max(1, len(s.effects)))()
         for j, e in enumerate(s.effects):
@@ -125,6 +138,9 @@ def _pack(streams: Sequence[Stream]):
                 fx[j].f32[k] = float(e.f32[k])
             for k in range(2):
                 fx[j].ns[k] = int(e.ns[k])
+            if int(e.kind) == FX_MIX:
+                addr = base + C.sizeof(_Stream) * next(k for k, f in enumerate(flat) if f is e.other)
+                fx[j].u32[1], fx[j].u32[2] = addr & 0xFFFFFFFF, addr >> 32
         keep += [pcm, fx]
         arr[i].sample_rate = s.sample_rate
         arr[i].channels = s.channels
@@ -133,7 +149,7 @@ def _pack(streams: Sequence[Stream]):
         arr[i].span_len = s.span_len
         arr[i].n_effects = len(s.effects)
         arr[i].effects = C.cast(fx, C.POINTER(_Effect))
-        arr[i].mix_start = s.mix_start
+        arr[i].mix_start = s.mix_start if i < len(streams) else MIX_START_CONSUMED
         arr[i].pcm = _fptr(pcm)
     return arr, keep
 

@@ -274,6 +274,8 @@ struct PlanNode {
     rb_node_dev d{};       // src/dst filled at layout time
     uint32_t rate_out = 0;
     uint32_t span_out = 0;
+    uint32_t level = 0;    // launch level: one more than the node in front, for a MIX also behind the second input's last node
+    int64_t other = -1;    // RB_N_MIX2: the stream whose final samples are the second input
 };
 struct PlanStream {
     rb_stream_desc desc{};
@@ -288,6 +290,12 @@ struct PlanStream {
     size_t buf_off = 0;        // float offset in each ping-pong arena
     uint64_t buf_cap = 0;      // floats
     const float* final_ptr = nullptr;
+    // second input of another stream's RB_FX_MIX (mix_start == RB_MIX_START_CONSUMED): never added to the mixer
+    bool consumed = false, planned = false, planning = false;
+    int64_t consumer = -1;
+    uint32_t end_span = 0;     // what the end of the chain reports / leaves for the UniformSourceIterator that wraps it
+    uint64_t end_tail_pad = 0;
+    int64_t end_cv_last = -1;
 };
 
 static rb_uniform_seg uniform_seg(uint64_t in_samples, uint32_t c_in, uint32_t c_out, uint32_t from, uint32_t to) {
@@ -357,8 +365,10 @@ static rb_status plan_uniform(PlanNode& nd, uint64_t n_in, uint32_t c_in, uint32
     return RB_OK;
 }
 
-static rb_status plan_stream(PlanStream& ps, uint16_t mixer_ch, uint32_t mixer_rate) {
+static rb_status plan_stream(PlanStream& ps, uint16_t mixer_ch, uint32_t mixer_rate, std::vector<PlanStream>* all = nullptr, size_t self = 0) {
     const rb_stream_desc& d = ps.desc;
+    ps.consumed = d.mix_start == RB_MIX_START_CONSUMED;
+    ps.planning = true;
     if (d.sample_rate == 0 || d.channels == 0) return fail(RB_ERR_INVALID_ARGUMENT, "zero sample rate or channels");
     if (d.channels > RB_MAX_CHANNELS) return fail(RB_ERR_UNSUPPORTED, "more than 12 channels");
     if (d.format > RB_FMT_I24_IN_I32) return fail(RB_ERR_INVALID_ARGUMENT, "unknown sample format");
@@ -382,6 +392,51 @@ static rb_status plan_stream(PlanStream& ps, uint16_t mixer_ch, uint32_t mixer_r
         const bool is_first = first_fx;
         first_fx = false;
         switch (e.kind) {
+            case RB_FX_MIX: {
+                if (!all) return fail(RB_ERR_UNSUPPORTED, "mix: the second input is another descriptor of the batch (rb_batch_create)");
+                const size_t idx = e.u32[0];
+                if (idx >= all->size() || idx == self) return fail(RB_ERR_INVALID_ARGUMENT, "mix: bad index of the second input");
+                PlanStream& o = (*all)[idx];
+                if (o.desc.mix_start != RB_MIX_START_CONSUMED)
+                    return fail(RB_ERR_INVALID_ARGUMENT, "mix: the second input must carry mix_start = RB_MIX_START_CONSUMED");
+                if (o.consumer >= 0 || o.planning) return fail(RB_ERR_INVALID_ARGUMENT, "mix: the second input is consumed twice (or by itself)");
+                if (!o.planned) {
+                    rb_status so = plan_stream(o, mixer_ch, mixer_rate, all, idx);
+                    if (so != RB_OK) return so;
+                }
+                o.consumer = (int64_t)self;
+                // input1: UniformSourceIterator::new(self, channels, rate) (mix.rs:19) -- the identity on whole frames, but it never
+                // pulls the frame padding of a TakeDuration and re-bootstraps per span like any other
+                {
+                    PlanNode u1;
+                    rb_status s1 = plan_uniform(u1, (span && tail_pad) ? n - tail_pad : n, c, rate, span, c, rate, cv_last);
+                    if (s1 != RB_OK) return s1;
+                    if (u1.d.n_out != n) {
+                        u1.level = ps.nodes.empty() ? 0u : ps.nodes.back().level + 1u;
+                        ps.nodes.push_back(u1);
+                        n = u1.d.n_out;
+                    }
+                }
+                // input2: UniformSourceIterator::new(other, channels, rate) (mix.rs:20), appended to the OTHER stream's nodes
+                uint64_t n2 = o.chain_len;
+                {
+                    PlanNode u2;
+                    rb_status s2 = plan_uniform(u2, (o.end_span && o.end_tail_pad) ? o.chain_len - o.end_tail_pad : o.chain_len,
+                                                o.chain_channels, o.chain_rate, o.end_span, c, rate, o.end_cv_last);
+                    if (s2 != RB_OK) return s2;
+                    if (!(u2.d.p.uni.from == u2.d.p.uni.to && u2.d.c_in == u2.d.c_out) || u2.d.n_out != o.chain_len) {
+                        u2.level = o.nodes.empty() ? 0u : o.nodes.back().level + 1u;
+                        o.nodes.push_back(u2);
+                    }
+                    n2 = u2.d.n_out;
+                }
+                nd.d.kind = RB_N_MIX2, nd.d.p.mix2.n2 = n2, nd.other = (int64_t)idx;
+                nd.d.n_in = n, nd.d.n_out = std::max(n, n2);
+                nd.span_out = 0;           // Mix::current_span_len of two UniformSourceIterators == None (mix.rs:80-88)
+                nd.level = o.nodes.empty() ? 0u : o.nodes.back().level + 1u;
+                cv_last = -1, tail_pad = 0;
+                break;
+            }
             case RB_FX_SIGNAL: {
                 // SignalGenerator::with_function (signal_generator.rs:107-128): mono, span-less, endless; `.take(n)` bounds it
                 if (!is_first || d.n_samples != 0 || d.channels != 1 || d.format != RB_FMT_F32 || d.span_len != 0)
@@ -514,16 +569,24 @@ static rb_status plan_stream(PlanStream& ps, uint16_t mixer_ch, uint32_t mixer_r
             }
             default: return fail(RB_ERR_INVALID_ARGUMENT, "unknown effect kind");
         }
+        nd.level = std::max(nd.level, ps.nodes.empty() ? 0u : ps.nodes.back().level + 1u);
         ps.nodes.push_back(nd);
         n = nd.d.n_out, c = nd.d.c_out, rate = nd.rate_out, span = nd.span_out;
     }
     ps.chain_len = n, ps.chain_channels = c, ps.chain_rate = rate;
+    ps.end_span = span, ps.end_tail_pad = tail_pad, ps.end_cv_last = cv_last;
+    ps.planning = false, ps.planned = true;
+    if (ps.consumed) {   // the MIX that consumes it appends the conversion to ITS format; the mixer never sees this stream
+        ps.out_len = 0, ps.mix_start = 0;
+        return RB_OK;
+    }
     // Mixer::add wraps the source in UniformSourceIterator::new(source, mixer_ch, mixer_rate) (mixer.rs:62-63)
     {
         PlanNode nd;
         rb_status s = plan_uniform(nd, (span && tail_pad) ? n - tail_pad : n, c, rate, span, mixer_ch, mixer_rate, cv_last);
         if (s != RB_OK) return s;
         if (!(nd.d.p.uni.from == nd.d.p.uni.to && nd.d.c_in == nd.d.c_out) || nd.d.n_out != n) {
+            nd.level = ps.nodes.empty() ? 0u : ps.nodes.back().level + 1u;
             ps.nodes.push_back(nd);
             n = nd.d.n_out;
         }
@@ -631,26 +694,36 @@ extern "C" rb_status rb_batch_create(rb_context* ctx, uint16_t mixer_ch, uint32_
     b->uploaded.assign(n_streams, 0);
     size_t in_bytes = 0, buf_floats = 0;
     uint64_t mix_len = 0, algo = 0;
-    size_t max_nodes = 0;
+    bool any_consumed = false;
     for (size_t i = 0; i < n_streams; i++) {
         PlanStream& ps = b->streams[i];
         ps.desc = descs[i];
         if (descs[i].n_effects && !descs[i].effects) return fail(RB_ERR_INVALID_ARGUMENT, "effects is NULL");
         ps.fx.assign(descs[i].effects, descs[i].effects + descs[i].n_effects);
         ps.desc.effects = nullptr;
-        rb_status s = plan_stream(ps, mixer_ch, mixer_rate);
+        any_consumed = any_consumed || descs[i].mix_start == RB_MIX_START_CONSUMED;
+    }
+    for (size_t i = 0; i < n_streams; i++) {
+        PlanStream& ps = b->streams[i];
+        if (ps.planned) continue;   // the second input of a MIX further up: planned when that MIX was reached
+        rb_status s = plan_stream(ps, mixer_ch, mixer_rate, &b->streams, i);
         if (s != RB_OK) {
             g_last_error = "stream " + std::to_string(i) + ": " + g_last_error;
             return s;
         }
+    }
+    uint32_t max_level = 0;
+    for (size_t i = 0; i < n_streams; i++) {
+        PlanStream& ps = b->streams[i];
+        if (ps.consumed && ps.consumer < 0)
+            return fail(RB_ERR_INVALID_ARGUMENT, "stream " + std::to_string(i) + ": mix_start = RB_MIX_START_CONSUMED but no RB_FX_MIX names it");
         ps.in_off = in_bytes;
         in_bytes += align_up((size_t)ps.desc.n_samples * fmt_size(ps.desc.format) + 16, 128);
         uint64_t cap = 0;
-        for (auto& nd : ps.nodes) cap = std::max(cap, nd.d.n_out);
+        for (auto& nd : ps.nodes) cap = std::max(cap, nd.d.n_out), max_level = std::max(max_level, nd.level + 1u);
         ps.buf_cap = align_up((size_t)cap + 4, 32);
         ps.buf_off = buf_floats;
         buf_floats += ps.buf_cap;
-        max_nodes = std::max(max_nodes, ps.nodes.size());
         if (ps.out_len) mix_len = std::max(mix_len, ps.mix_start + ps.out_len);
         algo += ps.desc.n_samples * fmt_size(ps.desc.format);
     }
@@ -670,7 +743,7 @@ extern "C" rb_status rb_batch_create(rb_context* ctx, uint16_t mixer_ch, uint32_
     });
 
     // Fast path: one fused kernel family when the whole batch has a chain shape it understands.
-    if (!(flags & RB_NO_FUSION)) {
+    if (!(flags & RB_NO_FUSION) && !any_consumed) {   // a two-input MIX: general path
         std::vector<rb_fused_stream> fs(n_streams);
         bool ok = true;
         // every stream integer PCM: plan the fused kernels on a resident f32 copy (converted once per upload)
@@ -743,21 +816,28 @@ extern "C" rb_status rb_batch_create(rb_context* ctx, uint16_t mixer_ch, uint32_
             RB_CUDA(cudaMalloc(&b->d_aux[1], std::max<size_t>(buf_floats * 4, 256)));
         }
         std::vector<rb_node_dev> host_nodes;
-        for (size_t lvl = 0; lvl < max_nodes; lvl++) {
+        auto final_of = [&](const PlanStream& ps) -> const float* {
+            const size_t k = ps.nodes.size();
+            return (k == 0) ? (const float*)(b->d_in + ps.in_off) : b->d_buf[(k - 1) & 1] + ps.buf_off;
+        };
+        for (uint32_t lvl = 0; lvl < max_level; lvl++) {
             for (uint32_t kind = 0; kind < RB_N_KINDS; kind++) {
                 LaunchGroup g{kind, (uint32_t)host_nodes.size(), 0, 0, 0};
                 for (auto& ps : b->streams) {
-                    if (lvl >= ps.nodes.size() || ps.nodes[lvl].d.kind != kind) continue;
-                    rb_node_dev nd = ps.nodes[lvl].d;
-                    nd.src = (lvl == 0) ? (const void*)(b->d_in + ps.in_off)
-                                        : (const void*)(b->d_buf[(lvl - 1) & 1] + ps.buf_off);
-                    nd.dst = b->d_buf[lvl & 1] + ps.buf_off;
-                    nd.aux0 = b->d_aux[0] ? b->d_aux[0] + ps.buf_off : nullptr;
-                    nd.aux1 = b->d_aux[1] ? b->d_aux[1] + ps.buf_off : nullptr;
-                    host_nodes.push_back(nd);
-                    g.count++;
-                    g.max_n_out = std::max(g.max_n_out, nd.n_out);
-                    g.max_channels = std::max(g.max_channels, nd.c_in);
+                    for (size_t j = 0; j < ps.nodes.size(); j++) {   // node j reads arena (j-1)&1 and writes arena j&1, at launch level `level`
+                        if (ps.nodes[j].level != lvl || ps.nodes[j].d.kind != kind) continue;
+                        rb_node_dev nd = ps.nodes[j].d;
+                        nd.src = (j == 0) ? (const void*)(b->d_in + ps.in_off)
+                                          : (const void*)(b->d_buf[(j - 1) & 1] + ps.buf_off);
+                        nd.dst = b->d_buf[j & 1] + ps.buf_off;
+                        nd.aux0 = b->d_aux[0] ? b->d_aux[0] + ps.buf_off : nullptr;
+                        nd.aux1 = b->d_aux[1] ? b->d_aux[1] + ps.buf_off : nullptr;
+                        if (kind == RB_N_MIX2) nd.aux0 = const_cast<float*>(final_of(b->streams[(size_t)ps.nodes[j].other]));
+                        host_nodes.push_back(nd);
+                        g.count++;
+                        g.max_n_out = std::max(g.max_n_out, nd.n_out);
+                        g.max_channels = std::max(g.max_channels, nd.c_in);
+                    }
                 }
                 if (g.count) b->groups.push_back(g);
             }

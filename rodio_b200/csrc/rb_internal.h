@@ -25,7 +25,8 @@ enum rb_node_kind : uint32_t {
     RB_N_RAMP = 10,     // src/source/linear_ramp.rs:79-104 (also fade_in / fade_out)
     RB_N_TAKE = 11,     // src/source/take.rs:107-148 (+ fade-out filter :34-41)
     RB_N_SIGNAL = 12,   // src/source/signal_generator.rs:107-135 (a source: no input)
-    RB_N_KINDS = 13
+    RB_N_MIX2 = 13,     // src/source/mix.rs:43-53 (second input: aux0, p.mix2.n2 samples)
+    RB_N_KINDS = 14
 };
 
 // Closed-form description of one UniformSourceIterator application.
@@ -72,6 +73,7 @@ struct alignas(16) rb_node_dev {
         struct { uint64_t total_ns, dt_ns; float start, end; uint32_t clamp_end; } ramp;
         struct { uint64_t total_ns, dps_ns, count; float total_ms_f; uint32_t fadeout; } take;
         struct { float step; uint32_t fn; } sig;
+        struct { uint64_t n2; } mix2;
         rb_uniform_params uni;
     } p;
 };

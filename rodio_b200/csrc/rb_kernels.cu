@@ -52,6 +52,16 @@ __global__ void __launch_bounds__(TPB) k_echo(const rb_node_dev* __restrict__ no
     });
 }
 
+// Mix of two sources (src/source/mix.rs:43-53; crossfade.rs:10-23 is built from it): s1 + s2 while both run, then whichever is left.
+// Both inputs already went through their UniformSourceIterator (planner).  Second input: aux0, p.mix2.n2 samples.
+__global__ void __launch_bounds__(TPB) k_mix2(const rb_node_dev* __restrict__ nodes) {
+    const rb_node_dev& nd = nodes[blockIdx.x];
+    const float* __restrict__ x1 = (const float*)nd.src;
+    const float* __restrict__ x2 = nd.aux0;
+    const uint64_t n1 = nd.n_in, n2 = nd.p.mix2.n2;
+    for_each_out(nd, [&](uint64_t o) { nd.dst[o] = (o < n1 && o < n2) ? add(x1[o], x2[o]) : (o < n1 ? x1[o] : x2[o]); });
+}
+
 __global__ void __launch_bounds__(TPB) k_delay(const rb_node_dev* __restrict__ nodes) {
     const rb_node_dev& nd = nodes[blockIdx.x];
     const float* __restrict__ x = (const float*)nd.src;
@@ -667,6 +677,7 @@ cudaError_t rb_launch_nodes(uint32_t kind, const rb_node_dev* d_nodes, uint32_t 
         case RB_N_AMPLIFY: k_amplify<<<grid, TPB, 0, st>>>(d_nodes); break;
         case RB_N_ECHO: k_echo<<<grid, TPB, 0, st>>>(d_nodes); break;
         case RB_N_DELAY: k_delay<<<grid, TPB, 0, st>>>(d_nodes); break;
+        case RB_N_MIX2: k_mix2<<<grid, TPB, 0, st>>>(d_nodes); break;
         case RB_N_CHANVOL: k_chanvol<<<grid, TPB, 0, st>>>(d_nodes); break;
         case RB_N_DISTORT: k_distort<<<grid, TPB, 0, st>>>(d_nodes); break;
         case RB_N_RAMP: k_ramp<<<grid, TPB, 0, st>>>(d_nodes); break;

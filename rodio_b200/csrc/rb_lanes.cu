@@ -63,98 +63,123 @@ __global__ void __launch_bounds__(64) k_fused_duo_split(lanes::Args a) {
 // Arithmetic per sample: a + ((b - a) * num) / den with the division as the exact reciprocal step of the lane kernels for streams
 // whose inputs are inside the class (k_classify_inputs), __fdiv_rn otherwise; (-0) / den keeps its sign.
 // ---------------------------------------------------------------------------------------------------
-constexpr int LM_U = 4;        // positions per thread
-constexpr int LM_R = 4;        // rows whose loads are in flight together (2 * LM_U * LM_R independent loads per thread)
-constexpr int LM_STAGE = 64;   // row descriptors staged in shared memory at a time
+constexpr int LM_U = 4;          // positions per thread: a tile is 256 * LM_U = 1024 timeline frames
+constexpr int LM_ROWS = 8;       // rows per pipeline stage
+constexpr int LM_STAGES = 3;     // stages in shared memory: one being summed, two in flight
+constexpr int LM_GROUP = 64;     // row descriptors staged at a time (= the largest group the planner makes)
+constexpr int LM_WQ = 260;       // 16-byte quads of one row's window: 1024 * from / to + 2 frames (from < to) + alignment slack
+constexpr uint32_t LM_SMEM = LM_STAGES * LM_ROWS * LM_WQ * 16;
+__device__ __forceinline__ void lm_cp16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void lm_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void lm_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// The input window of a (row, tile) -- the frames [i_tile, i_tile + n_win) of the row, 1024 * 147 / 160 + 2 of them at 44.1 -> 48 kHz --
+// travels HBM -> shared memory by 16-byte cp.async (SASS LDGSTS.E.BYPASS.128), LM_ROWS rows per stage and two stages ahead of the
+// sums: the copies of 16 rows are in flight while 8 are summed, whatever order the compiler gives the arithmetic (the first
+// version left every load to LDG.32 pairs in front of their use: long-scoreboard stalls of 21 cycles per issued instruction,
+// 1.8 TB/s).  Rows that do not interpolate on the whole tile (a stream starts or ends inside it) or whose inputs are outside
+// the exact-reciprocal class skip the window and read global memory directly, with the IEEE division.
 template <int NPOST>
 __global__ void __launch_bounds__(256) k_lerp_mix(rb_lerpmix_args a) {
-    __shared__ rb_lerpmix_row s_rows[LM_STAGE];
+    extern __shared__ __align__(16) unsigned char lm_smem[];
+    __shared__ rb_lerpmix_row s_rows[LM_GROUP];
+    float4* const win = reinterpret_cast<float4*>(lm_smem);
     const uint64_t tile_lo = (uint64_t)blockIdx.x * (256 * LM_U);
     if (tile_lo >= a.mix_len) return;
     const uint64_t tile_hi = min(a.mix_len, tile_lo + 256 * LM_U);
     const uint32_t g = blockIdx.y;
     const uint32_t r_lo = g * a.rows_per_group, r_hi = min(a.n_rows, r_lo + a.rows_per_group);
-    uint32_t idx[LM_U], pos[LM_U];
+    uint32_t tap[LM_U], pos[LM_U];     // tap: left input frame of the position, relative to the tile's first
     float numf[LM_U], acc[LM_U];
     bool any[LM_U];
+    const uint64_t i_tile = ((tile_lo - a.origin) * (uint64_t)a.from) / a.to;   // origin <= every position that any stream covers
+    const uint32_t n_win = (uint32_t)((((tile_hi - 1 - a.origin) * (uint64_t)a.from) / a.to) - i_tile) + 2;   // frames a full row needs
 #pragma unroll
     for (int u = 0; u < LM_U; u++) {
         const uint64_t n = tile_lo + (uint64_t)u * 256 + threadIdx.x;
-        const uint64_t rel = n - a.origin;                       // origin <= every position that any stream covers
-        const uint64_t prod = rel * (uint64_t)a.from;
+        const uint64_t prod = (n - a.origin) * (uint64_t)a.from;
         const uint64_t i = prod / a.to;
-        idx[u] = (uint32_t)i, numf[u] = __uint2float_rn((uint32_t)(prod - i * a.to)), pos[u] = (uint32_t)n;
+        tap[u] = (uint32_t)(i - i_tile), numf[u] = __uint2float_rn((uint32_t)(prod - i * a.to)), pos[u] = (uint32_t)n;
         acc[u] = 0.0f, any[u] = false;
     }
     const float den = a.den_f, rcp = a.rcp_den;
     const uint32_t t_lo = (uint32_t)tile_lo, t_hi = (uint32_t)tile_hi;
-    for (uint32_t rs = r_lo; rs < r_hi; rs += LM_STAGE) {
-        // stage the next descriptors (and the classification verdict of their streams) once per CTA: the row loop below then
-        // issues its input loads without a dependent global load in front of them
-        const uint32_t n_st = min((uint32_t)LM_STAGE, r_hi - rs);
-        __syncthreads();
+    const bool win_ok = n_win + 3 <= LM_WQ * 4;   // the planner only sends from < to here; anything else reads global memory
+    for (uint32_t rs = r_lo; rs < r_hi; rs += LM_GROUP) {
+        const uint32_t n_st = min((uint32_t)LM_GROUP, r_hi - rs);
+        __syncthreads();               // the previous group's descriptors and windows are no longer read
         if (threadIdx.x < n_st) {
             rb_lerpmix_row row = a.rows[rs + threadIdx.x];
-            row.pad_ = (a.lane_rows[row.row].flags & lanes::ROW_UNSAFE) ? 1u : 0u;
+            const bool unsafe = (a.lane_rows[row.row].flags & lanes::ROW_UNSAFE) != 0;
+            // pad_: 1 = the window path (interpolates on the whole tile, inputs inside the class), 0 = global memory
+            row.pad_ = (win_ok && !unsafe && row.lo <= t_lo && row.hi_int >= t_hi) ? 1u : 0u;
             s_rows[threadIdx.x] = row;
         }
         __syncthreads();
-        for (uint32_t r0 = 0; r0 < n_st; r0 += LM_R) {
-            // a run of LM_R rows that all interpolate on the whole tile: every load first, then the sums in row order
-            bool fast = r0 + LM_R <= n_st;
-#pragma unroll
-            for (int j = 0; j < LM_R; j++) {
-                const rb_lerpmix_row& row = s_rows[min(r0 + j, n_st - 1)];
-                fast = fast && !row.pad_ && row.lo <= t_lo && row.hi_int >= t_hi;
-            }
-            if (fast) {
-                float xa[LM_R][LM_U], xb[LM_R][LM_U];
-#pragma unroll
-                for (int j = 0; j < LM_R; j++) {
-                    const float* __restrict__ p = s_rows[r0 + j].p;
-#pragma unroll
-                    for (int u = 0; u < LM_U; u++) xa[j][u] = __ldg(p + idx[u]), xb[j][u] = __ldg(p + idx[u] + 1);
+        const uint32_t n_stages = (n_st + LM_ROWS - 1) / LM_ROWS;
+        auto issue = [&](uint32_t stage) {
+            if (stage < n_stages) {
+                float4* buf = win + (size_t)(stage % LM_STAGES) * LM_ROWS * LM_WQ;
+                const uint32_t j_hi = min((uint32_t)LM_ROWS, n_st - stage * LM_ROWS);
+                for (uint32_t j = 0; j < j_hi; j++) {
+                    const rb_lerpmix_row& row = s_rows[stage * LM_ROWS + j];
+                    if (!row.pad_) continue;
+                    const float* src = row.p + i_tile;
+                    const uint32_t off = (uint32_t)((reinterpret_cast<uintptr_t>(src) >> 2) & 3u);
+                    const float4* src4 = reinterpret_cast<const float4*>(src - off);
+                    const uint32_t nq = (off + n_win + 3) >> 2;
+                    for (uint32_t q = threadIdx.x; q < nq; q += 256) lm_cp16(buf + j * LM_WQ + q, src4 + q);
                 }
+            }
+            lm_commit();               // an empty group keeps the wait counts uniform
+        };
+        issue(0);
+        issue(1);
+        for (uint32_t stage = 0; stage < n_stages; stage++) {
+            lm_wait<1>();              // this thread's copies of `stage` have landed ...
+            __syncthreads();           // ... and everybody else's; everybody is also done reading stage - 1
+            issue(stage + 2);          // into the buffer of stage - 1
+            const float* buf = reinterpret_cast<const float*>(win + (size_t)(stage % LM_STAGES) * LM_ROWS * LM_WQ);
+            const uint32_t j_hi = min((uint32_t)LM_ROWS, n_st - stage * LM_ROWS);
+            for (uint32_t j = 0; j < j_hi; j++) {
+                const rb_lerpmix_row& row = s_rows[stage * LM_ROWS + j];
+                if (row.pad_) {
+                    const uint32_t off = (uint32_t)((reinterpret_cast<uintptr_t>(row.p + i_tile) >> 2) & 3u);
+                    const float* __restrict__ w = buf + j * (LM_WQ * 4) + off;
+                    const float post = row.post;
+                    float xa[LM_U], xb[LM_U];
 #pragma unroll
-                for (int j = 0; j < LM_R; j++) {
-                    const float post = s_rows[r0 + j].post;
+                    for (int u = 0; u < LM_U; u++) xa[u] = w[tap[u]], xb[u] = w[tap[u] + 1];
 #pragma unroll
                     for (int u = 0; u < LM_U; u++) {
-                        const float m = __fmul_rn(__fsub_rn(xb[j][u], xa[j][u]), numf[u]);
+                        if (pos[u] >= t_hi) continue;      // the last tile of the timeline may be partial
+                        const float m = __fmul_rn(__fsub_rn(xb[u], xa[u]), numf[u]);
                         const float q0 = __fmul_rn(m, rcp);
                         float q = __fmaf_rn(__fmaf_rn(-q0, den, m), rcp, q0);
                         q = m == 0.0f ? m : q;
-                        float x = __fadd_rn(xa[j][u], q);
+                        float x = __fadd_rn(xa[u], q);
                         if (NPOST) x = __fmul_rn(x, post);
                         acc[u] = __fadd_rn(acc[u], x), any[u] = true;
                     }
+                    continue;
                 }
-                continue;
-            }
-            for (uint32_t j = r0; j < min(r0 + LM_R, n_st); j++) {
-                const rb_lerpmix_row row = s_rows[j];
                 if (row.hi <= t_lo || row.lo >= t_hi) continue;          // the stream is silent on this tile
-                const float* __restrict__ p = row.p;
+                const float* __restrict__ p = row.p + i_tile;
 #pragma unroll
                 for (int u = 0; u < LM_U; u++) {
                     if (pos[u] < row.lo || pos[u] >= row.hi || pos[u] >= t_hi) continue;
-                    const float xa = __ldg(p + idx[u]);
+                    const float xa = __ldg(p + tap[u]);
                     float x = xa;
-                    if (pos[u] < row.hi_int) {
-                        const float m = __fmul_rn(__fsub_rn(__ldg(p + idx[u] + 1), xa), numf[u]);
-                        float q = __fdiv_rn(m, den);
-                        if (!row.pad_) {
-                            const float q0 = __fmul_rn(m, rcp);
-                            q = __fmaf_rn(__fmaf_rn(-q0, den, m), rcp, q0);
-                            q = m == 0.0f ? m : q;
-                        }
-                        x = __fadd_rn(xa, q);
-                    }
+                    if (pos[u] < row.hi_int) x = __fadd_rn(xa, __fdiv_rn(__fmul_rn(__fsub_rn(__ldg(p + tap[u] + 1), xa), numf[u]), den));
                     if (NPOST) x = __fmul_rn(x, row.post);
                     acc[u] = __fadd_rn(acc[u], x), any[u] = true;
                 }
             }
         }
+        lm_wait<0>();
     }
     float* __restrict__ out = a.out + (uint64_t)g * a.pstride;
 #pragma unroll
@@ -321,8 +346,15 @@ cudaError_t rb_duo_launch_kernel(const lanes::Args& a, bool has_biquad, bool ff2
 cudaError_t rb_lerpmix_launch(const rb_lerpmix_args& a, cudaStream_t st) {
     if (a.mix_len == 0 || a.n_rows == 0) return cudaSuccess;
     const dim3 grid((uint32_t)((a.mix_len + 256 * LM_U - 1) / (256 * LM_U)), a.n_groups);
-    if (a.has_post) k_lerp_mix<1><<<grid, 256, 0, st>>>(a);
-    else k_lerp_mix<0><<<grid, 256, 0, st>>>(a);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_lerp_mix<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LM_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lerp_mix<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LM_SMEM);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    if (a.has_post) k_lerp_mix<1><<<grid, 256, LM_SMEM, st>>>(a);
+    else k_lerp_mix<0><<<grid, 256, LM_SMEM, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -69,13 +69,14 @@ class Effect:
     u32: Tuple[int, int, int] = (0, 0, 0)
     f32: Tuple[float, ...] = (0.0,) * 12
     ns: Tuple[int, int] = (0, 0)
+    other: Optional["Source"] = None      # RB_FX_MIX: the second input (packed as a descriptor of its own, u32[0] = its index)
 
     @staticmethod
-    def make(kind, u32=(), f32=(), ns=()):
+    def make(kind, u32=(), f32=(), ns=(), other=None):
         u = tuple(int(x) for x in u32) + (0,) * (3 - len(u32))
         f = tuple(float(x) for x in f32) + (0.0,) * (12 - len(f32))
         n = tuple(int(x) for x in ns) + (0,) * (2 - len(ns))
-        return Effect(kind, u, f, n)
+        return Effect(kind, u, f, n, other)
 
 
 @dataclass
@@ -233,6 +234,15 @@ class Source:
     def take_duration(self, duration: int, filter_fadeout: bool = False) -> "Source":
         """Source::take_duration (+ TakeDuration::set_filter_fadeout) — src/source/take.rs:9-26,:89-96."""
         return self._with(Effect.make(capi.RB_FX_TAKE_DURATION, u32=[1 if filter_fadeout else 0], ns=[duration]))
+
+    def mix(self, other: "Source") -> "Source":
+        """Source::mix(other) -- src/source/mod.rs:253-261, mix.rs:10-53: both inputs converted to THIS source's channels and rate,
+        summed while both run, then whichever is left."""
+        return self._with(Effect.make(capi.RB_FX_MIX, other=other))
+
+    def take_crossfade_with(self, other: "Source", duration: int) -> "Source":
+        """Source::take_crossfade_with -- src/source/mod.rs:444-454 = crossfade::crossfade (crossfade.rs:10-23)."""
+        return self.take_duration(duration, filter_fadeout=True).mix(other.take_duration(duration).fade_in(duration))
 
     def automatic_gain_control(self, settings: Optional[AutomaticGainControlSettings] = None) -> "Source":
         """Source::automatic_gain_control — src/source/mod.rs:415-446."""
@@ -443,12 +453,26 @@ def default_context(device: int = 0) -> Context:
     return _default_ctx[device]
 
 
+def flatten_sources(sources: Sequence[Source]) -> List[Source]:
+    """`sources` followed by every second input of a mix() inside them (depth first): the descriptor array of a batch."""
+    flat = list(sources)
+    i = 0
+    while i < len(flat):
+        for e in flat[i].effects:
+            if e.kind == capi.RB_FX_MIX and e.other is not None and not any(e.other is f for f in flat):
+                flat.append(e.other)
+        i += 1
+    return flat
+
+
 def pack_descs(sources: Sequence[Source], mix_starts: Optional[Sequence[int]] = None):
-    """Build the rb_stream_desc array for `sources` (returns the array and the objects it points into)."""
-    n = len(sources)
+    """Build the rb_stream_desc array for `sources` (returns the array and the objects it points into).  Second inputs of a
+    mix() are appended as descriptors of their own with mix_start = RB_MIX_START_CONSUMED."""
+    flat = flatten_sources(sources)
+    n = len(flat)
     descs = (capi.rb_stream_desc * max(1, n))()
-    keep = []
-    for i, s in enumerate(sources):
+    keep = [flat]
+    for i, s in enumerate(flat):
         fx = (capi.rb_effect * max(1, len(s.effects)))()
         for j, e in enumerate(s.effects):
             fx[j].kind = e.kind
@@ -458,6 +482,8 @@ def pack_descs(sources: Sequence[Source], mix_starts: Optional[Sequence[int]] = 
                 fx[j].f32[k] = e.f32[k]
             for k in range(2):
                 fx[j].ns[k] = e.ns[k]
+            if e.kind == capi.RB_FX_MIX and e.other is not None:
+                fx[j].u32[0] = next(k for k, f in enumerate(flat) if f is e.other)
         keep.append(fx)
         d = descs[i]
         d.sample_rate = s.base_rate
@@ -467,7 +493,10 @@ def pack_descs(sources: Sequence[Source], mix_starts: Optional[Sequence[int]] = 
         d.span_len = s.span_len
         d.n_effects = len(s.effects)
         d.effects = C.cast(fx, C.POINTER(capi.rb_effect))
-        d.mix_start = int(mix_starts[i]) if mix_starts is not None else 0
+        if i >= len(sources):
+            d.mix_start = capi.RB_MIX_START_CONSUMED
+        else:
+            d.mix_start = int(mix_starts[i]) if mix_starts is not None else 0
     return descs, keep
 
 
@@ -486,8 +515,8 @@ class Batch:
     def __init__(self, sources: Sequence[Source], mixer_channels: int, mixer_rate: int, flags: int = 0,
                  mix_starts: Optional[Sequence[int]] = None, ctx: Optional[Context] = None):
         self.ctx = ctx or default_context()
-        self.sources = list(sources)
-        self._descs, self._keep = pack_descs(self.sources, mix_starts)
+        self._descs, self._keep = pack_descs(list(sources), mix_starts)
+        self.sources = self._keep[0]          # the sources handed in, then the second inputs of their mix() adapters
         self._h = C.c_void_p()
         check(lib().rb_batch_create(self.ctx._h, mixer_channels, mixer_rate, self._descs, len(self.sources), flags,
                                     C.byref(self._h)), "rb_batch_create")

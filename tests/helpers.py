@@ -15,7 +15,9 @@ def to_oracle(src: rb.Source, mix_start: int = 0) -> oracle.Stream:
         if getattr(src, "fmt_override", None) is not None:
             fmt = src.fmt_override
         pcm = oracle.convert(pcm, fmt, 0)
-    return oracle.Stream(pcm=pcm, channels=src.base_channels, sample_rate=src.base_rate, effects=src.effects,
+    effects = [oracle.Fx(e.kind, e.u32, e.f32, e.ns, to_oracle(e.other)) if getattr(e, "other", None) is not None else e
+               for e in src.effects]
+    return oracle.Stream(pcm=pcm, channels=src.base_channels, sample_rate=src.base_rate, effects=effects,
                          span_len=src.span_len, mix_start=mix_start)
 
 
