@@ -185,8 +185,12 @@ static cudaError_t fused_lanes_hook(const std::vector<FusedRow>& rows, size_t n_
     // for bit, and a batch of a few thousand mono streams fills the machine that way (measured against k_fused_hot<1, false>)
     // (k_lerp_mix, parallel over the timeline: from 64 streams on, and for RB_MIX_EXACT_ORDER, whose order it keeps)
     // RB_FUSED_DUO names the lane-pair kernel itself: k_lerp_mix stays out, and the segment plan starts where it was measured
+    // Measured (profiles/README.md R2.3): at 4096 streams x 2 s the segment rows on k_fused_duo take 0.402 ms, k_lerp_mix 0.422 ms;
+    // at 512 streams k_lerp_mix 0.147 ms against 0.20 ms for the generic fused kernel -> k_lerp_mix below 1024 streams and for
+    // RB_MIX_EXACT_ORDER (any size), the segment plan from 1024 streams on
     const bool name_duo = (flags & RB_FUSED_DUO) != 0;
     size_t seg_min = name_duo ? 1024 : 64;
+    const bool lerpmix_small = !name_duo && (n_streams < 1024 || getenv("RB_LERPMIX"));   // RB_LERPMIX=1: A/B runs at any size
     if (const char* e = getenv("RB_SEGMENTS_FROM")) seg_min = (size_t)atoll(e);
     const bool exact_order = (flags & RB_MIX_EXACT_ORDER) != 0;
     if (!has_b && has_u && !front && mixer_channels == 1 && (n_streams >= seg_min || exact_order) && !(flags & RB_FUSED_LANES)) want_tp = true;
@@ -223,7 +227,7 @@ static cudaError_t fused_lanes_hook(const std::vector<FusedRow>& rows, size_t n_
     }
     cudaError_t e = rb_lanes_try_create(ls.data(), n_streams, C, has_b != 0, front ? n_post != 0 : (n_mid + n_post) != 0, n_pre != 0, front != 0, d_out,
                                         mix_len / C, sm_count, st, lanes,
-                                        (want_tp ? LANES_TIME_PARALLEL : 0u) | ((flags & RB_FUSED_LANES) ? LANES_NO_DUO : 0u) | (exact_order ? LANES_ONE_GROUP : 0u) | (name_duo ? LANES_NO_LERPMIX : 0u));   // RB_FUSED_LANES names k_fused_lanes itself
+                                        (want_tp ? LANES_TIME_PARALLEL : 0u) | ((flags & RB_FUSED_LANES) ? LANES_NO_DUO : 0u) | (exact_order ? LANES_ONE_GROUP : 0u) | ((name_duo || !(lerpmix_small || exact_order)) ? LANES_NO_LERPMIX : 0u));   // RB_FUSED_LANES names k_fused_lanes itself
     if (e == cudaSuccess && *lanes && !want_lanes && rb_lanes_kind(*lanes) != 4 && rb_lanes_kind(*lanes) != 6) {   // asked for the time-parallel plan only, and it was not built
         rb_lanes_destroy(*lanes);
         *lanes = nullptr;

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(64) k_fused_duo_split(lanes::Args a) {
 // whose inputs are inside the class (k_classify_inputs), __fdiv_rn otherwise; (-0) / den keeps its sign.
 // ---------------------------------------------------------------------------------------------------
 constexpr int LM_U = 4;          // positions per thread: a tile is 256 * LM_U = 1024 timeline frames
-constexpr int LM_ROWS = 8;       // rows per pipeline stage
+constexpr int LM_ROWS = 4;       // rows per pipeline stage (50 KB of windows per CTA: four CTAs per SM)
 constexpr int LM_STAGES = 3;     // stages in shared memory: one being summed, two in flight
 constexpr int LM_GROUP = 64;     // row descriptors staged at a time (= the largest group the planner makes)
 constexpr int LM_WQ = 260;       // 16-byte quads of one row's window: 1024 * from / to + 2 frames (from < to) + alignment slack
@@ -82,15 +82,21 @@ __device__ __forceinline__ void lm_wait() { asm volatile("cp.async.wait_group %0
 // version left every load to LDG.32 pairs in front of their use: long-scoreboard stalls of 21 cycles per issued instruction,
 // 1.8 TB/s).  Rows that do not interpolate on the whole tile (a stream starts or ends inside it) or whose inputs are outside
 // the exact-reciprocal class skip the window and read global memory directly, with the IEEE division.
+struct LmSlot {       // what the summing loop needs of a row: 8 bytes, one LDS.64
+    float post;       // the one gain (1.0: none)
+    uint32_t woff;    // float offset of the row's first frame inside its stage buffer; LM_GLOBAL: the row reads global memory
+};
+constexpr uint32_t LM_GLOBAL = 0xffffffffu;
 template <int NPOST>
 __global__ void __launch_bounds__(256) k_lerp_mix(rb_lerpmix_args a) {
     extern __shared__ __align__(16) unsigned char lm_smem[];
     __shared__ rb_lerpmix_row s_rows[LM_GROUP];
+    __shared__ LmSlot s_slot[LM_GROUP];
     float4* const win = reinterpret_cast<float4*>(lm_smem);
     const uint64_t tile_lo = (uint64_t)blockIdx.x * (256 * LM_U);
     if (tile_lo >= a.mix_len) return;
     const uint64_t tile_hi = min(a.mix_len, tile_lo + 256 * LM_U);
-    const uint32_t g = blockIdx.y;
+    const uint32_t g = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t r_lo = g * a.rows_per_group, r_hi = min(a.n_rows, r_lo + a.rows_per_group);
     uint32_t tap[LM_U], pos[LM_U];     // tap: left input frame of the position, relative to the tile's first
     float numf[LM_U], acc[LM_U];
@@ -108,30 +114,33 @@ __global__ void __launch_bounds__(256) k_lerp_mix(rb_lerpmix_args a) {
     const float den = a.den_f, rcp = a.rcp_den;
     const uint32_t t_lo = (uint32_t)tile_lo, t_hi = (uint32_t)tile_hi;
     const bool win_ok = n_win + 3 <= LM_WQ * 4;   // the planner only sends from < to here; anything else reads global memory
+    const bool full_tile = tile_hi - tile_lo == 256 * LM_U;
+    bool any_win = false;                          // a window row covers every position of the tile
     for (uint32_t rs = r_lo; rs < r_hi; rs += LM_GROUP) {
         const uint32_t n_st = min((uint32_t)LM_GROUP, r_hi - rs);
         __syncthreads();               // the previous group's descriptors and windows are no longer read
         if (threadIdx.x < n_st) {
-            rb_lerpmix_row row = a.rows[rs + threadIdx.x];
+            const rb_lerpmix_row row = a.rows[rs + threadIdx.x];
             const bool unsafe = (a.lane_rows[row.row].flags & lanes::ROW_UNSAFE) != 0;
-            // pad_: 1 = the window path (interpolates on the whole tile, inputs inside the class), 0 = global memory
-            row.pad_ = (win_ok && !unsafe && row.lo <= t_lo && row.hi_int >= t_hi) ? 1u : 0u;
+            // the window path: the row interpolates on the whole tile and its inputs are inside the exact-reciprocal class
+            const bool w_ok = win_ok && !unsafe && row.lo <= t_lo && row.hi_int >= t_hi;
+            const uint32_t off = (uint32_t)((reinterpret_cast<uintptr_t>(row.p + i_tile) >> 2) & 3u);
             s_rows[threadIdx.x] = row;
+            s_slot[threadIdx.x] = LmSlot{row.post, w_ok ? (threadIdx.x % LM_ROWS) * (LM_WQ * 4) + off : LM_GLOBAL};
         }
         __syncthreads();
         const uint32_t n_stages = (n_st + LM_ROWS - 1) / LM_ROWS;
-        auto issue = [&](uint32_t stage) {
-            if (stage < n_stages) {
-                float4* buf = win + (size_t)(stage % LM_STAGES) * LM_ROWS * LM_WQ;
-                const uint32_t j_hi = min((uint32_t)LM_ROWS, n_st - stage * LM_ROWS);
-                for (uint32_t j = 0; j < j_hi; j++) {
-                    const rb_lerpmix_row& row = s_rows[stage * LM_ROWS + j];
-                    if (!row.pad_) continue;
-                    const float* src = row.p + i_tile;
-                    const uint32_t off = (uint32_t)((reinterpret_cast<uintptr_t>(src) >> 2) & 3u);
-                    const float4* src4 = reinterpret_cast<const float4*>(src - off);
+        auto issue = [&](uint32_t stage) {          // warps 2j and 2j + 1 copy row j of the stage: 16 bytes per lane and step
+            const uint32_t jrow = warp >> 1;
+            const uint32_t r = stage * LM_ROWS + jrow;
+            if (stage < n_stages && r < n_st) {
+                const uint32_t woff = s_slot[r].woff;
+                if (woff != LM_GLOBAL) {
+                    const uint32_t off = woff & 3u;
+                    const float4* src4 = reinterpret_cast<const float4*>(s_rows[r].p + i_tile - off);
+                    float4* dst4 = win + (size_t)(stage % LM_STAGES) * LM_ROWS * LM_WQ + jrow * LM_WQ;
                     const uint32_t nq = (off + n_win + 3) >> 2;
-                    for (uint32_t q = threadIdx.x; q < nq; q += 256) lm_cp16(buf + j * LM_WQ + q, src4 + q);
+                    for (uint32_t q = lane + 32 * (warp & 1); q < nq; q += 64) lm_cp16(dst4 + q, src4 + q);
                 }
             }
             lm_commit();               // an empty group keeps the wait counts uniform
@@ -145,27 +154,27 @@ __global__ void __launch_bounds__(256) k_lerp_mix(rb_lerpmix_args a) {
             const float* buf = reinterpret_cast<const float*>(win + (size_t)(stage % LM_STAGES) * LM_ROWS * LM_WQ);
             const uint32_t j_hi = min((uint32_t)LM_ROWS, n_st - stage * LM_ROWS);
             for (uint32_t j = 0; j < j_hi; j++) {
-                const rb_lerpmix_row& row = s_rows[stage * LM_ROWS + j];
-                if (row.pad_) {
-                    const uint32_t off = (uint32_t)((reinterpret_cast<uintptr_t>(row.p + i_tile) >> 2) & 3u);
-                    const float* __restrict__ w = buf + j * (LM_WQ * 4) + off;
-                    const float post = row.post;
+                const LmSlot sl = s_slot[stage * LM_ROWS + j];
+                if (sl.woff != LM_GLOBAL) {
+                    const float* __restrict__ w = buf + sl.woff;
                     float xa[LM_U], xb[LM_U];
 #pragma unroll
                     for (int u = 0; u < LM_U; u++) xa[u] = w[tap[u]], xb[u] = w[tap[u] + 1];
 #pragma unroll
                     for (int u = 0; u < LM_U; u++) {
-                        if (pos[u] >= t_hi) continue;      // the last tile of the timeline may be partial
+                        // a + ((b - a) * num) / den with the division as the exact reciprocal step; m = -0 gives q = +0 here where the
+                        // division gives -0: x can then differ in the sign of a zero only, which a sum that starts from +0.0 cannot see
                         const float m = __fmul_rn(__fsub_rn(xb[u], xa[u]), numf[u]);
                         const float q0 = __fmul_rn(m, rcp);
-                        float q = __fmaf_rn(__fmaf_rn(-q0, den, m), rcp, q0);
-                        q = m == 0.0f ? m : q;
+                        const float q = __fmaf_rn(__fmaf_rn(-q0, den, m), rcp, q0);
                         float x = __fadd_rn(xa[u], q);
-                        if (NPOST) x = __fmul_rn(x, post);
-                        acc[u] = __fadd_rn(acc[u], x), any[u] = true;
+                        if (NPOST) x = __fmul_rn(x, sl.post);
+                        if (full_tile || pos[u] < t_hi) acc[u] = __fadd_rn(acc[u], x);      // the last tile of the timeline may be partial
                     }
+                    any_win = true;
                     continue;
                 }
+                const rb_lerpmix_row row = s_rows[stage * LM_ROWS + j];
                 if (row.hi <= t_lo || row.lo >= t_hi) continue;          // the stream is silent on this tile
                 const float* __restrict__ p = row.p + i_tile;
 #pragma unroll
@@ -184,7 +193,7 @@ __global__ void __launch_bounds__(256) k_lerp_mix(rb_lerpmix_args a) {
     float* __restrict__ out = a.out + (uint64_t)g * a.pstride;
 #pragma unroll
     for (int u = 0; u < LM_U; u++)
-        if (pos[u] < t_hi && (any[u] || a.n_groups == 1)) out[pos[u]] = acc[u];
+        if (pos[u] < t_hi && (any[u] || any_win || a.n_groups == 1)) out[pos[u]] = acc[u];
 }
 
 // One CTA per stream: does every non-zero |x| lie inside [2^-70, 2^60]?  (rb_lanes_core.h, "Exact division".)

@@ -1,8 +1,8 @@
 #!/usr/bin/env bash
-# pass 19: k_lerp_mix with cp.async-staged windows (parity, memcheck, timing, ncu)
+# pass 21: k_lerp_mix with cp.async-staged windows (parity, memcheck, timing, ncu)
 set -u
 cd "$(dirname "$0")/.."
-OUT=gpurun_out/r2_pass19
+OUT=gpurun_out/r2_pass21
 mkdir -p "$OUT"
 timeout 900 python -m pytest tests -q -m gpu -x -k "lerp or nofilter" > "$OUT/pytest_gpu.log" 2>&1; echo "pytest exit $?" | tee -a "$OUT/summary.txt"
 tail -15 "$OUT/pytest_gpu.log" >> "$OUT/summary.txt"
