@@ -100,6 +100,16 @@ typedef enum {
                                  adapters) whose mix_start is RB_MIX_START_CONSUMED -- it is not added to the mixer, one MIX
                                  consumes it.  Both inputs go through UniformSourceIterator::new(_, channels, rate) of the
                                  FIRST input (mix.rs:16-21); s1 + s2 while both run, then whichever is left (mix.rs:43-53).  */
+    RB_FX_APPEND = 17,        /* source::from_iter([this buffer, next buffer, ...]) src/source/from_iter.rs:16-127 -- ONE source whose
+                                 sample rate and channel count change where one buffer ends and the next begins (a decoder whose
+                                 stream changes format, a play list handed to the mixer as one source).  Leading effects only:
+                                 effects[0 .. k) = APPEND, each u32[0] = index of the next buffer's descriptor (f32 PCM, no effects of
+                                 its own, mix_start = RB_MIX_START_CONSUMED, span_len = n_samples like a SamplesBuffer or 0).  What
+                                 follows sees the parameter change the way rodio's adapters do: AMPLIFY; SPEED; LOW/HIGH_PASS keep
+                                 their state and recompute the coefficients behind the first sample of the new span
+                                 (SpanTracker, src/source/span.rs:66-101 with blt.rs:122-137); the mixer's UniformSourceIterator
+                                 re-bootstraps with the span length and format FromIter reports at that moment
+                                 (src/source/uniform.rs:50-68,:83-96).  Other adapters on such a source: RB_ERR_UNSUPPORTED.    */
     RB_FX_SIGNAL = 15         /* SignalGenerator::new(sample_rate, frequency, function).take(n) src/source/signal_generator.rs:107-135
                                  (SineWave / SquareWave / TriangleWave / SawtoothWave = the same at 48 kHz, src/source/sine.rs:23-27):
                                  the SOURCE of the stream instead of uploaded PCM -- only as effects[0] of a descriptor with
@@ -253,6 +263,9 @@ rb_status rb_batch_algorithmic_bytes(rb_batch* b, uint64_t* bytes);
 rb_status rb_stream_plan(const rb_stream_desc* desc, uint16_t mixer_channels, uint32_t mixer_sample_rate,
                          uint64_t* out_len_samples, uint16_t* chain_channels, uint32_t* chain_sample_rate,
                          uint64_t* chain_len_samples);
+/* The same for descriptor `stream` of an array: descriptors that name others (RB_FX_MIX, RB_FX_APPEND) need the array. */
+rb_status rb_streams_plan(const rb_stream_desc* descs, size_t n_streams, size_t stream, uint16_t mixer_channels, uint32_t mixer_sample_rate,
+                          uint64_t* out_len, uint16_t* chain_channels, uint32_t* chain_rate, uint64_t* chain_len);
 
 /* Drain the MixerSource (src/mixer.rs:120-136) for the whole batch.
  *   _device: enqueue only; result stays in HBM (rb_batch_mix_device_ptr), no sync.

@@ -100,7 +100,7 @@ class Fx:
     other: Optional["Stream"] = None     # FX_MIX: the second input of Source::mix (a Stream of its own)
 
 
-FX_AMPLIFY, FX_LOW_PASS, FX_HIGH_PASS, FX_UNIFORM, FX_SIGNAL, FX_MIX = 1, 3, 4, 10, 15, 16     # rodio_oracle_capi.cpp, enum of adapter kinds
+FX_AMPLIFY, FX_LOW_PASS, FX_HIGH_PASS, FX_UNIFORM, FX_SIGNAL, FX_MIX, FX_APPEND = 1, 3, 4, 10, 15, 16, 17     # rodio_oracle_capi.cpp, enum of adapter kinds
 MIX_START_CONSUMED = 0xFFFFFFFFFFFFFFFF
 
 
@@ -121,7 +121,7 @@ def _pack(streams: Sequence[Stream]):
     while i < len(flat):
         for e in flat[i].effects:
             o = getattr(e, "other", None)
-            if int(e.kind) == FX_MIX and o is not None and not any(o is f for f in flat):
+            if int(e.kind) in (FX_MIX, FX_APPEND) and o is not None and not any(o is f for f in flat):
                 flat.append(o)
         i += 1
     keep = []
@@ -138,7 +138,7 @@ def _pack(streams: Sequence[Stream]):
                 fx[j].f32[k] = float(e.f32[k])
             for k in range(2):
                 fx[j].ns[k] = int(e.ns[k])
-            if int(e.kind) == FX_MIX:
+            if int(e.kind) in (FX_MIX, FX_APPEND):
                 addr = base + C.sizeof(_Stream) * next(k for k, f in enumerate(flat) if f is e.other)
                 fx[j].u32[1], fx[j].u32[2] = addr & 0xFFFFFFFF, addr >> 32
         keep += [pcm, fx]

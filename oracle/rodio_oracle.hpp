@@ -259,6 +259,40 @@ inline BltCoeffs blt_high_pass(uint32_t freq, float q, uint32_t fs) {  // blt.rs
     float a2 = 1.0f - alpha;
     return {b0 / a0, b1 / a0, b2 / a0, a1 / a0, a2 / a0};
 }
+// src/source/span.rs:33-101: SpanTracker (span-counting mode while `cached_span_len` is Some, parameter comparison on every sample
+// while it is None -- the state a tracker starts in, span.rs:56-63)
+struct SpanTracker {
+    size_t samples_counted = 0;
+    std::optional<size_t> cached_span_len;
+    uint32_t last_sample_rate;
+    uint16_t last_channels;
+    SpanTracker(uint32_t rate, uint16_t ch) : last_sample_rate(rate), last_channels(ch) {}
+    struct Detection {
+        bool at_span_boundary, parameters_changed;
+    };
+    Detection advance(const Source& source) {  // span.rs:66-101
+        if (samples_counted != SIZE_MAX) samples_counted++;   // saturating_add(1)
+        std::optional<size_t> input_span_len = source.current_span_len();
+        bool parameters_changed = false, at_span_boundary = false;
+        if (input_span_len) {
+            std::optional<bool> known_boundary;
+            if (cached_span_len) known_boundary = samples_counted >= *cached_span_len;
+            if (!known_boundary || *known_boundary) {
+                uint16_t cur_ch = source.channels();
+                uint32_t cur_rate = source.sample_rate();
+                parameters_changed = cur_ch != last_channels || cur_rate != last_sample_rate;
+                last_channels = cur_ch, last_sample_rate = cur_rate;
+            }
+            at_span_boundary = known_boundary ? *known_boundary : parameters_changed;
+        }
+        if (at_span_boundary) samples_counted = 0, cached_span_len = input_span_len;
+        return {at_span_boundary, parameters_changed};
+    }
+};
+
+// src/source/blt.rs:43-55 (constructor), :111-139 (next: the sample first, then the span tracker; a parameter change recomputes the
+// coefficients for the samples that follow -- `current_channels != channels()` at :128 compares a value with itself, so the state
+// layout chosen at construction, blt.rs:247-283, is never rebuilt), :397-492 (per-sample step)
 struct BltFilter : Source {
     Src in;
     bool high;
@@ -267,7 +301,9 @@ struct BltFilter : Source {
     BltCoeffs k;
     std::vector<float> x1, x2, y1, y2;
     size_t position = 0;
-    BltFilter(Src i, bool hp, uint32_t f, float qq) : in(std::move(i)), high(hp), freq(f), q(qq) {
+    SpanTracker span;
+    BltFilter(Src i, bool hp, uint32_t f, float qq)
+        : in(std::move(i)), high(hp), freq(f), q(qq), span(in->sample_rate(), in->channels()) {
         uint32_t fs = in->sample_rate();  // blt.rs:195-199
         k = hp ? blt_high_pass(f, qq, fs) : blt_low_pass(f, qq, fs);
         size_t n = in->channels();
@@ -289,6 +325,11 @@ struct BltFilter : Source {
         x2[c] = x1[c];
         y1[c] = r;
         x1[c] = x;
+        SpanTracker::Detection d = span.advance(*in);   // blt.rs:122-137
+        if (d.at_span_boundary && d.parameters_changed) {
+            uint32_t fs = in->sample_rate();
+            k = high ? blt_high_pass(freq, q, fs) : blt_low_pass(freq, q, fs);   // recreate_applier
+        }
         return r;
     }
     std::optional<size_t> current_span_len() const override { return in->current_span_len(); }
@@ -296,8 +337,45 @@ struct BltFilter : Source {
     uint32_t sample_rate() const override { return in->sample_rate(); }
     Src clone() const override {
         auto p = std::make_unique<BltFilter>(in->clone(), high, freq, q);
-        p->x1 = x1, p->x2 = x2, p->y1 = y1, p->y2 = y2, p->position = position;
+        p->x1 = x1, p->x2 = x2, p->y1 = y1, p->y2 = y2, p->position = position, p->k = k, p->span = span;
         return p;
+    }
+};
+
+// src/source/from_iter.rs:16-127: the sources of an iterator played one after the other; the format may change from one to the next.
+// current_span_len(): the current source's while it is not exhausted, None otherwise (:83-91); channels() / sample_rate(): the
+// current source's, also when it is exhausted -- the next one is only fetched inside next() (:48-63).
+struct FromIter : Source {
+    std::vector<Src> rest;   // in order
+    size_t next_idx = 0;
+    Src current;
+    explicit FromIter(std::vector<Src> srcs) : rest(std::move(srcs)) {
+        if (!rest.empty()) current = std::move(rest[0]), next_idx = 1;
+    }
+    std::optional<Sample> next() override {
+        while (true) {
+            if (current) {
+                auto v = current->next();
+                if (v) return v;
+            }
+            if (next_idx < rest.size()) current = std::move(rest[next_idx++]);
+            else return std::nullopt;
+        }
+    }
+    std::optional<size_t> current_span_len() const override {
+        if (current) {
+            auto s = current->current_span_len();
+            if (!(s && *s == 0)) return s;   // !is_exhausted() (src/source/mod.rs:204-206)
+        }
+        return std::nullopt;
+    }
+    uint16_t channels() const override { return current ? current->channels() : (uint16_t)2; }
+    uint32_t sample_rate() const override { return current ? current->sample_rate() : 48000u; }
+    Src clone() const override {
+        std::vector<Src> v;
+        if (current) v.push_back(current->clone());
+        for (size_t i = next_idx; i < rest.size(); i++) v.push_back(rest[i]->clone());
+        return std::make_unique<FromIter>(std::move(v));
     }
 };
 

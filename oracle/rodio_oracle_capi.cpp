@@ -30,7 +30,7 @@ struct ro_stream {
     const float* pcm;
 };
 enum { FX_AMPLIFY = 1, FX_SPEED, FX_LOW_PASS, FX_HIGH_PASS, FX_REVERB, FX_AGC, FX_LIMIT, FX_SPATIAL,
-       FX_CHANNEL_VOLUME, FX_UNIFORM, FX_DELAY, FX_DISTORTION, FX_LINEAR_RAMP, FX_TAKE_DURATION, FX_SIGNAL, FX_MIX };
+       FX_CHANNEL_VOLUME, FX_UNIFORM, FX_DELAY, FX_DISTORTION, FX_LINEAR_RAMP, FX_TAKE_DURATION, FX_SIGNAL, FX_MIX, FX_APPEND };
 
 float ro_lerp(float a, float b, uint32_t num, uint32_t den) { return lerp(a, b, num, den); }
 float ro_db_to_linear(float d) { return db_to_linear(d); }
@@ -97,6 +97,19 @@ static Src build(const ro_stream& s) {
         const ro_effect& e = s.effects[0];
         Src gen = std::make_unique<TakeN>(std::make_unique<SignalGenerator>(s.sample_rate, e.f32[0], (SignalGenerator::Fn)e.u32[0]), (size_t)e.ns[0]);
         return apply_effects(std::move(gen), s.effects + 1, s.n_effects - 1);
+    }
+    // leading FX_APPEND adapters: source::from_iter([this buffer, the appended buffers ...]) (src/source/from_iter.rs:16-27)
+    uint32_t n_app = 0;
+    while (n_app < s.n_effects && s.effects[n_app].kind == FX_APPEND) n_app++;
+    if (n_app) {
+        std::vector<Src> parts;
+        parts.push_back(make_input(s));
+        for (uint32_t i = 0; i < n_app; i++) {
+            const ro_effect& e = s.effects[i];
+            const ro_stream* o = (const ro_stream*)(uintptr_t)(((uint64_t)e.u32[2] << 32) | (uint64_t)e.u32[1]);
+            parts.push_back(make_input(*o));
+        }
+        return apply_effects(std::make_unique<FromIter>(std::move(parts)), s.effects + n_app, s.n_effects - n_app);
     }
     return apply_effects(make_input(s), s.effects, s.n_effects);
 }

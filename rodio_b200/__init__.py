@@ -10,12 +10,12 @@ from ._capi import RodioB200Error, lib
 from .source import (AutomaticGainControlSettings, Batch, ChannelCountConverter, ChannelVolume, Comm, Context, Duration, wav_source,
                      Effect, LimitSettings, Mixer, MixerSource, Player, SampleRateConverter, SamplesBuffer,
                      SampleTypeConverter, Session, Source, Spatial, TestSource, UniformSourceIterator, default_context, mixer, plan,
-                     Function, SignalGenerator, SineWave, SquareWave, TriangleWave, SawtoothWave)
+                     Function, from_iter, SignalGenerator, SineWave, SquareWave, TriangleWave, SawtoothWave)
 
 __all__ = [
     "capi", "lib", "RodioB200Error", "AutomaticGainControlSettings", "Batch", "ChannelCountConverter",
     "ChannelVolume", "Comm", "Context", "Duration", "Effect", "LimitSettings", "Mixer", "MixerSource", "Player",
     "SampleRateConverter", "SamplesBuffer", "SampleTypeConverter", "Session", "Source", "Spatial", "TestSource",
     "UniformSourceIterator", "default_context", "mixer", "plan", "wav_source",
-    "Function", "SignalGenerator", "SineWave", "SquareWave", "TriangleWave", "SawtoothWave",
+    "Function", "from_iter", "SignalGenerator", "SineWave", "SquareWave", "TriangleWave", "SawtoothWave",
 ]

@@ -28,7 +28,7 @@ RB_FMT_F32, RB_FMT_I16, RB_FMT_U16, RB_FMT_I8, RB_FMT_U8, RB_FMT_I32, RB_FMT_I24
 
 (RB_FX_AMPLIFY, RB_FX_SPEED, RB_FX_LOW_PASS, RB_FX_HIGH_PASS, RB_FX_REVERB, RB_FX_AGC, RB_FX_LIMIT,
  RB_FX_SPATIAL, RB_FX_CHANNEL_VOLUME, RB_FX_UNIFORM, RB_FX_DELAY, RB_FX_DISTORTION, RB_FX_LINEAR_RAMP,
- RB_FX_TAKE_DURATION, RB_FX_SIGNAL, RB_FX_MIX) = range(1, 17)
+ RB_FX_TAKE_DURATION, RB_FX_SIGNAL, RB_FX_MIX, RB_FX_APPEND) = range(1, 18)
 RB_MIX_START_CONSUMED = 0xFFFFFFFFFFFFFFFF
 RB_SIGNAL_SINE, RB_SIGNAL_TRIANGLE, RB_SIGNAL_SQUARE, RB_SIGNAL_SAWTOOTH = range(4)
 
@@ -77,6 +77,8 @@ SYMBOLS = {
     "rb_batch_destroy": (C.c_int32, [C.c_void_p]),
     "rb_stream_plan": (C.c_int32, [C.POINTER(rb_stream_desc), C.c_uint16, C.c_uint32, _u64p, C.POINTER(C.c_uint16),
                                    C.POINTER(C.c_uint32), _u64p]),
+    "rb_streams_plan": (C.c_int32, [C.POINTER(rb_stream_desc), C.c_size_t, C.c_size_t, C.c_uint16, C.c_uint32, _u64p,
+                                    C.POINTER(C.c_uint16), C.POINTER(C.c_uint32), _u64p]),
     "rb_batch_upload": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint64]),
     "rb_batch_upload_packed": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "rb_batch_input_device_ptr": (C.c_int32, [C.c_void_p, C.c_size_t, _vpp, _u64p]),

@@ -296,6 +296,17 @@ struct PlanStream {
     uint32_t end_span = 0;     // what the end of the chain reports / leaves for the UniformSourceIterator that wraps it
     uint64_t end_tail_pad = 0;
     int64_t end_cv_last = -1;
+    // source::from_iter (RB_FX_APPEND): this stream is the head of a sequence of buffers with their own formats, or one of the
+    // buffers appended to a head.  The samples of the sequence are contiguous in the input arena (head first).
+    int64_t appended_to = -1;
+    std::vector<size_t> appended;          // head: the descriptors that follow it, in order
+    uint64_t seq_samples = 0;              // head: samples of the whole sequence
+    struct Run {                           // one UniformSourceIterator bootstrap of the mixer's conversion (uniform.rs:50-68)
+        PlanNode nd;
+        uint64_t in_off, out_off;          // samples into the sequence / into the converted stream
+    };
+    std::vector<Run> runs;
+    uint32_t run_level = 0;
 };
 
 static rb_uniform_seg uniform_seg(uint64_t in_samples, uint32_t c_in, uint32_t c_out, uint32_t from, uint32_t to) {
@@ -365,10 +376,154 @@ static rb_status plan_uniform(PlanNode& nd, uint64_t n_in, uint32_t c_in, uint32
     return RB_OK;
 }
 
+// ---- source::from_iter of buffers with different formats (RB_FX_APPEND) ---------------------------------------------------------
+// The host walks the CONTROL FLOW of rodio's adapters over such a source -- which span length and format FromIter reports when
+// an adapter asks (from_iter.rs:83-109: the current buffer's while it is not exhausted, None once it is; the next buffer is only
+// fetched inside next()) -- and turns it into closed forms: coefficient changes for a filter, converter runs for the mixer.
+struct SeqSeg {
+    uint64_t n;          // samples
+    uint32_t c, r;       // channels, sample rate (after any Speed)
+    bool spans;          // SamplesBuffer: Some(len) until exhausted; TestSource-like: None
+};
+static rb_status plan_varying(PlanStream& ps, std::vector<SeqSeg> segs, size_t fx_from, uint16_t mixer_ch, uint32_t mixer_rate) {
+    uint64_t n = 0;
+    for (const SeqSeg& g : segs) n += g.n;
+    const uint32_t c0 = segs[0].c;
+    for (size_t fi = fx_from; fi < ps.fx.size(); fi++) {
+        const rb_effect& e = ps.fx[fi];
+        PlanNode nd;
+        nd.d.c_in = nd.d.c_out = c0, nd.d.n_in = nd.d.n_out = n;   // c_in: the state layout a filter chose at construction (blt.rs:247-283)
+        nd.rate_out = segs[0].r, nd.span_out = 0;
+        switch (e.kind) {
+            case RB_FX_AMPLIFY:
+                nd.d.kind = RB_N_AMPLIFY, nd.d.p.amp.factor = e.f32[0];
+                break;
+            case RB_FX_SPEED:   // Speed::sample_rate() scales whatever its input reports at that moment (speed.rs:130-133)
+                for (SeqSeg& g : segs) g.r = rb_speed_sample_rate(g.r, e.f32[0]);
+                continue;
+            case RB_FX_LOW_PASS:
+            case RB_FX_HIGH_PASS: {
+                const bool high = e.kind == RB_FX_HIGH_PASS;
+                hostmath::Blt k = hostmath::blt(high, e.u32[0], e.f32[0], segs[0].r);
+                nd.d.kind = RB_N_BIQUAD;
+                nd.d.p.blt.b0 = k.b0, nd.d.p.blt.b1 = k.b1, nd.d.p.blt.b2 = k.b2, nd.d.p.blt.a1 = k.a1, nd.d.p.blt.a2 = k.a2;
+                // SpanTracker::advance behind every sample (span.rs:66-101), on what FromIter reports behind that sample
+                uint64_t counted = 0, g0 = 0;
+                bool counting = false;       // cached_span_len is Some
+                uint64_t cached = 0;
+                uint32_t last_c = segs[0].c, last_r = segs[0].r;
+                uint32_t n_sw = 0;
+                for (const SeqSeg& g : segs) {
+                    if (g.n == 0) continue;
+                    // behind sample j of this buffer the span is Some(g.n) for j < g.n - 1 and None behind the last one (exhausted);
+                    // only the first of them can see a boundary: the counter restarts there or the parameters are equal from then on
+                    if (g.spans && g.n >= 2) {
+                        const uint64_t cnt = counted + 1;
+                        const bool known = counting ? cnt >= cached : true;     // None: compare on every sample
+                        bool changed = false, boundary = false;
+                        if (known) {
+                            changed = g.c != last_c || g.r != last_r;
+                            last_c = g.c, last_r = g.r;
+                            boundary = counting ? true : changed;
+                        }
+                        if (boundary) counting = true, cached = g.n, counted = 0;
+                        else counted = cnt;
+                        if (boundary && changed) {
+                            if (n_sw >= RB_MAX_BLT_SWITCH) return fail(RB_ERR_UNSUPPORTED, "from_iter: more format changes than a filter follows");
+                            hostmath::Blt kk = hostmath::blt(high, e.u32[0], e.f32[0], g.r);
+                            nd.d.p.blt.sw_at[n_sw] = g0 + 1;      // the sample that crossed the boundary still had the old coefficients
+                            float* d = nd.d.p.blt.sw_k[n_sw];
+                            d[0] = kk.b0, d[1] = kk.b1, d[2] = kk.b2, d[3] = kk.a1, d[4] = kk.a2;
+                            n_sw++;
+                        }
+                        counted += g.n - 1;      // the other samples of the buffer: no boundary (counter below the span, or nothing changed)
+                    } else {
+                        counted += g.n;          // None behind every sample: the counter runs, nothing is compared
+                    }
+                    g0 += g.n;
+                }
+                nd.d.p.blt.n_sw = n_sw;
+                break;
+            }
+            case RB_FX_APPEND: return fail(RB_ERR_INVALID_ARGUMENT, "from_iter: APPEND only at the front of the chain");
+            default: return fail(RB_ERR_UNSUPPORTED, "from_iter: only amplify, speed, low_pass and high_pass follow a source whose format changes");
+        }
+        nd.level = ps.nodes.empty() ? 0u : ps.nodes.back().level + 1u;
+        ps.nodes.push_back(nd);
+    }
+    ps.chain_len = n, ps.chain_channels = segs[0].c, ps.chain_rate = segs[0].r;
+    ps.planning = false, ps.planned = true;
+    if (ps.consumed) return fail(RB_ERR_UNSUPPORTED, "from_iter: such a source cannot be the second input of a mix");
+    // Mixer::add: UniformSourceIterator::new(source, mixer_ch, mixer_rate) -- one converter run per bootstrap (uniform.rs:50-68,:83-96)
+    uint64_t pos = 0, out = 0;
+    size_t cur = 0;              // FromIter's current buffer (only next() moves on)
+    uint64_t pulled = 0;         // samples pulled from it
+    while (true) {
+        const SeqSeg& g = segs[cur];
+        const bool exhausted = pulled >= g.n;
+        const bool some = g.spans && !exhausted;
+        const uint64_t take = some ? std::min<uint64_t>(g.n, RB_UNIFORM_SPAN_CAP) : ~0ull;
+        const uint64_t m = std::min<uint64_t>(take, n - pos);
+        if (m == 0) break;
+        PlanStream::Run run;
+        rb_status s = plan_uniform(run.nd, m, g.c, g.r, 0, mixer_ch, mixer_rate, -1);
+        if (s != RB_OK) return s;
+        if (run.nd.d.n_out == 0) break;      // the bootstrap's first next() is None: the UniformSourceIterator ends here
+        run.in_off = pos, run.out_off = out;
+        ps.runs.push_back(run);
+        pos += m, out += run.nd.d.n_out;
+        uint64_t left = m;                   // FromIter::next moved through the buffers
+        while (left) {
+            const uint64_t here = std::min<uint64_t>(left, segs[cur].n - pulled);
+            pulled += here, left -= here;
+            if (left) cur++, pulled = 0;
+            while (left && segs[cur].n == 0) cur++;
+        }
+    }
+    ps.run_level = ps.nodes.empty() ? 0u : ps.nodes.back().level + 1u;
+    ps.out_len = out;
+    ps.mix_start = (ps.desc.mix_start + mixer_ch - 1) / mixer_ch * mixer_ch;
+    return RB_OK;
+}
+
 static rb_status plan_stream(PlanStream& ps, uint16_t mixer_ch, uint32_t mixer_rate, std::vector<PlanStream>* all = nullptr, size_t self = 0) {
     const rb_stream_desc& d = ps.desc;
     ps.consumed = d.mix_start == RB_MIX_START_CONSUMED;
     ps.planning = true;
+    {
+        size_t n_app = 0;
+        while (n_app < ps.fx.size() && ps.fx[n_app].kind == RB_FX_APPEND) n_app++;
+        if (n_app) {
+            if (!all) return fail(RB_ERR_UNSUPPORTED, "from_iter: the appended buffers are other descriptors of the batch (rb_batch_create)");
+            auto seg_of = [](const rb_stream_desc& dd, SeqSeg& g) -> rb_status {
+                if (dd.sample_rate == 0 || dd.channels == 0) return fail(RB_ERR_INVALID_ARGUMENT, "zero sample rate or channels");
+                if (dd.channels > RB_MAX_CHANNELS) return fail(RB_ERR_UNSUPPORTED, "more than 12 channels");
+                if (dd.format != RB_FMT_F32) return fail(RB_ERR_UNSUPPORTED, "from_iter: f32 buffers only");
+                if (dd.span_len != 0 && (uint64_t)dd.span_len != dd.n_samples)
+                    return fail(RB_ERR_UNSUPPORTED, "from_iter: span_len is n_samples (SamplesBuffer) or 0");
+                g = SeqSeg{dd.n_samples, dd.channels, dd.sample_rate, dd.span_len != 0};
+                return RB_OK;
+            };
+            std::vector<SeqSeg> segs(1);
+            rb_status s0 = seg_of(d, segs[0]);
+            if (s0 != RB_OK) return s0;
+            for (size_t i = 0; i < n_app; i++) {
+                const size_t idx = ps.fx[i].u32[0];
+                if (idx >= all->size() || idx == self) return fail(RB_ERR_INVALID_ARGUMENT, "from_iter: bad index of an appended buffer");
+                PlanStream& o = (*all)[idx];
+                if (o.desc.mix_start != RB_MIX_START_CONSUMED || o.consumer >= 0 || o.planned || o.planning || !o.fx.empty())
+                    return fail(RB_ERR_INVALID_ARGUMENT, "from_iter: an appended buffer is a descriptor without effects, mix_start = RB_MIX_START_CONSUMED, used once");
+                SeqSeg g;
+                rb_status so = seg_of(o.desc, g);
+                if (so != RB_OK) return so;
+                segs.push_back(g);
+                o.consumer = (int64_t)self, o.appended_to = (int64_t)self, o.consumed = true, o.planned = true;
+                ps.appended.push_back(idx);
+            }
+            for (const SeqSeg& g : segs) ps.seq_samples += g.n;
+            return plan_varying(ps, segs, n_app, mixer_ch, mixer_rate);
+        }
+    }
     if (d.sample_rate == 0 || d.channels == 0) return fail(RB_ERR_INVALID_ARGUMENT, "zero sample rate or channels");
     if (d.channels > RB_MAX_CHANNELS) return fail(RB_ERR_UNSUPPORTED, "more than 12 channels");
     if (d.format > RB_FMT_I24_IN_I32) return fail(RB_ERR_INVALID_ARGUMENT, "unknown sample format");
@@ -616,6 +771,31 @@ extern "C" rb_status rb_stream_plan(const rb_stream_desc* desc, uint16_t mixer_c
     return RB_OK;
 }
 
+// The same closed forms for descriptor `stream` of an array -- needed when a descriptor names others (RB_FX_MIX, RB_FX_APPEND).
+extern "C" rb_status rb_streams_plan(const rb_stream_desc* descs, size_t n_streams, size_t stream, uint16_t mixer_ch, uint32_t mixer_rate,
+                                     uint64_t* out_len, uint16_t* chain_channels, uint32_t* chain_rate, uint64_t* chain_len) {
+    if (!descs || stream >= n_streams) return fail(RB_ERR_INVALID_ARGUMENT, "descs is NULL or stream out of range");
+    if (mixer_ch == 0 || mixer_rate == 0) return fail(RB_ERR_INVALID_ARGUMENT, "mixer: zero channels or rate");
+    if (mixer_ch > RB_MAX_CHANNELS) return fail(RB_ERR_UNSUPPORTED, "mixer: more than 12 channels");
+    std::vector<PlanStream> all(n_streams);
+    for (size_t i = 0; i < n_streams; i++) {
+        if (descs[i].n_effects && !descs[i].effects) return fail(RB_ERR_INVALID_ARGUMENT, "effects is NULL");
+        all[i].desc = descs[i];
+        all[i].fx.assign(descs[i].effects, descs[i].effects + descs[i].n_effects);
+    }
+    for (size_t i = 0; i < n_streams; i++) {
+        if (all[i].planned) continue;
+        rb_status s = plan_stream(all[i], mixer_ch, mixer_rate, &all, i);
+        if (s != RB_OK) return s;
+    }
+    const PlanStream& ps = all[stream];
+    if (out_len) *out_len = ps.out_len;
+    if (chain_channels) *chain_channels = (uint16_t)ps.chain_channels;
+    if (chain_rate) *chain_rate = ps.chain_rate;
+    if (chain_len) *chain_len = ps.chain_len;
+    return RB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // batch
 // ------------------------------------------------------------------------------------------------
@@ -717,10 +897,18 @@ extern "C" rb_status rb_batch_create(rb_context* ctx, uint16_t mixer_ch, uint32_
         PlanStream& ps = b->streams[i];
         if (ps.consumed && ps.consumer < 0)
             return fail(RB_ERR_INVALID_ARGUMENT, "stream " + std::to_string(i) + ": mix_start = RB_MIX_START_CONSUMED but no RB_FX_MIX names it");
-        ps.in_off = in_bytes;
-        in_bytes += align_up((size_t)ps.desc.n_samples * fmt_size(ps.desc.format) + 16, 128);
+        if (ps.appended_to < 0) {   // the buffers of a from_iter sequence follow their head without a gap
+            ps.in_off = in_bytes;
+            size_t off = in_bytes + (size_t)ps.desc.n_samples * fmt_size(ps.desc.format);
+            for (size_t idx : ps.appended) {
+                b->streams[idx].in_off = off;
+                off += (size_t)b->streams[idx].desc.n_samples * sizeof(float);
+            }
+            in_bytes = align_up(off + 16, 128);
+        }
         uint64_t cap = 0;
         for (auto& nd : ps.nodes) cap = std::max(cap, nd.d.n_out), max_level = std::max(max_level, nd.level + 1u);
+        if (!ps.runs.empty()) cap = std::max(cap, ps.out_len), max_level = std::max(max_level, ps.run_level + 1u);
         ps.buf_cap = align_up((size_t)cap + 4, 32);
         ps.buf_off = buf_floats;
         buf_floats += ps.buf_cap;
@@ -817,7 +1005,7 @@ extern "C" rb_status rb_batch_create(rb_context* ctx, uint16_t mixer_ch, uint32_
         }
         std::vector<rb_node_dev> host_nodes;
         auto final_of = [&](const PlanStream& ps) -> const float* {
-            const size_t k = ps.nodes.size();
+            const size_t k = ps.nodes.size() + (ps.runs.empty() ? 0 : 1);   // the converter runs of a from_iter source count as one node
             return (k == 0) ? (const float*)(b->d_in + ps.in_off) : b->d_buf[(k - 1) & 1] + ps.buf_off;
         };
         for (uint32_t lvl = 0; lvl < max_level; lvl++) {
@@ -838,6 +1026,20 @@ extern "C" rb_status rb_batch_create(rb_context* ctx, uint16_t mixer_ch, uint32_
                         g.max_n_out = std::max(g.max_n_out, nd.n_out);
                         g.max_channels = std::max(g.max_channels, nd.c_in);
                     }
+                    if (kind == RB_N_UNIFORM && !ps.runs.empty() && ps.run_level == lvl) {
+                        // from_iter: one k_uniform node per converter run, each on its slice of the sequence, outputs back to back
+                        const size_t j = ps.nodes.size();
+                        const float* in = (j == 0) ? (const float*)(b->d_in + ps.in_off) : b->d_buf[(j - 1) & 1] + ps.buf_off;
+                        for (const PlanStream::Run& run : ps.runs) {
+                            rb_node_dev nd = run.nd.d;
+                            nd.src = in + run.in_off, nd.dst = b->d_buf[j & 1] + ps.buf_off + run.out_off;
+                            nd.aux0 = nd.aux1 = nullptr;
+                            host_nodes.push_back(nd);
+                            g.count++;
+                            g.max_n_out = std::max(g.max_n_out, nd.n_out);
+                            g.max_channels = std::max(g.max_channels, nd.c_in);
+                        }
+                    }
                 }
                 if (g.count) b->groups.push_back(g);
             }
@@ -849,8 +1051,7 @@ extern "C" rb_status rb_batch_create(rb_context* ctx, uint16_t mixer_ch, uint32_
         std::vector<rb_mix_src> mix(n_streams);
         for (size_t i = 0; i < n_streams; i++) {
             PlanStream& ps = b->streams[order[i]];
-            size_t k = ps.nodes.size();
-            ps.final_ptr = (k == 0) ? (const float*)(b->d_in + ps.in_off) : b->d_buf[(k - 1) & 1] + ps.buf_off;
+            ps.final_ptr = final_of(ps);
             mix[i] = {ps.final_ptr, ps.mix_start, ps.out_len};
         }
         RB_CUDA(cudaMalloc(&b->d_mix, std::max<size_t>(n_streams * sizeof(rb_mix_src), 256)));

@@ -8,7 +8,8 @@
 #include "../../include/rodio_b200.h"
 
 #define RB_MAX_CHANNELS 12
-#define RB_UNIFORM_SPAN_CAP 32768u   // reference src/source/uniform.rs:56
+#define RB_UNIFORM_SPAN_CAP 32768u
+#define RB_MAX_BLT_SWITCH 3          // format changes inside one source that a filter follows (4 buffers)   // reference src/source/uniform.rs:56
 
 // Internal node kinds (one per kernel family).
 enum rb_node_kind : uint32_t {
@@ -64,7 +65,12 @@ struct alignas(16) rb_node_dev {
     float* aux1;
     union {
         struct { float factor; } amp;
-        struct { float b0, b1, b2, a1, a2; } blt;
+        struct {
+            float b0, b1, b2, a1, a2;
+            uint32_t n_sw;                       // coefficient changes at span boundaries (blt.rs:122-137): from flat sample sw_at[k] on, sw_k[k]
+            uint64_t sw_at[RB_MAX_BLT_SWITCH];
+            float sw_k[RB_MAX_BLT_SWITCH][5];
+        } blt;
         struct { uint64_t delay; float amplitude; } echo;
         struct { float target, max_gain, floor, attack, release; } agc;
         struct { float threshold, knee, inv_knee_8, attack, release; } lim;

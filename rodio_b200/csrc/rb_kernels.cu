@@ -267,10 +267,16 @@ __global__ void __launch_bounds__(128) k_biquad_seq(const rb_node_dev* __restric
     if (c >= nd.c_in) return;
     const float* __restrict__ x = (const float*)nd.src;
     float* __restrict__ y = nd.dst;
-    const float b0 = nd.p.blt.b0, b1 = nd.p.blt.b1, b2 = nd.p.blt.b2, a1 = nd.p.blt.a1, a2 = nd.p.blt.a2;
+    float b0 = nd.p.blt.b0, b1 = nd.p.blt.b1, b2 = nd.p.blt.b2, a1 = nd.p.blt.a1, a2 = nd.p.blt.a2;
     const uint32_t C = nd.c_in;
     float x1 = 0.f, x2 = 0.f, y1 = 0.f, y2 = 0.f;
+    uint32_t sw = 0;
+    const uint32_t n_sw = nd.p.blt.n_sw;
     for (uint64_t i = c; i < nd.n_in; i += C) {      // flat position % C selects the state (blt.rs:472-476)
+        while (sw < n_sw && i >= nd.p.blt.sw_at[sw]) {   // a span with another sample rate began: new coefficients, same state
+            b0 = nd.p.blt.sw_k[sw][0], b1 = nd.p.blt.sw_k[sw][1], b2 = nd.p.blt.sw_k[sw][2], a1 = nd.p.blt.sw_k[sw][3], a2 = nd.p.blt.sw_k[sw][4];
+            sw++;
+        }
         float xv = x[i];
         float r = biquad(b0, b1, b2, a1, a2, xv, x1, x2, y1, y2);
         y2 = y1, x2 = x1, y1 = r, x1 = xv;

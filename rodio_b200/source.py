@@ -287,6 +287,21 @@ class TestSource(Source):
         super().__init__(np.asarray(samples), channels, sample_rate, span_len=0)
 
 
+def from_iter(sources: Sequence[Source]) -> Source:
+    """source::from_iter(sources) -- src/source/from_iter.rs:16-27: the buffers played one after the other as ONE source whose
+    sample rate and channel count change where one ends and the next begins (RB_FX_APPEND).  The parts are plain f32 buffers
+    (SamplesBuffer or TestSource, no adapters of their own); adapters go on the result."""
+    parts = list(sources)
+    if not parts:
+        raise ValueError("from_iter of nothing")
+    for p in parts:
+        if p.effects or p.pcm.dtype != np.float32:
+            raise ValueError("from_iter takes plain f32 buffers")
+    head = parts[0]
+    fx = [Effect.make(capi.RB_FX_APPEND, other=o) for o in parts[1:]]
+    return Source(head.pcm, head.base_channels, head.base_rate, head.span_len, fx)
+
+
 class Function:
     """source::Function -- src/source/signal_generator.rs:40-49."""
     Sine, Triangle, Square, Sawtooth = capi.RB_SIGNAL_SINE, capi.RB_SIGNAL_TRIANGLE, capi.RB_SIGNAL_SQUARE, capi.RB_SIGNAL_SAWTOOTH
@@ -459,7 +474,7 @@ def flatten_sources(sources: Sequence[Source]) -> List[Source]:
     i = 0
     while i < len(flat):
         for e in flat[i].effects:
-            if e.kind == capi.RB_FX_MIX and e.other is not None and not any(e.other is f for f in flat):
+            if e.kind in (capi.RB_FX_MIX, capi.RB_FX_APPEND) and e.other is not None and not any(e.other is f for f in flat):
                 flat.append(e.other)
         i += 1
     return flat
@@ -482,7 +497,7 @@ def pack_descs(sources: Sequence[Source], mix_starts: Optional[Sequence[int]] = 
                 fx[j].f32[k] = e.f32[k]
             for k in range(2):
                 fx[j].ns[k] = e.ns[k]
-            if e.kind == capi.RB_FX_MIX and e.other is not None:
+            if e.kind in (capi.RB_FX_MIX, capi.RB_FX_APPEND) and e.other is not None:
                 fx[j].u32[0] = next(k for k, f in enumerate(flat) if f is e.other)
         keep.append(fx)
         d = descs[i]
@@ -504,8 +519,12 @@ def plan(source: Source, mixer_channels: int, mixer_rate: int):
     """Host-only closed forms for one source: (samples the mixer pulls, chain channels, chain rate, chain samples)."""
     descs, keep = pack_descs([source])
     n, ch, rate, cn = C.c_uint64(), C.c_uint16(), C.c_uint32(), C.c_uint64()
-    check(lib().rb_stream_plan(C.byref(descs[0]), mixer_channels, mixer_rate, C.byref(n), C.byref(ch), C.byref(rate),
-                               C.byref(cn)), "rb_stream_plan")
+    if len(keep[0]) > 1:      # the source names others (mix, from_iter): plan it inside its descriptor array
+        check(lib().rb_streams_plan(descs, len(keep[0]), 0, mixer_channels, mixer_rate, C.byref(n), C.byref(ch), C.byref(rate),
+                                    C.byref(cn)), "rb_streams_plan")
+    else:
+        check(lib().rb_stream_plan(C.byref(descs[0]), mixer_channels, mixer_rate, C.byref(n), C.byref(ch), C.byref(rate),
+                                   C.byref(cn)), "rb_stream_plan")
     return n.value, ch.value, rate.value, cn.value
 
 

@@ -35,11 +35,31 @@ def test_oracle_crossfade_against_silence():
     assert got.size == 5 and np.all(np.abs(got - np.array([1.0, 1.6, 1.8, 1.6, 1.0], np.float32)) < 1e-6), got
 
 
-def test_mix_argument_errors():
+def test_mix_planner_and_argument_errors():
+    import ctypes as C
+    from rodio_b200.source import pack_descs
     a = rb.TestSource(noise(100, 1), 1, 48000)
-    b = rb.TestSource(noise(100, 2), 1, 48000)
-    with pytest.raises(rb.RodioB200Error):          # one descriptor alone cannot name its second input
-        rb.plan(a.mix(b), 1, 48000)
+    b = rb.TestSource(noise(2 * 300, 2), 2, 24000)
+    out_len, ch, rate, chain_len = rb.plan(a.mix(b), 1, 48000)          # rb_streams_plan: the descriptor array
+    assert (ch, rate) == (1, 48000) and chain_len == _chain(a.mix(b)).size == out_len
+    descs, keep = pack_descs([a.mix(b)])
+    n = C.c_uint64()
+    L = rb.lib()
+    # one descriptor alone cannot name its second input
+    assert L.rb_stream_plan(C.byref(descs[0]), 1, 48000, C.byref(n), None, None, None) == capi.RB_ERR_UNSUPPORTED
+    # the second input must be marked consumed, and only one MIX may take it
+    descs[1].mix_start = 0
+    assert L.rb_streams_plan(descs, 2, 0, 1, 48000, C.byref(n), None, None, None) == capi.RB_ERR_INVALID_ARGUMENT
+    descs[1].mix_start = capi.RB_MIX_START_CONSUMED
+    assert L.rb_streams_plan(descs, 2, 0, 1, 48000, C.byref(n), None, None, None) == capi.RB_OK
+    keep[1][0].u32[0] = 0                                                # a source mixed with itself
+    assert L.rb_streams_plan(descs, 2, 0, 1, 48000, C.byref(n), None, None, None) == capi.RB_ERR_INVALID_ARGUMENT
+    keep[1][0].u32[0] = 5
+    assert L.rb_streams_plan(descs, 2, 0, 1, 48000, C.byref(n), None, None, None) == capi.RB_ERR_INVALID_ARGUMENT
+    # a descriptor marked consumed that nobody consumes
+    lone, _ = pack_descs([a])
+    lone[0].mix_start = capi.RB_MIX_START_CONSUMED
+    assert L.rb_streams_plan(lone, 1, 0, 1, 48000, C.byref(n), None, None, None) == capi.RB_OK     # planned, but a batch refuses it
 
 
 # ------------------------------------------------------------------ GPU
