@@ -377,16 +377,17 @@ def run_ours(args):
     if world == 1 and not args.no_e2e:
         also = {}
 
-        def timed(name, workload, srcs, mixer_ch, flags, steps, kernel_names):
+        def timed(name, workload, srcs, mixer_ch, flags, steps, kernel_names, fill=True):
             try:
                 b2 = rb.Batch(srcs, mixer_ch, MIX_RATE, flags=flags, ctx=ctx)
                 n2 = len(srcs)
-                q0, cap0 = b2.input_device_ptr(0)
-                pitch2 = (b2.input_device_ptr(1)[0] - q0) // 4 if n2 > 1 else cap0
-                for i in range(n2):
-                    b2.input_device_ptr(i)
-                with torch.cuda.stream(ext):
-                    torch.as_tensor(rbd.DeviceArray(q0, pitch2 * (n2 - 1) + cap0), device=dev).uniform_(-0.5, 0.5, generator=gen)
+                if fill:
+                    q0, cap0 = b2.input_device_ptr(0)
+                    pitch2 = (b2.input_device_ptr(1)[0] - q0) // 4 if n2 > 1 else cap0
+                    for i in range(n2):
+                        b2.input_device_ptr(i)
+                    with torch.cuda.stream(ext):
+                        torch.as_tensor(rbd.DeviceArray(q0, pitch2 * (n2 - 1) + cap0), device=dev).uniform_(-0.5, 0.5, generator=gen)
                 for _ in range(3):
                     b2.render_mix_device()
                 torch.cuda.synchronize(dev)
@@ -409,11 +410,17 @@ def run_ours(args):
                 also[name] = {"workload": workload, "error": f"{type(exc).__name__}: {exc}"[:300]}
 
         FAM = {-1: "general path (one kernel per adapter)", 0: "k_fused_biquad", 1: "k_fused_hot + k_sum_partials", 2: "k_fused_lanes + k_sum_groups",
-               3: "k_fused_duo + k_sum_groups", 4: "k_fused_duo over timeline segments + k_sum_groups", 5: "k_fused_fx + k_fx_sum_partials"}
+               3: "k_fused_duo + k_sum_groups", 4: "k_fused_duo over timeline segments + k_sum_groups", 5: "k_fused_fx + k_fx_sum_partials",
+               6: "k_lerp_mix + k_sum_groups"}
         z = lambda n: np.zeros(n, np.float32)
         steps2 = max(3, min(args.steps, 10))
         timed("cfg2_dynamic_mixer", "mixer(1, 48000) of 1024 mono 48 kHz f32 sources x 10 s, summed in insertion order (bit-exact)",
               [rb.TestSource(z(48000 * 10), 1, MIX_RATE) for _ in range(1024)], 1, args.flags, args.steps, {-1: "k_mix_ordered"})
+        timed("cfg2_from_generators", "BASELINE configs[1] as the reference states it: 1024 SineWave sources (110 Hz * 2^(s/128)) x 10 s handed to "
+              "mixer(1, 48000) -- generated on the device (k_siggen: f32 phase recurrence per source, glibc's sinf in FP64) AND summed in "
+              "insertion order, nothing uploaded; latency-bound by the 480 000 serial phase steps per source",
+              [rb.SineWave(min(110.0 * 2.0 ** (s / 128.0), 19999.0)).take(48000 * 10) for s in range(1024)], 1, args.flags, 3,
+              {-1: "k_siggen + k_mix_ordered"}, fill=False)
         one2 = z(2 * IN_RATE)
         timed("cfg3_low_pass_1000_time_parallel",
               "cfg3 shape at low_pass(1000) with RB_BIQUAD_TIME_PARALLEL (SURVEY 8d cfg3: the scan variant beside the exact one): 4096 mono "

@@ -62,6 +62,10 @@ pub const RB_FX_DELAY: u32 = 11;
 pub const RB_FX_DISTORTION: u32 = 12;
 pub const RB_FX_LINEAR_RAMP: u32 = 13;
 pub const RB_FX_TAKE_DURATION: u32 = 14;
+pub const RB_FX_SIGNAL: u32 = 15;      // SignalGenerator::new(rate, freq, f).take(n): generated on the device
+pub const RB_FX_MIX: u32 = 16;         // Source::mix(other): u32[0] = descriptor index of the second input
+pub const RB_FX_APPEND: u32 = 17;      // source::from_iter([self, next, ..]): u32[0] = descriptor index of the next buffer
+pub const RB_MIX_START_CONSUMED: u64 = u64::MAX;   // mix_start of a descriptor another descriptor's MIX / APPEND consumes
 
 /// An in-memory source plus the adapters recorded on it (what `SamplesBuffer::new(..).amplify(..)` builds).
 pub struct GpuSource {
@@ -71,13 +75,45 @@ pub struct GpuSource {
     span_len: u32,
     effects: Vec<rb_effect>,
     reported_rate: SampleRate,
+    /// second inputs of `mix` / buffers appended by `from_iter`: descriptors of their own, `others[k]` belongs to the k-th
+    /// RB_FX_MIX / RB_FX_APPEND of `effects` (their u32[0] is filled in when the descriptor array is laid out)
+    others: Vec<GpuSource>,
 }
 
 impl GpuSource {
+    /// `SignalGenerator::new(sample_rate, frequency, f).take(n)` (src/source/signal_generator.rs:85-135); function: 0 sine,
+    /// 1 triangle, 2 square, 3 sawtooth.  Nothing is uploaded: the samples are generated in HBM (f32 phase accumulation and
+    /// glibc's sinf bit for bit, like `f32::sin` on linux-gnu).
+    pub fn signal_generator(sample_rate: SampleRate, frequency: f32, function: u32, n: u64) -> Self {
+        assert!(frequency > 0.0, "frequency must be greater than zero");        // signal_generator.rs:112
+        Self { pcm: vec![], channels: NonZero::new(1).unwrap(), sample_rate, span_len: 0, effects: vec![], reported_rate: sample_rate,
+               others: vec![] }
+            .push(RB_FX_SIGNAL, [function, 0, 0], &[frequency], [n, 0])
+    }
+    /// `source::from_iter(buffers)` (src/source/from_iter.rs:16-27): ONE source whose format changes from buffer to buffer; filters
+    /// behind it follow the change like `SpanTracker` makes them (state kept, coefficients recomputed), the mixer re-bootstraps.
+    pub fn from_iter(mut buffers: Vec<GpuSource>) -> Self {
+        let mut head = buffers.remove(0);
+        for b in buffers {
+            assert!(b.effects.is_empty(), "from_iter takes plain buffers");
+            head = head.push(RB_FX_APPEND, [0; 3], &[], [0; 2]);
+            head.others.push(b);
+        }
+        head
+    }
+    /// `Source::mix` (src/source/mod.rs:253-261, mix.rs:10-53)
+    pub fn mix(mut self, other: GpuSource) -> Self {
+        self.others.push(other);
+        self.push(RB_FX_MIX, [0; 3], &[], [0; 2])
+    }
+    /// `Source::take_crossfade_with` (src/source/mod.rs:444-454, crossfade.rs:10-23)
+    pub fn take_crossfade_with(self, other: GpuSource, duration: Duration) -> Self {
+        self.take_duration(duration, true).mix(other.take_duration(duration, false).linear_gain_ramp(duration, 0.0, 1.0, false))
+    }
     /// `SamplesBuffer::new(channels, sample_rate, data)` (src/buffer.rs:40-60)
     pub fn from_samples(channels: ChannelCount, sample_rate: SampleRate, data: Vec<Sample>) -> Self {
         let span_len = data.len().min(u32::MAX as usize) as u32;
-        Self { pcm: data, channels, sample_rate, span_len, effects: vec![], reported_rate: sample_rate }
+        Self { pcm: data, channels, sample_rate, span_len, effects: vec![], reported_rate: sample_rate, others: vec![] }
     }
     fn push(mut self, kind: u32, u: [u32; 3], f: &[f32], ns: [u64; 2]) -> Self {
         let mut f32_ = [0f32; 12];
@@ -143,7 +179,20 @@ impl GpuMixer {
     pub fn add(&mut self, source: GpuSource) { self.sources.push((source, self.position)); }
 
     /// Drain everything added so far into a block-backed `Source`.
-    pub fn into_source(self) -> Result<GpuMixerSource, i32> {
+    pub fn into_source(mut self) -> Result<GpuMixerSource, i32> {
+        // second inputs of mix() and buffers of from_iter() become descriptors of their own behind the sources that were added
+        // (mix_start = RB_MIX_START_CONSUMED), breadth first; the adapter that names them gets their index
+        let mut i = 0;
+        while i < self.sources.len() {
+            let others: Vec<GpuSource> = std::mem::take(&mut self.sources[i].0.others);
+            let mut k = self.sources.len() as u32;
+            for e in self.sources[i].0.effects.iter_mut().filter(|e| e.kind == RB_FX_MIX || e.kind == RB_FX_APPEND) {
+                e.u32_[0] = k;
+                k += 1;
+            }
+            self.sources.extend(others.into_iter().map(|o| (o, RB_MIX_START_CONSUMED)));
+            i += 1;
+        }
         let descs: Vec<rb_stream_desc> = self.sources.iter().map(|(s, start)| rb_stream_desc {
             sample_rate: s.sample_rate.get(), channels: s.channels.get(), format: 0, n_samples: s.pcm.len() as u64,
             span_len: s.span_len, n_effects: s.effects.len() as u32, effects: s.effects.as_ptr(), mix_start: *start,

@@ -99,7 +99,12 @@ def test_from_iter_bit_exact(ctx):
         with rb.Batch([src], *mixer, flags=capi.RB_MIX_EXACT_ORDER, ctx=ctx) as b:
             b.upload_all()
             got = b.render_mix()
-        assert_bit_exact(got, want, f"from_iter case {t}")
+        # a filter above the Nyquist rate of an 8 kHz buffer diverges to inf - inf = NaN on both sides: x86 hands on the payload of
+        # an operand, the device the canonical NaN -- not a parity question, so NaNs compare equal here
+        assert got.shape == want.shape
+        nan = np.isnan(want)
+        assert np.array_equal(np.isnan(got), nan), f"from_iter case {t}: NaNs in other places"
+        assert_bit_exact(np.where(nan, np.float32(0), got), np.where(nan, np.float32(0), want), f"from_iter case {t}")
 
 
 @pytest.mark.gpu
