@@ -53,7 +53,10 @@ struct FusedArgs {
     float* partial;                // [n_ctas][mix_len]
     uint64_t mix_len;
     uint32_t direct;               // single CTA: `partial` is the mixer output itself, cover the whole timeline
-    uint32_t pad_;
+    uint32_t chain;                // RB_MIX_EXACT_ORDER on k_fused_hot: CTA c starts every tile's sum from the running sum CTA c - 1
+                                   // left for that tile -- the reference's sequential order over ALL streams (src/mixer.rs:185-198)
+    float* out;                    // chain: the last CTA's row is the mixer output
+    uint32_t* flags;               // chain: [n_ctas][2] tiles finished by (CTA, stage-C warp)
 };
 
 // ---- per (row, tile) index state -------------------------------------------------------------------
@@ -319,15 +322,14 @@ __device__ __forceinline__ void cta_span(const FusedRow* s_rows, uint32_t G, con
         lo = min(lo, s_rows[g].mix_start);
         hi = max(hi, s_rows[g].mix_start + s_rows[g].out_len);
     }
-    if (a.direct) lo = 0, hi = a.mix_len;
+    if (a.direct || a.chain) lo = 0, hi = a.mix_len;   // chain: every CTA hands the running sum on for every tile
 }
 
 // Stage C for one tile position: post-gains and the ordered sum over the CTA's rows.
 // `full`: every row of the CTA is active over the whole tile (the common interior case) -> no range checks.
 template <int NPOST, class TileState>   // NPOST: 0, 1 or -1 (runtime count); TileState begins with {uint32 lo, hi}
 __device__ __forceinline__ float mix_rows_n(const float* tile, const TileState* rts, const FusedRow* s_rows, uint32_t G,
-                                            uint32_t n_post, uint32_t t, bool full) {
-    float acc = 0.0f;
+                                            uint32_t n_post, uint32_t t, bool full, float acc = 0.0f) {
     if (full) {
 #pragma unroll 4
         for (uint32_t g = 0; g < G; g++) {
@@ -351,10 +353,10 @@ __device__ __forceinline__ float mix_rows_n(const float* tile, const TileState* 
 }
 template <class TileState>
 __device__ __forceinline__ float mix_rows(const float* tile, const TileState* rts, const FusedRow* s_rows, uint32_t G,
-                                          uint32_t n_post, uint32_t t, bool full) {
-    if (n_post == 0) return mix_rows_n<0>(tile, rts, s_rows, G, n_post, t, full);
-    if (n_post == 1) return mix_rows_n<1>(tile, rts, s_rows, G, n_post, t, full);
-    return mix_rows_n<-1>(tile, rts, s_rows, G, n_post, t, full);
+                                          uint32_t n_post, uint32_t t, bool full, float acc0 = 0.0f) {
+    if (n_post == 0) return mix_rows_n<0>(tile, rts, s_rows, G, n_post, t, full, acc0);
+    if (n_post == 1) return mix_rows_n<1>(tile, rts, s_rows, G, n_post, t, full, acc0);
+    return mix_rows_n<-1>(tile, rts, s_rows, G, n_post, t, full, acc0);
 }
 
 // Mixer-timeline interval on which every row of the CTA is active: tiles inside it need no range checks.
@@ -836,8 +838,8 @@ __device__ __forceinline__ int hot_second_row(int slot) {
 // Stage C of the HOT kernel: one thread sums FOUR consecutive tile positions over the CTA's rows (row order =
 // the mixer's insertion order), 16-byte loads of y, the post-gain applied on the fly.  64 threads cover a tile.
 template <int NPOST>
-__device__ __forceinline__ float4 hot_mix4_full(const float* tile, const FusedRow* s_rows, uint32_t G, uint32_t n_post, uint32_t t4) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+__device__ __forceinline__ float4 hot_mix4_full(const float* tile, const FusedRow* s_rows, uint32_t G, uint32_t n_post, uint32_t t4,
+                                                float4 acc) {
 #pragma unroll 4
     for (uint32_t g = 0; g < G; g++) {
         float4 v = *reinterpret_cast<const float4*>(tile + g * ROW_STRIDE + t4);
@@ -852,29 +854,67 @@ __device__ __forceinline__ float4 hot_mix4_full(const float* tile, const FusedRo
     }
     return acc;
 }
+// Chain mode (RB_MIX_EXACT_ORDER): the sum of a tile starts from the row CTA c - 1 wrote for it (`carry_row`, the running sum over
+// all earlier streams) instead of +0.0, so the last CTA's row is the reference's sequential sum over every stream.  A CTA only ever
+// waits for the CTA in front of it, which was scheduled before it: no co-residency is needed.  Every lane polls the flag itself
+// (one broadcast transaction) with an acquire load, reads the carry past L1, and the warp publishes its own tile count with a
+// release store after its partial row is written.
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void hot_mix4(const float* tile, const HotTile* hts, const FusedRow* s_rows, uint32_t G,
                                          uint32_t n_post, uint32_t t4, bool full, uint64_t m0, uint64_t mix_len,
-                                         float* __restrict__ partial) {
-    if (m0 + t4 >= mix_len) return;
-    float4 acc;
-    if (full) {
-        acc = n_post == 0 ? hot_mix4_full<0>(tile, s_rows, G, n_post, t4)
-              : n_post == 1 ? hot_mix4_full<1>(tile, s_rows, G, n_post, t4)
-                            : hot_mix4_full<-1>(tile, s_rows, G, n_post, t4);
-    } else {
-        acc.x = mix_rows(tile, hts, s_rows, G, n_post, t4, false);
-        acc.y = mix_rows(tile, hts, s_rows, G, n_post, t4 + 1, false);
-        acc.z = mix_rows(tile, hts, s_rows, G, n_post, t4 + 2, false);
-        acc.w = mix_rows(tile, hts, s_rows, G, n_post, t4 + 3, false);
+                                         float* __restrict__ partial, const float* carry_row = nullptr, const uint32_t* flag_prev = nullptr,
+                                         uint32_t* flag_own = nullptr, uint32_t tile_no = 0) {
+    const bool in_range = m0 + t4 < mix_len;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (flag_prev) {
+        uint32_t spins = 0;
+        while (ld_acquire_u32(flag_prev) <= tile_no) {
+            if (++spins > (1u << 22)) __trap();      // the CTA in front never arrived: fail loudly instead of hanging the device
+        }
+        if (in_range) {
+            const float* c = carry_row + m0 + t4;
+            if (m0 + t4 + 4 <= mix_len && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
+                acc = __ldcg(reinterpret_cast<const float4*>(c));
+            } else {
+                acc.x = __ldcg(c);
+                if (m0 + t4 + 1 < mix_len) acc.y = __ldcg(c + 1);
+                if (m0 + t4 + 2 < mix_len) acc.z = __ldcg(c + 2);
+                if (m0 + t4 + 3 < mix_len) acc.w = __ldcg(c + 3);
+            }
+        }
     }
-    float* o = partial + m0 + t4;
-    if (m0 + t4 + 4 <= mix_len && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
-        *reinterpret_cast<float4*>(o) = acc;
-    } else {
-        o[0] = acc.x;
-        if (m0 + t4 + 1 < mix_len) o[1] = acc.y;
-        if (m0 + t4 + 2 < mix_len) o[2] = acc.z;
-        if (m0 + t4 + 3 < mix_len) o[3] = acc.w;
+    if (in_range) {
+        if (full) {
+            acc = n_post == 0 ? hot_mix4_full<0>(tile, s_rows, G, n_post, t4, acc)
+                  : n_post == 1 ? hot_mix4_full<1>(tile, s_rows, G, n_post, t4, acc)
+                                : hot_mix4_full<-1>(tile, s_rows, G, n_post, t4, acc);
+        } else {
+            acc.x = mix_rows(tile, hts, s_rows, G, n_post, t4, false, acc.x);
+            acc.y = mix_rows(tile, hts, s_rows, G, n_post, t4 + 1, false, acc.y);
+            acc.z = mix_rows(tile, hts, s_rows, G, n_post, t4 + 2, false, acc.z);
+            acc.w = mix_rows(tile, hts, s_rows, G, n_post, t4 + 3, false, acc.w);
+        }
+        float* o = partial + m0 + t4;
+        if (m0 + t4 + 4 <= mix_len && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+            *reinterpret_cast<float4*>(o) = acc;
+        } else {
+            o[0] = acc.x;
+            if (m0 + t4 + 1 < mix_len) o[1] = acc.y;
+            if (m0 + t4 + 2 < mix_len) o[2] = acc.z;
+            if (m0 + t4 + 3 < mix_len) o[3] = acc.w;
+        }
+    }
+    if (flag_own) {
+        __threadfence();
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) st_release_u32(flag_own, tile_no + 1);
     }
 }
 
@@ -886,7 +926,15 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
     __shared__ __align__(16) FusedRow s_rows[MAX_G];
     __shared__ __align__(8) HotTile s_ht[NHT][MAX_G];
     __shared__ __align__(8) uint64_t s_full[NWIN];
-    const uint32_t row0 = blockIdx.x * a.rows_per_cta;
+    // chain mode: the CTA's place in the chain is the order in which the CTAs START (a ticket), not blockIdx.x -- a CTA then only
+    // ever waits for one that is already running, whatever order the hardware hands the blocks out in
+    __shared__ uint32_t s_cta;
+    if (a.chain) {
+        if (threadIdx.x == 0) s_cta = atomicAdd(a.flags + 2 * gridDim.x, 1u);
+        __syncthreads();
+    }
+    const uint32_t cta = a.chain ? s_cta : blockIdx.x;
+    const uint32_t row0 = cta * a.rows_per_cta;
     const uint32_t G = min(a.rows_per_cta, a.n_rows - row0);
     load_rows(s_rows, a.rows + row0, G);
     if (threadIdx.x == 0) {
@@ -898,7 +946,12 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
     float* tiles = smem;                                               // [NBUF][rows_per_cta][ROW_STRIDE]
     float* wins = smem + (size_t)NBUF * a.rows_per_cta * ROW_STRIDE;   // [NWIN][rows_per_cta][WSTRIDE]
     const size_t tile_sz = (size_t)a.rows_per_cta * ROW_STRIDE, win_sz = (size_t)a.rows_per_cta * WSTRIDE;
-    float* partial = a.partial + (uint64_t)blockIdx.x * a.mix_len;
+    float* partial = a.partial + (uint64_t)cta * a.mix_len;
+    const float* carry_row = nullptr;
+    if (a.chain) {
+        if (cta + 1 == gridDim.x) partial = a.out;
+        if (cta > 0) carry_row = a.partial + (uint64_t)(cta - 1) * a.mix_len;
+    }
     uint64_t lo, hi;
     cta_span(s_rows, G, a, lo, hi);
     if (lo >= hi) return;
@@ -1112,7 +1165,11 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
                 if (mix_block >= 0 && !HOT_SKIP(4)) {
                     const uint64_t m0 = m_begin + (uint64_t)(it - 2) * TT;
                     const bool full = m0 >= f_lo && m0 + TT <= f_hi;
-                    hot_mix4(tiles + cb * tile_sz + HOT_PAD, s_ht[ch], s_rows, G, a.n_post, mix_t, full, m0, a.mix_len, partial);
+                    if (a.chain)
+                        hot_mix4(tiles + cb * tile_sz + HOT_PAD, s_ht[ch], s_rows, G, a.n_post, mix_t, full, m0, a.mix_len, partial, carry_row,
+                                 carry_row ? a.flags + 2 * (cta - 1) + mix_block : nullptr, a.flags + 2 * cta + mix_block, it - 2);
+                    else
+                        hot_mix4(tiles + cb * tile_sz + HOT_PAD, s_ht[ch], s_rows, G, a.n_post, mix_t, full, m0, a.mix_len, partial);
                 }
                 cb = cb + 1 == NBUF ? 0 : cb + 1;
                 ch = ch + 1 == NHT ? 0 : ch + 1;
@@ -1154,6 +1211,8 @@ struct rb_fused_plan {
     bool all_f32 = true;
     bool hot = false;
     size_t hot_smem = 0;
+    bool chain = false;               // RB_MIX_EXACT_ORDER on k_fused_hot: sequential sum across the CTAs (FusedArgs::chain)
+    uint32_t* d_flags = nullptr;
     rb_lanes_plan* lanes = nullptr;   // RB_FUSED_LANES: the lane-per-stream kernel serves the batch (rb_lanes.cu)
     rb_fx_plan* fx = nullptr;         // the effect-chain kernel serves the batch (rb_fx.cu)
 };
@@ -1180,7 +1239,25 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     uint32_t n_pre = 0, n_mid = 0, n_post = 0, has_u = 0, has_b = 0, front = 0;
     bool mixed_u = false;   // some rows lost an identity conversion: only the lane kernel may take such a batch
     if (!fused_parse_rows(streams, n_streams, mixer_channels, rows, n_pre, n_mid, n_post, has_u, has_b, mixed_u, front)) return cudaSuccess;
-    if (exact_order && (has_b || front || !has_u || mixer_channels != 1 || (flags & RB_FUSED_LANES))) return cudaSuccess;
+    // RB_MIX_EXACT_ORDER: filter-free mono chains -> k_lerp_mix in one group; chains with a filter -> k_fused_hot with the running sum
+    // handed from CTA to CTA (below); everything else -> the general path
+    // (filter-free batches from 1024 streams on take the chain as well: k_lerp_mix in ONE group is one CTA per tile of the timeline
+    // walking every stream -- 6.9 ms at 4096 streams x 2 s against 1.8 ms for the chain)
+    auto hot_capable = [&]() {     // the same test as below, before anything is planned
+        const uint32_t C = mixer_channels;
+        bool ok = (has_b || has_u) && (C == 1 || C == 2);
+        for (size_t i = 0; i < n_streams && ok; i++) {
+            const FusedRow& r = rows[i];
+            const uint64_t qT = (uint64_t)(TT / C) * r.uni.from / r.uni.to;
+            ok = streams[i].fmt == RB_FMT_F32 && r.c_in == C && r.n_in % C == 0 && r.out_len % C == 0 && r.mix_start % C == 0 &&
+                 (r.mode == ROW_DIRECT || r.mode == ROW_PASS || (r.mode == ROW_LERP && 3 + (qT + 3) * C <= (uint64_t)WSTRIDE)) &&
+                 (has_b || r.mode == ROW_LERP);
+        }
+        return ok;
+    };
+    const bool exact_chain = exact_order && !front && !mixed_u && !(flags & (RB_FUSED_LANES | RB_FUSED_DUO)) &&
+                             (has_b || (has_u && n_streams >= 1024 && !getenv("RB_EXACT_LERPMIX"))) && hot_capable();
+    if (exact_order && !exact_chain && (has_b || front || !has_u || mixer_channels != 1 || (flags & RB_FUSED_LANES))) return cudaSuccess;
     if (has_b && (uint32_t)mixer_channels * 1u > 32u) return cudaSuccess;
 
     // Plain mixer of f32 sources at the mixer's own rate/channels (BASELINE cfg2): nothing to fuse -- the ordered
@@ -1193,7 +1270,7 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     auto plan = new rb_fused_plan;
     plan->all_f32 = true;
     for (size_t i = 0; i < n_streams; i++) plan->all_f32 = plan->all_f32 && streams[i].fmt == RB_FMT_F32;
-    {
+    if (!exact_chain) {
         cudaError_t e = fused_lanes_hook(rows, n_streams, mixer_channels, plan->all_f32, n_pre, n_mid, n_post, has_u, has_b, front, flags, sm_count,
                                          d_out, mix_len, st, &plan->lanes);
         if (e != cudaSuccess) {
@@ -1227,6 +1304,10 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
         // without a filter only rows that really interpolate take the HOT pipeline (the time axis is parallel as
         // well there: small batches are spread over the machine in time slices, see grid_y below)
         if (!has_b) plan->hot = plan->hot && r.mode == ROW_LERP;
+    }
+    if (exact_chain && !plan->hot) {   // only the HOT kernel hands the running sum on
+        delete plan;
+        return cudaSuccess;
     }
     if (plan->hot && !has_b && n_post == 0) {
         // no filter: the gains behind the resampler are the last thing before the sum -- apply them in stage C
@@ -1272,6 +1353,8 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     if (e == cudaSuccess) e = cudaMemcpyAsync(plan->d_rows, rows.data(), n_streams * sizeof(FusedRow), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     plan->single_cta_direct = (n_ctas == 1);
+    plan->chain = exact_chain && !plan->single_cta_direct;
+    if (e == cudaSuccess && plan->chain) e = cudaMalloc(&plan->d_flags, ((size_t)n_ctas * 2 + 1) * sizeof(uint32_t));   // + the ticket counter
     if (e == cudaSuccess && !plan->single_cta_direct) e = cudaMalloc(&plan->d_partial, (size_t)n_ctas * mix_len * sizeof(float));
     if (e == cudaSuccess && !plan->single_cta_direct) e = cudaMemsetAsync(plan->d_partial, 0, (size_t)n_ctas * mix_len * sizeof(float), st);
     plan->hot_smem = ((size_t)NBUF * ROW_STRIDE + (size_t)NWIN * WSTRIDE) * G * sizeof(float);
@@ -1299,10 +1382,12 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     a.partial = plan->single_cta_direct ? d_out : plan->d_partial;
     a.mix_len = mix_len;
     a.direct = plan->single_cta_direct ? 1u : 0u;
+    a.chain = plan->chain ? 1u : 0u, a.out = d_out, a.flags = plan->d_flags;
     // no-biquad variant: spread the timeline of each CTA over blockIdx.y so small batches still fill the GPU
     uint64_t tiles = (mix_len + TT - 1) / TT;
     uint64_t want_y = ((uint64_t)sm_count * 8 + n_ctas - 1) / n_ctas;
     if (plan->hot) want_y = has_b ? 1 : std::min<uint64_t>(((uint64_t)sm_count + n_ctas - 1) / n_ctas, std::max<uint64_t>(1, tiles / 8));
+    if (plan->chain) want_y = 1;   // the chain walks the whole timeline in every CTA
     plan->grid_y = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(tiles, want_y), 65535));
     *out = plan;
     return cudaSuccess;
@@ -1316,6 +1401,10 @@ cudaError_t rb_fused_run(rb_fused_plan* p, cudaStream_t st) {
     if (p->fx) return rb_fx_run(p->fx, st);
     if (p->lanes) return rb_lanes_run(p->lanes, st);
     const FusedArgs& a = p->args;
+    if (p->chain) {
+        cudaError_t ef = cudaMemsetAsync(p->d_flags, 0, ((size_t)p->n_ctas * 2 + 1) * sizeof(uint32_t), st);
+        if (ef != cudaSuccess) return ef;
+    }
     if (p->hot) {
         if (a.c_mix == 1) {
             if (a.has_biquad) k_fused_hot<1, true><<<p->n_ctas, 1024, p->hot_smem, st>>>(a);
@@ -1337,7 +1426,7 @@ cudaError_t rb_fused_run(rb_fused_plan* p, cudaStream_t st) {
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    if (!p->single_cta_direct) {
+    if (!p->single_cta_direct && !p->chain) {
         uint64_t blocks = (a.mix_len + 255) / 256;
         if (blocks > 148ull * 8) blocks = 148ull * 8;
         k_sum_partials<<<(uint32_t)blocks, 256, 0, st>>>(p->d_partial, p->n_ctas, a.mix_len, p->d_out);
@@ -1352,16 +1441,19 @@ void rb_fused_destroy(rb_fused_plan* p) {
     rb_fx_destroy(p->fx);
     cudaFree(p->d_rows);
     cudaFree(p->d_partial);
+    cudaFree(p->d_flags);
     delete p;
 }
 
 uint32_t rb_fused_launch_count(const rb_fused_plan* p) {
     if (p->fx) return 2u;
     if (p->lanes) return rb_lanes_launch_count(p->lanes);
-    return p->single_cta_direct ? 1u : 2u;
+    return (p->single_cta_direct || p->chain) ? 1u : 2u;
 }
 int rb_fused_kind(const rb_fused_plan* p) { return p->fx ? 5 : p->lanes ? rb_lanes_kind(p->lanes) : (p->hot ? 1 : 0); }
-uint32_t rb_fused_mix_group(const rb_fused_plan* p) { return p->fx ? 4u : p->lanes ? rb_lanes_mix_group(p->lanes) : p->args.rows_per_cta; }
+uint32_t rb_fused_mix_group(const rb_fused_plan* p) {
+    return p->fx ? 4u : p->lanes ? rb_lanes_mix_group(p->lanes) : p->chain ? 0u : p->args.rows_per_cta;   // chain: one sequential sum
+}
 
 #ifdef RB_HOT_TIMING
 extern "C" int rb_debug_hot_skip(int mask) { return (int)cudaMemcpyToSymbol(g_hot_skip, &mask, sizeof(int)); }

@@ -119,16 +119,17 @@ __device__ __forceinline__ float signal_value(uint32_t fn, float phase) {   // s
         default: return mul(2.0f, sub(phase, floorf(add(phase, 0.5f))));
     }
 }
-// A CTA owns 32 generators.  The phase is a serial f32 recurrence per generator (`phase = (phase + step).rem_euclid(1.0)`,
+// A CTA owns SIG_GENS generators (8: the waveform -- ~100 instructions per sine -- is what the seven worker warps have to keep up
+// with; with 32 generators per CTA the first version spent 220 cycles per sample step on 32 SMs).  The phase is a serial f32 recurrence per generator (`phase = (phase + step).rem_euclid(1.0)`,
 // signal_generator.rs:133: it drifts by design, so it cannot be computed from the sample index): warp 0, lane = generator, walks
 // it a tile ahead into shared memory; the other seven warps evaluate the waveform of the previous tile and store it with
 // consecutive threads on consecutive samples.  Latency-bound by the recurrence (3 dependent operations per sample) -- input
 // generation, outside every timed region.
-constexpr int SIG_TILE = 128, SIG_THREADS = 256, SIG_PITCH = SIG_TILE + 1;
+constexpr int SIG_TILE = 128, SIG_THREADS = 256, SIG_PITCH = SIG_TILE + 1, SIG_GENS = 8;
 __global__ void __launch_bounds__(SIG_THREADS) k_siggen(const rb_node_dev* __restrict__ nodes, uint32_t n_nodes) {
-    __shared__ float s_phase[2][32 * SIG_PITCH];
-    const uint32_t g0 = blockIdx.x * 32, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t n_g = min(32u, n_nodes - g0);
+    __shared__ float s_phase[2][SIG_GENS * SIG_PITCH];
+    const uint32_t g0 = blockIdx.x * SIG_GENS, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t n_g = min((uint32_t)SIG_GENS, n_nodes - g0);
     uint64_t max_n = 0;
     for (uint32_t g = 0; g < n_g; g++) max_n = max(max_n, nodes[g0 + g].n_out);
     const uint64_t n_tiles = (max_n + SIG_TILE - 1) / SIG_TILE;
@@ -155,12 +156,11 @@ __global__ void __launch_bounds__(SIG_THREADS) k_siggen(const rb_node_dev* __res
             }
         } else if (it > 0) {
             const uint64_t base = (it - 1) * SIG_TILE;
-            for (uint32_t g = 0; g < n_g; g++) {
+            // the tile's n_g * 128 values dealt out over the 224 worker threads: consecutive threads on consecutive samples
+            for (uint32_t w = threadIdx.x - 32; w < n_g * SIG_TILE; w += SIG_THREADS - 32) {
+                const uint32_t g = w / SIG_TILE, t = w % SIG_TILE;
                 const rb_node_dev& nd = nodes[g0 + g];
-                const uint32_t fn = nd.p.sig.fn;
-                const float* row = &s_phase[(it - 1) & 1][g * SIG_PITCH];
-                for (uint32_t t = threadIdx.x - 32; t < SIG_TILE; t += SIG_THREADS - 32)
-                    if (base + t < nd.n_out) nd.dst[base + t] = signal_value(fn, row[t]);
+                if (base + t < nd.n_out) nd.dst[base + t] = signal_value(nd.p.sig.fn, s_phase[(it - 1) & 1][g * SIG_PITCH + t]);
             }
         }
         __syncthreads();
@@ -705,7 +705,7 @@ cudaError_t rb_launch_nodes(uint32_t kind, const rb_node_dev* d_nodes, uint32_t 
             break;
         }
         case RB_N_LIMIT: k_limit_tile<<<(n_nodes + 31) / 32, 32, 0, st>>>(d_nodes, n_nodes); break;
-        case RB_N_SIGNAL: k_siggen<<<(n_nodes + 31) / 32, SIG_THREADS, 0, st>>>(d_nodes, n_nodes); break;
+        case RB_N_SIGNAL: k_siggen<<<(n_nodes + SIG_GENS - 1) / SIG_GENS, SIG_THREADS, 0, st>>>(d_nodes, n_nodes); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

@@ -370,3 +370,47 @@ def test_lerp_mix_other_ratio_no_gain_and_out_of_phase_fallback(ctx):
         b.upload_all()
         got = b.render_mix()
     assert_close_peak(got, oracle.mixer([to_oracle(s, st) for s, st in zip(srcs, starts)], 1, 48000), 1e-5, "out of phase")
+
+
+# ------------------------------------------------------------------ RB_MIX_EXACT_ORDER on k_fused_hot: the running sum handed from CTA to CTA
+def _check_exact_chain(ctx, srcs, ch, starts=None, family=1):
+    streams = [to_oracle(s, st) for s, st in zip(srcs, starts or [0] * len(srcs))]
+    ref = oracle.mixer(streams, ch, 48000)
+    with rb.Batch(srcs, ch, 48000, flags=capi.RB_MIX_EXACT_ORDER, mix_starts=starts, ctx=ctx) as b:
+        assert b.kernel_family == family, b.kernel_family
+        if family == 1:
+            assert b.mix_group == 0 and b.launches_per_render == 1
+        b.upload_all()
+        got = b.render_mix()
+        again = b.render_mix()
+    assert_bit_exact(got, ref, "exact order on the fused kernel vs the reference's sequential mixer")
+    assert_bit_exact(again, ref, "second render (flags and ticket reset)")
+
+
+def test_exact_order_headline_geometry_mono_4096(ctx):
+    """The benchmarked batch with RB_MIX_EXACT_ORDER: k_fused_hot, 147 CTAs x 28 rows, every tile's sum started from the running sum of
+    the CTA in front -- the WHOLE mixer output bit-identical to the reference's sequential sum over 4096 streams."""
+    _check_exact_chain(ctx, _cfg3(4096, 4410), 1)
+
+
+def test_exact_order_stereo_2048_and_two_waves(ctx):
+    _check_exact_chain(ctx, _cfg3(2048, 2205, ch=2, seed=33000), 2)
+    _check_exact_chain(ctx, _cfg3(5000, 700, seed=37000), 1)          # more CTAs than SMs: the ticket orders the chain
+
+
+def test_exact_order_ragged_and_late_starts(ctx):
+    """Streams of different lengths joining at different frames: partial tiles, CTAs whose rows are silent on a tile still hand the
+    running sum on."""
+    rng = np.random.default_rng(12)
+    n = 700
+    lens = [int(v) for v in rng.integers(1, 5000, n)]
+    lens[:5] = [0, 1, 2, 300, 4999]
+    starts = sorted(int(v) for v in rng.integers(0, 3000, n))
+    srcs = [rb.UniformSourceIterator(rb.TestSource(noise(L, 91000 + i), 1, 44100), 1, 48000).low_pass(200).amplify(1.2) for i, L in enumerate(lens)]
+    _check_exact_chain(ctx, srcs, 1, starts=starts)
+
+
+def test_exact_order_filter_free_4096(ctx):
+    """resample -> amplify -> mix with RB_MIX_EXACT_ORDER at 4096 streams: the chain on k_fused_hot<1, false> (below 1024 streams:
+    k_lerp_mix in one group, tests above)."""
+    _check_exact_chain(ctx, _cfg3(4096, 3000, lp=None, seed=38000), 1)

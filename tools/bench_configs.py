@@ -21,7 +21,7 @@ def time_batch(name, srcs, mixer, flags=0, steps=10, fill="uniform"):
         S = len(srcs)
         gen = torch.Generator(device=dev)
         gen.manual_seed(1)
-        for i in range(S):
+        for i in range(S if fill is not None else 0):
             p, cap = b.input_device_ptr(i)
             t = torch.as_tensor(rbd.DeviceArray(p, cap), device=dev)
             with torch.cuda.stream(ext):
@@ -126,6 +126,17 @@ def main():
         for S in (16384, 32768, 65536):
             srcs = [rb.UniformSourceIterator(rb.TestSource(one, 1, 44100), 1, 48000).low_pass(200).amplify(1.2) for _ in range(S)]
             time_batch(f"cfg5 S={S} x 1s low_pass(200) [RB_FUSED_DUO]", srcs, (1, 48000), flags=rb.capi.RB_FUSED_DUO, steps=5)
+    if "exact" in which:
+        # the benchmarked batch with RB_MIX_EXACT_ORDER (the reference's sequential sum over all streams) beside the default grouping
+        x = z(44100 * 2)
+        srcs = [rb.UniformSourceIterator(rb.TestSource(x, 1, 44100), 1, 48000).low_pass(200).amplify(1.2) for _ in range(4096)]
+        time_batch("cfg3 4096 x 2s, default order (partial sums per CTA)", srcs, (1, 48000), steps=10)
+        time_batch("cfg3 4096 x 2s, RB_MIX_EXACT_ORDER (running sum handed from CTA to CTA)", srcs, (1, 48000), flags=rb.capi.RB_MIX_EXACT_ORDER, steps=10)
+        srcs = [rb.UniformSourceIterator(rb.TestSource(x, 1, 44100), 1, 48000).amplify(1.2) for _ in range(4096)]
+        time_batch("no filter 4096 x 2s, RB_MIX_EXACT_ORDER (k_lerp_mix, one group)", srcs, (1, 48000), flags=rb.capi.RB_MIX_EXACT_ORDER, steps=5)
+    if "gen" in which:
+        srcs = [rb.SineWave(min(110.0 * 2.0 ** (s / 128.0), 19999.0)).take(48000 * 10) for s in range(1024)]
+        time_batch("cfg2 from generators: 1024 SineWave x 10 s generated and mixed on the device", srcs, (1, 48000), steps=3, fill=None)
     if "tp" in which:
         # the two plans that cut the timeline into segments: time-parallel low_pass(1000) and the filter-free chain, 4096 x 2 s
         x = z(44100 * 2)
