@@ -56,7 +56,9 @@ struct FusedArgs {
     uint32_t chain;                // RB_MIX_EXACT_ORDER on k_fused_hot: CTA c starts every tile's sum from the running sum CTA c - 1
                                    // left for that tile -- the reference's sequential order over ALL streams (src/mixer.rs:185-198)
     float* out;                    // chain: the last CTA's row is the mixer output
-    uint32_t* flags;               // chain: [n_ctas][2] tiles finished by (CTA, stage-C warp)
+    uint32_t* flags;               // chain: one word, the ticket counter (never reset: tickets of render e start at e * n_ctas)
+    uint32_t epoch;                // chain: render number, part of every tag
+    uint32_t pad_;
 };
 
 // ---- per (row, tile) index state -------------------------------------------------------------------
@@ -854,67 +856,71 @@ __device__ __forceinline__ float4 hot_mix4_full(const float* tile, const FusedRo
     }
     return acc;
 }
-// Chain mode (RB_MIX_EXACT_ORDER): the sum of a tile starts from the row CTA c - 1 wrote for it (`carry_row`, the running sum over
-// all earlier streams) instead of +0.0, so the last CTA's row is the reference's sequential sum over every stream.  A CTA only ever
-// waits for the CTA in front of it, which was scheduled before it: no co-residency is needed.  Every lane polls the flag itself
-// (one broadcast transaction) with an acquire load, reads the carry past L1, and the warp publishes its own tile count with a
-// release store after its partial row is written.
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+// Chain mode (RB_MIX_EXACT_ORDER): the sum of a tile starts from the row CTA c - 1 wrote for it (the running sum over all earlier
+// streams) instead of +0.0, so the last CTA's row is the reference's sequential sum over every stream.  A CTA only ever waits for
+// the CTA in front of it, which holds an earlier ticket and is therefore already running: no co-residency is needed.
+// The hand-over carries its own flag: a row of the chain is an array of (value, tag) pairs written and read as single 8-byte
+// accesses (single-copy atomic), tag = render number and tile -- the reader polls the DATA until the tag is the one it expects.
+// One L2 round trip per hop, no fences, no separate flag (the first version -- release store of a tile counter behind a fenced row,
+// acquire poll, then the carry load -- cost 4.8 us per tile and CTA: two fences and three dependent round trips).
+__device__ __forceinline__ uint2 ld_relaxed_v2(const uint2* p) {
+    uint2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_v2(uint2* p, uint2 v) {
+    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
 __device__ __forceinline__ void hot_mix4(const float* tile, const HotTile* hts, const FusedRow* s_rows, uint32_t G,
                                          uint32_t n_post, uint32_t t4, bool full, uint64_t m0, uint64_t mix_len,
-                                         float* __restrict__ partial, const float* carry_row = nullptr, const uint32_t* flag_prev = nullptr,
-                                         uint32_t* flag_own = nullptr, uint32_t tile_no = 0) {
-    const bool in_range = m0 + t4 < mix_len;
+                                         float* __restrict__ partial, bool chain = false, const uint2* carry_row = nullptr,
+                                         uint2* tagged_row = nullptr, uint32_t tag = 0) {
+    if (m0 + t4 >= mix_len) return;
+    const uint32_t n_here = (uint32_t)min((uint64_t)4, mix_len - (m0 + t4));
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (flag_prev) {
+    if (carry_row) {
+        const uint2* c = carry_row + m0 + t4;
+        uint2 w[4];
         uint32_t spins = 0;
-        while (ld_acquire_u32(flag_prev) <= tile_no) {
+        while (true) {
+            bool ok = true;
+#pragma unroll
+            for (uint32_t k = 0; k < 4; k++)
+                if (k < n_here) w[k] = ld_relaxed_v2(c + k), ok = ok && w[k].y == tag;
+            if (ok) break;
             if (++spins > (1u << 22)) __trap();      // the CTA in front never arrived: fail loudly instead of hanging the device
         }
-        if (in_range) {
-            const float* c = carry_row + m0 + t4;
-            if (m0 + t4 + 4 <= mix_len && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
-                acc = __ldcg(reinterpret_cast<const float4*>(c));
-            } else {
-                acc.x = __ldcg(c);
-                if (m0 + t4 + 1 < mix_len) acc.y = __ldcg(c + 1);
-                if (m0 + t4 + 2 < mix_len) acc.z = __ldcg(c + 2);
-                if (m0 + t4 + 3 < mix_len) acc.w = __ldcg(c + 3);
-            }
-        }
+        acc.x = __uint_as_float(w[0].x);
+        if (n_here > 1) acc.y = __uint_as_float(w[1].x);
+        if (n_here > 2) acc.z = __uint_as_float(w[2].x);
+        if (n_here > 3) acc.w = __uint_as_float(w[3].x);
     }
-    if (in_range) {
-        if (full) {
-            acc = n_post == 0 ? hot_mix4_full<0>(tile, s_rows, G, n_post, t4, acc)
-                  : n_post == 1 ? hot_mix4_full<1>(tile, s_rows, G, n_post, t4, acc)
-                                : hot_mix4_full<-1>(tile, s_rows, G, n_post, t4, acc);
-        } else {
-            acc.x = mix_rows(tile, hts, s_rows, G, n_post, t4, false, acc.x);
-            acc.y = mix_rows(tile, hts, s_rows, G, n_post, t4 + 1, false, acc.y);
-            acc.z = mix_rows(tile, hts, s_rows, G, n_post, t4 + 2, false, acc.z);
-            acc.w = mix_rows(tile, hts, s_rows, G, n_post, t4 + 3, false, acc.w);
-        }
-        float* o = partial + m0 + t4;
-        if (m0 + t4 + 4 <= mix_len && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
-            *reinterpret_cast<float4*>(o) = acc;
-        } else {
-            o[0] = acc.x;
-            if (m0 + t4 + 1 < mix_len) o[1] = acc.y;
-            if (m0 + t4 + 2 < mix_len) o[2] = acc.z;
-            if (m0 + t4 + 3 < mix_len) o[3] = acc.w;
-        }
+    if (full) {
+        acc = n_post == 0 ? hot_mix4_full<0>(tile, s_rows, G, n_post, t4, acc)
+              : n_post == 1 ? hot_mix4_full<1>(tile, s_rows, G, n_post, t4, acc)
+                            : hot_mix4_full<-1>(tile, s_rows, G, n_post, t4, acc);
+    } else {
+        acc.x = mix_rows(tile, hts, s_rows, G, n_post, t4, false, acc.x);
+        acc.y = mix_rows(tile, hts, s_rows, G, n_post, t4 + 1, false, acc.y);
+        acc.z = mix_rows(tile, hts, s_rows, G, n_post, t4 + 2, false, acc.z);
+        acc.w = mix_rows(tile, hts, s_rows, G, n_post, t4 + 3, false, acc.w);
     }
-    if (flag_own) {
-        __threadfence();
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) st_release_u32(flag_own, tile_no + 1);
+    if (chain && tagged_row) {     // hand the running sum on: (value, tag) pairs
+        uint2* o = tagged_row + m0 + t4;
+        st_relaxed_v2(o, make_uint2(__float_as_uint(acc.x), tag));
+        if (n_here > 1) st_relaxed_v2(o + 1, make_uint2(__float_as_uint(acc.y), tag));
+        if (n_here > 2) st_relaxed_v2(o + 2, make_uint2(__float_as_uint(acc.z), tag));
+        if (n_here > 3) st_relaxed_v2(o + 3, make_uint2(__float_as_uint(acc.w), tag));
+        return;
+    }
+    float* o = partial + m0 + t4;
+    if (n_here == 4 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+        *reinterpret_cast<float4*>(o) = acc;
+    } else {
+        o[0] = acc.x;
+        if (n_here > 1) o[1] = acc.y;
+        if (n_here > 2) o[2] = acc.z;
+        if (n_here > 3) o[3] = acc.w;
     }
 }
 
@@ -930,7 +936,7 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
     // ever waits for one that is already running, whatever order the hardware hands the blocks out in
     __shared__ uint32_t s_cta;
     if (a.chain) {
-        if (threadIdx.x == 0) s_cta = atomicAdd(a.flags + 2 * gridDim.x, 1u);
+        if (threadIdx.x == 0) s_cta = atomicAdd(a.flags, 1u) - a.epoch * gridDim.x;
         __syncthreads();
     }
     const uint32_t cta = a.chain ? s_cta : blockIdx.x;
@@ -947,10 +953,13 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
     float* wins = smem + (size_t)NBUF * a.rows_per_cta * ROW_STRIDE;   // [NWIN][rows_per_cta][WSTRIDE]
     const size_t tile_sz = (size_t)a.rows_per_cta * ROW_STRIDE, win_sz = (size_t)a.rows_per_cta * WSTRIDE;
     float* partial = a.partial + (uint64_t)cta * a.mix_len;
-    const float* carry_row = nullptr;
+    const uint2* carry_row = nullptr;      // chain: rows of (value, tag) pairs, `partial` is then [n_ctas][mix_len] of those
+    uint2* tagged_row = nullptr;
     if (a.chain) {
-        if (cta + 1 == gridDim.x) partial = a.out;
-        if (cta > 0) carry_row = a.partial + (uint64_t)(cta - 1) * a.mix_len;
+        uint2* rows2 = reinterpret_cast<uint2*>(a.partial);
+        if (cta + 1 == gridDim.x) partial = a.out;                       // the last CTA writes the mixer output itself
+        else tagged_row = rows2 + (uint64_t)cta * a.mix_len;
+        if (cta > 0) carry_row = rows2 + (uint64_t)(cta - 1) * a.mix_len;
     }
     uint64_t lo, hi;
     cta_span(s_rows, G, a, lo, hi);
@@ -1113,7 +1122,8 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
         const int second = hot_second_row(slot);
         const bool has_second = second >= 0 && (uint32_t)second < G;
         // stage C: two warps, 4 positions per thread (slots without a second row, on different sub-partitions)
-        const int mix_block = slot == 6 ? 0 : slot == 7 ? 1 : -1;
+        // (chain mode: stage C moves to two warps of its own, below -- the hand-over is latency, not work, and must not sit behind a row's stage A)
+        const int mix_block = a.chain ? -1 : slot == 6 ? 0 : slot == 7 ? 1 : -1;
         // (lane's first frame * from) divmod to for the rows this warp owns
         uint32_t lane_q0 = 0, lane_r0 = 0, lane_q1 = 0, lane_r1 = 0;
         if (has_first) {
@@ -1165,11 +1175,26 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
                 if (mix_block >= 0 && !HOT_SKIP(4)) {
                     const uint64_t m0 = m_begin + (uint64_t)(it - 2) * TT;
                     const bool full = m0 >= f_lo && m0 + TT <= f_hi;
-                    if (a.chain)
-                        hot_mix4(tiles + cb * tile_sz + HOT_PAD, s_ht[ch], s_rows, G, a.n_post, mix_t, full, m0, a.mix_len, partial, carry_row,
-                                 carry_row ? a.flags + 2 * (cta - 1) + mix_block : nullptr, a.flags + 2 * cta + mix_block, it - 2);
-                    else
-                        hot_mix4(tiles + cb * tile_sz + HOT_PAD, s_ht[ch], s_rows, G, a.n_post, mix_t, full, m0, a.mix_len, partial);
+                    hot_mix4(tiles + cb * tile_sz + HOT_PAD, s_ht[ch], s_rows, G, a.n_post, mix_t, full, m0, a.mix_len, partial);
+                }
+                cb = cb + 1 == NBUF ? 0 : cb + 1;
+                ch = ch + 1 == NHT ? 0 : ch + 1;
+            }
+            HOT_BAR();
+        }
+    } else if (a.chain && (warp == 3 || warp == 7)) {
+        // ---- chain mode, stage C on tile it-2: warps 3 and 7 (idle otherwise; the recurrence warp's sub-partition has issue slots to
+        // spare) wait for the CTA in front, add this CTA's rows to its running sum and hand it on ----
+        const int mix_block = warp == 3 ? 0 : 1;
+        const uint32_t mix_t = ((uint32_t)mix_block * 32 + lane) * 4;
+        uint32_t cb = 0, ch = 0;
+        for (uint32_t it = 0; it < n_iter; it++) {
+            if (it >= 2) {
+                if (!HOT_SKIP(4)) {
+                    const uint64_t m0 = m_begin + (uint64_t)(it - 2) * TT;
+                    const bool full = m0 >= f_lo && m0 + TT <= f_hi;
+                    hot_mix4(tiles + cb * tile_sz + HOT_PAD, s_ht[ch], s_rows, G, a.n_post, mix_t, full, m0, a.mix_len, partial, true, carry_row,
+                             tagged_row, a.epoch * (n_iter + 1u) + (it - 2) + 1u);
                 }
                 cb = cb + 1 == NBUF ? 0 : cb + 1;
                 ch = ch + 1 == NHT ? 0 : ch + 1;
@@ -1212,7 +1237,8 @@ struct rb_fused_plan {
     bool hot = false;
     size_t hot_smem = 0;
     bool chain = false;               // RB_MIX_EXACT_ORDER on k_fused_hot: sequential sum across the CTAs (FusedArgs::chain)
-    uint32_t* d_flags = nullptr;
+    uint32_t* d_flags = nullptr;      // the ticket counter
+    uint32_t epoch = 0;
     rb_lanes_plan* lanes = nullptr;   // RB_FUSED_LANES: the lane-per-stream kernel serves the batch (rb_lanes.cu)
     rb_fx_plan* fx = nullptr;         // the effect-chain kernel serves the batch (rb_fx.cu)
 };
@@ -1354,9 +1380,11 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     plan->single_cta_direct = (n_ctas == 1);
     plan->chain = exact_chain && !plan->single_cta_direct;
-    if (e == cudaSuccess && plan->chain) e = cudaMalloc(&plan->d_flags, ((size_t)n_ctas * 2 + 1) * sizeof(uint32_t));   // + the ticket counter
-    if (e == cudaSuccess && !plan->single_cta_direct) e = cudaMalloc(&plan->d_partial, (size_t)n_ctas * mix_len * sizeof(float));
-    if (e == cudaSuccess && !plan->single_cta_direct) e = cudaMemsetAsync(plan->d_partial, 0, (size_t)n_ctas * mix_len * sizeof(float), st);
+    if (e == cudaSuccess && plan->chain) e = cudaMalloc(&plan->d_flags, sizeof(uint32_t));   // the ticket counter
+    if (e == cudaSuccess && plan->chain) e = cudaMemsetAsync(plan->d_flags, 0, sizeof(uint32_t), st);
+    const size_t row_bytes = plan->chain ? sizeof(uint2) : sizeof(float);   // chain: (value, tag) pairs, tag 0 = never written
+    if (e == cudaSuccess && !plan->single_cta_direct) e = cudaMalloc(&plan->d_partial, (size_t)n_ctas * mix_len * row_bytes);
+    if (e == cudaSuccess && !plan->single_cta_direct) e = cudaMemsetAsync(plan->d_partial, 0, (size_t)n_ctas * mix_len * row_bytes, st);
     plan->hot_smem = ((size_t)NBUF * ROW_STRIDE + (size_t)NWIN * WSTRIDE) * G * sizeof(float);
     if (e == cudaSuccess && plan->hot) {
         const int hs = (int)plan->hot_smem;
@@ -1400,11 +1428,8 @@ void rb_fused_inputs_changed(rb_fused_plan* p) {
 cudaError_t rb_fused_run(rb_fused_plan* p, cudaStream_t st) {
     if (p->fx) return rb_fx_run(p->fx, st);
     if (p->lanes) return rb_lanes_run(p->lanes, st);
+    if (p->chain) p->args.epoch = p->epoch++;     // tickets and tags of this render
     const FusedArgs& a = p->args;
-    if (p->chain) {
-        cudaError_t ef = cudaMemsetAsync(p->d_flags, 0, ((size_t)p->n_ctas * 2 + 1) * sizeof(uint32_t), st);
-        if (ef != cudaSuccess) return ef;
-    }
     if (p->hot) {
         if (a.c_mix == 1) {
             if (a.has_biquad) k_fused_hot<1, true><<<p->n_ctas, 1024, p->hot_smem, st>>>(a);
