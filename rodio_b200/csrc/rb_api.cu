@@ -1114,9 +1114,10 @@ extern "C" rb_status rb_batch_upload_packed(rb_batch* b, const void* pcm, uint64
     while (i < n) {
         size_t bytes = (size_t)b->streams[i].desc.n_samples * fmt_size(b->streams[i].desc.format);
         size_t j = i + 1;
-        size_t pitch = (j < n) ? b->streams[j].in_off - b->streams[i].in_off : 0;
-        while (j < n && (size_t)b->streams[j].desc.n_samples * fmt_size(b->streams[j].desc.format) == bytes &&
-               b->streams[j].in_off - b->streams[j - 1].in_off == pitch)
+        // (the buffers of a from_iter sequence sit inside their head's region: only ascending, non-overlapping offsets form a pitch)
+        size_t pitch = (j < n && b->streams[j].in_off >= b->streams[i].in_off + bytes) ? b->streams[j].in_off - b->streams[i].in_off : 0;
+        while (pitch && j < n && (size_t)b->streams[j].desc.n_samples * fmt_size(b->streams[j].desc.format) == bytes &&
+               b->streams[j].in_off > b->streams[j - 1].in_off && b->streams[j].in_off - b->streams[j - 1].in_off == pitch)
             j++;
         size_t rows = j - i;
         if (bytes) {
