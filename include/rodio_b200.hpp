@@ -117,8 +117,40 @@ class Source {
         return s;
     }
 
+    // Source::mix(other) -- mod.rs:253-261, mix.rs:10-53: the second input becomes a descriptor of its own (RB_FX_MIX)
+    Source mix(const Source& other) const {
+        Source s = with(fx(RB_FX_MIX, {}, {}, {}));
+        s.others_.push_back(std::make_shared<Source>(other));
+        return s;
+    }
+    // Source::take_crossfade_with(other, duration) -- mod.rs:444-454 = crossfade.rs:10-23
+    Source take_crossfade_with(const Source& other, Duration d) const {
+        return take_duration(d, true).mix(other.take_duration(d).fade_in(d));
+    }
+    // source::from_iter(buffers) -- from_iter.rs:16-27: one source whose format changes from buffer to buffer (RB_FX_APPEND)
+    static Source from_iter(const std::vector<Source>& buffers) {
+        if (buffers.empty()) throw std::invalid_argument("from_iter of nothing");
+        Source s = buffers[0];
+        if (!s.effects_.empty()) throw std::invalid_argument("from_iter takes plain buffers");
+        for (size_t i = 1; i < buffers.size(); i++) {
+            if (!buffers[i].effects_.empty()) throw std::invalid_argument("from_iter takes plain buffers");
+            s.effects_.push_back(fx(RB_FX_APPEND, {}, {}, {}));
+            s.others_.push_back(std::make_shared<Source>(buffers[i]));
+        }
+        return s;
+    }
+    // SignalGenerator::new(sample_rate, frequency, function).take(n) -- signal_generator.rs:85-135: generated on the device
+    static Source signal_generator(uint32_t sample_rate, float frequency, rb_signal_function f, uint64_t n) {
+        if (!(frequency > 0.0f)) throw std::invalid_argument("frequency must be greater than zero");   // :112
+        Source s(1, sample_rate, {}, 0);
+        s.effects_.push_back(fx(RB_FX_SIGNAL, {(uint32_t)f}, {frequency}, {n}));
+        return s;
+    }
+
     // `.collect::<Vec<f32>>()` of this source (its own chain, no mixer conversion)
     std::vector<Sample> collect() const;
+    const std::vector<std::shared_ptr<Source>>& others() const { return others_; }
+    const std::vector<rb_effect>& effects() const { return effects_; }
 
     rb_stream_desc desc(uint64_t mix_start = 0) const {
         rb_stream_desc d{};
@@ -152,6 +184,7 @@ class Source {
     uint16_t base_channels_;
     uint32_t base_rate_, span_len_;
     std::vector<rb_effect> effects_;
+    std::vector<std::shared_ptr<Source>> others_;   // second inputs of mix() / buffers of from_iter(), one per RB_FX_MIX / RB_FX_APPEND in order
     uint16_t channels_;
     uint32_t rate_;
 };
@@ -174,12 +207,42 @@ struct Batch {
     }
     ~Batch() { rb_batch_destroy(h); }
 };
+// The descriptor array of `sources`: the sources themselves, then (breadth first) the second inputs of their mix() adapters and the
+// buffers of their from_iter() sequences as descriptors of their own (mix_start = RB_MIX_START_CONSUMED), the adapter that names
+// one carrying its index.  Owns the patched effect arrays the descriptors point into.
+struct Flat {
+    std::vector<const Source*> src;
+    std::vector<std::vector<rb_effect>> fx;
+    std::vector<rb_stream_desc> descs;
+    Flat(const std::vector<const Source*>& sources, const std::vector<uint64_t>& starts) {
+        src = sources;
+        for (size_t i = 0; i < src.size(); i++) {
+            std::vector<rb_effect> e = src[i]->effects();
+            size_t k = 0;
+            for (rb_effect& x : e)
+                if (x.kind == RB_FX_MIX || x.kind == RB_FX_APPEND) {
+                    x.u32[0] = (uint32_t)src.size();
+                    src.push_back(src[i]->others().at(k++).get());
+                }
+            fx.push_back(std::move(e));
+        }
+        for (size_t i = 0; i < src.size(); i++) {
+            rb_stream_desc d = src[i]->desc(i < starts.size() ? starts[i] : RB_MIX_START_CONSUMED);
+            d.effects = fx[i].data();
+            descs.push_back(d);
+        }
+    }
+    void upload(rb_batch* b) const {
+        for (size_t i = 0; i < src.size(); i++)
+            check(rb_batch_upload(b, i, src[i]->pcm().data(), src[i]->pcm().size()), "rb_batch_upload");
+    }
+};
 }  // namespace detail
 
 inline std::vector<Sample> Source::collect() const {
-    std::vector<rb_stream_desc> d{desc()};
-    detail::Batch b(d, channels_, rate_, RB_KEEP_STREAM_OUTPUTS | RB_NO_FUSION);
-    check(rb_batch_upload(b.h, 0, pcm_->data(), pcm_->size()), "rb_batch_upload");
+    detail::Flat flat({this}, {0});
+    detail::Batch b(flat.descs, channels_, rate_, RB_KEEP_STREAM_OUTPUTS | RB_NO_FUSION);
+    flat.upload(b.h);
     check(rb_batch_render_mix_device(b.h), "rb_batch_render_mix_device");
     uint64_t n = 0, w = 0;
     check(rb_batch_stream_out_len(b.h, 0, &n), "rb_batch_stream_out_len");
@@ -239,11 +302,11 @@ class MixerSource {
         s.dirty = false;
         s.rendered.clear(), s.active.clear();
         if (s.sources.empty()) return;
-        std::vector<rb_stream_desc> descs;
-        for (size_t i = 0; i < s.sources.size(); i++) descs.push_back(s.sources[i].desc(s.starts[i]));
-        detail::Batch b(descs, s.channels, s.rate, 0);
-        for (size_t i = 0; i < s.sources.size(); i++)
-            check(rb_batch_upload(b.h, i, s.sources[i].pcm().data(), s.sources[i].pcm().size()), "rb_batch_upload");
+        std::vector<const Source*> ptrs;
+        for (const Source& src : s.sources) ptrs.push_back(&src);
+        detail::Flat flat(ptrs, s.starts);
+        detail::Batch b(flat.descs, s.channels, s.rate, 0);
+        flat.upload(b.h);
         uint64_t n = 0, w = 0;
         check(rb_batch_mix_len(b.h, &n), "rb_batch_mix_len");
         s.rendered.resize(n);

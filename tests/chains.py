@@ -62,6 +62,17 @@ CHAINS = {
         .delay(rb.Duration.from_secs_f32(0.1)).fade_in(rb.Duration.from_secs_f32(0.4))
         .take_duration(rb.Duration.from_secs(1), filter_fadeout=True).reverb(rb.Duration.from_secs_f32(0.05), 0.3), 2, 40000),
     "i16_input": lambda: rb.SamplesBuffer(2, 44100, (noise(4000, 21) * 30000).astype(np.int16)).amplify(0.5).low_pass(500),
+    # round 2, second half: sources generated on the device, two-input adapters
+    "signal_sine_chain": lambda: rb.SineWave(440.0).take(5000).amplify(0.5).low_pass(2000),
+    "signal_triangle": lambda: rb.SignalGenerator(44100, 523.25, rb.Function.Triangle).take(3000),
+    "signal_square_fade": lambda: rb.SquareWave(80.0).take(4000).fade_in(rb.Duration.from_millis(30)),
+    "mix_other_rate_and_channels": lambda: rb.TestSource(_stereo(3000, 60), 2, 44100).mix(rb.TestSource(noise(1000, 61), 1, 32000)),
+    "mix_generator_longer": lambda: rb.SamplesBuffer(1, 48000, noise(700, 62)).amplify(0.5)
+        .mix(rb.SawtoothWave(220.0).take(2500).amplify(0.25)).high_pass(100),
+    "crossfade_stereo": lambda: rb.TestSource(_stereo(30000, 63), 2, 44100).take_crossfade_with(
+        rb.TestSource(_stereo(20000, 64), 2, 44100), rb.Duration.from_millis(250)),
+    "crossfade_other_format": lambda: rb.SamplesBuffer(2, 44100, _stereo(30000, 65)).take_crossfade_with(
+        rb.SamplesBuffer(1, 22050, noise(9000, 66)), rb.Duration.from_millis(150)).amplify(0.7),
 }
 
 

@@ -100,10 +100,47 @@ static void errors() {
     EXPECT(SamplesBuffer(2, 44100, {0, 0}).speed(0.9f).sample_rate() == 39690);   // speed.rs:130-133
 }
 
+static V one_to(int n) {   // crossfade.rs:40-43 dummy_source
+    V v;
+    for (int i = 1; i <= n; i++) v.push_back((float)i);
+    return v;
+}
+static void crossfade_with_self() {   // crossfade.rs:45-63
+    const Duration d = std::chrono::seconds(5) + std::chrono::nanoseconds(1);
+    V y = SamplesBuffer(1, 1, one_to(10)).take_crossfade_with(SamplesBuffer(1, 1, one_to(10)), d).collect();
+    EXPECT(y.size() == 5);
+    for (size_t i = 0; i < y.size() && i < 5; i++) EXPECT(std::fabs(y[i] - (float)(i + 1)) < 1e-6f);
+}
+static void crossfade_against_silence() {   // crossfade.rs:65-80 (source2 = Zero: endless silence)
+    const Duration d = std::chrono::seconds(5) + std::chrono::nanoseconds(1);
+    V y = SamplesBuffer(1, 1, one_to(10)).take_crossfade_with(TestSource(V(64, 0.0f), 1, 1), d).collect();
+    const float want[5] = {1.0f, 2.0f * 0.8f, 3.0f * 0.6f, 4.0f * 0.4f, 5.0f * 0.2f};
+    EXPECT(y.size() == 5);
+    for (size_t i = 0; i < y.size() && i < 5; i++) EXPECT(std::fabs(y[i] - want[i]) < 1e-6f);
+}
+static void from_iter_basic() {   // from_iter.rs:129-157: the format changes between the two buffers
+    Source seq = Source::from_iter({SamplesBuffer(1, 48000, {10.0f, -10.0f, 10.0f, -10.0f}), SamplesBuffer(2, 96000, {5.0f, 5.0f, 5.0f, 5.0f})});
+    EXPECT(seq.channels() == 1 && seq.sample_rate() == 48000);
+    V y = seq.collect();
+    const V want{10.0f, -10.0f, 10.0f, -10.0f, 5.0f, 5.0f, 5.0f, 5.0f};
+    EXPECT(y == want);
+}
+static void signal_generators() {   // signal_generator.rs:181-238
+    V sq = Source::signal_generator(2000, 500.0f, RB_SIGNAL_SQUARE, 8).collect();
+    EXPECT((sq == V{1.0f, 1.0f, -1.0f, -1.0f, 1.0f, 1.0f, -1.0f, -1.0f}));
+    V saw = Source::signal_generator(200, 50.0f, RB_SIGNAL_SAWTOOTH, 7).collect();
+    EXPECT((saw == V{0.0f, 0.5f, -1.0f, -0.5f, 0.0f, 0.5f, -1.0f}));
+    V sine = Source::signal_generator(1000, 100.0f, RB_SIGNAL_SINE, 7).collect();
+    const float want[7] = {0.0f, 0.58778524f, 0.95105654f, 0.95105654f, 0.58778524f, 0.0f, -0.58778554f};
+    EXPECT(sine.size() == 7);
+    for (size_t i = 0; i < sine.size() && i < 7; i++) EXPECT(std::fabs(sine[i] - want[i]) < 1e-4f);   // TEST_EPSILON
+}
+
 int main() {
     try {
         mixer_basic(); mixer_channels_conv(); mixer_rate_conv(); mixer_start_afterwards(); mixer_phase();
         channels(); sample_rate(); amplify_is_volume(); errors();
+        crossfade_with_self(); crossfade_against_silence(); from_iter_basic(); signal_generators();
     } catch (const std::exception& e) {
         std::fprintf(stderr, "exception: %s\n", e.what());
         return 2;

@@ -65,6 +65,28 @@ REFERENCE_VECTORS = {
         {"cite": "src/source/channel_volume.rs:157-166", "channels": 2, "rate": 44100, "pcm": [1.0, 3.0, 2.0, 4.0],
          "volumes": [0.5, 2.0], "output": [1.0, 4.0, 1.5, 6.0]},
     ],
+    # src/source/crossfade.rs:45-80: 1 Hz mono sources 1..=10, crossfade(a, b, 5 s + 1 ns); within 1e-6
+    "crossfade": [
+        {"cite": "src/source/crossfade.rs:45-63", "a": list(range(1, 11)), "b": list(range(1, 11)), "rate": 1,
+         "duration_ns": 5_000_000_001, "tolerance": 1e-6, "output": [1, 2, 3, 4, 5]},
+        {"cite": "src/source/crossfade.rs:65-80", "a": list(range(1, 11)), "b": [0] * 64, "b_spanless": True, "rate": 1,
+         "duration_ns": 5_000_000_001, "tolerance": 1e-6, "output": [1.0, 1.6, 1.8, 1.6, 1.0]},
+    ],
+    # src/source/from_iter.rs:129-157 (the same vector as src/queue.rs:280-303): the format changes between the buffers
+    "from_iter": [
+        {"cite": "src/source/from_iter.rs:129-157",
+         "buffers": [{"channels": 1, "rate": 48000, "pcm": [10, -10, 10, -10]}, {"channels": 2, "rate": 96000, "pcm": [5, 5, 5, 5]}],
+         "output": [10, -10, 10, -10, 5, 5, 5, 5]},
+    ],
+    # src/source/signal_generator.rs:181-238
+    "signal_generator": [
+        {"cite": "src/source/signal_generator.rs:182-193", "function": 2, "rate": 2000, "frequency": 500.0, "output": [1, 1, -1, -1, 1, 1, -1, -1]},
+        {"cite": "src/source/signal_generator.rs:195-214", "function": 1, "rate": 8000, "frequency": 1000.0,
+         "output": [-1.0, -0.5, 0.0, 0.5, 1.0, 0.5, 0.0, -0.5, -1.0, -0.5, 0.0, 0.5, 1.0, 0.5, 0.0, -0.5]},
+        {"cite": "src/source/signal_generator.rs:216-226", "function": 3, "rate": 200, "frequency": 50.0, "output": [0.0, 0.5, -1.0, -0.5, 0.0, 0.5, -1.0]},
+        {"cite": "src/source/signal_generator.rs:228-238", "function": 0, "rate": 1000, "frequency": 100.0, "tolerance": 1e-4,
+         "output": [0.0, 0.58778525, 0.95105652, 0.95105652, 0.58778525, 0.0, -0.58778554]},
+    ],
     # src/math.rs:238-266 DECIBELS_LINEAR_TABLE (Wikipedia values; the reference asserts a ratio within 1 %, :268-316)
     "db_table": {"cite": "src/math.rs:238-316", "ratio_tolerance": 0.01, "rows": [
         [100., 100000.], [90., 31623.], [80., 10000.], [70., 3162.], [60., 1000.], [50., 316.2], [40., 100.],

@@ -40,7 +40,7 @@ def _random_sequence(rng, seed):
 
 # ------------------------------------------------------------------ CPU
 def test_oracle_from_iter_reference_vector():
-    """from_iter.rs:130-162 `basic` (the same vector as queue.rs:274-300): four mono 48 kHz samples, then four stereo 96 kHz ones."""
+    """from_iter.rs:129-157 `basic` (the same vector as queue.rs:280-303): four mono 48 kHz samples, then four stereo 96 kHz ones."""
     src = rb.from_iter([rb.SamplesBuffer(1, 48000, [10.0, -10.0, 10.0, -10.0]), rb.SamplesBuffer(2, 96000, [5.0, 5.0, 5.0, 5.0])])
     out, ch, rate = oracle.chain(to_oracle(src))
     assert out.tolist() == [10.0, -10.0, 10.0, -10.0, 5.0, 5.0, 5.0, 5.0]

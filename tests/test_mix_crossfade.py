@@ -1,6 +1,6 @@
 """Source::mix / take_crossfade_with (src/source/mod.rs:253-261,:444-454, mix.rs:10-53, crossfade.rs:10-23): the two-input adapter
 (RB_FX_MIX: the second input is a descriptor of its own, consumed by the MIX).  CPU: the oracle against the two tests the
-reference holds (crossfade.rs:45-88) and the planner's argument checks.  GPU: the general path bit for bit against the oracle."""
+reference holds (crossfade.rs:45-80) and the planner's argument checks.  GPU: the general path bit for bit against the oracle."""
 import numpy as np
 import pytest
 
@@ -9,10 +9,10 @@ import rodio_b200 as rb
 from helpers import assert_bit_exact, noise, to_oracle
 from rodio_b200 import capi
 
-S5 = rb.Duration.from_secs(5) + 1          # Duration::from_secs(5) + Duration::from_nanos(1), crossfade.rs:51,:70
+S5 = rb.Duration.from_secs(5) + 1          # Duration::from_secs(5) + Duration::from_nanos(1), crossfade.rs:52,:72
 
 
-def _dummy(length):                        # crossfade.rs:39-42: SamplesBuffer::new(1 ch, 1 Hz, 1..=length)
+def _dummy(length):                        # crossfade.rs:40-43: SamplesBuffer::new(1 ch, 1 Hz, 1..=length)
     return rb.SamplesBuffer(1, 1, np.arange(1, length + 1, dtype=np.float32))
 
 
@@ -23,13 +23,13 @@ def _chain(src):
 
 # ------------------------------------------------------------------ CPU: the oracle on the reference's own vectors
 def test_oracle_crossfade_with_self():
-    """crossfade.rs:45-61: 1 2 3 4 5 within 1e-6, then None."""
+    """crossfade.rs:45-63: 1 2 3 4 5 within 1e-6, then None."""
     got = _chain(_dummy(10).take_crossfade_with(_dummy(10), S5))
     assert got.size == 5 and np.all(np.abs(got - np.array([1, 2, 3, 4, 5], np.float32)) < 1e-6), got
 
 
 def test_oracle_crossfade_against_silence():
-    """crossfade.rs:63-88: source2 = Zero (endless silence): [1.0, 2*0.8, 3*0.6, 4*0.4, 5*0.2] within 1e-6."""
+    """crossfade.rs:65-80: source2 = Zero (endless silence): [1.0, 2*0.8, 3*0.6, 4*0.4, 5*0.2] within 1e-6."""
     zero = rb.TestSource(np.zeros(64, np.float32), 1, 1)
     got = _chain(_dummy(10).take_crossfade_with(zero, S5))
     assert got.size == 5 and np.all(np.abs(got - np.array([1.0, 1.6, 1.8, 1.6, 1.0], np.float32)) < 1e-6), got
