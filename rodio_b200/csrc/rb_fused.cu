@@ -926,7 +926,7 @@ __device__ __forceinline__ void hot_mix4(const float* tile, const HotTile* hts, 
 
 // C == 2 (stereo source into a stereo mixer): a row carries two recurrence chains; the recurrence lane is
 // (row, channel) and a second recurrence warp on the same sub-partition takes the chains of rows 16..27.
-template <int C, bool HASB>
+template <int C, bool HASB, bool CHAIN>   // CHAIN: RB_MIX_EXACT_ORDER, an instantiation of its own (the default launch keeps its code: measured)
 __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(16) FusedRow s_rows[MAX_G];
@@ -935,11 +935,11 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
     // chain mode: the CTA's place in the chain is the order in which the CTAs START (a ticket), not blockIdx.x -- a CTA then only
     // ever waits for one that is already running, whatever order the hardware hands the blocks out in
     __shared__ uint32_t s_cta;
-    if (a.chain) {
+    if (CHAIN) {
         if (threadIdx.x == 0) s_cta = atomicAdd(a.flags, 1u) - a.epoch * gridDim.x;
         __syncthreads();
     }
-    const uint32_t cta = a.chain ? s_cta : blockIdx.x;
+    const uint32_t cta = CHAIN ? s_cta : blockIdx.x;
     const uint32_t row0 = cta * a.rows_per_cta;
     const uint32_t G = min(a.rows_per_cta, a.n_rows - row0);
     load_rows(s_rows, a.rows + row0, G);
@@ -955,7 +955,7 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
     float* partial = a.partial + (uint64_t)cta * a.mix_len;
     const uint2* carry_row = nullptr;      // chain: rows of (value, tag) pairs, `partial` is then [n_ctas][mix_len] of those
     uint2* tagged_row = nullptr;
-    if (a.chain) {
+    if (CHAIN) {
         uint2* rows2 = reinterpret_cast<uint2*>(a.partial);
         if (cta + 1 == gridDim.x) partial = a.out;                       // the last CTA writes the mixer output itself
         else tagged_row = rows2 + (uint64_t)cta * a.mix_len;
@@ -1123,7 +1123,7 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
         const bool has_second = second >= 0 && (uint32_t)second < G;
         // stage C: two warps, 4 positions per thread (slots without a second row, on different sub-partitions)
         // (chain mode: stage C moves to two warps of its own, below -- the hand-over is latency, not work, and must not sit behind a row's stage A)
-        const int mix_block = a.chain ? -1 : slot == 6 ? 0 : slot == 7 ? 1 : -1;
+        const int mix_block = CHAIN ? -1 : slot == 6 ? 0 : slot == 7 ? 1 : -1;
         // (lane's first frame * from) divmod to for the rows this warp owns
         uint32_t lane_q0 = 0, lane_r0 = 0, lane_q1 = 0, lane_r1 = 0;
         if (has_first) {
@@ -1182,7 +1182,7 @@ __global__ void __launch_bounds__(1024, 1) k_fused_hot(FusedArgs a) {
             }
             HOT_BAR();
         }
-    } else if (a.chain && (warp == 3 || warp == 7)) {
+    } else if (CHAIN && (warp == 3 || warp == 7)) {
         // ---- chain mode, stage C on tile it-2: warps 3 and 7 (idle otherwise; the recurrence warp's sub-partition has issue slots to
         // spare) wait for the CTA in front, add this CTA's rows to its running sum and hand it on ----
         const int mix_block = warp == 3 ? 0 : 1;
@@ -1388,10 +1388,12 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     plan->hot_smem = ((size_t)NBUF * ROW_STRIDE + (size_t)NWIN * WSTRIDE) * G * sizeof(float);
     if (e == cudaSuccess && plan->hot) {
         const int hs = (int)plan->hot_smem;
-        e = C == 2 ? (has_b ? cudaFuncSetAttribute(k_fused_hot<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hs)
-                            : cudaFuncSetAttribute(k_fused_hot<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hs))
-                   : (has_b ? cudaFuncSetAttribute(k_fused_hot<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hs)
-                            : cudaFuncSetAttribute(k_fused_hot<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hs));
+        const bool ch = plan->chain;
+        auto set = [&](auto kern) { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, hs); };
+        e = C == 2 ? (has_b ? (ch ? set(k_fused_hot<2, true, true>) : set(k_fused_hot<2, true, false>))
+                            : (ch ? set(k_fused_hot<2, false, true>) : set(k_fused_hot<2, false, false>)))
+                   : (has_b ? (ch ? set(k_fused_hot<1, true, true>) : set(k_fused_hot<1, true, false>))
+                            : (ch ? set(k_fused_hot<1, false, true>) : set(k_fused_hot<1, false, false>)));
     }
     if (e == cudaSuccess && has_b) {
         const int sb = (int)plan->smem_bytes;
@@ -1431,12 +1433,21 @@ cudaError_t rb_fused_run(rb_fused_plan* p, cudaStream_t st) {
     if (p->chain) p->args.epoch = p->epoch++;     // tickets and tags of this render
     const FusedArgs& a = p->args;
     if (p->hot) {
-        if (a.c_mix == 1) {
-            if (a.has_biquad) k_fused_hot<1, true><<<p->n_ctas, 1024, p->hot_smem, st>>>(a);
-            else k_fused_hot<1, false><<<dim3(p->n_ctas, p->grid_y), 1024, p->hot_smem, st>>>(a);
+        const dim3 gb(p->n_ctas), gn(p->n_ctas, p->grid_y);
+        if (p->chain) {
+            if (a.c_mix == 1) {
+                if (a.has_biquad) k_fused_hot<1, true, true><<<gb, 1024, p->hot_smem, st>>>(a);
+                else k_fused_hot<1, false, true><<<gn, 1024, p->hot_smem, st>>>(a);
+            } else {
+                if (a.has_biquad) k_fused_hot<2, true, true><<<gb, 1024, p->hot_smem, st>>>(a);
+                else k_fused_hot<2, false, true><<<gn, 1024, p->hot_smem, st>>>(a);
+            }
+        } else if (a.c_mix == 1) {
+            if (a.has_biquad) k_fused_hot<1, true, false><<<gb, 1024, p->hot_smem, st>>>(a);
+            else k_fused_hot<1, false, false><<<gn, 1024, p->hot_smem, st>>>(a);
         } else {
-            if (a.has_biquad) k_fused_hot<2, true><<<p->n_ctas, 1024, p->hot_smem, st>>>(a);
-            else k_fused_hot<2, false><<<dim3(p->n_ctas, p->grid_y), 1024, p->hot_smem, st>>>(a);
+            if (a.has_biquad) k_fused_hot<2, true, false><<<gb, 1024, p->hot_smem, st>>>(a);
+            else k_fused_hot<2, false, false><<<gn, 1024, p->hot_smem, st>>>(a);
         }
     } else if (a.has_biquad) {
         const uint32_t threads = 512;
