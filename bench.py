@@ -215,7 +215,8 @@ def run_ours(args):
     comm = None
     if world > 1:
         # torch.distributed is the plumbing (barrier, max over ranks, handing out the communicator id); the data-path
-        # collective is the library's own: rb_batch_render_mix_allreduce = render + ncclAllReduce on the context's stream
+        # collective is the library's own: rb_batch_render_mix_allreduce = render + k_mix_exchange over NVLink peer memory (NCCL's
+        # all-reduce where the ranks cannot map each other's memory; RB_COMM_NCCL_ONLY=1 forces it for A/B runs)
         rbd.init_process_group("nccl")
         ids = [rb.Comm.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
@@ -529,7 +530,7 @@ def run_ours(args):
             "e2e": e2e,
             "also": also,
             "strong_scaling": strong,
-            "allreduce": None if world == 1 else {"impl": "rb_batch_render_mix_allreduce (ncclAllReduce sum f32 on the render stream)", "floats": mix_len,
+            "allreduce": None if world == 1 else {"impl": "rb_batch_render_mix_allreduce: " + comm.transport, "floats": mix_len,
                                                   "ms": max(0.0, ms_step - ms_kernel)},
             "gpu_launches": launches * args.steps,
             "clocks": clocks,

@@ -255,6 +255,12 @@ rb_status rb_comm_unique_id(rb_comm_id* id);
 rb_status rb_comm_init_rank(rb_context* ctx, int n_ranks, int rank, const rb_comm_id* id, rb_comm** out);
 rb_status rb_comm_init_all(rb_context** ctxs, int n_gpus, rb_comm** out);
 rb_status rb_comm_destroy(rb_comm* comm);
+/* How the mixes travel on this communicator, known after the first rb_batch_render_mix_allreduce: "p2p ..." -- ONE kernel per GPU
+ * (k_mix_exchange) forms the shard's mix (adding the fused kernel's partial rows itself), pushes it as (value, tag) pairs into a
+ * mailbox in every peer's HBM over NVLink and sums the shards in rank order from +0.0: deterministic and identical on every rank --
+ * or "nccl ... (why)": ncclAllReduce, where the ranks cannot map each other's memory (another node, IPC not permitted) or with
+ * RB_COMM_NCCL_ONLY=1 in the environment. */
+rb_status rb_comm_transport(rb_comm* comm, char* buf, uint64_t cap);
 rb_status rb_batch_render_mix_allreduce(rb_batch** batches, int n_local, rb_comm* comm);
 
 /* Algorithmic bytes of one render: 4*sum(in_samples)(or format size) + 4*mix_len. */

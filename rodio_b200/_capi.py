@@ -93,6 +93,7 @@ SYMBOLS = {
     "rb_comm_init_rank": (C.c_int32, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "rb_comm_init_all": (C.c_int32, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]),
     "rb_comm_destroy": (C.c_int32, [C.c_void_p]),
+    "rb_comm_transport": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_uint64]),
     "rb_batch_render_mix_allreduce": (C.c_int32, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
     "rb_session_create": (C.c_int32, [C.c_void_p, C.c_uint16, C.c_uint32, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
     "rb_session_destroy": (C.c_int32, [C.c_void_p]),

@@ -19,6 +19,7 @@
 #include "rb_lanes.h"
 #include "rb_lanes_plan.h"
 #include "rb_session_plan.h"
+#include "rb_p2p.h"
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -1192,7 +1193,10 @@ static rb_status run_general(rb_batch* b, bool with_mix) {
     return RB_OK;
 }
 
-extern "C" rb_status rb_batch_render_mix_device(rb_batch* b) {
+static rb_status render_device(rb_batch* b, bool skip_final_sum);
+extern "C" rb_status rb_batch_render_mix_device(rb_batch* b) { return render_device(b, false); }
+// skip_final_sum: the fused plan's last launch (the ordered sum of its per-CTA partial rows) is left to the caller (rb_p2p)
+static rb_status render_device(rb_batch* b, bool skip_final_sum) {
     if (!b) return fail(RB_ERR_INVALID_ARGUMENT, "batch is NULL");
     for (size_t i = 0; i < b->streams.size(); i++)
         if (!b->uploaded[i] && b->streams[i].desc.n_samples)
@@ -1203,7 +1207,7 @@ extern "C" rb_status rb_batch_render_mix_device(rb_batch* b) {
             RB_CUDA(rb_launch_nodes(RB_N_CONVERT, b->d_conv_nodes, (uint32_t)b->streams.size(), b->conv_max_n, 1, b->ctx->stream));
             b->conv_dirty = false;
         }
-        RB_CUDA(rb_fused_run(b->fused, b->ctx->stream));
+        RB_CUDA(rb_fused_run(b->fused, b->ctx->stream, skip_final_sum));
         if (b->flags & RB_KEEP_STREAM_OUTPUTS) {
             rb_status s = run_general(b, false);
             if (s != RB_OK) return s;
@@ -1231,6 +1235,7 @@ struct NcclApi {
     int (*CommInitRank)(void**, int, rb_comm_id, int) = nullptr;
     int (*CommInitAll)(void**, int, const int*) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
@@ -1257,6 +1262,7 @@ NcclApi* nccl_api(std::string* why) {
             api.CommInitRank = (int (*)(void**, int, rb_comm_id, int))sym("ncclCommInitRank");
             api.CommInitAll = (int (*)(void**, int, const int*))sym("ncclCommInitAll");
             api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))sym("ncclAllReduce");
+            api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))sym("ncclAllGather");
             api.CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
             api.GroupStart = (int (*)())sym("ncclGroupStart");
             api.GroupEnd = (int (*)())sym("ncclGroupEnd");
@@ -1269,13 +1275,19 @@ NcclApi* nccl_api(std::string* why) {
     }
     return &api;
 }
-constexpr int NCCL_FLOAT32 = 7, NCCL_SUM = 0;   // ncclFloat32, ncclSum (nccl.h)
+constexpr int NCCL_FLOAT32 = 7, NCCL_SUM = 0, NCCL_INT8 = 0;   // ncclFloat32, ncclSum, ncclInt8 (nccl.h)
 }  // namespace
 
 struct rb_comm {
     std::vector<void*> comms;           // one per local rank (one entry for the process-per-GPU form)
     std::vector<rb_context*> ctxs;
     int n_ranks = 0;
+    int rank = 0;                       // process-per-GPU form
+    // the mixes are exchanged by k_mix_exchange over NVLink peer memory (rb_p2p.h) where the ranks can map each other's
+    // mailboxes; NCCL's all-reduce otherwise (other nodes, IPC not permitted, RB_COMM_NCCL_ONLY=1).  Set up at the first call.
+    std::vector<rb_p2p*> p2p;           // one per local rank, or empty
+    bool p2p_tried = false;
+    std::string transport = "nccl (ncclAllReduce sum f32 on the render stream)";
 };
 
 #define RB_NCCL(call, api)                                                                             \
@@ -1300,7 +1312,7 @@ extern "C" rb_status rb_comm_init_rank(rb_context* ctx, int n_ranks, int rank, c
     if (!api) return fail(RB_ERR_UNSUPPORTED, why);
     RB_CUDA(cudaSetDevice(ctx->device));
     auto c = std::make_unique<rb_comm>();
-    c->comms.resize(1), c->ctxs = {ctx}, c->n_ranks = n_ranks;
+    c->comms.resize(1), c->ctxs = {ctx}, c->n_ranks = n_ranks, c->rank = rank;
     RB_NCCL(api->CommInitRank(&c->comms[0], n_ranks, *id, rank), api);
     *out = c.release();
     return RB_OK;
@@ -1326,11 +1338,53 @@ extern "C" rb_status rb_comm_init_all(rb_context** ctxs, int n_gpus, rb_comm** o
 extern "C" rb_status rb_comm_destroy(rb_comm* c) {
     if (!c) return RB_OK;
     NcclApi* api = nccl_api(nullptr);
+    for (rb_p2p* q : c->p2p) rb_p2p_destroy(q);
     if (api)
         for (void* k : c->comms)
             if (k) api->CommDestroy(k);
     delete c;
     return RB_OK;
+}
+
+// "p2p ..." or "nccl ...": how rb_batch_render_mix_allreduce exchanges the mixes on this communicator (known after the first call)
+extern "C" rb_status rb_comm_transport(rb_comm* c, char* buf, uint64_t cap) {
+    if (!c || !buf || cap == 0) return fail(RB_ERR_INVALID_ARGUMENT, "NULL argument");
+    snprintf(buf, (size_t)cap, "%s", c->transport.c_str());
+    return RB_OK;
+}
+
+// Collective: every rank calls it with the same mix_len.  Leaves c->p2p empty (NCCL) when the ranks cannot map each other's memory.
+static void comm_setup_p2p(rb_comm* c, NcclApi* api, uint64_t mix_len) {
+    if (!c->p2p.empty() && rb_p2p_capacity(c->p2p[0]) >= mix_len) return;
+    if (c->p2p_tried && c->p2p.empty()) return;                  // settled on NCCL
+    c->p2p_tried = true;
+    for (rb_p2p* q : c->p2p) rb_p2p_destroy(q);
+    c->p2p.clear();
+    const char* only = getenv("RB_COMM_NCCL_ONLY");
+    if ((only && *only && *only != '0') || c->n_ranks < 2 || c->n_ranks > RB_P2P_MAX_RANKS) return;
+    const uint64_t cap = std::max<uint64_t>(mix_len, 1ull << 16);
+    std::string why;
+    cudaError_t e;
+    if (c->comms.size() == 1) {
+        void* comm = c->comms[0];
+        rb_p2p* p = nullptr;
+        e = rb_p2p_create_rank(c->n_ranks, c->rank, c->ctxs[0]->device, c->ctxs[0]->stream, cap,
+                               [api, comm](const void* s, void* r, size_t bytes, cudaStream_t st) {
+                                   return api->AllGather(s, r, bytes, NCCL_INT8, comm, st) == 0 ? cudaSuccess : cudaErrorInvalidValue;
+                               }, &p, &why);
+        if (e == cudaSuccess && p) c->p2p = {p};
+    } else {
+        std::vector<int> devs;
+        std::vector<cudaStream_t> sts;
+        for (rb_context* x : c->ctxs) devs.push_back(x->device), sts.push_back(x->stream);
+        std::vector<rb_p2p*> ps(c->ctxs.size(), nullptr);
+        e = rb_p2p_create_local((int)ps.size(), devs.data(), sts.data(), cap, ps.data(), &why);
+        if (e == cudaSuccess) c->p2p = ps;
+    }
+    if (!c->p2p.empty())
+        c->transport = "p2p (k_mix_exchange: (value, tag) pairs pushed into every peer's mailbox over NVLink, summed in rank order)";
+    else
+        c->transport = "nccl (ncclAllReduce sum f32 on the render stream; peer memory not used: " + why + ")";
 }
 
 // Render every batch (one per local rank of the communicator, in rank order) and all-reduce the mixes in place: afterwards
@@ -1342,10 +1396,23 @@ extern "C" rb_status rb_batch_render_mix_allreduce(rb_batch** batches, int n_loc
     for (int i = 0; i < n_local; i++) {
         if (!batches[i] || batches[i]->ctx != c->ctxs[i]) return fail(RB_ERR_INVALID_ARGUMENT, "batch i must live on the context of local rank i");
         if (batches[i]->mix_len != batches[0]->mix_len) return fail(RB_ERR_INVALID_ARGUMENT, "the shards must share the mixer timeline (equal mix_len)");
-        rb_status s = rb_batch_render_mix_device(batches[i]);
-        if (s != RB_OK) return s;
     }
-    if (c->n_ranks == 1 || batches[0]->mix_len == 0) return RB_OK;
+    if (c->n_ranks > 1 && batches[0]->mix_len) comm_setup_p2p(c, api, batches[0]->mix_len);
+    const bool p2p = !c->p2p.empty() && c->n_ranks > 1 && batches[0]->mix_len;
+    for (int i = 0; i < n_local; i++) {
+        const float* partial = nullptr;
+        uint32_t n_rows = 0;
+        uint64_t pstride = 0;
+        const bool fuse = p2p && batches[i]->fused && !(batches[i]->flags & RB_KEEP_STREAM_OUTPUTS) &&
+                          rb_fused_partial_rows(batches[i]->fused, &partial, &n_rows, &pstride);
+        rb_status s = render_device(batches[i], fuse);
+        if (s != RB_OK) return s;
+        if (p2p) {   // ONE kernel: [the ordered sum of the shard's partial rows +] push to the peers + the rank-ordered sum
+            RB_CUDA(cudaSetDevice(c->ctxs[i]->device));
+            RB_CUDA(rb_p2p_allreduce(c->p2p[i], batches[i]->d_out, batches[i]->mix_len, fuse ? partial : nullptr, n_rows, pstride, c->ctxs[i]->stream));
+        }
+    }
+    if (c->n_ranks == 1 || batches[0]->mix_len == 0 || p2p) return RB_OK;
     if (n_local > 1) RB_NCCL(api->GroupStart(), api);
     for (int i = 0; i < n_local; i++) {
         RB_CUDA(cudaSetDevice(c->ctxs[i]->device));

@@ -863,13 +863,15 @@ __device__ __forceinline__ float4 hot_mix4_full(const float* tile, const FusedRo
 // accesses (single-copy atomic), tag = render number and tile -- the reader polls the DATA until the tag is the one it expects.
 // One L2 round trip per hop, no fences, no separate flag (the first version -- release store of a tile counter behind a fenced row,
 // acquire poll, then the carry load -- cost 4.8 us per tile and CTA: two fences and three dependent round trips).
+// one 64-bit access each (naturally aligned: single-copy atomic -- a .v2.u32 access is formally two scalar accesses)
 __device__ __forceinline__ uint2 ld_relaxed_v2(const uint2* p) {
-    uint2 v;
-    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
-    return v;
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return make_uint2((uint32_t)v, (uint32_t)(v >> 32));
 }
 __device__ __forceinline__ void st_relaxed_v2(uint2* p, uint2 v) {
-    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+    const unsigned long long w = (unsigned long long)v.x | ((unsigned long long)v.y << 32);
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
 __device__ __forceinline__ void hot_mix4(const float* tile, const HotTile* hts, const FusedRow* s_rows, uint32_t G,
                                          uint32_t n_post, uint32_t t4, bool full, uint64_t m0, uint64_t mix_len,
@@ -1427,7 +1429,7 @@ void rb_fused_inputs_changed(rb_fused_plan* p) {
     if (p && p->lanes) rb_lanes_inputs_changed(p->lanes);
 }
 
-cudaError_t rb_fused_run(rb_fused_plan* p, cudaStream_t st) {
+cudaError_t rb_fused_run(rb_fused_plan* p, cudaStream_t st, bool skip_final_sum) {
     if (p->fx) return rb_fx_run(p->fx, st);
     if (p->lanes) return rb_lanes_run(p->lanes, st);
     if (p->chain) p->args.epoch = p->epoch++;     // tickets and tags of this render
@@ -1462,7 +1464,7 @@ cudaError_t rb_fused_run(rb_fused_plan* p, cudaStream_t st) {
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    if (!p->single_cta_direct && !p->chain) {
+    if (!p->single_cta_direct && !p->chain && !skip_final_sum) {
         uint64_t blocks = (a.mix_len + 255) / 256;
         if (blocks > 148ull * 8) blocks = 148ull * 8;
         k_sum_partials<<<(uint32_t)blocks, 256, 0, st>>>(p->d_partial, p->n_ctas, a.mix_len, p->d_out);
@@ -1481,6 +1483,11 @@ void rb_fused_destroy(rb_fused_plan* p) {
     delete p;
 }
 
+bool rb_fused_partial_rows(const rb_fused_plan* p, const float** partial, uint32_t* n_rows, uint64_t* pstride) {
+    if (!p || p->fx || p->lanes || p->single_cta_direct || p->chain || !p->d_partial) return false;
+    *partial = p->d_partial, *n_rows = p->n_ctas, *pstride = p->args.mix_len;
+    return true;
+}
 uint32_t rb_fused_launch_count(const rb_fused_plan* p) {
     if (p->fx) return 2u;
     if (p->lanes) return rb_lanes_launch_count(p->lanes);

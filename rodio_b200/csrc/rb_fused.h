@@ -26,7 +26,10 @@ struct rb_fused_plan;
 // else leaves it NULL (the general per-adapter path then serves the batch).
 cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams, uint16_t mixer_channels, float* d_out,
                                 uint64_t mix_len, uint32_t flags, int sm_count, cudaStream_t st, rb_fused_plan** out);
-cudaError_t rb_fused_run(rb_fused_plan* plan, cudaStream_t st);
+cudaError_t rb_fused_run(rb_fused_plan* plan, cudaStream_t st, bool skip_final_sum = false);
+// The per-CTA partial rows of a plan whose last launch is k_sum_partials (rows added in order give the mix): the cross-GPU sum can
+// then take the place of that launch (rb_p2p.h).  false: the plan has another shape (large-batch kernels, effect chain, one CTA, chain).
+bool rb_fused_partial_rows(const rb_fused_plan* plan, const float** partial, uint32_t* n_rows, uint64_t* pstride);
 void rb_fused_destroy(rb_fused_plan* plan);
 uint32_t rb_fused_launch_count(const rb_fused_plan* plan);
 // The input PCM of the batch was (re)written: plans that keep per-stream facts about it refresh them at the next run.

@@ -447,6 +447,13 @@ class Comm:
         check(lib().rb_comm_init_all(arr, len(ctxs), C.byref(self._h)), "rb_comm_init_all")
         return self
 
+    @property
+    def transport(self) -> str:
+        """"p2p ..." (k_mix_exchange over NVLink peer memory) or "nccl ... (why)" -- known after the first render_mix_allreduce."""
+        buf = C.create_string_buffer(400)
+        check(lib().rb_comm_transport(self._h, buf, 400), "rb_comm_transport")
+        return buf.value.decode()
+
     def render_mix_allreduce(self, batches):
         """Render the batch of every local rank and sum the mixes over all ranks in place (asynchronous like a render)."""
         batches = [batches] if isinstance(batches, Batch) else list(batches)

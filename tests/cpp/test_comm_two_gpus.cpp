@@ -1,10 +1,13 @@
 // The cross-shard mixer sum through the C ABI alone (include/rodio_b200.h rb_comm_*): one process drives N GPUs (default 2),
-// each renders the partial mix of its shard of a cfg3-shaped batch, rb_batch_render_mix_allreduce sums them with NCCL, and
-// every GPU must then hold (within the fused kernels' tolerance, 1e-5 * peak) the mix a single GPU renders from all sources.
+// each renders the partial mix of its shard of a cfg3-shaped batch, rb_batch_render_mix_allreduce sums the shards -- by
+// k_mix_exchange over NVLink peer memory, and once more by NCCL (RB_COMM_NCCL_ONLY=1) -- and every GPU must then hold (within the
+// fused kernels' tolerance, 1e-5 * peak) the mix a single GPU renders from all sources.  On the peer-memory path the result is also
+// the shards added in RANK ORDER from +0.0, bit for bit, and identical on every GPU.
 // Exit code 0 = passed, 77 = fewer GPUs than ranks (skipped).
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "rodio_b200.h"
@@ -58,24 +61,49 @@ int main(int argc, char** argv) {
     CHECK(rb_batch_mix_len(whole, &mix_len));
     std::vector<float> ref(mix_len);
     CHECK(rb_batch_render_mix(whole, ref.data(), mix_len, &got));
-    // sharded over the GPUs + all-reduce
-    rb_comm* comm = nullptr;
-    CHECK(rb_comm_init_all(ctxs.data(), n_gpus, &comm));
+    // sharded over the GPUs
     std::vector<rb_batch*> shard(n_gpus, nullptr);
     for (int g = 0; g < n_gpus; g++) CHECK(build(ctxs[g], S * g / n_gpus, S * (g + 1) / n_gpus, &shard[g]));
-    for (int rep = 0; rep < 2; rep++) CHECK(rb_batch_render_mix_allreduce(shard.data(), n_gpus, comm));
+    // every shard's own mix, added in rank order from +0.0 on the host: what the peer-memory exchange must give, bit for bit
+    std::vector<float> ordered(mix_len, 0.0f);
+    for (int g = 0; g < n_gpus; g++) {
+        std::vector<float> own(mix_len);
+        CHECK(rb_batch_render_mix(shard[g], own.data(), mix_len, &got));
+        for (uint64_t i = 0; i < mix_len; i++) ordered[i] = ordered[i] + own[i];
+    }
     float peak = 0.f;
     for (float v : ref) peak = std::fmax(peak, std::fabs(v));
-    for (int g = 0; g < n_gpus; g++) {
-        std::vector<float> out(mix_len);
-        CHECK(rb_batch_read_mix(shard[g], 0, out.data(), mix_len, &got));
-        if (got != mix_len) return std::fprintf(stderr, "short read on GPU %d\n", g), 1;
-        float err = 0.f;
-        for (uint64_t i = 0; i < mix_len; i++) err = std::fmax(err, std::fabs(out[i] - ref[i]));
-        std::printf("GPU %d: max |sharded - single| = %.3e (peak %.3e)\n", g, err, peak);
-        if (!(err <= 1e-5f * peak)) return std::fprintf(stderr, "all-reduced mix differs on GPU %d\n", g), 1;
+    for (int pass = 0; pass < 2; pass++) {           // 0: whatever the communicator picks (peer memory on an NVLink box), 1: NCCL
+        if (pass == 1) setenv("RB_COMM_NCCL_ONLY", "1", 1);
+        rb_comm* comm = nullptr;
+        CHECK(rb_comm_init_all(ctxs.data(), n_gpus, &comm));
+        for (int rep = 0; rep < 3; rep++) CHECK(rb_batch_render_mix_allreduce(shard.data(), n_gpus, comm));
+        char how[400];
+        CHECK(rb_comm_transport(comm, how, sizeof how));
+        std::printf("pass %d transport: %s\n", pass, how);
+        const bool p2p = how[0] == 'p';
+        if (pass == 1 && p2p) return std::fprintf(stderr, "RB_COMM_NCCL_ONLY=1 was ignored\n"), 1;
+        std::vector<float> first;
+        for (int g = 0; g < n_gpus; g++) {
+            std::vector<float> out(mix_len);
+            CHECK(rb_batch_read_mix(shard[g], 0, out.data(), mix_len, &got));
+            if (got != mix_len) return std::fprintf(stderr, "short read on GPU %d\n", g), 1;
+            float err = 0.f;
+            uint64_t bits_differ = 0;
+            for (uint64_t i = 0; i < mix_len; i++) {
+                err = std::fmax(err, std::fabs(out[i] - ref[i]));
+                bits_differ += std::memcmp(&out[i], &ordered[i], 4) != 0;
+            }
+            std::printf("GPU %d: max |sharded - single| = %.3e (peak %.3e), %llu samples differ from the rank-ordered sum\n", g, err, peak,
+                        (unsigned long long)bits_differ);
+            if (!(err <= 1e-5f * peak)) return std::fprintf(stderr, "all-reduced mix differs on GPU %d\n", g), 1;
+            if (p2p && bits_differ) return std::fprintf(stderr, "peer-memory exchange: not the rank-ordered sum on GPU %d\n", g), 1;
+            if (g == 0) first = out;
+            else if (p2p && std::memcmp(first.data(), out.data(), mix_len * 4) != 0) return std::fprintf(stderr, "GPUs disagree\n"), 1;
+        }
+        CHECK(rb_comm_destroy(comm));
     }
-    CHECK(rb_comm_destroy(comm));
+    unsetenv("RB_COMM_NCCL_ONLY");
     for (auto* b : shard) rb_batch_destroy(b);
     rb_batch_destroy(whole);
     for (auto* c : ctxs) rb_context_destroy(c);

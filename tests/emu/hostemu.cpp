@@ -11,6 +11,7 @@
 
 #include "warp_variants.h"
 #include "../../rodio_b200/csrc/rb_fused.h"
+#include "../../rodio_b200/csrc/rb_p2p.h"
 #include "../../rodio_b200/csrc/rb_fused_rows.h"
 #include "../../rodio_b200/csrc/rb_lanes.h"
 #include "../../rodio_b200/csrc/rb_lanes_plan.h"
@@ -174,7 +175,8 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     *out = new rb_fused_plan{lanes};
     return cudaSuccess;
 }
-cudaError_t rb_fused_run(rb_fused_plan* p, cudaStream_t st) { return rb_lanes_run(p->lanes, st); }
+cudaError_t rb_fused_run(rb_fused_plan* p, cudaStream_t st, bool) { return rb_lanes_run(p->lanes, st); }
+bool rb_fused_partial_rows(const rb_fused_plan*, const float**, uint32_t*, uint64_t*) { return false; }
 void rb_fused_destroy(rb_fused_plan* p) {
     if (p) rb_lanes_destroy(p->lanes), delete p;
 }
@@ -185,6 +187,20 @@ void rb_fused_inputs_changed(rb_fused_plan* p) {
 int rb_fused_kind(const rb_fused_plan* p) { return rb_lanes_kind(p->lanes); }
 uint32_t rb_fused_mix_group(const rb_fused_plan* p) { return rb_lanes_mix_group(p->lanes); }
 cudaError_t rb_launch_nodes(uint32_t, const rb_node_dev*, uint32_t, uint64_t, uint32_t, cudaStream_t) { return cudaErrorInvalidValue; }
+// the NVLink peer-memory exchange (rb_p2p.cu) has no host emulation: the communicator stays on NCCL here
+cudaError_t rb_p2p_create_rank(int, int, int, cudaStream_t, uint64_t, const rb_p2p_allgather&, rb_p2p** out, std::string* why) {
+    *out = nullptr;
+    if (why) *why = "host emulation";
+    return cudaErrorInvalidValue;
+}
+cudaError_t rb_p2p_create_local(int n, const int*, const cudaStream_t*, uint64_t, rb_p2p** out, std::string* why) {
+    for (int i = 0; i < n; i++) out[i] = nullptr;
+    if (why) *why = "host emulation";
+    return cudaErrorInvalidValue;
+}
+uint64_t rb_p2p_capacity(const rb_p2p*) { return 0; }
+cudaError_t rb_p2p_allreduce(rb_p2p*, float*, uint64_t, const float*, uint32_t, uint64_t, cudaStream_t) { return cudaErrorInvalidValue; }
+void rb_p2p_destroy(rb_p2p*) {}
 cudaError_t rb_launch_mix(const rb_mix_src*, uint32_t, float*, uint64_t, cudaStream_t, float*, uint32_t) { return cudaErrorInvalidValue; }
 cudaError_t rb_launch_convert(const void*, uint32_t, void*, uint32_t, uint64_t, cudaStream_t) { return cudaErrorInvalidValue; }
 
