@@ -238,3 +238,47 @@ def test_planner_take_ramp_distortion_lengths(built):
         rb.TestSource(np.zeros(4, np.float32), 1, 48000).fade_in(0)
     with pytest.raises(rb.RodioB200Error):
         rb.plan(rb.TestSource(np.zeros(4, np.float32), 1, 48000).distortion(2.0, -1.0), 1, 48000)
+
+
+def test_streams_plan_survives_random_descriptor_graphs(built):
+    """rb_streams_plan on random descriptor arrays -- MIX / APPEND pointing anywhere (themselves, each other in cycles, out of
+    range), consumed marks on and off, generators in odd places: every call returns a status, none crashes, and an accepted array
+    never has a consumed descriptor that reaches the mixer."""
+    import ctypes as C
+    rng = np.random.default_rng(99)
+    L = rb.lib()
+    ok = 0
+    for _ in range(3000):
+        n = int(rng.integers(1, 6))
+        descs = (capi.rb_stream_desc * n)()
+        keep = []
+        for i in range(n):
+            k = int(rng.integers(0, 4))
+            fx = (capi.rb_effect * max(1, k))()
+            for j in range(k):
+                kind = int(rng.choice([capi.RB_FX_AMPLIFY, capi.RB_FX_LOW_PASS, capi.RB_FX_MIX, capi.RB_FX_APPEND, capi.RB_FX_SIGNAL,
+                                       capi.RB_FX_UNIFORM, capi.RB_FX_TAKE_DURATION, 99]))
+                fx[j].kind = kind
+                fx[j].u32[0] = int(rng.integers(0, n + 2))
+                fx[j].u32[1] = int(rng.choice([0, 8000, 48000]))
+                fx[j].f32[0] = float(rng.choice([0.5, 440.0, -1.0]))
+                fx[j].ns[0] = int(rng.choice([0, 100, 10_000_000]))
+            keep.append(fx)
+            d = descs[i]
+            d.sample_rate = int(rng.choice([0, 8000, 44100, 48000]))
+            d.channels = int(rng.choice([0, 1, 2, 3]))
+            d.format = capi.RB_FMT_F32
+            d.n_samples = int(rng.choice([0, 1, 6, 600]))
+            d.span_len = int(rng.choice([0, 0, d.n_samples, 7]))
+            d.n_effects = k
+            d.effects = C.cast(fx, C.POINTER(capi.rb_effect))
+            d.mix_start = capi.RB_MIX_START_CONSUMED if rng.integers(0, 2) else int(rng.integers(0, 100))
+        out_len = C.c_uint64()
+        for i in range(n):
+            st = L.rb_streams_plan(descs, n, i, 2, 48000, C.byref(out_len), None, None, None)
+            assert 0 <= st <= 9
+            if st == capi.RB_OK:
+                ok += 1
+                if descs[i].mix_start == capi.RB_MIX_START_CONSUMED:
+                    assert out_len.value == 0
+    assert ok > 100      # the generator does produce valid arrays too
