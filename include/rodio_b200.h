@@ -110,6 +110,11 @@ typedef enum {
                                  (SpanTracker, src/source/span.rs:66-101 with blt.rs:122-137); the mixer's UniformSourceIterator
                                  re-bootstraps with the span length and format FromIter reports at that moment
                                  (src/source/uniform.rs:50-68,:83-96).  Other adapters on such a source: RB_ERR_UNSUPPORTED.    */
+    RB_FX_PAUSE = 18,         /* Pausable (src/source/pausable.rs:8-21,:85-97), what Player::pause / play drive: from inner sample ns[0]
+                                 on the adapters in FRONT of this one are not pulled -- a filter there keeps its state -- and ns[1]
+                                 whole frames of literal 0.0 are emitted instead (`channels` zeros per frame, wherever in a frame the
+                                 pause sets in), then the source carries on where it stopped.  Adapters behind it (the Player's
+                                 volume, the mixer's conversion) see the zeros as samples.  ns[0] > the source's length: no effect. */
     RB_FX_SIGNAL = 15         /* SignalGenerator::new(sample_rate, frequency, function).take(n) src/source/signal_generator.rs:107-135
                                  (SineWave / SquareWave / TriangleWave / SawtoothWave = the same at 48 kHz, src/source/sine.rs:23-27):
                                  the SOURCE of the stream instead of uploaded PCM -- only as effects[0] of a descriptor with

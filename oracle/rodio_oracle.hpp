@@ -342,6 +342,47 @@ struct BltFilter : Source {
     }
 };
 
+// src/source/pausable.rs:8-21,:31-50,:85-97 with the control calls of a Player scripted: set_paused(true) is observed when `at`
+// samples have been pulled from the input, set_paused(false) after `frames` whole frames of silence.
+struct Pausable : Source {
+    Src in;
+    std::optional<uint16_t> paused_channels;
+    uint16_t remaining_paused_samples = 0;
+    uint64_t at, frames, pulled = 0, silent_frames = 0;
+    bool done = false;
+    Pausable(Src i, uint64_t at_sample, uint64_t n_frames) : in(std::move(i)), at(at_sample), frames(n_frames) {}
+    void set_paused(bool paused) {  // :42-50
+        if (!paused_channels && paused) paused_channels = in->channels();
+        else if (paused_channels && !paused) paused_channels.reset();
+    }
+    std::optional<Sample> next() override {  // :85-97
+        // the script (what Player's periodic access does between two calls)
+        if (!done && frames && pulled == at && !paused_channels && silent_frames == 0) set_paused(true);
+        if (paused_channels && remaining_paused_samples == 0 && silent_frames == frames) set_paused(false), done = true;
+        if (remaining_paused_samples > 0) {
+            remaining_paused_samples--;
+            return 0.0f;
+        }
+        if (paused_channels) {
+            remaining_paused_samples = (uint16_t)(*paused_channels - 1);
+            silent_frames++;
+            return 0.0f;
+        }
+        auto v = in->next();
+        if (v) pulled++;
+        return v;
+    }
+    std::optional<size_t> current_span_len() const override { return in->current_span_len(); }
+    uint16_t channels() const override { return in->channels(); }
+    uint32_t sample_rate() const override { return in->sample_rate(); }
+    Src clone() const override {
+        auto p = std::make_unique<Pausable>(in->clone(), at, frames);
+        p->paused_channels = paused_channels, p->remaining_paused_samples = remaining_paused_samples;
+        p->pulled = pulled, p->silent_frames = silent_frames, p->done = done;
+        return p;
+    }
+};
+
 // src/source/from_iter.rs:16-127: the sources of an iterator played one after the other; the format may change from one to the next.
 // current_span_len(): the current source's while it is not exhausted, None otherwise (:83-91); channels() / sample_rate(): the
 // current source's, also when it is exhausted -- the next one is only fetched inside next() (:48-63).

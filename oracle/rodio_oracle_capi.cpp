@@ -30,7 +30,7 @@ struct ro_stream {
     const float* pcm;
 };
 enum { FX_AMPLIFY = 1, FX_SPEED, FX_LOW_PASS, FX_HIGH_PASS, FX_REVERB, FX_AGC, FX_LIMIT, FX_SPATIAL,
-       FX_CHANNEL_VOLUME, FX_UNIFORM, FX_DELAY, FX_DISTORTION, FX_LINEAR_RAMP, FX_TAKE_DURATION, FX_SIGNAL, FX_MIX, FX_APPEND };
+       FX_CHANNEL_VOLUME, FX_UNIFORM, FX_DELAY, FX_DISTORTION, FX_LINEAR_RAMP, FX_TAKE_DURATION, FX_SIGNAL, FX_MIX, FX_APPEND, FX_PAUSE };
 
 float ro_lerp(float a, float b, uint32_t num, uint32_t den) { return lerp(a, b, num, den); }
 float ro_db_to_linear(float d) { return db_to_linear(d); }
@@ -79,6 +79,7 @@ static Src apply_effects(Src src, const ro_effect* fx, uint32_t n) {
                 src = std::make_unique<LinearGainRamp>(std::move(src), e.ns[0], e.f32[0], e.f32[1], e.u32[0] != 0);
                 break;
             case FX_TAKE_DURATION: src = std::make_unique<TakeDuration>(std::move(src), e.ns[0], e.u32[0] != 0); break;
+            case FX_PAUSE: src = std::make_unique<Pausable>(std::move(src), e.ns[0], e.ns[1]); break;
             case FX_MIX: {   // Source::mix(other): the second input is another ro_stream, its address in u32[1] (low) / u32[2] (high)
                 const ro_stream* o = (const ro_stream*)(uintptr_t)(((uint64_t)e.u32[2] << 32) | (uint64_t)e.u32[1]);
                 Src other = build(*o);

@@ -28,7 +28,7 @@ RB_FMT_F32, RB_FMT_I16, RB_FMT_U16, RB_FMT_I8, RB_FMT_U8, RB_FMT_I32, RB_FMT_I24
 
 (RB_FX_AMPLIFY, RB_FX_SPEED, RB_FX_LOW_PASS, RB_FX_HIGH_PASS, RB_FX_REVERB, RB_FX_AGC, RB_FX_LIMIT,
  RB_FX_SPATIAL, RB_FX_CHANNEL_VOLUME, RB_FX_UNIFORM, RB_FX_DELAY, RB_FX_DISTORTION, RB_FX_LINEAR_RAMP,
- RB_FX_TAKE_DURATION, RB_FX_SIGNAL, RB_FX_MIX, RB_FX_APPEND) = range(1, 18)
+ RB_FX_TAKE_DURATION, RB_FX_SIGNAL, RB_FX_MIX, RB_FX_APPEND, RB_FX_PAUSE) = range(1, 19)
 RB_MIX_START_CONSUMED = 0xFFFFFFFFFFFFFFFF
 RB_SIGNAL_SINE, RB_SIGNAL_TRIANGLE, RB_SIGNAL_SQUARE, RB_SIGNAL_SAWTOOTH = range(4)
 

@@ -593,6 +593,16 @@ static rb_status plan_stream(PlanStream& ps, uint16_t mixer_ch, uint32_t mixer_r
                 cv_last = -1, tail_pad = 0;
                 break;
             }
+            case RB_FX_PAUSE: {
+                // Pausable: while paused it hands out `channels` zeros per call round without pulling its input (pausable.rs:85-97);
+                // a pause that would set in behind the source's last sample never does
+                if (e.ns[0] > n || e.ns[1] == 0) continue;
+                if (tail_pad) return fail(RB_ERR_UNSUPPORTED, "pause directly on a padded take_duration");
+                nd.d.kind = RB_N_PAUSE, nd.d.p.pause.at = e.ns[0], nd.d.p.pause.n = e.ns[1] * c;
+                nd.d.n_out = n + nd.d.p.pause.n;
+                if (cv_last >= 0) cv_last = -1;
+                break;
+            }
             case RB_FX_SIGNAL: {
                 // SignalGenerator::with_function (signal_generator.rs:107-128): mono, span-less, endless; `.take(n)` bounds it
                 if (!is_first || d.n_samples != 0 || d.channels != 1 || d.format != RB_FMT_F32 || d.span_len != 0)

@@ -27,7 +27,8 @@ enum rb_node_kind : uint32_t {
     RB_N_TAKE = 11,     // src/source/take.rs:107-148 (+ fade-out filter :34-41)
     RB_N_SIGNAL = 12,   // src/source/signal_generator.rs:107-135 (a source: no input)
     RB_N_MIX2 = 13,     // src/source/mix.rs:43-53 (second input: aux0, p.mix2.n2 samples)
-    RB_N_KINDS = 14
+    RB_N_PAUSE = 14,    // src/source/pausable.rs:85-97: p.pause.n zeros in front of input sample p.pause.at
+    RB_N_KINDS = 15
 };
 
 // Closed-form description of one UniformSourceIterator application.
@@ -80,6 +81,7 @@ struct alignas(16) rb_node_dev {
         struct { uint64_t total_ns, dps_ns, count; float total_ms_f; uint32_t fadeout; } take;
         struct { float step; uint32_t fn; } sig;
         struct { uint64_t n2; } mix2;
+        struct { uint64_t at, n; } pause;
         rb_uniform_params uni;
     } p;
 };

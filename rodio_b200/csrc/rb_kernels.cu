@@ -62,6 +62,14 @@ __global__ void __launch_bounds__(TPB) k_mix2(const rb_node_dev* __restrict__ no
     for_each_out(nd, [&](uint64_t o) { nd.dst[o] = (o < n1 && o < n2) ? add(x1[o], x2[o]) : (o < n1 ? x1[o] : x2[o]); });
 }
 
+// Pausable (src/source/pausable.rs:85-97): `n` zeros (whole frames) in front of input sample `at`, everything behind them shifted
+__global__ void __launch_bounds__(TPB) k_pause(const rb_node_dev* __restrict__ nodes) {
+    const rb_node_dev& nd = nodes[blockIdx.x];
+    const float* __restrict__ x = (const float*)nd.src;
+    const uint64_t at = nd.p.pause.at, n = nd.p.pause.n;
+    for_each_out(nd, [&](uint64_t o) { nd.dst[o] = o < at ? x[o] : (o < at + n ? 0.0f : x[o - n]); });
+}
+
 __global__ void __launch_bounds__(TPB) k_delay(const rb_node_dev* __restrict__ nodes) {
     const rb_node_dev& nd = nodes[blockIdx.x];
     const float* __restrict__ x = (const float*)nd.src;
@@ -684,6 +692,7 @@ cudaError_t rb_launch_nodes(uint32_t kind, const rb_node_dev* d_nodes, uint32_t 
         case RB_N_ECHO: k_echo<<<grid, TPB, 0, st>>>(d_nodes); break;
         case RB_N_DELAY: k_delay<<<grid, TPB, 0, st>>>(d_nodes); break;
         case RB_N_MIX2: k_mix2<<<grid, TPB, 0, st>>>(d_nodes); break;
+        case RB_N_PAUSE: k_pause<<<grid, TPB, 0, st>>>(d_nodes); break;
         case RB_N_CHANVOL: k_chanvol<<<grid, TPB, 0, st>>>(d_nodes); break;
         case RB_N_DISTORT: k_distort<<<grid, TPB, 0, st>>>(d_nodes); break;
         case RB_N_RAMP: k_ramp<<<grid, TPB, 0, st>>>(d_nodes); break;

@@ -235,6 +235,12 @@ class Source:
         """Source::take_duration (+ TakeDuration::set_filter_fadeout) — src/source/take.rs:9-26,:89-96."""
         return self._with(Effect.make(capi.RB_FX_TAKE_DURATION, u32=[1 if filter_fadeout else 0], ns=[duration]))
 
+    def pause_at(self, at_sample: int, n_frames: int) -> "Source":
+        """Pausable (src/source/pausable.rs:85-97) with Player::pause / play scripted: when `at_sample` samples have been pulled
+        from this source it stops being pulled -- filters in front keep their state -- and `n_frames` whole frames of zeros follow,
+        then it carries on."""
+        return self._with(Effect.make(capi.RB_FX_PAUSE, ns=[int(at_sample), int(n_frames)]))
+
     def mix(self, other: "Source") -> "Source":
         """Source::mix(other) -- src/source/mod.rs:253-261, mix.rs:10-53: both inputs converted to THIS source's channels and rate,
         summed while both run, then whichever is left."""

@@ -71,6 +71,10 @@ CHAINS = {
         .mix(rb.SawtoothWave(220.0).take(2500).amplify(0.25)).high_pass(100),
     "crossfade_stereo": lambda: rb.TestSource(_stereo(30000, 63), 2, 44100).take_crossfade_with(
         rb.TestSource(_stereo(20000, 64), 2, 44100), rb.Duration.from_millis(250)),
+    # Pausable with Player::pause / play scripted (pausable.rs:85-97): the filter in front is not pulled while paused
+    "pause_behind_filter": lambda: rb.TestSource(_stereo(4000, 67), 2, 44100).low_pass(300).pause_at(1001, 50).amplify(0.5),
+    "pause_at_start_and_end": lambda: rb.SamplesBuffer(1, 48000, noise(700, 68)).pause_at(0, 10).pause_at(710, 7),
+    "pause_then_mixer_conversion": lambda: rb.UniformSourceIterator(rb.TestSource(noise(3 * 900, 69), 3, 32000).pause_at(300, 40), 2, 48000),
     "crossfade_other_format": lambda: rb.SamplesBuffer(2, 44100, _stereo(30000, 65)).take_crossfade_with(
         rb.SamplesBuffer(1, 22050, noise(9000, 66)), rb.Duration.from_millis(150)).amplify(0.7),
 }
