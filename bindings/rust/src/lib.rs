@@ -65,6 +65,7 @@ pub const RB_FX_TAKE_DURATION: u32 = 14;
 pub const RB_FX_SIGNAL: u32 = 15;      // SignalGenerator::new(rate, freq, f).take(n): generated on the device
 pub const RB_FX_MIX: u32 = 16;         // Source::mix(other): u32[0] = descriptor index of the second input
 pub const RB_FX_APPEND: u32 = 17;      // source::from_iter([self, next, ..]): u32[0] = descriptor index of the next buffer
+pub const RB_FX_PAUSE: u32 = 18;       // Pausable with pause()/play() at known positions: ns[0] = inner sample, ns[1] = frames of silence
 pub const RB_MIX_START_CONSUMED: u64 = u64::MAX;   // mix_start of a descriptor another descriptor's MIX / APPEND consumes
 
 /// An in-memory source plus the adapters recorded on it (what `SamplesBuffer::new(..).amplify(..)` builds).
@@ -101,6 +102,9 @@ impl GpuSource {
         }
         head
     }
+    /// `Pausable` (src/source/pausable.rs:85-97) with `pause()` observed after `at_sample` inner samples and `play()` `n_frames` later:
+    /// the adapters recorded so far are not pulled in between (a filter keeps its state), whole frames of zeros are emitted
+    pub fn pause_at(self, at_sample: u64, n_frames: u64) -> Self { self.push(RB_FX_PAUSE, [0; 3], &[], [at_sample, n_frames]) }
     /// `Source::mix` (src/source/mod.rs:253-261, mix.rs:10-53)
     pub fn mix(mut self, other: GpuSource) -> Self {
         self.others.push(other);

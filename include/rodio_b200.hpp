@@ -117,6 +117,8 @@ class Source {
         return s;
     }
 
+    // Pausable with Player::pause / play at known positions -- pausable.rs:85-97 (RB_FX_PAUSE)
+    Source pause_at(uint64_t at_sample, uint64_t n_frames) const { return with(fx(RB_FX_PAUSE, {}, {}, {at_sample, n_frames})); }
     // Source::mix(other) -- mod.rs:253-261, mix.rs:10-53: the second input becomes a descriptor of its own (RB_FX_MIX)
     Source mix(const Source& other) const {
         Source s = with(fx(RB_FX_MIX, {}, {}, {}));
