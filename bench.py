@@ -428,6 +428,11 @@ def run_ours(args):
               "streams x 2 s, timeline segments with a warm-up; <= 1e-5 * peak of the reference (tests), most segments bit-identical",
               [rb.UniformSourceIterator(rb.TestSource(one2, 1, IN_RATE), 1, MIX_RATE).low_pass(1000).amplify(AMPLIFY) for _ in range(4096)],
               1, rb.capi.RB_BIQUAD_TIME_PARALLEL, steps2, FAM)
+        timed("cfg3_exact_order", "the headline batch (4096 mono x 2 s, 44.1 -> 48 kHz -> low_pass(200) -> amplify -> mix) with RB_MIX_EXACT_ORDER: "
+              "k_fused_hot hands the running sum of every tile from CTA to CTA, so the WHOLE mix is the reference's sequential sum over "
+              "all 4096 sources bit for bit (tests/test_bench_geometries_gpu.py::test_exact_order_*); the default grouping above is <= 1e-5 * peak",
+              [rb.UniformSourceIterator(rb.TestSource(one2, 1, IN_RATE), 1, MIX_RATE).low_pass(LOW_PASS_HZ).amplify(AMPLIFY) for _ in range(4096)],
+              1, rb.capi.RB_MIX_EXACT_ORDER, steps2, {1: "k_fused_hot<1, true, CHAIN> (one launch)"})
         timed("cfg3_no_filter", "4096 mono streams x 2 s, 44.1 -> 48 kHz -> amplify(1.2) -> mix (bit-exact per stream)",
               [rb.UniformSourceIterator(rb.TestSource(one2, 1, IN_RATE), 1, MIX_RATE).amplify(AMPLIFY) for _ in range(4096)], 1, 0, steps2, FAM)
         timed("cfg4_effect_chain", "512 stereo 48 kHz sources x 1 s: Spatial -> reverb(50 ms, 0.3) -> automatic_gain_control -> mix(2 ch); "
