@@ -107,9 +107,11 @@ typedef enum {
                                  its own, mix_start = RB_MIX_START_CONSUMED, span_len = n_samples like a SamplesBuffer or 0).  What
                                  follows sees the parameter change the way rodio's adapters do: AMPLIFY; SPEED; LOW/HIGH_PASS keep
                                  their state and recompute the coefficients behind the first sample of the new span
-                                 (SpanTracker, src/source/span.rs:66-101 with blt.rs:122-137); the mixer's UniformSourceIterator
-                                 re-bootstraps with the span length and format FromIter reports at that moment
-                                 (src/source/uniform.rs:50-68,:83-96).  Other adapters on such a source: RB_ERR_UNSUPPORTED.    */
+                                 (SpanTracker, src/source/span.rs:66-101 with blt.rs:122-137); AGC recomputes its coefficients and
+                                 starts RMS window, peak and gain from scratch (agc.rs:524-548); LIMIT rebuilds its per-channel state
+                                 when the channel count changed (limit.rs:651-697); the mixer's UniformSourceIterator re-bootstraps
+                                 with the span length and format FromIter reports at that moment (src/source/uniform.rs:50-68,
+                                 :83-96).  Other adapters on such a source: RB_ERR_UNSUPPORTED.                                  */
     RB_FX_PAUSE = 18,         /* Pausable (src/source/pausable.rs:8-21,:85-97), what Player::pause / play drive: from inner sample ns[0]
                                  on the adapters in FRONT of this one are not pulled -- a filter there keeps its state -- and ns[1]
                                  whole frames of literal 0.0 are emitted instead (`channels` zeros per frame, wherever in a frame the

@@ -757,13 +757,16 @@ struct AutomaticGainControl : Source {
     float sum = 0.0f;
     size_t index = 0;
     bool is_enabled = true;
+    uint64_t attack_time_ns, release_time_ns;
+    SpanTracker span;
     AutomaticGainControl(Src i, float target, uint64_t attack_ns, uint64_t release_ns, float max_gain, float floor_v)
         : in(std::move(i)), target_level(target), floor_(floor_v), absolute_max_gain(max_gain),
-          buffer(RMS_WINDOW_SIZE, 0.0f) {
+          buffer(RMS_WINDOW_SIZE, 0.0f), span(in->sample_rate(), in->channels()) {
         // src/source/mod.rs:432-433 : times limited to 10 s
         uint64_t ten = 10ull * 1000000000ull;
         attack_ns = std::min(attack_ns, ten);
         release_ns = std::min(release_ns, ten);
+        attack_time_ns = attack_ns, release_time_ns = release_ns;
         attack_coeff = duration_to_coefficient(attack_ns, in->sample_rate());
         release_coeff = duration_to_coefficient(release_ns, in->sample_rate());
     }
@@ -792,7 +795,16 @@ struct AutomaticGainControl : Source {
         current_gain = clampf(current_gain, 0.1f, absolute_max_gain);
         return sample * current_gain;
     }
-    std::optional<Sample> next() override {  // agc.rs:524-557 (span branch never taken: stable params)
+    std::optional<Sample> next() override {  // agc.rs:524-557: the tracker BEFORE the sample is pulled
+        SpanTracker::Detection d = span.advance(*in);
+        if (d.at_span_boundary && d.parameters_changed) {   // :527-548: coefficients for the new rate, everything else from scratch
+            uint32_t rate = in->sample_rate();
+            attack_coeff = duration_to_coefficient(attack_time_ns, rate);
+            release_coeff = duration_to_coefficient(release_time_ns, rate);
+            buffer.assign(RMS_WINDOW_SIZE, 0.0f), sum = 0.0f, index = 0;   // CircularBuffer::new()
+            peak_level = 0.0f;
+            current_gain = 1.0f;
+        }
         auto s = in->next();
         if (!s) return std::nullopt;
         return is_enabled ? process_sample(*s) : *s;
@@ -804,6 +816,7 @@ struct AutomaticGainControl : Source {
         auto p = std::make_unique<AutomaticGainControl>(in->clone(), target_level, 0, 0, absolute_max_gain, floor_);
         p->attack_coeff = attack_coeff, p->release_coeff = release_coeff, p->current_gain = current_gain;
         p->peak_level = peak_level, p->buffer = buffer, p->sum = sum, p->index = index, p->is_enabled = is_enabled;
+        p->attack_time_ns = attack_time_ns, p->release_time_ns = release_time_ns, p->span = span;
         return p;
     }
 };
@@ -814,8 +827,9 @@ struct Limit : Source {
     float threshold, knee_width, inv_knee_8, attack, release;
     std::vector<float> integrators, peaks;
     size_t position = 0;
+    SpanTracker span;
     Limit(Src i, float thr, float knee, uint64_t attack_ns, uint64_t release_ns)
-        : in(std::move(i)), threshold(thr), knee_width(knee) {
+        : in(std::move(i)), threshold(thr), knee_width(knee), span(in->sample_rate(), in->channels()) {
         attack = duration_to_coefficient(attack_ns, in->sample_rate());
         release = duration_to_coefficient(release_ns, in->sample_rate());
         inv_knee_8 = 1.0f / (8.0f * knee_width);  // :877
@@ -852,7 +866,15 @@ struct Limit : Source {
             max_peak = 0.0f;  // :971-988 fold(0.0, max)
             for (float p : peaks) max_peak = fmaxf(max_peak, p);
         }
-        return sample * db_to_linear(-max_peak);
+        const float out = sample * db_to_linear(-max_peak);
+        // limit.rs:651-697: the tracker behind the sample; another channel count rebuilds the per-channel state (`base`, with the
+        // coefficients of the rate at construction, is kept)
+        SpanTracker::Detection d = span.advance(*in);
+        if (d.at_span_boundary && d.parameters_changed) {
+            size_t nc = in->channels();
+            if (nc != integrators.size()) integrators.assign(nc, 0.0f), peaks.assign(nc, 0.0f), position = 0;
+        }
+        return out;
     }
     std::optional<size_t> current_span_len() const override { return in->current_span_len(); }
     uint16_t channels() const override { return in->channels(); }
@@ -860,6 +882,7 @@ struct Limit : Source {
     Src clone() const override {
         auto p = std::make_unique<Limit>(in->clone(), threshold, knee_width, 0, 0);
         p->attack = attack, p->release = release, p->integrators = integrators, p->peaks = peaks, p->position = position;
+        p->span = span;
         return p;
     }
 };

@@ -277,6 +277,12 @@ struct PlanNode {
     uint32_t span_out = 0;
     uint32_t level = 0;    // launch level: one more than the node in front, for a MIX also behind the second input's last node
     int64_t other = -1;    // RB_N_MIX2: the stream whose final samples are the second input
+    // from_iter: an adapter that starts from scratch at a span boundary (AGC, limiter) is launched as one node per run of samples
+    struct Split {
+        uint64_t off, n;   // samples
+        rb_node_dev d;     // the run's parameters (kind, coefficients, channels); src / dst / aux are filled at layout time
+    };
+    std::vector<Split> splits;
 };
 struct PlanStream {
     rb_stream_desc desc{};
@@ -386,6 +392,45 @@ struct SeqSeg {
     uint32_t c, r;       // channels, sample rate (after any Speed)
     bool spans;          // SamplesBuffer: Some(len) until exhausted; TestSource-like: None
 };
+// SpanTracker::advance (span.rs:66-101) over what FromIter reports, as events: `at` = flat index of the first sample that sees the
+// new parameters, `seg` = the buffer whose format they are.  The same list serves a tracker that runs behind the sample (filters,
+// limiter: blt.rs:122, limit.rs:651) and one that runs in front of the next pull (AGC, agc.rs:525): both notice the change between
+// the first and the second sample of the new buffer -- FromIter fetches a buffer inside next(), so the first sample is out before
+// anybody sees the new format.
+struct SpanEvent {
+    uint64_t at;
+    size_t seg;
+};
+static std::vector<SpanEvent> span_events(const std::vector<SeqSeg>& segs) {
+    std::vector<SpanEvent> ev;
+    uint64_t counted = 0, g0 = 0, cached = 0;
+    bool counting = false;       // cached_span_len is Some
+    uint32_t last_c = segs[0].c, last_r = segs[0].r;
+    for (size_t k = 0; k < segs.size(); k++) {
+        const SeqSeg& g = segs[k];
+        if (g.n == 0) continue;
+        // behind sample j of this buffer the span is Some(g.n) for j < g.n - 1 and None behind the last one (exhausted); only the
+        // first of them can see a boundary: the counter restarts there or the parameters are equal from then on
+        if (g.spans && g.n >= 2) {
+            const uint64_t cnt = counted + 1;
+            const bool known = counting ? cnt >= cached : true;     // None: compare on every sample
+            bool changed = false, boundary = false;
+            if (known) {
+                changed = g.c != last_c || g.r != last_r;
+                last_c = g.c, last_r = g.r;
+                boundary = counting ? true : changed;
+            }
+            if (boundary) counting = true, cached = g.n, counted = 0;
+            else counted = cnt;
+            if (boundary && changed) ev.push_back({g0 + 1, k});
+            counted += g.n - 1;      // the other samples of the buffer: no boundary (counter below the span, or nothing changed)
+        } else {
+            counted += g.n;          // None behind every sample: the counter runs, nothing is compared
+        }
+        g0 += g.n;
+    }
+    return ev;
+}
 static rb_status plan_varying(PlanStream& ps, std::vector<SeqSeg> segs, size_t fx_from, uint16_t mixer_ch, uint32_t mixer_rate) {
     uint64_t n = 0;
     for (const SeqSeg& g : segs) n += g.n;
@@ -408,46 +453,69 @@ static rb_status plan_varying(PlanStream& ps, std::vector<SeqSeg> segs, size_t f
                 hostmath::Blt k = hostmath::blt(high, e.u32[0], e.f32[0], segs[0].r);
                 nd.d.kind = RB_N_BIQUAD;
                 nd.d.p.blt.b0 = k.b0, nd.d.p.blt.b1 = k.b1, nd.d.p.blt.b2 = k.b2, nd.d.p.blt.a1 = k.a1, nd.d.p.blt.a2 = k.a2;
-                // SpanTracker::advance behind every sample (span.rs:66-101), on what FromIter reports behind that sample
-                uint64_t counted = 0, g0 = 0;
-                bool counting = false;       // cached_span_len is Some
-                uint64_t cached = 0;
-                uint32_t last_c = segs[0].c, last_r = segs[0].r;
                 uint32_t n_sw = 0;
-                for (const SeqSeg& g : segs) {
-                    if (g.n == 0) continue;
-                    // behind sample j of this buffer the span is Some(g.n) for j < g.n - 1 and None behind the last one (exhausted);
-                    // only the first of them can see a boundary: the counter restarts there or the parameters are equal from then on
-                    if (g.spans && g.n >= 2) {
-                        const uint64_t cnt = counted + 1;
-                        const bool known = counting ? cnt >= cached : true;     // None: compare on every sample
-                        bool changed = false, boundary = false;
-                        if (known) {
-                            changed = g.c != last_c || g.r != last_r;
-                            last_c = g.c, last_r = g.r;
-                            boundary = counting ? true : changed;
-                        }
-                        if (boundary) counting = true, cached = g.n, counted = 0;
-                        else counted = cnt;
-                        if (boundary && changed) {
-                            if (n_sw >= RB_MAX_BLT_SWITCH) return fail(RB_ERR_UNSUPPORTED, "from_iter: more format changes than a filter follows");
-                            hostmath::Blt kk = hostmath::blt(high, e.u32[0], e.f32[0], g.r);
-                            nd.d.p.blt.sw_at[n_sw] = g0 + 1;      // the sample that crossed the boundary still had the old coefficients
-                            float* d = nd.d.p.blt.sw_k[n_sw];
-                            d[0] = kk.b0, d[1] = kk.b1, d[2] = kk.b2, d[3] = kk.a1, d[4] = kk.a2;
-                            n_sw++;
-                        }
-                        counted += g.n - 1;      // the other samples of the buffer: no boundary (counter below the span, or nothing changed)
-                    } else {
-                        counted += g.n;          // None behind every sample: the counter runs, nothing is compared
-                    }
-                    g0 += g.n;
+                for (const SpanEvent& ev : span_events(segs)) {
+                    if (n_sw >= RB_MAX_BLT_SWITCH) return fail(RB_ERR_UNSUPPORTED, "from_iter: more format changes than a filter follows");
+                    hostmath::Blt kk = hostmath::blt(high, e.u32[0], e.f32[0], segs[ev.seg].r);
+                    nd.d.p.blt.sw_at[n_sw] = ev.at;      // the sample that crossed the boundary still had the old coefficients
+                    float* d = nd.d.p.blt.sw_k[n_sw];
+                    d[0] = kk.b0, d[1] = kk.b1, d[2] = kk.b2, d[3] = kk.a1, d[4] = kk.a2;
+                    n_sw++;
                 }
                 nd.d.p.blt.n_sw = n_sw;
                 break;
             }
+            case RB_FX_AGC: {
+                // agc.rs:524-548: the tracker in FRONT of every pull; a changed format recomputes the coefficients and starts the RMS
+                // window, the peak follower and the gain from scratch -- from the second sample of the new span on (the first one is
+                // pulled before FromIter reports the new buffer).  Every stretch between two such points is an AGC of its own.
+                const float mg = e.f32[1];
+                if (!(mg >= 0.1f)) return fail(RB_ERR_INVALID_ARGUMENT, "agc: clamp(0.1, absolute_max_gain) would panic");
+                const uint64_t ten = 10ull * 1000000000ull;
+                auto params = [&](uint32_t rate) {
+                    rb_node_dev d{};
+                    d.kind = RB_N_AGC, d.c_in = d.c_out = c0;
+                    d.p.agc.target = e.f32[0], d.p.agc.max_gain = mg, d.p.agc.floor = e.f32[2];
+                    d.p.agc.attack = hostmath::duration_to_coefficient(std::min(e.ns[0], ten), rate);
+                    d.p.agc.release = hostmath::duration_to_coefficient(std::min(e.ns[1], ten), rate);
+                    return d;
+                };
+                nd.d = params(segs[0].r);
+                nd.d.n_in = nd.d.n_out = n;
+                uint64_t from = 0;
+                rb_node_dev cur = nd.d;
+                for (const SpanEvent& ev : span_events(segs)) {
+                    if (ev.at >= n) break;
+                    nd.splits.push_back({from, ev.at - from, cur});
+                    from = ev.at, cur = params(segs[ev.seg].r);
+                }
+                if (!nd.splits.empty()) nd.splits.push_back({from, n - from, cur});
+                break;
+            }
+            case RB_FX_LIMIT: {
+                // limit.rs:651-697: the tracker BEHIND the sample; another channel count rebuilds the per-channel state, the
+                // coefficients (of the rate at construction) stay
+                rb_node_dev base{};
+                base.kind = RB_N_LIMIT, base.c_in = base.c_out = c0;
+                base.p.lim.threshold = e.f32[0], base.p.lim.knee = e.f32[1];
+                volatile float k8 = 8.0f * e.f32[1];
+                base.p.lim.inv_knee_8 = 1.0f / k8;
+                base.p.lim.attack = hostmath::duration_to_coefficient(e.ns[0], segs[0].r);
+                base.p.lim.release = hostmath::duration_to_coefficient(e.ns[1], segs[0].r);
+                nd.d = base;
+                nd.d.n_in = nd.d.n_out = n;
+                uint64_t from = 0;
+                rb_node_dev cur = base;
+                for (const SpanEvent& ev : span_events(segs)) {
+                    if (ev.at >= n || segs[ev.seg].c == cur.c_in) continue;
+                    nd.splits.push_back({from, ev.at - from, cur});
+                    from = ev.at, cur.c_in = cur.c_out = segs[ev.seg].c;
+                }
+                if (!nd.splits.empty()) nd.splits.push_back({from, n - from, cur});
+                break;
+            }
             case RB_FX_APPEND: return fail(RB_ERR_INVALID_ARGUMENT, "from_iter: APPEND only at the front of the chain");
-            default: return fail(RB_ERR_UNSUPPORTED, "from_iter: only amplify, speed, low_pass and high_pass follow a source whose format changes");
+            default: return fail(RB_ERR_UNSUPPORTED, "from_iter: amplify, speed, low_pass, high_pass, automatic_gain_control and limit follow a source whose format changes");
         }
         nd.level = ps.nodes.empty() ? 0u : ps.nodes.back().level + 1u;
         ps.nodes.push_back(nd);
@@ -1032,6 +1100,21 @@ extern "C" rb_status rb_batch_create(rb_context* ctx, uint16_t mixer_ch, uint32_
                         nd.aux0 = b->d_aux[0] ? b->d_aux[0] + ps.buf_off : nullptr;
                         nd.aux1 = b->d_aux[1] ? b->d_aux[1] + ps.buf_off : nullptr;
                         if (kind == RB_N_MIX2) nd.aux0 = const_cast<float*>(final_of(b->streams[(size_t)ps.nodes[j].other]));
+                        if (!ps.nodes[j].splits.empty()) {
+                            // from_iter: the adapter starts from scratch at a span boundary -- one node per run of samples
+                            for (const PlanNode::Split& sp : ps.nodes[j].splits) {
+                                if (sp.n == 0) continue;
+                                rb_node_dev r = sp.d;
+                                r.src = (const float*)nd.src + sp.off, r.dst = nd.dst + sp.off;
+                                r.aux0 = nd.aux0 ? nd.aux0 + sp.off : nullptr, r.aux1 = nd.aux1 ? nd.aux1 + sp.off : nullptr;
+                                r.n_in = r.n_out = sp.n;
+                                host_nodes.push_back(r);
+                                g.count++;
+                                g.max_n_out = std::max(g.max_n_out, r.n_out);
+                                g.max_channels = std::max(g.max_channels, r.c_in);
+                            }
+                            continue;
+                        }
                         host_nodes.push_back(nd);
                         g.count++;
                         g.max_n_out = std::max(g.max_n_out, nd.n_out);

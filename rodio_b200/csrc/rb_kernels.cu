@@ -335,6 +335,7 @@ __global__ void __launch_bounds__(AGC_THREADS) k_agc_pipe(const rb_node_dev* __r
     __shared__ float* s_out0[32];
     __shared__ float* s_out1[32];
     __shared__ uint64_t s_n[32];
+    __shared__ uint8_t s_al[32];     // every pointer of the row 16-byte aligned (a run of a from_iter source starts anywhere)
     __shared__ uint64_t s_max_n;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t s0 = blockIdx.x * 32;
@@ -349,6 +350,9 @@ __global__ void __launch_bounds__(AGC_THREADS) k_agc_pipe(const rb_node_dev* __r
             s_in1[lane] = PASS == 0 ? (const float*)nd.src - 8192 : nd.aux0;   // A: x[n-8192] (tiles below 8192 skip it), C: desired[n]
             s_out0[lane] = PASS == 0 ? nd.aux0 : nd.dst;
             s_out1[lane] = nd.aux1;
+            s_al[lane] = (((uintptr_t)nd.src | (uintptr_t)nd.dst | (uintptr_t)nd.aux0 | (uintptr_t)nd.aux1) & 15u) == 0;
+        } else {
+            s_al[lane] = 1;
         }
         s_n[lane] = n;
         for (int o = 16; o; o >>= 1) n = max(n, __shfl_xor_sync(0xffffffffu, n, o));
@@ -390,7 +394,7 @@ __global__ void __launch_bounds__(AGC_THREADS) k_agc_pipe(const rb_node_dev* __r
                     vx[j] = make_float4(0.f, 0.f, 0.f, 0.f), vo[j] = vx[j];
                     if (r >= 32) continue;
                     const uint64_t nr = s_n[r];
-                    if (n + 4 <= nr) {
+                    if (n + 4 <= nr && s_al[r]) {
                         vx[j] = __ldg(reinterpret_cast<const float4*>(s_in0[r] + n));
                         if (second_on) vo[j] = PASS == 0 ? __ldg(reinterpret_cast<const float4*>(s_in1[r] + n))
                                                          : *reinterpret_cast<const float4*>(s_in1[r] + n);
@@ -423,7 +427,7 @@ __global__ void __launch_bounds__(AGC_THREADS) k_agc_pipe(const rb_node_dev* __r
                     float4 a = *reinterpret_cast<const float4*>(base + (PASS == 0 ? AGC_ARR : 0) + r * ATS + 4 * lane);
                     const float4 b = *reinterpret_cast<const float4*>(base + (PASS == 0 ? 2 * AGC_ARR : AGC_ARR) + r * ATS + 4 * lane);
                     if (PASS == 2) a.x = mul(a.x, b.x), a.y = mul(a.y, b.y), a.z = mul(a.z, b.z), a.w = mul(a.w, b.w);
-                    if (n + 4 <= nr) {
+                    if (n + 4 <= nr && s_al[r]) {
                         *reinterpret_cast<float4*>(s_out0[r] + n) = a;
                         if (PASS == 0) *reinterpret_cast<float4*>(s_out1[r] + n) = b;
                     } else {
