@@ -29,3 +29,15 @@ timeout 120 python tools/hot_timing.py 4096 --skips > gpurun_out/r1_hot_timing.t
 # python -m pytest tests -m gpu -x -q -k "lanes or session"      (round 1: with RB_TEST_LANES=1, the gate of the time)
 # python tools/bench_configs.py lanes > gpurun_out/lanes_sweep.jsonl
 # ncu --set full --clock-control none --import-source on -k regex:k_fused_lanes -s 3 -c 1 -o gpurun_out/lanes_full python tools/bench_configs.py lanes
+
+# --- round 2: one script per GPU call, tools/r2_pass1.sh ... r2_pass37.sh (each writes gpurun_out/r2_passNN/; profiles/README.md says
+#     which file came from which pass).  The ones behind the second half of the round:
+#   bash tools/r2_pass17.sh      whole GPU suite + bench line + k_lerp_mix (first version) with a full ncu capture
+#   bash tools/r2_pass21.sh      k_lerp_mix as it is now: parity, memcheck, timing, ncu
+#   bash tools/r2_pass28.sh      RB_MIX_EXACT_ORDER on k_fused_hot (tagged-pair chain): parity + python tools/bench_configs.py exact gen
+#   bash tools/r2_pass29.sh      final-state evidence: suite, smoke(), bench, reference arm, launch list, ncu of the chain kernel and k_siggen
+#   bash tools/r2_pass31.sh      A/B of the default k_fused_hot launch against the kernel before the chain (needs a pre-chain build)
+#   gpurun --gpus 2 -- 'bash tools/r2_pass33.sh'; gpurun --gpus 2 -- 'bash tools/r2_pass34.sh'     the peer-memory exchange: tests, A/B against NCCL
+#   gpurun --gpus 4 -- 'bash tools/r2_pass35.sh 4'; gpurun --gpus 8 -- 'bash tools/r2_pass35.sh 8'
+#   bash tools/r2_pass36.sh      whole GPU suite + smoke() + bench line with the final code
+#   bash tools/r2_pass37.sh      AGC / limiter over from_iter sources, memcheck
