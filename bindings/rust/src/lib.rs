@@ -46,7 +46,45 @@ extern "C" {
     fn rb_batch_mix_len(b: *mut rb_batch, n: *mut u64) -> i32;
     fn rb_batch_render_mix(b: *mut rb_batch, out: *mut f32, max_samples: u64, written: *mut u64) -> i32;
     fn rb_speed_sample_rate(input_rate: u32, factor: f32) -> u32;
+    fn rb_batch_mix_device_ptr(b: *mut rb_batch, dptr: *mut *mut f32) -> i32;
+    fn rb_batch_read_mix(b: *mut rb_batch, offset: u64, out: *mut f32, n_samples: u64, written: *mut u64) -> i32;
+    // multi-GPU: one process per GPU; rank 0 makes the id, the host hands its 128 bytes to the others
+    fn rb_comm_unique_id(id: *mut rb_comm_id) -> i32;
+    fn rb_comm_init_rank(ctx: *mut rb_context, n_ranks: i32, rank: i32, id: *const rb_comm_id, out: *mut *mut rb_comm) -> i32;
+    fn rb_comm_destroy(comm: *mut rb_comm) -> i32;
+    fn rb_comm_transport(comm: *mut rb_comm, buf: *mut std::os::raw::c_char, cap: u64) -> i32;   // "p2p ..." (NVLink peer memory) or "nccl ... (why)"
+    fn rb_batch_render_mix_allreduce(batches: *mut *mut rb_batch, n_local: i32, comm: *mut rb_comm) -> i32;
 }
+#[repr(C)] pub struct rb_comm { _private: [u8; 0] }
+#[repr(C)] #[derive(Clone, Copy)] pub struct rb_comm_id { pub bytes: [u8; 128] }
+
+/// This rank's shard of a mixer that is spread over several GPUs: `render()` leaves the sum over ALL shards on every rank
+/// (src/mixer.rs:185-198 is the sum being distributed; shards in rank order = the sources' insertion order).
+pub struct GpuShard { batch: *mut rb_batch, comm: *mut rb_comm, mix_len: u64 }
+impl GpuShard {
+    /// `batch`: the rank's contiguous slice of the sources (already uploaded); `id` from rank 0's `rb_comm_unique_id`.
+    pub unsafe fn new(ctx: *mut rb_context, batch: *mut rb_batch, n_ranks: i32, rank: i32, id: &rb_comm_id) -> Result<Self, i32> {
+        let mut comm = std::ptr::null_mut();
+        let st = rb_comm_init_rank(ctx, n_ranks, rank, id, &mut comm);
+        if st != 0 { return Err(st); }
+        let mut mix_len = 0u64;
+        rb_batch_mix_len(batch, &mut mix_len);
+        Ok(Self { batch, comm, mix_len })
+    }
+    /// render + the cross-shard sum (one kernel over NVLink peer memory, or ncclAllReduce), then the mix on the host
+    pub fn render(&mut self) -> Result<Vec<Sample>, i32> {
+        let mut b = self.batch;
+        let st = unsafe { rb_batch_render_mix_allreduce(&mut b, 1, self.comm) };
+        if st != 0 { return Err(st); }
+        let mut out = vec![0f32; self.mix_len as usize];
+        let mut w = 0u64;
+        let st = unsafe { rb_batch_read_mix(self.batch, 0, out.as_mut_ptr(), self.mix_len, &mut w) };
+        if st != 0 { return Err(st); }
+        out.truncate(w as usize);
+        Ok(out)
+    }
+}
+impl Drop for GpuShard { fn drop(&mut self) { unsafe { rb_comm_destroy(self.comm); } } }
 
 pub const RB_FX_AMPLIFY: u32 = 1;
 pub const RB_FX_SPEED: u32 = 2;
