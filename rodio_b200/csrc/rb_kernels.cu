@@ -127,13 +127,13 @@ __device__ __forceinline__ float signal_value(uint32_t fn, float phase) {   // s
         default: return mul(2.0f, sub(phase, floorf(add(phase, 0.5f))));
     }
 }
-// A CTA owns SIG_GENS generators (8: the waveform -- ~100 instructions per sine -- is what the seven worker warps have to keep up
-// with; with 32 generators per CTA the first version spent 220 cycles per sample step on 32 SMs).  The phase is a serial f32 recurrence per generator (`phase = (phase + step).rem_euclid(1.0)`,
+// A CTA owns SIG_GENS generators (4: the waveform -- ~100 instructions per sine -- is what the seven worker warps have to keep up
+// with; with 32 generators per CTA the first version spent 220 cycles per sample step on 32 SMs, with 8 still 29).  The phase is a serial f32 recurrence per generator (`phase = (phase + step).rem_euclid(1.0)`,
 // signal_generator.rs:133: it drifts by design, so it cannot be computed from the sample index): warp 0, lane = generator, walks
 // it a tile ahead into shared memory; the other seven warps evaluate the waveform of the previous tile and store it with
 // consecutive threads on consecutive samples.  Latency-bound by the recurrence (3 dependent operations per sample) -- input
 // generation, outside every timed region.
-constexpr int SIG_TILE = 128, SIG_THREADS = 256, SIG_PITCH = SIG_TILE + 1, SIG_GENS = 8;
+constexpr int SIG_TILE = 256, SIG_THREADS = 256, SIG_PITCH = SIG_TILE + 1, SIG_GENS = 4;
 __global__ void __launch_bounds__(SIG_THREADS) k_siggen(const rb_node_dev* __restrict__ nodes, uint32_t n_nodes) {
     __shared__ float s_phase[2][SIG_GENS * SIG_PITCH];
     const uint32_t g0 = blockIdx.x * SIG_GENS, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
