@@ -780,7 +780,9 @@ static rb_status plan_stream(PlanStream& ps, uint16_t mixer_ch, uint32_t mixer_r
                 nd.d.p.take.total_ms_f = (float)(e.ns[0] / 1000000ull);
                 nd.d.p.take.fadeout = e.u32[0] ? 1u : 0u;
                 nd.d.n_out = count + pad;
-                tail_pad = pad;
+                // a take that does not cut (it outlasts its input) hands the padding of a take INSIDE it on: the span it reports is still
+                // the inner one's, so a UniformSourceIterator behind it stops in front of that padding all the same
+                tail_pad = (dps && take_n >= n) ? tail_pad : pad;
                 // TakeDuration::current_span_len: the inner span when it is shorter than what is left, else what is left
                 uint64_t so = span ? std::min<uint64_t>(span, take_n) : take_n;
                 nd.span_out = (uint32_t)std::min<uint64_t>(so, 0xFFFFFFFFull);

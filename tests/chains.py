@@ -75,6 +75,12 @@ CHAINS = {
     "pause_behind_filter": lambda: rb.TestSource(_stereo(4000, 67), 2, 44100).low_pass(300).pause_at(1001, 50).amplify(0.5),
     "pause_at_start_and_end": lambda: rb.SamplesBuffer(1, 48000, noise(700, 68)).pause_at(0, 10).pause_at(710, 7),
     "pause_then_mixer_conversion": lambda: rb.UniformSourceIterator(rb.TestSource(noise(3 * 900, 69), 3, 32000).pause_at(300, 40), 2, 48000),
+    # a take inside a take that outlasts it: the inner padding is handed on and still never pulled by a UniformSourceIterator
+    "take_inside_take_then_uniform": lambda: rb.UniformSourceIterator(
+        rb.SamplesBuffer(2, 44100, _stereo(1500, 70)).take_duration(rb.Duration.from_millis(26))
+        .take_duration(rb.Duration.from_millis(28)).fade_in(rb.Duration.from_millis(28)), 1, 48000),
+    "crossfade_of_a_taken_source": lambda: rb.TestSource(noise(1, 71), 1, 48000).amplify(0.5).take_crossfade_with(
+        rb.SamplesBuffer(2, 44100, _stereo(1500, 72)).take_duration(rb.Duration.from_millis(26)), rb.Duration.from_millis(28)),
     "crossfade_other_format": lambda: rb.SamplesBuffer(2, 44100, _stereo(30000, 65)).take_crossfade_with(
         rb.SamplesBuffer(1, 22050, noise(9000, 66)), rb.Duration.from_millis(150)).amplify(0.7),
 }

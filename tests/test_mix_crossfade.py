@@ -114,3 +114,35 @@ def test_crossfade_in_a_mixer_with_other_sources(ctx):
         assert b.kernel_family == -1
         got = b.render_mix()
     assert np.max(np.abs(got - want)) <= 1e-5 * np.max(np.abs(want))
+
+
+def test_planner_of_random_mixes_against_the_literal_iterators():
+    """Closed forms for Source::mix / take_crossfade_with (the second input converted to the first one's format, the longer one
+    wins; take_duration's frame padding is never pulled by Mix's UniformSourceIterators) against the oracle's pull iterators."""
+    rng = np.random.default_rng(4242)
+
+    def rand_src(seed):
+        ch = int(rng.integers(1, 4))
+        rate = int(rng.choice([8000, 22050, 32000, 44100, 48000]))
+        n = int(rng.choice([0, ch, 3 * ch, 200 * ch, 1500 * ch]))      # whole frames (the C ABI refuses anything else)
+        x = noise(n, seed)
+        s = rb.SamplesBuffer(ch, rate, x) if rng.integers(0, 2) else rb.TestSource(x, ch, rate)
+        k = int(rng.integers(0, 4))
+        if k == 1:
+            s = s.amplify(0.5)
+        elif k == 2:
+            s = s.low_pass(500)
+        elif k == 3:
+            s = s.take_duration(rb.Duration.from_millis(int(rng.integers(1, 40))))
+        return s
+
+    for t in range(200):
+        a, b = rand_src(9000 + 2 * t), rand_src(9001 + 2 * t)
+        src = a.mix(b) if t % 3 else a.take_crossfade_with(b, rb.Duration.from_millis(int(rng.integers(1, 30))))
+        if t % 5 == 0:
+            src = src.amplify(0.9)
+        want = _chain(src)
+        for mixer in ((1, 48000), (2, 44100)):
+            out_len, ch, rate, chain_len = rb.plan(src, *mixer)
+            assert chain_len == want.size, (t, chain_len, want.size)
+            assert out_len == oracle.chain_uniform(to_oracle(src), *mixer).size, (t, mixer)
