@@ -9,9 +9,8 @@ import rodio_b200 as rb
 from helpers import noise, to_oracle
 
 
-def test_random_chains_plan_like_the_literal_iterators():
-    rng = np.random.default_rng(20260923)
-
+def random_chain(rng, sd, depth=0):
+    """(source, description): a random adapter chain drawn from `rng`."""
     def base(sd):
         k=int(rng.integers(0,3)); ch=int(rng.integers(1,4)); rate=int(rng.choice([8000,22050,32000,44100,48000]))
         n=int(rng.choice([0,ch,3*ch,200*ch,1500*ch,12000*ch]))
@@ -19,7 +18,7 @@ def test_random_chains_plan_like_the_literal_iterators():
         if k==1: return rb.TestSource(noise(n,sd),ch,rate), f"TS{ch}/{rate}/{n}"
         f=float(rng.choice([50.0,440.0,9000.0])); m=int(rng.choice([0,1,500,5000]))
         return rb.SignalGenerator(rate,f,int(rng.integers(0,4))).take(m), f"GEN{rate}/{f}/{m}"
-    def chain(sd, depth=0):
+    if True:
         s,d=base(sd)
         for _ in range(int(rng.integers(0,4))):
             k=int(rng.integers(0,10))
@@ -38,12 +37,16 @@ def test_random_chains_plan_like_the_literal_iterators():
             elif k==8:
                 c=int(rng.integers(1,4)); r=int(rng.choice([22050,44100,48000])); s=rb.UniformSourceIterator(s,c,r); d+=f".uni{c}/{r}"
             elif k==9 and depth<2:
-                o,do=chain(sd+1000,depth+1); s=s.mix(o); d+=f".mix({do})"
+                o,do=random_chain(rng,sd+1000,depth+1); s=s.mix(o); d+=f".mix({do})"
         return s,d
 
+
+
+def test_random_chains_plan_like_the_literal_iterators():
+    rng = np.random.default_rng(20260923)
     checked = refused = 0
     for t in range(500):
-        s, d = chain(7 * t)
+        s, d = random_chain(rng, 7 * t)
         want = oracle.chain(to_oracle(s))[0]
         for mixer in ((1, 48000), (2, 44100)):
             try:
@@ -55,3 +58,32 @@ def test_random_chains_plan_like_the_literal_iterators():
             assert out_len == oracle.chain_uniform(to_oracle(s), *mixer).size, (d, mixer)
             checked += 1
     assert checked > 900 and refused < 20, (checked, refused)
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_random_chains_bit_exact_on_the_device(ctx):
+    """The same random chains rendered by the CUDA path (general path, exact order) into two different mixers: bit for bit what
+    the oracle's MixerSource pulls (NaNs -- a filter driven above its Nyquist rate -- compare as NaNs)."""
+    from helpers import assert_bit_exact
+    from rodio_b200 import capi
+    rng = np.random.default_rng(777)
+    done = 0
+    for t in range(120):
+        s, d = random_chain(rng, 50000 + 7 * t)
+        mixer = ((1, 48000), (2, 44100), (3, 32000))[t % 3]
+        want = oracle.mixer([to_oracle(s)], *mixer)
+        try:
+            with rb.Batch([s], *mixer, flags=capi.RB_MIX_EXACT_ORDER, ctx=ctx) as b:
+                b.upload_all()
+                got = b.render_mix()
+        except rb.RodioB200Error:
+            continue                                     # a combination the block path refuses (documented RB_ERR_UNSUPPORTED)
+        assert got.shape == want.shape, (d, got.shape, want.shape)
+        nan = np.isnan(want)
+        assert np.array_equal(np.isnan(got), nan), d
+        assert_bit_exact(np.where(nan, np.float32(0), got), np.where(nan, np.float32(0), want), d)
+        done += 1
+    assert done > 100
