@@ -167,8 +167,8 @@ enum {
                                        src/mixer.rs:185-198 on one GPU).  resample -> [low/high_pass] -> [amplify] -> mix batches
                                        keep their fused kernel: k_fused_hot hands the running sum of every tile from CTA to
                                        CTA (the whole mix of 4096 sources bit-identical to the reference's, 1.3 ms against 0.85 ms
-                                       for the default grouping), small filter-free batches use k_lerp_mix in one group; every
-                                       other chain takes the general path.  Default = ordered partial sums over
+                                       for the default grouping), so does the effect-chain kernel (cfg4: 1.8 ms), small filter-free
+                                       batches use k_lerp_mix in one group; every other chain takes the general path.  Default = ordered partial sums over
                                        contiguous groups of sources (rows of a fused CTA; runs of a short, wide
                                        mix of >= 256 sources) combined in group order: deterministic,
                                        <= 1e-5 * peak, and still the sequential sum for <= 148 fused streams  */

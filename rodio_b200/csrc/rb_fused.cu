@@ -1252,7 +1252,7 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
     // RB_MIX_EXACT_ORDER: the general path, except for filter-free resample -> gain -> mix batches, which k_lerp_mix sums in
     // one sequential chain per timeline position -- the reference's order (see below)
     const bool exact_order = (flags & RB_MIX_EXACT_ORDER) != 0;
-    if (!exact_order) {   // spatial / reverb / AGC chains have a kernel of their own
+    {   // spatial / reverb / AGC chains have a kernel of their own (with RB_MIX_EXACT_ORDER: its chain form, or nothing)
         rb_fx_plan* fx = nullptr;
         cudaError_t e = rb_fx_try_create(streams, n_streams, mixer_channels, d_out, mix_len, flags, st, &fx);
         if (e != cudaSuccess) return e;
@@ -1489,13 +1489,13 @@ bool rb_fused_partial_rows(const rb_fused_plan* p, const float** partial, uint32
     return true;
 }
 uint32_t rb_fused_launch_count(const rb_fused_plan* p) {
-    if (p->fx) return 2u;
+    if (p->fx) return rb_fx_chain(p->fx) ? 1u : 2u;
     if (p->lanes) return rb_lanes_launch_count(p->lanes);
     return (p->single_cta_direct || p->chain) ? 1u : 2u;
 }
 int rb_fused_kind(const rb_fused_plan* p) { return p->fx ? 5 : p->lanes ? rb_lanes_kind(p->lanes) : (p->hot ? 1 : 0); }
 uint32_t rb_fused_mix_group(const rb_fused_plan* p) {
-    return p->fx ? 4u : p->lanes ? rb_lanes_mix_group(p->lanes) : p->chain ? 0u : p->args.rows_per_cta;   // chain: one sequential sum
+    return p->fx ? (rb_fx_chain(p->fx) ? 0u : 4u) : p->lanes ? rb_lanes_mix_group(p->lanes) : p->chain ? 0u : p->args.rows_per_cta;   // chain: one sequential sum
 }
 
 #ifdef RB_HOT_TIMING

@@ -47,3 +47,4 @@ cudaError_t rb_fx_try_create(const rb_fused_stream* streams, size_t n_streams, u
                              uint32_t flags, cudaStream_t st, rb_fx_plan** out);
 cudaError_t rb_fx_run(rb_fx_plan* plan, cudaStream_t st);
 void rb_fx_destroy(rb_fx_plan* plan);
+bool rb_fx_chain(const rb_fx_plan* plan);   // RB_MIX_EXACT_ORDER: the running sum handed from CTA to CTA (one launch, one sequential sum)

@@ -33,7 +33,9 @@
 // chains are latency-bound and gain nothing from sharing an SM, the parallel stages need the SMs.  The 8192-entry ring of
 // squares is not stored: the square that leaves the window is recomputed from the input, bit-identical (as k_agc_pipe does).
 // Mixer sum: sequential over the 4 streams of a CTA from +0.0, the partial rows added in CTA order (rb_batch_mix_group = 4):
-// the tolerance class of the other fused kernels; per-stream samples are bit-exact (RB_MIX_EXACT_ORDER keeps the general path).
+// the tolerance class of the other fused kernels; per-stream samples are bit-exact.  RB_MIX_EXACT_ORDER: k_fused_fx<C, true> hands the
+// running sum of every tile from CTA to CTA (one sequential sum over all streams: the reference's, bit for bit; streams that join late
+// keep the general path).
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -73,9 +75,24 @@ struct FxArgs {
     uint32_t n_rows;
     uint32_t channels;    // 1 or 2 (source == mixer)
     uint32_t has_cv, has_echo, has_agc, has_lim;
-    float* partial;       // [n_ctas][mix_len]
+    float* partial;       // [n_ctas][mix_len]  (chain: [n_ctas][mix_len] of (value, tag) pairs)
     uint64_t mix_len;
+    // RB_MIX_EXACT_ORDER (k_fused_fx<C, true>): the running sum of every tile is handed from CTA to CTA like in k_fused_hot
+    // (rb_fused.cu, "Chain mode"): tickets order the chain, (value, tag) pairs are the hand-over, the last CTA writes `out`
+    float* out;
+    uint32_t* ticket;
+    uint32_t epoch, pad_;
 };
+
+__device__ __forceinline__ uint2 fx_ld_pair(const uint2* p) {      // one 64-bit relaxed access: single-copy atomic
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return make_uint2((uint32_t)v, (uint32_t)(v >> 32));
+}
+__device__ __forceinline__ void fx_st_pair(uint2* p, float v, uint32_t tag) {
+    const unsigned long long w = (unsigned long long)__float_as_uint(v) | ((unsigned long long)tag << 32);
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
 
 // e[n] of one stream: channel volume, then the echo (mix.rs:47-52: both / whichever exists)
 template <int C>
@@ -95,13 +112,19 @@ __device__ __forceinline__ float fx_e(const FxRow& r, bool has_cv, bool has_echo
     return n < r.n_in ? add(fx_cv<C>(r, has_cv, n), s2) : s2;
 }
 
-template <int C>
+template <int C, bool CHAIN>
 __global__ void __launch_bounds__(FX_THREADS) k_fused_fx(FxArgs a) {
     extern __shared__ __align__(16) float fx_sm[];   // [FX_SLOTS][4][FX_R][FX_TS]
     __shared__ FxRow s_rows[FX_R];
     __shared__ uint64_t s_max_n;
+    __shared__ uint32_t s_cta;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t s0 = blockIdx.x * FX_R;
+    if (CHAIN) {   // the CTA's place in the chain is the order in which the CTAs start
+        if (threadIdx.x == 0) s_cta = atomicAdd(a.ticket, 1u) - a.epoch * gridDim.x;
+        __syncthreads();
+    }
+    const uint32_t cta = CHAIN ? s_cta : blockIdx.x;
+    const uint32_t s0 = cta * FX_R;
     const uint32_t cnt = min((uint32_t)FX_R, a.n_rows - s0);
     if (threadIdx.x < FX_R) {
         FxRow r;
@@ -113,7 +136,7 @@ __global__ void __launch_bounds__(FX_THREADS) k_fused_fx(FxArgs a) {
     if (threadIdx.x == 0) {
         uint64_t m = 0;
         for (uint32_t i = 0; i < cnt; i++) m = max(m, s_rows[i].n_out);
-        s_max_n = m;
+        s_max_n = CHAIN ? a.mix_len : m;      // chain: every CTA hands the running sum on for every tile of the timeline (mix_start = 0)
     }
     __syncthreads();
     const uint32_t n_tiles = (uint32_t)((s_max_n + FX_T - 1) / FX_T);
@@ -124,7 +147,15 @@ __global__ void __launch_bounds__(FX_THREADS) k_fused_fx(FxArgs a) {
     const int worker = warp == 0 ? 0 : warp == 4 ? 1 : warp == 8 ? 2 : warp == 1 ? 3 : warp == 5 ? 4 : warp == 9 ? 5 : warp == 10 ? 6 : warp == 12 ? 7 : -1;
     const bool chain_p = warp == 2, chain_s = warp == 6, chain_g = warp == 3, chain_l = warp == 14;
     const uint64_t mix_start = s_rows[0].mix_start;      // equal for the CTA's streams (planner)
-    float* const prow = a.partial + (uint64_t)blockIdx.x * a.mix_len + mix_start;
+    float* const prow = a.partial + (uint64_t)cta * a.mix_len + mix_start;
+    const uint2* carry_row = nullptr;      // chain: the row of (value, tag) pairs the CTA in front wrote
+    uint2* tagged_row = nullptr;           // chain: this CTA's row (the last CTA writes a.out instead)
+    if (CHAIN) {
+        uint2* rows2 = reinterpret_cast<uint2*>(a.partial);
+        if (cta + 1 != gridDim.x) tagged_row = rows2 + (uint64_t)cta * a.mix_len;
+        if (cta > 0) carry_row = rows2 + (uint64_t)(cta - 1) * a.mix_len;
+    }
+    const int chain_out = !CHAIN ? -1 : warp == 7 ? 0 : warp == 11 ? 1 : warp == 13 ? 2 : -1;   // the mixer sum moves to the idle warps
 
     // chain state, lane = stream
     float peak = 0.0f, sum = 0.0f, gain = 1.0f;
@@ -215,7 +246,7 @@ __global__ void __launch_bounds__(FX_THREADS) k_fused_fx(FxArgs a) {
                                                                         limiter_db(ev.z, r.l_thr, r.l_knee, r.l_ik8), limiter_db(ev.w, r.l_thr, r.l_knee, r.l_ik8));
             }
             // ---- out, tile `it - out_lag`: the last factor, summed over the CTA's streams; one position per worker lane ----
-            if (it >= out_lag) {
+            if (!CHAIN && it >= out_lag) {
                 const float* base = fx_sm + ((it - out_lag) % FX_SLOTS) * FX_SLOT;
                 const uint32_t pos = 32 * (uint32_t)worker + lane;
                 const uint64_t n = (uint64_t)(it - out_lag) * FX_T + pos;
@@ -230,6 +261,35 @@ __global__ void __launch_bounds__(FX_THREADS) k_fused_fx(FxArgs a) {
                         acc = add(acc, y), any = true;
                     }
                 if (any && mix_start + n < a.mix_len) prow[n] = acc;
+            }
+        } else if (CHAIN && chain_out >= 0) {
+            // ---- chain mode, out, tile `it - out_lag`: start from the running sum of the CTA in front, add this CTA's streams in
+            // insertion order, hand the sum on (three otherwise idle warps, 96 lanes over the 256 positions of a tile) ----
+            if (it >= out_lag) {
+                const float* base = fx_sm + ((it - out_lag) % FX_SLOTS) * FX_SLOT;
+                const uint32_t tag = a.epoch * (n_tiles + out_lag + 1u) + (it - out_lag) + 1u;
+                for (uint32_t pos = 32 * (uint32_t)chain_out + lane; pos < (uint32_t)FX_T; pos += 96) {
+                    const uint64_t n = (uint64_t)(it - out_lag) * FX_T + pos;
+                    if (n >= a.mix_len) continue;
+                    float acc = 0.0f;
+                    if (carry_row) {
+                        uint2 w;
+                        uint32_t spins = 0;
+                        while ((w = fx_ld_pair(carry_row + n)).y != tag)
+                            if (++spins > (1u << 22)) __trap();      // the CTA in front never arrived: fail loudly
+                        acc = __uint_as_float(w.x);
+                    }
+#pragma unroll
+                    for (uint32_t s = 0; s < FX_R; s++)
+                        if (n < s_rows[s].n_out) {
+                            float y = base[s * FX_TS + pos];
+                            if (has_lim) y = mul(y, db_to_linear(-base[FX_ARR + s * FX_TS + pos]));
+                            else if (has_agc) y = mul(y, base[2 * FX_ARR + s * FX_TS + pos]);
+                            acc = add(acc, y);
+                        }
+                    if (tagged_row) fx_st_pair(tagged_row + n, acc, tag);
+                    else a.out[n] = acc;
+                }
             }
         } else if (has_agc && it >= 1 && it - 1 < n_tiles && (chain_p || chain_s)) {
             // ---- chains P and S, tile `it - 1`, lane = stream ----
@@ -342,6 +402,9 @@ struct rb_fx_plan {
     float* d_partial = nullptr;
     float* d_out = nullptr;
     uint32_t n_ctas = 0;
+    bool chain = false;          // RB_MIX_EXACT_ORDER: k_fused_fx<C, true>, no k_fx_sum_partials
+    uint32_t* d_ticket = nullptr;
+    uint32_t epoch = 0;
 };
 
 // Shape: every stream f32 with the mixer's channel count (1 or 2) and no conversion, nodes = [CHANVOL]? [ECHO]? [AGC]? [LIMIT]? with
@@ -350,7 +413,8 @@ struct rb_fx_plan {
 cudaError_t rb_fx_try_create(const rb_fused_stream* streams, size_t n_streams, uint16_t mixer_channels, float* d_out, uint64_t mix_len,
                              uint32_t flags, cudaStream_t st, rb_fx_plan** out) {
     *out = nullptr;
-    if (n_streams == 0 || mix_len == 0 || (flags & RB_MIX_EXACT_ORDER) || (mixer_channels != 1 && mixer_channels != 2)) return cudaSuccess;
+    if (n_streams == 0 || mix_len == 0 || (mixer_channels != 1 && mixer_channels != 2)) return cudaSuccess;
+    const bool exact = (flags & RB_MIX_EXACT_ORDER) != 0;
     std::vector<FxRow> rows(n_streams);
     uint32_t has_cv = 0, has_echo = 0, has_agc = 0, has_lim = 0;
     for (size_t i = 0; i < n_streams; i++) {
@@ -388,31 +452,46 @@ cudaError_t rb_fx_try_create(const rb_fused_stream* streams, size_t n_streams, u
         if (i == 0) has_cv = cv, has_echo = echo, has_agc = agc, has_lim = lim;
         else if (cv != has_cv || echo != has_echo || agc != has_agc || lim != has_lim) return cudaSuccess;
         if (i % FX_R && r.mix_start != rows[i - 1].mix_start) return cudaSuccess;
+        if (exact && r.mix_start != 0) return cudaSuccess;      // the chain walks one common timeline: late joiners keep the general path
     }
     auto p = new rb_fx_plan;
     p->n_ctas = (uint32_t)((n_streams + FX_R - 1) / FX_R);
     p->d_out = d_out;
-    const size_t partial_bytes = (size_t)p->n_ctas * mix_len * sizeof(float);
+    p->chain = exact && p->n_ctas > 1;
+    if (exact && !p->chain) {      // one CTA: its partial row is the sequential sum already; keep the plain launch
+    }
+    const size_t partial_bytes = (size_t)p->n_ctas * mix_len * (p->chain ? sizeof(uint2) : sizeof(float));
     cudaError_t e = cudaMalloc(&p->d_rows, n_streams * sizeof(FxRow));
+    if (e == cudaSuccess && p->chain) e = cudaMalloc(&p->d_ticket, sizeof(uint32_t));
+    if (e == cudaSuccess && p->chain) e = cudaMemsetAsync(p->d_ticket, 0, sizeof(uint32_t), st);
     if (e == cudaSuccess) e = cudaMalloc(&p->d_partial, partial_bytes);
     if (e == cudaSuccess) e = cudaMemsetAsync(p->d_partial, 0, partial_bytes, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_rows, rows.data(), n_streams * sizeof(FxRow), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused_fx<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FX_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused_fx<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FX_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused_fx<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FX_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused_fx<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FX_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused_fx<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FX_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused_fx<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FX_SMEM);
     if (e != cudaSuccess) {
         rb_fx_destroy(p);
         return e;
     }
     p->args.rows = p->d_rows, p->args.n_rows = (uint32_t)n_streams, p->args.channels = mixer_channels;
     p->args.has_cv = has_cv, p->args.has_echo = has_echo, p->args.has_agc = has_agc, p->args.has_lim = has_lim, p->args.partial = p->d_partial, p->args.mix_len = mix_len;
+    p->args.out = d_out, p->args.ticket = p->d_ticket;
     *out = p;
     return cudaSuccess;
 }
 
 cudaError_t rb_fx_run(rb_fx_plan* p, cudaStream_t st) {
-    if (p->args.channels == 2) k_fused_fx<2><<<p->n_ctas, FX_THREADS, FX_SMEM, st>>>(p->args);
-    else k_fused_fx<1><<<p->n_ctas, FX_THREADS, FX_SMEM, st>>>(p->args);
+    if (p->chain) {
+        p->args.epoch = p->epoch++;      // tickets and tags of this render
+        if (p->args.channels == 2) k_fused_fx<2, true><<<p->n_ctas, FX_THREADS, FX_SMEM, st>>>(p->args);
+        else k_fused_fx<1, true><<<p->n_ctas, FX_THREADS, FX_SMEM, st>>>(p->args);
+        return cudaGetLastError();
+    }
+    if (p->args.channels == 2) k_fused_fx<2, false><<<p->n_ctas, FX_THREADS, FX_SMEM, st>>>(p->args);
+    else k_fused_fx<1, false><<<p->n_ctas, FX_THREADS, FX_SMEM, st>>>(p->args);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     uint64_t blocks = (p->args.mix_len + 255) / 256;
@@ -425,5 +504,7 @@ void rb_fx_destroy(rb_fx_plan* p) {
     if (!p) return;
     cudaFree(p->d_rows);
     cudaFree(p->d_partial);
+    cudaFree(p->d_ticket);
     delete p;
 }
+bool rb_fx_chain(const rb_fx_plan* p) { return p && p->chain; }

@@ -177,6 +177,7 @@ cudaError_t rb_fused_try_create(const rb_fused_stream* streams, size_t n_streams
 }
 cudaError_t rb_fused_run(rb_fused_plan* p, cudaStream_t st, bool) { return rb_lanes_run(p->lanes, st); }
 bool rb_fused_partial_rows(const rb_fused_plan*, const float**, uint32_t*, uint64_t*) { return false; }
+bool rb_fx_chain(const rb_fx_plan*) { return false; }
 void rb_fused_destroy(rb_fused_plan* p) {
     if (p) rb_lanes_destroy(p->lanes), delete p;
 }

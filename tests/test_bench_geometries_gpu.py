@@ -414,3 +414,33 @@ def test_exact_order_filter_free_4096(ctx):
     """resample -> amplify -> mix with RB_MIX_EXACT_ORDER at 4096 streams: the chain on k_fused_hot<1, false> (below 1024 streams:
     k_lerp_mix in one group, tests above)."""
     _check_exact_chain(ctx, _cfg3(4096, 3000, lp=None, seed=38000), 1)
+
+
+def test_exact_order_effect_chain_cfg4(ctx):
+    """BASELINE cfg4 with RB_MIX_EXACT_ORDER alone: k_fused_fx in its chain form (the running sum handed from CTA to CTA, one launch) --
+    the whole stereo mix bit-identical to the reference's sequential mixer; also with a limiter behind the AGC within the limiter's
+    tolerance, ragged lengths, and a render repeated (tickets and tags come round)."""
+    n, frames = 512, 2400 + 2400
+    srcs = cfg4_sources(n, frames)
+    want = oracle.mixer([to_oracle(s) for s in srcs], 2, 48000)
+    with rb.Batch(srcs, 2, 48000, flags=capi.RB_MIX_EXACT_ORDER, ctx=ctx) as b:
+        assert b.kernel_family == 5 and b.mix_group == 0 and b.launches_per_render == 1, (b.kernel_family, b.mix_group, b.launches_per_render)
+        b.upload_all()
+        got = b.render_mix()
+        again = b.render_mix()
+    assert_bit_exact(got, want, "cfg4, exact order on k_fused_fx")
+    assert_bit_exact(again, want, "cfg4, exact order, second render")
+    rng = np.random.default_rng(23)
+    ragged = [rb.TestSource(noise(2 * int(rng.integers(1, 3000)), 95000 + i), 2, 48000).reverb(rb.Duration.from_millis(10), 0.4)
+              .automatic_gain_control() for i in range(203)]
+    want = oracle.mixer([to_oracle(s) for s in ragged], 2, 48000)
+    with rb.Batch(ragged, 2, 48000, flags=capi.RB_MIX_EXACT_ORDER, ctx=ctx) as b:
+        assert b.kernel_family == 5 and b.mix_group == 0
+        b.upload_all()
+        assert_bit_exact(b.render_mix(), want, "ragged effect chains, exact order")
+    lim = [s.limit() for s in srcs[:100]]
+    want = oracle.mixer([to_oracle(s) for s in lim], 2, 48000)
+    with rb.Batch(lim, 2, 48000, flags=capi.RB_MIX_EXACT_ORDER, ctx=ctx) as b:
+        assert b.kernel_family == 5
+        b.upload_all()
+        assert_close_peak(b.render_mix(), want, 1e-5, "limiter behind the AGC, exact order")

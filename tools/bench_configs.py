@@ -134,6 +134,12 @@ def main():
         time_batch("cfg3 4096 x 2s, RB_MIX_EXACT_ORDER (running sum handed from CTA to CTA)", srcs, (1, 48000), flags=rb.capi.RB_MIX_EXACT_ORDER, steps=10)
         srcs = [rb.UniformSourceIterator(rb.TestSource(x, 1, 44100), 1, 48000).amplify(1.2) for _ in range(4096)]
         time_batch("no filter 4096 x 2s, RB_MIX_EXACT_ORDER (k_lerp_mix, one group)", srcs, (1, 48000), flags=rb.capi.RB_MIX_EXACT_ORDER, steps=5)
+    if "exact4" in which:
+        S, frames = 512, 48000
+        srcs = [rb.Spatial(rb.TestSource(z(2 * frames), 2, 48000), [float(s % 7 - 3), 1.0, 0.0], [-1, 0, 0], [1, 0, 0])
+                .reverb(rb.Duration.from_millis(50), 0.3).automatic_gain_control() for s in range(S)]
+        time_batch("cfg4 512 stereo, default order [k_fused_fx]", srcs, (2, 48000), steps=5)
+        time_batch("cfg4 512 stereo, RB_MIX_EXACT_ORDER [k_fused_fx, chain]", srcs, (2, 48000), flags=rb.capi.RB_MIX_EXACT_ORDER, steps=5)
     if "gen" in which:
         srcs = [rb.SineWave(min(110.0 * 2.0 ** (s / 128.0), 19999.0)).take(48000 * 10) for s in range(1024)]
         time_batch("cfg2 from generators: 1024 SineWave x 10 s generated and mixed on the device", srcs, (1, 48000), steps=3, fill=None)
