@@ -439,6 +439,11 @@ def run_ours(args):
               "latency-bound: three serial recurrences per stream, 100 800 steps of >= 22 cycles",
               [rb.Spatial(rb.TestSource(z(2 * 48000), 2, MIX_RATE), [float(s % 7 - 3), 1.0, 0.0], [-1, 0, 0], [1, 0, 0])
                .reverb(rb.Duration.from_millis(50), 0.3).automatic_gain_control() for s in range(512)], 2, 0, 3, FAM)
+        timed("cfg4_exact_order", "cfg4 with RB_MIX_EXACT_ORDER: k_fused_fx hands the running sum from CTA to CTA -- the whole stereo mix is the "
+              "reference's sequential sum bit for bit (tests/test_bench_geometries_gpu.py::test_exact_order_effect_chain_cfg4)",
+              [rb.Spatial(rb.TestSource(z(2 * 48000), 2, MIX_RATE), [float(s % 7 - 3), 1.0, 0.0], [-1, 0, 0], [1, 0, 0])
+               .reverb(rb.Duration.from_millis(50), 0.3).automatic_gain_control() for s in range(512)], 2, rb.capi.RB_MIX_EXACT_ORDER, 3,
+              {5: "k_fused_fx<2, CHAIN> (one launch)"})
         one1 = z(IN_RATE)
         sweep = {}
         for n3 in (1, 16, 256, 1024, 4096, 16384, 65536):
