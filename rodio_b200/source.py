@@ -862,7 +862,9 @@ class Player:
     stoppable (src/player.rs:122-166) and samples the controls every 5 ms of audio.  On blocks the controls are
     read when a source is appended: its chain becomes `source.speed(speed).amplify(volume)` and it is queued
     behind the sources appended before it (src/queue.rs: one source after the other, each converted to the
-    mixer's format on its own).  This class renders offline; the controls WHILE playing live on a `Session`: `follow` (append),
+    mixer's format on its own); `pause()` / `play()` at known positions are the `pauses` of `append` (Pausable sits between the
+    speed and the volume, player.rs:122-128: the source and its filters are not pulled while paused, whole frames of zeros go
+    out -- RB_FX_PAUSE).  This class renders offline; the controls WHILE playing live on a `Session`: `follow` (append),
     `set_volume` (the Amplify in front of the mixer's conversion, per pulled frame), pausing = pushing zero frames, stop / skip =
     end_of_stream (examples/live_player.c).  Seeking is a control-plane feature of the decoders and out of
     scope."""
@@ -892,10 +894,16 @@ class Player:
         """Player::set_speed (src/player.rs:203-207): rescales the reported sample rate like Source::speed."""
         self._speed = float(value)
 
-    def append(self, source: Source):
-        """Player::append — src/player.rs:104-170."""
+    def append(self, source: Source, pauses: Sequence[Tuple[int, int]] = ()):
+        """Player::append — src/player.rs:104-170.  `pauses`: (sample of the source at which Player::pause() is observed, frames of
+        silence until Player::play()), in increasing order of the sample -- positions count the source's own samples."""
         s = self._mixer._s
-        chain = source.speed(self._speed).amplify(self._volume)
+        chain = source.speed(self._speed)
+        shift = 0
+        for at, frames in pauses:                       # a later pause sees the zeros of the earlier ones in front of it
+            chain = chain.pause_at(int(at) + shift, int(frames))
+            shift += int(frames) * chain.channels()
+        chain = chain.amplify(self._volume)
         n = plan(chain, s.channels, s.rate)[0]
         start = (self._next_start + s.channels - 1) // s.channels * s.channels
         s.sources.append(chain)
