@@ -282,3 +282,27 @@ def test_streams_plan_survives_random_descriptor_graphs(built):
                 if descs[i].mix_start == capi.RB_MIX_START_CONSUMED:
                     assert out_len.value == 0
     assert ok > 100      # the generator does produce valid arrays too
+
+
+def test_enum_values_agree_across_header_mirrors_and_oracle(built):
+    """RB_FX_* / RB_FMT_* / RB_SIGNAL_* / flag values: include/rodio_b200.h is the definition; the ctypes mirror, the Rust binding's
+    constants and the oracle's own enum (declared independently) must say the same numbers."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "rodio_b200.h")).read()
+    values = {m.group(1): int(m.group(2)) for m in re.finditer(r"\b(RB_(?:FX|FMT|SIGNAL)_[A-Z0-9_]+)\s*=\s*(\d+)", hdr)}
+    flags = {m.group(1): 1 << int(m.group(2)) for m in re.finditer(r"\b(RB_[A-Z_]+)\s*=\s*1u\s*<<\s*(\d+)", hdr)}
+    assert len(values) >= 29 and "RB_FX_PAUSE" in values and "RB_MIX_EXACT_ORDER" in flags
+    for name, v in {**values, **flags}.items():
+        if hasattr(capi, name):
+            assert getattr(capi, name) == v, name
+    for name in [n for n in values if n.startswith("RB_FX_")]:
+        assert hasattr(capi, name), f"{name} missing from rodio_b200/_capi.py"
+    rust = open(os.path.join(root, "bindings", "rust", "src", "lib.rs")).read()
+    for m in re.finditer(r"pub const (RB_FX_[A-Z_]+): u32 = (\d+);", rust):
+        assert values[m.group(1)] == int(m.group(2)), m.group(1)
+    cap = open(os.path.join(root, "oracle", "rodio_oracle_capi.cpp")).read()
+    m = re.search(r"enum \{ FX_AMPLIFY = 1,([^}]*)\}", cap)
+    names = ["FX_AMPLIFY"] + [t.strip() for t in m.group(1).replace("\n", " ").split(",") if t.strip()]
+    for i, n in enumerate(names, start=1):
+        assert values["RB_" + n] == i, n
